@@ -1,0 +1,477 @@
+"""ctypes mirror of include/b2q.h (the C ABI of the path) plus small builders for its POD inputs.
+
+The structs here are field-for-field the ones declared in ``include/b2q.h``; the enum values are the reference's
+own (Shared/sqltypes.h:65-99, Shared/sqldefs.h:31-40,76-90, QueryEngine/enums.h:54-60).  ``tests/test_abi.py``
+checks sizes/offsets against the C compiler's view of the header.
+
+Nothing in this module touches a GPU; it is shared by the product host wrapper (``executor.py``) and by the test
+oracle's loader (``tests/oracle_lib.py``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+# ---- SQLTypes subset -------------------------------------------------------------------------------------
+kINT, kSMALLINT, kFLOAT, kDOUBLE, kBIGINT, kTINYINT = 6, 7, 8, 9, 12, 22
+# ---- SQLOps subset ---------------------------------------------------------------------------------------
+kEQ, kNE, kLT, kGT, kLE, kGE, kAND, kOR = 0, 2, 3, 4, 5, 6, 7, 8
+# ---- SQLAgg subset ---------------------------------------------------------------------------------------
+kAVG, kMIN, kMAX, kSUM, kCOUNT = 0, 1, 2, 3, 4
+# ---- QueryDescriptionType --------------------------------------------------------------------------------
+GroupByPerfectHash, GroupByBaselineHash, Projection, TableFunction, NonGroupedAggregate, Estimator = range(6)
+
+# ---- error codes -----------------------------------------------------------------------------------------
+OK = 0
+ERR_OUT_OF_SLOTS = 3
+ERR_UNSUPPORTED = 1000
+ERR_CARDINALITY_ESTIMATION_REQUIRED = 1001
+ERR_INVALID_ARGUMENT = 1002
+ERR_NO_DEVICE = 1003
+ERR_CUDA = 1004
+ERR_KEY_OUT_OF_RANGE = 1005
+
+EXPR_COLUMN_VAR, EXPR_CONSTANT, EXPR_BIN_OPER, EXPR_AGG = 1, 2, 3, 4
+CPU_LEVEL, GPU_LEVEL = 1, 2
+DEVICE_CPU, DEVICE_GPU = 0, 1
+KERNEL_AUTO, KERNEL_NON_GROUPED, KERNEL_PERFECT_SMEM, KERNEL_PERFECT_GLOBAL, KERNEL_BASELINE_GLOBAL = range(5)
+DT_INT64, DT_FLOAT64 = 0, 1
+RED_SUM, RED_MIN, RED_MAX = 0, 1, 2
+
+MAX_SLOTS = 16
+MAX_TARGETS = 16
+
+# Shared/InlineNullValues.h:30-36
+NULL_TINYINT = -(2**7)
+NULL_SMALLINT = -(2**15)
+NULL_INT = -(2**31)
+NULL_BIGINT = -(2**63)
+NULL_DOUBLE = float(np.finfo(np.float64).tiny)  # DBL_MIN: smallest NORMAL double
+EMPTY_KEY_64 = 2**63 - 1
+EMPTY_KEY_32 = 2**31 - 1
+
+NUMPY_OF = {kTINYINT: np.int8, kSMALLINT: np.int16, kINT: np.int32, kBIGINT: np.int64, kDOUBLE: np.float64}
+SIZE_OF = {kTINYINT: 1, kSMALLINT: 2, kINT: 4, kBIGINT: 8, kDOUBLE: 8}
+NULL_OF = {kTINYINT: NULL_TINYINT, kSMALLINT: NULL_SMALLINT, kINT: NULL_INT, kBIGINT: NULL_BIGINT, kDOUBLE: NULL_DOUBLE}
+
+
+class TypeInfo(C.Structure):
+    _fields_ = [("type", C.c_int32), ("notnull", C.c_int32)]
+
+
+class Expr(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("ti", TypeInfo),
+        ("col_id", C.c_int32),
+        ("op", C.c_int32),
+        ("left", C.c_int32),
+        ("right", C.c_int32),
+        ("ival", C.c_int64),
+        ("dval", C.c_double),
+        ("is_null", C.c_int32),
+        ("pad_", C.c_int32),
+    ]
+
+
+class ExecUnit(C.Structure):
+    _fields_ = [
+        ("exprs", C.POINTER(Expr)),
+        ("num_exprs", C.c_int32),
+        ("simple_quals", C.POINTER(C.c_int32)),
+        ("num_simple_quals", C.c_int32),
+        ("quals", C.POINTER(C.c_int32)),
+        ("num_quals", C.c_int32),
+        ("groupby_exprs", C.POINTER(C.c_int32)),
+        ("num_groupby_exprs", C.c_int32),
+        ("target_exprs", C.POINTER(C.c_int32)),
+        ("num_target_exprs", C.c_int32),
+        ("scan_limit", C.c_int64),
+        ("num_join_quals", C.c_int32),
+        ("has_estimator", C.c_int32),
+        ("num_order_entries", C.c_int32),
+        ("has_union_all", C.c_int32),
+        ("has_window_function", C.c_int32),
+        ("pad_", C.c_int32),
+    ]
+
+
+class ChunkStats(C.Structure):
+    _fields_ = [
+        ("int_min", C.c_int64),
+        ("int_max", C.c_int64),
+        ("fp_min", C.c_double),
+        ("fp_max", C.c_double),
+        ("has_nulls", C.c_int32),
+        ("pad_", C.c_int32),
+    ]
+
+
+class FragmentInfo(C.Structure):
+    _fields_ = [
+        ("fragment_id", C.c_int32),
+        ("device_id", C.c_int32),
+        ("num_tuples", C.c_int64),
+        ("col_buffers", C.POINTER(C.c_void_p)),
+        ("col_stats", C.POINTER(ChunkStats)),
+    ]
+
+
+class TableInfo(C.Structure):
+    _fields_ = [
+        ("num_cols", C.c_int32),
+        ("col_types", C.POINTER(TypeInfo)),
+        ("num_fragments", C.c_int32),
+        ("fragments", C.POINTER(FragmentInfo)),
+        ("memory_level", C.c_int32),
+        ("pad_", C.c_int32),
+    ]
+
+
+class CompilationOptions(C.Structure):
+    _fields_ = [("device_type", C.c_int32), ("hoist_literals", C.c_int32)]
+
+
+class ExecutionOptions(C.Structure):
+    _fields_ = [
+        ("allow_multifrag", C.c_int32),
+        ("output_columnar_hint", C.c_int32),
+        ("bigint_count", C.c_int32),
+        ("force_kernel", C.c_int32),
+        ("device_ordinal", C.c_int32),
+        ("pad_", C.c_int32),
+    ]
+
+
+class TargetInfo(C.Structure):
+    _fields_ = [
+        ("is_agg", C.c_int32),
+        ("agg_kind", C.c_int32),
+        ("sql_type", TypeInfo),
+        ("agg_arg_type", TypeInfo),
+        ("skip_null_val", C.c_int32),
+        ("is_distinct", C.c_int32),
+        ("arg_col_id", C.c_int32),
+        ("first_slot", C.c_int32),
+    ]
+
+
+class Plan(C.Structure):
+    _fields_ = [
+        ("query_desc_type", C.c_int32),
+        ("keyless_hash", C.c_int32),
+        ("idx_target_as_key", C.c_int32),
+        ("output_columnar", C.c_int32),
+        ("interleaved_bins_on_gpu", C.c_int32),
+        ("group_col_width", C.c_int32),
+        ("effective_key_width", C.c_int32),
+        ("num_targets", C.c_int32),
+        ("num_slots", C.c_int32),
+        ("key_col_id", C.c_int32),
+        ("entry_count", C.c_int64),
+        ("min_val", C.c_int64),
+        ("max_val", C.c_int64),
+        ("bucket", C.c_int64),
+        ("has_nulls", C.c_int32),
+        ("kernel", C.c_int32),
+        ("row_size", C.c_int64),
+        ("buffer_size", C.c_int64),
+        ("slot_padded_width", C.c_int8 * MAX_SLOTS),
+        ("slot_logical_width", C.c_int8 * MAX_SLOTS),
+        ("slot_offset", C.c_int64 * MAX_SLOTS),
+        ("init_vals", C.c_int64 * MAX_SLOTS),
+        ("targets", TargetInfo * MAX_TARGETS),
+    ]
+
+    #: fields that must agree between the product planner and the oracle planner
+    PARITY_FIELDS = (
+        "query_desc_type", "keyless_hash", "idx_target_as_key", "output_columnar", "group_col_width",
+        "effective_key_width", "num_targets", "num_slots", "key_col_id", "entry_count", "min_val", "max_val",
+        "bucket", "has_nulls", "row_size", "buffer_size",
+    )
+
+    def as_dict(self) -> dict:
+        d = {k: getattr(self, k) for k in self.PARITY_FIELDS}
+        n = self.num_slots
+        d["slot_padded_width"] = list(self.slot_padded_width[:n])
+        d["slot_logical_width"] = list(self.slot_logical_width[:n])
+        d["slot_offset"] = list(self.slot_offset[:n])
+        d["init_vals"] = list(self.init_vals[:n])
+        d["targets"] = [
+            (t.is_agg, t.agg_kind, t.sql_type.type, t.sql_type.notnull, t.agg_arg_type.type,
+             t.agg_arg_type.notnull, t.skip_null_val, t.arg_col_id, t.first_slot)
+            for t in self.targets[: self.num_targets]
+        ]
+        return d
+
+
+class TargetValue(C.Structure):
+    _fields_ = [("is_fp", C.c_int32), ("is_null", C.c_int32), ("ival", C.c_int64), ("dval", C.c_double)]
+
+    def py(self):
+        """Python value: None for NULL, float for fp targets, int otherwise."""
+        if self.is_null:
+            return None
+        return self.dval if self.is_fp else self.ival
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("error_codes", C.c_void_p),
+        ("total_matched", C.c_void_p),
+        ("group_by_buffers", C.c_void_p),
+        ("num_fragments", C.POINTER(C.c_uint32)),
+        ("num_tables", C.POINTER(C.c_uint32)),
+        ("row_index_resume", C.c_void_p),
+        ("col_buffers", C.POINTER(C.POINTER(C.c_void_p))),
+        ("literals", C.c_void_p),
+        ("num_rows", C.POINTER(C.c_int64)),
+        ("frag_row_offsets", C.c_void_p),
+        ("frag_ids", C.c_void_p),
+        ("max_matched", C.c_void_p),
+        ("init_agg_value", C.POINTER(C.c_int64)),
+        ("join_hash_tables", C.c_void_p),
+        ("row_func_mgr", C.c_void_p),
+    ]
+
+
+# =========================================================================================================
+# Builders (host-side conveniences; they only assemble the POD structs above)
+# =========================================================================================================
+@dataclass
+class _Node:
+    kind: int
+    type: int = 0
+    notnull: bool = False
+    col_id: int = -1
+    op: int = 0
+    left: int = -1
+    right: int = -1
+    ival: int = 0
+    dval: float = 0.0
+    is_null: bool = False
+
+
+class UnitBuilder:
+    """Assembles a RelAlgExecutionUnit mirror.  Mirrors how Tests/GroupByTest.cpp:121-130 builds one by hand:
+    ColumnVar / Constant / BinOper / AggExpr nodes, then quals / groupby_exprs / target_exprs lists."""
+
+    def __init__(self, table: "Table"):
+        self.table = table
+        self.nodes: List[_Node] = []
+        self.simple_quals: List[int] = []
+        self.quals: List[int] = []
+        self.groupby: List[int] = []
+        self.targets: List[int] = []
+        self.scan_limit = 0
+        self.unsupported: Dict[str, int] = {}
+
+    # -- expression nodes ---------------------------------------------------------------------------------
+    def col(self, col_id: int) -> int:
+        t, nn = self.table.col_types[col_id]
+        self.nodes.append(_Node(EXPR_COLUMN_VAR, t, nn, col_id=col_id))
+        return len(self.nodes) - 1
+
+    def const(self, value, sql_type: Optional[int] = None, is_null: bool = False) -> int:
+        if sql_type is None:
+            sql_type = kDOUBLE if isinstance(value, float) else kBIGINT
+        n = _Node(EXPR_CONSTANT, sql_type, True, is_null=is_null)
+        if sql_type == kDOUBLE:
+            n.dval = float(value)
+        else:
+            n.ival = int(value)
+        self.nodes.append(n)
+        return len(self.nodes) - 1
+
+    def binop(self, op: int, left: int, right: int) -> int:
+        self.nodes.append(_Node(EXPR_BIN_OPER, kTINYINT, False, op=op, left=left, right=right))
+        return len(self.nodes) - 1
+
+    def cmp(self, col_id: int, op: int, value, const_type: Optional[int] = None) -> int:
+        return self.binop(op, self.col(col_id), self.const(value, const_type))
+
+    def agg(self, kind: int, col_id: Optional[int] = None, bigint_count: bool = False) -> int:
+        """AggExpr.  Result type as RelAlgTranslator assigns it: COUNT -> INT/BIGINT notnull... SUM(int) -> BIGINT,
+        MIN/MAX -> arg type, AVG -> DOUBLE."""
+        arg = -1
+        if col_id is None:
+            assert kind == kCOUNT
+            ti = (kBIGINT if bigint_count else kINT, False)
+        else:
+            arg = self.col(col_id)
+            at, ann = self.table.col_types[col_id]
+            if kind == kCOUNT:
+                ti = (kBIGINT if bigint_count else kINT, False)
+            elif kind == kSUM:
+                ti = (kDOUBLE if at == kDOUBLE else kBIGINT, ann)
+            elif kind == kAVG:
+                ti = (kDOUBLE, ann)
+            else:
+                ti = (at, ann)
+        self.nodes.append(_Node(EXPR_AGG, ti[0], ti[1], op=kind, left=arg))
+        return len(self.nodes) - 1
+
+    # -- unit lists ---------------------------------------------------------------------------------------
+    def add_qual(self, e: int, simple: bool = False):
+        (self.simple_quals if simple else self.quals).append(e)
+        return self
+
+    def group_by(self, col_id: int):
+        self.groupby.append(self.col(col_id))
+        return self
+
+    def target(self, e: int):
+        self.targets.append(e)
+        return self
+
+    def target_col(self, col_id: int):
+        return self.target(self.col(col_id))
+
+    def build(self) -> "BuiltUnit":
+        return BuiltUnit(self)
+
+
+class BuiltUnit:
+    """Owns the ctypes arrays an ExecUnit points into."""
+
+    def __init__(self, b: UnitBuilder):
+        n = len(b.nodes)
+        self.exprs = (Expr * max(n, 1))()
+        for i, nd in enumerate(b.nodes):
+            e = self.exprs[i]
+            e.kind = nd.kind
+            e.ti = TypeInfo(nd.type, int(nd.notnull))
+            e.col_id, e.op, e.left, e.right = nd.col_id, nd.op, nd.left, nd.right
+            e.ival, e.dval, e.is_null = nd.ival, nd.dval, int(nd.is_null)
+
+        def arr(xs):
+            return (C.c_int32 * max(len(xs), 1))(*xs)
+
+        self._sq, self._q, self._g, self._t = arr(b.simple_quals), arr(b.quals), arr(b.groupby), arr(b.targets)
+        u = ExecUnit()
+        u.exprs, u.num_exprs = self.exprs, n
+        u.simple_quals, u.num_simple_quals = self._sq, len(b.simple_quals)
+        u.quals, u.num_quals = self._q, len(b.quals)
+        u.groupby_exprs, u.num_groupby_exprs = self._g, len(b.groupby)
+        u.target_exprs, u.num_target_exprs = self._t, len(b.targets)
+        u.scan_limit = b.scan_limit
+        for k, v in b.unsupported.items():
+            setattr(u, k, v)
+        self.unit = u
+
+
+def chunk_stats(arr: np.ndarray, sql_type: int, notnull: bool) -> ChunkStats:
+    """ChunkMetadata::chunkStats as the reference's encoders maintain them: min/max over NON-NULL values,
+    has_nulls when a NULL sentinel is present (DataMgr/Encoder.h; FixedLengthEncoder::updateStats)."""
+    st = ChunkStats()
+    null = NULL_OF[sql_type]
+    if arr.size == 0:
+        st.int_min, st.int_max = 2**63 - 1, -(2**63)
+        st.fp_min, st.fp_max = float(np.finfo(np.float64).max), float(np.finfo(np.float64).min)
+        return st
+    if notnull:
+        vals = arr
+        st.has_nulls = 0
+    else:
+        mask = arr != null
+        vals = arr[mask]
+        st.has_nulls = int(vals.size != arr.size)
+    if sql_type == kDOUBLE:
+        if vals.size:
+            st.fp_min, st.fp_max = float(vals.min()), float(vals.max())
+        else:
+            st.fp_min, st.fp_max = float(np.finfo(np.float64).max), float(np.finfo(np.float64).min)
+    else:
+        if vals.size:
+            st.int_min, st.int_max = int(vals.min()), int(vals.max())
+        else:
+            st.int_min, st.int_max = 2**63 - 1, -(2**63)
+    return st
+
+
+@dataclass
+class Fragment:
+    """One fragment: per-column either a host ndarray or a raw device pointer (int) + explicit stats."""
+    num_tuples: int
+    host_cols: List[Optional[np.ndarray]] = field(default_factory=list)
+    dev_ptrs: List[int] = field(default_factory=list)
+    stats: List[ChunkStats] = field(default_factory=list)
+    fragment_id: int = 0
+    device_id: int = 0
+
+
+class Table:
+    """InputTableInfo mirror: column types + fragments (Fragmenter::FragmentInfo + chunk pointers + chunk stats)."""
+
+    def __init__(self, col_types: Sequence[tuple]):
+        # col_types: [(sql_type, notnull), ...]
+        self.col_types = [(int(t), bool(nn)) for t, nn in col_types]
+        self.fragments: List[Fragment] = []
+
+    @property
+    def num_cols(self):
+        return len(self.col_types)
+
+    def add_host_fragment(self, cols: Sequence[Optional[np.ndarray]], fragment_id: Optional[int] = None):
+        n = None
+        fixed = []
+        stats = []
+        for (t, nn), a in zip(self.col_types, cols):
+            if a is None:
+                fixed.append(None)
+                stats.append(ChunkStats())
+                continue
+            a = np.ascontiguousarray(a, dtype=NUMPY_OF[t])
+            n = a.size if n is None else n
+            assert a.size == n, "ragged fragment"
+            fixed.append(a)
+            stats.append(chunk_stats(a, t, nn))
+        fid = len(self.fragments) if fragment_id is None else fragment_id
+        self.fragments.append(Fragment(n or 0, host_cols=fixed, stats=stats, fragment_id=fid))
+        return self
+
+    def add_device_fragment(self, num_tuples: int, dev_ptrs: Sequence[int], stats: Sequence[ChunkStats],
+                            fragment_id: Optional[int] = None, device_id: int = 0):
+        fid = len(self.fragments) if fragment_id is None else fragment_id
+        self.fragments.append(Fragment(int(num_tuples), dev_ptrs=[int(p) for p in dev_ptrs], stats=list(stats),
+                                       fragment_id=fid, device_id=device_id))
+        return self
+
+    def total_tuples(self):
+        return sum(f.num_tuples for f in self.fragments)
+
+    def build(self, memory_level: int) -> "BuiltTable":
+        return BuiltTable(self, memory_level)
+
+
+class BuiltTable:
+    """Owns the ctypes arrays a TableInfo points into."""
+
+    def __init__(self, t: Table, memory_level: int):
+        self.src = t
+        nc = t.num_cols
+        self.col_types = (TypeInfo * nc)(*[TypeInfo(ty, int(nn)) for ty, nn in t.col_types])
+        nf = len(t.fragments)
+        self.frags = (FragmentInfo * max(nf, 1))()
+        self._keep = []
+        for i, f in enumerate(t.fragments):
+            bufs = (C.c_void_p * nc)()
+            for c in range(nc):
+                if memory_level == CPU_LEVEL:
+                    a = f.host_cols[c] if f.host_cols else None
+                    bufs[c] = a.ctypes.data if a is not None and a.size else None
+                else:
+                    bufs[c] = f.dev_ptrs[c] if f.dev_ptrs and f.dev_ptrs[c] else None
+            stats = (ChunkStats * nc)(*f.stats)
+            self._keep += [bufs, stats]
+            fi = self.frags[i]
+            fi.fragment_id, fi.device_id, fi.num_tuples = f.fragment_id, f.device_id, f.num_tuples
+            fi.col_buffers, fi.col_stats = bufs, stats
+        ti = TableInfo()
+        ti.num_cols, ti.col_types = nc, self.col_types
+        ti.num_fragments, ti.fragments = nf, self.frags
+        ti.memory_level = memory_level
+        self.info = ti

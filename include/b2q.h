@@ -1,0 +1,334 @@
+/*
+ * b2q.h — C ABI of the B200-native scan -> filter -> hash-group-by/aggregate path.
+ *
+ * This is the drop-in boundary for ONE path of a HeavyDB-style engine: everything that runs below
+ *     ResultSetPtr Executor::executeWorkUnit(size_t& max_groups_buffer_entry_guess, const bool is_agg,
+ *         const std::vector<InputTableInfo>&, const RelAlgExecutionUnit&, const CompilationOptions&,
+ *         const ExecutionOptions&, RenderInfo*, const bool has_cardinality_estimation, ColumnCacheMap&)
+ *     (reference: QueryEngine/Execute.h:719-727, QueryEngine/Execute.cpp:2144)
+ * for single-table filter + optional GROUP BY + COUNT/SUM/MIN/MAX/AVG.
+ *
+ * Two levels, both plain C (pointers + sizes, no C++/torch types):
+ *
+ *   outer  b2q_execute_work_unit()   — POD mirror of executeWorkUnit(); plans, launches, merges, materialises.
+ *          b2q_execute_partial() / b2q_partial_*() / b2q_partial_finalize() — the same, split at the point
+ *          where the reference merges per-device results on the host (Execute.cpp:1696,1772-1792) so the
+ *          caller can run the NCCL all-reduce of the dense partial tables between the two halves.
+ *          b2q_rs_*()                — the ResultSet output surface (QueryEngine/ResultSet.h:183-330).
+ *
+ *   inner  b2q_launch()              — the static-kernel replacement of the JIT'd
+ *          multifrag_query_hoisted_literals(...) entry (QueryEngine/RuntimeFunctions.cpp:2434-2449); takes the
+ *          same 15-slot parameter block (enum KernelParam, QueryEngine/enums.h:64-79) plus the restated
+ *          QueryMemoryDescriptor (B2QPlan) that the JIT would have baked into the code.
+ *
+ * Enum VALUES below are the reference's own (Shared/sqltypes.h:65-99, Shared/sqldefs.h:31-40,76-90,
+ * QueryEngine/enums.h:27-60) so that a reference-side binding is a cast, not a translation table.
+ *
+ * Everything outside the supported subset is REJECTED with B2Q_ERR_UNSUPPORTED — never silently ignored,
+ * and there is no CPU fallback: without a CUDA device every compute entry returns B2Q_ERR_NO_DEVICE.
+ */
+#ifndef B2Q_H
+#define B2Q_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2Q_ABI_VERSION 1
+
+/* ---- SQLTypes subset (Shared/sqltypes.h:65-99) -------------------------------------------------------- */
+enum {
+  B2Q_kINT = 6,
+  B2Q_kSMALLINT = 7,
+  B2Q_kFLOAT = 8,
+  B2Q_kDOUBLE = 9,
+  B2Q_kBIGINT = 12,
+  B2Q_kTINYINT = 22
+};
+
+/* ---- SQLOps subset (Shared/sqldefs.h:31-40) ----------------------------------------------------------- */
+enum { B2Q_kEQ = 0, B2Q_kNE = 2, B2Q_kLT = 3, B2Q_kGT = 4, B2Q_kLE = 5, B2Q_kGE = 6, B2Q_kAND = 7, B2Q_kOR = 8 };
+
+/* ---- SQLAgg subset (Shared/sqldefs.h:76-90) ----------------------------------------------------------- */
+enum { B2Q_kAVG = 0, B2Q_kMIN = 1, B2Q_kMAX = 2, B2Q_kSUM = 3, B2Q_kCOUNT = 4 };
+
+/* ---- QueryDescriptionType (QueryEngine/enums.h:54-60) ------------------------------------------------- */
+enum {
+  B2Q_GroupByPerfectHash = 0,
+  B2Q_GroupByBaselineHash = 1,
+  B2Q_Projection = 2,
+  B2Q_TableFunction = 3,
+  B2Q_NonGroupedAggregate = 4,
+  B2Q_Estimator = 5
+};
+
+/* ---- error codes ----------------------------------------------------------------------------------------
+ * 0..18 are heavyai::ErrorCode (QueryEngine/enums.h:27-47); a NEGATIVE return from the inner entry is the
+ * reference's "-pos" out-of-slots convention (GroupByAndAggregate.cpp:1149-1154).  Codes >= 1000 mirror the
+ * C++ exceptions that cross the reference's outer boundary (SURVEY §8b "errors"). */
+enum {
+  B2Q_OK = 0,
+  B2Q_ERR_DIV_BY_ZERO = 1,
+  B2Q_ERR_OUT_OF_GPU_MEM = 2,
+  B2Q_ERR_OUT_OF_SLOTS = 3,
+  B2Q_ERR_OVERFLOW_OR_UNDERFLOW = 7,
+  B2Q_ERR_OUT_OF_TIME = 8,
+  B2Q_ERR_INTERRUPTED = 9,
+  B2Q_ERR_UNSUPPORTED = 1000,                      /* feature outside the path (joins, sort, window, ...) */
+  B2Q_ERR_CARDINALITY_ESTIMATION_REQUIRED = 1001,  /* CardinalityEstimationRequired (NativeCodegen.cpp:2972-2979) */
+  B2Q_ERR_INVALID_ARGUMENT = 1002,
+  B2Q_ERR_NO_DEVICE = 1003,                        /* no CUDA device: there is no CPU fallback */
+  B2Q_ERR_CUDA = 1004,
+  B2Q_ERR_KEY_OUT_OF_RANGE = 1005                  /* a key outside the chunk-stats range (stale metadata) */
+};
+
+/* ---- SQLTypeInfo subset -------------------------------------------------------------------------------- */
+typedef struct B2QTypeInfo {
+  int32_t type;    /* B2Q_k* SQLTypes value */
+  int32_t notnull; /* SQLTypeInfo::get_notnull() */
+} B2QTypeInfo;
+
+/* ---- Analyzer::Expr subset (Analyzer/Analyzer.h:193 ColumnVar, :319 Constant, :434 BinOper, :1381 AggExpr)
+ * Nodes live in one flat array; children are indices into it (-1 = none). */
+enum { B2Q_EXPR_COLUMN_VAR = 1, B2Q_EXPR_CONSTANT = 2, B2Q_EXPR_BIN_OPER = 3, B2Q_EXPR_AGG = 4 };
+
+typedef struct B2QExpr {
+  int32_t kind;   /* B2Q_EXPR_* */
+  B2QTypeInfo ti; /* Expr::get_type_info() */
+  int32_t col_id; /* ColumnVar: column index in B2QTableInfo */
+  int32_t op;     /* BinOper: SQLOps; AggExpr: SQLAgg */
+  int32_t left;   /* BinOper: left operand; AggExpr: argument (-1 = COUNT(*)) */
+  int32_t right;  /* BinOper: right operand */
+  int64_t ival;   /* Constant: Datum for integer types */
+  double dval;    /* Constant: Datum for fp types */
+  int32_t is_null;/* Constant::get_is_null() */
+  int32_t pad_;
+} B2QExpr;
+
+/* ---- RelAlgExecutionUnit subset (QueryEngine/RelAlgExecutionUnit.h:166-216) ---------------------------- */
+typedef struct B2QExecUnit {
+  const B2QExpr* exprs;
+  int32_t num_exprs;
+  const int32_t* simple_quals; /* expr indices; "col OP const" comparisons (narrow the key range, a21) */
+  int32_t num_simple_quals;
+  const int32_t* quals;        /* expr indices; AND-ed together */
+  int32_t num_quals;
+  const int32_t* groupby_exprs;/* expr indices; num_groupby_exprs == 0 <=> reference's {nullptr} */
+  int32_t num_groupby_exprs;
+  const int32_t* target_exprs; /* expr indices */
+  int32_t num_target_exprs;
+  int64_t scan_limit;
+  /* Fields of the reference struct that are outside this path.  Must be zero or the call is rejected. */
+  int32_t num_join_quals;
+  int32_t has_estimator;
+  int32_t num_order_entries;
+  int32_t has_union_all;
+  int32_t has_window_function;
+  int32_t pad_;
+} B2QExecUnit;
+
+/* ---- ChunkMetadata::chunkStats per (fragment, column)  (Fragmenter/Fragmenter.h:73-146) ---------------- */
+typedef struct B2QChunkStats {
+  int64_t int_min, int_max; /* integer columns */
+  double fp_min, fp_max;    /* fp columns */
+  int32_t has_nulls;
+  int32_t pad_;
+} B2QChunkStats;
+
+/* ---- Fragmenter::FragmentInfo + the column pointers ColumnFetcher would return (ColumnFetcher.cpp:214) - */
+typedef struct B2QFragmentInfo {
+  int32_t fragment_id;
+  int32_t device_id;                /* reference rule: fragment_id % num_devices (InsertOrderFragmenter.cpp:435) */
+  int64_t num_tuples;
+  const void* const* col_buffers;   /* [num_cols]; flat fixed-width arrays; NULL for unreferenced columns */
+  const B2QChunkStats* col_stats;   /* [num_cols] */
+} B2QFragmentInfo;
+
+/* ---- InputTableInfo (QueryEngine/InputMetadata.h:32-35) ------------------------------------------------ */
+enum { B2Q_CPU_LEVEL = 1, B2Q_GPU_LEVEL = 2 }; /* Data_Namespace::MemoryLevel values */
+typedef struct B2QTableInfo {
+  int32_t num_cols;
+  const B2QTypeInfo* col_types;     /* [num_cols] */
+  int32_t num_fragments;
+  const B2QFragmentInfo* fragments; /* [num_fragments] */
+  int32_t memory_level;             /* where col_buffers live: B2Q_GPU_LEVEL (HBM resident) or B2Q_CPU_LEVEL
+                                       (host; copied H2D inside the call, chunk by chunk) */
+  int32_t pad_;
+} B2QTableInfo;
+
+/* ---- CompilationOptions / ExecutionOptions subsets (QueryEngine/CompilationOptions.h:31-66,70-122) ----- */
+enum { B2Q_DEVICE_CPU = 0, B2Q_DEVICE_GPU = 1 }; /* ExecutorDeviceType */
+typedef struct B2QCompilationOptions {
+  int32_t device_type;    /* must be B2Q_DEVICE_GPU: no CPU fallback */
+  int32_t hoist_literals; /* accepted, meaningless for static kernels */
+} B2QCompilationOptions;
+
+typedef struct B2QExecutionOptions {
+  int32_t allow_multifrag;       /* one launch over all fragments of this device (Execute.cpp:3075-3101) */
+  int32_t output_columnar_hint;  /* --enable-columnar-output */
+  int32_t bigint_count;          /* g_bigint_count (--bigint-count) */
+  int32_t force_kernel;          /* 0 = planner's choice; else B2Q_KERNEL_* (for tests / benchmarks) */
+  int32_t device_ordinal;        /* CUDA device to run on (-1 = current) */
+  int32_t pad_;
+} B2QExecutionOptions;
+
+/* static kernel families (one per C symbol b2q_k_*) */
+enum {
+  B2Q_KERNEL_AUTO = 0,
+  B2Q_KERNEL_NON_GROUPED = 1,     /* register accumulators + warp/block reduce            */
+  B2Q_KERNEL_PERFECT_SMEM = 2,    /* per-CTA private table in shared memory               */
+  B2Q_KERNEL_PERFECT_GLOBAL = 3,  /* one dense table in HBM/L2, global reductions          */
+  B2Q_KERNEL_BASELINE_GLOBAL = 4  /* open-addressing table in HBM (MurmurHash3, linear probe) */
+};
+
+/* =========================================================================================================
+ * Restated QueryMemoryDescriptor (QueryEngine/Descriptors/QueryMemoryDescriptor.h:69) — what the planner
+ * decided.  Filled by b2q_plan(); consumed by b2q_launch() and by the result-set accessors.
+ * ======================================================================================================= */
+#define B2Q_MAX_SLOTS 16
+#define B2Q_MAX_TARGETS 16
+#define B2Q_MAX_FILTER_TERMS 8
+
+typedef struct B2QTargetInfo { /* Shared/TargetInfo.h:49-78 */
+  int32_t is_agg;
+  int32_t agg_kind;        /* SQLAgg */
+  B2QTypeInfo sql_type;
+  B2QTypeInfo agg_arg_type;/* type = 0 (kNULLT) when there is no argument */
+  int32_t skip_null_val;
+  int32_t is_distinct;     /* always 0 here */
+  int32_t arg_col_id;      /* -1 when no argument */
+  int32_t first_slot;      /* slot index of this target (AVG owns first_slot and first_slot+1) */
+} B2QTargetInfo;
+
+typedef struct B2QPlan {
+  int32_t query_desc_type;   /* QueryDescriptionType */
+  int32_t keyless_hash;
+  int32_t idx_target_as_key; /* slot index whose value != init marks a non-empty keyless entry */
+  int32_t output_columnar;
+  int32_t interleaved_bins_on_gpu; /* reported for parity; our kernels never interleave */
+  int32_t group_col_width;   /* byte width of the GROUP BY column */
+  int32_t effective_key_width;/* 8 for perfect hash; 4 or 8 for baseline */
+  int32_t num_targets;
+  int32_t num_slots;
+  int32_t key_col_id;
+  int64_t entry_count;
+  int64_t min_val, max_val, bucket;
+  int32_t has_nulls;
+  int32_t kernel;            /* B2Q_KERNEL_* chosen */
+  int64_t row_size;          /* bytes, row-wise */
+  int64_t buffer_size;       /* bytes of the whole result buffer */
+  int8_t slot_padded_width[B2Q_MAX_SLOTS];
+  int8_t slot_logical_width[B2Q_MAX_SLOTS];
+  int64_t slot_offset[B2Q_MAX_SLOTS]; /* row-wise: byte offset inside the row; columnar: offset of the column */
+  int64_t init_vals[B2Q_MAX_SLOTS];   /* init_agg_val_vec (OutputBufferInitialization.cpp:26-86) */
+  B2QTargetInfo targets[B2Q_MAX_TARGETS];
+} B2QPlan;
+
+/* The 15-slot kernel parameter block of the reference's JIT entry (enums.h:64-79), device pointers. */
+typedef struct B2QParams {
+  int32_t* error_codes;            /* ERROR_CODE      */
+  int32_t* total_matched;          /* TOTAL_MATCHED   */
+  int64_t** group_by_buffers;      /* GROUPBY_BUF     — [0] = the output buffer in reference layout */
+  const uint32_t* num_fragments;   /* NUM_FRAGMENTS   (host pointer, read on the host)   */
+  const uint32_t* num_tables;      /* NUM_TABLES      (must point at 1) */
+  const uint32_t* row_index_resume;/* ROW_INDEX_RESUME (unused) */
+  const int8_t*** col_buffers;     /* COL_BUFFERS     host array [frag][col] of DEVICE pointers */
+  const int8_t* literals;          /* LITERALS        (unused: literals live in the plan) */
+  const int64_t* num_rows;         /* NUM_ROWS        host array [frag] */
+  const uint64_t* frag_row_offsets;/* FRAG_ROW_OFFSETS (unused) */
+  const int32_t* frag_ids;         /* FRAG_IDS        (unused) */
+  const int32_t* max_matched;      /* MAX_MATCHED     (unused) */
+  const int64_t* init_agg_value;   /* INIT_AGG_VALS   host array [num_slots]; NULL = plan->init_vals */
+  const int64_t* join_hash_tables; /* JOIN_HASH_TABLES must be NULL */
+  const int8_t* row_func_mgr;      /* ROW_FUNC_MGR    must be NULL */
+} B2QParams;
+
+typedef struct B2QQuery B2QQuery;         /* plan + compiled filter/aggregate program (opaque) */
+typedef struct B2QPartial B2QPartial;     /* per-device dense partial-aggregate table in HBM (opaque) */
+typedef struct B2QResultSet B2QResultSet; /* ResultSet output surface (opaque) */
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int32_t b2q_abi_version(void);
+const char* b2q_error_string(int32_t code);
+const char* b2q_last_error_message(void); /* thread-local detail for the last failing call */
+int32_t b2q_device_count(void);           /* 0 when no CUDA device is visible */
+
+/* ---- planning (host only; usable without a GPU) --------------------------------------------------------- */
+/* Restates GroupByAndAggregate::initQueryMemoryDescriptor + QueryMemoryDescriptor::init.
+ * max_groups_buffer_entry_guess / has_cardinality_estimation have executeWorkUnit()'s meaning. */
+int32_t b2q_plan(const B2QExecUnit* ra_exe_unit, const B2QTableInfo* query_info,
+                 const B2QCompilationOptions* co, const B2QExecutionOptions* eo,
+                 size_t max_groups_buffer_entry_guess, int32_t has_cardinality_estimation, B2QQuery** out);
+const B2QPlan* b2q_query_plan(const B2QQuery* q);
+void b2q_query_free(B2QQuery* q);
+
+/* ---- outer entry: Executor::executeWorkUnit --------------------------------------------------------------
+ * Same parameter order as the reference (RenderInfo* and ColumnCacheMap& have no meaning here and are
+ * dropped).  *max_groups_buffer_entry_guess is in/out like the reference's size_t&. */
+int32_t b2q_execute_work_unit(size_t* max_groups_buffer_entry_guess, int32_t is_agg,
+                              const B2QTableInfo* query_infos, const B2QExecUnit* ra_exe_unit,
+                              const B2QCompilationOptions* co, const B2QExecutionOptions* eo,
+                              int32_t has_cardinality_estimation, B2QResultSet** out);
+
+/* ---- split form for multi-GPU: [scan+aggregate] -> (caller's NCCL all-reduce) -> [materialise] ----------- */
+int32_t b2q_execute_partial(size_t* max_groups_buffer_entry_guess, int32_t is_agg,
+                            const B2QTableInfo* query_infos, const B2QExecUnit* ra_exe_unit,
+                            const B2QCompilationOptions* co, const B2QExecutionOptions* eo,
+                            int32_t has_cardinality_estimation, void* cuda_stream, B2QPartial** out);
+/* Dense per-slot arrays of the partial table.  Every array is position-aligned across devices (perfect-hash /
+ * non-grouped layouts), initialised to the identity of its reduction, so the merge of N devices is exactly
+ * one all-reduce per array — the device-side replacement of ResultSetStorage::reduce
+ * (ResultSetReduction.cpp:203-396, slot op :1496-1566). */
+enum { B2Q_DT_INT64 = 0, B2Q_DT_FLOAT64 = 1 };
+enum { B2Q_RED_SUM = 0, B2Q_RED_MIN = 1, B2Q_RED_MAX = 2 };
+int32_t b2q_partial_num_arrays(const B2QPartial* p);
+int32_t b2q_partial_array(const B2QPartial* p, int32_t i, void** device_ptr, int64_t* count, int32_t* dtype,
+                          int32_t* redop);
+int32_t b2q_partial_is_mergeable(const B2QPartial* p); /* 0 for baseline-hash (not position aligned) */
+const B2QPlan* b2q_partial_plan(const B2QPartial* p);
+double b2q_partial_kernel_ms(const B2QPartial* p);     /* CUDA-event time of the scan kernel(s) */
+int32_t b2q_partial_finalize(B2QPartial* p, void* cuda_stream, B2QResultSet** out);
+void b2q_partial_free(B2QPartial* p);
+
+/* ---- inner entry: the static-kernel replacement of multifrag_query_hoisted_literals ---------------------- */
+int32_t b2q_launch(const B2QQuery* query, const B2QParams* params, void* cuda_stream);
+
+/* ---- ResultSet surface (QueryEngine/ResultSet.h) --------------------------------------------------------- */
+typedef struct B2QTargetValue { /* ScalarTargetValue for the numeric subset (QueryEngine/TargetValue.h) */
+  int32_t is_fp;   /* 0: ival holds int64_t, 1: dval holds double (FLOAT targets are widened like getNextRow) */
+  int32_t is_null; /* value equals the type's NULL sentinel (Shared/InlineNullValues.h:30-36) */
+  int64_t ival;
+  double dval;
+} B2QTargetValue;
+
+size_t b2q_rs_row_count(const B2QResultSet* rs);   /* ResultSet::rowCount()  :306 */
+size_t b2q_rs_col_count(const B2QResultSet* rs);   /* ResultSet::colCount() */
+size_t b2q_rs_entry_count(const B2QResultSet* rs); /* ResultSet::entryCount() */
+int32_t b2q_rs_is_empty(const B2QResultSet* rs);   /* ResultSet::isEmpty() */
+B2QTypeInfo b2q_rs_get_col_type(const B2QResultSet* rs, size_t col_idx); /* ResultSet::getColType() */
+/* ResultSet::getNextRow(translate_strings, decimal_to_double) :259 — returns 1 and fills row[colCount()],
+ * or 0 at the end.  b2q_rs_move_to_begin() == ResultSet::moveToBegin(). */
+int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row);
+void b2q_rs_move_to_begin(B2QResultSet* rs);
+int32_t b2q_rs_is_row_at_empty(const B2QResultSet* rs, size_t entry_idx); /* ResultSet::isRowAtEmpty() */
+/* getStorage()->getUnderlyingBuffer(): host copy of the output buffer in the reference's own row-wise /
+ * columnar layout (ResultSet.h:55-84, QueryMemoryDescriptor.cpp:848-955). */
+const int8_t* b2q_rs_storage_buffer(const B2QResultSet* rs, size_t* size_bytes);
+const B2QPlan* b2q_rs_query_mem_desc(const B2QResultSet* rs); /* getQueryMemDesc() */
+double b2q_rs_kernel_ms(const B2QResultSet* rs);
+void b2q_rs_free(B2QResultSet* rs);
+
+/* ---- synthetic data (bench / tests): counter-based generator, identical to oracle/oracle_gen.h ----------
+ * value(row) = lo + splitmix64(seed ^ (col_tag << 56) ^ row) % span   (integers)
+ *            = (splitmix64(...) >> 11) * 2^-53                        (doubles in [0,1))
+ * Writes `count` elements of `width` bytes starting at global row `row0` into a DEVICE buffer. */
+int32_t b2q_gen_column(void* device_dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
+                       int64_t count, int64_t lo, int64_t span, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2Q_H */

@@ -1,0 +1,1260 @@
+/*
+ * oracle.cpp — CPU restatement of the reference's scan -> filter -> hash-group-by/aggregate path.
+ *
+ * >>> TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * >>> `--impl reference` legs may build, load or call anything under oracle/.  The product
+ * >>> (heavydb_b200/, include/) never links or imports it.
+ *
+ * What it is: a plain scalar C++17 restatement of what heavyai/heavydb executes below
+ * Executor::executeWorkUnit (QueryEngine/Execute.cpp:2144) with --cpu-only, for the subset
+ * single table, quals = AND/OR tree of `column OP constant`, optional single-column GROUP BY,
+ * targets in {group key, COUNT(*), COUNT(c), SUM(c), MIN(c), MAX(c), AVG(c)},
+ * column types TINYINT/SMALLINT/INT/BIGINT/DOUBLE.  Each function cites the reference lines it follows
+ * (paths relative to /root/reference).
+ *
+ * Parity pinning: the whole reference executor cannot be built here (needs LLVM 14, Boost,
+ * Thrift, TBB, a JVM).  The oracle is pinned instead by
+ *   (1) the reference's own hash/probe runtime compiled verbatim from /root/reference into
+ *       oracle/_ref/libref_groupby.so (QueryEngine/GroupByRuntime.cpp + MurmurHash.cpp) and compared against
+ *       oracle_murmur3 / oracle_get_group_value (tests/test_oracle_ref.py), plus the probe constants
+ *       MurmurHash3(&int64{12345},8,0)=342635441 and MurmurHash3(&int32{7},4,0)=1343918321;
+ *   (2) the reference's SQL golden tests: table `test` of Tests/ExecuteTest.cpp:30063-30115 and the
+ *       FilterAndSimpleAggregation / FilterAndGroupBy / GroupByKeylessAndNotKeyless query shapes, with expected
+ *       values computed by SQLite exactly as the reference's own comparator does
+ *       (ExecuteTest.cpp:383-520) — tests/test_oracle_golden.py;
+ *   (3) the ResultSetTest generator pattern (Tests/ResultSetTestUtils.h:33-70, ResultSetTest.cpp:1081-1098)
+ *       for the reduction — tests/test_oracle_reduce.py.
+ */
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../include/b2q.h" /* POD input structs of the boundary only */
+#include "oracle_gen.h"
+
+#define ORACLE_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+/* ---- Shared/InlineNullValues.h:30-36 ---- */
+constexpr int64_t kNullTinyint = INT8_MIN;
+constexpr int64_t kNullSmallint = INT16_MIN;
+constexpr int64_t kNullInt = INT32_MIN;
+constexpr int64_t kNullBigint = INT64_MIN;
+constexpr double kNullDouble = DBL_MIN; /* NULL_DOUBLE is the smallest NORMAL double */
+/* QueryEngine/GpuRtConstants.h: EMPTY_KEY_64 / EMPTY_KEY_32 */
+constexpr int64_t kEmptyKey64 = std::numeric_limits<int64_t>::max();
+constexpr int32_t kEmptyKey32 = std::numeric_limits<int32_t>::max();
+
+struct Ti {
+  int type{0};
+  bool notnull{false};
+};
+
+bool is_integer(int t) { return t == B2Q_kTINYINT || t == B2Q_kSMALLINT || t == B2Q_kINT || t == B2Q_kBIGINT; }
+bool is_fp(int t) { return t == B2Q_kDOUBLE; }
+int type_size(int t) { /* SQLTypeInfo::get_size() for the fixed-width subset */
+  switch (t) {
+    case B2Q_kTINYINT: return 1;
+    case B2Q_kSMALLINT: return 2;
+    case B2Q_kINT: return 4;
+    case B2Q_kBIGINT: return 8;
+    case B2Q_kDOUBLE: return 8;
+    default: return -1;
+  }
+}
+int64_t inline_int_null_val(int t) { /* Shared/InlineNullValues.h inline_int_null_val */
+  switch (t) {
+    case B2Q_kTINYINT: return kNullTinyint;
+    case B2Q_kSMALLINT: return kNullSmallint;
+    case B2Q_kINT: return kNullInt;
+    case B2Q_kBIGINT: return kNullBigint;
+    default: abort();
+  }
+}
+int64_t bits_of(double d) {
+  int64_t r;
+  memcpy(&r, &d, 8);
+  return r;
+}
+double double_of(int64_t b) {
+  double r;
+  memcpy(&r, &b, 8);
+  return r;
+}
+int64_t align_to_int64(int64_t x) { return (x + 7) & ~int64_t(7); } /* BufferCompaction.h:42-45 */
+
+struct OracleError {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void fail(int code, const std::string& msg) { throw OracleError{code, msg}; }
+
+/* ---------------------------------------------------------------------------------------------------
+ * MurmurHash3 x86_32 — QueryEngine/MurmurHash3Inl.h:11-72 (restated; pinned against _ref and constants)
+ * ------------------------------------------------------------------------------------------------- */
+uint32_t rotl32(uint32_t x, int8_t r) { return (x << r) | (x >> (32 - r)); }
+uint32_t murmur3(const void* key, int len, uint32_t seed) {
+  const uint8_t* data = static_cast<const uint8_t*>(key);
+  const int nblocks = len / 4;
+  uint32_t h1 = seed;
+  const uint32_t c1 = 0xcc9e2d51, c2 = 0x1b873593;
+  for (int i = 0; i < nblocks; ++i) {
+    uint32_t k1;
+    memcpy(&k1, data + 4 * i, 4);
+    k1 *= c1;
+    k1 = rotl32(k1, 15);
+    k1 *= c2;
+    h1 ^= k1;
+    h1 = rotl32(h1, 13);
+    h1 = h1 * 5 + 0xe6546b64;
+  }
+  const uint8_t* tail = data + nblocks * 4;
+  uint32_t k1 = 0;
+  switch (len & 3) {
+    case 3: k1 ^= tail[2] << 16; /* fallthrough */
+    case 2: k1 ^= tail[1] << 8;  /* fallthrough */
+    case 1:
+      k1 ^= tail[0];
+      k1 *= c1;
+      k1 = rotl32(k1, 15);
+      k1 *= c2;
+      h1 ^= k1;
+  }
+  h1 ^= static_cast<uint32_t>(len);
+  h1 ^= h1 >> 16;
+  h1 *= 0x85ebca6b;
+  h1 ^= h1 >> 13;
+  h1 *= 0xc2b2ae35;
+  h1 ^= h1 >> 16;
+  return h1;
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * Baseline-hash group lookup — QueryEngine/GroupByRuntime.cpp:20-48 (key_hash, get_group_value) with the CPU
+ * get_matching_group_value of QueryEngine/RuntimeFunctions.cpp:1953-2005 (match or claim an EMPTY slot).
+ * Row-wise layout: [key: key_count * key_width bytes, padded to 8][slots...], row_size_quad int64 per row.
+ * Returns pointer to the first slot of the row, or nullptr when the table is full.
+ * ------------------------------------------------------------------------------------------------- */
+template <typename T>
+int64_t* get_matching_group_value_t(int64_t* groups_buffer, uint32_t h, const T* key, uint32_t key_count,
+                                    uint32_t row_size_quad) {
+  auto off = static_cast<uint64_t>(h) * row_size_quad;
+  auto row_ptr = reinterpret_cast<T*>(groups_buffer + off);
+  const T empty = sizeof(T) == 4 ? static_cast<T>(kEmptyKey32) : static_cast<T>(kEmptyKey64);
+  if (*row_ptr == empty) {
+    memcpy(row_ptr, key, key_count * sizeof(T));
+    auto row_ptr_i8 = reinterpret_cast<int8_t*>(row_ptr + key_count);
+    return reinterpret_cast<int64_t*>(align_to_int64(reinterpret_cast<int64_t>(row_ptr_i8)));
+  }
+  if (memcmp(row_ptr, key, key_count * sizeof(T)) == 0) {
+    auto row_ptr_i8 = reinterpret_cast<int8_t*>(row_ptr + key_count);
+    return reinterpret_cast<int64_t*>(align_to_int64(reinterpret_cast<int64_t>(row_ptr_i8)));
+  }
+  return nullptr;
+}
+
+int64_t* get_matching_group_value(int64_t* groups_buffer, uint32_t h, const int64_t* key, uint32_t key_count,
+                                  uint32_t key_width, uint32_t row_size_quad) {
+  switch (key_width) {
+    case 4:
+      return get_matching_group_value_t(groups_buffer, h, reinterpret_cast<const int32_t*>(key), key_count,
+                                        row_size_quad);
+    case 8:
+      return get_matching_group_value_t(groups_buffer, h, key, key_count, row_size_quad);
+    default:
+      return nullptr;
+  }
+}
+
+int64_t* get_group_value(int64_t* groups_buffer, uint32_t entry_count, const int64_t* key, uint32_t key_count,
+                         uint32_t key_width, uint32_t row_size_quad) {
+  uint32_t h = murmur3(key, key_width * key_count, 0) % entry_count;
+  int64_t* m = get_matching_group_value(groups_buffer, h, key, key_count, key_width, row_size_quad);
+  if (m) return m;
+  uint32_t h_probe = (h + 1) % entry_count;
+  while (h_probe != h) {
+    m = get_matching_group_value(groups_buffer, h_probe, key, key_count, key_width, row_size_quad);
+    if (m) return m;
+    h_probe = (h_probe + 1) % entry_count;
+  }
+  return nullptr;
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * Aggregate update functions — QueryEngine/RuntimeFunctions.cpp:362 (agg_count), :1151-1173 (agg_sum/max/min/id),
+ * :1313-1431 (*_skip_val), :1439-1473 (double), :1558-1593 (fp skip_val)
+ * ------------------------------------------------------------------------------------------------- */
+void agg_count(int64_t* agg) { *reinterpret_cast<uint64_t*>(agg) += 1; }
+void agg_sum(int64_t* agg, int64_t val) { /* wraps silently, like the reference (:1151-1155) */
+  *agg = static_cast<int64_t>(static_cast<uint64_t>(*agg) + static_cast<uint64_t>(val));
+}
+void agg_max(int64_t* agg, int64_t val) { *agg = std::max(*agg, val); }
+void agg_min(int64_t* agg, int64_t val) { *agg = std::min(*agg, val); }
+void agg_id(int64_t* agg, int64_t val) { *agg = val; }
+void agg_sum_skip_val(int64_t* agg, int64_t val, int64_t skip_val) { /* :1313-1325 */
+  const auto old = *agg;
+  if (val != skip_val) {
+    if (old != skip_val) {
+      agg_sum(agg, val);
+    } else {
+      *agg = val;
+    }
+  }
+}
+void agg_count_skip_val(int64_t* agg, int64_t val, int64_t skip_val) { /* :1363-1369 */
+  if (val != skip_val) agg_count(agg);
+}
+void agg_max_skip_val(int64_t* agg, int64_t val, int64_t skip_val) { /* DEF_SKIP_AGG :1405-1416 */
+  if (val != skip_val) {
+    const int64_t old_agg = *agg;
+    if (old_agg != skip_val) agg_max(agg, val); else *agg = val;
+  }
+}
+void agg_min_skip_val(int64_t* agg, int64_t val, int64_t skip_val) {
+  if (val != skip_val) {
+    const int64_t old_agg = *agg;
+    if (old_agg != skip_val) agg_min(agg, val); else *agg = val;
+  }
+}
+void agg_sum_double(int64_t* agg, double val) { *agg = bits_of(double_of(*agg) + val); } /* :1444-1448 */
+void agg_max_double(int64_t* agg, double val) { *agg = bits_of(std::max(double_of(*agg), val)); }
+void agg_min_double(int64_t* agg, double val) { *agg = bits_of(std::min(double_of(*agg), val)); }
+/* DEF_SKIP_AGG for doubles (:1558-1570): `val != skip_val` is an fp compare, `old_agg` is compared bitwise */
+void agg_sum_double_skip_val(int64_t* agg, double val, double skip_val) {
+  if (val != skip_val) {
+    if (*agg != bits_of(skip_val)) agg_sum_double(agg, val); else *agg = bits_of(val);
+  }
+}
+void agg_max_double_skip_val(int64_t* agg, double val, double skip_val) {
+  if (val != skip_val) {
+    if (*agg != bits_of(skip_val)) agg_max_double(agg, val); else *agg = bits_of(val);
+  }
+}
+void agg_min_double_skip_val(int64_t* agg, double val, double skip_val) {
+  if (val != skip_val) {
+    if (*agg != bits_of(skip_val)) agg_min_double(agg, val); else *agg = bits_of(val);
+  }
+}
+void agg_count_double_skip_val(int64_t* agg, double val, double skip_val) { /* :1541-1547 */
+  if (val != skip_val) agg_count(agg);
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * Column decode — QueryEngine/DecodersImpl.h:30-61 (fixed_width_int_decode: sign-extending load),
+ * :112-136 (fixed_width_double_decode)
+ * ------------------------------------------------------------------------------------------------- */
+int64_t fixed_width_int_decode(const int8_t* byte_stream, int byte_width, int64_t pos) {
+  switch (byte_width) {
+    case 1: return static_cast<int64_t>(byte_stream[pos]);
+    case 2: { int16_t v; memcpy(&v, byte_stream + pos * 2, 2); return v; }
+    case 4: { int32_t v; memcpy(&v, byte_stream + pos * 4, 4); return v; }
+    case 8: { int64_t v; memcpy(&v, byte_stream + pos * 8, 8); return v; }
+    default: abort();
+  }
+}
+double fixed_width_double_decode(const int8_t* byte_stream, int64_t pos) {
+  double v;
+  memcpy(&v, byte_stream + pos * 8, 8);
+  return v;
+}
+
+/* ===================================================================================================
+ * Planner
+ * ================================================================================================= */
+struct Target {
+  /* Shared/TargetInfo.h:49-78 */
+  bool is_agg{false};
+  int agg_kind{B2Q_kMIN};
+  Ti sql_type;
+  Ti agg_arg_type; /* type 0 == kNULLT */
+  bool skip_null_val{false};
+  /* ours */
+  int arg_col{-1};
+  Ti arg_ti;      /* argument expression's own type info */
+  int first_slot{0};
+};
+
+struct Range { /* ExpressionRange (Integer or Double or Invalid) */
+  enum Kind { Invalid, Integer, Double } kind{Invalid};
+  int64_t imin{0}, imax{-1}, bucket{0};
+  double fmin{0}, fmax{-1};
+  bool has_nulls{false};
+};
+
+struct Plan {
+  B2QPlan p{};
+  std::vector<Target> targets;
+  std::vector<Ti> slot_compact_ti;
+};
+
+const B2QExpr& expr_at(const B2QExecUnit& u, int idx) {
+  if (idx < 0 || idx >= u.num_exprs) fail(B2Q_ERR_INVALID_ARGUMENT, "expr index out of range");
+  return u.exprs[idx];
+}
+Ti ti_of(const B2QTypeInfo& t) { return Ti{t.type, t.notnull != 0}; }
+
+/* Shared/TargetInfo.cpp:25-78 get_target_info_impl */
+Target get_target_info(const B2QExecUnit& u, int expr_idx, bool bigint_count) {
+  const B2QExpr& e = expr_at(u, expr_idx);
+  Target t;
+  const bool notnull = e.ti.notnull != 0;
+  if (e.kind != B2Q_EXPR_AGG) {
+    if (e.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "non-aggregate target must be a ColumnVar");
+    t.is_agg = false;
+    t.agg_kind = B2Q_kMIN;
+    t.sql_type = ti_of(e.ti); /* get_logical_type_info: identity for the numeric subset */
+    t.agg_arg_type = Ti{0, false};
+    t.skip_null_val = false;
+    t.arg_col = e.col_id;
+    t.arg_ti = ti_of(e.ti);
+    return t;
+  }
+  t.is_agg = true;
+  t.agg_kind = e.op;
+  if (e.left < 0) {
+    if (e.op != B2Q_kCOUNT) fail(B2Q_ERR_INVALID_ARGUMENT, "only COUNT may have no argument");
+    t.sql_type = Ti{bigint_count ? B2Q_kBIGINT : B2Q_kINT, notnull};
+    t.agg_arg_type = Ti{0, false};
+    t.skip_null_val = false;
+    return t;
+  }
+  const B2QExpr& arg = expr_at(u, e.left);
+  if (arg.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "aggregate argument must be a ColumnVar");
+  const Ti arg_ti = ti_of(arg.ti);
+  t.arg_col = arg.col_id;
+  t.arg_ti = arg_ti;
+  if (e.op == B2Q_kAVG) {
+    t.sql_type = is_integer(arg_ti.type) ? Ti{B2Q_kBIGINT, arg_ti.notnull} : arg_ti;
+    t.agg_arg_type = arg_ti;
+    t.skip_null_val = !arg_ti.notnull;
+    return t;
+  }
+  t.sql_type = (e.op == B2Q_kCOUNT) ? Ti{bigint_count ? B2Q_kBIGINT : B2Q_kINT, notnull} : ti_of(e.ti);
+  t.agg_arg_type = arg_ti;
+  t.skip_null_val = !arg_ti.notnull;
+  return t;
+}
+
+bool is_agg_domain_range_equivalent(int agg_kind) { return agg_kind == B2Q_kMIN || agg_kind == B2Q_kMAX; }
+
+/* Shared/SqlTypesLayout.h:37-63 get_compact_type */
+Ti get_compact_type(const Target& t) {
+  if (!t.is_agg) return t.sql_type;
+  if (t.agg_arg_type.type == 0) return t.sql_type;
+  if (is_agg_domain_range_equivalent(t.agg_kind)) return t.agg_arg_type;
+  Ti m = t.sql_type;
+  m.notnull = t.agg_arg_type.notnull;
+  return m;
+}
+
+/* ExpressionRange.cpp:521-632 getLeafColumnRange, then :144-200 apply_simple_quals when asked */
+Range leaf_column_range(const B2QTableInfo& tbl, int col_id) {
+  Range r;
+  if (col_id < 0 || col_id >= tbl.num_cols) fail(B2Q_ERR_INVALID_ARGUMENT, "column id out of range");
+  const int type = tbl.col_types[col_id].type;
+  int64_t total = 0;
+  for (int f = 0; f < tbl.num_fragments; ++f) total += tbl.fragments[f].num_tuples;
+  const bool fp = is_fp(type);
+  r.kind = fp ? Range::Double : Range::Integer;
+  if (total == 0) { /* :567-575 empty table => [0,-1] */
+    r.imin = 0; r.imax = -1; r.fmin = 0; r.fmax = -1; r.has_nulls = false;
+    return r;
+  }
+  bool first = true;
+  for (int f = 0; f < tbl.num_fragments; ++f) {
+    const auto& fr = tbl.fragments[f];
+    if (fr.num_tuples == 0) continue; /* isEmptyPhysicalFragment */
+    const auto& st = fr.col_stats[col_id];
+    if (first) {
+      r.imin = st.int_min; r.imax = st.int_max; r.fmin = st.fp_min; r.fmax = st.fp_max;
+      first = false;
+    } else {
+      r.imin = std::min(r.imin, st.int_min); r.imax = std::max(r.imax, st.int_max);
+      r.fmin = std::min(r.fmin, st.fp_min); r.fmax = std::max(r.fmax, st.fp_max);
+    }
+  }
+  for (int f = 0; f < tbl.num_fragments; ++f) {
+    if (tbl.fragments[f].col_stats[col_id].has_nulls) { r.has_nulls = true; break; }
+  }
+  if (!fp && r.imax < r.imin) { /* :617-621 only nulls */
+    r.imin = 0; r.imax = -1;
+  }
+  r.bucket = 0;
+  return r;
+}
+
+void apply_simple_quals(const B2QExecUnit& u, int key_col_id, Range& r) { /* ExpressionRange.cpp:144-200, :95-123 */
+  for (int i = 0; i < u.num_simple_quals; ++i) {
+    const B2QExpr& q = expr_at(u, u.simple_quals[i]);
+    if (q.kind != B2Q_EXPR_BIN_OPER) continue;
+    const B2QExpr& l = expr_at(u, q.left);
+    const B2QExpr& c = expr_at(u, q.right);
+    if (l.kind != B2Q_EXPR_COLUMN_VAR || l.col_id != key_col_id || c.kind != B2Q_EXPR_CONSTANT) continue;
+    if (r.kind == Range::Double) {
+      const double v = is_fp(c.ti.type) ? c.dval : static_cast<double>(c.ival);
+      switch (q.op) {
+        case B2Q_kGT: case B2Q_kGE: r.fmin = std::max(r.fmin, v); break;
+        case B2Q_kLT: case B2Q_kLE: r.fmax = std::min(r.fmax, v); break;
+        case B2Q_kEQ: r.fmin = std::max(r.fmin, v); r.fmax = std::min(r.fmax, v); break;
+        default: break;
+      }
+    } else if (r.kind == Range::Integer) {
+      const int64_t v = is_fp(c.ti.type) ? static_cast<int64_t>(c.dval) : c.ival;
+      switch (q.op) {
+        case B2Q_kGT: r.imin = std::max(r.imin, v + 1); break;
+        case B2Q_kGE: r.imin = std::max(r.imin, v); break;
+        case B2Q_kLT: r.imax = std::min(r.imax, v - 1); break;
+        case B2Q_kLE: r.imax = std::min(r.imax, v); break;
+        case B2Q_kEQ: r.imin = std::max(r.imin, v); r.imax = std::min(r.imax, v); break;
+        default: break;
+      }
+    }
+  }
+}
+
+/* QueryEngine/OutputBufferInitialization.cpp:124-262 get_agg_initial_val (numeric subset) */
+int64_t get_agg_initial_val(int agg, const Ti& ti, bool enable_compaction, unsigned min_byte_width_to_compact) {
+  const unsigned byte_width = enable_compaction
+                                  ? std::max(static_cast<unsigned>(type_size(ti.type)), min_byte_width_to_compact)
+                                  : 8u;
+  const bool fp = is_fp(ti.type);
+  auto int_max_of = [](unsigned w) -> int64_t {
+    switch (w) { case 1: return INT8_MAX; case 2: return INT16_MAX; case 4: return INT32_MAX; default: return INT64_MAX; }
+  };
+  auto int_min_of = [](unsigned w) -> int64_t {
+    switch (w) { case 1: return INT8_MIN; case 2: return INT16_MIN; case 4: return INT32_MIN; default: return INT64_MIN; }
+  };
+  switch (agg) {
+    case B2Q_kSUM:
+      if (!ti.notnull) return fp ? bits_of(kNullDouble) : inline_int_null_val(ti.type);
+      return fp ? bits_of(0.0) : 0;
+    case B2Q_kAVG:
+    case B2Q_kCOUNT:
+      return 0;
+    case B2Q_kMIN:
+      if (fp) return ti.notnull ? bits_of(DBL_MAX) : bits_of(kNullDouble);
+      return ti.notnull ? int_max_of(byte_width) : inline_int_null_val(ti.type);
+    case B2Q_kMAX:
+      if (fp) return ti.notnull ? bits_of(-DBL_MAX) : bits_of(kNullDouble);
+      return ti.notnull ? int_min_of(byte_width) : inline_int_null_val(ti.type);
+    default:
+      abort();
+  }
+}
+
+/* GroupByAndAggregate.cpp:489-648 get_keyless_info */
+void get_keyless_info(const B2QExecUnit& u, const B2QTableInfo& tbl, const std::vector<Target>& targets,
+                      bool is_group_by, bool& keyless_out, int32_t& index_out) {
+  bool keyless = true, found = false;
+  int32_t index = 0;
+  for (const auto& agg_info : targets) {
+    const Ti chosen_type = get_compact_type(agg_info);
+    if (!found && agg_info.is_agg) {
+      const bool has_arg = agg_info.arg_col >= 0;
+      switch (agg_info.agg_kind) {
+        case B2Q_kAVG:
+          ++index;
+          if (has_arg && !agg_info.arg_ti.notnull) {
+            const Range er = leaf_column_range(tbl, agg_info.arg_col);
+            if (er.kind == Range::Invalid || er.has_nulls) break;
+          }
+          found = true;
+          break;
+        case B2Q_kCOUNT:
+          if (has_arg && !agg_info.arg_ti.notnull) {
+            const Range er = leaf_column_range(tbl, agg_info.arg_col);
+            if (er.kind == Range::Invalid || er.has_nulls) break;
+          }
+          found = true;
+          break;
+        case B2Q_kSUM: {
+          const Range er = leaf_column_range(tbl, agg_info.arg_col);
+          if (!agg_info.arg_ti.notnull) {
+            if (er.kind != Range::Invalid && !er.has_nulls) found = true;
+          } else {
+            if (er.kind == Range::Double) {
+              if (er.fmax < 0 || er.fmin > 0) found = true;
+            } else if (er.kind == Range::Integer) {
+              if (er.imax < 0 || er.imin > 0) found = true;
+            }
+          }
+          break;
+        }
+        case B2Q_kMIN: {
+          const Range er = leaf_column_range(tbl, agg_info.arg_col);
+          const int64_t init_max = get_agg_initial_val(agg_info.agg_kind, chosen_type, is_group_by, 8);
+          if (er.kind == Range::Double) {
+            if (er.fmax < double_of(init_max)) found = true;
+          } else if (er.kind == Range::Integer) {
+            if (er.imax < init_max) found = true;
+          }
+          break;
+        }
+        case B2Q_kMAX: {
+          const Range er = leaf_column_range(tbl, agg_info.arg_col);
+          if (er.kind == Range::Invalid || er.has_nulls) break;
+          const int64_t init_min = get_agg_initial_val(agg_info.agg_kind, chosen_type, is_group_by, 8);
+          if (er.kind == Range::Double) {
+            if (er.fmin > double_of(init_min)) found = true;
+          } else if (er.kind == Range::Integer) {
+            if (er.imin > init_min) found = true;
+          }
+          break;
+        }
+        default:
+          keyless = false;
+          break;
+      }
+    }
+    if (!keyless) break;
+    if (!found) ++index;
+  }
+  keyless_out = keyless && found;
+  index_out = index;
+}
+
+constexpr int64_t kMaxBufferSize = int64_t(1) << 30;   /* GroupByAndAggregate.cpp:57 */
+
+Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecutionOptions& eo,
+               size_t max_groups_buffer_entry_guess, bool has_cardinality_estimation) {
+  if (u.num_join_quals || u.has_estimator || u.num_order_entries || u.has_union_all || u.has_window_function)
+    fail(B2Q_ERR_UNSUPPORTED, "joins / estimator / sort / union / window functions are outside this path");
+  if (u.num_groupby_exprs > 1) fail(B2Q_ERR_UNSUPPORTED, "multi-column GROUP BY");
+  if (u.num_target_exprs <= 0 || u.num_target_exprs > B2Q_MAX_TARGETS)
+    fail(B2Q_ERR_INVALID_ARGUMENT, "bad target count");
+  if (eo.output_columnar_hint) fail(B2Q_ERR_UNSUPPORTED, "columnar output");
+  for (int c = 0; c < tbl.num_cols; ++c)
+    if (type_size(tbl.col_types[c].type) < 0) fail(B2Q_ERR_UNSUPPORTED, "column type outside the numeric subset");
+
+  Plan plan;
+  B2QPlan& p = plan.p;
+  const bool bigint_count = eo.bigint_count != 0;
+  const bool is_group_by = u.num_groupby_exprs == 1;
+
+  for (int i = 0; i < u.num_target_exprs; ++i) plan.targets.push_back(get_target_info(u, u.target_exprs[i], bigint_count));
+  bool any_agg = false;
+  for (auto& t : plan.targets) any_agg |= t.is_agg;
+  if (!any_agg) fail(B2Q_ERR_UNSUPPORTED, "projection queries are outside this path");
+
+  /* ---- hash type: GroupByAndAggregate::getColRangeInfo (:232-365) + get_expr_range_info (:181-218) ---- */
+  int key_col = -1;
+  Range key_range;
+  if (is_group_by) {
+    const B2QExpr& g = expr_at(u, u.groupby_exprs[0]);
+    if (g.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "GROUP BY expression must be a ColumnVar");
+    key_col = g.col_id;
+    key_range = leaf_column_range(tbl, key_col);
+    apply_simple_quals(u, key_col, key_range);
+    p.group_col_width = type_size(tbl.col_types[key_col].type);
+    int hash_type;
+    int64_t cmin = 0, cmax = 0, cbucket = 0;
+    bool chas_nulls = false;
+    if (key_range.kind == Range::Integer) {
+      if (key_range.imin > key_range.imax) { /* :193-196 */
+        hash_type = B2Q_GroupByBaselineHash; cmin = 0; cmax = -1; chas_nulls = key_range.has_nulls;
+      } else {
+        hash_type = B2Q_GroupByPerfectHash;
+        cmin = key_range.imin; cmax = key_range.imax; cbucket = key_range.bucket; chas_nulls = key_range.has_nulls;
+      }
+    } else { /* Float/Double/Invalid => baseline (:203-212) */
+      hash_type = B2Q_GroupByBaselineHash;
+      if (key_range.kind == Range::Double && key_range.fmin > key_range.fmax) { cmax = -1; chas_nulls = key_range.has_nulls; }
+    }
+    if (hash_type == B2Q_GroupByPerfectHash) {
+      /* :298-304 max_entry_count, :131-139 is_column_range_too_big_for_perfect_hash */
+      const int64_t col_count = u.num_groupby_exprs + u.num_target_exprs;
+      const int64_t max_entry_count = kMaxBufferSize / (col_count * static_cast<int64_t>(sizeof(int64_t)));
+      bool too_big;
+      int64_t diff;
+      if (__builtin_sub_overflow(cmax, cmin, &diff)) too_big = true; else too_big = diff >= max_entry_count;
+      if (too_big && !cbucket) hash_type = B2Q_GroupByBaselineHash; /* :354-360, min/max kept */
+    }
+    p.query_desc_type = hash_type;
+    p.min_val = cmin; p.max_val = cmax; p.bucket = cbucket; p.has_nulls = chas_nulls;
+  } else {
+    p.query_desc_type = B2Q_NonGroupedAggregate;
+    p.group_col_width = 0;
+  }
+  p.key_col_id = key_col;
+
+  /* ---- keyless: initQueryMemoryDescriptorImpl :943-947 ---- */
+  bool keyless = false;
+  int32_t keyless_index = -1;
+  if (is_group_by && p.query_desc_type == B2Q_GroupByPerfectHash)
+    get_keyless_info(u, tbl, plan.targets, is_group_by, keyless, keyless_index);
+
+  /* ---- slots: ColSlotContext ctor (ColSlotContext.cpp:35-101) ---- */
+  std::vector<int8_t> logical;
+  for (size_t ti = 0; ti < plan.targets.size(); ++ti) {
+    auto& t = plan.targets[ti];
+    t.first_slot = static_cast<int>(logical.size());
+    const Ti chosen = get_compact_type(t);
+    logical.push_back(static_cast<int8_t>(type_size(chosen.type)));
+    plan.slot_compact_ti.push_back(chosen);
+    if (t.is_agg && t.agg_kind == B2Q_kAVG) {
+      logical.push_back(8);
+      plan.slot_compact_ti.push_back(Ti{B2Q_kBIGINT, true});
+    }
+  }
+  if (logical.size() > B2Q_MAX_SLOTS) fail(B2Q_ERR_UNSUPPORTED, "too many slots");
+
+  /* ---- pick_target_compact_width (QueryMemoryDescriptor.cpp:748-842), crt_min_byte_width = 8 ---- */
+  int8_t min_slot_size;
+  {
+    const int8_t crt_min_byte_width = 8;
+    if (bigint_count) {
+      min_slot_size = 8;
+    } else {
+      int8_t compact_width = 0;
+      if (!is_group_by) compact_width = crt_min_byte_width; /* groupby_exprs == {nullptr} (:775-778) */
+      if (!compact_width) {
+        for (int i = 0; i < u.num_target_exprs; ++i) {
+          const B2QExpr& e = expr_at(u, u.target_exprs[i]);
+          if (e.kind == B2Q_EXPR_AGG && e.left >= 0) { compact_width = crt_min_byte_width; break; }
+          if (e.kind == B2Q_EXPR_AGG) continue; /* COUNT(*) */
+          if (is_integer(e.ti.type) && type_size(e.ti.type) <= 4) continue; /* is_int_and_no_bigger_than(ti,4) */
+          compact_width = crt_min_byte_width;
+          break;
+        }
+      }
+      if (!compact_width) {
+        uint64_t total_tuples = 0;
+        for (int f = 0; f < tbl.num_fragments; ++f) total_tuples += tbl.fragments[f].num_tuples;
+        min_slot_size = total_tuples <= std::numeric_limits<uint32_t>::max() ? 4 : crt_min_byte_width;
+      } else {
+        for (int i = 0; i < u.num_target_exprs; ++i) /* get_col_byte_widths(target_exprs) */
+          compact_width = std::max<int8_t>(compact_width, static_cast<int8_t>(type_size(expr_at(u, u.target_exprs[i]).ti.type)));
+        min_slot_size = compact_width;
+      }
+    }
+  }
+
+  /* ---- QueryMemoryDescriptor::init (:240-444) ---- */
+  p.num_targets = static_cast<int32_t>(plan.targets.size());
+  p.output_columnar = 0;
+  p.interleaved_bins_on_gpu = 0;
+  p.keyless_hash = 0;
+  p.idx_target_as_key = -1;
+  p.effective_key_width = 8;
+  std::vector<bool> slot_is_key_ref(logical.size(), false); /* target_groupby_indices != -1 => 0-width slot */
+  if (!is_group_by) {
+    p.entry_count = 1;
+  } else if (p.query_desc_type == B2Q_GroupByPerfectHash) {
+    /* keyless_hash (:327-333): no sort hint, no bucket, no baseline sort in this path */
+    p.keyless_hash = (!p.bucket && keyless) ? 1 : 0;
+    p.idx_target_as_key = keyless_index;
+    /* getBucketedCardinality (:367-375) */
+    int64_t card = p.max_val - p.min_val;
+    if (p.bucket) card /= p.bucket;
+    card += 1 + (p.has_nulls ? 1 : 0);
+    p.entry_count = std::max<int64_t>(card, 1);
+    /* interleaved_bins_on_gpu (:364-369) is a GPU-layout detail of the reference; the CPU path never has it */
+  } else { /* baseline (:380-398) */
+    if (!has_cardinality_estimation) fail(B2Q_ERR_CARDINALITY_ESTIMATION_REQUIRED, "baseline hash needs a cardinality estimate");
+    p.entry_count = static_cast<int64_t>(max_groups_buffer_entry_guess);
+    if (p.entry_count <= 0) fail(B2Q_ERR_INVALID_ARGUMENT, "entry guess must be positive");
+    /* target_expr_group_by_indices: targets that ARE the group key get 0-width slots */
+    for (size_t ti = 0; ti < plan.targets.size(); ++ti) {
+      const auto& t = plan.targets[ti];
+      if (!t.is_agg && t.arg_col == key_col) slot_is_key_ref[t.first_slot] = true;
+    }
+    /* pick_baseline_key_width (:112-147) */
+    int8_t kw = 4;
+    {
+      const Range er = leaf_column_range(tbl, key_col); /* no simple quals here (getExpressionRange w/o quals) */
+      int8_t w;
+      if (er.kind == Range::Invalid) w = 8;
+      else if (er.kind == Range::Integer) {
+        if (p.group_col_width == 8 && er.has_nulls) w = 8;
+        else {
+          /* is_valid_int32_range (QueryMemoryDescriptor.cpp:40-42): min > INT32_MIN && max < EMPTY_KEY_32 - 1 */
+          const bool ok = er.imin > static_cast<int64_t>(INT32_MIN) && er.imax < static_cast<int64_t>(kEmptyKey32) - 1;
+          w = ok ? 4 : 8;
+        }
+      } else w = 8;
+      kw = std::max(kw, w);
+    }
+    p.effective_key_width = kw;
+    p.min_val = 0; p.max_val = 0; p.bucket = 0; p.has_nulls = 0; /* actual_col_range_info reset (:396-397) */
+  }
+
+  /* padded widths: setAllSlotsPaddedSize(min_slot_size); 0-width for key-ref slots (addSlotForColumn(0,0)) */
+  p.num_slots = static_cast<int32_t>(logical.size());
+  for (size_t s = 0; s < logical.size(); ++s) {
+    if (slot_is_key_ref[s]) { p.slot_logical_width[s] = 0; p.slot_padded_width[s] = 0; continue; }
+    p.slot_logical_width[s] = logical[s];
+    p.slot_padded_width[s] = min_slot_size;
+    if (logical[s] > min_slot_size) fail(B2Q_ERR_UNSUPPORTED, "slot wider than compact width (ColSlotContext::validate)");
+  }
+  /* TargetExprCodegenBuilder::operator() (:614-621): non-grouped + slot < 8 => CompilationRetryNoCompaction;
+   * the retry (Execute.cpp:2260) re-plans with 8-byte slots.  Non-grouped already forces 8 above. */
+
+  /* ---- row size / offsets: getRowSize (:848-860), getColOffInBytes (:918-955), ColSlotContext alignment ---- */
+  int64_t off = 0;
+  if (is_group_by && !p.keyless_hash) off = align_to_int64(1 * p.effective_key_width);
+  const int64_t key_bytes = off;
+  int64_t cols = 0;
+  for (int s = 0; s < p.num_slots; ++s) {
+    const int w = p.slot_padded_width[s];
+    if (w == 8) cols = align_to_int64(cols);
+    p.slot_offset[s] = key_bytes + cols;
+    cols += w;
+  }
+  p.row_size = align_to_int64(key_bytes + cols);
+  p.buffer_size = p.row_size * p.entry_count;
+
+  /* ---- init vals: init_agg_val_vec (OutputBufferInitialization.cpp:26-86, :264-293) ---- */
+  {
+    int8_t compact_byte_width = 8; /* ColSlotContext::getCompactByteWidth: first non-zero padded size */
+    for (int s = 0; s < p.num_slots; ++s) if (p.slot_padded_width[s]) { compact_byte_width = p.slot_padded_width[s]; break; }
+    int s = 0;
+    for (auto t : plan.targets) { /* by value: set_notnull only affects the init computation (:283-288) */
+      if (t.arg_col >= 0 && t.is_agg && p.query_desc_type == B2Q_NonGroupedAggregate &&
+          (t.agg_kind == B2Q_kMIN || t.agg_kind == B2Q_kMAX || t.agg_kind == B2Q_kSUM || t.agg_kind == B2Q_kAVG)) {
+        t.sql_type.notnull = false; t.agg_arg_type.notnull = false; t.skip_null_val = true; /* set_notnull(target,false) */
+      }
+      if (!t.is_agg) {
+        p.init_vals[s] = 0;
+        ++s;
+        continue;
+      }
+      Ti init_ti = get_compact_type(t);
+      if (!is_group_by) init_ti.notnull = false;
+      p.init_vals[s++] = get_agg_initial_val(t.agg_kind, init_ti, is_group_by, compact_byte_width);
+      if (t.agg_kind == B2Q_kAVG) p.init_vals[s++] = 0;
+    }
+  }
+
+  /* ---- skip_null_val as the code generator sees it (TargetExprBuilder.cpp:648-662) + public target infos ---- */
+  for (size_t i = 0; i < plan.targets.size(); ++i) {
+    auto& t = plan.targets[i];
+    if (t.arg_col >= 0 && t.is_agg && p.query_desc_type == B2Q_NonGroupedAggregate) t.skip_null_val = true;
+    B2QTargetInfo& o = p.targets[i];
+    o.is_agg = t.is_agg; o.agg_kind = t.agg_kind;
+    o.sql_type = B2QTypeInfo{t.sql_type.type, t.sql_type.notnull};
+    o.agg_arg_type = B2QTypeInfo{t.agg_arg_type.type, t.agg_arg_type.notnull};
+    o.skip_null_val = t.skip_null_val; o.is_distinct = 0; o.arg_col_id = t.arg_col; o.first_slot = t.first_slot;
+  }
+  p.kernel = 0;
+  return plan;
+}
+
+/* ===================================================================================================
+ * Filter: quals evaluated with the nullable compare semantics of RuntimeFunctions.cpp:73-107
+ * (DEF_CMP_NULLABLE: lhs OP rhs if neither is the NULL sentinel else null_bool_val = INT8_MIN) and the
+ * nullable logical_and / logical_or of RuntimeFunctions.cpp:320-357; a row passes iff the final value > 0
+ * (CodeGenerator::toBool, LogicalIR.cpp:344-352).
+ * ================================================================================================= */
+constexpr int8_t kNullBool = INT8_MIN;
+
+struct Frag {
+  const B2QFragmentInfo* fi;
+};
+
+int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr, int expr_idx, int64_t pos) {
+  const B2QExpr& e = expr_at(u, expr_idx);
+  if (e.kind != B2Q_EXPR_BIN_OPER) fail(B2Q_ERR_UNSUPPORTED, "qual must be a BinOper");
+  if (e.op == B2Q_kAND || e.op == B2Q_kOR) {
+    const int8_t lhs = eval_bool(u, tbl, fr, e.left, pos);
+    const int8_t rhs = eval_bool(u, tbl, fr, e.right, pos);
+    if (e.op == B2Q_kAND) { /* logical_and (:320-337) */
+      if (lhs == kNullBool) return rhs == 0 ? rhs : kNullBool;
+      if (rhs == kNullBool) return lhs == 0 ? lhs : kNullBool;
+      return (lhs && rhs) ? 1 : 0;
+    }
+    /* logical_or (:339-357) */
+    if (lhs == kNullBool) return rhs == 0 ? kNullBool : rhs;
+    if (rhs == kNullBool) return lhs == 0 ? kNullBool : lhs;
+    return (lhs || rhs) ? 1 : 0;
+  }
+  const B2QExpr& l = expr_at(u, e.left);
+  const B2QExpr& r = expr_at(u, e.right);
+  if (l.kind != B2Q_EXPR_COLUMN_VAR || r.kind != B2Q_EXPR_CONSTANT)
+    fail(B2Q_ERR_UNSUPPORTED, "comparison must be ColumnVar OP Constant");
+  const int col = l.col_id;
+  const int ctype = tbl.col_types[col].type;
+  const bool col_notnull = tbl.col_types[col].notnull != 0;
+  const int8_t* buf = static_cast<const int8_t*>(fr.col_buffers[col]);
+  if (r.is_null) return kNullBool;
+  if (is_fp(ctype) || is_fp(r.ti.type)) {
+    /* fp compare: the integer side is cast to double (CompareIR.cpp codegenCmp after normalisation) */
+    double lv;
+    bool lnull;
+    if (is_fp(ctype)) { lv = fixed_width_double_decode(buf, pos); lnull = !col_notnull && lv == kNullDouble; }
+    else { const int64_t iv = fixed_width_int_decode(buf, type_size(ctype), pos); lnull = !col_notnull && iv == inline_int_null_val(ctype); lv = static_cast<double>(iv); }
+    if (lnull) return kNullBool;
+    const double rv = is_fp(r.ti.type) ? r.dval : static_cast<double>(r.ival);
+    switch (e.op) {
+      case B2Q_kEQ: return lv == rv; case B2Q_kNE: return lv != rv; case B2Q_kLT: return lv < rv;
+      case B2Q_kGT: return lv > rv; case B2Q_kLE: return lv <= rv; case B2Q_kGE: return lv >= rv;
+      default: fail(B2Q_ERR_UNSUPPORTED, "comparison operator");
+    }
+  }
+  const int64_t lv = fixed_width_int_decode(buf, type_size(ctype), pos);
+  if (!col_notnull && lv == inline_int_null_val(ctype)) return kNullBool;
+  const int64_t rv = r.ival;
+  switch (e.op) {
+    case B2Q_kEQ: return lv == rv; case B2Q_kNE: return lv != rv; case B2Q_kLT: return lv < rv;
+    case B2Q_kGT: return lv > rv; case B2Q_kLE: return lv <= rv; case B2Q_kGE: return lv >= rv;
+    default: fail(B2Q_ERR_UNSUPPORTED, "comparison operator");
+  }
+}
+
+bool row_passes(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr, int64_t pos) {
+  /* simple_quals and quals are AND-ed: each must be TRUE (`filter_lv = AND of toBool(qual)`, NativeCodegen.cpp:3455+) */
+  for (int i = 0; i < u.num_simple_quals; ++i) if (!(eval_bool(u, tbl, fr, u.simple_quals[i], pos) > 0)) return false;
+  for (int i = 0; i < u.num_quals; ++i) if (!(eval_bool(u, tbl, fr, u.quals[i], pos) > 0)) return false;
+  return true;
+}
+
+/* ===================================================================================================
+ * Per-target aggregate update, as emitted by TargetExprCodegen::codegenAggregate
+ * (TargetExprBuilder.cpp:470-583): value conversion (convertNullIfAny, GroupByAndAggregate.cpp:1599-1660),
+ * cast to the slot width, `_skip_val` variant when target_info.skip_null_val.
+ * All slots are 8 bytes wide here except the COUNT(*)-only 4-byte layout, which uses the _int32 variants.
+ * ================================================================================================= */
+struct SlotWriter {
+  int8_t* row; /* points at the start of the row (after nothing): offsets are absolute inside the row */
+};
+
+void update_target(const Plan& plan, const Target& t, int8_t* row_base, const B2QTableInfo& tbl,
+                   const B2QFragmentInfo& fr, int64_t pos) {
+  const B2QPlan& p = plan.p;
+  const int s = t.first_slot;
+  const int w = p.slot_padded_width[s];
+  if (w == 0) return; /* baseline: group-key targets are read from the key columns */
+  int8_t* slot = row_base + p.slot_offset[s];
+  if (w == 4) {
+    /* only reachable for COUNT(*) / small-int key projections (pick_target_compact_width) */
+    int32_t* a = reinterpret_cast<int32_t*>(slot);
+    if (!t.is_agg) { *a = static_cast<int32_t>(fixed_width_int_decode(static_cast<const int8_t*>(fr.col_buffers[t.arg_col]), type_size(tbl.col_types[t.arg_col].type), pos)); return; } /* agg_id_int32 */
+    if (t.agg_kind == B2Q_kCOUNT && t.arg_col < 0) { *reinterpret_cast<uint32_t*>(a) += 1; return; } /* agg_count_int32 */
+    fail(B2Q_ERR_UNSUPPORTED, "4-byte slot with an aggregate argument");
+  }
+  int64_t* a = reinterpret_cast<int64_t*>(slot);
+  if (!t.is_agg) { /* agg_id on the projected group key, sign-extended to the slot */
+    const int ctype = tbl.col_types[t.arg_col].type;
+    if (is_fp(ctype)) agg_id(a, bits_of(fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[t.arg_col]), pos)));
+    else agg_id(a, fixed_width_int_decode(static_cast<const int8_t*>(fr.col_buffers[t.arg_col]), type_size(ctype), pos));
+    return;
+  }
+  if (t.agg_kind == B2Q_kCOUNT && t.arg_col < 0) { agg_count(a); return; }
+  const int ctype = tbl.col_types[t.arg_col].type;
+  const bool arg_notnull = t.arg_ti.notnull;
+  const int8_t* buf = static_cast<const int8_t*>(fr.col_buffers[t.arg_col]);
+  const bool need_skip_null = t.skip_null_val;
+  if (is_fp(ctype)) {
+    const double v = fixed_width_double_decode(buf, pos);
+    const double null_v = kNullDouble; /* arg null == agg null for DOUBLE: no conversion needed */
+    switch (t.agg_kind) {
+      case B2Q_kCOUNT: if (need_skip_null) agg_count_double_skip_val(a, v, null_v); else agg_count(a); break;
+      case B2Q_kSUM: if (need_skip_null) agg_sum_double_skip_val(a, v, null_v); else agg_sum_double(a, v); break;
+      case B2Q_kMIN: if (need_skip_null) agg_min_double_skip_val(a, v, null_v); else agg_min_double(a, v); break;
+      case B2Q_kMAX: if (need_skip_null) agg_max_double_skip_val(a, v, null_v); else agg_max_double(a, v); break;
+      case B2Q_kAVG: {
+        int64_t* cnt = reinterpret_cast<int64_t*>(row_base + p.slot_offset[s + 1]);
+        if (need_skip_null) { agg_sum_double_skip_val(a, v, null_v); agg_count_double_skip_val(cnt, v, null_v); }
+        else { agg_sum_double(a, v); agg_count(cnt); }
+        break;
+      }
+      default: abort();
+    }
+    return;
+  }
+  /* integer argument */
+  int64_t v = fixed_width_int_decode(buf, type_size(ctype), pos);
+  int64_t null_v;
+  if (is_agg_domain_range_equivalent(t.agg_kind)) {
+    null_v = inline_int_null_val(ctype); /* inlineIntNull(arg_ti) sign-extended to 64 bits (:548-556) */
+  } else {
+    const int agg_type = t.sql_type.type; /* BIGINT for SUM/AVG over ints; INT/BIGINT for COUNT */
+    null_v = inline_int_null_val(agg_type);
+    if (need_skip_null && !arg_notnull) { /* convertNullIfAny: arg NULL -> agg NULL, else cast to the agg type */
+      if (v == inline_int_null_val(ctype)) v = null_v;
+      else if (type_size(agg_type) == 4) v = static_cast<int32_t>(v); /* castToTypeIn(32) then sext to the slot */
+    }
+  }
+  switch (t.agg_kind) {
+    case B2Q_kCOUNT: if (need_skip_null) agg_count_skip_val(a, v, null_v); else agg_count(a); break;
+    case B2Q_kSUM: if (need_skip_null) agg_sum_skip_val(a, v, null_v); else agg_sum(a, v); break;
+    case B2Q_kMIN: if (need_skip_null) agg_min_skip_val(a, v, null_v); else agg_min(a, v); break;
+    case B2Q_kMAX: if (need_skip_null) agg_max_skip_val(a, v, null_v); else agg_max(a, v); break;
+    case B2Q_kAVG: {
+      int64_t* cnt = reinterpret_cast<int64_t*>(row_base + p.slot_offset[s + 1]);
+      if (need_skip_null) { agg_sum_skip_val(a, v, null_v); agg_count_skip_val(cnt, v, null_v); }
+      else { agg_sum(a, v); agg_count(cnt); }
+      break;
+    }
+    default: abort();
+  }
+}
+
+/* ---- buffer init: QueryMemoryInitializer::initRowGroups (QueryMemoryInitializer.cpp:620-700) ---- */
+void init_buffer(const Plan& plan, std::vector<int8_t>& buf) {
+  const B2QPlan& p = plan.p;
+  buf.assign(static_cast<size_t>(p.buffer_size), 0);
+  const bool has_key = p.query_desc_type != B2Q_NonGroupedAggregate && !p.keyless_hash;
+  for (int64_t e = 0; e < p.entry_count; ++e) {
+    int8_t* row = buf.data() + e * p.row_size;
+    if (has_key) {
+      if (p.effective_key_width == 4) { int32_t k = kEmptyKey32; memcpy(row, &k, 4); }
+      else { int64_t k = kEmptyKey64; memcpy(row, &k, 8); }
+    }
+    for (int s = 0; s < p.num_slots; ++s) {
+      const int w = p.slot_padded_width[s];
+      if (w == 8) memcpy(row + p.slot_offset[s], &p.init_vals[s], 8);
+      else if (w == 4) { int32_t v = static_cast<int32_t>(p.init_vals[s]); memcpy(row + p.slot_offset[s], &v, 4); }
+    }
+  }
+}
+
+/* ---- the fragment row loop: multifrag_query_hoisted_literals -> query_group_by_template / query_template
+ * (RuntimeFunctions.cpp:2434-2472, QueryTemplateGenerator.cpp:552-815): pos_start = 0, pos_step = 1 on CPU ---- */
+int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr,
+                     std::vector<int8_t>& buf) {
+  const B2QPlan& p = plan.p;
+  init_buffer(plan, buf);
+  const int key_col = p.key_col_id;
+  const int key_type = key_col >= 0 ? tbl.col_types[key_col].type : 0;
+  const bool key_nullable = key_col >= 0 && !tbl.col_types[key_col].notnull;
+  const uint32_t row_size_quad = static_cast<uint32_t>(p.row_size / 8);
+  for (int64_t pos = 0; pos < fr.num_tuples; ++pos) {
+    if (!row_passes(u, tbl, fr, pos)) continue;
+    int8_t* row_base;
+    if (p.query_desc_type == B2Q_NonGroupedAggregate) {
+      row_base = buf.data();
+    } else {
+      if (is_fp(key_type)) fail(B2Q_ERR_UNSUPPORTED, "floating-point GROUP BY key");
+      int64_t key = fixed_width_int_decode(static_cast<const int8_t*>(fr.col_buffers[key_col]), type_size(key_type), pos);
+      if (p.query_desc_type == B2Q_GroupByPerfectHash) {
+        /* NULL key -> max+1 bucket (GroupByAndAggregate.cpp:1337-1350, GroupByRuntime.cpp:414-425) */
+        if (p.has_nulls && key_nullable && key == inline_int_null_val(key_type)) key = p.max_val + (p.bucket ? p.bucket : 1);
+        /* get_group_value_fast[_keyless] (GroupByRuntime.cpp:194-209, RuntimeFunctions.cpp:2126-2133) */
+        int64_t key_diff = key - p.min_val;
+        if (p.bucket) key_diff /= p.bucket;
+        if (key_diff < 0 || key_diff >= p.entry_count) return B2Q_ERR_KEY_OUT_OF_RANGE; /* stale stats: reference would corrupt memory */
+        row_base = buf.data() + key_diff * p.row_size;
+        if (!p.keyless_hash) {
+          int64_t* k = reinterpret_cast<int64_t*>(row_base);
+          if (*k == kEmptyKey64) *k = key;
+        }
+      } else {
+        int64_t key_store = key;
+        int64_t* slots;
+        if (p.effective_key_width == 4) {
+          int32_t k32 = static_cast<int32_t>(key);
+          int64_t keybuf = 0;
+          memcpy(&keybuf, &k32, 4);
+          slots = get_group_value(reinterpret_cast<int64_t*>(buf.data()), static_cast<uint32_t>(p.entry_count), &keybuf, 1, 4, row_size_quad);
+        } else {
+          slots = get_group_value(reinterpret_cast<int64_t*>(buf.data()), static_cast<uint32_t>(p.entry_count), &key_store, 1, 8, row_size_quad);
+        }
+        if (!slots) return -static_cast<int32_t>(std::min<int64_t>(pos + 1, INT32_MAX)); /* out of slots: -pos (GroupByAndAggregate.cpp:1149-1154) */
+        /* row_base such that slot_offset (which includes the key bytes) lands on `slots` */
+        row_base = reinterpret_cast<int8_t*>(slots) - align_to_int64(p.effective_key_width);
+      }
+    }
+    for (const auto& t : plan.targets) update_target(plan, t, row_base, tbl, fr, pos);
+  }
+  return 0;
+}
+
+/* ---- is the entry empty?  ResultSetStorage::isEmptyEntry (ResultSetIteration.cpp:2457-2492) ---- */
+bool is_empty_entry(const B2QPlan& p, const int8_t* buf, int64_t entry) {
+  if (p.query_desc_type == B2Q_NonGroupedAggregate) return false;
+  const int8_t* row = buf + entry * p.row_size;
+  if (p.keyless_hash) {
+    const int s = p.idx_target_as_key;
+    const int w = p.slot_padded_width[s];
+    int64_t v;
+    if (w == 4) { int32_t x; memcpy(&x, row + p.slot_offset[s], 4); v = x; } else memcpy(&v, row + p.slot_offset[s], 8);
+    return v == p.init_vals[s];
+  }
+  if (p.effective_key_width == 4) { int32_t k; memcpy(&k, row, 4); return k == kEmptyKey32; }
+  int64_t k;
+  memcpy(&k, row, 8);
+  return k == kEmptyKey64;
+}
+
+/* ---- ResultSetStorage::reduceOneSlot (ResultSetReduction.cpp:1496-1566) with the AGGREGATE_ONE_* macros
+ * (:1290-1437): COUNT merges as SUM, AVG merges (sum, count) separately, nullable values use *_skip_val with the
+ * slot's init value as the skip value. ---- */
+void reduce_one_row(const Plan& plan, int8_t* this_row, const int8_t* that_row) {
+  const B2QPlan& p = plan.p;
+  for (const auto& t : plan.targets) {
+    const int s = t.first_slot;
+    const int w = p.slot_padded_width[s];
+    if (w == 0) continue;
+    int8_t* tp = this_row + p.slot_offset[s];
+    const int8_t* op = that_row + p.slot_offset[s];
+    const int64_t init_val = p.init_vals[s];
+    if (w == 4) {
+      int32_t a, b;
+      memcpy(&a, tp, 4); memcpy(&b, op, 4);
+      if (!t.is_agg) { if (b != static_cast<int32_t>(init_val)) a = b; }
+      else a = static_cast<int32_t>(static_cast<uint32_t>(a) + static_cast<uint32_t>(b)); /* agg_sum_int32 */
+      memcpy(tp, &a, 4);
+      continue;
+    }
+    int64_t* a = reinterpret_cast<int64_t*>(tp);
+    int64_t b;
+    memcpy(&b, op, 8);
+    if (!t.is_agg) { if (b != init_val) *a = b; continue; } /* projection: :1585-1640 case 8 */
+    const bool fp = is_fp(get_compact_type(t).type);
+    switch (t.agg_kind) {
+      case B2Q_kCOUNT: agg_sum(a, b); break; /* AGGREGATE_ONE_COUNT */
+      case B2Q_kAVG: {
+        int64_t* ac = reinterpret_cast<int64_t*>(this_row + p.slot_offset[s + 1]);
+        int64_t bc;
+        memcpy(&bc, that_row + p.slot_offset[s + 1], 8);
+        agg_sum(ac, bc);
+      } /* fall thru */
+      case B2Q_kSUM:
+        if (t.skip_null_val) { if (fp) agg_sum_double_skip_val(a, double_of(b), double_of(init_val)); else agg_sum_skip_val(a, b, init_val); }
+        else { if (fp) agg_sum_double(a, double_of(b)); else agg_sum(a, b); }
+        break;
+      case B2Q_kMIN:
+        if (t.skip_null_val) { if (fp) agg_min_double_skip_val(a, double_of(b), double_of(init_val)); else agg_min_skip_val(a, b, init_val); }
+        else { if (fp) agg_min_double(a, double_of(b)); else agg_min(a, b); }
+        break;
+      case B2Q_kMAX:
+        if (t.skip_null_val) { if (fp) agg_max_double_skip_val(a, double_of(b), double_of(init_val)); else agg_max_skip_val(a, b, init_val); }
+        else { if (fp) agg_max_double(a, double_of(b)); else agg_max(a, b); }
+        break;
+      default: abort();
+    }
+  }
+}
+
+/* ResultSetStorage::reduce (ResultSetReduction.cpp:203-396): perfect hash => entry-wise
+ * (reduceOneEntryNoCollisions :398-450: skip empty `that` entries, copy key); baseline => re-probe every
+ * non-empty `that` entry into `this` (:698-828). */
+int32_t reduce_buffers(const Plan& plan, std::vector<int8_t>& this_buf, const std::vector<int8_t>& that_buf) {
+  const B2QPlan& p = plan.p;
+  if (p.query_desc_type == B2Q_NonGroupedAggregate) {
+    reduce_one_row(plan, this_buf.data(), that_buf.data());
+    return 0;
+  }
+  for (int64_t e = 0; e < p.entry_count; ++e) {
+    if (is_empty_entry(p, that_buf.data(), e)) continue;
+    const int8_t* that_row = that_buf.data() + e * p.row_size;
+    if (p.query_desc_type == B2Q_GroupByPerfectHash) {
+      int8_t* this_row = this_buf.data() + e * p.row_size;
+      if (!p.keyless_hash) memcpy(this_row, that_row, align_to_int64(p.effective_key_width)); /* copyKeyColWise / key copy */
+      reduce_one_row(plan, this_row, that_row);
+    } else {
+      int64_t keybuf = 0;
+      memcpy(&keybuf, that_row, p.effective_key_width);
+      int64_t* slots = get_group_value(reinterpret_cast<int64_t*>(this_buf.data()), static_cast<uint32_t>(p.entry_count), &keybuf, 1,
+                                       static_cast<uint32_t>(p.effective_key_width), static_cast<uint32_t>(p.row_size / 8));
+      if (!slots) return B2Q_ERR_OUT_OF_SLOTS;
+      int8_t* this_row = reinterpret_cast<int8_t*>(slots) - align_to_int64(p.effective_key_width);
+      reduce_one_row(plan, this_row, that_row);
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+/* ===================================================================================================
+ * C API (ctypes-friendly)
+ * ================================================================================================= */
+struct OracleResult {
+  Plan plan;
+  std::vector<int8_t> buf;
+  int64_t cursor{0};
+  double exec_seconds{0};
+};
+
+static thread_local std::string g_last_error;
+
+ORACLE_EXPORT const char* oracle_last_error() { return g_last_error.c_str(); }
+
+ORACLE_EXPORT uint32_t oracle_murmur3(const void* key, int len, uint32_t seed) { return murmur3(key, len, seed); }
+
+/* get_group_value over a caller-provided row-wise buffer; returns the int64 offset of the slot pointer or -1 */
+ORACLE_EXPORT int64_t oracle_get_group_value(int64_t* groups_buffer, uint32_t entry_count, const int64_t* key,
+                                             uint32_t key_count, uint32_t key_width, uint32_t row_size_quad) {
+  int64_t* r = get_group_value(groups_buffer, entry_count, key, key_count, key_width, row_size_quad);
+  return r ? (r - groups_buffer) : -1;
+}
+
+ORACLE_EXPORT int32_t oracle_plan(const B2QExecUnit* u, const B2QTableInfo* tbl, const B2QExecutionOptions* eo,
+                                  size_t entry_guess, int32_t has_cardinality_estimation, B2QPlan* out) {
+  try {
+    Plan plan = make_plan(*u, *tbl, *eo, entry_guess, has_cardinality_estimation != 0);
+    *out = plan.p;
+    return 0;
+  } catch (const OracleError& e) {
+    g_last_error = e.msg;
+    return e.code;
+  }
+}
+
+/* The CPU executor: one buffer per fragment (KernelPerFragment, Execute.cpp:3102-3153), `num_threads` worker
+ * threads each taking fragments round-robin (the reference runs one thread per fragment, capped at
+ * cpu_threads(), Shared/thread_count.h:25-28), then a host reduce in fragment order
+ * (Execute.cpp:2833-2864 -> reduceMultiDeviceResultSets :1772). */
+ORACLE_EXPORT int32_t oracle_execute(const B2QExecUnit* u, const B2QTableInfo* tbl, const B2QExecutionOptions* eo,
+                                     size_t entry_guess, int32_t has_cardinality_estimation, int32_t num_threads,
+                                     OracleResult** out) {
+  try {
+    auto res = new OracleResult();
+    res->plan = make_plan(*u, *tbl, *eo, entry_guess, has_cardinality_estimation != 0);
+    if (tbl->memory_level != B2Q_CPU_LEVEL) fail(B2Q_ERR_INVALID_ARGUMENT, "oracle needs host column buffers");
+    const int nf = tbl->num_fragments;
+    std::vector<std::vector<int8_t>> bufs(std::max(nf, 1));
+    std::vector<int32_t> errs(std::max(nf, 1), 0);
+    std::vector<std::string> msgs(std::max(nf, 1));
+    if (nf == 0) init_buffer(res->plan, bufs[0]);
+    const int nt = std::max(1, std::min(num_threads, nf));
+    auto work = [&](int tid) {
+      for (int f = tid; f < nf; f += nt) {
+        try {
+          errs[f] = run_fragment(res->plan, *u, *tbl, tbl->fragments[f], bufs[f]);
+        } catch (const OracleError& e) {
+          errs[f] = e.code;
+          msgs[f] = e.msg;
+        }
+      }
+    };
+    if (nt == 1) work(0);
+    else {
+      std::vector<std::thread> ths;
+      for (int t = 0; t < nt; ++t) ths.emplace_back(work, t);
+      for (auto& t : ths) t.join();
+    }
+    for (int f = 0; f < nf; ++f) if (errs[f]) { g_last_error = msgs[f]; int32_t c = errs[f]; delete res; return c; }
+    for (int f = 1; f < nf; ++f) {
+      int32_t rc = reduce_buffers(res->plan, bufs[0], bufs[f]);
+      if (rc) { delete res; return rc; }
+      std::vector<int8_t>().swap(bufs[f]);
+    }
+    res->buf = std::move(bufs[0]);
+    *out = res;
+    return 0;
+  } catch (const OracleError& e) {
+    g_last_error = e.msg;
+    return e.code;
+  }
+}
+
+ORACLE_EXPORT const B2QPlan* oracle_result_plan(const OracleResult* r) { return &r->plan.p; }
+ORACLE_EXPORT const int8_t* oracle_result_buffer(const OracleResult* r, size_t* size) {
+  if (size) *size = r->buf.size();
+  return r->buf.data();
+}
+ORACLE_EXPORT size_t oracle_result_entry_count(const OracleResult* r) { return static_cast<size_t>(r->plan.p.entry_count); }
+ORACLE_EXPORT int32_t oracle_result_is_row_at_empty(const OracleResult* r, size_t e) { return is_empty_entry(r->plan.p, r->buf.data(), static_cast<int64_t>(e)); }
+ORACLE_EXPORT size_t oracle_result_row_count(const OracleResult* r) { /* ResultSet::rowCount(): non-empty entries */
+  size_t n = 0;
+  for (int64_t e = 0; e < r->plan.p.entry_count; ++e) n += !is_empty_entry(r->plan.p, r->buf.data(), e);
+  return n;
+}
+ORACLE_EXPORT size_t oracle_result_col_count(const OracleResult* r) { return r->plan.targets.size(); }
+ORACLE_EXPORT void oracle_result_move_to_begin(OracleResult* r) { r->cursor = 0; }
+ORACLE_EXPORT void oracle_result_free(OracleResult* r) { delete r; }
+
+/* ResultSet::getColType: AVG targets read out as DOUBLE (ResultSet.cpp getColType) */
+ORACLE_EXPORT B2QTypeInfo oracle_result_col_type(const OracleResult* r, size_t col) {
+  const Target& t = r->plan.targets[col];
+  if (t.is_agg && t.agg_kind == B2Q_kAVG) return B2QTypeInfo{B2Q_kDOUBLE, 0};
+  return B2QTypeInfo{t.sql_type.type, t.sql_type.notnull};
+}
+
+/* ResultSet::getNextRow -> getTargetValueFromBufferRowwise -> makeTargetValue (ResultSetIteration.cpp:2086-2220),
+ * AVG via make_avg_target_value (:43-82) + pair_to_double (ResultSetBufferAccessors.h:197-227). */
+ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue* row) {
+  const B2QPlan& p = r->plan.p;
+  while (r->cursor < p.entry_count && is_empty_entry(p, r->buf.data(), r->cursor)) ++r->cursor;
+  if (r->cursor >= p.entry_count) return 0;
+  const int8_t* rowp = r->buf.data() + r->cursor * p.row_size;
+  ++r->cursor;
+  for (size_t i = 0; i < r->plan.targets.size(); ++i) {
+    Target t = r->plan.targets[i];
+    /* ResultSet's targets_: non-grouped MIN/MAX/SUM/AVG are nullable (target_exprs_to_infos, set_notnull false) */
+    if (t.is_agg && t.arg_col >= 0 && p.query_desc_type == B2Q_NonGroupedAggregate && t.agg_kind != B2Q_kCOUNT) {
+      t.sql_type.notnull = false; t.agg_arg_type.notnull = false;
+    }
+    const int s = t.first_slot;
+    int w = p.slot_padded_width[s];
+    const int8_t* ptr = rowp + p.slot_offset[s];
+    if (w == 0) { /* baseline: key column (getTargetValueFromBufferRowwise, :2425-2452) */
+      ptr = rowp;
+      w = p.effective_key_width;
+    }
+    int64_t ival;
+    if (w == 4) { int32_t x; memcpy(&x, ptr, 4); ival = x; } else memcpy(&ival, ptr, 8);
+    B2QTargetValue& o = row[i];
+    o.is_fp = 0; o.is_null = 0; o.ival = 0; o.dval = 0;
+    const Ti chosen = get_compact_type(t);
+    if (t.is_agg && t.agg_kind == B2Q_kAVG) {
+      int64_t cnt;
+      memcpy(&cnt, rowp + p.slot_offset[s + 1], 8);
+      o.is_fp = 1;
+      if (cnt == 0) { o.dval = kNullDouble; o.is_null = 1; }
+      else {
+        const double dividend = is_fp(t.sql_type.type) ? double_of(ival) : static_cast<double>(ival);
+        o.dval = dividend / static_cast<double>(cnt);
+        o.is_null = o.dval == kNullDouble;
+      }
+      continue;
+    }
+    if (is_fp(chosen.type)) {
+      o.is_fp = 1;
+      o.dval = double_of(ival);
+      o.is_null = o.dval == kNullDouble;
+      continue;
+    }
+    /* :2184-2188: NULL iff the value, resized to the compact type's logical size, equals that type's sentinel;
+     * the returned value is then the TARGET type's sentinel */
+    int64_t resized;
+    switch (type_size(chosen.type)) {
+      case 1: resized = static_cast<int8_t>(ival); break;
+      case 2: resized = static_cast<int16_t>(ival); break;
+      case 4: resized = static_cast<int32_t>(ival); break;
+      default: resized = ival;
+    }
+    if (inline_int_null_val(chosen.type) == resized) { o.ival = inline_int_null_val(t.sql_type.type); o.is_null = 1; }
+    else o.ival = ival;
+  }
+  return 1;
+}
+
+/* ---- synthetic columns (bench / tests) ---- */
+ORACLE_EXPORT void oracle_gen_column(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
+                                     int64_t count, int64_t lo, int64_t span, int32_t num_threads) {
+  auto work = [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i) {
+      const int64_t row = row0 + i;
+      switch (sql_type) {
+        case B2Q_kDOUBLE: static_cast<double*>(dst)[i] = oracle_gen_double(seed, col_tag, row); break;
+        case B2Q_kBIGINT: static_cast<int64_t*>(dst)[i] = oracle_gen_int(seed, col_tag, row, lo, span); break;
+        case B2Q_kINT: static_cast<int32_t*>(dst)[i] = static_cast<int32_t>(oracle_gen_int(seed, col_tag, row, lo, span)); break;
+        case B2Q_kSMALLINT: static_cast<int16_t*>(dst)[i] = static_cast<int16_t>(oracle_gen_int(seed, col_tag, row, lo, span)); break;
+        case B2Q_kTINYINT: static_cast<int8_t*>(dst)[i] = static_cast<int8_t>(oracle_gen_int(seed, col_tag, row, lo, span)); break;
+        default: abort();
+      }
+    }
+  };
+  const int nt = std::max(1, num_threads);
+  if (nt == 1 || count < (1 << 16)) { work(0, count); return; }
+  std::vector<std::thread> ths;
+  const int64_t per = (count + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const int64_t b = t * per, e = std::min(count, b + per);
+    if (b < e) ths.emplace_back(work, b, e);
+  }
+  for (auto& t : ths) t.join();
+}

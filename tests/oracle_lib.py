@@ -1,0 +1,137 @@
+"""ctypes loader for the CPU oracle (oracle/_build/liboracle.so).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from heavydb_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle.so"))
+        L.oracle_last_error.restype = C.c_char_p
+        L.oracle_murmur3.restype = C.c_uint32
+        L.oracle_murmur3.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+        L.oracle_get_group_value.restype = C.c_int64
+        L.oracle_get_group_value.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.oracle_plan.restype = C.c_int32
+        L.oracle_plan.argtypes = [C.POINTER(abi.ExecUnit), C.POINTER(abi.TableInfo), C.POINTER(abi.ExecutionOptions),
+                                  C.c_size_t, C.c_int32, C.POINTER(abi.Plan)]
+        L.oracle_execute.restype = C.c_int32
+        L.oracle_execute.argtypes = [C.POINTER(abi.ExecUnit), C.POINTER(abi.TableInfo), C.POINTER(abi.ExecutionOptions),
+                                     C.c_size_t, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.oracle_result_plan.restype = C.POINTER(abi.Plan)
+        L.oracle_result_plan.argtypes = [C.c_void_p]
+        L.oracle_result_buffer.restype = C.c_void_p
+        L.oracle_result_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+        for name in ("oracle_result_entry_count", "oracle_result_row_count", "oracle_result_col_count"):
+            getattr(L, name).restype = C.c_size_t
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.oracle_result_is_row_at_empty.restype = C.c_int32
+        L.oracle_result_is_row_at_empty.argtypes = [C.c_void_p, C.c_size_t]
+        L.oracle_result_move_to_begin.argtypes = [C.c_void_p]
+        L.oracle_result_free.argtypes = [C.c_void_p]
+        L.oracle_result_col_type.restype = abi.TypeInfo
+        L.oracle_result_col_type.argtypes = [C.c_void_p, C.c_size_t]
+        L.oracle_result_get_next_row.restype = C.c_int32
+        L.oracle_result_get_next_row.argtypes = [C.c_void_p, C.POINTER(abi.TargetValue)]
+        L.oracle_gen_column.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
+                                        C.c_int64, C.c_int32]
+        _lib = L
+    return _lib
+
+
+class OracleError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"oracle error {code}: {msg}")
+        self.code = code
+
+
+class OracleResult:
+    def __init__(self, handle):
+        self.h = handle
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_result_free(self.h)
+            self.h = None
+
+    @property
+    def plan(self) -> abi.Plan:
+        return lib().oracle_result_plan(self.h).contents
+
+    def row_count(self):
+        return lib().oracle_result_row_count(self.h)
+
+    def col_count(self):
+        return lib().oracle_result_col_count(self.h)
+
+    def entry_count(self):
+        return lib().oracle_result_entry_count(self.h)
+
+    def col_type(self, i):
+        t = lib().oracle_result_col_type(self.h, i)
+        return (t.type, t.notnull)
+
+    def buffer(self) -> np.ndarray:
+        n = C.c_size_t()
+        p = lib().oracle_result_buffer(self.h, C.byref(n))
+        if n.value == 0:
+            return np.zeros(0, dtype=np.int8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int8)), shape=(n.value,)).copy()
+
+    def rows(self):
+        """All rows via getNextRow, as tuples of python values (None = NULL)."""
+        L = lib()
+        L.oracle_result_move_to_begin(self.h)
+        nc = self.col_count()
+        row = (abi.TargetValue * nc)()
+        out = []
+        while L.oracle_result_get_next_row(self.h, row):
+            out.append(tuple(v.py() for v in row))
+        return out
+
+
+def make_eo(bigint_count=False, force_kernel=0, output_columnar=False, device=-1):
+    eo = abi.ExecutionOptions()
+    eo.allow_multifrag = 1
+    eo.output_columnar_hint = int(output_columnar)
+    eo.bigint_count = int(bigint_count)
+    eo.force_kernel = force_kernel
+    eo.device_ordinal = device
+    return eo
+
+
+def plan(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=False, bigint_count=False) -> abi.Plan:
+    bt = table.build(abi.CPU_LEVEL)
+    out = abi.Plan()
+    eo = make_eo(bigint_count)
+    rc = lib().oracle_plan(C.byref(unit.unit), C.byref(bt.info), C.byref(eo), entry_guess, int(has_card), C.byref(out))
+    if rc:
+        raise OracleError(rc, lib().oracle_last_error().decode())
+    return out
+
+
+def execute(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=False, bigint_count=False,
+            num_threads=1) -> OracleResult:
+    bt = table.build(abi.CPU_LEVEL)
+    h = C.c_void_p()
+    eo = make_eo(bigint_count)
+    rc = lib().oracle_execute(C.byref(unit.unit), C.byref(bt.info), C.byref(eo), entry_guess, int(has_card),
+                              num_threads, C.byref(h))
+    if rc:
+        raise OracleError(rc, lib().oracle_last_error().decode())
+    return OracleResult(h)
+
+
+def gen_column(sql_type, seed, col_tag, row0, count, lo=0, span=1, threads=8) -> np.ndarray:
+    a = np.empty(count, dtype=abi.NUMPY_OF[sql_type])
+    lib().oracle_gen_column(a.ctypes.data, sql_type, seed, col_tag, row0, count, lo, span, threads)
+    return a
