@@ -1,0 +1,185 @@
+/*
+ * b2q_internal.h — structures shared by the host planner (planner.cpp), the executor (executor.cpp) and the
+ * sm_100a kernels (kernels.cu).  Not part of the ABI.
+ *
+ * The reference JIT-compiles one row function per query (QueryEngine/NativeCodegen.cpp:2917 compileWorkUnit).
+ * Here the query is lowered to a tiny *device program* (DevProgram) that static kernels interpret in a
+ * vector-at-a-time fashion: every switch on an operator / width is executed once per R rows per thread and is
+ * warp-uniform, so the interpretation overhead is amortised and never diverges.
+ */
+#pragma once
+#include <stdint.h>
+
+#include "../../include/b2q.h"
+
+#define B2Q_MAX_COLS 16   /* distinct columns a query may reference */
+#define B2Q_MAX_TERMS B2Q_MAX_FILTER_TERMS
+#define B2Q_MAX_FILTER_OPS 24
+#define B2Q_MAX_ACCS 12   /* internal accumulators */
+#define B2Q_MAX_FRAGS_INLINE 0
+
+/* ---- filter ---------------------------------------------------------------------------------------------
+ * A comparison `col OP literal` is normalised on the host to a closed range test plus flags:
+ *     pass = !is_null(v) && (negate ^ (lo <= v && v <= hi))
+ * (restates DEF_CMP_NULLABLE, RuntimeFunctions.cpp:73-107: NULL compares to null_bool_val which toBool()
+ * (LogicalIR.cpp:344-352) turns into "row fails").  AND/OR trees are evaluated in postfix order on "is TRUE"
+ * bits, which is exact for Kleene logic without NOT (logical_and/logical_or, RuntimeFunctions.cpp:320-357). */
+struct DevTerm {
+  int64_t lo, hi;       /* integer domain, inclusive */
+  double flo, fhi;      /* fp domain, inclusive */
+  int64_t null_bits;    /* column NULL sentinel: int value (sign-extended) or double bits */
+  int32_t col;          /* index into the launch's column table */
+  int8_t width;         /* 1,2,4,8 */
+  int8_t col_is_fp;     /* column holds doubles */
+  int8_t cmp_fp;        /* compare in the double domain (column or literal is fp) */
+  int8_t negate;        /* kNE */
+  int8_t nullable;
+  int8_t pad_[3];
+};
+
+enum { FOP_TERM = 0, FOP_AND = 1, FOP_OR = 2 };
+struct DevFilter {
+  int32_t n_terms;
+  int32_t n_ops;                 /* 0 => no filter */
+  uint8_t ops[B2Q_MAX_FILTER_OPS]; /* (kind << 4) | term index */
+  DevTerm terms[B2Q_MAX_TERMS];
+};
+
+/* ---- accumulators ---------------------------------------------------------------------------------------
+ * Internal dense arrays, one per accumulator, `entry_count` elements of 8 bytes in HBM, initialised to the
+ * identity of their reduction so partial tables of several GPUs merge with one all-reduce per array.  The
+ * reference's slot layout (NULL-sentinel init values, AVG pairs, key slots) is produced afterwards by the
+ * materialise kernel. */
+enum {
+  ACC_COUNT = 0,   /* rows (COUNT(*)) or non-skipped values of `col` (col >= 0) */
+  ACC_SUM_I64 = 1, /* wrap-around int64 sum (agg_sum, RuntimeFunctions.cpp:1151-1155) */
+  ACC_SUM_F64 = 2,
+  ACC_MIN_I64 = 3,
+  ACC_MAX_I64 = 4,
+  ACC_MIN_F64 = 5, /* stored as order-preserving int64 */
+  ACC_MAX_F64 = 6
+};
+
+struct DevAcc {
+  int64_t skip1_val;   /* skip the value when v == skip1_val (argument's own NULL sentinel) */
+  int64_t skip2_val;   /* ... or when (skip2_trunc32 ? (int32)v : v) == skip2_val (aggregate type's sentinel) */
+  int32_t col;         /* -1: no argument (COUNT(*)) */
+  int8_t op;           /* ACC_* */
+  int8_t width;        /* argument byte width */
+  int8_t is_fp;        /* argument holds doubles: skip test is an fp compare against skip1 (as double) */
+  int8_t skip1_en;
+  int8_t skip2_en;
+  int8_t skip2_trunc32;
+  int8_t pad_[2];
+};
+
+/* ---- group key ------------------------------------------------------------------------------------------ */
+struct DevKey {
+  int64_t min_val;     /* perfect hash: idx = key - min_val (bucket == 0 in this path) */
+  int64_t null_val;    /* key column NULL sentinel (sign-extended) */
+  int64_t null_idx;    /* perfect hash: entry index of the NULL group (= max - min + 1), -1 if none */
+  int64_t entry_count;
+  int32_t col;         /* -1: non-grouped */
+  int8_t width;
+  int8_t translate_null; /* has_nulls && column nullable (GroupByAndAggregate.cpp:1337-1350) */
+  int8_t hash_key_width; /* baseline: bytes hashed by MurmurHash3 (4 or 8) */
+  int8_t pad_;
+};
+
+struct DevProgram {
+  DevFilter filter;
+  DevKey key;
+  int32_t n_accs;
+  int32_t n_cols;
+  DevAcc accs[B2Q_MAX_ACCS];
+};
+
+/* ---- how a reference slot is produced from the accumulators (materialise kernel) ------------------------- */
+enum {
+  SLOT_KEY = 0,        /* projected group key (agg_id) */
+  SLOT_COUNT = 1,      /* accs[a] as integer */
+  SLOT_VALUE = 2,      /* accs[a] (int64 bits or double bits) ; if nn >= 0 and accs[nn] == 0 -> init (NULL sentinel) */
+  SLOT_VALUE_ORD = 3,  /* like SLOT_VALUE but accs[a] holds an order-preserving int64 image of a double */
+  SLOT_NONE = 4        /* zero-width slot (baseline key reference) */
+};
+struct DevSlot {
+  int64_t init_val;
+  int64_t offset;      /* byte offset inside the row */
+  int64_t identity;    /* identity of accs[acc] (used when nn == -2) */
+  int32_t acc;         /* accumulator index */
+  int32_t nn;          /* >= 0: accumulator whose value 0 means "no value seen" -> init_val;
+                          -2: "no value seen" <=> accs[acc] still holds its identity; -1: always valid */
+  int8_t kind;         /* SLOT_* */
+  int8_t width;        /* padded slot width: 0, 4 or 8 */
+  int8_t pad_[6];
+};
+struct DevLayout {
+  int64_t row_size;
+  int64_t entry_count;
+  int64_t key_min;       /* perfect: key = key_min + idx */
+  int64_t key_null_val;  /* value projected for the NULL group */
+  int64_t null_idx;
+  int32_t n_slots;
+  int32_t touched_acc;   /* accumulator whose value != 0 marks a non-empty entry (non-keyless layouts) */
+  int32_t keyless_marker;/* keyless: slot index whose init value marks an empty entry (idx_target_as_key), else -1 */
+  int8_t has_key_col;    /* row starts with the group key (non-keyless) */
+  int8_t key_width;      /* 4 or 8 */
+  int8_t baseline;       /* key comes from the keys[] array */
+  int8_t pad_[1];
+  DevSlot slots[B2Q_MAX_SLOTS];
+};
+
+/* identities ------------------------------------------------------------------------------------------------ */
+#define B2Q_I64_MAX 0x7FFFFFFFFFFFFFFFLL
+#define B2Q_I64_MIN (-B2Q_I64_MAX - 1)
+
+/* order-preserving map double -> int64 (NaNs excluded by the caller) and back */
+#if defined(__CUDACC__)
+#define B2Q_HD __host__ __device__ __forceinline__
+#else
+#define B2Q_HD inline
+#endif
+B2Q_HD int64_t b2q_f64_to_ord(int64_t bits) { return bits ^ ((bits >> 63) & B2Q_I64_MAX); }
+B2Q_HD int64_t b2q_ord_to_f64(int64_t ord) { return ord ^ ((ord >> 63) & B2Q_I64_MAX); }
+
+B2Q_HD int64_t b2q_acc_identity(int op) {
+  switch (op) {
+    case ACC_MIN_I64: case ACC_MIN_F64: return B2Q_I64_MAX; /* ord(+inf) < I64_MAX: fine as identity */
+    case ACC_MAX_I64: case ACC_MAX_F64: return B2Q_I64_MIN;
+    default: return 0; /* COUNT, SUM_I64; SUM_F64: +0.0 */
+  }
+}
+
+/* ---- launch description handed to the kernels ----------------------------------------------------------- */
+struct DevLaunch {
+  /* column table: col_ptrs[frag * n_cols + c] — device pointers (device array) */
+  const int8_t* const* col_ptrs;
+  const int64_t* frag_rows;        /* [n_frags] device */
+  const int64_t* frag_chunk_start; /* [n_frags + 1] device: prefix sum of chunks per fragment */
+  int32_t n_frags;
+  int32_t pad_;
+  int64_t total_chunks;
+  int64_t* accs[B2Q_MAX_ACCS];     /* dense accumulator arrays in HBM */
+  int64_t* keys;                   /* baseline: open-addressing key array (EMPTY_KEY_64 initialised) */
+  int32_t* error;                  /* device int: first error code */
+};
+
+/* chosen at plan time, needed at launch */
+struct SmemPlan {
+  int32_t use_smem;       /* per-CTA private table */
+  int32_t replicas;       /* power of two, >= 1 */
+  int32_t acc_bytes[B2Q_MAX_ACCS]; /* bytes per entry in shared memory (4 or 8) */
+  int32_t acc_off[B2Q_MAX_ACCS];   /* byte offset of the accumulator's array inside ONE replica */
+  int32_t replica_bytes;
+  int32_t total_bytes;
+};
+
+/* host-side query object behind B2QQuery */
+struct B2QQuery {
+  B2QPlan plan;
+  DevProgram prog;
+  DevLayout layout;
+  SmemPlan smem;
+  int32_t col_ids[B2Q_MAX_COLS]; /* launch column index -> table column id */
+  int32_t bigint_count;
+};

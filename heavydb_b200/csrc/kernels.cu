@@ -1,0 +1,775 @@
+/*
+ * kernels.cu — hand-written sm_100a kernels for the scan -> filter -> group-by/aggregate path.
+ *
+ * They replace what the reference JIT-compiles per query:
+ *   row loop            query_group_by_template / query_template + multifrag_query_hoisted_literals
+ *                       (QueryEngine/QueryTemplateGenerator.cpp:552-815,257-549; RuntimeFunctions.cpp:2434-2472)
+ *   column decode       fixed_width_int_decode / fixed_width_double_decode (QueryEngine/DecodersImpl.h:30-61,112-136)
+ *   filter              DEF_CMP_NULLABLE + toBool (RuntimeFunctions.cpp:73-107, LogicalIR.cpp:344-352)
+ *   group lookup        get_group_value_fast[_keyless] (GroupByRuntime.cpp:194-209, RuntimeFunctions.cpp:2126-2152),
+ *                       get_group_value + get_matching_group_value (GroupByRuntime.cpp:20-48, cuda_mapd_rt.cu:180-216)
+ *   aggregate update    agg_*_shared / agg_*_skip_val_shared (cuda_mapd_rt.cu:437-1198)
+ *   smem table          init_shared_mem + JIT'd reduce_from_smem_to_gmem (cuda_mapd_rt.cu:73-87,
+ *                       GpuSharedMemoryUtils.cpp:96-383)
+ *   buffer init         init_group_by_buffer_gpu (GpuInitGroups.cu:124-171)
+ *
+ * Design (DESIGN.md has the numbers):
+ *   - persistent CTAs, grid = #SMs x CTAs/SM, static chunk striding over all fragments of the launch;
+ *   - each thread owns R rows per chunk, lane-consecutive => every column load is a fully coalesced
+ *     ld.global.nc.L1::no_allocate of the column's own width; R independent loads per column are in flight;
+ *   - vector-at-a-time interpretation of the device program: all operator/width switches are warp-uniform and
+ *     executed once per R rows;
+ *   - group table private to the CTA in shared memory (TMA bulk copy of an identity image initialises it),
+ *     warp-private replicas for small tables; 32-bit native shared atomics only: a 64-bit integer SUM keeps its low
+ *     word in shared memory and sends the (rare) carries straight to the HBM table, because sm_100a has no native
+ *     64-bit shared-memory atomic add (ATOMS.CAST.SPIN loops otherwise);
+ *   - warp-aggregated update (shuffle reduction, one atomic per warp) for the non-grouped case;
+ *   - tables too large for shared memory go to one dense table in HBM/L2 with RED.E.ADD/MIN/MAX;
+ *   - sparse keys: open addressing in HBM, MurmurHash3 (same function and home slot as the reference), 64-bit CAS.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b2q_internal.h"
+
+namespace b2q {
+
+constexpr int R = 4;                 /* rows per thread per chunk */
+constexpr int kMaxBlock = 1024;
+
+enum { MODE_SMEM = 0, MODE_GLOBAL = 1, MODE_BASELINE = 2 };
+
+/* ---------------------------------------------------------------------------------------------------------
+ * loads: streaming, read-only, no L1 allocation
+ * ------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ int64_t ld_s8(const int8_t* p) { int32_t v; asm volatile("ld.global.nc.L1::no_allocate.s8 %0, [%1];" : "=r"(v) : "l"(p)); return (int64_t)(int8_t)v; }
+__device__ __forceinline__ int64_t ld_s16(const int8_t* p) { int32_t v; asm volatile("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=r"(v) : "l"(p)); return (int64_t)(int16_t)v; }
+__device__ __forceinline__ int64_t ld_s32(const int8_t* p) { int32_t v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return (int64_t)v; }
+__device__ __forceinline__ int64_t ld_s64(const int8_t* p) { int64_t v; asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
+
+/* load R sign-extended integers (or raw 8-byte words) of `width` bytes for rows row0 + j*stride, masked */
+__device__ __forceinline__ void load_rows(int64_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0,
+                                          int stride, uint32_t mask) {
+  switch (width) {
+    case 8:
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? ld_s64(base + (row0 + (int64_t)j * stride) * 8) : 0;
+      break;
+    case 4:
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? ld_s32(base + (row0 + (int64_t)j * stride) * 4) : 0;
+      break;
+    case 2:
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? ld_s16(base + (row0 + (int64_t)j * stride) * 2) : 0;
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? ld_s8(base + (row0 + (int64_t)j * stride)) : 0;
+      break;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * filter
+ * ------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* const* __restrict__ cols, int64_t row0,
+                                              int stride, uint32_t valid) {
+  int64_t v[R];
+  load_rows(v, cols[t.col], t.width, row0, stride, valid);
+  uint32_t m = 0;
+  if (!t.cmp_fp) {
+    const int64_t lo = t.lo, hi = t.hi, nullv = t.null_bits;
+    const bool neg = t.negate, nullable = t.nullable;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      bool in = (v[j] >= lo) & (v[j] <= hi);
+      bool ok = (in != neg) & !(nullable & (v[j] == nullv));
+      m |= (uint32_t)ok << j;
+    }
+  } else {
+    const double lo = t.flo, hi = t.fhi;
+    const bool neg = t.negate, nullable = t.nullable;
+    if (t.col_is_fp) {
+      const double nullv = __longlong_as_double(t.null_bits);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const double d = __longlong_as_double(v[j]);
+        bool in = (d >= lo) & (d <= hi);
+        bool ok = (in != neg) & !(nullable & (d == nullv));
+        m |= (uint32_t)ok << j;
+      }
+    } else {
+      const int64_t nullv = t.null_bits;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const double d = (double)v[j];
+        bool in = (d >= lo) & (d <= hi);
+        bool ok = (in != neg) & !(nullable & (v[j] == nullv));
+        m |= (uint32_t)ok << j;
+      }
+    }
+  }
+  return m & valid;
+}
+
+__device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t* const* __restrict__ cols,
+                                                int64_t row0, int stride, uint32_t valid) {
+  if (f.n_ops == 0) return valid;
+  uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int i = 0; i < f.n_ops; ++i) {
+    const uint32_t op = f.ops[i];
+    const uint32_t kind = op >> 4;
+    if (kind == FOP_TERM) {
+      const uint32_t m = eval_term(f.terms[op & 15], cols, row0, stride, valid);
+      s3 = s2; s2 = s1; s1 = s0; s0 = m;
+    } else {
+      s0 = (kind == FOP_AND) ? (s1 & s0) : (s1 | s0);
+      s1 = s2; s2 = s3; s3 = 0;
+    }
+  }
+  return s0 & valid;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * skip test (NULL handling of aggregate arguments), see DevAcc
+ * ------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t not_skipped(const DevAcc& a, const int64_t (&v)[R], uint32_t pass) {
+  if (!a.skip1_en && !a.skip2_en) return pass;
+  uint32_t m = 0;
+  if (a.is_fp) {
+    const double s = __longlong_as_double(a.skip1_val);
+#pragma unroll
+    for (int j = 0; j < R; ++j) m |= (uint32_t)(__longlong_as_double(v[j]) != s) << j;
+  } else {
+    const int64_t s1 = a.skip1_val, s2 = a.skip2_val;
+    const bool e1 = a.skip1_en, e2 = a.skip2_en, tr = a.skip2_trunc32;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int64_t w = tr ? (int64_t)(int32_t)v[j] : v[j];
+      bool skip = (e1 & (v[j] == s1)) | (e2 & (w == s2));
+      m |= (uint32_t)(!skip) << j;
+    }
+  }
+  return m & pass;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * MurmurHash3 x86_32 for one 4- or 8-byte key, seed 0 (QueryEngine/MurmurHash3Inl.h:11-72)
+ * ------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+__device__ __forceinline__ uint32_t murmur_block(uint32_t h1, uint32_t k1) {
+  k1 *= 0xcc9e2d51u; k1 = rotl32(k1, 15); k1 *= 0x1b873593u;
+  h1 ^= k1; h1 = rotl32(h1, 13); h1 = h1 * 5 + 0xe6546b64u;
+  return h1;
+}
+__device__ __forceinline__ uint32_t murmur3_key(int64_t key, int width) {
+  uint32_t h1 = 0;
+  h1 = murmur_block(h1, (uint32_t)key);
+  if (width == 8) h1 = murmur_block(h1, (uint32_t)((uint64_t)key >> 32));
+  h1 ^= (uint32_t)width;
+  h1 ^= h1 >> 16; h1 *= 0x85ebca6bu; h1 ^= h1 >> 13; h1 *= 0xc2b2ae35u; h1 ^= h1 >> 16;
+  return h1;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * global (HBM / L2) reductions without return value
+ * ------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void red_add_u64(int64_t* p, uint64_t v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_add_f64(int64_t* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void red_min_s64(int64_t* p, int64_t v) { asm volatile("red.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void red_max_s64(int64_t* p, int64_t v) { asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+__device__ __forceinline__ void global_update(int op, int64_t* arr, uint32_t e, int64_t v) {
+  switch (op) {
+    case ACC_COUNT: red_add_u64(arr + e, 1ull); break;
+    case ACC_SUM_I64: red_add_u64(arr + e, (uint64_t)v); break;
+    case ACC_SUM_F64: red_add_f64(arr + e, __longlong_as_double(v)); break;
+    case ACC_MIN_I64: red_min_s64(arr + e, v); break;
+    case ACC_MAX_I64: red_max_s64(arr + e, v); break;
+    case ACC_MIN_F64: { const double d = __longlong_as_double(v); if (d == d) red_min_s64(arr + e, b2q_f64_to_ord(v)); break; }
+    default: { const double d = __longlong_as_double(v); if (d == d) red_max_s64(arr + e, b2q_f64_to_ord(v)); break; }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * shared-memory table update.  `tab` points at the accumulator's array inside this warp's replica.
+ * ------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void smem_update(int op, int8_t* tab, int64_t* garr, uint32_t e, int64_t v) {
+  switch (op) {
+    case ACC_COUNT:
+      atomicAdd(reinterpret_cast<uint32_t*>(tab) + e, 1u);
+      break;
+    case ACC_SUM_I64: {
+      /* (hi:lo) += v with lo in shared memory (native 32-bit ATOMS.ADD) and hi deltas sent to the HBM table */
+      const uint32_t vl = (uint32_t)v;
+      const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(tab) + e, vl);
+      const int32_t carry = (uint32_t)(old + vl) < old;
+      const int32_t hi = (int32_t)(v >> 32) + carry;
+      if (hi != 0) red_add_u64(garr + e, (uint64_t)(int64_t)hi << 32);
+      break;
+    }
+    case ACC_SUM_F64:
+      atomicAdd(reinterpret_cast<double*>(tab) + e, __longlong_as_double(v));
+      break;
+    case ACC_MIN_I64: {
+      long long* p = reinterpret_cast<long long*>(tab) + e;
+      if (v < *reinterpret_cast<volatile long long*>(p)) atomicMin(p, (long long)v);
+      break;
+    }
+    case ACC_MAX_I64: {
+      long long* p = reinterpret_cast<long long*>(tab) + e;
+      if (v > *reinterpret_cast<volatile long long*>(p)) atomicMax(p, (long long)v);
+      break;
+    }
+    case ACC_MIN_F64: {
+      const double d = __longlong_as_double(v);
+      if (d == d) {
+        const long long o = b2q_f64_to_ord(v);
+        long long* p = reinterpret_cast<long long*>(tab) + e;
+        if (o < *reinterpret_cast<volatile long long*>(p)) atomicMin(p, o);
+      }
+      break;
+    }
+    default: {
+      const double d = __longlong_as_double(v);
+      if (d == d) {
+        const long long o = b2q_f64_to_ord(v);
+        long long* p = reinterpret_cast<long long*>(tab) + e;
+        if (o > *reinterpret_cast<volatile long long*>(p)) atomicMax(p, o);
+      }
+      break;
+    }
+  }
+}
+
+/* warp-level reductions for the single-group (non-grouped) case */
+__device__ __forceinline__ int64_t warp_sum_i64(int64_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int64_t warp_min_i64(int64_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { const int64_t w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+  return v;
+}
+__device__ __forceinline__ int64_t warp_max_i64(int64_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { const int64_t w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+  return v;
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * TMA bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) with mbarrier completion
+ * ------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * the scan kernel
+ * ------------------------------------------------------------------------------------------------------- */
+struct ScanArgs {
+  DevProgram prog;
+  DevLaunch launch;
+  SmemPlan smem;
+  const int8_t* smem_image; /* identity image of ONE replica in HBM (MODE_SMEM) */
+};
+
+extern __shared__ __align__(128) int8_t b2q_smem[];
+
+template <int MODE, bool WAGG>
+__global__ void __launch_bounds__(kMaxBlock, 1) b2q_k_scan(const __grid_constant__ ScanArgs A) {
+  const DevProgram& P = A.prog;
+  const DevLaunch& Lh = A.launch;
+  const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int64_t chunk_rows = (int64_t)nthr * R;
+  __shared__ uint64_t s_bar;
+  int8_t* my_tab = nullptr;
+
+  if (MODE == MODE_SMEM) {
+    /* TMA-stage the identity image into every replica of the CTA-private table */
+    const uint32_t rb = (uint32_t)A.smem.replica_bytes;
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&s_bar, rb * (uint32_t)A.smem.replicas);
+      for (int r = 0; r < A.smem.replicas; ++r) {
+        uint32_t off = 0;
+        while (off < rb) { /* bulk copies of <= 64 KB, 16-byte granularity (replica_bytes is a multiple of 16) */
+          const uint32_t n = min(rb - off, 65536u);
+          tma_bulk_g2s(b2q_smem + (size_t)r * rb + off, A.smem_image + off, n, &s_bar);
+          off += n;
+        }
+      }
+    }
+    mbar_wait(&s_bar, 0);
+    my_tab = b2q_smem + (size_t)(warp & (A.smem.replicas - 1)) * rb;
+  }
+
+  for (int64_t chunk = blockIdx.x; chunk < Lh.total_chunks; chunk += gridDim.x) {
+    /* chunk -> (fragment, first row): binary search in the per-fragment chunk prefix sums (warp-uniform) */
+    int lo = 0, hi = Lh.n_frags - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(Lh.frag_chunk_start + mid) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const int frag = lo;
+    const int64_t frag_rows = __ldg(Lh.frag_rows + frag);
+    const int64_t row0 = (chunk - __ldg(Lh.frag_chunk_start + frag)) * chunk_rows + tid;
+    const int8_t* const* __restrict__ cols = Lh.col_ptrs + (size_t)frag * P.n_cols;
+
+    uint32_t valid = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) valid |= (uint32_t)(row0 + (int64_t)j * nthr < frag_rows) << j;
+
+    uint32_t pass = eval_filter(P.filter, cols, row0, nthr, valid);
+
+    /* ---- group index ---- */
+    uint32_t e[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) e[j] = 0;
+    if (P.key.col >= 0) {
+      int64_t k[R];
+      load_rows(k, cols[P.key.col], P.key.width, row0, nthr, pass);
+      if (MODE != MODE_BASELINE) {
+        const int64_t mn = P.key.min_val, nullv = P.key.null_val, nidx = P.key.null_idx;
+        const uint64_t n = (uint64_t)P.key.entry_count;
+        const bool tr = P.key.translate_null;
+        uint32_t bad = 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          int64_t idx = k[j] - mn;
+          if (tr & (k[j] == nullv)) idx = nidx;
+          const bool oob = (uint64_t)idx >= n;
+          bad |= (uint32_t)oob << j;
+          e[j] = (uint32_t)idx;
+        }
+        bad &= pass;
+        if (bad) { atomicCAS(Lh.error, 0, B2Q_ERR_KEY_OUT_OF_RANGE); pass &= ~bad; }
+      } else {
+        const uint32_t n = (uint32_t)P.key.entry_count;
+        const int hw = P.key.hash_key_width;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          if (!(pass >> j & 1)) continue;
+          const int64_t key = k[j];
+          const uint32_t h = murmur3_key(key, hw) % n;
+          uint32_t p = h;
+          bool found = false;
+          unsigned long long* keys = reinterpret_cast<unsigned long long*>(Lh.keys);
+          do {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(keys + p);
+            if (cur == (unsigned long long)B2Q_I64_MAX) cur = atomicCAS(keys + p, (unsigned long long)B2Q_I64_MAX, (unsigned long long)key);
+            if (cur == (unsigned long long)B2Q_I64_MAX || cur == (unsigned long long)key) { found = true; break; }
+            p = p + 1 == n ? 0 : p + 1;
+          } while (p != h);
+          if (!found) { atomicCAS(Lh.error, 0, B2Q_ERR_OUT_OF_SLOTS); pass &= ~(1u << j); }
+          e[j] = p;
+        }
+      }
+    }
+
+    /* ---- aggregate updates: one warp-uniform switch per accumulator per R rows ---- */
+    for (int a = 0; a < P.n_accs; ++a) {
+      const DevAcc& acc = P.accs[a];
+      int64_t v[R];
+      uint32_t m = pass;
+      if (acc.col >= 0) {
+        load_rows(v, cols[acc.col], acc.width, row0, nthr, pass);
+        m = not_skipped(acc, v, pass);
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = 0;
+      }
+      const int op = acc.op;
+      if (WAGG) {
+        /* single group: thread-local combine over R rows, shuffle reduction, one shared-memory atomic per warp */
+        int8_t* tab = my_tab + A.smem.acc_off[a];
+        switch (op) {
+          case ACC_COUNT: {
+            uint32_t c = __popc(m);
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0 && c) atomicAdd(reinterpret_cast<uint32_t*>(tab), c);
+            break;
+          }
+          case ACC_SUM_I64: {
+            int64_t s = 0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) s += (m >> j & 1) ? v[j] : 0;
+            s = warp_sum_i64(s);
+            if (lane == 0 && s) smem_update(ACC_SUM_I64, tab, Lh.accs[a], 0, s);
+            break;
+          }
+          case ACC_SUM_F64: {
+            double s = 0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) s += (m >> j & 1) ? __longlong_as_double(v[j]) : 0.0;
+            const uint32_t any = __ballot_sync(0xffffffffu, m != 0);
+            s = warp_sum_f64(s);
+            if (lane == 0 && any) atomicAdd(reinterpret_cast<double*>(tab), s);
+            break;
+          }
+          default: {
+            const bool is_min = (op == ACC_MIN_I64) | (op == ACC_MIN_F64);
+            const bool fp = (op == ACC_MIN_F64) | (op == ACC_MAX_F64);
+            int64_t r = is_min ? B2Q_I64_MAX : B2Q_I64_MIN;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              if (!(m >> j & 1)) continue;
+              int64_t x = v[j];
+              if (fp) { const double d = __longlong_as_double(x); if (d != d) continue; x = b2q_f64_to_ord(x); }
+              r = is_min ? (x < r ? x : r) : (x > r ? x : r);
+            }
+            r = is_min ? warp_min_i64(r) : warp_max_i64(r);
+            if (lane == 0) {
+              long long* p = reinterpret_cast<long long*>(tab);
+              if (is_min) { if (r < *reinterpret_cast<volatile long long*>(p)) atomicMin(p, (long long)r); }
+              else { if (r > *reinterpret_cast<volatile long long*>(p)) atomicMax(p, (long long)r); }
+            }
+            break;
+          }
+        }
+      } else if (MODE == MODE_SMEM) {
+        int8_t* tab = my_tab + A.smem.acc_off[a];
+        int64_t* garr = Lh.accs[a];
+        switch (op) { /* switch hoisted out of the row loop */
+          case ACC_COUNT:
+#pragma unroll
+            for (int j = 0; j < R; ++j) if (m >> j & 1) atomicAdd(reinterpret_cast<uint32_t*>(tab) + e[j], 1u);
+            break;
+          case ACC_SUM_I64:
+#pragma unroll
+            for (int j = 0; j < R; ++j) if (m >> j & 1) smem_update(ACC_SUM_I64, tab, garr, e[j], v[j]);
+            break;
+          case ACC_SUM_F64:
+#pragma unroll
+            for (int j = 0; j < R; ++j) if (m >> j & 1) atomicAdd(reinterpret_cast<double*>(tab) + e[j], __longlong_as_double(v[j]));
+            break;
+          default:
+#pragma unroll
+            for (int j = 0; j < R; ++j) if (m >> j & 1) smem_update(op, tab, garr, e[j], v[j]);
+            break;
+        }
+      } else {
+        int64_t* garr = Lh.accs[a];
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, e[j], v[j]);
+      }
+    }
+  }
+
+  if (MODE == MODE_SMEM) {
+    /* flush the CTA-private table into the dense HBM table: one RED per (entry, accumulator) that moved */
+    __syncthreads();
+    const uint32_t rb = (uint32_t)A.smem.replica_bytes;
+    const int nrep = A.smem.replicas;
+    const int64_t n = P.key.entry_count;
+    for (int a = 0; a < P.n_accs; ++a) {
+      const int op = P.accs[a].op;
+      int64_t* garr = Lh.accs[a];
+      const int8_t* base = b2q_smem + A.smem.acc_off[a];
+      for (int64_t i = tid; i < n; i += nthr) {
+        switch (op) {
+          case ACC_COUNT:
+          case ACC_SUM_I64: {
+            uint64_t s = 0;
+            for (int r = 0; r < nrep; ++r) s += reinterpret_cast<const uint32_t*>(base + (size_t)r * rb)[i];
+            if (s) red_add_u64(garr + i, s);
+            break;
+          }
+          case ACC_SUM_F64: {
+            double s = 0;
+            bool any = false;
+            for (int r = 0; r < nrep; ++r) { const double x = reinterpret_cast<const double*>(base + (size_t)r * rb)[i]; any |= (x != 0.0); s += x; }
+            if (any) red_add_f64(garr + i, s);
+            break;
+          }
+          case ACC_MIN_I64:
+          case ACC_MIN_F64: {
+            int64_t s = B2Q_I64_MAX;
+            for (int r = 0; r < nrep; ++r) { const int64_t x = reinterpret_cast<const int64_t*>(base + (size_t)r * rb)[i]; s = x < s ? x : s; }
+            if (s != B2Q_I64_MAX) red_min_s64(garr + i, s);
+            break;
+          }
+          default: {
+            int64_t s = B2Q_I64_MIN;
+            for (int r = 0; r < nrep; ++r) { const int64_t x = reinterpret_cast<const int64_t*>(base + (size_t)r * rb)[i]; s = x > s ? x : s; }
+            if (s != B2Q_I64_MIN) red_max_s64(garr + i, s);
+            break;
+          }
+        }
+      }
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * table initialisation (replaces init_group_by_buffer_gpu, GpuInitGroups.cu:124-171): accumulators to the
+ * identity of their reduction, baseline keys to EMPTY_KEY_64, plus the one-replica shared-memory image.
+ * ------------------------------------------------------------------------------------------------------- */
+struct InitArgs {
+  int64_t* accs[B2Q_MAX_ACCS];
+  int8_t ops[B2Q_MAX_ACCS];
+  int32_t n_accs;
+  int64_t entry_count;
+  int64_t* keys;      /* or nullptr */
+  int8_t* smem_image; /* or nullptr */
+  SmemPlan smem;
+};
+
+__global__ void b2q_k_init(const __grid_constant__ InitArgs A) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.entry_count; i += stride) {
+    for (int a = 0; a < A.n_accs; ++a) {
+      const int64_t id = b2q_acc_identity(A.ops[a]);
+      A.accs[a][i] = id;
+      if (A.smem_image) {
+        int8_t* p = A.smem_image + A.smem.acc_off[a];
+        if (A.smem.acc_bytes[a] == 4) reinterpret_cast<uint32_t*>(p)[i] = 0u; else reinterpret_cast<int64_t*>(p)[i] = id;
+      }
+    }
+    if (A.keys) A.keys[i] = B2Q_I64_MAX;
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * materialise: dense accumulators -> the reference's row-wise output buffer
+ * (layout: QueryMemoryDescriptor.cpp:848-955; empty-entry conventions: ResultSetIteration.cpp:2457-2492)
+ * ------------------------------------------------------------------------------------------------------- */
+struct MatArgs {
+  DevLayout layout;
+  const int64_t* accs[B2Q_MAX_ACCS];
+  const int64_t* keys;
+  int8_t* out;
+};
+
+__global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
+  const DevLayout& L = A.layout;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.entry_count; i += stride) {
+    int8_t* row = A.out + i * L.row_size;
+    bool touched = true;
+    int64_t key = 0;
+    if (L.baseline) {
+      key = A.keys[i];
+      touched = key != B2Q_I64_MAX;
+      if (touched && L.key_width == 4) key = (int64_t)(int32_t)key;
+    } else {
+      key = (i == L.null_idx) ? L.key_null_val : L.key_min + i;
+      if (L.touched_acc >= 0) touched = A.accs[L.touched_acc][i] != 0;
+    }
+    if (L.has_key_col) {
+      if (L.key_width == 4) {
+        *reinterpret_cast<int32_t*>(row) = touched ? (int32_t)key : 0x7FFFFFFF;
+        *reinterpret_cast<int32_t*>(row + 4) = 0;
+      } else {
+        /* perfect hash stores the TRANSLATED key (NULL -> max+1), GroupByRuntime.cpp:194-209 */
+        const int64_t stored = (!L.baseline && i == L.null_idx) ? L.key_min + i : key;
+        *reinterpret_cast<int64_t*>(row) = touched ? stored : B2Q_I64_MAX;
+      }
+    }
+    int64_t vals[B2Q_MAX_SLOTS];
+    for (int s = 0; s < L.n_slots; ++s) {
+      const DevSlot& sl = L.slots[s];
+      int64_t val = sl.init_val;
+      if (touched && sl.kind != SLOT_NONE && sl.width != 0) {
+        switch (sl.kind) {
+          case SLOT_KEY: val = key; break;
+          case SLOT_COUNT: val = A.accs[sl.acc][i]; break;
+          default: {
+            const int64_t raw = A.accs[sl.acc][i];
+            bool is_null = false;
+            if (sl.nn >= 0) is_null = A.accs[sl.nn][i] == 0;
+            else if (sl.nn == -2) is_null = raw == sl.identity;
+            val = is_null ? sl.init_val : (sl.kind == SLOT_VALUE_ORD ? b2q_ord_to_f64(raw) : raw);
+            break;
+          }
+        }
+      }
+      vals[s] = val;
+    }
+    /* keyless layouts: an entry whose marker slot still holds its init value IS empty for every reader
+     * (ResultSetIteration.cpp:2457-2476); leave it entirely at the init pattern */
+    if (L.keyless_marker >= 0 && vals[L.keyless_marker] == L.slots[L.keyless_marker].init_val) {
+      for (int s = 0; s < L.n_slots; ++s) vals[s] = L.slots[s].init_val;
+    }
+    for (int s = 0; s < L.n_slots; ++s) {
+      const DevSlot& sl = L.slots[s];
+      if (sl.kind == SLOT_NONE || sl.width == 0) continue;
+      if (sl.width == 4) *reinterpret_cast<int32_t*>(row + sl.offset) = (int32_t)vals[s];
+      else *reinterpret_cast<int64_t*>(row + sl.offset) = vals[s];
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * synthetic columns: same counter-based generator as oracle/oracle_gen.h
+ * ------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void b2q_k_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count,
+                          int64_t lo, uint64_t span) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const uint64_t u = splitmix64(seed ^ ((uint64_t)col_tag << 56) ^ (uint64_t)(row0 + i));
+    switch (sql_type) {
+      case B2Q_kDOUBLE: static_cast<double*>(dst)[i] = (double)(u >> 11) * (1.0 / 9007199254740992.0); break;
+      case B2Q_kBIGINT: static_cast<int64_t*>(dst)[i] = lo + (int64_t)(u % span); break;
+      case B2Q_kINT: static_cast<int32_t*>(dst)[i] = (int32_t)(lo + (int64_t)(u % span)); break;
+      case B2Q_kSMALLINT: static_cast<int16_t*>(dst)[i] = (int16_t)(lo + (int64_t)(u % span)); break;
+      default: static_cast<int8_t*>(dst)[i] = (int8_t)(lo + (int64_t)(u % span)); break;
+    }
+  }
+}
+
+/* =========================================================================================================
+ * host-side launch wrappers (called from executor.cpp)
+ * ======================================================================================================= */
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+struct ScanConfig {
+  int block;
+  int grid;
+  size_t smem_bytes;
+};
+
+template <int MODE, bool WAGG>
+static cudaError_t launch_scan_t(const ScanArgs& a, const ScanConfig& c, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(b2q_k_scan<MODE, WAGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  b2q_k_scan<MODE, WAGG><<<c.grid, c.block, c.smem_bytes, st>>>(a);
+  return cudaGetLastError();
+}
+
+int scan_rows_per_chunk(int block) { return block * R; }
+
+/* block/grid policy: one CTA per SM with 1024 threads when the table needs more than half of the shared memory,
+ * otherwise two CTAs of 512 threads per SM (better tail behaviour, same number of resident threads). */
+void scan_config(const B2QQuery& q, int* block, int* ctas_per_sm) {
+  const bool big_table = q.smem.use_smem && q.smem.total_bytes > 100 * 1024;
+  *block = big_table ? 1024 : 512;
+  *ctas_per_sm = big_table ? 1 : 2;
+}
+
+cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t* smem_image, int block, int ctas_per_sm,
+                        cudaStream_t st) {
+  ScanArgs a;
+  a.prog = q.prog;
+  a.launch = launch;
+  a.smem = q.smem;
+  a.smem_image = smem_image;
+  ScanConfig c;
+  c.block = block;
+  const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
+  c.grid = (int)(launch.total_chunks < max_ctas ? (launch.total_chunks > 0 ? launch.total_chunks : 1) : max_ctas);
+  c.smem_bytes = 0;
+  const int kernel = q.plan.kernel;
+  if (kernel == B2Q_KERNEL_NON_GROUPED) {
+    c.smem_bytes = (size_t)q.smem.total_bytes;
+    return launch_scan_t<MODE_SMEM, true>(a, c, st);
+  }
+  if (kernel == B2Q_KERNEL_PERFECT_SMEM) {
+    c.smem_bytes = (size_t)q.smem.total_bytes;
+    return launch_scan_t<MODE_SMEM, false>(a, c, st);
+  }
+  if (kernel == B2Q_KERNEL_PERFECT_GLOBAL) return launch_scan_t<MODE_GLOBAL, false>(a, c, st);
+  return launch_scan_t<MODE_BASELINE, false>(a, c, st);
+}
+
+cudaError_t launch_init(const B2QQuery& q, int64_t* const* accs, int64_t* keys, int8_t* smem_image, cudaStream_t st) {
+  InitArgs a;
+  a.n_accs = q.prog.n_accs;
+  for (int i = 0; i < q.prog.n_accs; ++i) { a.accs[i] = accs[i]; a.ops[i] = q.prog.accs[i].op; }
+  a.entry_count = q.plan.entry_count;
+  a.keys = keys;
+  a.smem_image = smem_image;
+  a.smem = q.smem;
+  const int block = 256;
+  int64_t blocks = (q.plan.entry_count + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  b2q_k_init<<<(int)blocks, block, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_materialize(const B2QQuery& q, const int64_t* const* accs, const int64_t* keys, int8_t* out,
+                               cudaStream_t st) {
+  MatArgs a;
+  a.layout = q.layout;
+  for (int i = 0; i < q.prog.n_accs; ++i) a.accs[i] = accs[i];
+  a.keys = keys;
+  a.out = out;
+  const int block = 256;
+  int64_t blocks = (q.plan.entry_count + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  b2q_k_materialize<<<(int)blocks, block, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count, int64_t lo,
+                       int64_t span, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  const int block = 256;
+  int64_t blocks = (count + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  b2q_k_gen<<<(int)blocks, block, 0, st>>>(dst, sql_type, seed, col_tag, row0, count, lo, (uint64_t)(span > 0 ? span : 1));
+  return cudaGetLastError();
+}
+
+}  // namespace b2q

@@ -1,0 +1,698 @@
+/*
+ * planner.cpp — host-side planning for the B200 path: what GroupByAndAggregate + QueryMemoryDescriptor decide in
+ * the reference, then lowering of quals / targets to the device program the static kernels interpret.
+ *
+ * Reference behaviour restated (paths relative to the reference tree):
+ *   hash type          GroupByAndAggregate::getColRangeInfo        QueryEngine/GroupByAndAggregate.cpp:232-365
+ *   key range          getLeafColumnRange / apply_simple_quals     QueryEngine/ExpressionRange.cpp:521-632, :144-200
+ *   keyless decision   get_keyless_info                            QueryEngine/GroupByAndAggregate.cpp:489-648
+ *   entry count/layout QueryMemoryDescriptor::init, getRowSize     QueryEngine/Descriptors/QueryMemoryDescriptor.cpp:240-444,848-955
+ *   slot widths        pick_target_compact_width, ColSlotContext   QueryMemoryDescriptor.cpp:748-842, ColSlotContext.cpp:35-101
+ *   init values        init_agg_val_vec / get_agg_initial_val      QueryEngine/OutputBufferInitialization.cpp:26-262
+ *   target info        get_target_info_impl, get_compact_type      Shared/TargetInfo.cpp:25-78, Shared/SqlTypesLayout.h:37-63
+ *   null skipping      TargetExprCodegen::codegenAggregate         QueryEngine/TargetExprBuilder.cpp:470-583,
+ *                      convertNullIfAny                            QueryEngine/GroupByAndAggregate.cpp:1599-1660
+ */
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "b2q_internal.h"
+
+namespace b2q {
+
+struct PlanError {
+  int32_t code;
+  std::string msg;
+};
+
+namespace {
+
+[[noreturn]] void reject(int32_t code, const std::string& m) { throw PlanError{code, m}; }
+
+struct SqlType {
+  int32_t type = 0;
+  bool notnull = false;
+  bool is_int() const { return type == B2Q_kTINYINT || type == B2Q_kSMALLINT || type == B2Q_kINT || type == B2Q_kBIGINT; }
+  bool is_fp() const { return type == B2Q_kDOUBLE; }
+  int size() const {
+    switch (type) {
+      case B2Q_kTINYINT: return 1;
+      case B2Q_kSMALLINT: return 2;
+      case B2Q_kINT: return 4;
+      case B2Q_kBIGINT: case B2Q_kDOUBLE: return 8;
+      default: return -1;
+    }
+  }
+  int64_t int_null() const { /* Shared/InlineNullValues.h:30-36 */
+    switch (type) {
+      case B2Q_kTINYINT: return INT8_MIN;
+      case B2Q_kSMALLINT: return INT16_MIN;
+      case B2Q_kINT: return INT32_MIN;
+      default: return INT64_MIN;
+    }
+  }
+};
+SqlType from_abi(const B2QTypeInfo& t) { return SqlType{t.type, t.notnull != 0}; }
+B2QTypeInfo to_abi(const SqlType& t) { return B2QTypeInfo{t.type, t.notnull ? 1 : 0}; }
+
+int64_t dbl_bits(double d) { int64_t b; memcpy(&b, &d, 8); return b; }
+double bits_dbl(int64_t b) { double d; memcpy(&d, &b, 8); return d; }
+int64_t align8(int64_t v) { return (v + 7) & ~int64_t(7); }
+constexpr double kNullDouble = DBL_MIN;
+
+struct ColRange {
+  bool valid = false, fp = false, has_nulls = false;
+  int64_t imin = 0, imax = -1;
+  double fmin = 0, fmax = -1;
+};
+
+struct TargetDesc {
+  bool is_agg = false;
+  int agg = B2Q_kMIN;
+  SqlType sql_type, arg_type; /* arg_type.type == 0: no argument */
+  bool skip_null = false;
+  int arg_col = -1;
+  int first_slot = 0;
+  SqlType compact() const { /* get_compact_type */
+    if (!is_agg || arg_type.type == 0) return sql_type;
+    if (agg == B2Q_kMIN || agg == B2Q_kMAX) return arg_type;
+    SqlType t = sql_type;
+    t.notnull = arg_type.notnull;
+    return t;
+  }
+};
+
+class Planner {
+ public:
+  Planner(const B2QExecUnit& u, const B2QTableInfo& t, const B2QExecutionOptions& eo, size_t guess, bool has_card)
+      : u_(u), t_(t), eo_(eo), guess_(guess), has_card_(has_card) {}
+
+  void run(B2QQuery& q) {
+    memset(&q, 0, sizeof(q));
+    validate();
+    build_targets();
+    choose_hash_type(q.plan);
+    layout_slots(q.plan);
+    init_values(q.plan);
+    publish_targets(q.plan);
+    lower(q);
+    choose_kernel(q);
+  }
+
+ private:
+  const B2QExecUnit& u_;
+  const B2QTableInfo& t_;
+  const B2QExecutionOptions& eo_;
+  size_t guess_;
+  bool has_card_;
+  std::vector<TargetDesc> targets_;
+  bool grouped_ = false;
+  int key_col_ = -1;
+  bool keyless_ = false;
+  int keyless_idx_ = -1;
+  std::vector<bool> slot_key_ref_;
+
+  const B2QExpr& ex(int i) const {
+    if (i < 0 || i >= u_.num_exprs) reject(B2Q_ERR_INVALID_ARGUMENT, "expression index out of range");
+    return u_.exprs[i];
+  }
+  SqlType col_type(int c) const {
+    if (c < 0 || c >= t_.num_cols) reject(B2Q_ERR_INVALID_ARGUMENT, "column id out of range");
+    return from_abi(t_.col_types[c]);
+  }
+
+  void validate() {
+    if (u_.num_join_quals || u_.has_estimator || u_.num_order_entries || u_.has_union_all || u_.has_window_function)
+      reject(B2Q_ERR_UNSUPPORTED, "join_quals / estimator / sort_info / union_all / window functions are outside this path");
+    if (u_.num_groupby_exprs > 1) reject(B2Q_ERR_UNSUPPORTED, "multi-column GROUP BY is outside this path (SURVEY §8f-4)");
+    if (u_.num_groupby_exprs < 0 || u_.num_target_exprs <= 0 || u_.num_target_exprs > B2Q_MAX_TARGETS)
+      reject(B2Q_ERR_INVALID_ARGUMENT, "bad groupby/target counts");
+    if (eo_.output_columnar_hint) reject(B2Q_ERR_UNSUPPORTED, "columnar output layout");
+    for (int c = 0; c < t_.num_cols; ++c)
+      if (col_type(c).size() < 0) reject(B2Q_ERR_UNSUPPORTED, "column type outside TINYINT/SMALLINT/INT/BIGINT/DOUBLE");
+    if (t_.num_fragments < 0) reject(B2Q_ERR_INVALID_ARGUMENT, "negative fragment count");
+  }
+
+  void build_targets() {
+    const bool bigint_count = eo_.bigint_count != 0;
+    bool any_agg = false;
+    for (int i = 0; i < u_.num_target_exprs; ++i) {
+      const B2QExpr& e = ex(u_.target_exprs[i]);
+      TargetDesc d;
+      if (e.kind == B2Q_EXPR_COLUMN_VAR) {
+        d.is_agg = false;
+        d.sql_type = from_abi(e.ti);
+        d.arg_col = e.col_id;
+        col_type(e.col_id);
+      } else if (e.kind == B2Q_EXPR_AGG) {
+        d.is_agg = true;
+        d.agg = e.op;
+        any_agg = true;
+        if (e.op != B2Q_kCOUNT && e.op != B2Q_kSUM && e.op != B2Q_kMIN && e.op != B2Q_kMAX && e.op != B2Q_kAVG)
+          reject(B2Q_ERR_UNSUPPORTED, "aggregate kind outside COUNT/SUM/MIN/MAX/AVG");
+        if (e.left < 0) {
+          if (e.op != B2Q_kCOUNT) reject(B2Q_ERR_INVALID_ARGUMENT, "aggregate without argument must be COUNT");
+          d.sql_type = SqlType{bigint_count ? B2Q_kBIGINT : B2Q_kINT, e.ti.notnull != 0};
+        } else {
+          const B2QExpr& a = ex(e.left);
+          if (a.kind != B2Q_EXPR_COLUMN_VAR) reject(B2Q_ERR_UNSUPPORTED, "aggregate argument must be a ColumnVar");
+          d.arg_col = a.col_id;
+          d.arg_type = from_abi(a.ti);
+          if (d.arg_type.size() != col_type(a.col_id).size()) reject(B2Q_ERR_INVALID_ARGUMENT, "ColumnVar type does not match the table");
+          d.skip_null = !d.arg_type.notnull;
+          if (e.op == B2Q_kAVG) d.sql_type = d.arg_type.is_int() ? SqlType{B2Q_kBIGINT, d.arg_type.notnull} : d.arg_type;
+          else if (e.op == B2Q_kCOUNT) d.sql_type = SqlType{bigint_count ? B2Q_kBIGINT : B2Q_kINT, e.ti.notnull != 0};
+          else d.sql_type = from_abi(e.ti);
+        }
+      } else {
+        reject(B2Q_ERR_UNSUPPORTED, "target must be a ColumnVar or an AggExpr");
+      }
+      targets_.push_back(d);
+    }
+    if (!any_agg) reject(B2Q_ERR_UNSUPPORTED, "projection-only queries are outside this path");
+  }
+
+  ColRange leaf_range(int col) const {
+    ColRange r;
+    const SqlType ct = col_type(col);
+    r.valid = true;
+    r.fp = ct.is_fp();
+    int64_t total = 0;
+    for (int f = 0; f < t_.num_fragments; ++f) total += t_.fragments[f].num_tuples;
+    if (total == 0) return r; /* [0,-1], no nulls */
+    bool first = true;
+    for (int f = 0; f < t_.num_fragments; ++f) {
+      const B2QFragmentInfo& fr = t_.fragments[f];
+      if (fr.col_stats[col].has_nulls) r.has_nulls = true;
+      if (fr.num_tuples == 0) continue;
+      const B2QChunkStats& s = fr.col_stats[col];
+      if (first) { r.imin = s.int_min; r.imax = s.int_max; r.fmin = s.fp_min; r.fmax = s.fp_max; first = false; }
+      else {
+        r.imin = std::min(r.imin, s.int_min); r.imax = std::max(r.imax, s.int_max);
+        r.fmin = std::min(r.fmin, s.fp_min); r.fmax = std::max(r.fmax, s.fp_max);
+      }
+    }
+    if (!r.fp && r.imax < r.imin) { r.imin = 0; r.imax = -1; }
+    return r;
+  }
+
+  void narrow_by_simple_quals(int col, ColRange& r) const {
+    for (int i = 0; i < u_.num_simple_quals; ++i) {
+      const B2QExpr& q = ex(u_.simple_quals[i]);
+      if (q.kind != B2Q_EXPR_BIN_OPER) continue;
+      const B2QExpr& l = ex(q.left);
+      const B2QExpr& c = ex(q.right);
+      if (l.kind != B2Q_EXPR_COLUMN_VAR || l.col_id != col || c.kind != B2Q_EXPR_CONSTANT) continue;
+      const bool cfp = c.ti.type == B2Q_kDOUBLE;
+      if (r.fp) {
+        const double v = cfp ? c.dval : static_cast<double>(c.ival);
+        if (q.op == B2Q_kGT || q.op == B2Q_kGE || q.op == B2Q_kEQ) r.fmin = std::max(r.fmin, v);
+        if (q.op == B2Q_kLT || q.op == B2Q_kLE || q.op == B2Q_kEQ) r.fmax = std::min(r.fmax, v);
+      } else {
+        const int64_t v = cfp ? static_cast<int64_t>(c.dval) : c.ival;
+        switch (q.op) {
+          case B2Q_kGT: r.imin = std::max(r.imin, v + 1); break;
+          case B2Q_kGE: r.imin = std::max(r.imin, v); break;
+          case B2Q_kLT: r.imax = std::min(r.imax, v - 1); break;
+          case B2Q_kLE: r.imax = std::min(r.imax, v); break;
+          case B2Q_kEQ: r.imin = std::max(r.imin, v); r.imax = std::min(r.imax, v); break;
+          default: break;
+        }
+      }
+    }
+  }
+
+  static int64_t agg_init(int agg, const SqlType& ti, bool compaction, unsigned min_width) {
+    const unsigned bw = compaction ? std::max<unsigned>(ti.size(), min_width) : 8u;
+    const bool fp = ti.is_fp();
+    switch (agg) {
+      case B2Q_kSUM:
+        if (!ti.notnull) return fp ? dbl_bits(kNullDouble) : ti.int_null();
+        return 0; /* +0.0 has all-zero bits */
+      case B2Q_kAVG: case B2Q_kCOUNT: return 0;
+      case B2Q_kMIN:
+        if (fp) return dbl_bits(ti.notnull ? DBL_MAX : kNullDouble);
+        if (!ti.notnull) return ti.int_null();
+        return bw == 1 ? INT8_MAX : bw == 2 ? INT16_MAX : bw == 4 ? INT32_MAX : INT64_MAX;
+      case B2Q_kMAX:
+        if (fp) return dbl_bits(ti.notnull ? -DBL_MAX : kNullDouble);
+        if (!ti.notnull) return ti.int_null();
+        return bw == 1 ? INT8_MIN : bw == 2 ? INT16_MIN : bw == 4 ? INT32_MIN : INT64_MIN;
+      default: reject(B2Q_ERR_UNSUPPORTED, "aggregate kind");
+    }
+  }
+
+  void keyless_info() {
+    bool keyless = true, found = false;
+    int index = 0;
+    for (const TargetDesc& d : targets_) {
+      if (!found && d.is_agg) {
+        const bool has_arg = d.arg_col >= 0;
+        const ColRange r = has_arg ? leaf_range(d.arg_col) : ColRange{};
+        switch (d.agg) {
+          case B2Q_kAVG:
+            ++index; /* AVG's COUNT slot is the marker */
+            if (!(has_arg && !d.arg_type.notnull && (!r.valid || r.has_nulls))) found = true;
+            break;
+          case B2Q_kCOUNT:
+            if (!(has_arg && !d.arg_type.notnull && (!r.valid || r.has_nulls))) found = true;
+            break;
+          case B2Q_kSUM:
+            if (!d.arg_type.notnull) { if (r.valid && !r.has_nulls) found = true; }
+            else if (r.fp ? (r.fmax < 0 || r.fmin > 0) : (r.imax < 0 || r.imin > 0)) found = true;
+            break;
+          case B2Q_kMIN: { /* note: no has_nulls test in the reference (kMAX has one) */
+            const int64_t init_max = agg_init(d.agg, d.compact(), true, 8);
+            if (r.fp ? (r.fmax < bits_dbl(init_max)) : (r.imax < init_max)) found = true;
+            break;
+          }
+          case B2Q_kMAX: {
+            if (!r.valid || r.has_nulls) break;
+            const int64_t init_min = agg_init(d.agg, d.compact(), true, 8);
+            if (r.fp ? (r.fmin > bits_dbl(init_min)) : (r.imin > init_min)) found = true;
+            break;
+          }
+          default: keyless = false;
+        }
+      }
+      if (!keyless) break;
+      if (!found) ++index;
+    }
+    keyless_ = keyless && found;
+    keyless_idx_ = index;
+  }
+
+  void choose_hash_type(B2QPlan& p) {
+    grouped_ = u_.num_groupby_exprs == 1;
+    p.key_col_id = -1;
+    p.effective_key_width = 8;
+    p.idx_target_as_key = -1;
+    if (!grouped_) {
+      p.query_desc_type = B2Q_NonGroupedAggregate;
+      p.entry_count = 1;
+      return;
+    }
+    const B2QExpr& g = ex(u_.groupby_exprs[0]);
+    if (g.kind != B2Q_EXPR_COLUMN_VAR) reject(B2Q_ERR_UNSUPPORTED, "GROUP BY expression must be a ColumnVar");
+    key_col_ = g.col_id;
+    const SqlType kt = col_type(key_col_);
+    if (kt.is_fp()) reject(B2Q_ERR_UNSUPPORTED, "floating-point GROUP BY key (baseline double keys) is outside this path");
+    p.key_col_id = key_col_;
+    p.group_col_width = kt.size();
+    ColRange r = leaf_range(key_col_);
+    narrow_by_simple_quals(key_col_, r);
+    bool perfect = r.imin <= r.imax;
+    p.has_nulls = r.has_nulls;
+    if (perfect) {
+      p.min_val = r.imin; p.max_val = r.imax; p.bucket = 0;
+      const int64_t col_count = u_.num_groupby_exprs + u_.num_target_exprs;
+      const int64_t max_entries = (int64_t(1) << 30) / (col_count * 8); /* kMaxBufferSize, GroupByAndAggregate.cpp:57 */
+      int64_t span;
+      if (__builtin_sub_overflow(r.imax, r.imin, &span) || span >= max_entries) perfect = false; /* keeps min/max */
+    } else {
+      p.min_val = 0; p.max_val = -1;
+    }
+    if (perfect) {
+      p.query_desc_type = B2Q_GroupByPerfectHash;
+      keyless_info();
+      p.keyless_hash = keyless_ ? 1 : 0; /* bucket == 0, no sort hint, no baseline sort on this path */
+      p.idx_target_as_key = keyless_idx_;
+      p.entry_count = std::max<int64_t>(p.max_val - p.min_val + 1 + (p.has_nulls ? 1 : 0), 1);
+    } else {
+      p.query_desc_type = B2Q_GroupByBaselineHash;
+      if (!has_card_) reject(B2Q_ERR_CARDINALITY_ESTIMATION_REQUIRED, "baseline hash group-by needs a cardinality estimate (CardinalityEstimationRequired)");
+      if (guess_ == 0 || guess_ > 0xFFFFFFFFull) reject(B2Q_ERR_INVALID_ARGUMENT, "max_groups_buffer_entry_guess must be in [1, 2^32)");
+      p.entry_count = static_cast<int64_t>(guess_);
+      /* pick_baseline_key_width (QueryMemoryDescriptor.cpp:112-147) on the un-narrowed column range */
+      const ColRange kr = leaf_range(key_col_);
+      int w = 8;
+      if (!(p.group_col_width == 8 && kr.has_nulls) && kr.imin > INT32_MIN && kr.imax < int64_t(INT32_MAX) - 1) w = 4;
+      p.effective_key_width = std::max(4, w);
+      p.min_val = p.max_val = p.bucket = 0;
+      p.has_nulls = 0;
+    }
+  }
+
+  void layout_slots(B2QPlan& p) {
+    std::vector<int8_t> logical;
+    for (TargetDesc& d : targets_) {
+      d.first_slot = static_cast<int>(logical.size());
+      logical.push_back(static_cast<int8_t>(d.compact().size()));
+      if (d.is_agg && d.agg == B2Q_kAVG) logical.push_back(8);
+    }
+    if (logical.size() > B2Q_MAX_SLOTS) reject(B2Q_ERR_UNSUPPORTED, "too many output slots");
+    slot_key_ref_.assign(logical.size(), false);
+    if (p.query_desc_type == B2Q_GroupByBaselineHash)
+      for (const TargetDesc& d : targets_)
+        if (!d.is_agg && d.arg_col == key_col_) slot_key_ref_[d.first_slot] = true; /* target_groupby_indices */
+
+    /* pick_target_compact_width with crt_min_byte_width = 8 */
+    int8_t width = 0;
+    if (eo_.bigint_count) width = 8;
+    else {
+      int8_t compact = grouped_ ? 0 : 8;
+      if (!compact) {
+        for (int i = 0; i < u_.num_target_exprs && !compact; ++i) {
+          const B2QExpr& e = ex(u_.target_exprs[i]);
+          if (e.kind == B2Q_EXPR_AGG) { if (e.left >= 0) compact = 8; continue; }
+          const SqlType ti = from_abi(e.ti);
+          if (!(ti.is_int() && ti.size() <= 4)) compact = 8;
+        }
+      }
+      if (!compact) {
+        uint64_t tuples = 0;
+        for (int f = 0; f < t_.num_fragments; ++f) tuples += static_cast<uint64_t>(t_.fragments[f].num_tuples);
+        width = tuples <= UINT32_MAX ? 4 : 8;
+      } else {
+        for (int i = 0; i < u_.num_target_exprs; ++i) compact = std::max<int8_t>(compact, static_cast<int8_t>(from_abi(ex(u_.target_exprs[i]).ti).size()));
+        width = compact;
+      }
+    }
+    p.num_targets = static_cast<int32_t>(targets_.size());
+    p.num_slots = static_cast<int32_t>(logical.size());
+    const int64_t key_bytes = (grouped_ && !p.keyless_hash) ? align8(p.effective_key_width) : 0;
+    int64_t cols = 0;
+    for (size_t s = 0; s < logical.size(); ++s) {
+      if (slot_key_ref_[s]) { p.slot_logical_width[s] = p.slot_padded_width[s] = 0; p.slot_offset[s] = key_bytes + cols; continue; }
+      if (logical[s] > width) reject(B2Q_ERR_UNSUPPORTED, "slot wider than the compact width");
+      p.slot_logical_width[s] = logical[s];
+      p.slot_padded_width[s] = width;
+      if (width == 8) cols = align8(cols);
+      p.slot_offset[s] = key_bytes + cols;
+      cols += width;
+    }
+    p.row_size = align8(key_bytes + cols);
+    p.buffer_size = p.row_size * p.entry_count;
+  }
+
+  void init_values(B2QPlan& p) {
+    int8_t compact_width = 8;
+    for (int s = 0; s < p.num_slots; ++s) if (p.slot_padded_width[s]) { compact_width = p.slot_padded_width[s]; break; }
+    int s = 0;
+    for (const TargetDesc& d : targets_) {
+      if (!d.is_agg) { p.init_vals[s++] = 0; continue; }
+      SqlType ti = d.compact();
+      if (!grouped_) ti.notnull = false; /* non-grouped aggregates are nullable (OutputBufferInitialization.cpp:66-68,283-288) */
+      p.init_vals[s++] = agg_init(d.agg, ti, grouped_, compact_width);
+      if (d.agg == B2Q_kAVG) p.init_vals[s++] = 0;
+    }
+  }
+
+  void publish_targets(B2QPlan& p) {
+    for (size_t i = 0; i < targets_.size(); ++i) {
+      TargetDesc& d = targets_[i];
+      if (d.is_agg && d.arg_col >= 0 && !grouped_) d.skip_null = true; /* TargetExprBuilder.cpp:653-657 */
+      B2QTargetInfo& o = p.targets[i];
+      o.is_agg = d.is_agg; o.agg_kind = d.agg;
+      o.sql_type = to_abi(d.sql_type); o.agg_arg_type = to_abi(d.arg_type);
+      o.skip_null_val = d.skip_null; o.is_distinct = 0; o.arg_col_id = d.arg_col; o.first_slot = d.first_slot;
+    }
+  }
+
+  /* ---------------- lowering to the device program ---------------- */
+  int launch_col(B2QQuery& q, int table_col) {
+    for (int i = 0; i < q.prog.n_cols; ++i) if (q.col_ids[i] == table_col) return i;
+    if (q.prog.n_cols >= B2Q_MAX_COLS) reject(B2Q_ERR_UNSUPPORTED, "too many referenced columns");
+    q.col_ids[q.prog.n_cols] = table_col;
+    return q.prog.n_cols++;
+  }
+
+  void lower_cmp(B2QQuery& q, const B2QExpr& e) {
+    DevFilter& f = q.prog.filter;
+    const B2QExpr& l = ex(e.left);
+    const B2QExpr& c = ex(e.right);
+    if (l.kind != B2Q_EXPR_COLUMN_VAR || c.kind != B2Q_EXPR_CONSTANT) reject(B2Q_ERR_UNSUPPORTED, "comparison must be ColumnVar OP Constant");
+    if (f.n_terms >= B2Q_MAX_TERMS || f.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
+    const SqlType ct = col_type(l.col_id);
+    DevTerm t;
+    memset(&t, 0, sizeof(t));
+    t.col = launch_col(q, l.col_id);
+    t.width = static_cast<int8_t>(ct.size());
+    t.col_is_fp = ct.is_fp();
+    t.nullable = !ct.notnull;
+    t.null_bits = ct.is_fp() ? dbl_bits(kNullDouble) : ct.int_null();
+    const bool cfp = c.ti.type == B2Q_kDOUBLE;
+    t.cmp_fp = ct.is_fp() || cfp;
+    t.negate = e.op == B2Q_kNE;
+    const double inf = std::numeric_limits<double>::infinity();
+    /* default: empty range (always false; always true under negate) */
+    t.lo = 1; t.hi = 0; t.flo = inf; t.fhi = -inf;
+    if (c.is_null) {
+      t.negate = 0; /* comparison with a NULL literal is never TRUE */
+    } else if (t.cmp_fp) {
+      const double k = cfp ? c.dval : static_cast<double>(c.ival);
+      if (!std::isnan(k)) {
+        switch (e.op) {
+          case B2Q_kEQ: case B2Q_kNE: t.flo = k; t.fhi = k; break;
+          case B2Q_kLT: t.flo = -inf; t.fhi = std::nextafter(k, -inf); if (k == -inf) { t.flo = inf; t.fhi = -inf; } break;
+          case B2Q_kLE: t.flo = -inf; t.fhi = k; break;
+          case B2Q_kGT: t.flo = std::nextafter(k, inf); t.fhi = inf; if (k == inf) { t.flo = inf; t.fhi = -inf; } break;
+          case B2Q_kGE: t.flo = k; t.fhi = inf; break;
+          default: reject(B2Q_ERR_UNSUPPORTED, "comparison operator");
+        }
+      }
+    } else {
+      const int64_t k = c.ival;
+      switch (e.op) {
+        case B2Q_kEQ: case B2Q_kNE: t.lo = k; t.hi = k; break;
+        case B2Q_kLT: if (k != INT64_MIN) { t.lo = INT64_MIN; t.hi = k - 1; } break;
+        case B2Q_kLE: t.lo = INT64_MIN; t.hi = k; break;
+        case B2Q_kGT: if (k != INT64_MAX) { t.lo = k + 1; t.hi = INT64_MAX; } break;
+        case B2Q_kGE: t.lo = k; t.hi = INT64_MAX; break;
+        default: reject(B2Q_ERR_UNSUPPORTED, "comparison operator");
+      }
+    }
+    f.ops[f.n_ops++] = static_cast<uint8_t>((FOP_TERM << 4) | f.n_terms);
+    f.terms[f.n_terms++] = t;
+  }
+
+  int lower_bool(B2QQuery& q, int idx, int depth) { /* returns max stack depth used */
+    const B2QExpr& e = ex(idx);
+    if (e.kind != B2Q_EXPR_BIN_OPER) reject(B2Q_ERR_UNSUPPORTED, "qual must be a BinOper");
+    if (e.op == B2Q_kAND || e.op == B2Q_kOR) {
+      const int d1 = lower_bool(q, e.left, depth);
+      const int d2 = lower_bool(q, e.right, depth + 1);
+      DevFilter& f = q.prog.filter;
+      if (f.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
+      f.ops[f.n_ops++] = static_cast<uint8_t>((e.op == B2Q_kAND ? FOP_AND : FOP_OR) << 4);
+      return std::max(d1, d2);
+    }
+    lower_cmp(q, e);
+    return depth + 1;
+  }
+
+  int find_or_add_acc(B2QQuery& q, const DevAcc& a) {
+    for (int i = 0; i < q.prog.n_accs; ++i) if (!memcmp(&q.prog.accs[i], &a, sizeof(DevAcc))) return i;
+    if (q.prog.n_accs >= B2Q_MAX_ACCS) reject(B2Q_ERR_UNSUPPORTED, "too many aggregates");
+    q.prog.accs[q.prog.n_accs] = a;
+    return q.prog.n_accs++;
+  }
+
+  DevAcc make_acc(B2QQuery& q, int op, const TargetDesc* d) {
+    DevAcc a;
+    memset(&a, 0, sizeof(a));
+    a.op = static_cast<int8_t>(op);
+    a.col = -1;
+    if (!d || d->arg_col < 0) return a;
+    const SqlType at = d->arg_type;
+    a.col = launch_col(q, d->arg_col);
+    a.width = static_cast<int8_t>(at.size());
+    a.is_fp = at.is_fp();
+    if (!d->skip_null) return a;
+    if (at.is_fp()) { /* agg_*_double_skip_val: fp compare against NULL_DOUBLE */
+      a.skip1_en = 1;
+      a.skip1_val = dbl_bits(kNullDouble);
+      return a;
+    }
+    if (d->agg == B2Q_kMIN || d->agg == B2Q_kMAX) { /* null = inlineIntNull(arg_ti) sign-extended */
+      a.skip1_en = 1;
+      a.skip1_val = at.int_null();
+      return a;
+    }
+    /* SUM / AVG / COUNT: convertNullIfAny + cast to the aggregate type + compare with ITS sentinel */
+    const SqlType agg_t = d->sql_type;
+    if (!at.notnull) { a.skip1_en = 1; a.skip1_val = at.int_null(); }
+    a.skip2_en = 1;
+    a.skip2_val = agg_t.int_null();
+    a.skip2_trunc32 = (!at.notnull && agg_t.size() == 4) ? 1 : 0;
+    return a;
+  }
+
+  void lower(B2QQuery& q) {
+    B2QPlan& p = q.plan;
+    DevProgram& g = q.prog;
+    q.bigint_count = eo_.bigint_count;
+    /* filter: all simple_quals and quals AND-ed */
+    int n_quals = 0, max_depth = 0;
+    auto add_qual = [&](int idx) {
+      max_depth = std::max(max_depth, lower_bool(q, idx, n_quals ? 1 : 0));
+      if (n_quals) {
+        if (g.filter.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
+        g.filter.ops[g.filter.n_ops++] = static_cast<uint8_t>(FOP_AND << 4);
+      }
+      ++n_quals;
+    };
+    for (int i = 0; i < u_.num_simple_quals; ++i) add_qual(u_.simple_quals[i]);
+    for (int i = 0; i < u_.num_quals; ++i) add_qual(u_.quals[i]);
+    if (max_depth > 4) reject(B2Q_ERR_UNSUPPORTED, "filter expression nests deeper than 4");
+
+    /* key */
+    DevKey& k = g.key;
+    k.col = -1;
+    k.entry_count = p.entry_count;
+    k.null_idx = -1;
+    if (grouped_) {
+      const SqlType kt = col_type(key_col_);
+      k.col = launch_col(q, key_col_);
+      k.width = static_cast<int8_t>(kt.size());
+      k.min_val = p.min_val;
+      k.null_val = kt.int_null();
+      k.hash_key_width = static_cast<int8_t>(p.effective_key_width);
+      if (p.query_desc_type == B2Q_GroupByPerfectHash && p.has_nulls && !kt.notnull) {
+        k.translate_null = 1;
+        k.null_idx = p.max_val - p.min_val + 1;
+      }
+    }
+
+    /* accumulators + slot recipes */
+    DevLayout& L = q.layout;
+    L.row_size = p.row_size;
+    L.entry_count = p.entry_count;
+    L.n_slots = p.num_slots;
+    L.key_min = p.min_val;
+    L.null_idx = k.null_idx;
+    L.key_null_val = grouped_ ? col_type(key_col_).int_null() : 0;
+    L.has_key_col = grouped_ && !p.keyless_hash;
+    L.key_width = static_cast<int8_t>(p.effective_key_width);
+    L.baseline = p.query_desc_type == B2Q_GroupByBaselineHash;
+    L.touched_acc = -1;
+    L.keyless_marker = (grouped_ && p.keyless_hash) ? p.idx_target_as_key : -1;
+    for (const TargetDesc& d : targets_) {
+      const int s = d.first_slot;
+      DevSlot& sl = L.slots[s];
+      sl.init_val = p.init_vals[s];
+      sl.offset = p.slot_offset[s];
+      sl.width = p.slot_padded_width[s];
+      sl.acc = -1; sl.nn = -1;
+      if (sl.width == 0) { sl.kind = SLOT_NONE; continue; }
+      if (!d.is_agg) {
+        if (d.arg_col != key_col_) reject(B2Q_ERR_UNSUPPORTED, "non-aggregate target must be the GROUP BY column");
+        sl.kind = SLOT_KEY;
+        continue;
+      }
+      if (sl.width == 4 && !(d.agg == B2Q_kCOUNT && d.arg_col < 0)) reject(B2Q_ERR_UNSUPPORTED, "4-byte slot with an aggregate argument");
+      const bool fp = d.arg_col >= 0 && d.arg_type.is_fp();
+      /* the count of values that survive the skip test: decides NULL for SUM, is AVG's count, is COUNT(c) */
+      auto non_null_count = [&]() -> int {
+        if (!(d.arg_col >= 0 && d.skip_null)) return -1;
+        DevAcc c = make_acc(q, ACC_COUNT, &d);
+        if (!c.skip1_en && !c.skip2_en) { c.col = -1; c.width = 0; c.is_fp = 0; } /* nothing to skip: COUNT(*) */
+        return find_or_add_acc(q, c);
+      };
+      switch (d.agg) {
+        case B2Q_kCOUNT: {
+          sl.kind = SLOT_COUNT;
+          const int nn = non_null_count();
+          sl.acc = nn >= 0 ? nn : find_or_add_acc(q, make_acc(q, ACC_COUNT, nullptr));
+          break;
+        }
+        case B2Q_kSUM:
+        case B2Q_kAVG: {
+          sl.kind = SLOT_VALUE;
+          sl.acc = find_or_add_acc(q, make_acc(q, fp ? ACC_SUM_F64 : ACC_SUM_I64, &d));
+          const int nn = non_null_count();
+          sl.nn = nn;
+          if (d.agg == B2Q_kAVG) {
+            DevSlot& cs = L.slots[s + 1];
+            cs.init_val = 0; cs.offset = p.slot_offset[s + 1]; cs.width = p.slot_padded_width[s + 1];
+            cs.kind = SLOT_COUNT; cs.nn = -1;
+            cs.acc = nn >= 0 ? nn : find_or_add_acc(q, make_acc(q, ACC_COUNT, nullptr));
+          }
+          break;
+        }
+        case B2Q_kMIN:
+        case B2Q_kMAX: {
+          const int op = d.agg == B2Q_kMIN ? (fp ? ACC_MIN_F64 : ACC_MIN_I64) : (fp ? ACC_MAX_F64 : ACC_MAX_I64);
+          sl.kind = fp ? SLOT_VALUE_ORD : SLOT_VALUE;
+          sl.acc = find_or_add_acc(q, make_acc(q, op, &d));
+          sl.identity = b2q_acc_identity(op);
+          /* "no value seen" <=> the accumulator still holds its identity.  Exact except for a nullable BIGINT MIN
+           * whose only non-NULL values are INT64_MAX (the identity is a legal value there): that case counts. */
+          if (d.skip_null && !fp && d.arg_type.size() == 8 && d.agg == B2Q_kMIN) sl.nn = non_null_count();
+          else sl.nn = -2;
+          break;
+        }
+        default: reject(B2Q_ERR_UNSUPPORTED, "aggregate kind");
+      }
+    }
+    if (grouped_ && !p.keyless_hash && !L.baseline) L.touched_acc = find_or_add_acc(q, make_acc(q, ACC_COUNT, nullptr));
+  }
+
+  void choose_kernel(B2QQuery& q) {
+    B2QPlan& p = q.plan;
+    SmemPlan& sm = q.smem;
+    memset(&sm, 0, sizeof(sm));
+    sm.replicas = 1;
+    int kernel;
+    if (p.query_desc_type == B2Q_NonGroupedAggregate) kernel = B2Q_KERNEL_NON_GROUPED;
+    else if (p.query_desc_type == B2Q_GroupByBaselineHash) kernel = B2Q_KERNEL_BASELINE_GLOBAL;
+    else {
+      /* shared-memory footprint per entry: COUNT 4 B, SUM_I64 4 B (low word; carries go to HBM), others 8 B */
+      int off = 0;
+      /* 8-byte arrays first so they stay 8-byte aligned */
+      for (int pass = 0; pass < 2; ++pass)
+        for (int a = 0; a < q.prog.n_accs; ++a) {
+          const int op = q.prog.accs[a].op;
+          const int bytes = (op == ACC_COUNT || op == ACC_SUM_I64) ? 4 : 8;
+          if ((pass == 0) != (bytes == 8)) continue;
+          sm.acc_bytes[a] = bytes;
+          sm.acc_off[a] = off;
+          off += static_cast<int>(((p.entry_count * bytes + 15) / 16) * 16);
+          if (off > (1 << 24)) break;
+        }
+      const int64_t per_replica = off;
+      const int64_t budget = 200 * 1024; /* of the 227 KB a CTA may opt in to; the rest is left to L1 */
+      if (per_replica <= budget && p.entry_count <= (1 << 22)) {
+        kernel = B2Q_KERNEL_PERFECT_SMEM;
+        sm.use_smem = 1;
+        sm.replica_bytes = static_cast<int32_t>(per_replica);
+        int rep = 1;
+        while (rep < 32 && int64_t(rep) * 2 * per_replica <= 96 * 1024) rep *= 2; /* warp-private copies for small tables */
+        sm.replicas = rep;
+        sm.total_bytes = static_cast<int32_t>(per_replica * rep);
+      } else {
+        kernel = B2Q_KERNEL_PERFECT_GLOBAL;
+      }
+    }
+    if (eo_.force_kernel) {
+      const int f = eo_.force_kernel;
+      const bool ok = (f == kernel) || (f == B2Q_KERNEL_PERFECT_GLOBAL && kernel == B2Q_KERNEL_PERFECT_SMEM);
+      if (!ok) reject(B2Q_ERR_INVALID_ARGUMENT, "force_kernel is not applicable to this query");
+      if (f == B2Q_KERNEL_PERFECT_GLOBAL) { sm.use_smem = 0; sm.replicas = 1; sm.total_bytes = 0; }
+      kernel = f;
+    }
+    p.kernel = kernel;
+  }
+};
+
+}  // namespace
+
+int32_t make_query(const B2QExecUnit* u, const B2QTableInfo* t, const B2QExecutionOptions* eo, size_t guess,
+                   bool has_card, B2QQuery* out, std::string* err) {
+  try {
+    if (!u || !t || !eo || !out) throw PlanError{B2Q_ERR_INVALID_ARGUMENT, "null argument"};
+    Planner(*u, *t, *eo, guess, has_card).run(*out);
+    return B2Q_OK;
+  } catch (const PlanError& e) {
+    if (err) *err = e.msg;
+    return e.code;
+  }
+}
+
+}  // namespace b2q

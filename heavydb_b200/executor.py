@@ -1,0 +1,312 @@
+"""Host-side mirror of the reference's operator interface for this path, over the C ABI (``libb2q.so``).
+
+    Executor.executeWorkUnit(max_groups_buffer_entry_guess, is_agg, query_infos, ra_exe_unit, co, eo,
+                             has_cardinality_estimation)  ->  ResultSet
+
+has the parameter order and meaning of ``Executor::executeWorkUnit`` (QueryEngine/Execute.h:719-727); ``ResultSet``
+exposes ``rowCount/colCount/getColType/getNextRow/entryCount/isEmpty/getStorageBuffer`` like
+QueryEngine/ResultSet.h:183-330.  Errors that cross the reference's boundary as C++ exceptions are raised as the
+Python exceptions below (same names).
+
+This module only marshals arguments: all computation happens in the CUDA library.  If the library is missing the
+import of this module's ``lib()`` fails loudly — there is no Python or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2q.so")
+_lib = None
+
+
+class QueryExecutionError(RuntimeError):
+    """QueryExecutionError(ErrorCode) — QueryEngine/ExecutionKernel.cpp:133-160."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+class CardinalityEstimationRequired(QueryExecutionError):
+    """NativeCodegen.cpp:2972-2979: baseline hash without a cardinality estimate."""
+
+
+class UnsupportedOnThisPath(QueryExecutionError):
+    pass
+
+
+class NoDeviceError(QueryExecutionError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m heavydb_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.b2q_abi_version.restype = C.c_int32
+        L.b2q_error_string.restype = C.c_char_p
+        L.b2q_error_string.argtypes = [C.c_int32]
+        L.b2q_last_error_message.restype = C.c_char_p
+        L.b2q_device_count.restype = C.c_int32
+        L.b2q_plan.restype = C.c_int32
+        L.b2q_plan.argtypes = [C.POINTER(abi.ExecUnit), C.POINTER(abi.TableInfo), C.POINTER(abi.CompilationOptions),
+                               C.POINTER(abi.ExecutionOptions), C.c_size_t, C.c_int32, C.POINTER(C.c_void_p)]
+        L.b2q_query_plan.restype = C.POINTER(abi.Plan)
+        L.b2q_query_plan.argtypes = [C.c_void_p]
+        L.b2q_query_free.argtypes = [C.c_void_p]
+        ewu = [C.POINTER(C.c_size_t), C.c_int32, C.POINTER(abi.TableInfo), C.POINTER(abi.ExecUnit),
+               C.POINTER(abi.CompilationOptions), C.POINTER(abi.ExecutionOptions), C.c_int32]
+        L.b2q_execute_work_unit.restype = C.c_int32
+        L.b2q_execute_work_unit.argtypes = ewu + [C.POINTER(C.c_void_p)]
+        L.b2q_execute_partial.restype = C.c_int32
+        L.b2q_execute_partial.argtypes = ewu + [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.b2q_partial_num_arrays.restype = C.c_int32
+        L.b2q_partial_num_arrays.argtypes = [C.c_void_p]
+        L.b2q_partial_array.restype = C.c_int32
+        L.b2q_partial_array.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.b2q_partial_is_mergeable.restype = C.c_int32
+        L.b2q_partial_is_mergeable.argtypes = [C.c_void_p]
+        L.b2q_partial_plan.restype = C.POINTER(abi.Plan)
+        L.b2q_partial_plan.argtypes = [C.c_void_p]
+        L.b2q_partial_kernel_ms.restype = C.c_double
+        L.b2q_partial_kernel_ms.argtypes = [C.c_void_p]
+        L.b2q_partial_finalize.restype = C.c_int32
+        L.b2q_partial_finalize.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.b2q_partial_free.argtypes = [C.c_void_p]
+        L.b2q_launch.restype = C.c_int32
+        L.b2q_launch.argtypes = [C.c_void_p, C.POINTER(abi.Params), C.c_void_p]
+        for n in ("b2q_rs_row_count", "b2q_rs_col_count", "b2q_rs_entry_count"):
+            getattr(L, n).restype = C.c_size_t
+            getattr(L, n).argtypes = [C.c_void_p]
+        L.b2q_rs_is_empty.restype = C.c_int32
+        L.b2q_rs_is_empty.argtypes = [C.c_void_p]
+        L.b2q_rs_get_col_type.restype = abi.TypeInfo
+        L.b2q_rs_get_col_type.argtypes = [C.c_void_p, C.c_size_t]
+        L.b2q_rs_get_next_row.restype = C.c_int32
+        L.b2q_rs_get_next_row.argtypes = [C.c_void_p, C.POINTER(abi.TargetValue)]
+        L.b2q_rs_move_to_begin.argtypes = [C.c_void_p]
+        L.b2q_rs_is_row_at_empty.restype = C.c_int32
+        L.b2q_rs_is_row_at_empty.argtypes = [C.c_void_p, C.c_size_t]
+        L.b2q_rs_storage_buffer.restype = C.c_void_p
+        L.b2q_rs_storage_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+        L.b2q_rs_query_mem_desc.restype = C.POINTER(abi.Plan)
+        L.b2q_rs_query_mem_desc.argtypes = [C.c_void_p]
+        L.b2q_rs_kernel_ms.restype = C.c_double
+        L.b2q_rs_kernel_ms.argtypes = [C.c_void_p]
+        L.b2q_rs_free.argtypes = [C.c_void_p]
+        L.b2q_gen_column.restype = C.c_int32
+        L.b2q_gen_column.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
+                                     C.c_int64, C.c_void_p]
+        if L.b2q_abi_version() != 1:
+            raise ImportError("libb2q.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def _raise(code: int):
+    msg = lib().b2q_last_error_message().decode() or lib().b2q_error_string(code).decode()
+    if code == abi.ERR_CARDINALITY_ESTIMATION_REQUIRED:
+        raise CardinalityEstimationRequired(code, msg)
+    if code == abi.ERR_UNSUPPORTED:
+        raise UnsupportedOnThisPath(code, msg)
+    if code == abi.ERR_NO_DEVICE:
+        raise NoDeviceError(code, msg)
+    raise QueryExecutionError(code, msg)
+
+
+def compilation_options(device_type: int = abi.DEVICE_GPU, hoist_literals: bool = True) -> abi.CompilationOptions:
+    """CompilationOptions::defaults(ExecutorDeviceType::GPU) — QueryEngine/CompilationOptions.h:52-65."""
+    return abi.CompilationOptions(device_type, int(hoist_literals))
+
+
+def execution_options(allow_multifrag=True, output_columnar_hint=False, bigint_count=False, force_kernel=0,
+                      device_ordinal=-1) -> abi.ExecutionOptions:
+    eo = abi.ExecutionOptions()
+    eo.allow_multifrag = int(allow_multifrag)
+    eo.output_columnar_hint = int(output_columnar_hint)
+    eo.bigint_count = int(bigint_count)
+    eo.force_kernel = force_kernel
+    eo.device_ordinal = device_ordinal
+    return eo
+
+
+class ResultSet:
+    """Output surface of QueryEngine/ResultSet.h for the numeric subset."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().b2q_rs_free(self._h)
+            self._h = None
+
+    def rowCount(self) -> int:
+        return lib().b2q_rs_row_count(self._h)
+
+    def colCount(self) -> int:
+        return lib().b2q_rs_col_count(self._h)
+
+    def entryCount(self) -> int:
+        return lib().b2q_rs_entry_count(self._h)
+
+    def isEmpty(self) -> bool:
+        return bool(lib().b2q_rs_is_empty(self._h))
+
+    def getColType(self, i: int):
+        t = lib().b2q_rs_get_col_type(self._h, i)
+        return (t.type, t.notnull)
+
+    def moveToBegin(self):
+        lib().b2q_rs_move_to_begin(self._h)
+
+    def getNextRow(self, translate_strings: bool = True, decimal_to_double: bool = True):
+        nc = self.colCount()
+        row = (abi.TargetValue * nc)()
+        if not lib().b2q_rs_get_next_row(self._h, row):
+            return []
+        return [v.py() for v in row]
+
+    def rows(self) -> List[tuple]:
+        self.moveToBegin()
+        L = lib()
+        nc = self.colCount()
+        row = (abi.TargetValue * nc)()
+        out = []
+        while L.b2q_rs_get_next_row(self._h, row):
+            out.append(tuple(v.py() for v in row))
+        return out
+
+    def isRowAtEmpty(self, i: int) -> bool:
+        return bool(lib().b2q_rs_is_row_at_empty(self._h, i))
+
+    def getQueryMemDesc(self) -> abi.Plan:
+        return lib().b2q_rs_query_mem_desc(self._h).contents
+
+    def getStorageBuffer(self) -> np.ndarray:
+        """getStorage()->getUnderlyingBuffer() as bytes in the reference's row-wise layout."""
+        n = C.c_size_t()
+        p = lib().b2q_rs_storage_buffer(self._h, C.byref(n))
+        if not n.value:
+            return np.zeros(0, dtype=np.int8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int8)), shape=(n.value,)).copy()
+
+    def kernel_ms(self) -> float:
+        return lib().b2q_rs_kernel_ms(self._h)
+
+
+class Partial:
+    """Per-device dense partial-aggregate table (between the scan and the cross-device merge)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().b2q_partial_free(self._h)
+            self._h = None
+
+    def arrays(self):
+        """[(device_ptr, count, dtype, redop)] — what the caller all-reduces (one collective per array)."""
+        L = lib()
+        out = []
+        for i in range(L.b2q_partial_num_arrays(self._h)):
+            p, n, dt, op = C.c_void_p(), C.c_int64(), C.c_int32(), C.c_int32()
+            rc = L.b2q_partial_array(self._h, i, C.byref(p), C.byref(n), C.byref(dt), C.byref(op))
+            if rc:
+                _raise(rc)
+            out.append((p.value, n.value, dt.value, op.value))
+        return out
+
+    def is_mergeable(self) -> bool:
+        return bool(lib().b2q_partial_is_mergeable(self._h))
+
+    def plan(self) -> abi.Plan:
+        return lib().b2q_partial_plan(self._h).contents
+
+    def kernel_ms(self) -> float:
+        return lib().b2q_partial_kernel_ms(self._h)
+
+    def finalize(self, stream: int = 0) -> ResultSet:
+        h = C.c_void_p()
+        rc = lib().b2q_partial_finalize(self._h, C.c_void_p(stream), C.byref(h))
+        if rc:
+            _raise(rc)
+        return ResultSet(h)
+
+
+class Executor:
+    """Executor::executeWorkUnit for the scan/filter/group-by/aggregate path."""
+
+    def __init__(self, device_ordinal: int = -1):
+        self.device_ordinal = device_ordinal
+        lib()
+
+    @staticmethod
+    def _built_table(query_infos, memory_level):
+        if isinstance(query_infos, abi.BuiltTable):
+            return query_infos
+        return query_infos.build(memory_level)
+
+    def plan(self, ra_exe_unit: abi.BuiltUnit, query_infos, co=None, eo=None, max_groups_buffer_entry_guess: int = 0,
+             has_cardinality_estimation: bool = False, memory_level: int = abi.CPU_LEVEL) -> abi.Plan:
+        """Planning only (host; works without a GPU)."""
+        co = co or compilation_options()
+        eo = eo or execution_options(device_ordinal=self.device_ordinal)
+        bt = self._built_table(query_infos, memory_level)
+        h = C.c_void_p()
+        rc = lib().b2q_plan(C.byref(ra_exe_unit.unit), C.byref(bt.info), C.byref(co), C.byref(eo),
+                            max_groups_buffer_entry_guess, int(has_cardinality_estimation), C.byref(h))
+        if rc:
+            _raise(rc)
+        plan = abi.Plan()
+        C.memmove(C.byref(plan), lib().b2q_query_plan(h), C.sizeof(abi.Plan))
+        lib().b2q_query_free(h)
+        return plan
+
+    def executeWorkUnit(self, max_groups_buffer_entry_guess: int, is_agg: bool, query_infos, ra_exe_unit: abi.BuiltUnit,
+                        co: Optional[abi.CompilationOptions] = None, eo: Optional[abi.ExecutionOptions] = None,
+                        has_cardinality_estimation: bool = False, memory_level: int = abi.CPU_LEVEL) -> ResultSet:
+        co = co or compilation_options()
+        eo = eo or execution_options(device_ordinal=self.device_ordinal)
+        bt = self._built_table(query_infos, memory_level)
+        guess = C.c_size_t(max_groups_buffer_entry_guess)
+        h = C.c_void_p()
+        rc = lib().b2q_execute_work_unit(C.byref(guess), int(is_agg), C.byref(bt.info), C.byref(ra_exe_unit.unit),
+                                         C.byref(co), C.byref(eo), int(has_cardinality_estimation), C.byref(h))
+        if rc:
+            _raise(rc)
+        return ResultSet(h)
+
+    def executePartial(self, max_groups_buffer_entry_guess: int, is_agg: bool, query_infos, ra_exe_unit: abi.BuiltUnit,
+                       co=None, eo=None, has_cardinality_estimation: bool = False,
+                       memory_level: int = abi.CPU_LEVEL, stream: int = 0) -> Partial:
+        co = co or compilation_options()
+        eo = eo or execution_options(device_ordinal=self.device_ordinal)
+        bt = self._built_table(query_infos, memory_level)
+        guess = C.c_size_t(max_groups_buffer_entry_guess)
+        h = C.c_void_p()
+        rc = lib().b2q_execute_partial(C.byref(guess), int(is_agg), C.byref(bt.info), C.byref(ra_exe_unit.unit),
+                                       C.byref(co), C.byref(eo), int(has_cardinality_estimation), C.c_void_p(stream),
+                                       C.byref(h))
+        if rc:
+            _raise(rc)
+        return Partial(h)
+
+
+def gen_column_device(dst_ptr: int, sql_type: int, seed: int, col_tag: int, row0: int, count: int, lo: int = 0,
+                      span: int = 1, stream: int = 0):
+    rc = lib().b2q_gen_column(C.c_void_p(dst_ptr), sql_type, seed, col_tag, row0, count, lo, span, C.c_void_p(stream))
+    if rc:
+        _raise(rc)

@@ -1,0 +1,130 @@
+"""Helpers for the `-m gpu` parity tests: run a query through the C ABI (CUDA path) and through the oracle on the
+same inputs and compare rows + raw output buffers."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+import oracle_lib
+from heavydb_b200 import abi, executor
+
+FP_RTOL = 1e-6  # north_star: SUM/AVG(double) within 1e-6 relative; everything integer is bit-exact
+
+
+def _cudart():
+    """Device memory for tests comes from torch (plumbing only)."""
+    import torch
+    return torch
+
+
+def has_gpu() -> bool:
+    try:
+        return executor.lib().b2q_device_count() > 0
+    except Exception:
+        return False
+
+
+class DeviceTable:
+    """Copies a host abi.Table to the GPU (torch tensors own the memory) and exposes it as a GPU_LEVEL table."""
+
+    def __init__(self, table: abi.Table):
+        torch = _cudart()
+        self.keep = []
+        self.table = abi.Table(table.col_types)
+        for f in table.fragments:
+            ptrs = []
+            for a in f.host_cols:
+                if a is None or a.size == 0:
+                    ptrs.append(0)
+                    continue
+                t = torch.from_numpy(a.view(np.uint8).copy()).cuda()
+                self.keep.append(t)
+                ptrs.append(t.data_ptr())
+            self.table.add_device_fragment(f.num_tuples, ptrs, f.stats, fragment_id=f.fragment_id)
+        torch.cuda.synchronize()
+
+
+def rows_equal(got, want, fp_rtol=FP_RTOL):
+    def key(r):
+        return tuple((0, 0) if v is None else (1, v) for v in r)
+    g, w = sorted(got, key=key), sorted(want, key=key)
+    assert len(g) == len(w), f"row count {len(g)} != {len(w)}\n got={g[:8]}\nwant={w[:8]}"
+    for a, b in zip(g, w):
+        assert len(a) == len(b)
+        for va, vb in zip(a, b):
+            if va is None or vb is None:
+                assert va is None and vb is None, f"NULL mismatch: {a} vs {b}"
+            elif isinstance(vb, float):
+                assert isinstance(va, float)
+                if math.isnan(vb):
+                    assert math.isnan(va)
+                else:
+                    assert va == vb or abs(va - vb) <= fp_rtol * abs(vb), f"{a} vs {b}"
+            else:
+                assert va == vb, f"{a} vs {b}"
+
+
+def buffers_equal(got: np.ndarray, want: np.ndarray, plan: abi.Plan, fp_rtol=FP_RTOL, empty=None):
+    """Raw output buffers in the reference's row-wise layout.  Integer/bit-pattern slots must be identical; slots that
+    hold a floating-point SUM (order of additions differs on a GPU) are compared within fp_rtol."""
+    assert got.size == want.size == plan.buffer_size
+    if plan.buffer_size == 0:
+        return
+    rs = plan.row_size
+    g = got.view(np.int8).reshape(-1, rs)
+    w = want.view(np.int8).reshape(-1, rs)
+    fp_sum_slots = set()
+    for t in plan.targets[: plan.num_targets]:
+        if t.is_agg and t.agg_kind in (abi.kSUM, abi.kAVG) and t.agg_arg_type.type == abi.kDOUBLE:
+            fp_sum_slots.add(t.first_slot)
+    mask = np.ones(rs, dtype=bool)
+    for s in fp_sum_slots:
+        off = plan.slot_offset[s]
+        mask[off:off + 8] = False
+        a = np.ascontiguousarray(g[:, off:off + 8]).view(np.float64).ravel()
+        b = np.ascontiguousarray(w[:, off:off + 8]).view(np.float64).ravel()
+        if empty is not None:
+            a, b = a[~empty], b[~empty]
+        ok = (a == b) | (np.abs(a - b) <= fp_rtol * np.abs(b))
+        assert ok.all(), f"fp SUM slot {s}: {a[~ok][:4]} vs {b[~ok][:4]}"
+    if empty is not None:
+        # entries every reader treats as empty: only the emptiness itself must agree (checked by the caller)
+        g, w = g[~empty], w[~empty]
+    assert np.array_equal(g[:, mask], w[:, mask]), "integer part of the output buffer differs from the oracle"
+
+
+def run_both(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=False, bigint_count=False, force_kernel=0,
+             device_resident=True, compare_buffers=True, oracle_threads=4, dev_table: DeviceTable | None = None):
+    """Returns (gpu ResultSet, oracle result).  Asserts plan, rows and (unless baseline) buffers agree."""
+    ex = executor.Executor()
+    eo = executor.execution_options(bigint_count=bigint_count, force_kernel=force_kernel)
+    if device_resident:
+        dt = dev_table or DeviceTable(table)
+        rs = ex.executeWorkUnit(entry_guess, True, dt.table, unit, eo=eo, has_cardinality_estimation=has_card,
+                                memory_level=abi.GPU_LEVEL)
+    else:
+        rs = ex.executeWorkUnit(entry_guess, True, table, unit, eo=eo, has_cardinality_estimation=has_card,
+                                memory_level=abi.CPU_LEVEL)
+    ref = oracle_lib.execute(unit, table, entry_guess=entry_guess, has_card=has_card, bigint_count=bigint_count,
+                             num_threads=oracle_threads)
+    gp, op = rs.getQueryMemDesc(), ref.plan
+    assert gp.as_dict() == op.as_dict()
+    assert rs.colCount() == ref.col_count()
+    for i in range(rs.colCount()):
+        assert rs.getColType(i) == ref.col_type(i)
+    rows_equal(rs.rows(), ref.rows())
+    assert rs.rowCount() == ref.row_count()
+    if compare_buffers and gp.query_desc_type != abi.GroupByBaselineHash:
+        n = rs.entryCount()
+        assert n == ref.entry_count()
+        L = oracle_lib.lib()
+        if n <= 200_000:
+            empty = np.array([rs.isRowAtEmpty(i) for i in range(n)], dtype=bool)
+            empty_ref = np.array([bool(L.oracle_result_is_row_at_empty(ref.h, i)) for i in range(n)], dtype=bool)
+            assert np.array_equal(empty, empty_ref)
+        else:
+            empty = None
+        buffers_equal(rs.getStorageBuffer(), ref.buffer(), gp, empty=empty)
+    return rs, ref

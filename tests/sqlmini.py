@@ -1,129 +1,3 @@
-"""Tiny SQL front-end for tests: turns the reference's own test query strings (Tests/ExecuteTest.cpp) into the
-RelAlgExecutionUnit mirror, for the subset of the path:
-
-    SELECT <col | COUNT(*) | COUNT(c) | SUM(c) | MIN(c) | MAX(c) | AVG(c)>, ...
-    FROM <table> [WHERE <c OP literal> {AND|OR} ... with parentheses] [GROUP BY c]
-
-It plays the role Calcite + RelAlgTranslator play in the reference (kept, out of scope) and is test infrastructure.
-Like RelAlgTranslator/QualsConjunctiveForm, a top-level AND is split into separate quals, and a `col OP const`
-conjunct is a "simple qual" (Analyzer::BinOper::normalize_simple_predicate, QueryEngine/RelAlgExecutor.cpp
-translation of filters: simple_quals vs quals).
-"""
-from __future__ import annotations
-
-import re
-from typing import List, Tuple
-
-from heavydb_b200 import abi
-
-_TOK = re.compile(r"\s*(<>|<=|>=|!=|[(),*<>=]|[A-Za-z_][A-Za-z_0-9]*|-?\d+\.\d*(?:[eE][-+]?\d+)?|-?\d+)")
-_OPS = {"=": abi.kEQ, "<>": abi.kNE, "!=": abi.kNE, "<": abi.kLT, ">": abi.kGT, "<=": abi.kLE, ">=": abi.kGE}
-_AGGS = {"COUNT": abi.kCOUNT, "SUM": abi.kSUM, "MIN": abi.kMIN, "MAX": abi.kMAX, "AVG": abi.kAVG}
-
-
-def _tokens(s: str) -> List[str]:
-    s = s.strip().rstrip(";")
-    out, pos = [], 0
-    while pos < len(s):
-        m = _TOK.match(s, pos)
-        if not m:
-            raise ValueError(f"cannot tokenize at: {s[pos:]!r}")
-        out.append(m.group(1))
-        pos = m.end()
-    return out
-
-
-class _P:
-    def __init__(self, toks, table: abi.Table, names: List[str], bigint_count: bool):
-        self.t, self.i = toks, 0
-        self.b = abi.UnitBuilder(table)
-        self.names = [n.lower() for n in names]
-        self.bigint_count = bigint_count
-
-    def peek(self):
-        return self.t[self.i] if self.i < len(self.t) else None
-
-    def eat(self, expect=None):
-        tok = self.peek()
-        if tok is None or (expect is not None and tok.upper() != expect):
-            raise ValueError(f"expected {expect}, got {tok}")
-        self.i += 1
-        return tok
-
-    def colid(self, name):
-        return self.names.index(name.lower())
-
-    # cond := term {OR term}; term := factor {AND factor}; factor := '(' cond ')' | col OP literal
-    def cond(self):
-        e = self.term()
-        while self.peek() and self.peek().upper() == "OR":
-            self.eat()
-            e = self.b.binop(abi.kOR, e, self.term())
-        return e
-
-    def term(self):
-        e = self.factor()
-        while self.peek() and self.peek().upper() == "AND":
-            self.eat()
-            e = self.b.binop(abi.kAND, e, self.factor())
-        return e
-
-    def factor(self):
-        if self.peek() == "(":
-            self.eat()
-            e = self.cond()
-            self.eat(")")
-            return e
-        col = self.colid(self.eat())
-        op = _OPS[self.eat()]
-        lit = self.eat()
-        if re.fullmatch(r"-?\d+", lit):
-            return self.b.cmp(col, op, int(lit), abi.kBIGINT)
-        return self.b.cmp(col, op, float(lit), abi.kDOUBLE)
-
-    def target(self):
-        tok = self.eat()
-        if tok.upper() in _AGGS and self.peek() == "(":
-            self.eat("(")
-            if self.peek() == "*":
-                self.eat()
-                self.eat(")")
-                return self.b.agg(abi.kCOUNT, None, self.bigint_count)
-            col = self.colid(self.eat())
-            self.eat(")")
-            return self.b.agg(_AGGS[tok.upper()], col, self.bigint_count)
-        return self.b.col(self.colid(tok))
-
-
-def _conjuncts(b: abi.UnitBuilder, e: int) -> List[int]:
-    n = b.nodes[e]
-    if n.kind == abi.EXPR_BIN_OPER and n.op == abi.kAND:
-        return _conjuncts(b, n.left) + _conjuncts(b, n.right)
-    return [e]
-
-
-def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = False) -> abi.BuiltUnit:
-    p = _P(_tokens(sql), table, names, bigint_count)
-    p.eat("SELECT")
-    targets = [p.target()]
-    while p.peek() == ",":
-        p.eat()
-        targets.append(p.target())
-    p.eat("FROM")
-    p.eat()  # table name
-    if p.peek() and p.peek().upper() == "WHERE":
-        p.eat()
-        e = p.cond()
-        for c in _conjuncts(p.b, e):
-            n = p.b.nodes[c]
-            simple = n.op not in (abi.kAND, abi.kOR)
-            p.b.add_qual(c, simple=simple)
-    if p.peek() and p.peek().upper() == "GROUP":
-        p.eat()
-        p.eat("BY")
-        p.b.group_by(p.colid(p.eat()))
-    if p.peek() is not None:
-        raise ValueError(f"trailing tokens: {p.t[p.i:]}")
-    for t in targets:
-        p.b.target(t)
-    return p.b.build()
+"""Re-export of the mini SQL front-end (lives in the package so bench.py can use it too)."""
+from heavydb_b200.sqlmini import *  # noqa: F401,F403
+from heavydb_b200.sqlmini import parse  # noqa: F401

@@ -62,7 +62,7 @@ def test_get_group_value_matches_reference(ref, key_width, entry_count, nkeys):
         if key_width == 8:
             rows[:, 0] = empty
         else:
-            rows[:, 0].view(np.int32)[::2] = np.iinfo(np.int32).max
+            b.view(np.int32).reshape(entry_count, 2 * row_size_quad)[:, 0] = np.iinfo(np.int32).max
         return b
     ours, theirs = fresh(), fresh()
     keys = rng.integers(1, 50 if entry_count == 16 else 10**6, size=nkeys)

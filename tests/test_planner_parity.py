@@ -1,0 +1,92 @@
+"""Product planner (b2q_plan: restated GroupByAndAggregate / QueryMemoryDescriptor decisions, host-only) against
+the oracle's planner on the reference's golden table and on synthetic shapes of BASELINE.json's configs."""
+import numpy as np
+import pytest
+
+import oracle_lib
+import ref_tables as rt
+import sqlmini
+from heavydb_b200 import abi, executor
+from test_oracle_golden import PATH_QUERIES, REFERENCE_QUERIES
+
+EXTRA = [
+    "SELECT t, SUM(dn), AVG(dn), MIN(dn), MAX(dn), COUNT(dn) FROM test GROUP BY t;",
+    "SELECT x, MIN(ufd), MAX(ufd), SUM(ufd) FROM test GROUP BY x;",
+    "SELECT ofq, COUNT(*) FROM test GROUP BY ofq;",       # range too big for perfect hash -> baseline
+    "SELECT ufq, COUNT(*), SUM(x) FROM test GROUP BY ufq;",
+]
+
+
+@pytest.fixture(scope="module")
+def table():
+    return rt.make_table(rt.test_rows())
+
+
+@pytest.mark.parametrize("bigint_count", [False, True])
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA)
+def test_plan_matches_oracle(table, sql, bigint_count):
+    unit = sqlmini.parse(sql, table, rt.TEST_NAMES, bigint_count=bigint_count)
+    ex = executor.Executor()
+    eo = executor.execution_options(bigint_count=bigint_count)
+    want = oracle_lib.plan(unit, table, entry_guess=48, has_card=True, bigint_count=bigint_count).as_dict()
+    got = ex.plan(unit, table, eo=eo, max_groups_buffer_entry_guess=48, has_cardinality_estimation=True).as_dict()
+    assert got == want
+
+
+def test_cardinality_estimation_required(table):
+    unit = sqlmini.parse("SELECT ofq, COUNT(*) FROM test GROUP BY ofq;", table, rt.TEST_NAMES)
+    with pytest.raises(executor.CardinalityEstimationRequired):
+        executor.Executor().plan(unit, table)
+    with pytest.raises(oracle_lib.OracleError) as ei:
+        oracle_lib.plan(unit, table)
+    assert ei.value.code == abi.ERR_CARDINALITY_ESTIMATION_REQUIRED
+
+
+def test_unsupported_is_rejected_not_ignored(table):
+    for field in ("num_join_quals", "has_estimator", "num_order_entries", "has_union_all", "has_window_function"):
+        b = abi.UnitBuilder(table)
+        b.target(b.agg(abi.kCOUNT))
+        b.unsupported[field] = 1
+        with pytest.raises(executor.UnsupportedOnThisPath):
+            executor.Executor().plan(b.build(), table)
+    co = executor.compilation_options(device_type=abi.DEVICE_CPU)   # no CPU execution on this path
+    b = abi.UnitBuilder(table)
+    b.target(b.agg(abi.kCOUNT))
+    with pytest.raises(executor.UnsupportedOnThisPath):
+        executor.Executor().plan(b.build(), table, co=co)
+
+
+def _config_table(kind):
+    """Tiny stand-ins with the chunk statistics of BASELINE.json's configs (stats are what the planner reads)."""
+    if kind == "C2":   # c0..c3 int64 in [0,1e6), g int32 in [0,1e4)
+        t = abi.Table([(abi.kBIGINT, True)] * 4 + [(abi.kINT, True)])
+        cols = [np.array([0, 999999], dtype=np.int64)] * 4 + [np.array([0, 9999], dtype=np.int32)]
+        return t.add_host_fragment(cols), ["c0", "c1", "c2", "c3", "g"]
+    if kind == "C3":   # f int64, g int32 in [0,256), v double not null
+        t = abi.Table([(abi.kBIGINT, True), (abi.kINT, True), (abi.kDOUBLE, True)])
+        return t.add_host_fragment([np.array([0, 999999]), np.array([0, 255]), np.array([0.0, 0.999])]), ["f", "g", "v"]
+    if kind == "C4":   # key int64 in [0,1e7), v int64 in [0,1e6)
+        t = abi.Table([(abi.kBIGINT, True), (abi.kBIGINT, True)])
+        return t.add_host_fragment([np.array([0, 9999999]), np.array([0, 999999])]), ["key", "v"]
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,sql,expect", [
+    ("C2", "SELECT g, SUM(c1), COUNT(*) FROM t WHERE c0 < 500000 GROUP BY g;",
+     dict(query_desc_type=abi.GroupByPerfectHash, entry_count=10000, keyless_hash=1, idx_target_as_key=2, row_size=24)),
+    ("C2", "SELECT g, SUM(c1), SUM(c2), SUM(c3), COUNT(*) FROM t WHERE c0 < 500000 GROUP BY g;",
+     dict(query_desc_type=abi.GroupByPerfectHash, entry_count=10000, keyless_hash=1, idx_target_as_key=4, row_size=40)),
+    ("C3", "SELECT g, AVG(v) FROM t WHERE f < 500000 GROUP BY g;",
+     dict(query_desc_type=abi.GroupByPerfectHash, entry_count=256, keyless_hash=1, idx_target_as_key=2, row_size=24)),
+    ("C4", "SELECT key, SUM(v) FROM t GROUP BY key;",
+     dict(query_desc_type=abi.GroupByPerfectHash, entry_count=10000000, keyless_hash=0, row_size=24)),
+])
+def test_baseline_config_plans(kind, sql, expect):
+    """the layouts the reference picks for BASELINE.json's configs."""
+    table, names = _config_table(kind)
+    unit = sqlmini.parse(sql, table, names)
+    want = oracle_lib.plan(unit, table).as_dict()
+    got = executor.Executor().plan(unit, table).as_dict()
+    assert got == want
+    for k, v in expect.items():
+        assert got[k] == v, (k, got[k], v)
