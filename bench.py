@@ -297,7 +297,7 @@ def main():
             step_ms.append(float(t.item()))
             scan_ms.append(part.kernel_ms())
         result_rows = rs.rowCount()
-        plan = rs.getQueryMemDesc()
+        plan_kernel, plan_entries = int(rs.getQueryMemDesc().kernel), int(rs.getQueryMemDesc().entry_count)
         del rs, part
     clocks = sampler.stop()
     ms = float(np.mean(step_ms))
@@ -312,7 +312,7 @@ def main():
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic (counter-based splitmix64 columns generated in HBM; inputs 20 GB/GPU >> 126 MB L2, no flush needed)",
         "config": {"workload": workload, "query": sql, "rows_per_gpu": rows, "fragments_per_gpu": len(table.fragments),
-                   "fragment_rows": FRAG_ROWS, "kernel": int(plan.kernel), "entry_count": int(plan.entry_count),
+                   "fragment_rows": FRAG_ROWS, "kernel": plan_kernel, "entry_count": plan_entries,
                    "groups_out": int(result_rows), "l2": "inputs larger than L2"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": "b2q_k_scan", "kernel_ms": k_ms,

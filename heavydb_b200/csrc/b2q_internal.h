@@ -15,7 +15,7 @@
 #define B2Q_MAX_COLS 16   /* distinct columns a query may reference */
 #define B2Q_MAX_TERMS B2Q_MAX_FILTER_TERMS
 #define B2Q_MAX_FILTER_OPS 24
-#define B2Q_MAX_ACCS 12   /* internal accumulators */
+#define B2Q_MAX_ACCS 24   /* internal accumulators */
 #define B2Q_MAX_FRAGS_INLINE 0
 
 /* ---- filter ---------------------------------------------------------------------------------------------
@@ -25,15 +25,16 @@
  * (LogicalIR.cpp:344-352) turns into "row fails").  AND/OR trees are evaluated in postfix order on "is TRUE"
  * bits, which is exact for Kleene logic without NOT (logical_and/logical_or, RuntimeFunctions.cpp:320-357). */
 struct DevTerm {
-  int64_t lo, hi;       /* integer domain, inclusive */
+  int64_t lo;           /* integer domain: in_range = (unsigned)(v - lo) <= span  (32-bit columns: low words used) */
+  uint64_t span;
   double flo, fhi;      /* fp domain, inclusive */
   int64_t null_bits;    /* column NULL sentinel: int value (sign-extended) or double bits */
   int32_t col;          /* index into the launch's column table */
   int8_t width;         /* 1,2,4,8 */
   int8_t col_is_fp;     /* column holds doubles */
   int8_t cmp_fp;        /* compare in the double domain (column or literal is fp) */
-  int8_t negate;        /* kNE */
-  int8_t nullable;
+  int8_t negate;        /* result = in_range XOR negate */
+  int8_t null_check;    /* explicit `v != NULL` needed (the host folds it into the range whenever it can) */
   int8_t pad_[3];
 };
 
@@ -91,6 +92,10 @@ struct DevProgram {
   DevKey key;
   int32_t n_accs;
   int32_t n_cols;
+  float est_selectivity; /* planner's estimate from chunk stats (uniformity assumption) */
+  int8_t eager_key;      /* load the key column for every row, overlapped with the filter columns */
+  int8_t eager_args;     /* load aggregate arguments for every row instead of only the passing ones */
+  int8_t pad_[2];
   DevAcc accs[B2Q_MAX_ACCS];
 };
 

@@ -34,94 +34,155 @@
 
 namespace b2q {
 
-constexpr int R = 4;                 /* rows per thread per chunk */
+constexpr int R = 8;                 /* rows per thread per chunk */
 constexpr int kMaxBlock = 1024;
 
 enum { MODE_SMEM = 0, MODE_GLOBAL = 1, MODE_BASELINE = 2 };
 
 /* ---------------------------------------------------------------------------------------------------------
- * loads: streaming, read-only, no L1 allocation
+ * loads: streaming (read-only path, no L1 allocation), branch-free predication.
+ * The asm is deliberately NOT volatile: the data is immutable for the kernel, so the compiler may hoist and batch
+ * the loads of a vector, which is what puts R independent requests per column in flight.
  * ------------------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ int64_t ld_s8(const int8_t* p) { int32_t v; asm volatile("ld.global.nc.L1::no_allocate.s8 %0, [%1];" : "=r"(v) : "l"(p)); return (int64_t)(int8_t)v; }
-__device__ __forceinline__ int64_t ld_s16(const int8_t* p) { int32_t v; asm volatile("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=r"(v) : "l"(p)); return (int64_t)(int16_t)v; }
-__device__ __forceinline__ int64_t ld_s32(const int8_t* p) { int32_t v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return (int64_t)v; }
-__device__ __forceinline__ int64_t ld_s64(const int8_t* p) { int64_t v; asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p)); return v; }
+template <bool PRED>
+__device__ __forceinline__ int64_t ldg_b64(const int8_t* p, uint32_t pred) {
+  int64_t v;
+  if (PRED)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b64 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.b64 %0, [%1];\n\t}" : "=l"(v) : "l"(p), "r"(pred));
+  else
+    asm("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+template <bool PRED>
+__device__ __forceinline__ int32_t ldg_s32(const int8_t* p, uint32_t pred) {
+  int32_t v;
+  if (PRED)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.s32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(pred));
+  else
+    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+template <bool PRED>
+__device__ __forceinline__ int32_t ldg_s16(const int8_t* p, uint32_t pred) {
+  int32_t v;
+  if (PRED)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.s16 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(pred));
+  else
+    asm("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=r"(v) : "l"(p));
+  return (int32_t)(int16_t)v;
+}
+template <bool PRED>
+__device__ __forceinline__ int32_t ldg_s8(const int8_t* p, uint32_t pred) {
+  int32_t v;
+  if (PRED)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.s8 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(pred));
+  else
+    asm("ld.global.nc.L1::no_allocate.s8 %0, [%1];" : "=r"(v) : "l"(p));
+  return (int32_t)(int8_t)v;
+}
 
-/* load R sign-extended integers (or raw 8-byte words) of `width` bytes for rows row0 + j*stride, masked */
-__device__ __forceinline__ void load_rows(int64_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0,
-                                          int stride, uint32_t mask) {
-  switch (width) {
-    case 8:
+/* R rows of an 8-byte column: rows row0 + j*stride */
+template <bool PRED>
+__device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict__ base, int64_t row0, int stride, uint32_t mask) {
+  const int8_t* p = base + row0 * 8;
+  const int64_t step = (int64_t)stride * 8;
 #pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? ld_s64(base + (row0 + (int64_t)j * stride) * 8) : 0;
-      break;
-    case 4:
+  for (int j = 0; j < R; ++j) v[j] = ldg_b64<PRED>(p + j * step, mask >> j & 1);
+}
+/* R rows of a 1/2/4-byte integer column, sign-extended to 32 bits */
+template <bool PRED>
+__device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0, int stride, uint32_t mask) {
+  if (width == 4) {
+    const int8_t* p = base + row0 * 4;
+    const int64_t step = (int64_t)stride * 4;
 #pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? ld_s32(base + (row0 + (int64_t)j * stride) * 4) : 0;
-      break;
-    case 2:
+    for (int j = 0; j < R; ++j) v[j] = ldg_s32<PRED>(p + j * step, mask >> j & 1);
+  } else if (width == 2) {
+    const int8_t* p = base + row0 * 2;
+    const int64_t step = (int64_t)stride * 2;
 #pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? ld_s16(base + (row0 + (int64_t)j * stride) * 2) : 0;
-      break;
-    default:
+    for (int j = 0; j < R; ++j) v[j] = ldg_s16<PRED>(p + j * step, mask >> j & 1);
+  } else {
+    const int8_t* p = base + row0;
+    const int64_t step = (int64_t)stride;
 #pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? ld_s8(base + (row0 + (int64_t)j * stride)) : 0;
-      break;
+    for (int j = 0; j < R; ++j) v[j] = ldg_s8<PRED>(p + j * step, mask >> j & 1);
   }
 }
 
 /* ---------------------------------------------------------------------------------------------------------
- * filter
+ * filter: one comparison = one unsigned range test, (v - lo) <= span, in the column's register class
  * ------------------------------------------------------------------------------------------------------- */
+template <bool FULL>
 __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* const* __restrict__ cols, int64_t row0,
                                               int stride, uint32_t valid) {
-  int64_t v[R];
-  load_rows(v, cols[t.col], t.width, row0, stride, valid);
   uint32_t m = 0;
+  const bool neg = t.negate;
   if (!t.cmp_fp) {
-    const int64_t lo = t.lo, hi = t.hi, nullv = t.null_bits;
-    const bool neg = t.negate, nullable = t.nullable;
+    if (t.width == 8) {
+      int64_t v[R];
+      load64<!FULL>(v, cols[t.col], row0, stride, valid);
+      const uint64_t lo = (uint64_t)t.lo, span = t.span;
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      bool in = (v[j] >= lo) & (v[j] <= hi);
-      bool ok = (in != neg) & !(nullable & (v[j] == nullv));
-      m |= (uint32_t)ok << j;
+      for (int j = 0; j < R; ++j) m |= (uint32_t)(((uint64_t)v[j] - lo <= span) != neg) << j;
+      if (t.null_check) {
+        const int64_t nullv = t.null_bits;
+#pragma unroll
+        for (int j = 0; j < R; ++j) m &= ~((uint32_t)(v[j] == nullv) << j);
+      }
+    } else {
+      int32_t v[R];
+      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid);
+      const uint32_t lo = (uint32_t)t.lo, span = (uint32_t)t.span;
+#pragma unroll
+      for (int j = 0; j < R; ++j) m |= (uint32_t)(((uint32_t)v[j] - lo <= span) != neg) << j;
+      if (t.null_check) {
+        const int32_t nullv = (int32_t)t.null_bits;
+#pragma unroll
+        for (int j = 0; j < R; ++j) m &= ~((uint32_t)(v[j] == nullv) << j);
+      }
     }
   } else {
     const double lo = t.flo, hi = t.fhi;
-    const bool neg = t.negate, nullable = t.nullable;
+    double d[R];
+    uint32_t isnull = 0;
     if (t.col_is_fp) {
+      int64_t v[R];
+      load64<!FULL>(v, cols[t.col], row0, stride, valid);
       const double nullv = __longlong_as_double(t.null_bits);
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const double d = __longlong_as_double(v[j]);
-        bool in = (d >= lo) & (d <= hi);
-        bool ok = (in != neg) & !(nullable & (d == nullv));
-        m |= (uint32_t)ok << j;
-      }
-    } else {
+      for (int j = 0; j < R; ++j) { d[j] = __longlong_as_double(v[j]); isnull |= (uint32_t)(d[j] == nullv) << j; }
+    } else if (t.width == 8) {
+      int64_t v[R];
+      load64<!FULL>(v, cols[t.col], row0, stride, valid);
       const int64_t nullv = t.null_bits;
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const double d = (double)v[j];
-        bool in = (d >= lo) & (d <= hi);
-        bool ok = (in != neg) & !(nullable & (v[j] == nullv));
-        m |= (uint32_t)ok << j;
-      }
+      for (int j = 0; j < R; ++j) { d[j] = (double)v[j]; isnull |= (uint32_t)(v[j] == nullv) << j; }
+    } else {
+      int32_t v[R];
+      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid);
+      const int32_t nullv = (int32_t)t.null_bits;
+#pragma unroll
+      for (int j = 0; j < R; ++j) { d[j] = (double)v[j]; isnull |= (uint32_t)(v[j] == nullv) << j; }
     }
+#pragma unroll
+    for (int j = 0; j < R; ++j) m |= (uint32_t)(((d[j] >= lo) & (d[j] <= hi)) != neg) << j;
+    if (t.null_check) m &= ~isnull;
   }
   return m & valid;
 }
 
+template <bool FULL>
 __device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t* const* __restrict__ cols,
                                                 int64_t row0, int stride, uint32_t valid) {
   if (f.n_ops == 0) return valid;
+  if (f.n_ops == 1) return eval_term<FULL>(f.terms[0], cols, row0, stride, valid);
   uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
   for (int i = 0; i < f.n_ops; ++i) {
     const uint32_t op = f.ops[i];
     const uint32_t kind = op >> 4;
     if (kind == FOP_TERM) {
-      const uint32_t m = eval_term(f.terms[op & 15], cols, row0, stride, valid);
+      const uint32_t m = eval_term<FULL>(f.terms[op & 15], cols, row0, stride, valid);
       s3 = s2; s2 = s1; s1 = s0; s0 = m;
     } else {
       s0 = (kind == FOP_AND) ? (s1 & s0) : (s1 | s0);
@@ -134,7 +195,7 @@ __device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t
 /* ---------------------------------------------------------------------------------------------------------
  * skip test (NULL handling of aggregate arguments), see DevAcc
  * ------------------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ uint32_t not_skipped(const DevAcc& a, const int64_t (&v)[R], uint32_t pass) {
+__device__ __forceinline__ uint32_t not_skipped64(const DevAcc& a, const int64_t (&v)[R], uint32_t pass) {
   if (!a.skip1_en && !a.skip2_en) return pass;
   uint32_t m = 0;
   if (a.is_fp) {
@@ -147,9 +208,23 @@ __device__ __forceinline__ uint32_t not_skipped(const DevAcc& a, const int64_t (
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int64_t w = tr ? (int64_t)(int32_t)v[j] : v[j];
-      bool skip = (e1 & (v[j] == s1)) | (e2 & (w == s2));
+      const bool skip = (e1 & (v[j] == s1)) | (e2 & (w == s2));
       m |= (uint32_t)(!skip) << j;
     }
+  }
+  return m & pass;
+}
+__device__ __forceinline__ uint32_t not_skipped32(const DevAcc& a, const int32_t (&v)[R], uint32_t pass) {
+  if (!a.skip1_en && !a.skip2_en) return pass;
+  /* a sign-extended 32-bit value can only equal a skip value that itself fits in 32 bits */
+  const bool e1 = a.skip1_en && a.skip1_val == (int64_t)(int32_t)a.skip1_val;
+  const bool e2 = a.skip2_en && a.skip2_val == (int64_t)(int32_t)a.skip2_val;
+  const int32_t s1 = (int32_t)a.skip1_val, s2 = (int32_t)a.skip2_val;
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const bool skip = (e1 & (v[j] == s1)) | (e2 & (v[j] == s2));
+    m |= (uint32_t)(!skip) << j;
   }
   return m & pass;
 }
@@ -193,54 +268,27 @@ __device__ __forceinline__ void global_update(int op, int64_t* arr, uint32_t e, 
 }
 
 /* ---------------------------------------------------------------------------------------------------------
- * shared-memory table update.  `tab` points at the accumulator's array inside this warp's replica.
+ * shared-memory table updates.  `tab` points at the accumulator's array inside this warp's replica.
+ * 64-bit integer SUM: (hi:lo) += v with lo in shared memory (native 32-bit ATOMS.ADD) and the rare hi deltas
+ * (carry out of lo, or a value that does not fit 32 bits) sent to the HBM table with RED.ADD.64.
  * ------------------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ void smem_update(int op, int8_t* tab, int64_t* garr, uint32_t e, int64_t v) {
-  switch (op) {
-    case ACC_COUNT:
-      atomicAdd(reinterpret_cast<uint32_t*>(tab) + e, 1u);
-      break;
-    case ACC_SUM_I64: {
-      /* (hi:lo) += v with lo in shared memory (native 32-bit ATOMS.ADD) and hi deltas sent to the HBM table */
-      const uint32_t vl = (uint32_t)v;
-      const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(tab) + e, vl);
-      const int32_t carry = (uint32_t)(old + vl) < old;
-      const int32_t hi = (int32_t)(v >> 32) + carry;
-      if (hi != 0) red_add_u64(garr + e, (uint64_t)(int64_t)hi << 32);
-      break;
-    }
-    case ACC_SUM_F64:
-      atomicAdd(reinterpret_cast<double*>(tab) + e, __longlong_as_double(v));
-      break;
-    case ACC_MIN_I64: {
-      long long* p = reinterpret_cast<long long*>(tab) + e;
-      if (v < *reinterpret_cast<volatile long long*>(p)) atomicMin(p, (long long)v);
-      break;
-    }
-    case ACC_MAX_I64: {
-      long long* p = reinterpret_cast<long long*>(tab) + e;
-      if (v > *reinterpret_cast<volatile long long*>(p)) atomicMax(p, (long long)v);
-      break;
-    }
-    case ACC_MIN_F64: {
-      const double d = __longlong_as_double(v);
-      if (d == d) {
-        const long long o = b2q_f64_to_ord(v);
-        long long* p = reinterpret_cast<long long*>(tab) + e;
-        if (o < *reinterpret_cast<volatile long long*>(p)) atomicMin(p, o);
-      }
-      break;
-    }
-    default: {
-      const double d = __longlong_as_double(v);
-      if (d == d) {
-        const long long o = b2q_f64_to_ord(v);
-        long long* p = reinterpret_cast<long long*>(tab) + e;
-        if (o > *reinterpret_cast<volatile long long*>(p)) atomicMax(p, o);
-      }
-      break;
-    }
+__device__ __forceinline__ void smem_sum_i64(int8_t* tab, int64_t* garr, uint32_t e, uint32_t vl, int32_t vh) {
+  const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(tab) + e, vl);
+  const int32_t hi = vh + (int32_t)((uint32_t)(old + vl) < old);
+  if (hi != 0) red_add_u64(garr + e, (uint64_t)(int64_t)hi << 32);
+}
+
+__device__ __forceinline__ void smem_minmax(int op, int8_t* tab, uint32_t e, int64_t v) {
+  const bool fp = (op == ACC_MIN_F64) | (op == ACC_MAX_F64);
+  if (fp) {
+    const double d = __longlong_as_double(v);
+    if (d != d) return; /* std::min/std::max never pick up a NaN argument (RuntimeFunctions.cpp:1456-1466) */
+    v = b2q_f64_to_ord(v);
   }
+  long long* p = reinterpret_cast<long long*>(tab) + e;
+  const long long cur = *reinterpret_cast<volatile long long*>(p);
+  if ((op == ACC_MIN_I64) | (op == ACC_MIN_F64)) { if (v < cur) atomicMin(p, (long long)v); }
+  else { if (v > cur) atomicMax(p, (long long)v); }
 }
 
 /* warp-level reductions for the single-group (non-grouped) case */
@@ -305,7 +353,234 @@ struct ScanArgs {
 
 extern __shared__ __align__(128) int8_t b2q_smem[];
 
-template <int MODE, bool WAGG>
+/* one chunk: R rows per thread.  FULL = every row of the chunk exists (no tail masking). */
+template <int MODE, bool WAGG, bool KEY32, bool FULL>
+__device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* const* __restrict__ cols, int64_t row0,
+                                              int64_t frag_rows, int nthr, int lane, int8_t* my_tab) {
+  const DevProgram& P = A.prog;
+  const DevLaunch& Lh = A.launch;
+  uint32_t valid = (1u << R) - 1u;
+  if (!FULL) {
+    valid = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) valid |= (uint32_t)(row0 + (int64_t)j * nthr < frag_rows) << j;
+  }
+
+  /* ---- key column: issued before the filter when the planner expects most sectors to be needed anyway ---- */
+  int32_t k32[KEY32 ? R : 1];
+  int64_t k64[KEY32 ? 1 : R];
+  const bool has_key = !WAGG && P.key.col >= 0;
+  const bool eager_key = P.eager_key;
+  if (has_key && eager_key) {
+    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, valid);
+    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, valid);
+  }
+
+  uint32_t pass = eval_filter<FULL>(P.filter, cols, row0, nthr, valid);
+
+  if (has_key && !eager_key) {
+    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, pass);
+    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, pass);
+  }
+
+  /* ---- group index ---- */
+  uint32_t e[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) e[j] = 0;
+  if (has_key) {
+    if (MODE != MODE_BASELINE) {
+      uint32_t bad = 0;
+      const bool tr = P.key.translate_null;
+      if (KEY32) {
+        const uint32_t mn = (uint32_t)P.key.min_val, n = (uint32_t)P.key.entry_count, nidx = (uint32_t)P.key.null_idx;
+        const int32_t nullv = (int32_t)P.key.null_val;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          uint32_t idx = (uint32_t)k32[KEY32 ? j : 0] - mn;
+          if (tr) idx = (k32[KEY32 ? j : 0] == nullv) ? nidx : idx;
+          bad |= (uint32_t)(idx >= n) << j;
+          e[j] = idx;
+        }
+      } else {
+        const int64_t mn = P.key.min_val, nullv = P.key.null_val, nidx = P.key.null_idx;
+        const uint64_t n = (uint64_t)P.key.entry_count;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          int64_t idx = k64[KEY32 ? 0 : j] - mn;
+          if (tr) idx = (k64[KEY32 ? 0 : j] == nullv) ? nidx : idx;
+          bad |= (uint32_t)((uint64_t)idx >= n) << j;
+          e[j] = (uint32_t)idx;
+        }
+      }
+      bad &= pass;
+      if (bad) { atomicCAS(Lh.error, 0, B2Q_ERR_KEY_OUT_OF_RANGE); pass &= ~bad; }
+    } else {
+      const uint32_t n = (uint32_t)P.key.entry_count;
+      const int hw = P.key.hash_key_width;
+      unsigned long long* keys = reinterpret_cast<unsigned long long*>(Lh.keys);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (!(pass >> j & 1)) continue;
+        const int64_t key = KEY32 ? (int64_t)k32[KEY32 ? j : 0] : k64[KEY32 ? 0 : j];
+        const uint32_t h = murmur3_key(key, hw) % n;
+        uint32_t p = h;
+        bool found = false;
+        do { /* get_group_value's linear probe; claim an EMPTY_KEY_64 slot with a 64-bit CAS */
+          unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(keys + p);
+          if (cur == (unsigned long long)B2Q_I64_MAX) cur = atomicCAS(keys + p, (unsigned long long)B2Q_I64_MAX, (unsigned long long)key);
+          if (cur == (unsigned long long)B2Q_I64_MAX || cur == (unsigned long long)key) { found = true; break; }
+          p = p + 1 == n ? 0 : p + 1;
+        } while (p != h);
+        if (!found) { atomicCAS(Lh.error, 0, B2Q_ERR_OUT_OF_SLOTS); pass &= ~(1u << j); }
+        e[j] = p;
+      }
+    }
+  }
+
+  /* ---- aggregate updates: one warp-uniform dispatch per accumulator per R rows ---- */
+  const uint32_t arg_mask = P.eager_args ? valid : pass;
+  for (int a = 0; a < P.n_accs; ++a) {
+    const DevAcc& acc = P.accs[a];
+    const int op = acc.op;
+    int64_t* garr = Lh.accs[a];
+    int8_t* tab = (MODE == MODE_SMEM) ? my_tab + A.smem.acc_off[a] : nullptr;
+
+    if (op == ACC_COUNT && acc.col < 0) { /* COUNT(*) */
+      if (WAGG) {
+        const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(pass));
+        if (lane == 0 && c) atomicAdd(reinterpret_cast<uint32_t*>(tab), c);
+      } else if (MODE == MODE_SMEM) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (pass >> j & 1) atomicAdd(reinterpret_cast<uint32_t*>(tab) + e[j], 1u);
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (pass >> j & 1) red_add_u64(garr + e[j], 1ull);
+      }
+      continue;
+    }
+
+    const bool narrow = acc.width <= 4 && (op == ACC_COUNT || op == ACC_SUM_I64 || op == ACC_MIN_I64 || op == ACC_MAX_I64);
+    if (narrow) {
+      /* 1/2/4-byte integer argument: 32-bit registers */
+      int32_t v[R];
+      load32<true>(v, cols[acc.col], acc.width, row0, nthr, arg_mask);
+      const uint32_t m = not_skipped32(acc, v, pass);
+      if (WAGG) {
+        if (op == ACC_COUNT) {
+          const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m));
+          if (lane == 0 && c) atomicAdd(reinterpret_cast<uint32_t*>(tab), c);
+        } else if (op == ACC_SUM_I64) {
+          int64_t s = 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += (m >> j & 1) ? (int64_t)v[j] : 0;
+          s = warp_sum_i64(s);
+          if (lane == 0 && s) smem_sum_i64(tab, garr, 0, (uint32_t)s, (int32_t)(s >> 32));
+        } else {
+          const bool is_min = op == ACC_MIN_I64;
+          int64_t r = is_min ? B2Q_I64_MAX : B2Q_I64_MIN;
+#pragma unroll
+          for (int j = 0; j < R; ++j) if (m >> j & 1) r = is_min ? min(r, (int64_t)v[j]) : max(r, (int64_t)v[j]);
+          r = is_min ? warp_min_i64(r) : warp_max_i64(r);
+          if (lane == 0 && r != (is_min ? B2Q_I64_MAX : B2Q_I64_MIN)) smem_minmax(op, tab, 0, r);
+        }
+      } else if (MODE == MODE_SMEM) {
+        if (op == ACC_COUNT) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) if (m >> j & 1) atomicAdd(reinterpret_cast<uint32_t*>(tab) + e[j], 1u);
+        } else if (op == ACC_SUM_I64) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) if (m >> j & 1) smem_sum_i64(tab, garr, e[j], (uint32_t)v[j], v[j] >> 31);
+        } else {
+#pragma unroll
+          for (int j = 0; j < R; ++j) if (m >> j & 1) smem_minmax(op, tab, e[j], (int64_t)v[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, e[j], (int64_t)v[j]);
+      }
+      continue;
+    }
+
+    /* 8-byte argument (BIGINT or DOUBLE), or a narrow column feeding a double aggregate (not produced by the planner) */
+    int64_t v[R];
+    if (acc.width == 8) load64<true>(v, cols[acc.col], row0, nthr, arg_mask);
+    else {
+      int32_t t32[R];
+      load32<true>(t32, cols[acc.col], acc.width, row0, nthr, arg_mask);
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = t32[j];
+    }
+    const uint32_t m = not_skipped64(acc, v, pass);
+    if (WAGG) {
+      switch (op) {
+        case ACC_COUNT: {
+          const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m));
+          if (lane == 0 && c) atomicAdd(reinterpret_cast<uint32_t*>(tab), c);
+          break;
+        }
+        case ACC_SUM_I64: {
+          int64_t s = 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += (m >> j & 1) ? v[j] : 0;
+          s = warp_sum_i64(s);
+          if (lane == 0 && s) smem_sum_i64(tab, garr, 0, (uint32_t)s, (int32_t)(s >> 32));
+          break;
+        }
+        case ACC_SUM_F64: {
+          double s = 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j) s += (m >> j & 1) ? __longlong_as_double(v[j]) : 0.0;
+          const uint32_t any = __ballot_sync(0xffffffffu, m != 0);
+          s = warp_sum_f64(s);
+          if (lane == 0 && any) atomicAdd(reinterpret_cast<double*>(tab), s);
+          break;
+        }
+        default: {
+          const bool is_min = (op == ACC_MIN_I64) | (op == ACC_MIN_F64);
+          const bool fp = (op == ACC_MIN_F64) | (op == ACC_MAX_F64);
+          int64_t r = is_min ? B2Q_I64_MAX : B2Q_I64_MIN;
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            if (!(m >> j & 1)) continue;
+            int64_t x = v[j];
+            if (fp) { const double d = __longlong_as_double(x); if (d != d) continue; x = b2q_f64_to_ord(x); }
+            r = is_min ? min(r, x) : max(r, x);
+          }
+          r = is_min ? warp_min_i64(r) : warp_max_i64(r);
+          if (lane == 0 && r != (is_min ? B2Q_I64_MAX : B2Q_I64_MIN)) {
+            long long* p = reinterpret_cast<long long*>(tab);
+            if (is_min) atomicMin(p, (long long)r); else atomicMax(p, (long long)r);
+          }
+          break;
+        }
+      }
+    } else if (MODE == MODE_SMEM) {
+      switch (op) { /* dispatch hoisted out of the row loop */
+        case ACC_COUNT:
+#pragma unroll
+          for (int j = 0; j < R; ++j) if (m >> j & 1) atomicAdd(reinterpret_cast<uint32_t*>(tab) + e[j], 1u);
+          break;
+        case ACC_SUM_I64:
+#pragma unroll
+          for (int j = 0; j < R; ++j) if (m >> j & 1) smem_sum_i64(tab, garr, e[j], (uint32_t)v[j], (int32_t)(v[j] >> 32));
+          break;
+        case ACC_SUM_F64:
+#pragma unroll
+          for (int j = 0; j < R; ++j) if (m >> j & 1) atomicAdd(reinterpret_cast<double*>(tab) + e[j], __longlong_as_double(v[j]));
+          break;
+        default:
+#pragma unroll
+          for (int j = 0; j < R; ++j) if (m >> j & 1) smem_minmax(op, tab, e[j], v[j]);
+          break;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, e[j], v[j]);
+    }
+  }
+}
+
+template <int MODE, bool WAGG, bool KEY32>
 __global__ void __launch_bounds__(kMaxBlock, 1) b2q_k_scan(const __grid_constant__ ScanArgs A) {
   const DevProgram& P = A.prog;
   const DevLaunch& Lh = A.launch;
@@ -340,156 +615,23 @@ __global__ void __launch_bounds__(kMaxBlock, 1) b2q_k_scan(const __grid_constant
     my_tab = b2q_smem + (size_t)(warp & (A.smem.replicas - 1)) * rb;
   }
 
+  /* chunks are visited in increasing order, so the owning fragment is a moving cursor, not a search */
+  int frag = 0;
+  int64_t frag_first = 0;                                   /* first chunk of `frag` */
+  int64_t next_first = __ldg(Lh.frag_chunk_start + 1);      /* first chunk of frag + 1 */
   for (int64_t chunk = blockIdx.x; chunk < Lh.total_chunks; chunk += gridDim.x) {
-    /* chunk -> (fragment, first row): binary search in the per-fragment chunk prefix sums (warp-uniform) */
-    int lo = 0, hi = Lh.n_frags - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(Lh.frag_chunk_start + mid) <= chunk) lo = mid; else hi = mid - 1;
+    while (chunk >= next_first) {
+      ++frag;
+      frag_first = next_first;
+      next_first = __ldg(Lh.frag_chunk_start + frag + 1);
     }
-    const int frag = lo;
     const int64_t frag_rows = __ldg(Lh.frag_rows + frag);
-    const int64_t row0 = (chunk - __ldg(Lh.frag_chunk_start + frag)) * chunk_rows + tid;
+    const int64_t base_row = (chunk - frag_first) * chunk_rows;
     const int8_t* const* __restrict__ cols = Lh.col_ptrs + (size_t)frag * P.n_cols;
-
-    uint32_t valid = 0;
-#pragma unroll
-    for (int j = 0; j < R; ++j) valid |= (uint32_t)(row0 + (int64_t)j * nthr < frag_rows) << j;
-
-    uint32_t pass = eval_filter(P.filter, cols, row0, nthr, valid);
-
-    /* ---- group index ---- */
-    uint32_t e[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) e[j] = 0;
-    if (P.key.col >= 0) {
-      int64_t k[R];
-      load_rows(k, cols[P.key.col], P.key.width, row0, nthr, pass);
-      if (MODE != MODE_BASELINE) {
-        const int64_t mn = P.key.min_val, nullv = P.key.null_val, nidx = P.key.null_idx;
-        const uint64_t n = (uint64_t)P.key.entry_count;
-        const bool tr = P.key.translate_null;
-        uint32_t bad = 0;
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          int64_t idx = k[j] - mn;
-          if (tr & (k[j] == nullv)) idx = nidx;
-          const bool oob = (uint64_t)idx >= n;
-          bad |= (uint32_t)oob << j;
-          e[j] = (uint32_t)idx;
-        }
-        bad &= pass;
-        if (bad) { atomicCAS(Lh.error, 0, B2Q_ERR_KEY_OUT_OF_RANGE); pass &= ~bad; }
-      } else {
-        const uint32_t n = (uint32_t)P.key.entry_count;
-        const int hw = P.key.hash_key_width;
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          if (!(pass >> j & 1)) continue;
-          const int64_t key = k[j];
-          const uint32_t h = murmur3_key(key, hw) % n;
-          uint32_t p = h;
-          bool found = false;
-          unsigned long long* keys = reinterpret_cast<unsigned long long*>(Lh.keys);
-          do {
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(keys + p);
-            if (cur == (unsigned long long)B2Q_I64_MAX) cur = atomicCAS(keys + p, (unsigned long long)B2Q_I64_MAX, (unsigned long long)key);
-            if (cur == (unsigned long long)B2Q_I64_MAX || cur == (unsigned long long)key) { found = true; break; }
-            p = p + 1 == n ? 0 : p + 1;
-          } while (p != h);
-          if (!found) { atomicCAS(Lh.error, 0, B2Q_ERR_OUT_OF_SLOTS); pass &= ~(1u << j); }
-          e[j] = p;
-        }
-      }
-    }
-
-    /* ---- aggregate updates: one warp-uniform switch per accumulator per R rows ---- */
-    for (int a = 0; a < P.n_accs; ++a) {
-      const DevAcc& acc = P.accs[a];
-      int64_t v[R];
-      uint32_t m = pass;
-      if (acc.col >= 0) {
-        load_rows(v, cols[acc.col], acc.width, row0, nthr, pass);
-        m = not_skipped(acc, v, pass);
-      } else {
-#pragma unroll
-        for (int j = 0; j < R; ++j) v[j] = 0;
-      }
-      const int op = acc.op;
-      if (WAGG) {
-        /* single group: thread-local combine over R rows, shuffle reduction, one shared-memory atomic per warp */
-        int8_t* tab = my_tab + A.smem.acc_off[a];
-        switch (op) {
-          case ACC_COUNT: {
-            uint32_t c = __popc(m);
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (lane == 0 && c) atomicAdd(reinterpret_cast<uint32_t*>(tab), c);
-            break;
-          }
-          case ACC_SUM_I64: {
-            int64_t s = 0;
-#pragma unroll
-            for (int j = 0; j < R; ++j) s += (m >> j & 1) ? v[j] : 0;
-            s = warp_sum_i64(s);
-            if (lane == 0 && s) smem_update(ACC_SUM_I64, tab, Lh.accs[a], 0, s);
-            break;
-          }
-          case ACC_SUM_F64: {
-            double s = 0;
-#pragma unroll
-            for (int j = 0; j < R; ++j) s += (m >> j & 1) ? __longlong_as_double(v[j]) : 0.0;
-            const uint32_t any = __ballot_sync(0xffffffffu, m != 0);
-            s = warp_sum_f64(s);
-            if (lane == 0 && any) atomicAdd(reinterpret_cast<double*>(tab), s);
-            break;
-          }
-          default: {
-            const bool is_min = (op == ACC_MIN_I64) | (op == ACC_MIN_F64);
-            const bool fp = (op == ACC_MIN_F64) | (op == ACC_MAX_F64);
-            int64_t r = is_min ? B2Q_I64_MAX : B2Q_I64_MIN;
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-              if (!(m >> j & 1)) continue;
-              int64_t x = v[j];
-              if (fp) { const double d = __longlong_as_double(x); if (d != d) continue; x = b2q_f64_to_ord(x); }
-              r = is_min ? (x < r ? x : r) : (x > r ? x : r);
-            }
-            r = is_min ? warp_min_i64(r) : warp_max_i64(r);
-            if (lane == 0) {
-              long long* p = reinterpret_cast<long long*>(tab);
-              if (is_min) { if (r < *reinterpret_cast<volatile long long*>(p)) atomicMin(p, (long long)r); }
-              else { if (r > *reinterpret_cast<volatile long long*>(p)) atomicMax(p, (long long)r); }
-            }
-            break;
-          }
-        }
-      } else if (MODE == MODE_SMEM) {
-        int8_t* tab = my_tab + A.smem.acc_off[a];
-        int64_t* garr = Lh.accs[a];
-        switch (op) { /* switch hoisted out of the row loop */
-          case ACC_COUNT:
-#pragma unroll
-            for (int j = 0; j < R; ++j) if (m >> j & 1) atomicAdd(reinterpret_cast<uint32_t*>(tab) + e[j], 1u);
-            break;
-          case ACC_SUM_I64:
-#pragma unroll
-            for (int j = 0; j < R; ++j) if (m >> j & 1) smem_update(ACC_SUM_I64, tab, garr, e[j], v[j]);
-            break;
-          case ACC_SUM_F64:
-#pragma unroll
-            for (int j = 0; j < R; ++j) if (m >> j & 1) atomicAdd(reinterpret_cast<double*>(tab) + e[j], __longlong_as_double(v[j]));
-            break;
-          default:
-#pragma unroll
-            for (int j = 0; j < R; ++j) if (m >> j & 1) smem_update(op, tab, garr, e[j], v[j]);
-            break;
-        }
-      } else {
-        int64_t* garr = Lh.accs[a];
-#pragma unroll
-        for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, e[j], v[j]);
-      }
-    }
+    if (base_row + chunk_rows <= frag_rows)
+      process_chunk<MODE, WAGG, KEY32, true>(A, cols, base_row + tid, frag_rows, nthr, lane, my_tab);
+    else
+      process_chunk<MODE, WAGG, KEY32, false>(A, cols, base_row + tid, frag_rows, nthr, lane, my_tab);
   }
 
   if (MODE == MODE_SMEM) {
@@ -681,15 +823,21 @@ struct ScanConfig {
   size_t smem_bytes;
 };
 
-template <int MODE, bool WAGG>
+template <int MODE, bool WAGG, bool KEY32>
 static cudaError_t launch_scan_t(const ScanArgs& a, const ScanConfig& c, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(b2q_k_scan<MODE, WAGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, b2q_k_scan<MODE, WAGG, KEY32>);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(b2q_k_scan<MODE, WAGG, KEY32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  b2q_k_scan<MODE, WAGG><<<c.grid, c.block, c.smem_bytes, st>>>(a);
+  b2q_k_scan<MODE, WAGG, KEY32><<<c.grid, c.block, c.smem_bytes, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -716,16 +864,18 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
   c.grid = (int)(launch.total_chunks < max_ctas ? (launch.total_chunks > 0 ? launch.total_chunks : 1) : max_ctas);
   c.smem_bytes = 0;
   const int kernel = q.plan.kernel;
+  const bool key32 = q.prog.key.col >= 0 && q.prog.key.width <= 4;
   if (kernel == B2Q_KERNEL_NON_GROUPED) {
     c.smem_bytes = (size_t)q.smem.total_bytes;
-    return launch_scan_t<MODE_SMEM, true>(a, c, st);
+    return launch_scan_t<MODE_SMEM, true, false>(a, c, st);
   }
   if (kernel == B2Q_KERNEL_PERFECT_SMEM) {
     c.smem_bytes = (size_t)q.smem.total_bytes;
-    return launch_scan_t<MODE_SMEM, false>(a, c, st);
+    return key32 ? launch_scan_t<MODE_SMEM, false, true>(a, c, st) : launch_scan_t<MODE_SMEM, false, false>(a, c, st);
   }
-  if (kernel == B2Q_KERNEL_PERFECT_GLOBAL) return launch_scan_t<MODE_GLOBAL, false>(a, c, st);
-  return launch_scan_t<MODE_BASELINE, false>(a, c, st);
+  if (kernel == B2Q_KERNEL_PERFECT_GLOBAL)
+    return key32 ? launch_scan_t<MODE_GLOBAL, false, true>(a, c, st) : launch_scan_t<MODE_GLOBAL, false, false>(a, c, st);
+  return key32 ? launch_scan_t<MODE_BASELINE, false, true>(a, c, st) : launch_scan_t<MODE_BASELINE, false, false>(a, c, st);
 }
 
 cudaError_t launch_init(const B2QQuery& q, int64_t* const* accs, int64_t* keys, int8_t* smem_image, cudaStream_t st) {

@@ -423,6 +423,8 @@ class Planner {
     return q.prog.n_cols++;
   }
 
+  std::vector<double> term_sel_; /* estimated selectivity per filter term (uniformity assumption over chunk stats) */
+
   void lower_cmp(B2QQuery& q, const B2QExpr& e) {
     DevFilter& f = q.prog.filter;
     const B2QExpr& l = ex(e.left);
@@ -430,46 +432,102 @@ class Planner {
     if (l.kind != B2Q_EXPR_COLUMN_VAR || c.kind != B2Q_EXPR_CONSTANT) reject(B2Q_ERR_UNSUPPORTED, "comparison must be ColumnVar OP Constant");
     if (f.n_terms >= B2Q_MAX_TERMS || f.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
     const SqlType ct = col_type(l.col_id);
+    const ColRange cr = leaf_range(l.col_id);
     DevTerm t;
     memset(&t, 0, sizeof(t));
     t.col = launch_col(q, l.col_id);
     t.width = static_cast<int8_t>(ct.size());
     t.col_is_fp = ct.is_fp();
-    t.nullable = !ct.notnull;
+    const bool nullable = !ct.notnull;
     t.null_bits = ct.is_fp() ? dbl_bits(kNullDouble) : ct.int_null();
     const bool cfp = c.ti.type == B2Q_kDOUBLE;
     t.cmp_fp = ct.is_fp() || cfp;
-    t.negate = e.op == B2Q_kNE;
+    bool negate = e.op == B2Q_kNE;
     const double inf = std::numeric_limits<double>::infinity();
-    /* default: empty range (always false; always true under negate) */
-    t.lo = 1; t.hi = 0; t.flo = inf; t.fhi = -inf;
-    if (c.is_null) {
-      t.negate = 0; /* comparison with a NULL literal is never TRUE */
-    } else if (t.cmp_fp) {
-      const double k = cfp ? c.dval : static_cast<double>(c.ival);
-      if (!std::isnan(k)) {
+    double sel = 0.5;
+    if (t.cmp_fp) {
+      /* closed fp range; default empty (never TRUE; under negate always TRUE except NULL) */
+      t.flo = inf; t.fhi = -inf;
+      if (c.is_null) negate = false; /* comparison with a NULL literal is never TRUE */
+      else {
+        const double k = cfp ? c.dval : static_cast<double>(c.ival);
+        if (!std::isnan(k)) {
+          switch (e.op) {
+            case B2Q_kEQ: case B2Q_kNE: t.flo = k; t.fhi = k; break;
+            case B2Q_kLT: if (k != -inf) { t.flo = -inf; t.fhi = std::nextafter(k, -inf); } break;
+            case B2Q_kLE: t.flo = -inf; t.fhi = k; break;
+            case B2Q_kGT: if (k != inf) { t.flo = std::nextafter(k, inf); t.fhi = inf; } break;
+            case B2Q_kGE: t.flo = k; t.fhi = inf; break;
+            default: reject(B2Q_ERR_UNSUPPORTED, "comparison operator");
+          }
+        }
+      }
+      t.negate = negate;
+      t.null_check = nullable; /* NULL_DOUBLE sits inside the value range: always test explicitly */
+      const double cmin = cr.fp ? cr.fmin : static_cast<double>(cr.imin), cmax = cr.fp ? cr.fmax : static_cast<double>(cr.imax);
+      if (cmax > cmin && t.flo <= t.fhi) sel = std::max(0.0, std::min(t.fhi, cmax) - std::max(t.flo, cmin)) / (cmax - cmin);
+      else if (t.flo > t.fhi) sel = 0.0;
+      if (negate) sel = 1.0 - sel;
+    } else {
+      int64_t lo = 1, hi = 0; /* empty */
+      if (c.is_null) negate = false;
+      else {
+        const int64_t k = c.ival;
         switch (e.op) {
-          case B2Q_kEQ: case B2Q_kNE: t.flo = k; t.fhi = k; break;
-          case B2Q_kLT: t.flo = -inf; t.fhi = std::nextafter(k, -inf); if (k == -inf) { t.flo = inf; t.fhi = -inf; } break;
-          case B2Q_kLE: t.flo = -inf; t.fhi = k; break;
-          case B2Q_kGT: t.flo = std::nextafter(k, inf); t.fhi = inf; if (k == inf) { t.flo = inf; t.fhi = -inf; } break;
-          case B2Q_kGE: t.flo = k; t.fhi = inf; break;
+          case B2Q_kEQ: case B2Q_kNE: lo = k; hi = k; break;
+          case B2Q_kLT: if (k != INT64_MIN) { lo = INT64_MIN; hi = k - 1; } break;
+          case B2Q_kLE: lo = INT64_MIN; hi = k; break;
+          case B2Q_kGT: if (k != INT64_MAX) { lo = k + 1; hi = INT64_MAX; } break;
+          case B2Q_kGE: lo = k; hi = INT64_MAX; break;
           default: reject(B2Q_ERR_UNSUPPORTED, "comparison operator");
         }
       }
-    } else {
-      const int64_t k = c.ival;
-      switch (e.op) {
-        case B2Q_kEQ: case B2Q_kNE: t.lo = k; t.hi = k; break;
-        case B2Q_kLT: if (k != INT64_MIN) { t.lo = INT64_MIN; t.hi = k - 1; } break;
-        case B2Q_kLE: t.lo = INT64_MIN; t.hi = k; break;
-        case B2Q_kGT: if (k != INT64_MAX) { t.lo = k + 1; t.hi = INT64_MAX; } break;
-        case B2Q_kGE: t.lo = k; t.hi = INT64_MAX; break;
-        default: reject(B2Q_ERR_UNSUPPORTED, "comparison operator");
+      /* selectivity estimate on the un-clamped range */
+      if (cr.imax >= cr.imin && lo <= hi) {
+        const double ov = static_cast<double>(std::min(hi, cr.imax)) - static_cast<double>(std::max(lo, cr.imin)) + 1.0;
+        sel = std::max(0.0, ov) / (static_cast<double>(cr.imax) - static_cast<double>(cr.imin) + 1.0);
+      } else if (lo > hi) sel = 0.0;
+      if (negate) sel = 1.0 - sel;
+      /* clamp to the column's register class: 32-bit compares for 1/2/4-byte columns */
+      const int64_t dmin = t.width <= 4 ? INT32_MIN : INT64_MIN, dmax = t.width <= 4 ? INT32_MAX : INT64_MAX;
+      lo = std::max(lo, dmin);
+      hi = std::min(hi, dmax);
+      const int64_t nullv = ct.int_null();
+      bool null_check = false;
+      if (nullable) {
+        if (negate) null_check = true;                      /* v != k must still fail for NULL */
+        else if (lo <= hi && lo <= nullv && nullv <= hi) lo = nullv + 1; /* NULL is the type's minimum: cut it off the range */
       }
+      if (lo > hi) { /* never in range: encode as "always in range" with the negation flipped */
+        t.lo = 0;
+        t.span = t.width <= 4 ? 0xFFFFFFFFull : ~0ull;
+        negate = !negate;
+      } else {
+        t.lo = lo;
+        t.span = static_cast<uint64_t>(hi) - static_cast<uint64_t>(lo);
+      }
+      t.negate = negate;
+      t.null_check = null_check;
     }
+    term_sel_.push_back(std::min(1.0, std::max(0.0, sel)));
     f.ops[f.n_ops++] = static_cast<uint8_t>((FOP_TERM << 4) | f.n_terms);
     f.terms[f.n_terms++] = t;
+  }
+
+  double estimate_selectivity(const DevFilter& f) const {
+    if (f.n_ops == 0) return 1.0;
+    double st[8];
+    int sp = 0;
+    for (int i = 0; i < f.n_ops; ++i) {
+      const int kind = f.ops[i] >> 4;
+      if (kind == FOP_TERM) st[sp++] = term_sel_[f.ops[i] & 15];
+      else {
+        const double b = st[--sp], a = st[--sp];
+        st[sp++] = kind == FOP_AND ? a * b : 1.0 - (1.0 - a) * (1.0 - b);
+      }
+      if (sp >= 7) break;
+    }
+    return sp > 0 ? st[sp - 1] : 1.0;
   }
 
   int lower_bool(B2QQuery& q, int idx, int depth) { /* returns max stack depth used */
@@ -541,6 +599,11 @@ class Planner {
     for (int i = 0; i < u_.num_simple_quals; ++i) add_qual(u_.simple_quals[i]);
     for (int i = 0; i < u_.num_quals; ++i) add_qual(u_.quals[i]);
     if (max_depth > 4) reject(B2Q_ERR_UNSUPPORTED, "filter expression nests deeper than 4");
+    /* load scheduling hints: a 32-byte sector holds 4-8 rows, so predicating a column load on the filter only saves
+     * HBM traffic when almost every row fails; otherwise loading eagerly puts all column loads in flight at once */
+    g.est_selectivity = static_cast<float>(estimate_selectivity(g.filter));
+    g.eager_key = g.est_selectivity >= 0.10f;
+    g.eager_args = g.est_selectivity >= 0.25f;
 
     /* key */
     DevKey& k = g.key;
@@ -639,36 +702,40 @@ class Planner {
     SmemPlan& sm = q.smem;
     memset(&sm, 0, sizeof(sm));
     sm.replicas = 1;
-    int kernel;
-    if (p.query_desc_type == B2Q_NonGroupedAggregate) kernel = B2Q_KERNEL_NON_GROUPED;
-    else if (p.query_desc_type == B2Q_GroupByBaselineHash) kernel = B2Q_KERNEL_BASELINE_GLOBAL;
-    else {
-      /* shared-memory footprint per entry: COUNT 4 B, SUM_I64 4 B (low word; carries go to HBM), others 8 B */
-      int off = 0;
-      /* 8-byte arrays first so they stay 8-byte aligned */
-      for (int pass = 0; pass < 2; ++pass)
-        for (int a = 0; a < q.prog.n_accs; ++a) {
-          const int op = q.prog.accs[a].op;
-          const int bytes = (op == ACC_COUNT || op == ACC_SUM_I64) ? 4 : 8;
-          if ((pass == 0) != (bytes == 8)) continue;
-          sm.acc_bytes[a] = bytes;
-          sm.acc_off[a] = off;
-          off += static_cast<int>(((p.entry_count * bytes + 15) / 16) * 16);
-          if (off > (1 << 24)) break;
-        }
-      const int64_t per_replica = off;
-      const int64_t budget = 200 * 1024; /* of the 227 KB a CTA may opt in to; the rest is left to L1 */
-      if (per_replica <= budget && p.entry_count <= (1 << 22)) {
-        kernel = B2Q_KERNEL_PERFECT_SMEM;
-        sm.use_smem = 1;
-        sm.replica_bytes = static_cast<int32_t>(per_replica);
-        int rep = 1;
-        while (rep < 32 && int64_t(rep) * 2 * per_replica <= 96 * 1024) rep *= 2; /* warp-private copies for small tables */
-        sm.replicas = rep;
-        sm.total_bytes = static_cast<int32_t>(per_replica * rep);
-      } else {
-        kernel = B2Q_KERNEL_PERFECT_GLOBAL;
+    /* shared-memory footprint per entry: COUNT 4 B, SUM_I64 4 B (low word; carries go to HBM), others 8 B;
+     * 8-byte arrays first so they stay 8-byte aligned */
+    int off = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int a = 0; a < q.prog.n_accs; ++a) {
+        const int op = q.prog.accs[a].op;
+        const int bytes = (op == ACC_COUNT || op == ACC_SUM_I64) ? 4 : 8;
+        if ((pass == 0) != (bytes == 8)) continue;
+        sm.acc_bytes[a] = bytes;
+        sm.acc_off[a] = off;
+        const int64_t arr = ((p.entry_count * bytes + 15) / 16) * 16;
+        off = static_cast<int>(std::min<int64_t>(int64_t(off) + arr, int64_t(1) << 30));
       }
+    const int64_t per_replica = off;
+    const int64_t budget = 200 * 1024; /* of the 227 KB a CTA may opt in to */
+    auto use_smem_table = [&]() {
+      sm.use_smem = 1;
+      sm.replica_bytes = static_cast<int32_t>(per_replica);
+      int rep = 1;
+      while (rep < 32 && int64_t(rep) * 2 * per_replica <= 96 * 1024) rep *= 2; /* warp-private copies for small tables */
+      sm.replicas = rep;
+      sm.total_bytes = static_cast<int32_t>(per_replica * rep);
+    };
+    int kernel;
+    if (p.query_desc_type == B2Q_NonGroupedAggregate) {
+      kernel = B2Q_KERNEL_NON_GROUPED;
+      use_smem_table();
+    } else if (p.query_desc_type == B2Q_GroupByBaselineHash) {
+      kernel = B2Q_KERNEL_BASELINE_GLOBAL;
+    } else if (per_replica <= budget && p.entry_count <= (1 << 22)) {
+      kernel = B2Q_KERNEL_PERFECT_SMEM;
+      use_smem_table();
+    } else {
+      kernel = B2Q_KERNEL_PERFECT_GLOBAL;
     }
     if (eo_.force_kernel) {
       const int f = eo_.force_kernel;

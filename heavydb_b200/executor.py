@@ -192,7 +192,9 @@ class ResultSet:
         return bool(lib().b2q_rs_is_row_at_empty(self._h, i))
 
     def getQueryMemDesc(self) -> abi.Plan:
-        return lib().b2q_rs_query_mem_desc(self._h).contents
+        plan = abi.Plan()   # a copy: stays valid after the result set is freed
+        C.memmove(C.byref(plan), lib().b2q_rs_query_mem_desc(self._h), C.sizeof(abi.Plan))
+        return plan
 
     def getStorageBuffer(self) -> np.ndarray:
         """getStorage()->getUnderlyingBuffer() as bytes in the reference's row-wise layout."""
@@ -233,7 +235,9 @@ class Partial:
         return bool(lib().b2q_partial_is_mergeable(self._h))
 
     def plan(self) -> abi.Plan:
-        return lib().b2q_partial_plan(self._h).contents
+        plan = abi.Plan()
+        C.memmove(C.byref(plan), lib().b2q_partial_plan(self._h), C.sizeof(abi.Plan))
+        return plan
 
     def kernel_ms(self) -> float:
         return lib().b2q_partial_kernel_ms(self._h)
