@@ -154,7 +154,8 @@ def allreduce_partial(partial, torch, dist):
     """ResultSetStorage::reduce across devices == one NCCL all-reduce per dense accumulator array."""
     from heavydb_b200 import abi
     for ptr, n, dt, op in partial.arrays():
-        t = torch.as_tensor(CudaArray(ptr, n, "<f8" if dt == abi.DT_FLOAT64 else "<i8"), device="cuda")
+        typestr = {abi.DT_FLOAT64: "<f8", abi.DT_INT64: "<i8", abi.DT_UINT8: "|u1"}[dt]
+        t = torch.as_tensor(CudaArray(ptr, n, typestr), device="cuda")
         rop = {abi.RED_SUM: dist.ReduceOp.SUM, abi.RED_MIN: dist.ReduceOp.MIN, abi.RED_MAX: dist.ReduceOp.MAX}[op]
         dist.all_reduce(t, op=rop)
 
@@ -338,9 +339,40 @@ def main():
     return 0
 
 
+def gpu_numa_cpus(torch):
+    """CPUs of the NUMA node the GPU hangs off (so pinned host buffers are allocated next to its PCIe root)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None, node
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return cpus, node
+    except Exception as e:  # noqa
+        return None, str(e)
+
+
 def e2e_leg(args, torch, ex, eo, cols, sql, names):
     """Host (pinned) buffers -> C ABI -> host result.  H2D of every referenced column is inside the timed region."""
     import psutil
+    cpus, node = gpu_numa_cpus(torch)
+    old_aff = None
+    if cpus:
+        try:
+            old_aff = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus & old_aff or cpus)
+        except Exception:
+            old_aff = None
     from heavydb_b200 import abi, executor
     from heavydb_b200 import sqlmini
     bytes_per_row = sum(abi.SIZE_OF[np_type(t)] for _, t, _, _ in cols)
@@ -372,6 +404,8 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
             fr.stats.append(st)
         table.fragments.append(fr)
     torch.cuda.synchronize()
+    if old_aff:
+        os.sched_setaffinity(0, old_aff)
     unit = sqlmini.parse(sql, table, names)
     bt = table.build(abi.CPU_LEVEL)
     times = []
@@ -388,7 +422,7 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
         del rs
     dt = float(np.mean(times))
     return {"value": rows / dt, "unit": "rows/s", "h2d_bytes_per_step": int(rows * bytes_per_row), "d2h_bytes_per_step": d2h,
-            "rows": rows, "ms_per_step": dt * 1e3, "host_memory": "pinned", "h2d_gbs": rows * bytes_per_row / dt / 1e9,
+            "rows": rows, "ms_per_step": dt * 1e3, "host_memory": f"pinned, allocated on the GPU's NUMA node ({node})", "h2d_gbs": rows * bytes_per_row / dt / 1e9,
             "groups_out": int(n)}
 
 

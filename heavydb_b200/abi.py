@@ -38,7 +38,7 @@ EXPR_COLUMN_VAR, EXPR_CONSTANT, EXPR_BIN_OPER, EXPR_AGG = 1, 2, 3, 4
 CPU_LEVEL, GPU_LEVEL = 1, 2
 DEVICE_CPU, DEVICE_GPU = 0, 1
 KERNEL_AUTO, KERNEL_NON_GROUPED, KERNEL_PERFECT_SMEM, KERNEL_PERFECT_GLOBAL, KERNEL_BASELINE_GLOBAL = range(5)
-DT_INT64, DT_FLOAT64 = 0, 1
+DT_INT64, DT_FLOAT64, DT_UINT8 = 0, 1, 2
 RED_SUM, RED_MIN, RED_MAX = 0, 1, 2
 
 MAX_SLOTS = 16

@@ -58,7 +58,8 @@ enum {
   ACC_MIN_I64 = 3,
   ACC_MAX_I64 = 4,
   ACC_MIN_F64 = 5, /* stored as order-preserving int64 */
-  ACC_MAX_F64 = 6
+  ACC_MAX_F64 = 6,
+  ACC_TOUCH = 7    /* "some row reached this group": ONE BYTE per entry (the array holds uint8), merged with MAX */
 };
 
 struct DevAcc {
@@ -95,7 +96,9 @@ struct DevProgram {
   float est_selectivity; /* planner's estimate from chunk stats (uniformity assumption) */
   int8_t eager_key;      /* load the key column for every row, overlapped with the filter columns */
   int8_t eager_args;     /* load aggregate arguments for every row instead of only the passing ones */
-  int8_t pad_[2];
+  int8_t touch_acc;      /* index of the ACC_TOUCH accumulator, or -1 */
+  int8_t touch_piggyback;/* global-table kernels: accumulator (COUNT / SUM_I64 without a skip test) whose returning
+                            atomic also maintains the touched flag, or -1 (explicit flag check per row) */
   DevAcc accs[B2Q_MAX_ACCS];
 };
 

@@ -35,6 +35,7 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
 cudaError_t launch_init(const B2QQuery& q, int64_t* const* accs, int64_t* keys, int8_t* smem_image, cudaStream_t st);
 cudaError_t launch_materialize(const B2QQuery& q, const int64_t* const* accs, const int64_t* keys, int8_t* out,
                                cudaStream_t st);
+cudaError_t launch_join_split(const int64_t* split, int64_t* out, int64_t n, cudaStream_t st);
 cudaError_t launch_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count, int64_t lo,
                        int64_t span, cudaStream_t st);
 }  // namespace b2q
@@ -64,113 +65,204 @@ static bool have_device() {
 }
 
 /* ---------------------------------------------------------------------------------------------------------- */
+/* All device memory of one query comes from the CUDA stream-ordered pool in ONE allocation (the pool keeps freed
+ * memory, so steady-state calls do not touch the driver's allocator — the reference re-uses its CudaMgr slabs
+ * the same way, DataMgr/BufferMgr/GpuCudaBufferMgr). */
+static void configure_pool_once(int device) {
+  static std::mutex mu;
+  static bool done[64] = {};
+  std::lock_guard<std::mutex> g(mu);
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+  done[device] = true;
+}
+
+struct DeviceBlock {
+  int8_t* base = nullptr;
+  size_t size = 0;
+  size_t used = 0;
+  cudaError_t alloc(size_t n, cudaStream_t st) {
+    size = n;
+    used = 0;
+    return cudaMallocAsync(reinterpret_cast<void**>(&base), n, st);
+  }
+  static size_t pad(size_t n) { return (n + 255) & ~size_t(255); }
+  int8_t* take(size_t n) {
+    int8_t* p = base + used;
+    used += pad(n);
+    return p;
+  }
+  void release(cudaStream_t st) {
+    if (base) cudaFreeAsync(base, st);
+    base = nullptr;
+  }
+};
+
 struct B2QPartial {
   B2QQuery q;
   int device = 0;
+  DeviceBlock blk;
   int64_t* accs[B2Q_MAX_ACCS] = {};
   int64_t* keys = nullptr;
   int8_t* smem_image = nullptr;
   int32_t* d_error = nullptr;
+  std::vector<void*> extra;  /* stream-ordered allocations made after the main block */
+  bool split = false;        /* COUNT / SUM_I64 arrays are in the (lo[n] | hi[n]) layout of the global-table kernels */
+  cudaEvent_t ev[4] = {}; /* init begin/end, scan begin/end */
+  bool scan_timed = false;
   double scan_ms = 0, init_ms = 0, h2d_bytes = 0;
   int64_t launches = 0;
   ~B2QPartial() {
-    for (auto& a : accs) if (a) cudaFree(a);
-    if (keys) cudaFree(keys);
-    if (smem_image) cudaFree(smem_image);
-    if (d_error) cudaFree(d_error);
+    for (void* x : extra) cudaFreeAsync(x, nullptr);
+    blk.release(nullptr);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
   }
 };
+
+/* Result buffers are page-locked host memory so the copy-back is one asynchronous DMA at PCIe rate straight into
+ * the buffer the ResultSet owns.  Page-locking is expensive (~0.3 ms/MB), so released buffers are kept in a small
+ * cache and handed to the next result of a similar size. */
+struct PinnedCache {
+  struct Item { int8_t* p; size_t cap; };
+  std::mutex mu;
+  std::vector<Item> free_list;
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCached = size_t(2) << 30;
+  int8_t* get(size_t n, size_t* cap_out) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      int best = -1;
+      for (size_t i = 0; i < free_list.size(); ++i)
+        if (free_list[i].cap >= n && free_list[i].cap <= 2 * n + (1 << 20) && (best < 0 || free_list[i].cap < free_list[best].cap)) best = static_cast<int>(i);
+      if (best >= 0) {
+        Item it = free_list[best];
+        free_list.erase(free_list.begin() + best);
+        cached_bytes -= it.cap;
+        *cap_out = it.cap;
+        return it.p;
+      }
+    }
+    int8_t* p = nullptr;
+    const size_t cap = std::max<size_t>(n, 4096);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p), cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *cap_out = cap;
+    return p;
+  }
+  void put(int8_t* p, size_t cap) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(mu);
+    if (cached_bytes + cap > kMaxCached) { cudaFreeHost(p); return; }
+    free_list.push_back({p, cap});
+    cached_bytes += cap;
+  }
+};
+static PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }
 
 struct B2QResultSet {
   B2QQuery q;
-  std::vector<int8_t> buf;
+  int8_t* buf = nullptr;   /* pinned; every byte is written by the D2H copy */
+  size_t buf_size = 0, buf_cap = 0;
   int64_t cursor = 0;
   int64_t cached_rows = -1;
   double scan_ms = 0, init_ms = 0, mat_ms = 0;
+  ~B2QResultSet() { pinned_cache().put(buf, buf_cap); }
 };
 
-/* device-side launch tables for one scan launch over a set of (fragment, column pointer) rows */
-struct LaunchTables {
-  const int8_t** d_cols = nullptr;
-  int64_t* d_rows = nullptr;
-  int64_t* d_chunk_start = nullptr;
-  ~LaunchTables() {
-    if (d_cols) cudaFree(d_cols);
-    if (d_rows) cudaFree(d_rows);
-    if (d_chunk_start) cudaFree(d_chunk_start);
-  }
-};
+static size_t table_bytes(const B2QQuery& q) {
+  const size_t n = std::max<size_t>(static_cast<size_t>(q.plan.entry_count), 1);
+  size_t total = 0;
+  for (int a = 0; a < q.prog.n_accs; ++a) total += DeviceBlock::pad(n * 8);
+  if (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL) total += DeviceBlock::pad(n * 8);
+  if (q.smem.use_smem) total += DeviceBlock::pad(std::max<int>(q.smem.replica_bytes, 16));
+  total += 256; /* error word */
+  return total;
+}
 
-static int32_t alloc_partial(B2QPartial& p, cudaStream_t st) {
+static int32_t alloc_partial(B2QPartial& p, size_t extra_bytes, cudaStream_t st) {
   const B2QQuery& q = p.q;
-  const size_t n = static_cast<size_t>(q.plan.entry_count);
-  for (int a = 0; a < q.prog.n_accs; ++a) CU(cudaMalloc(&p.accs[a], std::max<size_t>(n, 1) * 8));
-  if (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL) CU(cudaMalloc(&p.keys, std::max<size_t>(n, 1) * 8));
-  if (q.smem.use_smem) CU(cudaMalloc(&p.smem_image, std::max<int>(q.smem.replica_bytes, 16)));
-  CU(cudaMalloc(&p.d_error, sizeof(int32_t)));
+  configure_pool_once(p.device);
+  const size_t n = std::max<size_t>(static_cast<size_t>(q.plan.entry_count), 1);
+  CU(p.blk.alloc(table_bytes(q) + DeviceBlock::pad(extra_bytes) + 4096, st));
+  for (int a = 0; a < q.prog.n_accs; ++a) p.accs[a] = reinterpret_cast<int64_t*>(p.blk.take(n * 8));
+  if (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL) p.keys = reinterpret_cast<int64_t*>(p.blk.take(n * 8));
+  if (q.smem.use_smem) p.smem_image = p.blk.take(std::max<int>(q.smem.replica_bytes, 16));
+  p.d_error = reinterpret_cast<int32_t*>(p.blk.take(256));
+  p.split = q.plan.kernel == B2Q_KERNEL_PERFECT_GLOBAL || q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL;
+  for (auto& e : p.ev) CU(cudaEventCreate(&e));
   CU(cudaMemsetAsync(p.d_error, 0, sizeof(int32_t), st));
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0));
-  CU(cudaEventCreate(&e1));
-  CU(cudaEventRecord(e0, st));
+  CU(cudaEventRecord(p.ev[0], st));
   CU(launch_init(q, p.accs, p.keys, p.smem_image, st));
-  CU(cudaEventRecord(e1, st));
-  CU(cudaEventSynchronize(e1));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
-  p.init_ms = ms;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  CU(cudaEventRecord(p.ev[1], st));
   return B2Q_OK;
 }
 
-/* one scan launch over `nf` fragments whose referenced columns are already in device memory */
+/* one scan launch over `nf` fragments whose referenced columns are already in device memory; the launch tables
+ * (column pointers, row counts, chunk prefix sums) travel in ONE H2D copy into the partial's block */
+static size_t launch_table_bytes(int nf, int nc) { return (static_cast<size_t>(nf) * nc + nf + nf + 1) * 8 + 64; }
+
 static int32_t scan_device_fragments(B2QPartial& p, int nf, const std::vector<const int8_t*>& cols /* nf * n_cols */,
                                      const std::vector<int64_t>& rows, cudaStream_t st, bool time_it) {
   const B2QQuery& q = p.q;
   int block, ctas;
   scan_config(q, &block, &ctas);
   const int64_t chunk_rows = scan_rows_per_chunk(block);
-  std::vector<int64_t> chunk_start(nf + 1, 0);
-  for (int f = 0; f < nf; ++f) chunk_start[f + 1] = chunk_start[f] + (rows[f] + chunk_rows - 1) / chunk_rows;
-  if (chunk_start[nf] == 0) return B2Q_OK;
-  LaunchTables t;
-  CU(cudaMalloc(&t.d_cols, std::max<size_t>(cols.size(), 1) * sizeof(void*)));
-  CU(cudaMalloc(&t.d_rows, nf * sizeof(int64_t)));
-  CU(cudaMalloc(&t.d_chunk_start, (nf + 1) * sizeof(int64_t)));
-  CU(cudaMemcpyAsync(t.d_cols, cols.data(), cols.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(t.d_rows, rows.data(), nf * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(t.d_chunk_start, chunk_start.data(), (nf + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  const size_t ncols = cols.size();
+  std::vector<int64_t> host(ncols + nf + nf + 1);
+  memcpy(host.data(), cols.data(), ncols * 8);
+  memcpy(host.data() + ncols, rows.data(), static_cast<size_t>(nf) * 8);
+  int64_t* cs = host.data() + ncols + nf;
+  cs[0] = 0;
+  for (int f = 0; f < nf; ++f) cs[f + 1] = cs[f] + (rows[f] + chunk_rows - 1) / chunk_rows;
+  if (cs[nf] == 0) return B2Q_OK;
+  int8_t* d_tab = p.blk.take(host.size() * 8);
+  if (p.blk.used > p.blk.size) return set_err(B2Q_ERR_CUDA, "internal: launch tables exceed the device block");
+  CU(cudaMemcpyAsync(d_tab, host.data(), host.size() * 8, cudaMemcpyHostToDevice, st));
   DevLaunch L;
   memset(&L, 0, sizeof(L));
-  L.col_ptrs = reinterpret_cast<const int8_t* const*>(t.d_cols);
-  L.frag_rows = t.d_rows;
-  L.frag_chunk_start = t.d_chunk_start;
+  L.col_ptrs = reinterpret_cast<const int8_t* const*>(d_tab);
+  L.frag_rows = reinterpret_cast<const int64_t*>(d_tab) + ncols;
+  L.frag_chunk_start = reinterpret_cast<const int64_t*>(d_tab) + ncols + nf;
   L.n_frags = nf;
-  L.total_chunks = chunk_start[nf];
+  L.total_chunks = cs[nf];
   for (int a = 0; a < q.prog.n_accs; ++a) L.accs[a] = p.accs[a];
   L.keys = p.keys;
   L.error = p.d_error;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (time_it) {
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, st));
-  }
+  if (time_it) CU(cudaEventRecord(p.ev[2], st));
   CU(launch_scan(q, L, p.smem_image, block, ctas, st));
   p.launches += 1;
-  if (time_it) {
-    CU(cudaEventRecord(e1, st));
-    CU(cudaEventSynchronize(e1));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    p.scan_ms += ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-  } else {
-    CU(cudaStreamSynchronize(st)); /* LaunchTables are freed on return */
-  }
+  if (time_it) { CU(cudaEventRecord(p.ev[3], st)); p.scan_timed = true; }
+  /* `host` is pageable: the copy above was staged by the runtime before cudaMemcpyAsync returned */
   return B2Q_OK;
+}
+
+/* global-table kernels keep COUNT / integer SUM as (lo[n] | hi[n]); everything downstream (NCCL merge,
+ * materialise) wants plain int64 */
+static int32_t normalize_partial(B2QPartial& p, cudaStream_t st) {
+  if (!p.split) return B2Q_OK;
+  const int64_t n = p.q.plan.entry_count;
+  for (int a = 0; a < p.q.prog.n_accs; ++a) {
+    const int op = p.q.prog.accs[a].op;
+    if (op != ACC_COUNT && op != ACC_SUM_I64) continue;
+    int64_t* out = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&out), std::max<int64_t>(n, 1) * 8, st));
+    p.extra.push_back(out);
+    CU(launch_join_split(p.accs[a], out, n, st));
+    p.accs[a] = out;
+  }
+  p.split = false;
+  return B2Q_OK;
+}
+
+static void collect_timings(B2QPartial& p) {
+  float ms = 0;
+  if (p.ev[0] && p.ev[1] && cudaEventElapsedTime(&ms, p.ev[0], p.ev[1]) == cudaSuccess) p.init_ms = ms;
+  if (p.scan_timed && cudaEventElapsedTime(&ms, p.ev[2], p.ev[3]) == cudaSuccess) p.scan_ms = ms;
+  cudaGetLastError();
 }
 
 /* host-resident table: stream the referenced columns through two staging buffer sets so that the H2D copy of
@@ -291,7 +383,8 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
   if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible; this path has no CPU fallback");
   if (eo->device_ordinal >= 0) CU(cudaSetDevice(eo->device_ordinal));
   CU(cudaGetDevice(&p->device));
-  rc = alloc_partial(*p, st);
+  const size_t extra = tbl->memory_level == B2Q_GPU_LEVEL ? launch_table_bytes(tbl->num_fragments, p->q.prog.n_cols) : 0;
+  rc = alloc_partial(*p, extra, st);
   if (rc != B2Q_OK) return rc;
   const B2QQuery& q = p->q;
   if (tbl->memory_level == B2Q_GPU_LEVEL) {
@@ -317,9 +410,12 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
   } else {
     return set_err(B2Q_ERR_INVALID_ARGUMENT, "memory_level must be B2Q_CPU_LEVEL or B2Q_GPU_LEVEL");
   }
+  rc = normalize_partial(*p, st);
+  if (rc != B2Q_OK) return rc;
   int32_t dev_err = 0;
   CU(cudaMemcpyAsync(&dev_err, p->d_error, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  collect_timings(*p);
   if (dev_err) return set_err(dev_err, dev_err == B2Q_ERR_OUT_OF_SLOTS ? "group-by table is full (OUT_OF_SLOTS)" : "group key outside the chunk-stats range");
   *out = p.release();
   return B2Q_OK;
@@ -333,26 +429,17 @@ static int32_t finalize_impl(B2QPartial* p, cudaStream_t st, B2QResultSet** out)
   rs->scan_ms = p->scan_ms;
   rs->init_ms = p->init_ms;
   const size_t nbytes = static_cast<size_t>(p->q.plan.buffer_size);
-  rs->buf.resize(nbytes);
+  rs->buf_size = nbytes;
   if (nbytes) {
+    rs->buf = pinned_cache().get(nbytes, &rs->buf_cap);
+    if (!rs->buf) return set_err(B2Q_ERR_INVALID_ARGUMENT, "out of (pinned) host memory for the result buffer");
     int8_t* d_out = nullptr;
-    CU(cudaMalloc(&d_out, nbytes));
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0, st);
-    cudaError_t e = cudaMemsetAsync(d_out, 0, nbytes, st);
-    if (e == cudaSuccess) e = launch_materialize(p->q, p->accs, p->keys, d_out, st);
-    cudaEventRecord(e1, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(rs->buf.data(), d_out, nbytes, cudaMemcpyDeviceToHost, st);
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&d_out), nbytes, st));
+    cudaError_t e = launch_materialize(p->q, p->accs, p->keys, d_out, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rs->buf, d_out, nbytes, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d_out, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    rs->mat_ms = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d_out);
-    if (e != cudaSuccess) return set_err(B2Q_ERR_CUDA, std::string("materialise: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(B2Q_ERR_CUDA, std::string("materialise: ") + cudaGetErrorString(e)); }
   }
   *out = rs.release();
   return B2Q_OK;
@@ -362,7 +449,7 @@ static int32_t finalize_impl(B2QPartial* p, cudaStream_t st, B2QResultSet** out)
 static bool rs_is_empty_entry(const B2QResultSet* rs, int64_t e) {
   const B2QPlan& p = rs->q.plan;
   if (p.query_desc_type == B2Q_NonGroupedAggregate) return false;
-  const int8_t* row = rs->buf.data() + e * p.row_size;
+  const int8_t* row = rs->buf + e * p.row_size;
   if (p.keyless_hash) {
     const int s = p.idx_target_as_key;
     int64_t v;
@@ -444,8 +531,8 @@ int32_t b2q_partial_array(const B2QPartial* p, int32_t i, void** ptr, int64_t* c
   const int op = p->q.prog.accs[i].op;
   if (ptr) *ptr = p->accs[i];
   if (count) *count = p->q.plan.entry_count;
-  if (dtype) *dtype = op == ACC_SUM_F64 ? B2Q_DT_FLOAT64 : B2Q_DT_INT64;
-  if (redop) *redop = (op == ACC_MIN_I64 || op == ACC_MIN_F64) ? B2Q_RED_MIN : (op == ACC_MAX_I64 || op == ACC_MAX_F64) ? B2Q_RED_MAX : B2Q_RED_SUM;
+  if (dtype) *dtype = op == ACC_SUM_F64 ? B2Q_DT_FLOAT64 : op == ACC_TOUCH ? B2Q_DT_UINT8 : B2Q_DT_INT64;
+  if (redop) *redop = (op == ACC_MIN_I64 || op == ACC_MIN_F64) ? B2Q_RED_MIN : (op == ACC_MAX_I64 || op == ACC_MAX_F64 || op == ACC_TOUCH) ? B2Q_RED_MAX : B2Q_RED_SUM;
   return B2Q_OK;
 }
 int32_t b2q_partial_is_mergeable(const B2QPartial* p) { return p && p->q.plan.kernel != B2Q_KERNEL_BASELINE_GLOBAL; }
@@ -470,10 +557,10 @@ int32_t b2q_launch(const B2QQuery* query, const B2QParams* prm, void* stream) {
     for (int s = 0; s < p.q.plan.num_slots; ++s) { p.q.plan.init_vals[s] = prm->init_agg_value[s]; p.q.layout.slots[s].init_val = prm->init_agg_value[s]; }
   }
   CU(cudaGetDevice(&p.device));
-  int32_t rc = alloc_partial(p, st);
-  if (rc != B2Q_OK) return rc;
   const int nf = static_cast<int>(*prm->num_fragments);
   const int nc = p.q.prog.n_cols;
+  int32_t rc = alloc_partial(p, launch_table_bytes(nf, nc), st);
+  if (rc != B2Q_OK) return rc;
   std::vector<const int8_t*> cols(static_cast<size_t>(nf) * nc);
   std::vector<int64_t> rows(nf);
   for (int f = 0; f < nf; ++f) {
@@ -487,6 +574,8 @@ int32_t b2q_launch(const B2QQuery* query, const B2QParams* prm, void* stream) {
   int64_t* d_out = nullptr;
   CU(cudaMemcpyAsync(&d_out, prm->group_by_buffers, sizeof(int64_t*), cudaMemcpyDefault, st));
   CU(cudaStreamSynchronize(st));
+  rc = normalize_partial(p, st);
+  if (rc != B2Q_OK) return rc;
   CU(launch_materialize(p.q, p.accs, p.keys, reinterpret_cast<int8_t*>(d_out), st));
   int32_t dev_err = 0;
   CU(cudaMemcpyAsync(&dev_err, p.d_error, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -520,7 +609,7 @@ int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
   const B2QPlan& p = rs->q.plan;
   while (rs->cursor < p.entry_count && rs_is_empty_entry(rs, rs->cursor)) ++rs->cursor;
   if (rs->cursor >= p.entry_count) return 0;
-  const int8_t* rowp = rs->buf.data() + rs->cursor * p.row_size;
+  const int8_t* rowp = rs->buf + rs->cursor * p.row_size;
   ++rs->cursor;
   for (int i = 0; i < p.num_targets; ++i) {
     const B2QTargetInfo& t = p.targets[i];
@@ -568,8 +657,8 @@ int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
 }
 
 const int8_t* b2q_rs_storage_buffer(const B2QResultSet* rs, size_t* size_bytes) {
-  if (size_bytes) *size_bytes = rs ? rs->buf.size() : 0;
-  return rs ? rs->buf.data() : nullptr;
+  if (size_bytes) *size_bytes = rs ? rs->buf_size : 0;
+  return rs ? rs->buf : nullptr;
 }
 const B2QPlan* b2q_rs_query_mem_desc(const B2QResultSet* rs) { return rs ? &rs->q.plan : nullptr; }
 double b2q_rs_kernel_ms(const B2QResultSet* rs) { return rs ? rs->scan_ms : 0; }

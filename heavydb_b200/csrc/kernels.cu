@@ -45,68 +45,68 @@ enum { MODE_SMEM = 0, MODE_GLOBAL = 1, MODE_BASELINE = 2 };
  * the loads of a vector, which is what puts R independent requests per column in flight.
  * ------------------------------------------------------------------------------------------------------- */
 template <bool PRED>
-__device__ __forceinline__ int64_t ldg_b64(const int8_t* p, uint32_t pred) {
+__device__ __forceinline__ int64_t ldg_b64(const int8_t* p, uint32_t pred, uint64_t pol) {
   int64_t v;
   if (PRED)
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b64 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.b64 %0, [%1];\n\t}" : "=l"(v) : "l"(p), "r"(pred));
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b64 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %3;\n\t}" : "=l"(v) : "l"(p), "r"(pred), "l"(pol));
   else
-    asm("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
   return v;
 }
 template <bool PRED>
-__device__ __forceinline__ int32_t ldg_s32(const int8_t* p, uint32_t pred) {
+__device__ __forceinline__ int32_t ldg_s32(const int8_t* p, uint32_t pred, uint64_t pol) {
   int32_t v;
   if (PRED)
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.s32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(pred));
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %3;\n\t}" : "=r"(v) : "l"(p), "r"(pred), "l"(pol));
   else
-    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
   return v;
 }
 template <bool PRED>
-__device__ __forceinline__ int32_t ldg_s16(const int8_t* p, uint32_t pred) {
+__device__ __forceinline__ int32_t ldg_s16(const int8_t* p, uint32_t pred, uint64_t pol) {
   int32_t v;
   if (PRED)
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.s16 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(pred));
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.L2::cache_hint.s16 %0, [%1], %3;\n\t}" : "=r"(v) : "l"(p), "r"(pred), "l"(pol));
   else
-    asm("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=r"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s16 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
   return (int32_t)(int16_t)v;
 }
 template <bool PRED>
-__device__ __forceinline__ int32_t ldg_s8(const int8_t* p, uint32_t pred) {
+__device__ __forceinline__ int32_t ldg_s8(const int8_t* p, uint32_t pred, uint64_t pol) {
   int32_t v;
   if (PRED)
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.s8 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(pred));
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.L2::cache_hint.s8 %0, [%1], %3;\n\t}" : "=r"(v) : "l"(p), "r"(pred), "l"(pol));
   else
-    asm("ld.global.nc.L1::no_allocate.s8 %0, [%1];" : "=r"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
   return (int32_t)(int8_t)v;
 }
 
 /* R rows of an 8-byte column: rows row0 + j*stride */
 template <bool PRED>
-__device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict__ base, int64_t row0, int stride, uint32_t mask) {
+__device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict__ base, int64_t row0, int stride, uint32_t mask, uint64_t pol) {
   const int8_t* p = base + row0 * 8;
   const int64_t step = (int64_t)stride * 8;
 #pragma unroll
-  for (int j = 0; j < R; ++j) v[j] = ldg_b64<PRED>(p + j * step, mask >> j & 1);
+  for (int j = 0; j < R; ++j) v[j] = ldg_b64<PRED>(p + j * step, mask >> j & 1, pol);
 }
 /* R rows of a 1/2/4-byte integer column, sign-extended to 32 bits */
 template <bool PRED>
-__device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0, int stride, uint32_t mask) {
+__device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0, int stride, uint32_t mask, uint64_t pol) {
   if (width == 4) {
     const int8_t* p = base + row0 * 4;
     const int64_t step = (int64_t)stride * 4;
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = ldg_s32<PRED>(p + j * step, mask >> j & 1);
+    for (int j = 0; j < R; ++j) v[j] = ldg_s32<PRED>(p + j * step, mask >> j & 1, pol);
   } else if (width == 2) {
     const int8_t* p = base + row0 * 2;
     const int64_t step = (int64_t)stride * 2;
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = ldg_s16<PRED>(p + j * step, mask >> j & 1);
+    for (int j = 0; j < R; ++j) v[j] = ldg_s16<PRED>(p + j * step, mask >> j & 1, pol);
   } else {
     const int8_t* p = base + row0;
     const int64_t step = (int64_t)stride;
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = ldg_s8<PRED>(p + j * step, mask >> j & 1);
+    for (int j = 0; j < R; ++j) v[j] = ldg_s8<PRED>(p + j * step, mask >> j & 1, pol);
   }
 }
 
@@ -115,13 +115,13 @@ __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict
  * ------------------------------------------------------------------------------------------------------- */
 template <bool FULL>
 __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* const* __restrict__ cols, int64_t row0,
-                                              int stride, uint32_t valid) {
+                                              int stride, uint32_t valid, uint64_t pol) {
   uint32_t m = 0;
   const bool neg = t.negate;
   if (!t.cmp_fp) {
     if (t.width == 8) {
       int64_t v[R];
-      load64<!FULL>(v, cols[t.col], row0, stride, valid);
+      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol);
       const uint64_t lo = (uint64_t)t.lo, span = t.span;
 #pragma unroll
       for (int j = 0; j < R; ++j) m |= (uint32_t)(((uint64_t)v[j] - lo <= span) != neg) << j;
@@ -132,7 +132,7 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
       }
     } else {
       int32_t v[R];
-      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid);
+      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol);
       const uint32_t lo = (uint32_t)t.lo, span = (uint32_t)t.span;
 #pragma unroll
       for (int j = 0; j < R; ++j) m |= (uint32_t)(((uint32_t)v[j] - lo <= span) != neg) << j;
@@ -148,19 +148,19 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
     uint32_t isnull = 0;
     if (t.col_is_fp) {
       int64_t v[R];
-      load64<!FULL>(v, cols[t.col], row0, stride, valid);
+      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol);
       const double nullv = __longlong_as_double(t.null_bits);
 #pragma unroll
       for (int j = 0; j < R; ++j) { d[j] = __longlong_as_double(v[j]); isnull |= (uint32_t)(d[j] == nullv) << j; }
     } else if (t.width == 8) {
       int64_t v[R];
-      load64<!FULL>(v, cols[t.col], row0, stride, valid);
+      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol);
       const int64_t nullv = t.null_bits;
 #pragma unroll
       for (int j = 0; j < R; ++j) { d[j] = (double)v[j]; isnull |= (uint32_t)(v[j] == nullv) << j; }
     } else {
       int32_t v[R];
-      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid);
+      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol);
       const int32_t nullv = (int32_t)t.null_bits;
 #pragma unroll
       for (int j = 0; j < R; ++j) { d[j] = (double)v[j]; isnull |= (uint32_t)(v[j] == nullv) << j; }
@@ -174,15 +174,15 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
 
 template <bool FULL>
 __device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t* const* __restrict__ cols,
-                                                int64_t row0, int stride, uint32_t valid) {
+                                                int64_t row0, int stride, uint32_t valid, uint64_t pol) {
   if (f.n_ops == 0) return valid;
-  if (f.n_ops == 1) return eval_term<FULL>(f.terms[0], cols, row0, stride, valid);
+  if (f.n_ops == 1) return eval_term<FULL>(f.terms[0], cols, row0, stride, valid, pol);
   uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
   for (int i = 0; i < f.n_ops; ++i) {
     const uint32_t op = f.ops[i];
     const uint32_t kind = op >> 4;
     if (kind == FOP_TERM) {
-      const uint32_t m = eval_term<FULL>(f.terms[op & 15], cols, row0, stride, valid);
+      const uint32_t m = eval_term<FULL>(f.terms[op & 15], cols, row0, stride, valid, pol);
       s3 = s2; s2 = s1; s1 = s0; s0 = m;
     } else {
       s0 = (kind == FOP_AND) ? (s1 & s0) : (s1 | s0);
@@ -255,10 +255,33 @@ __device__ __forceinline__ void red_add_f64(int64_t* p, double v) { asm volatile
 __device__ __forceinline__ void red_min_s64(int64_t* p, int64_t v) { asm volatile("red.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void red_max_s64(int64_t* p, int64_t v) { asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
-__device__ __forceinline__ void global_update(int op, int64_t* arr, uint32_t e, int64_t v) {
+/* HBM/L2-resident table (MODE_GLOBAL / MODE_BASELINE).  COUNT and integer SUM keep a SPLIT accumulator: the array's
+ * first 4n bytes are the low words, the next 4n bytes the high words.  Only the low words are hot (native 32-bit
+ * L2 atomics); the high word sees the rare carry / a value wider than 32 bits.  That halves the randomly accessed
+ * footprint — 40 MB instead of 80 MB for 1e7 groups — which is what lets the table stay L2-resident while 16 GB of
+ * column data streams through the same L2 (ncu: with 64-bit REDs on the 80 MB table, DRAM traffic was 2.9x the
+ * algorithmic bytes; see profiles/r1_scan_c4_*.txt).  Table accesses carry an evict_last L2 policy, the column
+ * stream evict_first. */
+__device__ __forceinline__ uint32_t global_split_add(int64_t* arr, uint32_t e, int64_t n, uint32_t vl, int32_t vh, uint64_t pol_tab) {
+  uint32_t* lo = reinterpret_cast<uint32_t*>(arr) + e;
+  uint32_t old;
+  asm volatile("atom.global.add.L2::cache_hint.u32 %0, [%1], %2, %3;" : "=r"(old) : "l"(lo), "r"(vl), "l"(pol_tab) : "memory");
+  const int32_t hi = vh + (int32_t)((uint32_t)(old + vl) < old);
+  if (hi != 0) atomicAdd(reinterpret_cast<int32_t*>(arr) + n + e, hi);
+  return old;
+}
+/* "group touched" flag piggy-backed on an accumulator that every passing row updates: the FIRST atomic on an entry
+ * always returns the initial 0, so storing the flag whenever 0 comes back marks every touched group and costs no
+ * extra L2 request for the (overwhelmingly common) rows that see a non-zero running value. */
+__device__ __forceinline__ void global_split_add_touch(int64_t* arr, uint8_t* flags, uint32_t e, int64_t n, uint32_t vl, int32_t vh, uint64_t pol_tab) {
+  const uint32_t old = global_split_add(arr, e, n, vl, vh, pol_tab);
+  if (flags && old == 0) flags[e] = 1;
+}
+
+__device__ __forceinline__ void global_update(int op, int64_t* arr, uint8_t* flags, uint32_t e, int64_t n, int64_t v, uint64_t pol_tab) {
   switch (op) {
-    case ACC_COUNT: red_add_u64(arr + e, 1ull); break;
-    case ACC_SUM_I64: red_add_u64(arr + e, (uint64_t)v); break;
+    case ACC_COUNT: global_split_add_touch(arr, flags, e, n, 1u, 0, pol_tab); break;
+    case ACC_SUM_I64: global_split_add_touch(arr, flags, e, n, (uint32_t)v, (int32_t)(v >> 32), pol_tab); break;
     case ACC_SUM_F64: red_add_f64(arr + e, __longlong_as_double(v)); break;
     case ACC_MIN_I64: red_min_s64(arr + e, v); break;
     case ACC_MAX_I64: red_max_s64(arr + e, v); break;
@@ -356,7 +379,7 @@ extern __shared__ __align__(128) int8_t b2q_smem[];
 /* one chunk: R rows per thread.  FULL = every row of the chunk exists (no tail masking). */
 template <int MODE, bool WAGG, bool KEY32, bool FULL>
 __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* const* __restrict__ cols, int64_t row0,
-                                              int64_t frag_rows, int nthr, int lane, int8_t* my_tab) {
+                                              int64_t frag_rows, int nthr, int lane, int8_t* my_tab, uint64_t pol, uint64_t pol_tab) {
   const DevProgram& P = A.prog;
   const DevLaunch& Lh = A.launch;
   uint32_t valid = (1u << R) - 1u;
@@ -372,15 +395,15 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
   const bool has_key = !WAGG && P.key.col >= 0;
   const bool eager_key = P.eager_key;
   if (has_key && eager_key) {
-    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, valid);
-    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, valid);
+    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, valid, pol);
+    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, valid, pol);
   }
 
-  uint32_t pass = eval_filter<FULL>(P.filter, cols, row0, nthr, valid);
+  uint32_t pass = eval_filter<FULL>(P.filter, cols, row0, nthr, valid, pol);
 
   if (has_key && !eager_key) {
-    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, pass);
-    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, pass);
+    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, pass, pol);
+    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, pass, pol);
   }
 
   /* ---- group index ---- */
@@ -444,6 +467,8 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     const int op = acc.op;
     int64_t* garr = Lh.accs[a];
     int8_t* tab = (MODE == MODE_SMEM) ? my_tab + A.smem.acc_off[a] : nullptr;
+    /* flags array when THIS accumulator carries the touched flag for the global-table kernels */
+    uint8_t* pig = (MODE != MODE_SMEM && P.touch_piggyback == a) ? reinterpret_cast<uint8_t*>(Lh.accs[P.touch_acc]) : nullptr;
 
     if (op == ACC_COUNT && acc.col < 0) { /* COUNT(*) */
       if (WAGG) {
@@ -454,7 +479,24 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         for (int j = 0; j < R; ++j) if (pass >> j & 1) atomicAdd(reinterpret_cast<uint32_t*>(tab) + e[j], 1u);
       } else {
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (pass >> j & 1) red_add_u64(garr + e[j], 1ull);
+        for (int j = 0; j < R; ++j) if (pass >> j & 1) global_split_add_touch(garr, pig, e[j], P.key.entry_count, 1u, 0, pol_tab);
+      }
+      continue;
+    }
+
+    if (op == ACC_TOUCH) { /* "a row reached this group": a byte flag, set at most once per thread view */
+      if (MODE == MODE_SMEM) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (pass >> j & 1) reinterpret_cast<uint8_t*>(tab)[e[j]] = 1;
+      } else if (P.touch_piggyback < 0) {
+        uint8_t* flags = reinterpret_cast<uint8_t*>(garr);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          if (!(pass >> j & 1)) continue;
+          uint32_t w;
+          asm volatile("ld.global.ca.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(w) : "l"(flags + e[j]), "l"(pol_tab)); /* a stale 0 only costs a redundant store */
+          if (!w) flags[e[j]] = 1;
+        }
       }
       continue;
     }
@@ -463,7 +505,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     if (narrow) {
       /* 1/2/4-byte integer argument: 32-bit registers */
       int32_t v[R];
-      load32<true>(v, cols[acc.col], acc.width, row0, nthr, arg_mask);
+      load32<true>(v, cols[acc.col], acc.width, row0, nthr, arg_mask, pol);
       const uint32_t m = not_skipped32(acc, v, pass);
       if (WAGG) {
         if (op == ACC_COUNT) {
@@ -496,17 +538,17 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, e[j], (int64_t)v[j]);
+        for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, pig, e[j], P.key.entry_count, (int64_t)v[j], pol_tab);
       }
       continue;
     }
 
     /* 8-byte argument (BIGINT or DOUBLE), or a narrow column feeding a double aggregate (not produced by the planner) */
     int64_t v[R];
-    if (acc.width == 8) load64<true>(v, cols[acc.col], row0, nthr, arg_mask);
+    if (acc.width == 8) load64<true>(v, cols[acc.col], row0, nthr, arg_mask, pol);
     else {
       int32_t t32[R];
-      load32<true>(t32, cols[acc.col], acc.width, row0, nthr, arg_mask);
+      load32<true>(t32, cols[acc.col], acc.width, row0, nthr, arg_mask, pol);
 #pragma unroll
       for (int j = 0; j < R; ++j) v[j] = t32[j];
     }
@@ -575,7 +617,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, e[j], v[j]);
+      for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, pig, e[j], P.key.entry_count, v[j], pol_tab);
     }
   }
 }
@@ -615,6 +657,13 @@ __global__ void __launch_bounds__(kMaxBlock, 1) b2q_k_scan(const __grid_constant
     my_tab = b2q_smem + (size_t)(warp & (A.smem.replicas - 1)) * rb;
   }
 
+  /* L2 policy for the column stream: it is read exactly once, so mark it evict-first and keep L2 for what is
+   * re-used (the HBM/L2-resident group table of the global-table kernels) */
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  uint64_t pol_tab;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_tab));
+
   /* chunks are visited in increasing order, so the owning fragment is a moving cursor, not a search */
   int frag = 0;
   int64_t frag_first = 0;                                   /* first chunk of `frag` */
@@ -629,9 +678,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) b2q_k_scan(const __grid_constant
     const int64_t base_row = (chunk - frag_first) * chunk_rows;
     const int8_t* const* __restrict__ cols = Lh.col_ptrs + (size_t)frag * P.n_cols;
     if (base_row + chunk_rows <= frag_rows)
-      process_chunk<MODE, WAGG, KEY32, true>(A, cols, base_row + tid, frag_rows, nthr, lane, my_tab);
+      process_chunk<MODE, WAGG, KEY32, true>(A, cols, base_row + tid, frag_rows, nthr, lane, my_tab, pol, pol_tab);
     else
-      process_chunk<MODE, WAGG, KEY32, false>(A, cols, base_row + tid, frag_rows, nthr, lane, my_tab);
+      process_chunk<MODE, WAGG, KEY32, false>(A, cols, base_row + tid, frag_rows, nthr, lane, my_tab, pol, pol_tab);
   }
 
   if (MODE == MODE_SMEM) {
@@ -646,6 +695,12 @@ __global__ void __launch_bounds__(kMaxBlock, 1) b2q_k_scan(const __grid_constant
       const int8_t* base = b2q_smem + A.smem.acc_off[a];
       for (int64_t i = tid; i < n; i += nthr) {
         switch (op) {
+          case ACC_TOUCH: {
+            uint32_t s = 0;
+            for (int r = 0; r < nrep; ++r) s |= reinterpret_cast<const uint8_t*>(base + (size_t)r * rb)[i];
+            if (s) reinterpret_cast<uint8_t*>(garr)[i] = 1;
+            break;
+          }
           case ACC_COUNT:
           case ACC_SUM_I64: {
             uint64_t s = 0;
@@ -698,14 +753,25 @@ __global__ void b2q_k_init(const __grid_constant__ InitArgs A) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.entry_count; i += stride) {
     for (int a = 0; a < A.n_accs; ++a) {
       const int64_t id = b2q_acc_identity(A.ops[a]);
-      A.accs[a][i] = id;
+      if (A.ops[a] == ACC_TOUCH) reinterpret_cast<uint8_t*>(A.accs[a])[i] = 0; else A.accs[a][i] = id;
       if (A.smem_image) {
         int8_t* p = A.smem_image + A.smem.acc_off[a];
-        if (A.smem.acc_bytes[a] == 4) reinterpret_cast<uint32_t*>(p)[i] = 0u; else reinterpret_cast<int64_t*>(p)[i] = id;
+        if (A.smem.acc_bytes[a] == 1) reinterpret_cast<uint8_t*>(p)[i] = 0;
+        else if (A.smem.acc_bytes[a] == 4) reinterpret_cast<uint32_t*>(p)[i] = 0u;
+        else reinterpret_cast<int64_t*>(p)[i] = id;
       }
     }
     if (A.keys) A.keys[i] = B2Q_I64_MAX;
   }
+}
+
+/* split (lo[n] | hi[n]) accumulator -> plain int64[n] (needed before the NCCL merge and by materialise) */
+__global__ void b2q_k_join_split(const int64_t* __restrict__ split, int64_t* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint32_t* lo = reinterpret_cast<const uint32_t*>(split);
+  const int32_t* hi = reinterpret_cast<const int32_t*>(split) + n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (int64_t)(((uint64_t)(uint32_t)hi[i] << 32) + lo[i]);
 }
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -732,7 +798,7 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
       if (touched && L.key_width == 4) key = (int64_t)(int32_t)key;
     } else {
       key = (i == L.null_idx) ? L.key_null_val : L.key_min + i;
-      if (L.touched_acc >= 0) touched = A.accs[L.touched_acc][i] != 0;
+      if (L.touched_acc >= 0) touched = reinterpret_cast<const uint8_t*>(A.accs[L.touched_acc])[i] != 0;
     }
     if (L.has_key_col) {
       if (L.key_width == 4) {
@@ -892,6 +958,16 @@ cudaError_t launch_init(const B2QQuery& q, int64_t* const* accs, int64_t* keys, 
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   b2q_k_init<<<(int)blocks, block, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_join_split(const int64_t* split, int64_t* out, int64_t n, cudaStream_t st) {
+  const int block = 256;
+  int64_t blocks = (n + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  b2q_k_join_split<<<(int)blocks, block, 0, st>>>(split, out, n);
   return cudaGetLastError();
 }
 

@@ -694,7 +694,14 @@ class Planner {
         default: reject(B2Q_ERR_UNSUPPORTED, "aggregate kind");
       }
     }
-    if (grouped_ && !p.keyless_hash && !L.baseline) L.touched_acc = find_or_add_acc(q, make_acc(q, ACC_COUNT, nullptr));
+    if (grouped_ && !p.keyless_hash && !L.baseline) L.touched_acc = find_or_add_acc(q, make_acc(q, ACC_TOUCH, nullptr));
+    g.touch_acc = static_cast<int8_t>(L.touched_acc);
+    g.touch_piggyback = -1;
+    if (L.touched_acc >= 0)
+      for (int a = 0; a < g.n_accs; ++a) {
+        const DevAcc& c = g.accs[a];
+        if ((c.op == ACC_COUNT || c.op == ACC_SUM_I64) && !c.skip1_en && !c.skip2_en) { g.touch_piggyback = static_cast<int8_t>(a); break; }
+      }
   }
 
   void choose_kernel(B2QQuery& q) {
@@ -708,7 +715,7 @@ class Planner {
     for (int pass = 0; pass < 2; ++pass)
       for (int a = 0; a < q.prog.n_accs; ++a) {
         const int op = q.prog.accs[a].op;
-        const int bytes = (op == ACC_COUNT || op == ACC_SUM_I64) ? 4 : 8;
+        const int bytes = op == ACC_TOUCH ? 1 : (op == ACC_COUNT || op == ACC_SUM_I64) ? 4 : 8;
         if ((pass == 0) != (bytes == 8)) continue;
         sm.acc_bytes[a] = bytes;
         sm.acc_off[a] = off;

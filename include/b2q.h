@@ -282,7 +282,7 @@ int32_t b2q_execute_partial(size_t* max_groups_buffer_entry_guess, int32_t is_ag
  * non-grouped layouts), initialised to the identity of its reduction, so the merge of N devices is exactly
  * one all-reduce per array — the device-side replacement of ResultSetStorage::reduce
  * (ResultSetReduction.cpp:203-396, slot op :1496-1566). */
-enum { B2Q_DT_INT64 = 0, B2Q_DT_FLOAT64 = 1 };
+enum { B2Q_DT_INT64 = 0, B2Q_DT_FLOAT64 = 1, B2Q_DT_UINT8 = 2 /* "group touched" flags, merged with MAX */ };
 enum { B2Q_RED_SUM = 0, B2Q_RED_MIN = 1, B2Q_RED_MAX = 2 };
 int32_t b2q_partial_num_arrays(const B2QPartial* p);
 int32_t b2q_partial_array(const B2QPartial* p, int32_t i, void** device_ptr, int64_t* count, int32_t* dtype,
