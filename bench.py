@@ -74,12 +74,13 @@ class ClockSampler:
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.load_start = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -87,15 +88,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples inside [t0, t1] (the timed region); if the region is shorter than the sampling period, the
+        samples of the whole loaded window (warm-up + timed steps) are used and the fact is reported."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [r for ts, r in self.rows if t0 is not None and t0 <= ts <= t1]
+        window = "timed region"
+        if len(inside) < 3:
+            inside = [r for ts, r in self.rows if self.load_start is not None and self.load_start <= ts <= (t1 or ts)]
+            window = "warm-up + timed region (timed region shorter than 3 sampling periods)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -105,7 +114,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def np_type(t):
@@ -141,23 +150,6 @@ def build_device_table(cfg, rows, frag_ids, torch):
         table.add_device_fragment(m, ptrs, stats, fragment_id=fid)
     torch.cuda.synchronize()
     return table, keep
-
-
-class CudaArray:
-    """Zero-copy view of a raw device pointer for torch (plumbing for the NCCL all-reduce)."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
-def allreduce_partial(partial, torch, dist):
-    """ResultSetStorage::reduce across devices == one NCCL all-reduce per dense accumulator array."""
-    from heavydb_b200 import abi
-    for ptr, n, dt, op in partial.arrays():
-        typestr = {abi.DT_FLOAT64: "<f8", abi.DT_INT64: "<i8", abi.DT_UINT8: "|u1"}[dt]
-        t = torch.as_tensor(CudaArray(ptr, n, typestr), device="cuda")
-        rop = {abi.RED_SUM: dist.ReduceOp.SUM, abi.RED_MIN: dist.ReduceOp.MIN, abi.RED_MAX: dist.ReduceOp.MAX}[op]
-        dist.all_reduce(t, op=rop)
 
 
 def run_reference(args):
@@ -246,7 +238,7 @@ def main():
         return run_reference(args)
 
     import torch
-    from heavydb_b200 import abi, build, executor
+    from heavydb_b200 import abi, build, executor, multigpu
     from heavydb_b200 import sqlmini
     build.build()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -265,7 +257,7 @@ def main():
     names = [c[0] for c in cols]
     rows = args.rows
     nfrag_per_rank = (rows + FRAG_ROWS - 1) // FRAG_ROWS
-    frag_ids = [rank + i * world for i in range(nfrag_per_rank)]  # fragment_id % num_devices == rank
+    frag_ids = multigpu.shard_fragments(range(nfrag_per_rank * world), rank, world)  # fragment_id % num_devices == rank
     table, keep = build_device_table(args.config, rows, frag_ids, torch)
     unit = sqlmini.parse(sql, table, names)
     ex = executor.Executor()
@@ -278,16 +270,20 @@ def main():
 
     scan_ms, step_ms = [], []
     sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)  # let nvidia-smi come up so that samples exist for a millisecond-scale timed region
     result_rows = None
+    t_begin = t_end = None
+    sampler.load_start = time.time()
     for i in range(args.warmup + args.steps):
-        if i == args.warmup:
-            sampler.start()
         barrier()
+        if i == args.warmup:
+            t_begin = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         part = ex.executePartial(0, True, table, unit, eo=eo, memory_level=abi.GPU_LEVEL)
         if dist is not None:
-            allreduce_partial(part, torch, dist)
+            multigpu.allreduce_partial(part, torch, dist)
         rs = part.finalize()
         e1.record()
         barrier()
@@ -297,10 +293,11 @@ def main():
         if i >= args.warmup:
             step_ms.append(float(t.item()))
             scan_ms.append(part.kernel_ms())
+        t_end = time.time()
         result_rows = rs.rowCount()
         plan_kernel, plan_entries = int(rs.getQueryMemDesc().kernel), int(rs.getQueryMemDesc().entry_count)
         del rs, part
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     ms = float(np.mean(step_ms))
     total_rows = rows * world
     value = total_rows / (ms / 1e3)

@@ -1,0 +1,207 @@
+/*
+ * b2q_executor.hpp — C++ host-side mirror of the reference's operator interface for this path, header-only, over the
+ * C ABI of b2q.h.  Names, argument order and error behaviour follow the reference so that a test written against
+ * it reads like Tests/GroupByTest.cpp:73-152 (which builds a RelAlgExecutionUnit by hand and calls
+ * executor->executeWorkUnit(...) directly):
+ *
+ *   Executor::executeWorkUnit(size_t& max_groups_buffer_entry_guess, const bool is_agg,
+ *                             const std::vector<InputTableInfo>&, const RelAlgExecutionUnit&,
+ *                             const CompilationOptions&, const ExecutionOptions&, RenderInfo*,
+ *                             const bool has_cardinality_estimation, ColumnCacheMap&)      (Execute.h:719-727)
+ *   ResultSet::rowCount / colCount / getColType / getNextRow / isEmpty / entryCount       (ResultSet.h:183-330)
+ *   exceptions: QueryExecutionError(code), CardinalityEstimationRequired, QueryNotSupported
+ *
+ * Only marshalling happens here; all computation is in libb2q (CUDA).  Link with -lb2q.
+ */
+#pragma once
+#include <cstdint>
+#include <list>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b2q.h"
+
+namespace b2q {
+
+/* ---- SQLTypeInfo / enums: the reference's own values ---- */
+enum SQLTypes { kINT = B2Q_kINT, kSMALLINT = B2Q_kSMALLINT, kDOUBLE = B2Q_kDOUBLE, kBIGINT = B2Q_kBIGINT, kTINYINT = B2Q_kTINYINT };
+enum SQLOps { kEQ = B2Q_kEQ, kNE = B2Q_kNE, kLT = B2Q_kLT, kGT = B2Q_kGT, kLE = B2Q_kLE, kGE = B2Q_kGE, kAND = B2Q_kAND, kOR = B2Q_kOR };
+enum SQLAgg { kAVG = B2Q_kAVG, kMIN = B2Q_kMIN, kMAX = B2Q_kMAX, kSUM = B2Q_kSUM, kCOUNT = B2Q_kCOUNT };
+enum class ExecutorDeviceType { CPU = B2Q_DEVICE_CPU, GPU = B2Q_DEVICE_GPU };
+
+struct SQLTypeInfo {
+  SQLTypes type{kBIGINT};
+  bool notnull{false};
+  SQLTypeInfo() = default;
+  SQLTypeInfo(SQLTypes t, bool nn) : type(t), notnull(nn) {}
+  SQLTypes get_type() const { return type; }
+  bool get_notnull() const { return notnull; }
+};
+
+/* ---- exceptions that cross the reference's boundary ---- */
+struct QueryExecutionError : std::runtime_error { /* ExecutionKernel.cpp:133-160 */
+  int32_t code;
+  QueryExecutionError(int32_t c, const std::string& m) : std::runtime_error(m), code(c) {}
+  int32_t getErrorCode() const { return code; }
+};
+struct CardinalityEstimationRequired : QueryExecutionError { using QueryExecutionError::QueryExecutionError; };
+struct QueryNotSupported : QueryExecutionError { using QueryExecutionError::QueryExecutionError; };
+
+/* ---- Analyzer:: expression subset; nodes are owned by the RelAlgExecutionUnit they are built into ---- */
+using ExprRef = int32_t;
+
+struct RelAlgExecutionUnit { /* RelAlgExecutionUnit.h:166-216 */
+  std::vector<B2QExpr> exprs;
+  std::list<ExprRef> simple_quals;
+  std::list<ExprRef> quals;
+  std::list<ExprRef> groupby_exprs; /* empty == the reference's {nullptr} (non-grouped) */
+  std::vector<ExprRef> target_exprs;
+  size_t scan_limit{0};
+  /* features outside this path: anything non-zero is rejected by the library */
+  int32_t num_join_quals{0}, has_estimator{0}, num_order_entries{0}, has_union_all{0}, has_window_function{0};
+
+  ExprRef makeColumnVar(const SQLTypeInfo& ti, int32_t column_id) {
+    B2QExpr e{};
+    e.kind = B2Q_EXPR_COLUMN_VAR; e.ti = {ti.type, ti.notnull}; e.col_id = column_id; e.left = e.right = -1;
+    exprs.push_back(e);
+    return static_cast<ExprRef>(exprs.size() - 1);
+  }
+  ExprRef makeConstant(int64_t v) {
+    B2QExpr e{};
+    e.kind = B2Q_EXPR_CONSTANT; e.ti = {B2Q_kBIGINT, 1}; e.ival = v; e.left = e.right = -1;
+    exprs.push_back(e);
+    return static_cast<ExprRef>(exprs.size() - 1);
+  }
+  ExprRef makeConstant(double v) {
+    B2QExpr e{};
+    e.kind = B2Q_EXPR_CONSTANT; e.ti = {B2Q_kDOUBLE, 1}; e.dval = v; e.left = e.right = -1;
+    exprs.push_back(e);
+    return static_cast<ExprRef>(exprs.size() - 1);
+  }
+  ExprRef makeBinOper(SQLOps op, ExprRef l, ExprRef r) { /* Analyzer::BinOper(kBOOLEAN, op, kONE, l, r) */
+    B2QExpr e{};
+    e.kind = B2Q_EXPR_BIN_OPER; e.ti = {B2Q_kTINYINT, 0}; e.op = op; e.left = l; e.right = r;
+    exprs.push_back(e);
+    return static_cast<ExprRef>(exprs.size() - 1);
+  }
+  ExprRef makeAggExpr(const SQLTypeInfo& ti, SQLAgg agg, ExprRef arg /* -1 = COUNT(*) */) { /* Analyzer::AggExpr */
+    B2QExpr e{};
+    e.kind = B2Q_EXPR_AGG; e.ti = {ti.type, ti.notnull}; e.op = agg; e.left = arg; e.right = -1;
+    exprs.push_back(e);
+    return static_cast<ExprRef>(exprs.size() - 1);
+  }
+};
+
+/* ---- InputTableInfo: Fragmenter::FragmentInfo + chunk stats + the column pointers ColumnFetcher returns ---- */
+struct ChunkStats { int64_t int_min{0}, int_max{-1}; double fp_min{0}, fp_max{-1}; bool has_nulls{false}; };
+struct FragmentInfo {
+  int fragmentId{0};
+  int deviceId{0};
+  size_t numTuples{0};
+  std::vector<const void*> col_buffers; /* [num_cols] */
+  std::vector<ChunkStats> chunkStats;   /* [num_cols] */
+};
+enum class MemoryLevel { CPU_LEVEL = B2Q_CPU_LEVEL, GPU_LEVEL = B2Q_GPU_LEVEL };
+struct InputTableInfo {
+  std::vector<SQLTypeInfo> col_types;
+  std::vector<FragmentInfo> fragments;
+  MemoryLevel memory_level{MemoryLevel::GPU_LEVEL};
+};
+
+struct CompilationOptions { /* CompilationOptions.h:31-66 */
+  ExecutorDeviceType device_type{ExecutorDeviceType::GPU};
+  bool hoist_literals{true};
+  static CompilationOptions defaults(ExecutorDeviceType dt = ExecutorDeviceType::GPU) { return CompilationOptions{dt, true}; }
+};
+struct ExecutionOptions { /* CompilationOptions.h:70-122 */
+  bool allow_multifrag{true};
+  bool output_columnar_hint{false};
+  bool bigint_count{false}; /* g_bigint_count */
+  static ExecutionOptions defaults() { return ExecutionOptions{}; }
+};
+struct RenderInfo;              /* unused on this path */
+struct ColumnCacheMap {};       /* unused on this path */
+
+using TargetValue = B2QTargetValue; /* ScalarTargetValue for the numeric subset */
+
+class ResultSet {
+ public:
+  explicit ResultSet(B2QResultSet* h) : h_(h) {}
+  ~ResultSet() { b2q_rs_free(h_); }
+  ResultSet(const ResultSet&) = delete;
+  ResultSet& operator=(const ResultSet&) = delete;
+  size_t rowCount() const { return b2q_rs_row_count(h_); }
+  size_t colCount() const { return b2q_rs_col_count(h_); }
+  size_t entryCount() const { return b2q_rs_entry_count(h_); }
+  bool isEmpty() const { return b2q_rs_is_empty(h_) != 0; }
+  bool definitelyHasNoRows() const { return isEmpty(); }
+  SQLTypeInfo getColType(size_t i) const { auto t = b2q_rs_get_col_type(h_, i); return SQLTypeInfo(static_cast<SQLTypes>(t.type), t.notnull != 0); }
+  void moveToBegin() const { b2q_rs_move_to_begin(h_); }
+  std::vector<TargetValue> getNextRow(const bool /*translate_strings*/, const bool /*decimal_to_double*/) const {
+    std::vector<TargetValue> row(colCount());
+    if (!b2q_rs_get_next_row(h_, row.data())) row.clear();
+    return row;
+  }
+  bool isRowAtEmpty(size_t i) const { return b2q_rs_is_row_at_empty(h_, i) != 0; }
+  const int8_t* getUnderlyingBuffer(size_t* size_bytes) const { return b2q_rs_storage_buffer(h_, size_bytes); }
+  const B2QPlan& getQueryMemDesc() const { return *b2q_rs_query_mem_desc(h_); }
+ private:
+  B2QResultSet* h_;
+};
+using ResultSetPtr = std::shared_ptr<ResultSet>;
+
+class Executor {
+ public:
+  ResultSetPtr executeWorkUnit(size_t& max_groups_buffer_entry_guess, const bool is_agg,
+                               const std::vector<InputTableInfo>& query_infos, const RelAlgExecutionUnit& ra_exe_unit,
+                               const CompilationOptions& co, const ExecutionOptions& options, RenderInfo* /*render_info*/,
+                               const bool has_cardinality_estimation, ColumnCacheMap& /*column_cache*/) {
+    if (query_infos.size() != 1) throw QueryNotSupported(B2Q_ERR_UNSUPPORTED, "exactly one input table on this path");
+    const InputTableInfo& ti = query_infos.front();
+    /* flatten to the POD structs of the C ABI */
+    std::vector<B2QTypeInfo> col_types;
+    for (const auto& t : ti.col_types) col_types.push_back({t.type, t.notnull});
+    const int nc = static_cast<int>(col_types.size());
+    std::vector<std::vector<B2QChunkStats>> stats(ti.fragments.size());
+    std::vector<B2QFragmentInfo> frags(ti.fragments.size());
+    for (size_t f = 0; f < ti.fragments.size(); ++f) {
+      const FragmentInfo& fi = ti.fragments[f];
+      stats[f].resize(nc);
+      for (int c = 0; c < nc; ++c) {
+        const ChunkStats& s = fi.chunkStats[c];
+        stats[f][c] = B2QChunkStats{s.int_min, s.int_max, s.fp_min, s.fp_max, s.has_nulls ? 1 : 0, 0};
+      }
+      frags[f] = B2QFragmentInfo{fi.fragmentId, fi.deviceId, static_cast<int64_t>(fi.numTuples), fi.col_buffers.data(), stats[f].data()};
+    }
+    B2QTableInfo tbl{nc, col_types.data(), static_cast<int32_t>(frags.size()), frags.data(), static_cast<int32_t>(ti.memory_level), 0};
+    std::vector<int32_t> sq(ra_exe_unit.simple_quals.begin(), ra_exe_unit.simple_quals.end());
+    std::vector<int32_t> q(ra_exe_unit.quals.begin(), ra_exe_unit.quals.end());
+    std::vector<int32_t> g(ra_exe_unit.groupby_exprs.begin(), ra_exe_unit.groupby_exprs.end());
+    B2QExecUnit u{};
+    u.exprs = ra_exe_unit.exprs.data(); u.num_exprs = static_cast<int32_t>(ra_exe_unit.exprs.size());
+    u.simple_quals = sq.data(); u.num_simple_quals = static_cast<int32_t>(sq.size());
+    u.quals = q.data(); u.num_quals = static_cast<int32_t>(q.size());
+    u.groupby_exprs = g.data(); u.num_groupby_exprs = static_cast<int32_t>(g.size());
+    u.target_exprs = ra_exe_unit.target_exprs.data(); u.num_target_exprs = static_cast<int32_t>(ra_exe_unit.target_exprs.size());
+    u.scan_limit = static_cast<int64_t>(ra_exe_unit.scan_limit);
+    u.num_join_quals = ra_exe_unit.num_join_quals; u.has_estimator = ra_exe_unit.has_estimator;
+    u.num_order_entries = ra_exe_unit.num_order_entries; u.has_union_all = ra_exe_unit.has_union_all;
+    u.has_window_function = ra_exe_unit.has_window_function;
+    B2QCompilationOptions cco{static_cast<int32_t>(co.device_type), co.hoist_literals ? 1 : 0};
+    B2QExecutionOptions ceo{options.allow_multifrag ? 1 : 0, options.output_columnar_hint ? 1 : 0, options.bigint_count ? 1 : 0, 0, -1, 0};
+    B2QResultSet* rs = nullptr;
+    const int32_t rc = b2q_execute_work_unit(&max_groups_buffer_entry_guess, is_agg ? 1 : 0, &tbl, &u, &cco, &ceo,
+                                             has_cardinality_estimation ? 1 : 0, &rs);
+    if (rc != B2Q_OK) {
+      const std::string msg = std::string(b2q_error_string(rc)) + ": " + b2q_last_error_message();
+      if (rc == B2Q_ERR_CARDINALITY_ESTIMATION_REQUIRED) throw CardinalityEstimationRequired(rc, msg);
+      if (rc == B2Q_ERR_UNSUPPORTED) throw QueryNotSupported(rc, msg);
+      throw QueryExecutionError(rc, msg);
+    }
+    return std::make_shared<ResultSet>(rs);
+  }
+};
+
+}  // namespace b2q

@@ -1,0 +1,31 @@
+"""The C++ mirror of the reference interface (include/b2q_executor.hpp) compiles against the C ABI (checked on CPU) and
+— on a GPU box — passes the GroupByTest-shaped boundary test (tests/cpp/test_executor_boundary.cpp)."""
+import os
+import subprocess
+
+import pytest
+
+from heavydb_b200 import build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _compile(tmp_path):
+    lib = build.build()
+    exe = tmp_path / "test_executor_boundary"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_executor_boundary.cpp"), "-o", str(exe),
+                           lib, f"-Wl,-rpath,{os.path.dirname(lib)}"])
+    return exe
+
+
+def test_cpp_mirror_compiles_and_links(tmp_path):
+    assert _compile(tmp_path).exists()
+
+
+@pytest.mark.gpu
+def test_cpp_boundary_like_groupbytest(tmp_path):
+    exe = _compile(tmp_path)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "boundary test ok" in out.stdout
