@@ -304,6 +304,14 @@ def main():
     k_ms = float(np.mean(scan_ms))
     peak, peak_src = measured_peak()
     achieved = rows * bytes_per_row / (k_ms / 1e3) / 1e9
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.config)
+        if tr:
+            traffic = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) * (rows / tr["rows"])
+            traffic_src = f"{tr['source']} (ncu --set full, {tr['rows']} rows/launch, scaled to {rows})"
+    except Exception:
+        pass
     out = {
         "metric": "rows/sec and HBM GB/s on 1e9-row filter+groupby",
         "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -313,7 +321,8 @@ def main():
                    "fragment_rows": FRAG_ROWS, "kernel": plan_kernel, "entry_count": plan_entries,
                    "groups_out": int(result_rows), "l2": "inputs larger than L2"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "b2q_k_scan", "kernel_ms": k_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": rows * bytes_per_row,
+                     "peak_source": peak_src, "kernel": "b2q_k_scan", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_row": bytes_per_row},
         "clocks": clocks,
         "gpu_launches": 3 * args.steps,  # per step: b2q_k_init, b2q_k_scan, b2q_k_materialize

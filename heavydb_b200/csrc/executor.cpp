@@ -116,7 +116,7 @@ struct B2QPartial {
   cudaEvent_t ev[4] = {}; /* init begin/end, scan begin/end */
   bool scan_timed = false;
   double scan_ms = 0, init_ms = 0, h2d_bytes = 0;
-  int64_t launches = 0;
+  int64_t launches = 0, frags_scanned = 0, frags_skipped = 0;
   ~B2QPartial() {
     for (void* x : extra) cudaFreeAsync(x, nullptr);
     blk.release(nullptr);
@@ -169,7 +169,8 @@ struct B2QResultSet {
   size_t buf_size = 0, buf_cap = 0;
   int64_t cursor = 0;
   int64_t cached_rows = -1;
-  double scan_ms = 0, init_ms = 0, mat_ms = 0;
+  double scan_ms = 0, init_ms = 0, mat_ms = 0, h2d_bytes = 0;
+  int64_t launches = 0, frags_scanned = 0, frags_skipped = 0;
   ~B2QResultSet() { pinned_cache().put(buf, buf_cap); }
 };
 
@@ -265,9 +266,11 @@ static void collect_timings(B2QPartial& p) {
   cudaGetLastError();
 }
 
+static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr);
+
 /* host-resident table: stream the referenced columns through two staging buffer sets so that the H2D copy of
  * slice k+1 overlaps the scan of slice k (the reference does the H2D in fetchChunks, unpipelined). */
-static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, cudaStream_t st) {
+static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2QExecUnit& u, cudaStream_t st) {
   const B2QQuery& q = p.q;
   const int nc = q.prog.n_cols;
   const int64_t slice_rows = int64_t(1) << 24; /* 16 Mi rows per slice */
@@ -309,9 +312,12 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, cudaStrea
   /* per-slice launch tables live in one device allocation, written once up front */
   struct Slice { int frag; int64_t row0, rows; };
   std::vector<Slice> slices;
-  for (int f = 0; f < tbl.num_fragments; ++f)
+  for (int f = 0; f < tbl.num_fragments; ++f) {
+    if (skip_fragment(u, tbl, tbl.fragments[f])) { p.frags_skipped += 1; continue; }
+    p.frags_scanned += 1;
     for (int64_t r = 0; r < tbl.fragments[f].num_tuples; r += cap_rows)
       slices.push_back({f, r, std::min<int64_t>(cap_rows, tbl.fragments[f].num_tuples - r)});
+  }
   const size_t ns = slices.size();
   if (ns == 0) { cleanup(); return B2Q_OK; }
   std::vector<const int8_t*> h_cols(ns * nc);
@@ -370,6 +376,52 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, cudaStrea
   return rc;
 }
 
+/* Executor::skipFragment (QueryEngine/Execute.cpp:4776-4935): a fragment whose chunk min/max cannot satisfy one of
+ * the simple quals (`col OP const`, AND-ed) is never scanned — and, for host-resident tables, never copied. */
+static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr) {
+  if (fr.num_tuples == 0) return true;
+  for (int i = 0; i < u.num_simple_quals; ++i) {
+    const int qi = u.simple_quals[i];
+    if (qi < 0 || qi >= u.num_exprs) return false;
+    const B2QExpr& q = u.exprs[qi];
+    if (q.kind != B2Q_EXPR_BIN_OPER) return false;
+    if (q.left < 0 || q.left >= u.num_exprs || q.right < 0 || q.right >= u.num_exprs) return false;
+    const B2QExpr& l = u.exprs[q.left];
+    const B2QExpr& c = u.exprs[q.right];
+    if (l.kind != B2Q_EXPR_COLUMN_VAR) continue;
+    if (c.kind != B2Q_EXPR_CONSTANT) return false;
+    if (c.is_null || l.col_id < 0 || l.col_id >= tbl.num_cols) continue;
+    const B2QChunkStats& st = fr.col_stats[l.col_id];
+    const bool col_fp = tbl.col_types[l.col_id].type == B2Q_kDOUBLE;
+    const bool const_fp = c.ti.type == B2Q_kDOUBLE;
+    if (col_fp) { /* canSkipFragmentForFpQual (Execute.cpp:4700-4774) */
+      const double mn = st.fp_min, mx = st.fp_max, v = const_fp ? c.dval : static_cast<double>(c.ival);
+      if (mn > mx) return false;
+      switch (q.op) {
+        case B2Q_kGE: if (mx < v) return true; break;
+        case B2Q_kGT: if (mx <= v) return true; break;
+        case B2Q_kLE: if (mn > v) return true; break;
+        case B2Q_kLT: if (mn >= v) return true; break;
+        case B2Q_kEQ: if (mn > v || mx < v) return true; break;
+        default: break;
+      }
+      continue;
+    }
+    if (const_fp) continue; /* integer column against an fp literal: not considered */
+    const int64_t mn = st.int_min, mx = st.int_max, v = c.ival;
+    if (mn > mx) return false;
+    switch (q.op) {
+      case B2Q_kGE: if (mx < v) return true; break;
+      case B2Q_kGT: if (mx <= v) return true; break;
+      case B2Q_kLE: if (mn > v) return true; break;
+      case B2Q_kLT: if (mn >= v) return true; break;
+      case B2Q_kEQ: if (mn > v || mx < v) return true; break;
+      default: break;
+    }
+  }
+  return false;
+}
+
 static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, const B2QExecUnit* u,
                                     const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card,
                                     cudaStream_t st, B2QPartial** out) {
@@ -389,23 +441,25 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
   const B2QQuery& q = p->q;
   if (tbl->memory_level == B2Q_GPU_LEVEL) {
     /* multi-fragment launch: one kernel over every fragment handed to this device (Execute.cpp:3075-3101) */
-    const int nf = tbl->num_fragments;
-    std::vector<const int8_t*> cols(static_cast<size_t>(nf) * q.prog.n_cols);
-    std::vector<int64_t> rows(nf);
-    for (int f = 0; f < nf; ++f) {
-      rows[f] = tbl->fragments[f].num_tuples;
+    std::vector<const int8_t*> cols;
+    std::vector<int64_t> rows;
+    for (int f = 0; f < tbl->num_fragments; ++f) {
+      if (skip_fragment(*u, *tbl, tbl->fragments[f])) { p->frags_skipped += 1; continue; }
+      p->frags_scanned += 1;
+      rows.push_back(tbl->fragments[f].num_tuples);
       for (int c = 0; c < q.prog.n_cols; ++c) {
         const void* ptr = tbl->fragments[f].col_buffers[q.col_ids[c]];
-        if (!ptr && rows[f] > 0) return set_err(B2Q_ERR_INVALID_ARGUMENT, "referenced column has a NULL buffer");
-        cols[static_cast<size_t>(f) * q.prog.n_cols + c] = static_cast<const int8_t*>(ptr);
+        if (!ptr) return set_err(B2Q_ERR_INVALID_ARGUMENT, "referenced column has a NULL buffer");
+        cols.push_back(static_cast<const int8_t*>(ptr));
       }
     }
+    const int nf = static_cast<int>(rows.size());
     if (nf > 0) {
       rc = scan_device_fragments(*p, nf, cols, rows, st, true);
       if (rc != B2Q_OK) return rc;
     }
   } else if (tbl->memory_level == B2Q_CPU_LEVEL) {
-    rc = scan_host_table(*p, *tbl, st);
+    rc = scan_host_table(*p, *tbl, *u, st);
     if (rc != B2Q_OK) return rc;
   } else {
     return set_err(B2Q_ERR_INVALID_ARGUMENT, "memory_level must be B2Q_CPU_LEVEL or B2Q_GPU_LEVEL");
@@ -428,6 +482,10 @@ static int32_t finalize_impl(B2QPartial* p, cudaStream_t st, B2QResultSet** out)
   rs->q = p->q;
   rs->scan_ms = p->scan_ms;
   rs->init_ms = p->init_ms;
+  rs->h2d_bytes = p->h2d_bytes;
+  rs->launches = p->launches + 2; /* + b2q_k_init + b2q_k_materialize */
+  rs->frags_scanned = p->frags_scanned;
+  rs->frags_skipped = p->frags_skipped;
   const size_t nbytes = static_cast<size_t>(p->q.plan.buffer_size);
   rs->buf_size = nbytes;
   if (nbytes) {
@@ -662,6 +720,16 @@ const int8_t* b2q_rs_storage_buffer(const B2QResultSet* rs, size_t* size_bytes) 
 }
 const B2QPlan* b2q_rs_query_mem_desc(const B2QResultSet* rs) { return rs ? &rs->q.plan : nullptr; }
 double b2q_rs_kernel_ms(const B2QResultSet* rs) { return rs ? rs->scan_ms : 0; }
+int64_t b2q_rs_stat(const B2QResultSet* rs, int32_t which) {
+  if (!rs) return -1;
+  switch (which) {
+    case B2Q_STAT_FRAGMENTS_SCANNED: return rs->frags_scanned;
+    case B2Q_STAT_FRAGMENTS_SKIPPED: return rs->frags_skipped;
+    case B2Q_STAT_KERNEL_LAUNCHES: return rs->launches;
+    case B2Q_STAT_H2D_BYTES: return static_cast<int64_t>(rs->h2d_bytes);
+    default: return -1;
+  }
+}
 void b2q_rs_free(B2QResultSet* rs) { delete rs; }
 
 int32_t b2q_gen_column(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count,

@@ -105,6 +105,8 @@ def lib():
         L.b2q_rs_kernel_ms.restype = C.c_double
         L.b2q_rs_kernel_ms.argtypes = [C.c_void_p]
         L.b2q_rs_free.argtypes = [C.c_void_p]
+        L.b2q_rs_stat.restype = C.c_int64
+        L.b2q_rs_stat.argtypes = [C.c_void_p, C.c_int32]
         L.b2q_gen_column.restype = C.c_int32
         L.b2q_gen_column.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
                                      C.c_int64, C.c_void_p]
@@ -206,6 +208,11 @@ class ResultSet:
 
     def kernel_ms(self) -> float:
         return lib().b2q_rs_kernel_ms(self._h)
+
+    def stats(self) -> dict:
+        L = lib()
+        return {"fragments_scanned": L.b2q_rs_stat(self._h, 0), "fragments_skipped": L.b2q_rs_stat(self._h, 1),
+                "kernel_launches": L.b2q_rs_stat(self._h, 2), "h2d_bytes": L.b2q_rs_stat(self._h, 3)}
 
 
 class Partial:

@@ -319,6 +319,10 @@ int32_t b2q_rs_is_row_at_empty(const B2QResultSet* rs, size_t entry_idx); /* Res
 const int8_t* b2q_rs_storage_buffer(const B2QResultSet* rs, size_t* size_bytes);
 const B2QPlan* b2q_rs_query_mem_desc(const B2QResultSet* rs); /* getQueryMemDesc() */
 double b2q_rs_kernel_ms(const B2QResultSet* rs);
+/* execution statistics of the call that produced the result set */
+enum { B2Q_STAT_FRAGMENTS_SCANNED = 0, B2Q_STAT_FRAGMENTS_SKIPPED = 1 /* Executor::skipFragment, Execute.cpp:4776 */,
+       B2Q_STAT_KERNEL_LAUNCHES = 2, B2Q_STAT_H2D_BYTES = 3 };
+int64_t b2q_rs_stat(const B2QResultSet* rs, int32_t which);
 void b2q_rs_free(B2QResultSet* rs);
 
 /* ---- synthetic data (bench / tests): counter-based generator, identical to oracle/oracle_gen.h ----------

@@ -309,3 +309,27 @@ def test_full_size_properties_2e8_rows():
     unit = sqlmini.parse("SELECT g, SUM(c1), COUNT(*) FROM t WHERE c0 < 500000 GROUP BY g;", host, names)
     got = ex.executeWorkUnit(0, True, pre, unit, memory_level=abi.GPU_LEVEL).rows()
     gu.rows_equal(got, oracle_lib.execute(unit, host, num_threads=8).rows())
+
+
+def test_fragment_skipping_on_chunk_stats():
+    """Executor::skipFragment (Execute.cpp:4776): fragments whose chunk min/max cannot satisfy a simple qual are not
+    scanned (nor copied, for host tables); the answer is unchanged."""
+    t = abi.Table([(abi.kINT, True), (abi.kBIGINT, True), (abi.kDOUBLE, True)])
+    rng = np.random.default_rng(3)
+    for f in range(6):   # disjoint key ranges per fragment: [100 f, 100 f + 99]
+        n = 5000
+        t.add_host_fragment([rng.integers(100 * f, 100 * f + 100, n).astype(np.int32), rng.integers(0, 1000, n),
+                             rng.random(n) + f])
+    names = ["a", "v", "d"]
+    for sql, skipped in [("SELECT COUNT(*), SUM(v) FROM t WHERE a >= 200 AND a < 400;", 4),
+                         ("SELECT a, COUNT(*) FROM t WHERE a = 350 GROUP BY a;", 5),
+                         ("SELECT COUNT(*) FROM t WHERE d > 4.5;", 4),
+                         ("SELECT COUNT(*) FROM t WHERE a > 1000;", 6),
+                         ("SELECT COUNT(*) FROM t WHERE a < 250 OR a > 450;", 0)]:
+        unit = sqlmini.parse(sql, t, names)
+        for resident in (True, False):
+            rs, _ = gu.run_both(unit, t, entry_guess=64, has_card=True, device_resident=resident)
+            st = rs.stats()
+            assert st["fragments_skipped"] == skipped and st["fragments_scanned"] == 6 - skipped, (sql, st)
+            if not resident:
+                assert (st["h2d_bytes"] == 0) == (skipped == 6)
