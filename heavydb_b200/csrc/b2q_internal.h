@@ -96,6 +96,8 @@ struct DevProgram {
   float est_selectivity; /* planner's estimate from chunk stats (uniformity assumption) */
   int8_t eager_key;      /* load the key column for every row, overlapped with the filter columns */
   int8_t eager_args;     /* load aggregate arguments for every row instead of only the passing ones */
+  int8_t col_width[B2Q_MAX_COLS];    /* byte width of launch column c */
+  int8_t col_prefetch[B2Q_MAX_COLS]; /* column is read for (nearly) every row: worth a bulk L2 prefetch ahead of the scan */
   int8_t touch_acc;      /* index of the ACC_TOUCH accumulator, or -1 */
   int8_t touch_piggyback;/* global-table kernels: accumulator (COUNT / SUM_I64 without a skip test) whose returning
                             atomic also maintains the touched flag, or -1 (explicit flag check per row) */

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -31,7 +32,7 @@ int32_t make_query(const B2QExecUnit* u, const B2QTableInfo* t, const B2QExecuti
 int scan_rows_per_chunk(int block);
 void scan_config(const B2QQuery& q, int* block, int* ctas_per_sm);
 cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t* smem_image, int block, int ctas_per_sm,
-                        cudaStream_t st);
+                        int prefetch_distance, cudaStream_t st);
 cudaError_t launch_init(const B2QQuery& q, int64_t* const* accs, int64_t* keys, int8_t* smem_image, cudaStream_t st);
 cudaError_t launch_materialize(const B2QQuery& q, const int64_t* const* accs, const int64_t* keys, int8_t* out,
                                cudaStream_t st);
@@ -57,6 +58,22 @@ static int32_t set_err(int32_t code, const std::string& m) {
                      std::string(#call) + ": " + cudaGetErrorString(e__));                                     \
     }                                                                                                          \
   } while (0)
+
+/* TMA bulk L2 prefetch distance (chunks ahead per CTA); needs 16-byte aligned column pointers.  B2Q_PREFETCH_DISTANCE
+ * overrides the default for experiments (0 disables). */
+static int prefetch_distance_for(const B2QQuery& q, const std::vector<const int8_t*>& cols) {
+  /* measured on B200 (profiles/r1_prefetch_sweep.txt): D=1 helps the shared-memory-table kernels (C2 +2 %, C2-all
+   * +7 %), D>=4 thrashes L2, and the L2-resident-table kernels want L2 for the table, not for the stream */
+  static int env = []() {
+    const char* e = getenv("B2Q_PREFETCH_DISTANCE");
+    return e ? atoi(e) : -1;
+  }();
+  const bool smem_kernel = q.plan.kernel == B2Q_KERNEL_PERFECT_SMEM || q.plan.kernel == B2Q_KERNEL_NON_GROUPED;
+  const int dist = env >= 0 ? env : (smem_kernel ? 1 : 0);
+  if (dist <= 0) return 0;
+  for (const int8_t* p : cols) if (reinterpret_cast<uintptr_t>(p) & 15) return 0;
+  return dist;
+}
 
 static bool have_device() {
   int n = 0;
@@ -234,7 +251,7 @@ static int32_t scan_device_fragments(B2QPartial& p, int nf, const std::vector<co
   L.keys = p.keys;
   L.error = p.d_error;
   if (time_it) CU(cudaEventRecord(p.ev[2], st));
-  CU(launch_scan(q, L, p.smem_image, block, ctas, st));
+  CU(launch_scan(q, L, p.smem_image, block, ctas, prefetch_distance_for(q, cols), st));
   p.launches += 1;
   if (time_it) { CU(cudaEventRecord(p.ev[3], st)); p.scan_timed = true; }
   /* `host` is pageable: the copy above was staged by the runtime before cudaMemcpyAsync returned */
@@ -363,7 +380,7 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
     for (int a = 0; a < q.prog.n_accs; ++a) L.accs[a] = p.accs[a];
     L.keys = p.keys;
     L.error = p.d_error;
-    cudaError_t e = launch_scan(q, L, p.smem_image, block, ctas, st);
+    cudaError_t e = launch_scan(q, L, p.smem_image, block, ctas, 0 /* slices arrive straight from PCIe */, st);
     if (e != cudaSuccess) { rc = set_err(B2Q_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e)); break; }
     p.launches += 1;
     cudaEventRecord(s.scanned, st);

@@ -420,6 +420,7 @@ class Planner {
     for (int i = 0; i < q.prog.n_cols; ++i) if (q.col_ids[i] == table_col) return i;
     if (q.prog.n_cols >= B2Q_MAX_COLS) reject(B2Q_ERR_UNSUPPORTED, "too many referenced columns");
     q.col_ids[q.prog.n_cols] = table_col;
+    q.prog.col_width[q.prog.n_cols] = static_cast<int8_t>(col_type(table_col).size());
     return q.prog.n_cols++;
   }
 
@@ -695,6 +696,11 @@ class Planner {
       }
     }
     if (grouped_ && !p.keyless_hash && !L.baseline) L.touched_acc = find_or_add_acc(q, make_acc(q, ACC_TOUCH, nullptr));
+    /* columns worth prefetching: filter columns always; key / arguments when they are loaded eagerly */
+    for (int t = 0; t < g.filter.n_terms; ++t) g.col_prefetch[g.filter.terms[t].col] = 1;
+    if (grouped_ && g.eager_key) g.col_prefetch[g.key.col] = 1;
+    if (g.eager_args)
+      for (int a = 0; a < g.n_accs; ++a) if (g.accs[a].col >= 0) g.col_prefetch[g.accs[a].col] = 1;
     g.touch_acc = static_cast<int8_t>(L.touched_acc);
     g.touch_piggyback = -1;
     if (L.touched_acc >= 0)
