@@ -50,7 +50,12 @@ CONFIGS = {
            "SELECT g, AVG(v) FROM t WHERE f < 500000 GROUP BY g;", 20, "configs[2]: 256 groups AVG(double)"),
     "c4": ([("key", "i64", 0, 10**7), ("v", "i64", 0, 10**6)],
            "SELECT key, SUM(v) FROM t GROUP BY key;", 16, "configs[3]: 1e7 dense int64 keys SUM (HBM/L2 table)"),
+    # sparse keys (key = U[0,1e7) * 900000000007): the range is too wide for a perfect hash => baseline hash,
+    # open addressing in HBM, entry_count = NDV * 1.5 like RelAlgExecutor's estimator path
+    "c4s": ([("key", "i64", 0, 10**7, 900_000_000_007), ("v", "i64", 0, 10**6)],
+            "SELECT key, SUM(v) FROM t GROUP BY key;", 16, "configs[3] sparse variant: 1e7 sparse int64 keys SUM (global-memory hash table, MurmurHash3 + CAS)"),
 }
+ENTRY_GUESS = {"c4s": 15_000_000}
 
 
 def log(*a):
@@ -126,7 +131,7 @@ def build_device_table(cfg, rows, frag_ids, torch):
     """Generate this rank's fragments directly in HBM with the counter-based generator (global row = frag_id*FRAG_ROWS+i)."""
     from heavydb_b200 import abi, executor
     cols, _, _, _ = CONFIGS[cfg]
-    table = abi.Table([(np_type(t), True) for _, t, _, _ in cols])
+    table = abi.Table([(np_type(c[1]), True) for c in cols])
     keep = []
     remaining = rows
     for fid in frag_ids:
@@ -135,17 +140,19 @@ def build_device_table(cfg, rows, frag_ids, torch):
             break
         remaining -= m
         ptrs, stats = [], []
-        for tag, (_, t, lo, span) in enumerate(cols):
+        for tag, col in enumerate(cols):
+            _, t, lo, span = col[:4]
+            stride = col[4] if len(col) > 4 else 1
             ty = np_type(t)
             buf = torch.empty(m * abi.SIZE_OF[ty], dtype=torch.uint8, device="cuda")
-            executor.gen_column_device(buf.data_ptr(), ty, SEED, tag, fid * FRAG_ROWS, m, lo, span)
+            executor.gen_column_device(buf.data_ptr(), ty, SEED, tag, fid * FRAG_ROWS, m, lo, span, stride=stride)
             keep.append(buf)
             ptrs.append(buf.data_ptr())
             st = abi.ChunkStats()
             if ty == abi.kDOUBLE:
                 st.fp_min, st.fp_max = 0.0, 1.0
             else:
-                st.int_min, st.int_max = lo, lo + span - 1
+                st.int_min, st.int_max = lo, lo + (span - 1) * stride
             stats.append(st)
         table.add_device_fragment(m, ptrs, stats, fragment_id=fid)
     torch.cuda.synchronize()
@@ -165,17 +172,18 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     frag_rows = 1 << 22  # 4 Mi rows per fragment, one fragment per thread (reference: one thread per fragment)
     nfrag = threads
-    table = abi.Table([(np_type(t), True) for _, t, _, _ in cols])
+    table = abi.Table([(np_type(c[1]), True) for c in cols])
     for f in range(nfrag):
-        table.add_host_fragment([oracle_lib.gen_column(np_type(t), SEED, tag, f * frag_rows, frag_rows, lo, span, threads)
-                                 for tag, (_, t, lo, span) in enumerate(cols)])
+        table.add_host_fragment([oracle_lib.gen_column(np_type(c[1]), SEED, tag, f * frag_rows, frag_rows, c[2], c[3], threads,
+                                                       stride=(c[4] if len(c) > 4 else 1)) for tag, c in enumerate(cols)])
     names = [c[0] for c in cols]
     unit = sqlmini.parse(sql, table, names)
     rows = nfrag * frag_rows
+    guess = ENTRY_GUESS.get(args.config, 0)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        res = oracle_lib.execute(unit, table, num_threads=threads)
+        res = oracle_lib.execute(unit, table, entry_guess=guess, has_card=guess > 0, num_threads=threads)
         n_out = res.row_count()
         dt = time.perf_counter() - t0
         if i >= args.warmup:
@@ -204,17 +212,18 @@ def cpu_baseline_sample(cfg, budget_s=15.0):
     threads = os.cpu_count() or 1
     frag_rows = 1 << 22
     nfrag = threads
-    table = abi.Table([(np_type(t), True) for _, t, _, _ in cols])
+    table = abi.Table([(np_type(c[1]), True) for c in cols])
     for f in range(nfrag):
-        table.add_host_fragment([oracle_lib.gen_column(np_type(t), SEED, tag, f * frag_rows, frag_rows, lo, span, threads)
-                                 for tag, (_, t, lo, span) in enumerate(cols)])
+        table.add_host_fragment([oracle_lib.gen_column(np_type(c[1]), SEED, tag, f * frag_rows, frag_rows, c[2], c[3], threads,
+                                                       stride=(c[4] if len(c) > 4 else 1)) for tag, c in enumerate(cols)])
     unit = sqlmini.parse(sql, table, [c[0] for c in cols])
     rows = nfrag * frag_rows
-    oracle_lib.execute(unit, table, num_threads=threads)  # warm
+    guess = ENTRY_GUESS.get(cfg, 0)
+    oracle_lib.execute(unit, table, entry_guess=guess, has_card=guess > 0, num_threads=threads)  # warm
     t0 = time.perf_counter()
     reps = 0
     while reps < 3 or (time.perf_counter() - t0 < budget_s and reps < 50):
-        oracle_lib.execute(unit, table, num_threads=threads)
+        oracle_lib.execute(unit, table, entry_guess=guess, has_card=guess > 0, num_threads=threads)
         reps += 1
     dt = (time.perf_counter() - t0) / reps
     return {"value": rows / dt, "unit": "rows/s", "cores": threads, "kind": "port",
@@ -262,6 +271,7 @@ def main():
     unit = sqlmini.parse(sql, table, names)
     ex = executor.Executor()
     eo = executor.execution_options(force_kernel=args.force_kernel)
+    guess = ENTRY_GUESS.get(args.config, 0)
 
     def barrier():
         if dist is not None:
@@ -281,7 +291,7 @@ def main():
             t_begin = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        part = ex.executePartial(0, True, table, unit, eo=eo, memory_level=abi.GPU_LEVEL)
+        part = ex.executePartial(guess, True, table, unit, eo=eo, has_cardinality_estimation=guess > 0, memory_level=abi.GPU_LEVEL)
         if dist is not None:
             multigpu.allreduce_partial(part, torch, dist)
         rs = part.finalize()
@@ -294,6 +304,7 @@ def main():
             step_ms.append(float(t.item()))
             scan_ms.append(part.kernel_ms())
         t_end = time.time()
+        launches_per_step = rs.stats()["kernel_launches"]
         result_rows = rs.rowCount()
         plan_kernel, plan_entries = int(rs.getQueryMemDesc().kernel), int(rs.getQueryMemDesc().entry_count)
         del rs, part
@@ -325,7 +336,7 @@ def main():
                      "peak_source": peak_src, "kernel": "b2q_k_scan", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_row": bytes_per_row},
         "clocks": clocks,
-        "gpu_launches": 3 * args.steps,  # per step: b2q_k_init, b2q_k_scan, b2q_k_materialize
+        "gpu_launches": int(launches_per_step) * args.steps,  # per step: b2q_k_init, b2q_k_scan (per launch), b2q_k_materialize
     }
     if rank == 0 and world == 1 and not args.no_e2e:
         out["e2e"] = e2e_leg(args, torch, ex, eo, cols, sql, names)
@@ -381,32 +392,35 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
             old_aff = None
     from heavydb_b200 import abi, executor
     from heavydb_b200 import sqlmini
-    bytes_per_row = sum(abi.SIZE_OF[np_type(t)] for _, t, _, _ in cols)
+    bytes_per_row = sum(abi.SIZE_OF[np_type(c[1])] for c in cols)
+    guess = ENTRY_GUESS.get(args.config, 0)
     avail = psutil.virtual_memory().available
     rows = args.e2e_rows or args.rows
     cap = int(avail * 0.4 // bytes_per_row)
     rows = max(FRAG_ROWS, min(rows, cap))
-    table = abi.Table([(np_type(t), True) for _, t, _, _ in cols])
+    table = abi.Table([(np_type(c[1]), True) for c in cols])
     keep = []
     for fi, b in enumerate(range(0, rows, FRAG_ROWS)):
         m = min(FRAG_ROWS, rows - b)
         harrs = []
-        for tag, (_, t, lo, span) in enumerate(cols):
+        for tag, col in enumerate(cols):
+            _, t, lo, span = col[:4]
             ty = np_type(t)
             dev = torch.empty(m * abi.SIZE_OF[ty], dtype=torch.uint8, device="cuda")
-            executor.gen_column_device(dev.data_ptr(), ty, SEED, tag, b, m, lo, span)
+            executor.gen_column_device(dev.data_ptr(), ty, SEED, tag, b, m, lo, span, stride=(col[4] if len(col) > 4 else 1))
             host = torch.empty(m * abi.SIZE_OF[ty], dtype=torch.uint8, pin_memory=True)
             host.copy_(dev)
             keep.append(host)
             harrs.append(host.numpy().view(abi.NUMPY_OF[ty]))
             del dev
         fr = abi.Fragment(m, host_cols=harrs, stats=[], fragment_id=fi)
-        for (_, t, lo, span) in cols:
+        for col in cols:
+            _, t, lo, span = col[:4]
             st = abi.ChunkStats()
             if t == "f64":
                 st.fp_min, st.fp_max = 0.0, 1.0
             else:
-                st.int_min, st.int_max = lo, lo + span - 1
+                st.int_min, st.int_max = lo, lo + (span - 1) * (col[4] if len(col) > 4 else 1)
             fr.stats.append(st)
         table.fragments.append(fr)
     torch.cuda.synchronize()
@@ -419,7 +433,7 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
     for i in range(2 + 3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        rs = ex.executeWorkUnit(0, True, bt, unit, eo=eo, memory_level=abi.CPU_LEVEL)
+        rs = ex.executeWorkUnit(guess, True, bt, unit, eo=eo, has_cardinality_estimation=guess > 0, memory_level=abi.CPU_LEVEL)
         n = rs.rowCount()
         dt = time.perf_counter() - t0
         d2h = int(rs.getQueryMemDesc().buffer_size)

@@ -38,7 +38,7 @@ cudaError_t launch_materialize(const B2QQuery& q, const int64_t* const* accs, co
                                cudaStream_t st);
 cudaError_t launch_join_split(const int64_t* split, int64_t* out, int64_t n, cudaStream_t st);
 cudaError_t launch_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count, int64_t lo,
-                       int64_t span, cudaStream_t st);
+                       int64_t span, int64_t stride, cudaStream_t st);
 }  // namespace b2q
 
 using namespace b2q;
@@ -752,7 +752,14 @@ void b2q_rs_free(B2QResultSet* rs) { delete rs; }
 int32_t b2q_gen_column(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count,
                        int64_t lo, int64_t span, void* stream) {
   if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible");
-  CU(launch_gen(dst, sql_type, seed, col_tag, row0, count, lo, span, static_cast<cudaStream_t>(stream)));
+  CU(launch_gen(dst, sql_type, seed, col_tag, row0, count, lo, span, 1, static_cast<cudaStream_t>(stream)));
+  return B2Q_OK;
+}
+
+int32_t b2q_gen_column_strided(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count,
+                               int64_t lo, int64_t span, int64_t stride, void* stream) {
+  if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible");
+  CU(launch_gen(dst, sql_type, seed, col_tag, row0, count, lo, span, stride, static_cast<cudaStream_t>(stream)));
   return B2Q_OK;
 }
 

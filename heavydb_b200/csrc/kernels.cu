@@ -885,13 +885,13 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 }
 
 __global__ void b2q_k_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count,
-                          int64_t lo, uint64_t span) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+                          int64_t lo, uint64_t span, int64_t key_stride) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += step) {
     const uint64_t u = splitmix64(seed ^ ((uint64_t)col_tag << 56) ^ (uint64_t)(row0 + i));
     switch (sql_type) {
       case B2Q_kDOUBLE: static_cast<double*>(dst)[i] = (double)(u >> 11) * (1.0 / 9007199254740992.0); break;
-      case B2Q_kBIGINT: static_cast<int64_t*>(dst)[i] = lo + (int64_t)(u % span); break;
+      case B2Q_kBIGINT: static_cast<int64_t*>(dst)[i] = lo + (int64_t)(u % span) * key_stride; break;
       case B2Q_kINT: static_cast<int32_t*>(dst)[i] = (int32_t)(lo + (int64_t)(u % span)); break;
       case B2Q_kSMALLINT: static_cast<int16_t*>(dst)[i] = (int16_t)(lo + (int64_t)(u % span)); break;
       default: static_cast<int8_t*>(dst)[i] = (int8_t)(lo + (int64_t)(u % span)); break;
@@ -1020,13 +1020,13 @@ cudaError_t launch_materialize(const B2QQuery& q, const int64_t* const* accs, co
 }
 
 cudaError_t launch_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count, int64_t lo,
-                       int64_t span, cudaStream_t st) {
+                       int64_t span, int64_t stride, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
   const int block = 256;
   int64_t blocks = (count + block - 1) / block;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  b2q_k_gen<<<(int)blocks, block, 0, st>>>(dst, sql_type, seed, col_tag, row0, count, lo, (uint64_t)(span > 0 ? span : 1));
+  b2q_k_gen<<<(int)blocks, block, 0, st>>>(dst, sql_type, seed, col_tag, row0, count, lo, (uint64_t)(span > 0 ? span : 1), stride ? stride : 1);
   return cudaGetLastError();
 }
 

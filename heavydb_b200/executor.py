@@ -110,6 +110,9 @@ def lib():
         L.b2q_gen_column.restype = C.c_int32
         L.b2q_gen_column.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
                                      C.c_int64, C.c_void_p]
+        L.b2q_gen_column_strided.restype = C.c_int32
+        L.b2q_gen_column_strided.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
+                                             C.c_int64, C.c_int64, C.c_void_p]
         if L.b2q_abi_version() != 1:
             raise ImportError("libb2q.so ABI version mismatch")
         _lib = L
@@ -317,7 +320,8 @@ class Executor:
 
 
 def gen_column_device(dst_ptr: int, sql_type: int, seed: int, col_tag: int, row0: int, count: int, lo: int = 0,
-                      span: int = 1, stream: int = 0):
-    rc = lib().b2q_gen_column(C.c_void_p(dst_ptr), sql_type, seed, col_tag, row0, count, lo, span, C.c_void_p(stream))
+                      span: int = 1, stream: int = 0, stride: int = 1):
+    rc = lib().b2q_gen_column_strided(C.c_void_p(dst_ptr), sql_type, seed, col_tag, row0, count, lo, span, stride,
+                                      C.c_void_p(stream))
     if rc:
         _raise(rc)

@@ -331,6 +331,9 @@ void b2q_rs_free(B2QResultSet* rs);
  * Writes `count` elements of `width` bytes starting at global row `row0` into a DEVICE buffer. */
 int32_t b2q_gen_column(void* device_dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
                        int64_t count, int64_t lo, int64_t span, void* cuda_stream);
+/* BIGINT only: value = lo + (u % span) * stride — sparse keys (range too wide for a perfect hash => baseline hash) */
+int32_t b2q_gen_column_strided(void* device_dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
+                               int64_t count, int64_t lo, int64_t span, int64_t stride, void* cuda_stream);
 
 #ifdef __cplusplus
 }

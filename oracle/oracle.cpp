@@ -1233,14 +1233,20 @@ ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue
 }
 
 /* ---- synthetic columns (bench / tests) ---- */
+ORACLE_EXPORT void oracle_gen_column_strided(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
+                                             int64_t count, int64_t lo, int64_t span, int64_t stride, int32_t num_threads);
 ORACLE_EXPORT void oracle_gen_column(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
                                      int64_t count, int64_t lo, int64_t span, int32_t num_threads) {
+  oracle_gen_column_strided(dst, sql_type, seed, col_tag, row0, count, lo, span, 1, num_threads);
+}
+ORACLE_EXPORT void oracle_gen_column_strided(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
+                                             int64_t count, int64_t lo, int64_t span, int64_t stride, int32_t num_threads) {
   auto work = [&](int64_t b, int64_t e) {
     for (int64_t i = b; i < e; ++i) {
       const int64_t row = row0 + i;
       switch (sql_type) {
         case B2Q_kDOUBLE: static_cast<double*>(dst)[i] = oracle_gen_double(seed, col_tag, row); break;
-        case B2Q_kBIGINT: static_cast<int64_t*>(dst)[i] = oracle_gen_int(seed, col_tag, row, lo, span); break;
+        case B2Q_kBIGINT: static_cast<int64_t*>(dst)[i] = lo + (oracle_gen_int(seed, col_tag, row, 0, span)) * stride; break;
         case B2Q_kINT: static_cast<int32_t*>(dst)[i] = static_cast<int32_t>(oracle_gen_int(seed, col_tag, row, lo, span)); break;
         case B2Q_kSMALLINT: static_cast<int16_t*>(dst)[i] = static_cast<int16_t>(oracle_gen_int(seed, col_tag, row, lo, span)); break;
         case B2Q_kTINYINT: static_cast<int8_t*>(dst)[i] = static_cast<int8_t>(oracle_gen_int(seed, col_tag, row, lo, span)); break;

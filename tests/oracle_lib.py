@@ -44,6 +44,8 @@ def lib():
         L.oracle_result_get_next_row.argtypes = [C.c_void_p, C.POINTER(abi.TargetValue)]
         L.oracle_gen_column.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_int32]
+        L.oracle_gen_column_strided.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
+                                                C.c_int64, C.c_int64, C.c_int32]
         _lib = L
     return _lib
 
@@ -131,7 +133,7 @@ def execute(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=False
     return OracleResult(h)
 
 
-def gen_column(sql_type, seed, col_tag, row0, count, lo=0, span=1, threads=8) -> np.ndarray:
+def gen_column(sql_type, seed, col_tag, row0, count, lo=0, span=1, threads=8, stride=1) -> np.ndarray:
     a = np.empty(count, dtype=abi.NUMPY_OF[sql_type])
-    lib().oracle_gen_column(a.ctypes.data, sql_type, seed, col_tag, row0, count, lo, span, threads)
+    lib().oracle_gen_column_strided(a.ctypes.data, sql_type, seed, col_tag, row0, count, lo, span, stride, threads)
     return a

@@ -333,3 +333,13 @@ def test_fragment_skipping_on_chunk_stats():
             assert st["fragments_skipped"] == skipped and st["fragments_scanned"] == 6 - skipped, (sql, st)
             if not resident:
                 assert (st["h2d_bytes"] == 0) == (skipped == 6)
+
+
+def test_strided_generator_matches_oracle():
+    import torch
+    n = 50001
+    want = oracle_lib.gen_column(abi.kBIGINT, SEED, 0, 777, n, 0, 10**7, stride=900_000_000_007)
+    buf = torch.empty(n * 8, dtype=torch.uint8, device="cuda")
+    executor.gen_column_device(buf.data_ptr(), abi.kBIGINT, SEED, 0, 777, n, 0, 10**7, stride=900_000_000_007)
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.cpu().numpy().view(np.int64), want)
