@@ -448,22 +448,40 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       const uint32_t n = (uint32_t)P.key.entry_count;
       const int hw = P.key.hash_key_width;
       unsigned long long* keys = reinterpret_cast<unsigned long long*>(Lh.keys);
+      /* get_group_value (GroupByRuntime.cpp:25-48): h = MurmurHash3(key) % entry_count, linear probe.
+       * Phase 1 puts the home-slot loads of all R rows in flight together (ld.global.cg: L2 is the coherence point,
+       * so a concurrent claim by another SM is visible); phase 2 resolves each row, falling back to the probe loop. */
+      int64_t key[R];
+      uint32_t h[R];
+      unsigned long long first[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        key[j] = KEY32 ? (int64_t)k32[KEY32 ? j : 0] : k64[KEY32 ? 0 : j];
+        h[j] = murmur3_key(key[j], hw) % n;
+      }
+#pragma unroll
+      for (int j = 0; j < R; ++j) first[j] = (pass >> j & 1) ? __ldcg(keys + h[j]) : 0ull;
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         if (!(pass >> j & 1)) continue;
-        const int64_t key = KEY32 ? (int64_t)k32[KEY32 ? j : 0] : k64[KEY32 ? 0 : j];
-        const uint32_t h = murmur3_key(key, hw) % n;
-        uint32_t p = h;
+        const unsigned long long want = (unsigned long long)key[j];
+        uint32_t p = h[j];
+        unsigned long long cur = first[j];
         bool found = false;
-        do { /* get_group_value's linear probe; claim an EMPTY_KEY_64 slot with a 64-bit CAS */
-          unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(keys + p);
-          if (cur == (unsigned long long)B2Q_I64_MAX) cur = atomicCAS(keys + p, (unsigned long long)B2Q_I64_MAX, (unsigned long long)key);
-          if (cur == (unsigned long long)B2Q_I64_MAX || cur == (unsigned long long)key) { found = true; break; }
+        for (;;) { /* claim an EMPTY_KEY_64 slot with a 64-bit CAS; a lost race re-examines the same slot */
+          if (cur == (unsigned long long)B2Q_I64_MAX) cur = atomicCAS(keys + p, (unsigned long long)B2Q_I64_MAX, want);
+          if (cur == (unsigned long long)B2Q_I64_MAX || cur == want) { found = true; break; }
           p = p + 1 == n ? 0 : p + 1;
-        } while (p != h);
+          if (p == h[j]) break;
+          cur = __ldcg(keys + p);
+        }
         if (!found) { atomicCAS(Lh.error, 0, B2Q_ERR_OUT_OF_SLOTS); pass &= ~(1u << j); }
         e[j] = p;
       }
+      /* the probe loops diverge per lane; without an explicit reconvergence the warp stays split for the rest of the
+       * kernel and every following column load is issued lane by lane (ncu: 3.8 active threads per LDG, one 32-B
+       * sector per thread, 23x the algorithmic DRAM traffic) */
+      __syncwarp();
     }
   }
 
