@@ -210,6 +210,7 @@ class Planner {
       const B2QExpr& c = ex(q.right);
       if (l.kind != B2Q_EXPR_COLUMN_VAR || l.col_id != col || c.kind != B2Q_EXPR_CONSTANT) continue;
       const bool cfp = c.ti.type == B2Q_kDOUBLE;
+      if (cfp != r.fp) continue; /* mixed int/fp comparisons are never simple quals in the reference (see sqlmini.py) */
       if (r.fp) {
         const double v = cfp ? c.dval : static_cast<double>(c.ival);
         if (q.op == B2Q_kGT || q.op == B2Q_kGE || q.op == B2Q_kEQ) r.fmin = std::max(r.fmin, v);

@@ -117,6 +117,12 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
         for c in _conjuncts(p.b, e):
             n = p.b.nodes[c]
             simple = n.op not in (abi.kAND, abi.kOR)
+            if simple:
+                # an integer column against an fp literal is `CAST(col AS DOUBLE) OP lit` in the reference; only
+                # int->int / timestamp casts survive BinOper::normalize_simple_predicate, so it is NOT a simple qual
+                col_fp = p.b.nodes[n.left].type == abi.kDOUBLE
+                lit_fp = p.b.nodes[n.right].type == abi.kDOUBLE
+                simple = col_fp == lit_fp
             p.b.add_qual(c, simple=simple)
     if p.peek() and p.peek().upper() == "GROUP":
         p.eat()

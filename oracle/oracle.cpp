@@ -400,6 +400,9 @@ void apply_simple_quals(const B2QExecUnit& u, int key_col_id, Range& r) { /* Exp
     const B2QExpr& l = expr_at(u, q.left);
     const B2QExpr& c = expr_at(u, q.right);
     if (l.kind != B2Q_EXPR_COLUMN_VAR || l.col_id != key_col_id || c.kind != B2Q_EXPR_CONSTANT) continue;
+    /* an int column against an fp literal is CAST(col AS DOUBLE) OP lit in the reference; such casts do not pass
+     * BinOper::normalize_simple_predicate, so the qual never reaches apply_simple_quals */
+    if (is_fp(c.ti.type) != (r.kind == Range::Double)) continue;
     if (r.kind == Range::Double) {
       const double v = is_fp(c.ti.type) ? c.dval : static_cast<double>(c.ival);
       switch (q.op) {

@@ -1,0 +1,84 @@
+"""Randomised query fuzzing on the GPU (`-m gpu`): random AND/OR filter trees, random target lists, random group key,
+over the mixed-type / nullable random table of test_gpu_parity — CUDA path vs oracle, bit-exact integers."""
+import random
+
+import numpy as np
+import pytest
+
+import gpu_util as gu
+from heavydb_b200 import abi, executor, sqlmini
+from test_gpu_parity import RAND_COLS, RAND_NAMES, random_table
+
+pytestmark = pytest.mark.gpu
+
+INT_COLS = [n for n, t, _ in RAND_COLS if t != abi.kDOUBLE and n != "sparse"]
+FP_COLS = ["d", "dnn"]
+KEY_COLS = ["k8", "k16", "k32", "k64", "nn32", "nn64", "a8", "sparse"]
+OPS = ["=", "<>", "<", ">", "<=", ">="]
+LIT = {"k8": (-6, 21), "k16": (90, 410), "k32": (-1100, 1100), "k64": (10**9 - 10, 10**9 + 5010), "nn32": (-5, 305),
+       "nn64": (-55, 55), "a8": (-130, 130), "a16": (-31000, 31000), "a32": (-2**31, 2**31), "a64": (-2**41, 2**41),
+       "big": (-2**62, 2**62)}
+
+
+def rand_cmp(rng):
+    if rng.random() < 0.75:
+        c = rng.choice(INT_COLS)
+        lo, hi = LIT[c]
+        lit = rng.randint(lo, hi)
+        if rng.random() < 0.15:
+            return f"{c} {rng.choice(OPS)} {lit + 0.5}"     # integer column against an fp literal
+        return f"{c} {rng.choice(OPS)} {lit}"
+    c = rng.choice(FP_COLS)
+    lit = rng.uniform(-1500, 1500) if c == "d" else rng.uniform(-0.1, 1.1)
+    return f"{c} {rng.choice(OPS)} {lit:.6f}"
+
+
+def rand_cond(rng, depth=0):
+    if depth >= 2 or rng.random() < 0.4:
+        return rand_cmp(rng)
+    op = rng.choice(["AND", "OR"])
+    a, b = rand_cond(rng, depth + 1), rand_cond(rng, depth + 1)
+    return f"({a} {op} {b})"
+
+
+def rand_query(rng):
+    key = rng.choice(KEY_COLS + [None, None])
+    targets = [key] if key and rng.random() < 0.8 else []
+    for _ in range(rng.randint(1, 5)):
+        agg = rng.choice(["COUNT", "SUM", "MIN", "MAX", "AVG", "COUNTSTAR"])
+        if agg == "COUNTSTAR":
+            targets.append("COUNT(*)")
+        else:
+            targets.append(f"{agg}({rng.choice(INT_COLS + FP_COLS)})")
+    if all(not t.endswith(")") for t in targets):
+        targets.append("COUNT(*)")
+    sql = "SELECT " + ", ".join(targets) + " FROM r"
+    n_conj = rng.choice([0, 1, 1, 2, 3])
+    if n_conj:
+        sql += " WHERE " + " AND ".join(rand_cond(rng) for _ in range(n_conj))
+    if key:
+        sql += f" GROUP BY {key}"
+    return sql + ";"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_queries(seed):
+    rng = random.Random(1234 + seed)
+    n = [1, 257, 5000, 40000, 40000, 120000][seed]
+    table = random_table(n, seed=100 + seed, frag_rows=[10, 100, 1700, 40000, 9000, 50000][seed])
+    dev = gu.DeviceTable(table)
+    ran = 0
+    for _ in range(60):
+        sql = rand_query(rng)
+        unit = sqlmini.parse(sql, table, RAND_NAMES)
+        try:
+            plan = executor.Executor().plan(unit, table, max_groups_buffer_entry_guess=3001, has_cardinality_estimation=True)
+        except executor.UnsupportedOnThisPath:
+            continue     # e.g. more slots than the ABI carries
+        force = abi.KERNEL_PERFECT_GLOBAL if (plan.query_desc_type == abi.GroupByPerfectHash and rng.random() < 0.3) else 0
+        try:
+            gu.run_both(unit, table, entry_guess=3001, has_card=True, dev_table=dev, force_kernel=force)
+        except Exception as e:
+            raise AssertionError(f"query: {sql}\nforce_kernel={force}\n{e}") from e
+        ran += 1
+    assert ran >= 40
