@@ -17,6 +17,7 @@ import numpy as np
 
 # ---- SQLTypes subset -------------------------------------------------------------------------------------
 kINT, kSMALLINT, kFLOAT, kDOUBLE, kBIGINT, kTINYINT = 6, 7, 8, 9, 12, 22
+kBOOLEAN = 1  # only as the type of the deleted-rows column
 # ---- SQLOps subset ---------------------------------------------------------------------------------------
 kEQ, kNE, kLT, kGT, kLE, kGE, kAND, kOR = 0, 2, 3, 4, 5, 6, 7, 8
 # ---- SQLAgg subset ---------------------------------------------------------------------------------------
@@ -53,9 +54,9 @@ NULL_DOUBLE = float(np.finfo(np.float64).tiny)  # DBL_MIN: smallest NORMAL doubl
 EMPTY_KEY_64 = 2**63 - 1
 EMPTY_KEY_32 = 2**31 - 1
 
-NUMPY_OF = {kTINYINT: np.int8, kSMALLINT: np.int16, kINT: np.int32, kBIGINT: np.int64, kDOUBLE: np.float64}
-SIZE_OF = {kTINYINT: 1, kSMALLINT: 2, kINT: 4, kBIGINT: 8, kDOUBLE: 8}
-NULL_OF = {kTINYINT: NULL_TINYINT, kSMALLINT: NULL_SMALLINT, kINT: NULL_INT, kBIGINT: NULL_BIGINT, kDOUBLE: NULL_DOUBLE}
+NUMPY_OF = {kBOOLEAN: np.int8, kTINYINT: np.int8, kSMALLINT: np.int16, kINT: np.int32, kBIGINT: np.int64, kDOUBLE: np.float64}
+SIZE_OF = {kBOOLEAN: 1, kTINYINT: 1, kSMALLINT: 2, kINT: 4, kBIGINT: 8, kDOUBLE: 8}
+NULL_OF = {kBOOLEAN: NULL_TINYINT, kTINYINT: NULL_TINYINT, kSMALLINT: NULL_SMALLINT, kINT: NULL_INT, kBIGINT: NULL_BIGINT, kDOUBLE: NULL_DOUBLE}
 
 
 class TypeInfo(C.Structure):
@@ -127,12 +128,14 @@ class TableInfo(C.Structure):
         ("num_fragments", C.c_int32),
         ("fragments", C.POINTER(FragmentInfo)),
         ("memory_level", C.c_int32),
-        ("pad_", C.c_int32),
+        ("deleted_column_plus1", C.c_int32),
+        ("col_encoded_sizes", C.POINTER(C.c_int8)),
     ]
 
 
 class CompilationOptions(C.Structure):
-    _fields_ = [("device_type", C.c_int32), ("hoist_literals", C.c_int32)]
+    _fields_ = [("device_type", C.c_int32), ("hoist_literals", C.c_int32), ("ignore_deleted_column", C.c_int32),
+                ("pad_", C.c_int32)]
 
 
 class ExecutionOptions(C.Structure):
@@ -363,11 +366,11 @@ class BuiltUnit:
         self.unit = u
 
 
-def chunk_stats(arr: np.ndarray, sql_type: int, notnull: bool) -> ChunkStats:
+def chunk_stats(arr: np.ndarray, sql_type: int, notnull: bool, null=None) -> ChunkStats:
     """ChunkMetadata::chunkStats as the reference's encoders maintain them: min/max over NON-NULL values,
     has_nulls when a NULL sentinel is present (DataMgr/Encoder.h; FixedLengthEncoder::updateStats)."""
     st = ChunkStats()
-    null = NULL_OF[sql_type]
+    null = NULL_OF[sql_type] if null is None else null
     if arr.size == 0:
         st.int_min, st.int_max = 2**63 - 1, -(2**63)
         st.fp_min, st.fp_max = float(np.finfo(np.float64).max), float(np.finfo(np.float64).min)
@@ -406,10 +409,26 @@ class Fragment:
 class Table:
     """InputTableInfo mirror: column types + fragments (Fragmenter::FragmentInfo + chunk pointers + chunk stats)."""
 
-    def __init__(self, col_types: Sequence[tuple]):
-        # col_types: [(sql_type, notnull), ...]
+    def __init__(self, col_types: Sequence[tuple], encoded_sizes: Optional[Sequence[int]] = None,
+                 deleted_column: Optional[int] = None):
+        # col_types: [(sql_type, notnull), ...]; encoded_sizes[c] = physical bytes of an `ENCODING FIXED` column (0 = none)
         self.col_types = [(int(t), bool(nn)) for t, nn in col_types]
+        self.encoded_sizes = [int(x) for x in encoded_sizes] if encoded_sizes is not None else [0] * len(self.col_types)
+        self.deleted_column = deleted_column
         self.fragments: List[Fragment] = []
+
+    def physical_dtype(self, c: int):
+        """numpy dtype of the chunk elements of column c (narrower than the logical type under ENCODING FIXED)."""
+        enc = self.encoded_sizes[c]
+        if enc:
+            return {1: np.int8, 2: np.int16, 4: np.int32}[enc]
+        return NUMPY_OF[self.col_types[c][0]]
+
+    def physical_null(self, c: int):
+        enc = self.encoded_sizes[c]
+        if enc:
+            return -(2 ** (8 * enc - 1))
+        return NULL_OF[self.col_types[c][0]]
 
     @property
     def num_cols(self):
@@ -419,16 +438,16 @@ class Table:
         n = None
         fixed = []
         stats = []
-        for (t, nn), a in zip(self.col_types, cols):
+        for c, ((t, nn), a) in enumerate(zip(self.col_types, cols)):
             if a is None:
                 fixed.append(None)
                 stats.append(ChunkStats())
                 continue
-            a = np.ascontiguousarray(a, dtype=NUMPY_OF[t])
+            a = np.ascontiguousarray(a, dtype=self.physical_dtype(c))
             n = a.size if n is None else n
             assert a.size == n, "ragged fragment"
             fixed.append(a)
-            stats.append(chunk_stats(a, t, nn))
+            stats.append(chunk_stats(a, t, nn, null=self.physical_null(c)))
         fid = len(self.fragments) if fragment_id is None else fragment_id
         self.fragments.append(Fragment(n or 0, host_cols=fixed, stats=stats, fragment_id=fid))
         return self
@@ -474,4 +493,8 @@ class BuiltTable:
         ti.num_cols, ti.col_types = nc, self.col_types
         ti.num_fragments, ti.fragments = nf, self.frags
         ti.memory_level = memory_level
+        ti.deleted_column_plus1 = 0 if t.deleted_column is None else t.deleted_column + 1
+        if any(t.encoded_sizes):
+            self.enc = (C.c_int8 * nc)(*t.encoded_sizes)
+            ti.col_encoded_sizes = self.enc
         self.info = ti

@@ -78,7 +78,8 @@ struct DevAcc {
 /* ---- group key ------------------------------------------------------------------------------------------ */
 struct DevKey {
   int64_t min_val;     /* perfect hash: idx = key - min_val (bucket == 0 in this path) */
-  int64_t null_val;    /* key column NULL sentinel (sign-extended) */
+  int64_t null_val;    /* key column NULL sentinel as stored in the chunk (physical width, sign-extended) */
+  int64_t null_logical;/* the logical type's sentinel (differs from null_val under ENCODING FIXED) */
   int64_t null_idx;    /* perfect hash: entry index of the NULL group (= max - min + 1), -1 if none */
   int64_t entry_count;
   int32_t col;         /* -1: non-grouped */

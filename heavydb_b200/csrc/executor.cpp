@@ -28,7 +28,7 @@
 
 namespace b2q {
 int32_t make_query(const B2QExecUnit* u, const B2QTableInfo* t, const B2QExecutionOptions* eo, size_t guess,
-                   bool has_card, B2QQuery* out, std::string* err);
+                   bool has_card, bool filter_deleted, B2QQuery* out, std::string* err);
 int scan_rows_per_chunk(int block);
 void scan_config(const B2QQuery& q, int* block, int* ctas_per_sm);
 cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t* smem_image, int block, int ctas_per_sm,
@@ -283,19 +283,18 @@ static void collect_timings(B2QPartial& p) {
   cudaGetLastError();
 }
 
-static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr);
+static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr, bool filter_deleted);
 
 /* host-resident table: stream the referenced columns through two staging buffer sets so that the H2D copy of
  * slice k+1 overlaps the scan of slice k (the reference does the H2D in fetchChunks, unpipelined). */
-static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2QExecUnit& u, cudaStream_t st) {
+static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2QExecUnit& u, bool filter_deleted, cudaStream_t st) {
   const B2QQuery& q = p.q;
   const int nc = q.prog.n_cols;
   const int64_t slice_rows = int64_t(1) << 24; /* 16 Mi rows per slice */
   int widths[B2Q_MAX_COLS];
   size_t bytes_per_row = 0;
   for (int c = 0; c < nc; ++c) {
-    const int t = tbl.col_types[q.col_ids[c]].type;
-    widths[c] = (t == B2Q_kTINYINT) ? 1 : (t == B2Q_kSMALLINT) ? 2 : (t == B2Q_kINT) ? 4 : 8;
+    widths[c] = q.prog.col_width[c]; /* physical element width (ENCODING FIXED aware) */
     bytes_per_row += widths[c];
   }
   int64_t max_frag = 0;
@@ -330,7 +329,7 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
   struct Slice { int frag; int64_t row0, rows; };
   std::vector<Slice> slices;
   for (int f = 0; f < tbl.num_fragments; ++f) {
-    if (skip_fragment(u, tbl, tbl.fragments[f])) { p.frags_skipped += 1; continue; }
+    if (skip_fragment(u, tbl, tbl.fragments[f], filter_deleted)) { p.frags_skipped += 1; continue; }
     p.frags_scanned += 1;
     for (int64_t r = 0; r < tbl.fragments[f].num_tuples; r += cap_rows)
       slices.push_back({f, r, std::min<int64_t>(cap_rows, tbl.fragments[f].num_tuples - r)});
@@ -395,8 +394,11 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
 
 /* Executor::skipFragment (QueryEngine/Execute.cpp:4776-4935): a fragment whose chunk min/max cannot satisfy one of
  * the simple quals (`col OP const`, AND-ed) is never scanned — and, for host-resident tables, never copied. */
-static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr) {
+static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr, bool filter_deleted) {
   if (fr.num_tuples == 0) return true;
+  /* isFragmentFullyDeleted (Execute.cpp:4740-4774): the $deleted$ chunk holds only `true` */
+  if (filter_deleted && tbl.deleted_column_plus1 > 0 && fr.col_stats[tbl.deleted_column_plus1 - 1].int_min >= 1 &&
+      fr.col_stats[tbl.deleted_column_plus1 - 1].int_max >= fr.col_stats[tbl.deleted_column_plus1 - 1].int_min) return true;
   for (int i = 0; i < u.num_simple_quals; ++i) {
     const int qi = u.simple_quals[i];
     if (qi < 0 || qi >= u.num_exprs) return false;
@@ -447,7 +449,7 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
   std::unique_ptr<B2QPartial> p(new B2QPartial());
   std::string err;
   const size_t g = guess ? *guess : 0;
-  int32_t rc = make_query(u, tbl, eo, g, has_card != 0, &p->q, &err);
+  int32_t rc = make_query(u, tbl, eo, g, has_card != 0, !co->ignore_deleted_column, &p->q, &err);
   if (rc != B2Q_OK) return set_err(rc, err);
   if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible; this path has no CPU fallback");
   if (eo->device_ordinal >= 0) CU(cudaSetDevice(eo->device_ordinal));
@@ -461,7 +463,7 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
     std::vector<const int8_t*> cols;
     std::vector<int64_t> rows;
     for (int f = 0; f < tbl->num_fragments; ++f) {
-      if (skip_fragment(*u, *tbl, tbl->fragments[f])) { p->frags_skipped += 1; continue; }
+      if (skip_fragment(*u, *tbl, tbl->fragments[f], !co->ignore_deleted_column)) { p->frags_skipped += 1; continue; }
       p->frags_scanned += 1;
       rows.push_back(tbl->fragments[f].num_tuples);
       for (int c = 0; c < q.prog.n_cols; ++c) {
@@ -476,7 +478,7 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
       if (rc != B2Q_OK) return rc;
     }
   } else if (tbl->memory_level == B2Q_CPU_LEVEL) {
-    rc = scan_host_table(*p, *tbl, *u, st);
+    rc = scan_host_table(*p, *tbl, *u, !co->ignore_deleted_column, st);
     if (rc != B2Q_OK) return rc;
   } else {
     return set_err(B2Q_ERR_INVALID_ARGUMENT, "memory_level must be B2Q_CPU_LEVEL or B2Q_GPU_LEVEL");
@@ -575,7 +577,7 @@ int32_t b2q_plan(const B2QExecUnit* u, const B2QTableInfo* t, const B2QCompilati
   if (co->device_type != B2Q_DEVICE_GPU) return set_err(B2Q_ERR_UNSUPPORTED, "device_type must be GPU: this path has no CPU execution");
   std::unique_ptr<B2QQuery> q(new B2QQuery());
   std::string err;
-  const int32_t rc = make_query(u, t, eo, guess, has_card != 0, q.get(), &err);
+  const int32_t rc = make_query(u, t, eo, guess, has_card != 0, !co->ignore_deleted_column, q.get(), &err);
   if (rc != B2Q_OK) return set_err(rc, err);
   *out = q.release();
   return B2Q_OK;

@@ -457,6 +457,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         key[j] = KEY32 ? (int64_t)k32[KEY32 ? j : 0] : k64[KEY32 ? 0 : j];
+        if (key[j] == P.key.null_val) key[j] = P.key.null_logical; /* ENCODING FIXED: physical NULL -> logical NULL */
         h[j] = murmur3_key(key[j], hw) % n;
       }
 #pragma unroll

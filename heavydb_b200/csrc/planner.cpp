@@ -90,8 +90,9 @@ struct TargetDesc {
 
 class Planner {
  public:
-  Planner(const B2QExecUnit& u, const B2QTableInfo& t, const B2QExecutionOptions& eo, size_t guess, bool has_card)
-      : u_(u), t_(t), eo_(eo), guess_(guess), has_card_(has_card) {}
+  Planner(const B2QExecUnit& u, const B2QTableInfo& t, const B2QExecutionOptions& eo, size_t guess, bool has_card,
+          bool filter_deleted)
+      : u_(u), t_(t), eo_(eo), guess_(guess), has_card_(has_card), filter_deleted_(filter_deleted) {}
 
   void run(B2QQuery& q) {
     memset(&q, 0, sizeof(q));
@@ -111,6 +112,7 @@ class Planner {
   const B2QExecutionOptions& eo_;
   size_t guess_;
   bool has_card_;
+  bool filter_deleted_;
   std::vector<TargetDesc> targets_;
   bool grouped_ = false;
   int key_col_ = -1;
@@ -126,6 +128,15 @@ class Planner {
     if (c < 0 || c >= t_.num_cols) reject(B2Q_ERR_INVALID_ARGUMENT, "column id out of range");
     return from_abi(t_.col_types[c]);
   }
+  /* physical element width / NULL sentinel of the chunk: narrower than the logical type under ENCODING FIXED
+   * (FixedWidthInt decode + codgenAdjustFixedEncNull, ColumnIR.cpp:456-500) */
+  int phys_size(int c) const {
+    if (t_.col_encoded_sizes && t_.col_encoded_sizes[c] > 0) return t_.col_encoded_sizes[c];
+    return col_type(c).size();
+  }
+  int64_t phys_int_null(int c) const {
+    switch (phys_size(c)) { case 1: return INT8_MIN; case 2: return INT16_MIN; case 4: return INT32_MIN; default: return INT64_MIN; }
+  }
 
   void validate() {
     if (u_.num_join_quals || u_.has_estimator || u_.num_order_entries || u_.has_union_all || u_.has_window_function)
@@ -134,8 +145,20 @@ class Planner {
     if (u_.num_groupby_exprs < 0 || u_.num_target_exprs <= 0 || u_.num_target_exprs > B2Q_MAX_TARGETS)
       reject(B2Q_ERR_INVALID_ARGUMENT, "bad groupby/target counts");
     if (eo_.output_columnar_hint) reject(B2Q_ERR_UNSUPPORTED, "columnar output layout");
-    for (int c = 0; c < t_.num_cols; ++c)
+    for (int c = 0; c < t_.num_cols; ++c) {
+      const bool is_deleted_col = t_.deleted_column_plus1 == c + 1;
+      if (t_.col_types[c].type == B2Q_kBOOLEAN) {
+        if (!is_deleted_col) reject(B2Q_ERR_UNSUPPORTED, "BOOLEAN is only supported as the deleted-rows column");
+        continue;
+      }
       if (col_type(c).size() < 0) reject(B2Q_ERR_UNSUPPORTED, "column type outside TINYINT/SMALLINT/INT/BIGINT/DOUBLE");
+      if (t_.col_encoded_sizes && t_.col_encoded_sizes[c]) {
+        const int e = t_.col_encoded_sizes[c];
+        if (!col_type(c).is_int() || (e != 1 && e != 2 && e != 4) || e >= col_type(c).size())
+          reject(B2Q_ERR_UNSUPPORTED, "ENCODING FIXED needs an integer column and a physical width below the logical one");
+      }
+    }
+    if (t_.deleted_column_plus1 < 0 || t_.deleted_column_plus1 > t_.num_cols) reject(B2Q_ERR_INVALID_ARGUMENT, "deleted column id out of range");
     if (t_.num_fragments < 0) reject(B2Q_ERR_INVALID_ARGUMENT, "negative fragment count");
   }
 
@@ -421,7 +444,7 @@ class Planner {
     for (int i = 0; i < q.prog.n_cols; ++i) if (q.col_ids[i] == table_col) return i;
     if (q.prog.n_cols >= B2Q_MAX_COLS) reject(B2Q_ERR_UNSUPPORTED, "too many referenced columns");
     q.col_ids[q.prog.n_cols] = table_col;
-    q.prog.col_width[q.prog.n_cols] = static_cast<int8_t>(col_type(table_col).size());
+    q.prog.col_width[q.prog.n_cols] = static_cast<int8_t>(t_.col_types[table_col].type == B2Q_kBOOLEAN ? 1 : phys_size(table_col));
     return q.prog.n_cols++;
   }
 
@@ -438,10 +461,10 @@ class Planner {
     DevTerm t;
     memset(&t, 0, sizeof(t));
     t.col = launch_col(q, l.col_id);
-    t.width = static_cast<int8_t>(ct.size());
+    t.width = static_cast<int8_t>(phys_size(l.col_id));
     t.col_is_fp = ct.is_fp();
     const bool nullable = !ct.notnull;
-    t.null_bits = ct.is_fp() ? dbl_bits(kNullDouble) : ct.int_null();
+    t.null_bits = ct.is_fp() ? dbl_bits(kNullDouble) : phys_int_null(l.col_id);
     const bool cfp = c.ti.type == B2Q_kDOUBLE;
     t.cmp_fp = ct.is_fp() || cfp;
     bool negate = e.op == B2Q_kNE;
@@ -494,7 +517,7 @@ class Planner {
       const int64_t dmin = t.width <= 4 ? INT32_MIN : INT64_MIN, dmax = t.width <= 4 ? INT32_MAX : INT64_MAX;
       lo = std::max(lo, dmin);
       hi = std::min(hi, dmax);
-      const int64_t nullv = ct.int_null();
+      const int64_t nullv = phys_int_null(l.col_id);
       bool null_check = false;
       if (nullable) {
         if (negate) null_check = true;                      /* v != k must still fail for NULL */
@@ -562,7 +585,8 @@ class Planner {
     if (!d || d->arg_col < 0) return a;
     const SqlType at = d->arg_type;
     a.col = launch_col(q, d->arg_col);
-    a.width = static_cast<int8_t>(at.size());
+    a.width = static_cast<int8_t>(phys_size(d->arg_col));
+    const int64_t arg_null = phys_int_null(d->arg_col); /* the sentinel as stored in the chunk */
     a.is_fp = at.is_fp();
     if (!d->skip_null) return a;
     if (at.is_fp()) { /* agg_*_double_skip_val: fp compare against NULL_DOUBLE */
@@ -572,12 +596,12 @@ class Planner {
     }
     if (d->agg == B2Q_kMIN || d->agg == B2Q_kMAX) { /* null = inlineIntNull(arg_ti) sign-extended */
       a.skip1_en = 1;
-      a.skip1_val = at.int_null();
+      a.skip1_val = arg_null;
       return a;
     }
     /* SUM / AVG / COUNT: convertNullIfAny + cast to the aggregate type + compare with ITS sentinel */
     const SqlType agg_t = d->sql_type;
-    if (!at.notnull) { a.skip1_en = 1; a.skip1_val = at.int_null(); }
+    if (!at.notnull) { a.skip1_en = 1; a.skip1_val = arg_null; }
     a.skip2_en = 1;
     a.skip2_val = agg_t.int_null();
     a.skip2_trunc32 = (!at.notnull && agg_t.size() == 4) ? 1 : 0;
@@ -598,6 +622,22 @@ class Planner {
       }
       ++n_quals;
     };
+    if (filter_deleted_ && t_.deleted_column_plus1 > 0) {
+      /* codegenSkipDeletedOuterTableRow (NativeCodegen.cpp:3419-3451): toBool($deleted$) => row skipped, before any
+       * qual.  As a filter term: pass iff the int8 flag is <= 0 (NULL_BOOLEAN = INT8_MIN is "not deleted"). */
+      DevFilter& f = g.filter;
+      DevTerm t;
+      memset(&t, 0, sizeof(t));
+      t.col = launch_col(q, t_.deleted_column_plus1 - 1);
+      t.width = 1;
+      t.lo = INT32_MIN;
+      t.span = static_cast<uint64_t>(0) - static_cast<uint64_t>(static_cast<int64_t>(INT32_MIN));
+      f.ops[f.n_ops++] = static_cast<uint8_t>((FOP_TERM << 4) | f.n_terms);
+      f.terms[f.n_terms++] = t;
+      term_sel_.push_back(1.0);
+      ++n_quals;
+      max_depth = std::max(max_depth, 1);
+    }
     for (int i = 0; i < u_.num_simple_quals; ++i) add_qual(u_.simple_quals[i]);
     for (int i = 0; i < u_.num_quals; ++i) add_qual(u_.quals[i]);
     if (max_depth > 4) reject(B2Q_ERR_UNSUPPORTED, "filter expression nests deeper than 4");
@@ -615,9 +655,10 @@ class Planner {
     if (grouped_) {
       const SqlType kt = col_type(key_col_);
       k.col = launch_col(q, key_col_);
-      k.width = static_cast<int8_t>(kt.size());
+      k.width = static_cast<int8_t>(phys_size(key_col_));
       k.min_val = p.min_val;
-      k.null_val = kt.int_null();
+      k.null_val = kt.notnull ? kt.int_null() : phys_int_null(key_col_);
+      k.null_logical = kt.int_null();
       k.hash_key_width = static_cast<int8_t>(p.effective_key_width);
       if (p.query_desc_type == B2Q_GroupByPerfectHash && p.has_nulls && !kt.notnull) {
         k.translate_null = 1;
@@ -765,10 +806,10 @@ class Planner {
 }  // namespace
 
 int32_t make_query(const B2QExecUnit* u, const B2QTableInfo* t, const B2QExecutionOptions* eo, size_t guess,
-                   bool has_card, B2QQuery* out, std::string* err) {
+                   bool has_card, bool filter_deleted, B2QQuery* out, std::string* err) {
   try {
     if (!u || !t || !eo || !out) throw PlanError{B2Q_ERR_INVALID_ARGUMENT, "null argument"};
-    Planner(*u, *t, *eo, guess, has_card).run(*out);
+    Planner(*u, *t, *eo, guess, has_card, filter_deleted).run(*out);
     return B2Q_OK;
   } catch (const PlanError& e) {
     if (err) *err = e.msg;

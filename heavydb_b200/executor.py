@@ -130,9 +130,10 @@ def _raise(code: int):
     raise QueryExecutionError(code, msg)
 
 
-def compilation_options(device_type: int = abi.DEVICE_GPU, hoist_literals: bool = True) -> abi.CompilationOptions:
+def compilation_options(device_type: int = abi.DEVICE_GPU, hoist_literals: bool = True,
+                        filter_on_deleted_column: bool = True) -> abi.CompilationOptions:
     """CompilationOptions::defaults(ExecutorDeviceType::GPU) — QueryEngine/CompilationOptions.h:52-65."""
-    return abi.CompilationOptions(device_type, int(hoist_literals))
+    return abi.CompilationOptions(device_type, int(hoist_literals), int(not filter_on_deleted_column), 0)
 
 
 def execution_options(allow_multifrag=True, output_columnar_hint=False, bigint_count=False, force_kernel=0,

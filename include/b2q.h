@@ -41,6 +41,7 @@ extern "C" {
 
 /* ---- SQLTypes subset (Shared/sqltypes.h:65-99) -------------------------------------------------------- */
 enum {
+  B2Q_kBOOLEAN = 1, /* only as the type of the deleted-rows column (B2QTableInfo.deleted_column_plus1) */
   B2Q_kINT = 6,
   B2Q_kSMALLINT = 7,
   B2Q_kFLOAT = 8,
@@ -156,7 +157,14 @@ typedef struct B2QTableInfo {
   const B2QFragmentInfo* fragments; /* [num_fragments] */
   int32_t memory_level;             /* where col_buffers live: B2Q_GPU_LEVEL (HBM resident) or B2Q_CPU_LEVEL
                                        (host; copied H2D inside the call, chunk by chunk) */
-  int32_t pad_;
+  int32_t deleted_column_plus1;     /* 1 + id of the table's BOOLEAN $deleted$ column, 0 = none.  Rows whose flag is
+                                       true are skipped before any qual (Executor::addDeletedColumn Execute.cpp:4593,
+                                       codegenSkipDeletedOuterTableRow NativeCodegen.cpp:3419-3451) */
+  const int8_t* col_encoded_sizes;  /* [num_cols] or NULL.  Byte width of the PHYSICAL chunk element when the column is
+                                       declared `ENCODING FIXED(bits)` (kENCODING_FIXED): 1, 2 or 4 for an integer
+                                       column of a wider logical type; 0 = not encoded.  NULL is stored as the minimum
+                                       of the physical width and decodes to the logical type's sentinel
+                                       (CodeGenerator::codgenAdjustFixedEncNull, ColumnIR.cpp:456-500) */
 } B2QTableInfo;
 
 /* ---- CompilationOptions / ExecutionOptions subsets (QueryEngine/CompilationOptions.h:31-66,70-122) ----- */
@@ -164,6 +172,8 @@ enum { B2Q_DEVICE_CPU = 0, B2Q_DEVICE_GPU = 1 }; /* ExecutorDeviceType */
 typedef struct B2QCompilationOptions {
   int32_t device_type;    /* must be B2Q_DEVICE_GPU: no CPU fallback */
   int32_t hoist_literals; /* accepted, meaningless for static kernels */
+  int32_t ignore_deleted_column; /* == !CompilationOptions::filter_on_deleted_column (default 0: deleted rows are skipped) */
+  int32_t pad_;
 } B2QCompilationOptions;
 
 typedef struct B2QExecutionOptions {

@@ -268,6 +268,25 @@ double fixed_width_double_decode(const int8_t* byte_stream, int64_t pos) {
   return v;
 }
 
+/* Physical element width of column c: narrower than the logical type under `ENCODING FIXED(bits)`. */
+int phys_width(const B2QTableInfo& tbl, int c) {
+  if (tbl.col_encoded_sizes && tbl.col_encoded_sizes[c] > 0) return tbl.col_encoded_sizes[c];
+  return type_size(tbl.col_types[c].type);
+}
+/* FixedWidthInt::codegenDecode (sign-extending load, DecodersImpl.h:30-61) followed by
+ * CodeGenerator::codgenAdjustFixedEncNull (ColumnIR.cpp:456-500): the physical width's minimum is NULL and becomes the
+ * logical type's sentinel (only for nullable columns, ColumnIR.cpp:286-291). */
+int64_t decode_int_column(const B2QTableInfo& tbl, const B2QFragmentInfo& fr, int c, int64_t pos) {
+  const int pw = phys_width(tbl, c);
+  const int lw = type_size(tbl.col_types[c].type);
+  int64_t v = fixed_width_int_decode(static_cast<const int8_t*>(fr.col_buffers[c]), pw, pos);
+  if (pw < lw && !tbl.col_types[c].notnull) {
+    const int64_t phys_null = pw == 1 ? INT8_MIN : pw == 2 ? INT16_MIN : INT32_MIN;
+    if (v == phys_null) v = inline_int_null_val(tbl.col_types[c].type);
+  }
+  return v;
+}
+
 /* ===================================================================================================
  * Planner
  * ================================================================================================= */
@@ -536,8 +555,16 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
   if (u.num_target_exprs <= 0 || u.num_target_exprs > B2Q_MAX_TARGETS)
     fail(B2Q_ERR_INVALID_ARGUMENT, "bad target count");
   if (eo.output_columnar_hint) fail(B2Q_ERR_UNSUPPORTED, "columnar output");
-  for (int c = 0; c < tbl.num_cols; ++c)
+  for (int c = 0; c < tbl.num_cols; ++c) {
+    const bool is_deleted_col = tbl.deleted_column_plus1 == c + 1;
+    if (tbl.col_types[c].type == B2Q_kBOOLEAN) { if (!is_deleted_col) fail(B2Q_ERR_UNSUPPORTED, "BOOLEAN is only supported as the deleted-rows column"); continue; }
     if (type_size(tbl.col_types[c].type) < 0) fail(B2Q_ERR_UNSUPPORTED, "column type outside the numeric subset");
+    if (tbl.col_encoded_sizes && tbl.col_encoded_sizes[c]) {
+      const int e = tbl.col_encoded_sizes[c];
+      if (!is_integer(tbl.col_types[c].type) || (e != 1 && e != 2 && e != 4) || e >= type_size(tbl.col_types[c].type))
+        fail(B2Q_ERR_UNSUPPORTED, "ENCODING FIXED needs an integer column and a physical width below the logical one");
+    }
+  }
 
   Plan plan;
   B2QPlan& p = plan.p;
@@ -794,7 +821,7 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
     double lv;
     bool lnull;
     if (is_fp(ctype)) { lv = fixed_width_double_decode(buf, pos); lnull = !col_notnull && lv == kNullDouble; }
-    else { const int64_t iv = fixed_width_int_decode(buf, type_size(ctype), pos); lnull = !col_notnull && iv == inline_int_null_val(ctype); lv = static_cast<double>(iv); }
+    else { const int64_t iv = decode_int_column(tbl, fr, col, pos); lnull = !col_notnull && iv == inline_int_null_val(ctype); lv = static_cast<double>(iv); }
     if (lnull) return kNullBool;
     const double rv = is_fp(r.ti.type) ? r.dval : static_cast<double>(r.ival);
     switch (e.op) {
@@ -803,7 +830,7 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
       default: fail(B2Q_ERR_UNSUPPORTED, "comparison operator");
     }
   }
-  const int64_t lv = fixed_width_int_decode(buf, type_size(ctype), pos);
+  const int64_t lv = decode_int_column(tbl, fr, col, pos);
   if (!col_notnull && lv == inline_int_null_val(ctype)) return kNullBool;
   const int64_t rv = r.ival;
   switch (e.op) {
@@ -813,7 +840,14 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
   }
 }
 
+bool g_filter_deleted = true; /* CompilationOptions::filter_on_deleted_column (set per oracle_execute call) */
+
 bool row_passes(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr, int64_t pos) {
+  /* codegenSkipDeletedOuterTableRow (NativeCodegen.cpp:3419-3451): toBool($deleted$) => the row function returns 0 */
+  if (g_filter_deleted && tbl.deleted_column_plus1 > 0) {
+    const int8_t d = static_cast<const int8_t*>(fr.col_buffers[tbl.deleted_column_plus1 - 1])[pos];
+    if (d > 0) return false;
+  }
   /* simple_quals and quals are AND-ed: each must be TRUE (`filter_lv = AND of toBool(qual)`, NativeCodegen.cpp:3455+) */
   for (int i = 0; i < u.num_simple_quals; ++i) if (!(eval_bool(u, tbl, fr, u.simple_quals[i], pos) > 0)) return false;
   for (int i = 0; i < u.num_quals; ++i) if (!(eval_bool(u, tbl, fr, u.quals[i], pos) > 0)) return false;
@@ -840,7 +874,7 @@ void update_target(const Plan& plan, const Target& t, int8_t* row_base, const B2
   if (w == 4) {
     /* only reachable for COUNT(*) / small-int key projections (pick_target_compact_width) */
     int32_t* a = reinterpret_cast<int32_t*>(slot);
-    if (!t.is_agg) { *a = static_cast<int32_t>(fixed_width_int_decode(static_cast<const int8_t*>(fr.col_buffers[t.arg_col]), type_size(tbl.col_types[t.arg_col].type), pos)); return; } /* agg_id_int32 */
+    if (!t.is_agg) { *a = static_cast<int32_t>(decode_int_column(tbl, fr, t.arg_col, pos)); return; } /* agg_id_int32 */
     if (t.agg_kind == B2Q_kCOUNT && t.arg_col < 0) { *reinterpret_cast<uint32_t*>(a) += 1; return; } /* agg_count_int32 */
     fail(B2Q_ERR_UNSUPPORTED, "4-byte slot with an aggregate argument");
   }
@@ -848,7 +882,7 @@ void update_target(const Plan& plan, const Target& t, int8_t* row_base, const B2
   if (!t.is_agg) { /* agg_id on the projected group key, sign-extended to the slot */
     const int ctype = tbl.col_types[t.arg_col].type;
     if (is_fp(ctype)) agg_id(a, bits_of(fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[t.arg_col]), pos)));
-    else agg_id(a, fixed_width_int_decode(static_cast<const int8_t*>(fr.col_buffers[t.arg_col]), type_size(ctype), pos));
+    else agg_id(a, decode_int_column(tbl, fr, t.arg_col, pos));
     return;
   }
   if (t.agg_kind == B2Q_kCOUNT && t.arg_col < 0) { agg_count(a); return; }
@@ -875,7 +909,7 @@ void update_target(const Plan& plan, const Target& t, int8_t* row_base, const B2
     return;
   }
   /* integer argument */
-  int64_t v = fixed_width_int_decode(buf, type_size(ctype), pos);
+  int64_t v = decode_int_column(tbl, fr, t.arg_col, pos);
   int64_t null_v;
   if (is_agg_domain_range_equivalent(t.agg_kind)) {
     null_v = inline_int_null_val(ctype); /* inlineIntNull(arg_ti) sign-extended to 64 bits (:548-556) */
@@ -938,7 +972,7 @@ int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo&
       row_base = buf.data();
     } else {
       if (is_fp(key_type)) fail(B2Q_ERR_UNSUPPORTED, "floating-point GROUP BY key");
-      int64_t key = fixed_width_int_decode(static_cast<const int8_t*>(fr.col_buffers[key_col]), type_size(key_type), pos);
+      int64_t key = decode_int_column(tbl, fr, key_col, pos);
       if (p.query_desc_type == B2Q_GroupByPerfectHash) {
         /* NULL key -> max+1 bucket (GroupByAndAggregate.cpp:1337-1350, GroupByRuntime.cpp:414-425) */
         if (p.has_nulls && key_nullable && key == inline_int_null_val(key_type)) key = p.max_val + (p.bucket ? p.bucket : 1);
@@ -1083,6 +1117,7 @@ struct OracleResult {
 static thread_local std::string g_last_error;
 
 ORACLE_EXPORT const char* oracle_last_error() { return g_last_error.c_str(); }
+ORACLE_EXPORT void oracle_set_filter_on_deleted_column(int32_t on) { g_filter_deleted = on != 0; }
 
 ORACLE_EXPORT uint32_t oracle_murmur3(const void* key, int len, uint32_t seed) { return murmur3(key, len, seed); }
 

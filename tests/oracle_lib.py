@@ -17,6 +17,7 @@ def lib():
     if _lib is None:
         L = C.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle.so"))
         L.oracle_last_error.restype = C.c_char_p
+        L.oracle_set_filter_on_deleted_column.argtypes = [C.c_int32]
         L.oracle_murmur3.restype = C.c_uint32
         L.oracle_murmur3.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
         L.oracle_get_group_value.restype = C.c_int64

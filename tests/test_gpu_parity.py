@@ -343,3 +343,35 @@ def test_strided_generator_matches_oracle():
     executor.gen_column_device(buf.data_ptr(), abi.kBIGINT, SEED, 0, 777, n, 0, 10**7, stride=900_000_000_007)
     torch.cuda.synchronize()
     assert np.array_equal(buf.cpu().numpy().view(np.int64), want)
+
+
+# ---- ENCODING FIXED chunks, deleted-rows column -----------------------------------------------
+import enc_tables as et  # noqa: E402
+
+
+@pytest.mark.parametrize("n,frag_rows", [(1, 5), (999, 100), (60000, 8192)])
+def test_fixed_encodings_and_deleted_rows(n, frag_rows):
+    table = et.enc_table(n, seed=n, frag_rows=frag_rows)
+    dev = gu.DeviceTable(table)
+    for sql in et.ENC_QUERIES:
+        unit = sqlmini.parse(sql, table, et.ENC_NAMES)
+        gu.run_both(unit, table, entry_guess=120001, has_card=True, dev_table=dev)
+    for sql in et.ENC_QUERIES[:4]:
+        gu.run_both(sqlmini.parse(sql, table, et.ENC_NAMES), table, entry_guess=120001, has_card=True, device_resident=False)
+
+
+def test_fully_deleted_fragment_is_skipped_and_flag_can_be_ignored():
+    table = et.enc_table(4000, seed=11, frag_rows=1000, fully_deleted_fragment=2)
+    unit = sqlmini.parse("SELECT k_i64_f32, COUNT(*), SUM(a_i64_f16) FROM e GROUP BY k_i64_f32;", table, et.ENC_NAMES)
+    rs, _ = gu.run_both(unit, table)
+    assert rs.stats()["fragments_skipped"] == 1          # isFragmentFullyDeleted
+    # filter_on_deleted_column = false: all 4000 rows counted
+    co = executor.compilation_options(filter_on_deleted_column=False)
+    unit = sqlmini.parse("SELECT COUNT(*) FROM e;", table, et.ENC_NAMES)
+    rs = executor.Executor().executeWorkUnit(0, True, table, unit, co=co)
+    assert rs.rows() == [(4000,)]
+    oracle_lib.lib().oracle_set_filter_on_deleted_column(0)
+    try:
+        assert oracle_lib.execute(unit, table).rows() == [(4000,)]
+    finally:
+        oracle_lib.lib().oracle_set_filter_on_deleted_column(1)
