@@ -55,7 +55,27 @@ CONFIGS = {
     "c4s": ([("key", "i64", 0, 10**7, 900_000_000_007), ("v", "i64", 0, 10**6)],
             "SELECT key, SUM(v) FROM t GROUP BY key;", 16, "configs[3] sparse variant: 1e7 sparse int64 keys SUM (global-memory hash table, MurmurHash3 + CAS)"),
 }
+CONFIGS["c2enc"] = (
+    # the same table declared with the reference's fixed-width encodings (BIGINT ENCODING FIXED(32), INT ENCODING
+    # FIXED(16)): 10 B/row instead of 20 — SURVEY.md §8f-2 "lets the kernels read real HeavyDB chunks"
+    [("c0", "i64", 0, 10**6, 1, 4), ("c1", "i64", 0, 10**6, 1, 4), ("g", "i32", 0, 10**4, 1, 2)],
+    CONFIGS["c2"][1], 10, "configs[1] with ENCODING FIXED chunks: c0,c1 BIGINT FIXED(32), g INT FIXED(16)")
 ENTRY_GUESS = {"c4s": 15_000_000}
+
+
+def col_enc(col):
+    return col[5] if len(col) > 5 else 0
+
+
+def col_stride(col):
+    return col[4] if len(col) > 4 else 1
+
+
+def phys_type(col):
+    """sql type of the PHYSICAL chunk elements (what the generator must write)."""
+    from heavydb_b200 import abi
+    e = col_enc(col)
+    return {0: np_type(col[1]), 1: abi.kTINYINT, 2: abi.kSMALLINT, 4: abi.kINT}[e]
 
 
 def log(*a):
@@ -131,7 +151,7 @@ def build_device_table(cfg, rows, frag_ids, torch):
     """Generate this rank's fragments directly in HBM with the counter-based generator (global row = frag_id*FRAG_ROWS+i)."""
     from heavydb_b200 import abi, executor
     cols, _, _, _ = CONFIGS[cfg]
-    table = abi.Table([(np_type(c[1]), True) for c in cols])
+    table = abi.Table([(np_type(c[1]), True) for c in cols], encoded_sizes=[col_enc(c) for c in cols])
     keep = []
     remaining = rows
     for fid in frag_ids:
@@ -142,8 +162,8 @@ def build_device_table(cfg, rows, frag_ids, torch):
         ptrs, stats = [], []
         for tag, col in enumerate(cols):
             _, t, lo, span = col[:4]
-            stride = col[4] if len(col) > 4 else 1
-            ty = np_type(t)
+            stride = col_stride(col)
+            ty = phys_type(col)
             buf = torch.empty(m * abi.SIZE_OF[ty], dtype=torch.uint8, device="cuda")
             executor.gen_column_device(buf.data_ptr(), ty, SEED, tag, fid * FRAG_ROWS, m, lo, span, stride=stride)
             keep.append(buf)
@@ -172,10 +192,10 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     frag_rows = 1 << 22  # 4 Mi rows per fragment, one fragment per thread (reference: one thread per fragment)
     nfrag = threads
-    table = abi.Table([(np_type(c[1]), True) for c in cols])
+    table = abi.Table([(np_type(c[1]), True) for c in cols], encoded_sizes=[col_enc(c) for c in cols])
     for f in range(nfrag):
-        table.add_host_fragment([oracle_lib.gen_column(np_type(c[1]), SEED, tag, f * frag_rows, frag_rows, c[2], c[3], threads,
-                                                       stride=(c[4] if len(c) > 4 else 1)) for tag, c in enumerate(cols)])
+        table.add_host_fragment([oracle_lib.gen_column(phys_type(c), SEED, tag, f * frag_rows, frag_rows, c[2], c[3], threads,
+                                                       stride=col_stride(c)) for tag, c in enumerate(cols)])
     names = [c[0] for c in cols]
     unit = sqlmini.parse(sql, table, names)
     rows = nfrag * frag_rows
@@ -212,10 +232,10 @@ def cpu_baseline_sample(cfg, budget_s=15.0):
     threads = os.cpu_count() or 1
     frag_rows = 1 << 22
     nfrag = threads
-    table = abi.Table([(np_type(c[1]), True) for c in cols])
+    table = abi.Table([(np_type(c[1]), True) for c in cols], encoded_sizes=[col_enc(c) for c in cols])
     for f in range(nfrag):
-        table.add_host_fragment([oracle_lib.gen_column(np_type(c[1]), SEED, tag, f * frag_rows, frag_rows, c[2], c[3], threads,
-                                                       stride=(c[4] if len(c) > 4 else 1)) for tag, c in enumerate(cols)])
+        table.add_host_fragment([oracle_lib.gen_column(phys_type(c), SEED, tag, f * frag_rows, frag_rows, c[2], c[3], threads,
+                                                       stride=col_stride(c)) for tag, c in enumerate(cols)])
     unit = sqlmini.parse(sql, table, [c[0] for c in cols])
     rows = nfrag * frag_rows
     guess = ENTRY_GUESS.get(cfg, 0)
@@ -392,22 +412,22 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
             old_aff = None
     from heavydb_b200 import abi, executor
     from heavydb_b200 import sqlmini
-    bytes_per_row = sum(abi.SIZE_OF[np_type(c[1])] for c in cols)
+    bytes_per_row = sum(abi.SIZE_OF[phys_type(c)] for c in cols)
     guess = ENTRY_GUESS.get(args.config, 0)
     avail = psutil.virtual_memory().available
     rows = args.e2e_rows or args.rows
     cap = int(avail * 0.4 // bytes_per_row)
     rows = max(FRAG_ROWS, min(rows, cap))
-    table = abi.Table([(np_type(c[1]), True) for c in cols])
+    table = abi.Table([(np_type(c[1]), True) for c in cols], encoded_sizes=[col_enc(c) for c in cols])
     keep = []
     for fi, b in enumerate(range(0, rows, FRAG_ROWS)):
         m = min(FRAG_ROWS, rows - b)
         harrs = []
         for tag, col in enumerate(cols):
             _, t, lo, span = col[:4]
-            ty = np_type(t)
+            ty = phys_type(col)
             dev = torch.empty(m * abi.SIZE_OF[ty], dtype=torch.uint8, device="cuda")
-            executor.gen_column_device(dev.data_ptr(), ty, SEED, tag, b, m, lo, span, stride=(col[4] if len(col) > 4 else 1))
+            executor.gen_column_device(dev.data_ptr(), ty, SEED, tag, b, m, lo, span, stride=col_stride(col))
             host = torch.empty(m * abi.SIZE_OF[ty], dtype=torch.uint8, pin_memory=True)
             host.copy_(dev)
             keep.append(host)
@@ -420,7 +440,7 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
             if t == "f64":
                 st.fp_min, st.fp_max = 0.0, 1.0
             else:
-                st.int_min, st.int_max = lo, lo + (span - 1) * (col[4] if len(col) > 4 else 1)
+                st.int_min, st.int_max = lo, lo + (span - 1) * col_stride(col)
             fr.stats.append(st)
         table.fragments.append(fr)
     torch.cuda.synchronize()

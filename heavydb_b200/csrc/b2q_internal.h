@@ -99,6 +99,10 @@ struct DevProgram {
   int8_t eager_args;     /* load aggregate arguments for every row instead of only the passing ones */
   int8_t col_width[B2Q_MAX_COLS];    /* byte width of launch column c */
   int8_t col_prefetch[B2Q_MAX_COLS]; /* column is read for (nearly) every row: worth a bulk L2 prefetch ahead of the scan */
+  int8_t fused;          /* shared-memory-table fast path: the program is {COUNT(*)} and/or {one integer SUM without a
+                            NULL test}: both updates of a row happen under ONE predicate region */
+  int8_t fused_cnt;      /* accumulator index of the COUNT(*), or -1 */
+  int8_t fused_sum;      /* accumulator index of the SUM_I64, or -1 */
   int8_t touch_acc;      /* index of the ACC_TOUCH accumulator, or -1 */
   int8_t touch_piggyback;/* global-table kernels: accumulator (COUNT / SUM_I64 without a skip test) whose returning
                             atomic also maintains the touched flag, or -1 (explicit flag check per row) */

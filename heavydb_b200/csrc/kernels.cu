@@ -123,8 +123,14 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
       int64_t v[R];
       load64<!FULL>(v, cols[t.col], row0, stride, valid, pol);
       const uint64_t lo = (uint64_t)t.lo, span = t.span;
+      if (lo == 0x8000000000000000ull) { /* only an upper bound (`<`, `<=`): one signed compare instead of subtract + compare */
+        const int64_t hi = (int64_t)(lo + span);
 #pragma unroll
-      for (int j = 0; j < R; ++j) m |= (uint32_t)(((uint64_t)v[j] - lo <= span) != neg) << j;
+        for (int j = 0; j < R; ++j) m |= (uint32_t)((v[j] <= hi) != neg) << j;
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) m |= (uint32_t)(((uint64_t)v[j] - lo <= span) != neg) << j;
+      }
       if (t.null_check) {
         const int64_t nullv = t.null_bits;
 #pragma unroll
@@ -295,6 +301,22 @@ __device__ __forceinline__ void global_update(int op, int64_t* arr, uint8_t* fla
  * 64-bit integer SUM: (hi:lo) += v with lo in shared memory (native 32-bit ATOMS.ADD) and the rare hi deltas
  * (carry out of lo, or a value that does not fit 32 bits) sent to the HBM table with RED.ADD.64.
  * ------------------------------------------------------------------------------------------------------- */
+/* branch-free predicated forms: the compiler wraps `if (p) atomicAdd(...)` in BSSY/BRA/BSYNC per row; a predicated
+ * ATOMS needs none of that (profiles/r1_scan_c2_v2: 587 warp-instructions per 8-row iteration, ~70 of them for this) */
+__device__ __forceinline__ void smem_inc_pred(uint32_t saddr, uint32_t pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(saddr), "r"(pred) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_add_ret_pred(uint32_t saddr, uint32_t v, uint32_t pred) {
+  uint32_t old = 0;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}" : "+r"(old) : "r"(saddr), "r"(v), "r"(pred) : "memory");
+  return old;
+}
+__device__ __forceinline__ void smem_sum_i64_pred(uint32_t saddr, int64_t* gslot, uint32_t vl, int32_t vh, uint32_t pred) {
+  const uint32_t old = smem_add_ret_pred(saddr, vl, pred);
+  const int32_t hi = vh + (int32_t)((uint32_t)(old + vl) < old);
+  if (pred && hi != 0) red_add_u64(gslot, (uint64_t)(int64_t)hi << 32);
+}
+
 __device__ __forceinline__ void smem_sum_i64(int8_t* tab, int64_t* garr, uint32_t e, uint32_t vl, int32_t vh) {
   const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(tab) + e, vl);
   const int32_t hi = vh + (int32_t)((uint32_t)(old + vl) < old);
@@ -384,9 +406,11 @@ struct ScanArgs {
 extern __shared__ __align__(128) int8_t b2q_smem[];
 
 /* one chunk: R rows per thread.  FULL = every row of the chunk exists (no tail masking). */
-template <int MODE, bool WAGG, bool KEY32, bool FULL>
+template <int MODE, bool WAGG, bool KEY32, bool FULL, int BLOCK>
 __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* const* __restrict__ cols, int64_t row0,
-                                              int64_t frag_rows, int nthr, int lane, int8_t* my_tab, uint64_t pol, uint64_t pol_tab) {
+                                              int64_t frag_rows, int lane, int8_t* my_tab, uint64_t pol, uint64_t pol_tab) {
+  /* BLOCK is a compile-time constant so that the R loads of a column are one base pointer + immediate offsets */
+  constexpr int nthr = BLOCK;
   const DevProgram& P = A.prog;
   const DevLaunch& Lh = A.launch;
   uint32_t valid = (1u << R) - 1u;
@@ -424,12 +448,21 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       if (KEY32) {
         const uint32_t mn = (uint32_t)P.key.min_val, n = (uint32_t)P.key.entry_count, nidx = (uint32_t)P.key.null_idx;
         const int32_t nullv = (int32_t)P.key.null_val;
+        if (tr) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          uint32_t idx = (uint32_t)k32[KEY32 ? j : 0] - mn;
-          if (tr) idx = (k32[KEY32 ? j : 0] == nullv) ? nidx : idx;
-          bad |= (uint32_t)(idx >= n) << j;
-          e[j] = idx;
+          for (int j = 0; j < R; ++j) {
+            uint32_t idx = (uint32_t)k32[KEY32 ? j : 0] - mn;
+            idx = (k32[KEY32 ? j : 0] == nullv) ? nidx : idx;
+            bad |= (uint32_t)(idx >= n) << j;
+            e[j] = idx;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const uint32_t idx = (uint32_t)k32[KEY32 ? j : 0] - mn;
+            bad |= (uint32_t)(idx >= n) << j;
+            e[j] = idx;
+          }
         }
       } else {
         const int64_t mn = P.key.min_val, nullv = P.key.null_val, nidx = P.key.null_idx;
@@ -486,8 +519,64 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     }
   }
 
-  /* ---- aggregate updates: one warp-uniform dispatch per accumulator per R rows ---- */
   const uint32_t arg_mask = P.eager_args ? valid : pass;
+
+  /* ---- fused fast path: COUNT(*) and/or one integer SUM, both updates of a row under one predicate region
+   * (ncu, profiles/r1_scan_c2_v3: the per-accumulator loops spend 30 of 70 instructions/row on predicate extraction,
+   * BSSY/BRA/BSYNC and address math; fusing them halves that) ---- */
+  if (MODE == MODE_SMEM && !WAGG && P.fused) {
+    const int ic = P.fused_cnt, is = P.fused_sum;
+    const uint32_t cnt32 = ic >= 0 ? smem_u32(my_tab + A.smem.acc_off[ic]) : 0u;
+    if (is < 0) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) if (pass >> j & 1) atomicAdd(reinterpret_cast<uint32_t*>(my_tab + A.smem.acc_off[ic]) + e[j], 1u);
+      return;
+    }
+    const DevAcc& sa = P.accs[is];
+    uint32_t* sum_tab = reinterpret_cast<uint32_t*>(my_tab + A.smem.acc_off[is]);
+    uint32_t* cnt_tab = reinterpret_cast<uint32_t*>(my_tab + A.smem.acc_off[ic >= 0 ? ic : is]);
+    int64_t* gsum = Lh.accs[is];
+    (void)cnt32;
+    if (sa.width == 8) {
+      int64_t v[R];
+      load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol);
+      if (ic >= 0) {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (pass >> j & 1) {
+            atomicAdd(cnt_tab + e[j], 1u);
+            const uint32_t vl = (uint32_t)v[j];
+            const uint32_t old = atomicAdd(sum_tab + e[j], vl);
+            const int32_t hi = (int32_t)(v[j] >> 32) + (int32_t)((uint32_t)(old + vl) < old);
+            if (hi != 0) red_add_u64(gsum + e[j], (uint64_t)(int64_t)hi << 32);
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (pass >> j & 1) {
+            const uint32_t vl = (uint32_t)v[j];
+            const uint32_t old = atomicAdd(sum_tab + e[j], vl);
+            const int32_t hi = (int32_t)(v[j] >> 32) + (int32_t)((uint32_t)(old + vl) < old);
+            if (hi != 0) red_add_u64(gsum + e[j], (uint64_t)(int64_t)hi << 32);
+          }
+      }
+    } else {
+      int32_t v[R];
+      load32<true>(v, cols[sa.col], sa.width, row0, nthr, arg_mask, pol);
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (pass >> j & 1) {
+          if (ic >= 0) atomicAdd(cnt_tab + e[j], 1u);
+          const uint32_t vl = (uint32_t)v[j];
+          const uint32_t old = atomicAdd(sum_tab + e[j], vl);
+          const int32_t hi = (v[j] >> 31) + (int32_t)((uint32_t)(old + vl) < old);
+          if (hi != 0) red_add_u64(gsum + e[j], (uint64_t)(int64_t)hi << 32);
+        }
+    }
+    return;
+  }
+
+  /* ---- aggregate updates: one warp-uniform dispatch per accumulator per R rows ---- */
   for (int a = 0; a < P.n_accs; ++a) {
     const DevAcc& acc = P.accs[a];
     const int op = acc.op;
@@ -501,8 +590,9 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(pass));
         if (lane == 0 && c) atomicAdd(reinterpret_cast<uint32_t*>(tab), c);
       } else if (MODE == MODE_SMEM) {
+        const uint32_t tab32 = smem_u32(tab);
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (pass >> j & 1) atomicAdd(reinterpret_cast<uint32_t*>(tab) + e[j], 1u);
+        for (int j = 0; j < R; ++j) smem_inc_pred(tab32 + e[j] * 4u, pass >> j & 1);
       } else {
 #pragma unroll
         for (int j = 0; j < R; ++j) if (pass >> j & 1) global_split_add_touch(garr, pig, e[j], P.key.entry_count, 1u, 0, pol_tab);
@@ -552,12 +642,13 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
           if (lane == 0 && r != (is_min ? B2Q_I64_MAX : B2Q_I64_MIN)) smem_minmax(op, tab, 0, r);
         }
       } else if (MODE == MODE_SMEM) {
+        const uint32_t tab32 = smem_u32(tab);
         if (op == ACC_COUNT) {
 #pragma unroll
-          for (int j = 0; j < R; ++j) if (m >> j & 1) atomicAdd(reinterpret_cast<uint32_t*>(tab) + e[j], 1u);
+          for (int j = 0; j < R; ++j) smem_inc_pred(tab32 + e[j] * 4u, m >> j & 1);
         } else if (op == ACC_SUM_I64) {
 #pragma unroll
-          for (int j = 0; j < R; ++j) if (m >> j & 1) smem_sum_i64(tab, garr, e[j], (uint32_t)v[j], v[j] >> 31);
+          for (int j = 0; j < R; ++j) smem_sum_i64_pred(tab32 + e[j] * 4u, garr + e[j], (uint32_t)v[j], v[j] >> 31, m >> j & 1);
         } else {
 #pragma unroll
           for (int j = 0; j < R; ++j) if (m >> j & 1) smem_minmax(op, tab, e[j], (int64_t)v[j]);
@@ -624,14 +715,18 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       }
     } else if (MODE == MODE_SMEM) {
       switch (op) { /* dispatch hoisted out of the row loop */
-        case ACC_COUNT:
+        case ACC_COUNT: {
+          const uint32_t tab32 = smem_u32(tab);
 #pragma unroll
-          for (int j = 0; j < R; ++j) if (m >> j & 1) atomicAdd(reinterpret_cast<uint32_t*>(tab) + e[j], 1u);
+          for (int j = 0; j < R; ++j) smem_inc_pred(tab32 + e[j] * 4u, m >> j & 1);
           break;
-        case ACC_SUM_I64:
+        }
+        case ACC_SUM_I64: {
+          const uint32_t tab32 = smem_u32(tab);
 #pragma unroll
-          for (int j = 0; j < R; ++j) if (m >> j & 1) smem_sum_i64(tab, garr, e[j], (uint32_t)v[j], (int32_t)(v[j] >> 32));
+          for (int j = 0; j < R; ++j) smem_sum_i64_pred(tab32 + e[j] * 4u, garr + e[j], (uint32_t)v[j], (int32_t)(v[j] >> 32), m >> j & 1);
           break;
+        }
         case ACC_SUM_F64:
 #pragma unroll
           for (int j = 0; j < R; ++j) if (m >> j & 1) atomicAdd(reinterpret_cast<double*>(tab) + e[j], __longlong_as_double(v[j]));
@@ -648,12 +743,12 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
   }
 }
 
-template <int MODE, bool WAGG, bool KEY32>
-__global__ void __launch_bounds__(kMaxBlock, 1) b2q_k_scan(const __grid_constant__ ScanArgs A) {
+template <int MODE, bool WAGG, bool KEY32, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) b2q_k_scan(const __grid_constant__ ScanArgs A) {
   const DevProgram& P = A.prog;
   const DevLaunch& Lh = A.launch;
   const int tid = threadIdx.x;
-  const int nthr = blockDim.x;
+  constexpr int nthr = BLOCK;
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int64_t chunk_rows = (int64_t)nthr * R;
@@ -727,9 +822,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) b2q_k_scan(const __grid_constant
     const int64_t base_row = (chunk - frag_first) * chunk_rows;
     const int8_t* const* __restrict__ cols = Lh.col_ptrs + (size_t)frag * P.n_cols;
     if (base_row + chunk_rows <= frag_rows)
-      process_chunk<MODE, WAGG, KEY32, true>(A, cols, base_row + tid, frag_rows, nthr, lane, my_tab, pol, pol_tab);
+      process_chunk<MODE, WAGG, KEY32, true, BLOCK>(A, cols, base_row + tid, frag_rows, lane, my_tab, pol, pol_tab);
     else
-      process_chunk<MODE, WAGG, KEY32, false>(A, cols, base_row + tid, frag_rows, nthr, lane, my_tab, pol, pol_tab);
+      process_chunk<MODE, WAGG, KEY32, false, BLOCK>(A, cols, base_row + tid, frag_rows, lane, my_tab, pol, pol_tab);
   }
 
   if (MODE == MODE_SMEM) {
@@ -938,22 +1033,27 @@ struct ScanConfig {
   size_t smem_bytes;
 };
 
-template <int MODE, bool WAGG, bool KEY32>
-static cudaError_t launch_scan_t(const ScanArgs& a, const ScanConfig& c, cudaStream_t st) {
+template <int MODE, bool WAGG, bool KEY32, int BLOCK>
+static cudaError_t launch_scan_tb(const ScanArgs& a, const ScanConfig& c, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, b2q_k_scan<MODE, WAGG, KEY32>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, b2q_k_scan<MODE, WAGG, KEY32, BLOCK>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(b2q_k_scan<MODE, WAGG, KEY32>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    e = cudaFuncSetAttribute(b2q_k_scan<MODE, WAGG, KEY32, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  b2q_k_scan<MODE, WAGG, KEY32><<<c.grid, c.block, c.smem_bytes, st>>>(a);
+  b2q_k_scan<MODE, WAGG, KEY32, BLOCK><<<c.grid, c.block, c.smem_bytes, st>>>(a);
   return cudaGetLastError();
+}
+
+template <int MODE, bool WAGG, bool KEY32>
+static cudaError_t launch_scan_t(const ScanArgs& a, const ScanConfig& c, cudaStream_t st) {
+  return c.block == 1024 ? launch_scan_tb<MODE, WAGG, KEY32, 1024>(a, c, st) : launch_scan_tb<MODE, WAGG, KEY32, 512>(a, c, st);
 }
 
 int scan_rows_per_chunk(int block) { return block * R; }

@@ -743,6 +743,19 @@ class Planner {
     if (grouped_ && g.eager_key) g.col_prefetch[g.key.col] = 1;
     if (g.eager_args)
       for (int a = 0; a < g.n_accs; ++a) if (g.accs[a].col >= 0) g.col_prefetch[g.accs[a].col] = 1;
+    /* fused fast path of the shared-memory-table kernel (the reference's JIT specialises per query; this is the
+     * static-kernel equivalent for the most common shape: GROUP BY k with COUNT(*) and/or one integer SUM) */
+    g.fused = 0; g.fused_cnt = -1; g.fused_sum = -1;
+    {
+      bool ok = g.n_accs >= 1 && g.n_accs <= 2;
+      for (int a = 0; a < g.n_accs && ok; ++a) {
+        const DevAcc& c = g.accs[a];
+        if (c.op == ACC_COUNT && c.col < 0 && g.fused_cnt < 0) g.fused_cnt = static_cast<int8_t>(a);
+        else if (c.op == ACC_SUM_I64 && !c.skip1_en && !c.skip2_en && g.fused_sum < 0) g.fused_sum = static_cast<int8_t>(a);
+        else ok = false;
+      }
+      g.fused = ok ? 1 : 0;
+    }
     g.touch_acc = static_cast<int8_t>(L.touched_acc);
     g.touch_piggyback = -1;
     if (L.touched_acc >= 0)
