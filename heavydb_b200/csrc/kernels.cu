@@ -537,7 +537,17 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     uint32_t* cnt_tab = reinterpret_cast<uint32_t*>(my_tab + A.smem.acc_off[ic >= 0 ? ic : is]);
     int64_t* gsum = Lh.accs[is];
     (void)cnt32;
-    if (sa.width == 8) {
+    if (sa.op == ACC_SUM_F64) { /* AVG/SUM(double): CAS-loop add on the (warp-private) replica + the count */
+      int64_t v[R];
+      load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol);
+      double* dsum = reinterpret_cast<double*>(sum_tab);
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (pass >> j & 1) {
+          if (ic >= 0) atomicAdd(cnt_tab + e[j], 1u);
+          atomicAdd(dsum + e[j], __longlong_as_double(v[j]));
+        }
+    } else if (sa.width == 8) {
       int64_t v[R];
       load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol);
       if (ic >= 0) {

@@ -751,7 +751,7 @@ class Planner {
       for (int a = 0; a < g.n_accs && ok; ++a) {
         const DevAcc& c = g.accs[a];
         if (c.op == ACC_COUNT && c.col < 0 && g.fused_cnt < 0) g.fused_cnt = static_cast<int8_t>(a);
-        else if (c.op == ACC_SUM_I64 && !c.skip1_en && !c.skip2_en && g.fused_sum < 0) g.fused_sum = static_cast<int8_t>(a);
+        else if ((c.op == ACC_SUM_I64 || c.op == ACC_SUM_F64) && !c.skip1_en && !c.skip2_en && g.fused_sum < 0) g.fused_sum = static_cast<int8_t>(a);
         else ok = false;
       }
       g.fused = ok ? 1 : 0;
