@@ -82,6 +82,7 @@ struct DevKey {
   int64_t null_logical;/* the logical type's sentinel (differs from null_val under ENCODING FIXED) */
   int64_t null_idx;    /* perfect hash: entry index of the NULL group (= max - min + 1), -1 if none */
   int64_t entry_count;
+  uint64_t hash_magic; /* baseline: 2^64 / entry_count + 1 — h % entry_count by two multiplies (Lemire fastmod, exact for 32-bit h) */
   int32_t col;         /* -1: non-grouped */
   int8_t width;
   int8_t translate_null; /* has_nulls && column nullable (GroupByAndAggregate.cpp:1337-1350) */

@@ -479,6 +479,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       if (bad) { atomicCAS(Lh.error, 0, B2Q_ERR_KEY_OUT_OF_RANGE); pass &= ~bad; }
     } else {
       const uint32_t n = (uint32_t)P.key.entry_count;
+      const uint64_t magic = P.key.hash_magic;
       const int hw = P.key.hash_key_width;
       unsigned long long* keys = reinterpret_cast<unsigned long long*>(Lh.keys);
       /* get_group_value (GroupByRuntime.cpp:25-48): h = MurmurHash3(key) % entry_count, linear probe.
@@ -491,7 +492,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       for (int j = 0; j < R; ++j) {
         key[j] = KEY32 ? (int64_t)k32[KEY32 ? j : 0] : k64[KEY32 ? 0 : j];
         if (key[j] == P.key.null_val) key[j] = P.key.null_logical; /* ENCODING FIXED: physical NULL -> logical NULL */
-        h[j] = murmur3_key(key[j], hw) % n;
+        h[j] = (uint32_t)__umul64hi(magic * (uint64_t)murmur3_key(key[j], hw), (uint64_t)n); /* == hash % n */
       }
 #pragma unroll
       for (int j = 0; j < R; ++j) first[j] = (pass >> j & 1) ? __ldcg(keys + h[j]) : 0ull;

@@ -651,6 +651,7 @@ class Planner {
     DevKey& k = g.key;
     k.col = -1;
     k.entry_count = p.entry_count;
+    k.hash_magic = p.entry_count > 0 ? ~0ull / static_cast<uint64_t>(p.entry_count) + 1 : 0;
     k.null_idx = -1;
     if (grouped_) {
       const SqlType kt = col_type(key_col_);
