@@ -1027,15 +1027,17 @@ __global__ void b2q_k_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_t
 /* =========================================================================================================
  * host-side launch wrappers (called from executor.cpp)
  * ======================================================================================================= */
-static int g_sm_count = 0;
 static int sm_count() {
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
   }
-  return g_sm_count;
+  return cached[dev];
 }
 
 struct ScanConfig {
@@ -1046,7 +1048,11 @@ struct ScanConfig {
 
 template <int MODE, bool WAGG, bool KEY32, int BLOCK>
 static cudaError_t launch_scan_tb(const ScanArgs& a, const ScanConfig& c, cudaStream_t st) {
-  static bool attr_set = false;
+  /* the opt-in shared-memory limit is a per-device function attribute: remember which devices have it */
+  static unsigned long long attr_set_mask = 0;
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  const bool attr_set = cur_dev < 64 && (attr_set_mask >> cur_dev & 1ull);
   if (!attr_set) {
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
@@ -1056,7 +1062,7 @@ static cudaError_t launch_scan_tb(const ScanArgs& a, const ScanConfig& c, cudaSt
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(b2q_k_scan<MODE, WAGG, KEY32, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (cur_dev < 64) attr_set_mask |= 1ull << cur_dev;
   }
   b2q_k_scan<MODE, WAGG, KEY32, BLOCK><<<c.grid, c.block, c.smem_bytes, st>>>(a);
   return cudaGetLastError();

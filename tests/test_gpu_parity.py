@@ -375,3 +375,49 @@ def test_fully_deleted_fragment_is_skipped_and_flag_can_be_ignored():
         assert oracle_lib.execute(unit, table).rows() == [(4000,)]
     finally:
         oracle_lib.lib().oracle_set_filter_on_deleted_column(1)
+
+
+def test_inner_entry_b2q_launch_param_block():
+    """The inner entry: the static-kernel replacement of the JIT'd multifrag_query_hoisted_literals call, driven with the
+    reference's own 15-slot parameter block (enum KernelParam, QueryEngine/enums.h:64-79): COL_BUFFERS, NUM_FRAGMENTS,
+    NUM_ROWS, GROUPBY_BUF (receives the finished reference-layout buffer on the DEVICE), ERROR_CODE."""
+    import ctypes as C
+    import torch
+    table = random_table(30000, seed=77, frag_rows=7000)
+    dev = gu.DeviceTable(table)
+    L = executor.lib()
+    for sql in ["SELECT nn32, COUNT(*), SUM(a64), MIN(a32), AVG(d) FROM r WHERE nn64 < 25 GROUP BY nn32;",
+                "SELECT COUNT(*), SUM(big), MAX(a16) FROM r WHERE a8 <> 3;",
+                "SELECT k64, SUM(a32) FROM r GROUP BY k64;"]:
+        unit = sqlmini.parse(sql, table, RAND_NAMES)
+        bt = dev.table.build(abi.GPU_LEVEL)
+        co, eo = executor.compilation_options(), executor.execution_options()
+        q = C.c_void_p()
+        assert L.b2q_plan(C.byref(unit.unit), C.byref(bt.info), C.byref(co), C.byref(eo), 0, 0, C.byref(q)) == 0
+        plan = L.b2q_query_plan(q).contents
+        nf, nc = len(dev.table.fragments), dev.table.num_cols
+        # COL_BUFFERS: host array [frag] of host arrays [col] of device pointers (QueryExecutionContext.cpp:751-765)
+        per_frag = [(C.c_void_p * nc)(*[p or None for p in f.dev_ptrs]) for f in dev.table.fragments]
+        col_buffers = (C.POINTER(C.c_void_p) * nf)(*[C.cast(a, C.POINTER(C.c_void_p)) for a in per_frag])
+        num_rows = (C.c_int64 * nf)(*[f.num_tuples for f in dev.table.fragments])
+        num_frags, num_tables = C.c_uint32(nf), C.c_uint32(1)
+        out = torch.zeros(max(int(plan.buffer_size), 8), dtype=torch.uint8, device="cuda")
+        gb = torch.tensor([out.data_ptr()], dtype=torch.int64, device="cuda")      # int64_t** on the device
+        err = torch.zeros(1, dtype=torch.int32, device="cuda")
+        prm = abi.Params()
+        prm.error_codes = err.data_ptr()
+        prm.group_by_buffers = gb.data_ptr()
+        prm.num_fragments, prm.num_tables = C.pointer(num_frags), C.pointer(num_tables)
+        prm.col_buffers = col_buffers
+        prm.num_rows = num_rows
+        torch.cuda.synchronize()
+        rc = L.b2q_launch(q, C.byref(prm), None)
+        assert rc == 0, L.b2q_last_error_message()
+        torch.cuda.synchronize()
+        assert int(err.item()) == 0
+        ref = oracle_lib.execute(unit, table, num_threads=4)
+        got = out.cpu().numpy()[: int(plan.buffer_size)].view(np.int8)
+        n = ref.entry_count()
+        empty = np.array([bool(oracle_lib.lib().oracle_result_is_row_at_empty(ref.h, i)) for i in range(n)], dtype=bool)
+        gu.buffers_equal(got, ref.buffer(), ref.plan, empty=empty)
+        L.b2q_query_free(q)
