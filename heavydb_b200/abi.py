@@ -44,6 +44,7 @@ RED_SUM, RED_MIN, RED_MAX = 0, 1, 2
 
 MAX_SLOTS = 16
 MAX_TARGETS = 16
+MAX_GROUP_COLS = 4
 
 # Shared/InlineNullValues.h:30-36
 NULL_TINYINT = -(2**7)
@@ -182,6 +183,10 @@ class Plan(C.Structure):
         ("kernel", C.c_int32),
         ("row_size", C.c_int64),
         ("buffer_size", C.c_int64),
+        ("num_group_cols", C.c_int32),
+        ("group_col_ids", C.c_int32 * MAX_GROUP_COLS),
+        ("group_col_widths", C.c_int8 * MAX_GROUP_COLS),
+        ("pad2_", C.c_int32),
         ("slot_padded_width", C.c_int8 * MAX_SLOTS),
         ("slot_logical_width", C.c_int8 * MAX_SLOTS),
         ("slot_offset", C.c_int64 * MAX_SLOTS),
@@ -193,7 +198,7 @@ class Plan(C.Structure):
     PARITY_FIELDS = (
         "query_desc_type", "keyless_hash", "idx_target_as_key", "output_columnar", "group_col_width",
         "effective_key_width", "num_targets", "num_slots", "key_col_id", "entry_count", "min_val", "max_val",
-        "bucket", "has_nulls", "row_size", "buffer_size",
+        "bucket", "has_nulls", "row_size", "buffer_size", "num_group_cols",
     )
 
     def as_dict(self) -> dict:
@@ -203,6 +208,8 @@ class Plan(C.Structure):
         d["slot_logical_width"] = list(self.slot_logical_width[:n])
         d["slot_offset"] = list(self.slot_offset[:n])
         d["init_vals"] = list(self.init_vals[:n])
+        d["group_col_ids"] = list(self.group_col_ids[: self.num_group_cols])
+        d["group_col_widths"] = list(self.group_col_widths[: self.num_group_cols])
         d["targets"] = [
             (t.is_agg, t.agg_kind, t.sql_type.type, t.sql_type.notnull, t.agg_arg_type.type,
              t.agg_arg_type.notnull, t.skip_null_val, t.arg_col_id, t.first_slot)

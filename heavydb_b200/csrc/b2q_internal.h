@@ -90,9 +90,26 @@ struct DevKey {
   int8_t pad_;
 };
 
+/* one GROUP BY column of a multi-column perfect hash (codegenPerfectHashFunction, GroupByAndAggregate.cpp:1549-1597):
+ * entry = sum_c d_c * mult_c with d_c = key_c - min_c (NULL -> card_c - 1, i.e. max_c + 1 - min_c) */
+struct DevKeyComp {
+  int64_t min_val;
+  int64_t null_val;     /* sentinel as stored in the chunk (sign-extended) */
+  int64_t null_logical; /* sentinel of the logical type (what a projected NULL key reads as) */
+  uint32_t card;        /* max - min + 1 (+1 when the column has NULLs) */
+  uint32_t mult;        /* product of the cardinalities of the preceding columns */
+  int32_t col;
+  int8_t width;
+  int8_t translate_null;
+  int8_t pad_[2];
+};
+
 struct DevProgram {
   DevFilter filter;
   DevKey key;
+  int32_t n_keys;       /* > 1: multi-column perfect hash, `keys` below; the single-column paths use `key` */
+  int32_t pad_keys_;
+  DevKeyComp keys[B2Q_MAX_GROUP_COLS];
   int32_t n_accs;
   int32_t n_cols;
   float est_selectivity; /* planner's estimate from chunk stats (uniformity assumption) */
@@ -127,7 +144,8 @@ struct DevSlot {
                           -2: "no value seen" <=> accs[acc] still holds its identity; -1: always valid */
   int8_t kind;         /* SLOT_* */
   int8_t width;        /* padded slot width: 0, 4 or 8 */
-  int8_t pad_[6];
+  int8_t key_comp;     /* SLOT_KEY of a multi-column key: which GROUP BY column */
+  int8_t pad_[5];
 };
 struct DevLayout {
   int64_t row_size;
@@ -138,7 +156,10 @@ struct DevLayout {
   int32_t n_slots;
   int32_t touched_acc;   /* accumulator whose value != 0 marks a non-empty entry (non-keyless layouts) */
   int32_t keyless_marker;/* keyless: slot index whose init value marks an empty entry (idx_target_as_key), else -1 */
-  int8_t has_key_col;    /* row starts with the group key (non-keyless) */
+  int32_t n_keys;        /* > 1: multi-column perfect hash */
+  int32_t pad_k_;
+  DevKeyComp keys[B2Q_MAX_GROUP_COLS];
+  int8_t has_key_col;    /* row starts with the group key(s) (non-keyless) */
   int8_t key_width;      /* 4 or 8 */
   int8_t baseline;       /* key comes from the keys[] array */
   int8_t pad_[1];

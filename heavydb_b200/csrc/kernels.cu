@@ -441,6 +441,42 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
   uint32_t e[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) e[j] = 0;
+  if (!WAGG && !KEY32 && MODE != MODE_BASELINE && P.n_keys > 1) {
+    /* multi-column perfect hash: perfect_key_hash (GroupByAndAggregate.cpp:1549-1597) — mixed-radix index over the
+     * NULL-translated keys; one warp-uniform pass per GROUP BY column */
+    uint32_t bad = 0;
+    const uint32_t kmask = P.eager_key ? valid : pass;
+    for (int c = 0; c < P.n_keys; ++c) {
+      const DevKeyComp& kc = P.keys[c];
+      const int64_t mn = kc.min_val, nullv = kc.null_val;
+      const uint64_t card = kc.card;
+      const uint32_t mult = kc.mult;
+      const bool tr = kc.translate_null;
+      if (kc.width == 8) {
+        int64_t k[R];
+        load64<true>(k, cols[kc.col], row0, nthr, kmask, pol);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          int64_t d = k[j] - mn;
+          if (tr) d = (k[j] == nullv) ? (int64_t)card - 1 : d;
+          bad |= (uint32_t)((uint64_t)d >= card) << j;
+          e[j] += (uint32_t)d * mult;
+        }
+      } else {
+        int32_t k[R];
+        load32<true>(k, cols[kc.col], kc.width, row0, nthr, kmask, pol);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          int64_t d = (int64_t)k[j] - mn;
+          if (tr) d = ((int64_t)k[j] == nullv) ? (int64_t)card - 1 : d;
+          bad |= (uint32_t)((uint64_t)d >= card) << j;
+          e[j] += (uint32_t)d * mult;
+        }
+      }
+    }
+    bad &= pass;
+    if (bad) { atomicCAS(Lh.error, 0, B2Q_ERR_KEY_OUT_OF_RANGE); pass &= ~bad; }
+  }
   if (has_key) {
     if (MODE != MODE_BASELINE) {
       uint32_t bad = 0;
@@ -947,7 +983,16 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
     int8_t* row = A.out + i * L.row_size;
     bool touched = true;
     int64_t key = 0;
-    if (L.baseline) {
+    int64_t mkey_stored[B2Q_MAX_GROUP_COLS], mkey_proj[B2Q_MAX_GROUP_COLS];
+    if (L.n_keys > 1) { /* mixed-radix decomposition of the entry index */
+      for (int c = 0; c < L.n_keys; ++c) {
+        const DevKeyComp& kc = L.keys[c];
+        const int64_t comp = (i / kc.mult) % kc.card;
+        mkey_stored[c] = kc.min_val + comp; /* a NULL key is stored translated: max + 1 */
+        mkey_proj[c] = (kc.translate_null && comp == (int64_t)kc.card - 1) ? kc.null_logical : kc.min_val + comp;
+      }
+      if (L.touched_acc >= 0) touched = reinterpret_cast<const uint8_t*>(A.accs[L.touched_acc])[i] != 0;
+    } else if (L.baseline) {
       key = A.keys[i];
       touched = key != B2Q_I64_MAX;
       if (touched && L.key_width == 4) key = (int64_t)(int32_t)key;
@@ -955,7 +1000,9 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
       key = (i == L.null_idx) ? L.key_null_val : L.key_min + i;
       if (L.touched_acc >= 0) touched = reinterpret_cast<const uint8_t*>(A.accs[L.touched_acc])[i] != 0;
     }
-    if (L.has_key_col) {
+    if (L.has_key_col && L.n_keys > 1) {
+      for (int c = 0; c < L.n_keys; ++c) reinterpret_cast<int64_t*>(row)[c] = touched ? mkey_stored[c] : B2Q_I64_MAX;
+    } else if (L.has_key_col) {
       if (L.key_width == 4) {
         *reinterpret_cast<int32_t*>(row) = touched ? (int32_t)key : 0x7FFFFFFF;
         *reinterpret_cast<int32_t*>(row + 4) = 0;
@@ -971,7 +1018,7 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
       int64_t val = sl.init_val;
       if (touched && sl.kind != SLOT_NONE && sl.width != 0) {
         switch (sl.kind) {
-          case SLOT_KEY: val = key; break;
+          case SLOT_KEY: val = L.n_keys > 1 ? mkey_proj[sl.key_comp] : key; break;
           case SLOT_COUNT: val = A.accs[sl.acc][i]; break;
           default: {
             const int64_t raw = A.accs[sl.acc][i];
@@ -990,12 +1037,17 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
     if (L.keyless_marker >= 0 && vals[L.keyless_marker] == L.slots[L.keyless_marker].init_val) {
       for (int s = 0; s < L.n_slots; ++s) vals[s] = L.slots[s].init_val;
     }
+    int end = 0;
     for (int s = 0; s < L.n_slots; ++s) {
       const DevSlot& sl = L.slots[s];
       if (sl.kind == SLOT_NONE || sl.width == 0) continue;
       if (sl.width == 4) *reinterpret_cast<int32_t*>(row + sl.offset) = (int32_t)vals[s];
       else *reinterpret_cast<int64_t*>(row + sl.offset) = vals[s];
+      end = max(end, (int)sl.offset + sl.width);
     }
+    /* an odd number of 4-byte slots leaves alignment padding (QueryMemoryDescriptor.cpp:848-860); the buffer comes from
+     * a recycled pool, so write the zeros the reference's freshly allocated buffer would hold */
+    if (end) for (; end + 4 <= L.row_size; end += 4) *reinterpret_cast<int32_t*>(row + end) = 0;
   }
 }
 
@@ -1098,7 +1150,7 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
   c.grid = (int)(launch.total_chunks < max_ctas ? (launch.total_chunks > 0 ? launch.total_chunks : 1) : max_ctas);
   c.smem_bytes = 0;
   const int kernel = q.plan.kernel;
-  const bool key32 = q.prog.key.col >= 0 && q.prog.key.width <= 4;
+  const bool key32 = q.prog.n_keys <= 1 && q.prog.key.col >= 0 && q.prog.key.width <= 4;
   if (kernel == B2Q_KERNEL_NON_GROUPED) {
     c.smem_bytes = (size_t)q.smem.total_bytes;
     return launch_scan_t<MODE_SMEM, true, false>(a, c, st);

@@ -115,6 +115,8 @@ class Planner {
   bool filter_deleted_;
   std::vector<TargetDesc> targets_;
   bool grouped_ = false;
+  struct KeyComp { int col; int64_t min, max, card, mult; bool has_nulls; };
+  std::vector<KeyComp> keycomps_; /* multi-column perfect hash */
   int key_col_ = -1;
   bool keyless_ = false;
   int keyless_idx_ = -1;
@@ -141,7 +143,7 @@ class Planner {
   void validate() {
     if (u_.num_join_quals || u_.has_estimator || u_.num_order_entries || u_.has_union_all || u_.has_window_function)
       reject(B2Q_ERR_UNSUPPORTED, "join_quals / estimator / sort_info / union_all / window functions are outside this path");
-    if (u_.num_groupby_exprs > 1) reject(B2Q_ERR_UNSUPPORTED, "multi-column GROUP BY is outside this path (SURVEY §8f-4)");
+    if (u_.num_groupby_exprs > B2Q_MAX_GROUP_COLS) reject(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
     if (u_.num_groupby_exprs < 0 || u_.num_target_exprs <= 0 || u_.num_target_exprs > B2Q_MAX_TARGETS)
       reject(B2Q_ERR_INVALID_ARGUMENT, "bad groupby/target counts");
     if (eo_.output_columnar_hint) reject(B2Q_ERR_UNSUPPORTED, "columnar output layout");
@@ -313,13 +315,49 @@ class Planner {
   }
 
   void choose_hash_type(B2QPlan& p) {
-    grouped_ = u_.num_groupby_exprs == 1;
+    grouped_ = u_.num_groupby_exprs >= 1;
     p.key_col_id = -1;
     p.effective_key_width = 8;
     p.idx_target_as_key = -1;
+    p.num_group_cols = u_.num_groupby_exprs;
     if (!grouped_) {
       p.query_desc_type = B2Q_NonGroupedAggregate;
       p.entry_count = 1;
+      return;
+    }
+    if (u_.num_groupby_exprs > 1) {
+      /* getColRangeInfo for several GROUP BY columns (GroupByAndAggregate.cpp:240-280): perfect hash over the product
+       * of the per-column cardinalities when every column has a valid integer range and the product is within
+       * g_baseline_groupby_threshold (1e6); otherwise baseline hash, which for composite keys is outside this path */
+      int64_t cardinality = 1;
+      bool has_nulls = false;
+      for (int i = 0; i < u_.num_groupby_exprs; ++i) {
+        const B2QExpr& g = ex(u_.groupby_exprs[i]);
+        if (g.kind != B2Q_EXPR_COLUMN_VAR) reject(B2Q_ERR_UNSUPPORTED, "GROUP BY expression must be a ColumnVar");
+        if (col_type(g.col_id).is_fp()) reject(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash (fp key) is outside this path");
+        ColRange r = leaf_range(g.col_id);
+        narrow_by_simple_quals(g.col_id, r);
+        if (r.imin > r.imax) reject(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
+        KeyComp k{g.col_id, r.imin, r.imax, 0, cardinality, r.has_nulls};
+        int64_t span;
+        if (__builtin_sub_overflow(r.imax, r.imin, &span) || __builtin_add_overflow(span, int64_t(1 + (r.has_nulls ? 1 : 0)), &k.card) ||
+            __builtin_mul_overflow(cardinality, k.card, &cardinality))
+          reject(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
+        has_nulls |= r.has_nulls;
+        keycomps_.push_back(k);
+        p.group_col_ids[i] = g.col_id;
+        p.group_col_widths[i] = static_cast<int8_t>(col_type(g.col_id).size());
+      }
+      if (!cardinality || cardinality > 1000000) reject(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
+      key_col_ = keycomps_[0].col;
+      p.key_col_id = key_col_;
+      p.group_col_width = p.group_col_widths[0];
+      p.query_desc_type = B2Q_GroupByPerfectHash;
+      p.min_val = 0; p.max_val = cardinality; p.bucket = 0; p.has_nulls = has_nulls;
+      keyless_info();
+      p.keyless_hash = keyless_ ? 1 : 0;
+      p.idx_target_as_key = keyless_idx_;
+      p.entry_count = cardinality;
       return;
     }
     const B2QExpr& g = ex(u_.groupby_exprs[0]);
@@ -329,6 +367,8 @@ class Planner {
     if (kt.is_fp()) reject(B2Q_ERR_UNSUPPORTED, "floating-point GROUP BY key (baseline double keys) is outside this path");
     p.key_col_id = key_col_;
     p.group_col_width = kt.size();
+    p.group_col_ids[0] = key_col_;
+    p.group_col_widths[0] = static_cast<int8_t>(kt.size());
     ColRange r = leaf_range(key_col_);
     narrow_by_simple_quals(key_col_, r);
     bool perfect = r.imin <= r.imax;
@@ -400,7 +440,7 @@ class Planner {
     }
     p.num_targets = static_cast<int32_t>(targets_.size());
     p.num_slots = static_cast<int32_t>(logical.size());
-    const int64_t key_bytes = (grouped_ && !p.keyless_hash) ? align8(p.effective_key_width) : 0;
+    const int64_t key_bytes = (grouped_ && !p.keyless_hash) ? align8(static_cast<int64_t>(u_.num_groupby_exprs) * p.effective_key_width) : 0;
     int64_t cols = 0;
     for (size_t s = 0; s < logical.size(); ++s) {
       if (slot_key_ref_[s]) { p.slot_logical_width[s] = p.slot_padded_width[s] = 0; p.slot_offset[s] = key_bytes + cols; continue; }
@@ -648,12 +688,26 @@ class Planner {
     g.eager_args = g.est_selectivity >= 0.25f;
 
     /* key */
+    g.n_keys = static_cast<int32_t>(keycomps_.size());
+    for (size_t i = 0; i < keycomps_.size(); ++i) {
+      const KeyComp& kc = keycomps_[i];
+      const SqlType kt = col_type(kc.col);
+      DevKeyComp& d = g.keys[i];
+      d.col = launch_col(q, kc.col);
+      d.width = static_cast<int8_t>(phys_size(kc.col));
+      d.min_val = kc.min;
+      d.card = static_cast<uint32_t>(kc.card);
+      d.mult = static_cast<uint32_t>(kc.mult);
+      d.translate_null = kc.has_nulls && !kt.notnull;
+      d.null_val = kt.notnull ? kt.int_null() : phys_int_null(kc.col);
+      d.null_logical = kt.int_null();
+    }
     DevKey& k = g.key;
     k.col = -1;
     k.entry_count = p.entry_count;
     k.hash_magic = p.entry_count > 0 ? ~0ull / static_cast<uint64_t>(p.entry_count) + 1 : 0;
     k.null_idx = -1;
-    if (grouped_) {
+    if (grouped_ && keycomps_.size() <= 1) {
       const SqlType kt = col_type(key_col_);
       k.col = launch_col(q, key_col_);
       k.width = static_cast<int8_t>(phys_size(key_col_));
@@ -679,6 +733,8 @@ class Planner {
     L.key_width = static_cast<int8_t>(p.effective_key_width);
     L.baseline = p.query_desc_type == B2Q_GroupByBaselineHash;
     L.touched_acc = -1;
+    L.n_keys = g.n_keys;
+    for (int i = 0; i < g.n_keys; ++i) L.keys[i] = g.keys[i];
     L.keyless_marker = (grouped_ && p.keyless_hash) ? p.idx_target_as_key : -1;
     for (const TargetDesc& d : targets_) {
       const int s = d.first_slot;
@@ -689,8 +745,16 @@ class Planner {
       sl.acc = -1; sl.nn = -1;
       if (sl.width == 0) { sl.kind = SLOT_NONE; continue; }
       if (!d.is_agg) {
-        if (d.arg_col != key_col_) reject(B2Q_ERR_UNSUPPORTED, "non-aggregate target must be the GROUP BY column");
         sl.kind = SLOT_KEY;
+        sl.key_comp = 0;
+        if (keycomps_.size() > 1) {
+          int comp = -1;
+          for (size_t c = 0; c < keycomps_.size(); ++c) if (keycomps_[c].col == d.arg_col) comp = static_cast<int>(c);
+          if (comp < 0) reject(B2Q_ERR_UNSUPPORTED, "non-aggregate target must be a GROUP BY column");
+          sl.key_comp = static_cast<int8_t>(comp);
+        } else if (d.arg_col != key_col_) {
+          reject(B2Q_ERR_UNSUPPORTED, "non-aggregate target must be the GROUP BY column");
+        }
         continue;
       }
       if (sl.width == 4 && !(d.agg == B2Q_kCOUNT && d.arg_col < 0)) reject(B2Q_ERR_UNSUPPORTED, "4-byte slot with an aggregate argument");
@@ -741,7 +805,7 @@ class Planner {
     if (grouped_ && !p.keyless_hash && !L.baseline) L.touched_acc = find_or_add_acc(q, make_acc(q, ACC_TOUCH, nullptr));
     /* columns worth prefetching: filter columns always; key / arguments when they are loaded eagerly */
     for (int t = 0; t < g.filter.n_terms; ++t) g.col_prefetch[g.filter.terms[t].col] = 1;
-    if (grouped_ && g.eager_key) g.col_prefetch[g.key.col] = 1;
+    if (grouped_ && g.eager_key) { if (g.n_keys > 1) { for (int i = 0; i < g.n_keys; ++i) g.col_prefetch[g.keys[i].col] = 1; } else g.col_prefetch[g.key.col] = 1; }
     if (g.eager_args)
       for (int a = 0; a < g.n_accs; ++a) if (g.accs[a].col >= 0) g.col_prefetch[g.accs[a].col] = 1;
     /* fused fast path of the shared-memory-table kernel (the reference's JIT specialises per query; this is the

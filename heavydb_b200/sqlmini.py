@@ -2,7 +2,7 @@
 RelAlgExecutionUnit mirror, for the subset of the path:
 
     SELECT <col | COUNT(*) | COUNT(c) | SUM(c) | MIN(c) | MAX(c) | AVG(c)>, ...
-    FROM <table> [WHERE <c OP literal> {AND|OR} ... with parentheses] [GROUP BY c]
+    FROM <table> [WHERE <c OP literal> {AND|OR} ... with parentheses] [GROUP BY c {, c}]
 
 It plays the role Calcite + RelAlgTranslator play in the reference (kept, out of scope) and is test infrastructure.
 Like RelAlgTranslator/QualsConjunctiveForm, a top-level AND is split into separate quals, and a `col OP const`
@@ -128,6 +128,9 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
         p.eat()
         p.eat("BY")
         p.b.group_by(p.colid(p.eat()))
+        while p.peek() == ",":
+            p.eat()
+            p.b.group_by(p.colid(p.eat()))
     if p.peek() is not None:
         raise ValueError(f"trailing tokens: {p.t[p.i:]}")
     for t in targets:

@@ -201,6 +201,7 @@ enum {
 #define B2Q_MAX_SLOTS 16
 #define B2Q_MAX_TARGETS 16
 #define B2Q_MAX_FILTER_TERMS 8
+#define B2Q_MAX_GROUP_COLS 4
 
 typedef struct B2QTargetInfo { /* Shared/TargetInfo.h:49-78 */
   int32_t is_agg;
@@ -230,6 +231,12 @@ typedef struct B2QPlan {
   int32_t kernel;            /* B2Q_KERNEL_* chosen */
   int64_t row_size;          /* bytes, row-wise */
   int64_t buffer_size;       /* bytes of the whole result buffer */
+  /* multi-column perfect hash (GroupByAndAggregate.cpp:232-280, codegenPerfectHashFunction :1549-1597):
+   * entry = sum_i (key_i - min_i) * prod_{j<i} cardinality_j; min_val = 0, max_val = the cardinality product */
+  int32_t num_group_cols;
+  int32_t group_col_ids[B2Q_MAX_GROUP_COLS];
+  int8_t group_col_widths[B2Q_MAX_GROUP_COLS];
+  int32_t pad2_;
   int8_t slot_padded_width[B2Q_MAX_SLOTS];
   int8_t slot_logical_width[B2Q_MAX_SLOTS];
   int64_t slot_offset[B2Q_MAX_SLOTS]; /* row-wise: byte offset inside the row; columnar: offset of the column */

@@ -310,10 +310,17 @@ struct Range { /* ExpressionRange (Integer or Double or Invalid) */
   bool has_nulls{false};
 };
 
+struct KeyCol { /* one GROUP BY column of a multi-column perfect hash */
+  int col{-1};
+  int64_t min{0}, max{-1}, card{0}, mult{1};
+  bool has_nulls{false};
+};
+
 struct Plan {
   B2QPlan p{};
   std::vector<Target> targets;
   std::vector<Ti> slot_compact_ti;
+  std::vector<KeyCol> keys; /* size > 1: multi-column perfect hash */
 };
 
 const B2QExpr& expr_at(const B2QExecUnit& u, int idx) {
@@ -551,7 +558,7 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
                size_t max_groups_buffer_entry_guess, bool has_cardinality_estimation) {
   if (u.num_join_quals || u.has_estimator || u.num_order_entries || u.has_union_all || u.has_window_function)
     fail(B2Q_ERR_UNSUPPORTED, "joins / estimator / sort / union / window functions are outside this path");
-  if (u.num_groupby_exprs > 1) fail(B2Q_ERR_UNSUPPORTED, "multi-column GROUP BY");
+  if (u.num_groupby_exprs > B2Q_MAX_GROUP_COLS) fail(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
   if (u.num_target_exprs <= 0 || u.num_target_exprs > B2Q_MAX_TARGETS)
     fail(B2Q_ERR_INVALID_ARGUMENT, "bad target count");
   if (eo.output_columnar_hint) fail(B2Q_ERR_UNSUPPORTED, "columnar output");
@@ -569,7 +576,8 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
   Plan plan;
   B2QPlan& p = plan.p;
   const bool bigint_count = eo.bigint_count != 0;
-  const bool is_group_by = u.num_groupby_exprs == 1;
+  const bool is_group_by = u.num_groupby_exprs >= 1;
+  const bool multi_key = u.num_groupby_exprs > 1;
 
   for (int i = 0; i < u.num_target_exprs; ++i) plan.targets.push_back(get_target_info(u, u.target_exprs[i], bigint_count));
   bool any_agg = false;
@@ -579,7 +587,37 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
   /* ---- hash type: GroupByAndAggregate::getColRangeInfo (:232-365) + get_expr_range_info (:181-218) ---- */
   int key_col = -1;
   Range key_range;
-  if (is_group_by) {
+  if (multi_key) {
+    /* getColRangeInfo, groupby_exprs.size() != 1 (GroupByAndAggregate.cpp:240-280): every column must have a valid
+     * integer range; cardinality = product of the bucketed cardinalities; zero or > g_baseline_groupby_threshold
+     * (1e6, Execute.cpp:111) => baseline hash, which for several key columns is outside this path. */
+    int64_t cardinality = 1;
+    bool has_nulls = false;
+    for (int i = 0; i < u.num_groupby_exprs; ++i) {
+      const B2QExpr& g = expr_at(u, u.groupby_exprs[i]);
+      if (g.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "GROUP BY expression must be a ColumnVar");
+      if (is_fp(tbl.col_types[g.col_id].type)) fail(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash (fp key) is outside this path");
+      Range r = leaf_column_range(tbl, g.col_id);
+      apply_simple_quals(u, g.col_id, r);
+      if (r.kind != Range::Integer || r.imin > r.imax) fail(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
+      KeyCol k;
+      k.col = g.col_id; k.min = r.imin; k.max = r.imax; k.has_nulls = r.has_nulls;
+      int64_t span;
+      if (__builtin_sub_overflow(r.imax, r.imin, &span) || __builtin_add_overflow(span, int64_t(1 + (r.has_nulls ? 1 : 0)), &k.card))
+        fail(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
+      k.mult = cardinality;
+      if (__builtin_mul_overflow(cardinality, k.card, &cardinality)) fail(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
+      has_nulls |= r.has_nulls;
+      plan.keys.push_back(k);
+      p.group_col_ids[i] = g.col_id;
+      p.group_col_widths[i] = static_cast<int8_t>(type_size(tbl.col_types[g.col_id].type));
+    }
+    if (!cardinality || cardinality > 1000000) fail(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
+    p.query_desc_type = B2Q_GroupByPerfectHash;
+    p.min_val = 0; p.max_val = cardinality; p.bucket = 0; p.has_nulls = has_nulls;
+    key_col = plan.keys[0].col;
+    p.group_col_width = p.group_col_widths[0];
+  } else if (is_group_by) {
     const B2QExpr& g = expr_at(u, u.groupby_exprs[0]);
     if (g.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "GROUP BY expression must be a ColumnVar");
     key_col = g.col_id;
@@ -616,6 +654,8 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
     p.group_col_width = 0;
   }
   p.key_col_id = key_col;
+  p.num_group_cols = u.num_groupby_exprs;
+  if (!multi_key && is_group_by) { p.group_col_ids[0] = key_col; p.group_col_widths[0] = static_cast<int8_t>(p.group_col_width); }
 
   /* ---- keyless: initQueryMemoryDescriptorImpl :943-947 ---- */
   bool keyless = false;
@@ -683,11 +723,15 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
     /* keyless_hash (:327-333): no sort hint, no bucket, no baseline sort in this path */
     p.keyless_hash = (!p.bucket && keyless) ? 1 : 0;
     p.idx_target_as_key = keyless_index;
-    /* getBucketedCardinality (:367-375) */
-    int64_t card = p.max_val - p.min_val;
-    if (p.bucket) card /= p.bucket;
-    card += 1 + (p.has_nulls ? 1 : 0);
-    p.entry_count = std::max<int64_t>(card, 1);
+    if (multi_key) {
+      p.entry_count = p.max_val; /* col range info max contains the expected cardinality (QueryMemoryDescriptor.cpp:339-342) */
+    } else {
+      /* getBucketedCardinality (:367-375) */
+      int64_t card = p.max_val - p.min_val;
+      if (p.bucket) card /= p.bucket;
+      card += 1 + (p.has_nulls ? 1 : 0);
+      p.entry_count = std::max<int64_t>(card, 1);
+    }
     /* interleaved_bins_on_gpu (:364-369) is a GPU-layout detail of the reference; the CPU path never has it */
   } else { /* baseline (:380-398) */
     if (!has_cardinality_estimation) fail(B2Q_ERR_CARDINALITY_ESTIMATION_REQUIRED, "baseline hash needs a cardinality estimate");
@@ -731,7 +775,7 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
 
   /* ---- row size / offsets: getRowSize (:848-860), getColOffInBytes (:918-955), ColSlotContext alignment ---- */
   int64_t off = 0;
-  if (is_group_by && !p.keyless_hash) off = align_to_int64(1 * p.effective_key_width);
+  if (is_group_by && !p.keyless_hash) off = align_to_int64(static_cast<int64_t>(u.num_groupby_exprs) * p.effective_key_width);
   const int64_t key_bytes = off;
   int64_t cols = 0;
   for (int s = 0; s < p.num_slots; ++s) {
@@ -945,7 +989,7 @@ void init_buffer(const Plan& plan, std::vector<int8_t>& buf) {
     int8_t* row = buf.data() + e * p.row_size;
     if (has_key) {
       if (p.effective_key_width == 4) { int32_t k = kEmptyKey32; memcpy(row, &k, 4); }
-      else { int64_t k = kEmptyKey64; memcpy(row, &k, 8); }
+      else for (int kc = 0; kc < std::max(p.num_group_cols, 1); ++kc) { int64_t k = kEmptyKey64; memcpy(row + 8 * kc, &k, 8); } /* fill_empty_key */
     }
     for (int s = 0; s < p.num_slots; ++s) {
       const int w = p.slot_padded_width[s];
@@ -971,6 +1015,30 @@ int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo&
     if (p.query_desc_type == B2Q_NonGroupedAggregate) {
       row_base = buf.data();
     } else {
+      if (plan.keys.size() > 1) {
+        /* perfect_key_hash (codegenPerfectHashFunction, GroupByAndAggregate.cpp:1549-1597) over the NULL-translated
+         * keys, then get_matching_group_value_perfect_hash[_keyless] (RuntimeFunctions.cpp:2077-2103) */
+        int64_t keyv[B2Q_MAX_GROUP_COLS];
+        int64_t hash = 0;
+        bool oob = false;
+        for (size_t i = 0; i < plan.keys.size(); ++i) {
+          const KeyCol& kc = plan.keys[i];
+          int64_t k = decode_int_column(tbl, fr, kc.col, pos);
+          if (kc.has_nulls && !tbl.col_types[kc.col].notnull && k == inline_int_null_val(tbl.col_types[kc.col].type)) k = kc.max + 1;
+          keyv[i] = k;
+          const int64_t d = k - kc.min;
+          oob |= d < 0 || d >= kc.card;
+          hash += d * kc.mult;
+        }
+        if (oob) return B2Q_ERR_KEY_OUT_OF_RANGE;
+        row_base = buf.data() + hash * p.row_size;
+        if (!p.keyless_hash) {
+          int64_t* kp = reinterpret_cast<int64_t*>(row_base);
+          if (kp[0] == kEmptyKey64) for (size_t i = 0; i < plan.keys.size(); ++i) kp[i] = keyv[i];
+        }
+        for (const auto& t : plan.targets) update_target(plan, t, row_base, tbl, fr, pos);
+        continue;
+      }
       if (is_fp(key_type)) fail(B2Q_ERR_UNSUPPORTED, "floating-point GROUP BY key");
       int64_t key = decode_int_column(tbl, fr, key_col, pos);
       if (p.query_desc_type == B2Q_GroupByPerfectHash) {
@@ -1087,7 +1155,7 @@ int32_t reduce_buffers(const Plan& plan, std::vector<int8_t>& this_buf, const st
     const int8_t* that_row = that_buf.data() + e * p.row_size;
     if (p.query_desc_type == B2Q_GroupByPerfectHash) {
       int8_t* this_row = this_buf.data() + e * p.row_size;
-      if (!p.keyless_hash) memcpy(this_row, that_row, align_to_int64(p.effective_key_width)); /* copyKeyColWise / key copy */
+      if (!p.keyless_hash) memcpy(this_row, that_row, align_to_int64(static_cast<int64_t>(std::max(p.num_group_cols, 1)) * p.effective_key_width)); /* key copy */
       reduce_one_row(plan, this_row, that_row);
     } else {
       int64_t keybuf = 0;

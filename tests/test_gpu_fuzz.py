@@ -41,9 +41,13 @@ def rand_cond(rng, depth=0):
     return f"({a} {op} {b})"
 
 
-def rand_query(rng):
+def rand_query(rng, multi_key=False):
     key = rng.choice(KEY_COLS + [None, None])
     targets = [key] if key and rng.random() < 0.8 else []
+    if multi_key:     # composite key: perfect hash over the cardinality product, or refused (baseline) when too large
+        keys = rng.sample(["k8", "nn64", "a8", "k16", "nn32", "k32", "k64"], rng.choice([2, 2, 3]))
+        key = ", ".join(keys)
+        targets = [k for k in rng.sample(keys, len(keys)) if rng.random() < 0.8]
     for _ in range(rng.randint(1, 5)):
         agg = rng.choice(["COUNT", "SUM", "MIN", "MAX", "AVG", "COUNTSTAR"])
         if agg == "COUNTSTAR":
@@ -59,6 +63,29 @@ def rand_query(rng):
     if key:
         sql += f" GROUP BY {key}"
     return sql + ";"
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz_multi_key_queries(seed):
+    rng = random.Random(99 + seed)
+    n = [3, 700, 30000, 90000][seed]
+    table = random_table(n, seed=200 + seed, frag_rows=[2, 128, 30000, 25000][seed])
+    dev = gu.DeviceTable(table)
+    ran = 0
+    for _ in range(60):
+        sql = rand_query(rng, multi_key=True)
+        unit = sqlmini.parse(sql, table, RAND_NAMES)
+        try:
+            plan = executor.Executor().plan(unit, table)
+        except executor.UnsupportedOnThisPath:
+            continue     # cardinality product above the perfect-hash threshold, or an all-NULL key column
+        force = abi.KERNEL_PERFECT_GLOBAL if rng.random() < 0.3 else 0
+        try:
+            gu.run_both(unit, table, dev_table=dev, force_kernel=force)
+        except Exception as e:
+            raise AssertionError(f"query: {sql}\nforce_kernel={force}\n{e}") from e
+        ran += 1
+    assert ran >= 15
 
 
 @pytest.mark.parametrize("seed", range(6))

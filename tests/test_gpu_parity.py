@@ -13,7 +13,7 @@ import oracle_lib
 import ref_tables as rt
 import sqlmini
 from heavydb_b200 import abi, executor
-from test_oracle_golden import PATH_QUERIES, REFERENCE_QUERIES
+from test_oracle_golden import MULTI_KEY_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
 from test_planner_parity import EXTRA
 
 pytestmark = pytest.mark.gpu
@@ -25,7 +25,7 @@ def golden():
     return table, gu.DeviceTable(table)
 
 
-@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA)
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES)
 def test_golden_table_device_resident(golden, sql):
     table, dev = golden
     unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
@@ -145,6 +145,12 @@ RAND_QUERIES = [
     "SELECT COUNT(*) FROM r WHERE (nn32 < 100 AND nn64 > 0) OR (a16 >= 100 AND a16 <= 20000 AND dnn <> 0.5);",
     "SELECT COUNT(*), SUM(nn64) FROM r WHERE a64 > 5.5;",
     "SELECT COUNT(*), SUM(nn64) FROM r WHERE d <= 10;",
+    "SELECT k8, nn64, COUNT(*), SUM(a32), MIN(big), AVG(d) FROM r GROUP BY k8, nn64;",            # multi-column keys
+    "SELECT nn32, k8, nn64, COUNT(*), SUM(a64) FROM r WHERE nn32 < 30 GROUP BY nn32, k8, nn64;",
+    "SELECT k32, k8, SUM(dnn), COUNT(a16) FROM r WHERE k32 >= -20 AND k32 < 20 GROUP BY k32, k8;",
+    "SELECT k8, nn64, MIN(d), MAX(d) FROM r GROUP BY k8, nn64;",                                   # keyed (not keyless) layouts
+    "SELECT k8, k16, SUM(a64) FROM r GROUP BY k8, k16;",
+    "SELECT nn64, k8, AVG(d) FROM r WHERE a32 > 0 GROUP BY nn64, k8;",
 ]
 
 
@@ -154,6 +160,13 @@ def test_random_tables(n, frag_rows):
     dev = gu.DeviceTable(table)
     for sql in RAND_QUERIES:
         unit = sqlmini.parse(sql, table, RAND_NAMES)
+        try:
+            oracle_lib.plan(unit, table, entry_guess=3001, has_card=True)
+        except oracle_lib.OracleError as e:   # e.g. an all-NULL key column of a composite key: both sides must refuse
+            assert e.code == abi.ERR_UNSUPPORTED
+            with pytest.raises(executor.UnsupportedOnThisPath):
+                executor.Executor().plan(unit, table, max_groups_buffer_entry_guess=3001, has_cardinality_estimation=True)
+            continue
         gu.run_both(unit, table, entry_guess=3001, has_card=True, dev_table=dev)
 
 

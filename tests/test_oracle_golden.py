@@ -40,6 +40,19 @@ REFERENCE_QUERIES = [
     "SELECT AVG(dn) FROM test;",
 ]
 
+# Multi-column GROUP BY (perfect hash over the cardinality product)
+MULTI_KEY_QUERIES = [
+    "SELECT x, y, COUNT(*) FROM test GROUP BY x, y;",                      # verbatim, Select.GroupBy ExecuteTest.cpp:2590
+    "SELECT x, z, COUNT(*), SUM(t), MIN(d), MAX(dn), AVG(y) FROM test GROUP BY x, z;",
+    "SELECT y, smallint_nulls, COUNT(*), SUM(x) FROM test GROUP BY y, smallint_nulls;",
+    "SELECT w, x, y, COUNT(*), AVG(t) FROM test GROUP BY w, x, y;",
+    "SELECT y, w, COUNT(ofq), SUM(ofd) FROM test WHERE x = 7 GROUP BY y, w;",
+    "SELECT z, y, MIN(t), MAX(t) FROM test WHERE z > 0 GROUP BY z, y;",
+    "SELECT t, w, COUNT(*), COUNT(u) FROM test GROUP BY t, w;",
+    "SELECT x, y, z, w, SUM(t) FROM test GROUP BY x, y, z, w;",
+    "SELECT SUM(t), x, COUNT(*), y FROM test GROUP BY x, y;",
+]
+
 # Same table, more shapes of the path (filter + GROUP BY + every aggregate, nullable keys and arguments).
 PATH_QUERIES = [
     "SELECT x, COUNT(*) FROM test GROUP BY x;",
@@ -79,7 +92,7 @@ def env():
     return rt.make_table(rows), rt.make_sqlite(rows)
 
 
-@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES)
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + MULTI_KEY_QUERIES)
 def test_oracle_vs_sqlite(env, sql):
     table, con = env
     unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
@@ -88,6 +101,17 @@ def test_oracle_vs_sqlite(env, sql):
     ref = [tuple(r) for r in con.execute(sql.rstrip(";")).fetchall()]
     rt.assert_rows_match(ours, ref)
     assert res.row_count() == len(ref)
+
+
+def test_multi_column_baseline_is_rejected():
+    """A cardinality product above g_baseline_groupby_threshold (1e6, Execute.cpp:111) means baseline hash in the
+    reference; multi-column baseline keys are outside this path and must be refused, not mis-executed."""
+    table = rt.make_table(rt.test_rows())
+    for sql in ["SELECT y, ofd, COUNT(*) FROM test GROUP BY y, ofd;", "SELECT smallint_nulls, z, COUNT(*) FROM test GROUP BY smallint_nulls, z;"]:
+        unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
+        with pytest.raises(oracle_lib.OracleError) as ei:
+            oracle_lib.execute(unit, table)
+        assert ei.value.code == abi.ERR_UNSUPPORTED
 
 
 def test_known_answers():
