@@ -137,7 +137,7 @@ enum {
 };
 struct DevSlot {
   int64_t init_val;
-  int64_t offset;      /* byte offset inside the row */
+  int64_t offset;      /* byte offset inside the row (row-wise) or of the slot column (columnar) */
   int64_t identity;    /* identity of accs[acc] (used when nn == -2) */
   int32_t acc;         /* accumulator index */
   int32_t nn;          /* >= 0: accumulator whose value 0 means "no value seen" -> init_val;
@@ -162,7 +162,8 @@ struct DevLayout {
   int8_t has_key_col;    /* row starts with the group key(s) (non-keyless) */
   int8_t key_width;      /* 4 or 8 */
   int8_t baseline;       /* key comes from the keys[] array */
-  int8_t pad_[1];
+  int8_t columnar;       /* ResultSet.h:72-84 layout: slot offsets are column offsets, keys are int64 columns */
+  int64_t key_col_stride;/* columnar: bytes per key column = align8(8 * entry_count) */
   DevSlot slots[B2Q_MAX_SLOTS];
 };
 

@@ -523,20 +523,30 @@ static int32_t finalize_impl(B2QPartial* p, cudaStream_t st, B2QResultSet** out)
 }
 
 /* ---- result-set iteration ------------------------------------------------------------------------------- */
+/* where entry `e` keeps slot `s` / its first key: row-wise (ResultSet.h:55-70) or columnar (:72-84) */
+static const int8_t* rs_slot_ptr(const B2QResultSet* rs, int64_t e, int s) {
+  const B2QPlan& p = rs->q.plan;
+  return p.output_columnar ? rs->buf + p.slot_offset[s] + e * p.slot_padded_width[s] : rs->buf + e * p.row_size + p.slot_offset[s];
+}
+static const int8_t* rs_key_ptr(const B2QResultSet* rs, int64_t e) {
+  const B2QPlan& p = rs->q.plan;
+  return p.output_columnar ? rs->buf + e * 8 : rs->buf + e * p.row_size;
+}
+
+/* ResultSetStorage::isEmptyEntry / isEmptyEntryColumnar (ResultSetIteration.cpp:2457-2545) */
 static bool rs_is_empty_entry(const B2QResultSet* rs, int64_t e) {
   const B2QPlan& p = rs->q.plan;
   if (p.query_desc_type == B2Q_NonGroupedAggregate) return false;
-  const int8_t* row = rs->buf + e * p.row_size;
   if (p.keyless_hash) {
     const int s = p.idx_target_as_key;
     int64_t v;
-    if (p.slot_padded_width[s] == 4) { int32_t x; memcpy(&x, row + p.slot_offset[s], 4); v = x; }
-    else memcpy(&v, row + p.slot_offset[s], 8);
+    if (p.slot_padded_width[s] == 4) { int32_t x; memcpy(&x, rs_slot_ptr(rs, e, s), 4); v = x; }
+    else memcpy(&v, rs_slot_ptr(rs, e, s), 8);
     return v == p.init_vals[s];
   }
-  if (p.effective_key_width == 4) { int32_t k; memcpy(&k, row, 4); return k == 0x7FFFFFFF; }
+  if (!p.output_columnar && p.effective_key_width == 4) { int32_t k; memcpy(&k, rs_key_ptr(rs, e), 4); return k == 0x7FFFFFFF; }
   int64_t k;
-  memcpy(&k, row, 8);
+  memcpy(&k, rs_key_ptr(rs, e), 8);
   return k == B2Q_I64_MAX;
 }
 
@@ -686,14 +696,14 @@ int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
   const B2QPlan& p = rs->q.plan;
   while (rs->cursor < p.entry_count && rs_is_empty_entry(rs, rs->cursor)) ++rs->cursor;
   if (rs->cursor >= p.entry_count) return 0;
-  const int8_t* rowp = rs->buf + rs->cursor * p.row_size;
+  const int64_t entry = rs->cursor;
   ++rs->cursor;
   for (int i = 0; i < p.num_targets; ++i) {
     const B2QTargetInfo& t = p.targets[i];
     const int s = t.first_slot;
     int w = p.slot_padded_width[s];
-    const int8_t* ptr = rowp + p.slot_offset[s];
-    if (w == 0) { ptr = rowp; w = p.effective_key_width; } /* baseline: the key column is the target */
+    const int8_t* ptr = rs_slot_ptr(rs, entry, s);
+    if (w == 0) { ptr = rs_key_ptr(rs, entry); w = p.effective_key_width; } /* baseline: the key column is the target */
     int64_t ival;
     if (w == 4) { int32_t x; memcpy(&x, ptr, 4); ival = x; } else memcpy(&ival, ptr, 8);
     B2QTargetValue& o = row[i];
@@ -703,7 +713,7 @@ int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
     const int compact_type = (t.is_agg && has_arg && (t.agg_kind == B2Q_kMIN || t.agg_kind == B2Q_kMAX)) ? t.agg_arg_type.type : t.sql_type.type;
     if (t.is_agg && t.agg_kind == B2Q_kAVG) { /* pair_to_double, ResultSetBufferAccessors.h:197-227 */
       int64_t cnt;
-      memcpy(&cnt, rowp + p.slot_offset[s + 1], 8);
+      memcpy(&cnt, rs_slot_ptr(rs, entry, s + 1), 8);
       o.is_fp = 1;
       if (cnt == 0) { o.dval = DBL_MIN; o.is_null = 1; }
       else {

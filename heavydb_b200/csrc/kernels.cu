@@ -1000,7 +1000,16 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
       key = (i == L.null_idx) ? L.key_null_val : L.key_min + i;
       if (L.touched_acc >= 0) touched = reinterpret_cast<const uint8_t*>(A.accs[L.touched_acc])[i] != 0;
     }
-    if (L.has_key_col && L.n_keys > 1) {
+    if (L.has_key_col && L.columnar) {
+      /* int64 key columns (initColumnarGroups, QueryMemoryInitializer.cpp:729-735; keys written by
+       * get_columnar_group_bin_offset / set_matching_group_value_perfect_hash_columnar / get_group_value_columnar) */
+      if (L.n_keys > 1) {
+        for (int c = 0; c < L.n_keys; ++c) reinterpret_cast<int64_t*>(A.out + c * L.key_col_stride)[i] = touched ? mkey_stored[c] : B2Q_I64_MAX;
+      } else {
+        const int64_t stored = (!L.baseline && i == L.null_idx) ? L.key_min + i : key;
+        reinterpret_cast<int64_t*>(A.out)[i] = touched ? stored : B2Q_I64_MAX;
+      }
+    } else if (L.has_key_col && L.n_keys > 1) {
       for (int c = 0; c < L.n_keys; ++c) reinterpret_cast<int64_t*>(row)[c] = touched ? mkey_stored[c] : B2Q_I64_MAX;
     } else if (L.has_key_col) {
       if (L.key_width == 4) {
@@ -1036,6 +1045,19 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
      * (ResultSetIteration.cpp:2457-2476); leave it entirely at the init pattern */
     if (L.keyless_marker >= 0 && vals[L.keyless_marker] == L.slots[L.keyless_marker].init_val) {
       for (int s = 0; s < L.n_slots; ++s) vals[s] = L.slots[s].init_val;
+    }
+    if (L.columnar) {
+      for (int s = 0; s < L.n_slots; ++s) {
+        const DevSlot& sl = L.slots[s];
+        if (sl.kind == SLOT_NONE || sl.width == 0) continue;
+        if (sl.width == 4) reinterpret_cast<int32_t*>(A.out + sl.offset)[i] = (int32_t)vals[s];
+        else reinterpret_cast<int64_t*>(A.out + sl.offset)[i] = vals[s];
+      }
+      /* an odd number of 4-byte entries leaves 4 bytes of column padding; the pool buffer is recycled */
+      if (i == L.entry_count - 1 && (L.entry_count & 1))
+        for (int s = 0; s < L.n_slots; ++s)
+          if (L.slots[s].width == 4 && L.slots[s].kind != SLOT_NONE) reinterpret_cast<int32_t*>(A.out + L.slots[s].offset)[L.entry_count] = 0;
+      continue;
     }
     int end = 0;
     for (int s = 0; s < L.n_slots; ++s) {

@@ -146,7 +146,6 @@ class Planner {
     if (u_.num_groupby_exprs > B2Q_MAX_GROUP_COLS) reject(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
     if (u_.num_groupby_exprs < 0 || u_.num_target_exprs <= 0 || u_.num_target_exprs > B2Q_MAX_TARGETS)
       reject(B2Q_ERR_INVALID_ARGUMENT, "bad groupby/target counts");
-    if (eo_.output_columnar_hint) reject(B2Q_ERR_UNSUPPORTED, "columnar output layout");
     for (int c = 0; c < t_.num_cols; ++c) {
       const bool is_deleted_col = t_.deleted_column_plus1 == c + 1;
       if (t_.col_types[c].type == B2Q_kBOOLEAN) {
@@ -397,7 +396,8 @@ class Planner {
       const ColRange kr = leaf_range(key_col_);
       int w = 8;
       if (!(p.group_col_width == 8 && kr.has_nulls) && kr.imin > INT32_MIN && kr.imax < int64_t(INT32_MAX) - 1) w = 4;
-      p.effective_key_width = std::max(4, w);
+      /* group_col_compact_width = output_columnar ? 8 : pick_baseline_key_width (QueryMemoryDescriptor.cpp:391-393) */
+      p.effective_key_width = eo_.output_columnar_hint ? 8 : std::max(4, w);
       p.min_val = p.max_val = p.bucket = 0;
       p.has_nulls = 0;
     }
@@ -440,6 +440,31 @@ class Planner {
     }
     p.num_targets = static_cast<int32_t>(targets_.size());
     p.num_slots = static_cast<int32_t>(logical.size());
+    /* QueryMemoryDescriptor ctor (:510-536): without GPU sort the columnar decision is the hint itself */
+    p.output_columnar = eo_.output_columnar_hint ? 1 : 0;
+    if (p.output_columnar) {
+      /* ResultSet.h:72-84: [key columns, int64 each, absent if keyless][slot columns], every column 8-byte aligned
+       * (getPrependedGroupBufferSizeInBytes :987-997, getColOffInBytes :920-944) */
+      if (grouped_ && !p.keyless_hash && p.group_col_widths[0] != 8)
+        /* isEmptyEntryColumnar (ResultSetIteration.cpp:2533-2543) reads the first key column at the COLUMN's width
+         * although initColumnarGroups stores int64 keys: the reference's own reader/reduce misjudge emptiness, so
+         * there is no defined result to reproduce */
+        reject(B2Q_ERR_UNSUPPORTED, "columnar output with a stored GROUP BY key narrower than 8 bytes (reference reader reads it at the column's width)");
+      int64_t off = (grouped_ && !p.keyless_hash) ? static_cast<int64_t>(u_.num_groupby_exprs) * align8(8 * p.entry_count) : 0;
+      int64_t cols_size = 0;
+      for (size_t s = 0; s < logical.size(); ++s) {
+        p.slot_offset[s] = off;
+        if (slot_key_ref_[s]) { p.slot_logical_width[s] = p.slot_padded_width[s] = 0; continue; }
+        if (logical[s] > width) reject(B2Q_ERR_UNSUPPORTED, "slot wider than the compact width");
+        p.slot_logical_width[s] = logical[s];
+        p.slot_padded_width[s] = width;
+        off += align8(static_cast<int64_t>(width) * p.entry_count);
+        cols_size += width;
+      }
+      p.row_size = align8(cols_size);
+      p.buffer_size = off;
+      return;
+    }
     const int64_t key_bytes = (grouped_ && !p.keyless_hash) ? align8(static_cast<int64_t>(u_.num_groupby_exprs) * p.effective_key_width) : 0;
     int64_t cols = 0;
     for (size_t s = 0; s < logical.size(); ++s) {
@@ -724,6 +749,8 @@ class Planner {
     /* accumulators + slot recipes */
     DevLayout& L = q.layout;
     L.row_size = p.row_size;
+    L.columnar = p.output_columnar;
+    L.key_col_stride = align8(8 * p.entry_count);
     L.entry_count = p.entry_count;
     L.n_slots = p.num_slots;
     L.key_min = p.min_val;

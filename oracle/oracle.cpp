@@ -190,6 +190,19 @@ int64_t* get_group_value(int64_t* groups_buffer, uint32_t entry_count, const int
   return nullptr;
 }
 
+/* get_matching_group_value_columnar + get_group_value_columnar (GroupByRuntime.cpp:136-157 and the matcher in
+ * RuntimeFunctions.cpp): one 8-byte key per entry in the leading key column; returns the entry index or -1. */
+int64_t get_group_value_columnar_slot(int64_t* groups_buffer, uint32_t entry_count, int64_t key) {
+  const uint32_t h = murmur3(&key, 8, 0) % entry_count;
+  uint32_t probe = h;
+  do {
+    if (groups_buffer[probe] == key) return probe;
+    if (groups_buffer[probe] == kEmptyKey64) { groups_buffer[probe] = key; return probe; }
+    probe = (probe + 1) % entry_count;
+  } while (probe != h);
+  return -1;
+}
+
 /* ---------------------------------------------------------------------------------------------------
  * Aggregate update functions — QueryEngine/RuntimeFunctions.cpp:362 (agg_count), :1151-1173 (agg_sum/max/min/id),
  * :1313-1431 (*_skip_val), :1439-1473 (double), :1558-1593 (fp skip_val)
@@ -561,7 +574,6 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
   if (u.num_groupby_exprs > B2Q_MAX_GROUP_COLS) fail(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
   if (u.num_target_exprs <= 0 || u.num_target_exprs > B2Q_MAX_TARGETS)
     fail(B2Q_ERR_INVALID_ARGUMENT, "bad target count");
-  if (eo.output_columnar_hint) fail(B2Q_ERR_UNSUPPORTED, "columnar output");
   for (int c = 0; c < tbl.num_cols; ++c) {
     const bool is_deleted_col = tbl.deleted_column_plus1 == c + 1;
     if (tbl.col_types[c].type == B2Q_kBOOLEAN) { if (!is_deleted_col) fail(B2Q_ERR_UNSUPPORTED, "BOOLEAN is only supported as the deleted-rows column"); continue; }
@@ -711,7 +723,9 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
 
   /* ---- QueryMemoryDescriptor::init (:240-444) ---- */
   p.num_targets = static_cast<int32_t>(plan.targets.size());
-  p.output_columnar = 0;
+  /* QueryMemoryDescriptor ctor (:510-536): no GPU sort on this path, so output_columnar_ is the hint for every
+   * descriptor type we plan (no count-distinct / quantile / mode targets here) */
+  p.output_columnar = eo.output_columnar_hint ? 1 : 0;
   p.interleaved_bins_on_gpu = 0;
   p.keyless_hash = 0;
   p.idx_target_as_key = -1;
@@ -758,7 +772,7 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
       } else w = 8;
       kw = std::max(kw, w);
     }
-    p.effective_key_width = kw;
+    p.effective_key_width = p.output_columnar ? 8 : kw; /* group_col_compact_width = output_columnar ? 8 : pick_baseline_key_width (:391-393) */
     p.min_val = 0; p.max_val = 0; p.bucket = 0; p.has_nulls = 0; /* actual_col_range_info reset (:396-397) */
   }
 
@@ -774,18 +788,39 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
    * the retry (Execute.cpp:2260) re-plans with 8-byte slots.  Non-grouped already forces 8 above. */
 
   /* ---- row size / offsets: getRowSize (:848-860), getColOffInBytes (:918-955), ColSlotContext alignment ---- */
-  int64_t off = 0;
-  if (is_group_by && !p.keyless_hash) off = align_to_int64(static_cast<int64_t>(u.num_groupby_exprs) * p.effective_key_width);
-  const int64_t key_bytes = off;
-  int64_t cols = 0;
-  for (int s = 0; s < p.num_slots; ++s) {
-    const int w = p.slot_padded_width[s];
-    if (w == 8) cols = align_to_int64(cols);
-    p.slot_offset[s] = key_bytes + cols;
-    cols += w;
+  if (p.output_columnar) {
+    /* columnar: [key columns: align8(max(width,8) * N) each, absent if keyless][slot columns: align8(w * N) each]
+     * (getPrependedGroupBufferSizeInBytes :987-997, getColOffInBytes :920-944, getBufferSizeBytes :1084-1111) */
+    if (is_group_by && !p.keyless_hash && p.group_col_widths[0] != 8)
+      /* ResultSetStorage::isEmptyEntryColumnar (ResultSetIteration.cpp:2533-2543) indexes the first key column by
+       * groupColWidth(0) — the COLUMN's width — although the column is stored as int64 (initColumnarGroups,
+       * QueryMemoryInitializer.cpp:729-735): with a narrower key the reference's own reader and reduce misjudge
+       * emptiness.  There is no well-defined result to match, so the layout is refused on both sides. */
+      fail(B2Q_ERR_UNSUPPORTED, "columnar output with a stored GROUP BY key narrower than 8 bytes (reference reader reads it at the column's width)");
+    int64_t off = 0;
+    if (is_group_by && !p.keyless_hash) off = static_cast<int64_t>(u.num_groupby_exprs) * align_to_int64(8 * p.entry_count);
+    for (int s = 0; s < p.num_slots; ++s) {
+      p.slot_offset[s] = off;
+      off += align_to_int64(static_cast<int64_t>(p.slot_padded_width[s]) * p.entry_count);
+    }
+    p.row_size = 0;
+    for (int s = 0; s < p.num_slots; ++s) p.row_size += p.slot_padded_width[s]; /* getColsSize(); informational for columnar */
+    p.row_size = align_to_int64(p.row_size);
+    p.buffer_size = off;
+  } else {
+    int64_t off = 0;
+    if (is_group_by && !p.keyless_hash) off = align_to_int64(static_cast<int64_t>(u.num_groupby_exprs) * p.effective_key_width);
+    const int64_t key_bytes = off;
+    int64_t cols = 0;
+    for (int s = 0; s < p.num_slots; ++s) {
+      const int w = p.slot_padded_width[s];
+      if (w == 8) cols = align_to_int64(cols);
+      p.slot_offset[s] = key_bytes + cols;
+      cols += w;
+    }
+    p.row_size = align_to_int64(key_bytes + cols);
+    p.buffer_size = p.row_size * p.entry_count;
   }
-  p.row_size = align_to_int64(key_bytes + cols);
-  p.buffer_size = p.row_size * p.entry_count;
 
   /* ---- init vals: init_agg_val_vec (OutputBufferInitialization.cpp:26-86, :264-293) ---- */
   {
@@ -904,17 +939,23 @@ bool row_passes(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragment
  * cast to the slot width, `_skip_val` variant when target_info.skip_null_val.
  * All slots are 8 bytes wide here except the COUNT(*)-only 4-byte layout, which uses the _int32 variants.
  * ================================================================================================= */
-struct SlotWriter {
-  int8_t* row; /* points at the start of the row (after nothing): offsets are absolute inside the row */
-};
+/* where entry `e` keeps slot `s` / key column `c`: row-wise rows (ResultSet.h:55-70) or columnar (:72-84) */
+template <class B>
+inline B* slot_ptr(const B2QPlan& p, B* buf, int64_t e, int s) {
+  return p.output_columnar ? buf + p.slot_offset[s] + e * p.slot_padded_width[s] : buf + e * p.row_size + p.slot_offset[s];
+}
+template <class B>
+inline B* key_ptr(const B2QPlan& p, B* buf, int64_t e, int c) {
+  return p.output_columnar ? buf + c * align_to_int64(8 * p.entry_count) + e * 8 : buf + e * p.row_size + c * p.effective_key_width;
+}
 
-void update_target(const Plan& plan, const Target& t, int8_t* row_base, const B2QTableInfo& tbl,
+void update_target(const Plan& plan, const Target& t, int8_t* out, int64_t entry, const B2QTableInfo& tbl,
                    const B2QFragmentInfo& fr, int64_t pos) {
   const B2QPlan& p = plan.p;
   const int s = t.first_slot;
   const int w = p.slot_padded_width[s];
   if (w == 0) return; /* baseline: group-key targets are read from the key columns */
-  int8_t* slot = row_base + p.slot_offset[s];
+  int8_t* slot = slot_ptr(p, out, entry, s);
   if (w == 4) {
     /* only reachable for COUNT(*) / small-int key projections (pick_target_compact_width) */
     int32_t* a = reinterpret_cast<int32_t*>(slot);
@@ -943,7 +984,7 @@ void update_target(const Plan& plan, const Target& t, int8_t* row_base, const B2
       case B2Q_kMIN: if (need_skip_null) agg_min_double_skip_val(a, v, null_v); else agg_min_double(a, v); break;
       case B2Q_kMAX: if (need_skip_null) agg_max_double_skip_val(a, v, null_v); else agg_max_double(a, v); break;
       case B2Q_kAVG: {
-        int64_t* cnt = reinterpret_cast<int64_t*>(row_base + p.slot_offset[s + 1]);
+        int64_t* cnt = reinterpret_cast<int64_t*>(slot_ptr(p, out, entry, s + 1));
         if (need_skip_null) { agg_sum_double_skip_val(a, v, null_v); agg_count_double_skip_val(cnt, v, null_v); }
         else { agg_sum_double(a, v); agg_count(cnt); }
         break;
@@ -971,7 +1012,7 @@ void update_target(const Plan& plan, const Target& t, int8_t* row_base, const B2
     case B2Q_kMIN: if (need_skip_null) agg_min_skip_val(a, v, null_v); else agg_min(a, v); break;
     case B2Q_kMAX: if (need_skip_null) agg_max_skip_val(a, v, null_v); else agg_max(a, v); break;
     case B2Q_kAVG: {
-      int64_t* cnt = reinterpret_cast<int64_t*>(row_base + p.slot_offset[s + 1]);
+      int64_t* cnt = reinterpret_cast<int64_t*>(slot_ptr(p, out, entry, s + 1));
       if (need_skip_null) { agg_sum_skip_val(a, v, null_v); agg_count_skip_val(cnt, v, null_v); }
       else { agg_sum(a, v); agg_count(cnt); }
       break;
@@ -986,15 +1027,14 @@ void init_buffer(const Plan& plan, std::vector<int8_t>& buf) {
   buf.assign(static_cast<size_t>(p.buffer_size), 0);
   const bool has_key = p.query_desc_type != B2Q_NonGroupedAggregate && !p.keyless_hash;
   for (int64_t e = 0; e < p.entry_count; ++e) {
-    int8_t* row = buf.data() + e * p.row_size;
     if (has_key) {
-      if (p.effective_key_width == 4) { int32_t k = kEmptyKey32; memcpy(row, &k, 4); }
-      else for (int kc = 0; kc < std::max(p.num_group_cols, 1); ++kc) { int64_t k = kEmptyKey64; memcpy(row + 8 * kc, &k, 8); } /* fill_empty_key */
+      if (p.effective_key_width == 4) { int32_t k = kEmptyKey32; memcpy(key_ptr(p, buf.data(), e, 0), &k, 4); }
+      else for (int kc = 0; kc < std::max(p.num_group_cols, 1); ++kc) { int64_t k = kEmptyKey64; memcpy(key_ptr(p, buf.data(), e, kc), &k, 8); } /* fill_empty_key / initColumnarGroups */
     }
     for (int s = 0; s < p.num_slots; ++s) {
       const int w = p.slot_padded_width[s];
-      if (w == 8) memcpy(row + p.slot_offset[s], &p.init_vals[s], 8);
-      else if (w == 4) { int32_t v = static_cast<int32_t>(p.init_vals[s]); memcpy(row + p.slot_offset[s], &v, 4); }
+      if (w == 8) memcpy(slot_ptr(p, buf.data(), e, s), &p.init_vals[s], 8);
+      else if (w == 4) { int32_t v = static_cast<int32_t>(p.init_vals[s]); memcpy(slot_ptr(p, buf.data(), e, s), &v, 4); }
     }
   }
 }
@@ -1011,13 +1051,12 @@ int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo&
   const uint32_t row_size_quad = static_cast<uint32_t>(p.row_size / 8);
   for (int64_t pos = 0; pos < fr.num_tuples; ++pos) {
     if (!row_passes(u, tbl, fr, pos)) continue;
-    int8_t* row_base;
-    if (p.query_desc_type == B2Q_NonGroupedAggregate) {
-      row_base = buf.data();
-    } else {
+    int64_t entry = 0;
+    if (p.query_desc_type != B2Q_NonGroupedAggregate) {
       if (plan.keys.size() > 1) {
         /* perfect_key_hash (codegenPerfectHashFunction, GroupByAndAggregate.cpp:1549-1597) over the NULL-translated
-         * keys, then get_matching_group_value_perfect_hash[_keyless] (RuntimeFunctions.cpp:2077-2103) */
+         * keys, then get_matching_group_value_perfect_hash[_keyless] (RuntimeFunctions.cpp:2077-2103) or, columnar,
+         * set_matching_group_value_perfect_hash_columnar (:2109-2124) */
         int64_t keyv[B2Q_MAX_GROUP_COLS];
         int64_t hash = 0;
         bool oob = false;
@@ -1031,45 +1070,51 @@ int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo&
           hash += d * kc.mult;
         }
         if (oob) return B2Q_ERR_KEY_OUT_OF_RANGE;
-        row_base = buf.data() + hash * p.row_size;
+        entry = hash;
         if (!p.keyless_hash) {
-          int64_t* kp = reinterpret_cast<int64_t*>(row_base);
-          if (kp[0] == kEmptyKey64) for (size_t i = 0; i < plan.keys.size(); ++i) kp[i] = keyv[i];
-        }
-        for (const auto& t : plan.targets) update_target(plan, t, row_base, tbl, fr, pos);
-        continue;
-      }
-      if (is_fp(key_type)) fail(B2Q_ERR_UNSUPPORTED, "floating-point GROUP BY key");
-      int64_t key = decode_int_column(tbl, fr, key_col, pos);
-      if (p.query_desc_type == B2Q_GroupByPerfectHash) {
-        /* NULL key -> max+1 bucket (GroupByAndAggregate.cpp:1337-1350, GroupByRuntime.cpp:414-425) */
-        if (p.has_nulls && key_nullable && key == inline_int_null_val(key_type)) key = p.max_val + (p.bucket ? p.bucket : 1);
-        /* get_group_value_fast[_keyless] (GroupByRuntime.cpp:194-209, RuntimeFunctions.cpp:2126-2133) */
-        int64_t key_diff = key - p.min_val;
-        if (p.bucket) key_diff /= p.bucket;
-        if (key_diff < 0 || key_diff >= p.entry_count) return B2Q_ERR_KEY_OUT_OF_RANGE; /* stale stats: reference would corrupt memory */
-        row_base = buf.data() + key_diff * p.row_size;
-        if (!p.keyless_hash) {
-          int64_t* k = reinterpret_cast<int64_t*>(row_base);
-          if (*k == kEmptyKey64) *k = key;
+          int64_t first;
+          memcpy(&first, key_ptr(p, buf.data(), entry, 0), 8);
+          if (first == kEmptyKey64) for (size_t i = 0; i < plan.keys.size(); ++i) memcpy(key_ptr(p, buf.data(), entry, static_cast<int>(i)), &keyv[i], 8);
         }
       } else {
-        int64_t key_store = key;
-        int64_t* slots;
-        if (p.effective_key_width == 4) {
-          int32_t k32 = static_cast<int32_t>(key);
-          int64_t keybuf = 0;
-          memcpy(&keybuf, &k32, 4);
-          slots = get_group_value(reinterpret_cast<int64_t*>(buf.data()), static_cast<uint32_t>(p.entry_count), &keybuf, 1, 4, row_size_quad);
+        if (is_fp(key_type)) fail(B2Q_ERR_UNSUPPORTED, "floating-point GROUP BY key");
+        int64_t key = decode_int_column(tbl, fr, key_col, pos);
+        if (p.query_desc_type == B2Q_GroupByPerfectHash) {
+          /* NULL key -> max+1 bucket (GroupByAndAggregate.cpp:1337-1350, GroupByRuntime.cpp:414-425) */
+          if (p.has_nulls && key_nullable && key == inline_int_null_val(key_type)) key = p.max_val + (p.bucket ? p.bucket : 1);
+          /* get_group_value_fast[_keyless] (GroupByRuntime.cpp:194-209, RuntimeFunctions.cpp:2126-2133);
+           * columnar: get_columnar_group_bin_offset (GroupByRuntime.cpp:228-241) */
+          int64_t key_diff = key - p.min_val;
+          if (p.bucket) key_diff /= p.bucket;
+          if (key_diff < 0 || key_diff >= p.entry_count) return B2Q_ERR_KEY_OUT_OF_RANGE; /* stale stats: reference would corrupt memory */
+          entry = key_diff;
+          if (!p.keyless_hash) {
+            int64_t cur;
+            memcpy(&cur, key_ptr(p, buf.data(), entry, 0), 8);
+            if (cur == kEmptyKey64) memcpy(key_ptr(p, buf.data(), entry, 0), &key, 8);
+          }
+        } else if (p.output_columnar) {
+          /* get_group_value_columnar (GroupByRuntime.cpp:136-157): same hash and probe order over 8-byte keys, the
+           * key lives in the key column at the slot index */
+          entry = get_group_value_columnar_slot(reinterpret_cast<int64_t*>(buf.data()), static_cast<uint32_t>(p.entry_count), key);
+          if (entry < 0) return -static_cast<int32_t>(std::min<int64_t>(pos + 1, INT32_MAX));
         } else {
-          slots = get_group_value(reinterpret_cast<int64_t*>(buf.data()), static_cast<uint32_t>(p.entry_count), &key_store, 1, 8, row_size_quad);
+          int64_t key_store = key;
+          int64_t* slots;
+          if (p.effective_key_width == 4) {
+            int32_t k32 = static_cast<int32_t>(key);
+            int64_t keybuf = 0;
+            memcpy(&keybuf, &k32, 4);
+            slots = get_group_value(reinterpret_cast<int64_t*>(buf.data()), static_cast<uint32_t>(p.entry_count), &keybuf, 1, 4, row_size_quad);
+          } else {
+            slots = get_group_value(reinterpret_cast<int64_t*>(buf.data()), static_cast<uint32_t>(p.entry_count), &key_store, 1, 8, row_size_quad);
+          }
+          if (!slots) return -static_cast<int32_t>(std::min<int64_t>(pos + 1, INT32_MAX)); /* out of slots: -pos (GroupByAndAggregate.cpp:1149-1154) */
+          entry = (reinterpret_cast<int8_t*>(slots) - buf.data()) / p.row_size;
         }
-        if (!slots) return -static_cast<int32_t>(std::min<int64_t>(pos + 1, INT32_MAX)); /* out of slots: -pos (GroupByAndAggregate.cpp:1149-1154) */
-        /* row_base such that slot_offset (which includes the key bytes) lands on `slots` */
-        row_base = reinterpret_cast<int8_t*>(slots) - align_to_int64(p.effective_key_width);
       }
     }
-    for (const auto& t : plan.targets) update_target(plan, t, row_base, tbl, fr, pos);
+    for (const auto& t : plan.targets) update_target(plan, t, buf.data(), entry, tbl, fr, pos);
   }
   return 0;
 }
@@ -1077,31 +1122,30 @@ int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo&
 /* ---- is the entry empty?  ResultSetStorage::isEmptyEntry (ResultSetIteration.cpp:2457-2492) ---- */
 bool is_empty_entry(const B2QPlan& p, const int8_t* buf, int64_t entry) {
   if (p.query_desc_type == B2Q_NonGroupedAggregate) return false;
-  const int8_t* row = buf + entry * p.row_size;
-  if (p.keyless_hash) {
+  if (p.keyless_hash) { /* also isEmptyEntryColumnar (:2498-2526) */
     const int s = p.idx_target_as_key;
     const int w = p.slot_padded_width[s];
     int64_t v;
-    if (w == 4) { int32_t x; memcpy(&x, row + p.slot_offset[s], 4); v = x; } else memcpy(&v, row + p.slot_offset[s], 8);
+    if (w == 4) { int32_t x; memcpy(&x, slot_ptr(p, buf, entry, s), 4); v = x; } else memcpy(&v, slot_ptr(p, buf, entry, s), 8);
     return v == p.init_vals[s];
   }
-  if (p.effective_key_width == 4) { int32_t k; memcpy(&k, row, 4); return k == kEmptyKey32; }
-  int64_t k;
-  memcpy(&k, row, 8);
+  if (!p.output_columnar && p.effective_key_width == 4) { int32_t k; memcpy(&k, key_ptr(p, buf, entry, 0), 4); return k == kEmptyKey32; }
+  int64_t k; /* columnar: first key column, stored as int64 (the plan refuses narrower first key columns) */
+  memcpy(&k, key_ptr(p, buf, entry, 0), 8);
   return k == kEmptyKey64;
 }
 
 /* ---- ResultSetStorage::reduceOneSlot (ResultSetReduction.cpp:1496-1566) with the AGGREGATE_ONE_* macros
  * (:1290-1437): COUNT merges as SUM, AVG merges (sum, count) separately, nullable values use *_skip_val with the
  * slot's init value as the skip value. ---- */
-void reduce_one_row(const Plan& plan, int8_t* this_row, const int8_t* that_row) {
+void reduce_one_row(const Plan& plan, int8_t* this_buf, int64_t this_e, const int8_t* that_buf, int64_t that_e) {
   const B2QPlan& p = plan.p;
   for (const auto& t : plan.targets) {
     const int s = t.first_slot;
     const int w = p.slot_padded_width[s];
     if (w == 0) continue;
-    int8_t* tp = this_row + p.slot_offset[s];
-    const int8_t* op = that_row + p.slot_offset[s];
+    int8_t* tp = slot_ptr(p, this_buf, this_e, s);
+    const int8_t* op = slot_ptr(p, that_buf, that_e, s);
     const int64_t init_val = p.init_vals[s];
     if (w == 4) {
       int32_t a, b;
@@ -1119,9 +1163,9 @@ void reduce_one_row(const Plan& plan, int8_t* this_row, const int8_t* that_row) 
     switch (t.agg_kind) {
       case B2Q_kCOUNT: agg_sum(a, b); break; /* AGGREGATE_ONE_COUNT */
       case B2Q_kAVG: {
-        int64_t* ac = reinterpret_cast<int64_t*>(this_row + p.slot_offset[s + 1]);
+        int64_t* ac = reinterpret_cast<int64_t*>(slot_ptr(p, this_buf, this_e, s + 1));
         int64_t bc;
-        memcpy(&bc, that_row + p.slot_offset[s + 1], 8);
+        memcpy(&bc, slot_ptr(p, that_buf, that_e, s + 1), 8);
         agg_sum(ac, bc);
       } /* fall thru */
       case B2Q_kSUM:
@@ -1147,24 +1191,30 @@ void reduce_one_row(const Plan& plan, int8_t* this_row, const int8_t* that_row) 
 int32_t reduce_buffers(const Plan& plan, std::vector<int8_t>& this_buf, const std::vector<int8_t>& that_buf) {
   const B2QPlan& p = plan.p;
   if (p.query_desc_type == B2Q_NonGroupedAggregate) {
-    reduce_one_row(plan, this_buf.data(), that_buf.data());
+    reduce_one_row(plan, this_buf.data(), 0, that_buf.data(), 0);
     return 0;
   }
   for (int64_t e = 0; e < p.entry_count; ++e) {
     if (is_empty_entry(p, that_buf.data(), e)) continue;
-    const int8_t* that_row = that_buf.data() + e * p.row_size;
     if (p.query_desc_type == B2Q_GroupByPerfectHash) {
-      int8_t* this_row = this_buf.data() + e * p.row_size;
-      if (!p.keyless_hash) memcpy(this_row, that_row, align_to_int64(static_cast<int64_t>(std::max(p.num_group_cols, 1)) * p.effective_key_width)); /* key copy */
-      reduce_one_row(plan, this_row, that_row);
+      if (!p.keyless_hash) /* key copy (copyKeyColWise :452-476 when columnar) */
+        for (int c = 0; c < std::max(p.num_group_cols, 1); ++c)
+          memcpy(key_ptr(p, this_buf.data(), e, c), key_ptr(p, that_buf.data(), e, c), p.output_columnar ? 8 : p.effective_key_width);
+      reduce_one_row(plan, this_buf.data(), e, that_buf.data(), e);
     } else {
       int64_t keybuf = 0;
-      memcpy(&keybuf, that_row, p.effective_key_width);
-      int64_t* slots = get_group_value(reinterpret_cast<int64_t*>(this_buf.data()), static_cast<uint32_t>(p.entry_count), &keybuf, 1,
-                                       static_cast<uint32_t>(p.effective_key_width), static_cast<uint32_t>(p.row_size / 8));
-      if (!slots) return B2Q_ERR_OUT_OF_SLOTS;
-      int8_t* this_row = reinterpret_cast<int8_t*>(slots) - align_to_int64(p.effective_key_width);
-      reduce_one_row(plan, this_row, that_row);
+      memcpy(&keybuf, key_ptr(p, that_buf.data(), e, 0), p.effective_key_width);
+      int64_t this_e;
+      if (p.output_columnar) {
+        this_e = get_group_value_columnar_slot(reinterpret_cast<int64_t*>(this_buf.data()), static_cast<uint32_t>(p.entry_count), keybuf);
+        if (this_e < 0) return B2Q_ERR_OUT_OF_SLOTS;
+      } else {
+        int64_t* slots = get_group_value(reinterpret_cast<int64_t*>(this_buf.data()), static_cast<uint32_t>(p.entry_count), &keybuf, 1,
+                                         static_cast<uint32_t>(p.effective_key_width), static_cast<uint32_t>(p.row_size / 8));
+        if (!slots) return B2Q_ERR_OUT_OF_SLOTS;
+        this_e = (reinterpret_cast<int8_t*>(slots) - this_buf.data()) / p.row_size;
+      }
+      reduce_one_row(plan, this_buf.data(), this_e, that_buf.data(), e);
     }
   }
   return 0;
@@ -1285,7 +1335,7 @@ ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue
   const B2QPlan& p = r->plan.p;
   while (r->cursor < p.entry_count && is_empty_entry(p, r->buf.data(), r->cursor)) ++r->cursor;
   if (r->cursor >= p.entry_count) return 0;
-  const int8_t* rowp = r->buf.data() + r->cursor * p.row_size;
+  const int64_t entry = r->cursor;
   ++r->cursor;
   for (size_t i = 0; i < r->plan.targets.size(); ++i) {
     Target t = r->plan.targets[i];
@@ -1295,9 +1345,9 @@ ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue
     }
     const int s = t.first_slot;
     int w = p.slot_padded_width[s];
-    const int8_t* ptr = rowp + p.slot_offset[s];
-    if (w == 0) { /* baseline: key column (getTargetValueFromBufferRowwise, :2425-2452) */
-      ptr = rowp;
+    const int8_t* ptr = slot_ptr(p, r->buf.data(), entry, s);
+    if (w == 0) { /* baseline: key column (getTargetValueFromBufferRowwise :2425-2452 / ...Colwise :2267-2340) */
+      ptr = key_ptr(p, r->buf.data(), entry, 0);
       w = p.effective_key_width;
     }
     int64_t ival;
@@ -1307,7 +1357,7 @@ ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue
     const Ti chosen = get_compact_type(t);
     if (t.is_agg && t.agg_kind == B2Q_kAVG) {
       int64_t cnt;
-      memcpy(&cnt, rowp + p.slot_offset[s + 1], 8);
+      memcpy(&cnt, slot_ptr(p, r->buf.data(), entry, s + 1), 8);
       o.is_fp = 1;
       if (cnt == 0) { o.dval = kNullDouble; o.is_null = 1; }
       else {

@@ -72,6 +72,8 @@ def buffers_equal(got: np.ndarray, want: np.ndarray, plan: abi.Plan, fp_rtol=FP_
     assert got.size == want.size == plan.buffer_size
     if plan.buffer_size == 0:
         return
+    if plan.output_columnar:
+        return columnar_buffers_equal(got, want, plan, fp_rtol, empty)
     rs = plan.row_size
     g = got.view(np.int8).reshape(-1, rs)
     w = want.view(np.int8).reshape(-1, rs)
@@ -95,11 +97,45 @@ def buffers_equal(got: np.ndarray, want: np.ndarray, plan: abi.Plan, fp_rtol=FP_
     assert np.array_equal(g[:, mask], w[:, mask]), "integer part of the output buffer differs from the oracle"
 
 
+def columnar_buffers_equal(got, want, plan, fp_rtol, empty):
+    """Columnar layout (ResultSet.h:72-84): int64 key columns (unless keyless), then one 8-byte-aligned column per slot."""
+    n = plan.entry_count
+    g, w = got.view(np.int8), want.view(np.int8)
+    keep = slice(None) if empty is None else ~empty
+    if plan.query_desc_type != abi.NonGroupedAggregate and not plan.keyless_hash:
+        stride = (8 * n + 7) // 8 * 8
+        for c in range(max(plan.num_group_cols, 1)):
+            a = g[c * stride:c * stride + 8 * n].view(np.int64)
+            b = w[c * stride:c * stride + 8 * n].view(np.int64)
+            assert np.array_equal(a[keep], b[keep]), f"key column {c} differs from the oracle"
+    fp_sum_slots = {t.first_slot for t in plan.targets[: plan.num_targets]
+                    if t.is_agg and t.agg_kind in (abi.kSUM, abi.kAVG) and t.agg_arg_type.type == abi.kDOUBLE}
+    for s in range(plan.num_slots):
+        wd = plan.slot_padded_width[s]
+        if wd == 0:
+            continue
+        off = plan.slot_offset[s]
+        dt = np.int32 if wd == 4 else np.int64
+        a, b = g[off:off + wd * n].view(dt)[keep], w[off:off + wd * n].view(dt)[keep]
+        if s in fp_sum_slots:
+            a, b = a.view(np.float64), b.view(np.float64)
+            ok = (a == b) | (np.abs(a - b) <= fp_rtol * np.abs(b))
+            assert ok.all(), f"fp SUM slot {s}: {a[~ok][:4]} vs {b[~ok][:4]}"
+        else:
+            assert np.array_equal(a, b), f"slot column {s} differs from the oracle"
+    if empty is None:
+        mask = np.ones(g.size, dtype=bool)      # whole buffer incl. alignment padding, minus the fp SUM columns
+        for s in fp_sum_slots:
+            mask[plan.slot_offset[s]:plan.slot_offset[s] + 8 * n] = False
+        assert np.array_equal(g[mask], w[mask]), "columnar buffer differs from the oracle outside the fp SUM columns"
+
+
 def run_both(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=False, bigint_count=False, force_kernel=0,
-             device_resident=True, compare_buffers=True, oracle_threads=4, dev_table: DeviceTable | None = None):
+             device_resident=True, compare_buffers=True, oracle_threads=4, dev_table: DeviceTable | None = None,
+             output_columnar=False):
     """Returns (gpu ResultSet, oracle result).  Asserts plan, rows and (unless baseline) buffers agree."""
     ex = executor.Executor()
-    eo = executor.execution_options(bigint_count=bigint_count, force_kernel=force_kernel)
+    eo = executor.execution_options(bigint_count=bigint_count, force_kernel=force_kernel, output_columnar_hint=output_columnar)
     if device_resident:
         dt = dev_table or DeviceTable(table)
         rs = ex.executeWorkUnit(entry_guess, True, dt.table, unit, eo=eo, has_cardinality_estimation=has_card,
@@ -108,7 +144,7 @@ def run_both(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=Fals
         rs = ex.executeWorkUnit(entry_guess, True, table, unit, eo=eo, has_cardinality_estimation=has_card,
                                 memory_level=abi.CPU_LEVEL)
     ref = oracle_lib.execute(unit, table, entry_guess=entry_guess, has_card=has_card, bigint_count=bigint_count,
-                             num_threads=oracle_threads)
+                             num_threads=oracle_threads, output_columnar=output_columnar)
     gp, op = rs.getQueryMemDesc(), ref.plan
     assert gp.as_dict() == op.as_dict()
     assert rs.colCount() == ref.col_count()

@@ -112,10 +112,11 @@ def make_eo(bigint_count=False, force_kernel=0, output_columnar=False, device=-1
     return eo
 
 
-def plan(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=False, bigint_count=False) -> abi.Plan:
+def plan(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=False, bigint_count=False,
+         output_columnar=False) -> abi.Plan:
     bt = table.build(abi.CPU_LEVEL)
     out = abi.Plan()
-    eo = make_eo(bigint_count)
+    eo = make_eo(bigint_count, output_columnar=output_columnar)
     rc = lib().oracle_plan(C.byref(unit.unit), C.byref(bt.info), C.byref(eo), entry_guess, int(has_card), C.byref(out))
     if rc:
         raise OracleError(rc, lib().oracle_last_error().decode())
@@ -123,10 +124,10 @@ def plan(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=False, b
 
 
 def execute(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=False, bigint_count=False,
-            num_threads=1) -> OracleResult:
+            num_threads=1, output_columnar=False) -> OracleResult:
     bt = table.build(abi.CPU_LEVEL)
     h = C.c_void_p()
-    eo = make_eo(bigint_count)
+    eo = make_eo(bigint_count, output_columnar=output_columnar)
     rc = lib().oracle_execute(C.byref(unit.unit), C.byref(bt.info), C.byref(eo), entry_guess, int(has_card),
                               num_threads, C.byref(h))
     if rc:

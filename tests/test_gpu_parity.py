@@ -82,6 +82,43 @@ def test_empty_table_and_empty_fragments():
 
 
 # ---- randomized tables -------------------------------------------------------------------------------------
+def _columnar_or_both_refuse(unit, table, dev, **kw):
+    """Run with the columnar hint; layouts the reference's reader cannot read (see planner.cpp) are refused by both."""
+    try:
+        oracle_lib.plan(unit, table, entry_guess=kw.get("entry_guess", 0), has_card=kw.get("has_card", False), output_columnar=True)
+    except oracle_lib.OracleError as e:
+        assert e.code == abi.ERR_UNSUPPORTED
+        with pytest.raises(executor.UnsupportedOnThisPath):
+            executor.Executor().plan(unit, table, eo=executor.execution_options(output_columnar_hint=True),
+                                     max_groups_buffer_entry_guess=kw.get("entry_guess", 0),
+                                     has_cardinality_estimation=kw.get("has_card", False))
+        return False
+    rs, _ = gu.run_both(unit, table, dev_table=dev, output_columnar=True, **kw)
+    assert rs.getQueryMemDesc().output_columnar == 1
+    return True
+
+
+def test_golden_table_columnar_output():
+    """eo.output_columnar_hint (--enable-columnar-output / the columnar hint): ResultSet.h:72-84 layout, bit-exact."""
+    table = rt.make_table(rt.test_rows())
+    dev = gu.DeviceTable(table)
+    ran = 0
+    for sql in REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES:
+        unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
+        ran += _columnar_or_both_refuse(unit, table, dev, entry_guess=48, has_card=True)
+    assert ran >= 40
+
+
+def test_random_table_columnar_output():
+    table = random_table(50000, seed=77, frag_rows=16384)
+    dev = gu.DeviceTable(table)
+    ran = 0
+    for sql in RAND_QUERIES:
+        unit = sqlmini.parse(sql, table, RAND_NAMES)
+        ran += _columnar_or_both_refuse(unit, table, dev, entry_guess=3001, has_card=True)
+    assert ran >= 15
+
+
 RAND_COLS = [
     ("k8", abi.kTINYINT, False), ("k16", abi.kSMALLINT, False), ("k32", abi.kINT, False), ("k64", abi.kBIGINT, False),
     ("nn32", abi.kINT, True), ("nn64", abi.kBIGINT, True), ("a8", abi.kTINYINT, False), ("a16", abi.kSMALLINT, True),

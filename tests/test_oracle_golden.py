@@ -103,6 +103,41 @@ def test_oracle_vs_sqlite(env, sql):
     assert res.row_count() == len(ref)
 
 
+COLUMNAR_EXTRA = [   # 8-byte stored keys: keyed (non-keyless) perfect hash and baseline hash in the columnar layout
+    "SELECT t, MIN(y), MAX(dn) FROM test GROUP BY t;",
+    "SELECT t, z, MIN(y) FROM test GROUP BY t, z;",
+    "SELECT ofq, COUNT(*), SUM(x), AVG(d) FROM test WHERE ofq < 100 OR x > 100 GROUP BY ofq;",   # baseline hash
+    "SELECT ufq, MIN(y) FROM test WHERE ufq > 0 OR x > 100 GROUP BY ufq;",
+]
+
+
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + MULTI_KEY_QUERIES + COLUMNAR_EXTRA)
+def test_oracle_columnar_vs_sqlite(env, sql):
+    """--enable-columnar-output / the columnar hint (eo.output_columnar_hint): same answers from the columnar buffer
+    (ResultSet.h:72-84), including the host reduce over the 2-row fragments."""
+    table, con = env
+    unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
+    try:
+        res = oracle_lib.execute(unit, table, entry_guess=64, has_card=True, output_columnar=True)
+    except oracle_lib.OracleError as e:
+        # keyed layout whose first stored key is narrower than 8 bytes: refused (see oracle.cpp, make_plan)
+        assert e.code == abi.ERR_UNSUPPORTED and "narrower than 8 bytes" in str(e)
+        rw = oracle_lib.plan(unit, table, entry_guess=64, has_card=True)
+        assert not rw.keyless_hash and rw.group_col_widths[0] < 8
+        return
+    p = res.plan
+    assert p.output_columnar == 1
+    ref = [tuple(r) for r in con.execute(sql.rstrip(";")).fetchall()]
+    rt.assert_rows_match(res.rows(), ref)
+    assert res.row_count() == len(ref)
+    if p.query_desc_type != abi.NonGroupedAggregate:   # the layout itself: slot columns back to back, 8-byte aligned
+        n, off = p.entry_count, (0 if p.keyless_hash else p.num_group_cols * ((8 * p.entry_count + 7) // 8 * 8))
+        for s in range(p.num_slots):
+            assert p.slot_offset[s] == off
+            off += (p.slot_padded_width[s] * n + 7) // 8 * 8
+        assert p.buffer_size == off
+
+
 def test_multi_column_baseline_is_rejected():
     """A cardinality product above g_baseline_groupby_threshold (1e6, Execute.cpp:111) means baseline hash in the
     reference; multi-column baseline keys are outside this path and must be refused, not mis-executed."""

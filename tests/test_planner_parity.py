@@ -33,6 +33,23 @@ def test_plan_matches_oracle(table, sql, bigint_count):
     assert got == want
 
 
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES)
+def test_columnar_plan_matches_oracle(table, sql):
+    """eo.output_columnar_hint: same layout decision (ResultSet.h:72-84 offsets) or the same refusal on both sides."""
+    unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
+    eo = executor.execution_options(output_columnar_hint=True)
+    kw = dict(max_groups_buffer_entry_guess=48, has_cardinality_estimation=True)
+    try:
+        want = oracle_lib.plan(unit, table, entry_guess=48, has_card=True, output_columnar=True).as_dict()
+    except oracle_lib.OracleError as e:
+        assert e.code == abi.ERR_UNSUPPORTED
+        with pytest.raises(executor.UnsupportedOnThisPath):
+            executor.Executor().plan(unit, table, eo=eo, **kw)
+        return
+    got = executor.Executor().plan(unit, table, eo=eo, **kw).as_dict()
+    assert got == want and got["output_columnar"] == 1
+
+
 def test_cardinality_estimation_required(table):
     unit = sqlmini.parse("SELECT ofq, COUNT(*) FROM test GROUP BY ofq;", table, rt.TEST_NAMES)
     with pytest.raises(executor.CardinalityEstimationRequired):
