@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -79,6 +79,11 @@ class Expr(C.Structure):
     ]
 
 
+class OrderEntry(C.Structure):
+    """Analyzer::OrderEntry (Analyzer/Analyzer.h:2960-2968)."""
+    _fields_ = [("tle_no", C.c_int32), ("is_desc", C.c_int8), ("nulls_first", C.c_int8), ("pad_", C.c_int8 * 2)]
+
+
 class ExecUnit(C.Structure):
     _fields_ = [
         ("exprs", C.POINTER(Expr)),
@@ -94,10 +99,13 @@ class ExecUnit(C.Structure):
         ("scan_limit", C.c_int64),
         ("num_join_quals", C.c_int32),
         ("has_estimator", C.c_int32),
-        ("num_order_entries", C.c_int32),
         ("has_union_all", C.c_int32),
         ("has_window_function", C.c_int32),
-        ("pad_", C.c_int32),
+        ("order_entries", C.POINTER(OrderEntry)),
+        ("num_order_entries", C.c_int32),
+        ("has_limit", C.c_int32),
+        ("limit", C.c_int64),
+        ("offset", C.c_int64),
     ]
 
 
@@ -278,6 +286,9 @@ class UnitBuilder:
         self.targets: List[int] = []
         self.scan_limit = 0
         self.unsupported: Dict[str, int] = {}
+        self.order: List[Tuple[int, bool, bool]] = []   # sort_info.order_entries: (tle_no 1-based, is_desc, nulls_first)
+        self.limit: Optional[int] = None
+        self.offset = 0
 
     # -- expression nodes ---------------------------------------------------------------------------------
     def col(self, col_id: int) -> int:
@@ -340,6 +351,12 @@ class UnitBuilder:
     def target_col(self, col_id: int):
         return self.target(self.col(col_id))
 
+    def order_by(self, tle_no: int, is_desc: bool = False, nulls_first: Optional[bool] = None):
+        """sort_info.order_entries.  Default NULL placement is the reference's (NULLs are the largest values:
+        last when ascending, first when descending — RelAlgTranslator / Calcite's default collation)."""
+        self.order.append((tle_no, bool(is_desc), bool(is_desc) if nulls_first is None else bool(nulls_first)))
+        return self
+
     def build(self) -> "BuiltUnit":
         return BuiltUnit(self)
 
@@ -368,6 +385,11 @@ class BuiltUnit:
         u.groupby_exprs, u.num_groupby_exprs = self._g, len(b.groupby)
         u.target_exprs, u.num_target_exprs = self._t, len(b.targets)
         u.scan_limit = b.scan_limit
+        self._order = (OrderEntry * max(len(b.order), 1))()
+        for i, (tle, desc, nf) in enumerate(b.order):
+            self._order[i].tle_no, self._order[i].is_desc, self._order[i].nulls_first = tle, int(desc), int(nf)
+        u.order_entries, u.num_order_entries = self._order, len(b.order)
+        u.has_limit, u.limit, u.offset = int(b.limit is not None), int(b.limit or 0), int(b.offset)
         for k, v in b.unsupported.items():
             setattr(u, k, v)
         self.unit = u

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2q.so")
-SOURCES = ["kernels.cu", "executor.cpp", "planner.cpp"]
+SOURCES = ["kernels.cu", "sort.cu", "executor.cpp", "planner.cpp"]
 HEADERS = [os.path.join(CSRC, "b2q_internal.h"), os.path.join(HERE, "..", "include", "b2q.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

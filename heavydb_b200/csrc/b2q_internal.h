@@ -212,6 +212,31 @@ struct SmemPlan {
   int32_t total_bytes;
 };
 
+/* ---- ORDER BY / LIMIT over the materialised table (sort.cu) ------------------------------------------------ */
+#define B2Q_MAX_ORDER_ENTRIES 8
+enum { SORTKEY_I64 = 0, SORTKEY_F64 = 1, SORTKEY_AVG_I64 = 2, SORTKEY_AVG_F64 = 3 };
+struct DevSortKey {        /* one Analyzer::OrderEntry resolved against the output layout */
+  int64_t off1, off2;      /* slot offsets (row-wise: inside the row; columnar: of the column); off2 = AVG's count slot */
+  int64_t null_pattern;    /* null_val_bit_pattern of the compact type (ResultSet::isNull, ResultSetIteration.cpp:2601-2618) */
+  int8_t w1;               /* 4 or 8 */
+  int8_t kind;             /* SORTKEY_* */
+  int8_t nullable;         /* !get_compact_type(target).get_notnull() */
+  int8_t is_desc, nulls_first;
+  int8_t pad_[3];
+};
+struct DevSortLayout {     /* what the kernels need to address an entry of a reference-layout buffer */
+  int64_t row_size, entry_count;
+  int64_t marker_off, marker_init; /* keyless: the idx_target_as_key slot and its init value */
+  int8_t columnar, grouped, keyless, marker_w, key_w;
+  int8_t pad_[3];
+};
+struct DevGatherCols {     /* columnar gather: every key / slot column, offsets for the source and the compact buffer */
+  int32_t n;
+  int32_t pad_;
+  int64_t in_off[B2Q_MAX_SLOTS + B2Q_MAX_GROUP_COLS], out_off[B2Q_MAX_SLOTS + B2Q_MAX_GROUP_COLS];
+  int8_t width[B2Q_MAX_SLOTS + B2Q_MAX_GROUP_COLS];
+};
+
 /* host-side query object behind B2QQuery */
 struct B2QQuery {
   B2QPlan plan;
@@ -220,4 +245,9 @@ struct B2QQuery {
   SmemPlan smem;
   int32_t col_ids[B2Q_MAX_COLS]; /* launch column index -> table column id */
   int32_t bigint_count;
+  /* sort_info of the execution unit (copied: the partial / finalize split outlives the caller's unit) */
+  int32_t n_order;
+  B2QOrderEntry order[B2Q_MAX_ORDER_ENTRIES];
+  int32_t has_limit;
+  int64_t limit, offset;
 };

@@ -39,6 +39,11 @@ cudaError_t launch_materialize(const B2QQuery& q, const int64_t* const* accs, co
 cudaError_t launch_join_split(const int64_t* split, int64_t* out, int64_t n, cudaStream_t st);
 cudaError_t launch_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count, int64_t lo,
                        int64_t span, int64_t stride, cudaStream_t st);
+size_t sort_scratch_bytes(int64_t entries);
+cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_keys, const int8_t* buf, int8_t* scratch,
+                        cudaStream_t st, const uint32_t** perm_out, int64_t* n_out, int* launches);
+cudaError_t sort_gather(const DevSortLayout& Lin, const DevGatherCols& G, const int8_t* in, int8_t* out, const uint32_t* perm,
+                        int64_t first, int64_t n_out, cudaStream_t st);
 }  // namespace b2q
 
 using namespace b2q;
@@ -186,6 +191,11 @@ struct B2QResultSet {
   size_t buf_size = 0, buf_cap = 0;
   int64_t cursor = 0;
   int64_t cached_rows = -1;
+  /* ResultSet::sort / dropFirstN / keepFirstN state (ResultSet.h: permutation_, drop_first_, keep_first_) */
+  std::vector<uint32_t> perm;
+  bool sorted = false;
+  size_t drop_first = 0, keep_first = 0, fetched = 0;
+  double sort_ms = 0;
   double scan_ms = 0, init_ms = 0, mat_ms = 0, h2d_bytes = 0;
   int64_t launches = 0, frags_scanned = 0, frags_skipped = 0;
   ~B2QResultSet() { pinned_cache().put(buf, buf_cap); }
@@ -494,6 +504,98 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
   return B2Q_OK;
 }
 
+/* ---- ORDER BY / LIMIT on the device (sort.cu) ---------------------------------------------------------------- */
+static DevSortLayout sort_layout_of(const B2QPlan& p) {
+  DevSortLayout L;
+  memset(&L, 0, sizeof(L));
+  L.row_size = p.row_size;
+  L.entry_count = p.entry_count;
+  L.columnar = static_cast<int8_t>(p.output_columnar);
+  L.grouped = p.query_desc_type != B2Q_NonGroupedAggregate;
+  L.keyless = static_cast<int8_t>(p.keyless_hash);
+  if (p.keyless_hash) {
+    L.marker_off = p.slot_offset[p.idx_target_as_key];
+    L.marker_w = p.slot_padded_width[p.idx_target_as_key];
+    L.marker_init = p.init_vals[p.idx_target_as_key];
+  }
+  L.key_w = static_cast<int8_t>(p.output_columnar ? 8 : p.effective_key_width);
+  return L;
+}
+
+/* one Analyzer::OrderEntry against the output layout; the value is read the way ResultSetComparator reads it
+ * (getColumnInternal at the padded slot width, AVG as a (sum, count) pair, baseline key targets from the key) */
+static DevSortKey sort_key_of(const B2QPlan& p, const B2QOrderEntry& oe) {
+  DevSortKey k;
+  memset(&k, 0, sizeof(k));
+  const B2QTargetInfo& t = p.targets[oe.tle_no - 1];
+  const int s = t.first_slot;
+  k.off1 = p.slot_offset[s];
+  k.w1 = p.slot_padded_width[s];
+  if (k.w1 == 0) { k.off1 = 0; k.w1 = static_cast<int8_t>(p.output_columnar ? 8 : p.effective_key_width); } /* baseline: the key is the target */
+  const bool has_arg = t.agg_arg_type.type != 0;
+  const bool minmax = t.is_agg && has_arg && (t.agg_kind == B2Q_kMIN || t.agg_kind == B2Q_kMAX);
+  const B2QTypeInfo compact = minmax ? t.agg_arg_type : t.sql_type; /* get_compact_type */
+  k.nullable = !compact.notnull;
+  k.is_desc = oe.is_desc;
+  k.nulls_first = oe.nulls_first;
+  if (t.is_agg && t.agg_kind == B2Q_kAVG) {
+    k.kind = t.sql_type.type == B2Q_kDOUBLE ? SORTKEY_AVG_F64 : SORTKEY_AVG_I64;
+    k.off2 = p.slot_offset[s + 1];
+  } else if (compact.type == B2Q_kDOUBLE) {
+    k.kind = SORTKEY_F64;
+    const double nd = DBL_MIN;
+    memcpy(&k.null_pattern, &nd, 8);
+  } else {
+    k.kind = SORTKEY_I64;
+    k.null_pattern = compact.type == B2Q_kTINYINT ? INT8_MIN : compact.type == B2Q_kSMALLINT ? INT16_MIN : compact.type == B2Q_kINT ? INT32_MIN : INT64_MIN;
+  }
+  return k;
+}
+
+/* the same descriptor for a buffer of `n` entries (compacted result): row-wise only the sizes change, columnar
+ * every column moves (getColOffInBytes, QueryMemoryDescriptor.cpp:918-955) */
+static void relayout_entries(B2QPlan& p, int64_t n) {
+  p.entry_count = n;
+  if (!p.output_columnar) { p.buffer_size = p.row_size * n; return; }
+  const bool keyed = p.query_desc_type != B2Q_NonGroupedAggregate && !p.keyless_hash;
+  int64_t off = keyed ? static_cast<int64_t>(std::max(p.num_group_cols, 1)) * ((8 * n + 7) & ~int64_t(7)) : 0;
+  for (int s = 0; s < p.num_slots; ++s) {
+    p.slot_offset[s] = off;
+    off += (static_cast<int64_t>(p.slot_padded_width[s]) * n + 7) & ~int64_t(7);
+  }
+  p.buffer_size = off;
+}
+
+static DevGatherCols gather_cols_of(const B2QPlan& in, const B2QPlan& out) {
+  DevGatherCols g;
+  memset(&g, 0, sizeof(g));
+  if (!in.output_columnar) return g;
+  const bool keyed = in.query_desc_type != B2Q_NonGroupedAggregate && !in.keyless_hash;
+  if (keyed)
+    for (int c = 0; c < std::max(in.num_group_cols, 1); ++c) {
+      g.in_off[g.n] = c * ((8 * in.entry_count + 7) & ~int64_t(7));
+      g.out_off[g.n] = c * ((8 * out.entry_count + 7) & ~int64_t(7));
+      g.width[g.n++] = 8;
+    }
+  for (int s = 0; s < in.num_slots; ++s) {
+    if (!in.slot_padded_width[s]) continue;
+    g.in_off[g.n] = in.slot_offset[s];
+    g.out_off[g.n] = out.slot_offset[s];
+    g.width[g.n++] = in.slot_padded_width[s];
+  }
+  return g;
+}
+
+/* get_truncated_row_count-style window over `n` sorted rows: [first, first + count) */
+static void limit_window(const B2QQuery& q, int64_t n, int64_t* first, int64_t* count) {
+  const int64_t top_n = (q.has_limit ? q.limit : 0) + q.offset; /* rs->sort(order_entries, limit + offset) */
+  int64_t kept = (q.n_order && top_n) ? std::min(top_n, n) : n;  /* topPermutation resizes to top_n */
+  *first = std::min<int64_t>(q.offset, kept);                   /* dropFirstN(offset) */
+  int64_t c = kept - *first;
+  if (q.has_limit && q.limit) c = std::min(c, q.limit);          /* keepFirstN(limit); keep_first_ == 0 means "no limit" */
+  *count = c;
+}
+
 static int32_t finalize_impl(B2QPartial* p, cudaStream_t st, B2QResultSet** out) {
   if (!p || !out) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(p->device));
@@ -506,6 +608,55 @@ static int32_t finalize_impl(B2QPartial* p, cudaStream_t st, B2QResultSet** out)
   rs->frags_scanned = p->frags_scanned;
   rs->frags_skipped = p->frags_skipped;
   const size_t nbytes = static_cast<size_t>(p->q.plan.buffer_size);
+  const bool want_sort = p->q.n_order > 0 || p->q.has_limit || p->q.offset > 0;
+  if (nbytes && want_sort) {
+    /* materialise on the device, sort / truncate there, copy back only the kept rows */
+    const B2QPlan& plan = p->q.plan;
+    int8_t* d_out = nullptr;
+    int8_t* d_scratch = nullptr;
+    int8_t* d_compact = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&d_out), nbytes, st));
+    cudaError_t e = launch_materialize(p->q, p->accs, p->keys, d_out, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&d_scratch), sort_scratch_bytes(plan.entry_count), st);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    const DevSortLayout L = sort_layout_of(plan);
+    DevSortKey keys[B2Q_MAX_ORDER_ENTRIES];
+    for (int i = 0; i < p->q.n_order; ++i) keys[i] = sort_key_of(plan, p->q.order[i]);
+    const uint32_t* d_perm = nullptr;
+    int64_t n = 0, first = 0, count = 0;
+    int sort_launches = 0;
+    if (e == cudaSuccess) e = cudaEventRecord(ev0, st);
+    if (e == cudaSuccess) e = sort_device(L, keys, p->q.n_order, d_out, d_scratch, st, &d_perm, &n, &sort_launches);
+    if (e == cudaSuccess) {
+      limit_window(p->q, n, &first, &count);
+      relayout_entries(rs->q.plan, count);
+      rs->buf_size = static_cast<size_t>(rs->q.plan.buffer_size);
+      if (rs->buf_size) {
+        rs->buf = pinned_cache().get(rs->buf_size, &rs->buf_cap);
+        if (!rs->buf) e = cudaErrorMemoryAllocation;
+        if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&d_compact), rs->buf_size, st);
+        const DevGatherCols G = gather_cols_of(plan, rs->q.plan);
+        if (e == cudaSuccess) e = sort_gather(L, G, d_out, d_compact, d_perm, first, count, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev1, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(rs->buf, d_compact, rs->buf_size, cudaMemcpyDeviceToHost, st);
+        sort_launches += 1;
+      } else if (e == cudaSuccess) {
+        e = cudaEventRecord(ev1, st);
+      }
+    }
+    if (d_compact) cudaFreeAsync(d_compact, st);
+    if (d_scratch) cudaFreeAsync(d_scratch, st);
+    cudaFreeAsync(d_out, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) { float ms = 0; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) rs->sort_ms = ms; }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(B2Q_ERR_CUDA, std::string("sort/materialise: ") + cudaGetErrorString(e)); }
+    rs->sorted = true;
+    rs->launches += sort_launches;
+    *out = rs.release();
+    return B2Q_OK;
+  }
   rs->buf_size = nbytes;
   if (nbytes) {
     rs->buf = pinned_cache().get(nbytes, &rs->buf_cap);
@@ -672,17 +823,27 @@ int32_t b2q_launch(const B2QQuery* query, const B2QParams* prm, void* stream) {
 }
 
 /* ---- ResultSet surface ---------------------------------------------------------------------------------- */
-size_t b2q_rs_entry_count(const B2QResultSet* rs) { return rs ? static_cast<size_t>(rs->q.plan.entry_count) : 0; }
+/* ResultSet::entryCount(): permutation_.size() once sorted, else the descriptor's entry count (ResultSetIteration.cpp:752-754) */
+size_t b2q_rs_entry_count(const B2QResultSet* rs) {
+  if (!rs) return 0;
+  return rs->perm.empty() ? static_cast<size_t>(rs->q.plan.entry_count) : rs->perm.size();
+}
 size_t b2q_rs_col_count(const B2QResultSet* rs) { return rs ? static_cast<size_t>(rs->q.plan.num_targets) : 0; }
 int32_t b2q_rs_is_row_at_empty(const B2QResultSet* rs, size_t e) { return rs_is_empty_entry(rs, static_cast<int64_t>(e)); }
-size_t b2q_rs_row_count(const B2QResultSet* rs) {
+static size_t truncated_row_count(size_t total, size_t keep_first, size_t drop_first) { /* get_truncated_row_count, ResultSet.cpp */
+  if (total <= drop_first) return 0;
+  const size_t rest = total - drop_first;
+  return keep_first ? std::min(rest, keep_first) : rest;
+}
+size_t b2q_rs_row_count(const B2QResultSet* rs) { /* ResultSet::rowCountImpl (ResultSet.cpp:565-600) */
   if (!rs) return 0;
+  if (!rs->perm.empty()) return truncated_row_count(rs->perm.size(), rs->keep_first, rs->drop_first);
   if (rs->cached_rows < 0) {
     int64_t n = 0;
     for (int64_t e = 0; e < rs->q.plan.entry_count; ++e) n += !rs_is_empty_entry(rs, e);
     const_cast<B2QResultSet*>(rs)->cached_rows = n;
   }
-  return static_cast<size_t>(rs->cached_rows);
+  return truncated_row_count(static_cast<size_t>(rs->cached_rows), rs->keep_first, rs->drop_first);
 }
 int32_t b2q_rs_is_empty(const B2QResultSet* rs) { return b2q_rs_row_count(rs) == 0; }
 B2QTypeInfo b2q_rs_get_col_type(const B2QResultSet* rs, size_t col) {
@@ -690,14 +851,21 @@ B2QTypeInfo b2q_rs_get_col_type(const B2QResultSet* rs, size_t col) {
   if (t.is_agg && t.agg_kind == B2Q_kAVG) return B2QTypeInfo{B2Q_kDOUBLE, 0};
   return t.sql_type;
 }
-void b2q_rs_move_to_begin(B2QResultSet* rs) { if (rs) rs->cursor = 0; }
+void b2q_rs_move_to_begin(B2QResultSet* rs) { if (rs) { rs->cursor = 0; rs->fetched = 0; } }
 
 int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
   const B2QPlan& p = rs->q.plan;
-  while (rs->cursor < p.entry_count && rs_is_empty_entry(rs, rs->cursor)) ++rs->cursor;
-  if (rs->cursor >= p.entry_count) return 0;
-  const int64_t entry = rs->cursor;
-  ++rs->cursor;
+  /* getNextRowImpl + advanceCursorToNextEntry (ResultSetIteration.cpp:320-340, :731-750) */
+  const int64_t n_entries = static_cast<int64_t>(b2q_rs_entry_count(rs));
+  int64_t entry = 0;
+  do {
+    if (rs->keep_first && rs->fetched >= rs->drop_first + rs->keep_first) return 0;
+    while (rs->cursor < n_entries && rs_is_empty_entry(rs, rs->perm.empty() ? rs->cursor : rs->perm[rs->cursor])) ++rs->cursor;
+    if (rs->cursor >= n_entries) return 0;
+    entry = rs->perm.empty() ? rs->cursor : rs->perm[rs->cursor];
+    ++rs->cursor;
+    ++rs->fetched;
+  } while (rs->drop_first && rs->fetched <= rs->drop_first);
   for (int i = 0; i < p.num_targets; ++i) {
     const B2QTargetInfo& t = p.targets[i];
     const int s = t.first_slot;
@@ -749,6 +917,47 @@ const int8_t* b2q_rs_storage_buffer(const B2QResultSet* rs, size_t* size_bytes) 
 }
 const B2QPlan* b2q_rs_query_mem_desc(const B2QResultSet* rs) { return rs ? &rs->q.plan : nullptr; }
 double b2q_rs_kernel_ms(const B2QResultSet* rs) { return rs ? rs->scan_ms : 0; }
+
+/* ResultSet::sort (ResultSet.cpp:781-849) on an existing result set: the storage buffer goes to the device, the
+ * kernels of sort.cu order the non-empty entries, the permutation comes back (the buffer itself is not moved). */
+int32_t b2q_rs_sort(B2QResultSet* rs, const B2QOrderEntry* order_entries, int32_t n_entries, size_t top_n) {
+  if (!rs || (n_entries && !order_entries)) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
+  if (n_entries < 0 || n_entries > B2Q_MAX_ORDER_ENTRIES) return set_err(B2Q_ERR_UNSUPPORTED, "more ORDER BY entries than the path carries");
+  const B2QPlan& plan = rs->q.plan;
+  for (int i = 0; i < n_entries; ++i)
+    if (order_entries[i].tle_no < 1 || order_entries[i].tle_no > plan.num_targets) return set_err(B2Q_ERR_INVALID_ARGUMENT, "order entry refers to a target that does not exist");
+  if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible; this path has no CPU fallback");
+  rs->perm.clear();
+  rs->cursor = 0; rs->fetched = 0;
+  if (!rs->buf_size || plan.entry_count <= 0) return B2Q_OK;
+  cudaStream_t st = nullptr;
+  int8_t* d_buf = nullptr;
+  int8_t* d_scratch = nullptr;
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&d_buf), rs->buf_size, st));
+  cudaError_t e = cudaMemcpyAsync(d_buf, rs->buf, rs->buf_size, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&d_scratch), sort_scratch_bytes(plan.entry_count), st);
+  const DevSortLayout L = sort_layout_of(plan);
+  DevSortKey keys[B2Q_MAX_ORDER_ENTRIES];
+  for (int i = 0; i < n_entries; ++i) keys[i] = sort_key_of(plan, order_entries[i]);
+  const uint32_t* d_perm = nullptr;
+  int64_t n = 0;
+  int launches = 0;
+  if (e == cudaSuccess) e = sort_device(L, keys, n_entries, d_buf, d_scratch, st, &d_perm, &n, &launches);
+  if (e == cudaSuccess) {
+    const int64_t keep = top_n && static_cast<int64_t>(top_n) < n ? static_cast<int64_t>(top_n) : n;
+    rs->perm.resize(static_cast<size_t>(keep));
+    if (keep) e = cudaMemcpyAsync(rs->perm.data(), d_perm, static_cast<size_t>(keep) * 4, cudaMemcpyDeviceToHost, st);
+  }
+  if (d_scratch) cudaFreeAsync(d_scratch, st);
+  cudaFreeAsync(d_buf, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cudaGetLastError(); rs->perm.clear(); return set_err(B2Q_ERR_CUDA, std::string("sort: ") + cudaGetErrorString(e)); }
+  rs->launches += launches;
+  rs->sorted = true;
+  return B2Q_OK;
+}
+void b2q_rs_drop_first_n(B2QResultSet* rs, size_t n) { if (rs) { rs->drop_first = n; rs->cursor = 0; rs->fetched = 0; } }   /* ResultSet::dropFirstN :63-66 */
+void b2q_rs_keep_first_n(B2QResultSet* rs, size_t n) { if (rs) { rs->keep_first = n; rs->cursor = 0; rs->fetched = 0; } }   /* ResultSet::keepFirstN :58-61 */
 int64_t b2q_rs_stat(const B2QResultSet* rs, int32_t which) {
   if (!rs) return -1;
   switch (which) {
@@ -756,6 +965,7 @@ int64_t b2q_rs_stat(const B2QResultSet* rs, int32_t which) {
     case B2Q_STAT_FRAGMENTS_SKIPPED: return rs->frags_skipped;
     case B2Q_STAT_KERNEL_LAUNCHES: return rs->launches;
     case B2Q_STAT_H2D_BYTES: return static_cast<int64_t>(rs->h2d_bytes);
+    case B2Q_STAT_SORT_US: return static_cast<int64_t>(rs->sort_ms * 1000.0);
     default: return -1;
   }
 }

@@ -104,6 +104,11 @@ class Planner {
     publish_targets(q.plan);
     lower(q);
     choose_kernel(q);
+    q.n_order = u_.num_order_entries;
+    for (int i = 0; i < u_.num_order_entries; ++i) q.order[i] = u_.order_entries[i];
+    q.has_limit = u_.has_limit ? 1 : 0;
+    q.limit = u_.limit;
+    q.offset = u_.offset;
   }
 
  private:
@@ -141,8 +146,14 @@ class Planner {
   }
 
   void validate() {
-    if (u_.num_join_quals || u_.has_estimator || u_.num_order_entries || u_.has_union_all || u_.has_window_function)
-      reject(B2Q_ERR_UNSUPPORTED, "join_quals / estimator / sort_info / union_all / window functions are outside this path");
+    if (u_.num_join_quals || u_.has_estimator || u_.has_union_all || u_.has_window_function)
+      reject(B2Q_ERR_UNSUPPORTED, "join_quals / estimator / union_all / window functions are outside this path");
+    if (u_.num_order_entries < 0 || u_.num_order_entries > B2Q_MAX_ORDER_ENTRIES) reject(B2Q_ERR_UNSUPPORTED, "more ORDER BY entries than the path carries");
+    if (u_.num_order_entries && !u_.order_entries) reject(B2Q_ERR_INVALID_ARGUMENT, "order_entries is null");
+    for (int i = 0; i < u_.num_order_entries; ++i)
+      if (u_.order_entries[i].tle_no < 1 || u_.order_entries[i].tle_no > u_.num_target_exprs)
+        reject(B2Q_ERR_INVALID_ARGUMENT, "order entry refers to a target that does not exist (tle_no is 1-based)");
+    if (u_.offset < 0 || (u_.has_limit && u_.limit < 0)) reject(B2Q_ERR_INVALID_ARGUMENT, "negative LIMIT / OFFSET");
     if (u_.num_groupby_exprs > B2Q_MAX_GROUP_COLS) reject(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
     if (u_.num_groupby_exprs < 0 || u_.num_target_exprs <= 0 || u_.num_target_exprs > B2Q_MAX_TARGETS)
       reject(B2Q_ERR_INVALID_ARGUMENT, "bad groupby/target counts");

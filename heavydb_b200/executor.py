@@ -107,6 +107,10 @@ def lib():
         L.b2q_rs_free.argtypes = [C.c_void_p]
         L.b2q_rs_stat.restype = C.c_int64
         L.b2q_rs_stat.argtypes = [C.c_void_p, C.c_int32]
+        L.b2q_rs_sort.restype = C.c_int32
+        L.b2q_rs_sort.argtypes = [C.c_void_p, C.POINTER(abi.OrderEntry), C.c_int32, C.c_size_t]
+        L.b2q_rs_drop_first_n.argtypes = [C.c_void_p, C.c_size_t]
+        L.b2q_rs_keep_first_n.argtypes = [C.c_void_p, C.c_size_t]
         L.b2q_gen_column.restype = C.c_int32
         L.b2q_gen_column.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
                                      C.c_int64, C.c_void_p]
@@ -216,7 +220,23 @@ class ResultSet:
     def stats(self) -> dict:
         L = lib()
         return {"fragments_scanned": L.b2q_rs_stat(self._h, 0), "fragments_skipped": L.b2q_rs_stat(self._h, 1),
-                "kernel_launches": L.b2q_rs_stat(self._h, 2), "h2d_bytes": L.b2q_rs_stat(self._h, 3)}
+                "kernel_launches": L.b2q_rs_stat(self._h, 2), "h2d_bytes": L.b2q_rs_stat(self._h, 3),
+                "sort_us": L.b2q_rs_stat(self._h, 4)}
+
+    def sort(self, order_entries, top_n: int = 0):
+        """ResultSet::sort(order_entries, top_n) (ResultSet.h:279): order_entries = [(tle_no, is_desc, nulls_first)]."""
+        arr = (abi.OrderEntry * max(len(order_entries), 1))()
+        for i, (tle, desc, nf) in enumerate(order_entries):
+            arr[i].tle_no, arr[i].is_desc, arr[i].nulls_first = tle, int(desc), int(nf)
+        rc = lib().b2q_rs_sort(self._h, arr, len(order_entries), top_n)
+        if rc:
+            _raise(rc)
+
+    def dropFirstN(self, n: int):
+        lib().b2q_rs_drop_first_n(self._h, n)
+
+    def keepFirstN(self, n: int):
+        lib().b2q_rs_keep_first_n(self._h, n)
 
 
 class Partial:

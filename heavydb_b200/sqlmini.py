@@ -3,6 +3,7 @@ RelAlgExecutionUnit mirror, for the subset of the path:
 
     SELECT <col | COUNT(*) | COUNT(c) | SUM(c) | MIN(c) | MAX(c) | AVG(c)>, ...
     FROM <table> [WHERE <c OP literal> {AND|OR} ... with parentheses] [GROUP BY c {, c}]
+    [ORDER BY <position | target text> [ASC|DESC] [NULLS FIRST|LAST] {, ...}] [LIMIT n] [OFFSET m]
 
 It plays the role Calcite + RelAlgTranslator play in the reference (kept, out of scope) and is test infrastructure.
 Like RelAlgTranslator/QualsConjunctiveForm, a top-level AND is split into separate quals, and a `col OP const`
@@ -81,6 +82,15 @@ class _P:
             return self.b.cmp(col, op, int(lit), abi.kBIGINT)
         return self.b.cmp(col, op, float(lit), abi.kDOUBLE)
 
+    def target_text(self):
+        """Canonical text of the target expression starting at the cursor (does not build nodes)."""
+        j = self.i
+        tok = self.t[j]
+        if tok.upper() in _AGGS and j + 1 < len(self.t) and self.t[j + 1] == "(":
+            k = self.t.index(")", j)
+            return "".join(self.t[j:k + 1]).upper(), k + 1
+        return tok.upper(), j + 1
+
     def target(self):
         tok = self.eat()
         if tok.upper() in _AGGS and self.peek() == "(":
@@ -105,9 +115,11 @@ def _conjuncts(b: abi.UnitBuilder, e: int) -> List[int]:
 def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = False) -> abi.BuiltUnit:
     p = _P(_tokens(sql), table, names, bigint_count)
     p.eat("SELECT")
+    texts = [p.target_text()[0]]
     targets = [p.target()]
     while p.peek() == ",":
         p.eat()
+        texts.append(p.target_text()[0])
         targets.append(p.target())
     p.eat("FROM")
     p.eat()  # table name
@@ -131,6 +143,32 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
         while p.peek() == ",":
             p.eat()
             p.b.group_by(p.colid(p.eat()))
+    if p.peek() and p.peek().upper() == "ORDER":
+        p.eat()
+        p.eat("BY")
+        while True:
+            if re.fullmatch(r"\d+", p.peek()):
+                tle = int(p.eat())
+            else:
+                text, nxt = p.target_text()
+                p.i = nxt
+                tle = texts.index(text) + 1
+            desc, nulls_first = False, None
+            if p.peek() and p.peek().upper() in ("ASC", "DESC"):
+                desc = p.eat().upper() == "DESC"
+            if p.peek() and p.peek().upper() == "NULLS":
+                p.eat()
+                nulls_first = p.eat().upper() == "FIRST"
+            p.b.order_by(tle, desc, nulls_first)
+            if p.peek() != ",":
+                break
+            p.eat()
+    if p.peek() and p.peek().upper() == "LIMIT":
+        p.eat()
+        p.b.limit = int(p.eat())
+    if p.peek() and p.peek().upper() == "OFFSET":
+        p.eat()
+        p.b.offset = int(p.eat())
     if p.peek() is not None:
         raise ValueError(f"trailing tokens: {p.t[p.i:]}")
     for t in targets:

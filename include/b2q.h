@@ -109,6 +109,14 @@ typedef struct B2QExpr {
   int32_t pad_;
 } B2QExpr;
 
+/* ---- Analyzer::OrderEntry (Analyzer/Analyzer.h:2960-2968) ------------------------------------------------ */
+typedef struct B2QOrderEntry {
+  int32_t tle_no;      /* target list entry number, 1-based */
+  int8_t is_desc;
+  int8_t nulls_first;
+  int8_t pad_[2];
+} B2QOrderEntry;
+
 /* ---- RelAlgExecutionUnit subset (QueryEngine/RelAlgExecutionUnit.h:166-216) ---------------------------- */
 typedef struct B2QExecUnit {
   const B2QExpr* exprs;
@@ -125,10 +133,18 @@ typedef struct B2QExecUnit {
   /* Fields of the reference struct that are outside this path.  Must be zero or the call is rejected. */
   int32_t num_join_quals;
   int32_t has_estimator;
-  int32_t num_order_entries;
   int32_t has_union_all;
   int32_t has_window_function;
-  int32_t pad_;
+  /* sort_info (SortInfo, RelAlgExecutionUnit.h:117-156).  When any of it is set the returned ResultSet is what
+   * RelAlgExecutor::executeSort makes of executeWorkUnit's result (RelAlgExecutor.cpp:3586-3610):
+   * rs->sort(order_entries, limit + offset); rs->dropFirstN(offset); rs->keepFirstN(limit) — done on the device
+   * over the aggregated table (compaction of non-empty entries, radix sort, gather), so only the kept rows are
+   * copied back.  Ties keep ascending entry order (the reference's std::sort leaves them unspecified). */
+  const B2QOrderEntry* order_entries;
+  int32_t num_order_entries;
+  int32_t has_limit;           /* std::optional<size_t> limit */
+  int64_t limit;
+  int64_t offset;
 } B2QExecUnit;
 
 /* ---- ChunkMetadata::chunkStats per (fragment, column)  (Fragmenter/Fragmenter.h:73-146) ---------------- */
@@ -336,9 +352,15 @@ int32_t b2q_rs_is_row_at_empty(const B2QResultSet* rs, size_t entry_idx); /* Res
 const int8_t* b2q_rs_storage_buffer(const B2QResultSet* rs, size_t* size_bytes);
 const B2QPlan* b2q_rs_query_mem_desc(const B2QResultSet* rs); /* getQueryMemDesc() */
 double b2q_rs_kernel_ms(const B2QResultSet* rs);
+/* ResultSet::sort(order_entries, top_n) (ResultSet.h:279, ResultSet.cpp:781-849) followed by iteration in sorted
+ * order; top_n == 0 sorts everything.  dropFirstN / keepFirstN are SQL OFFSET / LIMIT (ResultSet.cpp:58-66).
+ * The sort runs on the device (sort.cu); ties keep ascending entry order. */
+int32_t b2q_rs_sort(B2QResultSet* rs, const B2QOrderEntry* order_entries, int32_t num_order_entries, size_t top_n);
+void b2q_rs_drop_first_n(B2QResultSet* rs, size_t n);
+void b2q_rs_keep_first_n(B2QResultSet* rs, size_t n);
 /* execution statistics of the call that produced the result set */
 enum { B2Q_STAT_FRAGMENTS_SCANNED = 0, B2Q_STAT_FRAGMENTS_SKIPPED = 1 /* Executor::skipFragment, Execute.cpp:4776 */,
-       B2Q_STAT_KERNEL_LAUNCHES = 2, B2Q_STAT_H2D_BYTES = 3 };
+       B2Q_STAT_KERNEL_LAUNCHES = 2, B2Q_STAT_H2D_BYTES = 3, B2Q_STAT_SORT_US = 4 /* device time of compaction + sort + gather */ };
 int64_t b2q_rs_stat(const B2QResultSet* rs, int32_t which);
 void b2q_rs_free(B2QResultSet* rs);
 

@@ -16,6 +16,7 @@
 #pragma once
 #include <cstdint>
 #include <list>
+#include <optional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -60,7 +61,13 @@ struct RelAlgExecutionUnit { /* RelAlgExecutionUnit.h:166-216 */
   std::vector<ExprRef> target_exprs;
   size_t scan_limit{0};
   /* features outside this path: anything non-zero is rejected by the library */
-  int32_t num_join_quals{0}, has_estimator{0}, num_order_entries{0}, has_union_all{0}, has_window_function{0};
+  int32_t num_join_quals{0}, has_estimator{0}, has_union_all{0}, has_window_function{0};
+  /* SortInfo (RelAlgExecutionUnit.h:117-156); Analyzer::OrderEntry == B2QOrderEntry{tle_no, is_desc, nulls_first} */
+  struct SortInfo {
+    std::list<B2QOrderEntry> order_entries;
+    std::optional<size_t> limit;
+    size_t offset{0};
+  } sort_info;
 
   ExprRef makeColumnVar(const SQLTypeInfo& ti, int32_t column_id) {
     B2QExpr e{};
@@ -147,6 +154,14 @@ class ResultSet {
   bool isRowAtEmpty(size_t i) const { return b2q_rs_is_row_at_empty(h_, i) != 0; }
   const int8_t* getUnderlyingBuffer(size_t* size_bytes) const { return b2q_rs_storage_buffer(h_, size_bytes); }
   const B2QPlan& getQueryMemDesc() const { return *b2q_rs_query_mem_desc(h_); }
+  /* ResultSet::sort(order_entries, top_n, ...) ResultSet.h:279; dropFirstN / keepFirstN ResultSet.cpp:58-66 */
+  void sort(const std::list<B2QOrderEntry>& order_entries, size_t top_n) {
+    std::vector<B2QOrderEntry> oes(order_entries.begin(), order_entries.end());
+    const int32_t rc = b2q_rs_sort(h_, oes.data(), static_cast<int32_t>(oes.size()), top_n);
+    if (rc != B2Q_OK) throw QueryExecutionError(rc, b2q_last_error_message());
+  }
+  void dropFirstN(size_t n) { b2q_rs_drop_first_n(h_, n); }
+  void keepFirstN(size_t n) { b2q_rs_keep_first_n(h_, n); }
  private:
   B2QResultSet* h_;
 };
@@ -187,7 +202,12 @@ class Executor {
     u.target_exprs = ra_exe_unit.target_exprs.data(); u.num_target_exprs = static_cast<int32_t>(ra_exe_unit.target_exprs.size());
     u.scan_limit = static_cast<int64_t>(ra_exe_unit.scan_limit);
     u.num_join_quals = ra_exe_unit.num_join_quals; u.has_estimator = ra_exe_unit.has_estimator;
-    u.num_order_entries = ra_exe_unit.num_order_entries; u.has_union_all = ra_exe_unit.has_union_all;
+    u.has_union_all = ra_exe_unit.has_union_all;
+    std::vector<B2QOrderEntry> oes(ra_exe_unit.sort_info.order_entries.begin(), ra_exe_unit.sort_info.order_entries.end());
+    u.order_entries = oes.data(); u.num_order_entries = static_cast<int32_t>(oes.size());
+    u.has_limit = ra_exe_unit.sort_info.limit.has_value() ? 1 : 0;
+    u.limit = static_cast<int64_t>(ra_exe_unit.sort_info.limit.value_or(0));
+    u.offset = static_cast<int64_t>(ra_exe_unit.sort_info.offset);
     u.has_window_function = ra_exe_unit.has_window_function;
     B2QCompilationOptions cco{static_cast<int32_t>(co.device_type), co.hoist_literals ? 1 : 0};
     B2QExecutionOptions ceo{options.allow_multifrag ? 1 : 0, options.output_columnar_hint ? 1 : 0, options.bigint_count ? 1 : 0, 0, -1, 0};

@@ -569,8 +569,12 @@ constexpr int64_t kMaxBufferSize = int64_t(1) << 30;   /* GroupByAndAggregate.cp
 
 Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecutionOptions& eo,
                size_t max_groups_buffer_entry_guess, bool has_cardinality_estimation) {
-  if (u.num_join_quals || u.has_estimator || u.num_order_entries || u.has_union_all || u.has_window_function)
-    fail(B2Q_ERR_UNSUPPORTED, "joins / estimator / sort / union / window functions are outside this path");
+  if (u.num_join_quals || u.has_estimator || u.has_union_all || u.has_window_function)
+    fail(B2Q_ERR_UNSUPPORTED, "joins / estimator / union / window functions are outside this path");
+  if (u.num_order_entries < 0 || u.num_order_entries > 8) fail(B2Q_ERR_UNSUPPORTED, "more ORDER BY entries than the path carries");
+  for (int i = 0; i < u.num_order_entries; ++i)
+    if (u.order_entries[i].tle_no < 1 || u.order_entries[i].tle_no > u.num_target_exprs) fail(B2Q_ERR_INVALID_ARGUMENT, "order entry refers to a target that does not exist");
+  if (u.offset < 0 || (u.has_limit && u.limit < 0)) fail(B2Q_ERR_INVALID_ARGUMENT, "negative LIMIT / OFFSET");
   if (u.num_groupby_exprs > B2Q_MAX_GROUP_COLS) fail(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
   if (u.num_target_exprs <= 0 || u.num_target_exprs > B2Q_MAX_TARGETS)
     fail(B2Q_ERR_INVALID_ARGUMENT, "bad target count");
@@ -1230,7 +1234,79 @@ struct OracleResult {
   std::vector<int8_t> buf;
   int64_t cursor{0};
   double exec_seconds{0};
+  /* ResultSet::permutation_, drop_first_, keep_first_, fetched_so_far_ (ResultSet.h) */
+  std::vector<uint32_t> perm;
+  bool sorted{false};
+  size_t drop_first{0}, keep_first{0}, fetched{0};
 };
+
+namespace {
+
+/* ResultSet::ResultSetComparator::operator() (ResultSet.cpp:1310-1478) for the numeric subset: per order entry
+ * read the target like getColumnInternal (slot at its padded width; AVG as the (sum, count) pair; a baseline key
+ * target from the key), NULLs by ResultSet::isNull (ResultSetIteration.cpp:2601-2618), then int / double / pair compare. */
+struct ResultSetComparator {
+  const OracleResult* r;
+  std::vector<B2QOrderEntry> order_entries;
+  struct Val { int64_t i1, i2; bool pair; };
+  Val get(int64_t entry, const Target& t) const {
+    const B2QPlan& p = r->plan.p;
+    const int s = t.first_slot;
+    int w = p.slot_padded_width[s];
+    const int8_t* ptr = slot_ptr(p, r->buf.data(), entry, s);
+    if (w == 0) { ptr = key_ptr(p, r->buf.data(), entry, 0); w = p.effective_key_width; }
+    Val v{0, 0, false};
+    if (w == 4) { int32_t x; memcpy(&x, ptr, 4); v.i1 = x; } else memcpy(&v.i1, ptr, 8);
+    if (t.is_agg && t.agg_kind == B2Q_kAVG) { v.pair = true; memcpy(&v.i2, slot_ptr(p, r->buf.data(), entry, s + 1), 8); }
+    return v;
+  }
+  static bool is_null(const Ti& ti, const Val& v) {
+    if (ti.notnull) return false;
+    if (v.pair) return !v.i2;
+    return v.i1 == (is_fp(ti.type) ? bits_of(kNullDouble) : inline_int_null_val(ti.type)); /* null_val_bit_pattern */
+  }
+  static double pair_to_double(const Val& v, const Target& t) { /* ResultSetBufferAccessors.h:197-227 */
+    if (!v.i2) return kNullDouble;
+    return (is_fp(t.sql_type.type) ? double_of(v.i1) : static_cast<double>(v.i1)) / static_cast<double>(v.i2);
+  }
+  bool operator()(uint32_t lhs, uint32_t rhs) const {
+    for (const B2QOrderEntry& oe : order_entries) {
+      const Target& t = r->plan.targets[oe.tle_no - 1];
+      const Ti ti = get_compact_type(t);
+      const Val l = get(lhs, t), rv = get(rhs, t);
+      const bool ln = is_null(ti, l), rn = is_null(ti, rv);
+      if (ln && rn) continue;
+      if (ln && !rn) return oe.nulls_first;
+      if (rn && !ln) return !oe.nulls_first;
+      if (!l.pair) {
+        if (l.i1 == rv.i1) continue;
+        if (is_fp(ti.type)) return (double_of(l.i1) < double_of(rv.i1)) != static_cast<bool>(oe.is_desc);
+        return (l.i1 < rv.i1) != static_cast<bool>(oe.is_desc);
+      }
+      const double a = pair_to_double(l, t), b = pair_to_double(rv, t);
+      if (a == b) continue;
+      return (a < b) != static_cast<bool>(oe.is_desc);
+    }
+    return false;
+  }
+};
+
+/* ResultSet::sort (ResultSet.cpp:781-849): initPermutationBuffer (:870-885) + topPermutation (:1501-1527).
+ * The reference's std::partial_sort / std::sort leave ties in unspecified order; std::stable_sort over the
+ * ascending permutation pins them (ascending entry index), which is also what the device sort produces. */
+void result_sort(OracleResult* r, const B2QOrderEntry* oes, int n, size_t top_n) {
+  const B2QPlan& p = r->plan.p;
+  r->perm.clear();
+  r->cursor = 0; r->fetched = 0;
+  for (int64_t e = 0; e < p.entry_count; ++e) if (!is_empty_entry(p, r->buf.data(), e)) r->perm.push_back(static_cast<uint32_t>(e));
+  ResultSetComparator cmp{r, std::vector<B2QOrderEntry>(oes, oes + n)};
+  if (top_n == 0) top_n = r->perm.size();
+  std::stable_sort(r->perm.begin(), r->perm.end(), cmp);
+  if (top_n < r->perm.size()) r->perm.resize(top_n);
+  r->sorted = true;
+}
+
+}  // namespace
 
 static thread_local std::string g_last_error;
 
@@ -1298,6 +1374,12 @@ ORACLE_EXPORT int32_t oracle_execute(const B2QExecUnit* u, const B2QTableInfo* t
       std::vector<int8_t>().swap(bufs[f]);
     }
     res->buf = std::move(bufs[0]);
+    /* the tail of RelAlgExecutor::executeSort (RelAlgExecutor.cpp:3586-3610) when the unit carries sort_info */
+    if (u->num_order_entries) result_sort(res, u->order_entries, u->num_order_entries, static_cast<size_t>((u->has_limit ? u->limit : 0) + u->offset));
+    if (u->has_limit || u->offset) {
+      res->drop_first = static_cast<size_t>(u->offset);
+      if (u->has_limit) res->keep_first = static_cast<size_t>(u->limit);
+    }
     *out = res;
     return 0;
   } catch (const OracleError& e) {
@@ -1311,15 +1393,29 @@ ORACLE_EXPORT const int8_t* oracle_result_buffer(const OracleResult* r, size_t* 
   if (size) *size = r->buf.size();
   return r->buf.data();
 }
-ORACLE_EXPORT size_t oracle_result_entry_count(const OracleResult* r) { return static_cast<size_t>(r->plan.p.entry_count); }
+ORACLE_EXPORT size_t oracle_result_entry_count(const OracleResult* r) { /* ResultSet::entryCount() */
+  return r->sorted ? r->perm.size() : static_cast<size_t>(r->plan.p.entry_count);
+}
+ORACLE_EXPORT int32_t oracle_result_sort(OracleResult* r, const B2QOrderEntry* oes, int32_t n, size_t top_n) {
+  for (int i = 0; i < n; ++i) if (oes[i].tle_no < 1 || oes[i].tle_no > static_cast<int>(r->plan.targets.size())) return B2Q_ERR_INVALID_ARGUMENT;
+  result_sort(r, oes, n, top_n);
+  return 0;
+}
+ORACLE_EXPORT void oracle_result_drop_first_n(OracleResult* r, size_t n) { r->drop_first = n; r->cursor = 0; r->fetched = 0; }
+ORACLE_EXPORT void oracle_result_keep_first_n(OracleResult* r, size_t n) { r->keep_first = n; r->cursor = 0; r->fetched = 0; }
+/* the i-th entry index in iteration order (tests compare the device permutation with this one) */
+ORACLE_EXPORT int64_t oracle_result_permutation_at(const OracleResult* r, size_t i) { return r->sorted && i < r->perm.size() ? r->perm[i] : -1; }
 ORACLE_EXPORT int32_t oracle_result_is_row_at_empty(const OracleResult* r, size_t e) { return is_empty_entry(r->plan.p, r->buf.data(), static_cast<int64_t>(e)); }
-ORACLE_EXPORT size_t oracle_result_row_count(const OracleResult* r) { /* ResultSet::rowCount(): non-empty entries */
+ORACLE_EXPORT size_t oracle_result_row_count(const OracleResult* r) { /* ResultSet::rowCountImpl (ResultSet.cpp:565-600) */
   size_t n = 0;
-  for (int64_t e = 0; e < r->plan.p.entry_count; ++e) n += !is_empty_entry(r->plan.p, r->buf.data(), e);
-  return n;
+  if (r->sorted) n = r->perm.size();
+  else for (int64_t e = 0; e < r->plan.p.entry_count; ++e) n += !is_empty_entry(r->plan.p, r->buf.data(), e);
+  if (n <= r->drop_first) return 0; /* get_truncated_row_count */
+  n -= r->drop_first;
+  return r->keep_first ? std::min(n, r->keep_first) : n;
 }
 ORACLE_EXPORT size_t oracle_result_col_count(const OracleResult* r) { return r->plan.targets.size(); }
-ORACLE_EXPORT void oracle_result_move_to_begin(OracleResult* r) { r->cursor = 0; }
+ORACLE_EXPORT void oracle_result_move_to_begin(OracleResult* r) { r->cursor = 0; r->fetched = 0; }
 ORACLE_EXPORT void oracle_result_free(OracleResult* r) { delete r; }
 
 /* ResultSet::getColType: AVG targets read out as DOUBLE (ResultSet.cpp getColType) */
@@ -1333,10 +1429,17 @@ ORACLE_EXPORT B2QTypeInfo oracle_result_col_type(const OracleResult* r, size_t c
  * AVG via make_avg_target_value (:43-82) + pair_to_double (ResultSetBufferAccessors.h:197-227). */
 ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue* row) {
   const B2QPlan& p = r->plan.p;
-  while (r->cursor < p.entry_count && is_empty_entry(p, r->buf.data(), r->cursor)) ++r->cursor;
-  if (r->cursor >= p.entry_count) return 0;
-  const int64_t entry = r->cursor;
-  ++r->cursor;
+  /* getNextRowImpl + advanceCursorToNextEntry (ResultSetIteration.cpp:320-340, :731-750) */
+  const int64_t n_entries = r->sorted ? static_cast<int64_t>(r->perm.size()) : p.entry_count;
+  int64_t entry = 0;
+  do {
+    if (r->keep_first && r->fetched >= r->drop_first + r->keep_first) return 0;
+    while (r->cursor < n_entries && is_empty_entry(p, r->buf.data(), r->sorted ? r->perm[r->cursor] : r->cursor)) ++r->cursor;
+    if (r->cursor >= n_entries) return 0;
+    entry = r->sorted ? r->perm[r->cursor] : r->cursor;
+    ++r->cursor;
+    ++r->fetched;
+  } while (r->drop_first && r->fetched <= r->drop_first);
   for (size_t i = 0; i < r->plan.targets.size(); ++i) {
     Target t = r->plan.targets[i];
     /* ResultSet's targets_: non-grouped MIN/MAX/SUM/AVG are nullable (target_exprs_to_infos, set_notnull false) */

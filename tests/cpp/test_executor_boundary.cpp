@@ -93,6 +93,25 @@ int main() {
     CHECK(r0[0].ival == 1 && r0[1].ival == 10 && r0[2].dval == 10.0);
     CHECK(r1[0].ival == 2 && r1[1].ival == 20 && r1[2].dval == 20.0);
   }
+  { /* SELECT x, SUM(big) FROM t GROUP BY x ORDER BY 2 DESC LIMIT 1 — sort_info in the unit, and ResultSet::sort afterwards */
+    RelAlgExecutionUnit u;
+    u.groupby_exprs.push_back(u.makeColumnVar(info.col_types[0], 0));
+    u.target_exprs.push_back(u.makeColumnVar(info.col_types[0], 0));
+    u.target_exprs.push_back(u.makeAggExpr(SQLTypeInfo(kBIGINT, false), kSUM, u.makeColumnVar(info.col_types[1], 1)));
+    u.sort_info.order_entries.push_back(B2QOrderEntry{2, 1, 1, {0, 0}});
+    u.sort_info.limit = 1;
+    auto result = executor->executeWorkUnit(max_groups_buffer_entry_guess, true, {info}, u, CompilationOptions::defaults(), ExecutionOptions::defaults(), nullptr, false, column_cache);
+    CHECK(result->rowCount() == 1 && result->entryCount() == 1);
+    auto r0 = result->getNextRow(false, false);
+    CHECK(r0[0].ival == 2 && r0[1].ival == 20);
+    CHECK(result->getNextRow(false, false).empty());
+    u.sort_info = {};
+    auto all = executor->executeWorkUnit(max_groups_buffer_entry_guess, true, {info}, u, CompilationOptions::defaults(), ExecutionOptions::defaults(), nullptr, false, column_cache);
+    all->sort({B2QOrderEntry{1, 1, 0, {0, 0}}}, 0);
+    CHECK(all->rowCount() == 2);
+    CHECK(all->getNextRow(false, false)[0].ival == 2);
+    CHECK(all->getNextRow(false, false)[0].ival == 1);
+  }
   std::printf("boundary test ok\n");
   return 0;
 }

@@ -66,6 +66,66 @@ def rows_equal(got, want, fp_rtol=FP_RTOL):
                 assert va == vb, f"{a} vs {b}"
 
 
+def rows_equal_ordered(got, want, fp_rtol=FP_RTOL):
+    """Row by row, in order (ORDER BY results)."""
+    assert len(got) == len(want), f"row count {len(got)} != {len(want)}\n got={got[:8]}\nwant={want[:8]}"
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert len(a) == len(b)
+        for va, vb in zip(a, b):
+            if va is None or vb is None:
+                assert va is None and vb is None, f"row {i}: NULL mismatch: {a} vs {b}"
+            elif isinstance(vb, float):
+                assert isinstance(va, float) and (va == vb or abs(va - vb) <= fp_rtol * abs(vb)), f"row {i}: {a} vs {b}"
+            else:
+                assert va == vb, f"row {i}: {a} vs {b}"
+
+
+def _entry_bytes(buf, plan, entries):
+    """Per-entry byte image [keys | slots] of the given entries of a row-wise or columnar buffer, plus the byte
+    ranges (inside that image) of floating-point SUM slots."""
+    b = buf.view(np.int8)
+    n = plan.entry_count
+    entries = np.asarray(entries, dtype=np.int64)
+    fp_sum = {t.first_slot for t in plan.targets[: plan.num_targets]
+              if t.is_agg and t.agg_kind in (abi.kSUM, abi.kAVG) and t.agg_arg_type.type == abi.kDOUBLE}
+    parts, fp_ranges, off = [], [], 0
+    keyed = plan.query_desc_type != abi.NonGroupedAggregate and not plan.keyless_hash
+    if plan.output_columnar:
+        if keyed:
+            stride = (8 * n + 7) // 8 * 8
+            for c in range(max(plan.num_group_cols, 1)):
+                parts.append(b[c * stride:c * stride + 8 * n].reshape(n, 8)[entries]); off += 8
+        for s in range(plan.num_slots):
+            w = plan.slot_padded_width[s]
+            if not w:
+                continue
+            o = plan.slot_offset[s]
+            parts.append(b[o:o + w * n].reshape(n, w)[entries])
+            if s in fp_sum:
+                fp_ranges.append((off, off + 8))
+            off += w
+        return (np.concatenate(parts, axis=1) if parts else np.zeros((len(entries), 0), np.int8)), fp_ranges
+    rows = b.reshape(n, plan.row_size)[entries] if n else np.zeros((0, plan.row_size), np.int8)
+    for s in fp_sum:
+        fp_ranges.append((plan.slot_offset[s], plan.slot_offset[s] + 8))
+    return rows, fp_ranges
+
+
+def compact_buffer_equal(got, gplan, want, wplan, perm, fp_rtol=FP_RTOL):
+    """Entry i of the compacted/sorted product buffer must equal entry perm[i] of the oracle's full buffer."""
+    g, fr = _entry_bytes(got, gplan, np.arange(gplan.entry_count))
+    w, _ = _entry_bytes(want, wplan, perm)
+    assert g.shape == w.shape, (g.shape, w.shape)
+    mask = np.ones(g.shape[1], dtype=bool)
+    for lo, hi in fr:
+        mask[lo:hi] = False
+        a = np.ascontiguousarray(g[:, lo:hi]).view(np.float64).ravel()
+        b = np.ascontiguousarray(w[:, lo:hi]).view(np.float64).ravel()
+        ok = (a == b) | (np.abs(a - b) <= fp_rtol * np.abs(b))
+        assert ok.all(), f"fp SUM bytes {lo}:{hi}: {a[~ok][:4]} vs {b[~ok][:4]}"
+    assert np.array_equal(g[:, mask], w[:, mask]), "sorted/compacted buffer differs from the oracle's entries"
+
+
 def buffers_equal(got: np.ndarray, want: np.ndarray, plan: abi.Plan, fp_rtol=FP_RTOL, empty=None):
     """Raw output buffers in the reference's row-wise layout.  Integer/bit-pattern slots must be identical; slots that
     hold a floating-point SUM (order of additions differs on a GPU) are compared within fp_rtol."""

@@ -43,6 +43,12 @@ def lib():
         L.oracle_result_col_type.argtypes = [C.c_void_p, C.c_size_t]
         L.oracle_result_get_next_row.restype = C.c_int32
         L.oracle_result_get_next_row.argtypes = [C.c_void_p, C.POINTER(abi.TargetValue)]
+        L.oracle_result_sort.restype = C.c_int32
+        L.oracle_result_sort.argtypes = [C.c_void_p, C.POINTER(abi.OrderEntry), C.c_int32, C.c_size_t]
+        L.oracle_result_drop_first_n.argtypes = [C.c_void_p, C.c_size_t]
+        L.oracle_result_keep_first_n.argtypes = [C.c_void_p, C.c_size_t]
+        L.oracle_result_permutation_at.restype = C.c_int64
+        L.oracle_result_permutation_at.argtypes = [C.c_void_p, C.c_size_t]
         L.oracle_gen_column.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_int32]
         L.oracle_gen_column_strided.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
@@ -72,6 +78,24 @@ class OracleResult:
 
     def row_count(self):
         return lib().oracle_result_row_count(self.h)
+
+    def sort(self, order_entries, top_n=0):
+        """ResultSet::sort: order_entries = [(tle_no, is_desc, nulls_first)]."""
+        arr = (abi.OrderEntry * max(len(order_entries), 1))()
+        for i, (tle, desc, nf) in enumerate(order_entries):
+            arr[i].tle_no, arr[i].is_desc, arr[i].nulls_first = tle, int(desc), int(nf)
+        rc = lib().oracle_result_sort(self.h, arr, len(order_entries), top_n)
+        if rc:
+            raise OracleError(rc, "bad order entry")
+
+    def drop_first_n(self, n):
+        lib().oracle_result_drop_first_n(self.h, n)
+
+    def keep_first_n(self, n):
+        lib().oracle_result_keep_first_n(self.h, n)
+
+    def permutation(self):
+        return [lib().oracle_result_permutation_at(self.h, i) for i in range(self.entry_count())]
 
     def col_count(self):
         return lib().oracle_result_col_count(self.h)

@@ -60,7 +60,7 @@ def test_cardinality_estimation_required(table):
 
 
 def test_unsupported_is_rejected_not_ignored(table):
-    for field in ("num_join_quals", "has_estimator", "num_order_entries", "has_union_all", "has_window_function"):
+    for field in ("num_join_quals", "has_estimator", "has_union_all", "has_window_function"):
         b = abi.UnitBuilder(table)
         b.target(b.agg(abi.kCOUNT))
         b.unsupported[field] = 1
