@@ -60,6 +60,11 @@ CONFIGS["c2enc"] = (
     # FIXED(16)): 10 B/row instead of 20 — SURVEY.md §8f-2 "lets the kernels read real HeavyDB chunks"
     [("c0", "i64", 0, 10**6, 1, 4), ("c1", "i64", 0, 10**6, 1, 4), ("g", "i32", 0, 10**4, 1, 2)],
     CONFIGS["c2"][1], 10, "configs[1] with ENCODING FIXED chunks: c0,c1 BIGINT FIXED(32), g INT FIXED(16)")
+# the same aggregations ending in ORDER BY ... LIMIT (top-k on the device: only the kept rows are copied back)
+CONFIGS["c2top"] = (CONFIGS["c2"][0], "SELECT g, SUM(c1), COUNT(*) FROM t WHERE c0 < 500000 GROUP BY g ORDER BY 2 DESC, 1 LIMIT 10;", 20,
+                    "configs[1] + ORDER BY SUM DESC LIMIT 10 (device compaction + radix sort + gather)")
+CONFIGS["c4top"] = (CONFIGS["c4"][0], "SELECT key, SUM(v) FROM t GROUP BY key ORDER BY 2 DESC, 1 LIMIT 10;", 16,
+                    "configs[3] + ORDER BY SUM DESC LIMIT 10 over 1e7 groups (device compaction + radix sort + gather)")
 ENTRY_GUESS = {"c4s": 15_000_000}
 
 
@@ -325,6 +330,7 @@ def main():
             scan_ms.append(part.kernel_ms())
         t_end = time.time()
         launches_per_step = rs.stats()["kernel_launches"]
+        sort_us = rs.stats()["sort_us"]
         result_rows = rs.rowCount()
         plan_kernel, plan_entries = int(rs.getQueryMemDesc().kernel), int(rs.getQueryMemDesc().entry_count)
         del rs, part
@@ -350,7 +356,8 @@ def main():
         "data": "synthetic (counter-based splitmix64 columns generated in HBM; inputs 20 GB/GPU >> 126 MB L2, no flush needed)",
         "config": {"workload": workload, "query": sql, "rows_per_gpu": rows, "fragments_per_gpu": len(table.fragments),
                    "fragment_rows": FRAG_ROWS, "kernel": plan_kernel, "entry_count": plan_entries,
-                   "groups_out": int(result_rows), "l2": "inputs larger than L2"},
+                   "groups_out": int(result_rows), "l2": "inputs larger than L2",
+                   **({"sort_ms": sort_us / 1e3} if sort_us else {})},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": rows * bytes_per_row,
                      "peak_source": peak_src, "kernel": "b2q_k_scan", "kernel_ms": k_ms,

@@ -156,6 +156,15 @@ __global__ void b2q_k_sort_make_keys(const DevSortLayout L, const DevSortKey K, 
   }
 }
 
+/* OR / AND of all keys: a digit position whose bits are equal in both is uniform and its pass can be skipped */
+__global__ void b2q_k_sort_bits(const uint64_t* __restrict__ keys, int64_t n, unsigned long long* __restrict__ or_and) {
+  unsigned long long o = 0, a = ~0ull;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) { o |= keys[j]; a &= keys[j]; }
+  for (int s = 16; s; s >>= 1) { o |= __shfl_down_sync(~0u, o, s); a &= __shfl_down_sync(~0u, a, s); }
+  if ((threadIdx.x & 31) == 0) { atomicOr(or_and, o); atomicAnd(or_and + 1, a); }
+}
+
 /* ---- stable LSD radix pass (8-bit digit) -------------------------------------------------------------------- */
 __global__ void b2q_k_sort_hist(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist /* [256][nblocks] */,
                                 uint32_t* __restrict__ bin_total /* [256] */) {
@@ -171,6 +180,43 @@ __global__ void b2q_k_sort_hist(const uint64_t* __restrict__ keys, int64_t n, in
   const uint32_t c = s_h[threadIdx.x];
   hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = c;
   if (c) atomicAdd(&bin_total[threadIdx.x], c);
+}
+
+/* exclusive scan of the [256][nblocks] histogram in digit-major order, one CTA per digit: the digit's base is the
+ * sum of the totals of the smaller digits (bin_total, accumulated by the histogram kernel), then a tiled block scan
+ * along the row with a running carry — coalesced, 256 CTAs instead of one */
+__global__ void b2q_k_sort_scan_rows(uint32_t* __restrict__ hist, int nblocks, const uint32_t* __restrict__ bin_total) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int d = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t < 32) { /* base = sum of bin_total[0..d) */
+    uint32_t v = 0;
+    for (int i = t; i < d; i += 32) v += bin_total[i];
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(~0u, v, o);
+    if (t == 0) s_carry = v;
+  }
+  __syncthreads();
+  uint32_t* row = hist + (size_t)d * nblocks;
+  for (int base = 0; base < nblocks; base += blockDim.x) {
+    const int i = base + t;
+    const uint32_t v = i < nblocks ? row[i] : 0;
+    uint32_t inc = v; /* inclusive warp scan */
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(~0u, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < (blockDim.x >> 5) ? s_warp[lane] : 0;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(~0u, w, o); if (lane >= o) w += u; }
+      s_warp[lane] = w; /* inclusive scan of the warp totals */
+    }
+    __syncthreads();
+    const uint32_t carry = s_carry;
+    const uint32_t before = carry + (warp ? s_warp[warp - 1] : 0) + inc - v;
+    if (i < nblocks) row[i] = before;
+    __syncthreads();
+    if (t == blockDim.x - 1) s_carry = carry + s_warp[(blockDim.x >> 5) - 1];
+    __syncthreads();
+  }
 }
 
 /* uniform[0] = 1 when every key has the same digit: the scatter then degenerates to a copy */
@@ -295,6 +341,7 @@ cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_ke
   uint32_t* bin_total = reinterpret_cast<uint32_t*>(p); p += pad(256 * 4);
   uint32_t* d_total = reinterpret_cast<uint32_t*>(p);
   uint32_t* d_uniform = d_total + 1;
+  unsigned long long* d_bits = reinterpret_cast<unsigned long long*>(p + 64);
   *launches = 0;
   *perm_out = perm_a;
   *n_out = 0;
@@ -321,7 +368,7 @@ cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_ke
     cudaMemsetAsync(bin_total, 0, 256 * 4, st);
     b2q_k_sort_hist<<<nblocks, SORT_BLOCK, 0, st>>>(keys_a, n, shift, hist, bin_total);
     b2q_k_sort_uniform<<<1, 256, 0, st>>>(bin_total, n, d_uniform);
-    b2q_k_sort_scan<<<1, 1024, 0, st>>>(hist, (int64_t)256 * nblocks, nullptr);
+    b2q_k_sort_scan_rows<<<256, 1024, 0, st>>>(hist, nblocks, bin_total);
     b2q_k_sort_scatter<<<nblocks, SORT_BLOCK, 0, st>>>(keys_a, pin, keys_b, pout, n, shift, hist, d_uniform);
     *launches += 4;
     std::swap(keys_a, keys_b);
@@ -330,7 +377,16 @@ cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_ke
   for (int k = n_keys - 1; k >= 0; --k) {
     b2q_k_sort_make_keys<<<kgrid, 256, 0, st>>>(L, keys[k], buf, pin, n, keys_a, 0);
     *launches += 1;
-    for (int shift = 0; shift < 64; shift += 8) radix_pass(shift);
+    /* which digit positions actually differ: one tiny reduction + an 16-byte copy-back instead of up to 8 passes */
+    unsigned long long h_bits[2] = {0ull, ~0ull};
+    cudaMemcpyAsync(d_bits, h_bits, 16, cudaMemcpyHostToDevice, st);
+    b2q_k_sort_bits<<<kgrid, 256, 0, st>>>(keys_a, n, d_bits);
+    *launches += 1;
+    e = cudaMemcpyAsync(h_bits, d_bits, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    const unsigned long long diff = h_bits[0] ^ h_bits[1];
+    for (int shift = 0; shift < 64; shift += 8) if ((diff >> shift) & 255ull) radix_pass(shift);
     if (keys[k].nullable) {
       b2q_k_sort_make_keys<<<kgrid, 256, 0, st>>>(L, keys[k], buf, pin, n, keys_a, 1);
       *launches += 1;
