@@ -18,6 +18,10 @@ import numpy as np
 # ---- SQLTypes subset -------------------------------------------------------------------------------------
 kINT, kSMALLINT, kFLOAT, kDOUBLE, kBIGINT, kTINYINT = 6, 7, 8, 9, 12, 22
 kBOOLEAN = 1  # only as the type of the deleted-rows column
+kCHAR, kVARCHAR, kTEXT = 2, 3, 13   # dictionary-encoded strings: int32 ids (uint8 / uint16 under DICT(8) / DICT(16))
+kTIME, kTIMESTAMP, kDATE = 10, 11, 14   # int64
+STRING_TYPES = (kCHAR, kVARCHAR, kTEXT)
+TIME_TYPES = (kTIME, kTIMESTAMP, kDATE)
 # ---- SQLOps subset ---------------------------------------------------------------------------------------
 kEQ, kNE, kLT, kGT, kLE, kGE, kAND, kOR = 0, 2, 3, 4, 5, 6, 7, 8
 # ---- SQLAgg subset ---------------------------------------------------------------------------------------
@@ -55,9 +59,11 @@ NULL_DOUBLE = float(np.finfo(np.float64).tiny)  # DBL_MIN: smallest NORMAL doubl
 EMPTY_KEY_64 = 2**63 - 1
 EMPTY_KEY_32 = 2**31 - 1
 
-NUMPY_OF = {kBOOLEAN: np.int8, kTINYINT: np.int8, kSMALLINT: np.int16, kINT: np.int32, kBIGINT: np.int64, kDOUBLE: np.float64}
-SIZE_OF = {kBOOLEAN: 1, kTINYINT: 1, kSMALLINT: 2, kINT: 4, kBIGINT: 8, kDOUBLE: 8}
-NULL_OF = {kBOOLEAN: NULL_TINYINT, kTINYINT: NULL_TINYINT, kSMALLINT: NULL_SMALLINT, kINT: NULL_INT, kBIGINT: NULL_BIGINT, kDOUBLE: NULL_DOUBLE}
+NUMPY_OF = {kBOOLEAN: np.int8, kTINYINT: np.int8, kSMALLINT: np.int16, kINT: np.int32, kBIGINT: np.int64, kDOUBLE: np.float64,
+            kCHAR: np.int32, kVARCHAR: np.int32, kTEXT: np.int32, kTIME: np.int64, kTIMESTAMP: np.int64, kDATE: np.int64}
+SIZE_OF = {kBOOLEAN: 1, kTINYINT: 1, kSMALLINT: 2, kINT: 4, kBIGINT: 8, kDOUBLE: 8, kCHAR: 4, kVARCHAR: 4, kTEXT: 4, kTIME: 8, kTIMESTAMP: 8, kDATE: 8}
+NULL_OF = {kBOOLEAN: NULL_TINYINT, kTINYINT: NULL_TINYINT, kSMALLINT: NULL_SMALLINT, kINT: NULL_INT, kBIGINT: NULL_BIGINT, kDOUBLE: NULL_DOUBLE,
+           kCHAR: NULL_INT, kVARCHAR: NULL_INT, kTEXT: NULL_INT, kTIME: NULL_BIGINT, kTIMESTAMP: NULL_BIGINT, kDATE: NULL_BIGINT}
 
 
 class TypeInfo(C.Structure):
@@ -449,12 +455,16 @@ class Table:
     def physical_dtype(self, c: int):
         """numpy dtype of the chunk elements of column c (narrower than the logical type under ENCODING FIXED)."""
         enc = self.encoded_sizes[c]
+        if enc and self.col_types[c][0] in STRING_TYPES:   # DICT(8) / DICT(16): unsigned ids (ColumnIR.cpp:59-67)
+            return {1: np.uint8, 2: np.uint16, 4: np.int32}[enc]
         if enc:
             return {1: np.int8, 2: np.int16, 4: np.int32}[enc]
         return NUMPY_OF[self.col_types[c][0]]
 
     def physical_null(self, c: int):
         enc = self.encoded_sizes[c]
+        if enc in (1, 2) and self.col_types[c][0] in STRING_TYPES:   # inline_fixed_encoding_null_val: the unsigned maximum
+            return 2 ** (8 * enc) - 1
         if enc:
             return -(2 ** (8 * enc - 1))
         return NULL_OF[self.col_types[c][0]]

@@ -81,6 +81,26 @@ __device__ __forceinline__ int32_t ldg_s8(const int8_t* p, uint32_t pred, uint64
   return (int32_t)(int8_t)v;
 }
 
+/* zero-extending variants: dictionary ids stored on 1 / 2 bytes are unsigned (FixedWidthUnsigned, ColumnIR.cpp:59-67) */
+template <bool PRED>
+__device__ __forceinline__ int32_t ldg_u16(const int8_t* p, uint32_t pred, uint64_t pol) {
+  uint32_t v;
+  if (PRED)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %3;\n\t}" : "=r"(v) : "l"(p), "r"(pred), "l"(pol));
+  else
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return (int32_t)(v & 0xFFFFu);
+}
+template <bool PRED>
+__device__ __forceinline__ int32_t ldg_u8(const int8_t* p, uint32_t pred, uint64_t pol) {
+  uint32_t v;
+  if (PRED)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %3;\n\t}" : "=r"(v) : "l"(p), "r"(pred), "l"(pol));
+  else
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return (int32_t)(v & 0xFFu);
+}
+
 /* R rows of an 8-byte column: rows row0 + j*stride */
 template <bool PRED>
 __device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict__ base, int64_t row0, int stride, uint32_t mask, uint64_t pol) {
@@ -89,7 +109,7 @@ __device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict
 #pragma unroll
   for (int j = 0; j < R; ++j) v[j] = ldg_b64<PRED>(p + j * step, mask >> j & 1, pol);
 }
-/* R rows of a 1/2/4-byte integer column, sign-extended to 32 bits */
+/* R rows of a 1/2/4-byte integer column, sign-extended to 32 bits (width -1 / -2: zero-extended) */
 template <bool PRED>
 __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0, int stride, uint32_t mask, uint64_t pol) {
   if (width == 4) {
@@ -102,6 +122,16 @@ __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict
     const int64_t step = (int64_t)stride * 2;
 #pragma unroll
     for (int j = 0; j < R; ++j) v[j] = ldg_s16<PRED>(p + j * step, mask >> j & 1, pol);
+  } else if (width == -2) {
+    const int8_t* p = base + row0 * 2;
+    const int64_t step = (int64_t)stride * 2;
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = ldg_u16<PRED>(p + j * step, mask >> j & 1, pol);
+  } else if (width == -1) {
+    const int8_t* p = base + row0;
+    const int64_t step = (int64_t)stride;
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = ldg_u8<PRED>(p + j * step, mask >> j & 1, pol);
   } else {
     const int8_t* p = base + row0;
     const int64_t step = (int64_t)stride;

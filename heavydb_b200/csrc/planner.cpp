@@ -38,22 +38,27 @@ namespace {
 struct SqlType {
   int32_t type = 0;
   bool notnull = false;
-  bool is_int() const { return type == B2Q_kTINYINT || type == B2Q_kSMALLINT || type == B2Q_kINT || type == B2Q_kBIGINT; }
+  bool is_string() const { return type == B2Q_kTEXT || type == B2Q_kVARCHAR || type == B2Q_kCHAR; } /* dictionary ids */
+  bool is_time() const { return type == B2Q_kTIME || type == B2Q_kTIMESTAMP || type == B2Q_kDATE; }
+  /* everything the path handles as an integer: dictionary ids are int32 (is_int_and_no_bigger_than(ti, 4) ||
+   * dict string, QueryMemoryDescriptor.cpp:803-804), time types int64 (sqltypes.h is_time()) */
+  bool is_int() const { return type == B2Q_kTINYINT || type == B2Q_kSMALLINT || type == B2Q_kINT || type == B2Q_kBIGINT || is_string() || is_time(); }
+  bool is_number() const { return is_int() && !is_string() && !is_time(); }
   bool is_fp() const { return type == B2Q_kDOUBLE; }
-  int size() const {
+  int size() const { /* logical size */
     switch (type) {
       case B2Q_kTINYINT: return 1;
       case B2Q_kSMALLINT: return 2;
-      case B2Q_kINT: return 4;
-      case B2Q_kBIGINT: case B2Q_kDOUBLE: return 8;
+      case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4;
+      case B2Q_kBIGINT: case B2Q_kDOUBLE: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: return 8;
       default: return -1;
     }
   }
-  int64_t int_null() const { /* Shared/InlineNullValues.h:30-36 */
+  int64_t int_null() const { /* Shared/InlineNullValues.h:30-36, :100-150 */
     switch (type) {
       case B2Q_kTINYINT: return INT8_MIN;
       case B2Q_kSMALLINT: return INT16_MIN;
-      case B2Q_kINT: return INT32_MIN;
+      case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return INT32_MIN;
       default: return INT64_MIN;
     }
   }
@@ -141,7 +146,12 @@ class Planner {
     if (t_.col_encoded_sizes && t_.col_encoded_sizes[c] > 0) return t_.col_encoded_sizes[c];
     return col_type(c).size();
   }
+  /* dictionary ids stored on 1 or 2 bytes are UNSIGNED (FixedWidthUnsigned, ColumnIR.cpp:59-67) */
+  bool phys_unsigned(int c) const { return col_type(c).is_string() && phys_size(c) < 4; }
+  /* width as the kernels take it: bytes, negative for an unsigned (zero-extending) load */
+  int phys_width_code(int c) const { return phys_unsigned(c) ? -phys_size(c) : phys_size(c); }
   int64_t phys_int_null(int c) const {
+    if (phys_unsigned(c)) return phys_size(c) == 1 ? 255 : 65535; /* inline_fixed_encoding_null_val, InlineNullValues.h:173-182 */
     switch (phys_size(c)) { case 1: return INT8_MIN; case 2: return INT16_MIN; case 4: return INT32_MIN; default: return INT64_MIN; }
   }
 
@@ -163,7 +173,7 @@ class Planner {
         if (!is_deleted_col) reject(B2Q_ERR_UNSUPPORTED, "BOOLEAN is only supported as the deleted-rows column");
         continue;
       }
-      if (col_type(c).size() < 0) reject(B2Q_ERR_UNSUPPORTED, "column type outside TINYINT/SMALLINT/INT/BIGINT/DOUBLE");
+      if (col_type(c).size() < 0) reject(B2Q_ERR_UNSUPPORTED, "column type outside TINYINT/SMALLINT/INT/BIGINT/DOUBLE/TIME/TIMESTAMP/DATE/dictionary-encoded strings");
       if (t_.col_encoded_sizes && t_.col_encoded_sizes[c]) {
         const int e = t_.col_encoded_sizes[c];
         if (!col_type(c).is_int() || (e != 1 && e != 2 && e != 4) || e >= col_type(c).size())
@@ -201,6 +211,10 @@ class Planner {
           d.arg_type = from_abi(a.ti);
           if (d.arg_type.size() != col_type(a.col_id).size()) reject(B2Q_ERR_INVALID_ARGUMENT, "ColumnVar type does not match the table");
           d.skip_null = !d.arg_type.notnull;
+          /* what the analyzer lets through (Analyzer.cpp / RelAlgTranslator): no SUM / AVG of strings or time types,
+           * MIN / MAX of a dictionary string would need dictionary order */
+          if (d.arg_type.is_string() && e.op != B2Q_kCOUNT) reject(B2Q_ERR_UNSUPPORTED, "only COUNT of a dictionary-encoded string is on this path");
+          if (d.arg_type.is_time() && (e.op == B2Q_kSUM || e.op == B2Q_kAVG)) reject(B2Q_ERR_UNSUPPORTED, "SUM / AVG of a TIME / TIMESTAMP / DATE");
           if (e.op == B2Q_kAVG) d.sql_type = d.arg_type.is_int() ? SqlType{B2Q_kBIGINT, d.arg_type.notnull} : d.arg_type;
           else if (e.op == B2Q_kCOUNT) d.sql_type = SqlType{bigint_count ? B2Q_kBIGINT : B2Q_kINT, e.ti.notnull != 0};
           else d.sql_type = from_abi(e.ti);
@@ -211,6 +225,8 @@ class Planner {
       targets_.push_back(d);
     }
     if (!any_agg) reject(B2Q_ERR_UNSUPPORTED, "projection-only queries are outside this path");
+    for (int i = 0; i < u_.num_order_entries; ++i) /* ResultSet::sort orders dictionary strings through the dictionary (ResultSet.cpp:1431-1446) */
+      if (targets_[u_.order_entries[i].tle_no - 1].sql_type.is_string()) reject(B2Q_ERR_UNSUPPORTED, "ORDER BY a dictionary-encoded string needs the dictionary");
   }
 
   ColRange leaf_range(int col) const {
@@ -537,8 +553,10 @@ class Planner {
     DevTerm t;
     memset(&t, 0, sizeof(t));
     t.col = launch_col(q, l.col_id);
-    t.width = static_cast<int8_t>(phys_size(l.col_id));
+    t.width = static_cast<int8_t>(phys_width_code(l.col_id));
     t.col_is_fp = ct.is_fp();
+    if (ct.is_string() && e.op != B2Q_kEQ && e.op != B2Q_kNE) reject(B2Q_ERR_UNSUPPORTED, "dictionary-encoded strings compare by id: only = and <> are on this path");
+    if (ct.is_string() && c.ti.type == B2Q_kDOUBLE) reject(B2Q_ERR_INVALID_ARGUMENT, "string column compared with a floating-point constant");
     const bool nullable = !ct.notnull;
     t.null_bits = ct.is_fp() ? dbl_bits(kNullDouble) : phys_int_null(l.col_id);
     const bool cfp = c.ti.type == B2Q_kDOUBLE;
@@ -661,7 +679,7 @@ class Planner {
     if (!d || d->arg_col < 0) return a;
     const SqlType at = d->arg_type;
     a.col = launch_col(q, d->arg_col);
-    a.width = static_cast<int8_t>(phys_size(d->arg_col));
+    a.width = static_cast<int8_t>(phys_width_code(d->arg_col));
     const int64_t arg_null = phys_int_null(d->arg_col); /* the sentinel as stored in the chunk */
     a.is_fp = at.is_fp();
     if (!d->skip_null) return a;
@@ -730,7 +748,7 @@ class Planner {
       const SqlType kt = col_type(kc.col);
       DevKeyComp& d = g.keys[i];
       d.col = launch_col(q, kc.col);
-      d.width = static_cast<int8_t>(phys_size(kc.col));
+      d.width = static_cast<int8_t>(phys_width_code(kc.col));
       d.min_val = kc.min;
       d.card = static_cast<uint32_t>(kc.card);
       d.mult = static_cast<uint32_t>(kc.mult);
@@ -746,7 +764,7 @@ class Planner {
     if (grouped_ && keycomps_.size() <= 1) {
       const SqlType kt = col_type(key_col_);
       k.col = launch_col(q, key_col_);
-      k.width = static_cast<int8_t>(phys_size(key_col_));
+      k.width = static_cast<int8_t>(phys_width_code(key_col_));
       k.min_val = p.min_val;
       k.null_val = kt.notnull ? kt.int_null() : phys_int_null(key_col_);
       k.null_logical = kt.int_null();

@@ -42,11 +42,22 @@ extern "C" {
 /* ---- SQLTypes subset (Shared/sqltypes.h:65-99) -------------------------------------------------------- */
 enum {
   B2Q_kBOOLEAN = 1, /* only as the type of the deleted-rows column (B2QTableInfo.deleted_column_plus1) */
+  /* dictionary-encoded strings (kENCODING_DICT only): the chunk holds int32 ids, or uint8 / uint16 ids for
+   * `TEXT ENCODING DICT(8|16)` (col_encoded_sizes = 1 | 2, FixedWidthUnsigned decode, NULL = 255 / 65535,
+   * ColumnIR.cpp:59-67, InlineNullValues.h:173-182).  Usable as GROUP BY keys, projected keys, COUNT arguments and
+   * in `=` / `<>` against an id constant; results carry ids (getNextRow with translate_strings = false). */
+  B2Q_kCHAR = 2,
+  B2Q_kVARCHAR = 3,
   B2Q_kINT = 6,
   B2Q_kSMALLINT = 7,
   B2Q_kFLOAT = 8,
   B2Q_kDOUBLE = 9,
+  /* TIME / TIMESTAMP / DATE: int64 (optionally ENCODING FIXED(32)); keys, COUNT / MIN / MAX arguments, comparisons */
+  B2Q_kTIME = 10,
+  B2Q_kTIMESTAMP = 11,
   B2Q_kBIGINT = 12,
+  B2Q_kTEXT = 13,
+  B2Q_kDATE = 14,
   B2Q_kTINYINT = 22
 };
 

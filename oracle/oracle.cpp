@@ -60,14 +60,18 @@ struct Ti {
   bool notnull{false};
 };
 
-bool is_integer(int t) { return t == B2Q_kTINYINT || t == B2Q_kSMALLINT || t == B2Q_kINT || t == B2Q_kBIGINT; }
+/* dictionary-encoded strings are int32 ids on this path (sqltypes.h is_dict_encoded_string; treated like
+ * is_int_and_no_bigger_than(ti, 4) by QueryMemoryDescriptor.cpp:803-804), TIME / TIMESTAMP / DATE are int64 (is_time()) */
+bool is_string(int t) { return t == B2Q_kTEXT || t == B2Q_kVARCHAR || t == B2Q_kCHAR; }
+bool is_time(int t) { return t == B2Q_kTIME || t == B2Q_kTIMESTAMP || t == B2Q_kDATE; }
+bool is_integer(int t) { return t == B2Q_kTINYINT || t == B2Q_kSMALLINT || t == B2Q_kINT || t == B2Q_kBIGINT || is_string(t) || is_time(t); }
 bool is_fp(int t) { return t == B2Q_kDOUBLE; }
 int type_size(int t) { /* SQLTypeInfo::get_size() for the fixed-width subset */
   switch (t) {
     case B2Q_kTINYINT: return 1;
     case B2Q_kSMALLINT: return 2;
-    case B2Q_kINT: return 4;
-    case B2Q_kBIGINT: return 8;
+    case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4; /* logical size of a dictionary id */
+    case B2Q_kBIGINT: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: return 8;
     case B2Q_kDOUBLE: return 8;
     default: return -1;
   }
@@ -76,8 +80,8 @@ int64_t inline_int_null_val(int t) { /* Shared/InlineNullValues.h inline_int_nul
   switch (t) {
     case B2Q_kTINYINT: return kNullTinyint;
     case B2Q_kSMALLINT: return kNullSmallint;
-    case B2Q_kINT: return kNullInt;
-    case B2Q_kBIGINT: return kNullBigint;
+    case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return kNullInt;
+    case B2Q_kBIGINT: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: return kNullBigint;
     default: abort();
   }
 }
@@ -292,6 +296,15 @@ int phys_width(const B2QTableInfo& tbl, int c) {
 int64_t decode_int_column(const B2QTableInfo& tbl, const B2QFragmentInfo& fr, int c, int64_t pos) {
   const int pw = phys_width(tbl, c);
   const int lw = type_size(tbl.col_types[c].type);
+  if (is_string(tbl.col_types[c].type) && pw < lw) {
+    /* FixedWidthUnsigned (ColumnIR.cpp:59-67, fixed_width_unsigned_decode DecodersImpl.h:63-88); NULL is the maximum
+     * of the unsigned type (inline_fixed_encoding_null_val, InlineNullValues.h:173-182) */
+    const uint8_t* b = static_cast<const uint8_t*>(fr.col_buffers[c]);
+    int64_t u;
+    if (pw == 1) u = b[pos]; else { uint16_t x; memcpy(&x, b + 2 * pos, 2); u = x; }
+    if (!tbl.col_types[c].notnull && u == (pw == 1 ? 255 : 65535)) u = inline_int_null_val(tbl.col_types[c].type);
+    return u;
+  }
   int64_t v = fixed_width_int_decode(static_cast<const int8_t*>(fr.col_buffers[c]), pw, pos);
   if (pw < lw && !tbl.col_types[c].notnull) {
     const int64_t phys_null = pw == 1 ? INT8_MIN : pw == 2 ? INT16_MIN : INT32_MIN;
@@ -372,6 +385,8 @@ Target get_target_info(const B2QExecUnit& u, int expr_idx, bool bigint_count) {
   const Ti arg_ti = ti_of(arg.ti);
   t.arg_col = arg.col_id;
   t.arg_ti = arg_ti;
+  if (is_string(arg_ti.type) && e.op != B2Q_kCOUNT) fail(B2Q_ERR_UNSUPPORTED, "only COUNT of a dictionary-encoded string is on this path");
+  if (is_time(arg_ti.type) && (e.op == B2Q_kSUM || e.op == B2Q_kAVG)) fail(B2Q_ERR_UNSUPPORTED, "SUM / AVG of a TIME / TIMESTAMP / DATE");
   if (e.op == B2Q_kAVG) {
     t.sql_type = is_integer(arg_ti.type) ? Ti{B2Q_kBIGINT, arg_ti.notnull} : arg_ti;
     t.agg_arg_type = arg_ti;
@@ -575,13 +590,15 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
   for (int i = 0; i < u.num_order_entries; ++i)
     if (u.order_entries[i].tle_no < 1 || u.order_entries[i].tle_no > u.num_target_exprs) fail(B2Q_ERR_INVALID_ARGUMENT, "order entry refers to a target that does not exist");
   if (u.offset < 0 || (u.has_limit && u.limit < 0)) fail(B2Q_ERR_INVALID_ARGUMENT, "negative LIMIT / OFFSET");
+  for (int i = 0; i < u.num_order_entries; ++i) /* ResultSet::sort orders dictionary strings through the dictionary (ResultSet.cpp:1431-1446) */
+    if (is_string(expr_at(u, u.target_exprs[u.order_entries[i].tle_no - 1]).ti.type)) fail(B2Q_ERR_UNSUPPORTED, "ORDER BY a dictionary-encoded string needs the dictionary");
   if (u.num_groupby_exprs > B2Q_MAX_GROUP_COLS) fail(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
   if (u.num_target_exprs <= 0 || u.num_target_exprs > B2Q_MAX_TARGETS)
     fail(B2Q_ERR_INVALID_ARGUMENT, "bad target count");
   for (int c = 0; c < tbl.num_cols; ++c) {
     const bool is_deleted_col = tbl.deleted_column_plus1 == c + 1;
     if (tbl.col_types[c].type == B2Q_kBOOLEAN) { if (!is_deleted_col) fail(B2Q_ERR_UNSUPPORTED, "BOOLEAN is only supported as the deleted-rows column"); continue; }
-    if (type_size(tbl.col_types[c].type) < 0) fail(B2Q_ERR_UNSUPPORTED, "column type outside the numeric subset");
+    if (type_size(tbl.col_types[c].type) < 0) fail(B2Q_ERR_UNSUPPORTED, "column type outside the numeric / time / dictionary-string subset");
     if (tbl.col_encoded_sizes && tbl.col_encoded_sizes[c]) {
       const int e = tbl.col_encoded_sizes[c];
       if (!is_integer(tbl.col_types[c].type) || (e != 1 && e != 2 && e != 4) || e >= type_size(tbl.col_types[c].type))
@@ -898,6 +915,10 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
   const int ctype = tbl.col_types[col].type;
   const bool col_notnull = tbl.col_types[col].notnull != 0;
   const int8_t* buf = static_cast<const int8_t*>(fr.col_buffers[col]);
+  /* dictionary strings compare by id against a literal's id (CompareIR.cpp codegenStrCmp / translated literal):
+   * only = and <> mean anything without the dictionary */
+  if (is_string(ctype) && e.op != B2Q_kEQ && e.op != B2Q_kNE) fail(B2Q_ERR_UNSUPPORTED, "dictionary-encoded strings compare by id: only = and <> are on this path");
+  if (is_string(ctype) && is_fp(r.ti.type)) fail(B2Q_ERR_INVALID_ARGUMENT, "string column compared with a floating-point constant");
   if (r.is_null) return kNullBool;
   if (is_fp(ctype) || is_fp(r.ti.type)) {
     /* fp compare: the integer side is cast to double (CompareIR.cpp codegenCmp after normalisation) */

@@ -1,0 +1,56 @@
+"""Dictionary-encoded string keys and TIME-family columns: the oracle against SQLite on the
+ids, the known answers of Tests/GroupByTest.cpp, and planner parity."""
+import numpy as np
+import pytest
+
+import oracle_lib
+import order_queries as oq
+import ref_tables as rt
+import sqlmini
+import str_tables as st
+from heavydb_b200 import abi, executor
+from test_order_by import assert_ordered_rows_match
+
+
+@pytest.fixture(scope="module")
+def env():
+    table = st.str_table(4000, seed=12, frag_rows=900)
+    cols = [(n, t, nn) for n, t, nn, _ in st.STR_COLS]
+    return table, rt.make_sqlite(st.logical_rows(table), cols, "s")
+
+
+@pytest.mark.parametrize("sql", st.STR_QUERIES)
+def test_oracle_vs_sqlite(env, sql):
+    table, con = env
+    unit = sqlmini.parse(sql, table, st.STR_NAMES)
+    res = oracle_lib.execute(unit, table, num_threads=3)
+    ref = [tuple(r) for r in con.execute(oq.sqlite_sql(sql, unit, "s")).fetchall()]
+    if unit.unit.num_order_entries:
+        assert_ordered_rows_match(res.rows(), ref)
+    else:
+        rt.assert_rows_match(res.rows(), ref)
+    want = oracle_lib.plan(unit, table).as_dict()
+    assert executor.Executor().plan(unit, table).as_dict() == want
+
+
+@pytest.mark.parametrize("sql", st.STR_REJECTED)
+def test_rejected_on_both_sides(env, sql):
+    table, _ = env
+    unit = sqlmini.parse(sql, table, st.STR_NAMES)
+    with pytest.raises(oracle_lib.OracleError) as ei:
+        oracle_lib.execute(unit, table)
+    assert ei.value.code == abi.ERR_UNSUPPORTED
+    with pytest.raises(executor.UnsupportedOnThisPath):
+        executor.Executor().plan(unit, table)
+
+
+def test_groupbytest_known_answers():
+    """Tests/GroupByTest.cpp:60-152 PerfectHashNoFallback: rows (1,'hi'), (2,'bye'); SELECT COUNT(*) FROM t WHERE x = 1
+    GROUP BY str  =>  one row, value 1; :264-338 BaselineNoFilters => two rows, each 1."""
+    t = abi.Table([(abi.kINT, True), (abi.kTEXT, False)])
+    t.add_host_fragment([np.array([1, 2], dtype=np.int32), np.array([0, 1], dtype=np.int32)])   # 'hi' -> id 0, 'bye' -> id 1
+    unit = sqlmini.parse("SELECT COUNT(*) FROM t WHERE x = 1 GROUP BY str;", t, ["x", "str"])
+    res = oracle_lib.execute(unit, t)
+    assert res.plan.query_desc_type == abi.GroupByPerfectHash and res.rows() == [(1,)] and res.row_count() == 1
+    unit = sqlmini.parse("SELECT COUNT(*) FROM t GROUP BY str;", t, ["x", "str"])
+    assert oracle_lib.execute(unit, t).rows() == [(1,), (1,)]

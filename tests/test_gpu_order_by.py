@@ -83,6 +83,18 @@ def test_order_by_columnar_output():
     assert ran >= 5
 
 
+def test_order_by_on_time_and_dict_tables():
+    import str_tables as stt
+    table = stt.str_table(20000, seed=3, frag_rows=6000)
+    dev = gu.DeviceTable(table)
+    for sql in [q for q in stt.STR_QUERIES if " ORDER BY " in q] + [
+            "SELECT ts, COUNT(*), MAX(dt) FROM s GROUP BY ts ORDER BY 1 DESC NULLS LAST LIMIT 20;",
+            "SELECT s8, COUNT(str) FROM s GROUP BY s8 ORDER BY 2 DESC, 1 LIMIT 7;" if False else
+            "SELECT x, COUNT(str), MIN(ts) FROM s GROUP BY x ORDER BY 3 ASC NULLS FIRST, 1;"]:
+        unit = sqlmini.parse(sql, table, stt.STR_NAMES)
+        run_sorted(unit, table, dev)
+
+
 def test_result_set_sort_api():
     """b2q_rs_sort / drop_first_n / keep_first_n on a finished (unsorted) result set == sort_info in the unit."""
     table = random_table(40000, seed=5, frag_rows=9000)

@@ -397,6 +397,7 @@ def test_strided_generator_matches_oracle():
 
 # ---- ENCODING FIXED chunks, deleted-rows column -----------------------------------------------
 import enc_tables as et  # noqa: E402
+import str_tables as stt  # noqa: E402
 
 
 @pytest.mark.parametrize("n,frag_rows", [(1, 5), (999, 100), (60000, 8192)])
@@ -471,3 +472,29 @@ def test_inner_entry_b2q_launch_param_block():
         empty = np.array([bool(oracle_lib.lib().oracle_result_is_row_at_empty(ref.h, i)) for i in range(n)], dtype=bool)
         gu.buffers_equal(got, ref.buffer(), ref.plan, empty=empty)
         L.b2q_query_free(q)
+
+
+# ---- dictionary-encoded string keys (int32 / uint8 / uint16 ids) and TIME-family columns ---------------------
+@pytest.mark.parametrize("n,frag_rows", [(5, 2), (4000, 900), (150000, 40000)])
+def test_dict_string_and_time_columns(n, frag_rows):
+    table = stt.str_table(n, seed=12 + n, frag_rows=frag_rows)
+    dev = gu.DeviceTable(table)
+    for sql in stt.STR_QUERIES:
+        unit = sqlmini.parse(sql, table, stt.STR_NAMES)
+        if unit.unit.num_order_entries:
+            continue     # ordered variants: test_gpu_order_by
+        gu.run_both(unit, table, dev_table=dev)
+        gu.run_both(unit, table, device_resident=False)
+    for sql in stt.STR_REJECTED:
+        with pytest.raises(executor.UnsupportedOnThisPath):
+            executor.Executor().executeWorkUnit(0, True, dev.table, sqlmini.parse(sql, table, stt.STR_NAMES), memory_level=abi.GPU_LEVEL)
+
+
+def test_groupbytest_dictionary_key():
+    """Tests/GroupByTest.cpp:73-152 (PerfectHashNoFallback) with its own key type: GROUP BY a dictionary string."""
+    t = abi.Table([(abi.kINT, True), (abi.kTEXT, False)])
+    t.add_host_fragment([np.array([1, 2], dtype=np.int32), np.array([0, 1], dtype=np.int32)])
+    rs, _ = gu.run_both(sqlmini.parse("SELECT COUNT(*) FROM t WHERE x = 1 GROUP BY str;", t, ["x", "str"]), t)
+    assert rs.rowCount() == 1 and rs.rows() == [(1,)] and rs.getQueryMemDesc().query_desc_type == abi.GroupByPerfectHash
+    rs, _ = gu.run_both(sqlmini.parse("SELECT str, COUNT(*) FROM t GROUP BY str;", t, ["x", "str"]), t)
+    assert sorted(rs.rows()) == [(0, 1), (1, 1)]
