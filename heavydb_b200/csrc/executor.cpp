@@ -504,6 +504,11 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
   return B2Q_OK;
 }
 
+/* logical size / NULL sentinel (dictionary-encoded strings are int32 ids, TIME-family types int64) */
+static bool is_dict_string(int t) { return t == B2Q_kTEXT || t == B2Q_kVARCHAR || t == B2Q_kCHAR; }
+static int type_size(int t) { return t == B2Q_kTINYINT ? 1 : t == B2Q_kSMALLINT ? 2 : (t == B2Q_kINT || is_dict_string(t)) ? 4 : 8; }
+static int64_t int_null(int t) { return t == B2Q_kTINYINT ? INT8_MIN : t == B2Q_kSMALLINT ? INT16_MIN : (t == B2Q_kINT || is_dict_string(t)) ? INT32_MIN : INT64_MIN; }
+
 /* ---- ORDER BY / LIMIT on the device (sort.cu) ---------------------------------------------------------------- */
 static DevSortLayout sort_layout_of(const B2QPlan& p) {
   DevSortLayout L;
@@ -547,7 +552,7 @@ static DevSortKey sort_key_of(const B2QPlan& p, const B2QOrderEntry& oe) {
     memcpy(&k.null_pattern, &nd, 8);
   } else {
     k.kind = SORTKEY_I64;
-    k.null_pattern = compact.type == B2Q_kTINYINT ? INT8_MIN : compact.type == B2Q_kSMALLINT ? INT16_MIN : compact.type == B2Q_kINT ? INT32_MIN : INT64_MIN;
+    k.null_pattern = int_null(compact.type);
   }
   return k;
 }
@@ -701,8 +706,6 @@ static bool rs_is_empty_entry(const B2QResultSet* rs, int64_t e) {
   return k == B2Q_I64_MAX;
 }
 
-static int type_size(int t) { return t == B2Q_kTINYINT ? 1 : t == B2Q_kSMALLINT ? 2 : t == B2Q_kINT ? 4 : 8; }
-static int64_t int_null(int t) { return t == B2Q_kTINYINT ? INT8_MIN : t == B2Q_kSMALLINT ? INT16_MIN : t == B2Q_kINT ? INT32_MIN : INT64_MIN; }
 
 extern "C" {
 

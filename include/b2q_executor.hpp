@@ -27,7 +27,9 @@
 namespace b2q {
 
 /* ---- SQLTypeInfo / enums: the reference's own values ---- */
-enum SQLTypes { kINT = B2Q_kINT, kSMALLINT = B2Q_kSMALLINT, kDOUBLE = B2Q_kDOUBLE, kBIGINT = B2Q_kBIGINT, kTINYINT = B2Q_kTINYINT };
+enum SQLTypes { kCHAR = B2Q_kCHAR, kVARCHAR = B2Q_kVARCHAR, kINT = B2Q_kINT, kSMALLINT = B2Q_kSMALLINT, kDOUBLE = B2Q_kDOUBLE,
+                kTIME = B2Q_kTIME, kTIMESTAMP = B2Q_kTIMESTAMP, kBIGINT = B2Q_kBIGINT, kTEXT = B2Q_kTEXT /* dictionary-encoded */,
+                kDATE = B2Q_kDATE, kTINYINT = B2Q_kTINYINT };
 enum SQLOps { kEQ = B2Q_kEQ, kNE = B2Q_kNE, kLT = B2Q_kLT, kGT = B2Q_kGT, kLE = B2Q_kLE, kGE = B2Q_kGE, kAND = B2Q_kAND, kOR = B2Q_kOR };
 enum SQLAgg { kAVG = B2Q_kAVG, kMIN = B2Q_kMIN, kMAX = B2Q_kMAX, kSUM = B2Q_kSUM, kCOUNT = B2Q_kCOUNT };
 enum class ExecutorDeviceType { CPU = B2Q_DEVICE_CPU, GPU = B2Q_DEVICE_GPU };

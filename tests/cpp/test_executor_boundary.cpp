@@ -1,10 +1,10 @@
 /*
  * Boundary-level test in the shape of the reference's Tests/GroupByTest.cpp:73-152 (`PerfectHashNoFallback`) and
  * :173-338 (`BaselineFallbackTest`, `BaselineNoFilters`): build a RelAlgExecutionUnit by hand, call
- * executor->executeWorkUnit(...) directly, check rowCount()/getNextRow().  (The reference groups by a dictionary
- * string; string dictionaries are outside this path, so the key is the integer column itself.)
+ * executor->executeWorkUnit(...) directly, check rowCount()/getNextRow().  Like the reference the first test groups
+ * by a dictionary-encoded string column (the chunk holds the ids).
  *
- * Table: two rows (1, 10), (2, 20)   — GroupByTest.cpp:60-63 inserts (1,'hi'), (2,'bye').
+ * Table: (x, big, sparse, str) = (1, 10, 9e12, 'hi'), (2, 20, 7, 'bye')   — GroupByTest.cpp:60-63 inserts (1,'hi'), (2,'bye').
  */
 #include <cstdio>
 #include <cstdlib>
@@ -24,12 +24,14 @@ int main() {
   std::vector<int64_t> big{10, 20};
   std::vector<int64_t> sparse{9000000000000LL, 7};
   InputTableInfo info;
-  info.col_types = {SQLTypeInfo(kINT, true), SQLTypeInfo(kBIGINT, false), SQLTypeInfo(kBIGINT, true)};
+  std::vector<int32_t> str_ids{0, 1}; /* 'hi' -> 0, 'bye' -> 1 */
+  info.col_types = {SQLTypeInfo(kINT, true), SQLTypeInfo(kBIGINT, false), SQLTypeInfo(kBIGINT, true), SQLTypeInfo(kTEXT, false)};
   info.memory_level = MemoryLevel::CPU_LEVEL; /* host chunks: fetched to the GPU inside the call */
   FragmentInfo f;
   f.numTuples = 2;
-  f.col_buffers = {x.data(), big.data(), sparse.data()};
-  f.chunkStats.resize(3);
+  f.col_buffers = {x.data(), big.data(), sparse.data(), str_ids.data()};
+  f.chunkStats.resize(4);
+  f.chunkStats[3].int_min = 0; f.chunkStats[3].int_max = 1;
   f.chunkStats[0].int_min = 1; f.chunkStats[0].int_max = 2;
   f.chunkStats[1].int_min = 10; f.chunkStats[1].int_max = 20;
   f.chunkStats[2].int_min = 7; f.chunkStats[2].int_max = 9000000000000LL;
@@ -39,11 +41,11 @@ int main() {
   ColumnCacheMap column_cache;
   size_t max_groups_buffer_entry_guess = 1;
 
-  { /* PerfectHashNoFallback: SELECT COUNT(*) FROM t WHERE x = 1 GROUP BY x */
+  { /* PerfectHashNoFallback (GroupByTest.cpp:100-152): SELECT COUNT(*) FROM t WHERE x = 1 GROUP BY str */
     RelAlgExecutionUnit u;
     const auto col = u.makeColumnVar(info.col_types[0], 0);
     u.simple_quals.push_back(u.makeBinOper(kEQ, col, u.makeConstant(int64_t(1))));
-    u.groupby_exprs.push_back(u.makeColumnVar(info.col_types[0], 0));
+    u.groupby_exprs.push_back(u.makeColumnVar(info.col_types[3], 3));
     u.target_exprs.push_back(u.makeAggExpr(SQLTypeInfo(kINT, false), kCOUNT, -1));
     auto result = executor->executeWorkUnit(max_groups_buffer_entry_guess, true, {info}, u, CompilationOptions::defaults(ExecutorDeviceType::GPU),
                                             ExecutionOptions::defaults(), nullptr, false, column_cache);
