@@ -24,6 +24,7 @@ STRING_TYPES = (kCHAR, kVARCHAR, kTEXT)
 TIME_TYPES = (kTIME, kTIMESTAMP, kDATE)
 # ---- SQLOps subset ---------------------------------------------------------------------------------------
 kEQ, kNE, kLT, kGT, kLE, kGE, kAND, kOR = 0, 2, 3, 4, 5, 6, 7, 8
+kNOT, kISNULL = 9, 16   # Analyzer::UOper
 # ---- SQLAgg subset ---------------------------------------------------------------------------------------
 kAVG, kMIN, kMAX, kSUM, kCOUNT = 0, 1, 2, 3, 4
 # ---- QueryDescriptionType --------------------------------------------------------------------------------
@@ -39,7 +40,7 @@ ERR_NO_DEVICE = 1003
 ERR_CUDA = 1004
 ERR_KEY_OUT_OF_RANGE = 1005
 
-EXPR_COLUMN_VAR, EXPR_CONSTANT, EXPR_BIN_OPER, EXPR_AGG = 1, 2, 3, 4
+EXPR_COLUMN_VAR, EXPR_CONSTANT, EXPR_BIN_OPER, EXPR_AGG, EXPR_UOPER = 1, 2, 3, 4, 5
 CPU_LEVEL, GPU_LEVEL = 1, 2
 DEVICE_CPU, DEVICE_GPU = 0, 1
 KERNEL_AUTO, KERNEL_NON_GROUPED, KERNEL_PERFECT_SMEM, KERNEL_PERFECT_GLOBAL, KERNEL_BASELINE_GLOBAL = range(5)
@@ -315,6 +316,11 @@ class UnitBuilder:
 
     def binop(self, op: int, left: int, right: int) -> int:
         self.nodes.append(_Node(EXPR_BIN_OPER, kTINYINT, False, op=op, left=left, right=right))
+        return len(self.nodes) - 1
+
+    def uoper(self, op: int, operand: int) -> int:
+        """Analyzer::UOper: kNOT over a boolean expression, kISNULL over a ColumnVar (IS NOT NULL = NOT(ISNULL))."""
+        self.nodes.append(_Node(EXPR_UOPER, kBOOLEAN, op == kISNULL, op=op, left=operand))
         return len(self.nodes) - 1
 
     def cmp(self, col_id: int, op: int, value, const_type: Optional[int] = None) -> int:

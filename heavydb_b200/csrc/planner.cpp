@@ -649,19 +649,81 @@ class Planner {
     return sp > 0 ? st[sp - 1] : 1.0;
   }
 
-  int lower_bool(B2QQuery& q, int idx, int depth) { /* returns max stack depth used */
+  /* Quals are lowered to postfix AND / OR over "is TRUE" bits.  NOT never reaches the device: in Kleene logic
+   * (logical_and / logical_or / logical_not, RuntimeFunctions.cpp:331-357) NOT distributes over AND / OR by De Morgan,
+   * NOT(col OP k) is the inverse comparison (still NULL -> not TRUE), and NOT(col IS NULL) is two-valued, so the
+   * host pushes the negation down to the leaves. */
+  static int inverse_cmp(int op) {
+    switch (op) {
+      case B2Q_kEQ: return B2Q_kNE; case B2Q_kNE: return B2Q_kEQ;
+      case B2Q_kLT: return B2Q_kGE; case B2Q_kGE: return B2Q_kLT;
+      case B2Q_kGT: return B2Q_kLE; case B2Q_kLE: return B2Q_kGT;
+      default: return -1;
+    }
+  }
+  int lower_bool(B2QQuery& q, int idx, int depth, bool negated = false) { /* returns max stack depth used */
     const B2QExpr& e = ex(idx);
-    if (e.kind != B2Q_EXPR_BIN_OPER) reject(B2Q_ERR_UNSUPPORTED, "qual must be a BinOper");
+    if (e.kind == B2Q_EXPR_UOPER) {
+      if (e.op == B2Q_kNOT) return lower_bool(q, e.left, depth, !negated);
+      if (e.op == B2Q_kISNULL) { lower_is_null(q, e, negated); return depth + 1; }
+      reject(B2Q_ERR_UNSUPPORTED, "unary operator outside NOT / IS NULL");
+    }
+    if (e.kind != B2Q_EXPR_BIN_OPER) reject(B2Q_ERR_UNSUPPORTED, "qual must be a BinOper or NOT / IS NULL");
     if (e.op == B2Q_kAND || e.op == B2Q_kOR) {
-      const int d1 = lower_bool(q, e.left, depth);
-      const int d2 = lower_bool(q, e.right, depth + 1);
+      const int d1 = lower_bool(q, e.left, depth, negated);
+      const int d2 = lower_bool(q, e.right, depth + 1, negated);
       DevFilter& f = q.prog.filter;
       if (f.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
-      f.ops[f.n_ops++] = static_cast<uint8_t>((e.op == B2Q_kAND ? FOP_AND : FOP_OR) << 4);
+      const bool is_and = (e.op == B2Q_kAND) != negated; /* De Morgan */
+      f.ops[f.n_ops++] = static_cast<uint8_t>((is_and ? FOP_AND : FOP_OR) << 4);
       return std::max(d1, d2);
     }
-    lower_cmp(q, e);
+    if (negated) {
+      B2QExpr inv = e;
+      inv.op = inverse_cmp(e.op);
+      if (inv.op < 0) reject(B2Q_ERR_UNSUPPORTED, "comparison operator");
+      lower_cmp(q, inv);
+    } else {
+      lower_cmp(q, e);
+    }
     return depth + 1;
+  }
+
+  /* <ColumnVar> IS [NOT] NULL (CodeGenerator::codegenIsNull, LogicalIR.cpp:381-432): constant false for a NOT NULL
+   * column, else value == NULL sentinel — a closed range [null, null] without the usual NULL exclusion */
+  void lower_is_null(B2QQuery& q, const B2QExpr& e, bool negated) {
+    DevFilter& f = q.prog.filter;
+    const B2QExpr& l = ex(e.left);
+    if (l.kind != B2Q_EXPR_COLUMN_VAR) reject(B2Q_ERR_UNSUPPORTED, "IS NULL operand must be a ColumnVar");
+    if (f.n_terms >= B2Q_MAX_TERMS || f.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
+    const SqlType ct = col_type(l.col_id);
+    DevTerm t;
+    memset(&t, 0, sizeof(t));
+    t.col = launch_col(q, l.col_id);
+    t.width = static_cast<int8_t>(phys_width_code(l.col_id));
+    t.col_is_fp = ct.is_fp();
+    t.cmp_fp = ct.is_fp();
+    t.null_bits = ct.is_fp() ? dbl_bits(kNullDouble) : phys_int_null(l.col_id);
+    t.null_check = 0;
+    double sel;
+    if (ct.notnull) { /* never NULL: "always in range" + negate encodes the constant FALSE */
+      t.lo = 0;
+      t.span = t.width == 8 ? ~0ull : 0xFFFFFFFFull;
+      t.flo = -std::numeric_limits<double>::infinity(); t.fhi = std::numeric_limits<double>::infinity();
+      t.negate = !negated;
+      sel = negated ? 1.0 : 0.0;
+    } else {
+      const int64_t nullv = phys_int_null(l.col_id);
+      t.lo = nullv; t.span = 0;
+      t.flo = t.fhi = kNullDouble;
+      t.negate = negated;
+      const ColRange cr = leaf_range(l.col_id);
+      sel = cr.has_nulls ? 0.1 : 0.0;
+      if (negated) sel = 1.0 - sel;
+    }
+    term_sel_.push_back(sel);
+    f.ops[f.n_ops++] = static_cast<uint8_t>((FOP_TERM << 4) | f.n_terms);
+    f.terms[f.n_terms++] = t;
   }
 
   int find_or_add_acc(B2QQuery& q, const DevAcc& a) {

@@ -2,7 +2,8 @@
 RelAlgExecutionUnit mirror, for the subset of the path:
 
     SELECT <col | COUNT(*) | COUNT(c) | SUM(c) | MIN(c) | MAX(c) | AVG(c)>, ...
-    FROM <table> [WHERE <c OP literal> {AND|OR} ... with parentheses] [GROUP BY c {, c}]
+    FROM <table> [WHERE <c OP literal | c IS [NOT] NULL | c [NOT] IN (l, ...) | c BETWEEN l AND l | NOT <factor>>
+                  {AND|OR} ... with parentheses] [GROUP BY c {, c}]
     [ORDER BY <position | target text> [ASC|DESC] [NULLS FIRST|LAST] {, ...}] [LIMIT n] [OFFSET m]
 
 It plays the role Calcite + RelAlgTranslator play in the reference (kept, out of scope) and is test infrastructure.
@@ -69,18 +70,53 @@ class _P:
             e = self.b.binop(abi.kAND, e, self.factor())
         return e
 
+    def literal_cmp(self, col, op, lit):
+        if re.fullmatch(r"-?\d+", lit):
+            return self.b.cmp(col, op, int(lit), abi.kBIGINT)
+        return self.b.cmp(col, op, float(lit), abi.kDOUBLE)
+
     def factor(self):
         if self.peek() == "(":
             self.eat()
             e = self.cond()
             self.eat(")")
             return e
+        if self.peek().upper() == "NOT":          # Analyzer::UOper(kNOT, ...)
+            self.eat()
+            return self.b.uoper(abi.kNOT, self.factor())
         col = self.colid(self.eat())
+        nxt = self.peek().upper()
+        if nxt == "IS":                            # c IS NULL -> UOper(kISNULL, c); IS NOT NULL -> NOT(ISNULL), like RelAlgTranslator
+            self.eat()
+            neg = self.peek().upper() == "NOT"
+            if neg:
+                self.eat()
+            self.eat("NULL")
+            e = self.b.uoper(abi.kISNULL, self.b.col(col))
+            return self.b.uoper(abi.kNOT, e) if neg else e
+        neg = False
+        if nxt == "NOT":
+            self.eat()
+            neg = True
+            nxt = self.peek().upper()
+        if nxt == "IN":                            # c IN (a, b, ...) -> OR of equalities (InValues codegen for short lists)
+            self.eat()
+            self.eat("(")
+            e = self.literal_cmp(col, abi.kEQ, self.eat())
+            while self.peek() == ",":
+                self.eat()
+                e = self.b.binop(abi.kOR, e, self.literal_cmp(col, abi.kEQ, self.eat()))
+            self.eat(")")
+            return self.b.uoper(abi.kNOT, e) if neg else e
+        if nxt == "BETWEEN":                       # Calcite expands BETWEEN to >= AND <=
+            self.eat()
+            lo = self.eat()
+            self.eat("AND")
+            hi = self.eat()
+            e = self.b.binop(abi.kAND, self.literal_cmp(col, abi.kGE, lo), self.literal_cmp(col, abi.kLE, hi))
+            return self.b.uoper(abi.kNOT, e) if neg else e
         op = _OPS[self.eat()]
-        lit = self.eat()
-        if re.fullmatch(r"-?\d+", lit):
-            return self.b.cmp(col, op, int(lit), abi.kBIGINT)
-        return self.b.cmp(col, op, float(lit), abi.kDOUBLE)
+        return self.literal_cmp(col, op, self.eat())
 
     def target_text(self):
         """Canonical text of the target expression starting at the cursor (does not build nodes)."""
@@ -128,7 +164,7 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
         e = p.cond()
         for c in _conjuncts(p.b, e):
             n = p.b.nodes[c]
-            simple = n.op not in (abi.kAND, abi.kOR)
+            simple = n.kind == abi.EXPR_BIN_OPER and n.op not in (abi.kAND, abi.kOR)
             if simple:
                 # an integer column against an fp literal is `CAST(col AS DOUBLE) OP lit` in the reference; only
                 # int->int / timestamp casts survive BinOper::normalize_simple_predicate, so it is NOT a simple qual

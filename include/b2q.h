@@ -62,7 +62,8 @@ enum {
 };
 
 /* ---- SQLOps subset (Shared/sqldefs.h:31-40) ----------------------------------------------------------- */
-enum { B2Q_kEQ = 0, B2Q_kNE = 2, B2Q_kLT = 3, B2Q_kGT = 4, B2Q_kLE = 5, B2Q_kGE = 6, B2Q_kAND = 7, B2Q_kOR = 8 };
+enum { B2Q_kEQ = 0, B2Q_kNE = 2, B2Q_kLT = 3, B2Q_kGT = 4, B2Q_kLE = 5, B2Q_kGE = 6, B2Q_kAND = 7, B2Q_kOR = 8,
+       B2Q_kNOT = 9, B2Q_kISNULL = 16 /* Analyzer::UOper: NOT <bool expr>, <ColumnVar> IS NULL; IS NOT NULL = NOT(ISNULL) */ };
 
 /* ---- SQLAgg subset (Shared/sqldefs.h:76-90) ----------------------------------------------------------- */
 enum { B2Q_kAVG = 0, B2Q_kMIN = 1, B2Q_kMAX = 2, B2Q_kSUM = 3, B2Q_kCOUNT = 4 };
@@ -105,7 +106,8 @@ typedef struct B2QTypeInfo {
 
 /* ---- Analyzer::Expr subset (Analyzer/Analyzer.h:193 ColumnVar, :319 Constant, :434 BinOper, :1381 AggExpr)
  * Nodes live in one flat array; children are indices into it (-1 = none). */
-enum { B2Q_EXPR_COLUMN_VAR = 1, B2Q_EXPR_CONSTANT = 2, B2Q_EXPR_BIN_OPER = 3, B2Q_EXPR_AGG = 4 };
+enum { B2Q_EXPR_COLUMN_VAR = 1, B2Q_EXPR_CONSTANT = 2, B2Q_EXPR_BIN_OPER = 3, B2Q_EXPR_AGG = 4,
+       B2Q_EXPR_UOPER = 5 /* Analyzer::UOper with op in {kNOT, kISNULL}; operand = left */ };
 
 typedef struct B2QExpr {
   int32_t kind;   /* B2Q_EXPR_* */

@@ -893,7 +893,22 @@ struct Frag {
 
 int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr, int expr_idx, int64_t pos) {
   const B2QExpr& e = expr_at(u, expr_idx);
-  if (e.kind != B2Q_EXPR_BIN_OPER) fail(B2Q_ERR_UNSUPPORTED, "qual must be a BinOper");
+  if (e.kind == B2Q_EXPR_UOPER) {
+    if (e.op == B2Q_kNOT) { /* logical_not (RuntimeFunctions.cpp:331-334) */
+      const int8_t v = eval_bool(u, tbl, fr, e.left, pos);
+      return v == kNullBool ? v : (v ? 0 : 1);
+    }
+    if (e.op == B2Q_kISNULL) { /* CodeGenerator::codegenIsNull / codegenIsNullNumber (LogicalIR.cpp:381-432) */
+      const B2QExpr& o = expr_at(u, e.left);
+      if (o.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "IS NULL operand must be a ColumnVar");
+      const int ctype = tbl.col_types[o.col_id].type;
+      if (tbl.col_types[o.col_id].notnull) return 0; /* inferred non-null: short-circuit to false */
+      if (is_fp(ctype)) return fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[o.col_id]), pos) == kNullDouble;
+      return decode_int_column(tbl, fr, o.col_id, pos) == inline_int_null_val(ctype);
+    }
+    fail(B2Q_ERR_UNSUPPORTED, "unary operator outside NOT / IS NULL");
+  }
+  if (e.kind != B2Q_EXPR_BIN_OPER) fail(B2Q_ERR_UNSUPPORTED, "qual must be a BinOper or NOT / IS NULL");
   if (e.op == B2Q_kAND || e.op == B2Q_kOR) {
     const int8_t lhs = eval_bool(u, tbl, fr, e.left, pos);
     const int8_t rhs = eval_bool(u, tbl, fr, e.right, pos);

@@ -33,12 +33,32 @@ def rand_cmp(rng):
     return f"{c} {rng.choice(OPS)} {lit:.6f}"
 
 
+def rand_leaf(rng):
+    r = rng.random()
+    if r < 0.12:
+        c = rng.choice(INT_COLS + FP_COLS)
+        return f"{c} IS {'NOT ' if rng.random() < 0.5 else ''}NULL"
+    if r < 0.2:
+        c = rng.choice(INT_COLS)
+        lo, hi = LIT[c]
+        vals = ", ".join(str(rng.randint(lo, hi)) for _ in range(rng.randint(1, 3)))
+        return f"{c} {'NOT ' if rng.random() < 0.3 else ''}IN ({vals})"
+    return rand_cmp(rng)
+
+
 def rand_cond(rng, depth=0):
     if depth >= 2 or rng.random() < 0.4:
-        return rand_cmp(rng)
+        leaf = rand_leaf(rng)
+        return f"NOT ({leaf})" if rng.random() < 0.1 else leaf
+    if rng.random() < 0.1:
+        return f"NOT {rand_cond_paren(rng, depth + 1)}"
     op = rng.choice(["AND", "OR"])
     a, b = rand_cond(rng, depth + 1), rand_cond(rng, depth + 1)
     return f"({a} {op} {b})"
+
+
+def rand_cond_paren(rng, depth):
+    return "(" + rand_cond(rng, depth) + ")"
 
 
 def rand_query(rng, multi_key=False):

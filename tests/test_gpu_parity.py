@@ -13,7 +13,7 @@ import oracle_lib
 import ref_tables as rt
 import sqlmini
 from heavydb_b200 import abi, executor
-from test_oracle_golden import MULTI_KEY_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
+from test_oracle_golden import MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
 from test_planner_parity import EXTRA
 
 pytestmark = pytest.mark.gpu
@@ -25,7 +25,7 @@ def golden():
     return table, gu.DeviceTable(table)
 
 
-@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES)
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES)
 def test_golden_table_device_resident(golden, sql):
     table, dev = golden
     unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
@@ -188,6 +188,9 @@ RAND_QUERIES = [
     "SELECT k8, nn64, MIN(d), MAX(d) FROM r GROUP BY k8, nn64;",                                   # keyed (not keyless) layouts
     "SELECT k8, k16, SUM(a64) FROM r GROUP BY k8, k16;",
     "SELECT nn64, k8, AVG(d) FROM r WHERE a32 > 0 GROUP BY nn64, k8;",
+    "SELECT k8, COUNT(*), SUM(a64) FROM r WHERE a64 IS NOT NULL AND NOT (k16 IS NULL OR a8 IN (1, 2, 3, -4)) GROUP BY k8;",   # NOT / IS NULL / IN
+    "SELECT COUNT(*), COUNT(d), MIN(a32) FROM r WHERE d IS NULL OR NOT (a16 BETWEEN -1000 AND 1000 AND dnn < 0.5) OR big IS NULL;",
+    "SELECT nn32, COUNT(*) FROM r WHERE NOT (NOT (k32 >= 0)) AND k64 NOT IN (1000000001, 1000000002) AND nn64 IS NOT NULL GROUP BY nn32;",
 ]
 
 

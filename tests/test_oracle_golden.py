@@ -86,13 +86,39 @@ PATH_QUERIES = [
 ]
 
 
+# NOT / IS [NOT] NULL / IN / BETWEEN (Analyzer::UOper kNOT, kISNULL; IN lists and BETWEEN as the OR / AND they expand to)
+NULL_LOGIC_QUERIES = [
+    "SELECT SUM(z) FROM test WHERE z IS NOT NULL;",                          # verbatim, ExecuteTest.cpp:1955
+    "SELECT COUNT(*) FROM test WHERE u IS NOT NULL;",                        # :1989
+    "SELECT COUNT(*) FROM test WHERE ofq >= 0 OR ofq IS NULL;",              # :2016
+    "SELECT MAX(dn) FROM test WHERE dn IS NOT NULL;",                        # :2025
+    "SELECT x, MAX(dn) FROM test WHERE dn IS NOT NULL GROUP BY x;",          # :2026 without the ORDER BY
+    "SELECT x, SUM(z) FROM test WHERE z IS NOT NULL GROUP BY x;",            # :2868
+    "SELECT COUNT(*) FROM test WHERE x IN (7, 8);",                          # :7364
+    "SELECT COUNT(*) FROM test WHERE x IN (9, 10);",                         # :7365
+    "SELECT COUNT(*) FROM test WHERE z IN (101, 102);",                      # :7366
+    "SELECT COUNT(*) FROM test WHERE z IN (201, 202);",                      # :7367
+    "SELECT t, COUNT(*) FROM test WHERE t NOT IN (1001, 1003, 1005, 1007, 1009, -10) GROUP BY t;",   # :2521
+    "SELECT COUNT(*) FROM test WHERE x IS NULL;",                            # NOT NULL column: constant false
+    "SELECT COUNT(*) FROM test WHERE x IS NOT NULL;",
+    "SELECT COUNT(*), SUM(t) FROM test WHERE dn IS NULL OR y IS NULL;",
+    "SELECT y, COUNT(*) FROM test WHERE NOT (y = 42 OR z > 101) GROUP BY y;",        # NULL y: NOT(NULL OR FALSE) = NULL -> dropped
+    "SELECT COUNT(*) FROM test WHERE NOT (dn < -300.5 AND ofd IS NULL);",
+    "SELECT COUNT(*) FROM test WHERE NOT (NOT (smallint_nulls IS NULL)) AND NOT x = 8;",
+    "SELECT z, COUNT(*) FROM test WHERE z BETWEEN 100 AND 101 GROUP BY z;",
+    "SELECT COUNT(*) FROM test WHERE z NOT BETWEEN 100 AND 101 OR w IN (-8);",
+    "SELECT COUNT(*), MIN(ofd) FROM test WHERE NOT (ofd IN (1, 2, 3) OR ofd IS NULL);",
+    "SELECT COUNT(*) FROM test WHERE d IS NULL OR NOT dn IS NOT NULL;",
+]
+
+
 @pytest.fixture(scope="module")
 def env():
     rows = rt.test_rows()
     return rt.make_table(rows), rt.make_sqlite(rows)
 
 
-@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + MULTI_KEY_QUERIES)
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES)
 def test_oracle_vs_sqlite(env, sql):
     table, con = env
     unit = sqlmini.parse(sql, table, rt.TEST_NAMES)

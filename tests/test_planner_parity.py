@@ -7,7 +7,7 @@ import oracle_lib
 import ref_tables as rt
 import sqlmini
 from heavydb_b200 import abi, executor
-from test_oracle_golden import MULTI_KEY_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
+from test_oracle_golden import MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
 
 EXTRA = [
     "SELECT t, SUM(dn), AVG(dn), MIN(dn), MAX(dn), COUNT(dn) FROM test GROUP BY t;",
@@ -23,7 +23,7 @@ def table():
 
 
 @pytest.mark.parametrize("bigint_count", [False, True])
-@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES)
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES)
 def test_plan_matches_oracle(table, sql, bigint_count):
     unit = sqlmini.parse(sql, table, rt.TEST_NAMES, bigint_count=bigint_count)
     ex = executor.Executor()
