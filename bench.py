@@ -65,7 +65,28 @@ CONFIGS["c2top"] = (CONFIGS["c2"][0], "SELECT g, SUM(c1), COUNT(*) FROM t WHERE 
                     "configs[1] + ORDER BY SUM DESC LIMIT 10 (device compaction + radix sort + gather)")
 CONFIGS["c4top"] = (CONFIGS["c4"][0], "SELECT key, SUM(v) FROM t GROUP BY key ORDER BY 2 DESC, 1 LIMIT 10;", 16,
                     "configs[3] + ORDER BY SUM DESC LIMIT 10 over 1e7 groups (device compaction + radix sort + gather)")
+# star join — the fact table probes a 1e5-row dimension through a one-to-one perfect join table and
+# groups by a dimension attribute (the dimension is generated on the host: id = row, attr = splitmix64(row) % 1000)
+CONFIGS["c2join"] = ([("c0", "i64", 0, 10**6), ("c1", "i64", 0, 10**6), ("fk", "i32", 0, 10**5)],
+                     "SELECT d.attr, SUM(t.c1), COUNT(*) FROM t JOIN d ON t.fk = d.id WHERE t.c0 < 500000 GROUP BY d.attr;", 20,
+                     "configs[1] shape through a star join: filter c0<k (50%), INNER JOIN dim(1e5 rows) ON fk = id, GROUP BY dim.attr (1000 groups), SUM/COUNT")
 ENTRY_GUESS = {"c4s": 15_000_000}
+
+
+def join_inner(cfg):
+    """(inner abi.Table, names) for the join configs, else None.  Built on the host; the library copies it per query."""
+    if cfg != "c2join":
+        return None
+    from heavydb_b200 import abi
+    n = 10**5
+    ids = np.arange(n, dtype=np.int32)
+    x = ids.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    attr = ((x ^ (x >> np.uint64(31))) % np.uint64(1000)).astype(np.int32)
+    t = abi.Table([(abi.kINT, True), (abi.kINT, True)])
+    t.add_host_fragment([ids, attr])
+    return t, ["id", "attr"]
 
 
 def col_enc(col):
@@ -202,7 +223,7 @@ def run_reference(args):
         table.add_host_fragment([oracle_lib.gen_column(phys_type(c), SEED, tag, f * frag_rows, frag_rows, c[2], c[3], threads,
                                                        stride=col_stride(c)) for tag, c in enumerate(cols)])
     names = [c[0] for c in cols]
-    unit = sqlmini.parse(sql, table, names)
+    unit = sqlmini.parse(sql, table, names, inner=join_inner(args.config))
     rows = nfrag * frag_rows
     guess = ENTRY_GUESS.get(args.config, 0)
     times = []
@@ -241,7 +262,7 @@ def cpu_baseline_sample(cfg, budget_s=15.0):
     for f in range(nfrag):
         table.add_host_fragment([oracle_lib.gen_column(phys_type(c), SEED, tag, f * frag_rows, frag_rows, c[2], c[3], threads,
                                                        stride=col_stride(c)) for tag, c in enumerate(cols)])
-    unit = sqlmini.parse(sql, table, [c[0] for c in cols])
+    unit = sqlmini.parse(sql, table, [c[0] for c in cols], inner=join_inner(cfg))
     rows = nfrag * frag_rows
     guess = ENTRY_GUESS.get(cfg, 0)
     oracle_lib.execute(unit, table, entry_guess=guess, has_card=guess > 0, num_threads=threads)  # warm
@@ -293,7 +314,7 @@ def main():
     nfrag_per_rank = (rows + FRAG_ROWS - 1) // FRAG_ROWS
     frag_ids = multigpu.shard_fragments(range(nfrag_per_rank * world), rank, world)  # fragment_id % num_devices == rank
     table, keep = build_device_table(args.config, rows, frag_ids, torch)
-    unit = sqlmini.parse(sql, table, names)
+    unit = sqlmini.parse(sql, table, names, inner=join_inner(args.config))
     ex = executor.Executor()
     eo = executor.execution_options(force_kernel=args.force_kernel)
     guess = ENTRY_GUESS.get(args.config, 0)
@@ -453,7 +474,7 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
     torch.cuda.synchronize()
     if old_aff:
         os.sched_setaffinity(0, old_aff)
-    unit = sqlmini.parse(sql, table, names)
+    unit = sqlmini.parse(sql, table, names, inner=join_inner(args.config))
     bt = table.build(abi.CPU_LEVEL)
     times = []
     d2h = 0

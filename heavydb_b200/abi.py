@@ -82,7 +82,7 @@ class Expr(C.Structure):
         ("ival", C.c_int64),
         ("dval", C.c_double),
         ("is_null", C.c_int32),
-        ("pad_", C.c_int32),
+        ("rte_idx", C.c_int32),
     ]
 
 
@@ -113,6 +113,9 @@ class ExecUnit(C.Structure):
         ("has_limit", C.c_int32),
         ("limit", C.c_int64),
         ("offset", C.c_int64),
+        ("join_qual", C.c_int32),
+        ("join_type", C.c_int32),
+        ("inner_table", C.c_void_p),   # const B2QTableInfo*
     ]
 
 
@@ -207,6 +210,11 @@ class Plan(C.Structure):
         ("slot_offset", C.c_int64 * MAX_SLOTS),
         ("init_vals", C.c_int64 * MAX_SLOTS),
         ("targets", TargetInfo * MAX_TARGETS),
+        ("join_min_key", C.c_int64),
+        ("join_max_key", C.c_int64),
+        ("join_entry_count", C.c_int64),
+        ("join_outer_col", C.c_int32),
+        ("join_inner_col", C.c_int32),
     ]
 
     #: fields that must agree between the product planner and the oracle planner
@@ -214,6 +222,7 @@ class Plan(C.Structure):
         "query_desc_type", "keyless_hash", "idx_target_as_key", "output_columnar", "group_col_width",
         "effective_key_width", "num_targets", "num_slots", "key_col_id", "entry_count", "min_val", "max_val",
         "bucket", "has_nulls", "row_size", "buffer_size", "num_group_cols",
+        "join_min_key", "join_max_key", "join_entry_count", "join_outer_col", "join_inner_col",
     )
 
     def as_dict(self) -> dict:
@@ -278,6 +287,7 @@ class _Node:
     ival: int = 0
     dval: float = 0.0
     is_null: bool = False
+    rte_idx: int = 0
 
 
 class UnitBuilder:
@@ -293,15 +303,25 @@ class UnitBuilder:
         self.targets: List[int] = []
         self.scan_limit = 0
         self.unsupported: Dict[str, int] = {}
+        self.inner: Optional["Table"] = None            # input_descs[1] of a one-level INNER hash join
+        self.join_qual: int = -1
         self.order: List[Tuple[int, bool, bool]] = []   # sort_info.order_entries: (tle_no 1-based, is_desc, nulls_first)
         self.limit: Optional[int] = None
         self.offset = 0
 
     # -- expression nodes ---------------------------------------------------------------------------------
-    def col(self, col_id: int) -> int:
-        t, nn = self.table.col_types[col_id]
-        self.nodes.append(_Node(EXPR_COLUMN_VAR, t, nn, col_id=col_id))
+    def col(self, col_id: int, rte_idx: int = 0) -> int:
+        """ColumnVar; rte_idx 1 = a column of the joined inner table (set with join())."""
+        t, nn = (self.inner if rte_idx else self.table).col_types[col_id]
+        self.nodes.append(_Node(EXPR_COLUMN_VAR, t, nn, col_id=col_id, rte_idx=rte_idx))
         return len(self.nodes) - 1
+
+    def join(self, inner: "Table", outer_col: int, inner_col: int):
+        """join_quals[0] = {outer.col = inner.col}, JoinType::INNER; the inner table is passed as one concatenated
+        fragment, the way the hash-join column fetch sees it."""
+        self.inner = inner
+        self.join_qual = self.binop(kEQ, self.col(outer_col, 0), self.col(inner_col, 1))
+        return self
 
     def const(self, value, sql_type: Optional[int] = None, is_null: bool = False) -> int:
         if sql_type is None:
@@ -323,10 +343,10 @@ class UnitBuilder:
         self.nodes.append(_Node(EXPR_UOPER, kBOOLEAN, op == kISNULL, op=op, left=operand))
         return len(self.nodes) - 1
 
-    def cmp(self, col_id: int, op: int, value, const_type: Optional[int] = None) -> int:
-        return self.binop(op, self.col(col_id), self.const(value, const_type))
+    def cmp(self, col_id: int, op: int, value, const_type: Optional[int] = None, rte_idx: int = 0) -> int:
+        return self.binop(op, self.col(col_id, rte_idx), self.const(value, const_type))
 
-    def agg(self, kind: int, col_id: Optional[int] = None, bigint_count: bool = False) -> int:
+    def agg(self, kind: int, col_id: Optional[int] = None, bigint_count: bool = False, rte_idx: int = 0) -> int:
         """AggExpr.  Result type as RelAlgTranslator assigns it: COUNT -> INT/BIGINT notnull... SUM(int) -> BIGINT,
         MIN/MAX -> arg type, AVG -> DOUBLE."""
         arg = -1
@@ -334,8 +354,8 @@ class UnitBuilder:
             assert kind == kCOUNT
             ti = (kBIGINT if bigint_count else kINT, False)
         else:
-            arg = self.col(col_id)
-            at, ann = self.table.col_types[col_id]
+            arg = self.col(col_id, rte_idx)
+            at, ann = (self.inner if rte_idx else self.table).col_types[col_id]
             if kind == kCOUNT:
                 ti = (kBIGINT if bigint_count else kINT, False)
             elif kind == kSUM:
@@ -352,16 +372,16 @@ class UnitBuilder:
         (self.simple_quals if simple else self.quals).append(e)
         return self
 
-    def group_by(self, col_id: int):
-        self.groupby.append(self.col(col_id))
+    def group_by(self, col_id: int, rte_idx: int = 0):
+        self.groupby.append(self.col(col_id, rte_idx))
         return self
 
     def target(self, e: int):
         self.targets.append(e)
         return self
 
-    def target_col(self, col_id: int):
-        return self.target(self.col(col_id))
+    def target_col(self, col_id: int, rte_idx: int = 0):
+        return self.target(self.col(col_id, rte_idx))
 
     def order_by(self, tle_no: int, is_desc: bool = False, nulls_first: Optional[bool] = None):
         """sort_info.order_entries.  Default NULL placement is the reference's (NULLs are the largest values:
@@ -384,7 +404,7 @@ class BuiltUnit:
             e.kind = nd.kind
             e.ti = TypeInfo(nd.type, int(nd.notnull))
             e.col_id, e.op, e.left, e.right = nd.col_id, nd.op, nd.left, nd.right
-            e.ival, e.dval, e.is_null = nd.ival, nd.dval, int(nd.is_null)
+            e.ival, e.dval, e.is_null, e.rte_idx = nd.ival, nd.dval, int(nd.is_null), nd.rte_idx
 
         def arr(xs):
             return (C.c_int32 * max(len(xs), 1))(*xs)
@@ -402,6 +422,13 @@ class BuiltUnit:
             self._order[i].tle_no, self._order[i].is_desc, self._order[i].nulls_first = tle, int(desc), int(nf)
         u.order_entries, u.num_order_entries = self._order, len(b.order)
         u.has_limit, u.limit, u.offset = int(b.limit is not None), int(b.limit or 0), int(b.offset)
+        u.join_qual = -1
+        self.inner = b.inner
+        if b.inner is not None:
+            assert len(b.inner.fragments) <= 1, "the inner table must be one concatenated fragment"
+            self._inner_built = b.inner.build(CPU_LEVEL)     # host chunks; the library copies what it needs
+            u.num_join_quals, u.join_qual, u.join_type = 1, b.join_qual, 0
+            u.inner_table = C.cast(C.pointer(self._inner_built.info), C.c_void_p)
         for k, v in b.unsupported.items():
             setattr(u, k, v)
         self.unit = u

@@ -104,7 +104,20 @@ struct DevKeyComp {
   int8_t pad_[2];
 };
 
+/* ---- one INNER hash-join level (PerfectJoinHashTable one-to-one: int32 slots, -1 = no row) ------------------ */
+struct DevJoin {
+  int64_t min_key;      /* slot = key - min_key */
+  int64_t entry_count;  /* max_key - min_key + 1 */
+  int64_t null_val;     /* outer key's NULL as stored in the chunk */
+  int32_t fk_col;       /* launch column of the outer key, -1: no join */
+  int8_t fk_width;      /* width code of the outer key column */
+  int8_t nullable;      /* hash_join_idx_nullable: a NULL outer key never matches */
+  int8_t pad_[2];
+};
+
 struct DevProgram {
+  DevJoin join;
+  int8_t col_inner[B2Q_MAX_COLS];    /* launch column belongs to the joined inner table: read at the matching inner row */
   DevFilter filter;
   DevKey key;
   int32_t n_keys;       /* > 1: multi-column perfect hash, `keys` below; the single-column paths use `key` */
@@ -200,6 +213,7 @@ struct DevLaunch {
   int64_t* accs[B2Q_MAX_ACCS];     /* dense accumulator arrays in HBM */
   int64_t* keys;                   /* baseline: open-addressing key array (EMPTY_KEY_64 initialised) */
   int32_t* error;                  /* device int: first error code */
+  const int32_t* join_buff;        /* one-to-one join table (HashJoin::getJoinHashBuffer), or nullptr */
 };
 
 /* chosen at plan time, needed at launch */
@@ -243,8 +257,10 @@ struct B2QQuery {
   DevProgram prog;
   DevLayout layout;
   SmemPlan smem;
-  int32_t col_ids[B2Q_MAX_COLS]; /* launch column index -> table column id */
+  int32_t col_ids[B2Q_MAX_COLS]; /* launch column index -> table column id (>= n_outer_cols: inner column id + n_outer_cols) */
   int32_t bigint_count;
+  int32_t n_outer_cols;          /* columns of the scanned table; 0 < join_inner_key_col + 1 only with a join */
+  int32_t join_inner_key_col;    /* inner table column of the join key, -1 without a join */
   /* sort_info of the execution unit (copied: the partial / finalize split outlives the caller's unit) */
   int32_t n_order;
   B2QOrderEntry order[B2Q_MAX_ORDER_ENTRIES];

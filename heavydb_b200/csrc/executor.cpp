@@ -34,6 +34,8 @@ void scan_config(const B2QQuery& q, int* block, int* ctas_per_sm);
 cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t* smem_image, int block, int ctas_per_sm,
                         int prefetch_distance, cudaStream_t st);
 cudaError_t launch_init(const B2QQuery& q, int64_t* const* accs, int64_t* keys, int8_t* smem_image, cudaStream_t st);
+cudaError_t launch_join_build(const int8_t* keys, int width, int64_t n_rows, int64_t min_key, int64_t entry_count, int nullable,
+                              int64_t null_val, int32_t* buff, int32_t* error, cudaStream_t st);
 cudaError_t launch_materialize(const B2QQuery& q, const int64_t* const* accs, const int64_t* keys, int8_t* out,
                                cudaStream_t st);
 cudaError_t launch_join_split(const int64_t* split, int64_t* out, int64_t n, cudaStream_t st);
@@ -134,6 +136,9 @@ struct B2QPartial {
   int8_t* smem_image = nullptr;
   int32_t* d_error = nullptr;
   std::vector<void*> extra;  /* stream-ordered allocations made after the main block */
+  /* join level: the one-to-one table and, per launch column, the device copy of an inner-table column (else nullptr) */
+  const int32_t* join_buff = nullptr;
+  const int8_t* inner_cols[B2Q_MAX_COLS] = {};
   bool split = false;        /* COUNT / SUM_I64 arrays are in the (lo[n] | hi[n]) layout of the global-table kernels */
   cudaEvent_t ev[4] = {}; /* init begin/end, scan begin/end */
   bool scan_timed = false;
@@ -260,6 +265,7 @@ static int32_t scan_device_fragments(B2QPartial& p, int nf, const std::vector<co
   for (int a = 0; a < q.prog.n_accs; ++a) L.accs[a] = p.accs[a];
   L.keys = p.keys;
   L.error = p.d_error;
+  L.join_buff = p.join_buff;
   if (time_it) CU(cudaEventRecord(p.ev[2], st));
   CU(launch_scan(q, L, p.smem_image, block, ctas, prefetch_distance_for(q, cols), st));
   p.launches += 1;
@@ -327,8 +333,10 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
     cudaStreamDestroy(copy_st);
   };
   for (auto& s : stage) {
-    for (int c = 0; c < nc; ++c)
+    for (int c = 0; c < nc; ++c) {
+      if (q.prog.col_inner[c]) continue; /* inner-table columns are resident for the whole query */
       if (cudaMalloc(&s.buf[c], static_cast<size_t>(cap_rows) * widths[c] + 16) != cudaSuccess) { cleanup(); cudaGetLastError(); return set_err(B2Q_ERR_OUT_OF_GPU_MEM, "staging buffers"); }
+    }
     cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.scanned, cudaEventDisableTiming);
   }
@@ -349,7 +357,7 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
   std::vector<const int8_t*> h_cols(ns * nc);
   std::vector<int64_t> h_rows(ns), h_cs(ns * 2);
   for (size_t i = 0; i < ns; ++i) {
-    for (int c = 0; c < nc; ++c) h_cols[i * nc + c] = stage[i & 1].buf[c];
+    for (int c = 0; c < nc; ++c) h_cols[i * nc + c] = q.prog.col_inner[c] ? p.inner_cols[c] : stage[i & 1].buf[c];
     h_rows[i] = slices[i].rows;
     h_cs[2 * i] = 0;
     h_cs[2 * i + 1] = (slices[i].rows + chunk_rows - 1) / chunk_rows;
@@ -367,6 +375,7 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
     const Slice& sl = slices[i];
     if (s.busy) cudaStreamWaitEvent(copy_st, s.scanned, 0); /* the scan that used this buffer set is done */
     for (int c = 0; c < nc; ++c) {
+      if (q.prog.col_inner[c]) continue;
       const int8_t* src = static_cast<const int8_t*>(tbl.fragments[sl.frag].col_buffers[q.col_ids[c]]);
       if (!src) { rc = set_err(B2Q_ERR_INVALID_ARGUMENT, "referenced column has a NULL buffer"); break; }
       const size_t nbytes = static_cast<size_t>(sl.rows) * widths[c];
@@ -389,6 +398,7 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
     for (int a = 0; a < q.prog.n_accs; ++a) L.accs[a] = p.accs[a];
     L.keys = p.keys;
     L.error = p.d_error;
+    L.join_buff = p.join_buff;
     cudaError_t e = launch_scan(q, L, p.smem_image, block, ctas, 0 /* slices arrive straight from PCIe */, st);
     if (e != cudaSuccess) { rc = set_err(B2Q_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e)); break; }
     p.launches += 1;
@@ -417,7 +427,7 @@ static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B
     if (q.left < 0 || q.left >= u.num_exprs || q.right < 0 || q.right >= u.num_exprs) return false;
     const B2QExpr& l = u.exprs[q.left];
     const B2QExpr& c = u.exprs[q.right];
-    if (l.kind != B2Q_EXPR_COLUMN_VAR) continue;
+    if (l.kind != B2Q_EXPR_COLUMN_VAR || l.rte_idx != 0) continue; /* chunk stats of the scanned table only */
     if (c.kind != B2Q_EXPR_CONSTANT) return false;
     if (c.is_null || l.col_id < 0 || l.col_id >= tbl.num_cols) continue;
     const B2QChunkStats& st = fr.col_stats[l.col_id];
@@ -451,6 +461,58 @@ static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B
   return false;
 }
 
+/* The join level: inner-table columns to the device (they are small: dimension tables) and the one-to-one table
+ * built there (PerfectJoinHashTable::reify -> initHashTableOnGpu / fill_hash_join_buff on the device). */
+static int32_t prepare_join(B2QPartial& p, const B2QExecUnit& u, cudaStream_t st) {
+  const B2QQuery& q = p.q;
+  if (q.prog.join.fk_col < 0) return B2Q_OK;
+  const B2QTableInfo& inner = *u.inner_table;
+  const int64_t rows = inner.num_fragments ? inner.fragments[0].num_tuples : 0;
+  auto phys_bytes = [&](int c) -> int {
+    if (inner.col_encoded_sizes && inner.col_encoded_sizes[c] > 0) return inner.col_encoded_sizes[c];
+    switch (inner.col_types[c].type) {
+      case B2Q_kTINYINT: case B2Q_kBOOLEAN: return 1;
+      case B2Q_kSMALLINT: return 2;
+      case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4;
+      default: return 8;
+    }
+  };
+  std::vector<const int8_t*> dev(static_cast<size_t>(inner.num_cols), nullptr);
+  auto device_col = [&](int c, const int8_t** out) -> int32_t {
+    if (dev[c]) { *out = dev[c]; return B2Q_OK; }
+    const void* src = rows ? inner.fragments[0].col_buffers[c] : nullptr;
+    if (rows && !src) return set_err(B2Q_ERR_INVALID_ARGUMENT, "referenced inner column has a NULL buffer");
+    if (inner.memory_level == B2Q_GPU_LEVEL) { dev[c] = static_cast<const int8_t*>(src); *out = dev[c]; return B2Q_OK; }
+    if (inner.memory_level != B2Q_CPU_LEVEL) return set_err(B2Q_ERR_INVALID_ARGUMENT, "inner table memory_level must be B2Q_CPU_LEVEL or B2Q_GPU_LEVEL");
+    int8_t* d = nullptr;
+    const size_t nbytes = static_cast<size_t>(std::max<int64_t>(rows, 1)) * phys_bytes(c);
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&d), nbytes, st));
+    p.extra.push_back(d);
+    if (rows) { CU(cudaMemcpyAsync(d, src, static_cast<size_t>(rows) * phys_bytes(c), cudaMemcpyHostToDevice, st)); p.h2d_bytes += static_cast<double>(rows) * phys_bytes(c); }
+    dev[c] = d;
+    *out = d;
+    return B2Q_OK;
+  };
+  for (int c = 0; c < q.prog.n_cols; ++c) {
+    if (!q.prog.col_inner[c]) continue;
+    const int32_t rc = device_col(q.col_ids[c] - q.n_outer_cols, &p.inner_cols[c]);
+    if (rc != B2Q_OK) return rc;
+  }
+  const int8_t* d_key = nullptr;
+  int32_t rc = device_col(q.join_inner_key_col, &d_key);
+  if (rc != B2Q_OK) return rc;
+  int32_t* buff = nullptr;
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&buff), static_cast<size_t>(std::max<int64_t>(q.plan.join_entry_count, 1)) * 4, st));
+  p.extra.push_back(buff);
+  const B2QTypeInfo kt = inner.col_types[q.join_inner_key_col];
+  const int kw = phys_bytes(q.join_inner_key_col);
+  const int64_t knull = kw == 1 ? INT8_MIN : kw == 2 ? INT16_MIN : kw == 4 ? INT32_MIN : INT64_MIN;
+  CU(launch_join_build(d_key, kw, rows, q.plan.join_min_key, q.plan.join_entry_count, kt.notnull ? 0 : 1, knull, buff, p.d_error, st));
+  p.launches += 1;
+  p.join_buff = buff;
+  return B2Q_OK;
+}
+
 static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, const B2QExecUnit* u,
                                     const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card,
                                     cudaStream_t st, B2QPartial** out) {
@@ -467,6 +529,8 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
   const size_t extra = tbl->memory_level == B2Q_GPU_LEVEL ? launch_table_bytes(tbl->num_fragments, p->q.prog.n_cols) : 0;
   rc = alloc_partial(*p, extra, st);
   if (rc != B2Q_OK) return rc;
+  rc = prepare_join(*p, *u, st);
+  if (rc != B2Q_OK) return rc;
   const B2QQuery& q = p->q;
   if (tbl->memory_level == B2Q_GPU_LEVEL) {
     /* multi-fragment launch: one kernel over every fragment handed to this device (Execute.cpp:3075-3101) */
@@ -477,7 +541,7 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
       p->frags_scanned += 1;
       rows.push_back(tbl->fragments[f].num_tuples);
       for (int c = 0; c < q.prog.n_cols; ++c) {
-        const void* ptr = tbl->fragments[f].col_buffers[q.col_ids[c]];
+        const void* ptr = q.prog.col_inner[c] ? p->inner_cols[c] : tbl->fragments[f].col_buffers[q.col_ids[c]];
         if (!ptr) return set_err(B2Q_ERR_INVALID_ARGUMENT, "referenced column has a NULL buffer");
         cols.push_back(static_cast<const int8_t*>(ptr));
       }
@@ -499,7 +563,8 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
   CU(cudaMemcpyAsync(&dev_err, p->d_error, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   collect_timings(*p);
-  if (dev_err) return set_err(dev_err, dev_err == B2Q_ERR_OUT_OF_SLOTS ? "group-by table is full (OUT_OF_SLOTS)" : "group key outside the chunk-stats range");
+  if (dev_err == B2Q_ERR_UNSUPPORTED) return set_err(dev_err, "join is not one-to-one (the reference rebuilds a one-to-many table): outside this path");
+  if (dev_err) return set_err(dev_err, dev_err == B2Q_ERR_OUT_OF_SLOTS ? "group-by table is full (OUT_OF_SLOTS)" : "group or join key outside the chunk-stats range");
   *out = p.release();
   return B2Q_OK;
 }
@@ -787,10 +852,12 @@ void b2q_partial_free(B2QPartial* p) { delete p; }
 int32_t b2q_launch(const B2QQuery* query, const B2QParams* prm, void* stream) {
   if (!query || !prm) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
   if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible; this path has no CPU fallback");
-  if (prm->join_hash_tables || prm->row_func_mgr) return set_err(B2Q_ERR_UNSUPPORTED, "join hash tables / row function manager");
+  if (prm->row_func_mgr) return set_err(B2Q_ERR_UNSUPPORTED, "row function manager");
+  const bool has_join = query->prog.join.fk_col >= 0;
+  if (has_join != (prm->join_hash_tables != nullptr)) return set_err(B2Q_ERR_INVALID_ARGUMENT, "JOIN_HASH_TABLES must be given exactly when the plan has a join level");
   if (!prm->num_fragments || !prm->col_buffers || !prm->num_rows || !prm->group_by_buffers)
     return set_err(B2Q_ERR_INVALID_ARGUMENT, "missing kernel parameter");
-  if (prm->num_tables && *prm->num_tables != 1) return set_err(B2Q_ERR_UNSUPPORTED, "more than one input table");
+  if (prm->num_tables && *prm->num_tables != (has_join ? 2u : 1u)) return set_err(B2Q_ERR_UNSUPPORTED, "number of input tables does not match the plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   B2QPartial p;
   p.q = *query;
@@ -802,6 +869,9 @@ int32_t b2q_launch(const B2QQuery* query, const B2QParams* prm, void* stream) {
   const int nc = p.q.prog.n_cols;
   int32_t rc = alloc_partial(p, launch_table_bytes(nf, nc), st);
   if (rc != B2Q_OK) return rc;
+  /* with a join level col_buffers[frag] holds the scanned table's columns followed by the inner table's (the same
+   * device pointers in every fragment), and JOIN_HASH_TABLES[0] is the built one-to-one table */
+  if (has_join) p.join_buff = reinterpret_cast<const int32_t*>(static_cast<intptr_t>(prm->join_hash_tables[0]));
   std::vector<const int8_t*> cols(static_cast<size_t>(nf) * nc);
   std::vector<int64_t> rows(nf);
   for (int f = 0; f < nf; ++f) {

@@ -102,8 +102,17 @@ __device__ __forceinline__ int32_t ldg_u8(const int8_t* p, uint32_t pred, uint64
 }
 
 /* R rows of an 8-byte column: rows row0 + j*stride */
+/* jidx != nullptr: the column belongs to the joined inner table and is read at the matching inner rows (a gather
+ * through the normal cached path: dimension tables are small and re-read constantly).  Call sites pass a
+ * compile-time nullptr in the kernels without a join level, so the branch disappears there. */
 template <bool PRED>
-__device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict__ base, int64_t row0, int stride, uint32_t mask, uint64_t pol) {
+__device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict__ base, int64_t row0, int stride, uint32_t mask, uint64_t pol,
+                                       const int32_t* jidx = nullptr) {
+  if (jidx) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? __ldg(reinterpret_cast<const long long*>(base) + jidx[j]) : 0;
+    return;
+  }
   const int8_t* p = base + row0 * 8;
   const int64_t step = (int64_t)stride * 8;
 #pragma unroll
@@ -111,7 +120,26 @@ __device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict
 }
 /* R rows of a 1/2/4-byte integer column, sign-extended to 32 bits (width -1 / -2: zero-extended) */
 template <bool PRED>
-__device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0, int stride, uint32_t mask, uint64_t pol) {
+__device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0, int stride, uint32_t mask, uint64_t pol,
+                                       const int32_t* jidx = nullptr) {
+  if (jidx) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      int32_t x = 0;
+      if (mask >> j & 1) {
+        const int64_t i = jidx[j];
+        switch (width) {
+          case 4: x = __ldg(reinterpret_cast<const int32_t*>(base) + i); break;
+          case 2: x = __ldg(reinterpret_cast<const int16_t*>(base) + i); break;
+          case -2: x = __ldg(reinterpret_cast<const uint16_t*>(base) + i); break;
+          case -1: x = __ldg(reinterpret_cast<const uint8_t*>(base) + i); break;
+          default: x = __ldg(reinterpret_cast<const signed char*>(base) + i); break;
+        }
+      }
+      v[j] = x;
+    }
+    return;
+  }
   if (width == 4) {
     const int8_t* p = base + row0 * 4;
     const int64_t step = (int64_t)stride * 4;
@@ -145,13 +173,13 @@ __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict
  * ------------------------------------------------------------------------------------------------------- */
 template <bool FULL>
 __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* const* __restrict__ cols, int64_t row0,
-                                              int stride, uint32_t valid, uint64_t pol) {
+                                              int stride, uint32_t valid, uint64_t pol, const int32_t* jidx = nullptr) {
   uint32_t m = 0;
   const bool neg = t.negate;
   if (!t.cmp_fp) {
     if (t.width == 8) {
       int64_t v[R];
-      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol);
+      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol, jidx);
       const uint64_t lo = (uint64_t)t.lo, span = t.span;
       if (lo == 0x8000000000000000ull) { /* only an upper bound (`<`, `<=`): one signed compare instead of subtract + compare */
         const int64_t hi = (int64_t)(lo + span);
@@ -168,7 +196,7 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
       }
     } else {
       int32_t v[R];
-      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol);
+      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol, jidx);
       const uint32_t lo = (uint32_t)t.lo, span = (uint32_t)t.span;
 #pragma unroll
       for (int j = 0; j < R; ++j) m |= (uint32_t)(((uint32_t)v[j] - lo <= span) != neg) << j;
@@ -184,19 +212,19 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
     uint32_t isnull = 0;
     if (t.col_is_fp) {
       int64_t v[R];
-      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol);
+      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol, jidx);
       const double nullv = __longlong_as_double(t.null_bits);
 #pragma unroll
       for (int j = 0; j < R; ++j) { d[j] = __longlong_as_double(v[j]); isnull |= (uint32_t)(d[j] == nullv) << j; }
     } else if (t.width == 8) {
       int64_t v[R];
-      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol);
+      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol, jidx);
       const int64_t nullv = t.null_bits;
 #pragma unroll
       for (int j = 0; j < R; ++j) { d[j] = (double)v[j]; isnull |= (uint32_t)(v[j] == nullv) << j; }
     } else {
       int32_t v[R];
-      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol);
+      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol, jidx);
       const int32_t nullv = (int32_t)t.null_bits;
 #pragma unroll
       for (int j = 0; j < R; ++j) { d[j] = (double)v[j]; isnull |= (uint32_t)(v[j] == nullv) << j; }
@@ -208,17 +236,19 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
   return m & valid;
 }
 
-template <bool FULL>
+template <bool FULL, bool JOIN>
 __device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t* const* __restrict__ cols,
-                                                int64_t row0, int stride, uint32_t valid, uint64_t pol) {
+                                                int64_t row0, int stride, uint32_t valid, uint64_t pol,
+                                                const int8_t* __restrict__ col_inner, const int32_t* jidx) {
+#define B2Q_TERM_JX(t) ((JOIN && col_inner[(t).col]) ? jidx : nullptr)
   if (f.n_ops == 0) return valid;
-  if (f.n_ops == 1) return eval_term<FULL>(f.terms[0], cols, row0, stride, valid, pol);
+  if (f.n_ops == 1) return eval_term<FULL>(f.terms[0], cols, row0, stride, valid, pol, B2Q_TERM_JX(f.terms[0]));
   uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
   for (int i = 0; i < f.n_ops; ++i) {
     const uint32_t op = f.ops[i];
     const uint32_t kind = op >> 4;
     if (kind == FOP_TERM) {
-      const uint32_t m = eval_term<FULL>(f.terms[op & 15], cols, row0, stride, valid, pol);
+      const uint32_t m = eval_term<FULL>(f.terms[op & 15], cols, row0, stride, valid, pol, B2Q_TERM_JX(f.terms[op & 15]));
       s3 = s2; s2 = s1; s1 = s0; s0 = m;
     } else {
       s0 = (kind == FOP_AND) ? (s1 & s0) : (s1 | s0);
@@ -226,6 +256,7 @@ __device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t
     }
   }
   return s0 & valid;
+#undef B2Q_TERM_JX
 }
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -436,7 +467,7 @@ struct ScanArgs {
 extern __shared__ __align__(128) int8_t b2q_smem[];
 
 /* one chunk: R rows per thread.  FULL = every row of the chunk exists (no tail masking). */
-template <int MODE, bool WAGG, bool KEY32, bool FULL, int BLOCK>
+template <int MODE, bool WAGG, bool KEY32, bool FULL, int BLOCK, bool JOIN>
 __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* const* __restrict__ cols, int64_t row0,
                                               int64_t frag_rows, int lane, int8_t* my_tab, uint64_t pol, uint64_t pol_tab) {
   /* BLOCK is a compile-time constant so that the R loads of a column are one base pointer + immediate offsets */
@@ -450,21 +481,56 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     for (int j = 0; j < R; ++j) valid |= (uint32_t)(row0 + (int64_t)j * nthr < frag_rows) << j;
   }
 
+  /* ---- join level: probe the one-to-one table with the outer key; rows without a match leave `valid`
+   * (hash_join_idx[_nullable], GroupByRuntime.cpp:283-311; INNER join).  Columns of the inner table are then read at
+   * jidx[] — see load32 / load64. ---- */
+  int32_t jidx[JOIN ? R : 1];
+#define JX(c) ((JOIN && P.col_inner[c]) ? jidx : nullptr)
+  if (JOIN) {
+    const DevJoin& J = P.join;
+    const int32_t* __restrict__ buff = Lh.join_buff;
+    uint32_t matched = 0;
+    if (J.fk_width == 8) {
+      int64_t k[R];
+      load64<!FULL>(k, cols[J.fk_col], row0, nthr, valid, pol);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint64_t d = (uint64_t)(k[j] - J.min_key);
+        const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && k[j] == J.null_val);
+        const int32_t idx = ok ? __ldg(buff + d) : -1;
+        jidx[JOIN ? j : 0] = idx;
+        matched |= (uint32_t)(idx >= 0) << j;
+      }
+    } else {
+      int32_t k[R];
+      load32<!FULL>(k, cols[J.fk_col], J.fk_width, row0, nthr, valid, pol);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint64_t d = (uint64_t)((int64_t)k[j] - J.min_key);
+        const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && (int64_t)k[j] == J.null_val);
+        const int32_t idx = ok ? __ldg(buff + d) : -1;
+        jidx[JOIN ? j : 0] = idx;
+        matched |= (uint32_t)(idx >= 0) << j;
+      }
+    }
+    valid &= matched;
+  }
+
   /* ---- key column: issued before the filter when the planner expects most sectors to be needed anyway ---- */
   int32_t k32[KEY32 ? R : 1];
   int64_t k64[KEY32 ? 1 : R];
   const bool has_key = !WAGG && P.key.col >= 0;
   const bool eager_key = P.eager_key;
   if (has_key && eager_key) {
-    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, valid, pol);
-    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, valid, pol);
+    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, valid, pol, JX(P.key.col));
+    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, valid, pol, JX(P.key.col));
   }
 
-  uint32_t pass = eval_filter<FULL>(P.filter, cols, row0, nthr, valid, pol);
+  uint32_t pass = eval_filter<FULL, JOIN>(P.filter, cols, row0, nthr, valid, pol, P.col_inner, jidx);
 
   if (has_key && !eager_key) {
-    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, pass, pol);
-    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, pass, pol);
+    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, pass, pol, JX(P.key.col));
+    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, pass, pol, JX(P.key.col));
   }
 
   /* ---- group index ---- */
@@ -484,7 +550,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       const bool tr = kc.translate_null;
       if (kc.width == 8) {
         int64_t k[R];
-        load64<true>(k, cols[kc.col], row0, nthr, kmask, pol);
+        load64<true>(k, cols[kc.col], row0, nthr, kmask, pol, JX(kc.col));
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           int64_t d = k[j] - mn;
@@ -494,7 +560,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         }
       } else {
         int32_t k[R];
-        load32<true>(k, cols[kc.col], kc.width, row0, nthr, kmask, pol);
+        load32<true>(k, cols[kc.col], kc.width, row0, nthr, kmask, pol, JX(kc.col));
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           int64_t d = (int64_t)k[j] - mn;
@@ -606,7 +672,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     (void)cnt32;
     if (sa.op == ACC_SUM_F64) { /* AVG/SUM(double): CAS-loop add on the (warp-private) replica + the count */
       int64_t v[R];
-      load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol);
+      load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol, JX(sa.col));
       double* dsum = reinterpret_cast<double*>(sum_tab);
 #pragma unroll
       for (int j = 0; j < R; ++j)
@@ -616,7 +682,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         }
     } else if (sa.width == 8) {
       int64_t v[R];
-      load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol);
+      load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol, JX(sa.col));
       if (ic >= 0) {
 #pragma unroll
         for (int j = 0; j < R; ++j)
@@ -639,7 +705,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       }
     } else {
       int32_t v[R];
-      load32<true>(v, cols[sa.col], sa.width, row0, nthr, arg_mask, pol);
+      load32<true>(v, cols[sa.col], sa.width, row0, nthr, arg_mask, pol, JX(sa.col));
 #pragma unroll
       for (int j = 0; j < R; ++j)
         if (pass >> j & 1) {
@@ -698,7 +764,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     if (narrow) {
       /* 1/2/4-byte integer argument: 32-bit registers */
       int32_t v[R];
-      load32<true>(v, cols[acc.col], acc.width, row0, nthr, arg_mask, pol);
+      load32<true>(v, cols[acc.col], acc.width, row0, nthr, arg_mask, pol, JX(acc.col));
       const uint32_t m = not_skipped32(acc, v, pass);
       if (WAGG) {
         if (op == ACC_COUNT) {
@@ -739,10 +805,10 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
 
     /* 8-byte argument (BIGINT or DOUBLE), or a narrow column feeding a double aggregate (not produced by the planner) */
     int64_t v[R];
-    if (acc.width == 8) load64<true>(v, cols[acc.col], row0, nthr, arg_mask, pol);
+    if (acc.width == 8) load64<true>(v, cols[acc.col], row0, nthr, arg_mask, pol, JX(acc.col));
     else {
       int32_t t32[R];
-      load32<true>(t32, cols[acc.col], acc.width, row0, nthr, arg_mask, pol);
+      load32<true>(t32, cols[acc.col], acc.width, row0, nthr, arg_mask, pol, JX(acc.col));
 #pragma unroll
       for (int j = 0; j < R; ++j) v[j] = t32[j];
     }
@@ -819,8 +885,9 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     }
   }
 }
+#undef JX
 
-template <int MODE, bool WAGG, bool KEY32, int BLOCK>
+template <int MODE, bool WAGG, bool KEY32, int BLOCK, bool JOIN>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) b2q_k_scan(const __grid_constant__ ScanArgs A) {
   const DevProgram& P = A.prog;
   const DevLaunch& Lh = A.launch;
@@ -899,9 +966,9 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) b2q_k_scan(const __grid_c
     const int64_t base_row = (chunk - frag_first) * chunk_rows;
     const int8_t* const* __restrict__ cols = Lh.col_ptrs + (size_t)frag * P.n_cols;
     if (base_row + chunk_rows <= frag_rows)
-      process_chunk<MODE, WAGG, KEY32, true, BLOCK>(A, cols, base_row + tid, frag_rows, lane, my_tab, pol, pol_tab);
+      process_chunk<MODE, WAGG, KEY32, true, BLOCK, JOIN>(A, cols, base_row + tid, frag_rows, lane, my_tab, pol, pol_tab);
     else
-      process_chunk<MODE, WAGG, KEY32, false, BLOCK>(A, cols, base_row + tid, frag_rows, lane, my_tab, pol, pol_tab);
+      process_chunk<MODE, WAGG, KEY32, false, BLOCK, JOIN>(A, cols, base_row + tid, frag_rows, lane, my_tab, pol, pol_tab);
   }
 
   if (MODE == MODE_SMEM) {
@@ -952,6 +1019,29 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) b2q_k_scan(const __grid_c
         }
       }
     }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------------------
+ * one-to-one perfect join table (fill_hash_join_buff, JoinHashTable/Runtime/HashJoinRuntime.cpp:120-216, and its
+ * init_hash_join_buff): slot[key - min] = inner row index, NULL keys skipped; a slot claimed twice means the join is
+ * not one-to-one (the reference then rebuilds a one-to-many table — outside this path)
+ * ------------------------------------------------------------------------------------------------------- */
+__global__ void b2q_k_join_build(const int8_t* __restrict__ keys, int width, int64_t n_rows, int64_t min_key, int64_t entry_count,
+                                 int nullable, int64_t null_val, int32_t* __restrict__ buff, int32_t* __restrict__ error) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += stride) {
+    int64_t k;
+    switch (width) {
+      case 8: k = reinterpret_cast<const int64_t*>(keys)[row]; break;
+      case 4: k = reinterpret_cast<const int32_t*>(keys)[row]; break;
+      case 2: k = reinterpret_cast<const int16_t*>(keys)[row]; break;
+      default: k = reinterpret_cast<const signed char*>(keys)[row]; break;
+    }
+    if (nullable && k == null_val) continue;
+    const uint64_t d = (uint64_t)(k - min_key);
+    if (d >= (uint64_t)entry_count) { atomicCAS(error, 0, B2Q_ERR_KEY_OUT_OF_RANGE); continue; }
+    if (atomicCAS(buff + d, -1, (int32_t)row) != -1) atomicCAS(error, 0, B2Q_ERR_UNSUPPORTED);
   }
 }
 
@@ -1150,7 +1240,7 @@ struct ScanConfig {
   size_t smem_bytes;
 };
 
-template <int MODE, bool WAGG, bool KEY32, int BLOCK>
+template <int MODE, bool WAGG, bool KEY32, int BLOCK, bool JOIN>
 static cudaError_t launch_scan_tb(const ScanArgs& a, const ScanConfig& c, cudaStream_t st) {
   /* the opt-in shared-memory limit is a per-device function attribute: remember which devices have it */
   static unsigned long long attr_set_mask = 0;
@@ -1162,19 +1252,21 @@ static cudaError_t launch_scan_tb(const ScanArgs& a, const ScanConfig& c, cudaSt
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, b2q_k_scan<MODE, WAGG, KEY32, BLOCK>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, b2q_k_scan<MODE, WAGG, KEY32, BLOCK, JOIN>);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(b2q_k_scan<MODE, WAGG, KEY32, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    e = cudaFuncSetAttribute(b2q_k_scan<MODE, WAGG, KEY32, BLOCK, JOIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
     if (e != cudaSuccess) return e;
     if (cur_dev < 64) attr_set_mask |= 1ull << cur_dev;
   }
-  b2q_k_scan<MODE, WAGG, KEY32, BLOCK><<<c.grid, c.block, c.smem_bytes, st>>>(a);
+  b2q_k_scan<MODE, WAGG, KEY32, BLOCK, JOIN><<<c.grid, c.block, c.smem_bytes, st>>>(a);
   return cudaGetLastError();
 }
 
 template <int MODE, bool WAGG, bool KEY32>
 static cudaError_t launch_scan_t(const ScanArgs& a, const ScanConfig& c, cudaStream_t st) {
-  return c.block == 1024 ? launch_scan_tb<MODE, WAGG, KEY32, 1024>(a, c, st) : launch_scan_tb<MODE, WAGG, KEY32, 512>(a, c, st);
+  if (a.prog.join.fk_col >= 0) /* one INNER hash-join level: separate instantiations, the plain scan stays as it was */
+    return c.block == 1024 ? launch_scan_tb<MODE, WAGG, KEY32, 1024, true>(a, c, st) : launch_scan_tb<MODE, WAGG, KEY32, 512, true>(a, c, st);
+  return c.block == 1024 ? launch_scan_tb<MODE, WAGG, KEY32, 1024, false>(a, c, st) : launch_scan_tb<MODE, WAGG, KEY32, 512, false>(a, c, st);
 }
 
 int scan_rows_per_chunk(int block) { return block * R; }
@@ -1214,6 +1306,21 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
   if (kernel == B2Q_KERNEL_PERFECT_GLOBAL)
     return key32 ? launch_scan_t<MODE_GLOBAL, false, true>(a, c, st) : launch_scan_t<MODE_GLOBAL, false, false>(a, c, st);
   return key32 ? launch_scan_t<MODE_BASELINE, false, true>(a, c, st) : launch_scan_t<MODE_BASELINE, false, false>(a, c, st);
+}
+
+cudaError_t launch_join_build(const int8_t* keys, int width, int64_t n_rows, int64_t min_key, int64_t entry_count, int nullable,
+                              int64_t null_val, int32_t* buff, int32_t* error, cudaStream_t st) {
+  if (entry_count > 0) {
+    cudaError_t e = cudaMemsetAsync(buff, 0xFF, (size_t)entry_count * 4, st); /* init_hash_join_buff: every slot -1 */
+    if (e != cudaSuccess) return e;
+  }
+  if (n_rows <= 0 || entry_count <= 0) return cudaSuccess;
+  const int block = 256;
+  int64_t blocks = (n_rows + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  b2q_k_join_build<<<(int)blocks, block, 0, st>>>(keys, width, n_rows, min_key, entry_count, nullable, null_val, buff, error);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_init(const B2QQuery& q, int64_t* const* accs, int64_t* keys, int8_t* smem_image, cudaStream_t st) {

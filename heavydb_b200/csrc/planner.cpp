@@ -99,10 +99,22 @@ class Planner {
           bool filter_deleted)
       : u_(u), t_(t), eo_(eo), guess_(guess), has_card_(has_card), filter_deleted_(filter_deleted) {}
 
+  /* join level of the unit this planner was given in its combined form (make_query) */
+  void set_join(int n_outer, int outer_col, int inner_col, const B2QTableInfo& inner) {
+    join_ = true;
+    n_outer_ = n_outer;
+    join_outer_col_ = outer_col;
+    join_inner_col_ = inner_col;
+    inner_ = &inner;
+  }
+
   void run(B2QQuery& q) {
     memset(&q, 0, sizeof(q));
+    q.prog.join.fk_col = -1;
+    q.plan.join_outer_col = q.plan.join_inner_col = -1;
     validate();
     build_targets();
+    plan_join(q.plan);
     choose_hash_type(q.plan);
     layout_slots(q.plan);
     init_values(q.plan);
@@ -131,6 +143,39 @@ class Planner {
   bool keyless_ = false;
   int keyless_idx_ = -1;
   std::vector<bool> slot_key_ref_;
+  bool join_ = false;
+  int n_outer_ = 0, join_outer_col_ = -1, join_inner_col_ = -1;
+  const B2QTableInfo* inner_ = nullptr;
+
+  /* PerfectJoinHashTable::getInstance (JoinHashTable/PerfectJoinHashTable.cpp:168-300): the table spans the inner
+   * key's range (getExpressionRange(inner_col)), one int32 slot per value; a range much wider than the row count
+   * makes the reference switch to a baseline join table (deploy_baseline_join, :235-246) — outside this path */
+  void plan_join(B2QPlan& p) {
+    if (!join_) return;
+    const SqlType ot = col_type(join_outer_col_), it = col_type(n_outer_ + join_inner_col_);
+    if (!ot.is_int() || !it.is_int() || ot.is_string() || it.is_string())
+      reject(B2Q_ERR_UNSUPPORTED, "join keys must be integer columns (dictionary translation is outside this path)");
+    /* getExpressionRange(inner_col): over the inner table alone (getLeafColumnRange, ExpressionRange.cpp:521-632) */
+    ColRange r;
+    r.valid = true;
+    const int64_t inner_tuples = inner_->num_fragments ? inner_->fragments[0].num_tuples : 0;
+    if (inner_tuples > 0) {
+      const B2QChunkStats& st = inner_->fragments[0].col_stats[join_inner_col_];
+      r.imin = st.int_min; r.imax = st.int_max; r.has_nulls = st.has_nulls != 0;
+      if (r.imax < r.imin) { r.imin = 0; r.imax = -1; }
+    }
+    int64_t entries = 0;
+    if (r.imin <= r.imax && (__builtin_sub_overflow(r.imax, r.imin, &entries) || __builtin_add_overflow(entries, int64_t(1), &entries) || entries > INT32_MAX))
+      reject(B2Q_ERR_UNSUPPORTED, "too many hash entries for a perfect join table (TooManyHashEntries)");
+    const int64_t inner_rows = inner_->num_fragments ? inner_->fragments[0].num_tuples : 0;
+    if (inner_rows * 100 < entries) /* g_ratio_num_hash_entry_to_num_tuple_switch_to_baseline, Execute.cpp:104 */
+      reject(B2Q_ERR_UNSUPPORTED, "join column range too wide for its row count: the reference switches to a baseline join table");
+    p.join_min_key = r.imin;
+    p.join_max_key = r.imax;
+    p.join_entry_count = entries;
+    p.join_outer_col = join_outer_col_;
+    p.join_inner_col = join_inner_col_;
+  }
 
   const B2QExpr& ex(int i) const {
     if (i < 0 || i >= u_.num_exprs) reject(B2Q_ERR_INVALID_ARGUMENT, "expression index out of range");
@@ -536,6 +581,7 @@ class Planner {
     for (int i = 0; i < q.prog.n_cols; ++i) if (q.col_ids[i] == table_col) return i;
     if (q.prog.n_cols >= B2Q_MAX_COLS) reject(B2Q_ERR_UNSUPPORTED, "too many referenced columns");
     q.col_ids[q.prog.n_cols] = table_col;
+    q.prog.col_inner[q.prog.n_cols] = (join_ && table_col >= n_outer_) ? 1 : 0;
     q.prog.col_width[q.prog.n_cols] = static_cast<int8_t>(t_.col_types[table_col].type == B2Q_kBOOLEAN ? 1 : phys_size(table_col));
     return q.prog.n_cols++;
   }
@@ -768,6 +814,14 @@ class Planner {
     B2QPlan& p = q.plan;
     DevProgram& g = q.prog;
     q.bigint_count = eo_.bigint_count;
+    if (join_) { /* probe parameters: hash_join_idx[_nullable](buff, key, min, max[, null]) (GroupByRuntime.cpp:283-311) */
+      g.join.fk_col = launch_col(q, join_outer_col_);
+      g.join.fk_width = static_cast<int8_t>(phys_width_code(join_outer_col_));
+      g.join.min_key = p.join_min_key;
+      g.join.entry_count = p.join_entry_count;
+      g.join.nullable = !col_type(join_outer_col_).notnull;
+      g.join.null_val = phys_int_null(join_outer_col_);
+    }
     /* filter: all simple_quals and quals AND-ed */
     int n_quals = 0, max_depth = 0;
     auto add_qual = [&](int idx) {
@@ -926,6 +980,8 @@ class Planner {
     if (grouped_ && g.eager_key) { if (g.n_keys > 1) { for (int i = 0; i < g.n_keys; ++i) g.col_prefetch[g.keys[i].col] = 1; } else g.col_prefetch[g.key.col] = 1; }
     if (g.eager_args)
       for (int a = 0; a < g.n_accs; ++a) if (g.accs[a].col >= 0) g.col_prefetch[g.accs[a].col] = 1;
+    if (join_) g.col_prefetch[g.join.fk_col] = 1;
+    for (int c = 0; c < g.n_cols; ++c) if (g.col_inner[c]) g.col_prefetch[c] = 0; /* gathered by join index, not streamed */
     /* fused fast path of the shared-memory-table kernel (the reference's JIT specialises per query; this is the
      * static-kernel equivalent for the most common shape: GROUP BY k with COUNT(*) and/or one integer SUM) */
     g.fused = 0; g.fused_cnt = -1; g.fused_sum = -1;
@@ -1001,11 +1057,106 @@ class Planner {
 
 }  // namespace
 
+/* One INNER hash-join level: the unit is re-expressed over a combined table — columns [0, n_outer) of the scanned
+ * table followed by the inner table's — so that ranges, layouts and the device program are planned by the same code;
+ * every combined fragment carries the inner table's chunk stats for the inner columns. */
+struct JoinedInput {
+  std::vector<B2QExpr> exprs;
+  B2QExecUnit u{};
+  std::vector<B2QTypeInfo> col_types;
+  std::vector<int8_t> enc;
+  std::vector<std::vector<const void*>> bufs;
+  std::vector<std::vector<B2QChunkStats>> stats;
+  std::vector<B2QFragmentInfo> frags;
+  B2QTableInfo t{};
+  int n_outer = 0, outer_col = -1, inner_col = -1;
+};
+
+static void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, JoinedInput& ji) {
+  auto bad = [](int32_t code, const char* m) { throw PlanError{code, m}; };
+  if (u.num_join_quals != 1) bad(B2Q_ERR_UNSUPPORTED, "more than one join level is outside this path");
+  if (u.join_type != 0) bad(B2Q_ERR_UNSUPPORTED, "only INNER joins are on this path");
+  if (!u.inner_table) bad(B2Q_ERR_INVALID_ARGUMENT, "join without an inner table");
+  const B2QTableInfo& inner = *u.inner_table;
+  if (inner.num_fragments > 1) bad(B2Q_ERR_INVALID_ARGUMENT, "the inner table must come as one concatenated fragment (ColumnFetcher::getAllTableColumnFragments)");
+  if (inner.deleted_column_plus1) bad(B2Q_ERR_UNSUPPORTED, "inner table with a deleted-rows column");
+  if (inner.num_cols <= 0 || outer.num_cols <= 0) bad(B2Q_ERR_INVALID_ARGUMENT, "table without columns");
+  ji.n_outer = outer.num_cols;
+  ji.exprs.assign(u.exprs, u.exprs + std::max(u.num_exprs, 0));
+  for (B2QExpr& e : ji.exprs) {
+    if (e.kind != B2Q_EXPR_COLUMN_VAR) continue;
+    if (e.rte_idx == 1) {
+      if (e.col_id < 0 || e.col_id >= inner.num_cols) bad(B2Q_ERR_INVALID_ARGUMENT, "inner column id out of range");
+      e.col_id += ji.n_outer;
+      e.rte_idx = 0;
+    } else if (e.rte_idx != 0) bad(B2Q_ERR_UNSUPPORTED, "rte_idx beyond one join level");
+  }
+  ji.u = u;
+  ji.u.exprs = ji.exprs.data();
+  ji.u.num_join_quals = 0;
+  ji.u.inner_table = nullptr;
+  if (u.join_qual < 0 || u.join_qual >= u.num_exprs) bad(B2Q_ERR_INVALID_ARGUMENT, "join qual index out of range");
+  const B2QExpr& q = ji.exprs[u.join_qual];
+  if (q.kind != B2Q_EXPR_BIN_OPER || q.op != B2Q_kEQ) bad(B2Q_ERR_UNSUPPORTED, "join qual must be an equality");
+  if (q.left < 0 || q.left >= u.num_exprs || q.right < 0 || q.right >= u.num_exprs) bad(B2Q_ERR_INVALID_ARGUMENT, "join qual operand out of range");
+  const B2QExpr& a = ji.exprs[q.left];
+  const B2QExpr& b = ji.exprs[q.right];
+  if (a.kind != B2Q_EXPR_COLUMN_VAR || b.kind != B2Q_EXPR_COLUMN_VAR) bad(B2Q_ERR_UNSUPPORTED, "join qual must compare two ColumnVars");
+  const bool a_inner = a.col_id >= ji.n_outer, b_inner = b.col_id >= ji.n_outer;
+  if (a_inner == b_inner) bad(B2Q_ERR_UNSUPPORTED, "join qual must compare an outer with an inner column");
+  ji.outer_col = a_inner ? b.col_id : a.col_id;
+  ji.inner_col = (a_inner ? a.col_id : b.col_id) - ji.n_outer;
+  if (ji.outer_col < 0 || ji.outer_col >= ji.n_outer) bad(B2Q_ERR_INVALID_ARGUMENT, "outer join column out of range");
+  ji.col_types.assign(outer.col_types, outer.col_types + outer.num_cols);
+  ji.col_types.insert(ji.col_types.end(), inner.col_types, inner.col_types + inner.num_cols);
+  ji.enc.assign(ji.col_types.size(), 0);
+  for (int c = 0; c < outer.num_cols; ++c) if (outer.col_encoded_sizes) ji.enc[c] = outer.col_encoded_sizes[c];
+  for (int c = 0; c < inner.num_cols; ++c) if (inner.col_encoded_sizes) ji.enc[ji.n_outer + c] = inner.col_encoded_sizes[c];
+  const B2QFragmentInfo* inf = inner.num_fragments ? &inner.fragments[0] : nullptr;
+  const int nf = std::max(outer.num_fragments, 0);
+  ji.bufs.resize(nf);
+  ji.stats.resize(nf);
+  ji.frags.resize(nf);
+  for (int f = 0; f < nf; ++f) {
+    const B2QFragmentInfo& of = outer.fragments[f];
+    ji.bufs[f].assign(of.col_buffers, of.col_buffers + outer.num_cols);
+    ji.stats[f].assign(of.col_stats, of.col_stats + outer.num_cols);
+    for (int c = 0; c < inner.num_cols; ++c) {
+      ji.bufs[f].push_back(nullptr); /* inner columns are resolved by the executor, not through the fragment */
+      B2QChunkStats empty{};
+      empty.int_min = INT64_MAX; empty.int_max = INT64_MIN; empty.fp_min = DBL_MAX; empty.fp_max = -DBL_MAX;
+      ji.stats[f].push_back(inf ? inf->col_stats[c] : empty);
+    }
+    ji.frags[f] = of;
+    ji.frags[f].col_buffers = ji.bufs[f].data();
+    ji.frags[f].col_stats = ji.stats[f].data();
+  }
+  ji.t = outer;
+  ji.t.num_cols = static_cast<int32_t>(ji.col_types.size());
+  ji.t.col_types = ji.col_types.data();
+  ji.t.col_encoded_sizes = ji.enc.data();
+  ji.t.fragments = ji.frags.data();
+}
+
 int32_t make_query(const B2QExecUnit* u, const B2QTableInfo* t, const B2QExecutionOptions* eo, size_t guess,
                    bool has_card, bool filter_deleted, B2QQuery* out, std::string* err) {
   try {
     if (!u || !t || !eo || !out) throw PlanError{B2Q_ERR_INVALID_ARGUMENT, "null argument"};
-    Planner(*u, *t, *eo, guess, has_card, filter_deleted).run(*out);
+    if (!u->num_join_quals) {
+      Planner(*u, *t, *eo, guess, has_card, filter_deleted).run(*out);
+      out->n_outer_cols = t->num_cols;
+      out->join_inner_key_col = -1;
+      out->plan.join_outer_col = out->plan.join_inner_col = -1;
+      out->prog.join.fk_col = -1;
+      return B2Q_OK;
+    }
+    JoinedInput ji;
+    build_joined_input(*u, *t, ji);
+    Planner pl(ji.u, ji.t, *eo, guess, has_card, filter_deleted);
+    pl.set_join(ji.n_outer, ji.outer_col, ji.inner_col, *u->inner_table);
+    pl.run(*out);
+    out->n_outer_cols = ji.n_outer;
+    out->join_inner_key_col = ji.inner_col;
     return B2Q_OK;
   } catch (const PlanError& e) {
     if (err) *err = e.msg;

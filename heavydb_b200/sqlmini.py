@@ -2,7 +2,7 @@
 RelAlgExecutionUnit mirror, for the subset of the path:
 
     SELECT <col | COUNT(*) | COUNT(c) | SUM(c) | MIN(c) | MAX(c) | AVG(c)>, ...
-    FROM <table> [WHERE <c OP literal | c IS [NOT] NULL | c [NOT] IN (l, ...) | c BETWEEN l AND l | NOT <factor>>
+    FROM <table> [JOIN <inner> ON <table>.<c> = <inner>.<c>] [WHERE <c OP literal | c IS [NOT] NULL | c [NOT] IN (l, ...) | c BETWEEN l AND l | NOT <factor>>
                   {AND|OR} ... with parentheses] [GROUP BY c {, c}]
     [ORDER BY <position | target text> [ASC|DESC] [NULLS FIRST|LAST] {, ...}] [LIMIT n] [OFFSET m]
 
@@ -18,7 +18,7 @@ from typing import List, Tuple
 
 from heavydb_b200 import abi
 
-_TOK = re.compile(r"\s*(<>|<=|>=|!=|[(),*<>=]|[A-Za-z_][A-Za-z_0-9]*|-?\d+\.\d*(?:[eE][-+]?\d+)?|-?\d+)")
+_TOK = re.compile(r"\s*(<>|<=|>=|!=|[(),*<>=]|[A-Za-z_][A-Za-z_0-9]*(?:\.[A-Za-z_][A-Za-z_0-9]*)?|-?\d+\.\d*(?:[eE][-+]?\d+)?|-?\d+)")
 _OPS = {"=": abi.kEQ, "<>": abi.kNE, "!=": abi.kNE, "<": abi.kLT, ">": abi.kGT, "<=": abi.kLE, ">=": abi.kGE}
 _AGGS = {"COUNT": abi.kCOUNT, "SUM": abi.kSUM, "MIN": abi.kMIN, "MAX": abi.kMAX, "AVG": abi.kAVG}
 
@@ -36,11 +36,16 @@ def _tokens(s: str) -> List[str]:
 
 
 class _P:
-    def __init__(self, toks, table: abi.Table, names: List[str], bigint_count: bool):
+    def __init__(self, toks, table: abi.Table, names: List[str], bigint_count: bool, inner=None):
         self.t, self.i = toks, 0
         self.b = abi.UnitBuilder(table)
         self.names = [n.lower() for n in names]
         self.bigint_count = bigint_count
+        # one INNER join level: inner = (abi.Table, [column names]); set before any column is resolved
+        self.inner_names = [n.lower() for n in inner[1]] if inner else []
+        self.outer_alias = self.inner_alias = None
+        if inner:
+            self.b.inner = inner[0]
 
     def peek(self):
         return self.t[self.i] if self.i < len(self.t) else None
@@ -52,8 +57,22 @@ class _P:
         self.i += 1
         return tok
 
+    def colref(self, name):
+        """(column id, rte_idx).  `alias.col` is resolved by alias, a bare name in the outer table first."""
+        name = name.lower()
+        if "." in name:
+            alias, col = name.split(".", 1)
+            if self.inner_alias is not None and alias == self.inner_alias:
+                return self.inner_names.index(col), 1
+            return self.names.index(col), 0
+        if name in self.names:
+            return self.names.index(name), 0
+        return self.inner_names.index(name), 1
+
     def colid(self, name):
-        return self.names.index(name.lower())
+        c, rte = self.colref(name)
+        assert rte == 0, f"{name}: inner-table column where only outer columns are supported"
+        return c
 
     # cond := term {OR term}; term := factor {AND factor}; factor := '(' cond ')' | col OP literal
     def cond(self):
@@ -70,10 +89,10 @@ class _P:
             e = self.b.binop(abi.kAND, e, self.factor())
         return e
 
-    def literal_cmp(self, col, op, lit):
+    def literal_cmp(self, col, op, lit, rte=0):
         if re.fullmatch(r"-?\d+", lit):
-            return self.b.cmp(col, op, int(lit), abi.kBIGINT)
-        return self.b.cmp(col, op, float(lit), abi.kDOUBLE)
+            return self.b.cmp(col, op, int(lit), abi.kBIGINT, rte)
+        return self.b.cmp(col, op, float(lit), abi.kDOUBLE, rte)
 
     def factor(self):
         if self.peek() == "(":
@@ -84,7 +103,7 @@ class _P:
         if self.peek().upper() == "NOT":          # Analyzer::UOper(kNOT, ...)
             self.eat()
             return self.b.uoper(abi.kNOT, self.factor())
-        col = self.colid(self.eat())
+        col, rte = self.colref(self.eat())
         nxt = self.peek().upper()
         if nxt == "IS":                            # c IS NULL -> UOper(kISNULL, c); IS NOT NULL -> NOT(ISNULL), like RelAlgTranslator
             self.eat()
@@ -92,7 +111,7 @@ class _P:
             if neg:
                 self.eat()
             self.eat("NULL")
-            e = self.b.uoper(abi.kISNULL, self.b.col(col))
+            e = self.b.uoper(abi.kISNULL, self.b.col(col, rte))
             return self.b.uoper(abi.kNOT, e) if neg else e
         neg = False
         if nxt == "NOT":
@@ -102,10 +121,10 @@ class _P:
         if nxt == "IN":                            # c IN (a, b, ...) -> OR of equalities (InValues codegen for short lists)
             self.eat()
             self.eat("(")
-            e = self.literal_cmp(col, abi.kEQ, self.eat())
+            e = self.literal_cmp(col, abi.kEQ, self.eat(), rte)
             while self.peek() == ",":
                 self.eat()
-                e = self.b.binop(abi.kOR, e, self.literal_cmp(col, abi.kEQ, self.eat()))
+                e = self.b.binop(abi.kOR, e, self.literal_cmp(col, abi.kEQ, self.eat(), rte))
             self.eat(")")
             return self.b.uoper(abi.kNOT, e) if neg else e
         if nxt == "BETWEEN":                       # Calcite expands BETWEEN to >= AND <=
@@ -113,10 +132,10 @@ class _P:
             lo = self.eat()
             self.eat("AND")
             hi = self.eat()
-            e = self.b.binop(abi.kAND, self.literal_cmp(col, abi.kGE, lo), self.literal_cmp(col, abi.kLE, hi))
+            e = self.b.binop(abi.kAND, self.literal_cmp(col, abi.kGE, lo, rte), self.literal_cmp(col, abi.kLE, hi, rte))
             return self.b.uoper(abi.kNOT, e) if neg else e
         op = _OPS[self.eat()]
-        return self.literal_cmp(col, op, self.eat())
+        return self.literal_cmp(col, op, self.eat(), rte)
 
     def target_text(self):
         """Canonical text of the target expression starting at the cursor (does not build nodes)."""
@@ -135,10 +154,10 @@ class _P:
                 self.eat()
                 self.eat(")")
                 return self.b.agg(abi.kCOUNT, None, self.bigint_count)
-            col = self.colid(self.eat())
+            col, rte = self.colref(self.eat())
             self.eat(")")
-            return self.b.agg(_AGGS[tok.upper()], col, self.bigint_count)
-        return self.b.col(self.colid(tok))
+            return self.b.agg(_AGGS[tok.upper()], col, self.bigint_count, rte)
+        return self.b.col(*self.colref(tok))
 
 
 def _conjuncts(b: abi.UnitBuilder, e: int) -> List[int]:
@@ -148,8 +167,16 @@ def _conjuncts(b: abi.UnitBuilder, e: int) -> List[int]:
     return [e]
 
 
-def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = False) -> abi.BuiltUnit:
-    p = _P(_tokens(sql), table, names, bigint_count)
+def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = False, inner=None) -> abi.BuiltUnit:
+    """inner = (abi.Table, [names]) of the table named after JOIN (one concatenated fragment)."""
+    toks = _tokens(sql)
+    p = _P(toks, table, names, bigint_count, inner)
+    ups = [t.upper() for t in toks]
+    fi = ups.index("FROM")
+    p.outer_alias = toks[fi + 1].lower()
+    if fi + 2 < len(toks) and ups[fi + 2] == "JOIN":
+        assert inner is not None, "JOIN needs the inner table"
+        p.inner_alias = toks[fi + 3].lower()
     p.eat("SELECT")
     texts = [p.target_text()[0]]
     targets = [p.target()]
@@ -159,6 +186,13 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
         targets.append(p.target())
     p.eat("FROM")
     p.eat()  # table name
+    if p.peek() and p.peek().upper() == "JOIN":   # join_quals[0] = {a = b}, INNER
+        p.eat()
+        p.eat()  # inner table name
+        p.eat("ON")
+        (c1, r1), _, (c2, r2) = p.colref(p.eat()), p.eat("="), p.colref(p.eat())
+        assert {r1, r2} == {0, 1}, "ON must compare an outer with an inner column"
+        p.b.join(inner[0], c1 if r1 == 0 else c2, c2 if r1 == 0 else c1)
     if p.peek() and p.peek().upper() == "WHERE":
         p.eat()
         e = p.cond()
@@ -175,10 +209,10 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
     if p.peek() and p.peek().upper() == "GROUP":
         p.eat()
         p.eat("BY")
-        p.b.group_by(p.colid(p.eat()))
+        p.b.group_by(*p.colref(p.eat()))
         while p.peek() == ",":
             p.eat()
-            p.b.group_by(p.colid(p.eat()))
+            p.b.group_by(*p.colref(p.eat()))
     if p.peek() and p.peek().upper() == "ORDER":
         p.eat()
         p.eat("BY")

@@ -119,7 +119,7 @@ typedef struct B2QExpr {
   int64_t ival;   /* Constant: Datum for integer types */
   double dval;    /* Constant: Datum for fp types */
   int32_t is_null;/* Constant::get_is_null() */
-  int32_t pad_;
+  int32_t rte_idx;/* ColumnVar::get_rte_idx(): 0 = the scanned (outer) table, 1 = the joined inner table */
 } B2QExpr;
 
 /* ---- Analyzer::OrderEntry (Analyzer/Analyzer.h:2960-2968) ------------------------------------------------ */
@@ -131,6 +131,7 @@ typedef struct B2QOrderEntry {
 } B2QOrderEntry;
 
 /* ---- RelAlgExecutionUnit subset (QueryEngine/RelAlgExecutionUnit.h:166-216) ---------------------------- */
+struct B2QTableInfo;
 typedef struct B2QExecUnit {
   const B2QExpr* exprs;
   int32_t num_exprs;
@@ -143,8 +144,12 @@ typedef struct B2QExecUnit {
   const int32_t* target_exprs; /* expr indices */
   int32_t num_target_exprs;
   int64_t scan_limit;
+  /* join_quals (JoinQualsPerNestingLevel, RelAlgExecutionUnit.h:166-216): at most ONE nesting level, INNER, whose only
+   * qual is `ColumnVar(rte 0) = ColumnVar(rte 1)` over integer columns and for which the reference would build a
+   * one-to-one PerfectJoinHashTable (JoinHashTable/PerfectJoinHashTable.cpp:168-300; probe hash_join_idx[_nullable],
+   * GroupByRuntime.cpp:283-311).  Anything else (outer joins, one-to-many, baseline join tables) is rejected. */
+  int32_t num_join_quals;      /* 0 or 1 */
   /* Fields of the reference struct that are outside this path.  Must be zero or the call is rejected. */
-  int32_t num_join_quals;
   int32_t has_estimator;
   int32_t has_union_all;
   int32_t has_window_function;
@@ -158,6 +163,13 @@ typedef struct B2QExecUnit {
   int32_t has_limit;           /* std::optional<size_t> limit */
   int64_t limit;
   int64_t offset;
+  /* the join level (used when num_join_quals == 1) */
+  int32_t join_qual;           /* expr index of the equi-join BinOper(kEQ, ColumnVar, ColumnVar) */
+  int32_t join_type;           /* JoinType (Shared/sqldefs.h:252): only INNER = 0 */
+  /* input_descs[1]: the inner table the way the hash-join column fetch sees it — every column as ONE buffer over all
+   * fragments (ColumnFetcher::getAllTableColumnFragments, ColumnFetcher.cpp:290-360), i.e. exactly one fragment whose
+   * chunk stats cover the table; memory_level CPU (copied to the device per query) or GPU */
+  const struct B2QTableInfo* inner_table;
 } B2QExecUnit;
 
 /* ---- ChunkMetadata::chunkStats per (fragment, column)  (Fragmenter/Fragmenter.h:73-146) ---------------- */
@@ -271,6 +283,12 @@ typedef struct B2QPlan {
   int64_t slot_offset[B2Q_MAX_SLOTS]; /* row-wise: byte offset inside the row; columnar: offset of the column */
   int64_t init_vals[B2Q_MAX_SLOTS];   /* init_agg_val_vec (OutputBufferInitialization.cpp:26-86) */
   B2QTargetInfo targets[B2Q_MAX_TARGETS];
+  /* the join level, if any: a one-to-one perfect hash table over [join_min_key, join_max_key] of the inner key
+   * (PerfectJoinHashTable: hash_entry_count = max - min + 1, slots = inner row index or -1).  With a join, column ids
+   * in this descriptor (key_col_id, group_col_ids, targets[].arg_col_id) >= the outer table's num_cols denote inner
+   * table column (id - num_cols). */
+  int64_t join_min_key, join_max_key, join_entry_count;
+  int32_t join_outer_col, join_inner_col; /* -1 without a join */
 } B2QPlan;
 
 /* The 15-slot kernel parameter block of the reference's JIT entry (enums.h:64-79), device pointers. */
@@ -288,7 +306,8 @@ typedef struct B2QParams {
   const int32_t* frag_ids;         /* FRAG_IDS        (unused) */
   const int32_t* max_matched;      /* MAX_MATCHED     (unused) */
   const int64_t* init_agg_value;   /* INIT_AGG_VALS   host array [num_slots]; NULL = plan->init_vals */
-  const int64_t* join_hash_tables; /* JOIN_HASH_TABLES must be NULL */
+  const int64_t* join_hash_tables; /* JOIN_HASH_TABLES NULL, or [0] = device address of the int32 one-to-one table
+                                      (what HashJoin::getJoinHashBuffer returns) when the plan has a join level */
   const int8_t* row_func_mgr;      /* ROW_FUNC_MGR    must be NULL */
 } B2QParams;
 

@@ -34,6 +34,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -285,6 +286,16 @@ double fixed_width_double_decode(const int8_t* byte_stream, int64_t pos) {
   return v;
 }
 
+/* Hash join (one INNER level): the joined inner table's columns are addressed as columns n_outer.. of a combined
+ * ("virtual") table; their row position is the matching inner row (the join loop's iterator, IRCodegen.cpp
+ * buildJoinLoops), not the outer position.  Set per outer row by run_fragment; one row loop per thread. */
+struct JoinRowCtx {
+  int n_outer{INT32_MAX};
+  int64_t inner_pos{0};
+};
+thread_local JoinRowCtx g_join_row;
+inline int64_t row_pos_of(int c, int64_t pos) { return c >= g_join_row.n_outer ? g_join_row.inner_pos : pos; }
+
 /* Physical element width of column c: narrower than the logical type under `ENCODING FIXED(bits)`. */
 int phys_width(const B2QTableInfo& tbl, int c) {
   if (tbl.col_encoded_sizes && tbl.col_encoded_sizes[c] > 0) return tbl.col_encoded_sizes[c];
@@ -294,6 +305,7 @@ int phys_width(const B2QTableInfo& tbl, int c) {
  * CodeGenerator::codgenAdjustFixedEncNull (ColumnIR.cpp:456-500): the physical width's minimum is NULL and becomes the
  * logical type's sentinel (only for nullable columns, ColumnIR.cpp:286-291). */
 int64_t decode_int_column(const B2QTableInfo& tbl, const B2QFragmentInfo& fr, int c, int64_t pos) {
+  pos = row_pos_of(c, pos);
   const int pw = phys_width(tbl, c);
   const int lw = type_size(tbl.col_types[c].type);
   if (is_string(tbl.col_types[c].type) && pw < lw) {
@@ -347,6 +359,11 @@ struct Plan {
   std::vector<Target> targets;
   std::vector<Ti> slot_compact_ti;
   std::vector<KeyCol> keys; /* size > 1: multi-column perfect hash */
+  /* join level: probe parameters (the table itself is built per execution) */
+  bool join{false};
+  int join_outer_col{-1}, join_inner_vcol{-1}; /* virtual column ids */
+  bool join_outer_nullable{false};
+  std::shared_ptr<std::vector<int32_t>> join_buff;
 };
 
 const B2QExpr& expr_at(const B2QExecUnit& u, int idx) {
@@ -582,10 +599,10 @@ void get_keyless_info(const B2QExecUnit& u, const B2QTableInfo& tbl, const std::
 
 constexpr int64_t kMaxBufferSize = int64_t(1) << 30;   /* GroupByAndAggregate.cpp:57 */
 
-Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecutionOptions& eo,
-               size_t max_groups_buffer_entry_guess, bool has_cardinality_estimation) {
-  if (u.num_join_quals || u.has_estimator || u.has_union_all || u.has_window_function)
-    fail(B2Q_ERR_UNSUPPORTED, "joins / estimator / union / window functions are outside this path");
+Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecutionOptions& eo,
+                      size_t max_groups_buffer_entry_guess, bool has_cardinality_estimation) {
+  if (u.has_estimator || u.has_union_all || u.has_window_function)
+    fail(B2Q_ERR_UNSUPPORTED, "estimator / union / window functions are outside this path");
   if (u.num_order_entries < 0 || u.num_order_entries > 8) fail(B2Q_ERR_UNSUPPORTED, "more ORDER BY entries than the path carries");
   for (int i = 0; i < u.num_order_entries; ++i)
     if (u.order_entries[i].tle_no < 1 || u.order_entries[i].tle_no > u.num_target_exprs) fail(B2Q_ERR_INVALID_ARGUMENT, "order entry refers to a target that does not exist");
@@ -876,7 +893,149 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
     o.skip_null_val = t.skip_null_val; o.is_distinct = 0; o.arg_col_id = t.arg_col; o.first_slot = t.first_slot;
   }
   p.kernel = 0;
+  p.join_outer_col = p.join_inner_col = -1;
   return plan;
+}
+
+/* ---- one INNER hash-join level -------------------------------------------------------------------------------
+ * The unit is rewritten over a combined table: columns [0, n_outer) are the outer table's, [n_outer, n_outer +
+ * n_inner) the inner table's (ColumnVar rte_idx 1); every fragment of the combined table pairs one outer fragment
+ * with the (single, concatenated) inner fragment. */
+struct JoinedInput {
+  bool active{false};
+  std::vector<B2QExpr> exprs;
+  B2QExecUnit u{};
+  std::vector<B2QTypeInfo> col_types;
+  std::vector<int8_t> enc;
+  std::vector<std::vector<const void*>> bufs;
+  std::vector<std::vector<B2QChunkStats>> stats;
+  std::vector<B2QFragmentInfo> frags;
+  B2QTableInfo t{};
+  int n_outer{0};
+  int outer_col{-1}, inner_vcol{-1};
+};
+
+void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, JoinedInput& ji) {
+  if (u.num_join_quals != 1) fail(B2Q_ERR_UNSUPPORTED, "more than one join level is outside this path");
+  if (u.join_type != 0) fail(B2Q_ERR_UNSUPPORTED, "only INNER joins are on this path");
+  if (!u.inner_table) fail(B2Q_ERR_INVALID_ARGUMENT, "join without an inner table");
+  const B2QTableInfo& inner = *u.inner_table;
+  if (inner.num_fragments > 1) fail(B2Q_ERR_INVALID_ARGUMENT, "the inner table must come as one concatenated fragment (getAllTableColumnFragments)");
+  if (inner.deleted_column_plus1) fail(B2Q_ERR_UNSUPPORTED, "inner table with a deleted-rows column");
+  if (inner.memory_level != B2Q_CPU_LEVEL) fail(B2Q_ERR_INVALID_ARGUMENT, "oracle needs host column buffers");
+  ji.active = true;
+  ji.n_outer = outer.num_cols;
+  const int n_inner = inner.num_cols;
+  ji.exprs.assign(u.exprs, u.exprs + u.num_exprs);
+  for (auto& e : ji.exprs) {
+    if (e.kind != B2Q_EXPR_COLUMN_VAR) continue;
+    if (e.rte_idx == 1) {
+      if (e.col_id < 0 || e.col_id >= n_inner) fail(B2Q_ERR_INVALID_ARGUMENT, "inner column id out of range");
+      e.col_id += ji.n_outer;
+      e.rte_idx = 0;
+    } else if (e.rte_idx != 0) fail(B2Q_ERR_UNSUPPORTED, "rte_idx beyond one join level");
+  }
+  ji.u = u;
+  ji.u.exprs = ji.exprs.data();
+  ji.u.num_join_quals = 0;
+  ji.u.inner_table = nullptr;
+  /* the qual: ColumnVar = ColumnVar, one side per table (normalizeColumnPairs, HashJoin.cpp) */
+  const B2QExpr& q = expr_at(ji.u, u.join_qual);
+  if (q.kind != B2Q_EXPR_BIN_OPER || q.op != B2Q_kEQ) fail(B2Q_ERR_UNSUPPORTED, "join qual must be an equality");
+  const B2QExpr& a = expr_at(ji.u, q.left);
+  const B2QExpr& b = expr_at(ji.u, q.right);
+  if (a.kind != B2Q_EXPR_COLUMN_VAR || b.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "join qual must compare two ColumnVars");
+  const bool a_inner = a.col_id >= ji.n_outer, b_inner = b.col_id >= ji.n_outer;
+  if (a_inner == b_inner) fail(B2Q_ERR_UNSUPPORTED, "join qual must compare an outer with an inner column");
+  ji.outer_col = a_inner ? b.col_id : a.col_id;
+  ji.inner_vcol = a_inner ? a.col_id : b.col_id;
+  /* combined table */
+  ji.col_types.assign(outer.col_types, outer.col_types + outer.num_cols);
+  ji.col_types.insert(ji.col_types.end(), inner.col_types, inner.col_types + n_inner);
+  ji.enc.assign(ji.col_types.size(), 0);
+  for (int c = 0; c < outer.num_cols; ++c) if (outer.col_encoded_sizes) ji.enc[c] = outer.col_encoded_sizes[c];
+  for (int c = 0; c < n_inner; ++c) if (inner.col_encoded_sizes) ji.enc[ji.n_outer + c] = inner.col_encoded_sizes[c];
+  const B2QFragmentInfo* inf = inner.num_fragments ? &inner.fragments[0] : nullptr;
+  ji.bufs.resize(outer.num_fragments);
+  ji.stats.resize(outer.num_fragments);
+  ji.frags.resize(outer.num_fragments);
+  for (int f = 0; f < outer.num_fragments; ++f) {
+    const B2QFragmentInfo& of = outer.fragments[f];
+    ji.bufs[f].assign(of.col_buffers, of.col_buffers + outer.num_cols);
+    ji.stats[f].assign(of.col_stats, of.col_stats + outer.num_cols);
+    for (int c = 0; c < n_inner; ++c) {
+      ji.bufs[f].push_back(inf ? inf->col_buffers[c] : nullptr);
+      B2QChunkStats empty{};
+      empty.int_min = INT64_MAX; empty.int_max = INT64_MIN; empty.fp_min = DBL_MAX; empty.fp_max = -DBL_MAX;
+      ji.stats[f].push_back(inf ? inf->col_stats[c] : empty);
+    }
+    ji.frags[f] = of;
+    ji.frags[f].col_buffers = ji.bufs[f].data();
+    ji.frags[f].col_stats = ji.stats[f].data();
+  }
+  ji.t = outer;
+  ji.t.num_cols = static_cast<int32_t>(ji.col_types.size());
+  ji.t.col_types = ji.col_types.data();
+  ji.t.col_encoded_sizes = ji.enc.data();
+  ji.t.fragments = ji.frags.data();
+}
+
+/* PerfectJoinHashTable::getInstance (JoinHashTable/PerfectJoinHashTable.cpp:168-300): the table spans the INNER
+ * column's range; too sparse a range switches the reference to a baseline join table, outside this path. */
+Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecutionOptions& eo,
+               size_t max_groups_buffer_entry_guess, bool has_cardinality_estimation, JoinedInput* ji_out = nullptr) {
+  if (!u.num_join_quals) return make_plan_single(u, tbl, eo, max_groups_buffer_entry_guess, has_cardinality_estimation);
+  JoinedInput local;
+  JoinedInput& ji = ji_out ? *ji_out : local;
+  build_joined_input(u, tbl, ji);
+  const Ti oti = ti_of(ji.t.col_types[ji.outer_col]), iti = ti_of(ji.t.col_types[ji.inner_vcol]);
+  if (!is_integer(oti.type) || !is_integer(iti.type) || is_string(oti.type) || is_string(iti.type))
+    fail(B2Q_ERR_UNSUPPORTED, "join keys must be integer columns (dictionary translation is outside this path)");
+  Plan plan = make_plan_single(ji.u, ji.t, eo, max_groups_buffer_entry_guess, has_cardinality_estimation);
+  const B2QTableInfo& inner = *u.inner_table;
+  Range r; /* getExpressionRange(inner_col): over the inner table alone */
+  {
+    B2QTableInfo it = inner;
+    r = leaf_column_range(it, ji.inner_vcol - ji.n_outer);
+  }
+  if (r.kind != Range::Integer) fail(B2Q_ERR_UNSUPPORTED, "could not compute the range of the join column (HashJoinFail)");
+  int64_t entries = 0;
+  if (r.imin <= r.imax && (__builtin_sub_overflow(r.imax, r.imin, &entries) || __builtin_add_overflow(entries, int64_t(1), &entries) || entries > INT32_MAX))
+    fail(B2Q_ERR_UNSUPPORTED, "too many hash entries for a perfect join table (TooManyHashEntries)");
+  const int64_t inner_rows = inner.num_fragments ? inner.fragments[0].num_tuples : 0;
+  /* deploy_baseline_join (:235-246): g_ratio_num_hash_entry_to_num_tuple_switch_to_baseline = 100 (Execute.cpp:104) */
+  if (inner_rows * 100 < entries) fail(B2Q_ERR_UNSUPPORTED, "join column range too wide for its row count: the reference switches to a baseline join table");
+  plan.join = true;
+  plan.join_outer_col = ji.outer_col;
+  plan.join_inner_vcol = ji.inner_vcol;
+  plan.join_outer_nullable = !oti.notnull;
+  plan.p.join_min_key = r.imin;
+  plan.p.join_max_key = r.imax;
+  plan.p.join_entry_count = entries;
+  plan.p.join_outer_col = ji.outer_col;
+  plan.p.join_inner_col = ji.inner_vcol - ji.n_outer;
+  return plan;
+}
+
+/* fill_hash_join_buff (JoinHashTable/Runtime/HashJoinRuntime.cpp:120-216, one-to-one): slot[key - min] = inner row,
+ * NULL keys are skipped, a second row for a slot means the join is not one-to-one (NeedsOneToManyHash) */
+void build_join_table(Plan& plan, const JoinedInput& ji, const B2QTableInfo& inner) {
+  auto buff = std::make_shared<std::vector<int32_t>>(static_cast<size_t>(plan.p.join_entry_count), -1);
+  if (inner.num_fragments && plan.p.join_entry_count > 0) {
+    const B2QFragmentInfo& fr = inner.fragments[0];
+    const int c = ji.inner_vcol - ji.n_outer;
+    const int ctype = inner.col_types[c].type;
+    const bool nullable = !inner.col_types[c].notnull;
+    for (int64_t row = 0; row < fr.num_tuples; ++row) {
+      const int64_t key = decode_int_column(inner, fr, c, row);
+      if (nullable && key == inline_int_null_val(ctype)) continue;
+      if (key < plan.p.join_min_key || key > plan.p.join_max_key) fail(B2Q_ERR_KEY_OUT_OF_RANGE, "inner join key outside its chunk-stats range");
+      int32_t& slot = (*buff)[static_cast<size_t>(key - plan.p.join_min_key)];
+      if (slot != -1) fail(B2Q_ERR_UNSUPPORTED, "join is not one-to-one (the reference rebuilds a one-to-many table)");
+      slot = static_cast<int32_t>(row);
+    }
+  }
+  plan.join_buff = buff;
 }
 
 /* ===================================================================================================
@@ -903,7 +1062,7 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
       if (o.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "IS NULL operand must be a ColumnVar");
       const int ctype = tbl.col_types[o.col_id].type;
       if (tbl.col_types[o.col_id].notnull) return 0; /* inferred non-null: short-circuit to false */
-      if (is_fp(ctype)) return fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[o.col_id]), pos) == kNullDouble;
+      if (is_fp(ctype)) return fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[o.col_id]), row_pos_of(o.col_id, pos)) == kNullDouble;
       return decode_int_column(tbl, fr, o.col_id, pos) == inline_int_null_val(ctype);
     }
     fail(B2Q_ERR_UNSUPPORTED, "unary operator outside NOT / IS NULL");
@@ -939,7 +1098,7 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
     /* fp compare: the integer side is cast to double (CompareIR.cpp codegenCmp after normalisation) */
     double lv;
     bool lnull;
-    if (is_fp(ctype)) { lv = fixed_width_double_decode(buf, pos); lnull = !col_notnull && lv == kNullDouble; }
+    if (is_fp(ctype)) { lv = fixed_width_double_decode(buf, row_pos_of(col, pos)); lnull = !col_notnull && lv == kNullDouble; }
     else { const int64_t iv = decode_int_column(tbl, fr, col, pos); lnull = !col_notnull && iv == inline_int_null_val(ctype); lv = static_cast<double>(iv); }
     if (lnull) return kNullBool;
     const double rv = is_fp(r.ti.type) ? r.dval : static_cast<double>(r.ival);
@@ -1006,7 +1165,7 @@ void update_target(const Plan& plan, const Target& t, int8_t* out, int64_t entry
   int64_t* a = reinterpret_cast<int64_t*>(slot);
   if (!t.is_agg) { /* agg_id on the projected group key, sign-extended to the slot */
     const int ctype = tbl.col_types[t.arg_col].type;
-    if (is_fp(ctype)) agg_id(a, bits_of(fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[t.arg_col]), pos)));
+    if (is_fp(ctype)) agg_id(a, bits_of(fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[t.arg_col]), row_pos_of(t.arg_col, pos))));
     else agg_id(a, decode_int_column(tbl, fr, t.arg_col, pos));
     return;
   }
@@ -1016,7 +1175,7 @@ void update_target(const Plan& plan, const Target& t, int8_t* out, int64_t entry
   const int8_t* buf = static_cast<const int8_t*>(fr.col_buffers[t.arg_col]);
   const bool need_skip_null = t.skip_null_val;
   if (is_fp(ctype)) {
-    const double v = fixed_width_double_decode(buf, pos);
+    const double v = fixed_width_double_decode(buf, row_pos_of(t.arg_col, pos));
     const double null_v = kNullDouble; /* arg null == agg null for DOUBLE: no conversion needed */
     switch (t.agg_kind) {
       case B2Q_kCOUNT: if (need_skip_null) agg_count_double_skip_val(a, v, null_v); else agg_count(a); break;
@@ -1089,7 +1248,23 @@ int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo&
   const int key_type = key_col >= 0 ? tbl.col_types[key_col].type : 0;
   const bool key_nullable = key_col >= 0 && !tbl.col_types[key_col].notnull;
   const uint32_t row_size_quad = static_cast<uint32_t>(p.row_size / 8);
+  struct JoinScope { /* the inner-row iterator of this thread's row loop */
+    explicit JoinScope(int n_outer) { g_join_row.n_outer = n_outer; }
+    ~JoinScope() { g_join_row = JoinRowCtx{}; }
+  } join_scope(plan.join ? plan.join_inner_vcol - p.join_inner_col : INT32_MAX);
+  const int32_t* join_buff = plan.join && plan.join_buff ? plan.join_buff->data() : nullptr;
+  const int64_t join_null = plan.join ? inline_int_null_val(tbl.col_types[plan.join_outer_col].type) : 0;
   for (int64_t pos = 0; pos < fr.num_tuples; ++pos) {
+    if (plan.join) {
+      /* deleted outer rows never reach the join loop (codegenSkipDeletedOuterTableRow precedes it) */
+      if (g_filter_deleted && tbl.deleted_column_plus1 > 0 && static_cast<const int8_t*>(fr.col_buffers[tbl.deleted_column_plus1 - 1])[pos] > 0) continue;
+      /* hash_join_idx[_nullable] (GroupByRuntime.cpp:283-311): NULL never matches, keys outside [min, max] miss */
+      const int64_t key = decode_int_column(tbl, fr, plan.join_outer_col, pos);
+      int64_t idx = -1;
+      if (!(plan.join_outer_nullable && key == join_null) && key >= p.join_min_key && key <= p.join_max_key) idx = join_buff[key - p.join_min_key];
+      if (idx < 0) continue; /* INNER join: no match, no row */
+      g_join_row.inner_pos = idx;
+    }
     if (!row_passes(u, tbl, fr, pos)) continue;
     int64_t entry = 0;
     if (p.query_desc_type != B2Q_NonGroupedAggregate) {
@@ -1378,9 +1553,16 @@ ORACLE_EXPORT int32_t oracle_execute(const B2QExecUnit* u, const B2QTableInfo* t
                                      size_t entry_guess, int32_t has_cardinality_estimation, int32_t num_threads,
                                      OracleResult** out) {
   try {
-    auto res = new OracleResult();
-    res->plan = make_plan(*u, *tbl, *eo, entry_guess, has_cardinality_estimation != 0);
+    std::unique_ptr<OracleResult> holder(new OracleResult());
+    OracleResult* res = holder.get();
+    JoinedInput ji;
+    res->plan = make_plan(*u, *tbl, *eo, entry_guess, has_cardinality_estimation != 0, &ji);
     if (tbl->memory_level != B2Q_CPU_LEVEL) fail(B2Q_ERR_INVALID_ARGUMENT, "oracle needs host column buffers");
+    if (ji.active) { /* from here on the unit / table are the combined ones */
+      build_join_table(res->plan, ji, *u->inner_table);
+      u = &ji.u;
+      tbl = &ji.t;
+    }
     const int nf = tbl->num_fragments;
     std::vector<std::vector<int8_t>> bufs(std::max(nf, 1));
     std::vector<int32_t> errs(std::max(nf, 1), 0);
@@ -1403,10 +1585,10 @@ ORACLE_EXPORT int32_t oracle_execute(const B2QExecUnit* u, const B2QTableInfo* t
       for (int t = 0; t < nt; ++t) ths.emplace_back(work, t);
       for (auto& t : ths) t.join();
     }
-    for (int f = 0; f < nf; ++f) if (errs[f]) { g_last_error = msgs[f]; int32_t c = errs[f]; delete res; return c; }
+    for (int f = 0; f < nf; ++f) if (errs[f]) { g_last_error = msgs[f]; return errs[f]; }
     for (int f = 1; f < nf; ++f) {
       int32_t rc = reduce_buffers(res->plan, bufs[0], bufs[f]);
-      if (rc) { delete res; return rc; }
+      if (rc) return rc;
       std::vector<int8_t>().swap(bufs[f]);
     }
     res->buf = std::move(bufs[0]);
@@ -1416,7 +1598,7 @@ ORACLE_EXPORT int32_t oracle_execute(const B2QExecUnit* u, const B2QTableInfo* t
       res->drop_first = static_cast<size_t>(u->offset);
       if (u->has_limit) res->keep_first = static_cast<size_t>(u->limit);
     }
-    *out = res;
+    *out = holder.release();
     return 0;
   } catch (const OracleError& e) {
     g_last_error = e.msg;

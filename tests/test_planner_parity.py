@@ -60,10 +60,10 @@ def test_cardinality_estimation_required(table):
 
 
 def test_unsupported_is_rejected_not_ignored(table):
-    for field in ("num_join_quals", "has_estimator", "has_union_all", "has_window_function"):
+    for field, val in (("num_join_quals", 2), ("has_estimator", 1), ("has_union_all", 1), ("has_window_function", 1)):
         b = abi.UnitBuilder(table)
         b.target(b.agg(abi.kCOUNT))
-        b.unsupported[field] = 1
+        b.unsupported[field] = val
         with pytest.raises(executor.UnsupportedOnThisPath):
             executor.Executor().plan(b.build(), table)
     co = executor.compilation_options(device_type=abi.DEVICE_CPU)   # no CPU execution on this path
