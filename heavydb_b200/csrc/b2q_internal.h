@@ -112,7 +112,10 @@ struct DevJoin {
   int32_t fk_col;       /* launch column of the outer key, -1: no join */
   int8_t fk_width;      /* width code of the outer key column */
   int8_t nullable;      /* hash_join_idx_nullable: a NULL outer key never matches */
-  int8_t pad_[2];
+  int8_t packed_col;    /* >= 0: the table is {int32 row, int32 value-of-this-inner-launch-column} per slot, so the probe
+                           and the gather of that column are ONE 8-byte load (random 4-byte gathers are bound by L1 tag
+                           throughput, ~1 sector/clk/SM: two dependent gathers per row cost twice the scan itself) */
+  int8_t packed_width;  /* width code of that column in the inner table */
 };
 
 struct DevProgram {

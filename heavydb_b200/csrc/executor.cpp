@@ -35,7 +35,8 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
                         int prefetch_distance, cudaStream_t st);
 cudaError_t launch_init(const B2QQuery& q, int64_t* const* accs, int64_t* keys, int8_t* smem_image, cudaStream_t st);
 cudaError_t launch_join_build(const int8_t* keys, int width, int64_t n_rows, int64_t min_key, int64_t entry_count, int nullable,
-                              int64_t null_val, int32_t* buff, int32_t* error, cudaStream_t st);
+                              int64_t null_val, int32_t* buff, int32_t* error, const int8_t* packed_vals, int packed_width,
+                              cudaStream_t st);
 cudaError_t launch_materialize(const B2QQuery& q, const int64_t* const* accs, const int64_t* keys, int8_t* out,
                                cudaStream_t st);
 cudaError_t launch_join_split(const int64_t* split, int64_t* out, int64_t n, cudaStream_t st);
@@ -502,12 +503,14 @@ static int32_t prepare_join(B2QPartial& p, const B2QExecUnit& u, cudaStream_t st
   int32_t rc = device_col(q.join_inner_key_col, &d_key);
   if (rc != B2Q_OK) return rc;
   int32_t* buff = nullptr;
-  CU(cudaMallocAsync(reinterpret_cast<void**>(&buff), static_cast<size_t>(std::max<int64_t>(q.plan.join_entry_count, 1)) * 4, st));
+  const int pc = q.prog.join.packed_col; /* slots {row, value of that inner column}: see DevJoin */
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&buff), static_cast<size_t>(std::max<int64_t>(q.plan.join_entry_count, 1)) * (pc >= 0 ? 8 : 4), st));
   p.extra.push_back(buff);
   const B2QTypeInfo kt = inner.col_types[q.join_inner_key_col];
   const int kw = phys_bytes(q.join_inner_key_col);
   const int64_t knull = kw == 1 ? INT8_MIN : kw == 2 ? INT16_MIN : kw == 4 ? INT32_MIN : INT64_MIN;
-  CU(launch_join_build(d_key, kw, rows, q.plan.join_min_key, q.plan.join_entry_count, kt.notnull ? 0 : 1, knull, buff, p.d_error, st));
+  CU(launch_join_build(d_key, kw, rows, q.plan.join_min_key, q.plan.join_entry_count, kt.notnull ? 0 : 1, knull, buff, p.d_error,
+                       pc >= 0 ? p.inner_cols[pc] : nullptr, q.prog.join.packed_width, st));
   p.launches += 1;
   p.join_buff = buff;
   return B2Q_OK;
@@ -871,7 +874,10 @@ int32_t b2q_launch(const B2QQuery* query, const B2QParams* prm, void* stream) {
   if (rc != B2Q_OK) return rc;
   /* with a join level col_buffers[frag] holds the scanned table's columns followed by the inner table's (the same
    * device pointers in every fragment), and JOIN_HASH_TABLES[0] is the built one-to-one table */
-  if (has_join) p.join_buff = reinterpret_cast<const int32_t*>(static_cast<intptr_t>(prm->join_hash_tables[0]));
+  if (has_join) {
+    p.join_buff = reinterpret_cast<const int32_t*>(static_cast<intptr_t>(prm->join_hash_tables[0]));
+    p.q.prog.join.packed_col = -1; /* the caller's table is the reference's plain int32 layout */
+  }
   std::vector<const int8_t*> cols(static_cast<size_t>(nf) * nc);
   std::vector<int64_t> rows(nf);
   for (int f = 0; f < nf; ++f) {

@@ -107,7 +107,7 @@ __device__ __forceinline__ int32_t ldg_u8(const int8_t* p, uint32_t pred, uint64
  * compile-time nullptr in the kernels without a join level, so the branch disappears there. */
 template <bool PRED>
 __device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict__ base, int64_t row0, int stride, uint32_t mask, uint64_t pol,
-                                       const int32_t* jidx = nullptr) {
+                                       const int32_t* jidx = nullptr, const int32_t* /* jval: only 1/2/4-byte columns are packed */ = nullptr) {
   if (jidx) {
 #pragma unroll
     for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? __ldg(reinterpret_cast<const long long*>(base) + jidx[j]) : 0;
@@ -121,7 +121,12 @@ __device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict
 /* R rows of a 1/2/4-byte integer column, sign-extended to 32 bits (width -1 / -2: zero-extended) */
 template <bool PRED>
 __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0, int stride, uint32_t mask, uint64_t pol,
-                                       const int32_t* jidx = nullptr) {
+                                       const int32_t* jidx = nullptr, const int32_t* jval = nullptr) {
+  if (jval) { /* the column that rides in the packed join table: already in registers since the probe */
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? jval[j] : 0;
+    return;
+  }
   if (jidx) {
 #pragma unroll
     for (int j = 0; j < R; ++j) {
@@ -173,7 +178,8 @@ __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict
  * ------------------------------------------------------------------------------------------------------- */
 template <bool FULL>
 __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* const* __restrict__ cols, int64_t row0,
-                                              int stride, uint32_t valid, uint64_t pol, const int32_t* jidx = nullptr) {
+                                              int stride, uint32_t valid, uint64_t pol, const int32_t* jidx = nullptr,
+                                              const int32_t* jval = nullptr) {
   uint32_t m = 0;
   const bool neg = t.negate;
   if (!t.cmp_fp) {
@@ -196,7 +202,7 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
       }
     } else {
       int32_t v[R];
-      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol, jidx);
+      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol, jidx, jval);
       const uint32_t lo = (uint32_t)t.lo, span = (uint32_t)t.span;
 #pragma unroll
       for (int j = 0; j < R; ++j) m |= (uint32_t)(((uint32_t)v[j] - lo <= span) != neg) << j;
@@ -224,7 +230,7 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
       for (int j = 0; j < R; ++j) { d[j] = (double)v[j]; isnull |= (uint32_t)(v[j] == nullv) << j; }
     } else {
       int32_t v[R];
-      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol, jidx);
+      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol, jidx, jval);
       const int32_t nullv = (int32_t)t.null_bits;
 #pragma unroll
       for (int j = 0; j < R; ++j) { d[j] = (double)v[j]; isnull |= (uint32_t)(v[j] == nullv) << j; }
@@ -239,8 +245,9 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
 template <bool FULL, bool JOIN>
 __device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t* const* __restrict__ cols,
                                                 int64_t row0, int stride, uint32_t valid, uint64_t pol,
-                                                const int8_t* __restrict__ col_inner, const int32_t* jidx) {
-#define B2Q_TERM_JX(t) ((JOIN && col_inner[(t).col]) ? jidx : nullptr)
+                                                const int8_t* __restrict__ col_inner, const int32_t* jidx, int packed_col,
+                                                const int32_t* jval) {
+#define B2Q_TERM_JX(t) ((JOIN && col_inner[(t).col]) ? jidx : nullptr), ((JOIN && (t).col == packed_col) ? jval : nullptr)
   if (f.n_ops == 0) return valid;
   if (f.n_ops == 1) return eval_term<FULL>(f.terms[0], cols, row0, stride, valid, pol, B2Q_TERM_JX(f.terms[0]));
   uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -485,10 +492,12 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
    * (hash_join_idx[_nullable], GroupByRuntime.cpp:283-311; INNER join).  Columns of the inner table are then read at
    * jidx[] — see load32 / load64. ---- */
   int32_t jidx[JOIN ? R : 1];
-#define JX(c) ((JOIN && P.col_inner[c]) ? jidx : nullptr)
+  int32_t jval[JOIN ? R : 1]; /* value of the inner column that is packed into the join table (DevJoin::packed_col) */
+#define JX(c) ((JOIN && P.col_inner[c]) ? jidx : nullptr), ((JOIN && (c) == P.join.packed_col) ? jval : nullptr)
   if (JOIN) {
     const DevJoin& J = P.join;
     const int32_t* __restrict__ buff = Lh.join_buff;
+    const bool packed = J.packed_col >= 0;
     uint32_t matched = 0;
     if (J.fk_width == 8) {
       int64_t k[R];
@@ -497,8 +506,13 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       for (int j = 0; j < R; ++j) {
         const uint64_t d = (uint64_t)(k[j] - J.min_key);
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && k[j] == J.null_val);
-        const int32_t idx = ok ? __ldg(buff + d) : -1;
+        int32_t idx = -1, val = 0;
+        if (ok) {
+          if (packed) { const int2 e2 = __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.y; }
+          else idx = __ldg(buff + d);
+        }
         jidx[JOIN ? j : 0] = idx;
+        jval[JOIN ? j : 0] = val;
         matched |= (uint32_t)(idx >= 0) << j;
       }
     } else {
@@ -508,8 +522,13 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       for (int j = 0; j < R; ++j) {
         const uint64_t d = (uint64_t)((int64_t)k[j] - J.min_key);
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && (int64_t)k[j] == J.null_val);
-        const int32_t idx = ok ? __ldg(buff + d) : -1;
+        int32_t idx = -1, val = 0;
+        if (ok) {
+          if (packed) { const int2 e2 = __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.y; }
+          else idx = __ldg(buff + d);
+        }
         jidx[JOIN ? j : 0] = idx;
+        jval[JOIN ? j : 0] = val;
         matched |= (uint32_t)(idx >= 0) << j;
       }
     }
@@ -526,7 +545,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, valid, pol, JX(P.key.col));
   }
 
-  uint32_t pass = eval_filter<FULL, JOIN>(P.filter, cols, row0, nthr, valid, pol, P.col_inner, jidx);
+  uint32_t pass = eval_filter<FULL, JOIN>(P.filter, cols, row0, nthr, valid, pol, P.col_inner, jidx, P.join.packed_col, jval);
 
   if (has_key && !eager_key) {
     if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, pass, pol, JX(P.key.col));
@@ -1028,7 +1047,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) b2q_k_scan(const __grid_c
  * not one-to-one (the reference then rebuilds a one-to-many table — outside this path)
  * ------------------------------------------------------------------------------------------------------- */
 __global__ void b2q_k_join_build(const int8_t* __restrict__ keys, int width, int64_t n_rows, int64_t min_key, int64_t entry_count,
-                                 int nullable, int64_t null_val, int32_t* __restrict__ buff, int32_t* __restrict__ error) {
+                                 int nullable, int64_t null_val, int32_t* __restrict__ buff, int32_t* __restrict__ error,
+                                 const int8_t* __restrict__ packed_vals, int packed_width) {
+  /* packed_vals != nullptr: slots are {int32 row, int32 value}; the value of the winning row is written by the thread
+   * that claimed the slot (one winner per slot, so no race) */
+  const int slot_words = packed_vals ? 2 : 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += stride) {
     int64_t k;
@@ -1041,7 +1064,18 @@ __global__ void b2q_k_join_build(const int8_t* __restrict__ keys, int width, int
     if (nullable && k == null_val) continue;
     const uint64_t d = (uint64_t)(k - min_key);
     if (d >= (uint64_t)entry_count) { atomicCAS(error, 0, B2Q_ERR_KEY_OUT_OF_RANGE); continue; }
-    if (atomicCAS(buff + d, -1, (int32_t)row) != -1) atomicCAS(error, 0, B2Q_ERR_UNSUPPORTED);
+    if (atomicCAS(buff + d * slot_words, -1, (int32_t)row) != -1) { atomicCAS(error, 0, B2Q_ERR_UNSUPPORTED); continue; }
+    if (packed_vals) {
+      int32_t v;
+      switch (packed_width) {
+        case 4: v = reinterpret_cast<const int32_t*>(packed_vals)[row]; break;
+        case 2: v = reinterpret_cast<const int16_t*>(packed_vals)[row]; break;
+        case -2: v = reinterpret_cast<const uint16_t*>(packed_vals)[row]; break;
+        case -1: v = reinterpret_cast<const uint8_t*>(packed_vals)[row]; break;
+        default: v = reinterpret_cast<const signed char*>(packed_vals)[row]; break;
+      }
+      buff[d * 2 + 1] = v;
+    }
   }
 }
 
@@ -1309,9 +1343,10 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
 }
 
 cudaError_t launch_join_build(const int8_t* keys, int width, int64_t n_rows, int64_t min_key, int64_t entry_count, int nullable,
-                              int64_t null_val, int32_t* buff, int32_t* error, cudaStream_t st) {
+                              int64_t null_val, int32_t* buff, int32_t* error, const int8_t* packed_vals, int packed_width,
+                              cudaStream_t st) {
   if (entry_count > 0) {
-    cudaError_t e = cudaMemsetAsync(buff, 0xFF, (size_t)entry_count * 4, st); /* init_hash_join_buff: every slot -1 */
+    cudaError_t e = cudaMemsetAsync(buff, 0xFF, (size_t)entry_count * (packed_vals ? 8 : 4), st); /* init_hash_join_buff: every slot -1 */
     if (e != cudaSuccess) return e;
   }
   if (n_rows <= 0 || entry_count <= 0) return cudaSuccess;
@@ -1319,7 +1354,7 @@ cudaError_t launch_join_build(const int8_t* keys, int width, int64_t n_rows, int
   int64_t blocks = (n_rows + block - 1) / block;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  b2q_k_join_build<<<(int)blocks, block, 0, st>>>(keys, width, n_rows, min_key, entry_count, nullable, null_val, buff, error);
+  b2q_k_join_build<<<(int)blocks, block, 0, st>>>(keys, width, n_rows, min_key, entry_count, nullable, null_val, buff, error, packed_vals, packed_width);
   return cudaGetLastError();
 }
 

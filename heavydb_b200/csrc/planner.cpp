@@ -17,6 +17,7 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -981,6 +982,16 @@ class Planner {
     if (g.eager_args)
       for (int a = 0; a < g.n_accs; ++a) if (g.accs[a].col >= 0) g.col_prefetch[g.accs[a].col] = 1;
     if (join_) g.col_prefetch[g.join.fk_col] = 1;
+    g.join.packed_col = -1;
+    if (join_) { /* the first 1/2/4-byte inner column the program reads rides in the join table itself */
+      static const bool pack = []() { const char* e = getenv("B2Q_JOIN_PACK"); return !e || atoi(e) != 0; }();
+      for (int c = 0; c < g.n_cols && pack; ++c)
+        if (g.col_inner[c] && g.col_width[c] <= 4) {
+          g.join.packed_col = static_cast<int8_t>(c);
+          g.join.packed_width = static_cast<int8_t>(phys_width_code(q.col_ids[c]));
+          break;
+        }
+    }
     for (int c = 0; c < g.n_cols; ++c) if (g.col_inner[c]) g.col_prefetch[c] = 0; /* gathered by join index, not streamed */
     /* fused fast path of the shared-memory-table kernel (the reference's JIT specialises per query; this is the
      * static-kernel equivalent for the most common shape: GROUP BY k with COUNT(*) and/or one integer SUM) */
