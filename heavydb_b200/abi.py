@@ -472,6 +472,7 @@ class Fragment:
     stats: List[ChunkStats] = field(default_factory=list)
     fragment_id: int = 0
     device_id: int = 0
+    remote: bool = False   # lives on another device / rank: only its chunk stats are passed (col_buffers = NULL)
 
 
 class Table:
@@ -531,6 +532,13 @@ class Table:
                                        fragment_id=fid, device_id=device_id))
         return self
 
+    def add_remote_fragment(self, num_tuples: int, stats: Sequence[ChunkStats], fragment_id: int, device_id: int = 0):
+        """A fragment that another device / rank scans: it contributes its chunk statistics to planning (so that every
+        device derives the same key ranges and the partial tables are position-aligned) and nothing else."""
+        self.fragments.append(Fragment(int(num_tuples), stats=list(stats), fragment_id=fragment_id, device_id=device_id,
+                                       remote=True))
+        return self
+
     def total_tuples(self):
         return sum(f.num_tuples for f in self.fragments)
 
@@ -560,7 +568,7 @@ class BuiltTable:
             self._keep += [bufs, stats]
             fi = self.frags[i]
             fi.fragment_id, fi.device_id, fi.num_tuples = f.fragment_id, f.device_id, f.num_tuples
-            fi.col_buffers, fi.col_stats = bufs, stats
+            fi.col_buffers, fi.col_stats = (None if f.remote else bufs), stats
         ti = TableInfo()
         ti.num_cols, ti.col_types = nc, self.col_types
         ti.num_fragments, ti.fragments = nf, self.frags

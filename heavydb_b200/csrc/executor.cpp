@@ -417,6 +417,7 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
  * the simple quals (`col OP const`, AND-ed) is never scanned — and, for host-resident tables, never copied. */
 static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr, bool filter_deleted) {
   if (fr.num_tuples == 0) return true;
+  if (!fr.col_buffers) return true; /* a fragment of another device: passed for its chunk stats only (see b2q.h) */
   /* isFragmentFullyDeleted (Execute.cpp:4740-4774): the $deleted$ chunk holds only `true` */
   if (filter_deleted && tbl.deleted_column_plus1 > 0 && fr.col_stats[tbl.deleted_column_plus1 - 1].int_min >= 1 &&
       fr.col_stats[tbl.deleted_column_plus1 - 1].int_max >= fr.col_stats[tbl.deleted_column_plus1 - 1].int_min) return true;

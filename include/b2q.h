@@ -185,7 +185,10 @@ typedef struct B2QFragmentInfo {
   int32_t fragment_id;
   int32_t device_id;                /* reference rule: fragment_id % num_devices (InsertOrderFragmenter.cpp:435) */
   int64_t num_tuples;
-  const void* const* col_buffers;   /* [num_cols]; flat fixed-width arrays; NULL for unreferenced columns */
+  const void* const* col_buffers;   /* [num_cols]; flat fixed-width arrays; NULL for unreferenced columns.  The whole
+                                       pointer may be NULL for a fragment that ANOTHER device scans: it then only
+                                       contributes its chunk stats to planning, so that every device of a multi-GPU
+                                       query derives the same key ranges (the reference plans once for all devices) */
   const B2QChunkStats* col_stats;   /* [num_cols] */
 } B2QFragmentInfo;
 

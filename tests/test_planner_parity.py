@@ -107,3 +107,23 @@ def test_baseline_config_plans(kind, sql, expect):
     assert got == want
     for k, v in expect.items():
         assert got[k] == v, (k, got[k], v)
+
+
+def test_remote_fragments_carry_stats_only():
+    """Multi-GPU: a device is handed its own fragments plus the OTHER devices' fragments as chunk stats (col_buffers =
+    NULL), so every device derives the plan of the whole table — position-aligned partial tables (include/b2q.h)."""
+    from test_gpu_parity import RAND_NAMES, random_table
+    table = random_table(4000, seed=2, frag_rows=500)      # 8 fragments with different per-fragment ranges
+    view = abi.Table(table.col_types)
+    for f in table.fragments:
+        if f.fragment_id % 2 == 0:
+            view.fragments.append(f)
+        else:
+            view.add_remote_fragment(f.num_tuples, f.stats, f.fragment_id)
+    for sql in ["SELECT k32, COUNT(*), SUM(a64) FROM r GROUP BY k32;", "SELECT k8, k16, MIN(d) FROM r WHERE nn32 < 100 GROUP BY k8, k16;"]:
+        unit = sqlmini.parse(sql, table, RAND_NAMES)
+        whole = executor.Executor().plan(unit, table).as_dict()
+        assert executor.Executor().plan(unit, view).as_dict() == whole
+        local_only = abi.Table(table.col_types)
+        local_only.fragments = [f for f in table.fragments if f.fragment_id % 2 == 0]
+        assert executor.Executor().plan(unit, local_only).as_dict()["buffer_size"] > 0   # plans, but not necessarily the same ranges
