@@ -77,7 +77,10 @@ static int prefetch_distance_for(const B2QQuery& q, const std::vector<const int8
     return e ? atoi(e) : -1;
   }();
   const bool smem_kernel = q.plan.kernel == B2Q_KERNEL_PERFECT_SMEM || q.plan.kernel == B2Q_KERNEL_NON_GROUPED;
-  const int dist = env >= 0 ? env : (smem_kernel ? 1 : 0);
+  /* the join kernels are bound by the L2 gathers of the probe: a prefetched stream only competes with them
+   * (c2join, 1e9 rows: 6.29 ms with D=1, 5.67 ms with D=0) */
+  const bool join_kernel = q.prog.join.fk_col >= 0;
+  const int dist = env >= 0 ? env : (smem_kernel && !join_kernel ? 1 : 0);
   if (dist <= 0) return 0;
   for (const int8_t* p : cols) if (reinterpret_cast<uintptr_t>(p) & 15) return 0;
   return dist;

@@ -1130,7 +1130,8 @@ static void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, 
   ji.frags.resize(nf);
   for (int f = 0; f < nf; ++f) {
     const B2QFragmentInfo& of = outer.fragments[f];
-    ji.bufs[f].assign(of.col_buffers, of.col_buffers + outer.num_cols);
+    if (of.col_buffers) ji.bufs[f].assign(of.col_buffers, of.col_buffers + outer.num_cols);
+    else ji.bufs[f].assign(static_cast<size_t>(outer.num_cols), nullptr); /* another device's fragment: chunk stats only */
     ji.stats[f].assign(of.col_stats, of.col_stats + outer.num_cols);
     for (int c = 0; c < inner.num_cols; ++c) {
       ji.bufs[f].push_back(nullptr); /* inner columns are resolved by the executor, not through the fragment */
@@ -1139,7 +1140,7 @@ static void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, 
       ji.stats[f].push_back(inf ? inf->col_stats[c] : empty);
     }
     ji.frags[f] = of;
-    ji.frags[f].col_buffers = ji.bufs[f].data();
+    ji.frags[f].col_buffers = of.col_buffers ? ji.bufs[f].data() : nullptr;
     ji.frags[f].col_stats = ji.stats[f].data();
   }
   ji.t = outer;
