@@ -62,8 +62,12 @@ struct RelAlgExecutionUnit { /* RelAlgExecutionUnit.h:166-216 */
   std::list<ExprRef> groupby_exprs; /* empty == the reference's {nullptr} (non-grouped) */
   std::vector<ExprRef> target_exprs;
   size_t scan_limit{0};
+  /* join_quals (JoinQualsPerNestingLevel): at most one INNER level whose only qual is outer.col = inner.col */
+  enum class JoinType { INNER = 0, LEFT = 1 };
+  struct JoinCondition { std::list<ExprRef> quals; JoinType type{JoinType::INNER}; };
+  std::vector<JoinCondition> join_quals;
   /* features outside this path: anything non-zero is rejected by the library */
-  int32_t num_join_quals{0}, has_estimator{0}, has_union_all{0}, has_window_function{0};
+  int32_t has_estimator{0}, has_union_all{0}, has_window_function{0};
   /* SortInfo (RelAlgExecutionUnit.h:117-156); Analyzer::OrderEntry == B2QOrderEntry{tle_no, is_desc, nulls_first} */
   struct SortInfo {
     std::list<B2QOrderEntry> order_entries;
@@ -71,9 +75,9 @@ struct RelAlgExecutionUnit { /* RelAlgExecutionUnit.h:166-216 */
     size_t offset{0};
   } sort_info;
 
-  ExprRef makeColumnVar(const SQLTypeInfo& ti, int32_t column_id) {
+  ExprRef makeColumnVar(const SQLTypeInfo& ti, int32_t column_id, int32_t rte_idx = 0) { /* Analyzer::ColumnVar(ti, column_key, rte_idx) */
     B2QExpr e{};
-    e.kind = B2Q_EXPR_COLUMN_VAR; e.ti = {ti.type, ti.notnull}; e.col_id = column_id; e.left = e.right = -1;
+    e.kind = B2Q_EXPR_COLUMN_VAR; e.ti = {ti.type, ti.notnull}; e.col_id = column_id; e.left = e.right = -1; e.rte_idx = rte_idx;
     exprs.push_back(e);
     return static_cast<ExprRef>(exprs.size() - 1);
   }
@@ -175,24 +179,34 @@ class Executor {
                                const std::vector<InputTableInfo>& query_infos, const RelAlgExecutionUnit& ra_exe_unit,
                                const CompilationOptions& co, const ExecutionOptions& options, RenderInfo* /*render_info*/,
                                const bool has_cardinality_estimation, ColumnCacheMap& /*column_cache*/) {
-    if (query_infos.size() != 1) throw QueryNotSupported(B2Q_ERR_UNSUPPORTED, "exactly one input table on this path");
-    const InputTableInfo& ti = query_infos.front();
+    const size_t n_tables = 1 + ra_exe_unit.join_quals.size();
+    if (query_infos.size() != n_tables || n_tables > 2) throw QueryNotSupported(B2Q_ERR_UNSUPPORTED, "one input table, or two with one join level, on this path");
     /* flatten to the POD structs of the C ABI */
-    std::vector<B2QTypeInfo> col_types;
-    for (const auto& t : ti.col_types) col_types.push_back({t.type, t.notnull});
-    const int nc = static_cast<int>(col_types.size());
-    std::vector<std::vector<B2QChunkStats>> stats(ti.fragments.size());
-    std::vector<B2QFragmentInfo> frags(ti.fragments.size());
-    for (size_t f = 0; f < ti.fragments.size(); ++f) {
-      const FragmentInfo& fi = ti.fragments[f];
-      stats[f].resize(nc);
-      for (int c = 0; c < nc; ++c) {
-        const ChunkStats& s = fi.chunkStats[c];
-        stats[f][c] = B2QChunkStats{s.int_min, s.int_max, s.fp_min, s.fp_max, s.has_nulls ? 1 : 0, 0};
+    struct Flat {
+      std::vector<B2QTypeInfo> col_types;
+      std::vector<std::vector<B2QChunkStats>> stats;
+      std::vector<B2QFragmentInfo> frags;
+      B2QTableInfo tbl{};
+      void fill(const InputTableInfo& ti) {
+        for (const auto& t : ti.col_types) col_types.push_back({t.type, t.notnull});
+        const int nc = static_cast<int>(col_types.size());
+        stats.resize(ti.fragments.size());
+        frags.resize(ti.fragments.size());
+        for (size_t f = 0; f < ti.fragments.size(); ++f) {
+          const FragmentInfo& fi = ti.fragments[f];
+          stats[f].resize(nc);
+          for (int c = 0; c < nc; ++c) {
+            const ChunkStats& s = fi.chunkStats[c];
+            stats[f][c] = B2QChunkStats{s.int_min, s.int_max, s.fp_min, s.fp_max, s.has_nulls ? 1 : 0, 0};
+          }
+          frags[f] = B2QFragmentInfo{fi.fragmentId, fi.deviceId, static_cast<int64_t>(fi.numTuples), fi.col_buffers.data(), stats[f].data()};
+        }
+        tbl = B2QTableInfo{nc, col_types.data(), static_cast<int32_t>(frags.size()), frags.data(), static_cast<int32_t>(ti.memory_level), 0, nullptr};
       }
-      frags[f] = B2QFragmentInfo{fi.fragmentId, fi.deviceId, static_cast<int64_t>(fi.numTuples), fi.col_buffers.data(), stats[f].data()};
-    }
-    B2QTableInfo tbl{nc, col_types.data(), static_cast<int32_t>(frags.size()), frags.data(), static_cast<int32_t>(ti.memory_level), 0};
+    } outer, inner;
+    outer.fill(query_infos.front());
+    if (n_tables == 2) inner.fill(query_infos[1]);
+    const B2QTableInfo& tbl = outer.tbl;
     std::vector<int32_t> sq(ra_exe_unit.simple_quals.begin(), ra_exe_unit.simple_quals.end());
     std::vector<int32_t> q(ra_exe_unit.quals.begin(), ra_exe_unit.quals.end());
     std::vector<int32_t> g(ra_exe_unit.groupby_exprs.begin(), ra_exe_unit.groupby_exprs.end());
@@ -203,7 +217,16 @@ class Executor {
     u.groupby_exprs = g.data(); u.num_groupby_exprs = static_cast<int32_t>(g.size());
     u.target_exprs = ra_exe_unit.target_exprs.data(); u.num_target_exprs = static_cast<int32_t>(ra_exe_unit.target_exprs.size());
     u.scan_limit = static_cast<int64_t>(ra_exe_unit.scan_limit);
-    u.num_join_quals = ra_exe_unit.num_join_quals; u.has_estimator = ra_exe_unit.has_estimator;
+    u.has_estimator = ra_exe_unit.has_estimator;
+    u.num_join_quals = static_cast<int32_t>(ra_exe_unit.join_quals.size());
+    u.join_qual = -1;
+    if (u.num_join_quals == 1) {
+      const auto& jc = ra_exe_unit.join_quals.front();
+      if (jc.quals.size() != 1) throw QueryNotSupported(B2Q_ERR_UNSUPPORTED, "exactly one equi-join qual per level on this path");
+      u.join_qual = jc.quals.front();
+      u.join_type = static_cast<int32_t>(jc.type);
+      u.inner_table = &inner.tbl;
+    }
     u.has_union_all = ra_exe_unit.has_union_all;
     std::vector<B2QOrderEntry> oes(ra_exe_unit.sort_info.order_entries.begin(), ra_exe_unit.sort_info.order_entries.end());
     u.order_entries = oes.data(); u.num_order_entries = static_cast<int32_t>(oes.size());

@@ -114,6 +114,32 @@ int main() {
     CHECK(all->getNextRow(false, false)[0].ival == 2);
     CHECK(all->getNextRow(false, false)[0].ival == 1);
   }
+  { /* SELECT d.attr, COUNT(*), SUM(t.big) FROM t JOIN d ON t.x = d.id GROUP BY d.attr — one INNER hash-join level */
+    std::vector<int32_t> id{2, 1, 5}, attr{70, 70, 80};
+    InputTableInfo dim;
+    dim.col_types = {SQLTypeInfo(kINT, true), SQLTypeInfo(kINT, true)};
+    dim.memory_level = MemoryLevel::CPU_LEVEL;
+    FragmentInfo df;
+    df.numTuples = 3;
+    df.col_buffers = {id.data(), attr.data()};
+    df.chunkStats.resize(2);
+    df.chunkStats[0].int_min = 1; df.chunkStats[0].int_max = 5;
+    df.chunkStats[1].int_min = 70; df.chunkStats[1].int_max = 80;
+    dim.fragments.push_back(df);
+    RelAlgExecutionUnit u;
+    RelAlgExecutionUnit::JoinCondition jc;
+    jc.quals.push_back(u.makeBinOper(kEQ, u.makeColumnVar(info.col_types[0], 0, 0), u.makeColumnVar(dim.col_types[0], 0, 1)));
+    u.join_quals.push_back(jc);
+    u.groupby_exprs.push_back(u.makeColumnVar(dim.col_types[1], 1, 1));
+    u.target_exprs.push_back(u.makeColumnVar(dim.col_types[1], 1, 1));
+    u.target_exprs.push_back(u.makeAggExpr(SQLTypeInfo(kINT, false), kCOUNT, -1));
+    u.target_exprs.push_back(u.makeAggExpr(SQLTypeInfo(kBIGINT, false), kSUM, u.makeColumnVar(info.col_types[1], 1, 0)));
+    auto result = executor->executeWorkUnit(max_groups_buffer_entry_guess, true, {info, dim}, u, CompilationOptions::defaults(), ExecutionOptions::defaults(), nullptr, false, column_cache);
+    CHECK(result->rowCount() == 1);   /* both fact rows (x = 1, 2) map to attr 70 */
+    auto r0 = result->getNextRow(false, false);
+    CHECK(r0[0].ival == 70 && r0[1].ival == 2 && r0[2].ival == 30);
+    CHECK(result->getQueryMemDesc().join_entry_count == 5);
+  }
   std::printf("boundary test ok\n");
   return 0;
 }
