@@ -116,6 +116,8 @@ struct DevJoin {
                            and the gather of that column are ONE 8-byte load (random 4-byte gathers are bound by L1 tag
                            throughput, ~1 sector/clk/SM: two dependent gathers per row cost twice the scan itself) */
   int8_t packed_width;  /* width code of that column in the inner table */
+  int8_t pad_probe_cg;  /* experiment knob (B2Q_JOIN_CG): probe with ld.global.cg (L2 only) instead of the L1 path */
+  int8_t pad_[7];
 };
 
 struct DevProgram {

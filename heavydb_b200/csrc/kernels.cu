@@ -508,7 +508,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && k[j] == J.null_val);
         int32_t idx = -1, val = 0;
         if (ok) {
-          if (packed) { const int2 e2 = __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.y; }
+          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.y; }
           else idx = __ldg(buff + d);
         }
         jidx[JOIN ? j : 0] = idx;
@@ -524,7 +524,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && (int64_t)k[j] == J.null_val);
         int32_t idx = -1, val = 0;
         if (ok) {
-          if (packed) { const int2 e2 = __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.y; }
+          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.y; }
           else idx = __ldg(buff + d);
         }
         jidx[JOIN ? j : 0] = idx;

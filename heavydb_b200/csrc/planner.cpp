@@ -983,6 +983,7 @@ class Planner {
       for (int a = 0; a < g.n_accs; ++a) if (g.accs[a].col >= 0) g.col_prefetch[g.accs[a].col] = 1;
     if (join_) g.col_prefetch[g.join.fk_col] = 1;
     g.join.packed_col = -1;
+    g.join.pad_probe_cg = []() { const char* e = getenv("B2Q_JOIN_CG"); return e && atoi(e) != 0; }() ? 1 : 0;
     if (join_) { /* the first 1/2/4-byte inner column the program reads rides in the join table itself */
       static const bool pack = []() { const char* e = getenv("B2Q_JOIN_PACK"); return !e || atoi(e) != 0; }();
       for (int c = 0; c < g.n_cols && pack; ++c)
@@ -1039,7 +1040,11 @@ class Planner {
       sm.use_smem = 1;
       sm.replica_bytes = static_cast<int32_t>(per_replica);
       int rep = 1;
-      while (rep < 32 && int64_t(rep) * 2 * per_replica <= 96 * 1024) rep *= 2; /* warp-private copies for small tables */
+      /* the join kernels gather from the join table through L1/L2: shared memory left to the group-table replicas is L1
+       * taken from those gathers (B2Q_JOIN_SMEM_KB: experiment knob, default = the plain kernels' 96 KB) */
+      static const int64_t join_cap_kb = []() { const char* e = getenv("B2Q_JOIN_SMEM_KB"); return e ? atoll(e) : int64_t(96); }();
+      const int64_t cap = (join_ ? join_cap_kb : 96) * 1024;
+      while (rep < 32 && int64_t(rep) * 2 * per_replica <= cap) rep *= 2; /* warp-private copies for small tables */
       sm.replicas = rep;
       sm.total_bytes = static_cast<int32_t>(per_replica * rep);
     };
