@@ -117,7 +117,7 @@ def lib():
         L.b2q_gen_column_strided.restype = C.c_int32
         L.b2q_gen_column_strided.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
                                              C.c_int64, C.c_int64, C.c_void_p]
-        if L.b2q_abi_version() != 1:
+        if L.b2q_abi_version() != abi.ABI_VERSION:
             raise ImportError("libb2q.so ABI version mismatch")
         _lib = L
     return _lib

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define B2Q_ABI_VERSION 1
+#define B2Q_ABI_VERSION 2 /* 2: sort_info, join level, rte_idx, columnar, dictionary / time types, B2QPlan join fields */
 
 /* ---- SQLTypes subset (Shared/sqltypes.h:65-99) -------------------------------------------------------- */
 enum {
