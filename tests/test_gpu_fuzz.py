@@ -129,3 +129,77 @@ def test_fuzz_queries(seed):
             raise AssertionError(f"query: {sql}\nforce_kernel={force}\n{e}") from e
         ran += 1
     assert ran >= 40
+
+
+# ---- joins: random targets / filters / keys over both tables of the star schema -----------------------------
+import join_tables as jt  # noqa: E402
+
+J_INT = {"t.fk32": (-5, 1060), "t.x": (0, 100), "t.v": (-10**6, 10**6), "t.fk64": (-220, 1940),
+         "d.attr": (0, 20), "d.attr8": (-100, 100), "d.big": (-2**50, 2**50), "d.id32": (3, 1003), "d.id64": (-100, 1900)}
+J_FP = {"t.d": (0.0, 1.0), "d.w": (-30.0, 30.0)}
+J_KEYS = ["d.attr", "d.attr8", "t.x", "d.id32", "d.big", None, None]
+J_ON = ["t.fk32 = d.id32", "d.id32 = t.fk16", "t.fk64 = d.id64"]
+
+
+def rand_join_leaf(rng):
+    r = rng.random()
+    if r < 0.15:
+        c = rng.choice(list(J_INT) + list(J_FP))
+        return f"{c} IS {'NOT ' if rng.random() < 0.5 else ''}NULL"
+    if r < 0.75:
+        c = rng.choice(list(J_INT))
+        lo, hi = J_INT[c]
+        return f"{c} {rng.choice(OPS)} {rng.randint(lo, hi)}"
+    c = rng.choice(list(J_FP))
+    lo, hi = J_FP[c]
+    return f"{c} {rng.choice(OPS)} {rng.uniform(lo, hi):.6f}"
+
+
+def rand_join_query(rng):
+    keys = []
+    if rng.random() < 0.8:
+        keys = [k for k in rng.sample(J_KEYS, rng.choice([1, 1, 2])) if k]
+    targets = [k for k in keys if rng.random() < 0.8]
+    for _ in range(rng.randint(1, 4)):
+        agg = rng.choice(["COUNT", "SUM", "MIN", "MAX", "AVG", "COUNTSTAR"])
+        targets.append("COUNT(*)" if agg == "COUNTSTAR" else f"{agg}({rng.choice(list(J_INT) + list(J_FP))})")
+    if all(not t.endswith(")") for t in targets):
+        targets.append("COUNT(*)")
+    sql = "SELECT " + ", ".join(targets) + f" FROM t JOIN d ON {rng.choice(J_ON)}"
+    n = rng.choice([0, 1, 1, 2])
+    if n:
+        conds = []
+        for _ in range(n):
+            a = rand_join_leaf(rng)
+            if rng.random() < 0.4:
+                a = f"({a} {rng.choice(['AND', 'OR'])} {rand_join_leaf(rng)})"
+            if rng.random() < 0.15:
+                a = f"NOT {a}" if a.startswith("(") else f"NOT ({a})"
+            conds.append(a)
+        sql += " WHERE " + " AND ".join(conds)
+    if keys:
+        sql += " GROUP BY " + ", ".join(keys)
+    return sql + ";"
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_fuzz_join_queries(seed):
+    rng = random.Random(4242 + seed)
+    fact = jt.fact_table([50, 9000, 120000][seed], seed=60 + seed, frag_rows=[20, 2500, 50000][seed])
+    dim = jt.dim_table(seed=7 + seed)
+    dev = gu.DeviceTable(fact)
+    ran = 0
+    for _ in range(50):
+        sql = rand_join_query(rng)
+        unit = sqlmini.parse(sql, fact, jt.FACT_NAMES, inner=(dim, jt.DIM_NAMES))
+        try:
+            plan = executor.Executor().plan(unit, fact, max_groups_buffer_entry_guess=3001, has_cardinality_estimation=True)
+        except executor.UnsupportedOnThisPath:
+            continue
+        force = abi.KERNEL_PERFECT_GLOBAL if (plan.query_desc_type == abi.GroupByPerfectHash and rng.random() < 0.3) else 0
+        try:
+            gu.run_both(unit, fact, entry_guess=3001, has_card=True, dev_table=dev, force_kernel=force)
+        except Exception as e:
+            raise AssertionError(f"query: {sql}\nforce_kernel={force}\n{e}") from e
+        ran += 1
+    assert ran >= 30
