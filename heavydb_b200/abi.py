@@ -304,7 +304,8 @@ class UnitBuilder:
         self.targets: List[int] = []
         self.scan_limit = 0
         self.unsupported: Dict[str, int] = {}
-        self.inner: Optional["Table"] = None            # input_descs[1] of a one-level INNER hash join
+        self.inner: Optional["Table"] = None            # input_descs[1] of a one-level INNER / LEFT hash join
+        self.join_type = 0                              # JoinType: INNER = 0, LEFT = 1
         self.join_qual: int = -1
         self.order: List[Tuple[int, bool, bool]] = []   # sort_info.order_entries: (tle_no 1-based, is_desc, nulls_first)
         self.limit: Optional[int] = None
@@ -314,13 +315,16 @@ class UnitBuilder:
     def col(self, col_id: int, rte_idx: int = 0) -> int:
         """ColumnVar; rte_idx 1 = a column of the joined inner table (set with join())."""
         t, nn = (self.inner if rte_idx else self.table).col_types[col_id]
+        if rte_idx and self.join_type == 1:
+            nn = False      # the inner side of a LEFT join is nullable (RelAlgTranslator marks it so)
         self.nodes.append(_Node(EXPR_COLUMN_VAR, t, nn, col_id=col_id, rte_idx=rte_idx))
         return len(self.nodes) - 1
 
-    def join(self, inner: "Table", outer_col: int, inner_col: int):
-        """join_quals[0] = {outer.col = inner.col}, JoinType::INNER; the inner table is passed as one concatenated
-        fragment, the way the hash-join column fetch sees it."""
+    def join(self, inner: "Table", outer_col: int, inner_col: int, join_type: int = 0):
+        """join_quals[0] = {outer.col = inner.col}, JoinType INNER (0) or LEFT (1); the inner table is passed as one
+        concatenated fragment, the way the hash-join column fetch sees it."""
         self.inner = inner
+        self.join_type = join_type
         self.join_qual = self.binop(kEQ, self.col(outer_col, 0), self.col(inner_col, 1))
         return self
 
@@ -357,6 +361,8 @@ class UnitBuilder:
         else:
             arg = self.col(col_id, rte_idx)
             at, ann = (self.inner if rte_idx else self.table).col_types[col_id]
+            if rte_idx and self.join_type == 1:
+                ann = False
             if kind == kCOUNT:
                 ti = (kBIGINT if bigint_count else kINT, False)
             elif kind == kSUM:
@@ -428,7 +434,7 @@ class BuiltUnit:
         if b.inner is not None:
             assert len(b.inner.fragments) <= 1, "the inner table must be one concatenated fragment"
             self._inner_built = b.inner.build(CPU_LEVEL)     # host chunks; the library copies what it needs
-            u.num_join_quals, u.join_qual, u.join_type = 1, b.join_qual, 0
+            u.num_join_quals, u.join_qual, u.join_type = 1, b.join_qual, b.join_type
             u.inner_table = C.cast(C.pointer(self._inner_built.info), C.c_void_p)
         for k, v in b.unsupported.items():
             setattr(u, k, v)

@@ -117,12 +117,14 @@ struct DevJoin {
                            throughput, ~1 sector/clk/SM: two dependent gathers per row cost twice the scan itself) */
   int8_t packed_width;  /* width code of that column in the inner table */
   int8_t pad_probe_cg;  /* experiment knob (B2Q_JOIN_CG): probe with ld.global.cg (L2 only) instead of the L1 path */
-  int8_t pad_[7];
+  int8_t left;          /* LEFT join: a row without a match stays, its inner columns read col_null[] */
+  int8_t pad_[6];
 };
 
 struct DevProgram {
   DevJoin join;
   int8_t col_inner[B2Q_MAX_COLS];    /* launch column belongs to the joined inner table: read at the matching inner row */
+  int64_t col_null[B2Q_MAX_COLS];    /* inner columns: the NULL a LEFT join's unmatched row reads (chunk sentinel / NULL_DOUBLE bits) */
   DevFilter filter;
   DevKey key;
   int32_t n_keys;       /* > 1: multi-column perfect hash, `keys` below; the single-column paths use `key` */

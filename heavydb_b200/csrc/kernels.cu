@@ -107,10 +107,11 @@ __device__ __forceinline__ int32_t ldg_u8(const int8_t* p, uint32_t pred, uint64
  * compile-time nullptr in the kernels without a join level, so the branch disappears there. */
 template <bool PRED>
 __device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict__ base, int64_t row0, int stride, uint32_t mask, uint64_t pol,
-                                       const int32_t* jidx = nullptr, const int32_t* /* jval: only 1/2/4-byte columns are packed */ = nullptr) {
-  if (jidx) {
+                                       const int32_t* jidx = nullptr, const int32_t* /* jval: only 1/2/4-byte columns are packed */ = nullptr,
+                                       int64_t nullv = 0) {
+  if (jidx) { /* idx < 0 only under a LEFT join: the unmatched row reads NULL (codegenOuterJoinNullPlaceholder) */
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? __ldg(reinterpret_cast<const long long*>(base) + jidx[j]) : 0;
+    for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? (jidx[j] >= 0 ? __ldg(reinterpret_cast<const long long*>(base) + jidx[j]) : nullv) : 0;
     return;
   }
   const int8_t* p = base + row0 * 8;
@@ -121,7 +122,7 @@ __device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict
 /* R rows of a 1/2/4-byte integer column, sign-extended to 32 bits (width -1 / -2: zero-extended) */
 template <bool PRED>
 __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0, int stride, uint32_t mask, uint64_t pol,
-                                       const int32_t* jidx = nullptr, const int32_t* jval = nullptr) {
+                                       const int32_t* jidx = nullptr, const int32_t* jval = nullptr, int64_t nullv = 0) {
   if (jval) { /* the column that rides in the packed join table: already in registers since the probe */
 #pragma unroll
     for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? jval[j] : 0;
@@ -131,7 +132,8 @@ __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       int32_t x = 0;
-      if (mask >> j & 1) {
+      if ((mask >> j & 1) && jidx[j] < 0) x = (int32_t)nullv;
+      else if (mask >> j & 1) {
         const int64_t i = jidx[j];
         switch (width) {
           case 4: x = __ldg(reinterpret_cast<const int32_t*>(base) + i); break;
@@ -179,13 +181,13 @@ __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict
 template <bool FULL>
 __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* const* __restrict__ cols, int64_t row0,
                                               int stride, uint32_t valid, uint64_t pol, const int32_t* jidx = nullptr,
-                                              const int32_t* jval = nullptr) {
+                                              const int32_t* jval = nullptr, int64_t jnull = 0) {
   uint32_t m = 0;
   const bool neg = t.negate;
   if (!t.cmp_fp) {
     if (t.width == 8) {
       int64_t v[R];
-      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol, jidx);
+      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol, jidx, nullptr, jnull);
       const uint64_t lo = (uint64_t)t.lo, span = t.span;
       if (lo == 0x8000000000000000ull) { /* only an upper bound (`<`, `<=`): one signed compare instead of subtract + compare */
         const int64_t hi = (int64_t)(lo + span);
@@ -202,7 +204,7 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
       }
     } else {
       int32_t v[R];
-      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol, jidx, jval);
+      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol, jidx, jval, jnull);
       const uint32_t lo = (uint32_t)t.lo, span = (uint32_t)t.span;
 #pragma unroll
       for (int j = 0; j < R; ++j) m |= (uint32_t)(((uint32_t)v[j] - lo <= span) != neg) << j;
@@ -218,19 +220,19 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
     uint32_t isnull = 0;
     if (t.col_is_fp) {
       int64_t v[R];
-      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol, jidx);
+      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol, jidx, nullptr, jnull);
       const double nullv = __longlong_as_double(t.null_bits);
 #pragma unroll
       for (int j = 0; j < R; ++j) { d[j] = __longlong_as_double(v[j]); isnull |= (uint32_t)(d[j] == nullv) << j; }
     } else if (t.width == 8) {
       int64_t v[R];
-      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol, jidx);
+      load64<!FULL>(v, cols[t.col], row0, stride, valid, pol, jidx, nullptr, jnull);
       const int64_t nullv = t.null_bits;
 #pragma unroll
       for (int j = 0; j < R; ++j) { d[j] = (double)v[j]; isnull |= (uint32_t)(v[j] == nullv) << j; }
     } else {
       int32_t v[R];
-      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol, jidx, jval);
+      load32<!FULL>(v, cols[t.col], t.width, row0, stride, valid, pol, jidx, jval, jnull);
       const int32_t nullv = (int32_t)t.null_bits;
 #pragma unroll
       for (int j = 0; j < R; ++j) { d[j] = (double)v[j]; isnull |= (uint32_t)(v[j] == nullv) << j; }
@@ -246,8 +248,8 @@ template <bool FULL, bool JOIN>
 __device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t* const* __restrict__ cols,
                                                 int64_t row0, int stride, uint32_t valid, uint64_t pol,
                                                 const int8_t* __restrict__ col_inner, const int32_t* jidx, int packed_col,
-                                                const int32_t* jval) {
-#define B2Q_TERM_JX(t) ((JOIN && col_inner[(t).col]) ? jidx : nullptr), ((JOIN && (t).col == packed_col) ? jval : nullptr)
+                                                const int32_t* jval, const int64_t* __restrict__ col_null) {
+#define B2Q_TERM_JX(t) ((JOIN && col_inner[(t).col]) ? jidx : nullptr), ((JOIN && (t).col == packed_col) ? jval : nullptr), (JOIN ? col_null[(t).col] : 0)
   if (f.n_ops == 0) return valid;
   if (f.n_ops == 1) return eval_term<FULL>(f.terms[0], cols, row0, stride, valid, pol, B2Q_TERM_JX(f.terms[0]));
   uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -493,11 +495,12 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
    * jidx[] — see load32 / load64. ---- */
   int32_t jidx[JOIN ? R : 1];
   int32_t jval[JOIN ? R : 1]; /* value of the inner column that is packed into the join table (DevJoin::packed_col) */
-#define JX(c) ((JOIN && P.col_inner[c]) ? jidx : nullptr), ((JOIN && (c) == P.join.packed_col) ? jval : nullptr)
+#define JX(c) ((JOIN && P.col_inner[c]) ? jidx : nullptr), ((JOIN && (c) == P.join.packed_col) ? jval : nullptr), (JOIN ? P.col_null[c] : 0)
   if (JOIN) {
     const DevJoin& J = P.join;
     const int32_t* __restrict__ buff = Lh.join_buff;
     const bool packed = J.packed_col >= 0;
+    const int32_t packed_null = packed ? (int32_t)P.col_null[J.packed_col] : 0;
     uint32_t matched = 0;
     if (J.fk_width == 8) {
       int64_t k[R];
@@ -506,9 +509,9 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       for (int j = 0; j < R; ++j) {
         const uint64_t d = (uint64_t)(k[j] - J.min_key);
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && k[j] == J.null_val);
-        int32_t idx = -1, val = 0;
+        int32_t idx = -1, val = packed_null;
         if (ok) {
-          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.y; }
+          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.x >= 0 ? e2.y : packed_null; }
           else idx = __ldg(buff + d);
         }
         jidx[JOIN ? j : 0] = idx;
@@ -522,9 +525,9 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       for (int j = 0; j < R; ++j) {
         const uint64_t d = (uint64_t)((int64_t)k[j] - J.min_key);
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && (int64_t)k[j] == J.null_val);
-        int32_t idx = -1, val = 0;
+        int32_t idx = -1, val = packed_null;
         if (ok) {
-          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.y; }
+          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.x >= 0 ? e2.y : packed_null; }
           else idx = __ldg(buff + d);
         }
         jidx[JOIN ? j : 0] = idx;
@@ -532,7 +535,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         matched |= (uint32_t)(idx >= 0) << j;
       }
     }
-    valid &= matched;
+    if (!J.left) valid &= matched; /* INNER: no match, no row; LEFT: the row stays and its inner columns are NULL */
   }
 
   /* ---- key column: issued before the filter when the planner expects most sectors to be needed anyway ---- */
@@ -545,7 +548,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, valid, pol, JX(P.key.col));
   }
 
-  uint32_t pass = eval_filter<FULL, JOIN>(P.filter, cols, row0, nthr, valid, pol, P.col_inner, jidx, P.join.packed_col, jval);
+  uint32_t pass = eval_filter<FULL, JOIN>(P.filter, cols, row0, nthr, valid, pol, P.col_inner, jidx, P.join.packed_col, jval, P.col_null);
 
   if (has_key && !eager_key) {
     if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, pass, pol, JX(P.key.col));

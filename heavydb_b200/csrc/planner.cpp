@@ -101,8 +101,9 @@ class Planner {
       : u_(u), t_(t), eo_(eo), guess_(guess), has_card_(has_card), filter_deleted_(filter_deleted) {}
 
   /* join level of the unit this planner was given in its combined form (make_query) */
-  void set_join(int n_outer, int outer_col, int inner_col, const B2QTableInfo& inner) {
+  void set_join(int n_outer, int outer_col, int inner_col, const B2QTableInfo& inner, bool left) {
     join_ = true;
+    join_left_ = left;
     n_outer_ = n_outer;
     join_outer_col_ = outer_col;
     join_inner_col_ = inner_col;
@@ -144,7 +145,7 @@ class Planner {
   bool keyless_ = false;
   int keyless_idx_ = -1;
   std::vector<bool> slot_key_ref_;
-  bool join_ = false;
+  bool join_ = false, join_left_ = false;
   int n_outer_ = 0, join_outer_col_ = -1, join_inner_col_ = -1;
   const B2QTableInfo* inner_ = nullptr;
 
@@ -583,6 +584,7 @@ class Planner {
     if (q.prog.n_cols >= B2Q_MAX_COLS) reject(B2Q_ERR_UNSUPPORTED, "too many referenced columns");
     q.col_ids[q.prog.n_cols] = table_col;
     q.prog.col_inner[q.prog.n_cols] = (join_ && table_col >= n_outer_) ? 1 : 0;
+    q.prog.col_null[q.prog.n_cols] = col_type(table_col).is_fp() ? dbl_bits(kNullDouble) : (t_.col_types[table_col].type == B2Q_kBOOLEAN ? 0 : phys_int_null(table_col));
     q.prog.col_width[q.prog.n_cols] = static_cast<int8_t>(t_.col_types[table_col].type == B2Q_kBOOLEAN ? 1 : phys_size(table_col));
     return q.prog.n_cols++;
   }
@@ -822,6 +824,7 @@ class Planner {
       g.join.entry_count = p.join_entry_count;
       g.join.nullable = !col_type(join_outer_col_).notnull;
       g.join.null_val = phys_int_null(join_outer_col_);
+      g.join.left = join_left_ ? 1 : 0;
     }
     /* filter: all simple_quals and quals AND-ed */
     int n_quals = 0, max_depth = 0;
@@ -1086,12 +1089,14 @@ struct JoinedInput {
   std::vector<B2QFragmentInfo> frags;
   B2QTableInfo t{};
   int n_outer = 0, outer_col = -1, inner_col = -1;
+  bool left = false;
 };
 
 static void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, JoinedInput& ji) {
   auto bad = [](int32_t code, const char* m) { throw PlanError{code, m}; };
   if (u.num_join_quals != 1) bad(B2Q_ERR_UNSUPPORTED, "more than one join level is outside this path");
-  if (u.join_type != 0) bad(B2Q_ERR_UNSUPPORTED, "only INNER joins are on this path");
+  if (u.join_type != 0 && u.join_type != 1) bad(B2Q_ERR_UNSUPPORTED, "only INNER and LEFT joins are on this path");
+  const bool left = u.join_type == 1;
   if (!u.inner_table) bad(B2Q_ERR_INVALID_ARGUMENT, "join without an inner table");
   const B2QTableInfo& inner = *u.inner_table;
   if (inner.num_fragments > 1) bad(B2Q_ERR_INVALID_ARGUMENT, "the inner table must come as one concatenated fragment (ColumnFetcher::getAllTableColumnFragments)");
@@ -1103,6 +1108,7 @@ static void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, 
     if (e.kind != B2Q_EXPR_COLUMN_VAR) continue;
     if (e.rte_idx == 1) {
       if (e.col_id < 0 || e.col_id >= inner.num_cols) bad(B2Q_ERR_INVALID_ARGUMENT, "inner column id out of range");
+      if (left && e.ti.notnull) bad(B2Q_ERR_INVALID_ARGUMENT, "LEFT join: inner ColumnVars must be nullable");
       e.col_id += ji.n_outer;
       e.rte_idx = 0;
     } else if (e.rte_idx != 0) bad(B2Q_ERR_UNSUPPORTED, "rte_idx beyond one join level");
@@ -1125,6 +1131,8 @@ static void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, 
   if (ji.outer_col < 0 || ji.outer_col >= ji.n_outer) bad(B2Q_ERR_INVALID_ARGUMENT, "outer join column out of range");
   ji.col_types.assign(outer.col_types, outer.col_types + outer.num_cols);
   ji.col_types.insert(ji.col_types.end(), inner.col_types, inner.col_types + inner.num_cols);
+  if (left) for (int c = 0; c < inner.num_cols; ++c) ji.col_types[ji.n_outer + c].notnull = 0; /* codegenOuterJoinNullPlaceholder */
+  ji.left = left;
   ji.enc.assign(ji.col_types.size(), 0);
   for (int c = 0; c < outer.num_cols; ++c) if (outer.col_encoded_sizes) ji.enc[c] = outer.col_encoded_sizes[c];
   for (int c = 0; c < inner.num_cols; ++c) if (inner.col_encoded_sizes) ji.enc[ji.n_outer + c] = inner.col_encoded_sizes[c];
@@ -1143,6 +1151,7 @@ static void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, 
       B2QChunkStats empty{};
       empty.int_min = INT64_MAX; empty.int_max = INT64_MIN; empty.fp_min = DBL_MAX; empty.fp_max = -DBL_MAX;
       ji.stats[f].push_back(inf ? inf->col_stats[c] : empty);
+      if (left) ji.stats[f].back().has_nulls = 1; /* is_outer_join_proj (ExpressionRange.cpp:521-525, :642-652) */
     }
     ji.frags[f] = of;
     ji.frags[f].col_buffers = of.col_buffers ? ji.bufs[f].data() : nullptr;
@@ -1170,7 +1179,7 @@ int32_t make_query(const B2QExecUnit* u, const B2QTableInfo* t, const B2QExecuti
     JoinedInput ji;
     build_joined_input(*u, *t, ji);
     Planner pl(ji.u, ji.t, *eo, guess, has_card, filter_deleted);
-    pl.set_join(ji.n_outer, ji.outer_col, ji.inner_col, *u->inner_table);
+    pl.set_join(ji.n_outer, ji.outer_col, ji.inner_col, *u->inner_table, ji.left);
     pl.run(*out);
     out->n_outer_cols = ji.n_outer;
     out->join_inner_key_col = ji.inner_col;

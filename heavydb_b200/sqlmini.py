@@ -2,7 +2,7 @@
 RelAlgExecutionUnit mirror, for the subset of the path:
 
     SELECT <col | COUNT(*) | COUNT(c) | SUM(c) | MIN(c) | MAX(c) | AVG(c)>, ...
-    FROM <table> [JOIN <inner> ON <table>.<c> = <inner>.<c>] [WHERE <c OP literal | c IS [NOT] NULL | c [NOT] IN (l, ...) | c BETWEEN l AND l | NOT <factor>>
+    FROM <table> [[LEFT] JOIN <inner> ON <table>.<c> = <inner>.<c>] [WHERE <c OP literal | c IS [NOT] NULL | c [NOT] IN (l, ...) | c BETWEEN l AND l | NOT <factor>>
                   {AND|OR} ... with parentheses] [GROUP BY c {, c}]
     [ORDER BY <position | target text> [ASC|DESC] [NULLS FIRST|LAST] {, ...}] [LIMIT n] [OFFSET m]
 
@@ -174,9 +174,13 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
     ups = [t.upper() for t in toks]
     fi = ups.index("FROM")
     p.outer_alias = toks[fi + 1].lower()
-    if fi + 2 < len(toks) and ups[fi + 2] == "JOIN":
+    ji = fi + 2
+    if ji < len(toks) and ups[ji] == "LEFT":
+        p.b.join_type = 1          # known before any column of the inner table is resolved (they become nullable)
+        ji += 1
+    if ji < len(toks) and ups[ji] == "JOIN":
         assert inner is not None, "JOIN needs the inner table"
-        p.inner_alias = toks[fi + 3].lower()
+        p.inner_alias = toks[ji + 1].lower()
     p.eat("SELECT")
     texts = [p.target_text()[0]]
     targets = [p.target()]
@@ -186,13 +190,15 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
         targets.append(p.target())
     p.eat("FROM")
     p.eat()  # table name
-    if p.peek() and p.peek().upper() == "JOIN":   # join_quals[0] = {a = b}, INNER
+    if p.peek() and p.peek().upper() == "LEFT":
+        p.eat()
+    if p.peek() and p.peek().upper() == "JOIN":   # join_quals[0] = {a = b}, INNER or LEFT
         p.eat()
         p.eat()  # inner table name
         p.eat("ON")
         (c1, r1), _, (c2, r2) = p.colref(p.eat()), p.eat("="), p.colref(p.eat())
         assert {r1, r2} == {0, 1}, "ON must compare an outer with an inner column"
-        p.b.join(inner[0], c1 if r1 == 0 else c2, c2 if r1 == 0 else c1)
+        p.b.join(inner[0], c1 if r1 == 0 else c2, c2 if r1 == 0 else c1, p.b.join_type)
     if p.peek() and p.peek().upper() == "WHERE":
         p.eat()
         e = p.cond()

@@ -144,10 +144,13 @@ typedef struct B2QExecUnit {
   const int32_t* target_exprs; /* expr indices */
   int32_t num_target_exprs;
   int64_t scan_limit;
-  /* join_quals (JoinQualsPerNestingLevel, RelAlgExecutionUnit.h:166-216): at most ONE nesting level, INNER, whose only
-   * qual is `ColumnVar(rte 0) = ColumnVar(rte 1)` over integer columns and for which the reference would build a
-   * one-to-one PerfectJoinHashTable (JoinHashTable/PerfectJoinHashTable.cpp:168-300; probe hash_join_idx[_nullable],
-   * GroupByRuntime.cpp:283-311).  Anything else (outer joins, one-to-many, baseline join tables) is rejected. */
+  /* join_quals (JoinQualsPerNestingLevel, RelAlgExecutionUnit.h:166-216): at most ONE nesting level, INNER or LEFT,
+   * whose only qual is `ColumnVar(rte 0) = ColumnVar(rte 1)` over integer columns and for which the reference would
+   * build a one-to-one PerfectJoinHashTable (JoinHashTable/PerfectJoinHashTable.cpp:168-300; probe
+   * hash_join_idx[_nullable], GroupByRuntime.cpp:283-311).  LEFT: an outer row without a match continues with every
+   * inner column NULL (codegenOuterJoinNullPlaceholder, ColumnIR.cpp:504-560); the unit's inner ColumnVars must then
+   * be nullable, as RelAlgTranslator makes them.  Anything else (one-to-many, baseline join tables, more levels) is
+   * rejected. */
   int32_t num_join_quals;      /* 0 or 1 */
   /* Fields of the reference struct that are outside this path.  Must be zero or the call is rejected. */
   int32_t has_estimator;
@@ -165,7 +168,7 @@ typedef struct B2QExecUnit {
   int64_t offset;
   /* the join level (used when num_join_quals == 1) */
   int32_t join_qual;           /* expr index of the equi-join BinOper(kEQ, ColumnVar, ColumnVar) */
-  int32_t join_type;           /* JoinType (Shared/sqldefs.h:252): only INNER = 0 */
+  int32_t join_type;           /* JoinType (Shared/sqldefs.h:252): INNER = 0 or LEFT = 1 */
   /* input_descs[1]: the inner table the way the hash-join column fetch sees it — every column as ONE buffer over all
    * fragments (ColumnFetcher::getAllTableColumnFragments, ColumnFetcher.cpp:290-360), i.e. exactly one fragment whose
    * chunk stats cover the table; memory_level CPU (copied to the device per query) or GPU */

@@ -291,10 +291,11 @@ double fixed_width_double_decode(const int8_t* byte_stream, int64_t pos) {
  * buildJoinLoops), not the outer position.  Set per outer row by run_fragment; one row loop per thread. */
 struct JoinRowCtx {
   int n_outer{INT32_MAX};
-  int64_t inner_pos{0};
+  int64_t inner_pos{0}; /* -1: LEFT join without a match => every inner column reads NULL (codegenOuterJoinNullPlaceholder) */
 };
 thread_local JoinRowCtx g_join_row;
 inline int64_t row_pos_of(int c, int64_t pos) { return c >= g_join_row.n_outer ? g_join_row.inner_pos : pos; }
+inline bool outer_join_null(int c) { return c >= g_join_row.n_outer && g_join_row.inner_pos < 0; }
 
 /* Physical element width of column c: narrower than the logical type under `ENCODING FIXED(bits)`. */
 int phys_width(const B2QTableInfo& tbl, int c) {
@@ -305,6 +306,7 @@ int phys_width(const B2QTableInfo& tbl, int c) {
  * CodeGenerator::codgenAdjustFixedEncNull (ColumnIR.cpp:456-500): the physical width's minimum is NULL and becomes the
  * logical type's sentinel (only for nullable columns, ColumnIR.cpp:286-291). */
 int64_t decode_int_column(const B2QTableInfo& tbl, const B2QFragmentInfo& fr, int c, int64_t pos) {
+  if (outer_join_null(c)) return inline_int_null_val(tbl.col_types[c].type);
   pos = row_pos_of(c, pos);
   const int pw = phys_width(tbl, c);
   const int lw = type_size(tbl.col_types[c].type);
@@ -323,6 +325,11 @@ int64_t decode_int_column(const B2QTableInfo& tbl, const B2QFragmentInfo& fr, in
     if (v == phys_null) v = inline_int_null_val(tbl.col_types[c].type);
   }
   return v;
+}
+
+double decode_double_column(const B2QFragmentInfo& fr, int c, int64_t pos) {
+  if (outer_join_null(c)) return kNullDouble;
+  return fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[c]), row_pos_of(c, pos));
 }
 
 /* ===================================================================================================
@@ -363,6 +370,7 @@ struct Plan {
   bool join{false};
   int join_outer_col{-1}, join_inner_vcol{-1}; /* virtual column ids */
   bool join_outer_nullable{false};
+  bool join_left{false};
   std::shared_ptr<std::vector<int32_t>> join_buff;
 };
 
@@ -913,11 +921,13 @@ struct JoinedInput {
   B2QTableInfo t{};
   int n_outer{0};
   int outer_col{-1}, inner_vcol{-1};
+  bool left{false};
 };
 
 void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, JoinedInput& ji) {
   if (u.num_join_quals != 1) fail(B2Q_ERR_UNSUPPORTED, "more than one join level is outside this path");
-  if (u.join_type != 0) fail(B2Q_ERR_UNSUPPORTED, "only INNER joins are on this path");
+  if (u.join_type != 0 && u.join_type != 1) fail(B2Q_ERR_UNSUPPORTED, "only INNER and LEFT joins are on this path");
+  const bool left = u.join_type == 1;
   if (!u.inner_table) fail(B2Q_ERR_INVALID_ARGUMENT, "join without an inner table");
   const B2QTableInfo& inner = *u.inner_table;
   if (inner.num_fragments > 1) fail(B2Q_ERR_INVALID_ARGUMENT, "the inner table must come as one concatenated fragment (getAllTableColumnFragments)");
@@ -931,6 +941,8 @@ void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, JoinedI
     if (e.kind != B2Q_EXPR_COLUMN_VAR) continue;
     if (e.rte_idx == 1) {
       if (e.col_id < 0 || e.col_id >= n_inner) fail(B2Q_ERR_INVALID_ARGUMENT, "inner column id out of range");
+      /* RelAlgTranslator hands a LEFT join's inner columns over as nullable; a NOT NULL one would mis-plan */
+      if (left && e.ti.notnull) fail(B2Q_ERR_INVALID_ARGUMENT, "LEFT join: inner ColumnVars must be nullable");
       e.col_id += ji.n_outer;
       e.rte_idx = 0;
     } else if (e.rte_idx != 0) fail(B2Q_ERR_UNSUPPORTED, "rte_idx beyond one join level");
@@ -952,6 +964,8 @@ void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, JoinedI
   /* combined table */
   ji.col_types.assign(outer.col_types, outer.col_types + outer.num_cols);
   ji.col_types.insert(ji.col_types.end(), inner.col_types, inner.col_types + n_inner);
+  if (left) for (int c = 0; c < n_inner; ++c) ji.col_types[ji.n_outer + c].notnull = 0;
+  ji.left = left;
   ji.enc.assign(ji.col_types.size(), 0);
   for (int c = 0; c < outer.num_cols; ++c) if (outer.col_encoded_sizes) ji.enc[c] = outer.col_encoded_sizes[c];
   for (int c = 0; c < n_inner; ++c) if (inner.col_encoded_sizes) ji.enc[ji.n_outer + c] = inner.col_encoded_sizes[c];
@@ -968,6 +982,7 @@ void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, JoinedI
       B2QChunkStats empty{};
       empty.int_min = INT64_MAX; empty.int_max = INT64_MIN; empty.fp_min = DBL_MAX; empty.fp_max = -DBL_MAX;
       ji.stats[f].push_back(inf ? inf->col_stats[c] : empty);
+      if (left) ji.stats[f].back().has_nulls = 1; /* is_outer_join_proj: getLeafColumnRange starts from has_nulls = true (ExpressionRange.cpp:521-525, :642-652) */
     }
     ji.frags[f] = of;
     ji.frags[f].col_buffers = ji.bufs[f].data();
@@ -1009,6 +1024,7 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
   plan.join_outer_col = ji.outer_col;
   plan.join_inner_vcol = ji.inner_vcol;
   plan.join_outer_nullable = !oti.notnull;
+  plan.join_left = ji.left;
   plan.p.join_min_key = r.imin;
   plan.p.join_max_key = r.imax;
   plan.p.join_entry_count = entries;
@@ -1062,7 +1078,7 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
       if (o.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "IS NULL operand must be a ColumnVar");
       const int ctype = tbl.col_types[o.col_id].type;
       if (tbl.col_types[o.col_id].notnull) return 0; /* inferred non-null: short-circuit to false */
-      if (is_fp(ctype)) return fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[o.col_id]), row_pos_of(o.col_id, pos)) == kNullDouble;
+      if (is_fp(ctype)) return decode_double_column(fr, o.col_id, pos) == kNullDouble;
       return decode_int_column(tbl, fr, o.col_id, pos) == inline_int_null_val(ctype);
     }
     fail(B2Q_ERR_UNSUPPORTED, "unary operator outside NOT / IS NULL");
@@ -1088,7 +1104,6 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
   const int col = l.col_id;
   const int ctype = tbl.col_types[col].type;
   const bool col_notnull = tbl.col_types[col].notnull != 0;
-  const int8_t* buf = static_cast<const int8_t*>(fr.col_buffers[col]);
   /* dictionary strings compare by id against a literal's id (CompareIR.cpp codegenStrCmp / translated literal):
    * only = and <> mean anything without the dictionary */
   if (is_string(ctype) && e.op != B2Q_kEQ && e.op != B2Q_kNE) fail(B2Q_ERR_UNSUPPORTED, "dictionary-encoded strings compare by id: only = and <> are on this path");
@@ -1098,7 +1113,7 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
     /* fp compare: the integer side is cast to double (CompareIR.cpp codegenCmp after normalisation) */
     double lv;
     bool lnull;
-    if (is_fp(ctype)) { lv = fixed_width_double_decode(buf, row_pos_of(col, pos)); lnull = !col_notnull && lv == kNullDouble; }
+    if (is_fp(ctype)) { lv = decode_double_column(fr, col, pos); lnull = !col_notnull && lv == kNullDouble; }
     else { const int64_t iv = decode_int_column(tbl, fr, col, pos); lnull = !col_notnull && iv == inline_int_null_val(ctype); lv = static_cast<double>(iv); }
     if (lnull) return kNullBool;
     const double rv = is_fp(r.ti.type) ? r.dval : static_cast<double>(r.ival);
@@ -1165,17 +1180,16 @@ void update_target(const Plan& plan, const Target& t, int8_t* out, int64_t entry
   int64_t* a = reinterpret_cast<int64_t*>(slot);
   if (!t.is_agg) { /* agg_id on the projected group key, sign-extended to the slot */
     const int ctype = tbl.col_types[t.arg_col].type;
-    if (is_fp(ctype)) agg_id(a, bits_of(fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[t.arg_col]), row_pos_of(t.arg_col, pos))));
+    if (is_fp(ctype)) agg_id(a, bits_of(decode_double_column(fr, t.arg_col, pos)));
     else agg_id(a, decode_int_column(tbl, fr, t.arg_col, pos));
     return;
   }
   if (t.agg_kind == B2Q_kCOUNT && t.arg_col < 0) { agg_count(a); return; }
   const int ctype = tbl.col_types[t.arg_col].type;
   const bool arg_notnull = t.arg_ti.notnull;
-  const int8_t* buf = static_cast<const int8_t*>(fr.col_buffers[t.arg_col]);
   const bool need_skip_null = t.skip_null_val;
   if (is_fp(ctype)) {
-    const double v = fixed_width_double_decode(buf, row_pos_of(t.arg_col, pos));
+    const double v = decode_double_column(fr, t.arg_col, pos);
     const double null_v = kNullDouble; /* arg null == agg null for DOUBLE: no conversion needed */
     switch (t.agg_kind) {
       case B2Q_kCOUNT: if (need_skip_null) agg_count_double_skip_val(a, v, null_v); else agg_count(a); break;
@@ -1262,8 +1276,8 @@ int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo&
       const int64_t key = decode_int_column(tbl, fr, plan.join_outer_col, pos);
       int64_t idx = -1;
       if (!(plan.join_outer_nullable && key == join_null) && key >= p.join_min_key && key <= p.join_max_key) idx = join_buff[key - p.join_min_key];
-      if (idx < 0) continue; /* INNER join: no match, no row */
-      g_join_row.inner_pos = idx;
+      if (idx < 0 && !plan.join_left) continue; /* INNER join: no match, no row */
+      g_join_row.inner_pos = idx;        /* LEFT join: -1 => the inner columns read NULL */
     }
     if (!row_passes(u, tbl, fr, pos)) continue;
     int64_t entry = 0;

@@ -62,6 +62,19 @@ JOIN_QUERIES = [
 ]
 
 
+# LEFT joins: an outer row without a match stays, its inner columns read NULL (codegenOuterJoinNullPlaceholder)
+LEFT_JOIN_QUERIES = [
+    "SELECT d.attr, COUNT(*), SUM(t.v), COUNT(d.id32) FROM t LEFT JOIN d ON t.fk32 = d.id32 GROUP BY d.attr;",
+    "SELECT COUNT(*), COUNT(d.w), SUM(d.big), MIN(d.attr8), AVG(d.w), MAX(d.id64) FROM t LEFT JOIN d ON t.fk32 = d.id32 WHERE t.x < 50;",
+    "SELECT t.x, COUNT(*), COUNT(d.attr8), SUM(d.attr8) FROM t LEFT JOIN d ON t.fk64 = d.id64 WHERE d.attr8 IS NULL OR d.attr8 > 0 GROUP BY t.x;",
+    "SELECT d.attr8, COUNT(*), AVG(t.d) FROM t LEFT JOIN d ON t.fk16 = d.id32 GROUP BY d.attr8;",
+    "SELECT d.attr, t.x, COUNT(*), MIN(d.w) FROM t LEFT JOIN d ON t.fk32 = d.id32 WHERE t.x < 20 GROUP BY d.attr, t.x;",
+    "SELECT d.big, COUNT(*) FROM t LEFT JOIN d ON t.fk32 = d.id32 WHERE NOT (d.attr >= 2) OR d.attr IS NULL GROUP BY d.big;",        # baseline hash, NULL key
+    "SELECT d.attr, COUNT(*), AVG(d.w) FROM t LEFT JOIN d ON t.fk32 = d.id32 GROUP BY d.attr ORDER BY 2 DESC, 1 ASC NULLS FIRST LIMIT 6;",
+    "SELECT COUNT(*), COUNT(d.id32) FROM t LEFT JOIN d ON t.fk32 = d.id32 WHERE d.id32 IS NULL;",                                  # anti-join shape
+]
+
+
 def logical_rows(table, cols):
     out = []
     arrays = [np.concatenate([f.host_cols[c] for f in table.fragments]) for c in range(len(cols))]

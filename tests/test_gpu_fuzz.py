@@ -165,7 +165,7 @@ def rand_join_query(rng):
         targets.append("COUNT(*)" if agg == "COUNTSTAR" else f"{agg}({rng.choice(list(J_INT) + list(J_FP))})")
     if all(not t.endswith(")") for t in targets):
         targets.append("COUNT(*)")
-    sql = "SELECT " + ", ".join(targets) + f" FROM t JOIN d ON {rng.choice(J_ON)}"
+    sql = "SELECT " + ", ".join(targets) + f" FROM t {'LEFT ' if rng.random() < 0.4 else ''}JOIN d ON {rng.choice(J_ON)}"
     n = rng.choice([0, 1, 1, 2])
     if n:
         conds = []

@@ -22,7 +22,7 @@ def test_join_queries(n, frag_rows):
     fact = jt.fact_table(n, seed=3 + n, frag_rows=frag_rows)
     dim = jt.dim_table()
     dev = gu.DeviceTable(fact)
-    for sql in jt.JOIN_QUERIES:
+    for sql in jt.JOIN_QUERIES + jt.LEFT_JOIN_QUERIES:
         unit = parse(sql, fact, dim)
         try:
             if unit.unit.num_order_entries:

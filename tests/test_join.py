@@ -28,7 +28,7 @@ def parse(sql, fact, dim):
     return sqlmini.parse(sql, fact, jt.FACT_NAMES, inner=(dim, jt.DIM_NAMES))
 
 
-@pytest.mark.parametrize("sql", jt.JOIN_QUERIES)
+@pytest.mark.parametrize("sql", jt.JOIN_QUERIES + jt.LEFT_JOIN_QUERIES)
 def test_oracle_join_vs_sqlite(env, sql):
     fact, dim, con = env
     unit = parse(sql, fact, dim)
@@ -74,12 +74,19 @@ def test_refused_joins(env):
     dup = abi.Table([(abi.kINT, True), (abi.kINT, False)])
     dup.add_host_fragment([np.array([1, 2, 2, 3], dtype=np.int32), np.array([5, 6, 7, 8], dtype=np.int32)])
     _both_refuse(sqlmini.parse("SELECT COUNT(*) FROM t JOIN d ON t.fk32 = d.id;", fact, jt.FACT_NAMES, inner=(dup, ["id", "a"])), fact, plan_only=False)
-    # LEFT join
+    # SEMI join (JoinType 2)
     b = abi.UnitBuilder(fact)
     b.join(dim, 0, 0)
     b.target(b.agg(abi.kCOUNT))
-    b.unsupported["join_type"] = 1
+    b.unsupported["join_type"] = 2
     _both_refuse(b.build(), fact)
+    # LEFT join whose inner ColumnVars were left NOT NULL: the planner would mis-size the key range
+    b = abi.UnitBuilder(fact)
+    b.join(dim, 0, 0)            # INNER while the columns are created ...
+    b.group_by(0, 1)
+    b.target(b.agg(abi.kCOUNT))
+    b.unsupported["join_type"] = 1   # ... then declared LEFT
+    _both_refuse(b.build(), fact, code=abi.ERR_INVALID_ARGUMENT)
     # a double as join key
     _both_refuse(sqlmini.parse("SELECT COUNT(*) FROM t JOIN d ON t.d = d.w;", fact, jt.FACT_NAMES, inner=(dim, jt.DIM_NAMES)), fact)
 
