@@ -108,10 +108,10 @@ __device__ __forceinline__ int32_t ldg_u8(const int8_t* p, uint32_t pred, uint64
 template <bool PRED>
 __device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict__ base, int64_t row0, int stride, uint32_t mask, uint64_t pol,
                                        const int32_t* jidx = nullptr, const int32_t* /* jval: only 1/2/4-byte columns are packed */ = nullptr,
-                                       int64_t nullv = 0) {
-  if (jidx) { /* idx < 0 only under a LEFT join: the unmatched row reads NULL (codegenOuterJoinNullPlaceholder) */
+                                       const int64_t* nullp = nullptr) {
+  if (jidx) { /* nullp (LEFT join kernels only): an unmatched row (idx < 0) reads NULL (codegenOuterJoinNullPlaceholder) */
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? (jidx[j] >= 0 ? __ldg(reinterpret_cast<const long long*>(base) + jidx[j]) : nullv) : 0;
+    for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? ((nullp && jidx[j] < 0) ? *nullp : __ldg(reinterpret_cast<const long long*>(base) + jidx[j])) : 0;
     return;
   }
   const int8_t* p = base + row0 * 8;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void load64(int64_t (&v)[R], const int8_t* __restrict
 /* R rows of a 1/2/4-byte integer column, sign-extended to 32 bits (width -1 / -2: zero-extended) */
 template <bool PRED>
 __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict__ base, int width, int64_t row0, int stride, uint32_t mask, uint64_t pol,
-                                       const int32_t* jidx = nullptr, const int32_t* jval = nullptr, int64_t nullv = 0) {
+                                       const int32_t* jidx = nullptr, const int32_t* jval = nullptr, const int64_t* nullp = nullptr) {
   if (jval) { /* the column that rides in the packed join table: already in registers since the probe */
 #pragma unroll
     for (int j = 0; j < R; ++j) v[j] = (mask >> j & 1) ? jval[j] : 0;
@@ -132,7 +132,7 @@ __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       int32_t x = 0;
-      if ((mask >> j & 1) && jidx[j] < 0) x = (int32_t)nullv;
+      if (nullp && (mask >> j & 1) && jidx[j] < 0) x = (int32_t)*nullp;
       else if (mask >> j & 1) {
         const int64_t i = jidx[j];
         switch (width) {
@@ -181,7 +181,7 @@ __device__ __forceinline__ void load32(int32_t (&v)[R], const int8_t* __restrict
 template <bool FULL>
 __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* const* __restrict__ cols, int64_t row0,
                                               int stride, uint32_t valid, uint64_t pol, const int32_t* jidx = nullptr,
-                                              const int32_t* jval = nullptr, int64_t jnull = 0) {
+                                              const int32_t* jval = nullptr, const int64_t* jnull = nullptr) {
   uint32_t m = 0;
   const bool neg = t.negate;
   if (!t.cmp_fp) {
@@ -244,12 +244,12 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
   return m & valid;
 }
 
-template <bool FULL, bool JOIN>
+template <bool FULL, int JOIN>
 __device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t* const* __restrict__ cols,
                                                 int64_t row0, int stride, uint32_t valid, uint64_t pol,
                                                 const int8_t* __restrict__ col_inner, const int32_t* jidx, int packed_col,
                                                 const int32_t* jval, const int64_t* __restrict__ col_null) {
-#define B2Q_TERM_JX(t) ((JOIN && col_inner[(t).col]) ? jidx : nullptr), ((JOIN && (t).col == packed_col) ? jval : nullptr), (JOIN ? col_null[(t).col] : 0)
+#define B2Q_TERM_JX(t) ((JOIN && col_inner[(t).col]) ? jidx : nullptr), ((JOIN && (t).col == packed_col) ? jval : nullptr), (JOIN == 2 ? col_null + (t).col : nullptr)
   if (f.n_ops == 0) return valid;
   if (f.n_ops == 1) return eval_term<FULL>(f.terms[0], cols, row0, stride, valid, pol, B2Q_TERM_JX(f.terms[0]));
   uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -476,7 +476,9 @@ struct ScanArgs {
 extern __shared__ __align__(128) int8_t b2q_smem[];
 
 /* one chunk: R rows per thread.  FULL = every row of the chunk exists (no tail masking). */
-template <int MODE, bool WAGG, bool KEY32, bool FULL, int BLOCK, bool JOIN>
+/* JOIN: 0 = no join level, 1 = INNER, 2 = LEFT (separate instantiations: the plain scan and the INNER probe do not pay
+ * for the NULL placeholders of the outer join) */
+template <int MODE, bool WAGG, bool KEY32, bool FULL, int BLOCK, int JOIN>
 __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* const* __restrict__ cols, int64_t row0,
                                               int64_t frag_rows, int lane, int8_t* my_tab, uint64_t pol, uint64_t pol_tab) {
   /* BLOCK is a compile-time constant so that the R loads of a column are one base pointer + immediate offsets */
@@ -495,12 +497,12 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
    * jidx[] — see load32 / load64. ---- */
   int32_t jidx[JOIN ? R : 1];
   int32_t jval[JOIN ? R : 1]; /* value of the inner column that is packed into the join table (DevJoin::packed_col) */
-#define JX(c) ((JOIN && P.col_inner[c]) ? jidx : nullptr), ((JOIN && (c) == P.join.packed_col) ? jval : nullptr), (JOIN ? P.col_null[c] : 0)
+#define JX(c) ((JOIN && P.col_inner[c]) ? jidx : nullptr), ((JOIN && (c) == P.join.packed_col) ? jval : nullptr), (JOIN == 2 ? P.col_null + (c) : nullptr)
   if (JOIN) {
     const DevJoin& J = P.join;
     const int32_t* __restrict__ buff = Lh.join_buff;
     const bool packed = J.packed_col >= 0;
-    const int32_t packed_null = packed ? (int32_t)P.col_null[J.packed_col] : 0;
+    const int32_t packed_null = (JOIN == 2 && packed) ? (int32_t)P.col_null[J.packed_col] : 0;
     uint32_t matched = 0;
     if (J.fk_width == 8) {
       int64_t k[R];
@@ -511,7 +513,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && k[j] == J.null_val);
         int32_t idx = -1, val = packed_null;
         if (ok) {
-          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.x >= 0 ? e2.y : packed_null; }
+          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = (JOIN == 2 && e2.x < 0) ? packed_null : e2.y; }
           else idx = __ldg(buff + d);
         }
         jidx[JOIN ? j : 0] = idx;
@@ -527,7 +529,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && (int64_t)k[j] == J.null_val);
         int32_t idx = -1, val = packed_null;
         if (ok) {
-          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = e2.x >= 0 ? e2.y : packed_null; }
+          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = (JOIN == 2 && e2.x < 0) ? packed_null : e2.y; }
           else idx = __ldg(buff + d);
         }
         jidx[JOIN ? j : 0] = idx;
@@ -535,7 +537,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         matched |= (uint32_t)(idx >= 0) << j;
       }
     }
-    if (!J.left) valid &= matched; /* INNER: no match, no row; LEFT: the row stays and its inner columns are NULL */
+    if (JOIN != 2) valid &= matched; /* INNER: no match, no row; LEFT: the row stays and its inner columns are NULL */
   }
 
   /* ---- key column: issued before the filter when the planner expects most sectors to be needed anyway ---- */
@@ -909,7 +911,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
 }
 #undef JX
 
-template <int MODE, bool WAGG, bool KEY32, int BLOCK, bool JOIN>
+template <int MODE, bool WAGG, bool KEY32, int BLOCK, int JOIN>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) b2q_k_scan(const __grid_constant__ ScanArgs A) {
   const DevProgram& P = A.prog;
   const DevLaunch& Lh = A.launch;
@@ -1277,7 +1279,7 @@ struct ScanConfig {
   size_t smem_bytes;
 };
 
-template <int MODE, bool WAGG, bool KEY32, int BLOCK, bool JOIN>
+template <int MODE, bool WAGG, bool KEY32, int BLOCK, int JOIN>
 static cudaError_t launch_scan_tb(const ScanArgs& a, const ScanConfig& c, cudaStream_t st) {
   /* the opt-in shared-memory limit is a per-device function attribute: remember which devices have it */
   static unsigned long long attr_set_mask = 0;
@@ -1301,9 +1303,11 @@ static cudaError_t launch_scan_tb(const ScanArgs& a, const ScanConfig& c, cudaSt
 
 template <int MODE, bool WAGG, bool KEY32>
 static cudaError_t launch_scan_t(const ScanArgs& a, const ScanConfig& c, cudaStream_t st) {
-  if (a.prog.join.fk_col >= 0) /* one INNER hash-join level: separate instantiations, the plain scan stays as it was */
-    return c.block == 1024 ? launch_scan_tb<MODE, WAGG, KEY32, 1024, true>(a, c, st) : launch_scan_tb<MODE, WAGG, KEY32, 512, true>(a, c, st);
-  return c.block == 1024 ? launch_scan_tb<MODE, WAGG, KEY32, 1024, false>(a, c, st) : launch_scan_tb<MODE, WAGG, KEY32, 512, false>(a, c, st);
+  if (a.prog.join.fk_col >= 0 && a.prog.join.left) /* one hash-join level: separate instantiations, the plain scan stays as it was */
+    return c.block == 1024 ? launch_scan_tb<MODE, WAGG, KEY32, 1024, 2>(a, c, st) : launch_scan_tb<MODE, WAGG, KEY32, 512, 2>(a, c, st);
+  if (a.prog.join.fk_col >= 0)
+    return c.block == 1024 ? launch_scan_tb<MODE, WAGG, KEY32, 1024, 1>(a, c, st) : launch_scan_tb<MODE, WAGG, KEY32, 512, 1>(a, c, st);
+  return c.block == 1024 ? launch_scan_tb<MODE, WAGG, KEY32, 1024, 0>(a, c, st) : launch_scan_tb<MODE, WAGG, KEY32, 512, 0>(a, c, st);
 }
 
 int scan_rows_per_chunk(int block) { return block * R; }
