@@ -46,7 +46,7 @@ CPU_LEVEL, GPU_LEVEL = 1, 2
 DEVICE_CPU, DEVICE_GPU = 0, 1
 KERNEL_AUTO, KERNEL_NON_GROUPED, KERNEL_PERFECT_SMEM, KERNEL_PERFECT_GLOBAL, KERNEL_BASELINE_GLOBAL = range(5)
 DT_INT64, DT_FLOAT64, DT_UINT8 = 0, 1, 2
-RED_SUM, RED_MIN, RED_MAX = 0, 1, 2
+RED_SUM, RED_MIN, RED_MAX, RED_BOR = 0, 1, 2, 3
 
 MAX_SLOTS = 16
 MAX_TARGETS = 16
@@ -117,6 +117,9 @@ class ExecUnit(C.Structure):
         ("join_qual", C.c_int32),
         ("join_type", C.c_int32),
         ("inner_table", C.c_void_p),   # const B2QTableInfo*
+        ("estimator_args", C.POINTER(C.c_int32)),
+        ("num_estimator_args", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 
@@ -307,6 +310,8 @@ class UnitBuilder:
         self.inner: Optional["Table"] = None            # input_descs[1] of a one-level INNER / LEFT hash join
         self.join_type = 0                              # JoinType: INNER = 0, LEFT = 1
         self.join_qual: int = -1
+        self.estimator_kind = 0                         # 1 = NDVEstimator, 2 = LargeNDVEstimator
+        self.estimator_args: List[int] = []
         self.order: List[Tuple[int, bool, bool]] = []   # sort_info.order_entries: (tle_no 1-based, is_desc, nulls_first)
         self.limit: Optional[int] = None
         self.offset = 0
@@ -390,6 +395,13 @@ class UnitBuilder:
     def target_col(self, col_id: int, rte_idx: int = 0):
         return self.target(self.col(col_id, rte_idx))
 
+    def estimator(self, cols: Sequence, large: bool = False):
+        """RelAlgExecutionUnit::createNdvExecutionUnit: estimator = [Large]NDVEstimator over the GROUP BY tuple; the unit
+        keeps its quals (and join level) but has no groupby_exprs and no targets.  cols: column ids or (id, rte_idx)."""
+        self.estimator_kind = 2 if large else 1
+        self.estimator_args = [self.col(*c) if isinstance(c, tuple) else self.col(c) for c in cols]
+        return self
+
     def order_by(self, tle_no: int, is_desc: bool = False, nulls_first: Optional[bool] = None):
         """sort_info.order_entries.  Default NULL placement is the reference's (NULLs are the largest values:
         last when ascending, first when descending — RelAlgTranslator / Calcite's default collation)."""
@@ -429,6 +441,8 @@ class BuiltUnit:
             self._order[i].tle_no, self._order[i].is_desc, self._order[i].nulls_first = tle, int(desc), int(nf)
         u.order_entries, u.num_order_entries = self._order, len(b.order)
         u.has_limit, u.limit, u.offset = int(b.limit is not None), int(b.limit or 0), int(b.offset)
+        self._est = arr(b.estimator_args)
+        u.has_estimator, u.estimator_args, u.num_estimator_args = b.estimator_kind, self._est, len(b.estimator_args)
         u.join_qual = -1
         self.inner = b.inner
         if b.inner is not None:

@@ -59,7 +59,9 @@ enum {
   ACC_MAX_I64 = 4,
   ACC_MIN_F64 = 5, /* stored as order-preserving int64 */
   ACC_MAX_F64 = 6,
-  ACC_TOUCH = 7    /* "some row reached this group": ONE BYTE per entry (the array holds uint8), merged with MAX */
+  ACC_TOUCH = 7,   /* "some row reached this group": ONE BYTE per entry (the array holds uint8), merged with MAX */
+  ACC_NDV = 8      /* estimator query: the array is the linear-counting bitmap (plan.buffer_size bytes), one bit set per row
+                      at MurmurHash3(tuple of DevProgram::keys) % bits (linear_probabilistic_count), merged with OR */
 };
 
 struct DevAcc {

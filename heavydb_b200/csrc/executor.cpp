@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -210,10 +211,16 @@ struct B2QResultSet {
   ~B2QResultSet() { pinned_cache().put(buf, buf_cap); }
 };
 
+/* bytes of accumulator array a: entry_count x 8, except the estimator's bitmap */
+static size_t acc_array_bytes(const B2QQuery& q, int a) {
+  if (q.prog.accs[a].op == ACC_NDV) return static_cast<size_t>(q.plan.buffer_size);
+  return std::max<size_t>(static_cast<size_t>(q.plan.entry_count), 1) * 8;
+}
+
 static size_t table_bytes(const B2QQuery& q) {
   const size_t n = std::max<size_t>(static_cast<size_t>(q.plan.entry_count), 1);
   size_t total = 0;
-  for (int a = 0; a < q.prog.n_accs; ++a) total += DeviceBlock::pad(n * 8);
+  for (int a = 0; a < q.prog.n_accs; ++a) total += DeviceBlock::pad(acc_array_bytes(q, a));
   if (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL) total += DeviceBlock::pad(n * 8);
   if (q.smem.use_smem) total += DeviceBlock::pad(std::max<int>(q.smem.replica_bytes, 16));
   total += 256; /* error word */
@@ -225,7 +232,7 @@ static int32_t alloc_partial(B2QPartial& p, size_t extra_bytes, cudaStream_t st)
   configure_pool_once(p.device);
   const size_t n = std::max<size_t>(static_cast<size_t>(q.plan.entry_count), 1);
   CU(p.blk.alloc(table_bytes(q) + DeviceBlock::pad(extra_bytes) + 4096, st));
-  for (int a = 0; a < q.prog.n_accs; ++a) p.accs[a] = reinterpret_cast<int64_t*>(p.blk.take(n * 8));
+  for (int a = 0; a < q.prog.n_accs; ++a) p.accs[a] = reinterpret_cast<int64_t*>(p.blk.take(acc_array_bytes(q, a)));
   if (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL) p.keys = reinterpret_cast<int64_t*>(p.blk.take(n * 8));
   if (q.smem.use_smem) p.smem_image = p.blk.take(std::max<int>(q.smem.replica_bytes, 16));
   p.d_error = reinterpret_cast<int32_t*>(p.blk.take(256));
@@ -234,6 +241,8 @@ static int32_t alloc_partial(B2QPartial& p, size_t extra_bytes, cudaStream_t st)
   CU(cudaMemsetAsync(p.d_error, 0, sizeof(int32_t), st));
   CU(cudaEventRecord(p.ev[0], st));
   CU(launch_init(q, p.accs, p.keys, p.smem_image, st));
+  for (int a = 0; a < q.prog.n_accs; ++a) /* the estimator's bitmap starts all-zero */
+    if (q.prog.accs[a].op == ACC_NDV) CU(cudaMemsetAsync(p.accs[a], 0, acc_array_bytes(q, a), st));
   CU(cudaEventRecord(p.ev[1], st));
   return B2Q_OK;
 }
@@ -685,6 +694,17 @@ static int32_t finalize_impl(B2QPartial* p, cudaStream_t st, B2QResultSet** out)
   rs->frags_scanned = p->frags_scanned;
   rs->frags_skipped = p->frags_skipped;
   const size_t nbytes = static_cast<size_t>(p->q.plan.buffer_size);
+  if (p->q.plan.query_desc_type == B2Q_Estimator) { /* the result is the bitmap itself (ResultSet::getHostEstimatorBuffer) */
+    rs->launches = p->launches + 1; /* + b2q_k_init */
+    rs->buf_size = nbytes;
+    rs->buf = pinned_cache().get(nbytes, &rs->buf_cap);
+    if (!rs->buf) return set_err(B2Q_ERR_INVALID_ARGUMENT, "out of (pinned) host memory for the estimator buffer");
+    cudaError_t e = cudaMemcpyAsync(rs->buf, p->accs[0], nbytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(B2Q_ERR_CUDA, std::string("estimator buffer: ") + cudaGetErrorString(e)); }
+    *out = rs.release();
+    return B2Q_OK;
+  }
   const bool want_sort = p->q.n_order > 0 || p->q.has_limit || p->q.offset > 0;
   if (nbytes && want_sort) {
     /* materialise on the device, sort / truncate there, copy back only the kept rows */
@@ -764,6 +784,7 @@ static const int8_t* rs_key_ptr(const B2QResultSet* rs, int64_t e) {
 /* ResultSetStorage::isEmptyEntry / isEmptyEntryColumnar (ResultSetIteration.cpp:2457-2545) */
 static bool rs_is_empty_entry(const B2QResultSet* rs, int64_t e) {
   const B2QPlan& p = rs->q.plan;
+  if (p.query_desc_type == B2Q_Estimator) return true; /* an estimator result set has no storage, only the bitmap */
   if (p.query_desc_type == B2Q_NonGroupedAggregate) return false;
   if (p.keyless_hash) {
     const int s = p.idx_target_as_key;
@@ -843,9 +864,9 @@ int32_t b2q_partial_array(const B2QPartial* p, int32_t i, void** ptr, int64_t* c
   if (!p || i < 0 || i >= p->q.prog.n_accs) return set_err(B2Q_ERR_INVALID_ARGUMENT, "array index");
   const int op = p->q.prog.accs[i].op;
   if (ptr) *ptr = p->accs[i];
-  if (count) *count = p->q.plan.entry_count;
-  if (dtype) *dtype = op == ACC_SUM_F64 ? B2Q_DT_FLOAT64 : op == ACC_TOUCH ? B2Q_DT_UINT8 : B2Q_DT_INT64;
-  if (redop) *redop = (op == ACC_MIN_I64 || op == ACC_MIN_F64) ? B2Q_RED_MIN : (op == ACC_MAX_I64 || op == ACC_MAX_F64 || op == ACC_TOUCH) ? B2Q_RED_MAX : B2Q_RED_SUM;
+  if (count) *count = op == ACC_NDV ? p->q.plan.buffer_size : p->q.plan.entry_count;
+  if (dtype) *dtype = op == ACC_SUM_F64 ? B2Q_DT_FLOAT64 : (op == ACC_TOUCH || op == ACC_NDV) ? B2Q_DT_UINT8 : B2Q_DT_INT64;
+  if (redop) *redop = op == ACC_NDV ? B2Q_RED_BOR : (op == ACC_MIN_I64 || op == ACC_MIN_F64) ? B2Q_RED_MIN : (op == ACC_MAX_I64 || op == ACC_MAX_F64 || op == ACC_TOUCH) ? B2Q_RED_MAX : B2Q_RED_SUM;
   return B2Q_OK;
 }
 int32_t b2q_partial_is_mergeable(const B2QPartial* p) { return p && p->q.plan.kernel != B2Q_KERNEL_BASELINE_GLOBAL; }
@@ -860,6 +881,7 @@ int32_t b2q_launch(const B2QQuery* query, const B2QParams* prm, void* stream) {
   if (!query || !prm) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
   if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible; this path has no CPU fallback");
   if (prm->row_func_mgr) return set_err(B2Q_ERR_UNSUPPORTED, "row function manager");
+  if (query->plan.query_desc_type == B2Q_Estimator) return set_err(B2Q_ERR_UNSUPPORTED, "estimator queries run through b2q_execute_work_unit / b2q_execute_partial");
   const bool has_join = query->prog.join.fk_col >= 0;
   if (has_join != (prm->join_hash_tables != nullptr)) return set_err(B2Q_ERR_INVALID_ARGUMENT, "JOIN_HASH_TABLES must be given exactly when the plan has a join level");
   if (!prm->num_fragments || !prm->col_buffers || !prm->num_rows || !prm->group_by_buffers)
@@ -1000,6 +1022,24 @@ const int8_t* b2q_rs_storage_buffer(const B2QResultSet* rs, size_t* size_bytes) 
 }
 const B2QPlan* b2q_rs_query_mem_desc(const B2QResultSet* rs) { return rs ? &rs->q.plan : nullptr; }
 double b2q_rs_kernel_ms(const B2QResultSet* rs) { return rs ? rs->scan_ms : 0; }
+
+/* ResultSet::getNDVEstimator (CardinalityEstimator.cpp:33-52) */
+size_t b2q_rs_get_ndv_estimator(const B2QResultSet* rs) {
+  if (!rs || rs->q.plan.query_desc_type != B2Q_Estimator || !rs->buf) return 0;
+  size_t bits_set = 0;
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(rs->buf);
+  for (size_t i = 0; i < rs->buf_size / 8; ++i) bits_set += static_cast<size_t>(__builtin_popcountll(w[i]));
+  if (bits_set == 0) return 1; /* empty result: one slot is enough */
+  const size_t total_bits = rs->buf_size * 8;
+  const double ratio = static_cast<double>(total_bits - bits_set) / static_cast<double>(total_bits);
+  if (ratio == 0.) return 0;   /* saturated: no usable estimate */
+  return static_cast<size_t>(-static_cast<double>(total_bits) * log(ratio));
+}
+const int8_t* b2q_rs_estimator_buffer(const B2QResultSet* rs, size_t* size_bytes) {
+  const bool ok = rs && rs->q.plan.query_desc_type == B2Q_Estimator;
+  if (size_bytes) *size_bytes = ok ? rs->buf_size : 0;
+  return ok ? rs->buf : nullptr;
+}
 
 /* ResultSet::sort (ResultSet.cpp:781-849) on an existing result set: the storage buffer goes to the device, the
  * kernels of sort.cu order the non-empty entries, the permutation comes back (the buffer itself is not moved). */

@@ -323,6 +323,13 @@ __device__ __forceinline__ uint32_t murmur3_key(int64_t key, int width) {
   return h1;
 }
 
+/* MurmurHash3_x86_32 finalisation for a key of `len` bytes whose 4-byte blocks were folded with murmur_block */
+__device__ __forceinline__ uint32_t murmur3_fmix(uint32_t h1, uint32_t len) {
+  h1 ^= len;
+  h1 ^= h1 >> 16; h1 *= 0x85ebca6bu; h1 ^= h1 >> 13; h1 *= 0xc2b2ae35u; h1 ^= h1 >> 16;
+  return h1;
+}
+
 /* ---------------------------------------------------------------------------------------------------------
  * global (HBM / L2) reductions without return value
  * ------------------------------------------------------------------------------------------------------- */
@@ -471,6 +478,7 @@ struct ScanArgs {
   const int8_t* smem_image; /* identity image of ONE replica in HBM (MODE_SMEM) */
   int32_t prefetch_distance; /* > 0: TMA bulk-prefetch the column slabs of the chunk this CTA will scan D iterations ahead into L2 */
   int32_t pad_;
+  int64_t ndv_bitmap_bytes;  /* estimator query: size of the ACC_NDV bitmap (a power of two) */
 };
 
 extern __shared__ __align__(128) int8_t b2q_smem[];
@@ -752,6 +760,44 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     /* flags array when THIS accumulator carries the touched flag for the global-table kernels */
     uint8_t* pig = (MODE != MODE_SMEM && P.touch_piggyback == a) ? reinterpret_cast<uint8_t*>(Lh.accs[P.touch_acc]) : nullptr;
 
+    if (op == ACC_NDV) {
+      /* estimator query: linear_probabilistic_count (RuntimeFunctions.cpp:2399-2408, cuda_mapd_rt.cu:1300-1308) over
+       * the tuple of int64 sub-keys (codegenEstimator); the bitmap lives in HBM/L2 and saturates quickly, so a
+       * plain load filters out the bits that are already set before the atomic OR */
+      if (WAGG) {
+        uint32_t h[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) h[j] = 0;
+        for (int c = 0; c < P.n_keys; ++c) {
+          const DevKeyComp& kc = P.keys[c];
+          int64_t k[R];
+          if (kc.width == 8) load64<true>(k, cols[kc.col], row0, nthr, pass, pol, JX(kc.col));
+          else {
+            int32_t t32[R];
+            load32<true>(t32, cols[kc.col], kc.width, row0, nthr, pass, pol, JX(kc.col));
+#pragma unroll
+            for (int j = 0; j < R; ++j) k[j] = t32[j];
+          }
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const int64_t v = (kc.translate_null && k[j] == kc.null_val) ? kc.null_logical : k[j];
+            h[j] = murmur_block(murmur_block(h[j], (uint32_t)v), (uint32_t)((uint64_t)v >> 32));
+          }
+        }
+        uint32_t* bitmap = reinterpret_cast<uint32_t*>(garr);
+        const uint32_t bits_mask = (uint32_t)(A.ndv_bitmap_bytes * 8ull - 1ull); /* the buffer sizes are powers of two */
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          if (!(pass >> j & 1)) continue;
+          const uint32_t bit_pos = murmur3_fmix(h[j], (uint32_t)P.n_keys * 8u) & bits_mask;
+          const uint32_t bit = 1u << (bit_pos & 31u);
+          uint32_t* w = bitmap + (bit_pos >> 5);
+          if (!(__ldcg(w) & bit)) atomicOr(w, bit);
+        }
+      }
+      continue;
+    }
+
     if (op == ACC_COUNT && acc.col < 0) { /* COUNT(*) */
       if (WAGG) {
         const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(pass));
@@ -1007,6 +1053,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) b2q_k_scan(const __grid_c
       const int8_t* base = b2q_smem + A.smem.acc_off[a];
       for (int64_t i = tid; i < n; i += nthr) {
         switch (op) {
+          case ACC_NDV: break; /* lives in HBM only */
           case ACC_TOUCH: {
             uint32_t s = 0;
             for (int r = 0; r < nrep; ++r) s |= reinterpret_cast<const uint8_t*>(base + (size_t)r * rb)[i];
@@ -1329,6 +1376,7 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
   a.smem_image = smem_image;
   a.prefetch_distance = prefetch_distance;
   a.pad_ = 0;
+  a.ndv_bitmap_bytes = q.plan.query_desc_type == B2Q_Estimator ? q.plan.buffer_size : 0;
   ScanConfig c;
   c.block = block;
   const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;

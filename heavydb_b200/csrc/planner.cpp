@@ -115,6 +115,13 @@ class Planner {
     q.prog.join.fk_col = -1;
     q.plan.join_outer_col = q.plan.join_inner_col = -1;
     validate();
+    if (u_.has_estimator) { /* createNdvExecutionUnit: quals (+ join level) and the estimator's tuple, nothing else */
+      plan_join(q.plan);
+      plan_estimator(q.plan);
+      lower(q);
+      choose_kernel(q);
+      return;
+    }
     build_targets();
     plan_join(q.plan);
     choose_hash_type(q.plan);
@@ -179,6 +186,32 @@ class Planner {
     p.join_inner_col = join_inner_col_;
   }
 
+  /* QueryDescriptionType::Estimator (QueryMemoryDescriptor::init :270-300): entry_count 1, the output is the
+   * estimator's bitmap of Estimator::getBufferSize() bytes (CardinalityEstimator.h:89-116, .cpp:27-29) */
+  std::vector<int> estimator_cols_;
+  void plan_estimator(B2QPlan& p) {
+    if (u_.has_estimator != 1 && u_.has_estimator != 2) reject(B2Q_ERR_INVALID_ARGUMENT, "estimator kind");
+    if (u_.num_groupby_exprs || u_.num_target_exprs || u_.num_order_entries || u_.has_limit || u_.offset)
+      reject(B2Q_ERR_INVALID_ARGUMENT, "an estimator unit has no groupby_exprs, targets or sort_info");
+    if (u_.num_estimator_args <= 0 || u_.num_estimator_args > B2Q_MAX_GROUP_COLS || !u_.estimator_args)
+      reject(B2Q_ERR_UNSUPPORTED, "estimator argument count");
+    p.query_desc_type = B2Q_Estimator;
+    p.entry_count = 1;
+    p.key_col_id = -1;
+    p.idx_target_as_key = -1;
+    p.effective_key_width = 8;
+    p.buffer_size = (u_.has_estimator == 2 ? int64_t(256) : int64_t(1)) * 1024 * 1024;
+    for (int i = 0; i < u_.num_estimator_args; ++i) {
+      const B2QExpr& e = ex(u_.estimator_args[i]);
+      if (e.kind != B2Q_EXPR_COLUMN_VAR) reject(B2Q_ERR_UNSUPPORTED, "estimator argument must be a ColumnVar");
+      if (!col_type(e.col_id).is_int()) reject(B2Q_ERR_UNSUPPORTED, "estimator over a floating-point key");
+      estimator_cols_.push_back(e.col_id);
+      p.group_col_ids[i] = e.col_id;
+      p.group_col_widths[i] = static_cast<int8_t>(col_type(e.col_id).size());
+    }
+    p.num_group_cols = u_.num_estimator_args;
+  }
+
   const B2QExpr& ex(int i) const {
     if (i < 0 || i >= u_.num_exprs) reject(B2Q_ERR_INVALID_ARGUMENT, "expression index out of range");
     return u_.exprs[i];
@@ -203,8 +236,8 @@ class Planner {
   }
 
   void validate() {
-    if (u_.num_join_quals || u_.has_estimator || u_.has_union_all || u_.has_window_function)
-      reject(B2Q_ERR_UNSUPPORTED, "join_quals / estimator / union_all / window functions are outside this path");
+    if (u_.num_join_quals || u_.has_union_all || u_.has_window_function)
+      reject(B2Q_ERR_UNSUPPORTED, "join_quals / union_all / window functions are outside this path");
     if (u_.num_order_entries < 0 || u_.num_order_entries > B2Q_MAX_ORDER_ENTRIES) reject(B2Q_ERR_UNSUPPORTED, "more ORDER BY entries than the path carries");
     if (u_.num_order_entries && !u_.order_entries) reject(B2Q_ERR_INVALID_ARGUMENT, "order_entries is null");
     for (int i = 0; i < u_.num_order_entries; ++i)
@@ -212,7 +245,7 @@ class Planner {
         reject(B2Q_ERR_INVALID_ARGUMENT, "order entry refers to a target that does not exist (tle_no is 1-based)");
     if (u_.offset < 0 || (u_.has_limit && u_.limit < 0)) reject(B2Q_ERR_INVALID_ARGUMENT, "negative LIMIT / OFFSET");
     if (u_.num_groupby_exprs > B2Q_MAX_GROUP_COLS) reject(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
-    if (u_.num_groupby_exprs < 0 || u_.num_target_exprs <= 0 || u_.num_target_exprs > B2Q_MAX_TARGETS)
+    if (u_.num_groupby_exprs < 0 || (u_.num_target_exprs <= 0 && !u_.has_estimator) || u_.num_target_exprs > B2Q_MAX_TARGETS)
       reject(B2Q_ERR_INVALID_ARGUMENT, "bad groupby/target counts");
     for (int c = 0; c < t_.num_cols; ++c) {
       const bool is_deleted_col = t_.deleted_column_plus1 == c + 1;
@@ -861,6 +894,42 @@ class Planner {
     g.eager_key = g.est_selectivity >= 0.10f;
     g.eager_args = g.est_selectivity >= 0.25f;
 
+    if (u_.has_estimator) { /* the tuple rides in keys[]; ONE accumulator: the bitmap (see ACC_NDV) */
+      g.n_keys = static_cast<int32_t>(estimator_cols_.size());
+      for (size_t i = 0; i < estimator_cols_.size(); ++i) {
+        const int c = estimator_cols_[i];
+        const SqlType kt = col_type(c);
+        DevKeyComp& d = g.keys[i];
+        d.col = launch_col(q, c);
+        d.width = static_cast<int8_t>(phys_width_code(c));
+        /* groupByColumnCodegen without NULL translation: a NULL contributes the LOGICAL sentinel, so the chunk's
+         * physical sentinel (ENCODING FIXED / DICT(8|16)) is mapped back */
+        d.translate_null = !kt.notnull && phys_int_null(c) != kt.int_null();
+        d.null_val = phys_int_null(c);
+        d.null_logical = kt.int_null();
+        g.col_prefetch[d.col] = 1;
+      }
+      g.key.col = -1;
+      g.key.entry_count = 1;
+      DevAcc a;
+      memset(&a, 0, sizeof(a));
+      a.op = ACC_NDV;
+      a.col = -1;
+      g.accs[0] = a;
+      g.n_accs = 1;
+      g.fused = 0; g.fused_cnt = -1; g.fused_sum = -1; g.touch_acc = -1; g.touch_piggyback = -1;
+      DevLayout& EL = q.layout;
+      EL.entry_count = 1;
+      EL.n_slots = 0;
+      EL.touched_acc = -1;
+      EL.keyless_marker = -1;
+      for (int t = 0; t < g.filter.n_terms; ++t) g.col_prefetch[g.filter.terms[t].col] = 1;
+      if (join_) g.col_prefetch[g.join.fk_col] = 1;
+      g.join.packed_col = -1;
+      for (int c = 0; c < g.n_cols; ++c) if (g.col_inner[c]) g.col_prefetch[c] = 0;
+      return;
+    }
+
     /* key */
     g.n_keys = static_cast<int32_t>(keycomps_.size());
     for (size_t i = 0; i < keycomps_.size(); ++i) {
@@ -1052,7 +1121,7 @@ class Planner {
       sm.total_bytes = static_cast<int32_t>(per_replica * rep);
     };
     int kernel;
-    if (p.query_desc_type == B2Q_NonGroupedAggregate) {
+    if (p.query_desc_type == B2Q_NonGroupedAggregate || p.query_desc_type == B2Q_Estimator) {
       kernel = B2Q_KERNEL_NON_GROUPED;
       use_smem_table();
     } else if (p.query_desc_type == B2Q_GroupByBaselineHash) {

@@ -107,6 +107,10 @@ def lib():
         L.b2q_rs_free.argtypes = [C.c_void_p]
         L.b2q_rs_stat.restype = C.c_int64
         L.b2q_rs_stat.argtypes = [C.c_void_p, C.c_int32]
+        L.b2q_rs_get_ndv_estimator.restype = C.c_size_t
+        L.b2q_rs_get_ndv_estimator.argtypes = [C.c_void_p]
+        L.b2q_rs_estimator_buffer.restype = C.c_void_p
+        L.b2q_rs_estimator_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         L.b2q_rs_sort.restype = C.c_int32
         L.b2q_rs_sort.argtypes = [C.c_void_p, C.POINTER(abi.OrderEntry), C.c_int32, C.c_size_t]
         L.b2q_rs_drop_first_n.argtypes = [C.c_void_p, C.c_size_t]
@@ -222,6 +226,17 @@ class ResultSet:
         return {"fragments_scanned": L.b2q_rs_stat(self._h, 0), "fragments_skipped": L.b2q_rs_stat(self._h, 1),
                 "kernel_launches": L.b2q_rs_stat(self._h, 2), "h2d_bytes": L.b2q_rs_stat(self._h, 3),
                 "sort_us": L.b2q_rs_stat(self._h, 4)}
+
+    def getNDVEstimator(self) -> int:
+        """ResultSet::getNDVEstimator (CardinalityEstimator.cpp:33-52) of an estimator query."""
+        return lib().b2q_rs_get_ndv_estimator(self._h)
+
+    def getHostEstimatorBuffer(self) -> np.ndarray:
+        n = C.c_size_t()
+        p = lib().b2q_rs_estimator_buffer(self._h, C.byref(n))
+        if not p or n.value == 0:
+            return np.zeros(0, dtype=np.uint8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
 
     def sort(self, order_entries, top_n: int = 0):
         """ResultSet::sort(order_entries, top_n) (ResultSet.h:279): order_entries = [(tle_no, is_desc, nulls_first)]."""

@@ -39,8 +39,17 @@ def reduce_op(dist, redop: int):
 
 
 def allreduce_tensors(tensors_and_ops: Sequence[tuple], dist) -> None:
-    """[(tensor, redop)] -> in-place all-reduce of each (works for CUDA/NCCL and CPU/gloo tensors alike)."""
+    """[(tensor, redop)] -> in-place all-reduce of each (works for CUDA/NCCL and CPU/gloo tensors alike).  Bitwise OR
+    (the estimator bitmap, reduce_estimator_results CardinalityEstimator.cpp:142-161) is not an NCCL reduction: the
+    bitmaps are all-gathered and OR-ed locally."""
     for t, op in tensors_and_ops:
+        if op == abi.RED_BOR:
+            parts = [t.new_empty(t.shape) for _ in range(dist.get_world_size())]
+            dist.all_gather(parts, t)
+            t.zero_()
+            for p in parts:
+                t.bitwise_or_(p)
+            continue
         dist.all_reduce(t, op=reduce_op(dist, op))
 
 

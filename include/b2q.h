@@ -152,7 +152,11 @@ typedef struct B2QExecUnit {
    * be nullable, as RelAlgTranslator makes them.  Anything else (one-to-many, baseline join tables, more levels) is
    * rejected. */
   int32_t num_join_quals;      /* 0 or 1 */
-  /* Fields of the reference struct that are outside this path.  Must be zero or the call is rejected. */
+  /* estimator (RelAlgExecutionUnit::createNdvExecutionUnit, CardinalityEstimator.cpp:94-116): 0 = none, 1 =
+   * Analyzer::NDVEstimator (1 MiB bitmap), 2 = LargeNDVEstimator (256 MiB).  The unit then has no groupby_exprs and
+   * no target_exprs; every row that passes the quals hashes the tuple `estimator_args` (each widened to int64, NULLs
+   * as their sentinel) with MurmurHash3 and sets one bit (linear_probabilistic_count, RuntimeFunctions.cpp:2399-2408,
+   * codegenEstimator GroupByAndAggregate.cpp:1825-1864).  b2q_rs_get_ndv_estimator() is ResultSet::getNDVEstimator. */
   int32_t has_estimator;
   int32_t has_union_all;
   int32_t has_window_function;
@@ -173,6 +177,9 @@ typedef struct B2QExecUnit {
    * fragments (ColumnFetcher::getAllTableColumnFragments, ColumnFetcher.cpp:290-360), i.e. exactly one fragment whose
    * chunk stats cover the table; memory_level CPU (copied to the device per query) or GPU */
   const struct B2QTableInfo* inner_table;
+  const int32_t* estimator_args; /* expr indices of the estimator's argument tuple (ColumnVars) */
+  int32_t num_estimator_args;
+  int32_t pad_;
 } B2QExecUnit;
 
 /* ---- ChunkMetadata::chunkStats per (fragment, column)  (Fragmenter/Fragmenter.h:73-146) ---------------- */
@@ -354,7 +361,9 @@ int32_t b2q_execute_partial(size_t* max_groups_buffer_entry_guess, int32_t is_ag
  * one all-reduce per array — the device-side replacement of ResultSetStorage::reduce
  * (ResultSetReduction.cpp:203-396, slot op :1496-1566). */
 enum { B2Q_DT_INT64 = 0, B2Q_DT_FLOAT64 = 1, B2Q_DT_UINT8 = 2 /* "group touched" flags, merged with MAX */ };
-enum { B2Q_RED_SUM = 0, B2Q_RED_MIN = 1, B2Q_RED_MAX = 2 };
+enum { B2Q_RED_SUM = 0, B2Q_RED_MIN = 1, B2Q_RED_MAX = 2,
+       B2Q_RED_BOR = 3 /* bitwise OR: the estimator bitmap (reduce_estimator_results, CardinalityEstimator.cpp:142-161);
+                          NCCL has no OR — all-gather + OR, see heavydb_b200/multigpu.py */ };
 int32_t b2q_partial_num_arrays(const B2QPartial* p);
 int32_t b2q_partial_array(const B2QPartial* p, int32_t i, void** device_ptr, int64_t* count, int32_t* dtype,
                           int32_t* redop);
@@ -393,6 +402,10 @@ double b2q_rs_kernel_ms(const B2QResultSet* rs);
 /* ResultSet::sort(order_entries, top_n) (ResultSet.h:279, ResultSet.cpp:781-849) followed by iteration in sorted
  * order; top_n == 0 sorts everything.  dropFirstN / keepFirstN are SQL OFFSET / LIMIT (ResultSet.cpp:58-66).
  * The sort runs on the device (sort.cu); ties keep ascending entry order. */
+/* ResultSet::getNDVEstimator (CardinalityEstimator.cpp:33-52) of an estimator query: -total_bits * ln(unset/total),
+ * 1 for an empty bitmap, 0 when every bit is set; b2q_rs_estimator_buffer = getHostEstimatorBuffer(). */
+size_t b2q_rs_get_ndv_estimator(const B2QResultSet* rs);
+const int8_t* b2q_rs_estimator_buffer(const B2QResultSet* rs, size_t* size_bytes);
 int32_t b2q_rs_sort(B2QResultSet* rs, const B2QOrderEntry* order_entries, int32_t num_order_entries, size_t top_n);
 void b2q_rs_drop_first_n(B2QResultSet* rs, size_t n);
 void b2q_rs_keep_first_n(B2QResultSet* rs, size_t n);

@@ -372,6 +372,8 @@ struct Plan {
   bool join_outer_nullable{false};
   bool join_left{false};
   std::shared_ptr<std::vector<int32_t>> join_buff;
+  /* estimator query (QueryDescriptionType::Estimator): the argument tuple's (virtual) column ids */
+  std::vector<int> estimator_cols;
 };
 
 const B2QExpr& expr_at(const B2QExecUnit& u, int idx) {
@@ -609,8 +611,37 @@ constexpr int64_t kMaxBufferSize = int64_t(1) << 30;   /* GroupByAndAggregate.cp
 
 Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecutionOptions& eo,
                       size_t max_groups_buffer_entry_guess, bool has_cardinality_estimation) {
-  if (u.has_estimator || u.has_union_all || u.has_window_function)
-    fail(B2Q_ERR_UNSUPPORTED, "estimator / union / window functions are outside this path");
+  if (u.has_union_all || u.has_window_function)
+    fail(B2Q_ERR_UNSUPPORTED, "union / window functions are outside this path");
+  if (u.has_estimator) {
+    /* RelAlgExecutionUnit::createNdvExecutionUnit (CardinalityEstimator.cpp:94-116): no groupby_exprs, no targets,
+     * estimator = NDVEstimator / LargeNDVEstimator over the GROUP BY tuple; QueryMemoryDescriptor::init returns the
+     * Estimator descriptor with entry_count 1 (QueryMemoryDescriptor.cpp:270-300) */
+    if (u.has_estimator != 1 && u.has_estimator != 2) fail(B2Q_ERR_INVALID_ARGUMENT, "estimator kind");
+    if (u.num_groupby_exprs || u.num_target_exprs || u.num_order_entries || u.has_limit || u.offset)
+      fail(B2Q_ERR_INVALID_ARGUMENT, "an estimator unit has no groupby_exprs, targets or sort_info");
+    if (u.num_estimator_args <= 0 || u.num_estimator_args > B2Q_MAX_GROUP_COLS) fail(B2Q_ERR_UNSUPPORTED, "estimator argument count");
+    Plan plan;
+    B2QPlan& p = plan.p;
+    p.query_desc_type = B2Q_Estimator;
+    p.entry_count = 1;
+    p.key_col_id = -1;
+    p.idx_target_as_key = -1;
+    p.effective_key_width = 8;
+    p.join_outer_col = p.join_inner_col = -1;
+    p.buffer_size = (u.has_estimator == 2 ? int64_t(256) : int64_t(1)) * 1024 * 1024; /* Estimator::getBufferSize() */
+    for (int i = 0; i < u.num_estimator_args; ++i) {
+      const B2QExpr& e = expr_at(u, u.estimator_args[i]);
+      if (e.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "estimator argument must be a ColumnVar");
+      if (e.col_id < 0 || e.col_id >= tbl.num_cols) fail(B2Q_ERR_INVALID_ARGUMENT, "column id out of range");
+      if (!is_integer(tbl.col_types[e.col_id].type)) fail(B2Q_ERR_UNSUPPORTED, "estimator over a floating-point key");
+      plan.estimator_cols.push_back(e.col_id);
+      p.group_col_ids[i] = e.col_id;
+      p.group_col_widths[i] = static_cast<int8_t>(type_size(tbl.col_types[e.col_id].type));
+    }
+    p.num_group_cols = u.num_estimator_args;
+    return plan;
+  }
   if (u.num_order_entries < 0 || u.num_order_entries > 8) fail(B2Q_ERR_UNSUPPORTED, "more ORDER BY entries than the path carries");
   for (int i = 0; i < u.num_order_entries; ++i)
     if (u.order_entries[i].tle_no < 1 || u.order_entries[i].tle_no > u.num_target_exprs) fail(B2Q_ERR_INVALID_ARGUMENT, "order entry refers to a target that does not exist");
@@ -1238,6 +1269,7 @@ void update_target(const Plan& plan, const Target& t, int8_t* out, int64_t entry
 void init_buffer(const Plan& plan, std::vector<int8_t>& buf) {
   const B2QPlan& p = plan.p;
   buf.assign(static_cast<size_t>(p.buffer_size), 0);
+  if (p.query_desc_type == B2Q_Estimator) return; /* the estimator buffer is a zeroed bitmap (QueryMemoryInitializer: allocateCountDistinct... / estimator_result_set_) */
   const bool has_key = p.query_desc_type != B2Q_NonGroupedAggregate && !p.keyless_hash;
   for (int64_t e = 0; e < p.entry_count; ++e) {
     if (has_key) {
@@ -1280,6 +1312,17 @@ int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo&
       g_join_row.inner_pos = idx;        /* LEFT join: -1 => the inner columns read NULL */
     }
     if (!row_passes(u, tbl, fr, pos)) continue;
+    if (p.query_desc_type == B2Q_Estimator) {
+      /* codegenEstimator (GroupByAndAggregate.cpp:1825-1864): the tuple as int64 sub-keys (groupByColumnCodegen without
+       * NULL translation: a NULL is its sentinel) -> linear_probabilistic_count (RuntimeFunctions.cpp:2399-2408) */
+      int64_t key[B2Q_MAX_GROUP_COLS];
+      const int n = static_cast<int>(plan.estimator_cols.size());
+      for (int i = 0; i < n; ++i) key[i] = decode_int_column(tbl, fr, plan.estimator_cols[i], pos);
+      const uint32_t bitmap_bytes = static_cast<uint32_t>(p.buffer_size);
+      const uint32_t bit_pos = murmur3(key, n * 8, 0) % (bitmap_bytes * 8);
+      reinterpret_cast<uint32_t*>(buf.data())[bit_pos / 32] |= 1u << (bit_pos % 32);
+      continue;
+    }
     int64_t entry = 0;
     if (p.query_desc_type != B2Q_NonGroupedAggregate) {
       if (plan.keys.size() > 1) {
@@ -1419,6 +1462,10 @@ void reduce_one_row(const Plan& plan, int8_t* this_buf, int64_t this_e, const in
  * non-empty `that` entry into `this` (:698-828). */
 int32_t reduce_buffers(const Plan& plan, std::vector<int8_t>& this_buf, const std::vector<int8_t>& that_buf) {
   const B2QPlan& p = plan.p;
+  if (p.query_desc_type == B2Q_Estimator) { /* reduce_estimator_results (CardinalityEstimator.cpp:142-161) */
+    for (size_t i = 0; i < this_buf.size(); ++i) this_buf[i] |= that_buf[i];
+    return 0;
+  }
   if (p.query_desc_type == B2Q_NonGroupedAggregate) {
     reduce_one_row(plan, this_buf.data(), 0, that_buf.data(), 0);
     return 0;
@@ -1639,6 +1686,7 @@ ORACLE_EXPORT void oracle_result_keep_first_n(OracleResult* r, size_t n) { r->ke
 ORACLE_EXPORT int64_t oracle_result_permutation_at(const OracleResult* r, size_t i) { return r->sorted && i < r->perm.size() ? r->perm[i] : -1; }
 ORACLE_EXPORT int32_t oracle_result_is_row_at_empty(const OracleResult* r, size_t e) { return is_empty_entry(r->plan.p, r->buf.data(), static_cast<int64_t>(e)); }
 ORACLE_EXPORT size_t oracle_result_row_count(const OracleResult* r) { /* ResultSet::rowCountImpl (ResultSet.cpp:565-600) */
+  if (r->plan.p.query_desc_type == B2Q_Estimator) return 0; /* an estimator result set has no storage, only the bitmap */
   size_t n = 0;
   if (r->sorted) n = r->perm.size();
   else for (int64_t e = 0; e < r->plan.p.entry_count; ++e) n += !is_empty_entry(r->plan.p, r->buf.data(), e);
@@ -1647,6 +1695,18 @@ ORACLE_EXPORT size_t oracle_result_row_count(const OracleResult* r) { /* ResultS
   return r->keep_first ? std::min(n, r->keep_first) : n;
 }
 ORACLE_EXPORT size_t oracle_result_col_count(const OracleResult* r) { return r->plan.targets.size(); }
+/* ResultSet::getNDVEstimator (CardinalityEstimator.cpp:33-52) */
+ORACLE_EXPORT size_t oracle_result_ndv_estimator(const OracleResult* r) {
+  if (r->plan.p.query_desc_type != B2Q_Estimator) return 0;
+  size_t bits_set = 0;
+  for (int8_t b : r->buf) bits_set += static_cast<size_t>(__builtin_popcount(static_cast<uint8_t>(b)));
+  if (bits_set == 0) return 1;
+  const size_t total_bits = r->buf.size() * 8;
+  const size_t unset_bits = total_bits - bits_set;
+  const double ratio = static_cast<double>(unset_bits) / static_cast<double>(total_bits);
+  if (ratio == 0.) return 0;
+  return static_cast<size_t>(-static_cast<double>(total_bits) * log(ratio));
+}
 ORACLE_EXPORT void oracle_result_move_to_begin(OracleResult* r) { r->cursor = 0; r->fetched = 0; }
 ORACLE_EXPORT void oracle_result_free(OracleResult* r) { delete r; }
 
@@ -1661,6 +1721,7 @@ ORACLE_EXPORT B2QTypeInfo oracle_result_col_type(const OracleResult* r, size_t c
  * AVG via make_avg_target_value (:43-82) + pair_to_double (ResultSetBufferAccessors.h:197-227). */
 ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue* row) {
   const B2QPlan& p = r->plan.p;
+  if (p.query_desc_type == B2Q_Estimator) return 0;
   /* getNextRowImpl + advanceCursorToNextEntry (ResultSetIteration.cpp:320-340, :731-750) */
   const int64_t n_entries = r->sorted ? static_cast<int64_t>(r->perm.size()) : p.entry_count;
   int64_t entry = 0;

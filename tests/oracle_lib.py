@@ -43,6 +43,8 @@ def lib():
         L.oracle_result_col_type.argtypes = [C.c_void_p, C.c_size_t]
         L.oracle_result_get_next_row.restype = C.c_int32
         L.oracle_result_get_next_row.argtypes = [C.c_void_p, C.POINTER(abi.TargetValue)]
+        L.oracle_result_ndv_estimator.restype = C.c_size_t
+        L.oracle_result_ndv_estimator.argtypes = [C.c_void_p]
         L.oracle_result_sort.restype = C.c_int32
         L.oracle_result_sort.argtypes = [C.c_void_p, C.POINTER(abi.OrderEntry), C.c_int32, C.c_size_t]
         L.oracle_result_drop_first_n.argtypes = [C.c_void_p, C.c_size_t]
@@ -78,6 +80,9 @@ class OracleResult:
 
     def row_count(self):
         return lib().oracle_result_row_count(self.h)
+
+    def ndv_estimator(self):
+        return lib().oracle_result_ndv_estimator(self.h)
 
     def sort(self, order_entries, top_n=0):
         """ResultSet::sort: order_entries = [(tle_no, is_desc, nulls_first)]."""
