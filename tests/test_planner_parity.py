@@ -60,7 +60,7 @@ def test_cardinality_estimation_required(table):
 
 
 def test_unsupported_is_rejected_not_ignored(table):
-    for field, val in (("num_join_quals", 2), ("has_estimator", 1), ("has_union_all", 1), ("has_window_function", 1)):
+    for field, val in (("num_join_quals", 2), ("has_union_all", 1), ("has_window_function", 1)):
         b = abi.UnitBuilder(table)
         b.target(b.agg(abi.kCOUNT))
         b.unsupported[field] = val
