@@ -162,6 +162,17 @@ def _worker(rank, world, port, out_q):
             except AssertionError as e:  # noqa
                 ok = False
                 out_q.put((rank, sql, str(e)[:500]))
+        # the estimator query: per-rank linear-counting bitmaps merge with OR (reduce_estimator_results)
+        for cols in (["t"], ["x", "y"]):
+            b = abi.UnitBuilder(full)
+            b.estimator([rt.TEST_NAMES.index(c) for c in cols])
+            eu = b.build()
+            mine_bits = torch.from_numpy(oracle_lib.execute(eu, plan_table).buffer().view(np.uint8).copy())
+            multigpu.allreduce_tensors([(mine_bits, abi.RED_BOR)], dist)
+            want_bits = oracle_lib.execute(eu, full).buffer().view(np.uint8)
+            if not np.array_equal(mine_bits.numpy(), want_bits):
+                ok = False
+                out_q.put((rank, f"estimator {cols}", "OR-merged bitmap differs from the whole-table bitmap"))
         out_q.put((rank, "done", ok))
     finally:
         dist.destroy_process_group()
