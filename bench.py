@@ -70,7 +70,21 @@ CONFIGS["c4top"] = (CONFIGS["c4"][0], "SELECT key, SUM(v) FROM t GROUP BY key OR
 CONFIGS["c2join"] = ([("c0", "i64", 0, 10**6), ("c1", "i64", 0, 10**6), ("fk", "i32", 0, 10**5)],
                      "SELECT d.attr, SUM(t.c1), COUNT(*) FROM t JOIN d ON t.fk = d.id WHERE t.c0 < 500000 GROUP BY d.attr;", 20,
                      "configs[1] shape through a star join: filter c0<k (50%), INNER JOIN dim(1e5 rows) ON fk = id, GROUP BY dim.attr (1000 groups), SUM/COUNT")
+# the cardinality-estimation query that precedes c4s in the reference's flow (CardinalityEstimationRequired ->
+# RelAlgExecutor::getNDVEstimation): NDVEstimator over the sparse key, 8 B/row
+CONFIGS["c4sndv"] = ([("key", "i64", 0, 10**7, 900_000_000_007)], "ESTIMATOR NDV(key)", 8,
+                     "NDV estimator query over 1e7 sparse int64 keys (linear_probabilistic_count into a 1 MiB bitmap)")
 ENTRY_GUESS = {"c4s": 15_000_000}
+
+
+def make_unit(cfg, sql, table, names):
+    """The execution unit of a config: parsed SQL, or the estimator unit (no SQL form: RelAlgExecutor synthesises it)."""
+    from heavydb_b200 import abi, sqlmini
+    if sql.startswith("ESTIMATOR"):
+        b = abi.UnitBuilder(table)
+        b.estimator([names.index("key")])
+        return b.build()
+    return sqlmini.parse(sql, table, names, inner=join_inner(cfg))
 
 
 def join_inner(cfg):
@@ -223,7 +237,7 @@ def run_reference(args):
         table.add_host_fragment([oracle_lib.gen_column(phys_type(c), SEED, tag, f * frag_rows, frag_rows, c[2], c[3], threads,
                                                        stride=col_stride(c)) for tag, c in enumerate(cols)])
     names = [c[0] for c in cols]
-    unit = sqlmini.parse(sql, table, names, inner=join_inner(args.config))
+    unit = make_unit(args.config, sql, table, names)
     rows = nfrag * frag_rows
     guess = ENTRY_GUESS.get(args.config, 0)
     times = []
@@ -262,7 +276,7 @@ def cpu_baseline_sample(cfg, budget_s=15.0):
     for f in range(nfrag):
         table.add_host_fragment([oracle_lib.gen_column(phys_type(c), SEED, tag, f * frag_rows, frag_rows, c[2], c[3], threads,
                                                        stride=col_stride(c)) for tag, c in enumerate(cols)])
-    unit = sqlmini.parse(sql, table, [c[0] for c in cols], inner=join_inner(cfg))
+    unit = make_unit(cfg, sql, table, [c[0] for c in cols])
     rows = nfrag * frag_rows
     guess = ENTRY_GUESS.get(cfg, 0)
     oracle_lib.execute(unit, table, entry_guess=guess, has_card=guess > 0, num_threads=threads)  # warm
@@ -314,7 +328,7 @@ def main():
     nfrag_per_rank = (rows + FRAG_ROWS - 1) // FRAG_ROWS
     frag_ids = multigpu.shard_fragments(range(nfrag_per_rank * world), rank, world)  # fragment_id % num_devices == rank
     table, keep = build_device_table(args.config, rows, frag_ids, torch)
-    unit = sqlmini.parse(sql, table, names, inner=join_inner(args.config))
+    unit = make_unit(args.config, sql, table, names)
     ex = executor.Executor()
     eo = executor.execution_options(force_kernel=args.force_kernel)
     guess = ENTRY_GUESS.get(args.config, 0)
@@ -352,7 +366,7 @@ def main():
         t_end = time.time()
         launches_per_step = rs.stats()["kernel_launches"]
         sort_us = rs.stats()["sort_us"]
-        result_rows = rs.rowCount()
+        result_rows = rs.rowCount() if not sql.startswith("ESTIMATOR") else rs.getNDVEstimator()
         plan_kernel, plan_entries = int(rs.getQueryMemDesc().kernel), int(rs.getQueryMemDesc().entry_count)
         del rs, part
     clocks = sampler.stop(t_begin, t_end)
@@ -474,7 +488,7 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
     torch.cuda.synchronize()
     if old_aff:
         os.sched_setaffinity(0, old_aff)
-    unit = sqlmini.parse(sql, table, names, inner=join_inner(args.config))
+    unit = make_unit(args.config, sql, table, names)
     bt = table.build(abi.CPU_LEVEL)
     times = []
     d2h = 0
