@@ -70,6 +70,9 @@ CONFIGS["c4top"] = (CONFIGS["c4"][0], "SELECT key, SUM(v) FROM t GROUP BY key OR
 CONFIGS["c2join"] = ([("c0", "i64", 0, 10**6), ("c1", "i64", 0, 10**6), ("fk", "i32", 0, 10**5)],
                      "SELECT d.attr, SUM(t.c1), COUNT(*) FROM t JOIN d ON t.fk = d.id WHERE t.c0 < 500000 GROUP BY d.attr;", 20,
                      "configs[1] shape through a star join: filter c0<k (50%), INNER JOIN dim(1e5 rows) ON fk = id, GROUP BY dim.attr (1000 groups), SUM/COUNT")
+CONFIGS["c2joins"] = ([("c0", "i64", 0, 10**6), ("c1", "i64", 0, 10**6), ("fk", "i32", 0, 10**4)],
+                      CONFIGS["c2join"][1], 20,
+                      "star join with a 1e4-row dimension: the (packed) join table is TMA-staged into shared memory")
 # the cardinality-estimation query that precedes c4s in the reference's flow (CardinalityEstimationRequired ->
 # RelAlgExecutor::getNDVEstimation): NDVEstimator over the sparse key, 8 B/row
 CONFIGS["c4sndv"] = ([("key", "i64", 0, 10**7, 900_000_000_007)], "ESTIMATOR NDV(key)", 8,
@@ -89,10 +92,10 @@ def make_unit(cfg, sql, table, names):
 
 def join_inner(cfg):
     """(inner abi.Table, names) for the join configs, else None.  Built on the host; the library copies it per query."""
-    if cfg != "c2join":
+    if cfg not in ("c2join", "c2joins"):
         return None
     from heavydb_b200 import abi
-    n = 10**5
+    n = 10**5 if cfg == "c2join" else 10**4
     ids = np.arange(n, dtype=np.int32)
     x = ids.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
     x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)

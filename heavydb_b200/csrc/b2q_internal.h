@@ -233,6 +233,8 @@ struct SmemPlan {
   int32_t acc_off[B2Q_MAX_ACCS];   /* byte offset of the accumulator's array inside ONE replica */
   int32_t replica_bytes;
   int32_t total_bytes;
+  int32_t join_off;       /* >= 0: the join table is TMA-staged into shared memory at this byte offset (dimension-sized tables) */
+  int32_t join_bytes;     /* bytes staged (multiple of 16) */
 };
 
 /* ---- ORDER BY / LIMIT over the materialised table (sort.cu) ------------------------------------------------ */

@@ -517,7 +517,8 @@ static int32_t prepare_join(B2QPartial& p, const B2QExecUnit& u, cudaStream_t st
   if (rc != B2Q_OK) return rc;
   int32_t* buff = nullptr;
   const int pc = q.prog.join.packed_col; /* slots {row, value of that inner column}: see DevJoin */
-  CU(cudaMallocAsync(reinterpret_cast<void**>(&buff), static_cast<size_t>(std::max<int64_t>(q.plan.join_entry_count, 1)) * (pc >= 0 ? 8 : 4), st));
+  /* + 16: the shared-memory staging copies whole 16-byte units (SmemPlan::join_bytes) */
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&buff), static_cast<size_t>(std::max<int64_t>(q.plan.join_entry_count, 1)) * (pc >= 0 ? 8 : 4) + 16, st));
   p.extra.push_back(buff);
   const B2QTypeInfo kt = inner.col_types[q.join_inner_key_col];
   const int kw = phys_bytes(q.join_inner_key_col);
@@ -903,6 +904,7 @@ int32_t b2q_launch(const B2QQuery* query, const B2QParams* prm, void* stream) {
   if (has_join) {
     p.join_buff = reinterpret_cast<const int32_t*>(static_cast<intptr_t>(prm->join_hash_tables[0]));
     p.q.prog.join.packed_col = -1; /* the caller's table is the reference's plain int32 layout */
+    if (p.q.smem.join_off >= 0) { p.q.smem.total_bytes = p.q.smem.join_off; p.q.smem.join_off = -1; p.q.smem.join_bytes = 0; } /* ... and is read in place */
   }
   std::vector<const int8_t*> cols(static_cast<size_t>(nf) * nc);
   std::vector<int64_t> rows(nf);

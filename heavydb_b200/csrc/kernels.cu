@@ -509,6 +509,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
   if (JOIN) {
     const DevJoin& J = P.join;
     const int32_t* __restrict__ buff = Lh.join_buff;
+    const int32_t* jsm = A.smem.join_off >= 0 ? reinterpret_cast<const int32_t*>(b2q_smem + A.smem.join_off) : nullptr; /* staged copy */
     const bool packed = J.packed_col >= 0;
     const int32_t packed_null = (JOIN == 2 && packed) ? (int32_t)P.col_null[J.packed_col] : 0;
     uint32_t matched = 0;
@@ -521,8 +522,14 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && k[j] == J.null_val);
         int32_t idx = -1, val = packed_null;
         if (ok) {
-          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = (JOIN == 2 && e2.x < 0) ? packed_null : e2.y; }
-          else idx = __ldg(buff + d);
+          if (packed) {
+            const int2 e2 = jsm ? reinterpret_cast<const int2*>(jsm)[d]
+                                : (J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d));
+            idx = e2.x;
+            val = (JOIN == 2 && e2.x < 0) ? packed_null : e2.y;
+          } else {
+            idx = jsm ? jsm[d] : __ldg(buff + d);
+          }
         }
         jidx[JOIN ? j : 0] = idx;
         jval[JOIN ? j : 0] = val;
@@ -537,8 +544,14 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && (int64_t)k[j] == J.null_val);
         int32_t idx = -1, val = packed_null;
         if (ok) {
-          if (packed) { const int2 e2 = J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d); idx = e2.x; val = (JOIN == 2 && e2.x < 0) ? packed_null : e2.y; }
-          else idx = __ldg(buff + d);
+          if (packed) {
+            const int2 e2 = jsm ? reinterpret_cast<const int2*>(jsm)[d]
+                                : (J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d));
+            idx = e2.x;
+            val = (JOIN == 2 && e2.x < 0) ? packed_null : e2.y;
+          } else {
+            idx = jsm ? jsm[d] : __ldg(buff + d);
+          }
         }
         jidx[JOIN ? j : 0] = idx;
         jval[JOIN ? j : 0] = val;
@@ -969,17 +982,22 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) b2q_k_scan(const __grid_c
   __shared__ uint64_t s_bar;
   int8_t* my_tab = nullptr;
 
-  if (MODE == MODE_SMEM) {
+  /* a dimension-sized join table is staged into shared memory next to the group table: the probe is then a shared-memory
+   * load instead of one random L2 sector per row (profiles/r1_join_knob_sweep.txt: the L2 sector rate is what bounds
+   * the join kernels) */
+  const bool stage_join = JOIN && A.smem.join_off >= 0;
+  if (MODE == MODE_SMEM || stage_join) {
     /* TMA-stage the identity image into every replica of the CTA-private table */
     const uint32_t rb = (uint32_t)A.smem.replica_bytes;
+    const uint32_t nrep = MODE == MODE_SMEM ? (uint32_t)A.smem.replicas : 0u;
     if (tid == 0) {
       mbar_init(&s_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) {
-      mbar_expect_tx(&s_bar, rb * (uint32_t)A.smem.replicas);
-      for (int r = 0; r < A.smem.replicas; ++r) {
+      mbar_expect_tx(&s_bar, rb * nrep + (stage_join ? (uint32_t)A.smem.join_bytes : 0u));
+      for (uint32_t r = 0; r < nrep; ++r) {
         uint32_t off = 0;
         while (off < rb) { /* bulk copies of <= 64 KB, 16-byte granularity (replica_bytes is a multiple of 16) */
           const uint32_t n = min(rb - off, 65536u);
@@ -987,9 +1005,18 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) b2q_k_scan(const __grid_c
           off += n;
         }
       }
+      if (stage_join) {
+        const uint32_t jb = (uint32_t)A.smem.join_bytes;
+        uint32_t off = 0;
+        while (off < jb) {
+          const uint32_t n = min(jb - off, 65536u);
+          tma_bulk_g2s(b2q_smem + A.smem.join_off + off, reinterpret_cast<const int8_t*>(Lh.join_buff) + off, n, &s_bar);
+          off += n;
+        }
+      }
     }
     mbar_wait(&s_bar, 0);
-    my_tab = b2q_smem + (size_t)(warp & (A.smem.replicas - 1)) * rb;
+    if (MODE == MODE_SMEM) my_tab = b2q_smem + (size_t)(warp & (A.smem.replicas - 1)) * rb;
   }
 
   /* L2 policy for the column stream: it is read exactly once, so mark it evict-first and keep L2 for what is
@@ -1362,7 +1389,7 @@ int scan_rows_per_chunk(int block) { return block * R; }
 /* block/grid policy: one CTA per SM with 1024 threads when the table needs more than half of the shared memory,
  * otherwise two CTAs of 512 threads per SM (better tail behaviour, same number of resident threads). */
 void scan_config(const B2QQuery& q, int* block, int* ctas_per_sm) {
-  const bool big_table = q.smem.use_smem && q.smem.total_bytes > 100 * 1024;
+  const bool big_table = q.smem.total_bytes > 100 * 1024; /* group-table replicas and/or a staged join table */
   *block = big_table ? 1024 : 512;
   *ctas_per_sm = big_table ? 1 : 2;
 }
@@ -1381,7 +1408,7 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
   c.block = block;
   const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
   c.grid = (int)(launch.total_chunks < max_ctas ? (launch.total_chunks > 0 ? launch.total_chunks : 1) : max_ctas);
-  c.smem_bytes = 0;
+  c.smem_bytes = (size_t)q.smem.total_bytes; /* 0 for the HBM-table kernels unless a join table is staged */
   const int kernel = q.plan.kernel;
   const bool key32 = q.prog.n_keys <= 1 && q.prog.key.col >= 0 && q.prog.key.width <= 4;
   if (kernel == B2Q_KERNEL_NON_GROUPED) {

@@ -1140,6 +1140,24 @@ class Planner {
       kernel = f;
     }
     p.kernel = kernel;
+    /* a dimension-sized join table rides in shared memory (TMA-staged once per CTA) when it fits beside the group
+     * table; replicas give way first (they only relieve same-address serialisation) */
+    sm.join_off = -1;
+    sm.join_bytes = 0;
+    static const bool stage = []() { const char* e = getenv("B2Q_JOIN_SMEM"); return !e || atoi(e) != 0; }();
+    if (join_ && stage && p.join_entry_count > 0) {
+      const int64_t jb = ((p.join_entry_count * (q.prog.join.packed_col >= 0 ? 8 : 4) + 15) / 16) * 16;
+      const int64_t room = 200 * 1024;
+      if (sm.use_smem) {
+        while (sm.replicas > 1 && int64_t(sm.replica_bytes) * sm.replicas + jb > room) sm.replicas /= 2;
+        sm.total_bytes = sm.replica_bytes * sm.replicas;
+      }
+      if (int64_t(sm.total_bytes) + jb <= room) {
+        sm.join_off = ((sm.total_bytes + 127) / 128) * 128;
+        sm.join_bytes = static_cast<int32_t>(jb);
+        sm.total_bytes = sm.join_off + sm.join_bytes;
+      }
+    }
   }
 };
 
