@@ -45,7 +45,7 @@ cudaError_t launch_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_tag,
                        int64_t span, int64_t stride, cudaStream_t st);
 size_t sort_scratch_bytes(int64_t entries);
 cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_keys, const int8_t* buf, int8_t* scratch,
-                        cudaStream_t st, const uint32_t** perm_out, int64_t* n_out, int* launches);
+                        cudaStream_t st, const uint32_t** perm_out, int64_t* n_out, int* launches, int64_t top_n);
 cudaError_t sort_gather(const DevSortLayout& Lin, const DevGatherCols& G, const int8_t* in, int8_t* out, const uint32_t* perm,
                         int64_t first, int64_t n_out, cudaStream_t st);
 }  // namespace b2q
@@ -725,7 +725,8 @@ static int32_t finalize_impl(B2QPartial* p, cudaStream_t st, B2QResultSet** out)
     int64_t n = 0, first = 0, count = 0;
     int sort_launches = 0;
     if (e == cudaSuccess) e = cudaEventRecord(ev0, st);
-    if (e == cudaSuccess) e = sort_device(L, keys, p->q.n_order, d_out, d_scratch, st, &d_perm, &n, &sort_launches);
+    if (e == cudaSuccess) e = sort_device(L, keys, p->q.n_order, d_out, d_scratch, st, &d_perm, &n, &sort_launches,
+                                          (p->q.has_limit ? p->q.limit : 0) + p->q.offset);
     if (e == cudaSuccess) {
       limit_window(p->q, n, &first, &count);
       relayout_entries(rs->q.plan, count);
@@ -1067,7 +1068,7 @@ int32_t b2q_rs_sort(B2QResultSet* rs, const B2QOrderEntry* order_entries, int32_
   const uint32_t* d_perm = nullptr;
   int64_t n = 0;
   int launches = 0;
-  if (e == cudaSuccess) e = sort_device(L, keys, n_entries, d_buf, d_scratch, st, &d_perm, &n, &launches);
+  if (e == cudaSuccess) e = sort_device(L, keys, n_entries, d_buf, d_scratch, st, &d_perm, &n, &launches, static_cast<int64_t>(top_n));
   if (e == cudaSuccess) {
     const int64_t keep = top_n && static_cast<int64_t>(top_n) < n ? static_cast<int64_t>(top_n) : n;
     rs->perm.resize(static_cast<size_t>(keep));

@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <utility>
+#include <vector>
 
 #include "b2q_internal.h"
 
@@ -163,6 +164,65 @@ __global__ void b2q_k_sort_bits(const uint64_t* __restrict__ keys, int64_t n, un
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) { o |= keys[j]; a &= keys[j]; }
   for (int s = 16; s; s >>= 1) { o |= __shfl_down_sync(~0u, o, s); a &= __shfl_down_sync(~0u, a, s); }
   if ((threadIdx.x & 31) == 0) { atomicOr(or_and, o); atomicAnd(or_and + 1, a); }
+}
+
+/* ---- top-k pre-filter: with LIMIT << groups, only entries whose PRIMARY sort key falls into the leading 16-bit buckets
+ * that hold the first top_n entries can reach the output (the primary key dominates the order; ties and the further
+ * order entries are settled by the full sort of the survivors).  bucket = NULL rank (2 bits) | top 14 bits of the key. */
+__device__ __forceinline__ uint32_t topk_bucket(uint64_t key, uint64_t rank) { return (uint32_t)(rank << 14) | (uint32_t)(key >> 50); }
+
+__global__ void b2q_k_sort_bucket_hist(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ranks, int64_t n,
+                                       uint32_t* __restrict__ hist16) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+    atomicAdd(&hist16[topk_bucket(keys[j], ranks ? ranks[j] : 1ull)], 1u);
+}
+
+__global__ void b2q_k_sort_bucket_count(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ranks, int64_t n, uint32_t max_bucket,
+                                        uint32_t* __restrict__ block_counts) {
+  const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+  int c = 0;
+  for (int k = 0; k < SORT_ITEMS; ++k) {
+    const int64_t j = base + (int64_t)k * SORT_BLOCK + threadIdx.x;
+    c += (j < n && topk_bucket(keys[j], ranks ? ranks[j] : 1ull) <= max_bucket) ? 1 : 0;
+  }
+  __shared__ int s_sum[SORT_WARPS];
+  for (int o = 16; o; o >>= 1) c += __shfl_down_sync(~0u, c, o);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < SORT_WARPS; ++w) t += s_sum[w];
+    block_counts[blockIdx.x] = (uint32_t)t;
+  }
+}
+
+__global__ void b2q_k_sort_bucket_compact(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ranks, int64_t n, uint32_t max_bucket,
+                                          const uint32_t* __restrict__ block_offsets, const uint32_t* __restrict__ perm_in,
+                                          uint32_t* __restrict__ perm_out) {
+  __shared__ uint32_t s_warp[SORT_WARPS];
+  __shared__ uint32_t s_run;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_run = block_offsets[blockIdx.x];
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+  for (int k = 0; k < SORT_ITEMS; ++k) { /* ordered: the survivors keep ascending entry order (tie rule) */
+    const int64_t j = base + (int64_t)k * SORT_BLOCK + threadIdx.x;
+    const bool keep = j < n && topk_bucket(keys[j], ranks ? ranks[j] : 1ull) <= max_bucket;
+    const uint32_t m = __ballot_sync(~0u, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    uint32_t before = s_run;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (keep) perm_out[before + __popc(m & ((1u << lane) - 1u))] = perm_in[j];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int w = 0; w < SORT_WARPS; ++w) t += s_warp[w];
+      s_run += t;
+    }
+    __syncthreads();
+  }
 }
 
 /* ---- stable LSD radix pass (8-bit digit) -------------------------------------------------------------------- */
@@ -320,14 +380,14 @@ size_t sort_scratch_bytes(int64_t entries) {
   const size_t n = (size_t)(entries > 0 ? entries : 1);
   const size_t nblocks = (n + SORT_TILE - 1) / SORT_TILE;
   auto pad = [](size_t x) { return (x + 255) & ~size_t(255); };
-  return pad(nblocks * 4) + 2 * pad(n * 4) + 2 * pad(n * 8) + pad(256 * nblocks * 4) + pad(256 * 4) + 1024;
+  return pad(nblocks * 4) + 2 * pad(n * 4) + 2 * pad(n * 8) + pad(256 * nblocks * 4) + pad(256 * 4) + 1024 + pad(65536 * 4);
 }
 
 /* Sorts the non-empty entries of the device buffer `buf` (layout L) by `keys` (n_keys order entries).
  * Returns in *perm_out a pointer (inside `scratch`) to the sorted entry indices and in *n_out their count.
  * One stream synchronisation (the count of non-empty entries decides every later grid). */
 cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_keys, const int8_t* buf, int8_t* scratch,
-                        cudaStream_t st, const uint32_t** perm_out, int64_t* n_out, int* launches) {
+                        cudaStream_t st, const uint32_t** perm_out, int64_t* n_out, int* launches, int64_t top_n) {
   const int64_t n_entries = L.entry_count;
   const size_t nblocks_c = (size_t)((n_entries + SORT_TILE - 1) / SORT_TILE);
   auto pad = [](size_t x) { return (x + 255) & ~size_t(255); };
@@ -342,6 +402,7 @@ cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_ke
   uint32_t* d_total = reinterpret_cast<uint32_t*>(p);
   uint32_t* d_uniform = d_total + 1;
   unsigned long long* d_bits = reinterpret_cast<unsigned long long*>(p + 64);
+  uint32_t* hist16 = reinterpret_cast<uint32_t*>(p + 1024);
   *launches = 0;
   *perm_out = perm_a;
   *n_out = 0;
@@ -356,14 +417,44 @@ cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_ke
   if (e != cudaSuccess) return e;
   e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return e;
-  const int64_t n = h_total;
-  *n_out = n;
+  int64_t n = h_total;
+  *n_out = n; /* the number of non-empty entries, whatever is sorted below */
   if (n <= 1 || n_keys == 0) return cudaGetLastError();
+
+  uint32_t* pin = perm_a;
+  uint32_t* pout = perm_b;
+  if (top_n > 0 && n >= 65536 && top_n * 8 <= n) {
+    /* top-k pre-filter on the primary order entry (see topk_bucket) */
+    const int g0 = grid_for(n, 256, 148 * 8);
+    const int nb0 = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    b2q_k_sort_make_keys<<<g0, 256, 0, st>>>(L, keys[0], buf, pin, n, keys_a, 0);
+    const uint64_t* ranks = nullptr;
+    if (keys[0].nullable) { b2q_k_sort_make_keys<<<g0, 256, 0, st>>>(L, keys[0], buf, pin, n, keys_b, 1); ranks = keys_b; *launches += 1; }
+    cudaMemsetAsync(hist16, 0, 65536 * 4, st);
+    b2q_k_sort_bucket_hist<<<g0, 256, 0, st>>>(keys_a, ranks, n, hist16);
+    *launches += 2;
+    std::vector<uint32_t> h16(65536);
+    e = cudaMemcpyAsync(h16.data(), hist16, 65536 * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    uint32_t max_bucket = 65535;
+    int64_t cum = 0;
+    for (uint32_t b = 0; b < 65536; ++b) { cum += h16[b]; if (cum >= top_n) { max_bucket = b; break; } }
+    if (cum < n) { /* worth it: fewer survivors than entries */
+      b2q_k_sort_bucket_count<<<nb0, SORT_BLOCK, 0, st>>>(keys_a, ranks, n, max_bucket, block_counts);
+      b2q_k_sort_scan<<<1, 1024, 0, st>>>(block_counts, (int64_t)nb0, d_total);
+      b2q_k_sort_bucket_compact<<<nb0, SORT_BLOCK, 0, st>>>(keys_a, ranks, n, max_bucket, block_counts, pin, pout);
+      *launches += 3;
+      e = cudaMemcpyAsync(&h_total, d_total, 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return e;
+      std::swap(pin, pout);
+      n = h_total; /* >= top_n survivors, in ascending entry order */
+    }
+  }
 
   const int nblocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
   const int kgrid = grid_for(n, 256, 148 * 8);
-  uint32_t* pin = perm_a;
-  uint32_t* pout = perm_b;
   auto radix_pass = [&](int shift) {
     cudaMemsetAsync(bin_total, 0, 256 * 4, st);
     b2q_k_sort_hist<<<nblocks, SORT_BLOCK, 0, st>>>(keys_a, n, shift, hist, bin_total);

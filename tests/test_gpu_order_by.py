@@ -117,6 +117,20 @@ def test_result_set_sort_api():
     assert len(rows) == n_all and [r[0] for r in rows] == sorted(r[0] for r in rows)
 
 
+def test_topk_prefilter_with_nulls():
+    """> 65536 groups and a small LIMIT: the top-k pre-filter (sort.cu, topk_bucket) runs; NULL ranks, DESC, ties on the
+    primary key and a second order entry must all survive it."""
+    table = random_table(400000, seed=77, frag_rows=100000)
+    dev = gu.DeviceTable(table)
+    for sql in ["SELECT a64, COUNT(*), SUM(a32) FROM r GROUP BY a64 ORDER BY 3 DESC NULLS LAST, 1 LIMIT 20;",
+                "SELECT a64, COUNT(*), SUM(a32) FROM r GROUP BY a64 ORDER BY 3 ASC NULLS FIRST, 1 DESC NULLS LAST LIMIT 50 OFFSET 5;",
+                "SELECT a64, COUNT(*), MIN(a8) FROM r GROUP BY a64 ORDER BY 2 DESC, 3 ASC NULLS LAST, 1 LIMIT 100;",     # heavy ties on COUNT
+                "SELECT a64, AVG(d), COUNT(*) FROM r GROUP BY a64 ORDER BY 2 DESC NULLS LAST, 1 LIMIT 7;"]:
+        unit = sqlmini.parse(sql, table, RAND_NAMES)
+        rs, _ = run_sorted(unit, table, dev, entry_guess=1_000_000, has_card=True)
+        assert rs.rowCount() > 0
+
+
 def test_large_sort_c4_like():
     """1e6 dense int64 keys, ORDER BY SUM DESC LIMIT 10 / full sort: multi-block compaction, all radix passes."""
     n, keys = 4_000_000, 1_000_000
