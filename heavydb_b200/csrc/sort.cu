@@ -169,22 +169,31 @@ __global__ void b2q_k_sort_bits(const uint64_t* __restrict__ keys, int64_t n, un
 /* ---- top-k pre-filter: with LIMIT << groups, only entries whose PRIMARY sort key falls into the leading 16-bit buckets
  * that hold the first top_n entries can reach the output (the primary key dominates the order; ties and the further
  * order entries are settled by the full sort of the survivors).  bucket = NULL rank (2 bits) | top 14 bits of the key. */
-__device__ __forceinline__ uint32_t topk_bucket(uint64_t key, uint64_t rank) { return (uint32_t)(rank << 14) | (uint32_t)(key >> 50); }
-
-__global__ void b2q_k_sort_bucket_hist(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ranks, int64_t n,
-                                       uint32_t* __restrict__ hist16) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
-    atomicAdd(&hist16[topk_bucket(keys[j], ranks ? ranks[j] : 1ull)], 1u);
+/* `shift` drops the low bits so that the 14 bits kept are the highest ones in which the keys differ at all (bits above
+ * them are equal for every key and do not order anything) */
+__device__ __forceinline__ uint32_t topk_bucket(uint64_t key, uint64_t rank, int shift) {
+  return (uint32_t)(rank << 14) | (uint32_t)((key >> shift) & 0x3FFFull);
 }
 
-__global__ void b2q_k_sort_bucket_count(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ranks, int64_t n, uint32_t max_bucket,
+__global__ void b2q_k_sort_bucket_hist(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ranks, int64_t n, int shift,
+                                       uint32_t* __restrict__ hist16) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_round = (n + 31) & ~int64_t(31); /* whole warps stay in the loop for the match */
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += stride) {
+    const uint32_t b = j < n ? topk_bucket(keys[j], ranks ? ranks[j] : 1ull, shift) : 0xFFFFFFFFu;
+    /* clustered keys would hammer one L2 address: lanes with the same bucket send one atomic */
+    const uint32_t m = __match_any_sync(~0u, b);
+    if (j < n && (m & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&hist16[b], (uint32_t)__popc(m));
+  }
+}
+
+__global__ void b2q_k_sort_bucket_count(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ranks, int64_t n, int shift, uint32_t max_bucket,
                                         uint32_t* __restrict__ block_counts) {
   const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
   int c = 0;
   for (int k = 0; k < SORT_ITEMS; ++k) {
     const int64_t j = base + (int64_t)k * SORT_BLOCK + threadIdx.x;
-    c += (j < n && topk_bucket(keys[j], ranks ? ranks[j] : 1ull) <= max_bucket) ? 1 : 0;
+    c += (j < n && topk_bucket(keys[j], ranks ? ranks[j] : 1ull, shift) <= max_bucket) ? 1 : 0;
   }
   __shared__ int s_sum[SORT_WARPS];
   for (int o = 16; o; o >>= 1) c += __shfl_down_sync(~0u, c, o);
@@ -197,7 +206,7 @@ __global__ void b2q_k_sort_bucket_count(const uint64_t* __restrict__ keys, const
   }
 }
 
-__global__ void b2q_k_sort_bucket_compact(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ranks, int64_t n, uint32_t max_bucket,
+__global__ void b2q_k_sort_bucket_compact(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ranks, int64_t n, int shift, uint32_t max_bucket,
                                           const uint32_t* __restrict__ block_offsets, const uint32_t* __restrict__ perm_in,
                                           uint32_t* __restrict__ perm_out) {
   __shared__ uint32_t s_warp[SORT_WARPS];
@@ -208,7 +217,7 @@ __global__ void b2q_k_sort_bucket_compact(const uint64_t* __restrict__ keys, con
   const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
   for (int k = 0; k < SORT_ITEMS; ++k) { /* ordered: the survivors keep ascending entry order (tie rule) */
     const int64_t j = base + (int64_t)k * SORT_BLOCK + threadIdx.x;
-    const bool keep = j < n && topk_bucket(keys[j], ranks ? ranks[j] : 1ull) <= max_bucket;
+    const bool keep = j < n && topk_bucket(keys[j], ranks ? ranks[j] : 1ull, shift) <= max_bucket;
     const uint32_t m = __ballot_sync(~0u, keep);
     if (lane == 0) s_warp[warp] = __popc(m);
     __syncthreads();
@@ -430,9 +439,18 @@ cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_ke
     b2q_k_sort_make_keys<<<g0, 256, 0, st>>>(L, keys[0], buf, pin, n, keys_a, 0);
     const uint64_t* ranks = nullptr;
     if (keys[0].nullable) { b2q_k_sort_make_keys<<<g0, 256, 0, st>>>(L, keys[0], buf, pin, n, keys_b, 1); ranks = keys_b; *launches += 1; }
+    unsigned long long hb[2] = {0ull, ~0ull};
+    cudaMemcpyAsync(d_bits, hb, 16, cudaMemcpyHostToDevice, st);
+    b2q_k_sort_bits<<<g0, 256, 0, st>>>(keys_a, n, d_bits);
+    e = cudaMemcpyAsync(hb, d_bits, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    const unsigned long long kdiff = hb[0] ^ hb[1];
+    const int msb = kdiff ? 63 - __builtin_clzll(kdiff) : 0;
+    const int shift = msb > 13 ? msb - 13 : 0;
     cudaMemsetAsync(hist16, 0, 65536 * 4, st);
-    b2q_k_sort_bucket_hist<<<g0, 256, 0, st>>>(keys_a, ranks, n, hist16);
-    *launches += 2;
+    b2q_k_sort_bucket_hist<<<g0, 256, 0, st>>>(keys_a, ranks, n, shift, hist16);
+    *launches += 3;
     std::vector<uint32_t> h16(65536);
     e = cudaMemcpyAsync(h16.data(), hist16, 65536 * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -441,9 +459,9 @@ cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_ke
     int64_t cum = 0;
     for (uint32_t b = 0; b < 65536; ++b) { cum += h16[b]; if (cum >= top_n) { max_bucket = b; break; } }
     if (cum < n) { /* worth it: fewer survivors than entries */
-      b2q_k_sort_bucket_count<<<nb0, SORT_BLOCK, 0, st>>>(keys_a, ranks, n, max_bucket, block_counts);
+      b2q_k_sort_bucket_count<<<nb0, SORT_BLOCK, 0, st>>>(keys_a, ranks, n, shift, max_bucket, block_counts);
       b2q_k_sort_scan<<<1, 1024, 0, st>>>(block_counts, (int64_t)nb0, d_total);
-      b2q_k_sort_bucket_compact<<<nb0, SORT_BLOCK, 0, st>>>(keys_a, ranks, n, max_bucket, block_counts, pin, pout);
+      b2q_k_sort_bucket_compact<<<nb0, SORT_BLOCK, 0, st>>>(keys_a, ranks, n, shift, max_bucket, block_counts, pin, pout);
       *launches += 3;
       e = cudaMemcpyAsync(&h_total, d_total, 4, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
