@@ -87,6 +87,27 @@ def main():
             assert rs.rowCount() == ref.row_count(), sql
         checked += 1
         del rs, part
+    # the estimator query: per-rank bitmaps are OR-merged (all-gather + OR; reduce_estimator_results)
+    for cols in (["k32"], ["k16", "nn32"], ["sparse"]):
+        b = abi.UnitBuilder(table)
+        b.estimator([RAND_NAMES.index(c) for c in cols])
+        unit = b.build()
+        sub, _ = shards[id(table)]
+        view = abi.Table(table.col_types)
+        for f in sub.fragments:
+            view.fragments.append(f)
+        for f in table.fragments:
+            if f.fragment_id % world != rank:
+                view.add_remote_fragment(f.num_tuples, f.stats, f.fragment_id)
+        part = ex.executePartial(1, True, view, unit, memory_level=abi.GPU_LEVEL)
+        multigpu.allreduce_partial(part, torch, dist)
+        rs = part.finalize()
+        if rank == 0:
+            ref = oracle_lib.execute(unit, table, num_threads=8)
+            assert np.array_equal(rs.getHostEstimatorBuffer(), ref.buffer().view(np.uint8)), cols
+            assert rs.getNDVEstimator() == ref.ndv_estimator()
+        checked += 1
+        del rs, part
     dist.barrier()
     if rank == 0:
         print(f"multigpu_check ok: {checked} queries, world={world}", flush=True)
