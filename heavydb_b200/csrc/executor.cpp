@@ -43,6 +43,8 @@ cudaError_t launch_materialize(const B2QQuery& q, const int64_t* const* accs, co
 cudaError_t launch_join_split(const int64_t* split, int64_t* out, int64_t n, cudaStream_t st);
 cudaError_t launch_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count, int64_t lo,
                        int64_t span, int64_t stride, cudaStream_t st);
+cudaError_t launch_join_slot16(const int32_t* rows, int64_t entry_count, const int8_t* vals, int width, int64_t null_val, int64_t vmin,
+                               uint16_t* out, int32_t* error, cudaStream_t st);
 size_t sort_scratch_bytes(int64_t entries);
 cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_keys, const int8_t* buf, int8_t* scratch,
                         cudaStream_t st, const uint32_t** perm_out, int64_t* n_out, int* launches, int64_t top_n);
@@ -516,7 +518,8 @@ static int32_t prepare_join(B2QPartial& p, const B2QExecUnit& u, cudaStream_t st
   int32_t rc = device_col(q.join_inner_key_col, &d_key);
   if (rc != B2Q_OK) return rc;
   int32_t* buff = nullptr;
-  const int pc = q.prog.join.packed_col; /* slots {row, value of that inner column}: see DevJoin */
+  const bool slot16 = q.prog.join.slot16 != 0;
+  const int pc = slot16 ? -1 : q.prog.join.packed_col; /* slots {row, value of that inner column}: see DevJoin */
   /* + 16: the shared-memory staging copies whole 16-byte units (SmemPlan::join_bytes) */
   CU(cudaMallocAsync(reinterpret_cast<void**>(&buff), static_cast<size_t>(std::max<int64_t>(q.plan.join_entry_count, 1)) * (pc >= 0 ? 8 : 4) + 16, st));
   p.extra.push_back(buff);
@@ -527,6 +530,15 @@ static int32_t prepare_join(B2QPartial& p, const B2QExecUnit& u, cudaStream_t st
                        pc >= 0 ? p.inner_cols[pc] : nullptr, q.prog.join.packed_width, st));
   p.launches += 1;
   p.join_buff = buff;
+  if (slot16) { /* the row table only served to detect duplicates; the kernels probe the value-only 16-bit table */
+    uint16_t* t16 = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&t16), static_cast<size_t>(std::max<int64_t>(q.plan.join_entry_count, 1)) * 2 + 16, st));
+    p.extra.push_back(t16);
+    const int c = q.prog.join.packed_col;
+    CU(launch_join_slot16(buff, q.plan.join_entry_count, p.inner_cols[c], q.prog.join.packed_width, q.prog.col_null[c], q.prog.join.slot16_min, t16, p.d_error, st));
+    p.launches += 1;
+    p.join_buff = reinterpret_cast<const int32_t*>(t16);
+  }
   return B2Q_OK;
 }
 
@@ -905,6 +917,7 @@ int32_t b2q_launch(const B2QQuery* query, const B2QParams* prm, void* stream) {
   if (has_join) {
     p.join_buff = reinterpret_cast<const int32_t*>(static_cast<intptr_t>(prm->join_hash_tables[0]));
     p.q.prog.join.packed_col = -1; /* the caller's table is the reference's plain int32 layout */
+    p.q.prog.join.slot16 = 0;
     if (p.q.smem.join_off >= 0) { p.q.smem.total_bytes = p.q.smem.join_off; p.q.smem.join_off = -1; p.q.smem.join_bytes = 0; } /* ... and is read in place */
   }
   std::vector<const int8_t*> cols(static_cast<size_t>(nf) * nc);

@@ -512,6 +512,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     const int32_t* jsm = A.smem.join_off >= 0 ? reinterpret_cast<const int32_t*>(b2q_smem + A.smem.join_off) : nullptr; /* staged copy */
     const bool packed = J.packed_col >= 0;
     const int32_t packed_null = (JOIN == 2 && packed) ? (int32_t)P.col_null[J.packed_col] : 0;
+    const int32_t slot16_null = packed ? (int32_t)P.col_null[J.packed_col] : 0; /* a NULL attribute of a matched row */
     uint32_t matched = 0;
     if (J.fk_width == 8) {
       int64_t k[R];
@@ -521,7 +522,11 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         const uint64_t d = (uint64_t)(k[j] - J.min_key);
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && k[j] == J.null_val);
         int32_t idx = -1, val = packed_null;
-        if (ok) {
+        if (ok && J.slot16) { /* value-only 16-bit slot in shared memory (DevJoin::slot16) */
+          const uint32_t s16 = reinterpret_cast<const uint16_t*>(jsm)[d];
+          idx = s16 == 0xFFFFu ? -1 : 0;
+          val = s16 >= 0xFFFEu ? slot16_null : (int32_t)(J.slot16_min + (int64_t)s16);
+        } else if (ok) {
           if (packed) {
             const int2 e2 = jsm ? reinterpret_cast<const int2*>(jsm)[d]
                                 : (J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d));
@@ -543,7 +548,11 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         const uint64_t d = (uint64_t)((int64_t)k[j] - J.min_key);
         const bool ok = (valid >> j & 1) && d < (uint64_t)J.entry_count && !(J.nullable && (int64_t)k[j] == J.null_val);
         int32_t idx = -1, val = packed_null;
-        if (ok) {
+        if (ok && J.slot16) { /* value-only 16-bit slot in shared memory (DevJoin::slot16) */
+          const uint32_t s16 = reinterpret_cast<const uint16_t*>(jsm)[d];
+          idx = s16 == 0xFFFFu ? -1 : 0;
+          val = s16 >= 0xFFFEu ? slot16_null : (int32_t)(J.slot16_min + (int64_t)s16);
+        } else if (ok) {
           if (packed) {
             const int2 e2 = jsm ? reinterpret_cast<const int2*>(jsm)[d]
                                 : (J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d));
@@ -1158,6 +1167,30 @@ __global__ void b2q_k_join_build(const int8_t* __restrict__ keys, int width, int
   }
 }
 
+/* one-to-one row table -> value-only uint16 slots (DevJoin::slot16): value - vmin, 0xFFFE = NULL, 0xFFFF = no row */
+__global__ void b2q_k_join_slot16(const int32_t* __restrict__ rows, int64_t entry_count, const int8_t* __restrict__ vals, int width,
+                                  int64_t null_val, int64_t vmin, uint16_t* __restrict__ out, int32_t* __restrict__ error) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < entry_count; d += stride) {
+    const int32_t row = rows[d];
+    uint32_t code = 0xFFFFu;
+    if (row >= 0) {
+      int64_t v;
+      switch (width) {
+        case 4: v = reinterpret_cast<const int32_t*>(vals)[row]; break;
+        case 2: v = reinterpret_cast<const int16_t*>(vals)[row]; break;
+        case -2: v = reinterpret_cast<const uint16_t*>(vals)[row]; break;
+        case -1: v = reinterpret_cast<const uint8_t*>(vals)[row]; break;
+        default: v = reinterpret_cast<const signed char*>(vals)[row]; break;
+      }
+      if (v == null_val) code = 0xFFFEu;
+      else if ((uint64_t)(v - vmin) < 0xFFFEull) code = (uint32_t)(v - vmin);
+      else atomicCAS(error, 0, B2Q_ERR_KEY_OUT_OF_RANGE); /* a value outside its chunk-stats range (stale metadata) */
+    }
+    out[d] = (uint16_t)code;
+  }
+}
+
 /* ---------------------------------------------------------------------------------------------------------
  * table initialisation (replaces init_group_by_buffer_gpu, GpuInitGroups.cu:124-171): accumulators to the
  * identity of their reduction, baseline keys to EMPTY_KEY_64, plus the one-replica shared-memory image.
@@ -1437,6 +1470,17 @@ cudaError_t launch_join_build(const int8_t* keys, int width, int64_t n_rows, int
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   b2q_k_join_build<<<(int)blocks, block, 0, st>>>(keys, width, n_rows, min_key, entry_count, nullable, null_val, buff, error, packed_vals, packed_width);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_join_slot16(const int32_t* rows, int64_t entry_count, const int8_t* vals, int width, int64_t null_val, int64_t vmin,
+                               uint16_t* out, int32_t* error, cudaStream_t st) {
+  if (entry_count <= 0) return cudaSuccess;
+  const int block = 256;
+  int64_t blocks = (entry_count + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  b2q_k_join_slot16<<<(int)blocks, block, 0, st>>>(rows, entry_count, vals, width, null_val, vmin, out, error);
   return cudaGetLastError();
 }
 

@@ -1065,6 +1065,19 @@ class Planner {
           break;
         }
     }
+    /* value-only 16-bit slots: when the packed column is the ONLY inner column read and its values span < 65534 */
+    g.join.slot16 = 0;
+    if (join_ && g.join.packed_col >= 0) {
+      static const bool s16 = []() { const char* e = getenv("B2Q_JOIN_SLOT16"); return !e || atoi(e) != 0; }();
+      int n_inner = 0;
+      for (int c = 0; c < g.n_cols; ++c) n_inner += g.col_inner[c] ? 1 : 0;
+      const ColRange vr = leaf_range(q.col_ids[g.join.packed_col]);
+      int64_t span = 0;
+      if (s16 && n_inner == 1 && vr.valid && !vr.fp && vr.imin <= vr.imax && !__builtin_sub_overflow(vr.imax, vr.imin, &span) && span < 65534) {
+        g.join.slot16 = 1;
+        g.join.slot16_min = vr.imin;
+      }
+    }
     for (int c = 0; c < g.n_cols; ++c) if (g.col_inner[c]) g.col_prefetch[c] = 0; /* gathered by join index, not streamed */
     /* fused fast path of the shared-memory-table kernel (the reference's JIT specialises per query; this is the
      * static-kernel equivalent for the most common shape: GROUP BY k with COUNT(*) and/or one integer SUM) */
@@ -1146,17 +1159,28 @@ class Planner {
     sm.join_bytes = 0;
     static const bool stage = []() { const char* e = getenv("B2Q_JOIN_SMEM"); return !e || atoi(e) != 0; }();
     if (join_ && stage && p.join_entry_count > 0) {
-      const int64_t jb = ((p.join_entry_count * (q.prog.join.packed_col >= 0 ? 8 : 4) + 15) / 16) * 16;
-      const int64_t room = 200 * 1024;
-      if (sm.use_smem) {
-        while (sm.replicas > 1 && int64_t(sm.replica_bytes) * sm.replicas + jb > room) sm.replicas /= 2;
-        sm.total_bytes = sm.replica_bytes * sm.replicas;
-      }
-      if (int64_t(sm.total_bytes) + jb <= room) {
-        sm.join_off = ((sm.total_bytes + 127) / 128) * 128;
+      const int64_t room = 216 * 1024; /* of the 227 KB a CTA may opt in to */
+      auto try_stage = [&](int64_t slot_bytes) -> bool {
+        const int64_t jb = ((p.join_entry_count * slot_bytes + 15) / 16) * 16;
+        int rep = sm.replicas;
+        if (sm.use_smem) while (rep > 1 && int64_t(sm.replica_bytes) * rep + jb + 128 > room) rep /= 2;
+        const int64_t base = sm.use_smem ? int64_t(sm.replica_bytes) * rep : 0;
+        const int64_t off = ((base + 127) / 128) * 128;
+        if (off + jb > room) return false;
+        if (sm.use_smem) sm.replicas = rep;
+        sm.join_off = static_cast<int32_t>(off);
         sm.join_bytes = static_cast<int32_t>(jb);
-        sm.total_bytes = sm.join_off + sm.join_bytes;
+        sm.total_bytes = static_cast<int32_t>(off + jb);
+        return true;
+      };
+      bool staged = false;
+      if (q.prog.join.slot16) staged = try_stage(2);
+      if (!staged) {
+        q.prog.join.slot16 = 0; /* 16-bit slots exist only in shared memory */
+        staged = try_stage(q.prog.join.packed_col >= 0 ? 8 : 4);
       }
+    } else {
+      q.prog.join.slot16 = 0;
     }
   }
 };
