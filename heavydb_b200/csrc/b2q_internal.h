@@ -118,7 +118,7 @@ struct DevJoin {
                            and the gather of that column are ONE 8-byte load (random 4-byte gathers are bound by L1 tag
                            throughput, ~1 sector/clk/SM: two dependent gathers per row cost twice the scan itself) */
   int8_t packed_width;  /* width code of that column in the inner table */
-  int8_t pad_probe_cg;  /* experiment knob (B2Q_JOIN_CG): probe with ld.global.cg (L2 only) instead of the L1 path */
+  int8_t probe_cg;  /* experiment knob (B2Q_JOIN_CG): probe with ld.global.cg (L2 only) instead of the L1 path */
   int8_t left;          /* LEFT join: a row without a match stays, its inner columns read col_null[] */
   int8_t slot16;        /* the table is ONE uint16 per slot, staged in shared memory: value - slot16_min of packed_col
                            (the only inner column the query reads), 0xFFFE = that column is NULL, 0xFFFF = no row.

@@ -529,7 +529,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         } else if (ok) {
           if (packed) {
             const int2 e2 = jsm ? reinterpret_cast<const int2*>(jsm)[d]
-                                : (J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d));
+                                : (J.probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d));
             idx = e2.x;
             val = (JOIN == 2 && e2.x < 0) ? packed_null : e2.y;
           } else {
@@ -555,7 +555,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         } else if (ok) {
           if (packed) {
             const int2 e2 = jsm ? reinterpret_cast<const int2*>(jsm)[d]
-                                : (J.pad_probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d));
+                                : (J.probe_cg ? __ldcg(reinterpret_cast<const int2*>(buff) + d) : __ldg(reinterpret_cast<const int2*>(buff) + d));
             idx = e2.x;
             val = (JOIN == 2 && e2.x < 0) ? packed_null : e2.y;
           } else {

@@ -1055,7 +1055,7 @@ class Planner {
       for (int a = 0; a < g.n_accs; ++a) if (g.accs[a].col >= 0) g.col_prefetch[g.accs[a].col] = 1;
     if (join_) g.col_prefetch[g.join.fk_col] = 1;
     g.join.packed_col = -1;
-    g.join.pad_probe_cg = []() { const char* e = getenv("B2Q_JOIN_CG"); return e && atoi(e) != 0; }() ? 1 : 0;
+    g.join.probe_cg = []() { const char* e = getenv("B2Q_JOIN_CG"); return e && atoi(e) != 0; }() ? 1 : 0;
     if (join_) { /* the first 1/2/4-byte inner column the program reads rides in the join table itself */
       static const bool pack = []() { const char* e = getenv("B2Q_JOIN_PACK"); return !e || atoi(e) != 0; }();
       for (int c = 0; c < g.n_cols && pack; ++c)
