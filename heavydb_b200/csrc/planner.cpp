@@ -1173,12 +1173,12 @@ class Planner {
         sm.total_bytes = static_cast<int32_t>(off + jb);
         return true;
       };
-      bool staged = false;
-      if (q.prog.join.slot16) staged = try_stage(2);
-      if (!staged) {
-        q.prog.join.slot16 = 0; /* 16-bit slots exist only in shared memory */
-        staged = try_stage(q.prog.join.packed_col >= 0 ? 8 : 4);
-      }
+      /* measured (c2join / c2joins, 1e9 rows): a table that fits with its 8-byte slots is a little faster that way
+       * (4.02 vs 4.18 ms); the 16-bit slots are what lets a 1e5-row dimension fit at all (4.42 vs 5.60 ms from L2) */
+      bool staged = try_stage(q.prog.join.packed_col >= 0 ? 8 : 4);
+      if (staged) q.prog.join.slot16 = 0;
+      else if (q.prog.join.slot16) staged = try_stage(2);
+      if (!staged) q.prog.join.slot16 = 0; /* 16-bit slots exist only in shared memory */
     } else {
       q.prog.join.slot16 = 0;
     }
