@@ -86,3 +86,59 @@ def test_join_queries(seed):
             raise AssertionError(f"query: {sql}\n{e}") from e
         checked += 1
     assert checked >= 50
+
+
+def with_random_order(rng, sql: str):
+    """Append ORDER BY over random targets followed by every GROUP BY key (a total order), plus LIMIT / OFFSET.
+    Returns None when the keys are not all in the target list (positions could not name them)."""
+    body = sql.rstrip(";")
+    up = body.upper()
+    if " GROUP BY " not in up:
+        return None
+    targets = [t.strip() for t in body[len("SELECT "):up.index(" FROM ")].split(",")]
+    keys = [k.strip() for k in body[up.index(" GROUP BY ") + 10:].split(",")]
+    if any(k not in targets for k in keys):
+        return None
+    items = []
+    for pos in rng.sample(range(1, len(targets) + 1), rng.randint(1, min(3, len(targets)))):
+        if targets[pos - 1] in keys:
+            continue
+        items.append(f"{pos} {rng.choice(['ASC', 'DESC'])} NULLS {rng.choice(['FIRST', 'LAST'])}")
+    for k in keys:
+        items.append(f"{targets.index(k) + 1} {rng.choice(['ASC', 'DESC'])} NULLS {rng.choice(['FIRST', 'LAST'])}")
+    tail = ""
+    if rng.random() < 0.6:
+        tail = f" LIMIT {rng.randint(1, 40)}"
+        if rng.random() < 0.4:
+            tail += f" OFFSET {rng.randint(0, 10)}"
+    return body + " ORDER BY " + ", ".join(items) + tail + ";"
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_ordered_queries(seed):
+    """ResultSet::sort / dropFirstN / keepFirstN restatement on random ORDER BY lists, compared row by row."""
+    from test_order_by import assert_ordered_rows_match
+    rng = random.Random(5000 + seed)
+    table = random_table([300, 3000, 3000][seed], seed=500 + seed, frag_rows=[64, 700, 3000][seed])
+    con = rt.make_sqlite(oq.rows_of(table, RAND_COLS), RAND_COLS, "r")
+    checked = 0
+    for i in range(150):
+        sql = with_random_order(rng, rand_query(rng, multi_key=(i % 4 == 0)))
+        if sql is None or sqlite_overflows(sql):
+            continue
+        # AVG / SUM of doubles as an order key could tie-break differently on the last ulp: keep exact key types
+        unit = sqlmini.parse(sql, table, RAND_NAMES)
+        try:
+            res = oracle_lib.execute(unit, table, entry_guess=6000, has_card=True, num_threads=2)
+        except oracle_lib.OracleError as e:
+            assert e.code == abi.ERR_UNSUPPORTED, sql
+            continue
+        if known_reference_quirk(unit, res.plan):
+            continue
+        ref = [tuple(r) for r in con.execute(oq.sqlite_sql(sql, unit, "r")).fetchall()]
+        try:
+            assert_ordered_rows_match(res.rows(), ref)
+        except AssertionError as e:
+            raise AssertionError(f"query: {sql}\n{e}") from e
+        checked += 1
+    assert checked >= 40
