@@ -479,8 +479,6 @@ struct ScanArgs {
   int32_t prefetch_distance; /* > 0: TMA bulk-prefetch the column slabs of the chunk this CTA will scan D iterations ahead into L2 */
   int32_t pad_;
   int64_t ndv_bitmap_bytes;  /* estimator query: size of the ACC_NDV bitmap (a power of two) */
-  int32_t f64_match;         /* fused AVG/SUM(double) path: match-based plain updates on warp-private replicas (B2Q_F64_MATCH) */
-  int32_t pad2_;
 };
 
 extern __shared__ __align__(128) int8_t b2q_smem[];
@@ -730,33 +728,12 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       int64_t v[R];
       load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol, JX(sa.col));
       double* dsum = reinterpret_cast<double*>(sum_tab);
-      if (A.f64_match && A.smem.replicas >= BLOCK / 32) {
-        /* the replica is private to this warp: lanes whose group is unique within the instruction (match.any) update
-         * it with a plain load / add / store — shared memory has no native f64 add, atomicAdd(double) is a CAS loop —
-         * and only the lanes that collide fall back to the atomic; __syncwarp orders the rows */
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const bool act = pass >> j & 1;
-          const uint32_t m = __match_any_sync(~0u, act ? e[j] : 0xFFFFFFFFu);
-          if (act) {
-            if (m == (1u << lane)) {
-              if (ic >= 0) cnt_tab[e[j]] += 1u;
-              dsum[e[j]] += __longlong_as_double(v[j]);
-            } else {
-              if (ic >= 0) atomicAdd(cnt_tab + e[j], 1u);
-              atomicAdd(dsum + e[j], __longlong_as_double(v[j]));
-            }
-          }
-          __syncwarp();
+      for (int j = 0; j < R; ++j)
+        if (pass >> j & 1) {
+          if (ic >= 0) atomicAdd(cnt_tab + e[j], 1u);
+          atomicAdd(dsum + e[j], __longlong_as_double(v[j]));
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (pass >> j & 1) {
-            if (ic >= 0) atomicAdd(cnt_tab + e[j], 1u);
-            atomicAdd(dsum + e[j], __longlong_as_double(v[j]));
-          }
-      }
     } else if (sa.width == 8) {
       int64_t v[R];
       load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol, JX(sa.col));
@@ -1460,9 +1437,6 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
   a.prefetch_distance = prefetch_distance;
   a.pad_ = 0;
   a.ndv_bitmap_bytes = q.plan.query_desc_type == B2Q_Estimator ? q.plan.buffer_size : 0;
-  static const int f64_match = []() { const char* e = getenv("B2Q_F64_MATCH"); return e ? atoi(e) : 0; }();
-  a.f64_match = f64_match;
-  a.pad2_ = 0;
   ScanConfig c;
   c.block = block;
   const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
