@@ -493,6 +493,25 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
         os.sched_setaffinity(0, old_aff)
     unit = make_unit(args.config, sql, table, names)
     bt = table.build(abi.CPU_LEVEL)
+    # what this box's PCIe link delivers for plain copies out of the very same pinned buffers (no kernels, one stream):
+    # the ceiling the end-to-end leg can reach — boxes of the pool differ by almost 2x here
+    raw_gbs = None
+    try:
+        probe = [h for h in keep if h.numel() >= (64 << 20)][:8]
+        if probe:
+            scratch = torch.empty(max(h.numel() for h in probe), dtype=torch.uint8, device="cuda")
+            scratch[:probe[0].numel()].copy_(probe[0], non_blocking=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for h in probe:
+                scratch[:h.numel()].copy_(h, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            raw_gbs = sum(h.numel() for h in probe) / (e0.elapsed_time(e1) / 1e3) / 1e9
+            del scratch
+    except Exception:  # the probe is informational
+        raw_gbs = None
     times = []
     d2h = 0
     for i in range(2 + 3):
@@ -508,7 +527,7 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
     dt = float(np.mean(times))
     return {"value": rows / dt, "unit": "rows/s", "h2d_bytes_per_step": int(rows * bytes_per_row), "d2h_bytes_per_step": d2h,
             "rows": rows, "ms_per_step": dt * 1e3, "host_memory": f"pinned, allocated on the GPU's NUMA node ({node})", "h2d_gbs": rows * bytes_per_row / dt / 1e9,
-            "groups_out": int(n)}
+            "h2d_raw_gbs_same_buffers": raw_gbs, "groups_out": int(n)}
 
 
 if __name__ == "__main__":
