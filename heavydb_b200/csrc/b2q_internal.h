@@ -35,7 +35,15 @@ struct DevTerm {
   int8_t cmp_fp;        /* compare in the double domain (column or literal is fp) */
   int8_t negate;        /* result = in_range XOR negate */
   int8_t null_check;    /* explicit `v != NULL` needed (the host folds it into the range whenever it can) */
-  int8_t pad_[3];
+  /* column OP column (col2 >= 0): both sides loaded, compared as int64 or — if either side is fp — as double;
+   * TRUE only when neither side is NULL (DEF_CMP_NULLABLE, RuntimeFunctions.cpp:73-107) */
+  int8_t width2;
+  int8_t col2_is_fp;
+  int8_t op2;           /* B2Q_kEQ .. B2Q_kGE */
+  int32_t col2;         /* -1: comparison with a constant */
+  int8_t nullable1, nullable2;
+  int8_t pad_[2];
+  int64_t null_bits2;
 };
 
 enum { FOP_TERM = 0, FOP_AND = 1, FOP_OR = 2 };

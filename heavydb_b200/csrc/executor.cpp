@@ -443,7 +443,7 @@ static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B
     if (q.left < 0 || q.left >= u.num_exprs || q.right < 0 || q.right >= u.num_exprs) return false;
     const B2QExpr& l = u.exprs[q.left];
     const B2QExpr& c = u.exprs[q.right];
-    if (l.kind != B2Q_EXPR_COLUMN_VAR || l.rte_idx != 0) continue; /* chunk stats of the scanned table only */
+    if (l.kind != B2Q_EXPR_COLUMN_VAR || l.rte_idx != 0 || c.kind != B2Q_EXPR_CONSTANT) continue; /* chunk stats of the scanned table only */
     if (c.kind != B2Q_EXPR_CONSTANT) return false;
     if (c.is_null || l.col_id < 0 || l.col_id >= tbl.num_cols) continue;
     const B2QChunkStats& st = fr.col_stats[l.col_id];

@@ -244,20 +244,68 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
   return m & valid;
 }
 
+/* column OP column */
+template <bool FULL>
+__device__ __forceinline__ uint32_t eval_term2(const DevTerm& t, const int8_t* const* __restrict__ cols, int64_t row0, int stride,
+                                               uint32_t valid, uint64_t pol, const int32_t* jidx1, const int32_t* jval1,
+                                               const int64_t* jnull1, const int32_t* jidx2, const int32_t* jval2, const int64_t* jnull2) {
+  int64_t a[R], b[R];
+  if (t.width == 8) load64<!FULL>(a, cols[t.col], row0, stride, valid, pol, jidx1, jval1, jnull1);
+  else {
+    int32_t x[R];
+    load32<!FULL>(x, cols[t.col], t.width, row0, stride, valid, pol, jidx1, jval1, jnull1);
+#pragma unroll
+    for (int j = 0; j < R; ++j) a[j] = x[j];
+  }
+  if (t.width2 == 8) load64<!FULL>(b, cols[t.col2], row0, stride, valid, pol, jidx2, jval2, jnull2);
+  else {
+    int32_t x[R];
+    load32<!FULL>(x, cols[t.col2], t.width2, row0, stride, valid, pol, jidx2, jval2, jnull2);
+#pragma unroll
+    for (int j = 0; j < R; ++j) b[j] = x[j];
+  }
+  uint32_t isnull = 0, m = 0;
+  const int op = t.op2;
+  if (t.cmp_fp) {
+    const double n1 = __longlong_as_double(t.null_bits), n2 = __longlong_as_double(t.null_bits2);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      double x, y;
+      if (t.col_is_fp) { x = __longlong_as_double(a[j]); isnull |= (uint32_t)(t.nullable1 && x == n1) << j; }
+      else { x = (double)a[j]; isnull |= (uint32_t)(t.nullable1 && a[j] == t.null_bits) << j; }
+      if (t.col2_is_fp) { y = __longlong_as_double(b[j]); isnull |= (uint32_t)(t.nullable2 && y == n2) << j; }
+      else { y = (double)b[j]; isnull |= (uint32_t)(t.nullable2 && b[j] == t.null_bits2) << j; }
+      const bool r = op == B2Q_kEQ ? x == y : op == B2Q_kNE ? x != y : op == B2Q_kLT ? x < y : op == B2Q_kGT ? x > y : op == B2Q_kLE ? x <= y : x >= y;
+      m |= (uint32_t)r << j;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      isnull |= (uint32_t)((t.nullable1 && a[j] == t.null_bits) || (t.nullable2 && b[j] == t.null_bits2)) << j;
+      const bool r = op == B2Q_kEQ ? a[j] == b[j] : op == B2Q_kNE ? a[j] != b[j] : op == B2Q_kLT ? a[j] < b[j] : op == B2Q_kGT ? a[j] > b[j] : op == B2Q_kLE ? a[j] <= b[j] : a[j] >= b[j];
+      m |= (uint32_t)r << j;
+    }
+  }
+  return m & ~isnull & valid;
+}
+
 template <bool FULL, int JOIN>
 __device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t* const* __restrict__ cols,
                                                 int64_t row0, int stride, uint32_t valid, uint64_t pol,
                                                 const int8_t* __restrict__ col_inner, const int32_t* jidx, int packed_col,
                                                 const int32_t* jval, const int64_t* __restrict__ col_null) {
 #define B2Q_TERM_JX(t) ((JOIN && col_inner[(t).col]) ? jidx : nullptr), ((JOIN && (t).col == packed_col) ? jval : nullptr), (JOIN == 2 ? col_null + (t).col : nullptr)
+#define B2Q_TERM_JX2(t) ((JOIN && col_inner[(t).col2]) ? jidx : nullptr), ((JOIN && (t).col2 == packed_col) ? jval : nullptr), (JOIN == 2 ? col_null + (t).col2 : nullptr)
+#define B2Q_EVAL_TERM(t) ((t).col2 >= 0 ? eval_term2<FULL>((t), cols, row0, stride, valid, pol, B2Q_TERM_JX(t), B2Q_TERM_JX2(t)) \
+                                       : eval_term<FULL>((t), cols, row0, stride, valid, pol, B2Q_TERM_JX(t)))
   if (f.n_ops == 0) return valid;
-  if (f.n_ops == 1) return eval_term<FULL>(f.terms[0], cols, row0, stride, valid, pol, B2Q_TERM_JX(f.terms[0]));
+  if (f.n_ops == 1) return B2Q_EVAL_TERM(f.terms[0]);
   uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
   for (int i = 0; i < f.n_ops; ++i) {
     const uint32_t op = f.ops[i];
     const uint32_t kind = op >> 4;
     if (kind == FOP_TERM) {
-      const uint32_t m = eval_term<FULL>(f.terms[op & 15], cols, row0, stride, valid, pol, B2Q_TERM_JX(f.terms[op & 15]));
+      const uint32_t m = B2Q_EVAL_TERM(f.terms[op & 15]);
       s3 = s2; s2 = s1; s1 = s0; s0 = m;
     } else {
       s0 = (kind == FOP_AND) ? (s1 & s0) : (s1 | s0);
@@ -265,6 +313,8 @@ __device__ __forceinline__ uint32_t eval_filter(const DevFilter& f, const int8_t
     }
   }
   return s0 & valid;
+#undef B2Q_EVAL_TERM
+#undef B2Q_TERM_JX2
 #undef B2Q_TERM_JX
 }
 

@@ -628,12 +628,14 @@ class Planner {
     DevFilter& f = q.prog.filter;
     const B2QExpr& l = ex(e.left);
     const B2QExpr& c = ex(e.right);
-    if (l.kind != B2Q_EXPR_COLUMN_VAR || c.kind != B2Q_EXPR_CONSTANT) reject(B2Q_ERR_UNSUPPORTED, "comparison must be ColumnVar OP Constant");
+    if (l.kind == B2Q_EXPR_COLUMN_VAR && c.kind == B2Q_EXPR_COLUMN_VAR) { lower_cmp_cols(q, e, l, c); return; }
+    if (l.kind != B2Q_EXPR_COLUMN_VAR || c.kind != B2Q_EXPR_CONSTANT) reject(B2Q_ERR_UNSUPPORTED, "comparison must be ColumnVar OP Constant or ColumnVar OP ColumnVar");
     if (f.n_terms >= B2Q_MAX_TERMS || f.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
     const SqlType ct = col_type(l.col_id);
     const ColRange cr = leaf_range(l.col_id);
     DevTerm t;
     memset(&t, 0, sizeof(t));
+    t.col2 = -1;
     t.col = launch_col(q, l.col_id);
     t.width = static_cast<int8_t>(phys_width_code(l.col_id));
     t.col_is_fp = ct.is_fp();
@@ -715,6 +717,34 @@ class Planner {
     f.terms[f.n_terms++] = t;
   }
 
+  /* ColumnVar OP ColumnVar: the analyzer casts both sides to their common type (integers to the wider one, anything
+   * with a DOUBLE to DOUBLE) and DEF_CMP_NULLABLE yields TRUE only when neither side is NULL */
+  void lower_cmp_cols(B2QQuery& q, const B2QExpr& e, const B2QExpr& l, const B2QExpr& r) {
+    DevFilter& f = q.prog.filter;
+    if (f.n_terms >= B2Q_MAX_TERMS || f.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
+    if (e.op != B2Q_kEQ && e.op != B2Q_kNE && e.op != B2Q_kLT && e.op != B2Q_kGT && e.op != B2Q_kLE && e.op != B2Q_kGE) reject(B2Q_ERR_UNSUPPORTED, "comparison operator");
+    const SqlType lt = col_type(l.col_id), rt = col_type(r.col_id);
+    if (lt.is_string() != rt.is_string() || (lt.is_string() && e.op != B2Q_kEQ && e.op != B2Q_kNE))
+      reject(B2Q_ERR_UNSUPPORTED, "dictionary-encoded strings compare by id: only = and <> between two string columns of one dictionary");
+    DevTerm t;
+    memset(&t, 0, sizeof(t));
+    t.col = launch_col(q, l.col_id);
+    t.width = static_cast<int8_t>(phys_width_code(l.col_id));
+    t.col_is_fp = lt.is_fp();
+    t.null_bits = lt.is_fp() ? dbl_bits(kNullDouble) : phys_int_null(l.col_id);
+    t.nullable1 = !lt.notnull;
+    t.col2 = launch_col(q, r.col_id);
+    t.width2 = static_cast<int8_t>(phys_width_code(r.col_id));
+    t.col2_is_fp = rt.is_fp();
+    t.null_bits2 = rt.is_fp() ? dbl_bits(kNullDouble) : phys_int_null(r.col_id);
+    t.nullable2 = !rt.notnull;
+    t.cmp_fp = lt.is_fp() || rt.is_fp();
+    t.op2 = static_cast<int8_t>(e.op);
+    term_sel_.push_back(e.op == B2Q_kEQ ? 0.05 : e.op == B2Q_kNE ? 0.95 : 0.5);
+    f.ops[f.n_ops++] = static_cast<uint8_t>((FOP_TERM << 4) | f.n_terms);
+    f.terms[f.n_terms++] = t;
+  }
+
   double estimate_selectivity(const DevFilter& f) const {
     if (f.n_ops == 0) return 1.0;
     double st[8];
@@ -781,6 +811,7 @@ class Planner {
     const SqlType ct = col_type(l.col_id);
     DevTerm t;
     memset(&t, 0, sizeof(t));
+    t.col2 = -1;
     t.col = launch_col(q, l.col_id);
     t.width = static_cast<int8_t>(phys_width_code(l.col_id));
     t.col_is_fp = ct.is_fp();
@@ -875,6 +906,7 @@ class Planner {
       DevFilter& f = g.filter;
       DevTerm t;
       memset(&t, 0, sizeof(t));
+      t.col2 = -1;
       t.col = launch_col(q, t_.deleted_column_plus1 - 1);
       t.width = 1;
       t.lo = INT32_MIN;
@@ -923,7 +955,7 @@ class Planner {
       EL.n_slots = 0;
       EL.touched_acc = -1;
       EL.keyless_marker = -1;
-      for (int t = 0; t < g.filter.n_terms; ++t) g.col_prefetch[g.filter.terms[t].col] = 1;
+      for (int t = 0; t < g.filter.n_terms; ++t) { g.col_prefetch[g.filter.terms[t].col] = 1; if (g.filter.terms[t].col2 >= 0) g.col_prefetch[g.filter.terms[t].col2] = 1; }
       if (join_) g.col_prefetch[g.join.fk_col] = 1;
       g.join.packed_col = -1;
       for (int c = 0; c < g.n_cols; ++c) if (g.col_inner[c]) g.col_prefetch[c] = 0;
@@ -1049,7 +1081,7 @@ class Planner {
     }
     if (grouped_ && !p.keyless_hash && !L.baseline) L.touched_acc = find_or_add_acc(q, make_acc(q, ACC_TOUCH, nullptr));
     /* columns worth prefetching: filter columns always; key / arguments when they are loaded eagerly */
-    for (int t = 0; t < g.filter.n_terms; ++t) g.col_prefetch[g.filter.terms[t].col] = 1;
+    for (int t = 0; t < g.filter.n_terms; ++t) { g.col_prefetch[g.filter.terms[t].col] = 1; if (g.filter.terms[t].col2 >= 0) g.col_prefetch[g.filter.terms[t].col2] = 1; }
     if (grouped_ && g.eager_key) { if (g.n_keys > 1) { for (int i = 0; i < g.n_keys; ++i) g.col_prefetch[g.keys[i].col] = 1; } else g.col_prefetch[g.key.col] = 1; }
     if (g.eager_args)
       for (int a = 0; a < g.n_accs; ++a) if (g.accs[a].col >= 0) g.col_prefetch[g.accs[a].col] = 1;

@@ -135,7 +135,11 @@ class _P:
             e = self.b.binop(abi.kAND, self.literal_cmp(col, abi.kGE, lo, rte), self.literal_cmp(col, abi.kLE, hi, rte))
             return self.b.uoper(abi.kNOT, e) if neg else e
         op = _OPS[self.eat()]
-        return self.literal_cmp(col, op, self.eat(), rte)
+        rhs = self.eat()
+        if re.fullmatch(r"[A-Za-z_][A-Za-z_0-9.]*", rhs):     # column OP column
+            c2, rte2 = self.colref(rhs)
+            return self.b.binop(op, self.b.col(col, rte), self.b.col(c2, rte2))
+        return self.literal_cmp(col, op, rhs, rte)
 
     def target_text(self):
         """Canonical text of the target expression starting at the cursor (does not build nodes)."""
@@ -205,6 +209,8 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
         for c in _conjuncts(p.b, e):
             n = p.b.nodes[c]
             simple = n.kind == abi.EXPR_BIN_OPER and n.op not in (abi.kAND, abi.kOR)
+            if simple and p.b.nodes[n.right].kind != abi.EXPR_CONSTANT:
+                simple = False          # column OP column is never a simple qual
             if simple:
                 # an integer column against an fp literal is `CAST(col AS DOUBLE) OP lit` in the reference; only
                 # int->int / timestamp casts survive BinOper::normalize_simple_predicate, so it is NOT a simple qual

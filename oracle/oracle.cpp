@@ -1130,8 +1130,37 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
   }
   const B2QExpr& l = expr_at(u, e.left);
   const B2QExpr& r = expr_at(u, e.right);
+  if (l.kind == B2Q_EXPR_COLUMN_VAR && r.kind == B2Q_EXPR_COLUMN_VAR) {
+    /* ColumnVar OP ColumnVar: both sides cast to their common type by the analyzer (integers to the wider integer,
+     * anything with a DOUBLE to DOUBLE), then the nullable compare: NULL on either side -> NULL */
+    const int lt = tbl.col_types[l.col_id].type, rt = tbl.col_types[r.col_id].type;
+    if (is_string(lt) != is_string(rt) || (is_string(lt) && e.op != B2Q_kEQ && e.op != B2Q_kNE))
+      fail(B2Q_ERR_UNSUPPORTED, "dictionary-encoded strings compare by id: only = and <> between two string columns of one dictionary");
+    const bool lnn = tbl.col_types[l.col_id].notnull != 0, rnn = tbl.col_types[r.col_id].notnull != 0;
+    if (is_fp(lt) || is_fp(rt)) {
+      double a, b;
+      bool an, bn;
+      if (is_fp(lt)) { a = decode_double_column(fr, l.col_id, pos); an = !lnn && a == kNullDouble; }
+      else { const int64_t v = decode_int_column(tbl, fr, l.col_id, pos); an = !lnn && v == inline_int_null_val(lt); a = static_cast<double>(v); }
+      if (is_fp(rt)) { b = decode_double_column(fr, r.col_id, pos); bn = !rnn && b == kNullDouble; }
+      else { const int64_t v = decode_int_column(tbl, fr, r.col_id, pos); bn = !rnn && v == inline_int_null_val(rt); b = static_cast<double>(v); }
+      if (an || bn) return kNullBool;
+      switch (e.op) {
+        case B2Q_kEQ: return a == b; case B2Q_kNE: return a != b; case B2Q_kLT: return a < b;
+        case B2Q_kGT: return a > b; case B2Q_kLE: return a <= b; case B2Q_kGE: return a >= b;
+        default: fail(B2Q_ERR_UNSUPPORTED, "comparison operator");
+      }
+    }
+    const int64_t a = decode_int_column(tbl, fr, l.col_id, pos), b = decode_int_column(tbl, fr, r.col_id, pos);
+    if ((!lnn && a == inline_int_null_val(lt)) || (!rnn && b == inline_int_null_val(rt))) return kNullBool;
+    switch (e.op) {
+      case B2Q_kEQ: return a == b; case B2Q_kNE: return a != b; case B2Q_kLT: return a < b;
+      case B2Q_kGT: return a > b; case B2Q_kLE: return a <= b; case B2Q_kGE: return a >= b;
+      default: fail(B2Q_ERR_UNSUPPORTED, "comparison operator");
+    }
+  }
   if (l.kind != B2Q_EXPR_COLUMN_VAR || r.kind != B2Q_EXPR_CONSTANT)
-    fail(B2Q_ERR_UNSUPPORTED, "comparison must be ColumnVar OP Constant");
+    fail(B2Q_ERR_UNSUPPORTED, "comparison must be ColumnVar OP Constant or ColumnVar OP ColumnVar");
   const int col = l.col_id;
   const int ctype = tbl.col_types[col].type;
   const bool col_notnull = tbl.col_types[col].notnull != 0;

@@ -59,6 +59,7 @@ JOIN_QUERIES = [
     "SELECT d.attr, COUNT(*), AVG(d.w) FROM t JOIN d ON t.fk32 = d.id32 GROUP BY d.attr ORDER BY 2 DESC, 1 ASC NULLS FIRST LIMIT 5;",
     "SELECT COUNT(*) FROM t JOIN d ON t.fk32 = d.id32 WHERE d.attr IS NULL OR t.fk64 > 500;",
     "SELECT MIN(d.id64), MAX(d.id64), COUNT(d.id64), COUNT(*) FROM t JOIN d ON t.fk32 = d.id32;",
+    "SELECT d.attr, COUNT(*) FROM t JOIN d ON t.fk32 = d.id32 WHERE t.x < d.attr8 OR d.w > t.d GROUP BY d.attr;",   # column OP column across the tables
 ]
 
 

@@ -35,6 +35,9 @@ def rand_cmp(rng):
 
 def rand_leaf(rng):
     r = rng.random()
+    if r > 0.9:          # column OP column
+        a, b = rng.sample(INT_COLS + FP_COLS, 2)
+        return f"{a} {rng.choice(OPS)} {b}"
     if r < 0.12:
         c = rng.choice(INT_COLS + FP_COLS)
         return f"{c} IS {'NOT ' if rng.random() < 0.5 else ''}NULL"
@@ -143,6 +146,9 @@ J_ON = ["t.fk32 = d.id32", "d.id32 = t.fk16", "t.fk64 = d.id64"]
 
 def rand_join_leaf(rng):
     r = rng.random()
+    if r > 0.9:          # column OP column, possibly across the two tables
+        a, b = rng.sample(list(J_INT) + list(J_FP), 2)
+        return f"{a} {rng.choice(OPS)} {b}"
     if r < 0.15:
         c = rng.choice(list(J_INT) + list(J_FP))
         return f"{c} IS {'NOT ' if rng.random() < 0.5 else ''}NULL"

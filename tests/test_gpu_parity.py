@@ -191,6 +191,9 @@ RAND_QUERIES = [
     "SELECT k8, COUNT(*), SUM(a64) FROM r WHERE a64 IS NOT NULL AND NOT (k16 IS NULL OR a8 IN (1, 2, 3, -4)) GROUP BY k8;",   # NOT / IS NULL / IN
     "SELECT COUNT(*), COUNT(d), MIN(a32) FROM r WHERE d IS NULL OR NOT (a16 BETWEEN -1000 AND 1000 AND dnn < 0.5) OR big IS NULL;",
     "SELECT nn32, COUNT(*) FROM r WHERE NOT (NOT (k32 >= 0)) AND k64 NOT IN (1000000001, 1000000002) AND nn64 IS NOT NULL GROUP BY nn32;",
+    "SELECT k8, COUNT(*), SUM(a16) FROM r WHERE a8 < k8 OR a32 > a64 GROUP BY k8;",                       # column OP column: int8/int8, int32/int64
+    "SELECT COUNT(*), MIN(d), MAX(dnn) FROM r WHERE d <= dnn AND NOT (a16 = nn32) AND (k16 >= nn32 OR big < a64);",   # double/double, int16/int32
+    "SELECT nn64, COUNT(*) FROM r WHERE d > a32 AND nn32 <> nn64 GROUP BY nn64;",                       # double vs int32
 ]
 
 

@@ -109,6 +109,12 @@ NULL_LOGIC_QUERIES = [
     "SELECT COUNT(*) FROM test WHERE z NOT BETWEEN 100 AND 101 OR w IN (-8);",
     "SELECT COUNT(*), MIN(ofd) FROM test WHERE NOT (ofd IN (1, 2, 3) OR ofd IS NULL);",
     "SELECT COUNT(*) FROM test WHERE d IS NULL OR NOT dn IS NOT NULL;",
+    # column OP column (both sides cast to the common type; NULL on either side is not TRUE)
+    "SELECT COUNT(*) FROM test WHERE x < y;",
+    "SELECT COUNT(*), SUM(t) FROM test WHERE y >= z OR w = x;",
+    "SELECT x, COUNT(*) FROM test WHERE z <> smallint_nulls AND NOT (d > dn) GROUP BY x;",
+    "SELECT y, MIN(dn) FROM test WHERE dn < y OR t > ofq GROUP BY y;",        # double vs int, bigint vs bigint with NULLs
+    "SELECT COUNT(*) FROM test WHERE NOT (x <> w) OR ufd <= ofd;",
 ]
 
 
