@@ -497,7 +497,7 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
     # the ceiling the end-to-end leg can reach — boxes of the pool differ by almost 2x here
     raw_gbs = None
     try:
-        probe = [h for h in keep if h.numel() >= (64 << 20)][:8]
+        probe = [h for h in keep if h.numel() >= (64 << 20)]   # every buffer the timed leg will copy
         if probe:
             scratch = torch.empty(max(h.numel() for h in probe), dtype=torch.uint8, device="cuda")
             scratch[:probe[0].numel()].copy_(probe[0], non_blocking=True)
@@ -521,13 +521,15 @@ def e2e_leg(args, torch, ex, eo, cols, sql, names):
         n = rs.rowCount()
         dt = time.perf_counter() - t0
         d2h = int(rs.getQueryMemDesc().buffer_size)
+        phases = rs.stats()
         if i >= 2:
             times.append(dt)
         del rs
     dt = float(np.mean(times))
     return {"value": rows / dt, "unit": "rows/s", "h2d_bytes_per_step": int(rows * bytes_per_row), "d2h_bytes_per_step": d2h,
             "rows": rows, "ms_per_step": dt * 1e3, "host_memory": f"pinned, allocated on the GPU's NUMA node ({node})", "h2d_gbs": rows * bytes_per_row / dt / 1e9,
-            "h2d_raw_gbs_same_buffers": raw_gbs, "groups_out": int(n)}
+            "h2d_raw_gbs_same_buffers": raw_gbs, "groups_out": int(n),
+            "host_phases_ms": {k[5:-3]: phases[k] / 1e3 for k in ("host_setup_us", "host_stream_us", "host_teardown_us")}}
 
 
 if __name__ == "__main__":

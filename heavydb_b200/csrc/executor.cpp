@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +24,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "b2q_internal.h"
@@ -150,6 +152,7 @@ struct B2QPartial {
   cudaEvent_t ev[4] = {}; /* init begin/end, scan begin/end */
   bool scan_timed = false;
   double scan_ms = 0, init_ms = 0, h2d_bytes = 0;
+  double host_setup_us = 0, host_stream_us = 0, host_teardown_us = 0; /* scan_host_table wall-clock phases */
   int64_t launches = 0, frags_scanned = 0, frags_skipped = 0;
   ~B2QPartial() {
     for (void* x : extra) cudaFreeAsync(x, nullptr);
@@ -209,6 +212,7 @@ struct B2QResultSet {
   size_t drop_first = 0, keep_first = 0, fetched = 0;
   double sort_ms = 0;
   double scan_ms = 0, init_ms = 0, mat_ms = 0, h2d_bytes = 0;
+  double host_setup_us = 0, host_stream_us = 0, host_teardown_us = 0;
   int64_t launches = 0, frags_scanned = 0, frags_skipped = 0;
   ~B2QResultSet() { pinned_cache().put(buf, buf_cap); }
 };
@@ -324,6 +328,8 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
   const int64_t slice_rows = int64_t(1) << 24; /* 16 Mi rows per slice */
   int widths[B2Q_MAX_COLS];
   size_t bytes_per_row = 0;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto us_since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
   for (int c = 0; c < nc; ++c) {
     widths[c] = q.prog.col_width[c]; /* physical element width (ENCODING FIXED aware) */
     bytes_per_row += widths[c];
@@ -385,6 +391,8 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
   cudaMemcpyAsync(d_cols, h_cols.data(), h_cols.size() * sizeof(void*), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_rows, h_rows.data(), ns * 8, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_cs, h_cs.data(), ns * 16, cudaMemcpyHostToDevice, st);
+  p.host_setup_us += us_since(t_begin);
+  const auto t_stream = std::chrono::steady_clock::now();
   for (size_t i = 0; i < ns && rc == B2Q_OK; ++i) {
     Stage& s = stage[i & 1];
     const Slice& sl = slices[i];
@@ -422,8 +430,11 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
   }
   cudaStreamSynchronize(copy_st);
   cudaStreamSynchronize(st);
+  p.host_stream_us += us_since(t_stream);
+  const auto t_down = std::chrono::steady_clock::now();
   cleanup();
   cleanup2();
+  p.host_teardown_us += us_since(t_down);
   return rc;
 }
 
@@ -703,6 +714,9 @@ static int32_t finalize_impl(B2QPartial* p, cudaStream_t st, B2QResultSet** out)
   rs->scan_ms = p->scan_ms;
   rs->init_ms = p->init_ms;
   rs->h2d_bytes = p->h2d_bytes;
+  rs->host_setup_us = p->host_setup_us;
+  rs->host_stream_us = p->host_stream_us;
+  rs->host_teardown_us = p->host_teardown_us;
   rs->launches = p->launches + 2; /* + b2q_k_init + b2q_k_materialize */
   rs->frags_scanned = p->frags_scanned;
   rs->frags_skipped = p->frags_skipped;
@@ -1105,6 +1119,9 @@ int64_t b2q_rs_stat(const B2QResultSet* rs, int32_t which) {
     case B2Q_STAT_KERNEL_LAUNCHES: return rs->launches;
     case B2Q_STAT_H2D_BYTES: return static_cast<int64_t>(rs->h2d_bytes);
     case B2Q_STAT_SORT_US: return static_cast<int64_t>(rs->sort_ms * 1000.0);
+    case B2Q_STAT_HOST_SETUP_US: return static_cast<int64_t>(rs->host_setup_us);
+    case B2Q_STAT_HOST_STREAM_US: return static_cast<int64_t>(rs->host_stream_us);
+    case B2Q_STAT_HOST_TEARDOWN_US: return static_cast<int64_t>(rs->host_teardown_us);
     default: return -1;
   }
 }

@@ -225,7 +225,8 @@ class ResultSet:
         L = lib()
         return {"fragments_scanned": L.b2q_rs_stat(self._h, 0), "fragments_skipped": L.b2q_rs_stat(self._h, 1),
                 "kernel_launches": L.b2q_rs_stat(self._h, 2), "h2d_bytes": L.b2q_rs_stat(self._h, 3),
-                "sort_us": L.b2q_rs_stat(self._h, 4)}
+                "sort_us": L.b2q_rs_stat(self._h, 4), "host_setup_us": L.b2q_rs_stat(self._h, 5),
+                "host_stream_us": L.b2q_rs_stat(self._h, 6), "host_teardown_us": L.b2q_rs_stat(self._h, 7)}
 
     def getNDVEstimator(self) -> int:
         """ResultSet::getNDVEstimator (CardinalityEstimator.cpp:33-52) of an estimator query."""

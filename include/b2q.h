@@ -411,7 +411,9 @@ void b2q_rs_drop_first_n(B2QResultSet* rs, size_t n);
 void b2q_rs_keep_first_n(B2QResultSet* rs, size_t n);
 /* execution statistics of the call that produced the result set */
 enum { B2Q_STAT_FRAGMENTS_SCANNED = 0, B2Q_STAT_FRAGMENTS_SKIPPED = 1 /* Executor::skipFragment, Execute.cpp:4776 */,
-       B2Q_STAT_KERNEL_LAUNCHES = 2, B2Q_STAT_H2D_BYTES = 3, B2Q_STAT_SORT_US = 4 /* device time of compaction + sort + gather */ };
+       B2Q_STAT_KERNEL_LAUNCHES = 2, B2Q_STAT_H2D_BYTES = 3, B2Q_STAT_SORT_US = 4 /* device time of compaction + sort + gather */,
+       /* host wall-clock of the CPU_LEVEL streaming scan: staging setup, copy+scan pipeline, teardown */
+       B2Q_STAT_HOST_SETUP_US = 5, B2Q_STAT_HOST_STREAM_US = 6, B2Q_STAT_HOST_TEARDOWN_US = 7 };
 int64_t b2q_rs_stat(const B2QResultSet* rs, int32_t which);
 void b2q_rs_free(B2QResultSet* rs);
 
