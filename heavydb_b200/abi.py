@@ -501,7 +501,8 @@ class Table:
 
     def __init__(self, col_types: Sequence[tuple], encoded_sizes: Optional[Sequence[int]] = None,
                  deleted_column: Optional[int] = None):
-        # col_types: [(sql_type, notnull), ...]; encoded_sizes[c] = physical bytes of an `ENCODING FIXED` column (0 = none)
+        # col_types: [(sql_type, notnull), ...]; encoded_sizes[c] = physical bytes of an `ENCODING FIXED` column (0 = none),
+        # or -4 / -2 for a DATE column under `ENCODING DAYS(32|16)` (kENCODING_DATE_IN_DAYS: the chunk holds days)
         self.col_types = [(int(t), bool(nn)) for t, nn in col_types]
         self.encoded_sizes = [int(x) for x in encoded_sizes] if encoded_sizes is not None else [0] * len(self.col_types)
         self.deleted_column = deleted_column
@@ -510,6 +511,8 @@ class Table:
     def physical_dtype(self, c: int):
         """numpy dtype of the chunk elements of column c (narrower than the logical type under ENCODING FIXED)."""
         enc = self.encoded_sizes[c]
+        if enc < 0:                                        # DATE ENCODING DAYS(32|16)
+            return {4: np.int32, 2: np.int16}[-enc]
         if enc and self.col_types[c][0] in STRING_TYPES:   # DICT(8) / DICT(16): unsigned ids (ColumnIR.cpp:59-67)
             return {1: np.uint8, 2: np.uint16, 4: np.int32}[enc]
         if enc:
@@ -518,6 +521,8 @@ class Table:
 
     def physical_null(self, c: int):
         enc = self.encoded_sizes[c]
+        if enc < 0:
+            return -(2 ** (8 * -enc - 1))
         if enc in (1, 2) and self.col_types[c][0] in STRING_TYPES:   # inline_fixed_encoding_null_val: the unsigned maximum
             return 2 ** (8 * enc) - 1
         if enc:
@@ -541,6 +546,14 @@ class Table:
             n = a.size if n is None else n
             assert a.size == n, "ragged fragment"
             fixed.append(a)
+            if self.encoded_sizes[c] < 0:
+                # DateDaysEncoder (DataMgr/DateDaysEncoder.h:246-254): the physical minimum is NULL whatever the column's
+                # nullability, min / max are kept in epoch SECONDS
+                st = chunk_stats(a, t, False, null=self.physical_null(c))
+                if st.int_min <= st.int_max:
+                    st.int_min, st.int_max = st.int_min * 86400, st.int_max * 86400
+                stats.append(st)
+                continue
             stats.append(chunk_stats(a, t, nn, null=self.physical_null(c)))
         fid = len(self.fragments) if fragment_id is None else fragment_id
         self.fragments.append(Fragment(n or 0, host_cols=fixed, stats=stats, fragment_id=fid))

@@ -97,7 +97,7 @@ struct DevKey {
   int8_t width;
   int8_t translate_null; /* has_nulls && column nullable (GroupByAndAggregate.cpp:1337-1350) */
   int8_t hash_key_width; /* baseline: bytes hashed by MurmurHash3 (4 or 8) */
-  int8_t pad_;
+  int8_t div_day;        /* 8-byte DATE key: idx = (key - min_val) / 86400 (the day bucket of DATE ranges, ExpressionRange.cpp:622) */
 };
 
 /* one GROUP BY column of a multi-column perfect hash (codegenPerfectHashFunction, GroupByAndAggregate.cpp:1549-1597):
@@ -111,7 +111,11 @@ struct DevKeyComp {
   int32_t col;
   int8_t width;
   int8_t translate_null;
-  int8_t pad_[2];
+  int8_t div_day;       /* scan: 8-byte DATE component, d = (key - min_val) / 86400 */
+  int8_t pad_;
+  /* materialise only (DevLayout.keys): key of component index d = min_val + d * step, the NULL group stores null_stored */
+  int64_t step;
+  int64_t null_stored;
 };
 
 /* ---- one INNER hash-join level (PerfectJoinHashTable one-to-one: int32 slots, -1 = no row) ------------------ */
@@ -179,12 +183,15 @@ struct DevSlot {
   int8_t kind;         /* SLOT_* */
   int8_t width;        /* padded slot width: 0, 4 or 8 */
   int8_t key_comp;     /* SLOT_KEY of a multi-column key: which GROUP BY column */
-  int8_t pad_[5];
+  int8_t scale_day;    /* MIN / MAX over a days-encoded DATE chunk: the accumulator holds days, the slot seconds */
+  int8_t pad_[4];
 };
 struct DevLayout {
   int64_t row_size;
   int64_t entry_count;
-  int64_t key_min;       /* perfect: key = key_min + idx */
+  int64_t key_min;       /* perfect: key = key_min + idx * key_step */
+  int64_t key_step;      /* 1, or 86400 for a DATE key (bucketed range / days-encoded chunk) */
+  int64_t key_null_stored; /* perfect hash stores the TRANSLATED NULL key: max + (bucket ? bucket : 1) */
   int64_t key_null_val;  /* value projected for the NULL group */
   int64_t null_idx;
   int32_t n_slots;

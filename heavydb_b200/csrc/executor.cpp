@@ -347,7 +347,8 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
   int32_t rc = B2Q_OK;
   auto cleanup = [&]() {
     for (auto& s : stage) {
-      for (auto& b : s.buf) if (b) cudaFree(b);
+      /* back to the stream-ordered pool (kept there: cudaFree of staging buffers this size costs ~100 ms per call) */
+      for (auto& b : s.buf) if (b) cudaFreeAsync(b, st);
       if (s.copied) cudaEventDestroy(s.copied);
       if (s.scanned) cudaEventDestroy(s.scanned);
     }
@@ -356,7 +357,7 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
   for (auto& s : stage) {
     for (int c = 0; c < nc; ++c) {
       if (q.prog.col_inner[c]) continue; /* inner-table columns are resident for the whole query */
-      if (cudaMalloc(&s.buf[c], static_cast<size_t>(cap_rows) * widths[c] + 16) != cudaSuccess) { cleanup(); cudaGetLastError(); return set_err(B2Q_ERR_OUT_OF_GPU_MEM, "staging buffers"); }
+      if (cudaMallocAsync(reinterpret_cast<void**>(&s.buf[c]), static_cast<size_t>(cap_rows) * widths[c] + 16, st) != cudaSuccess) { cleanup(); cudaGetLastError(); return set_err(B2Q_ERR_OUT_OF_GPU_MEM, "staging buffers"); }
     }
     cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.scanned, cudaEventDisableTiming);
@@ -385,12 +386,20 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
   }
   const int8_t** d_cols = nullptr;
   int64_t *d_rows = nullptr, *d_cs = nullptr;
-  auto cleanup2 = [&]() { if (d_cols) cudaFree(d_cols); if (d_rows) cudaFree(d_rows); if (d_cs) cudaFree(d_cs); };
-  if (cudaMalloc(&d_cols, h_cols.size() * sizeof(void*)) != cudaSuccess || cudaMalloc(&d_rows, ns * 8) != cudaSuccess ||
-      cudaMalloc(&d_cs, ns * 16) != cudaSuccess) { cleanup(); cleanup2(); cudaGetLastError(); return set_err(B2Q_ERR_OUT_OF_GPU_MEM, "launch tables"); }
+  auto cleanup2 = [&]() { if (d_cols) cudaFreeAsync(d_cols, st); if (d_rows) cudaFreeAsync(d_rows, st); if (d_cs) cudaFreeAsync(d_cs, st); };
+  if (cudaMallocAsync(reinterpret_cast<void**>(&d_cols), h_cols.size() * sizeof(void*), st) != cudaSuccess || cudaMallocAsync(reinterpret_cast<void**>(&d_rows), ns * 8, st) != cudaSuccess ||
+      cudaMallocAsync(reinterpret_cast<void**>(&d_cs), ns * 16, st) != cudaSuccess) { cleanup(); cleanup2(); cudaGetLastError(); return set_err(B2Q_ERR_OUT_OF_GPU_MEM, "launch tables"); }
   cudaMemcpyAsync(d_cols, h_cols.data(), h_cols.size() * sizeof(void*), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_rows, h_rows.data(), ns * 8, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_cs, h_cs.data(), ns * 16, cudaMemcpyHostToDevice, st);
+  /* the staging buffers were allocated in st's order: the copy stream may touch them only after that point */
+  {
+    cudaEvent_t ready;
+    cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+    cudaEventRecord(ready, st);
+    cudaStreamWaitEvent(copy_st, ready, 0);
+    cudaEventDestroy(ready);
+  }
   p.host_setup_us += us_since(t_begin);
   const auto t_stream = std::chrono::steady_clock::now();
   for (size_t i = 0; i < ns && rc == B2Q_OK; ++i) {
@@ -497,6 +506,7 @@ static int32_t prepare_join(B2QPartial& p, const B2QExecUnit& u, cudaStream_t st
   const int64_t rows = inner.num_fragments ? inner.fragments[0].num_tuples : 0;
   auto phys_bytes = [&](int c) -> int {
     if (inner.col_encoded_sizes && inner.col_encoded_sizes[c] > 0) return inner.col_encoded_sizes[c];
+    if (inner.col_encoded_sizes && inner.col_encoded_sizes[c] < 0) return -inner.col_encoded_sizes[c]; /* DATE ENCODING DAYS */
     switch (inner.col_types[c].type) {
       case B2Q_kTINYINT: case B2Q_kBOOLEAN: return 1;
       case B2Q_kSMALLINT: return 2;

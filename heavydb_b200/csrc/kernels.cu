@@ -658,6 +658,10 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           int64_t d = k[j] - mn;
+          if (kc.div_day) { /* DATE: bucketed by day; a value off the day grid has no reconstructible key */
+            d = d / 86400;
+            if (k[j] % 86400 != 0 && !(tr && k[j] == nullv)) d = -1;
+          }
           if (tr) d = (k[j] == nullv) ? (int64_t)card - 1 : d;
           bad |= (uint32_t)((uint64_t)d >= card) << j;
           e[j] += (uint32_t)d * mult;
@@ -706,6 +710,10 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           int64_t idx = k64[KEY32 ? 0 : j] - mn;
+          if (P.key.div_day) { /* DATE: (key - min) / bucket (get_group_value_fast, GroupByRuntime.cpp:194-209) */
+            idx = idx / 86400;
+            if (k64[KEY32 ? 0 : j] % 86400 != 0 && !(tr && k64[KEY32 ? 0 : j] == nullv)) idx = -1;
+          }
           if (tr) idx = (k64[KEY32 ? 0 : j] == nullv) ? nidx : idx;
           bad |= (uint32_t)((uint64_t)idx >= n) << j;
           e[j] = (uint32_t)idx;
@@ -1304,8 +1312,9 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
       for (int c = 0; c < L.n_keys; ++c) {
         const DevKeyComp& kc = L.keys[c];
         const int64_t comp = (i / kc.mult) % kc.card;
-        mkey_stored[c] = kc.min_val + comp; /* a NULL key is stored translated: max + 1 */
-        mkey_proj[c] = (kc.translate_null && comp == (int64_t)kc.card - 1) ? kc.null_logical : kc.min_val + comp;
+        const bool is_null_comp = kc.translate_null && comp == (int64_t)kc.card - 1;
+        mkey_stored[c] = is_null_comp ? kc.null_stored : kc.min_val + comp * kc.step; /* a NULL key is stored translated: max + (bucket ? bucket : 1) */
+        mkey_proj[c] = is_null_comp ? kc.null_logical : kc.min_val + comp * kc.step;
       }
       if (L.touched_acc >= 0) touched = reinterpret_cast<const uint8_t*>(A.accs[L.touched_acc])[i] != 0;
     } else if (L.baseline) {
@@ -1313,7 +1322,7 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
       touched = key != B2Q_I64_MAX;
       if (touched && L.key_width == 4) key = (int64_t)(int32_t)key;
     } else {
-      key = (i == L.null_idx) ? L.key_null_val : L.key_min + i;
+      key = (i == L.null_idx) ? L.key_null_val : L.key_min + i * L.key_step;
       if (L.touched_acc >= 0) touched = reinterpret_cast<const uint8_t*>(A.accs[L.touched_acc])[i] != 0;
     }
     if (L.has_key_col && L.columnar) {
@@ -1322,7 +1331,7 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
       if (L.n_keys > 1) {
         for (int c = 0; c < L.n_keys; ++c) reinterpret_cast<int64_t*>(A.out + c * L.key_col_stride)[i] = touched ? mkey_stored[c] : B2Q_I64_MAX;
       } else {
-        const int64_t stored = (!L.baseline && i == L.null_idx) ? L.key_min + i : key;
+        const int64_t stored = (!L.baseline && i == L.null_idx) ? L.key_null_stored : key;
         reinterpret_cast<int64_t*>(A.out)[i] = touched ? stored : B2Q_I64_MAX;
       }
     } else if (L.has_key_col && L.n_keys > 1) {
@@ -1333,7 +1342,7 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
         *reinterpret_cast<int32_t*>(row + 4) = 0;
       } else {
         /* perfect hash stores the TRANSLATED key (NULL -> max+1), GroupByRuntime.cpp:194-209 */
-        const int64_t stored = (!L.baseline && i == L.null_idx) ? L.key_min + i : key;
+        const int64_t stored = (!L.baseline && i == L.null_idx) ? L.key_null_stored : key;
         *reinterpret_cast<int64_t*>(row) = touched ? stored : B2Q_I64_MAX;
       }
     }
@@ -1350,7 +1359,7 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
             bool is_null = false;
             if (sl.nn >= 0) is_null = A.accs[sl.nn][i] == 0;
             else if (sl.nn == -2) is_null = raw == sl.identity;
-            val = is_null ? sl.init_val : (sl.kind == SLOT_VALUE_ORD ? b2q_ord_to_f64(raw) : raw);
+            val = is_null ? sl.init_val : (sl.kind == SLOT_VALUE_ORD ? b2q_ord_to_f64(raw) : (sl.scale_day ? raw * 86400 : raw));
             break;
           }
         }

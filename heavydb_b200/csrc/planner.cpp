@@ -76,6 +76,7 @@ struct ColRange {
   bool valid = false, fp = false, has_nulls = false;
   int64_t imin = 0, imax = -1;
   double fmin = 0, fmax = -1;
+  int64_t bucket = 0; /* 86400 for DATE columns (getLeafColumnRange, ExpressionRange.cpp:622-624) */
 };
 
 struct TargetDesc {
@@ -146,7 +147,7 @@ class Planner {
   bool filter_deleted_;
   std::vector<TargetDesc> targets_;
   bool grouped_ = false;
-  struct KeyComp { int col; int64_t min, max, card, mult; bool has_nulls; };
+  struct KeyComp { int col; int64_t min, max, card, mult; bool has_nulls; int64_t bucket = 0; };
   std::vector<KeyComp> keycomps_; /* multi-column perfect hash */
   int key_col_ = -1;
   bool keyless_ = false;
@@ -164,6 +165,7 @@ class Planner {
     const SqlType ot = col_type(join_outer_col_), it = col_type(n_outer_ + join_inner_col_);
     if (!ot.is_int() || !it.is_int() || ot.is_string() || it.is_string())
       reject(B2Q_ERR_UNSUPPORTED, "join keys must be integer columns (dictionary translation is outside this path)");
+    if (is_days(join_outer_col_) || is_days(n_outer_ + join_inner_col_)) reject(B2Q_ERR_UNSUPPORTED, "days-encoded DATE join keys are outside this path");
     /* getExpressionRange(inner_col): over the inner table alone (getLeafColumnRange, ExpressionRange.cpp:521-632) */
     ColRange r;
     r.valid = true;
@@ -205,6 +207,7 @@ class Planner {
       const B2QExpr& e = ex(u_.estimator_args[i]);
       if (e.kind != B2Q_EXPR_COLUMN_VAR) reject(B2Q_ERR_UNSUPPORTED, "estimator argument must be a ColumnVar");
       if (!col_type(e.col_id).is_int()) reject(B2Q_ERR_UNSUPPORTED, "estimator over a floating-point key");
+      if (is_days(e.col_id)) reject(B2Q_ERR_UNSUPPORTED, "estimator over a days-encoded DATE is outside this path");
       estimator_cols_.push_back(e.col_id);
       p.group_col_ids[i] = e.col_id;
       p.group_col_widths[i] = static_cast<int8_t>(col_type(e.col_id).size());
@@ -224,8 +227,15 @@ class Planner {
    * (FixedWidthInt decode + codgenAdjustFixedEncNull, ColumnIR.cpp:456-500) */
   int phys_size(int c) const {
     if (t_.col_encoded_sizes && t_.col_encoded_sizes[c] > 0) return t_.col_encoded_sizes[c];
+    if (t_.col_encoded_sizes && t_.col_encoded_sizes[c] < 0) return -t_.col_encoded_sizes[c];
     return col_type(c).size();
   }
+  /* kENCODING_DATE_IN_DAYS (the default for DATE columns): the chunk holds int32 / int16 days, NULL = the physical
+   * minimum, decoded as days * 86400 (FixedWidthSmallDate, ColumnIR.cpp:73-81; DecodersImpl.h:138-146).  The scan never
+   * multiplies: constants and key ranges are divided on the host and materialise scales keys and MIN / MAX back. */
+  bool is_days(int c) const { return t_.col_encoded_sizes && t_.col_encoded_sizes[c] < 0; }
+  static int64_t floor_div(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+  static int64_t ceil_div(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) == (b < 0))) ? q + 1 : q; }
   /* dictionary ids stored on 1 or 2 bytes are UNSIGNED (FixedWidthUnsigned, ColumnIR.cpp:59-67) */
   bool phys_unsigned(int c) const { return col_type(c).is_string() && phys_size(c) < 4; }
   /* width as the kernels take it: bytes, negative for an unsigned (zero-extending) load */
@@ -256,7 +266,9 @@ class Planner {
       if (col_type(c).size() < 0) reject(B2Q_ERR_UNSUPPORTED, "column type outside TINYINT/SMALLINT/INT/BIGINT/DOUBLE/TIME/TIMESTAMP/DATE/dictionary-encoded strings");
       if (t_.col_encoded_sizes && t_.col_encoded_sizes[c]) {
         const int e = t_.col_encoded_sizes[c];
-        if (!col_type(c).is_int() || (e != 1 && e != 2 && e != 4) || e >= col_type(c).size())
+        if (e < 0) {
+          if (t_.col_types[c].type != B2Q_kDATE || (e != -4 && e != -2)) reject(B2Q_ERR_UNSUPPORTED, "ENCODING DAYS needs a DATE column and 32 or 16 bits");
+        } else if (!col_type(c).is_int() || (e != 1 && e != 2 && e != 4) || e >= col_type(c).size())
           reject(B2Q_ERR_UNSUPPORTED, "ENCODING FIXED needs an integer column and a physical width below the logical one");
       }
     }
@@ -330,6 +342,7 @@ class Planner {
       }
     }
     if (!r.fp && r.imax < r.imin) { r.imin = 0; r.imax = -1; }
+    r.bucket = t_.col_types[col].type == B2Q_kDATE ? 86400 : 0;
     return r;
   }
 
@@ -444,9 +457,11 @@ class Planner {
         ColRange r = leaf_range(g.col_id);
         narrow_by_simple_quals(g.col_id, r);
         if (r.imin > r.imax) reject(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
-        KeyComp k{g.col_id, r.imin, r.imax, 0, cardinality, r.has_nulls};
+        KeyComp k{g.col_id, r.imin, r.imax, 0, cardinality, r.has_nulls, r.bucket};
         int64_t span;
-        if (__builtin_sub_overflow(r.imax, r.imin, &span) || __builtin_add_overflow(span, int64_t(1 + (r.has_nulls ? 1 : 0)), &k.card) ||
+        const bool span_ovf = __builtin_sub_overflow(r.imax, r.imin, &span);
+        if (!span_ovf && r.bucket) span /= r.bucket; /* getBucketedCardinality (:367-375) */
+        if (span_ovf || __builtin_add_overflow(span, int64_t(1 + (r.has_nulls ? 1 : 0)), &k.card) ||
             __builtin_mul_overflow(cardinality, k.card, &cardinality))
           reject(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
         has_nulls |= r.has_nulls;
@@ -480,22 +495,36 @@ class Planner {
     bool perfect = r.imin <= r.imax;
     p.has_nulls = r.has_nulls;
     if (perfect) {
-      p.min_val = r.imin; p.max_val = r.imax; p.bucket = 0;
+      p.min_val = r.imin; p.max_val = r.imax; p.bucket = r.bucket;
       const int64_t col_count = u_.num_groupby_exprs + u_.num_target_exprs;
       const int64_t max_entries = (int64_t(1) << 30) / (col_count * 8); /* kMaxBufferSize, GroupByAndAggregate.cpp:57 */
       int64_t span;
-      if (__builtin_sub_overflow(r.imax, r.imin, &span) || span >= max_entries) perfect = false; /* keeps min/max */
+      const bool too_big = __builtin_sub_overflow(r.imax, r.imin, &span) || span >= max_entries;
+      if (kt.is_string() && !r.bucket) {
+        /* :311-356 dictionary ids are dense: a too-big range stays perfect hash unless a filter can be expected to
+         * thin it out — with filters and no sort, baseline when there is no estimate yet or 2 * estimate < range */
+        const bool has_filters = u_.num_quals > 0 || u_.num_simple_quals > 0;
+        if (has_filters && too_big && u_.num_order_entries == 0) {
+          int64_t twice;
+          const bool less = has_card_ && !__builtin_mul_overflow(static_cast<int64_t>(guess_), int64_t(2), &twice) && twice < span;
+          if (!has_card_ || less) perfect = false;
+        }
+      } else if (too_big && !r.bucket) perfect = false; /* :357-363, keeps min/max */
+      if (!perfect) p.bucket = 0;
     } else {
       p.min_val = 0; p.max_val = -1;
     }
     if (perfect) {
       p.query_desc_type = B2Q_GroupByPerfectHash;
       keyless_info();
-      p.keyless_hash = keyless_ ? 1 : 0; /* bucket == 0, no sort hint, no baseline sort on this path */
+      p.keyless_hash = (!p.bucket && keyless_) ? 1 : 0; /* QueryMemoryDescriptor.cpp:327-333; no sort hint, no baseline sort on this path */
       p.idx_target_as_key = keyless_idx_;
-      p.entry_count = std::max<int64_t>(p.max_val - p.min_val + 1 + (p.has_nulls ? 1 : 0), 1);
+      int64_t card = p.max_val - p.min_val;
+      if (p.bucket) card /= p.bucket; /* getBucketedCardinality (:367-375) */
+      p.entry_count = std::max<int64_t>(card + 1 + (p.has_nulls ? 1 : 0), 1);
     } else {
       p.query_desc_type = B2Q_GroupByBaselineHash;
+      if (is_days(key_col_)) reject(B2Q_ERR_UNSUPPORTED, "baseline hash over a days-encoded DATE key is outside this path");
       if (!has_card_) reject(B2Q_ERR_CARDINALITY_ESTIMATION_REQUIRED, "baseline hash group-by needs a cardinality estimate (CardinalityEstimationRequired)");
       if (guess_ == 0 || guess_ > 0xFFFFFFFFull) reject(B2Q_ERR_INVALID_ARGUMENT, "max_groups_buffer_entry_guess must be in [1, 2^32)");
       p.entry_count = static_cast<int64_t>(guess_);
@@ -644,6 +673,7 @@ class Planner {
     const bool nullable = !ct.notnull;
     t.null_bits = ct.is_fp() ? dbl_bits(kNullDouble) : phys_int_null(l.col_id);
     const bool cfp = c.ti.type == B2Q_kDOUBLE;
+    if (cfp && is_days(l.col_id)) reject(B2Q_ERR_UNSUPPORTED, "days-encoded DATE compared with a floating-point constant");
     t.cmp_fp = ct.is_fp() || cfp;
     bool negate = e.op == B2Q_kNE;
     const double inf = std::numeric_limits<double>::infinity();
@@ -691,6 +721,12 @@ class Planner {
         sel = std::max(0.0, ov) / (static_cast<double>(cr.imax) - static_cast<double>(cr.imin) + 1.0);
       } else if (lo > hi) sel = 0.0;
       if (negate) sel = 1.0 - sel;
+      if (is_days(l.col_id) && lo <= hi) {
+        /* days * 86400 in [lo, hi]  <=>  days in [ceil(lo / 86400), floor(hi / 86400)]: a constant off the day grid
+         * leaves `=` with an empty range, exactly as the decoded comparison would */
+        if (lo != INT64_MIN) lo = ceil_div(lo, 86400);
+        if (hi != INT64_MAX) hi = floor_div(hi, 86400);
+      }
       /* clamp to the column's register class: 32-bit compares for 1/2/4-byte columns */
       const int64_t dmin = t.width <= 4 ? INT32_MIN : INT64_MIN, dmax = t.width <= 4 ? INT32_MAX : INT64_MAX;
       lo = std::max(lo, dmin);
@@ -724,6 +760,7 @@ class Planner {
     if (f.n_terms >= B2Q_MAX_TERMS || f.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
     if (e.op != B2Q_kEQ && e.op != B2Q_kNE && e.op != B2Q_kLT && e.op != B2Q_kGT && e.op != B2Q_kLE && e.op != B2Q_kGE) reject(B2Q_ERR_UNSUPPORTED, "comparison operator");
     const SqlType lt = col_type(l.col_id), rt = col_type(r.col_id);
+    if (is_days(l.col_id) != is_days(r.col_id)) reject(B2Q_ERR_UNSUPPORTED, "days-encoded DATE compared with a column of another encoding");
     if (lt.is_string() != rt.is_string() || (lt.is_string() && e.op != B2Q_kEQ && e.op != B2Q_kNE))
       reject(B2Q_ERR_UNSUPPORTED, "dictionary-encoded strings compare by id: only = and <> between two string columns of one dictionary");
     DevTerm t;
@@ -837,6 +874,16 @@ class Planner {
     term_sel_.push_back(sel);
     f.ops[f.n_ops++] = static_cast<uint8_t>((FOP_TERM << 4) | f.n_terms);
     f.terms[f.n_terms++] = t;
+  }
+
+  /* scan-side parameters of a DATE key with the day bucket.  Days-encoded chunk: idx = days - first_day (no division
+   * on the device).  8-byte chunk: idx = (seconds - min) / 86400, the kernel divides and checks the day grid.
+   * A DATE under ENCODING FIXED(32) (legacy seconds-in-int32) would need the division on the 32-bit key path. */
+  void day_key(int col, int64_t min_secs, int64_t* min_out, int8_t* div_day) const {
+    if (is_days(col)) { *min_out = ceil_div(min_secs, 86400); *div_day = 0; return; }
+    if (phys_size(col) != 8) reject(B2Q_ERR_UNSUPPORTED, "DATE ENCODING FIXED(32) as a GROUP BY key is outside this path");
+    *min_out = min_secs;
+    *div_day = 1;
   }
 
   int find_or_add_acc(B2QQuery& q, const DevAcc& a) {
@@ -976,6 +1023,9 @@ class Planner {
       d.translate_null = kc.has_nulls && !kt.notnull;
       d.null_val = kt.notnull ? kt.int_null() : phys_int_null(kc.col);
       d.null_logical = kt.int_null();
+      d.step = kc.bucket ? kc.bucket : 1;
+      d.null_stored = kc.max + d.step;
+      if (kc.bucket) day_key(kc.col, kc.min, &d.min_val, &d.div_day);
     }
     DevKey& k = g.key;
     k.col = -1;
@@ -990,9 +1040,10 @@ class Planner {
       k.null_val = kt.notnull ? kt.int_null() : phys_int_null(key_col_);
       k.null_logical = kt.int_null();
       k.hash_key_width = static_cast<int8_t>(p.effective_key_width);
+      if (p.query_desc_type == B2Q_GroupByPerfectHash && p.bucket) day_key(key_col_, p.min_val, &k.min_val, &k.div_day);
       if (p.query_desc_type == B2Q_GroupByPerfectHash && p.has_nulls && !kt.notnull) {
         k.translate_null = 1;
-        k.null_idx = p.max_val - p.min_val + 1;
+        k.null_idx = (p.max_val - p.min_val) / (p.bucket ? p.bucket : 1) + 1;
       }
     }
 
@@ -1003,7 +1054,10 @@ class Planner {
     L.key_col_stride = align8(8 * p.entry_count);
     L.entry_count = p.entry_count;
     L.n_slots = p.num_slots;
-    L.key_min = p.min_val;
+    /* with a day bucket entry i holds the i-th day on or after min: (key - min) / 86400 == i  <=>  key = first + i * 86400 */
+    L.key_step = p.bucket ? p.bucket : 1;
+    L.key_min = p.bucket ? ceil_div(p.min_val, p.bucket) * p.bucket : p.min_val;
+    L.key_null_stored = p.max_val + L.key_step;
     L.null_idx = k.null_idx;
     L.key_null_val = grouped_ ? col_type(key_col_).int_null() : 0;
     L.has_key_col = grouped_ && !p.keyless_hash;
@@ -1011,7 +1065,10 @@ class Planner {
     L.baseline = p.query_desc_type == B2Q_GroupByBaselineHash;
     L.touched_acc = -1;
     L.n_keys = g.n_keys;
-    for (int i = 0; i < g.n_keys; ++i) L.keys[i] = g.keys[i];
+    for (int i = 0; i < g.n_keys; ++i) {
+      L.keys[i] = g.keys[i];
+      if (keycomps_[i].bucket) L.keys[i].min_val = ceil_div(keycomps_[i].min, keycomps_[i].bucket) * keycomps_[i].bucket;
+    }
     L.keyless_marker = (grouped_ && p.keyless_hash) ? p.idx_target_as_key : -1;
     for (const TargetDesc& d : targets_) {
       const int s = d.first_slot;
@@ -1070,6 +1127,7 @@ class Planner {
           sl.kind = fp ? SLOT_VALUE_ORD : SLOT_VALUE;
           sl.acc = find_or_add_acc(q, make_acc(q, op, &d));
           sl.identity = b2q_acc_identity(op);
+          sl.scale_day = is_days(d.arg_col) ? 1 : 0;
           /* "no value seen" <=> the accumulator still holds its identity.  Exact except for a nullable BIGINT MIN
            * whose only non-NULL values are INT64_MAX (the identity is a legal value there): that case counts. */
           if (d.skip_null && !fp && d.arg_type.size() == 8 && d.agg == B2Q_kMIN) sl.nn = non_null_count();

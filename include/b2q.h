@@ -218,7 +218,12 @@ typedef struct B2QTableInfo {
                                        declared `ENCODING FIXED(bits)` (kENCODING_FIXED): 1, 2 or 4 for an integer
                                        column of a wider logical type; 0 = not encoded.  NULL is stored as the minimum
                                        of the physical width and decodes to the logical type's sentinel
-                                       (CodeGenerator::codgenAdjustFixedEncNull, ColumnIR.cpp:456-500) */
+                                       (CodeGenerator::codgenAdjustFixedEncNull, ColumnIR.cpp:456-500).
+                                       NEGATIVE = kENCODING_DATE_IN_DAYS (the default encoding of DATE columns): -4 / -2
+                                       for `DATE ENCODING DAYS(32|16)`; the chunk holds int32 / int16 days since the
+                                       epoch, the physical minimum is NULL, values decode as days * 86400
+                                       (FixedWidthSmallDate, ColumnIR.cpp:73-81, DecodersImpl.h:138-146) and the chunk
+                                       stats are in epoch seconds (DateDaysEncoder.h:246-254) */
 } B2QTableInfo;
 
 /* ---- CompilationOptions / ExecutionOptions subsets (QueryEngine/CompilationOptions.h:31-66,70-122) ----- */

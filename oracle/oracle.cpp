@@ -300,8 +300,12 @@ inline bool outer_join_null(int c) { return c >= g_join_row.n_outer && g_join_ro
 /* Physical element width of column c: narrower than the logical type under `ENCODING FIXED(bits)`. */
 int phys_width(const B2QTableInfo& tbl, int c) {
   if (tbl.col_encoded_sizes && tbl.col_encoded_sizes[c] > 0) return tbl.col_encoded_sizes[c];
+  if (tbl.col_encoded_sizes && tbl.col_encoded_sizes[c] < 0) return -tbl.col_encoded_sizes[c]; /* DATE ENCODING DAYS(32|16) */
   return type_size(tbl.col_types[c].type);
 }
+/* kENCODING_DATE_IN_DAYS (the default encoding of DATE columns): the chunk holds int32 / int16 days since the epoch */
+bool is_date_in_days(const B2QTableInfo& tbl, int c) { return tbl.col_encoded_sizes && tbl.col_encoded_sizes[c] < 0; }
+constexpr int64_t kSecsPerDay = 86400;
 /* FixedWidthInt::codegenDecode (sign-extending load, DecodersImpl.h:30-61) followed by
  * CodeGenerator::codgenAdjustFixedEncNull (ColumnIR.cpp:456-500): the physical width's minimum is NULL and becomes the
  * logical type's sentinel (only for nullable columns, ColumnIR.cpp:286-291). */
@@ -320,6 +324,12 @@ int64_t decode_int_column(const B2QTableInfo& tbl, const B2QFragmentInfo& fr, in
     return u;
   }
   int64_t v = fixed_width_int_decode(static_cast<const int8_t*>(fr.col_buffers[c]), pw, pos);
+  if (is_date_in_days(tbl, c)) {
+    /* FixedWidthSmallDate (ColumnIR.cpp:73-81), fixed_width_small_date_decode (DecodersImpl.h:138-146): the physical
+     * minimum is NULL whatever the column's nullability, everything else is days * 86400 */
+    const int64_t phys_null = pw == 2 ? INT16_MIN : INT32_MIN;
+    return v == phys_null ? inline_int_null_val(tbl.col_types[c].type) : v * kSecsPerDay;
+  }
   if (pw < lw && !tbl.col_types[c].notnull) {
     const int64_t phys_null = pw == 1 ? INT8_MIN : pw == 2 ? INT16_MIN : INT32_MIN;
     if (v == phys_null) v = inline_int_null_val(tbl.col_types[c].type);
@@ -357,7 +367,7 @@ struct Range { /* ExpressionRange (Integer or Double or Invalid) */
 
 struct KeyCol { /* one GROUP BY column of a multi-column perfect hash */
   int col{-1};
-  int64_t min{0}, max{-1}, card{0}, mult{1};
+  int64_t min{0}, max{-1}, card{0}, mult{1}, bucket{0};
   bool has_nulls{false};
 };
 
@@ -470,7 +480,8 @@ Range leaf_column_range(const B2QTableInfo& tbl, int col_id) {
   if (!fp && r.imax < r.imin) { /* :617-621 only nulls */
     r.imin = 0; r.imax = -1;
   }
-  r.bucket = 0;
+  /* :622-624: DATE columns carry the day bucket (get_conservative_datetrunc_bucket(dtDAY)) */
+  r.bucket = type == B2Q_kDATE ? kSecsPerDay : 0;
   return r;
 }
 
@@ -635,6 +646,7 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
       if (e.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "estimator argument must be a ColumnVar");
       if (e.col_id < 0 || e.col_id >= tbl.num_cols) fail(B2Q_ERR_INVALID_ARGUMENT, "column id out of range");
       if (!is_integer(tbl.col_types[e.col_id].type)) fail(B2Q_ERR_UNSUPPORTED, "estimator over a floating-point key");
+      if (is_date_in_days(tbl, e.col_id)) fail(B2Q_ERR_UNSUPPORTED, "estimator over a days-encoded DATE is outside the product path");
       plan.estimator_cols.push_back(e.col_id);
       p.group_col_ids[i] = e.col_id;
       p.group_col_widths[i] = static_cast<int8_t>(type_size(tbl.col_types[e.col_id].type));
@@ -657,7 +669,9 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
     if (type_size(tbl.col_types[c].type) < 0) fail(B2Q_ERR_UNSUPPORTED, "column type outside the numeric / time / dictionary-string subset");
     if (tbl.col_encoded_sizes && tbl.col_encoded_sizes[c]) {
       const int e = tbl.col_encoded_sizes[c];
-      if (!is_integer(tbl.col_types[c].type) || (e != 1 && e != 2 && e != 4) || e >= type_size(tbl.col_types[c].type))
+      if (e < 0) {
+        if (tbl.col_types[c].type != B2Q_kDATE || (e != -4 && e != -2)) fail(B2Q_ERR_UNSUPPORTED, "ENCODING DAYS needs a DATE column and 32 or 16 bits");
+      } else if (!is_integer(tbl.col_types[c].type) || (e != 1 && e != 2 && e != 4) || e >= type_size(tbl.col_types[c].type))
         fail(B2Q_ERR_UNSUPPORTED, "ENCODING FIXED needs an integer column and a physical width below the logical one");
     }
   }
@@ -690,9 +704,11 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
       apply_simple_quals(u, g.col_id, r);
       if (r.kind != Range::Integer || r.imin > r.imax) fail(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
       KeyCol k;
-      k.col = g.col_id; k.min = r.imin; k.max = r.imax; k.has_nulls = r.has_nulls;
+      k.col = g.col_id; k.min = r.imin; k.max = r.imax; k.has_nulls = r.has_nulls; k.bucket = r.bucket;
       int64_t span;
-      if (__builtin_sub_overflow(r.imax, r.imin, &span) || __builtin_add_overflow(span, int64_t(1 + (r.has_nulls ? 1 : 0)), &k.card))
+      const bool span_ovf = __builtin_sub_overflow(r.imax, r.imin, &span);
+      if (!span_ovf && r.bucket) span /= r.bucket; /* getBucketedCardinality (:367-375) */
+      if (span_ovf || __builtin_add_overflow(span, int64_t(1 + (r.has_nulls ? 1 : 0)), &k.card))
         fail(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
       k.mult = cardinality;
       if (__builtin_mul_overflow(cardinality, k.card, &cardinality)) fail(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
@@ -734,7 +750,17 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
       bool too_big;
       int64_t diff;
       if (__builtin_sub_overflow(cmax, cmin, &diff)) too_big = true; else too_big = diff >= max_entry_count;
-      if (too_big && !cbucket) hash_type = B2Q_GroupByBaselineHash; /* :354-360, min/max kept */
+      if (is_string(tbl.col_types[key_col].type) && !cbucket) {
+        /* :311-356 dictionary ids are dense, so a too-big range stays perfect hash unless a filter can be expected to
+         * thin it out: with filters and no sort, baseline when there is no estimate yet or 2 * estimate < range */
+        const bool has_filters = u.num_quals > 0 || u.num_simple_quals > 0;
+        if (has_filters && too_big && u.num_order_entries == 0) {
+          int64_t twice;
+          const bool less = has_cardinality_estimation &&
+                            !__builtin_mul_overflow(static_cast<int64_t>(max_groups_buffer_entry_guess), int64_t(2), &twice) && twice < diff;
+          if (!has_cardinality_estimation || less) hash_type = B2Q_GroupByBaselineHash; /* min/max kept */
+        }
+      } else if (too_big && !cbucket) hash_type = B2Q_GroupByBaselineHash; /* :357-363, min/max kept */
     }
     p.query_desc_type = hash_type;
     p.min_val = cmin; p.max_val = cmax; p.bucket = cbucket; p.has_nulls = chas_nulls;
@@ -825,6 +851,7 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
     }
     /* interleaved_bins_on_gpu (:364-369) is a GPU-layout detail of the reference; the CPU path never has it */
   } else { /* baseline (:380-398) */
+    if (is_date_in_days(tbl, key_col)) fail(B2Q_ERR_UNSUPPORTED, "baseline hash over a days-encoded DATE key is outside the product path");
     if (!has_cardinality_estimation) fail(B2Q_ERR_CARDINALITY_ESTIMATION_REQUIRED, "baseline hash needs a cardinality estimate");
     p.entry_count = static_cast<int64_t>(max_groups_buffer_entry_guess);
     if (p.entry_count <= 0) fail(B2Q_ERR_INVALID_ARGUMENT, "entry guess must be positive");
@@ -1037,6 +1064,7 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
   const Ti oti = ti_of(ji.t.col_types[ji.outer_col]), iti = ti_of(ji.t.col_types[ji.inner_vcol]);
   if (!is_integer(oti.type) || !is_integer(iti.type) || is_string(oti.type) || is_string(iti.type))
     fail(B2Q_ERR_UNSUPPORTED, "join keys must be integer columns (dictionary translation is outside this path)");
+  if (is_date_in_days(ji.t, ji.outer_col) || is_date_in_days(ji.t, ji.inner_vcol)) fail(B2Q_ERR_UNSUPPORTED, "days-encoded DATE join keys are outside the product path");
   Plan plan = make_plan_single(ji.u, ji.t, eo, max_groups_buffer_entry_guess, has_cardinality_estimation);
   const B2QTableInfo& inner = *u.inner_table;
   Range r; /* getExpressionRange(inner_col): over the inner table alone */
@@ -1136,6 +1164,7 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
     const int lt = tbl.col_types[l.col_id].type, rt = tbl.col_types[r.col_id].type;
     if (is_string(lt) != is_string(rt) || (is_string(lt) && e.op != B2Q_kEQ && e.op != B2Q_kNE))
       fail(B2Q_ERR_UNSUPPORTED, "dictionary-encoded strings compare by id: only = and <> between two string columns of one dictionary");
+    if (is_date_in_days(tbl, l.col_id) != is_date_in_days(tbl, r.col_id)) fail(B2Q_ERR_UNSUPPORTED, "days-encoded DATE compared with a column of another encoding is outside the product path");
     const bool lnn = tbl.col_types[l.col_id].notnull != 0, rnn = tbl.col_types[r.col_id].notnull != 0;
     if (is_fp(lt) || is_fp(rt)) {
       double a, b;
@@ -1364,9 +1393,10 @@ int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo&
         for (size_t i = 0; i < plan.keys.size(); ++i) {
           const KeyCol& kc = plan.keys[i];
           int64_t k = decode_int_column(tbl, fr, kc.col, pos);
-          if (kc.has_nulls && !tbl.col_types[kc.col].notnull && k == inline_int_null_val(tbl.col_types[kc.col].type)) k = kc.max + 1;
+          if (kc.has_nulls && !tbl.col_types[kc.col].notnull && k == inline_int_null_val(tbl.col_types[kc.col].type)) k = kc.max + (kc.bucket ? kc.bucket : 1);
           keyv[i] = k;
-          const int64_t d = k - kc.min;
+          int64_t d = k - kc.min;
+          if (kc.bucket) d /= kc.bucket; /* codegenPerfectHashFunction :1583-1586 */
           oob |= d < 0 || d >= kc.card;
           hash += d * kc.mult;
         }

@@ -127,3 +127,69 @@ def test_remote_fragments_carry_stats_only():
         local_only = abi.Table(table.col_types)
         local_only.fragments = [f for f in table.fragments if f.fragment_id % 2 == 0]
         assert executor.Executor().plan(unit, local_only).as_dict()["buffer_size"] > 0   # plans, but not necessarily the same ranges
+
+
+def _stats_only_table(col_types, stats_per_col, tuples=1000, encoded_sizes=None):
+    t = abi.Table(col_types, encoded_sizes=encoded_sizes)
+    stats = []
+    for lo, hi, has_nulls in stats_per_col:
+        s = abi.ChunkStats()
+        s.int_min, s.int_max, s.has_nulls = lo, hi, int(has_nulls)
+        stats.append(s)
+    t.add_remote_fragment(tuples, stats, fragment_id=0)
+    return t
+
+
+def _both_plans(unit, table, **kw):
+    outs = []
+    for side in ("oracle", "product"):
+        try:
+            if side == "oracle":
+                outs.append(oracle_lib.plan(unit, table, entry_guess=kw.get("guess", 0), has_card=kw.get("has_card", False)).as_dict())
+            else:
+                outs.append(executor.Executor().plan(unit, table, max_groups_buffer_entry_guess=kw.get("guess", 0),
+                                                     has_cardinality_estimation=kw.get("has_card", False)).as_dict())
+        except oracle_lib.OracleError as e:
+            outs.append(("error", e.code))
+        except executor.CardinalityEstimationRequired:
+            outs.append(("error", abi.ERR_CARDINALITY_ESTIMATION_REQUIRED))
+    return outs
+
+
+def test_dictionary_key_range_too_big_for_perfect_hash():
+    """getColRangeInfo's string-key branch (GroupByAndAggregate.cpp:311-356): dictionary ids are dense, so a range past
+    max_entry_count stays perfect hash unless a filter may thin it out; with filters and no sort, baseline when no
+    estimate exists yet or 2 * estimate < range."""
+    big = 60_000_000     # > 2^30 / (2 cols * 8)
+    t = _stats_only_table([(abi.kTEXT, False), (abi.kINT, True)], [(0, big, True), (0, 9, False)])
+    names = ["str", "x"]
+    o, p = _both_plans(sqlmini.parse("SELECT str, COUNT(*) FROM t GROUP BY str;", t, names), t)
+    assert o == p and o["query_desc_type"] == abi.GroupByPerfectHash and o["entry_count"] == big + 2
+    unit = sqlmini.parse("SELECT str, COUNT(*) FROM t WHERE x < 3 GROUP BY str;", t, names)
+    assert _both_plans(unit, t) == [("error", abi.ERR_CARDINALITY_ESTIMATION_REQUIRED)] * 2
+    o, p = _both_plans(unit, t, guess=1000, has_card=True)
+    assert o == p and o["query_desc_type"] == abi.GroupByBaselineHash and o["entry_count"] == 1000
+    o, p = _both_plans(unit, t, guess=big, has_card=True)          # 2 * estimate >= range: perfect hash after all
+    assert o == p and o["query_desc_type"] == abi.GroupByPerfectHash
+    o, p = _both_plans(sqlmini.parse("SELECT str, COUNT(*) FROM t WHERE x < 3 GROUP BY str ORDER BY 2 DESC LIMIT 3;", t, names), t)
+    assert o == p and o["query_desc_type"] == abi.GroupByPerfectHash
+    # an integer key of the same range goes baseline whatever the filters
+    ti = _stats_only_table([(abi.kINT, False), (abi.kINT, True)], [(0, big, True), (0, 9, False)])
+    assert _both_plans(sqlmini.parse("SELECT k, COUNT(*) FROM t GROUP BY k;", ti, ["k", "x"]), ti) == [("error", abi.ERR_CARDINALITY_ESTIMATION_REQUIRED)] * 2
+
+
+def test_date_keys_carry_the_day_bucket():
+    """getLeafColumnRange gives DATE columns bucket = 86400 (ExpressionRange.cpp:622-624): perfect hash over
+    (max - min) / 86400 + 1 entries, never keyless (QueryMemoryDescriptor.cpp:327-333), never 'too big' (:357)."""
+    day = 86400
+    for enc in (0, -4):
+        t = _stats_only_table([(abi.kDATE, False), (abi.kINT, True)], [(18000 * day, 58000 * day, True), (0, 9, False)], encoded_sizes=[enc, 0])
+        o, p = _both_plans(sqlmini.parse("SELECT d, COUNT(*) FROM t GROUP BY d;", t, ["d", "x"]), t)
+        assert o == p
+        assert (o["query_desc_type"], o["bucket"], o["entry_count"], o["keyless_hash"]) == (abi.GroupByPerfectHash, day, 40000 + 2, 0)
+        # a simple qual narrows min off the day grid; the entry count follows (max - min) / bucket
+        o, p = _both_plans(sqlmini.parse("SELECT d, COUNT(*) FROM t WHERE d > %d GROUP BY d;" % (57990 * day + 5), t, ["d", "x"]), t)
+        assert o == p and o["min_val"] == 57990 * day + 6 and o["entry_count"] == 9 + 2
+    # TIMESTAMP of the same range: no bucket, too big => baseline
+    t = _stats_only_table([(abi.kTIMESTAMP, False), (abi.kINT, True)], [(18000 * day, 58000 * day, True), (0, 9, False)])
+    assert _both_plans(sqlmini.parse("SELECT d, COUNT(*) FROM t GROUP BY d;", t, ["d", "x"]), t) == [("error", abi.ERR_CARDINALITY_ESTIMATION_REQUIRED)] * 2
