@@ -491,6 +491,8 @@ def test_dict_string_and_time_columns(n, frag_rows):
             continue     # ordered variants: test_gpu_order_by
         gu.run_both(unit, table, dev_table=dev)
         gu.run_both(unit, table, device_resident=False)
+        if " GROUP BY dd" in sql or " GROUP BY dt" in sql:     # DATE keys are 8-byte keys: the columnar layout applies
+            gu.run_both(unit, table, dev_table=dev, output_columnar=True)
     for sql in stt.STR_REJECTED:
         with pytest.raises(executor.UnsupportedOnThisPath):
             executor.Executor().executeWorkUnit(0, True, dev.table, sqlmini.parse(sql, table, stt.STR_NAMES), memory_level=abi.GPU_LEVEL)
