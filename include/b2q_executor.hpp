@@ -27,20 +27,37 @@
 namespace b2q {
 
 /* ---- SQLTypeInfo / enums: the reference's own values ---- */
-enum SQLTypes { kCHAR = B2Q_kCHAR, kVARCHAR = B2Q_kVARCHAR, kINT = B2Q_kINT, kSMALLINT = B2Q_kSMALLINT, kDOUBLE = B2Q_kDOUBLE,
+enum SQLTypes { kBOOLEAN = B2Q_kBOOLEAN /* the $deleted$ column only */, kCHAR = B2Q_kCHAR, kVARCHAR = B2Q_kVARCHAR, kINT = B2Q_kINT, kSMALLINT = B2Q_kSMALLINT, kDOUBLE = B2Q_kDOUBLE,
                 kTIME = B2Q_kTIME, kTIMESTAMP = B2Q_kTIMESTAMP, kBIGINT = B2Q_kBIGINT, kTEXT = B2Q_kTEXT /* dictionary-encoded */,
                 kDATE = B2Q_kDATE, kTINYINT = B2Q_kTINYINT };
-enum SQLOps { kEQ = B2Q_kEQ, kNE = B2Q_kNE, kLT = B2Q_kLT, kGT = B2Q_kGT, kLE = B2Q_kLE, kGE = B2Q_kGE, kAND = B2Q_kAND, kOR = B2Q_kOR };
+enum SQLOps { kEQ = B2Q_kEQ, kNE = B2Q_kNE, kLT = B2Q_kLT, kGT = B2Q_kGT, kLE = B2Q_kLE, kGE = B2Q_kGE, kAND = B2Q_kAND, kOR = B2Q_kOR,
+              kNOT = B2Q_kNOT, kISNULL = B2Q_kISNULL };
 enum SQLAgg { kAVG = B2Q_kAVG, kMIN = B2Q_kMIN, kMAX = B2Q_kMAX, kSUM = B2Q_kSUM, kCOUNT = B2Q_kCOUNT };
 enum class ExecutorDeviceType { CPU = B2Q_DEVICE_CPU, GPU = B2Q_DEVICE_GPU };
+
+/* EncodingType (Shared/sqltypes.h:261-273), the values this path can read */
+enum EncodingType { kENCODING_NONE = 0, kENCODING_FIXED = 1, kENCODING_DICT = 4, kENCODING_DATE_IN_DAYS = 7 };
 
 struct SQLTypeInfo {
   SQLTypes type{kBIGINT};
   bool notnull{false};
+  EncodingType compression{kENCODING_NONE};
+  int comp_param{0}; /* bits for kENCODING_FIXED / kENCODING_DATE_IN_DAYS / DICT(8|16); the dictionary id otherwise */
   SQLTypeInfo() = default;
   SQLTypeInfo(SQLTypes t, bool nn) : type(t), notnull(nn) {}
+  SQLTypeInfo(SQLTypes t, bool nn, EncodingType c, int p) : type(t), notnull(nn), compression(c), comp_param(p) {}
   SQLTypes get_type() const { return type; }
   bool get_notnull() const { return notnull; }
+  EncodingType get_compression() const { return compression; }
+  int get_comp_param() const { return comp_param; }
+  /* B2QTableInfo.col_encoded_sizes entry: physical bytes under FIXED / DICT(8|16), minus the bytes under
+   * DATE_IN_DAYS (comp_param 0 means 32 there, as in SQLTypeInfo::get_size), 0 when the chunk has the logical width */
+  int8_t encoded_size() const {
+    if (compression == kENCODING_FIXED) return static_cast<int8_t>(comp_param / 8);
+    if (compression == kENCODING_DATE_IN_DAYS) return static_cast<int8_t>(comp_param == 16 ? -2 : -4);
+    if (compression == kENCODING_DICT && (comp_param == 8 || comp_param == 16)) return static_cast<int8_t>(comp_param / 8);
+    return 0;
+  }
 };
 
 /* ---- exceptions that cross the reference's boundary ---- */
@@ -87,6 +104,18 @@ struct RelAlgExecutionUnit { /* RelAlgExecutionUnit.h:166-216 */
     exprs.push_back(e);
     return static_cast<ExprRef>(exprs.size() - 1);
   }
+  ExprRef makeConstant(const SQLTypeInfo& ti, int64_t v) { /* Analyzer::Constant(ti, false, Datum) of an integer / time type */
+    B2QExpr e{};
+    e.kind = B2Q_EXPR_CONSTANT; e.ti = {ti.type, ti.notnull}; e.ival = v; e.left = e.right = -1;
+    exprs.push_back(e);
+    return static_cast<ExprRef>(exprs.size() - 1);
+  }
+  ExprRef makeUOper(SQLOps op, ExprRef operand) { /* Analyzer::UOper(kBOOLEAN, kNOT | kISNULL, operand) */
+    B2QExpr e{};
+    e.kind = B2Q_EXPR_UOPER; e.ti = {B2Q_kBOOLEAN, 0}; e.op = op; e.left = operand; e.right = -1;
+    exprs.push_back(e);
+    return static_cast<ExprRef>(exprs.size() - 1);
+  }
   ExprRef makeConstant(double v) {
     B2QExpr e{};
     e.kind = B2Q_EXPR_CONSTANT; e.ti = {B2Q_kDOUBLE, 1}; e.dval = v; e.left = e.right = -1;
@@ -121,6 +150,7 @@ struct InputTableInfo {
   std::vector<SQLTypeInfo> col_types;
   std::vector<FragmentInfo> fragments;
   MemoryLevel memory_level{MemoryLevel::GPU_LEVEL};
+  int deleted_column{-1}; /* id of the BOOLEAN $deleted$ column (Executor::addDeletedColumn, Execute.cpp:4593), -1 = none */
 };
 
 struct CompilationOptions { /* CompilationOptions.h:31-66 */
@@ -184,11 +214,17 @@ class Executor {
     /* flatten to the POD structs of the C ABI */
     struct Flat {
       std::vector<B2QTypeInfo> col_types;
+      std::vector<int8_t> enc;
       std::vector<std::vector<B2QChunkStats>> stats;
       std::vector<B2QFragmentInfo> frags;
       B2QTableInfo tbl{};
       void fill(const InputTableInfo& ti) {
-        for (const auto& t : ti.col_types) col_types.push_back({t.type, t.notnull});
+        bool any_enc = false;
+        for (const auto& t : ti.col_types) {
+          col_types.push_back({t.type, t.notnull});
+          enc.push_back(t.encoded_size());
+          any_enc |= enc.back() != 0;
+        }
         const int nc = static_cast<int>(col_types.size());
         stats.resize(ti.fragments.size());
         frags.resize(ti.fragments.size());
@@ -201,7 +237,7 @@ class Executor {
           }
           frags[f] = B2QFragmentInfo{fi.fragmentId, fi.deviceId, static_cast<int64_t>(fi.numTuples), fi.col_buffers.data(), stats[f].data()};
         }
-        tbl = B2QTableInfo{nc, col_types.data(), static_cast<int32_t>(frags.size()), frags.data(), static_cast<int32_t>(ti.memory_level), 0, nullptr};
+        tbl = B2QTableInfo{nc, col_types.data(), static_cast<int32_t>(frags.size()), frags.data(), static_cast<int32_t>(ti.memory_level), ti.deleted_column + 1, any_enc ? enc.data() : nullptr};
       }
     } outer, inner;
     outer.fill(query_infos.front());

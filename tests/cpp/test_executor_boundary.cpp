@@ -140,6 +140,35 @@ int main() {
     CHECK(r0[0].ival == 70 && r0[1].ival == 2 && r0[2].ival == 30);
     CHECK(result->getQueryMemDesc().join_entry_count == 5);
   }
+  { /* SELECT dd, COUNT(*), MAX(dd) FROM e WHERE dd >= DATE '1970-01-03' GROUP BY dd — DATE ENCODING DAYS(32) chunk
+     * (SQLTypeInfo::get_compression() == kENCODING_DATE_IN_DAYS) with a $deleted$ column; row 3 is deleted */
+    std::vector<int32_t> days{1, 2, 2, 4, INT32_MIN};
+    std::vector<int8_t> deleted{0, 0, 0, 1, 0};
+    InputTableInfo e;
+    const SQLTypeInfo date_days(kDATE, false, kENCODING_DATE_IN_DAYS, 32);
+    e.col_types = {date_days, SQLTypeInfo(kBOOLEAN, true)};
+    e.memory_level = MemoryLevel::CPU_LEVEL;
+    e.deleted_column = 1;
+    FragmentInfo f;
+    f.numTuples = 5;
+    f.col_buffers = {days.data(), deleted.data()};
+    f.chunkStats.resize(2);
+    f.chunkStats[0].int_min = 1 * 86400; f.chunkStats[0].int_max = 4 * 86400; f.chunkStats[0].has_nulls = true; /* DateDaysEncoder keeps seconds */
+    f.chunkStats[1].int_min = 0; f.chunkStats[1].int_max = 1;
+    e.fragments.push_back(f);
+    RelAlgExecutionUnit u;
+    const ExprRef dd = u.makeColumnVar(date_days, 0, 0);
+    u.simple_quals.push_back(u.makeBinOper(kGE, dd, u.makeConstant(SQLTypeInfo(kDATE, true), int64_t(2 * 86400))));
+    u.groupby_exprs.push_back(dd);
+    u.target_exprs.push_back(dd);
+    u.target_exprs.push_back(u.makeAggExpr(SQLTypeInfo(kINT, false), kCOUNT, -1));
+    u.target_exprs.push_back(u.makeAggExpr(date_days, kMAX, dd));
+    auto result = executor->executeWorkUnit(max_groups_buffer_entry_guess, true, {e}, u, CompilationOptions::defaults(), ExecutionOptions::defaults(), nullptr, false, column_cache);
+    CHECK(result->getQueryMemDesc().bucket == 86400 && result->getQueryMemDesc().entry_count == 4); /* days 2..4 + the NULL group */
+    CHECK(result->rowCount() == 1);
+    auto r0 = result->getNextRow(false, false);
+    CHECK(r0[0].ival == 2 * 86400 && r0[1].ival == 2 && r0[2].ival == 2 * 86400);
+  }
   std::printf("boundary test ok\n");
   return 0;
 }
