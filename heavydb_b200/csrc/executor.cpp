@@ -24,6 +24,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <chrono>
 #include <vector>
 
@@ -998,8 +999,9 @@ B2QTypeInfo b2q_rs_get_col_type(const B2QResultSet* rs, size_t col) {
 }
 void b2q_rs_move_to_begin(B2QResultSet* rs) { if (rs) { rs->cursor = 0; rs->fetched = 0; } }
 
+static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* row);
+
 int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
-  const B2QPlan& p = rs->q.plan;
   /* getNextRowImpl + advanceCursorToNextEntry (ResultSetIteration.cpp:320-340, :731-750) */
   const int64_t n_entries = static_cast<int64_t>(b2q_rs_entry_count(rs));
   int64_t entry = 0;
@@ -1011,6 +1013,13 @@ int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
     ++rs->cursor;
     ++rs->fetched;
   } while (rs->drop_first && rs->fetched <= rs->drop_first);
+  read_entry(rs, entry, row);
+  return 1;
+}
+
+/* getRowAt / getTargetValueFromBufferRowwise|Colwise (ResultSetIteration.cpp:820-1000) for one storage entry */
+static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* row) {
+  const B2QPlan& p = rs->q.plan;
   for (int i = 0; i < p.num_targets; ++i) {
     const B2QTargetInfo& t = p.targets[i];
     const int s = t.first_slot;
@@ -1053,8 +1062,79 @@ int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
     if (resized == int_null(compact_type)) { o.ival = int_null(t.sql_type.type); o.is_null = 1; }
     else o.ival = ival;
   }
-  return 1;
 }
+
+/* ---- ColumnarResults (QueryEngine/ColumnarResults.cpp:256-392, materializeAllColumnsThroughIteration :1043-1140):
+ * the rows of a result set, in iteration order (permutation, OFFSET and LIMIT applied), as one contiguous array per
+ * target in the target type's own width; NULLs stay the type's inline sentinel (toBuffer, ColumnarResults.cpp:42-90).
+ * Host code in the reference as well; rows are converted by blocks on `num_threads` threads. */
+struct B2QColumnarResults {
+  size_t num_rows = 0;
+  std::vector<B2QTypeInfo> types;
+  std::vector<std::vector<int8_t>> cols;
+};
+
+int32_t b2q_columnar_results_create(const B2QResultSet* rs, int32_t num_threads, B2QColumnarResults** out) {
+  if (!rs || !out) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
+  if (rs->q.plan.query_desc_type == B2Q_Estimator) return set_err(B2Q_ERR_UNSUPPORTED, "an estimator result has no rows");
+  const B2QPlan& p = rs->q.plan;
+  /* the storage entries the cursor would visit */
+  std::vector<int64_t> entries;
+  const int64_t n_entries = static_cast<int64_t>(b2q_rs_entry_count(rs));
+  for (int64_t i = 0; i < n_entries; ++i) {
+    const int64_t e = rs->perm.empty() ? i : rs->perm[i];
+    if (!rs_is_empty_entry(rs, e)) entries.push_back(e);
+  }
+  const size_t first = std::min(entries.size(), rs->drop_first);
+  const size_t n = truncated_row_count(entries.size(), rs->keep_first, rs->drop_first);
+  std::unique_ptr<B2QColumnarResults> cr(new B2QColumnarResults);
+  cr->num_rows = n;
+  const int nt = p.num_targets;
+  cr->types.resize(nt);
+  cr->cols.resize(nt);
+  std::vector<int> width(nt);
+  for (int c = 0; c < nt; ++c) {
+    cr->types[c] = b2q_rs_get_col_type(rs, c);
+    width[c] = type_size(cr->types[c].type);
+    if (width[c] <= 0) return set_err(B2Q_ERR_UNSUPPORTED, "target type has no fixed width");
+    cr->cols[c].resize(std::max<size_t>(n, 1) * width[c]);
+  }
+  auto convert = [&](size_t lo, size_t hi) {
+    B2QTargetValue row[B2Q_MAX_TARGETS];
+    for (size_t r = lo; r < hi; ++r) {
+      read_entry(rs, entries[first + r], row);
+      for (int c = 0; c < nt; ++c) {
+        int8_t* dst = cr->cols[c].data() + r * width[c];
+        if (row[c].is_fp) { memcpy(dst, &row[c].dval, 8); continue; }
+        const int64_t v = row[c].ival;
+        switch (width[c]) {
+          case 1: { const int8_t x = static_cast<int8_t>(v); memcpy(dst, &x, 1); break; }
+          case 2: { const int16_t x = static_cast<int16_t>(v); memcpy(dst, &x, 2); break; }
+          case 4: { const int32_t x = static_cast<int32_t>(v); memcpy(dst, &x, 4); break; }
+          default: memcpy(dst, &v, 8);
+        }
+      }
+    }
+  };
+  const size_t threads = std::max<size_t>(1, std::min<size_t>(num_threads > 0 ? num_threads : 1, n / 65536 + 1));
+  if (threads == 1) convert(0, n);
+  else {
+    std::vector<std::thread> pool;
+    const size_t step = (n + threads - 1) / threads;
+    for (size_t t = 0; t < threads; ++t) pool.emplace_back(convert, std::min(n, t * step), std::min(n, (t + 1) * step));
+    for (auto& th : pool) th.join();
+  }
+  *out = cr.release();
+  return B2Q_OK;
+}
+size_t b2q_columnar_results_size(const B2QColumnarResults* cr) { return cr ? cr->num_rows : 0; }
+size_t b2q_columnar_results_num_columns(const B2QColumnarResults* cr) { return cr ? cr->cols.size() : 0; }
+const int8_t* b2q_columnar_results_column(const B2QColumnarResults* cr, size_t col, B2QTypeInfo* ti) {
+  if (!cr || col >= cr->cols.size()) return nullptr;
+  if (ti) *ti = cr->types[col];
+  return cr->cols[col].data();
+}
+void b2q_columnar_results_free(B2QColumnarResults* cr) { delete cr; }
 
 const int8_t* b2q_rs_storage_buffer(const B2QResultSet* rs, size_t* size_bytes) {
   if (size_bytes) *size_bytes = rs ? rs->buf_size : 0;

@@ -113,6 +113,15 @@ def lib():
         L.b2q_rs_estimator_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         L.b2q_rs_sort.restype = C.c_int32
         L.b2q_rs_sort.argtypes = [C.c_void_p, C.POINTER(abi.OrderEntry), C.c_int32, C.c_size_t]
+        L.b2q_columnar_results_create.restype = C.c_int32
+        L.b2q_columnar_results_create.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.b2q_columnar_results_size.restype = C.c_size_t
+        L.b2q_columnar_results_size.argtypes = [C.c_void_p]
+        L.b2q_columnar_results_num_columns.restype = C.c_size_t
+        L.b2q_columnar_results_num_columns.argtypes = [C.c_void_p]
+        L.b2q_columnar_results_column.restype = C.c_void_p
+        L.b2q_columnar_results_column.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(abi.TypeInfo)]
+        L.b2q_columnar_results_free.argtypes = [C.c_void_p]
         L.b2q_rs_drop_first_n.argtypes = [C.c_void_p, C.c_size_t]
         L.b2q_rs_keep_first_n.argtypes = [C.c_void_p, C.c_size_t]
         L.b2q_gen_column.restype = C.c_int32
@@ -227,6 +236,42 @@ class ResultSet:
                 "kernel_launches": L.b2q_rs_stat(self._h, 2), "h2d_bytes": L.b2q_rs_stat(self._h, 3),
                 "sort_us": L.b2q_rs_stat(self._h, 4), "host_setup_us": L.b2q_rs_stat(self._h, 5),
                 "host_stream_us": L.b2q_rs_stat(self._h, 6), "host_teardown_us": L.b2q_rs_stat(self._h, 7)}
+
+    def columnarResults(self, num_threads: int = 8):
+        """ColumnarResults(rows, num_columns, target_types) (QueryEngine/ColumnarResults.cpp:256-392): one numpy array per
+        target in the target type's own dtype, rows in iteration order, NULLs as the type's inline sentinel.
+        Returns [(sql_type, notnull, array), ...]."""
+        L = lib()
+        h = C.c_void_p()
+        rc = L.b2q_columnar_results_create(self._h, int(num_threads), C.byref(h))
+        if rc:
+            _raise(rc)
+        try:
+            n = L.b2q_columnar_results_size(h)
+            out = []
+            for c in range(L.b2q_columnar_results_num_columns(h)):
+                ti = abi.TypeInfo()
+                ptr = L.b2q_columnar_results_column(h, c, C.byref(ti))
+                dt = np.dtype(abi.NUMPY_OF[ti.type])
+                arr = np.frombuffer(C.string_at(ptr, n * dt.itemsize), dtype=dt).copy() if n else np.empty(0, dtype=dt)
+                out.append((ti.type, bool(ti.notnull), arr))
+            return out
+        finally:
+            L.b2q_columnar_results_free(h)
+
+    def toArrow(self, names=None, num_threads: int = 8):
+        """ArrowResultSetConverter::convertToArrow (QueryEngine/ArrowResultSetConverter.cpp): a pyarrow RecordBatch
+        over the columnar results; the validity bitmap marks the inline NULL sentinels (dictionary-encoded strings
+        travel as their int32 ids, as with translate_strings = false)."""
+        import pyarrow as pa
+        cols = self.columnarResults(num_threads)
+        arrays = []
+        for ty, _nn, a in cols:
+            null = abi.NULL_OF[ty]
+            mask = (a == null) if a.size else None
+            arrays.append(pa.array(a, mask=mask if mask is not None and mask.any() else None))
+        names = list(names) if names is not None else [f"col{i}" for i in range(len(arrays))]
+        return pa.RecordBatch.from_arrays(arrays, names=names)
 
     def getNDVEstimator(self) -> int:
         """ResultSet::getNDVEstimator (CardinalityEstimator.cpp:33-52) of an estimator query."""

@@ -397,6 +397,18 @@ B2QTypeInfo b2q_rs_get_col_type(const B2QResultSet* rs, size_t col_idx); /* Resu
 /* ResultSet::getNextRow(translate_strings, decimal_to_double) :259 — returns 1 and fills row[colCount()],
  * or 0 at the end.  b2q_rs_move_to_begin() == ResultSet::moveToBegin(). */
 int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row);
+
+/* ColumnarResults (QueryEngine/ColumnarResults.h:60-232, .cpp:256-392): the rows of a result set, in iteration order
+ * (ResultSet::sort permutation, OFFSET, LIMIT applied), as one contiguous array per target in the target type's own
+ * width (COUNT int32 / int64, SUM(int) int64, AVG double, keys at their column type); NULLs keep the type's inline
+ * sentinel.  This is what ColumnFetcher hands to the next step and what ArrowResultSetConverter reads; host code in
+ * the reference too.  `num_threads` conversion threads (is_parallel_execution_enforced). */
+typedef struct B2QColumnarResults B2QColumnarResults;
+int32_t b2q_columnar_results_create(const B2QResultSet* rs, int32_t num_threads, B2QColumnarResults** out);
+size_t b2q_columnar_results_size(const B2QColumnarResults* cr);                                  /* ColumnarResults::size() */
+size_t b2q_columnar_results_num_columns(const B2QColumnarResults* cr);
+const int8_t* b2q_columnar_results_column(const B2QColumnarResults* cr, size_t col, B2QTypeInfo* ti); /* getColumnBuffers()[col], getColumnType(col) */
+void b2q_columnar_results_free(B2QColumnarResults* cr);
 void b2q_rs_move_to_begin(B2QResultSet* rs);
 int32_t b2q_rs_is_row_at_empty(const B2QResultSet* rs, size_t entry_idx); /* ResultSet::isRowAtEmpty() */
 /* getStorage()->getUnderlyingBuffer(): host copy of the output buffer in the reference's own row-wise /

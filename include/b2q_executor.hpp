@@ -198,10 +198,39 @@ class ResultSet {
   }
   void dropFirstN(size_t n) { b2q_rs_drop_first_n(h_, n); }
   void keepFirstN(size_t n) { b2q_rs_keep_first_n(h_, n); }
+  const B2QResultSet* handle() const { return h_; }
  private:
   B2QResultSet* h_;
 };
 using ResultSetPtr = std::shared_ptr<ResultSet>;
+
+/* ColumnarResults (QueryEngine/ColumnarResults.h:60-232): ColumnarResults(row_set_mem_owner, rows, num_columns,
+ * target_types, executor_id, thread_idx, is_parallel_execution_enforced) — the memory owner, executor id and thread
+ * index have no counterpart here; the buffers live as long as this object. */
+class ColumnarResults {
+ public:
+  ColumnarResults(const ResultSet& rows, const size_t num_columns, const std::vector<SQLTypeInfo>& /*target_types*/,
+                  const bool is_parallel_execution_enforced = false) {
+    const int32_t rc = b2q_columnar_results_create(rows.handle(), is_parallel_execution_enforced ? 8 : 1, &h_);
+    if (rc != B2Q_OK) throw QueryExecutionError(rc, b2q_last_error_message());
+    if (num_columns != b2q_columnar_results_num_columns(h_)) { b2q_columnar_results_free(h_); throw QueryExecutionError(B2Q_ERR_INVALID_ARGUMENT, "num_columns"); }
+    for (size_t c = 0; c < num_columns; ++c) {
+      B2QTypeInfo ti;
+      column_buffers_.push_back(b2q_columnar_results_column(h_, c, &ti));
+      target_types_.emplace_back(static_cast<SQLTypes>(ti.type), ti.notnull != 0);
+    }
+  }
+  ~ColumnarResults() { b2q_columnar_results_free(h_); }
+  ColumnarResults(const ColumnarResults&) = delete;
+  ColumnarResults& operator=(const ColumnarResults&) = delete;
+  const std::vector<const int8_t*>& getColumnBuffers() const { return column_buffers_; }
+  size_t size() const { return b2q_columnar_results_size(h_); }
+  const SQLTypeInfo& getColumnType(const int col_id) const { return target_types_[col_id]; }
+ private:
+  B2QColumnarResults* h_{nullptr};
+  std::vector<const int8_t*> column_buffers_;
+  std::vector<SQLTypeInfo> target_types_;
+};
 
 class Executor {
  public:

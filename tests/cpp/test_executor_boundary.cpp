@@ -168,6 +168,12 @@ int main() {
     CHECK(result->rowCount() == 1);
     auto r0 = result->getNextRow(false, false);
     CHECK(r0[0].ival == 2 * 86400 && r0[1].ival == 2 && r0[2].ival == 2 * 86400);
+    /* ColumnarResults of the same rows: DATE as int64, COUNT as int32 */
+    ColumnarResults cols(*result, result->colCount(), {});
+    CHECK(cols.size() == 1 && cols.getColumnBuffers().size() == 3);
+    CHECK(*reinterpret_cast<const int64_t*>(cols.getColumnBuffers()[0]) == 2 * 86400);
+    CHECK(*reinterpret_cast<const int32_t*>(cols.getColumnBuffers()[1]) == 2);
+    CHECK(cols.getColumnType(1).get_type() == kINT && cols.getColumnType(0).get_type() == kDATE);
   }
   std::printf("boundary test ok\n");
   return 0;
