@@ -55,3 +55,7 @@ extern "C" bool dynamic_watchdog() { return false; }
 
 #include "QueryEngine/MurmurHash.cpp"
 #include "QueryEngine/GroupByRuntime.cpp"
+
+/* The reference's chunk decoders, header-only (QueryEngine/DecodersImpl.h): fixed_width_int_decode,
+ * fixed_width_unsigned_decode, fixed_width_small_date_decode (days-encoded DATE), fixed_width_double_decode. */
+#include "QueryEngine/DecodersImpl.h"

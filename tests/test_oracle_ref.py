@@ -95,3 +95,107 @@ def test_get_group_value_fast_reference(ref):
             d //= bucket
         assert (r - buf.ctypes.data) // 8 == d * row_size_quad + 1
         assert buf[d * row_size_quad] == key
+
+
+# ---- chunk decoders (QueryEngine/DecodersImpl.h, compiled from the reference) --------------------------------
+def _decoders(ref):
+    for name in ("fixed_width_int_decode", "fixed_width_unsigned_decode"):
+        f = getattr(ref, name)
+        f.restype = C.c_int64
+        f.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
+    ref.fixed_width_small_date_decode.restype = C.c_int64
+    ref.fixed_width_small_date_decode.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64]
+    return ref
+
+
+def test_chunk_decoders_match_reference(ref):
+    """The oracle reads ENCODING FIXED, DICT(8|16) and DATE ENCODING DAYS chunks exactly like the reference's
+    decoders: per column, MIN / MAX / COUNT over the values the REFERENCE decodes == the oracle's answer."""
+    import sqlmini
+    import str_tables as stt
+    from heavydb_b200 import abi
+    _decoders(ref)
+    table = stt.str_table(3000, seed=21, frag_rows=700)
+    names = stt.STR_NAMES
+    null64 = abi.NULL_BIGINT
+    for col, kind in [("dd", "days"), ("dd16", "days"), ("ts", "fixed"), ("s8", "unsigned"), ("s16", "unsigned")]:
+        c = names.index(col)
+        width = np.dtype(table.physical_dtype(c)).itemsize
+        vals = []
+        for f in table.fragments:
+            a = f.host_cols[c]
+            for pos in range(a.size):
+                if kind == "days":
+                    v = ref.fixed_width_small_date_decode(a.ctypes.data, width, table.physical_null(c), null64, pos)
+                    if v != null64:
+                        vals.append(v)
+                elif kind == "fixed":
+                    v = ref.fixed_width_int_decode(a.ctypes.data, width, pos)
+                    if v != table.physical_null(c):     # codgenAdjustFixedEncNull maps it to the logical NULL
+                        vals.append(v)
+                else:
+                    v = ref.fixed_width_unsigned_decode(a.ctypes.data, width, pos)
+                    if stt.STR_COLS[c][2] or v != table.physical_null(c):
+                        vals.append(v)
+        agg = "COUNT({0})" if kind == "unsigned" else "MIN({0}), MAX({0}), COUNT({0})"
+        res = oracle_lib.execute(sqlmini.parse(f"SELECT {agg.format(col)}, COUNT(*) FROM s;", table, names), table).rows()[0]
+        if kind == "unsigned":
+            assert res == (len(vals), 3000)
+        else:
+            assert res == (min(vals), max(vals), len(vals), 3000), col
+
+
+def test_day_bucket_index_matches_reference(ref):
+    """DATE keys: entry = (key - min) / 86400 with min possibly off the day grid (a simple qual narrowed it) — every
+    non-empty entry of the oracle's buffer sits where the reference's get_group_value_fast puts its key."""
+    import sqlmini
+    import str_tables as stt
+    table = stt.str_table(3000, seed=22, frag_rows=700)
+    for sql in ["SELECT dt, COUNT(*) FROM s WHERE dt > 1555286410 GROUP BY dt;", "SELECT dd, COUNT(*) FROM s WHERE dd >= 1555372801 GROUP BY dd;"]:
+        res = oracle_lib.execute(sqlmini.parse(sql, table, stt.STR_NAMES), table)
+        p = res.plan
+        assert p.bucket == 86400 and p.min_val % 86400 != 0 and not p.keyless_hash
+        row_quad = p.row_size // 8
+        buf = res.buffer().view(np.int64).reshape(p.entry_count, row_quad)
+        seen = 0
+        for i in range(p.entry_count):
+            key = int(buf[i, 0])
+            if key == np.iinfo(np.int64).max:
+                continue
+            scratch = np.full(p.entry_count * row_quad, np.iinfo(np.int64).max, dtype=np.int64)
+            r = ref.get_group_value_fast(scratch.ctypes.data, key, p.min_val, p.bucket, row_quad)
+            assert (r - scratch.ctypes.data) // 8 == i * row_quad + 1, (sql, i, key)
+            seen += 1
+        assert seen == res.row_count() > 5
+
+
+def test_one_to_one_join_table_matches_reference(ref):
+    """fill_one_to_one_hashtable + get_hash_slot + hash_join_idx[_nullable] (JoinHashImpl.h, GroupByRuntime.cpp:283-316),
+    the reference's own code, drive a Python join; the oracle's joined aggregates must agree."""
+    import join_tables as jt
+    import sqlmini
+    from heavydb_b200 import abi
+    ref.fill_one_to_one_hashtable.restype = C.c_int
+    ref.fill_one_to_one_hashtable.argtypes = [C.c_size_t, C.c_void_p, C.c_int32]
+    ref.get_hash_slot.restype = C.c_void_p
+    ref.get_hash_slot.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    ref.hash_join_idx_nullable.restype = C.c_int64
+    ref.hash_join_idx_nullable.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
+    dim, fact = jt.dim_table(), jt.fact_table(5000, seed=9, frag_rows=1300)
+    ids = dim.fragments[0].host_cols[jt.DIM_NAMES.index("id32")]
+    big = dim.fragments[0].host_cols[jt.DIM_NAMES.index("big")]
+    mn, mx = int(ids.min()), int(ids.max())
+    buff = np.full(mx - mn + 1, -1, dtype=np.int32)
+    for row, k in enumerate(ids):
+        slot = ref.get_hash_slot(buff.ctypes.data, int(k), mn)
+        assert ref.fill_one_to_one_hashtable(row, slot, -1) == 0
+    matches, total = 0, 0
+    for f in fact.fragments:
+        for k in f.host_cols[jt.FACT_NAMES.index("fk32")]:
+            idx = ref.hash_join_idx_nullable(buff.ctypes.data, int(k), mn, mx, abi.NULL_INT)
+            if idx >= 0:
+                matches += 1
+                total += int(big[idx])
+    unit = sqlmini.parse("SELECT COUNT(*), SUM(d.big) FROM t JOIN d ON t.fk32 = d.id32;", fact, jt.FACT_NAMES, inner=(dim, jt.DIM_NAMES))
+    assert oracle_lib.execute(unit, fact).rows() == [(matches, total)]
+    assert 0 < matches < 5000
