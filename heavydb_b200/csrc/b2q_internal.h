@@ -14,7 +14,7 @@
 
 #define B2Q_MAX_COLS 16   /* distinct columns a query may reference */
 #define B2Q_MAX_TERMS B2Q_MAX_FILTER_TERMS
-#define B2Q_MAX_FILTER_OPS 24
+#define B2Q_MAX_FILTER_OPS 34 /* 16 leaves + 15 connectives (+ the deleted-rows term and its AND) */
 #define B2Q_MAX_ACCS 24   /* internal accumulators */
 #define B2Q_MAX_FRAGS_INLINE 0
 

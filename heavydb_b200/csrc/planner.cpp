@@ -810,6 +810,16 @@ class Planner {
       default: return -1;
     }
   }
+  int stack_need(int idx) const { /* mask-stack slots the postfix evaluation of this subtree needs */
+    const B2QExpr& e = ex(idx);
+    if (e.kind == B2Q_EXPR_UOPER) return e.op == B2Q_kNOT ? stack_need(e.left) : 1;
+    if (e.kind == B2Q_EXPR_BIN_OPER && (e.op == B2Q_kAND || e.op == B2Q_kOR)) {
+      const int l = stack_need(e.left), r = stack_need(e.right);
+      return l == r ? l + 1 : std::max(l, r);
+    }
+    return 1;
+  }
+
   int lower_bool(B2QQuery& q, int idx, int depth, bool negated = false) { /* returns max stack depth used */
     const B2QExpr& e = ex(idx);
     if (e.kind == B2Q_EXPR_UOPER) {
@@ -819,8 +829,12 @@ class Planner {
     }
     if (e.kind != B2Q_EXPR_BIN_OPER) reject(B2Q_ERR_UNSUPPORTED, "qual must be a BinOper or NOT / IS NULL");
     if (e.op == B2Q_kAND || e.op == B2Q_kOR) {
-      const int d1 = lower_bool(q, e.left, depth, negated);
-      const int d2 = lower_bool(q, e.right, depth + 1, negated);
+      /* the device evaluates the postfix program on a 4-deep stack of row masks: lowering the operand that needs the
+       * deeper stack FIRST (Sethi-Ullman; AND / OR are symmetric in the reference's three-valued logic too,
+       * RuntimeFunctions.cpp:331-357) lets any tree of up to 16 terms fit */
+      const bool right_first = stack_need(e.right) > stack_need(e.left);
+      const int d1 = lower_bool(q, right_first ? e.right : e.left, depth, negated);
+      const int d2 = lower_bool(q, right_first ? e.left : e.right, depth + 1, negated);
       DevFilter& f = q.prog.filter;
       if (f.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
       const bool is_and = (e.op == B2Q_kAND) != negated; /* De Morgan */

@@ -259,7 +259,7 @@ enum {
  * ======================================================================================================= */
 #define B2Q_MAX_SLOTS 16
 #define B2Q_MAX_TARGETS 16
-#define B2Q_MAX_FILTER_TERMS 8
+#define B2Q_MAX_FILTER_TERMS 16 /* comparison / IS NULL leaves of all quals together (an IN list is one leaf per value) */
 #define B2Q_MAX_GROUP_COLS 4
 
 typedef struct B2QTargetInfo { /* Shared/TargetInfo.h:49-78 */
