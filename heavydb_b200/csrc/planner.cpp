@@ -1175,7 +1175,11 @@ class Planner {
       static const bool s16 = []() { const char* e = getenv("B2Q_JOIN_SLOT16"); return !e || atoi(e) != 0; }();
       int n_inner = 0;
       for (int c = 0; c < g.n_cols; ++c) n_inner += g.col_inner[c] ? 1 : 0;
-      const ColRange vr = leaf_range(q.col_ids[g.join.packed_col]);
+      ColRange vr = leaf_range(q.col_ids[g.join.packed_col]);
+      if (is_days(q.col_ids[g.join.packed_col]) && vr.imin <= vr.imax) { /* the slot holds the chunk's raw days, the stats are seconds */
+        vr.imin = floor_div(vr.imin, 86400);
+        vr.imax = floor_div(vr.imax, 86400);
+      }
       int64_t span = 0;
       if (s16 && n_inner == 1 && vr.valid && !vr.fp && vr.imin <= vr.imax && !__builtin_sub_overflow(vr.imax, vr.imin, &span) && span < 65534) {
         g.join.slot16 = 1;
