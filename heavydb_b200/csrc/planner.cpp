@@ -254,6 +254,13 @@ class Planner {
       if (u_.order_entries[i].tle_no < 1 || u_.order_entries[i].tle_no > u_.num_target_exprs)
         reject(B2Q_ERR_INVALID_ARGUMENT, "order entry refers to a target that does not exist (tle_no is 1-based)");
     if (u_.offset < 0 || (u_.has_limit && u_.limit < 0)) reject(B2Q_ERR_INVALID_ARGUMENT, "negative LIMIT / OFFSET");
+    if (u_.num_exprs < 0 || (u_.num_exprs && !u_.exprs)) reject(B2Q_ERR_INVALID_ARGUMENT, "exprs");
+    /* the node array is in construction order: operands precede the node that uses them (no cycles, bounded recursion) */
+    for (int i = 0; i < u_.num_exprs; ++i) {
+      const B2QExpr& e = u_.exprs[i];
+      if (e.left < -1 || e.left >= i || e.right < -1 || e.right >= i)
+        reject(B2Q_ERR_INVALID_ARGUMENT, "expression operands must be earlier nodes of the array (or -1)");
+    }
     if (u_.num_groupby_exprs > B2Q_MAX_GROUP_COLS) reject(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
     if (u_.num_groupby_exprs < 0 || (u_.num_target_exprs <= 0 && !u_.has_estimator) || u_.num_target_exprs > B2Q_MAX_TARGETS)
       reject(B2Q_ERR_INVALID_ARGUMENT, "bad groupby/target counts");
@@ -273,7 +280,11 @@ class Planner {
       }
     }
     if (t_.deleted_column_plus1 < 0 || t_.deleted_column_plus1 > t_.num_cols) reject(B2Q_ERR_INVALID_ARGUMENT, "deleted column id out of range");
-    if (t_.num_fragments < 0) reject(B2Q_ERR_INVALID_ARGUMENT, "negative fragment count");
+    if (t_.num_fragments < 0 || (t_.num_fragments && !t_.fragments)) reject(B2Q_ERR_INVALID_ARGUMENT, "fragments");
+    for (int f = 0; f < t_.num_fragments; ++f) {
+      if (t_.fragments[f].num_tuples < 0) reject(B2Q_ERR_INVALID_ARGUMENT, "negative fragment row count");
+      if (t_.num_cols && !t_.fragments[f].col_stats) reject(B2Q_ERR_INVALID_ARGUMENT, "fragment without chunk stats");
+    }
   }
 
   void build_targets() {

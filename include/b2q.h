@@ -105,7 +105,8 @@ typedef struct B2QTypeInfo {
 } B2QTypeInfo;
 
 /* ---- Analyzer::Expr subset (Analyzer/Analyzer.h:193 ColumnVar, :319 Constant, :434 BinOper, :1381 AggExpr)
- * Nodes live in one flat array; children are indices into it (-1 = none). */
+ * Nodes live in one flat array in construction order; children are indices of EARLIER nodes (-1 = none) — anything
+ * else is B2Q_ERR_INVALID_ARGUMENT. */
 enum { B2Q_EXPR_COLUMN_VAR = 1, B2Q_EXPR_CONSTANT = 2, B2Q_EXPR_BIN_OPER = 3, B2Q_EXPR_AGG = 4,
        B2Q_EXPR_UOPER = 5 /* Analyzer::UOper with op in {kNOT, kISNULL}; operand = left */ };
 

@@ -68,3 +68,28 @@ def test_no_device_is_an_error_not_a_fallback(libpath):
     unit = sqlmini.parse("SELECT COUNT(*) FROM test;", table, rt.TEST_NAMES)
     with pytest.raises(executor.NoDeviceError):
         executor.Executor().executeWorkUnit(0, True, table, unit)
+
+
+def test_malformed_units_are_refused_not_followed():
+    """Operands must be earlier nodes of the expression array: a self-referencing / forward-referencing node (a cycle
+    would recurse forever) and negative fragment row counts come back as INVALID_ARGUMENT from the host-only planner."""
+    import ref_tables as rt
+    import sqlmini
+    from heavydb_b200 import executor
+    table = rt.make_table(rt.test_rows())
+    unit = sqlmini.parse("SELECT x, COUNT(*) FROM test WHERE y > 42 OR z < 100 GROUP BY x;", table, rt.TEST_NAMES)
+    u = unit.unit
+    ors = [i for i in range(u.num_exprs) if u.exprs[i].kind == abi.EXPR_BIN_OPER and u.exprs[i].op == abi.kOR]
+    assert ors
+    saved = u.exprs[ors[0]].right
+    for bad in (ors[0], u.num_exprs, -7):
+        u.exprs[ors[0]].right = bad
+        with pytest.raises(executor.QueryExecutionError) as ei:
+            executor.Executor().plan(unit, table)
+        assert ei.value.code == abi.ERR_INVALID_ARGUMENT
+    u.exprs[ors[0]].right = saved
+    executor.Executor().plan(unit, table)
+    table.fragments[0].num_tuples = -1
+    with pytest.raises(executor.QueryExecutionError) as ei:
+        executor.Executor().plan(unit, table)
+    assert ei.value.code == abi.ERR_INVALID_ARGUMENT
