@@ -975,7 +975,10 @@ size_t b2q_rs_entry_count(const B2QResultSet* rs) {
   return rs->perm.empty() ? static_cast<size_t>(rs->q.plan.entry_count) : rs->perm.size();
 }
 size_t b2q_rs_col_count(const B2QResultSet* rs) { return rs ? static_cast<size_t>(rs->q.plan.num_targets) : 0; }
-int32_t b2q_rs_is_row_at_empty(const B2QResultSet* rs, size_t e) { return rs_is_empty_entry(rs, static_cast<int64_t>(e)); }
+int32_t b2q_rs_is_row_at_empty(const B2QResultSet* rs, size_t e) { /* ResultSet::isRowAtEmpty; an index past the storage is empty */
+  if (!rs || e >= static_cast<size_t>(rs->q.plan.entry_count)) return 1;
+  return rs_is_empty_entry(rs, static_cast<int64_t>(e));
+}
 static size_t truncated_row_count(size_t total, size_t keep_first, size_t drop_first) { /* get_truncated_row_count, ResultSet.cpp */
   if (total <= drop_first) return 0;
   const size_t rest = total - drop_first;
@@ -993,6 +996,7 @@ size_t b2q_rs_row_count(const B2QResultSet* rs) { /* ResultSet::rowCountImpl (Re
 }
 int32_t b2q_rs_is_empty(const B2QResultSet* rs) { return b2q_rs_row_count(rs) == 0; }
 B2QTypeInfo b2q_rs_get_col_type(const B2QResultSet* rs, size_t col) {
+  if (!rs || col >= static_cast<size_t>(rs->q.plan.num_targets)) return B2QTypeInfo{0, 0}; /* kNULLT */
   const B2QTargetInfo& t = rs->q.plan.targets[col];
   if (t.is_agg && t.agg_kind == B2Q_kAVG) return B2QTypeInfo{B2Q_kDOUBLE, 0};
   return t.sql_type;
@@ -1002,6 +1006,7 @@ void b2q_rs_move_to_begin(B2QResultSet* rs) { if (rs) { rs->cursor = 0; rs->fetc
 static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* row);
 
 int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
+  if (!rs || !row || rs->q.plan.query_desc_type == B2Q_Estimator) return 0;
   /* getNextRowImpl + advanceCursorToNextEntry (ResultSetIteration.cpp:320-340, :731-750) */
   const int64_t n_entries = static_cast<int64_t>(b2q_rs_entry_count(rs));
   int64_t entry = 0;
