@@ -21,6 +21,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "b2q_internal.h"
@@ -664,7 +665,8 @@ class Planner {
 
   std::vector<double> term_sel_; /* estimated selectivity per filter term (uniformity assumption over chunk stats) */
 
-  void lower_cmp(B2QQuery& q, const B2QExpr& e) {
+  /* `range_hi`: the comparison is `=` / `<>` against the run of consecutive values [constant, *range_hi] of an IN list */
+  void lower_cmp(B2QQuery& q, const B2QExpr& e, const int64_t* range_hi = nullptr) {
     DevFilter& f = q.prog.filter;
     const B2QExpr& l = ex(e.left);
     const B2QExpr& c = ex(e.right);
@@ -718,7 +720,7 @@ class Planner {
       else {
         const int64_t k = c.ival;
         switch (e.op) {
-          case B2Q_kEQ: case B2Q_kNE: lo = k; hi = k; break;
+          case B2Q_kEQ: case B2Q_kNE: lo = k; hi = range_hi ? *range_hi : k; break;
           case B2Q_kLT: if (k != INT64_MIN) { lo = INT64_MIN; hi = k - 1; } break;
           case B2Q_kLE: lo = INT64_MIN; hi = k; break;
           case B2Q_kGT: if (k != INT64_MAX) { lo = k + 1; hi = INT64_MAX; } break;
@@ -831,6 +833,92 @@ class Planner {
     return 1;
   }
 
+  /* ---- IN lists: `c = v1 OR c = v2 OR ...` (what the analyzer expands a short IN list to) and its negation
+   * `c <> v1 AND c <> v2 AND ...`.  Values that are consecutive in the column's domain (step 1; one day for a
+   * days-encoded DATE) fold into ONE range term — fewer loads and compares per row, and long dense lists fit the
+   * 16-leaf program. ---- */
+  struct ChainItem { int idx; bool negated; };
+  void flatten_chain(int idx, bool negated, bool want_and, std::vector<ChainItem>& out) const {
+    const B2QExpr& e = ex(idx);
+    if (e.kind == B2Q_EXPR_UOPER && e.op == B2Q_kNOT) { flatten_chain(e.left, !negated, want_and, out); return; }
+    if (e.kind == B2Q_EXPR_BIN_OPER && (e.op == B2Q_kAND || e.op == B2Q_kOR) && ((e.op == B2Q_kAND) != negated) == want_and) {
+      flatten_chain(e.left, negated, want_and, out);
+      flatten_chain(e.right, negated, want_and, out);
+      return;
+    }
+    out.push_back({idx, negated});
+  }
+  bool point_leaf(const ChainItem& it, bool want_and, int* col, int64_t* val) const {
+    const B2QExpr& e = ex(it.idx);
+    if (e.kind != B2Q_EXPR_BIN_OPER || e.op == B2Q_kAND || e.op == B2Q_kOR) return false;
+    const int op = it.negated ? inverse_cmp(e.op) : e.op;
+    if (op != (want_and ? B2Q_kNE : B2Q_kEQ)) return false;
+    const B2QExpr& l = ex(e.left);
+    const B2QExpr& c = ex(e.right);
+    if (l.kind != B2Q_EXPR_COLUMN_VAR || c.kind != B2Q_EXPR_CONSTANT || c.is_null || c.ti.type == B2Q_kDOUBLE) return false;
+    if (col_type(l.col_id).is_fp()) return false;
+    *col = l.col_id;
+    *val = c.ival;
+    return true;
+  }
+  /* returns -1 when the chain has nothing to fold (the caller lowers it as the binary tree it is) */
+  int lower_in_list_chain(B2QQuery& q, int idx, int depth, bool negated, bool want_and) {
+    std::vector<ChainItem> items;
+    flatten_chain(idx, negated, want_and, items);
+    std::map<int, std::vector<std::pair<int64_t, size_t>>> groups; /* column -> (value, item) */
+    for (size_t i = 0; i < items.size(); ++i) {
+      int col;
+      int64_t val;
+      if (point_leaf(items[i], want_and, &col, &val)) groups[col].push_back({val, i});
+    }
+    struct Emit { int need; bool is_run; size_t item; int64_t hi; };
+    std::vector<Emit> emits;
+    std::vector<bool> consumed(items.size(), false);
+    bool folded = false;
+    for (auto& g : groups) {
+      auto& vals = g.second;
+      if (vals.size() < 2) continue;
+      const int64_t step = is_days(g.first) ? 86400 : 1;
+      bool on_grid = true;
+      for (const auto& v : vals) on_grid &= v.first % step == 0;
+      if (!on_grid) continue; /* a DATE constant off the day grid matches nothing: leave those leaves as they are */
+      std::sort(vals.begin(), vals.end());
+      size_t run_begin = 0;
+      for (size_t i = 1; i <= vals.size(); ++i) {
+        int64_t gap = 0;
+        const bool joins = i < vals.size() && !__builtin_sub_overflow(vals[i].first, vals[i - 1].first, &gap) && (gap == step || gap == 0);
+        if (joins) continue;
+        emits.push_back({1, true, vals[run_begin].second, vals[i - 1].first});
+        if (i - run_begin > 1) folded = true;
+        for (size_t k = run_begin; k < i; ++k) consumed[vals[k].second] = true;
+        run_begin = i;
+      }
+    }
+    if (!folded) return -1;
+    for (size_t i = 0; i < items.size(); ++i)
+      if (!consumed[i]) emits.push_back({stack_need(items[i].idx), false, i, 0});
+    std::stable_sort(emits.begin(), emits.end(), [](const Emit& a, const Emit& b) { return a.need > b.need; });
+    DevFilter& f = q.prog.filter;
+    int max_depth = depth;
+    for (size_t i = 0; i < emits.size(); ++i) {
+      const Emit& em = emits[i];
+      const int at = depth + (i ? 1 : 0);
+      if (em.is_run) {
+        B2QExpr leaf = ex(items[em.item].idx);
+        leaf.op = want_and ? B2Q_kNE : B2Q_kEQ; /* the negation is already applied */
+        lower_cmp(q, leaf, &em.hi);
+        max_depth = std::max(max_depth, at + 1);
+      } else {
+        max_depth = std::max(max_depth, lower_bool(q, items[em.item].idx, at, items[em.item].negated));
+      }
+      if (i) {
+        if (f.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
+        f.ops[f.n_ops++] = static_cast<uint8_t>((want_and ? FOP_AND : FOP_OR) << 4);
+      }
+    }
+    return max_depth;
+  }
+
   int lower_bool(B2QQuery& q, int idx, int depth, bool negated = false) { /* returns max stack depth used */
     const B2QExpr& e = ex(idx);
     if (e.kind == B2Q_EXPR_UOPER) {
@@ -843,6 +931,10 @@ class Planner {
       /* the device evaluates the postfix program on a 4-deep stack of row masks: lowering the operand that needs the
        * deeper stack FIRST (Sethi-Ullman; AND / OR are symmetric in the reference's three-valued logic too,
        * RuntimeFunctions.cpp:331-357) lets any tree of up to 16 terms fit */
+      {
+        const int folded = lower_in_list_chain(q, idx, depth, negated, (e.op == B2Q_kAND) != negated);
+        if (folded >= 0) return folded;
+      }
       const bool right_first = stack_need(e.right) > stack_need(e.left);
       const int d1 = lower_bool(q, right_first ? e.right : e.left, depth, negated);
       const int d2 = lower_bool(q, right_first ? e.left : e.right, depth + 1, negated);

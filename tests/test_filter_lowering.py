@@ -98,3 +98,60 @@ def test_golden_time_table(emu):
     for q in tt.TIME_QUERIES:
         if where_of(q):
             check(emu, table, tt.TIME_NAMES, "test", where_of(q))
+
+
+def n_terms(emu, unit, table):
+    L = executor.lib()
+    bt = table.build(abi.CPU_LEVEL)
+    co, eo = executor.compilation_options(), executor.execution_options()
+    h = C.c_void_p()
+    assert L.b2q_plan(C.byref(unit.unit), C.byref(bt.info), C.byref(co), C.byref(eo), 0, 0, C.byref(h)) == 0
+    emu.b2q_test_filter_terms.restype = C.c_int32
+    emu.b2q_test_filter_terms.argtypes = [C.c_void_p]
+    n = emu.b2q_test_filter_terms(h)
+    L.b2q_query_free(h)
+    return n
+
+
+def test_in_lists_fold_consecutive_values_into_ranges(emu):
+    """`c IN (...)` is an OR chain of equalities (NOT IN: an AND chain of <>): runs of consecutive values become ONE range
+    term, so a dense 30-value list — past the 16-leaf program as written — is two terms here."""
+    table = random_table(900, seed=61, frag_rows=250)
+    dense = ", ".join(str(v) for v in range(-3, 27))
+    cases = [
+        (f"k8 IN ({dense})", 1), (f"k8 NOT IN ({dense})", 1), ("k8 IN (1, 2, 3, 7, 8, 20)", 3), ("NOT (k8 IN (5, 4, 3) OR k16 = 7)", 2),
+        ("k16 IN (100, 101, 102) AND a8 NOT IN (-1, 0, 1, 2)", 2), ("nn32 IN (3, 4, 5) OR nn32 IN (6, 7) OR d < 0.5", 2),
+        ("k8 = 2 OR (k32 < 10 AND k16 > 5) OR k8 = 3 OR k8 = 4 OR a16 IS NULL", 4), ("k64 IN (1000000001, 1000000002, 1000000004)", 2),
+        ("a8 IN (5, 5, 6) OR a8 = 127", 2), ("NOT (a16 <> 10 AND a16 <> 11 AND a16 <> 12)", 1),
+    ]
+    for where, terms in cases:
+        check(emu, table, RAND_NAMES, "r", where)
+        assert n_terms(emu, sqlmini.parse(f"SELECT COUNT(*) FROM r WHERE {where};", table, RAND_NAMES), table) == terms, where
+    s = stt.str_table(1500, seed=9, frag_rows=400)
+    for where, terms in [("dd IN (1555286400, 1555372800, 1555459200)", 1), ("dd16 NOT IN (864000000, 864086400, 863913600, 5)", 2),
+                         ("s8 IN (3, 4, 5, 6, 200) OR str = 7 OR str = 8", 3), ("dt IN (1555200000, 1555286400) OR dt = 1555372801", 3)]:
+        check(emu, s, stt.STR_NAMES, "s", where)
+        assert n_terms(emu, sqlmini.parse(f"SELECT COUNT(*) FROM s WHERE {where};", s, stt.STR_NAMES), s) == terms, where
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_random_dense_in_lists(emu, seed):
+    rng = random.Random(880 + seed)
+    table = random_table(600, seed=70 + seed, frag_rows=170)
+    cols = {"k8": (-2, 12), "k16": (90, 140), "nn32": (0, 40), "a8": (-128, 127), "k64": (1000000000, 1000000040), "nn64": (-50, 50)}
+    for _ in range(120):
+        parts = []
+        for _ in range(rng.randint(1, 3)):
+            c = rng.choice(sorted(cols))
+            lo, hi = cols[c]
+            start = rng.randint(lo, hi)
+            vals = [start + i for i in range(rng.randint(1, 6))] + [rng.randint(lo, hi) for _ in range(rng.randint(0, 2))]
+            rng.shuffle(vals)
+            parts.append(f"{c} {'NOT IN' if rng.random() < 0.4 else 'IN'} ({', '.join(map(str, vals))})")
+        where = parts[0]
+        for p in parts[1:]:
+            where = f"({where}) {rng.choice(['AND', 'OR'])} {'NOT ' if rng.random() < 0.2 else ''}({p})"
+        try:
+            check(emu, table, RAND_NAMES, "r", where)
+        except executor.UnsupportedOnThisPath:
+            continue
