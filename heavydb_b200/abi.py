@@ -40,7 +40,7 @@ ERR_NO_DEVICE = 1003
 ERR_CUDA = 1004
 ERR_KEY_OUT_OF_RANGE = 1005
 
-ABI_VERSION = 2   # B2Q_ABI_VERSION of include/b2q.h this mirror was written against
+ABI_VERSION = 3   # B2Q_ABI_VERSION of include/b2q.h this mirror was written against
 EXPR_COLUMN_VAR, EXPR_CONSTANT, EXPR_BIN_OPER, EXPR_AGG, EXPR_UOPER = 1, 2, 3, 4, 5
 CPU_LEVEL, GPU_LEVEL = 1, 2
 DEVICE_CPU, DEVICE_GPU = 0, 1

@@ -37,7 +37,9 @@
 extern "C" {
 #endif
 
-#define B2Q_ABI_VERSION 2 /* 2: sort_info, join level, rte_idx, columnar, dictionary / time types, B2QPlan join fields */
+#define B2Q_ABI_VERSION 3 /* 2: sort_info, join level, rte_idx, columnar, dictionary / time types, B2QPlan join fields;
+                            3: DATE_IN_DAYS chunks (negative col_encoded_sizes), column-vs-column quals, 16 filter leaves,
+                               operands-before-node rule, b2q_columnar_results_*, host-phase stats */
 
 /* ---- SQLTypes subset (Shared/sqltypes.h:65-99) -------------------------------------------------------- */
 enum {
