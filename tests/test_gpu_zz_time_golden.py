@@ -67,3 +67,18 @@ def test_join_single_days_column_rides_in_the_join_table():
         unit = sqlmini.parse(sql, fact, ["fk", "v"], inner=(dim, ["id", "dday"]))
         gu.run_both(unit, fact)
         gu.run_both(unit, fact, device_resident=False)
+
+
+@pytest.mark.parametrize("entry_count", [1, 2, 3, 5, 13, 31, 63, 126, 241, 511, 1021])
+def test_reduction_ladder_of_gpu_shared_memory_test(entry_count):
+    """Tests/GpuSharedMemoryTest.cpp:457-617's ladder (tests/reduce_ladder.py): per-CTA shared-memory tables merged into
+    the HBM table on the device, one launch over all fragments and one per fragment, against the oracle's host reduce."""
+    import reduce_ladder as rl
+    from heavydb_b200 import abi
+    for i, step in enumerate(rl.STEPS[:3] if entry_count < 100 else rl.STEPS[3:]):
+        num_buffers = [2, 8, 64][i]
+        table, _ = rl.ladder_table(entry_count, step, num_buffers, rows_per_buffer=300, seed=entry_count * 100 + step)
+        unit = sqlmini.parse(rl.QUERY, table, rl.NAMES)
+        gu.run_both(unit, table)                                   # the planner's kernel (shared-memory table)
+        gu.run_both(unit, table, device_resident=False)           # streamed from the host, slice by slice
+        gu.run_both(unit, table, force_kernel=abi.KERNEL_PERFECT_GLOBAL)   # the HBM-table kernel on the same shape
