@@ -665,8 +665,9 @@ class Planner {
 
   std::vector<double> term_sel_; /* estimated selectivity per filter term (uniformity assumption over chunk stats) */
 
-  /* `range_hi`: the comparison is `=` / `<>` against the run of consecutive values [constant, *range_hi] of an IN list */
-  void lower_cmp(B2QQuery& q, const B2QExpr& e, const int64_t* range_hi = nullptr) {
+  /* `range`: the comparison is `=` ("in") / `<>` ("not in") against the closed interval [range[0], range[1]] that a
+   * chain of leaves on this column folded into (lower_chain_items); its own constant only supplies the type */
+  void lower_cmp(B2QQuery& q, const B2QExpr& e, const int64_t* range = nullptr) {
     DevFilter& f = q.prog.filter;
     const B2QExpr& l = ex(e.left);
     const B2QExpr& c = ex(e.right);
@@ -720,7 +721,7 @@ class Planner {
       else {
         const int64_t k = c.ival;
         switch (e.op) {
-          case B2Q_kEQ: case B2Q_kNE: lo = k; hi = range_hi ? *range_hi : k; break;
+          case B2Q_kEQ: case B2Q_kNE: lo = range ? range[0] : k; hi = range ? range[1] : k; break;
           case B2Q_kLT: if (k != INT64_MIN) { lo = INT64_MIN; hi = k - 1; } break;
           case B2Q_kLE: lo = INT64_MIN; hi = k; break;
           case B2Q_kGT: if (k != INT64_MAX) { lo = k + 1; hi = INT64_MAX; } break;
@@ -848,65 +849,112 @@ class Planner {
     }
     out.push_back({idx, negated});
   }
-  bool point_leaf(const ChainItem& it, bool want_and, int* col, int64_t* val) const {
+  /* a leaf `int column OP k` (k a non-NULL integer constant) as the closed interval of values that satisfy it, after the
+   * pending negation is applied; `<>` is not an interval (is_ne) */
+  bool interval_leaf(const ChainItem& it, int* col, int64_t* lo, int64_t* hi, bool* is_ne) const {
     const B2QExpr& e = ex(it.idx);
     if (e.kind != B2Q_EXPR_BIN_OPER || e.op == B2Q_kAND || e.op == B2Q_kOR) return false;
     const int op = it.negated ? inverse_cmp(e.op) : e.op;
-    if (op != (want_and ? B2Q_kNE : B2Q_kEQ)) return false;
     const B2QExpr& l = ex(e.left);
     const B2QExpr& c = ex(e.right);
     if (l.kind != B2Q_EXPR_COLUMN_VAR || c.kind != B2Q_EXPR_CONSTANT || c.is_null || c.ti.type == B2Q_kDOUBLE) return false;
     if (col_type(l.col_id).is_fp()) return false;
+    const int64_t k = c.ival;
     *col = l.col_id;
-    *val = c.ival;
-    return true;
+    *is_ne = false;
+    switch (op) {
+      case B2Q_kEQ: *lo = k; *hi = k; return true;
+      case B2Q_kNE: *lo = k; *hi = k; *is_ne = true; return true;
+      case B2Q_kLT: if (k == INT64_MIN) { *lo = 1; *hi = 0; } else { *lo = INT64_MIN; *hi = k - 1; } return true;
+      case B2Q_kLE: *lo = INT64_MIN; *hi = k; return true;
+      case B2Q_kGT: if (k == INT64_MAX) { *lo = 1; *hi = 0; } else { *lo = k + 1; *hi = INT64_MAX; } return true;
+      case B2Q_kGE: *lo = k; *hi = INT64_MAX; return true;
+      default: return false;
+    }
   }
-  /* returns -1 when the chain has nothing to fold (the caller lowers it as the binary tree it is) */
-  int lower_in_list_chain(B2QQuery& q, int idx, int depth, bool negated, bool want_and) {
-    std::vector<ChainItem> items;
-    flatten_chain(idx, negated, want_and, items);
-    std::map<int, std::vector<std::pair<int64_t, size_t>>> groups; /* column -> (value, item) */
+
+  /* Lowers the items of one AND / OR chain.  Leaves on the SAME integer column fold:
+   *  - AND: every `=`, `<`, `<=`, `>`, `>=` leaf into the intersection of their intervals (BETWEEN is one range test);
+   *         runs of consecutive values of `<>` leaves (NOT IN) into one negated range each;
+   *  - OR:  runs of consecutive values of `=` leaves (IN) into one range each; `c < a OR c > b` (NOT BETWEEN) into the
+   *         negated range [a, b].
+   * NULL behaves as in the unfolded chain: every leaf on a NULL value is NULL, so the chain's contribution is "not
+   * TRUE" — exactly what one range term yields (lower_cmp keeps NULL out of the range / adds the NULL check).
+   * Returns -1 when nothing folds (the caller lowers the binary tree as it is). */
+  struct ChainEmit { int need; bool is_range; size_t item; int64_t lo, hi; bool negate; };
+  int lower_chain_items(B2QQuery& q, const std::vector<ChainItem>& items, int depth, bool want_and) {
+    struct Leaf { size_t item; int64_t lo, hi; bool is_ne; };
+    std::map<int, std::vector<Leaf>> by_col;
     for (size_t i = 0; i < items.size(); ++i) {
       int col;
-      int64_t val;
-      if (point_leaf(items[i], want_and, &col, &val)) groups[col].push_back({val, i});
+      Leaf lf{i, 0, 0, false};
+      if (interval_leaf(items[i], &col, &lf.lo, &lf.hi, &lf.is_ne)) by_col[col].push_back(lf);
     }
-    struct Emit { int need; bool is_run; size_t item; int64_t hi; };
-    std::vector<Emit> emits;
+    std::vector<ChainEmit> emits;
     std::vector<bool> consumed(items.size(), false);
     bool folded = false;
-    for (auto& g : groups) {
-      auto& vals = g.second;
-      if (vals.size() < 2) continue;
+    for (auto& g : by_col) {
       const int64_t step = is_days(g.first) ? 86400 : 1;
+      /* points to fold into runs: `<>` leaves of an AND chain, `=` leaves of an OR chain */
+      std::vector<std::pair<int64_t, size_t>> pts;
+      std::vector<Leaf> ranges; /* AND: every non-`<>` leaf; OR: the one-sided leaves */
+      for (const Leaf& lf : g.second) {
+        const bool point = lf.lo == lf.hi;
+        if (want_and ? lf.is_ne : (point && !lf.is_ne)) pts.push_back({lf.lo, lf.item});
+        else if (!lf.is_ne) ranges.push_back(lf);
+      }
       bool on_grid = true;
-      for (const auto& v : vals) on_grid &= v.first % step == 0;
-      if (!on_grid) continue; /* a DATE constant off the day grid matches nothing: leave those leaves as they are */
-      std::sort(vals.begin(), vals.end());
-      size_t run_begin = 0;
-      for (size_t i = 1; i <= vals.size(); ++i) {
-        int64_t gap = 0;
-        const bool joins = i < vals.size() && !__builtin_sub_overflow(vals[i].first, vals[i - 1].first, &gap) && (gap == step || gap == 0);
-        if (joins) continue;
-        emits.push_back({1, true, vals[run_begin].second, vals[i - 1].first});
-        if (i - run_begin > 1) folded = true;
-        for (size_t k = run_begin; k < i; ++k) consumed[vals[k].second] = true;
-        run_begin = i;
+      for (const auto& v : pts) on_grid &= v.first % step == 0;
+      if (pts.size() >= 2 && on_grid) { /* a DATE constant off the day grid matches nothing: those stay single leaves */
+        std::sort(pts.begin(), pts.end());
+        size_t run_begin = 0;
+        for (size_t i = 1; i <= pts.size(); ++i) {
+          int64_t gap = 0;
+          if (i < pts.size() && !__builtin_sub_overflow(pts[i].first, pts[i - 1].first, &gap) && (gap == step || gap == 0)) continue;
+          if (i - run_begin > 1) {
+            emits.push_back({1, true, pts[run_begin].second, pts[run_begin].first, pts[i - 1].first, want_and});
+            for (size_t k = run_begin; k < i; ++k) consumed[pts[k].second] = true;
+            folded = true;
+          }
+          run_begin = i;
+        }
+      }
+      if (want_and && ranges.size() >= 2) {
+        int64_t lo = INT64_MIN, hi = INT64_MAX;
+        bool empty = false;
+        for (const Leaf& lf : ranges) {
+          if (lf.lo > lf.hi) empty = true;
+          lo = std::max(lo, lf.lo);
+          hi = std::min(hi, lf.hi);
+        }
+        if (empty || lo > hi) { lo = 1; hi = 0; }
+        emits.push_back({1, true, ranges[0].item, lo, hi, false});
+        for (const Leaf& lf : ranges) consumed[lf.item] = true;
+        folded = true;
+      } else if (!want_and && ranges.size() == 2) {
+        const Leaf& a = ranges[0].lo == INT64_MIN ? ranges[0] : ranges[1]; /* upper-bounded: c <= a.hi */
+        const Leaf& b = ranges[0].lo == INT64_MIN ? ranges[1] : ranges[0]; /* lower-bounded: c >= b.lo */
+        if (a.lo == INT64_MIN && a.lo <= a.hi && a.hi != INT64_MAX && b.hi == INT64_MAX && b.lo <= b.hi && b.lo != INT64_MIN && a.hi < b.lo) {
+          emits.push_back({1, true, a.item, a.hi + 1, b.lo - 1, true}); /* NOT in (a.hi, b.lo) */
+          consumed[a.item] = consumed[b.item] = true;
+          folded = true;
+        }
       }
     }
     if (!folded) return -1;
     for (size_t i = 0; i < items.size(); ++i)
-      if (!consumed[i]) emits.push_back({stack_need(items[i].idx), false, i, 0});
-    std::stable_sort(emits.begin(), emits.end(), [](const Emit& a, const Emit& b) { return a.need > b.need; });
+      if (!consumed[i]) emits.push_back({stack_need(items[i].idx), false, i, 0, 0, false});
+    std::stable_sort(emits.begin(), emits.end(), [](const ChainEmit& a, const ChainEmit& b) { return a.need > b.need; });
     DevFilter& f = q.prog.filter;
     int max_depth = depth;
     for (size_t i = 0; i < emits.size(); ++i) {
-      const Emit& em = emits[i];
+      const ChainEmit& em = emits[i];
       const int at = depth + (i ? 1 : 0);
-      if (em.is_run) {
+      if (em.is_range) {
         B2QExpr leaf = ex(items[em.item].idx);
-        leaf.op = want_and ? B2Q_kNE : B2Q_kEQ; /* the negation is already applied */
-        lower_cmp(q, leaf, &em.hi);
+        leaf.op = em.negate ? B2Q_kNE : B2Q_kEQ; /* the pending negation is already applied */
+        const int64_t range[2] = {em.lo, em.hi};
+        lower_cmp(q, leaf, range);
         max_depth = std::max(max_depth, at + 1);
       } else {
         max_depth = std::max(max_depth, lower_bool(q, items[em.item].idx, at, items[em.item].negated));
@@ -917,6 +965,11 @@ class Planner {
       }
     }
     return max_depth;
+  }
+  int lower_in_list_chain(B2QQuery& q, int idx, int depth, bool negated, bool want_and) {
+    std::vector<ChainItem> items;
+    flatten_chain(idx, negated, want_and, items);
+    return lower_chain_items(q, items, depth, want_and);
   }
 
   int lower_bool(B2QQuery& q, int idx, int depth, bool negated = false) { /* returns max stack depth used */
@@ -1081,8 +1134,25 @@ class Planner {
       ++n_quals;
       max_depth = std::max(max_depth, 1);
     }
-    for (int i = 0; i < u_.num_simple_quals; ++i) add_qual(u_.simple_quals[i]);
-    for (int i = 0; i < u_.num_quals; ++i) add_qual(u_.quals[i]);
+    {
+      /* simple_quals and quals are the conjuncts of ONE AND chain (the analyzer split the WHERE clause at its top-level
+       * ANDs): leaves on the same column fold across them — `c >= a` and `c <= b` arrive as two quals */
+      std::vector<ChainItem> conjuncts;
+      for (int i = 0; i < u_.num_simple_quals; ++i) flatten_chain(u_.simple_quals[i], false, true, conjuncts);
+      for (int i = 0; i < u_.num_quals; ++i) flatten_chain(u_.quals[i], false, true, conjuncts);
+      const int d = conjuncts.size() >= 2 ? lower_chain_items(q, conjuncts, n_quals ? 1 : 0, true) : -1;
+      if (d >= 0) {
+        max_depth = std::max(max_depth, d);
+        if (n_quals) {
+          if (g.filter.n_ops >= B2Q_MAX_FILTER_OPS) reject(B2Q_ERR_UNSUPPORTED, "filter too large");
+          g.filter.ops[g.filter.n_ops++] = static_cast<uint8_t>(FOP_AND << 4);
+        }
+        ++n_quals;
+      } else {
+        for (int i = 0; i < u_.num_simple_quals; ++i) add_qual(u_.simple_quals[i]);
+        for (int i = 0; i < u_.num_quals; ++i) add_qual(u_.quals[i]);
+      }
+    }
     if (max_depth > 4) reject(B2Q_ERR_UNSUPPORTED, "filter expression nests deeper than 4");
     /* load scheduling hints: a 32-byte sector holds 4-8 rows, so predicating a column load on the filter only saves
      * HBM traffic when almost every row fails; otherwise loading eagerly puts all column loads in flight at once */

@@ -155,3 +155,47 @@ def test_random_dense_in_lists(emu, seed):
             check(emu, table, RAND_NAMES, "r", where)
         except executor.UnsupportedOnThisPath:
             continue
+
+
+def test_range_leaves_on_one_column_fold_into_one_term(emu):
+    """BETWEEN (two conjuncts, possibly two separate quals), redundant bounds, `=` with bounds, NOT BETWEEN (an OR of two
+    one-sided leaves): one range test per column."""
+    table = random_table(900, seed=62, frag_rows=250)
+    cases = [
+        ("k16 BETWEEN 100 AND 130", 1), ("k16 >= 100 AND k16 <= 130 AND k16 < 125 AND k16 > 90", 1),
+        ("k16 NOT BETWEEN 100 AND 130", 1), ("NOT (k16 >= 100 AND k16 <= 130)", 1), ("k16 < 100 OR k16 > 130 OR k16 = 110", 2),
+        ("a8 > 5 AND d < 0.5 AND a8 <= 60 AND nn32 <> 7", 3), ("k8 = 3 AND k8 < 10 AND k8 > 0", 1), ("k8 = 3 AND k8 > 5", 1),
+        ("k8 >= 2 AND k8 <= 9 AND k8 NOT IN (4, 5, 6)", 2), ("(a16 > 100 AND a16 < 20000) OR (a16 > -20000 AND a16 < -100)", 2),
+        ("k64 > 1000000010 AND k64 <= 1000000400 AND k32 BETWEEN -50 AND 50 AND a64 IS NOT NULL", 3),
+        ("a16 < 100 OR a16 > 99", 1), ("a16 <= 5 OR a16 >= 6", 1), ("NOT (a32 BETWEEN -1000000 AND 1000000) AND a32 < 2000000000", 2),
+    ]
+    for where, terms in cases:
+        check(emu, table, RAND_NAMES, "r", where)
+        assert n_terms(emu, sqlmini.parse(f"SELECT COUNT(*) FROM r WHERE {where};", table, RAND_NAMES), table) == terms, where
+    s = stt.str_table(1500, seed=10, frag_rows=400)
+    for where, terms in [("dd BETWEEN 1555200000 AND 1556000000", 1), ("dd > 1555286399 AND dd < 1555459201 AND dd16 >= 863308800", 2),
+                         ("dd16 NOT BETWEEN 863913601 AND 864086399", 1), ("ts >= 1600000050 AND ts < 1600000200 AND dt <= 1556000000 AND dt > 1555200001", 2)]:
+        check(emu, s, stt.STR_NAMES, "s", where)
+        assert n_terms(emu, sqlmini.parse(f"SELECT COUNT(*) FROM s WHERE {where};", s, stt.STR_NAMES), s) == terms, where
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_random_range_chains(emu, seed):
+    rng = random.Random(990 + seed)
+    table = random_table(600, seed=75 + seed, frag_rows=170)
+    cols = {"k8": (-2, 12), "k16": (90, 140), "nn32": (0, 40), "a8": (-128, 127), "k64": (1000000000, 1000000040), "a16": (-32768, 32767), "big": (-2**62, 2**62)}
+    for _ in range(150):
+        leaves = []
+        for _ in range(rng.randint(2, 6)):
+            c = rng.choice(sorted(cols))
+            lo, hi = cols[c]
+            leaves.append(f"{'NOT ' if rng.random() < 0.15 else ''}({c} {rng.choice(['<', '<=', '>', '>=', '=', '<>'])} {rng.randint(lo, hi)})")
+        where = leaves[0]
+        for lf in leaves[1:]:
+            where = f"{where} {rng.choice(['AND', 'AND', 'OR'])} {lf}" if rng.random() < 0.7 else f"({where}) {rng.choice(['AND', 'OR'])} {lf}"
+        if rng.random() < 0.2:
+            where = f"NOT ({where})"
+        try:
+            check(emu, table, RAND_NAMES, "r", where)
+        except executor.UnsupportedOnThisPath:
+            continue
