@@ -667,7 +667,7 @@ class Planner {
 
   /* `range`: the comparison is `=` ("in") / `<>` ("not in") against the closed interval [range[0], range[1]] that a
    * chain of leaves on this column folded into (lower_chain_items); its own constant only supplies the type */
-  void lower_cmp(B2QQuery& q, const B2QExpr& e, const int64_t* range = nullptr) {
+  void lower_cmp(B2QQuery& q, const B2QExpr& e, const int64_t* range = nullptr, const double* frange = nullptr) {
     DevFilter& f = q.prog.filter;
     const B2QExpr& l = ex(e.left);
     const B2QExpr& c = ex(e.right);
@@ -700,7 +700,7 @@ class Planner {
         const double k = cfp ? c.dval : static_cast<double>(c.ival);
         if (!std::isnan(k)) {
           switch (e.op) {
-            case B2Q_kEQ: case B2Q_kNE: t.flo = k; t.fhi = k; break;
+            case B2Q_kEQ: case B2Q_kNE: t.flo = frange ? frange[0] : k; t.fhi = frange ? frange[1] : k; break;
             case B2Q_kLT: if (k != -inf) { t.flo = -inf; t.fhi = std::nextafter(k, -inf); } break;
             case B2Q_kLE: t.flo = -inf; t.fhi = k; break;
             case B2Q_kGT: if (k != inf) { t.flo = std::nextafter(k, inf); t.fhi = inf; } break;
@@ -873,6 +873,30 @@ class Planner {
     }
   }
 
+  /* the same for a DOUBLE column: closed interval of doubles (`<` / `>` step to the neighbouring double) */
+  bool interval_leaf_fp(const ChainItem& it, int* col, double* lo, double* hi, bool* is_ne) const {
+    const B2QExpr& e = ex(it.idx);
+    if (e.kind != B2Q_EXPR_BIN_OPER || e.op == B2Q_kAND || e.op == B2Q_kOR) return false;
+    const int op = it.negated ? inverse_cmp(e.op) : e.op;
+    const B2QExpr& l = ex(e.left);
+    const B2QExpr& c = ex(e.right);
+    if (l.kind != B2Q_EXPR_COLUMN_VAR || c.kind != B2Q_EXPR_CONSTANT || c.is_null || !col_type(l.col_id).is_fp()) return false;
+    const double k = c.ti.type == B2Q_kDOUBLE ? c.dval : static_cast<double>(c.ival);
+    if (std::isnan(k)) return false;
+    const double inf = std::numeric_limits<double>::infinity();
+    *col = l.col_id;
+    *is_ne = false;
+    switch (op) {
+      case B2Q_kEQ: *lo = k; *hi = k; return true;
+      case B2Q_kNE: *lo = k; *hi = k; *is_ne = true; return true;
+      case B2Q_kLT: if (k == -inf) { *lo = inf; *hi = -inf; } else { *lo = -inf; *hi = std::nextafter(k, -inf); } return true;
+      case B2Q_kLE: *lo = -inf; *hi = k; return true;
+      case B2Q_kGT: if (k == inf) { *lo = inf; *hi = -inf; } else { *lo = std::nextafter(k, inf); *hi = inf; } return true;
+      case B2Q_kGE: *lo = k; *hi = inf; return true;
+      default: return false;
+    }
+  }
+
   /* Lowers the items of one AND / OR chain.  Leaves on the SAME integer column fold:
    *  - AND: every `=`, `<`, `<=`, `>`, `>=` leaf into the intersection of their intervals (BETWEEN is one range test);
    *         runs of consecutive values of `<>` leaves (NOT IN) into one negated range each;
@@ -881,7 +905,7 @@ class Planner {
    * NULL behaves as in the unfolded chain: every leaf on a NULL value is NULL, so the chain's contribution is "not
    * TRUE" — exactly what one range term yields (lower_cmp keeps NULL out of the range / adds the NULL check).
    * Returns -1 when nothing folds (the caller lowers the binary tree as it is). */
-  struct ChainEmit { int need; bool is_range; size_t item; int64_t lo, hi; bool negate; };
+  struct ChainEmit { int need; bool is_range; size_t item; int64_t lo, hi; bool negate; bool is_fp = false; double flo = 0, fhi = 0; };
   int lower_chain_items(B2QQuery& q, const std::vector<ChainItem>& items, int depth, bool want_and) {
     struct Leaf { size_t item; int64_t lo, hi; bool is_ne; };
     std::map<int, std::vector<Leaf>> by_col;
@@ -941,6 +965,41 @@ class Planner {
         }
       }
     }
+    /* DOUBLE columns: bounds intersect (AND), `d < a OR d > b` is the negated range (OR); no runs of points */
+    {
+      struct FLeaf { size_t item; double lo, hi; };
+      std::map<int, std::vector<FLeaf>> fby_col;
+      for (size_t i = 0; i < items.size(); ++i) {
+        int col;
+        double lo, hi;
+        bool is_ne;
+        if (!consumed[i] && interval_leaf_fp(items[i], &col, &lo, &hi, &is_ne) && !is_ne) fby_col[col].push_back({i, lo, hi});
+      }
+      const double inf = std::numeric_limits<double>::infinity();
+      for (auto& g : fby_col) {
+        std::vector<FLeaf>& ranges = g.second;
+        if (want_and && ranges.size() >= 2) {
+          double lo = -inf, hi = inf;
+          for (const FLeaf& lf : ranges) { lo = std::max(lo, lf.lo); hi = std::min(hi, lf.hi); }
+          if (lo > hi) { lo = inf; hi = -inf; }
+          ChainEmit em{1, true, ranges[0].item, 0, 0, false};
+          em.is_fp = true; em.flo = lo; em.fhi = hi;
+          emits.push_back(em);
+          for (const FLeaf& lf : ranges) consumed[lf.item] = true;
+          folded = true;
+        } else if (!want_and && ranges.size() == 2) {
+          const FLeaf& a = ranges[0].lo == -inf ? ranges[0] : ranges[1]; /* d <= a.hi */
+          const FLeaf& b = ranges[0].lo == -inf ? ranges[1] : ranges[0]; /* d >= b.lo */
+          if (a.lo == -inf && a.hi != inf && a.hi != -inf && b.hi == inf && b.lo != -inf && b.lo != inf && a.hi < b.lo) {
+            ChainEmit em{1, true, a.item, 0, 0, true};
+            em.is_fp = true; em.flo = std::nextafter(a.hi, inf); em.fhi = std::nextafter(b.lo, -inf); /* NOT in the open gap */
+            emits.push_back(em);
+            consumed[a.item] = consumed[b.item] = true;
+            folded = true;
+          }
+        }
+      }
+    }
     if (!folded) return -1;
     for (size_t i = 0; i < items.size(); ++i)
       if (!consumed[i]) emits.push_back({stack_need(items[i].idx), false, i, 0, 0, false});
@@ -954,7 +1013,9 @@ class Planner {
         B2QExpr leaf = ex(items[em.item].idx);
         leaf.op = em.negate ? B2Q_kNE : B2Q_kEQ; /* the pending negation is already applied */
         const int64_t range[2] = {em.lo, em.hi};
-        lower_cmp(q, leaf, range);
+        const double frange[2] = {em.flo, em.fhi};
+        if (em.is_fp) lower_cmp(q, leaf, nullptr, frange);
+        else lower_cmp(q, leaf, range);
         max_depth = std::max(max_depth, at + 1);
       } else {
         max_depth = std::max(max_depth, lower_bool(q, items[em.item].idx, at, items[em.item].negated));

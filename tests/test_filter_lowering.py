@@ -199,3 +199,26 @@ def test_random_range_chains(emu, seed):
             check(emu, table, RAND_NAMES, "r", where)
         except executor.UnsupportedOnThisPath:
             continue
+
+
+def test_double_bounds_fold_too(emu):
+    """Bounding boxes: `d BETWEEN a AND b` on a DOUBLE column is one closed-range test; `<` / `>` step to the neighbouring
+    double; `d < a OR d > b` is the negated range; NULL_DOUBLE never passes."""
+    table = random_table(900, seed=63, frag_rows=250)
+    cases = [
+        ("d BETWEEN -500.5 AND 700.25", 1), ("d > -500.5 AND d < 700.25 AND dnn >= 0.25 AND dnn <= 0.75", 2),
+        ("d NOT BETWEEN -500.5 AND 700.25", 1), ("d < -500 OR d > 700", 1), ("dnn > 0.5 AND dnn < 0.5", 1), ("dnn >= 0.5 AND dnn <= 0.5", 1),
+        ("d >= 0 AND d < 1000 AND k8 BETWEEN 2 AND 9 AND d > 10", 2), ("NOT (d >= -100 AND d <= 100) AND d IS NOT NULL", 2),
+        ("d < 5 OR d >= 5", 1), ("d <= 5 OR d >= 5", 2), ("d > 100 AND d > 200 AND d > 5", 1), ("dnn < 0.3 OR dnn > 0.6 OR dnn = 0.45", 2),
+    ]
+    for where, terms in cases:
+        check(emu, table, RAND_NAMES, "r", where)
+        assert n_terms(emu, sqlmini.parse(f"SELECT COUNT(*) FROM r WHERE {where};", table, RAND_NAMES), table) == terms, where
+    rng = random.Random(5)
+    for _ in range(150):
+        leaves = [f"{'NOT ' if rng.random() < 0.15 else ''}({rng.choice(['d', 'dnn', 'd'])} {rng.choice(['<', '<=', '>', '>=', '=', '<>'])} {rng.choice([round(rng.uniform(-1500, 1500), 3), round(rng.random(), 4), rng.randint(-5, 5)])})"
+                  for _ in range(rng.randint(2, 5))]
+        where = leaves[0]
+        for lf in leaves[1:]:
+            where = f"{where} {rng.choice(['AND', 'AND', 'OR'])} {lf}" if rng.random() < 0.7 else f"({where}) {rng.choice(['AND', 'OR'])} {lf}"
+        check(emu, table, RAND_NAMES, "r", where)
