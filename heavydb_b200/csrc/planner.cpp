@@ -1000,6 +1000,26 @@ class Planner {
         }
       }
     }
+    if (want_and) {
+      /* `c IS NOT NULL` next to a comparison on c in the same AND chain adds nothing: a comparison is never TRUE on NULL */
+      std::vector<bool> compared(static_cast<size_t>(t_.num_cols), false);
+      for (size_t i = 0; i < items.size(); ++i) {
+        int col;
+        int64_t lo, hi;
+        double flo, fhi;
+        bool ne;
+        if (interval_leaf(items[i], &col, &lo, &hi, &ne) || interval_leaf_fp(items[i], &col, &flo, &fhi, &ne)) compared[col] = true;
+      }
+      for (size_t i = 0; i < items.size(); ++i) {
+        const B2QExpr& e = ex(items[i].idx);
+        if (consumed[i] || e.kind != B2Q_EXPR_UOPER || e.op != B2Q_kISNULL || !items[i].negated) continue;
+        const B2QExpr& l = ex(e.left);
+        if (l.kind == B2Q_EXPR_COLUMN_VAR && l.col_id >= 0 && l.col_id < t_.num_cols && compared[l.col_id]) {
+          consumed[i] = true;
+          folded = true;
+        }
+      }
+    }
     if (!folded) return -1;
     for (size_t i = 0; i < items.size(); ++i)
       if (!consumed[i]) emits.push_back({stack_need(items[i].idx), false, i, 0, 0, false});

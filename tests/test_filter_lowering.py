@@ -222,3 +222,15 @@ def test_double_bounds_fold_too(emu):
         for lf in leaves[1:]:
             where = f"{where} {rng.choice(['AND', 'AND', 'OR'])} {lf}" if rng.random() < 0.7 else f"({where}) {rng.choice(['AND', 'OR'])} {lf}"
         check(emu, table, RAND_NAMES, "r", where)
+
+
+def test_is_not_null_next_to_a_comparison_is_dropped(emu):
+    """Calcite adds `c IS NOT NULL` next to filters and join keys; a comparison on c in the same AND chain already fails on
+    NULL, so the leaf costs nothing on the device."""
+    table = random_table(900, seed=64, frag_rows=250)
+    cases = [("a16 IS NOT NULL AND a16 > 100", 1), ("a16 > 100 AND k16 < 120 AND NOT (a16 IS NULL)", 2), ("d IS NOT NULL AND d < 0.5 AND a8 IS NOT NULL", 2),
+             ("a16 IS NOT NULL AND a16 <> 5", 1), ("a16 IS NOT NULL OR a16 > 100", 2), ("a16 IS NULL AND a16 > 100", 2),
+             ("(a16 IS NOT NULL AND k8 = 3) OR (a8 IS NOT NULL AND a8 BETWEEN 1 AND 50)", 3), ("a64 IS NOT NULL AND a64 IN (5, 6, 7) AND nn64 IS NOT NULL", 3)]
+    for where, terms in cases:
+        check(emu, table, RAND_NAMES, "r", where)
+        assert n_terms(emu, sqlmini.parse(f"SELECT COUNT(*) FROM r WHERE {where};", table, RAND_NAMES), table) == terms, where
