@@ -83,8 +83,13 @@ struct RelAlgExecutionUnit { /* RelAlgExecutionUnit.h:166-216 */
   enum class JoinType { INNER = 0, LEFT = 1 };
   struct JoinCondition { std::list<ExprRef> quals; JoinType type{JoinType::INNER}; };
   std::vector<JoinCondition> join_quals;
+  /* ra_exe_unit.estimator (Analyzer::NDVEstimator / LargeNDVEstimator over the GROUP BY tuple,
+   * RelAlgExecutionUnit::createNdvExecutionUnit, CardinalityEstimator.cpp:94-116): such a unit has no groupby_exprs,
+   * no targets and no sort_info; the result answers ResultSet::getNDVEstimator() */
+  struct NDVEstimator { std::list<ExprRef> expr_tuple; bool large{false}; };
+  std::optional<NDVEstimator> estimator;
   /* features outside this path: anything non-zero is rejected by the library */
-  int32_t has_estimator{0}, has_union_all{0}, has_window_function{0};
+  int32_t has_union_all{0}, has_window_function{0};
   /* SortInfo (RelAlgExecutionUnit.h:117-156); Analyzer::OrderEntry == B2QOrderEntry{tle_no, is_desc, nulls_first} */
   struct SortInfo {
     std::list<B2QOrderEntry> order_entries;
@@ -156,6 +161,7 @@ struct InputTableInfo {
 struct CompilationOptions { /* CompilationOptions.h:31-66 */
   ExecutorDeviceType device_type{ExecutorDeviceType::GPU};
   bool hoist_literals{true};
+  bool filter_on_deleted_column{true}; /* false: rows flagged in the $deleted$ column are scanned like any other */
   static CompilationOptions defaults(ExecutorDeviceType dt = ExecutorDeviceType::GPU) { return CompilationOptions{dt, true}; }
 };
 struct ExecutionOptions { /* CompilationOptions.h:70-122 */
@@ -196,6 +202,7 @@ class ResultSet {
     const int32_t rc = b2q_rs_sort(h_, oes.data(), static_cast<int32_t>(oes.size()), top_n);
     if (rc != B2Q_OK) throw QueryExecutionError(rc, b2q_last_error_message());
   }
+  size_t getNDVEstimator() const { return b2q_rs_get_ndv_estimator(h_); } /* CardinalityEstimator.cpp:33-52 */
   void dropFirstN(size_t n) { b2q_rs_drop_first_n(h_, n); }
   void keepFirstN(size_t n) { b2q_rs_keep_first_n(h_, n); }
   const B2QResultSet* handle() const { return h_; }
@@ -282,7 +289,13 @@ class Executor {
     u.groupby_exprs = g.data(); u.num_groupby_exprs = static_cast<int32_t>(g.size());
     u.target_exprs = ra_exe_unit.target_exprs.data(); u.num_target_exprs = static_cast<int32_t>(ra_exe_unit.target_exprs.size());
     u.scan_limit = static_cast<int64_t>(ra_exe_unit.scan_limit);
-    u.has_estimator = ra_exe_unit.has_estimator;
+    std::vector<int32_t> est;
+    if (ra_exe_unit.estimator) {
+      est.assign(ra_exe_unit.estimator->expr_tuple.begin(), ra_exe_unit.estimator->expr_tuple.end());
+      u.has_estimator = ra_exe_unit.estimator->large ? 2 : 1;
+      u.estimator_args = est.data();
+      u.num_estimator_args = static_cast<int32_t>(est.size());
+    }
     u.num_join_quals = static_cast<int32_t>(ra_exe_unit.join_quals.size());
     u.join_qual = -1;
     if (u.num_join_quals == 1) {
@@ -299,7 +312,7 @@ class Executor {
     u.limit = static_cast<int64_t>(ra_exe_unit.sort_info.limit.value_or(0));
     u.offset = static_cast<int64_t>(ra_exe_unit.sort_info.offset);
     u.has_window_function = ra_exe_unit.has_window_function;
-    B2QCompilationOptions cco{static_cast<int32_t>(co.device_type), co.hoist_literals ? 1 : 0};
+    B2QCompilationOptions cco{static_cast<int32_t>(co.device_type), co.hoist_literals ? 1 : 0, co.filter_on_deleted_column ? 0 : 1, 0};
     B2QExecutionOptions ceo{options.allow_multifrag ? 1 : 0, options.output_columnar_hint ? 1 : 0, options.bigint_count ? 1 : 0, 0, -1, 0};
     B2QResultSet* rs = nullptr;
     const int32_t rc = b2q_execute_work_unit(&max_groups_buffer_entry_guess, is_agg ? 1 : 0, &tbl, &u, &cco, &ceo,

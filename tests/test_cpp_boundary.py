@@ -23,6 +23,17 @@ def test_cpp_mirror_compiles_and_links(tmp_path):
     assert _compile(tmp_path).exists()
 
 
+def test_cpp_mirror_surface_links(tmp_path):
+    """Estimator unit, getNDVEstimator, deleted-column option, ColumnarResults: compiled and linked, nothing executed."""
+    lib = build.build()
+    exe = tmp_path / "mirror_surface"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "mirror_surface.cpp"), "-o", str(exe),
+                           lib, f"-Wl,-rpath,{os.path.dirname(lib)}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "mirror surface links" in out.stdout
+
+
 @pytest.mark.gpu
 def test_cpp_boundary_like_groupbytest(tmp_path):
     exe = _compile(tmp_path)
