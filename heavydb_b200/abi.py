@@ -356,7 +356,8 @@ class UnitBuilder:
     def cmp(self, col_id: int, op: int, value, const_type: Optional[int] = None, rte_idx: int = 0) -> int:
         return self.binop(op, self.col(col_id, rte_idx), self.const(value, const_type))
 
-    def agg(self, kind: int, col_id: Optional[int] = None, bigint_count: bool = False, rte_idx: int = 0) -> int:
+    def agg(self, kind: int, col_id: Optional[int] = None, bigint_count: bool = False, rte_idx: int = 0,
+            is_distinct: bool = False) -> int:
         """AggExpr.  Result type as RelAlgTranslator assigns it: COUNT -> INT/BIGINT notnull... SUM(int) -> BIGINT,
         MIN/MAX -> arg type, AVG -> DOUBLE."""
         arg = -1
@@ -376,7 +377,7 @@ class UnitBuilder:
                 ti = (kDOUBLE, ann)
             else:
                 ti = (at, ann)
-        self.nodes.append(_Node(EXPR_AGG, ti[0], ti[1], op=kind, left=arg))
+        self.nodes.append(_Node(EXPR_AGG, ti[0], ti[1], op=kind, left=arg, ival=int(is_distinct)))   # ival: AggExpr::get_is_distinct()
         return len(self.nodes) - 1
 
     # -- unit lists ---------------------------------------------------------------------------------------

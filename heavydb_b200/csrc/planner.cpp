@@ -305,6 +305,7 @@ class Planner {
         any_agg = true;
         if (e.op != B2Q_kCOUNT && e.op != B2Q_kSUM && e.op != B2Q_kMIN && e.op != B2Q_kMAX && e.op != B2Q_kAVG)
           reject(B2Q_ERR_UNSUPPORTED, "aggregate kind outside COUNT/SUM/MIN/MAX/AVG");
+        if (e.ival != 0) reject(B2Q_ERR_UNSUPPORTED, "DISTINCT aggregates (count-distinct bitmaps / sets) are outside this path");
         if (e.left < 0) {
           if (e.op != B2Q_kCOUNT) reject(B2Q_ERR_INVALID_ARGUMENT, "aggregate without argument must be COUNT");
           d.sql_type = SqlType{bigint_count ? B2Q_kBIGINT : B2Q_kINT, e.ti.notnull != 0};

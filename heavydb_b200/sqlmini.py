@@ -158,9 +158,13 @@ class _P:
                 self.eat()
                 self.eat(")")
                 return self.b.agg(abi.kCOUNT, None, self.bigint_count)
+            distinct = False
+            if self.peek().upper() == "DISTINCT":
+                self.eat()
+                distinct = True
             col, rte = self.colref(self.eat())
             self.eat(")")
-            return self.b.agg(_AGGS[tok.upper()], col, self.bigint_count, rte)
+            return self.b.agg(_AGGS[tok.upper()], col, self.bigint_count, rte, is_distinct=distinct)
         return self.b.col(*self.colref(tok))
 
 

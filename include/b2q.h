@@ -119,7 +119,8 @@ typedef struct B2QExpr {
   int32_t op;     /* BinOper: SQLOps; AggExpr: SQLAgg */
   int32_t left;   /* BinOper: left operand; AggExpr: argument (-1 = COUNT(*)) */
   int32_t right;  /* BinOper: right operand */
-  int64_t ival;   /* Constant: Datum for integer types */
+  int64_t ival;   /* Constant: Datum for integer types; AggExpr: get_is_distinct() (COUNT(DISTINCT c) is refused on this path,
+                     not silently counted as COUNT(c)) */
   double dval;    /* Constant: Datum for fp types */
   int32_t is_null;/* Constant::get_is_null() */
   int32_t rte_idx;/* ColumnVar::get_rte_idx(): 0 = the scanned (outer) table, 1 = the joined inner table */

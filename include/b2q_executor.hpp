@@ -133,9 +133,9 @@ struct RelAlgExecutionUnit { /* RelAlgExecutionUnit.h:166-216 */
     exprs.push_back(e);
     return static_cast<ExprRef>(exprs.size() - 1);
   }
-  ExprRef makeAggExpr(const SQLTypeInfo& ti, SQLAgg agg, ExprRef arg /* -1 = COUNT(*) */) { /* Analyzer::AggExpr */
+  ExprRef makeAggExpr(const SQLTypeInfo& ti, SQLAgg agg, ExprRef arg /* -1 = COUNT(*) */, bool is_distinct = false) { /* Analyzer::AggExpr(ti, agg, arg, is_distinct, ...) */
     B2QExpr e{};
-    e.kind = B2Q_EXPR_AGG; e.ti = {ti.type, ti.notnull}; e.op = agg; e.left = arg; e.right = -1;
+    e.kind = B2Q_EXPR_AGG; e.ti = {ti.type, ti.notnull}; e.op = agg; e.left = arg; e.right = -1; e.ival = is_distinct ? 1 : 0;
     exprs.push_back(e);
     return static_cast<ExprRef>(exprs.size() - 1);
   }

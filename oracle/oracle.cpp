@@ -410,6 +410,7 @@ Target get_target_info(const B2QExecUnit& u, int expr_idx, bool bigint_count) {
   }
   t.is_agg = true;
   t.agg_kind = e.op;
+  if (e.ival != 0) fail(B2Q_ERR_UNSUPPORTED, "DISTINCT aggregates (count-distinct descriptors, GroupByAndAggregate.cpp:650-855) are not restated yet");
   if (e.left < 0) {
     if (e.op != B2Q_kCOUNT) fail(B2Q_ERR_INVALID_ARGUMENT, "only COUNT may have no argument");
     t.sql_type = Ti{bigint_count ? B2Q_kBIGINT : B2Q_kINT, notnull};

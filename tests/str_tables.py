@@ -88,6 +88,7 @@ STR_QUERIES = [
 ]
 
 STR_REJECTED = [
+    "SELECT x, COUNT(DISTINCT str) FROM s GROUP BY x;",          # AggExpr::get_is_distinct(): refused, never counted as COUNT(str)
     "SELECT COUNT(*) FROM s WHERE dd < dt;",                      # days-encoded vs seconds chunk
     "SELECT x, SUM(dd) FROM s GROUP BY x;",
     "SELECT s8, SUM(ts) FROM s GROUP BY s8;",
