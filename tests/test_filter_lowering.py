@@ -234,3 +234,23 @@ def test_is_not_null_next_to_a_comparison_is_dropped(emu):
     for where, terms in cases:
         check(emu, table, RAND_NAMES, "r", where)
         assert n_terms(emu, sqlmini.parse(f"SELECT COUNT(*) FROM r WHERE {where};", table, RAND_NAMES), table) == terms, where
+
+
+def test_deleted_rows_term_precedes_the_folded_chain(emu):
+    """A $deleted$ column adds one term in front of the quals (codegenSkipDeletedOuterTableRow); the folded chain starts one
+    stack slot higher and is AND-ed to it."""
+    import numpy as np
+    rng = np.random.default_rng(12)
+    n = 800
+    t = abi.Table([(abi.kINT, False), (abi.kDOUBLE, False), (abi.kBOOLEAN, True), (abi.kBIGINT, True)], deleted_column=2)
+    for b in range(0, n, 300):
+        m = min(300, n - b)
+        x = rng.integers(-50, 50, m).astype(np.int32)
+        x[rng.random(m) < 0.1] = abi.NULL_INT
+        d = rng.normal(0, 10, m)
+        d[rng.random(m) < 0.1] = abi.NULL_DOUBLE
+        t.add_host_fragment([x, d, (rng.random(m) < 0.3).astype(np.int8), rng.integers(0, 1000, m).astype(np.int64)])
+    names = ["x", "d", "del", "v"]
+    for where in ["x BETWEEN -10 AND 10", "x >= -10 AND x <= 10 AND d > -5 AND d < 5", "x IN (1, 2, 3) OR (d < -3 AND v BETWEEN 100 AND 900 AND v <> 500)",
+                  "x IS NOT NULL AND x > 0 AND NOT (d BETWEEN -1 AND 1)", "(x < -20 OR x > 20) AND (v IN (5, 6, 7, 8) OR d >= 0)", "x = 5"]:
+        check(emu, t, names, "t", where)
