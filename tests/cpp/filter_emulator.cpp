@@ -71,8 +71,19 @@ bool eval_term2(const DevTerm& t, const int8_t* c1, const int8_t* c2, int64_t ro
 
 /* 1 / 0 = the row passes / fails the lowered filter; -1 = the program is not one this emulator reads (join level,
  * stack deeper than the device's).  table_cols[c] = chunk of table column c for the fragment, `row` inside it. */
+static int32_t eval_filter_impl(const B2QQuery* q, const void* const* table_cols, int64_t row);
 extern "C" int32_t b2q_test_eval_filter(const B2QQuery* q, const void* const* table_cols, int64_t row) {
   if (!q || q->prog.join.fk_col >= 0) return -1;
+  return eval_filter_impl(q, table_cols, row);
+}
+/* Join programs: the caller has already done the probe — table_cols[n_outer + c] is inner column c GATHERED at the matching
+ * inner row for every outer row (the chunk's NULL sentinel where a LEFT join found no match), so the filter reads one
+ * denormalised row exactly as the kernel reads it through the join index. */
+extern "C" int32_t b2q_test_eval_filter_joined(const B2QQuery* q, const void* const* table_cols, int64_t row) {
+  if (!q || q->prog.join.fk_col < 0) return -1;
+  return eval_filter_impl(q, table_cols, row);
+}
+static int32_t eval_filter_impl(const B2QQuery* q, const void* const* table_cols, int64_t row) {
   const DevFilter& f = q->prog.filter;
   if (f.n_ops == 0) return 1;
   bool st[4];

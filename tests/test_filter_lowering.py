@@ -254,3 +254,49 @@ def test_deleted_rows_term_precedes_the_folded_chain(emu):
     for where in ["x BETWEEN -10 AND 10", "x >= -10 AND x <= 10 AND d > -5 AND d < 5", "x IN (1, 2, 3) OR (d < -3 AND v BETWEEN 100 AND 900 AND v <> 500)",
                   "x IS NOT NULL AND x > 0 AND NOT (d BETWEEN -1 AND 1)", "(x < -20 OR x > 20) AND (v IN (5, 6, 7, 8) OR d >= 0)", "x = 5"]:
         check(emu, t, names, "t", where)
+
+
+def test_join_queries_read_the_same_filter_through_the_join_index(emu):
+    """INNER / LEFT star joins: the probe is done here in numpy (inner columns gathered at the matching row, the chunk's NULL
+    where a LEFT join has no match), the lowered filter — with the LEFT join's nullable inner columns — runs on that
+    denormalised row, and the count must be the oracle's."""
+    import numpy as np
+    import join_tables as jt
+    emu.b2q_test_eval_filter_joined.restype = C.c_int32
+    emu.b2q_test_eval_filter_joined.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64]
+    fact, dim = jt.fact_table(1200, seed=31, frag_rows=500), jt.dim_table(seed=11)
+    dcols = dim.fragments[0].host_cols
+    ids = dcols[jt.DIM_NAMES.index("id32")]
+    pos = {int(k): i for i, k in enumerate(ids)}
+    L = executor.lib()
+    wheres = ["t.x BETWEEN 10 AND 60 AND d.attr8 >= -50 AND d.attr8 < 50", "d.attr IN (1, 2, 3, 9) OR t.x < 5", "d.w > -5 AND d.w <= 5 AND d.attr IS NOT NULL AND d.attr <> 4",
+              "NOT (d.attr8 BETWEEN -20 AND 20) AND t.v IS NOT NULL AND t.v > 0", "d.big > 0 AND d.big < 900000000000000 AND t.x <> 7 AND t.x <> 8 AND t.x <> 9",
+              "d.attr8 < t.x OR d.attr8 IN (5, 6, 7)", "d.attr IS NULL OR d.attr >= 10"]
+    for left in (False, True):
+        for where in wheres:
+            sql = f"SELECT COUNT(*) FROM t {'LEFT ' if left else ''}JOIN d ON t.fk32 = d.id32 WHERE {where};"
+            unit = sqlmini.parse(sql, fact, jt.FACT_NAMES, inner=(dim, jt.DIM_NAMES))
+            want = oracle_lib.execute(unit, fact).rows()[0][0]
+            bt = fact.build(abi.CPU_LEVEL)
+            co, eo = executor.compilation_options(), executor.execution_options()
+            h = C.c_void_p()
+            assert L.b2q_plan(C.byref(unit.unit), C.byref(bt.info), C.byref(co), C.byref(eo), 0, 0, C.byref(h)) == 0, L.b2q_last_error_message()
+            got = 0
+            for f in fact.fragments:
+                fk = f.host_cols[jt.FACT_NAMES.index("fk32")]
+                idx = np.array([pos.get(int(k), -1) if k != abi.NULL_INT else -1 for k in fk], dtype=np.int64)
+                gathered = []
+                for c, a in enumerate(dcols):
+                    g = a[np.maximum(idx, 0)].copy()
+                    g[idx < 0] = dim.physical_null(c)
+                    gathered.append(g)
+                arrays = list(f.host_cols) + gathered
+                ptrs = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+                for row in range(f.num_tuples):
+                    if not left and idx[row] < 0:
+                        continue          # INNER: no match, no row
+                    r = emu.b2q_test_eval_filter_joined(h, ptrs, row)
+                    assert r >= 0
+                    got += r
+            L.b2q_query_free(h)
+            assert got == want, sql
