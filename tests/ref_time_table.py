@@ -54,6 +54,36 @@ def make_sqlite(rows, name="test"):
     return con
 
 
+def fold_time_literals(sql: str) -> str:
+    """'YYYY-MM-DD[ hh:mm:ss]' / 'hh:mm:ss' literals -> the epoch seconds the analyzer folds them to (Constant of type
+    DATE / TIMESTAMP / TIME), so that ExecuteTest.cpp query strings can be used verbatim."""
+    import datetime as dt
+    import re
+
+    def repl(m):
+        txt = m.group(1)
+        if re.fullmatch(r"\d\d:\d\d:\d\d", txt):
+            h, mi, se = map(int, txt.split(":"))
+            return str(h * 3600 + mi * 60 + se)
+        fmt = "%Y-%m-%d %H:%M:%S" if " " in txt else "%Y-%m-%d"
+        return str(int((dt.datetime.strptime(txt, fmt) - dt.datetime(1970, 1, 1)).total_seconds()))
+    return re.sub(r"'(\d{4}-\d\d-\d\d(?: \d\d:\d\d:\d\d)?|\d\d:\d\d:\d\d)'", repl, sql)
+
+
+# verbatim strings of Tests/ExecuteTest.cpp (Select.FilterAndSimpleAggregation :2040-2050, Select.Time :27998)
+VERBATIM = [
+    "SELECT COUNT(*) FROM test WHERE o1 > '1999-09-08';",
+    "SELECT COUNT(*) FROM test WHERE o1 <= '1999-09-08';",
+    "SELECT COUNT(*) FROM test WHERE o1 = '1999-09-08';",
+    "SELECT COUNT(*) FROM test WHERE o1 <> '1999-09-08';",
+    "SELECT COUNT(*) FROM test WHERE o2 > '1999-09-08';",
+    "SELECT COUNT(*) FROM test WHERE o2 <= '1999-09-08';",
+    "SELECT COUNT(*) FROM test WHERE o2 = '1999-09-08';",
+    "SELECT COUNT(*) FROM test WHERE o2 <> '1999-09-08';",
+    "SELECT COUNT(*) FROM test WHERE o1 = o2;",
+    "SELECT COUNT(*) FROM test WHERE o1 <> o2;",
+]
+
 # ExecuteTest.cpp queries over these columns (date / time literals written as the epoch values the analyzer folds them to)
 TIME_QUERIES = [
     f"SELECT COUNT(*) FROM test WHERE o1 > {D_1999_09_08};",       # :2040

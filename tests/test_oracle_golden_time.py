@@ -44,3 +44,16 @@ def test_known_answers(env):
     res = oracle_lib.execute(sqlmini.parse(f"SELECT o, COUNT(*) FROM test WHERE o <= {tt.D_1999_09_09} GROUP BY o ORDER BY 2;", table, tt.TIME_NAMES), table)
     assert res.rows() == [(tt.D_1999_09_09, 15)]
     assert res.plan.query_desc_type == abi.GroupByPerfectHash and res.plan.bucket == 86400
+
+
+def test_verbatim_strings_fold_to_the_same_queries(env):
+    """The quoted-literal strings of ExecuteTest.cpp:2040-2050, folded like the analyzer folds them, are the queries above."""
+    table, con = env
+    for i, sql in enumerate(tt.VERBATIM):
+        folded = tt.fold_time_literals(sql)
+        assert "'" not in folded
+        unit = sqlmini.parse(folded, table, tt.TIME_NAMES)
+        got = oracle_lib.execute(unit, table).rows()
+        assert got == [tuple(r) for r in con.execute(folded.rstrip(";")).fetchall()]
+    assert tt.fold_time_literals("SELECT COUNT(*) FROM test WHERE m > '2014-12-13 22:23:15' AND n = '15:13:14';") == \
+        f"SELECT COUNT(*) FROM test WHERE m > {tt.TS_A} AND n = {tt.T_151314};"
