@@ -104,3 +104,38 @@ static int32_t eval_filter_impl(const B2QQuery* q, const void* const* table_cols
   return sp == 1 ? (st[0] ? 1 : 0) : -1;
 }
 extern "C" int32_t b2q_test_filter_terms(const B2QQuery* q) { return q ? q->prog.filter.n_terms : -1; }
+
+/* The entry a passing row aggregates into under PERFECT hash, read from the lowered key mapping (DevKey / DevKeyComp) with
+ * the semantics of process_chunk's "group index" block: idx = key - min (raw chunk value: days for a days-encoded DATE),
+ * `/ 86400` for an 8-byte DATE, NULL -> the translated NULL entry; several GROUP BY columns: mixed radix.
+ * -1 = out of range (the kernel raises KEY_OUT_OF_RANGE), -2 = not a perfect-hash program. */
+extern "C" int64_t b2q_test_group_index(const B2QQuery* q, const void* const* table_cols, int64_t row) {
+  if (!q || q->plan.query_desc_type != B2Q_GroupByPerfectHash) return -2;
+  const DevProgram& P = q->prog;
+  if (P.n_keys > 1) {
+    int64_t e = 0;
+    for (int c = 0; c < P.n_keys; ++c) {
+      const DevKeyComp& kc = P.keys[c];
+      const int64_t k = load_int(static_cast<const int8_t*>(table_cols[q->col_ids[kc.col]]), kc.width, row);
+      int64_t d = k - kc.min_val;
+      if (kc.div_day) { d = d / 86400; if (k % 86400 != 0 && !(kc.translate_null && k == kc.null_val)) d = -1; }
+      if (kc.translate_null && k == kc.null_val) d = static_cast<int64_t>(kc.card) - 1;
+      if (static_cast<uint64_t>(d) >= kc.card) return -1;
+      e += d * static_cast<int64_t>(kc.mult);
+    }
+    return e;
+  }
+  const DevKey& K = P.key;
+  if (K.col < 0) return -2;
+  const int64_t k = load_int(static_cast<const int8_t*>(table_cols[q->col_ids[K.col]]), K.width, row);
+  int64_t idx;
+  if (K.width != 8) { /* the 32-bit key path: unsigned difference of the low words */
+    idx = static_cast<uint32_t>(static_cast<uint32_t>(static_cast<int32_t>(k)) - static_cast<uint32_t>(K.min_val));
+    if (K.translate_null && static_cast<int32_t>(k) == static_cast<int32_t>(K.null_val)) idx = K.null_idx;
+  } else {
+    idx = k - K.min_val;
+    if (K.div_day) { idx = idx / 86400; if (k % 86400 != 0 && !(K.translate_null && k == K.null_val)) idx = -1; }
+    if (K.translate_null && k == K.null_val) idx = K.null_idx;
+  }
+  return static_cast<uint64_t>(idx) < static_cast<uint64_t>(K.entry_count) ? idx : -1;
+}

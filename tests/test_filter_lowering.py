@@ -300,3 +300,62 @@ def test_join_queries_read_the_same_filter_through_the_join_index(emu):
                     got += r
             L.b2q_query_free(h)
             assert got == want, sql
+
+
+def per_entry_counts(emu, unit, table):
+    """COUNT(*) per ENTRY from the lowered program: filter, then the key mapping (perfect hash)."""
+    import numpy as np
+    emu.b2q_test_group_index.restype = C.c_int64
+    emu.b2q_test_group_index.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64]
+    L = executor.lib()
+    bt = table.build(abi.CPU_LEVEL)
+    co, eo = executor.compilation_options(), executor.execution_options()
+    h = C.c_void_p()
+    assert L.b2q_plan(C.byref(unit.unit), C.byref(bt.info), C.byref(co), C.byref(eo), 0, 0, C.byref(h)) == 0, L.b2q_last_error_message()
+    plan = L.b2q_query_plan(h).contents
+    counts = np.zeros(plan.entry_count, dtype=np.int64)
+    for f in table.fragments:
+        ptrs = (C.c_void_p * table.num_cols)(*[a.ctypes.data if a is not None else None for a in f.host_cols])
+        for row in range(f.num_tuples):
+            if emu.b2q_test_eval_filter(h, ptrs, row) == 1:
+                e = emu.b2q_test_group_index(h, ptrs, row)
+                assert e >= 0, (e, row)
+                counts[e] += 1
+    L.b2q_query_free(h)
+    return counts
+
+
+def oracle_count_column(res, slot):
+    """The COUNT slot of every entry of the oracle's (row-wise) buffer."""
+    import numpy as np
+    p = res.plan
+    buf = res.buffer()
+    w = p.slot_padded_width[slot]
+    rows = buf.reshape(p.entry_count, p.row_size)
+    col = rows[:, p.slot_offset[slot]:p.slot_offset[slot] + w].copy()
+    return col.view(np.int32 if w == 4 else np.int64).reshape(-1).astype(np.int64)
+
+
+def test_key_mapping_places_every_row_in_the_oracles_entry(emu):
+    """GROUP BY keys -> entry index as the planner lowers it (min, NULL entry, mixed radix, the DATE day bucket with a min off
+    the day grid, days-encoded chunks indexed in days): per-entry COUNT(*) equals the oracle's buffer, entry by entry."""
+    cases = [
+        (random_table(900, seed=65, frag_rows=250), RAND_NAMES, "r",
+         ["SELECT k8, COUNT(*) FROM r GROUP BY k8;", "SELECT k16, COUNT(*) FROM r WHERE a8 > 0 GROUP BY k16;", "SELECT nn64, COUNT(*) FROM r WHERE nn64 > -20 GROUP BY nn64;",
+          "SELECT k8, k16, COUNT(*) FROM r WHERE d < 500 GROUP BY k8, k16;", "SELECT nn32, k8, COUNT(*) FROM r GROUP BY nn32, k8;", "SELECT k64, COUNT(*) FROM r WHERE k64 >= 1000000100 GROUP BY k64;"]),
+        (stt.str_table(1500, seed=11, frag_rows=400), stt.STR_NAMES, "s",
+         ["SELECT dd, COUNT(*) FROM s GROUP BY dd;", "SELECT dd16, COUNT(*) FROM s WHERE dd > 1555286400 GROUP BY dd16;", "SELECT dt, COUNT(*) FROM s WHERE dt > 1555286410 GROUP BY dt;",
+          "SELECT dd, dt, COUNT(*) FROM s WHERE dd <= 1557000000 GROUP BY dd, dt;", "SELECT s8, COUNT(*) FROM s GROUP BY s8;", "SELECT str, s8, COUNT(*) FROM s GROUP BY str, s8;",
+          "SELECT ts, COUNT(*) FROM s GROUP BY ts;"]),
+        (tt.make_table(tt.time_rows()), tt.TIME_NAMES, "test",
+         ["SELECT o, COUNT(*) FROM test WHERE o <= 936835200 GROUP BY o;", "SELECT fx, COUNT(*) FROM test GROUP BY fx;", "SELECT o1, o2, COUNT(*) FROM test GROUP BY o1, o2;", "SELECT m, COUNT(*) FROM test GROUP BY m;"]),
+    ]
+    for table, names, _tname, sqls in cases:
+        for sql in sqls:
+            unit = sqlmini.parse(sql, table, names)
+            res = oracle_lib.execute(unit, table)
+            assert res.plan.query_desc_type == abi.GroupByPerfectHash and not res.plan.output_columnar, sql
+            n_keys = max(res.plan.num_group_cols, 1)
+            got = per_entry_counts(emu, unit, table)
+            want = oracle_count_column(res, slot=n_keys)       # targets: the key column(s), then COUNT(*)
+            assert (got == want).all(), sql
