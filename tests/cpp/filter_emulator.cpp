@@ -5,9 +5,11 @@
  * (kernels.cu: eval_term, eval_term2, eval_filter).  tests/test_filter_lowering.py uses it to check the planner's
  * lowering — range encoding of comparisons, NULL folding, De Morgan push-down, operand ordering on the 4-deep mask stack,
  * constants of days-encoded DATE columns — against the oracle on the CPU, where no kernel can run. */
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../heavydb_b200/csrc/b2q_internal.h"
 
@@ -138,4 +140,144 @@ extern "C" int64_t b2q_test_group_index(const B2QQuery* q, const void* const* ta
     if (K.translate_null && k == K.null_val) idx = K.null_idx;
   }
   return static_cast<uint64_t>(idx) < static_cast<uint64_t>(K.entry_count) ? idx : -1;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * The whole lowered program on the host: filter -> entry -> accumulators (DevAcc skip rules) -> materialise (DevLayout),
+ * for non-grouped and perfect-hash programs without a join.  Accumulator semantics follow process_chunk /
+ * not_skipped64 (kernels.cu); materialise is the host reading of b2q_k_materialize.  DOUBLE sums are accumulated per
+ * fragment and folded in fragment order, the order of the oracle's host reduce.
+ * Returns 0, or a B2Q error code (KEY_OUT_OF_RANGE), or -2 for programs outside this emulator.
+ * ------------------------------------------------------------------------------------------------------------------- */
+namespace {
+bool skipped(const DevAcc& a, int64_t v) {
+  if (!a.skip1_en && !a.skip2_en) return false;
+  if (a.is_fp) return as_double(v) == as_double(a.skip1_val);
+  const int64_t w = a.skip2_trunc32 ? static_cast<int64_t>(static_cast<int32_t>(v)) : v;
+  return (a.skip1_en && v == a.skip1_val) || (a.skip2_en && w == a.skip2_val);
+}
+}  // namespace
+
+extern "C" int32_t b2q_test_run_program(const B2QQuery* q, int32_t n_frags, const void* const* const* frag_cols,
+                                        const int64_t* frag_rows, int8_t* out) {
+  if (!q || q->prog.join.fk_col >= 0) return -2;
+  const B2QPlan& plan = q->plan;
+  if (plan.query_desc_type != B2Q_GroupByPerfectHash && plan.query_desc_type != B2Q_NonGroupedAggregate) return -2;
+  const DevProgram& P = q->prog;
+  const int64_t n = plan.entry_count;
+  std::vector<std::vector<int64_t>> accs(P.n_accs, std::vector<int64_t>(static_cast<size_t>(n)));
+  std::vector<uint8_t> touch(static_cast<size_t>(n), 0);
+  for (int a = 0; a < P.n_accs; ++a) for (int64_t i = 0; i < n; ++i) accs[a][i] = b2q_acc_identity(P.accs[a].op);
+  std::vector<std::vector<double>> fsum(P.n_accs);
+  for (int f = 0; f < n_frags; ++f) {
+    for (int a = 0; a < P.n_accs; ++a) if (P.accs[a].op == ACC_SUM_F64) fsum[a].assign(static_cast<size_t>(n), 0.0);
+    std::vector<uint8_t> ftouch(static_cast<size_t>(n), 0);
+    for (int64_t row = 0; row < frag_rows[f]; ++row) {
+      const int32_t pass = eval_filter_impl(q, frag_cols[f], row);
+      if (pass < 0) return -2;
+      if (!pass) continue;
+      int64_t e = 0;
+      if (plan.query_desc_type == B2Q_GroupByPerfectHash) {
+        e = b2q_test_group_index(q, frag_cols[f], row);
+        if (e == -1) return B2Q_ERR_KEY_OUT_OF_RANGE;
+        if (e < 0) return -2;
+      }
+      ftouch[e] = 1;
+      for (int a = 0; a < P.n_accs; ++a) {
+        const DevAcc& A = P.accs[a];
+        if (A.op == ACC_TOUCH) { touch[e] = 1; continue; }
+        int64_t v = 0;
+        if (A.col >= 0) {
+          const int8_t* col = static_cast<const int8_t*>(frag_cols[f][q->col_ids[A.col]]);
+          v = A.is_fp ? load_int(col, 8, row) : load_int(col, A.width, row);
+          if (skipped(A, v)) continue;
+        }
+        int64_t& acc = accs[a][e];
+        switch (A.op) {
+          case ACC_COUNT: acc += 1; break;
+          case ACC_SUM_I64: acc = static_cast<int64_t>(static_cast<uint64_t>(acc) + static_cast<uint64_t>(v)); break;
+          case ACC_SUM_F64: fsum[a][e] += as_double(v); break;
+          case ACC_MIN_I64: acc = v < acc ? v : acc; break;
+          case ACC_MAX_I64: acc = v > acc ? v : acc; break;
+          case ACC_MIN_F64: { const int64_t o = b2q_f64_to_ord(v); acc = o < acc ? o : acc; break; }
+          case ACC_MAX_F64: { const int64_t o = b2q_f64_to_ord(v); acc = o > acc ? o : acc; break; }
+          default: return -2;
+        }
+      }
+    }
+    for (int a = 0; a < P.n_accs; ++a)
+      if (P.accs[a].op == ACC_SUM_F64)
+        for (int64_t i = 0; i < n; ++i)
+          if (ftouch[i]) { const double s = as_double(accs[a][i]) + fsum[a][i]; memcpy(&accs[a][i], &s, 8); }
+  }
+  /* ---- materialise (b2q_k_materialize) ---- */
+  const DevLayout& L = q->layout;
+  if (L.baseline) return -2;
+  for (int64_t i = 0; i < L.entry_count; ++i) {
+    int8_t* row = out + i * L.row_size;
+    bool touched = true;
+    int64_t key = 0, mkey_stored[B2Q_MAX_GROUP_COLS], mkey_proj[B2Q_MAX_GROUP_COLS];
+    if (L.n_keys > 1) {
+      for (int c = 0; c < L.n_keys; ++c) {
+        const DevKeyComp& kc = L.keys[c];
+        const int64_t comp = (i / kc.mult) % kc.card;
+        const bool is_null_comp = kc.translate_null && comp == static_cast<int64_t>(kc.card) - 1;
+        mkey_stored[c] = is_null_comp ? kc.null_stored : kc.min_val + comp * kc.step;
+        mkey_proj[c] = is_null_comp ? kc.null_logical : kc.min_val + comp * kc.step;
+      }
+      if (L.touched_acc >= 0) touched = touch[i] != 0;
+    } else {
+      key = (i == L.null_idx) ? L.key_null_val : L.key_min + i * L.key_step;
+      if (L.touched_acc >= 0) touched = touch[i] != 0;
+    }
+    auto put64 = [](int8_t* p, int64_t v) { memcpy(p, &v, 8); };
+    auto put32 = [](int8_t* p, int32_t v) { memcpy(p, &v, 4); };
+    if (L.has_key_col && L.columnar) {
+      if (L.n_keys > 1) for (int c = 0; c < L.n_keys; ++c) put64(out + c * L.key_col_stride + i * 8, touched ? mkey_stored[c] : B2Q_I64_MAX);
+      else put64(out + i * 8, touched ? ((i == L.null_idx) ? L.key_null_stored : key) : B2Q_I64_MAX);
+    } else if (L.has_key_col && L.n_keys > 1) {
+      for (int c = 0; c < L.n_keys; ++c) put64(row + c * 8, touched ? mkey_stored[c] : B2Q_I64_MAX);
+    } else if (L.has_key_col) {
+      if (L.key_width == 4) { put32(row, touched ? static_cast<int32_t>(key) : 0x7FFFFFFF); put32(row + 4, 0); }
+      else put64(row, touched ? ((i == L.null_idx) ? L.key_null_stored : key) : B2Q_I64_MAX);
+    }
+    int64_t vals[B2Q_MAX_SLOTS];
+    for (int s = 0; s < L.n_slots; ++s) {
+      const DevSlot& sl = L.slots[s];
+      int64_t val = sl.init_val;
+      if (touched && sl.kind != SLOT_NONE && sl.width != 0) {
+        switch (sl.kind) {
+          case SLOT_KEY: val = L.n_keys > 1 ? mkey_proj[sl.key_comp] : key; break;
+          case SLOT_COUNT: val = accs[sl.acc][i]; break;
+          default: {
+            const int64_t raw = accs[sl.acc][i];
+            bool is_null = false;
+            if (sl.nn >= 0) is_null = accs[sl.nn][i] == 0;
+            else if (sl.nn == -2) is_null = raw == sl.identity;
+            val = is_null ? sl.init_val : (sl.kind == SLOT_VALUE_ORD ? b2q_ord_to_f64(raw) : (sl.scale_day ? raw * 86400 : raw));
+          }
+        }
+      }
+      vals[s] = val;
+    }
+    if (L.keyless_marker >= 0 && vals[L.keyless_marker] == L.slots[L.keyless_marker].init_val)
+      for (int s = 0; s < L.n_slots; ++s) vals[s] = L.slots[s].init_val;
+    if (L.columnar) {
+      for (int s = 0; s < L.n_slots; ++s) {
+        const DevSlot& sl = L.slots[s];
+        if (sl.kind == SLOT_NONE || sl.width == 0) continue;
+        if (sl.width == 4) put32(out + sl.offset + i * 4, static_cast<int32_t>(vals[s])); else put64(out + sl.offset + i * 8, vals[s]);
+      }
+      continue;
+    }
+    int end = 0;
+    for (int s = 0; s < L.n_slots; ++s) {
+      const DevSlot& sl = L.slots[s];
+      if (sl.kind == SLOT_NONE || sl.width == 0) continue;
+      if (sl.width == 4) put32(row + sl.offset, static_cast<int32_t>(vals[s])); else put64(row + sl.offset, vals[s]);
+      end = std::max(end, static_cast<int>(sl.offset) + sl.width);
+    }
+    if (end) for (; end + 4 <= L.row_size; end += 4) put32(row + end, 0);
+  }
+  return 0;
 }

@@ -359,3 +359,65 @@ def test_key_mapping_places_every_row_in_the_oracles_entry(emu):
             got = per_entry_counts(emu, unit, table)
             want = oracle_count_column(res, slot=n_keys)       # targets: the key column(s), then COUNT(*)
             assert (got == want).all(), sql
+
+
+def run_program(emu, unit, table, output_columnar=False, entry_guess=0, has_card=False):
+    """The whole lowered program on the host (tests/cpp/filter_emulator.cpp: b2q_test_run_program) -> result buffer bytes."""
+    import numpy as np
+    emu.b2q_test_run_program.restype = C.c_int32
+    emu.b2q_test_run_program.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.c_int64), C.c_void_p]
+    L = executor.lib()
+    bt = table.build(abi.CPU_LEVEL)
+    co, eo = executor.compilation_options(), executor.execution_options(output_columnar_hint=output_columnar)
+    h = C.c_void_p()
+    rc = L.b2q_plan(C.byref(unit.unit), C.byref(bt.info), C.byref(co), C.byref(eo), entry_guess, int(has_card), C.byref(h))
+    assert rc == 0, L.b2q_last_error_message()
+    plan = L.b2q_query_plan(h).contents
+    nf = len(table.fragments)
+    keep = [(C.c_void_p * table.num_cols)(*[a.ctypes.data if a is not None else None for a in f.host_cols]) for f in table.fragments]
+    frag_cols = (C.POINTER(C.c_void_p) * max(nf, 1))(*[C.cast(k, C.POINTER(C.c_void_p)) for k in keep])
+    frag_rows = (C.c_int64 * max(nf, 1))(*[f.num_tuples for f in table.fragments])
+    out = np.zeros(max(plan.buffer_size, 8), dtype=np.uint8)
+    rc = emu.b2q_test_run_program(h, nf, frag_cols, frag_rows, out.ctypes.data)
+    L.b2q_query_free(h)
+    return rc, out[:plan.buffer_size]
+
+
+def assert_buffers_match(got, want, sql):
+    """Bit-exact, except that 8-byte words which read as doubles may differ in the last bits (fp summation order)."""
+    import numpy as np
+    if np.array_equal(got, want):
+        return
+    assert got.size == want.size and got.size % 8 == 0, sql
+    g, w = got.view(np.int64), want.view(np.int64)
+    bad = np.nonzero(g != w)[0]
+    gd, wd = got.view(np.float64)[bad], want.view(np.float64)[bad]
+    assert np.allclose(gd, wd, rtol=1e-9, atol=0) and np.all(np.isfinite(gd)), (sql, bad[:5], g[bad][:5], w[bad][:5])
+
+
+def test_whole_program_reproduces_the_oracles_buffer(emu):
+    """filter -> entry -> accumulators with their NULL-skip rules -> materialise, all read from the lowered program on the
+    host: the result buffer is the oracle's (row-wise and columnar; keyless and keyed; single, composite and DATE keys;
+    non-grouped)."""
+    from test_gpu_parity import RAND_QUERIES
+    import reduce_ladder as rl
+    ran = 0
+    cases = [(random_table(1200, seed=66, frag_rows=350), RAND_NAMES, list(RAND_QUERIES)),
+             (stt.str_table(1500, seed=12, frag_rows=400), stt.STR_NAMES, [q for q in stt.STR_QUERIES if " ORDER BY " not in q]),
+             (tt.make_table(tt.time_rows()), tt.TIME_NAMES, [q for q in tt.TIME_QUERIES if " ORDER BY " not in q]),
+             (rl.ladder_table(241, 7, 17, 60, seed=5)[0], rl.NAMES, [rl.QUERY])]
+    for table, names, sqls in cases:
+        for sql in sqls:
+            unit = sqlmini.parse(sql, table, names)
+            for columnar in (False, True):
+                try:
+                    res = oracle_lib.execute(unit, table, entry_guess=3001, has_card=True, output_columnar=columnar)
+                except oracle_lib.OracleError:
+                    continue
+                if res.plan.query_desc_type not in (abi.GroupByPerfectHash, abi.NonGroupedAggregate):
+                    continue
+                rc, got = run_program(emu, unit, table, output_columnar=columnar, entry_guess=3001, has_card=True)
+                assert rc == 0, (sql, rc)
+                assert_buffers_match(got, res.buffer(), sql)
+                ran += 1
+    assert ran >= 60
