@@ -421,3 +421,27 @@ def test_whole_program_reproduces_the_oracles_buffer(emu):
                 assert_buffers_match(got, res.buffer(), sql)
                 ran += 1
     assert ran >= 60
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_queries_whole_program(emu, seed):
+    """The GPU fuzz generator's queries (filters, single / composite keys, every aggregate over every column type), planned
+    on the host and run through the host reading of the lowered program: same buffer as the oracle, both layouts."""
+    rng = random.Random(31000 + seed)
+    table = random_table([40, 900, 2000][seed], seed=520 + seed, frag_rows=[11, 300, 2000][seed])
+    ran = 0
+    for i in range(70):
+        sql = rand_query(rng, multi_key=(i % 3 == 0))
+        unit = sqlmini.parse(sql, table, RAND_NAMES)
+        for columnar in (False, True):
+            try:
+                res = oracle_lib.execute(unit, table, entry_guess=6000, has_card=True, output_columnar=columnar)
+            except oracle_lib.OracleError:
+                continue
+            if res.plan.query_desc_type not in (abi.GroupByPerfectHash, abi.NonGroupedAggregate):
+                continue
+            rc, got = run_program(emu, unit, table, output_columnar=columnar, entry_guess=6000, has_card=True)
+            assert rc == 0, sql
+            assert_buffers_match(got, res.buffer(), sql)
+            ran += 1
+    assert ran >= 40
