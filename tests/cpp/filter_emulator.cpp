@@ -158,9 +158,22 @@ bool skipped(const DevAcc& a, int64_t v) {
 }
 }  // namespace
 
+static int32_t run_program_impl(const B2QQuery* q, int32_t n_frags, const void* const* const* frag_cols,
+                                const int64_t* frag_rows, const uint8_t* const* frag_valid, int8_t* out);
 extern "C" int32_t b2q_test_run_program(const B2QQuery* q, int32_t n_frags, const void* const* const* frag_cols,
                                         const int64_t* frag_rows, int8_t* out) {
   if (!q || q->prog.join.fk_col >= 0) return -2;
+  return run_program_impl(q, n_frags, frag_cols, frag_rows, nullptr, out);
+}
+/* Join programs on denormalised rows (see b2q_test_eval_filter_joined); frag_valid[f][row] == 0: an INNER join found no
+ * match for the row, which then does not exist. */
+extern "C" int32_t b2q_test_run_program_joined(const B2QQuery* q, int32_t n_frags, const void* const* const* frag_cols,
+                                               const int64_t* frag_rows, const uint8_t* const* frag_valid, int8_t* out) {
+  if (!q || q->prog.join.fk_col < 0) return -2;
+  return run_program_impl(q, n_frags, frag_cols, frag_rows, frag_valid, out);
+}
+static int32_t run_program_impl(const B2QQuery* q, int32_t n_frags, const void* const* const* frag_cols,
+                                const int64_t* frag_rows, const uint8_t* const* frag_valid, int8_t* out) {
   const B2QPlan& plan = q->plan;
   if (plan.query_desc_type != B2Q_GroupByPerfectHash && plan.query_desc_type != B2Q_NonGroupedAggregate) return -2;
   const DevProgram& P = q->prog;
@@ -173,6 +186,7 @@ extern "C" int32_t b2q_test_run_program(const B2QQuery* q, int32_t n_frags, cons
     for (int a = 0; a < P.n_accs; ++a) if (P.accs[a].op == ACC_SUM_F64) fsum[a].assign(static_cast<size_t>(n), 0.0);
     std::vector<uint8_t> ftouch(static_cast<size_t>(n), 0);
     for (int64_t row = 0; row < frag_rows[f]; ++row) {
+      if (frag_valid && !frag_valid[f][row]) continue;
       const int32_t pass = eval_filter_impl(q, frag_cols[f], row);
       if (pass < 0) return -2;
       if (!pass) continue;
