@@ -447,58 +447,68 @@ def test_random_queries_whole_program(emu, seed):
     assert ran >= 40
 
 
-def test_join_programs_reproduce_the_oracles_buffer(emu):
-    """INNER and LEFT star joins: probe in numpy, then the whole lowered program on the denormalised rows — inner columns as
-    keys, filter operands and aggregate arguments, nullable under a LEFT join — gives the oracle's buffer."""
+def run_join_program(emu, unit, fact, dim, left, entry_guess=4000):
+    """Probe in numpy, then the whole lowered join program on the denormalised rows -> (rc, result buffer bytes)."""
     import numpy as np
-    import join_tables as jt
     emu.b2q_test_run_program_joined.restype = C.c_int32
     emu.b2q_test_run_program_joined.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.POINTER(C.c_void_p)), C.POINTER(C.c_int64),
                                                 C.POINTER(C.POINTER(C.c_uint8)), C.c_void_p]
-    fact, dim = jt.fact_table(1500, seed=41, frag_rows=600), jt.dim_table(seed=13)
-    dcols = dim.fragments[0].host_cols
     L = executor.lib()
+    dcols = dim.fragments[0].host_cols
+    e = unit.unit.exprs[unit.unit.join_qual]
+    a, b = unit.unit.exprs[e.left], unit.unit.exprs[e.right]
+    outer, inner = (a, b) if a.rte_idx == 0 else (b, a)
+    ikeys = dcols[inner.col_id]
+    inull = dim.physical_null(inner.col_id)
+    pos = {int(k): i for i, k in enumerate(ikeys) if dim.col_types[inner.col_id][1] or k != inull}
+    bt = fact.build(abi.CPU_LEVEL)
+    co, eo = executor.compilation_options(), executor.execution_options()
+    h = C.c_void_p()
+    assert L.b2q_plan(C.byref(unit.unit), C.byref(bt.info), C.byref(co), C.byref(eo), entry_guess, 1, C.byref(h)) == 0, L.b2q_last_error_message()
+    plan = L.b2q_query_plan(h).contents
+    keep, valids = [], []
+    for f in fact.fragments:
+        fk = f.host_cols[outer.col_id]
+        onull = fact.physical_null(outer.col_id)
+        idx = np.array([-1 if (not fact.col_types[outer.col_id][1] and k == onull) else pos.get(int(k), -1) for k in fk], dtype=np.int64)
+        gathered = []
+        for c, col in enumerate(dcols):
+            g = col[np.maximum(idx, 0)].copy() if len(col) else np.full(len(fk), dim.physical_null(c), dtype=col.dtype)
+            g[idx < 0] = dim.physical_null(c)
+            gathered.append(g)
+        arrays = list(f.host_cols) + gathered
+        keep.append((arrays, (C.c_void_p * len(arrays))(*[x.ctypes.data for x in arrays])))
+        valids.append(np.ascontiguousarray(np.ones(len(fk), dtype=np.uint8) if left else (idx >= 0).astype(np.uint8)))
+    nf = len(keep)
+    frag_cols = (C.POINTER(C.c_void_p) * nf)(*[C.cast(k[1], C.POINTER(C.c_void_p)) for k in keep])
+    frag_rows = (C.c_int64 * nf)(*[f.num_tuples for f in fact.fragments])
+    frag_valid = (C.POINTER(C.c_uint8) * nf)(*[v.ctypes.data_as(C.POINTER(C.c_uint8)) for v in valids])
+    out = np.zeros(max(plan.buffer_size, 8), dtype=np.uint8)
+    rc = emu.b2q_test_run_program_joined(h, nf, frag_cols, frag_rows, frag_valid, out.ctypes.data)
+    L.b2q_query_free(h)
+    return rc, out[:plan.buffer_size]
+
+
+def test_join_programs_reproduce_the_oracles_buffer(emu):
+    """INNER and LEFT star joins: probe in numpy, then the whole lowered program on the denormalised rows — inner columns as
+    keys, filter operands and aggregate arguments, nullable under a LEFT join — gives the oracle's buffer."""
+    import join_tables as jt
+    from test_gpu_fuzz import rand_join_query
+    fact, dim = jt.fact_table(1500, seed=41, frag_rows=600), jt.dim_table(seed=13)
+    rng = random.Random(77)
     ran = 0
-    for sql in jt.JOIN_QUERIES + jt.LEFT_JOIN_QUERIES:
+    for sql in jt.JOIN_QUERIES + jt.LEFT_JOIN_QUERIES + [rand_join_query(rng) for _ in range(60)]:
         unit = sqlmini.parse(sql, fact, jt.FACT_NAMES, inner=(dim, jt.DIM_NAMES))
         if unit.unit.num_order_entries:
             continue
-        res = oracle_lib.execute(unit, fact, entry_guess=4000, has_card=True)
+        try:
+            res = oracle_lib.execute(unit, fact, entry_guess=4000, has_card=True)
+        except oracle_lib.OracleError:
+            continue
         if res.plan.query_desc_type not in (abi.GroupByPerfectHash, abi.NonGroupedAggregate):
             continue
-        left = " LEFT JOIN " in sql
-        e = unit.unit.exprs[unit.unit.join_qual]
-        a, b = unit.unit.exprs[e.left], unit.unit.exprs[e.right]
-        outer, inner = (a, b) if a.rte_idx == 0 else (b, a)
-        ikeys = dcols[inner.col_id]
-        inull = dim.physical_null(inner.col_id)
-        pos = {int(k): i for i, k in enumerate(ikeys) if dim.col_types[inner.col_id][1] or k != inull}
-        bt = fact.build(abi.CPU_LEVEL)
-        co, eo = executor.compilation_options(), executor.execution_options()
-        h = C.c_void_p()
-        assert L.b2q_plan(C.byref(unit.unit), C.byref(bt.info), C.byref(co), C.byref(eo), 4000, 1, C.byref(h)) == 0, L.b2q_last_error_message()
-        plan = L.b2q_query_plan(h).contents
-        keep, valids = [], []
-        for f in fact.fragments:
-            fk = f.host_cols[outer.col_id]
-            onull = fact.physical_null(outer.col_id)
-            idx = np.array([-1 if (not fact.col_types[outer.col_id][1] and k == onull) else pos.get(int(k), -1) for k in fk], dtype=np.int64)
-            gathered = []
-            for c, col in enumerate(dcols):
-                g = col[np.maximum(idx, 0)].copy()
-                g[idx < 0] = dim.physical_null(c)
-                gathered.append(g)
-            arrays = list(f.host_cols) + gathered
-            keep.append((arrays, (C.c_void_p * len(arrays))(*[x.ctypes.data for x in arrays])))
-            valids.append(np.ascontiguousarray(np.ones(len(fk), dtype=np.uint8) if left else (idx >= 0).astype(np.uint8)))
-        nf = len(keep)
-        frag_cols = (C.POINTER(C.c_void_p) * nf)(*[C.cast(k[1], C.POINTER(C.c_void_p)) for k in keep])
-        frag_rows = (C.c_int64 * nf)(*[f.num_tuples for f in fact.fragments])
-        frag_valid = (C.POINTER(C.c_uint8) * nf)(*[v.ctypes.data_as(C.POINTER(C.c_uint8)) for v in valids])
-        out = np.zeros(max(plan.buffer_size, 8), dtype=np.uint8)
-        rc = emu.b2q_test_run_program_joined(h, nf, frag_cols, frag_rows, frag_valid, out.ctypes.data)
-        L.b2q_query_free(h)
+        rc, got = run_join_program(emu, unit, fact, dim, left=" LEFT JOIN " in sql)
         assert rc == 0, (sql, rc)
-        assert_buffers_match(out[:plan.buffer_size], res.buffer(), sql)
+        assert_buffers_match(got, res.buffer(), sql)
         ran += 1
-    assert ran >= 12
+    assert ran >= 30
