@@ -20,6 +20,8 @@ kINT, kSMALLINT, kFLOAT, kDOUBLE, kBIGINT, kTINYINT = 6, 7, 8, 9, 12, 22
 kBOOLEAN = 1  # only as the type of the deleted-rows column
 kCHAR, kVARCHAR, kTEXT = 2, 3, 13   # dictionary-encoded strings: int32 ids (uint8 / uint16 under DICT(8) / DICT(16))
 kTIME, kTIMESTAMP, kDATE = 10, 11, 14   # int64
+kNUMERIC, kDECIMAL = 4, 5               # value * 10**scale as int64 (int32 / int16 under the DDL's ENCODING FIXED)
+DECIMAL_TYPES = (kNUMERIC, kDECIMAL)
 STRING_TYPES = (kCHAR, kVARCHAR, kTEXT)
 TIME_TYPES = (kTIME, kTIMESTAMP, kDATE)
 # ---- SQLOps subset ---------------------------------------------------------------------------------------
@@ -40,7 +42,7 @@ ERR_NO_DEVICE = 1003
 ERR_CUDA = 1004
 ERR_KEY_OUT_OF_RANGE = 1005
 
-ABI_VERSION = 3   # B2Q_ABI_VERSION of include/b2q.h this mirror was written against
+ABI_VERSION = 4   # B2Q_ABI_VERSION of include/b2q.h this mirror was written against
 EXPR_COLUMN_VAR, EXPR_CONSTANT, EXPR_BIN_OPER, EXPR_AGG, EXPR_UOPER = 1, 2, 3, 4, 5
 CPU_LEVEL, GPU_LEVEL = 1, 2
 DEVICE_CPU, DEVICE_GPU = 0, 1
@@ -62,14 +64,17 @@ EMPTY_KEY_64 = 2**63 - 1
 EMPTY_KEY_32 = 2**31 - 1
 
 NUMPY_OF = {kBOOLEAN: np.int8, kTINYINT: np.int8, kSMALLINT: np.int16, kINT: np.int32, kBIGINT: np.int64, kDOUBLE: np.float64,
-            kCHAR: np.int32, kVARCHAR: np.int32, kTEXT: np.int32, kTIME: np.int64, kTIMESTAMP: np.int64, kDATE: np.int64}
-SIZE_OF = {kBOOLEAN: 1, kTINYINT: 1, kSMALLINT: 2, kINT: 4, kBIGINT: 8, kDOUBLE: 8, kCHAR: 4, kVARCHAR: 4, kTEXT: 4, kTIME: 8, kTIMESTAMP: 8, kDATE: 8}
+            kCHAR: np.int32, kVARCHAR: np.int32, kTEXT: np.int32, kTIME: np.int64, kTIMESTAMP: np.int64, kDATE: np.int64,
+            kNUMERIC: np.int64, kDECIMAL: np.int64}
+SIZE_OF = {kBOOLEAN: 1, kTINYINT: 1, kSMALLINT: 2, kINT: 4, kBIGINT: 8, kDOUBLE: 8, kCHAR: 4, kVARCHAR: 4, kTEXT: 4, kTIME: 8, kTIMESTAMP: 8, kDATE: 8,
+           kNUMERIC: 8, kDECIMAL: 8}
 NULL_OF = {kBOOLEAN: NULL_TINYINT, kTINYINT: NULL_TINYINT, kSMALLINT: NULL_SMALLINT, kINT: NULL_INT, kBIGINT: NULL_BIGINT, kDOUBLE: NULL_DOUBLE,
-           kCHAR: NULL_INT, kVARCHAR: NULL_INT, kTEXT: NULL_INT, kTIME: NULL_BIGINT, kTIMESTAMP: NULL_BIGINT, kDATE: NULL_BIGINT}
+           kCHAR: NULL_INT, kVARCHAR: NULL_INT, kTEXT: NULL_INT, kTIME: NULL_BIGINT, kTIMESTAMP: NULL_BIGINT, kDATE: NULL_BIGINT,
+           kNUMERIC: NULL_BIGINT, kDECIMAL: NULL_BIGINT}
 
 
 class TypeInfo(C.Structure):
-    _fields_ = [("type", C.c_int32), ("notnull", C.c_int32)]
+    _fields_ = [("type", C.c_int32), ("notnull", C.c_int32), ("scale", C.c_int32)]
 
 
 class Expr(C.Structure):
@@ -240,7 +245,7 @@ class Plan(C.Structure):
         d["group_col_widths"] = list(self.group_col_widths[: self.num_group_cols])
         d["targets"] = [
             (t.is_agg, t.agg_kind, t.sql_type.type, t.sql_type.notnull, t.agg_arg_type.type,
-             t.agg_arg_type.notnull, t.skip_null_val, t.arg_col_id, t.first_slot)
+             t.agg_arg_type.notnull, t.skip_null_val, t.arg_col_id, t.first_slot, t.sql_type.scale, t.agg_arg_type.scale)
             for t in self.targets[: self.num_targets]
         ]
         return d
@@ -292,6 +297,7 @@ class _Node:
     dval: float = 0.0
     is_null: bool = False
     rte_idx: int = 0
+    scale: int = 0      # SQLTypeInfo::get_scale() of a DECIMAL / NUMERIC
 
 
 class UnitBuilder:
@@ -322,7 +328,8 @@ class UnitBuilder:
         t, nn = (self.inner if rte_idx else self.table).col_types[col_id]
         if rte_idx and self.join_type == 1:
             nn = False      # the inner side of a LEFT join is nullable (RelAlgTranslator marks it so)
-        self.nodes.append(_Node(EXPR_COLUMN_VAR, t, nn, col_id=col_id, rte_idx=rte_idx))
+        self.nodes.append(_Node(EXPR_COLUMN_VAR, t, nn, col_id=col_id, rte_idx=rte_idx,
+                                scale=(self.inner if rte_idx else self.table).col_scales.get(col_id, 0)))
         return len(self.nodes) - 1
 
     def join(self, inner: "Table", outer_col: int, inner_col: int, join_type: int = 0):
@@ -333,10 +340,12 @@ class UnitBuilder:
         self.join_qual = self.binop(kEQ, self.col(outer_col, 0), self.col(inner_col, 1))
         return self
 
-    def const(self, value, sql_type: Optional[int] = None, is_null: bool = False) -> int:
+    def const(self, value, sql_type: Optional[int] = None, is_null: bool = False, scale: int = 0) -> int:
+        """Constant.  A DECIMAL constant carries its Datum the way the analyzer folds it: bigintval = value * 10**scale
+        (pass the already scaled integer)."""
         if sql_type is None:
             sql_type = kDOUBLE if isinstance(value, float) else kBIGINT
-        n = _Node(EXPR_CONSTANT, sql_type, True, is_null=is_null)
+        n = _Node(EXPR_CONSTANT, sql_type, True, is_null=is_null, scale=scale)
         if sql_type == kDOUBLE:
             n.dval = float(value)
         else:
@@ -353,14 +362,15 @@ class UnitBuilder:
         self.nodes.append(_Node(EXPR_UOPER, kBOOLEAN, op == kISNULL, op=op, left=operand))
         return len(self.nodes) - 1
 
-    def cmp(self, col_id: int, op: int, value, const_type: Optional[int] = None, rte_idx: int = 0) -> int:
-        return self.binop(op, self.col(col_id, rte_idx), self.const(value, const_type))
+    def cmp(self, col_id: int, op: int, value, const_type: Optional[int] = None, rte_idx: int = 0, scale: int = 0) -> int:
+        return self.binop(op, self.col(col_id, rte_idx), self.const(value, const_type, scale=scale))
 
     def agg(self, kind: int, col_id: Optional[int] = None, bigint_count: bool = False, rte_idx: int = 0,
             is_distinct: bool = False) -> int:
         """AggExpr.  Result type as RelAlgTranslator assigns it: COUNT -> INT/BIGINT notnull... SUM(int) -> BIGINT,
         MIN/MAX -> arg type, AVG -> DOUBLE."""
         arg = -1
+        scale = 0
         if col_id is None:
             assert kind == kCOUNT
             ti = (kBIGINT if bigint_count else kINT, False)
@@ -372,12 +382,14 @@ class UnitBuilder:
             if kind == kCOUNT:
                 ti = (kBIGINT if bigint_count else kINT, False)
             elif kind == kSUM:
-                ti = (kDOUBLE if at == kDOUBLE else kBIGINT, ann)
+                ti = (at if at in DECIMAL_TYPES else kDOUBLE if at == kDOUBLE else kBIGINT, ann)   # SUM(DECIMAL) keeps type and scale
+                scale = self.nodes[arg].scale
             elif kind == kAVG:
                 ti = (kDOUBLE, ann)
             else:
                 ti = (at, ann)
-        self.nodes.append(_Node(EXPR_AGG, ti[0], ti[1], op=kind, left=arg, ival=int(is_distinct)))   # ival: AggExpr::get_is_distinct()
+                scale = self.nodes[arg].scale
+        self.nodes.append(_Node(EXPR_AGG, ti[0], ti[1], op=kind, left=arg, ival=int(is_distinct), scale=scale))   # ival: AggExpr::get_is_distinct()
         return len(self.nodes) - 1
 
     # -- unit lists ---------------------------------------------------------------------------------------
@@ -422,7 +434,7 @@ class BuiltUnit:
         for i, nd in enumerate(b.nodes):
             e = self.exprs[i]
             e.kind = nd.kind
-            e.ti = TypeInfo(nd.type, int(nd.notnull))
+            e.ti = TypeInfo(nd.type, int(nd.notnull), nd.scale)
             e.col_id, e.op, e.left, e.right = nd.col_id, nd.op, nd.left, nd.right
             e.ival, e.dval, e.is_null, e.rte_idx = nd.ival, nd.dval, int(nd.is_null), nd.rte_idx
 
@@ -501,12 +513,13 @@ class Table:
     """InputTableInfo mirror: column types + fragments (Fragmenter::FragmentInfo + chunk pointers + chunk stats)."""
 
     def __init__(self, col_types: Sequence[tuple], encoded_sizes: Optional[Sequence[int]] = None,
-                 deleted_column: Optional[int] = None):
+                 deleted_column: Optional[int] = None, col_scales: Optional[Dict[int, int]] = None):
         # col_types: [(sql_type, notnull), ...]; encoded_sizes[c] = physical bytes of an `ENCODING FIXED` column (0 = none),
         # or -4 / -2 for a DATE column under `ENCODING DAYS(32|16)` (kENCODING_DATE_IN_DAYS: the chunk holds days)
         self.col_types = [(int(t), bool(nn)) for t, nn in col_types]
         self.encoded_sizes = [int(x) for x in encoded_sizes] if encoded_sizes is not None else [0] * len(self.col_types)
         self.deleted_column = deleted_column
+        self.col_scales: Dict[int, int] = dict(col_scales or {})   # DECIMAL / NUMERIC columns: column index -> scale
         self.fragments: List[Fragment] = []
 
     def physical_dtype(self, c: int):
@@ -587,7 +600,7 @@ class BuiltTable:
     def __init__(self, t: Table, memory_level: int):
         self.src = t
         nc = t.num_cols
-        self.col_types = (TypeInfo * nc)(*[TypeInfo(ty, int(nn)) for ty, nn in t.col_types])
+        self.col_types = (TypeInfo * nc)(*[TypeInfo(ty, int(nn), t.col_scales.get(c, 0)) for c, (ty, nn) in enumerate(t.col_types)])
         nf = len(t.fragments)
         self.frags = (FragmentInfo * max(nf, 1))()
         self._keep = []

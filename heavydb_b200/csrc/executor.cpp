@@ -996,16 +996,16 @@ size_t b2q_rs_row_count(const B2QResultSet* rs) { /* ResultSet::rowCountImpl (Re
 }
 int32_t b2q_rs_is_empty(const B2QResultSet* rs) { return b2q_rs_row_count(rs) == 0; }
 B2QTypeInfo b2q_rs_get_col_type(const B2QResultSet* rs, size_t col) {
-  if (!rs || col >= static_cast<size_t>(rs->q.plan.num_targets)) return B2QTypeInfo{0, 0}; /* kNULLT */
+  if (!rs || col >= static_cast<size_t>(rs->q.plan.num_targets)) return B2QTypeInfo{0, 0, 0}; /* kNULLT */
   const B2QTargetInfo& t = rs->q.plan.targets[col];
-  if (t.is_agg && t.agg_kind == B2Q_kAVG) return B2QTypeInfo{B2Q_kDOUBLE, 0};
+  if (t.is_agg && t.agg_kind == B2Q_kAVG) return B2QTypeInfo{B2Q_kDOUBLE, 0, 0};
   return t.sql_type;
 }
 void b2q_rs_move_to_begin(B2QResultSet* rs) { if (rs) { rs->cursor = 0; rs->fetched = 0; } }
 
-static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* row);
+static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* row, bool decimal_to_double);
 
-int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
+int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row, int32_t /*translate_strings: results carry ids*/, int32_t decimal_to_double) {
   if (!rs || !row || rs->q.plan.query_desc_type == B2Q_Estimator) return 0;
   /* getNextRowImpl + advanceCursorToNextEntry (ResultSetIteration.cpp:320-340, :731-750) */
   const int64_t n_entries = static_cast<int64_t>(b2q_rs_entry_count(rs));
@@ -1018,12 +1018,15 @@ int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row) {
     ++rs->cursor;
     ++rs->fetched;
   } while (rs->drop_first && rs->fetched <= rs->drop_first);
-  read_entry(rs, entry, row);
+  read_entry(rs, entry, row, decimal_to_double != 0);
   return 1;
 }
 
 /* getRowAt / getTargetValueFromBufferRowwise|Colwise (ResultSetIteration.cpp:820-1000) for one storage entry */
-static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* row) {
+static bool is_decimal(int t) { return t == B2Q_kDECIMAL || t == B2Q_kNUMERIC; }
+static double exp_to_scale(int scale) { double d = 1; for (int i = 0; i < scale; ++i) d *= 10; return d; }
+
+static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* row, bool decimal_to_double) {
   const B2QPlan& p = rs->q.plan;
   for (int i = 0; i < p.num_targets; ++i) {
     const B2QTargetInfo& t = p.targets[i];
@@ -1046,7 +1049,9 @@ static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* ro
       else {
         double dividend;
         if (t.sql_type.type == B2Q_kDOUBLE) memcpy(&dividend, &ival, 8); else dividend = static_cast<double>(ival);
-        o.dval = dividend / static_cast<double>(cnt);
+        /* DECIMAL: one division by count x 10^scale, ResultSetBufferAccessors.h:222-225 */
+        o.dval = is_decimal(t.sql_type.type) && t.sql_type.scale ? dividend / (static_cast<double>(cnt) * exp_to_scale(t.sql_type.scale))
+                                                                 : dividend / static_cast<double>(cnt);
         o.is_null = o.dval == DBL_MIN;
       }
       continue;
@@ -1055,6 +1060,16 @@ static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* ro
       o.is_fp = 1;
       memcpy(&o.dval, &ival, 8);
       o.is_null = o.dval == DBL_MIN;
+      continue;
+    }
+    if (is_decimal(compact_type)) { /* makeTargetValue, ResultSetIteration.cpp:2193-2210 */
+      const B2QTypeInfo& ct = compact_type == t.sql_type.type ? t.sql_type : t.agg_arg_type;
+      const bool agg_null = t.is_agg && (t.agg_kind == B2Q_kSUM || t.agg_kind == B2Q_kMIN || t.agg_kind == B2Q_kMAX);
+      o.is_null = ival == INT64_MIN && (agg_null || !ct.notnull);
+      if (decimal_to_double) {
+        o.is_fp = 1;
+        o.dval = o.is_null ? DBL_MIN : static_cast<double>(ival) / exp_to_scale(ct.scale);
+      } else o.ival = ival;
       continue;
     }
     int64_t resized = ival;
@@ -1107,7 +1122,7 @@ int32_t b2q_columnar_results_create(const B2QResultSet* rs, int32_t num_threads,
   auto convert = [&](size_t lo, size_t hi) {
     B2QTargetValue row[B2Q_MAX_TARGETS];
     for (size_t r = lo; r < hi; ++r) {
-      read_entry(rs, entries[first + r], row);
+      read_entry(rs, entries[first + r], row, false); /* decimals stay scaled int64 (ColumnarResults.cpp:155,550 getRowAtNoTranslations / getNextRow(false, false)) */
       for (int c = 0; c < nt; ++c) {
         int8_t* dst = cr->cols[c].data() + r * width[c];
         if (row[c].is_fp) { memcpy(dst, &row[c].dval, 8); continue; }

@@ -40,11 +40,15 @@ namespace {
 struct SqlType {
   int32_t type = 0;
   bool notnull = false;
+  int32_t scale = 0; /* SQLTypeInfo::get_scale() of a DECIMAL / NUMERIC */
   bool is_string() const { return type == B2Q_kTEXT || type == B2Q_kVARCHAR || type == B2Q_kCHAR; } /* dictionary ids */
   bool is_time() const { return type == B2Q_kTIME || type == B2Q_kTIMESTAMP || type == B2Q_kDATE; }
   /* everything the path handles as an integer: dictionary ids are int32 (is_int_and_no_bigger_than(ti, 4) ||
    * dict string, QueryMemoryDescriptor.cpp:803-804), time types int64 (sqltypes.h is_time()) */
-  bool is_int() const { return type == B2Q_kTINYINT || type == B2Q_kSMALLINT || type == B2Q_kINT || type == B2Q_kBIGINT || is_string() || is_time(); }
+  /* DECIMAL / NUMERIC: value x 10^scale as int64; every decision that is not is_fp() treats it like BIGINT, the scale only
+   * matters at read-out (makeTargetValue, pair_to_double) */
+  bool is_decimal() const { return type == B2Q_kDECIMAL || type == B2Q_kNUMERIC; }
+  bool is_int() const { return type == B2Q_kTINYINT || type == B2Q_kSMALLINT || type == B2Q_kINT || type == B2Q_kBIGINT || is_string() || is_time() || is_decimal(); }
   bool is_number() const { return is_int() && !is_string() && !is_time(); }
   bool is_fp() const { return type == B2Q_kDOUBLE; }
   int size() const { /* logical size */
@@ -52,7 +56,7 @@ struct SqlType {
       case B2Q_kTINYINT: return 1;
       case B2Q_kSMALLINT: return 2;
       case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4;
-      case B2Q_kBIGINT: case B2Q_kDOUBLE: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: return 8;
+      case B2Q_kBIGINT: case B2Q_kDOUBLE: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: case B2Q_kDECIMAL: case B2Q_kNUMERIC: return 8;
       default: return -1;
     }
   }
@@ -65,8 +69,8 @@ struct SqlType {
     }
   }
 };
-SqlType from_abi(const B2QTypeInfo& t) { return SqlType{t.type, t.notnull != 0}; }
-B2QTypeInfo to_abi(const SqlType& t) { return B2QTypeInfo{t.type, t.notnull ? 1 : 0}; }
+SqlType from_abi(const B2QTypeInfo& t) { return SqlType{t.type, t.notnull != 0, t.scale}; }
+B2QTypeInfo to_abi(const SqlType& t) { return B2QTypeInfo{t.type, t.notnull ? 1 : 0, t.scale}; }
 
 int64_t dbl_bits(double d) { int64_t b; memcpy(&b, &d, 8); return b; }
 double bits_dbl(int64_t b) { double d; memcpy(&d, &b, 8); return d; }
@@ -166,6 +170,7 @@ class Planner {
     const SqlType ot = col_type(join_outer_col_), it = col_type(n_outer_ + join_inner_col_);
     if (!ot.is_int() || !it.is_int() || ot.is_string() || it.is_string())
       reject(B2Q_ERR_UNSUPPORTED, "join keys must be integer columns (dictionary translation is outside this path)");
+    if (ot.is_decimal() || it.is_decimal()) reject(B2Q_ERR_UNSUPPORTED, "DECIMAL join keys are outside this path");
     if (is_days(join_outer_col_) || is_days(n_outer_ + join_inner_col_)) reject(B2Q_ERR_UNSUPPORTED, "days-encoded DATE join keys are outside this path");
     /* getExpressionRange(inner_col): over the inner table alone (getLeafColumnRange, ExpressionRange.cpp:521-632) */
     ColRange r;
@@ -261,6 +266,13 @@ class Planner {
       const B2QExpr& e = u_.exprs[i];
       if (e.left < -1 || e.left >= i || e.right < -1 || e.right >= i)
         reject(B2Q_ERR_INVALID_ARGUMENT, "expression operands must be earlier nodes of the array (or -1)");
+      /* a DECIMAL compares as its scaled integer, so both sides must be DECIMALs of one scale — what the analyzer leaves
+       * when the common type is the column's (constants are folded to it); otherwise it wraps the column in a CAST */
+      if (e.kind == B2Q_EXPR_BIN_OPER && e.op != B2Q_kAND && e.op != B2Q_kOR && e.left >= 0 && e.right >= 0) {
+        const SqlType a = from_abi(u_.exprs[e.left].ti), b = from_abi(u_.exprs[e.right].ti);
+        if ((a.is_decimal() || b.is_decimal()) && !(a.is_decimal() && b.is_decimal() && a.scale == b.scale))
+          reject(B2Q_ERR_UNSUPPORTED, "DECIMAL compared with a value of another type / scale needs the analyzer's cast");
+      }
     }
     if (u_.num_groupby_exprs > B2Q_MAX_GROUP_COLS) reject(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
     if (u_.num_groupby_exprs < 0 || (u_.num_target_exprs <= 0 && !u_.has_estimator) || u_.num_target_exprs > B2Q_MAX_TARGETS)
@@ -320,7 +332,8 @@ class Planner {
            * MIN / MAX of a dictionary string would need dictionary order */
           if (d.arg_type.is_string() && e.op != B2Q_kCOUNT) reject(B2Q_ERR_UNSUPPORTED, "only COUNT of a dictionary-encoded string is on this path");
           if (d.arg_type.is_time() && (e.op == B2Q_kSUM || e.op == B2Q_kAVG)) reject(B2Q_ERR_UNSUPPORTED, "SUM / AVG of a TIME / TIMESTAMP / DATE");
-          if (e.op == B2Q_kAVG) d.sql_type = d.arg_type.is_int() ? SqlType{B2Q_kBIGINT, d.arg_type.notnull} : d.arg_type;
+          /* SQLTypeInfo::is_integer() is false for a DECIMAL: its AVG keeps type and scale (TargetInfo.cpp:57-67) for pair_to_double */
+          if (e.op == B2Q_kAVG) d.sql_type = (d.arg_type.is_int() && !d.arg_type.is_decimal()) ? SqlType{B2Q_kBIGINT, d.arg_type.notnull} : d.arg_type;
           else if (e.op == B2Q_kCOUNT) d.sql_type = SqlType{bigint_count ? B2Q_kBIGINT : B2Q_kINT, e.ti.notnull != 0};
           else d.sql_type = from_abi(e.ti);
         }

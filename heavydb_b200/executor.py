@@ -94,7 +94,7 @@ def lib():
         L.b2q_rs_get_col_type.restype = abi.TypeInfo
         L.b2q_rs_get_col_type.argtypes = [C.c_void_p, C.c_size_t]
         L.b2q_rs_get_next_row.restype = C.c_int32
-        L.b2q_rs_get_next_row.argtypes = [C.c_void_p, C.POINTER(abi.TargetValue)]
+        L.b2q_rs_get_next_row.argtypes = [C.c_void_p, C.POINTER(abi.TargetValue), C.c_int32, C.c_int32]
         L.b2q_rs_move_to_begin.argtypes = [C.c_void_p]
         L.b2q_rs_is_row_at_empty.restype = C.c_int32
         L.b2q_rs_is_row_at_empty.argtypes = [C.c_void_p, C.c_size_t]
@@ -189,7 +189,7 @@ class ResultSet:
 
     def getColType(self, i: int):
         t = lib().b2q_rs_get_col_type(self._h, i)
-        return (t.type, t.notnull)
+        return (t.type, t.notnull, t.scale)
 
     def moveToBegin(self):
         lib().b2q_rs_move_to_begin(self._h)
@@ -197,17 +197,17 @@ class ResultSet:
     def getNextRow(self, translate_strings: bool = True, decimal_to_double: bool = True):
         nc = self.colCount()
         row = (abi.TargetValue * nc)()
-        if not lib().b2q_rs_get_next_row(self._h, row):
+        if not lib().b2q_rs_get_next_row(self._h, row, int(translate_strings), int(decimal_to_double)):
             return []
         return [v.py() for v in row]
 
-    def rows(self) -> List[tuple]:
+    def rows(self, decimal_to_double: bool = True) -> List[tuple]:
         self.moveToBegin()
         L = lib()
         nc = self.colCount()
         row = (abi.TargetValue * nc)()
         out = []
-        while L.b2q_rs_get_next_row(self._h, row):
+        while L.b2q_rs_get_next_row(self._h, row, 0, int(decimal_to_double)):
             out.append(tuple(v.py() for v in row))
         return out
 

@@ -90,6 +90,16 @@ class _P:
         return e
 
     def literal_cmp(self, col, op, lit, rte=0):
+        tbl = self.b.inner if rte else self.b.table
+        if tbl.col_types[col][0] in abi.DECIMAL_TYPES:
+            # the analyzer folds the literal to the common DECIMAL type: same scale as the column when the literal has no
+            # more fraction digits than the column (Constant::do_cast); otherwise the COLUMN would be cast — not this path
+            import decimal
+            scale = tbl.col_scales.get(col, 0)
+            v = decimal.Decimal(lit).scaleb(scale)
+            if v != v.to_integral_value():
+                raise ValueError(f"literal {lit} has more fraction digits than DECIMAL scale {scale}")
+            return self.b.cmp(col, op, int(v), tbl.col_types[col][0], rte, scale=scale)
         if re.fullmatch(r"-?\d+", lit):
             return self.b.cmp(col, op, int(lit), abi.kBIGINT, rte)
         return self.b.cmp(col, op, float(lit), abi.kDOUBLE, rte)

@@ -37,9 +37,10 @@
 extern "C" {
 #endif
 
-#define B2Q_ABI_VERSION 3 /* 2: sort_info, join level, rte_idx, columnar, dictionary / time types, B2QPlan join fields;
+#define B2Q_ABI_VERSION 4 /* 2: sort_info, join level, rte_idx, columnar, dictionary / time types, B2QPlan join fields;
                             3: DATE_IN_DAYS chunks (negative col_encoded_sizes), column-vs-column quals, 16 filter leaves,
-                               operands-before-node rule, b2q_columnar_results_*, host-phase stats */
+                               operands-before-node rule, b2q_columnar_results_*, host-phase stats;
+                            4: DECIMAL / NUMERIC columns (B2QTypeInfo.scale), decimal_to_double of b2q_rs_get_next_row */
 
 /* ---- SQLTypes subset (Shared/sqltypes.h:65-99) -------------------------------------------------------- */
 enum {
@@ -50,6 +51,12 @@ enum {
    * in `=` / `<>` against an id constant; results carry ids (getNextRow with translate_strings = false). */
   B2Q_kCHAR = 2,
   B2Q_kVARCHAR = 3,
+  /* NUMERIC / DECIMAL(p, s): the chunk holds value x 10^s as int64, or int32 / int16 under the ENCODING FIXED the DDL
+   * picks for p <= 9 / p <= 4 (col_encoded_sizes = 4 | 2); an integer to everything on the path (keys, quals against a
+   * constant / column of the SAME scale, COUNT / SUM / MIN / MAX / AVG); the scale is applied at read-out only
+   * (makeTargetValue ResultSetIteration.cpp:2193-2210, pair_to_double ResultSetBufferAccessors.h:222-225) */
+  B2Q_kNUMERIC = 4,
+  B2Q_kDECIMAL = 5,
   B2Q_kINT = 6,
   B2Q_kSMALLINT = 7,
   B2Q_kFLOAT = 8,
@@ -104,6 +111,7 @@ enum {
 typedef struct B2QTypeInfo {
   int32_t type;    /* B2Q_k* SQLTypes value */
   int32_t notnull; /* SQLTypeInfo::get_notnull() */
+  int32_t scale;   /* SQLTypeInfo::get_scale(): digits after the point of a DECIMAL / NUMERIC (0 for every other type) */
 } B2QTypeInfo;
 
 /* ---- Analyzer::Expr subset (Analyzer/Analyzer.h:193 ColumnVar, :319 Constant, :434 BinOper, :1381 AggExpr)
@@ -399,8 +407,10 @@ size_t b2q_rs_entry_count(const B2QResultSet* rs); /* ResultSet::entryCount() */
 int32_t b2q_rs_is_empty(const B2QResultSet* rs);   /* ResultSet::isEmpty() */
 B2QTypeInfo b2q_rs_get_col_type(const B2QResultSet* rs, size_t col_idx); /* ResultSet::getColType() */
 /* ResultSet::getNextRow(translate_strings, decimal_to_double) :259 — returns 1 and fills row[colCount()],
- * or 0 at the end.  b2q_rs_move_to_begin() == ResultSet::moveToBegin(). */
-int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row);
+ * or 0 at the end.  Dictionary strings always come back as ids (translate_strings is accepted and ignored); a DECIMAL
+ * target is a double (value / 10^scale, NULL_DOUBLE for NULL) under decimal_to_double, else the scaled int64.
+ * b2q_rs_move_to_begin() == ResultSet::moveToBegin(). */
+int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row, int32_t translate_strings, int32_t decimal_to_double);
 
 /* ColumnarResults (QueryEngine/ColumnarResults.h:60-232, .cpp:256-392): the rows of a result set, in iteration order
  * (ResultSet::sort permutation, OFFSET, LIMIT applied), as one contiguous array per target in the target type's own

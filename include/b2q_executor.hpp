@@ -27,7 +27,7 @@
 namespace b2q {
 
 /* ---- SQLTypeInfo / enums: the reference's own values ---- */
-enum SQLTypes { kBOOLEAN = B2Q_kBOOLEAN /* the $deleted$ column only */, kCHAR = B2Q_kCHAR, kVARCHAR = B2Q_kVARCHAR, kINT = B2Q_kINT, kSMALLINT = B2Q_kSMALLINT, kDOUBLE = B2Q_kDOUBLE,
+enum SQLTypes { kBOOLEAN = B2Q_kBOOLEAN /* the $deleted$ column only */, kCHAR = B2Q_kCHAR, kVARCHAR = B2Q_kVARCHAR, kNUMERIC = B2Q_kNUMERIC, kDECIMAL = B2Q_kDECIMAL, kINT = B2Q_kINT, kSMALLINT = B2Q_kSMALLINT, kDOUBLE = B2Q_kDOUBLE,
                 kTIME = B2Q_kTIME, kTIMESTAMP = B2Q_kTIMESTAMP, kBIGINT = B2Q_kBIGINT, kTEXT = B2Q_kTEXT /* dictionary-encoded */,
                 kDATE = B2Q_kDATE, kTINYINT = B2Q_kTINYINT };
 enum SQLOps { kEQ = B2Q_kEQ, kNE = B2Q_kNE, kLT = B2Q_kLT, kGT = B2Q_kGT, kLE = B2Q_kLE, kGE = B2Q_kGE, kAND = B2Q_kAND, kOR = B2Q_kOR,
@@ -43,11 +43,18 @@ struct SQLTypeInfo {
   bool notnull{false};
   EncodingType compression{kENCODING_NONE};
   int comp_param{0}; /* bits for kENCODING_FIXED / kENCODING_DATE_IN_DAYS / DICT(8|16); the dictionary id otherwise */
+  int dimension{0};  /* precision of a DECIMAL / NUMERIC (informational on this path) */
+  int scale{0};      /* digits after the point of a DECIMAL / NUMERIC */
   SQLTypeInfo() = default;
+  SQLTypeInfo(SQLTypes t, int d, int s, bool nn) : type(t), notnull(nn), dimension(d), scale(s) {} /* SQLTypeInfo(kDECIMAL, 10, 4, false) */
   SQLTypeInfo(SQLTypes t, bool nn) : type(t), notnull(nn) {}
   SQLTypeInfo(SQLTypes t, bool nn, EncodingType c, int p) : type(t), notnull(nn), compression(c), comp_param(p) {}
   SQLTypes get_type() const { return type; }
   bool get_notnull() const { return notnull; }
+  int get_dimension() const { return dimension; }
+  int get_scale() const { return scale; }
+  bool is_decimal() const { return type == kDECIMAL || type == kNUMERIC; }
+  B2QTypeInfo pod() const { return B2QTypeInfo{type, notnull ? 1 : 0, scale}; }
   EncodingType get_compression() const { return compression; }
   int get_comp_param() const { return comp_param; }
   /* B2QTableInfo.col_encoded_sizes entry: physical bytes under FIXED / DICT(8|16), minus the bytes under
@@ -99,7 +106,7 @@ struct RelAlgExecutionUnit { /* RelAlgExecutionUnit.h:166-216 */
 
   ExprRef makeColumnVar(const SQLTypeInfo& ti, int32_t column_id, int32_t rte_idx = 0) { /* Analyzer::ColumnVar(ti, column_key, rte_idx) */
     B2QExpr e{};
-    e.kind = B2Q_EXPR_COLUMN_VAR; e.ti = {ti.type, ti.notnull}; e.col_id = column_id; e.left = e.right = -1; e.rte_idx = rte_idx;
+    e.kind = B2Q_EXPR_COLUMN_VAR; e.ti = ti.pod(); e.col_id = column_id; e.left = e.right = -1; e.rte_idx = rte_idx;
     exprs.push_back(e);
     return static_cast<ExprRef>(exprs.size() - 1);
   }
@@ -111,7 +118,7 @@ struct RelAlgExecutionUnit { /* RelAlgExecutionUnit.h:166-216 */
   }
   ExprRef makeConstant(const SQLTypeInfo& ti, int64_t v) { /* Analyzer::Constant(ti, false, Datum) of an integer / time type */
     B2QExpr e{};
-    e.kind = B2Q_EXPR_CONSTANT; e.ti = {ti.type, ti.notnull}; e.ival = v; e.left = e.right = -1;
+    e.kind = B2Q_EXPR_CONSTANT; e.ti = ti.pod(); e.ival = v; /* DECIMAL: Datum.bigintval = value x 10^scale */ e.left = e.right = -1;
     exprs.push_back(e);
     return static_cast<ExprRef>(exprs.size() - 1);
   }
@@ -135,7 +142,7 @@ struct RelAlgExecutionUnit { /* RelAlgExecutionUnit.h:166-216 */
   }
   ExprRef makeAggExpr(const SQLTypeInfo& ti, SQLAgg agg, ExprRef arg /* -1 = COUNT(*) */, bool is_distinct = false) { /* Analyzer::AggExpr(ti, agg, arg, is_distinct, ...) */
     B2QExpr e{};
-    e.kind = B2Q_EXPR_AGG; e.ti = {ti.type, ti.notnull}; e.op = agg; e.left = arg; e.right = -1; e.ival = is_distinct ? 1 : 0;
+    e.kind = B2Q_EXPR_AGG; e.ti = ti.pod(); e.op = agg; e.left = arg; e.right = -1; e.ival = is_distinct ? 1 : 0;
     exprs.push_back(e);
     return static_cast<ExprRef>(exprs.size() - 1);
   }
@@ -186,11 +193,11 @@ class ResultSet {
   size_t entryCount() const { return b2q_rs_entry_count(h_); }
   bool isEmpty() const { return b2q_rs_is_empty(h_) != 0; }
   bool definitelyHasNoRows() const { return isEmpty(); }
-  SQLTypeInfo getColType(size_t i) const { auto t = b2q_rs_get_col_type(h_, i); return SQLTypeInfo(static_cast<SQLTypes>(t.type), t.notnull != 0); }
+  SQLTypeInfo getColType(size_t i) const { auto t = b2q_rs_get_col_type(h_, i); SQLTypeInfo r(static_cast<SQLTypes>(t.type), t.notnull != 0); r.scale = t.scale; return r; }
   void moveToBegin() const { b2q_rs_move_to_begin(h_); }
-  std::vector<TargetValue> getNextRow(const bool /*translate_strings*/, const bool /*decimal_to_double*/) const {
+  std::vector<TargetValue> getNextRow(const bool translate_strings, const bool decimal_to_double) const {
     std::vector<TargetValue> row(colCount());
-    if (!b2q_rs_get_next_row(h_, row.data())) row.clear();
+    if (!b2q_rs_get_next_row(h_, row.data(), translate_strings, decimal_to_double)) row.clear();
     return row;
   }
   bool isRowAtEmpty(size_t i) const { return b2q_rs_is_row_at_empty(h_, i) != 0; }
@@ -225,6 +232,7 @@ class ColumnarResults {
       B2QTypeInfo ti;
       column_buffers_.push_back(b2q_columnar_results_column(h_, c, &ti));
       target_types_.emplace_back(static_cast<SQLTypes>(ti.type), ti.notnull != 0);
+      target_types_.back().scale = ti.scale;
     }
   }
   ~ColumnarResults() { b2q_columnar_results_free(h_); }
@@ -257,7 +265,7 @@ class Executor {
       void fill(const InputTableInfo& ti) {
         bool any_enc = false;
         for (const auto& t : ti.col_types) {
-          col_types.push_back({t.type, t.notnull});
+          col_types.push_back(t.pod());
           enc.push_back(t.encoded_size());
           any_enc |= enc.back() != 0;
         }

@@ -59,20 +59,24 @@ constexpr int32_t kEmptyKey32 = std::numeric_limits<int32_t>::max();
 struct Ti {
   int type{0};
   bool notnull{false};
+  int scale{0}; /* SQLTypeInfo::get_scale() of a DECIMAL / NUMERIC */
 };
 
 /* dictionary-encoded strings are int32 ids on this path (sqltypes.h is_dict_encoded_string; treated like
  * is_int_and_no_bigger_than(ti, 4) by QueryMemoryDescriptor.cpp:803-804), TIME / TIMESTAMP / DATE are int64 (is_time()) */
 bool is_string(int t) { return t == B2Q_kTEXT || t == B2Q_kVARCHAR || t == B2Q_kCHAR; }
 bool is_time(int t) { return t == B2Q_kTIME || t == B2Q_kTIMESTAMP || t == B2Q_kDATE; }
-bool is_integer(int t) { return t == B2Q_kTINYINT || t == B2Q_kSMALLINT || t == B2Q_kINT || t == B2Q_kBIGINT || is_string(t) || is_time(t); }
+/* DECIMAL / NUMERIC: value x 10^scale as int64 (sqltypes.h is_decimal(); every branch of the planner and of the row
+ * function that is not is_fp() treats it like BIGINT; the scale only matters at read-out) */
+bool is_decimal(int t) { return t == B2Q_kDECIMAL || t == B2Q_kNUMERIC; }
+bool is_integer(int t) { return t == B2Q_kTINYINT || t == B2Q_kSMALLINT || t == B2Q_kINT || t == B2Q_kBIGINT || is_string(t) || is_time(t) || is_decimal(t); }
 bool is_fp(int t) { return t == B2Q_kDOUBLE; }
 int type_size(int t) { /* SQLTypeInfo::get_size() for the fixed-width subset */
   switch (t) {
     case B2Q_kTINYINT: return 1;
     case B2Q_kSMALLINT: return 2;
     case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4; /* logical size of a dictionary id */
-    case B2Q_kBIGINT: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: return 8;
+    case B2Q_kBIGINT: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: case B2Q_kDECIMAL: case B2Q_kNUMERIC: return 8;
     case B2Q_kDOUBLE: return 8;
     default: return -1;
   }
@@ -82,9 +86,14 @@ int64_t inline_int_null_val(int t) { /* Shared/InlineNullValues.h inline_int_nul
     case B2Q_kTINYINT: return kNullTinyint;
     case B2Q_kSMALLINT: return kNullSmallint;
     case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return kNullInt;
-    case B2Q_kBIGINT: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: return kNullBigint;
+    case B2Q_kBIGINT: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: case B2Q_kDECIMAL: case B2Q_kNUMERIC: return kNullBigint;
     default: abort();
   }
+}
+double exp_to_scale(int scale) { /* Shared/sqltypes.h exp_to_scale */
+  double d = 1;
+  for (int i = 0; i < scale; ++i) d *= 10;
+  return d;
 }
 int64_t bits_of(double d) {
   int64_t r;
@@ -390,7 +399,7 @@ const B2QExpr& expr_at(const B2QExecUnit& u, int idx) {
   if (idx < 0 || idx >= u.num_exprs) fail(B2Q_ERR_INVALID_ARGUMENT, "expr index out of range");
   return u.exprs[idx];
 }
-Ti ti_of(const B2QTypeInfo& t) { return Ti{t.type, t.notnull != 0}; }
+Ti ti_of(const B2QTypeInfo& t) { return Ti{t.type, t.notnull != 0, t.scale}; }
 
 /* Shared/TargetInfo.cpp:25-78 get_target_info_impl */
 Target get_target_info(const B2QExecUnit& u, int expr_idx, bool bigint_count) {
@@ -426,7 +435,7 @@ Target get_target_info(const B2QExecUnit& u, int expr_idx, bool bigint_count) {
   if (is_string(arg_ti.type) && e.op != B2Q_kCOUNT) fail(B2Q_ERR_UNSUPPORTED, "only COUNT of a dictionary-encoded string is on this path");
   if (is_time(arg_ti.type) && (e.op == B2Q_kSUM || e.op == B2Q_kAVG)) fail(B2Q_ERR_UNSUPPORTED, "SUM / AVG of a TIME / TIMESTAMP / DATE");
   if (e.op == B2Q_kAVG) {
-    t.sql_type = is_integer(arg_ti.type) ? Ti{B2Q_kBIGINT, arg_ti.notnull} : arg_ti;
+    t.sql_type = (is_integer(arg_ti.type) && !is_decimal(arg_ti.type)) ? Ti{B2Q_kBIGINT, arg_ti.notnull} : arg_ti; /* SQLTypeInfo::is_integer() is false for a DECIMAL: AVG keeps the scale for pair_to_double */
     t.agg_arg_type = arg_ti;
     t.skip_null_val = !arg_ti.notnull;
     return t;
@@ -661,6 +670,16 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
   if (u.offset < 0 || (u.has_limit && u.limit < 0)) fail(B2Q_ERR_INVALID_ARGUMENT, "negative LIMIT / OFFSET");
   for (int i = 0; i < u.num_order_entries; ++i) /* ResultSet::sort orders dictionary strings through the dictionary (ResultSet.cpp:1431-1446) */
     if (is_string(expr_at(u, u.target_exprs[u.order_entries[i].tle_no - 1]).ti.type)) fail(B2Q_ERR_UNSUPPORTED, "ORDER BY a dictionary-encoded string needs the dictionary");
+  /* a DECIMAL compares as its scaled integer: both sides must already be at one scale, which is what the analyzer's
+   * common_numeric_type + folded constant casts leave when the types agree (Analyzer.cpp BinOper::normalize); anything
+   * else reaches the executor as a CAST node, which is outside this path */
+  for (int i = 0; i < u.num_exprs; ++i) {
+    const B2QExpr& e = u.exprs[i];
+    if (e.kind != B2Q_EXPR_BIN_OPER || e.op == B2Q_kAND || e.op == B2Q_kOR || e.left < 0 || e.right < 0 || e.left >= u.num_exprs || e.right >= u.num_exprs) continue;
+    const B2QTypeInfo& a = u.exprs[e.left].ti, &b = u.exprs[e.right].ti;
+    if ((is_decimal(a.type) || is_decimal(b.type)) && !(is_decimal(a.type) && is_decimal(b.type) && a.scale == b.scale))
+      fail(B2Q_ERR_UNSUPPORTED, "DECIMAL compared with a value of another type / scale needs the analyzer's cast");
+  }
   if (u.num_groupby_exprs > B2Q_MAX_GROUP_COLS) fail(B2Q_ERR_UNSUPPORTED, "more GROUP BY columns than the path carries");
   if (u.num_target_exprs <= 0 || u.num_target_exprs > B2Q_MAX_TARGETS)
     fail(B2Q_ERR_INVALID_ARGUMENT, "bad target count");
@@ -955,8 +974,8 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
     if (t.arg_col >= 0 && t.is_agg && p.query_desc_type == B2Q_NonGroupedAggregate) t.skip_null_val = true;
     B2QTargetInfo& o = p.targets[i];
     o.is_agg = t.is_agg; o.agg_kind = t.agg_kind;
-    o.sql_type = B2QTypeInfo{t.sql_type.type, t.sql_type.notnull};
-    o.agg_arg_type = B2QTypeInfo{t.agg_arg_type.type, t.agg_arg_type.notnull};
+    o.sql_type = B2QTypeInfo{t.sql_type.type, t.sql_type.notnull, t.sql_type.scale};
+    o.agg_arg_type = B2QTypeInfo{t.agg_arg_type.type, t.agg_arg_type.notnull, t.agg_arg_type.scale};
     o.skip_null_val = t.skip_null_val; o.is_distinct = 0; o.arg_col_id = t.arg_col; o.first_slot = t.first_slot;
   }
   p.kernel = 0;
@@ -1065,6 +1084,7 @@ Plan make_plan(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QExecution
   const Ti oti = ti_of(ji.t.col_types[ji.outer_col]), iti = ti_of(ji.t.col_types[ji.inner_vcol]);
   if (!is_integer(oti.type) || !is_integer(iti.type) || is_string(oti.type) || is_string(iti.type))
     fail(B2Q_ERR_UNSUPPORTED, "join keys must be integer columns (dictionary translation is outside this path)");
+  if (is_decimal(oti.type) || is_decimal(iti.type)) fail(B2Q_ERR_UNSUPPORTED, "DECIMAL join keys are outside this path");
   if (is_date_in_days(ji.t, ji.outer_col) || is_date_in_days(ji.t, ji.inner_vcol)) fail(B2Q_ERR_UNSUPPORTED, "days-encoded DATE join keys are outside the product path");
   Plan plan = make_plan_single(ji.u, ji.t, eo, max_groups_buffer_entry_guess, has_cardinality_estimation);
   const B2QTableInfo& inner = *u.inner_table;
@@ -1599,7 +1619,9 @@ struct ResultSetComparator {
   }
   static double pair_to_double(const Val& v, const Target& t) { /* ResultSetBufferAccessors.h:197-227 */
     if (!v.i2) return kNullDouble;
-    return (is_fp(t.sql_type.type) ? double_of(v.i1) : static_cast<double>(v.i1)) / static_cast<double>(v.i2);
+    const double dividend = is_fp(t.sql_type.type) ? double_of(v.i1) : static_cast<double>(v.i1);
+    return is_decimal(t.sql_type.type) && t.sql_type.scale ? dividend / (static_cast<double>(v.i2) * exp_to_scale(t.sql_type.scale)) /* :222-225 */
+                                                           : dividend / static_cast<double>(v.i2);
   }
   bool operator()(uint32_t lhs, uint32_t rhs) const {
     for (const B2QOrderEntry& oe : order_entries) {
@@ -1773,13 +1795,13 @@ ORACLE_EXPORT void oracle_result_free(OracleResult* r) { delete r; }
 /* ResultSet::getColType: AVG targets read out as DOUBLE (ResultSet.cpp getColType) */
 ORACLE_EXPORT B2QTypeInfo oracle_result_col_type(const OracleResult* r, size_t col) {
   const Target& t = r->plan.targets[col];
-  if (t.is_agg && t.agg_kind == B2Q_kAVG) return B2QTypeInfo{B2Q_kDOUBLE, 0};
-  return B2QTypeInfo{t.sql_type.type, t.sql_type.notnull};
+  if (t.is_agg && t.agg_kind == B2Q_kAVG) return B2QTypeInfo{B2Q_kDOUBLE, 0, 0};
+  return B2QTypeInfo{t.sql_type.type, t.sql_type.notnull, t.sql_type.scale};
 }
 
 /* ResultSet::getNextRow -> getTargetValueFromBufferRowwise -> makeTargetValue (ResultSetIteration.cpp:2086-2220),
  * AVG via make_avg_target_value (:43-82) + pair_to_double (ResultSetBufferAccessors.h:197-227). */
-ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue* row) {
+ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue* row, int32_t decimal_to_double) {
   const B2QPlan& p = r->plan.p;
   if (p.query_desc_type == B2Q_Estimator) return 0;
   /* getNextRowImpl + advanceCursorToNextEntry (ResultSetIteration.cpp:320-340, :731-750) */
@@ -1818,7 +1840,8 @@ ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue
       if (cnt == 0) { o.dval = kNullDouble; o.is_null = 1; }
       else {
         const double dividend = is_fp(t.sql_type.type) ? double_of(ival) : static_cast<double>(ival);
-        o.dval = dividend / static_cast<double>(cnt);
+        o.dval = is_decimal(t.sql_type.type) && t.sql_type.scale ? dividend / (static_cast<double>(cnt) * exp_to_scale(t.sql_type.scale))
+                                                                 : dividend / static_cast<double>(cnt);
         o.is_null = o.dval == kNullDouble;
       }
       continue;
@@ -1827,6 +1850,13 @@ ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue
       o.is_fp = 1;
       o.dval = double_of(ival);
       o.is_null = o.dval == kNullDouble;
+      continue;
+    }
+    if (is_decimal(chosen.type)) { /* makeTargetValue :2193-2210: the agg kinds test against the BIGINT sentinel whatever notnull says */
+      const bool agg_null = t.is_agg && (t.agg_kind == B2Q_kSUM || t.agg_kind == B2Q_kMIN || t.agg_kind == B2Q_kMAX);
+      o.is_null = ival == kNullBigint && (agg_null || !chosen.notnull);
+      if (decimal_to_double) { o.is_fp = 1; o.dval = o.is_null ? kNullDouble : static_cast<double>(ival) / exp_to_scale(chosen.scale); }
+      else o.ival = ival;
       continue;
     }
     /* :2184-2188: NULL iff the value, resized to the compact type's logical size, equals that type's sentinel;

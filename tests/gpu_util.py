@@ -32,7 +32,7 @@ class DeviceTable:
     def __init__(self, table: abi.Table):
         torch = _cudart()
         self.keep = []
-        self.table = abi.Table(table.col_types, encoded_sizes=table.encoded_sizes, deleted_column=table.deleted_column)
+        self.table = abi.Table(table.col_types, encoded_sizes=table.encoded_sizes, deleted_column=table.deleted_column, col_scales=table.col_scales)
         for f in table.fragments:
             ptrs = []
             for a in f.host_cols:

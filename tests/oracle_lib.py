@@ -42,7 +42,7 @@ def lib():
         L.oracle_result_col_type.restype = abi.TypeInfo
         L.oracle_result_col_type.argtypes = [C.c_void_p, C.c_size_t]
         L.oracle_result_get_next_row.restype = C.c_int32
-        L.oracle_result_get_next_row.argtypes = [C.c_void_p, C.POINTER(abi.TargetValue)]
+        L.oracle_result_get_next_row.argtypes = [C.c_void_p, C.POINTER(abi.TargetValue), C.c_int32]
         L.oracle_result_ndv_estimator.restype = C.c_size_t
         L.oracle_result_ndv_estimator.argtypes = [C.c_void_p]
         L.oracle_result_sort.restype = C.c_int32
@@ -110,7 +110,7 @@ class OracleResult:
 
     def col_type(self, i):
         t = lib().oracle_result_col_type(self.h, i)
-        return (t.type, t.notnull)
+        return (t.type, t.notnull, t.scale)
 
     def buffer(self) -> np.ndarray:
         n = C.c_size_t()
@@ -119,14 +119,14 @@ class OracleResult:
             return np.zeros(0, dtype=np.int8)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int8)), shape=(n.value,)).copy()
 
-    def rows(self):
+    def rows(self, decimal_to_double=True):
         """All rows via getNextRow, as tuples of python values (None = NULL)."""
         L = lib()
         L.oracle_result_move_to_begin(self.h)
         nc = self.col_count()
         row = (abi.TargetValue * nc)()
         out = []
-        while L.oracle_result_get_next_row(self.h, row):
+        while L.oracle_result_get_next_row(self.h, row, int(decimal_to_double)):
             out.append(tuple(v.py() for v in row))
         return out
 

@@ -1,0 +1,49 @@
+"""DECIMAL / NUMERIC columns on the CUDA path against the oracle (tests/dec_tables.py: the reference's golden `dd`
+columns, ExecuteTest.cpp:1971-1986, :2823, :12022, and a table with NULLs and 32 / 16-bit FIXED decimal chunks) —
+device-resident and host-resident chunks, row-wise and columnar output, and the scaled-integer read-out."""
+import pytest
+
+import dec_tables as dt
+import gpu_util as gu
+import oracle_lib
+import sqlmini
+from test_gpu_order_by import run_sorted
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("which", ["golden", "mixed"])
+def test_decimal_queries_on_the_gpu(which):
+    table = dt.make_table(dt.golden_rows()) if which == "golden" else dt.make_table(dt.mixed_rows(), fragment_size=170)
+    dev = gu.DeviceTable(table)
+    for sql in dt.GOLDEN_QUERIES + dt.MORE_QUERIES:
+        unit = sqlmini.parse(sql, table, dt.DEC_NAMES)
+        try:
+            if unit.unit.num_order_entries:
+                run_sorted(unit, table, dev)
+            else:
+                rs, ref = gu.run_both(unit, table, dev_table=dev)
+                assert rs.rows(decimal_to_double=False) == ref.rows(decimal_to_double=False)
+                gu.run_both(unit, table, device_resident=False)
+                try:   # one columnar layout is refused on both sides (keyed output under a narrow first key)
+                    oracle_lib.execute(unit, table, output_columnar=True)
+                except oracle_lib.OracleError:
+                    continue
+                gu.run_both(unit, table, dev_table=dev, output_columnar=True)
+        except Exception as e:
+            raise AssertionError(f"query: {sql}\n{e}") from e
+
+
+def test_decimal_columnar_results_keep_the_scaled_integers():
+    """ColumnarResults reads rows with decimal_to_double = false (ColumnarResults.cpp:155, :550)."""
+    import numpy as np
+    from heavydb_b200 import abi
+    table = dt.make_table(dt.golden_rows())
+    unit = sqlmini.parse("SELECT dd, COUNT(*), SUM(dd), AVG(dd) FROM test GROUP BY dd;", table, dt.DEC_NAMES)
+    rs, _ = gu.run_both(unit, table)
+    cols = rs.columnarResults()
+    assert [c[0] for c in cols] == [abi.kDECIMAL, abi.kINT, abi.kDECIMAL, abi.kDOUBLE]
+    order = np.argsort(cols[0][2])
+    assert cols[0][2][order].tolist() == [11110, 22220, 33330]
+    assert cols[2][2][order].tolist() == [111100, 111100, 166650]
+    assert np.allclose(cols[3][2][order], [111.1, 222.2, 333.3], rtol=1e-12)
