@@ -117,3 +117,74 @@ def test_lowered_program_reproduces_the_oracles_buffer(emu, mixed):  # noqa: F81
             assert_buffers_match(got, res.buffer(), sql)
             ran += 1
     assert ran >= 30
+
+
+def _rand_decimal_query(rng):
+    """Random filter tree + aggregates + keys over the DECIMAL table; literals are written at the column's scale or coarser."""
+    lits = {"x": lambda: str(rng.randint(0, 9)), "y": lambda: str(rng.randint(39, 45)),
+            "dd": lambda: f"{rng.randint(-5200, 5200) / 100:.2f}", "dd_notnull": lambda: f"{rng.randint(0, 40) * 25 / 100:.2f}",
+            "p": lambda: rng.choice([f"{rng.randint(-9999999, 9999999) / 1000:.3f}", str(rng.randint(-9999, 9999))]),
+            "q": lambda: f"{rng.randint(-9999, 9999) / 100:.2f}"}
+    def leaf():
+        c = rng.choice(list(lits))
+        k = rng.random()
+        if k < 0.12 and c not in ("x", "dd_notnull"):
+            return f"{c} IS {'NOT ' if rng.random() < 0.5 else ''}NULL"
+        if k < 0.22:
+            lo, hi = sorted([float(lits[c]()), float(lits[c]())])
+            fmt = {"x": "%d", "y": "%d", "p": "%.3f"}.get(c, "%.2f")
+            return f"{c} BETWEEN {fmt % lo} AND {fmt % hi}"
+        if k < 0.3:
+            return f"{c} IN ({', '.join(lits[c]() for _ in range(rng.randint(2, 4)))})"
+        return f"{c} {rng.choice(['=', '<>', '<', '>', '<=', '>='])} {lits[c]()}"
+    def tree(depth):
+        if depth == 0 or rng.random() < 0.4:
+            return leaf()
+        return f"({tree(depth - 1)} {rng.choice(['AND', 'OR'])} {tree(depth - 1)})"
+    aggs = ["COUNT(*)"]
+    for _ in range(rng.randint(1, 4)):
+        kind = rng.choice(["COUNT", "SUM", "MIN", "MAX", "AVG"])
+        col = "dd_notnull" if kind in ("SUM", "AVG") else rng.choice(["dd", "dd_notnull", "p", "q", "y"])   # exact in binary: SQLite's REAL sums stay comparable
+        aggs.append(f"{kind}({col})")
+    keys = rng.sample(["x", "y", "dd_notnull", "q", "dd"], rng.choice([0, 1, 1, 2]))
+    where = f" WHERE {tree(2)}" if rng.random() < 0.8 else ""
+    group = f" GROUP BY {', '.join(keys)}" if keys else ""
+    return f"SELECT {', '.join(keys + aggs)} FROM test{where}{group};"
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_decimal_queries(emu, mixed, seed):  # noqa: F811
+    """Oracle vs SQLite, the product's planner vs the oracle's, and the lowered program read on the host vs the oracle's buffer."""
+    import random
+    from test_oracle_fuzz import known_reference_quirk
+    table, con = mixed
+    rng = random.Random(4200 + seed)
+    checked = emulated = 0
+    for _ in range(80):
+        sql = _rand_decimal_query(rng)
+        unit = sqlmini.parse(sql, table, dt.DEC_NAMES)
+        try:
+            res = oracle_lib.execute(unit, table, entry_guess=6000, has_card=True, num_threads=2)
+        except oracle_lib.OracleError as e:
+            assert e.code == abi.ERR_UNSUPPORTED, sql
+            continue
+        try:
+            got = executor.Executor().plan(unit, table, max_groups_buffer_entry_guess=6000, has_cardinality_estimation=True).as_dict()
+            assert got == res.plan.as_dict(), sql
+        except executor.UnsupportedOnThisPath as e:
+            assert "filter" in str(e), sql
+            continue
+        if res.plan.query_desc_type in (abi.GroupByPerfectHash, abi.NonGroupedAggregate):
+            rc, buf = run_program(emu, unit, table, entry_guess=6000, has_card=True)
+            assert rc == 0, (sql, rc)
+            assert_buffers_match(buf, res.buffer(), sql)
+            emulated += 1
+        if known_reference_quirk(unit, res.plan):
+            continue
+        ref = [tuple(r) for r in con.execute(sql.rstrip(";")).fetchall()]
+        try:
+            rt.assert_rows_match(res.rows(), ref)
+        except AssertionError as e:
+            raise AssertionError(f"query: {sql}\n{e}") from e
+        checked += 1
+    assert checked >= 40 and emulated >= 40
