@@ -25,6 +25,13 @@ static std::shared_ptr<ResultSet> never_called(Executor& ex, const InputTableInf
   std::printf("%zu\n", rs->getNDVEstimator());
   ColumnarResults cols(*rs, rs->colCount(), {}, true);
   std::printf("%zu %d\n", cols.size(), static_cast<int>(cols.getColumnType(0).get_type()));
+  /* DECIMAL(10, 2): the constant's Datum is the scaled integer; getNextRow's decimal_to_double picks the read-out */
+  const SQLTypeInfo dd(kDECIMAL, 10, 2, false);
+  const ExprRef c = u.makeColumnVar(dd, 1, 0);
+  u.quals.push_back(u.makeBinOper(kGT, c, u.makeConstant(SQLTypeInfo(kDECIMAL, 10, 2, true), int64_t(11100))));
+  u.target_exprs.push_back(u.makeAggExpr(dd, kSUM, c));
+  const auto row = rs->getNextRow(false, true);
+  std::printf("%zu %d %d\n", row.size(), rs->getColType(0).get_scale(), static_cast<int>(dd.is_decimal()));
   return rs;
 }
 
