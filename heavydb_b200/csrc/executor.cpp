@@ -215,7 +215,8 @@ struct B2QResultSet {
   double scan_ms = 0, init_ms = 0, mat_ms = 0, h2d_bytes = 0;
   double host_setup_us = 0, host_stream_us = 0, host_teardown_us = 0;
   int64_t launches = 0, frags_scanned = 0, frags_skipped = 0;
-  ~B2QResultSet() { pinned_cache().put(buf, buf_cap); }
+  bool heap_buf = false; /* b2q_rs_create_from_storage: a plain heap copy of the caller's buffer (no device involved) */
+  ~B2QResultSet() { if (heap_buf) free(buf); else pinned_cache().put(buf, buf_cap); }
 };
 
 /* bytes of accumulator array a: entry_count x 8, except the estimator's bitmap */
@@ -1236,6 +1237,26 @@ int64_t b2q_rs_stat(const B2QResultSet* rs, int32_t which) {
   }
 }
 void b2q_rs_free(B2QResultSet* rs) { delete rs; }
+
+/* A ResultSet over storage the caller already holds: ResultSet(targets, device_type, query_mem_desc, row_set_mem_owner, ...)
+ * followed by allocateStorage(buffer, ...) (ResultSet.h:183-217, ResultSet.cpp allocateStorage) — how ResultSetTest and the
+ * reduction code wrap a filled group-by buffer.  The descriptor is the planned query's; the bytes are copied.  Nothing
+ * is computed here: it is the read-out half (rowCount / getNextRow / isRowAtEmpty / ColumnarResults) on its own. */
+int32_t b2q_rs_create_from_storage(const B2QQuery* q, const int8_t* storage, size_t size_bytes, B2QResultSet** out) {
+  if (!q || !out || (!storage && size_bytes)) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
+  if (q->plan.query_desc_type == B2Q_Estimator) return set_err(B2Q_ERR_UNSUPPORTED, "an estimator result is a bitmap, not a group-by buffer");
+  if (size_bytes != static_cast<size_t>(q->plan.buffer_size)) return set_err(B2Q_ERR_INVALID_ARGUMENT, "storage size differs from the descriptor's buffer size");
+  std::unique_ptr<B2QResultSet> rs(new B2QResultSet());
+  rs->q = *q;
+  rs->heap_buf = true;
+  rs->buf_cap = std::max<size_t>(size_bytes, 8);
+  rs->buf = static_cast<int8_t*>(malloc(rs->buf_cap));
+  if (!rs->buf) return set_err(B2Q_ERR_INVALID_ARGUMENT, "out of host memory");
+  if (size_bytes) memcpy(rs->buf, storage, size_bytes);
+  rs->buf_size = size_bytes;
+  *out = rs.release();
+  return B2Q_OK;
+}
 
 int32_t b2q_gen_column(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0, int64_t count,
                        int64_t lo, int64_t span, void* stream) {

@@ -58,6 +58,8 @@ def lib():
         L.b2q_error_string.argtypes = [C.c_int32]
         L.b2q_last_error_message.restype = C.c_char_p
         L.b2q_device_count.restype = C.c_int32
+        L.b2q_rs_create_from_storage.restype = C.c_int32
+        L.b2q_rs_create_from_storage.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.b2q_plan.restype = C.c_int32
         L.b2q_plan.argtypes = [C.POINTER(abi.ExecUnit), C.POINTER(abi.TableInfo), C.POINTER(abi.CompilationOptions),
                                C.POINTER(abi.ExecutionOptions), C.c_size_t, C.c_int32, C.POINTER(C.c_void_p)]
@@ -370,6 +372,29 @@ class Executor:
         C.memmove(C.byref(plan), lib().b2q_query_plan(h), C.sizeof(abi.Plan))
         lib().b2q_query_free(h)
         return plan
+
+    def resultSetFromStorage(self, storage: np.ndarray, ra_exe_unit: abi.BuiltUnit, query_infos, co=None, eo=None,
+                             max_groups_buffer_entry_guess: int = 0, has_cardinality_estimation: bool = False,
+                             memory_level: int = abi.CPU_LEVEL) -> ResultSet:
+        """ResultSet(targets, device_type, query_mem_desc, ...) + allocateStorage(buffer) (ResultSet.h:183-217): the read-out
+        surface over a group-by buffer the caller already holds, laid out as this unit's descriptor says.  Host only."""
+        co = co or compilation_options()
+        eo = eo or execution_options(device_ordinal=self.device_ordinal)
+        bt = self._built_table(query_infos, memory_level)
+        q = C.c_void_p()
+        rc = lib().b2q_plan(C.byref(ra_exe_unit.unit), C.byref(bt.info), C.byref(co), C.byref(eo),
+                            max_groups_buffer_entry_guess, int(has_cardinality_estimation), C.byref(q))
+        if rc:
+            _raise(rc)
+        try:
+            buf = np.ascontiguousarray(storage).view(np.uint8)
+            h = C.c_void_p()
+            rc = lib().b2q_rs_create_from_storage(q, buf.ctypes.data if buf.size else None, buf.size, C.byref(h))
+            if rc:
+                _raise(rc)
+        finally:
+            lib().b2q_query_free(q)
+        return ResultSet(h)
 
     def executeWorkUnit(self, max_groups_buffer_entry_guess: int, is_agg: bool, query_infos, ra_exe_unit: abi.BuiltUnit,
                         co: Optional[abi.CompilationOptions] = None, eo: Optional[abi.ExecutionOptions] = None,

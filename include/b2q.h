@@ -447,6 +447,11 @@ enum { B2Q_STAT_FRAGMENTS_SCANNED = 0, B2Q_STAT_FRAGMENTS_SKIPPED = 1 /* Executo
        B2Q_STAT_HOST_SETUP_US = 5, B2Q_STAT_HOST_STREAM_US = 6, B2Q_STAT_HOST_TEARDOWN_US = 7 };
 int64_t b2q_rs_stat(const B2QResultSet* rs, int32_t which);
 void b2q_rs_free(B2QResultSet* rs);
+/* ResultSet(targets, device_type, query_mem_desc, ...) + allocateStorage(buffer) (ResultSet.h:183-217): a result set over a
+ * group-by buffer the caller already holds, laid out as the planned query's descriptor says (b2q_plan); the bytes are
+ * copied.  Read-out only (rowCount / getNextRow / isRowAtEmpty / ColumnarResults) — nothing is computed and no device is
+ * needed, the way ResultSetTest wraps hand-filled storage. */
+int32_t b2q_rs_create_from_storage(const B2QQuery* q, const int8_t* storage, size_t size_bytes, B2QResultSet** out);
 
 /* ---- synthetic data (bench / tests): counter-based generator, identical to oracle/oracle_gen.h ----------
  * value(row) = lo + splitmix64(seed ^ (col_tag << 56) ^ row) % span   (integers)
