@@ -239,7 +239,7 @@ class ResultSet:
                 "sort_us": L.b2q_rs_stat(self._h, 4), "host_setup_us": L.b2q_rs_stat(self._h, 5),
                 "host_stream_us": L.b2q_rs_stat(self._h, 6), "host_teardown_us": L.b2q_rs_stat(self._h, 7)}
 
-    def columnarResults(self, num_threads: int = 8):
+    def columnarResults(self, num_threads: int = 8, with_scale: bool = False):
         """ColumnarResults(rows, num_columns, target_types) (QueryEngine/ColumnarResults.cpp:256-392): one numpy array per
         target in the target type's own dtype, rows in iteration order, NULLs as the type's inline sentinel.
         Returns [(sql_type, notnull, array), ...]."""
@@ -256,7 +256,7 @@ class ResultSet:
                 ptr = L.b2q_columnar_results_column(h, c, C.byref(ti))
                 dt = np.dtype(abi.NUMPY_OF[ti.type])
                 arr = np.frombuffer(C.string_at(ptr, n * dt.itemsize), dtype=dt).copy() if n else np.empty(0, dtype=dt)
-                out.append((ti.type, bool(ti.notnull), arr))
+                out.append((ti.type, bool(ti.notnull), arr, ti.scale) if with_scale else (ti.type, bool(ti.notnull), arr))
             return out
         finally:
             L.b2q_columnar_results_free(h)
@@ -266,11 +266,21 @@ class ResultSet:
         over the columnar results; the validity bitmap marks the inline NULL sentinels (dictionary-encoded strings
         travel as their int32 ids, as with translate_strings = false)."""
         import pyarrow as pa
-        cols = self.columnarResults(num_threads)
+        cols = self.columnarResults(num_threads, with_scale=True)
         arrays = []
-        for ty, _nn, a in cols:
+        for ty, _nn, a, scale in cols:
             null = abi.NULL_OF[ty]
             mask = (a == null) if a.size else None
+            if ty in abi.DECIMAL_TYPES:
+                # arrow::decimal128(precision, scale) fed from the scaled int64 (ArrowResultSetConverter.cpp:1141, :1425-1440);
+                # the precision is not carried across the C ABI: 19 digits hold every int64
+                words = np.empty((a.size, 2), dtype=np.int64)
+                words[:, 0] = a
+                words[:, 1] = a >> 63                      # sign extension to 128 bits, little endian
+                nulls = int(mask.sum()) if mask is not None else 0
+                validity = pa.py_buffer(np.packbits(~mask, bitorder="little").tobytes()) if nulls else None
+                arrays.append(pa.Array.from_buffers(pa.decimal128(19, scale), a.size, [validity, pa.py_buffer(words.tobytes())], nulls))
+                continue
             arrays.append(pa.array(a, mask=mask if mask is not None and mask.any() else None))
         names = list(names) if names is not None else [f"col{i}" for i in range(len(arrays))]
         return pa.RecordBatch.from_arrays(arrays, names=names)

@@ -81,3 +81,29 @@ def test_refusals():
         executor.Executor().resultSetFromStorage(ref.buffer()[:-8], unit, table)       # not the descriptor's size
     rs = executor.Executor().resultSetFromStorage(ref.buffer(), unit, table)
     assert sorted(rs.rows()) == [(7, 15), (8, 5)]
+
+
+def test_arrow_hand_off_on_the_cpu():
+    """ResultSet.toArrow over wrapped storage: validity bitmaps mark the inline sentinels, DECIMALs become decimal128(…, scale)
+    fed from the scaled integers (ArrowResultSetConverter.cpp:1141, :1425-1440)."""
+    import decimal
+    import pyarrow as pa
+    table = dt.make_table(dt.mixed_rows(), fragment_size=170)
+    unit = sqlmini.parse("SELECT dd, COUNT(*), SUM(p), MIN(q), AVG(dd_notnull), MAX(y) FROM test GROUP BY dd;", table, dt.DEC_NAMES)
+    ref = oracle_lib.execute(unit, table)
+    rs = executor.Executor().resultSetFromStorage(ref.buffer(), unit, table)
+    batch = rs.toArrow(names=["dd", "n", "sp", "mq", "avg", "my"])
+    assert [str(f.type) for f in batch.schema] == ["decimal128(19, 2)", "int32", "decimal128(19, 3)", "decimal128(19, 2)", "double", "int32"]
+    rows = ref.rows(decimal_to_double=False)
+    assert batch.num_rows == len(rows)
+    scales = {0: 2, 2: 3, 3: 2}
+    for c in range(6):
+        got = batch.column(c).to_pylist()
+        for g, r in zip(got, rows):
+            if r[c] is None:
+                assert g is None
+            elif c in scales:
+                assert isinstance(g, decimal.Decimal) and g == decimal.Decimal(r[c]).scaleb(-scales[c])
+            else:
+                assert g == r[c]
+    assert any(r[0] is None for r in rows) and any(r[2] is not None and r[2] < 0 for r in rows)   # NULL key group, negative sums
