@@ -253,6 +253,25 @@ class Executor {
                                const std::vector<InputTableInfo>& query_infos, const RelAlgExecutionUnit& ra_exe_unit,
                                const CompilationOptions& co, const ExecutionOptions& options, RenderInfo* /*render_info*/,
                                const bool has_cardinality_estimation, ColumnCacheMap& /*column_cache*/) {
+    return dispatch(max_groups_buffer_entry_guess, is_agg, query_infos, ra_exe_unit, co, options, has_cardinality_estimation, nullptr, 0);
+  }
+
+  /* ResultSet(targets, device_type, query_mem_desc, row_set_mem_owner, ...) + allocateStorage(buffer) (ResultSet.h:183-217):
+   * the read-out surface over a group-by buffer the caller already holds, laid out as this unit's descriptor says (the bytes
+   * are copied; host only, nothing is computed) */
+  ResultSetPtr resultSetFromStorage(const int8_t* storage, const size_t size_bytes, size_t max_groups_buffer_entry_guess,
+                                    const std::vector<InputTableInfo>& query_infos, const RelAlgExecutionUnit& ra_exe_unit,
+                                    const CompilationOptions& co, const ExecutionOptions& options,
+                                    const bool has_cardinality_estimation = false) {
+    static const int8_t empty = 0;
+    return dispatch(max_groups_buffer_entry_guess, true, query_infos, ra_exe_unit, co, options, has_cardinality_estimation,
+                    storage ? storage : &empty, size_bytes);
+  }
+
+ private:
+  ResultSetPtr dispatch(size_t& max_groups_buffer_entry_guess, const bool is_agg, const std::vector<InputTableInfo>& query_infos,
+                        const RelAlgExecutionUnit& ra_exe_unit, const CompilationOptions& co, const ExecutionOptions& options,
+                        const bool has_cardinality_estimation, const int8_t* storage, const size_t storage_bytes) {
     const size_t n_tables = 1 + ra_exe_unit.join_quals.size();
     if (query_infos.size() != n_tables || n_tables > 2) throw QueryNotSupported(B2Q_ERR_UNSUPPORTED, "one input table, or two with one join level, on this path");
     /* flatten to the POD structs of the C ABI */
@@ -323,8 +342,15 @@ class Executor {
     B2QCompilationOptions cco{static_cast<int32_t>(co.device_type), co.hoist_literals ? 1 : 0, co.filter_on_deleted_column ? 0 : 1, 0};
     B2QExecutionOptions ceo{options.allow_multifrag ? 1 : 0, options.output_columnar_hint ? 1 : 0, options.bigint_count ? 1 : 0, 0, -1, 0};
     B2QResultSet* rs = nullptr;
-    const int32_t rc = b2q_execute_work_unit(&max_groups_buffer_entry_guess, is_agg ? 1 : 0, &tbl, &u, &cco, &ceo,
-                                             has_cardinality_estimation ? 1 : 0, &rs);
+    int32_t rc;
+    if (storage) {
+      B2QQuery* planned = nullptr;
+      rc = b2q_plan(&u, &tbl, &cco, &ceo, max_groups_buffer_entry_guess, has_cardinality_estimation ? 1 : 0, &planned);
+      if (rc == B2Q_OK) rc = b2q_rs_create_from_storage(planned, storage, storage_bytes, &rs);
+      b2q_query_free(planned);
+    } else {
+      rc = b2q_execute_work_unit(&max_groups_buffer_entry_guess, is_agg ? 1 : 0, &tbl, &u, &cco, &ceo, has_cardinality_estimation ? 1 : 0, &rs);
+    }
     if (rc != B2Q_OK) {
       const std::string msg = std::string(b2q_error_string(rc)) + ": " + b2q_last_error_message();
       if (rc == B2Q_ERR_CARDINALITY_ESTIMATION_REQUIRED) throw CardinalityEstimationRequired(rc, msg);

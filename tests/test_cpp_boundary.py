@@ -24,7 +24,8 @@ def test_cpp_mirror_compiles_and_links(tmp_path):
 
 
 def test_cpp_mirror_surface_links(tmp_path):
-    """Estimator unit, getNDVEstimator, deleted-column option, ColumnarResults: compiled and linked, nothing executed."""
+    """Estimator unit, getNDVEstimator, deleted-column option, ColumnarResults: compiled and linked, not executed; the
+    read-out half (resultSetFromStorage over hand-filled storage, a DECIMAL SUM / AVG among the targets) RUNS, on the CPU."""
     lib = build.build()
     exe = tmp_path / "mirror_surface"
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
