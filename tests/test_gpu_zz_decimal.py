@@ -47,3 +47,28 @@ def test_decimal_columnar_results_keep_the_scaled_integers():
     assert cols[0][2][order].tolist() == [11110, 22220, 33330]
     assert cols[2][2][order].tolist() == [111100, 111100, 166650]
     assert np.allclose(cols[3][2][order], [111.1, 222.2, 333.3], rtol=1e-12)
+
+
+def test_sort_over_wrapped_storage():
+    """b2q_rs_create_from_storage + ResultSet::sort on the device: the ORACLE's buffer, wrapped, sorted by the CUDA radix path,
+    against the oracle's own ResultSet::sort restatement (DECIMAL SUM / AVG and a nullable DECIMAL key among the order keys)."""
+    import oracle_lib
+    from heavydb_b200 import executor
+    table = dt.make_table(dt.mixed_rows(n=3000, seed=3), fragment_size=800)
+    unit = sqlmini.parse("SELECT dd, COUNT(*), SUM(p), AVG(q) FROM test GROUP BY dd;", table, dt.DEC_NAMES)
+    for order, top_n, drop, keep in [([(3, True, False), (1, False, True)], 0, 0, 0),
+                                     ([(2, True, False), (1, True, True)], 40, 5, 20),
+                                     ([(4, False, True), (1, False, False)], 0, 17, 0),
+                                     ([(1, True, True)], 25, 0, 25)]:
+        ref = oracle_lib.execute(unit, table)
+        rs = executor.Executor().resultSetFromStorage(ref.buffer(), unit, table)
+        ref.sort(order, top_n)
+        rs.sort(order, top_n)
+        for r in (ref,):
+            r.drop_first_n(drop)
+            r.keep_first_n(keep)
+        rs.dropFirstN(drop)
+        rs.keepFirstN(keep)
+        assert rs.entryCount() == ref.entry_count() and rs.rowCount() == ref.row_count()
+        gu.rows_equal_ordered(rs.rows(), ref.rows())
+        assert rs.rows(decimal_to_double=False) == ref.rows(decimal_to_double=False)
