@@ -64,9 +64,8 @@ def test_sort_over_wrapped_storage():
         rs = executor.Executor().resultSetFromStorage(ref.buffer(), unit, table)
         ref.sort(order, top_n)
         rs.sort(order, top_n)
-        for r in (ref,):
-            r.drop_first_n(drop)
-            r.keep_first_n(keep)
+        ref.drop_first_n(drop)
+        ref.keep_first_n(keep)
         rs.dropFirstN(drop)
         rs.keepFirstN(keep)
         assert rs.entryCount() == ref.entry_count() and rs.rowCount() == ref.row_count()

@@ -13,6 +13,7 @@ import ref_time_table as tt
 import sqlmini
 import str_tables as stt
 from heavydb_b200 import abi, executor
+from test_filter_lowering import emu, run_program  # noqa: F401  (emu is a fixture)
 from test_gpu_parity import RAND_NAMES, RAND_QUERIES, random_table
 from test_oracle_golden import COLUMNAR_EXTRA, MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
 
@@ -107,3 +108,41 @@ def test_arrow_hand_off_on_the_cpu():
             else:
                 assert g == r[c]
     assert any(r[0] is None for r in rows) and any(r[2] is not None and r[2] < 0 for r in rows)   # NULL key group, negative sums
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_host_side_end_to_end_against_sqlite(emu, seed):  # noqa: F811
+    """Everything of the product except the CUDA kernels, against an independent engine: SQL -> b2q_plan -> the lowered
+    program read on the host (tests/cpp/filter_emulator.cpp stands in for the kernels) -> b2q_rs_create_from_storage ->
+    getNextRow, compared with SQLite like the reference's SQLiteComparator."""
+    import random
+    import order_queries as oq
+    from test_gpu_fuzz import rand_query
+    from test_gpu_parity import RAND_COLS
+    from test_oracle_fuzz import known_reference_quirk, sqlite_overflows
+    rng = random.Random(31000 + seed)
+    table = random_table([900, 2500][seed], seed=700 + seed, frag_rows=[250, 2500][seed])
+    con = rt.make_sqlite(oq.rows_of(table, RAND_COLS), RAND_COLS, "r")
+    ex = executor.Executor()
+    checked = 0
+    for i in range(90):
+        sql = rand_query(rng, multi_key=(i % 3 == 0))
+        if sqlite_overflows(sql):
+            continue
+        unit = sqlmini.parse(sql, table, RAND_NAMES)
+        try:
+            plan = ex.plan(unit, table, max_groups_buffer_entry_guess=6000, has_cardinality_estimation=True)
+        except executor.QueryExecutionError:
+            continue
+        if plan.query_desc_type not in (abi.GroupByPerfectHash, abi.NonGroupedAggregate) or known_reference_quirk(unit, plan):
+            continue
+        rc, buf = run_program(emu, unit, table, entry_guess=6000, has_card=True)
+        assert rc == 0, (sql, rc)
+        rs = ex.resultSetFromStorage(buf, unit, table, max_groups_buffer_entry_guess=6000, has_cardinality_estimation=True)
+        ref = [tuple(r) for r in con.execute(sql.rstrip(";")).fetchall()]
+        try:
+            rt.assert_rows_match(rs.rows(), ref)
+        except AssertionError as e:
+            raise AssertionError(f"query: {sql}\n{e}") from e
+        checked += 1
+    assert checked >= 40
