@@ -92,3 +92,31 @@ MORE_QUERIES = [
     "SELECT dd_notnull, SUM(dd) FROM test GROUP BY dd_notnull ORDER BY 2 LIMIT 5 OFFSET 2;",
     "SELECT MIN(dd), MAX(dd), SUM(dd), AVG(dd), COUNT(dd) FROM test WHERE x > 100;",
 ]
+
+
+FACT_NAMES, DIM_NAMES = ["fk", "v"], ["id", "price"]
+JOIN_QUERIES = [
+    "SELECT d.price, COUNT(*), SUM(t.v) FROM t JOIN d ON t.fk = d.id GROUP BY d.price;",
+    "SELECT COUNT(*), SUM(d.price), AVG(d.price), MIN(d.price), MAX(d.price), COUNT(d.price) FROM t JOIN d ON t.fk = d.id WHERE d.price > 2.5;",
+    "SELECT COUNT(*), SUM(d.price), AVG(d.price) FROM t LEFT JOIN d ON t.fk = d.id WHERE d.price <= 7.25 OR d.price IS NULL;",
+    "SELECT d.price, COUNT(*), AVG(t.v) FROM t LEFT JOIN d ON t.fk = d.id WHERE t.v < 50 GROUP BY d.price;",
+]
+
+
+def star_join(seed: int = 8):
+    """fact(fk INT, v BIGINT NOT NULL) x dim(id INT NOT NULL, price DECIMAL(7, 2) as FIXED(32), three NULL prices)."""
+    rng = np.random.default_rng(seed)
+    dim = abi.Table([(abi.kINT, True), (abi.kDECIMAL, False)], encoded_sizes=[0, 4], col_scales={1: 2})
+    price = rng.integers(0, 60, 50).astype(np.int32) * 25           # multiples of 0.25: exact as REAL
+    price[[3, 17, 40]] = -2**31                                      # NULL (the FIXED(32) sentinel)
+    dim.add_host_fragment([np.arange(50, dtype=np.int32), price])
+    fact = abi.Table([(abi.kINT, False), (abi.kBIGINT, True)])
+    fk_all, v_all = [], []
+    for _ in range(3):
+        fk = rng.integers(-3, 55, 800).astype(np.int32)
+        fk[rng.random(800) < 0.05] = abi.NULL_INT
+        v = rng.integers(0, 100, 800).astype(np.int64)
+        fact.add_host_fragment([fk, v])
+        fk_all += fk.tolist()
+        v_all += v.tolist()
+    return fact, dim, price, fk_all, v_all

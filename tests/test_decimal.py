@@ -188,3 +188,25 @@ def test_random_decimal_queries(emu, mixed, seed):  # noqa: F811
             raise AssertionError(f"query: {sql}\n{e}") from e
         checked += 1
     assert checked >= 40 and emulated >= 40
+
+
+def test_decimal_attribute_of_a_joined_dimension(emu):  # noqa: F811
+    """Star join whose dimension carries a DECIMAL(7, 2) price stored as FIXED(32): filter, key and aggregate argument read
+    through the join index — oracle vs SQLite, product planner vs oracle, lowered join program vs the oracle's buffer (INNER and LEFT)."""
+    import sqlite3
+    fact, dim, price, fk_all, v_all = dt.star_join()
+    con = sqlite3.connect(":memory:")
+    con.execute("CREATE TABLE t(fk bigint, v bigint)")
+    con.execute("CREATE TABLE d(id bigint, price double)")
+    con.executemany("INSERT INTO t VALUES(?, ?)", [(None if a == abi.NULL_INT else a, b) for a, b in zip(fk_all, v_all)])
+    con.executemany("INSERT INTO d VALUES(?, ?)", [(i, None if p == -2**31 else p / 100) for i, p in enumerate(price.tolist())])
+    for sql in dt.JOIN_QUERIES:
+        unit = sqlmini.parse(sql, fact, dt.FACT_NAMES, inner=(dim, dt.DIM_NAMES))
+        res = oracle_lib.execute(unit, fact, num_threads=2)
+        rt.assert_rows_match(res.rows(), [tuple(r) for r in con.execute(sql.rstrip(";")).fetchall()])
+        assert executor.Executor().plan(unit, fact).as_dict() == res.plan.as_dict(), sql
+        # the lowered join program, read on the host over the denormalised rows, gives the oracle's buffer
+        from test_filter_lowering import run_join_program
+        rc, got = run_join_program(emu, unit, fact, dim, left=" LEFT JOIN " in sql, entry_guess=0)
+        assert rc == 0, (sql, rc)
+        assert_buffers_match(got, res.buffer(), sql)

@@ -71,3 +71,17 @@ def test_sort_over_wrapped_storage():
         assert rs.entryCount() == ref.entry_count() and rs.rowCount() == ref.row_count()
         gu.rows_equal_ordered(rs.rows(), ref.rows())
         assert rs.rows(decimal_to_double=False) == ref.rows(decimal_to_double=False)
+
+
+def test_decimal_attribute_of_a_joined_dimension_on_the_gpu():
+    """A DECIMAL(7, 2) dimension attribute stored as FIXED(32), read through the join index (packed / 16-bit / shared-memory
+    join-table variants are the planner's choice) as filter operand, group key and aggregate argument; INNER and LEFT."""
+    fact, dim, *_ = dt.star_join()
+    for sql in dt.JOIN_QUERIES:
+        unit = sqlmini.parse(sql, fact, dt.FACT_NAMES, inner=(dim, dt.DIM_NAMES))
+        try:
+            rs, ref = gu.run_both(unit, fact)
+            assert rs.rows(decimal_to_double=False) == ref.rows(decimal_to_double=False)
+            gu.run_both(unit, fact, device_resident=False)
+        except Exception as e:
+            raise AssertionError(f"query: {sql}\n{e}") from e
