@@ -89,6 +89,7 @@ struct TargetDesc {
   int agg = B2Q_kMIN;
   SqlType sql_type, arg_type; /* arg_type.type == 0: no argument */
   bool skip_null = false;
+  bool constrained = false; /* the quals hold a top-level `arg IS NOT NULL` (constrained_not_null, OutputBufferInitialization.cpp:301-324) */
   int arg_col = -1;
   int first_slot = 0;
   SqlType compact() const { /* get_compact_type */
@@ -300,6 +301,20 @@ class Planner {
     }
   }
 
+  /* constrained_not_null (OutputBufferInitialization.cpp:301-324): one of ra_exe_unit.quals — the simple_quals are not
+   * consulted — is NOT(ISNULL(col)) at its top level, for the very ColumnVar the aggregate reads */
+  bool quals_constrain_not_null(const B2QExpr& col) const {
+    for (int i = 0; i < u_.num_quals; ++i) {
+      const B2QExpr& n = ex(u_.quals[i]);
+      if (n.kind != B2Q_EXPR_UOPER || n.op != B2Q_kNOT) continue;
+      const B2QExpr& isn = ex(n.left);
+      if (isn.kind != B2Q_EXPR_UOPER || isn.op != B2Q_kISNULL) continue;
+      const B2QExpr& c = ex(isn.left);
+      if (c.kind == B2Q_EXPR_COLUMN_VAR && c.col_id == col.col_id && c.rte_idx == col.rte_idx) return true;
+    }
+    return false;
+  }
+
   void build_targets() {
     const bool bigint_count = eo_.bigint_count != 0;
     bool any_agg = false;
@@ -328,6 +343,7 @@ class Planner {
           d.arg_type = from_abi(a.ti);
           if (d.arg_type.size() != col_type(a.col_id).size()) reject(B2Q_ERR_INVALID_ARGUMENT, "ColumnVar type does not match the table");
           d.skip_null = !d.arg_type.notnull;
+          d.constrained = quals_constrain_not_null(a);
           /* what the analyzer lets through (Analyzer.cpp / RelAlgTranslator): no SUM / AVG of strings or time types,
            * MIN / MAX of a dictionary string would need dictionary order */
           if (d.arg_type.is_string() && e.op != B2Q_kCOUNT) reject(B2Q_ERR_UNSUPPORTED, "only COUNT of a dictionary-encoded string is on this path");
@@ -434,8 +450,8 @@ class Planner {
           case B2Q_kCOUNT:
             if (!(has_arg && !d.arg_type.notnull && (!r.valid || r.has_nulls))) found = true;
             break;
-          case B2Q_kSUM:
-            if (!d.arg_type.notnull) { if (r.valid && !r.has_nulls) found = true; }
+          case B2Q_kSUM: /* the one aggregate whose keyless test honours `arg IS NOT NULL` (GroupByAndAggregate.cpp:531-533) */
+            if (!d.arg_type.notnull && !d.constrained) { if (r.valid && !r.has_nulls) found = true; }
             else if (r.fp ? (r.fmax < 0 || r.fmin > 0) : (r.imax < 0 || r.imin > 0)) found = true;
             break;
           case B2Q_kMIN: { /* note: no has_nulls test in the reference (kMAX has one) */
@@ -649,6 +665,7 @@ class Planner {
     for (const TargetDesc& d : targets_) {
       if (!d.is_agg) { p.init_vals[s++] = 0; continue; }
       SqlType ti = d.compact();
+      if (d.constrained && d.arg_col >= 0) ti.notnull = true; /* set_notnull(target, true), OutputBufferInitialization.cpp:287-289 */
       if (!grouped_) ti.notnull = false; /* non-grouped aggregates are nullable (OutputBufferInitialization.cpp:66-68,283-288) */
       p.init_vals[s++] = agg_init(d.agg, ti, grouped_, compact_width);
       if (d.agg == B2Q_kAVG) p.init_vals[s++] = 0;
@@ -659,6 +676,7 @@ class Planner {
     for (size_t i = 0; i < targets_.size(); ++i) {
       TargetDesc& d = targets_[i];
       if (d.is_agg && d.arg_col >= 0 && !grouped_) d.skip_null = true; /* TargetExprBuilder.cpp:653-657 */
+      else if (d.is_agg && d.arg_col >= 0 && d.constrained) d.skip_null = false; /* :690-692 */
       B2QTargetInfo& o = p.targets[i];
       o.is_agg = d.is_agg; o.agg_kind = d.agg;
       o.sql_type = to_abi(d.sql_type); o.agg_arg_type = to_abi(d.arg_type);

@@ -365,6 +365,7 @@ struct Target {
   int arg_col{-1};
   Ti arg_ti;      /* argument expression's own type info */
   int first_slot{0};
+  bool arg_constrained_not_null{false}; /* constrained_not_null(agg_arg(target_expr), ra_exe_unit.quals) */
 };
 
 struct Range { /* ExpressionRange (Integer or Double or Invalid) */
@@ -401,6 +402,32 @@ const B2QExpr& expr_at(const B2QExecUnit& u, int idx) {
 }
 Ti ti_of(const B2QTypeInfo& t) { return Ti{t.type, t.notnull != 0, t.scale}; }
 
+/* OutputBufferInitialization.cpp:301-324 constrained_not_null: some member of ra_exe_unit.quals (NOT simple_quals) is,
+ * at its top level, `expr IS NOT NULL` — which reaches the executor as UOper(kNOT, UOper(kISNULL, expr)) — over an
+ * operand equal to `expr` (ColumnVar::operator==: same table / column / rte_idx). */
+bool constrained_not_null(const B2QExecUnit& u, int arg_expr_idx) {
+  if (arg_expr_idx < 0) return false;
+  const B2QExpr& arg = expr_at(u, arg_expr_idx);
+  for (int i = 0; i < u.num_quals; ++i) {
+    const B2QExpr* uoper = &expr_at(u, u.quals[i]);
+    if (uoper->kind != B2Q_EXPR_UOPER) continue;
+    bool is_negated = false;
+    if (uoper->op == B2Q_kNOT) {
+      const B2QExpr& operand = expr_at(u, uoper->left);
+      if (operand.kind != B2Q_EXPR_UOPER) continue;
+      uoper = &operand;
+      is_negated = true;
+    }
+    if (is_negated && uoper->op == B2Q_kISNULL) { /* kISNOTNULL itself never reaches this boundary */
+      const B2QExpr& operand = expr_at(u, uoper->left);
+      if (operand.kind == B2Q_EXPR_COLUMN_VAR && arg.kind == B2Q_EXPR_COLUMN_VAR && operand.col_id == arg.col_id &&
+          operand.rte_idx == arg.rte_idx)
+        return true;
+    }
+  }
+  return false;
+}
+
 /* Shared/TargetInfo.cpp:25-78 get_target_info_impl */
 Target get_target_info(const B2QExecUnit& u, int expr_idx, bool bigint_count) {
   const B2QExpr& e = expr_at(u, expr_idx);
@@ -432,6 +459,7 @@ Target get_target_info(const B2QExecUnit& u, int expr_idx, bool bigint_count) {
   const Ti arg_ti = ti_of(arg.ti);
   t.arg_col = arg.col_id;
   t.arg_ti = arg_ti;
+  t.arg_constrained_not_null = constrained_not_null(u, e.left); /* evaluated where the reference evaluates it; kept here once */
   if (is_string(arg_ti.type) && e.op != B2Q_kCOUNT) fail(B2Q_ERR_UNSUPPORTED, "only COUNT of a dictionary-encoded string is on this path");
   if (is_time(arg_ti.type) && (e.op == B2Q_kSUM || e.op == B2Q_kAVG)) fail(B2Q_ERR_UNSUPPORTED, "SUM / AVG of a TIME / TIMESTAMP / DATE");
   if (e.op == B2Q_kAVG) {
@@ -584,7 +612,9 @@ void get_keyless_info(const B2QExecUnit& u, const B2QTableInfo& tbl, const std::
           break;
         case B2Q_kSUM: {
           const Range er = leaf_column_range(tbl, agg_info.arg_col);
-          if (!agg_info.arg_ti.notnull) {
+          Ti arg_ti = agg_info.arg_ti;
+          if (agg_info.arg_constrained_not_null) arg_ti.notnull = true; /* GroupByAndAggregate.cpp:531-533 */
+          if (!arg_ti.notnull) {
             if (er.kind != Range::Invalid && !er.has_nulls) found = true;
           } else {
             if (er.kind == Range::Double) {
@@ -955,6 +985,8 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
       if (t.arg_col >= 0 && t.is_agg && p.query_desc_type == B2Q_NonGroupedAggregate &&
           (t.agg_kind == B2Q_kMIN || t.agg_kind == B2Q_kMAX || t.agg_kind == B2Q_kSUM || t.agg_kind == B2Q_kAVG)) {
         t.sql_type.notnull = false; t.agg_arg_type.notnull = false; t.skip_null_val = true; /* set_notnull(target,false) */
+      } else if (t.arg_col >= 0 && t.is_agg && t.arg_constrained_not_null) { /* :287-289 set_notnull(target, true) */
+        t.sql_type.notnull = true; t.agg_arg_type.notnull = true; t.skip_null_val = false;
       }
       if (!t.is_agg) {
         p.init_vals[s] = 0;
@@ -972,6 +1004,7 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
   for (size_t i = 0; i < plan.targets.size(); ++i) {
     auto& t = plan.targets[i];
     if (t.arg_col >= 0 && t.is_agg && p.query_desc_type == B2Q_NonGroupedAggregate) t.skip_null_val = true;
+    else if (t.arg_col >= 0 && t.is_agg && t.arg_constrained_not_null) t.skip_null_val = false; /* TargetExprBuilder.cpp:690-692 */
     B2QTargetInfo& o = p.targets[i];
     o.is_agg = t.is_agg; o.agg_kind = t.agg_kind;
     o.sql_type = B2QTypeInfo{t.sql_type.type, t.sql_type.notnull, t.sql_type.scale};

@@ -225,3 +225,50 @@ def test_empty_table():
         oracle_lib.execute(unit, table)
     assert ei.value.code == abi.ERR_CARDINALITY_ESTIMATION_REQUIRED
     assert oracle_lib.execute(unit, table, entry_guess=16, has_card=True).rows() == []
+
+
+# constrained_not_null (OutputBufferInitialization.cpp:301-324): a top-level `arg IS NOT NULL` qual makes the aggregate's
+# target NOT NULL for (1) get_keyless_info's kSUM case (GroupByAndAggregate.cpp:531), (2) the init values
+# (OutputBufferInitialization.cpp:287) and (3) the skip-val choice (TargetExprBuilder.cpp:690).  Expected plans derived BY HAND
+# from those three places and the golden table's values (z in {101, -78, 102}, t in {1001, 1002}, dn in {NULL, -2002.4, -220.6}).
+#   sql, keyless, idx_target_as_key, init_vals, skip_null_val per target
+I64_MIN, I64_MAX = -(1 << 63), (1 << 63) - 1
+CONSTRAINED_NOT_NULL_PLANS = [
+    # :2868 — z spans zero, so a NOT NULL SUM cannot mark emptiness: keyed layout, SUM starts at 0 and adds without a skip test
+    ("SELECT x, SUM(z) FROM test WHERE z IS NOT NULL GROUP BY x;", 0, -1, [0, 0], [0, 0]),
+    # the same without the qual: nullable argument without NULLs in the chunk stats -> keyless on SUM, NULL-sentinel init
+    ("SELECT x, SUM(z) FROM test GROUP BY x;", 1, 1, [0, I64_MIN], [0, 1]),
+    # t > 0 everywhere: NOT NULL SUM over a strictly positive range IS a marker; init 0
+    ("SELECT x, SUM(t) FROM test WHERE t IS NOT NULL GROUP BY x;", 1, 1, [0, 0], [0, 0]),
+    ("SELECT x, SUM(t) FROM test WHERE NOT (t IS NULL) AND x > 0 GROUP BY x;", 1, 1, [0, 0], [0, 0]),
+    # the qual must be a top-level conjunct over the SAME column
+    ("SELECT x, SUM(t) FROM test WHERE t IS NOT NULL OR x > 7 GROUP BY x;", 1, 1, [0, I64_MIN], [0, 1]),
+    ("SELECT x, SUM(t) FROM test WHERE y IS NOT NULL GROUP BY x;", 1, 1, [0, I64_MIN], [0, 1]),
+    # :2026 — kMAX's keyless test does not consult the quals (dn has NULLs -> keyed); init becomes -DBL_MAX, no skip test
+    ("SELECT x, MAX(dn) FROM test WHERE dn IS NOT NULL GROUP BY x;", 0, -1, [0, "-dblmax"], [0, 0]),
+    ("SELECT x, MAX(dn) FROM test GROUP BY x;", 0, -1, [0, "nulldbl"], [0, 1]),
+    # MIN / COUNT / AVG over a constrained argument: 8-byte slot -> INT64_MAX; COUNT(z) counts every row
+    ("SELECT x, MIN(z), COUNT(z), AVG(z) FROM test WHERE z IS NOT NULL GROUP BY x;", 1, 2, [0, I64_MAX, 0, 0, 0], [0, 0, 0, 0]),
+    # non-grouped (:1955, :2025): set_notnull(target, false) wins for MIN / MAX / SUM / AVG; the code generator forces skip_null_val
+    ("SELECT SUM(z) FROM test WHERE z IS NOT NULL;", 0, -1, [I64_MIN], [1]),
+    ("SELECT MAX(dn) FROM test WHERE dn IS NOT NULL;", 0, -1, ["nulldbl"], [1]),
+]
+
+
+@pytest.mark.parametrize("case", CONSTRAINED_NOT_NULL_PLANS, ids=[c[0][:60] for c in CONSTRAINED_NOT_NULL_PLANS])
+def test_constrained_not_null_plan(env, case):
+    import struct
+    sql, keyless, idx, inits, skips = case
+    table, con = env
+    unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
+    res = oracle_lib.execute(unit, table, entry_guess=64, has_card=True)
+    p = res.plan
+    bits = {"-dblmax": struct.unpack("<q", struct.pack("<d", -1.7976931348623157e308))[0],
+            "nulldbl": struct.unpack("<q", struct.pack("<d", 2.2250738585072014e-308))[0]}
+    assert p.keyless_hash == keyless
+    if keyless:   # KeylessInfo::target_index only means something for a keyless layout
+        assert p.idx_target_as_key == idx
+    assert [p.init_vals[s] for s in range(p.num_slots)] == [bits.get(v, v) for v in inits]
+    assert [p.targets[i].skip_null_val for i in range(p.num_targets)] == skips
+    ref = [tuple(r) for r in con.execute(sql.rstrip(";")).fetchall()]
+    rt.assert_rows_match(res.rows(), ref)
