@@ -42,11 +42,12 @@ ERR_NO_DEVICE = 1003
 ERR_CUDA = 1004
 ERR_KEY_OUT_OF_RANGE = 1005
 
-ABI_VERSION = 4   # B2Q_ABI_VERSION of include/b2q.h this mirror was written against
+COMM_ID_BYTES = 128
+ABI_VERSION = 5   # B2Q_ABI_VERSION of include/b2q.h this mirror was written against
 EXPR_COLUMN_VAR, EXPR_CONSTANT, EXPR_BIN_OPER, EXPR_AGG, EXPR_UOPER = 1, 2, 3, 4, 5
 CPU_LEVEL, GPU_LEVEL = 1, 2
 DEVICE_CPU, DEVICE_GPU = 0, 1
-KERNEL_AUTO, KERNEL_NON_GROUPED, KERNEL_PERFECT_SMEM, KERNEL_PERFECT_GLOBAL, KERNEL_BASELINE_GLOBAL = range(5)
+KERNEL_AUTO, KERNEL_NON_GROUPED, KERNEL_PERFECT_SMEM, KERNEL_PERFECT_GLOBAL, KERNEL_BASELINE_GLOBAL, KERNEL_BASELINE_PROBE = range(6)
 DT_INT64, DT_FLOAT64, DT_UINT8 = 0, 1, 2
 RED_SUM, RED_MIN, RED_MAX, RED_BOR = 0, 1, 2, 3
 

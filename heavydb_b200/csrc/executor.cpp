@@ -29,6 +29,8 @@
 #include <vector>
 
 #include "b2q_internal.h"
+#include "multi.h"
+#include "radix_agg.h"
 
 namespace b2q {
 int32_t make_query(const B2QExecUnit* u, const B2QTableInfo* t, const B2QExecutionOptions* eo, size_t guess,
@@ -48,6 +50,7 @@ cudaError_t launch_gen(void* dst, int sql_type, uint64_t seed, uint32_t col_tag,
                        int64_t span, int64_t stride, cudaStream_t st);
 cudaError_t launch_join_slot16(const int32_t* rows, int64_t entry_count, const int8_t* vals, int width, int64_t null_val, int64_t vmin,
                                uint16_t* out, int32_t* error, cudaStream_t st);
+cudaError_t launch_bitmap_or(uint64_t* dst, const uint64_t* gathered, int64_t words, int copies, cudaStream_t st);
 size_t sort_scratch_bytes(int64_t entries);
 cudaError_t sort_device(const DevSortLayout& L, const DevSortKey* keys, int n_keys, const int8_t* buf, int8_t* scratch,
                         cudaStream_t st, const uint32_t** perm_out, int64_t* n_out, int* launches, int64_t top_n);
@@ -150,16 +153,39 @@ struct B2QPartial {
   const int32_t* join_buff = nullptr;
   const int8_t* inner_cols[B2Q_MAX_COLS] = {};
   bool split = false;        /* COUNT / SUM_I64 arrays are in the (lo[n] | hi[n]) layout of the global-table kernels */
+  /* baseline hash as a two-pass radix-partitioned aggregation (radix_agg.cu); buffers sized for `radix_batch_chunks` chunks a launch */
+  bool radix = false;
+  RadixPlan rp;
+  RadixBuffers rb = {};
+  int64_t radix_batch_chunks = 0;
+  int radix_n_cta1 = 0;
+  uint32_t radix_cap = 0;
+  cudaStream_t stream = nullptr; /* the stream the work was enqueued on: frees are ordered after it */
+  /* deferred completion (single-sync calls): the device error word is copied into this pinned word on the stream and read
+   * after the call's one synchronize at the end of finalize */
+  bool deferred = false;
+  int32_t* h_err = nullptr;
+  size_t h_err_cap = 0;
   cudaEvent_t ev[4] = {}; /* init begin/end, scan begin/end */
   bool scan_timed = false;
   double scan_ms = 0, init_ms = 0, h2d_bytes = 0;
   double host_setup_us = 0, host_stream_us = 0, host_teardown_us = 0; /* scan_host_table wall-clock phases */
   int64_t launches = 0, frags_scanned = 0, frags_skipped = 0;
   ~B2QPartial() {
-    for (void* x : extra) cudaFreeAsync(x, nullptr);
-    blk.release(nullptr);
+    /* Kernels may still be running on `stream` (error paths return before the synchronize), and the caller's current
+     * device may be another one: free on the owning device, in the order of the stream the work was enqueued on. */
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != device) cudaSetDevice(device);
+    for (void* x : extra) cudaFreeAsync(x, stream);
+    blk.release(stream);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (cur >= 0 && cur != device) cudaSetDevice(cur);
+    cudaGetLastError();
+    release_h_err();
   }
+  void release_h_err();
+  bool stream_busy() const { return cudaStreamQuery(stream) == cudaErrorNotReady; }
 };
 
 /* Result buffers are page-locked host memory so the copy-back is one asynchronous DMA at PCIe rate straight into
@@ -200,6 +226,13 @@ struct PinnedCache {
   }
 };
 static PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }
+void B2QPartial::release_h_err() {
+  if (h_err) {
+    if (stream_busy()) cudaStreamSynchronize(stream); /* the async copy into the word must have landed before it is recycled */
+    pinned_cache().put(reinterpret_cast<int8_t*>(h_err), h_err_cap);
+  }
+  h_err = nullptr;
+}
 
 struct B2QResultSet {
   B2QQuery q;
@@ -218,6 +251,19 @@ struct B2QResultSet {
   bool heap_buf = false; /* b2q_rs_create_from_storage: a plain heap copy of the caller's buffer (no device involved) */
   ~B2QResultSet() { if (heap_buf) free(buf); else pinned_cache().put(buf, buf_cap); }
 };
+
+/* reduction class of an accumulator across devices (ResultSetStorage::reduceOneSlot's algebra on the internal arrays) */
+enum { MERGE_SUM_I64 = 0, MERGE_SUM_F64 = 1, MERGE_MIN = 2, MERGE_MAX = 3, MERGE_FLAG = 4, MERGE_BOR = 5, kMergeClasses = 6 };
+static int merge_class(int op) {
+  switch (op) {
+    case ACC_COUNT: case ACC_SUM_I64: return MERGE_SUM_I64;
+    case ACC_SUM_F64: return MERGE_SUM_F64;
+    case ACC_MIN_I64: case ACC_MIN_F64: return MERGE_MIN;
+    case ACC_MAX_I64: case ACC_MAX_F64: return MERGE_MAX;
+    case ACC_TOUCH: return MERGE_FLAG;
+    default: return MERGE_BOR;
+  }
+}
 
 /* bytes of accumulator array a: entry_count x 8, except the estimator's bitmap */
 static size_t acc_array_bytes(const B2QQuery& q, int a) {
@@ -238,13 +284,18 @@ static size_t table_bytes(const B2QQuery& q) {
 static int32_t alloc_partial(B2QPartial& p, size_t extra_bytes, cudaStream_t st) {
   const B2QQuery& q = p.q;
   configure_pool_once(p.device);
+  p.stream = st;
   const size_t n = std::max<size_t>(static_cast<size_t>(q.plan.entry_count), 1);
   CU(p.blk.alloc(table_bytes(q) + DeviceBlock::pad(extra_bytes) + 4096, st));
-  for (int a = 0; a < q.prog.n_accs; ++a) p.accs[a] = reinterpret_cast<int64_t*>(p.blk.take(acc_array_bytes(q, a)));
+  /* arrays of one reduction class (int64 SUM: COUNT / SUM_I64; f64 SUM; MIN; MAX; flags; bitmap) sit next to each other, so
+   * that the cross-GPU merge is ONE collective per class over a contiguous range (C2: COUNT + SUM = one all-reduce) */
+  for (int cls = 0; cls < kMergeClasses; ++cls)
+    for (int a = 0; a < q.prog.n_accs; ++a)
+      if (merge_class(q.prog.accs[a].op) == cls) p.accs[a] = reinterpret_cast<int64_t*>(p.blk.take(acc_array_bytes(q, a)));
   if (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL) p.keys = reinterpret_cast<int64_t*>(p.blk.take(n * 8));
   if (q.smem.use_smem) p.smem_image = p.blk.take(std::max<int>(q.smem.replica_bytes, 16));
   p.d_error = reinterpret_cast<int32_t*>(p.blk.take(256));
-  p.split = q.plan.kernel == B2Q_KERNEL_PERFECT_GLOBAL || q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL;
+  p.split = q.plan.kernel == B2Q_KERNEL_PERFECT_GLOBAL || (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL && !p.radix);
   for (auto& e : p.ev) CU(cudaEventCreate(&e));
   CU(cudaMemsetAsync(p.d_error, 0, sizeof(int32_t), st));
   CU(cudaEventRecord(p.ev[0], st));
@@ -252,6 +303,79 @@ static int32_t alloc_partial(B2QPartial& p, size_t extra_bytes, cudaStream_t st)
   for (int a = 0; a < q.prog.n_accs; ++a) /* the estimator's bitmap starts all-zero */
     if (q.prog.accs[a].op == ACC_NDV) CU(cudaMemsetAsync(p.accs[a], 0, acc_array_bytes(q, a), st));
   CU(cudaEventRecord(p.ev[1], st));
+  return B2Q_OK;
+}
+
+/* ---- baseline hash through the radix-partitioned aggregation ------------------------------------------------------
+ * B2Q_BASELINE_RADIX=0 keeps the per-row probe kernel (experiments / the fallback's own tests). */
+static bool radix_enabled() {
+  static const bool on = []() { const char* e = getenv("B2Q_BASELINE_RADIX"); return !e || atoi(e) != 0; }();
+  return on;
+}
+
+/* memory a new stream-ordered allocation can count on: free device memory + what the pool holds but does not use */
+static size_t pool_headroom(int device) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return size_t(1) << 30; }
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+      free_b += static_cast<size_t>(reserved - used);
+  }
+  cudaGetLastError();
+  return free_b;
+}
+
+/* buffers for launches of up to `max_chunks` chunks; larger launches run in batches over the same buffers */
+static int32_t radix_prepare(B2QPartial& p, int64_t max_chunks, cudaStream_t st) {
+  const B2QQuery& q = p.q;
+  const size_t budget = std::max<size_t>(pool_headroom(p.device) / 2, size_t(256) << 20);
+  int64_t batch = std::max<int64_t>(max_chunks, 1);
+  int n_cta1 = 0;
+  uint32_t cap = 0;
+  size_t tuples = 0;
+  for (;;) {
+    radix_geometry(q, p.rp, batch, &n_cta1, &cap);
+    tuples = static_cast<size_t>(p.rp.n_parts) * n_cta1 * cap;
+    if ((tuples < (size_t(1) << 32) - 2 && tuples * p.rp.tuple_words * 8 <= budget) || batch <= n_cta1) break;
+    batch = (batch + 1) / 2;
+  }
+  if (tuples >= (size_t(1) << 32) - 2) return set_err(B2Q_ERR_OUT_OF_GPU_MEM, "radix scratch does not fit");
+  const size_t b_scratch = DeviceBlock::pad(tuples * p.rp.tuple_words * 8);
+  const size_t b_counts = DeviceBlock::pad(static_cast<size_t>(p.rp.n_parts) * n_cta1 * 4);
+  const size_t b_ov = DeviceBlock::pad(static_cast<size_t>(p.rp.n_parts) * B2Q_RADIX_OV * (1 + q.prog.n_accs) * 8);
+  const uint32_t list_cap = 1u << 18;
+  const size_t b_list = DeviceBlock::pad(static_cast<size_t>(list_cap) * p.rp.tuple_words * 8);
+  int8_t* base = nullptr;
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&base), b_scratch + b_counts + b_ov + b_list + 256, st));
+  p.extra.push_back(base);
+  p.rb.scratch = reinterpret_cast<int64_t*>(base);
+  p.rb.counts = reinterpret_cast<uint32_t*>(base + b_scratch);
+  p.rb.ov = reinterpret_cast<int64_t*>(base + b_scratch + b_counts);
+  p.rb.list = reinterpret_cast<int64_t*>(base + b_scratch + b_counts + b_ov);
+  p.rb.work_counter = reinterpret_cast<uint32_t*>(base + b_scratch + b_counts + b_ov + b_list);
+  p.rb.list_count = p.rb.work_counter + 1;
+  p.rb.list_cap = list_cap;
+  p.radix_batch_chunks = batch;
+  p.radix_n_cta1 = n_cta1;
+  p.radix_cap = cap;
+  return B2Q_OK;
+}
+
+static int32_t radix_launch(B2QPartial& p, const DevLaunch& L, cudaStream_t st) {
+  for (int64_t c0 = 0; c0 < L.total_chunks; c0 += p.radix_batch_chunks) {
+    const int64_t c1 = std::min(L.total_chunks, c0 + p.radix_batch_chunks);
+    int n_cta1 = p.radix_n_cta1;
+    uint32_t cap = p.radix_cap;
+    if (c1 - c0 < p.radix_batch_chunks) { /* a short (last) batch: fewer CTAs / smaller regions inside the same buffers */
+      radix_geometry(p.q, p.rp, c1 - c0, &n_cta1, &cap);
+      if (static_cast<size_t>(n_cta1) * cap > static_cast<size_t>(p.radix_n_cta1) * p.radix_cap) { n_cta1 = p.radix_n_cta1; cap = p.radix_cap; }
+    }
+    CU(launch_radix(p.q, p.rp, L, p.rb, c0, c1, n_cta1, cap, st));
+    p.launches += 3;
+  }
   return B2Q_OK;
 }
 
@@ -264,7 +388,7 @@ static int32_t scan_device_fragments(B2QPartial& p, int nf, const std::vector<co
   const B2QQuery& q = p.q;
   int block, ctas;
   scan_config(q, &block, &ctas);
-  const int64_t chunk_rows = scan_rows_per_chunk(block);
+  const int64_t chunk_rows = p.radix ? radix_chunk_rows() : scan_rows_per_chunk(block);
   const size_t ncols = cols.size();
   std::vector<int64_t> host(ncols + nf + nf + 1);
   memcpy(host.data(), cols.data(), ncols * 8);
@@ -287,9 +411,18 @@ static int32_t scan_device_fragments(B2QPartial& p, int nf, const std::vector<co
   L.keys = p.keys;
   L.error = p.d_error;
   L.join_buff = p.join_buff;
+  if (p.radix) {
+    const int32_t rc = radix_prepare(p, L.total_chunks, st);
+    if (rc != B2Q_OK) return rc;
+  }
   if (time_it) CU(cudaEventRecord(p.ev[2], st));
-  CU(launch_scan(q, L, p.smem_image, block, ctas, prefetch_distance_for(q, cols), st));
-  p.launches += 1;
+  if (p.radix) {
+    const int32_t rc = radix_launch(p, L, st);
+    if (rc != B2Q_OK) return rc;
+  } else {
+    CU(launch_scan(q, L, p.smem_image, block, ctas, prefetch_distance_for(q, cols), st));
+    p.launches += 1;
+  }
   if (time_it) { CU(cudaEventRecord(p.ev[3], st)); p.scan_timed = true; }
   /* `host` is pageable: the copy above was staged by the runtime before cudaMemcpyAsync returned */
   return B2Q_OK;
@@ -366,7 +499,11 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
   }
   int block, ctas;
   scan_config(q, &block, &ctas);
-  const int64_t chunk_rows = scan_rows_per_chunk(block);
+  const int64_t chunk_rows = p.radix ? radix_chunk_rows() : scan_rows_per_chunk(block);
+  if (p.radix) {
+    const int32_t prc = radix_prepare(p, (cap_rows + chunk_rows - 1) / chunk_rows, st);
+    if (prc != B2Q_OK) { cleanup(); return prc; }
+  }
   /* per-slice launch tables live in one device allocation, written once up front */
   struct Slice { int frag; int64_t row0, rows; };
   std::vector<Slice> slices;
@@ -433,9 +570,14 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
     L.keys = p.keys;
     L.error = p.d_error;
     L.join_buff = p.join_buff;
-    cudaError_t e = launch_scan(q, L, p.smem_image, block, ctas, 0 /* slices arrive straight from PCIe */, st);
-    if (e != cudaSuccess) { rc = set_err(B2Q_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e)); break; }
-    p.launches += 1;
+    if (p.radix) {
+      rc = radix_launch(p, L, st);
+      if (rc != B2Q_OK) break;
+    } else {
+      cudaError_t e = launch_scan(q, L, p.smem_image, block, ctas, 0 /* slices arrive straight from PCIe */, st);
+      if (e != cudaSuccess) { rc = set_err(B2Q_ERR_CUDA, std::string("scan launch: ") + cudaGetErrorString(e)); break; }
+      p.launches += 1;
+    }
     cudaEventRecord(s.scanned, st);
     s.busy = true;
   }
@@ -565,9 +707,34 @@ static int32_t prepare_join(B2QPartial& p, const B2QExecUnit& u, cudaStream_t st
   return B2Q_OK;
 }
 
+static int32_t execute_partial_attempt(size_t* guess, const B2QTableInfo* tbl, const B2QExecUnit* u,
+                                       const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card,
+                                       cudaStream_t st, bool allow_radix, bool defer, B2QPartial** out);
+
 static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, const B2QExecUnit* u,
                                     const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card,
                                     cudaStream_t st, B2QPartial** out) {
+  int32_t rc = execute_partial_attempt(guess, tbl, u, co, eo, has_card, st, radix_enabled(), false, out);
+  /* a structure of the radix path was too small for this input (hash clusters longer than its overflow areas): the
+   * per-row probe kernel handles anything */
+  if (rc == B2Q_RADIX_RETRY) rc = execute_partial_attempt(guess, tbl, u, co, eo, has_card, st, false, false, out);
+  return rc;
+}
+
+/* what a non-zero device error word means at the boundary */
+static int32_t device_error(int32_t dev_err) {
+  if (dev_err == B2Q_RADIX_RETRY) return set_err(dev_err, "radix path: retry with the probe kernel");
+  if (dev_err == B2Q_ERR_UNSUPPORTED) return set_err(dev_err, "join is not one-to-one (the reference rebuilds a one-to-many table): outside this path");
+  if (dev_err) return set_err(dev_err, dev_err == B2Q_ERR_OUT_OF_SLOTS ? "group-by table is full (OUT_OF_SLOTS)" : "group or join key outside the chunk-stats range");
+  return B2Q_OK;
+}
+
+/* defer = true: nothing is synchronised here — the error word travels to the pinned p->h_err on the stream and the
+ * caller checks it (partial_complete) after its own synchronize: scan -> merge -> materialise -> D2H is then ONE stream
+ * of work with one host wait at the end. */
+static int32_t execute_partial_attempt(size_t* guess, const B2QTableInfo* tbl, const B2QExecUnit* u,
+                                       const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card,
+                                       cudaStream_t st, bool allow_radix, bool defer, B2QPartial** out) {
   if (!tbl || !u || !co || !eo || !out) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
   if (co->device_type != B2Q_DEVICE_GPU) return set_err(B2Q_ERR_UNSUPPORTED, "device_type must be GPU: this path has no CPU execution");
   std::unique_ptr<B2QPartial> p(new B2QPartial());
@@ -578,6 +745,7 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
   if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible; this path has no CPU fallback");
   if (eo->device_ordinal >= 0) CU(cudaSetDevice(eo->device_ordinal));
   CU(cudaGetDevice(&p->device));
+  p->radix = allow_radix && eo->force_kernel != B2Q_KERNEL_BASELINE_PROBE && radix_plan(p->q, &p->rp);
   const size_t extra = tbl->memory_level == B2Q_GPU_LEVEL ? launch_table_bytes(tbl->num_fragments, p->q.prog.n_cols) : 0;
   rc = alloc_partial(*p, extra, st);
   if (rc != B2Q_OK) return rc;
@@ -611,13 +779,27 @@ static int32_t execute_partial_impl(size_t* guess, const B2QTableInfo* tbl, cons
   }
   rc = normalize_partial(*p, st);
   if (rc != B2Q_OK) return rc;
+  if (defer && tbl->memory_level == B2Q_GPU_LEVEL) {
+    p->h_err = reinterpret_cast<int32_t*>(pinned_cache().get(64, &p->h_err_cap));
+    if (!p->h_err) return set_err(B2Q_ERR_INVALID_ARGUMENT, "out of (pinned) host memory");
+    *p->h_err = 0;
+    p->deferred = true;
+    *out = p.release();
+    return B2Q_OK;
+  }
   int32_t dev_err = 0;
   CU(cudaMemcpyAsync(&dev_err, p->d_error, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   collect_timings(*p);
-  if (dev_err == B2Q_ERR_UNSUPPORTED) return set_err(dev_err, "join is not one-to-one (the reference rebuilds a one-to-many table): outside this path");
-  if (dev_err) return set_err(dev_err, dev_err == B2Q_ERR_OUT_OF_SLOTS ? "group-by table is full (OUT_OF_SLOTS)" : "group or join key outside the chunk-stats range");
+  rc = device_error(dev_err);
+  if (rc != B2Q_OK) return rc;
   *out = p.release();
+  return B2Q_OK;
+}
+
+/* deferred partial: enqueue the copy of the error word (after whatever merged it across devices) */
+static int32_t partial_enqueue_error_copy(B2QPartial& p, cudaStream_t st) {
+  if (p.deferred) CU(cudaMemcpyAsync(p.h_err, p.d_error, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   return B2Q_OK;
 }
 
@@ -710,6 +892,9 @@ static DevGatherCols gather_cols_of(const B2QPlan& in, const B2QPlan& out) {
 
 /* get_truncated_row_count-style window over `n` sorted rows: [first, first + count) */
 static void limit_window(const B2QQuery& q, int64_t n, int64_t* first, int64_t* count) {
+  /* LIMIT 0: RelSort::isEmptyResult() (RelAlgDag.h:2557) turns the step into just_validate and an empty result
+   * (RelAlgExecutor.cpp:1277, :3559); a unit that still carries it gets exactly that */
+  if (q.has_limit && q.limit == 0) { *first = 0; *count = 0; return; }
   const int64_t top_n = (q.has_limit ? q.limit : 0) + q.offset; /* rs->sort(order_entries, limit + offset) */
   int64_t kept = (q.n_order && top_n) ? std::min(top_n, n) : n;  /* topPermutation resizes to top_n */
   *first = std::min<int64_t>(q.offset, kept);                   /* dropFirstN(offset) */
@@ -718,8 +903,28 @@ static void limit_window(const B2QQuery& q, int64_t n, int64_t* first, int64_t* 
   *count = c;
 }
 
+static int32_t finalize_core(B2QPartial* p, cudaStream_t st, B2QResultSet** out);
+
 static int32_t finalize_impl(B2QPartial* p, cudaStream_t st, B2QResultSet** out) {
   if (!p || !out) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
+  if (p->deferred) {
+    const int32_t rc0 = partial_enqueue_error_copy(*p, st);
+    if (rc0 != B2Q_OK) return rc0;
+  }
+  int32_t rc = finalize_core(p, st, out);
+  if (!p->deferred) return rc;
+  /* the call's one host wait has happened inside finalize_core (or happens here when nothing was copied back) */
+  if (cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); if (rc == B2Q_OK) { delete *out; *out = nullptr; } return set_err(B2Q_ERR_CUDA, "stream synchronize"); }
+  collect_timings(*p);
+  p->deferred = false;
+  const int32_t dev_err = *p->h_err;
+  if (rc == B2Q_OK && dev_err) { delete *out; *out = nullptr; }
+  if (dev_err) return device_error(dev_err);
+  if (rc == B2Q_OK) { (*out)->scan_ms = p->scan_ms; (*out)->init_ms = p->init_ms; }
+  return rc;
+}
+
+static int32_t finalize_core(B2QPartial* p, cudaStream_t st, B2QResultSet** out) {
   CU(cudaSetDevice(p->device));
   std::unique_ptr<B2QResultSet> rs(new B2QResultSet());
   rs->q = p->q;
@@ -840,6 +1045,115 @@ static bool rs_is_empty_entry(const B2QResultSet* rs, int64_t e) {
 }
 
 
+/* ---- cross-GPU merge of a partial (NCCL, on the stream that produced it) -------------------------------------------
+ * Dense tables are position-aligned on every device (all devices plan over the same key ranges) and initialised to the
+ * identity of their reduction: the merge is one in-place all-reduce per reduction class, grouped into one NCCL launch,
+ * with the device error word riding along (MAX) so that every rank reports the same outcome.  No host synchronisation
+ * between scan, merge and materialise. */
+#define NC(call)                                                                                                      \
+  do {                                                                                                                \
+    ncclResult_t r__ = (call);                                                                                        \
+    if (r__ != ncclSuccess) return set_err(B2Q_ERR_CUDA, std::string(#call) + ": " + api->GetErrorString(r__));       \
+  } while (0)
+
+/* Baseline-hash tables are not position-aligned across devices (each device claimed its slots in its own order): every rank
+ * gathers the peers' key / accumulator arrays and re-probes their entries into its own table — ResultSetStorage::reduce for
+ * baseline layouts (ResultSetReduction.cpp:698-828) on the device.  Afterwards every rank holds the same set of rows. */
+static int32_t b2q_baseline_merge(B2QPartial& p, const B2QComm* comm, const NcclApi* api, cudaStream_t st) {
+  const B2QQuery& q = p.q;
+  if (p.split) return set_err(B2Q_ERR_CUDA, "internal: split accumulators reached the baseline merge");
+  const int64_t E = q.plan.entry_count;
+  const int na = q.prog.n_accs;
+  const size_t arr = static_cast<size_t>(E) * 8;
+  int8_t* stage = nullptr;
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&stage), arr * comm->nranks * (1 + na) + 256, st));
+  p.extra.push_back(stage);
+  const int64_t* g_keys = reinterpret_cast<const int64_t*>(stage);
+  const int64_t* g_accs[B2Q_MAX_ACCS];
+  NC(api->GroupStart());
+  NC(api->AllGather(p.keys, stage, static_cast<size_t>(E), ncclInt64, comm->comm, st));
+  for (int a = 0; a < na; ++a) {
+    int8_t* dst = stage + arr * comm->nranks * (1 + a);
+    g_accs[a] = reinterpret_cast<const int64_t*>(dst);
+    NC(api->AllGather(p.accs[a], dst, static_cast<size_t>(E), ncclInt64, comm->comm, st));
+  }
+  NC(api->AllReduce(p.d_error, p.d_error, 1, ncclInt32, ncclMax, comm->comm, st));
+  NC(api->GroupEnd());
+  CU(launch_baseline_merge(q, g_keys, g_accs, E * comm->nranks, E * comm->rank, E * (comm->rank + 1), p.keys, p.accs, p.d_error, st));
+  p.launches += 1;
+  /* a rank whose merged table ran out of slots must not be the only one to say so */
+  NC(api->AllReduce(p.d_error, p.d_error, 1, ncclInt32, ncclMax, comm->comm, st));
+  return B2Q_OK;
+}
+
+static int32_t merge_partial(B2QPartial& p, const B2QComm* comm, cudaStream_t st) {
+  if (!comm || comm->nranks <= 1) return B2Q_OK;
+  std::string why;
+  const NcclApi* api = nccl_api(&why);
+  if (!api) return set_err(B2Q_ERR_UNSUPPORTED, why);
+  const B2QQuery& q = p.q;
+  if (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL) return b2q_baseline_merge(p, comm, api, st);
+  struct Span { int8_t* lo; int8_t* hi; int cls; };
+  std::vector<Span> spans;
+  for (int cls = 0; cls < kMergeClasses; ++cls)
+    for (int a = 0; a < q.prog.n_accs; ++a) {
+      if (merge_class(q.prog.accs[a].op) != cls) continue;
+      int8_t* lo = reinterpret_cast<int8_t*>(p.accs[a]);
+      int8_t* hi = lo + DeviceBlock::pad(acc_array_bytes(q, a));
+      if (q.prog.accs[a].op == ACC_TOUCH) hi = lo + DeviceBlock::pad(std::max<size_t>(static_cast<size_t>(q.plan.entry_count), 1));
+      if (!spans.empty() && spans.back().cls == cls && spans.back().hi == lo) spans.back().hi = hi; /* contiguous: one collective */
+      else spans.push_back({lo, hi, cls});
+    }
+  int8_t* gathered = nullptr; /* estimator bitmaps: NCCL has no OR — all-gather, then OR on the device */
+  NC(api->GroupStart());
+  for (const Span& sp : spans) {
+    const size_t bytes = static_cast<size_t>(sp.hi - sp.lo);
+    switch (sp.cls) {
+      case MERGE_SUM_I64: NC(api->AllReduce(sp.lo, sp.lo, bytes / 8, ncclInt64, ncclSum, comm->comm, st)); break;
+      case MERGE_SUM_F64: NC(api->AllReduce(sp.lo, sp.lo, bytes / 8, ncclFloat64, ncclSum, comm->comm, st)); break;
+      case MERGE_MIN: NC(api->AllReduce(sp.lo, sp.lo, bytes / 8, ncclInt64, ncclMin, comm->comm, st)); break;
+      case MERGE_MAX: NC(api->AllReduce(sp.lo, sp.lo, bytes / 8, ncclInt64, ncclMax, comm->comm, st)); break;
+      case MERGE_FLAG: NC(api->AllReduce(sp.lo, sp.lo, bytes, ncclUint8, ncclMax, comm->comm, st)); break;
+      default: {
+        if (cudaMallocAsync(reinterpret_cast<void**>(&gathered), bytes * comm->nranks, st) != cudaSuccess) { cudaGetLastError(); api->GroupEnd(); return set_err(B2Q_ERR_OUT_OF_GPU_MEM, "estimator merge buffer"); }
+        p.extra.push_back(gathered);
+        NC(api->AllGather(sp.lo, gathered, bytes, ncclUint8, comm->comm, st));
+        break;
+      }
+    }
+  }
+  NC(api->AllReduce(p.d_error, p.d_error, 1, ncclInt32, ncclMax, comm->comm, st));
+  NC(api->GroupEnd());
+  if (gathered)
+    for (const Span& sp : spans)
+      if (sp.cls == MERGE_BOR) CU(launch_bitmap_or(reinterpret_cast<uint64_t*>(sp.lo), reinterpret_cast<const uint64_t*>(gathered), static_cast<int64_t>(sp.hi - sp.lo) / 8, comm->nranks, st));
+  return B2Q_OK;
+}
+
+/* one rank's share of a multi-device work unit: scan -> merge -> materialise -> D2H, one host wait at the end */
+static int32_t execute_work_unit_rank(const B2QComm* comm, size_t* guess, const B2QTableInfo* tbl, const B2QExecUnit* u,
+                                      const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card,
+                                      cudaStream_t st, bool finalize, B2QResultSet** out, double* kernel_ms) {
+  B2QExecutionOptions eo_dev = *eo;
+  if (comm) eo_dev.device_ordinal = comm->device;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    B2QPartial* p = nullptr;
+    int32_t rc = execute_partial_attempt(guess, tbl, u, co, &eo_dev, has_card, st, attempt == 0 && radix_enabled(), tbl->memory_level == B2Q_GPU_LEVEL, &p);
+    if (rc != B2Q_OK) return rc; /* planning errors are the same on every rank: nobody reaches the collective */
+    rc = merge_partial(*p, comm, st);
+    if (rc == B2Q_OK && finalize) rc = finalize_impl(p, st, out);
+    else if (rc == B2Q_OK) { /* a device that only contributes: wait for its part, report its error word */
+      if (p->deferred) rc = partial_enqueue_error_copy(*p, st);
+      if (rc == B2Q_OK && cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); rc = set_err(B2Q_ERR_CUDA, "stream synchronize"); }
+      if (rc == B2Q_OK) { collect_timings(*p); if (p->deferred) { p->deferred = false; rc = device_error(*p->h_err); } }
+    }
+    if (kernel_ms) *kernel_ms = p->scan_ms;
+    delete p;
+    if (rc != B2Q_RADIX_RETRY) return rc; /* the error word was MAX-merged: every rank retries together */
+  }
+  return set_err(B2Q_ERR_CUDA, "internal: radix retry did not converge");
+}
+
 extern "C" {
 
 int32_t b2q_abi_version(void) { return B2Q_ABI_VERSION; }
@@ -891,12 +1205,17 @@ int32_t b2q_execute_partial(size_t* guess, int32_t /*is_agg*/, const B2QTableInf
 int32_t b2q_execute_work_unit(size_t* guess, int32_t is_agg, const B2QTableInfo* tbl, const B2QExecUnit* u,
                               const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card,
                               B2QResultSet** out) {
-  B2QPartial* p = nullptr;
-  int32_t rc = b2q_execute_partial(guess, is_agg, tbl, u, co, eo, has_card, nullptr, &p);
-  if (rc != B2Q_OK) return rc;
-  rc = finalize_impl(p, nullptr, out);
-  delete p;
-  return rc;
+  (void)is_agg;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    B2QPartial* p = nullptr;
+    int32_t rc = execute_partial_attempt(guess, tbl, u, co, eo, has_card, nullptr, attempt == 0 && radix_enabled(), true, &p);
+    if (rc == B2Q_OK) {
+      rc = finalize_impl(p, nullptr, out);
+      delete p;
+    }
+    if (rc != B2Q_RADIX_RETRY) return rc;
+  }
+  return set_err(B2Q_ERR_CUDA, "internal: radix retry did not converge");
 }
 
 int32_t b2q_partial_num_arrays(const B2QPartial* p) { return p ? p->q.prog.n_accs : 0; }
@@ -1255,6 +1574,108 @@ int32_t b2q_rs_create_from_storage(const B2QQuery* q, const int8_t* storage, siz
   if (size_bytes) memcpy(rs->buf, storage, size_bytes);
   rs->buf_size = size_bytes;
   *out = rs.release();
+  return B2Q_OK;
+}
+
+/* ---- multi-GPU entry points ------------------------------------------------------------------------------------ */
+int32_t b2q_comm_unique_id(void* id128) {
+  std::string why;
+  const NcclApi* api = nccl_api(&why);
+  if (!api) return set_err(B2Q_ERR_UNSUPPORTED, why);
+  if (!id128) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
+  static_assert(sizeof(ncclUniqueId) == B2Q_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  const ncclResult_t r = api->GetUniqueId(&id);
+  if (r != ncclSuccess) return set_err(B2Q_ERR_CUDA, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
+  memcpy(id128, &id, sizeof(id));
+  return B2Q_OK;
+}
+
+int32_t b2q_comm_init_rank(const void* id128, int32_t nranks, int32_t rank, int32_t device, B2QComm** out) {
+  std::string why;
+  const NcclApi* api = nccl_api(&why);
+  if (!api) return set_err(B2Q_ERR_UNSUPPORTED, why);
+  if (!id128 || !out || nranks < 1 || rank < 0 || rank >= nranks) return set_err(B2Q_ERR_INVALID_ARGUMENT, "communicator arguments");
+  if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible");
+  if (device >= 0) CU(cudaSetDevice(device));
+  std::unique_ptr<B2QComm> c(new B2QComm());
+  CU(cudaGetDevice(&c->device));
+  c->rank = rank;
+  c->nranks = nranks;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  const ncclResult_t r = api->CommInitRank(&c->comm, nranks, id, rank);
+  if (r != ncclSuccess) return set_err(B2Q_ERR_CUDA, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
+  *out = c.release();
+  return B2Q_OK;
+}
+
+int32_t b2q_comm_init_all(const int32_t* devices, int32_t ndev, B2QComm** out) {
+  std::string why;
+  const NcclApi* api = nccl_api(&why);
+  if (!api) return set_err(B2Q_ERR_UNSUPPORTED, why);
+  if (!devices || !out || ndev < 1 || ndev > 64) return set_err(B2Q_ERR_INVALID_ARGUMENT, "communicator arguments");
+  if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible");
+  std::vector<ncclComm_t> comms(ndev);
+  std::vector<int> devs(devices, devices + ndev);
+  const ncclResult_t r = api->CommInitAll(comms.data(), ndev, devs.data());
+  if (r != ncclSuccess) return set_err(B2Q_ERR_CUDA, std::string("ncclCommInitAll: ") + api->GetErrorString(r));
+  for (int i = 0; i < ndev; ++i) {
+    out[i] = new B2QComm();
+    out[i]->comm = comms[i];
+    out[i]->rank = i;
+    out[i]->nranks = ndev;
+    out[i]->device = devs[i];
+  }
+  return B2Q_OK;
+}
+
+void b2q_comm_destroy(B2QComm* c) {
+  if (!c) return;
+  const NcclApi* api = nccl_api(nullptr);
+  if (api && c->comm) api->CommDestroy(c->comm);
+  delete c;
+}
+int32_t b2q_comm_rank(const B2QComm* c) { return c ? c->rank : -1; }
+int32_t b2q_comm_size(const B2QComm* c) { return c ? c->nranks : 0; }
+
+int32_t b2q_execute_work_unit_dist(B2QComm* comm, size_t* guess, int32_t /*is_agg*/, const B2QTableInfo* tbl, const B2QExecUnit* u,
+                                   const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card, void* stream,
+                                   B2QResultSet** out) {
+  if (!comm || !eo) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
+  return execute_work_unit_rank(comm, guess, tbl, u, co, eo, has_card, static_cast<cudaStream_t>(stream), true, out, nullptr);
+}
+
+int32_t b2q_execute_work_unit_multi(B2QComm* const* comms, int32_t ndev, size_t* guess, int32_t /*is_agg*/, const B2QTableInfo* const* tbls,
+                                    const B2QExecUnit* u, const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card,
+                                    B2QResultSet** out) {
+  if (!comms || !tbls || !eo || !out || ndev < 1) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
+  /* one host thread per device (Executor::launchKernelsViaResourceMgr -> ExecutionKernel::run, Execute.cpp:3055-3101,
+   * ExecutionKernel.cpp:215-218); device 0 of the list materialises the merged table */
+  std::vector<int32_t> rcs(ndev, B2Q_OK);
+  std::vector<std::string> msgs(ndev);
+  std::vector<std::thread> ths;
+  const size_t g = guess ? *guess : 0;
+  for (int i = 0; i < ndev; ++i)
+    ths.emplace_back([&, i]() {
+      size_t gi = g;
+      cudaStream_t st = nullptr;
+      if (cudaSetDevice(comms[i]->device) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        rcs[i] = B2Q_ERR_CUDA;
+        msgs[i] = "device / stream setup";
+        return;
+      }
+      rcs[i] = execute_work_unit_rank(comms[i], &gi, tbls[i], u, co, eo, has_card, st, i == 0, i == 0 ? out : nullptr, nullptr);
+      if (rcs[i] != B2Q_OK) msgs[i] = g_err;
+      cudaStreamDestroy(st);
+    });
+  for (auto& t : ths) t.join();
+  for (int i = 0; i < ndev; ++i)
+    if (rcs[i] != B2Q_OK) {
+      if (i != 0 && rcs[0] == B2Q_OK && out && *out) { delete *out; *out = nullptr; }
+      return set_err(rcs[i], msgs[i]);
+    }
   return B2Q_OK;
 }
 

@@ -109,6 +109,16 @@ __global__ void b2q_k_join_split(const int64_t* __restrict__ split, int64_t* __r
     out[i] = (int64_t)(((uint64_t)(uint32_t)hi[i] << 32) + lo[i]);
 }
 
+/* estimator bitmaps of several devices (reduce_estimator_results, CardinalityEstimator.cpp:142-161): dst |= every gathered copy */
+__global__ void b2q_k_bitmap_or(uint64_t* __restrict__ dst, const uint64_t* __restrict__ gathered, int64_t words, int copies) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
+    uint64_t v = dst[i];
+    for (int c = 0; c < copies; ++c) v |= gathered[(size_t)c * words + i];
+    dst[i] = v;
+  }
+}
+
 /* ---------------------------------------------------------------------------------------------------------
  * materialise: dense accumulators -> the reference's row-wise output buffer
  * (layout: QueryMemoryDescriptor.cpp:848-955; empty-entry conventions: ResultSetIteration.cpp:2457-2492)
@@ -339,6 +349,15 @@ cudaError_t launch_init(const B2QQuery& q, int64_t* const* accs, int64_t* keys, 
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   b2q_k_init<<<(int)blocks, block, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bitmap_or(uint64_t* dst, const uint64_t* gathered, int64_t words, int copies, cudaStream_t st) {
+  if (words <= 0) return cudaSuccess;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  int64_t blocks = (words + 255) / 256;
+  if (blocks > cap) blocks = cap;
+  b2q_k_bitmap_or<<<(int)blocks, 256, 0, st>>>(dst, gathered, words, copies);
   return cudaGetLastError();
 }
 

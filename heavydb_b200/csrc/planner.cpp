@@ -1540,7 +1540,8 @@ class Planner {
       kernel = B2Q_KERNEL_PERFECT_GLOBAL;
     }
     if (eo_.force_kernel) {
-      const int f = eo_.force_kernel;
+      int f = eo_.force_kernel;
+      if (f == B2Q_KERNEL_BASELINE_PROBE && kernel == B2Q_KERNEL_BASELINE_GLOBAL) f = kernel; /* the executor reads the option: per-row probe instead of the radix passes */
       const bool ok = (f == kernel) || (f == B2Q_KERNEL_PERFECT_GLOBAL && kernel == B2Q_KERNEL_PERFECT_SMEM);
       if (!ok) reject(B2Q_ERR_INVALID_ARGUMENT, "force_kernel is not applicable to this query");
       if (f == B2Q_KERNEL_PERFECT_GLOBAL) { sm.use_smem = 0; sm.replicas = 1; sm.total_bytes = 0; }

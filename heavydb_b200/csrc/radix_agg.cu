@@ -1,0 +1,612 @@
+/*
+ * radix_agg.cu — baseline-hash GROUP BY (sparse / high-cardinality keys) as a two-pass radix-partitioned aggregation.
+ *
+ * Replaces, for the sparse-key case, what the reference does per row with get_group_value + get_matching_group_value
+ * (GroupByRuntime.cpp:25-48, cuda_mapd_rt.cu:180-216: MurmurHash3 home slot, linear probe, CAS claim on a table in
+ * global memory) followed by agg_*_shared atomics on the claimed row.  The table that comes out is the same kind of
+ * table — open addressing, h = MurmurHash3(key) % entry_count, every key reachable from its home slot by a linear probe
+ * over occupied slots — but no row ever touches it in HBM:
+ *
+ *   pass 1  b2q_k_radix_partition   streams the fragments once (same coalesced column loads and filter program as
+ *           b2q_k_scan), hashes the key and appends the tuple {key, argument values} of every passing row to the region
+ *           of (partition = home slot / S, this CTA).  Regions are private to a CTA, so the append cursor is a shared-
+ *           memory counter and the 16-byte tuple stores of one region land in consecutive addresses: the open 128-byte
+ *           lines of all regions (148 x P x 128 B ~ 35 MB) stay in L2 until complete, HBM sees full lines once.
+ *   pass 2  b2q_k_radix_aggregate   one CTA per partition: the partition's slice of the key / accumulator arrays
+ *           (S entries) is bulk-copied into shared memory (cp.async.bulk, TMA), the partition's tuples are streamed
+ *           through it — probe, claim and update are shared-memory operations —, and the slice is bulk-copied back.
+ *           Keys whose probe runs off the end of the slice go to a small overflow area per partition.
+ *   pass 3  b2q_k_radix_insert      merges the overflow areas (a few keys per partition) into the table in HBM with the
+ *           reference's global-memory probe.
+ *
+ * Algorithmic traffic: read columns + write tuples + read tuples ~ 3x the column bytes, sequential, instead of two
+ * random 32-byte sectors per row (profiles/r1_scan_c4s_v2_ncu.txt: 9.7x, 514 instructions/row).
+ * Rows a region has no room for (skewed keys) are inserted by pass 1 straight into the HBM table with the probe of the
+ * old kernel — any input is handled, uniform ones fast.
+ */
+#include "scan_kernel.cuh"
+#include "radix_agg.h"
+
+namespace b2q {
+
+constexpr int kRadixBlock = 1024;  /* pass 1 and pass 2: one CTA per SM */
+constexpr int kTupleBlock = 128;   /* pass 2: tuples a warp takes at a time (4 per lane) */
+
+/* ---- table in HBM: the reference's probe (get_group_value, GroupByRuntime.cpp:25-48) with plain 64-bit accumulators ---- */
+__device__ __forceinline__ uint32_t home_slot(int64_t key, int hw, uint64_t magic, uint32_t n) {
+  return (uint32_t)__umul64hi(magic * (uint64_t)murmur3_key(key, hw), (uint64_t)n); /* == MurmurHash3(key) % n */
+}
+
+__device__ __forceinline__ int64_t global_probe(unsigned long long* keys, uint32_t n, uint32_t h, int64_t key) {
+  const unsigned long long want = (unsigned long long)key;
+  uint32_t p = h;
+  for (;;) {
+    unsigned long long cur = __ldcg(keys + p);
+    if (cur == (unsigned long long)B2Q_I64_MAX) cur = atomicCAS(keys + p, (unsigned long long)B2Q_I64_MAX, want);
+    if (cur == (unsigned long long)B2Q_I64_MAX || cur == want) return p;
+    p = p + 1 == n ? 0 : p + 1;
+    if (p == h) return -1;
+  }
+}
+
+/* raw value -> accumulator, HBM table */
+__device__ __forceinline__ void global_acc_raw(int op, int64_t* slot, int64_t v) {
+  switch (op) {
+    case ACC_COUNT: atomicAdd(reinterpret_cast<unsigned long long*>(slot), 1ull); break;
+    case ACC_SUM_I64: atomicAdd(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)v); break;
+    case ACC_SUM_F64: red_add_f64(slot, __longlong_as_double(v)); break;
+    case ACC_MIN_I64: red_min_s64(slot, v); break;
+    case ACC_MAX_I64: red_max_s64(slot, v); break;
+    case ACC_MIN_F64: { const double d = __longlong_as_double(v); if (d == d) red_min_s64(slot, b2q_f64_to_ord(v)); break; }
+    case ACC_MAX_F64: { const double d = __longlong_as_double(v); if (d == d) red_max_s64(slot, b2q_f64_to_ord(v)); break; }
+    default: break;
+  }
+}
+/* partial accumulator -> accumulator (ResultSetStorage::reduceOneSlot's algebra on the internal arrays) */
+__device__ __forceinline__ void global_acc_merge(int op, int64_t* slot, int64_t v) {
+  switch (op) {
+    case ACC_COUNT: case ACC_SUM_I64: if (v) atomicAdd(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)v); break;
+    case ACC_SUM_F64: if (__longlong_as_double(v) != 0.0) red_add_f64(slot, __longlong_as_double(v)); break;
+    case ACC_MIN_I64: case ACC_MIN_F64: if (v != B2Q_I64_MAX) red_min_s64(slot, v); break;
+    case ACC_MAX_I64: case ACC_MAX_F64: if (v != B2Q_I64_MIN) red_max_s64(slot, v); break;
+    default: break;
+  }
+}
+
+__device__ __forceinline__ bool value_skipped(const DevAcc& a, int64_t v) {
+  if (a.is_fp) return a.skip1_en && __longlong_as_double(v) == __longlong_as_double(a.skip1_val);
+  const int64_t w = a.skip2_trunc32 ? (int64_t)(int32_t)v : v;
+  return (a.skip1_en && v == a.skip1_val) || (a.skip2_en && w == a.skip2_val);
+}
+
+/* one raw tuple {key, vals[]} into the HBM table */
+__device__ __forceinline__ void global_insert_raw(const RadixArgs& A, int64_t key, const int64_t* vals) {
+  const DevProgram& P = A.prog;
+  const uint32_t n = (uint32_t)P.key.entry_count;
+  const int64_t e = global_probe(reinterpret_cast<unsigned long long*>(A.launch.keys), n, home_slot(key, P.key.hash_key_width, P.key.hash_magic, n), key);
+  if (e < 0) { atomicCAS(A.launch.error, 0, B2Q_ERR_OUT_OF_SLOTS); return; }
+  for (int a = 0; a < P.n_accs; ++a) {
+    const DevAcc& acc = P.accs[a];
+    const int vi = A.acc_val[a];
+    const int64_t v = vi >= 0 ? vals[vi] : 0;
+    if (vi >= 0 && value_skipped(acc, v)) continue;
+    global_acc_raw(acc.op, A.launch.accs[a] + e, v);
+  }
+}
+
+/* ---- shared-memory slice (pass 2): 64-bit slots, 32-bit native atomics ---- */
+__device__ __forceinline__ void smem_add64(int64_t* slot, int64_t v) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(slot);
+  const uint32_t vl = (uint32_t)v;
+  const uint32_t old = atomicAdd(w, vl);
+  const int32_t hi = (int32_t)(v >> 32) + (int32_t)((uint32_t)(old + vl) < old);
+  if (hi != 0) atomicAdd(w + 1, (uint32_t)hi);
+}
+__device__ __forceinline__ void smem_acc_raw(int op, int64_t* slot, int64_t v) {
+  switch (op) {
+    case ACC_COUNT: smem_add64(slot, 1); break;
+    case ACC_SUM_I64: smem_add64(slot, v); break;
+    case ACC_SUM_F64: atomicAdd(reinterpret_cast<double*>(slot), __longlong_as_double(v)); break;
+    case ACC_MIN_I64: if (v < *reinterpret_cast<volatile long long*>(slot)) atomicMin(reinterpret_cast<long long*>(slot), (long long)v); break;
+    case ACC_MAX_I64: if (v > *reinterpret_cast<volatile long long*>(slot)) atomicMax(reinterpret_cast<long long*>(slot), (long long)v); break;
+    case ACC_MIN_F64: { const double d = __longlong_as_double(v); if (d == d) { const long long o = b2q_f64_to_ord(v); if (o < *reinterpret_cast<volatile long long*>(slot)) atomicMin(reinterpret_cast<long long*>(slot), o); } break; }
+    case ACC_MAX_F64: { const double d = __longlong_as_double(v); if (d == d) { const long long o = b2q_f64_to_ord(v); if (o > *reinterpret_cast<volatile long long*>(slot)) atomicMax(reinterpret_cast<long long*>(slot), o); } break; }
+    default: break;
+  }
+}
+
+/* ==========================================================================================================
+ * pass 1: partition
+ * ======================================================================================================== */
+template <bool KEY32, bool FULL>
+__device__ __forceinline__ void partition_chunk(const RadixArgs& A, const int8_t* const* __restrict__ cols, int64_t row0, int64_t frag_rows,
+                                                uint32_t* s_cnt, uint64_t pol) {
+  constexpr int nthr = kRadixBlock;
+  const DevProgram& P = A.prog;
+  uint32_t valid = (1u << R) - 1u;
+  if (!FULL) {
+    valid = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) valid |= (uint32_t)(row0 + (int64_t)j * nthr < frag_rows) << j;
+  }
+  int32_t k32[KEY32 ? R : 1];
+  int64_t k64[KEY32 ? 1 : R];
+  const bool eager_key = P.eager_key;
+  if (eager_key) {
+    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, valid, pol);
+    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, valid, pol);
+  }
+  const uint32_t pass = eval_filter<FULL, 0>(P.filter, cols, row0, nthr, valid, pol, P.col_inner, nullptr, -1, nullptr, P.col_null);
+  if (!eager_key) {
+    if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, pass, pol);
+    else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, pass, pol);
+  }
+  const uint32_t n = (uint32_t)P.key.entry_count;
+  const uint64_t magic = P.key.hash_magic;
+  const int hw = P.key.hash_key_width;
+  const int tw = A.tuple_words;
+  const uint32_t region0 = blockIdx.x * A.cap;          /* this CTA's region inside a partition's block of regions */
+  const uint32_t part_stride = gridDim.x * A.cap;
+#define B2Q_KEY_OF(j) (KEY32 ? (int64_t)k32[KEY32 ? (j) : 0] : k64[KEY32 ? 0 : (j)])
+  /* The append cursor of (partition, this CTA) is a shared-memory counter; the tuple goes to the region's next free place.
+   * Register budget (64 at 1024 threads): keys and ONE value vector stay live, places are computed row by row. */
+  if (tw == 2) { /* {key, one value}: one 16-byte store per row */
+    int64_t v[R];
+    if (A.val_width[0] == 8) load64<true>(v, cols[A.val_col[0]], row0, nthr, pass, pol);
+    else {
+      int32_t t32[R];
+      load32<true>(t32, cols[A.val_col[0]], A.val_width[0], row0, nthr, pass, pol);
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = t32[j];
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (!(pass >> j & 1)) continue;
+      int64_t key = B2Q_KEY_OF(j);
+      if (key == P.key.null_val) key = P.key.null_logical; /* ENCODING FIXED: physical NULL -> logical NULL */
+      const uint32_t part = home_slot(key, hw, magic, n) >> A.log_s;
+      const uint32_t pos = atomicAdd(s_cnt + part, 1u);
+      if (pos < A.cap) {
+        int64_t* dst = A.scratch + ((uint64_t)part * part_stride + region0 + pos) * 2u;
+        asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(dst), "l"(key), "l"(v[j]) : "memory");
+      } else {
+        global_insert_raw(A, key, &v[j]); /* no room (skewed keys): the reference's probe on the table in HBM */
+      }
+    }
+    return;
+  }
+  uint32_t place[R]; /* tuple index inside the scratch area; ~0u: no room */
+  uint32_t direct = 0;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    place[j] = ~0u;
+    if (!(pass >> j & 1)) continue;
+    int64_t key = B2Q_KEY_OF(j);
+    if (key == P.key.null_val) key = P.key.null_logical;
+    const uint32_t part = home_slot(key, hw, magic, n) >> A.log_s;
+    const uint32_t pos = atomicAdd(s_cnt + part, 1u);
+    if (pos < A.cap) {
+      place[j] = part * part_stride + region0 + pos;
+      A.scratch[(uint64_t)place[j] * (uint64_t)tw] = key;
+    } else direct |= 1u << j;
+  }
+  for (int c = 0; c < A.n_vals; ++c) {
+    int64_t v[R];
+    if (A.val_width[c] == 8) load64<true>(v, cols[A.val_col[c]], row0, nthr, pass, pol);
+    else {
+      int32_t t32[R];
+      load32<true>(t32, cols[A.val_col[c]], A.val_width[c], row0, nthr, pass, pol);
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = t32[j];
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) if (place[j] != ~0u) A.scratch[(uint64_t)place[j] * (uint64_t)tw + 1 + c] = v[j];
+  }
+  if (direct) { /* rare: re-read the row's values one by one */
+#pragma unroll 1
+    for (int j = 0; j < R; ++j) {
+      if (!(direct >> j & 1)) continue;
+      int64_t key = B2Q_KEY_OF(j);
+      if (key == P.key.null_val) key = P.key.null_logical;
+      int64_t vals[B2Q_RADIX_MAX_VALS];
+      const int64_t row = row0 + (int64_t)j * nthr;
+      for (int c = 0; c < A.n_vals; ++c) {
+        const int8_t* b = cols[A.val_col[c]];
+        switch (A.val_width[c]) {
+          case 8: vals[c] = reinterpret_cast<const int64_t*>(b)[row]; break;
+          case 4: vals[c] = reinterpret_cast<const int32_t*>(b)[row]; break;
+          case 2: vals[c] = reinterpret_cast<const int16_t*>(b)[row]; break;
+          case -2: vals[c] = reinterpret_cast<const uint16_t*>(b)[row]; break;
+          case -1: vals[c] = reinterpret_cast<const uint8_t*>(b)[row]; break;
+          default: vals[c] = reinterpret_cast<const signed char*>(b)[row]; break;
+        }
+      }
+      global_insert_raw(A, key, vals);
+    }
+  }
+#undef B2Q_KEY_OF
+}
+
+template <bool KEY32>
+__global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_partition(const __grid_constant__ RadixArgs A) {
+  extern __shared__ __align__(16) uint32_t s_cnt[]; /* [n_parts] */
+  const DevProgram& P = A.prog;
+  const DevLaunch& Lh = A.launch;
+  const int tid = threadIdx.x;
+  constexpr int nthr = kRadixBlock;
+  const int64_t chunk_rows = (int64_t)nthr * R;
+  for (int i = tid; i < A.n_parts; i += nthr) s_cnt[i] = 0;
+  __syncthreads();
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  int frag = 0;
+  int64_t frag_first = 0;
+  int64_t next_first = __ldg(Lh.frag_chunk_start + 1);
+  for (int64_t chunk = A.chunk_begin + blockIdx.x; chunk < A.chunk_end; chunk += gridDim.x) {
+    while (chunk >= next_first) {
+      ++frag;
+      frag_first = next_first;
+      next_first = __ldg(Lh.frag_chunk_start + frag + 1);
+    }
+    const int64_t frag_rows = __ldg(Lh.frag_rows + frag);
+    const int64_t base_row = (chunk - frag_first) * chunk_rows;
+    const int8_t* const* __restrict__ cols = Lh.col_ptrs + (size_t)frag * P.n_cols;
+    if (base_row + chunk_rows <= frag_rows) partition_chunk<KEY32, true>(A, cols, base_row + tid, frag_rows, s_cnt, pol);
+    else partition_chunk<KEY32, false>(A, cols, base_row + tid, frag_rows, s_cnt, pol);
+    __syncwarp(); /* the (rare) probe of a row without room diverges per lane */
+  }
+  __syncthreads();
+  /* how many tuples each region holds: counts[part * n_cta + cta] */
+  for (int i = tid; i < A.n_parts; i += nthr) A.counts[(size_t)i * gridDim.x + blockIdx.x] = min(s_cnt[i], A.cap);
+}
+
+/* ==========================================================================================================
+ * pass 2: aggregate one partition at a time in shared memory
+ * ======================================================================================================== */
+__device__ __forceinline__ void tma_bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __grid_constant__ RadixArgs A) {
+  extern __shared__ __align__(128) int8_t s_raw[];
+  const DevProgram& P = A.prog;
+  const DevLaunch& Lh = A.launch;
+  const int tid = threadIdx.x, lane = tid & 31;
+  constexpr int nthr = kRadixBlock;
+  const uint32_t S = 1u << A.log_s;
+  const uint32_t SO = S + B2Q_RADIX_OV;             /* slice + overflow area */
+  const int n_accs = P.n_accs;
+  int64_t* s_keys = reinterpret_cast<int64_t*>(s_raw);
+  int64_t* s_acc = s_keys + SO;                     /* accumulator a: s_acc + a * SO */
+  uint32_t* s_blk = reinterpret_cast<uint32_t*>(s_acc + (size_t)n_accs * SO); /* [n_cta1 + 1] block prefix of the partition's regions */
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_part, s_next;
+  const uint32_t n = (uint32_t)P.key.entry_count;
+  const uint64_t magic = P.key.hash_magic;
+  const int hw = P.key.hash_key_width;
+  const int tw = A.tuple_words;
+  const int n_cta1 = A.n_cta1;
+  uint32_t phase = 0;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  for (;;) {
+    if (tid == 0) { s_part = atomicAdd(A.work_counter, 1u); s_next = 0; }
+    __syncthreads();
+    const uint32_t part = s_part;
+    if (part >= (uint32_t)A.n_parts) break;
+    const uint32_t first = part << A.log_s;
+    const uint32_t Sp = min(S, n - first);          /* entries of this slice (the last one may be short) */
+    const uint32_t bulk = (Sp * 8u) & ~15u;         /* bytes per array that move as TMA bulk copies */
+    /* ---- slice in: keys + every accumulator array, cp.async.bulk global -> shared ---- */
+    if (tid == 0 && bulk) {
+      mbar_expect_tx(&s_bar, bulk * (uint32_t)(1 + n_accs));
+      for (int a = -1; a < n_accs; ++a) {
+        const int8_t* src = reinterpret_cast<const int8_t*>((a < 0 ? Lh.keys : Lh.accs[a]) + first);
+        int8_t* dst = reinterpret_cast<int8_t*>(a < 0 ? s_keys : s_acc + (size_t)a * SO);
+        for (uint32_t off = 0; off < bulk; off += 65536u) tma_bulk_g2s(dst + off, src + off, min(bulk - off, 65536u), &s_bar);
+      }
+    }
+    /* the odd last entry of a short slice, the overflow area, and the block prefix of the regions */
+    if ((Sp & 1u) && tid <= n_accs) {
+      const int a = tid - 1;
+      (a < 0 ? s_keys : s_acc + (size_t)a * SO)[Sp - 1] = (a < 0 ? Lh.keys : Lh.accs[a])[first + Sp - 1];
+    }
+    for (uint32_t i = tid; i < B2Q_RADIX_OV; i += nthr) {
+      s_keys[Sp + i] = B2Q_I64_MAX;
+      for (int a = 0; a < n_accs; ++a) s_acc[(size_t)a * SO + Sp + i] = b2q_acc_identity(P.accs[a].op);
+    }
+    if (tid < 32) { /* warp 0: inclusive scan of ceil(count / kTupleBlock) over the n_cta1 regions */
+      uint32_t run = 0;
+      for (int base = 0; base < n_cta1; base += 32) {
+        const int c = base + lane;
+        uint32_t b = c < n_cta1 ? (__ldg(A.counts + (size_t)part * n_cta1 + c) + kTupleBlock - 1) / kTupleBlock : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, b, o); if (lane >= o) b += t; }
+        if (c < n_cta1) s_blk[c + 1] = run + b;
+        run += __shfl_sync(0xffffffffu, b, 31);
+      }
+      if (lane == 0) s_blk[0] = 0;
+    }
+    if (bulk) mbar_wait(&s_bar, phase);
+    phase ^= bulk ? 1u : 0u;
+    __syncthreads();
+    /* ---- stream the partition's tuples through the slice ---- */
+    const uint32_t total_blocks = s_blk[n_cta1];
+    for (;;) {
+      uint32_t b = 0;
+      if (lane == 0) b = atomicAdd(&s_next, 1u);
+      b = __shfl_sync(0xffffffffu, b, 0);
+      if (b >= total_blocks) break;
+      int lo = 0, hi = n_cta1 - 1; /* region c with s_blk[c] <= b < s_blk[c + 1] */
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_blk[mid + 1] > b) hi = mid; else lo = mid + 1; }
+      const int c = lo;
+      const uint32_t cnt = __ldg(A.counts + (size_t)part * n_cta1 + c);
+      const uint32_t off = (b - s_blk[c]) * kTupleBlock;
+      const int64_t* tp = A.scratch + (((uint64_t)part * n_cta1 + c) * A.cap + off) * (uint64_t)tw;
+      const uint32_t m = min((uint32_t)kTupleBlock, cnt - off);
+      constexpr int U = kTupleBlock / 32;
+      int64_t key[U], v0[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t i = lane + 32u * u;
+        key[u] = B2Q_I64_MAX; v0[u] = 0;
+        if (i < m) {
+          if (tw == 2) asm volatile("ld.global.cg.v2.b64 {%0, %1}, [%2];" : "=l"(key[u]), "=l"(v0[u]) : "l"(tp + (size_t)i * 2));
+          else key[u] = __ldcg(tp + (size_t)i * tw);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t i = lane + 32u * u;
+        if (i >= m) continue;
+        /* get_group_value's probe inside the slice: home slot, then linear; past the slice end -> the overflow area */
+        uint32_t pos = home_slot(key[u], hw, magic, n) - first;
+        const unsigned long long want = (unsigned long long)key[u];
+        bool found = false;
+        for (; pos < Sp + B2Q_RADIX_OV; ++pos) {
+          unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_keys + pos);
+          if (cur == (unsigned long long)B2Q_I64_MAX) cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_keys + pos), (unsigned long long)B2Q_I64_MAX, want);
+          if (cur == (unsigned long long)B2Q_I64_MAX || cur == want) { found = true; break; }
+        }
+        const int64_t* vals = tp + (size_t)i * tw + 1;
+        if (!found) { /* a cluster longer than the overflow area: keep the raw tuple for pass 3 */
+          const uint32_t li = atomicAdd(A.list_count, 1u);
+          if (li < A.list_cap) {
+            int64_t* d = A.list + (size_t)li * tw;
+            d[0] = key[u];
+            for (int cidx = 0; cidx < A.n_vals; ++cidx) d[1 + cidx] = tw == 2 ? v0[u] : __ldcg(vals + cidx);
+          } else atomicCAS(Lh.error, 0, B2Q_RADIX_RETRY);
+          continue;
+        }
+        for (int a = 0; a < n_accs; ++a) {
+          const DevAcc& acc = P.accs[a];
+          const int vi = A.acc_val[a];
+          const int64_t v = vi < 0 ? 0 : (tw == 2 ? v0[u] : __ldcg(vals + vi));
+          if (vi >= 0 && value_skipped(acc, v)) continue;
+          smem_acc_raw(acc.op, s_acc + (size_t)a * SO + pos, v);
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    /* ---- slice out (TMA bulk shared -> global), overflow area to its place in HBM ---- */
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes above -> visible to the bulk copy */
+    __syncthreads();
+    if (tid == 0 && bulk) {
+      for (int a = -1; a < n_accs; ++a) {
+        int8_t* dst = reinterpret_cast<int8_t*>((a < 0 ? Lh.keys : Lh.accs[a]) + first);
+        const int8_t* src = reinterpret_cast<const int8_t*>(a < 0 ? s_keys : s_acc + (size_t)a * SO);
+        for (uint32_t off = 0; off < bulk; off += 65536u) tma_bulk_s2g(dst + off, src + off, min(bulk - off, 65536u));
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if ((Sp & 1u) && tid <= n_accs) {
+      const int a = tid - 1;
+      (a < 0 ? Lh.keys : Lh.accs[a])[first + Sp - 1] = (a < 0 ? s_keys : s_acc + (size_t)a * SO)[Sp - 1];
+    }
+    for (uint32_t i = tid; i < B2Q_RADIX_OV; i += nthr) {
+      int64_t* o = A.ov + ((size_t)part * B2Q_RADIX_OV + i) * (size_t)(1 + n_accs);
+      o[0] = s_keys[Sp + i];
+      for (int a = 0; a < n_accs; ++a) o[1 + a] = s_acc[(size_t)a * SO + Sp + i];
+    }
+    if (tid == 0 && bulk) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); /* shared memory may be overwritten */
+    __syncthreads();
+  }
+}
+
+/* ==========================================================================================================
+ * pass 3: overflow areas (aggregated entries) and listed raw tuples -> the table in HBM
+ * ======================================================================================================== */
+__global__ void b2q_k_radix_insert(const __grid_constant__ RadixArgs A) {
+  const DevProgram& P = A.prog;
+  const DevLaunch& Lh = A.launch;
+  const int n_accs = P.n_accs;
+  const uint32_t n = (uint32_t)P.key.entry_count;
+  const int64_t n_ov = (int64_t)A.n_parts * B2Q_RADIX_OV;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ov; i += stride) {
+    const int64_t* o = A.ov + (size_t)i * (size_t)(1 + n_accs);
+    const int64_t key = o[0];
+    if (key == B2Q_I64_MAX) continue;
+    const int64_t e = global_probe(reinterpret_cast<unsigned long long*>(Lh.keys), n, home_slot(key, P.key.hash_key_width, P.key.hash_magic, n), key);
+    if (e < 0) { atomicCAS(Lh.error, 0, B2Q_ERR_OUT_OF_SLOTS); continue; }
+    for (int a = 0; a < n_accs; ++a) global_acc_merge(P.accs[a].op, Lh.accs[a] + e, o[1 + a]);
+  }
+  const uint32_t n_list = min(*A.list_count, A.list_cap);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_list; i += stride) {
+    const int64_t* t = A.list + (size_t)i * A.tuple_words;
+    global_insert_raw(A, t[0], t + 1);
+  }
+}
+
+/* ==========================================================================================================
+ * cross-device merge of baseline-hash tables: ResultSetStorage::reduce's re-probe (ResultSetReduction.cpp:698-828 — every
+ * non-empty entry of `that` is looked up / claimed in `this` with the group-by probe and its slots are reduced one by one)
+ * run by a grid over the peers' tables instead of a host loop
+ * ======================================================================================================== */
+struct MergeArgs {
+  const int64_t* src_keys;             /* [n_src] entries of the peers' key arrays, EMPTY_KEY_64 = no entry */
+  const int64_t* src_accs[B2Q_MAX_ACCS];
+  int64_t n_src;
+  int64_t skip_begin, skip_end;        /* entries of this rank's own block inside the gathered arrays */
+  int64_t* keys;
+  int64_t* accs[B2Q_MAX_ACCS];
+  int32_t* error;
+  int8_t ops[B2Q_MAX_ACCS];
+  int32_t n_accs, hash_key_width;
+  uint32_t entry_count;
+  uint64_t hash_magic;
+};
+
+__global__ void b2q_k_baseline_merge(const __grid_constant__ MergeArgs A) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_src; i += stride) {
+    if (i >= A.skip_begin && i < A.skip_end) continue;
+    const int64_t key = A.src_keys[i];
+    if (key == B2Q_I64_MAX) continue;
+    const int64_t e = global_probe(reinterpret_cast<unsigned long long*>(A.keys), A.entry_count, home_slot(key, A.hash_key_width, A.hash_magic, A.entry_count), key);
+    if (e < 0) { atomicCAS(A.error, 0, B2Q_ERR_OUT_OF_SLOTS); continue; }
+    for (int a = 0; a < A.n_accs; ++a) global_acc_merge(A.ops[a], A.accs[a] + e, A.src_accs[a][i]);
+  }
+}
+
+/* ==========================================================================================================
+ * host side
+ * ======================================================================================================== */
+int sm_count();
+
+cudaError_t launch_baseline_merge(const B2QQuery& q, const int64_t* src_keys, const int64_t* const* src_accs, int64_t n_src, int64_t skip_begin,
+                                  int64_t skip_end, int64_t* keys, int64_t* const* accs, int32_t* error, cudaStream_t st) {
+  MergeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src_keys = src_keys;
+  a.n_src = n_src;
+  a.skip_begin = skip_begin;
+  a.skip_end = skip_end;
+  a.keys = keys;
+  a.error = error;
+  a.n_accs = q.prog.n_accs;
+  for (int i = 0; i < q.prog.n_accs; ++i) { a.src_accs[i] = src_accs[i]; a.accs[i] = accs[i]; a.ops[i] = q.prog.accs[i].op; }
+  a.hash_key_width = q.prog.key.hash_key_width;
+  a.entry_count = static_cast<uint32_t>(q.prog.key.entry_count);
+  a.hash_magic = q.prog.key.hash_magic;
+  if (n_src <= 0) return cudaSuccess;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n_src + 255) / 256, sm_count() * 8)));
+  b2q_k_baseline_merge<<<grid, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+bool radix_plan(const B2QQuery& q, RadixPlan* rp) {
+  const DevProgram& P = q.prog;
+  memset(rp, 0, sizeof(*rp));
+  if (q.plan.kernel != B2Q_KERNEL_BASELINE_GLOBAL || P.join.fk_col >= 0 || P.n_keys > 1 || P.key.col < 0) return false;
+  if (q.plan.entry_count < 1 || q.plan.entry_count > (int64_t(1) << 31)) return false;
+  /* tuple = {key, one word per distinct aggregate argument column} */
+  int n_vals = 0;
+  for (int a = 0; a < P.n_accs; ++a) {
+    const DevAcc& acc = P.accs[a];
+    if (acc.op == ACC_TOUCH || acc.op == ACC_NDV) return false;
+    rp->acc_val[a] = -1;
+    if (acc.col < 0) continue;
+    int vi = -1;
+    for (int c = 0; c < n_vals; ++c) if (rp->val_col[c] == acc.col) vi = c;
+    if (vi < 0) {
+      if (n_vals == B2Q_RADIX_MAX_VALS) return false;
+      rp->val_col[n_vals] = static_cast<int8_t>(acc.col);
+      rp->val_width[n_vals] = acc.width;
+      vi = n_vals++;
+    }
+    rp->acc_val[a] = static_cast<int8_t>(vi);
+  }
+  rp->n_vals = n_vals;
+  rp->tuple_words = 1 + n_vals;
+  /* slice: the largest power of two of entries whose keys + accumulators (+ overflow area) fit the shared memory of a CTA */
+  const int64_t entry_bytes = 8 * (1 + P.n_accs);
+  const int64_t budget = 200 * 1024;
+  int log_s = 3;
+  while (log_s < 20 && ((int64_t(2) << log_s) + B2Q_RADIX_OV) * entry_bytes <= budget) ++log_s;
+  if (((int64_t(1) << log_s) + B2Q_RADIX_OV) * entry_bytes > budget) return false;
+  rp->log_s = log_s;
+  const int64_t S = int64_t(1) << log_s;
+  rp->n_parts = static_cast<int32_t>((q.plan.entry_count + S - 1) / S);
+  if (rp->n_parts > 8192) return false; /* the open lines of 148 x n_parts regions must stay L2-resident */
+  return true;
+}
+
+size_t radix_smem_pass2(const B2QQuery& q, const RadixPlan& rp, int n_cta1) {
+  const size_t SO = (size_t(1) << rp.log_s) + B2Q_RADIX_OV;
+  return SO * 8 * (1 + q.prog.n_accs) + (static_cast<size_t>(n_cta1) + 1) * 4 + 16;
+}
+
+/* grid of pass 1 and the region capacity for a batch of `chunks` scan chunks */
+void radix_geometry(const B2QQuery& q, const RadixPlan& rp, int64_t chunks, int* n_cta1, uint32_t* cap) {
+  const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(sm_count(), chunks));
+  const double rows_per_cta = static_cast<double>((chunks + ctas - 1) / ctas) * kRadixBlock * R;
+  const double S = static_cast<double>(int64_t(1) << rp.log_s);
+  const double mean = rows_per_cta * std::min(1.0, S / static_cast<double>(q.plan.entry_count));
+  const double c = mean + 6.0 * sqrt(mean) + 16.0;
+  *n_cta1 = static_cast<int>(ctas);
+  *cap = static_cast<uint32_t>(std::min<double>(c, rows_per_cta + 1)) + 1u;
+}
+
+int radix_chunk_rows() { return kRadixBlock * R; }
+
+cudaError_t launch_radix(const B2QQuery& q, const RadixPlan& rp, const DevLaunch& launch, const RadixBuffers& buf, int64_t chunk_begin,
+                         int64_t chunk_end, int n_cta1, uint32_t cap, cudaStream_t st) {
+  static std::atomic<unsigned long long> attr_mask{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  RadixArgs a;
+  a.prog = q.prog;
+  a.launch = launch;
+  a.scratch = buf.scratch;
+  a.counts = buf.counts;
+  a.ov = buf.ov;
+  a.list = buf.list;
+  a.list_count = buf.list_count;
+  a.list_cap = buf.list_cap;
+  a.work_counter = buf.work_counter;
+  a.n_parts = rp.n_parts;
+  a.log_s = rp.log_s;
+  a.n_cta1 = n_cta1;
+  a.cap = cap;
+  a.n_vals = rp.n_vals;
+  a.tuple_words = rp.tuple_words;
+  memcpy(a.val_col, rp.val_col, sizeof(a.val_col));
+  memcpy(a.val_width, rp.val_width, sizeof(a.val_width));
+  memcpy(a.acc_val, rp.acc_val, sizeof(a.acc_val));
+  a.chunk_begin = chunk_begin;
+  a.chunk_end = chunk_end;
+  const size_t smem2 = radix_smem_pass2(q, rp, n_cta1);
+  if (dev < 64 && !(attr_mask.load(std::memory_order_acquire) >> dev & 1ull)) {
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, b2q_k_radix_aggregate);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(b2q_k_radix_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return e;
+    attr_mask.fetch_or(1ull << dev, std::memory_order_release);
+  }
+  cudaError_t e = cudaMemsetAsync(buf.work_counter, 0, 8, st); /* work_counter + list_count are adjacent words */
+  if (e != cudaSuccess) return e;
+  const bool key32 = q.prog.key.width <= 4 && q.prog.key.width >= -2 && q.prog.key.width != 8;
+  const size_t smem1 = static_cast<size_t>(rp.n_parts) * 4;
+  if (key32) b2q_k_radix_partition<true><<<n_cta1, kRadixBlock, smem1, st>>>(a);
+  else b2q_k_radix_partition<false><<<n_cta1, kRadixBlock, smem1, st>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int grid2 = std::max(1, std::min(sm_count(), rp.n_parts));
+  b2q_k_radix_aggregate<<<grid2, kRadixBlock, smem2, st>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int64_t n_ov = static_cast<int64_t>(rp.n_parts) * B2Q_RADIX_OV;
+  const int grid3 = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n_ov + 255) / 256, sm_count() * 8)));
+  b2q_k_radix_insert<<<grid3, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace b2q

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Optional
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -132,6 +132,24 @@ def lib():
         L.b2q_gen_column_strided.restype = C.c_int32
         L.b2q_gen_column_strided.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
                                              C.c_int64, C.c_int64, C.c_void_p]
+        L.b2q_comm_unique_id.restype = C.c_int32
+        L.b2q_comm_unique_id.argtypes = [C.c_void_p]
+        L.b2q_comm_init_rank.restype = C.c_int32
+        L.b2q_comm_init_rank.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.b2q_comm_init_all.restype = C.c_int32
+        L.b2q_comm_init_all.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]
+        L.b2q_comm_destroy.argtypes = [C.c_void_p]
+        L.b2q_comm_rank.restype = C.c_int32
+        L.b2q_comm_rank.argtypes = [C.c_void_p]
+        L.b2q_comm_size.restype = C.c_int32
+        L.b2q_comm_size.argtypes = [C.c_void_p]
+        L.b2q_execute_work_unit_dist.restype = C.c_int32
+        L.b2q_execute_work_unit_dist.argtypes = [C.c_void_p] + ewu + [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.b2q_execute_work_unit_multi.restype = C.c_int32
+        L.b2q_execute_work_unit_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_size_t), C.c_int32,
+                                                  C.POINTER(C.POINTER(abi.TableInfo)), C.POINTER(abi.ExecUnit),
+                                                  C.POINTER(abi.CompilationOptions), C.POINTER(abi.ExecutionOptions), C.c_int32,
+                                                  C.POINTER(C.c_void_p)]
         if L.b2q_abi_version() != abi.ABI_VERSION:
             raise ImportError("libb2q.so ABI version mismatch")
         _lib = L
@@ -434,6 +452,86 @@ class Executor:
         if rc:
             _raise(rc)
         return Partial(h)
+
+
+class Comm:
+    """One rank of a multi-GPU communicator inside libb2q (NCCL).  `Comm.init_rank` for one process per GPU (the 128-byte id
+    is made by rank 0 with `Comm.unique_id()` and broadcast by the caller's own plumbing, e.g. torch.distributed);
+    `Comm.init_all` for one process driving several devices."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(abi.COMM_ID_BYTES)
+        rc = lib().b2q_comm_unique_id(buf)
+        if rc:
+            _raise(rc)
+        return buf.raw
+
+    @classmethod
+    def init_rank(cls, unique_id: bytes, nranks: int, rank: int, device: int = -1) -> "Comm":
+        h = C.c_void_p()
+        rc = lib().b2q_comm_init_rank(C.c_char_p(unique_id), nranks, rank, device, C.byref(h))
+        if rc:
+            _raise(rc)
+        return cls(h)
+
+    @classmethod
+    def init_all(cls, devices: Sequence[int]):
+        arr = (C.c_int32 * len(devices))(*devices)
+        out = (C.c_void_p * len(devices))()
+        rc = lib().b2q_comm_init_all(arr, len(devices), out)
+        if rc:
+            _raise(rc)
+        return [cls(C.c_void_p(h)) for h in out]
+
+    def rank(self):
+        return lib().b2q_comm_rank(self.h)
+
+    def size(self):
+        return lib().b2q_comm_size(self.h)
+
+    def destroy(self):
+        if getattr(self, "h", None):
+            lib().b2q_comm_destroy(self.h)
+            self.h = None
+
+
+def execute_work_unit_dist(comm: Comm, executor: "Executor", max_groups_buffer_entry_guess: int, is_agg: bool, query_infos,
+                           ra_exe_unit: abi.BuiltUnit, co=None, eo=None, has_cardinality_estimation: bool = False,
+                           memory_level: int = abi.GPU_LEVEL, stream: int = 0) -> ResultSet:
+    """This rank's share of a multi-GPU work unit: scan -> NCCL merge inside libb2q -> materialise.  `query_infos` holds this
+    rank's fragments plus the other ranks' fragments as chunk stats (abi.Table.add_remote_fragment)."""
+    co = co or compilation_options()
+    eo = eo or execution_options(device_ordinal=executor.device_ordinal)
+    bt = executor._built_table(query_infos, memory_level)
+    guess = C.c_size_t(max_groups_buffer_entry_guess)
+    h = C.c_void_p()
+    rc = lib().b2q_execute_work_unit_dist(comm.h, C.byref(guess), int(is_agg), C.byref(bt.info), C.byref(ra_exe_unit.unit), C.byref(co),
+                                          C.byref(eo), int(has_cardinality_estimation), C.c_void_p(stream), C.byref(h))
+    if rc:
+        _raise(rc)
+    return ResultSet(h)
+
+
+def execute_work_unit_multi(comms: Sequence[Comm], executor: "Executor", max_groups_buffer_entry_guess: int, is_agg: bool,
+                            tables_per_device, ra_exe_unit: abi.BuiltUnit, co=None, eo=None,
+                            has_cardinality_estimation: bool = False, memory_level: int = abi.GPU_LEVEL) -> ResultSet:
+    """One call, one host thread per device inside libb2q (Execute.cpp:3055-3101): tables_per_device[i] is what device i scans."""
+    co = co or compilation_options()
+    eo = eo or execution_options()
+    bts = [executor._built_table(t, memory_level) for t in tables_per_device]
+    infos = (C.POINTER(abi.TableInfo) * len(bts))(*[C.pointer(bt.info) for bt in bts])
+    hs = (C.c_void_p * len(comms))(*[c.h for c in comms])
+    guess = C.c_size_t(max_groups_buffer_entry_guess)
+    h = C.c_void_p()
+    rc = lib().b2q_execute_work_unit_multi(hs, len(comms), C.byref(guess), int(is_agg), infos, C.byref(ra_exe_unit.unit), C.byref(co),
+                                           C.byref(eo), int(has_cardinality_estimation), C.byref(h))
+    if rc:
+        _raise(rc)
+    return ResultSet(h)
 
 
 def gen_column_device(dst_ptr: int, sql_type: int, seed: int, col_tag: int, row0: int, count: int, lo: int = 0,

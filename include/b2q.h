@@ -37,10 +37,12 @@
 extern "C" {
 #endif
 
-#define B2Q_ABI_VERSION 4 /* 2: sort_info, join level, rte_idx, columnar, dictionary / time types, B2QPlan join fields;
+#define B2Q_ABI_VERSION 5 /* 2: sort_info, join level, rte_idx, columnar, dictionary / time types, B2QPlan join fields;
                             3: DATE_IN_DAYS chunks (negative col_encoded_sizes), column-vs-column quals, 16 filter leaves,
                                operands-before-node rule, b2q_columnar_results_*, host-phase stats;
-                            4: DECIMAL / NUMERIC columns (B2QTypeInfo.scale), decimal_to_double of b2q_rs_get_next_row */
+                            4: DECIMAL / NUMERIC columns (B2QTypeInfo.scale), decimal_to_double of b2q_rs_get_next_row;
+                            5: b2q_comm_* / b2q_execute_work_unit_dist / _multi (merge of the per-device tables inside the
+                               library, NCCL), B2Q_KERNEL_BASELINE_PROBE, LIMIT 0 = empty result */
 
 /* ---- SQLTypes subset (Shared/sqltypes.h:65-99) -------------------------------------------------------- */
 enum {
@@ -262,7 +264,10 @@ enum {
   B2Q_KERNEL_NON_GROUPED = 1,     /* register accumulators + warp/block reduce            */
   B2Q_KERNEL_PERFECT_SMEM = 2,    /* per-CTA private table in shared memory               */
   B2Q_KERNEL_PERFECT_GLOBAL = 3,  /* one dense table in HBM/L2, global reductions          */
-  B2Q_KERNEL_BASELINE_GLOBAL = 4  /* open-addressing table in HBM (MurmurHash3, linear probe) */
+  B2Q_KERNEL_BASELINE_GLOBAL = 4, /* open-addressing table in HBM (MurmurHash3, linear probe): built by the radix-partitioned
+                                     aggregation (partition by home-slot range, aggregate each slice in shared memory) when the
+                                     query's shape allows, else row by row with the reference's probe */
+  B2Q_KERNEL_BASELINE_PROBE = 5   /* force_kernel only: baseline hash with the per-row probe kernel (plan.kernel stays 4) */
 };
 
 /* =========================================================================================================
@@ -389,6 +394,41 @@ const B2QPlan* b2q_partial_plan(const B2QPartial* p);
 double b2q_partial_kernel_ms(const B2QPartial* p);     /* CUDA-event time of the scan kernel(s) */
 int32_t b2q_partial_finalize(B2QPartial* p, void* cuda_stream, B2QResultSet** out);
 void b2q_partial_free(B2QPartial* p);
+
+/* ---- multi-GPU with the merge inside the library ---------------------------------------------------------
+ * The reference runs ONE process with one host thread per device (Executor::launchKernelsViaResourceMgr,
+ * Execute.cpp:3055-3101; ExecutionKernel::run, ExecutionKernel.cpp:215-218) and reduces the per-device result sets on the
+ * HOST (Executor::reduceMultiDeviceResults, Execute.cpp:1696,1772-1792 -> ResultSetStorage::reduce).  Here each device's
+ * scan is followed, on the same CUDA stream and without a host synchronisation, by NCCL collectives over NVLink that
+ * merge the tables in HBM: dense (perfect-hash / non-grouped) tables by ONE all-reduce per reduction class — COUNT and
+ * integer SUM arrays are adjacent, so configs[1] is a single 160 KB all-reduce —, baseline-hash tables by an all-gather of
+ * the peers' key / accumulator arrays and a device-side re-probe (ResultSetReduction.cpp:698-828), estimator bitmaps by
+ * all-gather + OR.  libnccl.so.2 is bound at run time; without it these entries return B2Q_ERR_UNSUPPORTED.
+ *
+ *   b2q_comm_init_all     ncclCommInitAll: all devices driven by this process (b2q_execute_work_unit_multi)
+ *   b2q_comm_init_rank    ncclCommInitRank: one process per device (torchrun & co.); the 128-byte id comes from
+ *                         b2q_comm_unique_id on rank 0 and travels by whatever the host already has
+ *   ..._dist              this rank's share: `query_infos` = its own fragments plus the other ranks' fragments as chunk
+ *                         stats only (col_buffers == NULL), so that every rank plans the same layout; every rank gets the
+ *                         merged ResultSet
+ *   ..._multi             one call, one host thread per device, tables[i] = what device comms[i] scans; the ResultSet
+ *                         is materialised by comms[0]'s device */
+#define B2Q_COMM_ID_BYTES 128
+typedef struct B2QComm B2QComm;
+int32_t b2q_comm_unique_id(void* id128);
+int32_t b2q_comm_init_rank(const void* id128, int32_t nranks, int32_t rank, int32_t device_ordinal, B2QComm** out);
+int32_t b2q_comm_init_all(const int32_t* devices, int32_t ndev, B2QComm** out /* [ndev] */);
+void b2q_comm_destroy(B2QComm* comm);
+int32_t b2q_comm_rank(const B2QComm* comm);
+int32_t b2q_comm_size(const B2QComm* comm);
+int32_t b2q_execute_work_unit_dist(B2QComm* comm, size_t* max_groups_buffer_entry_guess, int32_t is_agg,
+                                   const B2QTableInfo* query_infos, const B2QExecUnit* ra_exe_unit,
+                                   const B2QCompilationOptions* co, const B2QExecutionOptions* eo,
+                                   int32_t has_cardinality_estimation, void* cuda_stream, B2QResultSet** out);
+int32_t b2q_execute_work_unit_multi(B2QComm* const* comms, int32_t ndev, size_t* max_groups_buffer_entry_guess, int32_t is_agg,
+                                    const B2QTableInfo* const* query_infos_per_device, const B2QExecUnit* ra_exe_unit,
+                                    const B2QCompilationOptions* co, const B2QExecutionOptions* eo,
+                                    int32_t has_cardinality_estimation, B2QResultSet** out);
 
 /* ---- inner entry: the static-kernel replacement of multifrag_query_hoisted_literals ---------------------- */
 int32_t b2q_launch(const B2QQuery* query, const B2QParams* params, void* cuda_stream);

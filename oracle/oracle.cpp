@@ -26,6 +26,7 @@
  *       for the reduction — tests/test_oracle_reduce.py.
  */
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -1398,10 +1399,18 @@ void init_buffer(const Plan& plan, std::vector<int8_t>& buf) {
 
 /* ---- the fragment row loop: multifrag_query_hoisted_literals -> query_group_by_template / query_template
  * (RuntimeFunctions.cpp:2434-2472, QueryTemplateGenerator.cpp:552-815): pos_start = 0, pos_step = 1 on CPU ---- */
+int32_t run_rows(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr, std::vector<int8_t>& buf);
+
 int32_t run_fragment(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr,
                      std::vector<int8_t>& buf) {
-  const B2QPlan& p = plan.p;
   init_buffer(plan, buf);
+  return run_rows(plan, u, tbl, fr, buf);
+}
+
+/* the row function over one fragment into an ALREADY initialised buffer: what one iteration of the fragment loop of
+ * multifrag_query_hoisted_literals does (RuntimeFunctions.cpp:2434-2472: every fragment of a kernel shares `out`) */
+int32_t run_rows(const Plan& plan, const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmentInfo& fr, std::vector<int8_t>& buf) {
+  const B2QPlan& p = plan.p;
   const int key_col = p.key_col_id;
   const int key_type = key_col >= 0 ? tbl.col_types[key_col].type : 0;
   const bool key_nullable = key_col >= 0 && !tbl.col_types[key_col].notnull;
@@ -1623,6 +1632,7 @@ struct OracleResult {
   std::vector<uint32_t> perm;
   bool sorted{false};
   size_t drop_first{0}, keep_first{0}, fetched{0};
+  bool empty_result{false}; /* LIMIT 0: RelSort::isEmptyResult() -> just_validate -> an empty result set (RelAlgDag.h:2557, RelAlgExecutor.cpp:1277,3559) */
 };
 
 namespace {
@@ -1696,6 +1706,8 @@ void result_sort(OracleResult* r, const B2QOrderEntry* oes, int n, size_t top_n)
 }  // namespace
 
 static thread_local std::string g_last_error;
+ORACLE_EXPORT void oracle_gen_column_strided(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
+                                             int64_t count, int64_t lo, int64_t span, int64_t stride, int32_t num_threads);
 
 ORACLE_EXPORT const char* oracle_last_error() { return g_last_error.c_str(); }
 ORACLE_EXPORT void oracle_set_filter_on_deleted_column(int32_t on) { g_filter_deleted = on != 0; }
@@ -1774,6 +1786,109 @@ ORACLE_EXPORT int32_t oracle_execute(const B2QExecUnit* u, const B2QTableInfo* t
       res->drop_first = static_cast<size_t>(u->offset);
       if (u->has_limit) res->keep_first = static_cast<size_t>(u->limit);
     }
+    if (u->has_limit && u->limit == 0) { res->empty_result = true; res->perm.clear(); res->sorted = true; }
+    *out = holder.release();
+    return 0;
+  } catch (const OracleError& e) {
+    g_last_error = e.msg;
+    return e.code;
+  }
+}
+
+/* ---- full-size check of the benchmark configurations -----------------------------------------------------------
+ * The same executor over a table that is never materialised: column c of global row r is the counter-based generator's
+ * value (oracle_gen.h), produced slab by slab into thread-local buffers right before the row function reads it.  Work is
+ * cut into slabs of 64 Ki rows; each worker thread owns ONE output buffer for all its slabs — the multi-fragment kernel
+ * of the reference (multifrag_query_hoisted_literals, RuntimeFunctions.cpp:2434-2472: one `out` per kernel, the row loop
+ * run fragment after fragment; ExecutionOptions::allow_multifrag) — and the per-thread buffers are reduced with
+ * ResultSetStorage::reduce: perfect hash entry range by entry range in thread order (the order a sequential reduce
+ * visits each entry), baseline hash pairwise (the re-probe reduce is associative on the set of rows).
+ * Fragments of `tbl` need no column buffers (num_tuples, fragment_id and chunk stats only); global row of tuple i of
+ * fragment f = fragment_id * rows_per_fragment_id + i. */
+struct OracleGenCol { int32_t sql_type; uint32_t col_tag; int64_t lo, span, stride; };
+
+ORACLE_EXPORT int32_t oracle_execute_generated(const B2QExecUnit* u, const B2QTableInfo* tbl, const B2QExecutionOptions* eo,
+                                               size_t entry_guess, int32_t has_cardinality_estimation, int32_t num_threads,
+                                               uint64_t seed, const OracleGenCol* gen, int64_t rows_per_fragment_id,
+                                               OracleResult** out) {
+  try {
+    std::unique_ptr<OracleResult> holder(new OracleResult());
+    OracleResult* res = holder.get();
+    res->plan = make_plan(*u, *tbl, *eo, entry_guess, has_cardinality_estimation != 0, nullptr);
+    if (res->plan.join) fail(B2Q_ERR_UNSUPPORTED, "generated tables have no join level");
+    const int nc = tbl->num_cols;
+    const int64_t slab = int64_t(1) << 16;
+    struct Item { int frag; int64_t row0, rows; };
+    std::vector<Item> items;
+    for (int f = 0; f < tbl->num_fragments; ++f)
+      for (int64_t r = 0; r < tbl->fragments[f].num_tuples; r += slab) items.push_back({f, r, std::min(slab, tbl->fragments[f].num_tuples - r)});
+    const int nt = std::max<int>(1, std::min<int64_t>(num_threads, std::max<size_t>(items.size(), 1)));
+    std::vector<std::vector<int8_t>> bufs(nt);
+    std::vector<int32_t> errs(nt, 0);
+    std::vector<std::string> msgs(nt);
+    std::atomic<size_t> next{0};
+    auto width_of = [](int t) { return t == B2Q_kTINYINT ? 1 : t == B2Q_kSMALLINT ? 2 : t == B2Q_kINT ? 4 : 8; };
+    auto work = [&](int tid) {
+      try {
+        init_buffer(res->plan, bufs[tid]);
+        std::vector<std::vector<int8_t>> cols(nc);
+        std::vector<const void*> ptrs(nc, nullptr);
+        for (int c = 0; c < nc; ++c) { cols[c].resize(static_cast<size_t>(slab) * width_of(gen[c].sql_type)); ptrs[c] = cols[c].data(); }
+        for (;;) {
+          const size_t i = next.fetch_add(1);
+          if (i >= items.size() || errs[tid]) break;
+          const Item& it = items[i];
+          const B2QFragmentInfo& src = tbl->fragments[it.frag];
+          const int64_t g0 = static_cast<int64_t>(src.fragment_id) * rows_per_fragment_id + it.row0;
+          for (int c = 0; c < nc; ++c) oracle_gen_column_strided(cols[c].data(), gen[c].sql_type, seed, gen[c].col_tag, g0, it.rows, gen[c].lo, gen[c].span, gen[c].stride, 1);
+          B2QFragmentInfo fr = src;
+          fr.num_tuples = it.rows;
+          fr.col_buffers = ptrs.data();
+          errs[tid] = run_rows(res->plan, *u, *tbl, fr, bufs[tid]);
+        }
+      } catch (const OracleError& e) {
+        errs[tid] = e.code;
+        msgs[tid] = e.msg;
+      }
+    };
+    {
+      std::vector<std::thread> ths;
+      for (int t = 0; t < nt; ++t) ths.emplace_back(work, t);
+      for (auto& t : ths) t.join();
+    }
+    for (int t = 0; t < nt; ++t) if (errs[t]) { g_last_error = msgs[t]; return errs[t]; }
+    const B2QPlan& p = res->plan.p;
+    if (p.query_desc_type == B2Q_GroupByPerfectHash && nt > 1) {
+      /* reduceOneEntryNoCollisions is entry-local: thread j folds its entry range of buffers 1..nt-1 into buffer 0, in order */
+      auto fold = [&](int j) {
+        const int64_t e0 = p.entry_count * j / nt, e1 = p.entry_count * (j + 1) / nt;
+        for (int t = 1; t < nt; ++t)
+          for (int64_t e = e0; e < e1; ++e) {
+            if (is_empty_entry(p, bufs[t].data(), e)) continue;
+            if (!p.keyless_hash)
+              for (int c = 0; c < std::max(p.num_group_cols, 1); ++c)
+                memcpy(key_ptr(p, bufs[0].data(), e, c), key_ptr(p, bufs[t].data(), e, c), p.output_columnar ? 8 : p.effective_key_width);
+            reduce_one_row(res->plan, bufs[0].data(), e, bufs[t].data(), e);
+          }
+      };
+      std::vector<std::thread> ths;
+      for (int j = 0; j < nt; ++j) ths.emplace_back(fold, j);
+      for (auto& t : ths) t.join();
+    } else {
+      std::atomic<int32_t> rerr{0};
+      for (int step = 1; step < nt; step *= 2) { /* pairwise: (0,1)(2,3).. then (0,2)(4,6).. */
+        std::vector<std::thread> ths;
+        for (int a = 0; a + step < nt; a += 2 * step)
+          ths.emplace_back([&, a, step]() {
+            const int32_t rc = reduce_buffers(res->plan, bufs[a], bufs[a + step]);
+            if (rc) rerr = rc;
+            std::vector<int8_t>().swap(bufs[a + step]);
+          });
+        for (auto& t : ths) t.join();
+        if (rerr) return rerr.load();
+      }
+    }
+    res->buf = std::move(bufs[0]);
     *out = holder.release();
     return 0;
   } catch (const OracleError& e) {
@@ -1802,6 +1917,7 @@ ORACLE_EXPORT int64_t oracle_result_permutation_at(const OracleResult* r, size_t
 ORACLE_EXPORT int32_t oracle_result_is_row_at_empty(const OracleResult* r, size_t e) { return is_empty_entry(r->plan.p, r->buf.data(), static_cast<int64_t>(e)); }
 ORACLE_EXPORT size_t oracle_result_row_count(const OracleResult* r) { /* ResultSet::rowCountImpl (ResultSet.cpp:565-600) */
   if (r->plan.p.query_desc_type == B2Q_Estimator) return 0; /* an estimator result set has no storage, only the bitmap */
+  if (r->empty_result) return 0;
   size_t n = 0;
   if (r->sorted) n = r->perm.size();
   else for (int64_t e = 0; e < r->plan.p.entry_count; ++e) n += !is_empty_entry(r->plan.p, r->buf.data(), e);
@@ -1836,7 +1952,7 @@ ORACLE_EXPORT B2QTypeInfo oracle_result_col_type(const OracleResult* r, size_t c
  * AVG via make_avg_target_value (:43-82) + pair_to_double (ResultSetBufferAccessors.h:197-227). */
 ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue* row, int32_t decimal_to_double) {
   const B2QPlan& p = r->plan.p;
-  if (p.query_desc_type == B2Q_Estimator) return 0;
+  if (p.query_desc_type == B2Q_Estimator || r->empty_result) return 0;
   /* getNextRowImpl + advanceCursorToNextEntry (ResultSetIteration.cpp:320-340, :731-750) */
   const int64_t n_entries = r->sorted ? static_cast<int64_t>(r->perm.size()) : p.entry_count;
   int64_t entry = 0;

@@ -55,8 +55,17 @@ def lib():
                                         C.c_int64, C.c_int32]
         L.oracle_gen_column_strided.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64,
                                                 C.c_int64, C.c_int64, C.c_int32]
+        L.oracle_execute_generated.restype = C.c_int32
+        L.oracle_execute_generated.argtypes = [C.POINTER(abi.ExecUnit), C.POINTER(abi.TableInfo), C.POINTER(abi.ExecutionOptions),
+                                               C.c_size_t, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(GenCol), C.c_int64,
+                                               C.POINTER(C.c_void_p)]
         _lib = L
     return _lib
+
+
+class GenCol(C.Structure):
+    """One column of a generated table (oracle.cpp OracleGenCol): the PHYSICAL element type and the generator's parameters."""
+    _fields_ = [("sql_type", C.c_int32), ("col_tag", C.c_uint32), ("lo", C.c_int64), ("span", C.c_int64), ("stride", C.c_int64)]
 
 
 class OracleError(RuntimeError):
@@ -159,6 +168,22 @@ def execute(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=False
     eo = make_eo(bigint_count, output_columnar=output_columnar)
     rc = lib().oracle_execute(C.byref(unit.unit), C.byref(bt.info), C.byref(eo), entry_guess, int(has_card),
                               num_threads, C.byref(h))
+    if rc:
+        raise OracleError(rc, lib().oracle_last_error().decode())
+    return OracleResult(h)
+
+
+def execute_generated(unit: abi.BuiltUnit, table: abi.Table, gen_cols, seed, rows_per_fragment_id, entry_guess=0, has_card=False,
+                      bigint_count=False, num_threads=1, output_columnar=False) -> OracleResult:
+    """The oracle over a table that is generated on the fly (never materialised): `table` carries fragment sizes, ids and
+    chunk stats only; gen_cols = [(physical sql type, col_tag, lo, span, stride)] per column; global row of tuple i of
+    fragment f = fragment_id * rows_per_fragment_id + i.  One output buffer per worker thread (multi-fragment kernels)."""
+    bt = table.build(abi.CPU_LEVEL)
+    arr = (GenCol * len(gen_cols))(*[GenCol(int(t), int(tag), int(lo), int(span), int(stride)) for t, tag, lo, span, stride in gen_cols])
+    h = C.c_void_p()
+    eo = make_eo(bigint_count, output_columnar=output_columnar)
+    rc = lib().oracle_execute_generated(C.byref(unit.unit), C.byref(bt.info), C.byref(eo), entry_guess, int(has_card), num_threads,
+                                        seed, arr, rows_per_fragment_id, C.byref(h))
     if rc:
         raise OracleError(rc, lib().oracle_last_error().decode())
     return OracleResult(h)

@@ -23,6 +23,8 @@ GOLDEN_ORDER_QUERIES = [
     "SELECT COUNT(*), SUM(x) FROM test ORDER BY 1;",
     "SELECT x, COUNT(*) FROM test GROUP BY x LIMIT 1;",          # LIMIT without ORDER BY: first entries in buffer order
     "SELECT x, COUNT(*) FROM test WHERE x > 100 GROUP BY x ORDER BY 2 DESC, 1 LIMIT 3;",   # empty result
+    "SELECT x, COUNT(*) FROM test GROUP BY x ORDER BY 2 DESC LIMIT 0;",     # RelSort::isEmptyResult(): LIMIT 0 is an empty result, not "no limit"
+    "SELECT y, SUM(t) FROM test GROUP BY y LIMIT 0 OFFSET 1;",
 ]
 
 # on the mixed-type random table of test_gpu_parity.random_table

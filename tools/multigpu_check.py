@@ -3,10 +3,12 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multigpu_check.py
 
-Every rank takes the fragments `fragment_id % world == rank` (InsertOrderFragmenter.cpp:435-443), scans them into its
-dense partial table (b2q_execute_partial), all ranks all-reduce the arrays (multigpu.allreduce_partial, replacing the
-host-side reduceMultiDeviceResults), every rank finalises — incl. ORDER BY / LIMIT and the join level — and rank 0
-compares the result with the oracle run over the WHOLE table.  Test infrastructure: the oracle is the checker only."""
+Every rank takes the fragments `fragment_id % world == rank` (InsertOrderFragmenter.cpp:435-443) and calls
+b2q_execute_work_unit_dist: scan -> merge of the per-device tables by NCCL collectives INSIDE libb2q (all-reduce of the dense
+arrays; all-gather + re-probe for baseline hash; all-gather + OR for estimator bitmaps — replacing the host-side
+reduceMultiDeviceResults) -> materialise incl. ORDER BY / LIMIT and the join level; rank 0 compares the result with the
+oracle run over the WHOLE table.  `--merge python` keeps the older harness (b2q_execute_partial + torch.distributed
+all-reduce per array + finalize) for the dense layouts.  Test infrastructure: the oracle is the checker only."""
 import os
 import sys
 
@@ -48,6 +50,12 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ex = executor.Executor()
+    lib_merge = "--merge" not in sys.argv or sys.argv[sys.argv.index("--merge") + 1] != "python"
+    comm = None
+    if lib_merge:   # the 128-byte NCCL id travels over the process group the launcher already gave us
+        box = [executor.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = executor.Comm.init_rank(box[0], world, rank, device=local)
     checked = 0
     cases = []
     table = random_table(200000, seed=17, frag_rows=12500)    # 16 fragments
@@ -64,8 +72,8 @@ def main():
             shards[id(tbl)] = shard(tbl, rank, world)
         sub, _ = shards[id(tbl)]
         plan = ex.plan(unit, tbl, max_groups_buffer_entry_guess=4000, has_cardinality_estimation=True)
-        if plan.query_desc_type == abi.GroupByBaselineHash:
-            continue    # not position-aligned across devices
+        if plan.query_desc_type == abi.GroupByBaselineHash and not lib_merge:
+            continue    # not position-aligned across devices: only the library's re-probe merge handles it
         # the other ranks' fragments travel as chunk stats only, so that every rank derives the same key ranges
         view = abi.Table(tbl.col_types, encoded_sizes=tbl.encoded_sizes, deleted_column=tbl.deleted_column)
         for f in sub.fragments:
@@ -73,9 +81,13 @@ def main():
         for f in tbl.fragments:
             if f.fragment_id % world != rank:
                 view.add_remote_fragment(f.num_tuples, f.stats, f.fragment_id)
-        part = ex.executePartial(4000, True, view, unit, has_cardinality_estimation=True, memory_level=abi.GPU_LEVEL)
-        multigpu.allreduce_partial(part, torch, dist)
-        rs = part.finalize()
+        part = None
+        if lib_merge:
+            rs = executor.execute_work_unit_dist(comm, ex, 4000, True, view, unit, has_cardinality_estimation=True)
+        else:
+            part = ex.executePartial(4000, True, view, unit, has_cardinality_estimation=True, memory_level=abi.GPU_LEVEL)
+            multigpu.allreduce_partial(part, torch, dist)
+            rs = part.finalize()
         rows = rs.rows()
         if rank == 0:
             ref = oracle_lib.execute(unit, tbl, entry_guess=4000, has_card=True, num_threads=8)
@@ -99,9 +111,13 @@ def main():
         for f in table.fragments:
             if f.fragment_id % world != rank:
                 view.add_remote_fragment(f.num_tuples, f.stats, f.fragment_id)
-        part = ex.executePartial(1, True, view, unit, memory_level=abi.GPU_LEVEL)
-        multigpu.allreduce_partial(part, torch, dist)
-        rs = part.finalize()
+        part = None
+        if lib_merge:
+            rs = executor.execute_work_unit_dist(comm, ex, 1, True, view, unit)
+        else:
+            part = ex.executePartial(1, True, view, unit, memory_level=abi.GPU_LEVEL)
+            multigpu.allreduce_partial(part, torch, dist)
+            rs = part.finalize()
         if rank == 0:
             ref = oracle_lib.execute(unit, table, num_threads=8)
             assert np.array_equal(rs.getHostEstimatorBuffer(), ref.buffer().view(np.uint8)), cols
@@ -110,7 +126,9 @@ def main():
         del rs, part
     dist.barrier()
     if rank == 0:
-        print(f"multigpu_check ok: {checked} queries, world={world}", flush=True)
+        print(f"multigpu_check ok: {checked} queries, world={world}, merge={'libb2q/NCCL' if lib_merge else 'python'}", flush=True)
+    if comm is not None:
+        comm.destroy()
     dist.destroy_process_group()
 
 
