@@ -348,14 +348,17 @@ static int32_t radix_prepare(B2QPartial& p, int64_t max_chunks, cudaStream_t st)
   const size_t b_ov = DeviceBlock::pad(static_cast<size_t>(p.rp.n_parts) * B2Q_RADIX_OV * (1 + q.prog.n_accs) * 8);
   const uint32_t list_cap = 1u << 18;
   const size_t b_list = DeviceBlock::pad(static_cast<size_t>(list_cap) * p.rp.tuple_words * 8);
+  const size_t b_ovhi = DeviceBlock::pad(static_cast<size_t>(p.rp.n_parts) * B2Q_RADIX_OV * std::max(q.prog.n_accs, 1) * 8);
   int8_t* base = nullptr;
-  CU(cudaMallocAsync(reinterpret_cast<void**>(&base), b_scratch + b_counts + b_ov + b_list + 256, st));
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&base), b_scratch + b_counts + b_ov + b_list + b_ovhi + 256, st));
   p.extra.push_back(base);
   p.rb.scratch = reinterpret_cast<int64_t*>(base);
   p.rb.counts = reinterpret_cast<uint32_t*>(base + b_scratch);
   p.rb.ov = reinterpret_cast<int64_t*>(base + b_scratch + b_counts);
   p.rb.list = reinterpret_cast<int64_t*>(base + b_scratch + b_counts + b_ov);
-  p.rb.work_counter = reinterpret_cast<uint32_t*>(base + b_scratch + b_counts + b_ov + b_list);
+  p.rb.ov_hi = reinterpret_cast<int64_t*>(base + b_scratch + b_counts + b_ov + b_list);
+  p.rb.ov_hi_bytes = b_ovhi;
+  p.rb.work_counter = reinterpret_cast<uint32_t*>(base + b_scratch + b_counts + b_ov + b_list + b_ovhi);
   p.rb.list_count = p.rb.work_counter + 1;
   p.rb.list_cap = list_cap;
   p.radix_batch_chunks = batch;

@@ -227,6 +227,8 @@ __device__ __forceinline__ void partition_chunk(const RadixArgs& A, const int8_t
 #undef B2Q_KEY_OF
 }
 
+/* direct variant (tuples of three words and more): every tuple goes straight to its place — 32 different lines per warp store.
+ * profiles/r2_scatter_bench.txt: 1.2 TB/s of (read + written) bytes whatever the number of partitions. */
 template <bool KEY32>
 __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_partition(const __grid_constant__ RadixArgs A) {
   extern __shared__ __align__(16) uint32_t s_cnt[]; /* [n_parts] */
@@ -260,6 +262,143 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_partition(const __
   for (int i = tid; i < A.n_parts; i += nthr) A.counts[(size_t)i * gridDim.x + blockIdx.x] = min(s_cnt[i], A.cap);
 }
 
+/* tile variant (tuples of one or two words): the passing rows of a chunk (BLOCK x R = 8192 rows) are bucketed by partition in
+ * shared memory — count with a shared atomic (which also ranks the row inside its bucket), scan, place — and written out
+ * with consecutive lanes on consecutive tuples of a region, i.e. in runs of chunk / n_parts tuples instead of one tuple per
+ * line.  profiles/r2_scatter_bench.txt: 2.1 TB/s at 1832 partitions, 2.8 TB/s at 916, 3.1 TB/s at 458. */
+template <bool KEY32, int TW>
+__global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_partition_tile(const __grid_constant__ RadixArgs A) {
+  extern __shared__ __align__(16) int8_t s_tile_raw[];
+  constexpr int nthr = kRadixBlock;
+  constexpr int TILE = nthr * R;
+  const DevProgram& P = A.prog;
+  const DevLaunch& Lh = A.launch;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NP = A.n_parts;
+  int64_t* tile = reinterpret_cast<int64_t*>(s_tile_raw);                 /* [TILE][TW] tuples in partition order */
+  uint32_t* s_cur = reinterpret_cast<uint32_t*>(tile + (size_t)TILE * TW);  /* [NP] tuples of the region so far */
+  uint32_t* s_cnt = s_cur + NP;                                           /* [NP] tuples of this chunk */
+  uint32_t* s_off = s_cnt + NP;                                           /* [NP + 1] exclusive scan of s_cnt */
+  uint16_t* s_pid = reinterpret_cast<uint16_t*>(s_off + NP + 1);          /* [TILE] partition of a tile slot */
+  __shared__ uint32_t s_warp[32];
+  const int64_t chunk_rows = (int64_t)TILE;
+  for (int i = tid; i < NP; i += nthr) { s_cur[i] = 0; s_cnt[i] = 0; }
+  __syncthreads();
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  const uint32_t n = (uint32_t)P.key.entry_count;
+  const uint64_t magic = P.key.hash_magic;
+  const int hw = P.key.hash_key_width;
+  const uint32_t region0 = blockIdx.x * A.cap;
+  const uint32_t part_stride = gridDim.x * A.cap;
+  const int per = (NP + nthr - 1) / nthr; /* scan: partitions per thread */
+  int frag = 0;
+  int64_t frag_first = 0;
+  int64_t next_first = __ldg(Lh.frag_chunk_start + 1);
+  for (int64_t chunk = A.chunk_begin + blockIdx.x; chunk < A.chunk_end; chunk += gridDim.x) {
+    while (chunk >= next_first) {
+      ++frag;
+      frag_first = next_first;
+      next_first = __ldg(Lh.frag_chunk_start + frag + 1);
+    }
+    const int64_t frag_rows = __ldg(Lh.frag_rows + frag);
+    const int64_t row0 = (chunk - frag_first) * chunk_rows + tid;
+    const int8_t* const* __restrict__ cols = Lh.col_ptrs + (size_t)frag * P.n_cols;
+    const bool full = (chunk - frag_first + 1) * chunk_rows <= frag_rows;
+    uint32_t valid = (1u << R) - 1u;
+    if (!full) {
+      valid = 0;
+#pragma unroll
+      for (int j = 0; j < R; ++j) valid |= (uint32_t)(row0 + (int64_t)j * nthr < frag_rows) << j;
+    }
+    /* ---- rows in: key, filter, value (all loads predicated, so the ragged last chunk of a fragment takes the same path) ---- */
+    int32_t k32[KEY32 ? R : 1];
+    int64_t k64[KEY32 ? 1 : R];
+    const bool eager_key = P.eager_key;
+    if (eager_key) {
+      if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, valid, pol);
+      else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, valid, pol);
+    }
+    const uint32_t pass = eval_filter<false, 0>(P.filter, cols, row0, nthr, valid, pol, P.col_inner, nullptr, -1, nullptr, P.col_null);
+    if (!eager_key) {
+      if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, pass, pol);
+      else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, pass, pol);
+    }
+    int64_t v[TW == 2 ? R : 1];
+    if (TW == 2) {
+      if (A.val_width[0] == 8) load64<true>(reinterpret_cast<int64_t(&)[R]>(v), cols[A.val_col[0]], row0, nthr, pass, pol);
+      else {
+        int32_t t32[R];
+        load32<true>(t32, cols[A.val_col[0]], A.val_width[0], row0, nthr, pass, pol);
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[TW == 2 ? j : 0] = t32[j];
+      }
+    }
+    /* ---- count + rank: (partition << 16 | rank inside the chunk's bucket); TILE <= 65536 ---- */
+    uint32_t pr[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      pr[j] = ~0u;
+      if (!(pass >> j & 1)) continue;
+      int64_t key = KEY32 ? (int64_t)k32[KEY32 ? j : 0] : k64[KEY32 ? 0 : j];
+      if (key == P.key.null_val) key = P.key.null_logical; /* ENCODING FIXED: physical NULL -> logical NULL */
+      if (KEY32) k32[KEY32 ? j : 0] = (int32_t)key; else k64[KEY32 ? 0 : j] = key;
+      const uint32_t part = home_slot(key, hw, magic, n) >> A.log_s;
+      pr[j] = part << 16 | atomicAdd(s_cnt + part, 1u);
+    }
+    __syncthreads();
+    /* ---- exclusive scan of the bucket sizes ---- */
+    uint32_t loc = 0;
+    for (int q = 0; q < per; ++q) { const int i = tid * per + q; if (i < NP) loc += s_cnt[i]; }
+    uint32_t inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    uint32_t run = inc - loc + (warp ? s_warp[warp - 1] : 0u);
+    for (int q = 0; q < per; ++q) { const int i = tid * per + q; if (i < NP) { s_off[i] = run; run += s_cnt[i]; } }
+    if (tid == nthr - 1) s_off[NP] = run;
+    __syncthreads();
+    /* ---- place ---- */
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (pr[j] == ~0u) continue;
+      const uint32_t part = pr[j] >> 16, slot = s_off[part] + (pr[j] & 0xFFFFu);
+      const int64_t key = KEY32 ? (int64_t)k32[KEY32 ? j : 0] : k64[KEY32 ? 0 : j];
+      if (TW == 2) { tile[(size_t)slot * 2] = key; tile[(size_t)slot * 2 + 1] = v[TW == 2 ? j : 0]; }
+      else tile[slot] = key;
+      s_pid[slot] = (uint16_t)part;
+    }
+    __syncthreads();
+    /* ---- runs out: lane i takes tile slot i ---- */
+    const uint32_t total = s_off[NP];
+    for (uint32_t slot = tid; slot < total; slot += nthr) {
+      const uint32_t part = s_pid[slot];
+      const uint32_t pos = s_cur[part] + (slot - s_off[part]);
+      if (pos < A.cap) {
+        int64_t* dst = A.scratch + ((uint64_t)part * part_stride + region0 + pos) * (uint64_t)TW;
+        if (TW == 2) {
+          const longlong2 t = *reinterpret_cast<const longlong2*>(tile + (size_t)slot * 2);
+          asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(dst), "l"(t.x), "l"(t.y) : "memory");
+        } else *dst = tile[slot];
+      } else { /* no room in the region (skewed keys): the reference's probe on the table in HBM */
+        global_insert_raw(A, tile[(size_t)slot * TW], tile + (size_t)slot * TW + 1);
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < NP; i += nthr) { s_cur[i] += s_cnt[i]; s_cnt[i] = 0; }
+    __syncthreads();
+  }
+  for (int i = tid; i < NP; i += nthr) A.counts[(size_t)i * gridDim.x + blockIdx.x] = min(s_cur[i], A.cap);
+}
+
 /* ==========================================================================================================
  * pass 2: aggregate one partition at a time in shared memory
  * ======================================================================================================== */
@@ -267,6 +406,10 @@ __device__ __forceinline__ void tma_bulk_s2g(void* gdst, const void* smem_src, u
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 
+/* The slice of the KEY array is bulk-copied in and out (the probe needs the keys earlier launches and pass 1's direct
+ * inserts left there).  Accumulators start at their identity in shared memory — COUNT / integer SUM as a 32-bit low word
+ * (native ATOMS.ADD; the carry or a value wider than 32 bits goes straight to the HBM array as RED.ADD.64 of hi << 32, as in
+ * b2q_k_scan), the others as 64-bit slots — and are merged into the HBM arrays entry by entry when the partition is done. */
 __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __grid_constant__ RadixArgs A) {
   extern __shared__ __align__(128) int8_t s_raw[];
   const DevProgram& P = A.prog;
@@ -277,8 +420,8 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
   const uint32_t SO = S + B2Q_RADIX_OV;             /* slice + overflow area */
   const int n_accs = P.n_accs;
   int64_t* s_keys = reinterpret_cast<int64_t*>(s_raw);
-  int64_t* s_acc = s_keys + SO;                     /* accumulator a: s_acc + a * SO */
-  uint32_t* s_blk = reinterpret_cast<uint32_t*>(s_acc + (size_t)n_accs * SO); /* [n_cta1 + 1] block prefix of the partition's regions */
+  int8_t* s_acc = s_raw + (size_t)SO * 8;           /* accumulator a: s_acc + acc_off[a] * SO, 4 or 8 bytes per entry */
+  uint32_t* s_blk = reinterpret_cast<uint32_t*>(s_acc + (size_t)A.acc_bytes_total * SO); /* [n_cta1 + 1] block prefix of the partition's regions */
   __shared__ uint64_t s_bar;
   __shared__ uint32_t s_part, s_next;
   const uint32_t n = (uint32_t)P.key.entry_count;
@@ -287,6 +430,8 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
   const int tw = A.tuple_words;
   const int n_cta1 = A.n_cta1;
   uint32_t phase = 0;
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -299,24 +444,19 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
     if (part >= (uint32_t)A.n_parts) break;
     const uint32_t first = part << A.log_s;
     const uint32_t Sp = min(S, n - first);          /* entries of this slice (the last one may be short) */
-    const uint32_t bulk = (Sp * 8u) & ~15u;         /* bytes per array that move as TMA bulk copies */
-    /* ---- slice in: keys + every accumulator array, cp.async.bulk global -> shared ---- */
+    const uint32_t bulk = (Sp * 8u) & ~15u;         /* bytes of the key slice that move as TMA bulk copies */
+    /* ---- key slice in: cp.async.bulk global -> shared ---- */
     if (tid == 0 && bulk) {
-      mbar_expect_tx(&s_bar, bulk * (uint32_t)(1 + n_accs));
-      for (int a = -1; a < n_accs; ++a) {
-        const int8_t* src = reinterpret_cast<const int8_t*>((a < 0 ? Lh.keys : Lh.accs[a]) + first);
-        int8_t* dst = reinterpret_cast<int8_t*>(a < 0 ? s_keys : s_acc + (size_t)a * SO);
-        for (uint32_t off = 0; off < bulk; off += 65536u) tma_bulk_g2s(dst + off, src + off, min(bulk - off, 65536u), &s_bar);
-      }
+      mbar_expect_tx(&s_bar, bulk);
+      const int8_t* src = reinterpret_cast<const int8_t*>(Lh.keys + first);
+      for (uint32_t off = 0; off < bulk; off += 65536u) tma_bulk_g2s(reinterpret_cast<int8_t*>(s_keys) + off, src + off, min(bulk - off, 65536u), &s_bar);
     }
-    /* the odd last entry of a short slice, the overflow area, and the block prefix of the regions */
-    if ((Sp & 1u) && tid <= n_accs) {
-      const int a = tid - 1;
-      (a < 0 ? s_keys : s_acc + (size_t)a * SO)[Sp - 1] = (a < 0 ? Lh.keys : Lh.accs[a])[first + Sp - 1];
-    }
-    for (uint32_t i = tid; i < B2Q_RADIX_OV; i += nthr) {
-      s_keys[Sp + i] = B2Q_I64_MAX;
-      for (int a = 0; a < n_accs; ++a) s_acc[(size_t)a * SO + Sp + i] = b2q_acc_identity(P.accs[a].op);
+    if ((Sp & 1u) && tid == 0) s_keys[Sp - 1] = Lh.keys[first + Sp - 1]; /* the odd last entry of a short slice */
+    for (uint32_t i = tid; i < B2Q_RADIX_OV; i += nthr) s_keys[Sp + i] = B2Q_I64_MAX;
+    for (int a = 0; a < n_accs; ++a) { /* accumulators at their identity (slice and overflow area) */
+      int8_t* base = s_acc + (size_t)A.acc_off[a] * SO;
+      if (A.acc_bytes[a] == 4) for (uint32_t i = tid; i < Sp + B2Q_RADIX_OV; i += nthr) reinterpret_cast<uint32_t*>(base)[i] = 0u;
+      else { const int64_t id = b2q_acc_identity(P.accs[a].op); for (uint32_t i = tid; i < Sp + B2Q_RADIX_OV; i += nthr) reinterpret_cast<int64_t*>(base)[i] = id; }
     }
     if (tid < 32) { /* warp 0: inclusive scan of ceil(count / kTupleBlock) over the n_cta1 regions */
       uint32_t run = 0;
@@ -349,68 +489,92 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
       const uint32_t m = min((uint32_t)kTupleBlock, cnt - off);
       constexpr int U = kTupleBlock / 32;
       int64_t key[U], v0[U];
+      uint32_t pos[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const uint32_t i = lane + 32u * u;
         key[u] = B2Q_I64_MAX; v0[u] = 0;
         if (i < m) {
-          if (tw == 2) asm volatile("ld.global.cg.v2.b64 {%0, %1}, [%2];" : "=l"(key[u]), "=l"(v0[u]) : "l"(tp + (size_t)i * 2));
+          if (tw == 2) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;" : "=l"(key[u]), "=l"(v0[u]) : "l"(tp + (size_t)i * 2), "l"(pol));
           else key[u] = __ldcg(tp + (size_t)i * tw);
         }
       }
 #pragma unroll
+      for (int u = 0; u < U; ++u) pos[u] = home_slot(key[u], hw, magic, n) - first;
+#pragma unroll
       for (int u = 0; u < U; ++u) {
         const uint32_t i = lane + 32u * u;
-        if (i >= m) continue;
+        const bool live = i < m;
         /* get_group_value's probe inside the slice: home slot, then linear; past the slice end -> the overflow area */
-        uint32_t pos = home_slot(key[u], hw, magic, n) - first;
-        const unsigned long long want = (unsigned long long)key[u];
+        uint32_t e = pos[u];
         bool found = false;
-        for (; pos < Sp + B2Q_RADIX_OV; ++pos) {
-          unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_keys + pos);
-          if (cur == (unsigned long long)B2Q_I64_MAX) cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_keys + pos), (unsigned long long)B2Q_I64_MAX, want);
-          if (cur == (unsigned long long)B2Q_I64_MAX || cur == want) { found = true; break; }
+        if (live) {
+          const unsigned long long want = (unsigned long long)key[u];
+          for (; e < Sp + B2Q_RADIX_OV; ++e) {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_keys + e);
+            if (cur == (unsigned long long)B2Q_I64_MAX) cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_keys + e), (unsigned long long)B2Q_I64_MAX, want);
+            if (cur == (unsigned long long)B2Q_I64_MAX || cur == want) { found = true; break; }
+          }
         }
+        __syncwarp(); /* probe lengths differ per lane: reconverge before the updates, or every lane group runs them on its own */
         const int64_t* vals = tp + (size_t)i * tw + 1;
-        if (!found) { /* a cluster longer than the overflow area: keep the raw tuple for pass 3 */
+        if (live && !found) { /* a cluster longer than the overflow area: keep the raw tuple for pass 3 */
           const uint32_t li = atomicAdd(A.list_count, 1u);
           if (li < A.list_cap) {
             int64_t* d = A.list + (size_t)li * tw;
             d[0] = key[u];
             for (int cidx = 0; cidx < A.n_vals; ++cidx) d[1 + cidx] = tw == 2 ? v0[u] : __ldcg(vals + cidx);
           } else atomicCAS(Lh.error, 0, B2Q_RADIX_RETRY);
-          continue;
         }
-        for (int a = 0; a < n_accs; ++a) {
-          const DevAcc& acc = P.accs[a];
-          const int vi = A.acc_val[a];
-          const int64_t v = vi < 0 ? 0 : (tw == 2 ? v0[u] : __ldcg(vals + vi));
-          if (vi >= 0 && value_skipped(acc, v)) continue;
-          smem_acc_raw(acc.op, s_acc + (size_t)a * SO + pos, v);
+        if (live && found) {
+          for (int a = 0; a < n_accs; ++a) {
+            const DevAcc& acc = P.accs[a];
+            const int vi = A.acc_val[a];
+            const int64_t v = vi < 0 ? 0 : (tw == 2 ? v0[u] : __ldcg(vals + vi));
+            if (vi >= 0 && value_skipped(acc, v)) continue;
+            int8_t* base = s_acc + (size_t)A.acc_off[a] * SO;
+            if (A.acc_bytes[a] == 4) { /* COUNT / integer SUM: low word here, the rare high-word delta straight to HBM */
+              const int64_t add = acc.op == ACC_COUNT ? 1 : v;
+              const uint32_t vl = (uint32_t)add;
+              const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(base) + e, vl);
+              const int32_t hi = (int32_t)(add >> 32) + (int32_t)((uint32_t)(old + vl) < old);
+              if (hi != 0) {
+                if (e < Sp) red_add_u64(Lh.accs[a] + first + e, (uint64_t)(int64_t)hi << 32);
+                else atomicAdd(reinterpret_cast<unsigned long long*>(A.ov_hi + ((size_t)part * B2Q_RADIX_OV + (e - Sp)) * n_accs + a), (unsigned long long)((uint64_t)(int64_t)hi << 32));
+              }
+            } else smem_acc_raw(acc.op, reinterpret_cast<int64_t*>(base) + e, v);
+          }
         }
       }
       __syncwarp();
     }
     __syncthreads();
-    /* ---- slice out (TMA bulk shared -> global), overflow area to its place in HBM ---- */
+    /* ---- key slice out (TMA bulk shared -> global); accumulators merged into the HBM arrays; overflow area to its place ---- */
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes above -> visible to the bulk copy */
     __syncthreads();
     if (tid == 0 && bulk) {
-      for (int a = -1; a < n_accs; ++a) {
-        int8_t* dst = reinterpret_cast<int8_t*>((a < 0 ? Lh.keys : Lh.accs[a]) + first);
-        const int8_t* src = reinterpret_cast<const int8_t*>(a < 0 ? s_keys : s_acc + (size_t)a * SO);
-        for (uint32_t off = 0; off < bulk; off += 65536u) tma_bulk_s2g(dst + off, src + off, min(bulk - off, 65536u));
-      }
+      int8_t* dst = reinterpret_cast<int8_t*>(Lh.keys + first);
+      for (uint32_t off = 0; off < bulk; off += 65536u) tma_bulk_s2g(dst + off, reinterpret_cast<const int8_t*>(s_keys) + off, min(bulk - off, 65536u));
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    if ((Sp & 1u) && tid <= n_accs) {
-      const int a = tid - 1;
-      (a < 0 ? Lh.keys : Lh.accs[a])[first + Sp - 1] = (a < 0 ? s_keys : s_acc + (size_t)a * SO)[Sp - 1];
+    if ((Sp & 1u) && tid == 0) Lh.keys[first + Sp - 1] = s_keys[Sp - 1];
+    for (int a = 0; a < n_accs; ++a) {
+      const int8_t* base = s_acc + (size_t)A.acc_off[a] * SO;
+      const int op = P.accs[a].op;
+      int64_t* g = Lh.accs[a] + first;
+      if (A.acc_bytes[a] == 4) {
+        for (uint32_t i = tid; i < Sp; i += nthr) { const uint32_t x = reinterpret_cast<const uint32_t*>(base)[i]; if (x) red_add_u64(g + i, (uint64_t)x); }
+      } else {
+        for (uint32_t i = tid; i < Sp; i += nthr) global_acc_merge(op, g + i, reinterpret_cast<const int64_t*>(base)[i]);
+      }
     }
     for (uint32_t i = tid; i < B2Q_RADIX_OV; i += nthr) {
       int64_t* o = A.ov + ((size_t)part * B2Q_RADIX_OV + i) * (size_t)(1 + n_accs);
       o[0] = s_keys[Sp + i];
-      for (int a = 0; a < n_accs; ++a) o[1 + a] = s_acc[(size_t)a * SO + Sp + i];
+      for (int a = 0; a < n_accs; ++a) {
+        const int8_t* base = s_acc + (size_t)A.acc_off[a] * SO;
+        o[1 + a] = A.acc_bytes[a] == 4 ? (int64_t)(uint64_t)reinterpret_cast<const uint32_t*>(base)[Sp + i] : reinterpret_cast<const int64_t*>(base)[Sp + i];
+      }
     }
     if (tid == 0 && bulk) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); /* shared memory may be overwritten */
     __syncthreads();
@@ -433,7 +597,8 @@ __global__ void b2q_k_radix_insert(const __grid_constant__ RadixArgs A) {
     if (key == B2Q_I64_MAX) continue;
     const int64_t e = global_probe(reinterpret_cast<unsigned long long*>(Lh.keys), n, home_slot(key, P.key.hash_key_width, P.key.hash_magic, n), key);
     if (e < 0) { atomicCAS(Lh.error, 0, B2Q_ERR_OUT_OF_SLOTS); continue; }
-    for (int a = 0; a < n_accs; ++a) global_acc_merge(P.accs[a].op, Lh.accs[a] + e, o[1 + a]);
+    for (int a = 0; a < n_accs; ++a)
+      global_acc_merge(P.accs[a].op, Lh.accs[a] + e, A.acc_bytes[a] == 4 ? o[1 + a] + A.ov_hi[(size_t)i * n_accs + a] : o[1 + a]);
   }
   const uint32_t n_list = min(*A.list_count, A.list_cap);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_list; i += stride) {
@@ -477,6 +642,7 @@ __global__ void b2q_k_baseline_merge(const __grid_constant__ MergeArgs A) {
  * host side
  * ======================================================================================================== */
 int sm_count();
+static size_t radix_tile_smem(const RadixPlan& rp);
 
 cudaError_t launch_baseline_merge(const B2QQuery& q, const int64_t* src_keys, const int64_t* const* src_accs, int64_t n_src, int64_t skip_begin,
                                   int64_t skip_end, int64_t* keys, int64_t* const* accs, int32_t* error, cudaStream_t st) {
@@ -523,22 +689,41 @@ bool radix_plan(const B2QQuery& q, RadixPlan* rp) {
   }
   rp->n_vals = n_vals;
   rp->tuple_words = 1 + n_vals;
+  /* pass 2, shared-memory bytes per entry: key + 4 (COUNT / integer SUM) or 8 per accumulator, 8-byte arrays first */
+  int off = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int a = 0; a < P.n_accs; ++a) {
+      const int bytes = (P.accs[a].op == ACC_COUNT || P.accs[a].op == ACC_SUM_I64) ? 4 : 8;
+      if ((pass == 0) != (bytes == 8)) continue;
+      rp->acc_bytes[a] = static_cast<int8_t>(bytes);
+      rp->acc_off[a] = static_cast<int16_t>(off);
+      off += bytes;
+    }
+  rp->acc_bytes_total = off;
   /* slice: the largest power of two of entries whose keys + accumulators (+ overflow area) fit the shared memory of a CTA */
-  const int64_t entry_bytes = 8 * (1 + P.n_accs);
-  const int64_t budget = 200 * 1024;
-  int log_s = 3;
+  const int64_t entry_bytes = 8 + off;
+  const int64_t budget = 208 * 1024;
+  int log_s = 4;
   while (log_s < 20 && ((int64_t(2) << log_s) + B2Q_RADIX_OV) * entry_bytes <= budget) ++log_s;
   if (((int64_t(1) << log_s) + B2Q_RADIX_OV) * entry_bytes > budget) return false;
   rp->log_s = log_s;
   const int64_t S = int64_t(1) << log_s;
   rp->n_parts = static_cast<int32_t>((q.plan.entry_count + S - 1) / S);
-  if (rp->n_parts > 8192) return false; /* the open lines of 148 x n_parts regions must stay L2-resident */
+  if (rp->n_parts > 8192) return false; /* per-CTA counters / the open lines of 148 x n_parts regions */
+  /* pass 1 buckets a chunk in shared memory when the tile (8192 tuples), its partition ids and three counters per partition fit */
+  rp->tile = rp->tuple_words <= 2 && radix_tile_smem(*rp) <= 220 * 1024;
   return true;
 }
 
-size_t radix_smem_pass2(const B2QQuery& q, const RadixPlan& rp, int n_cta1) {
+static size_t radix_tile_smem(const RadixPlan& rp) {
+  const size_t tile = static_cast<size_t>(kRadixBlock) * R;
+  return tile * rp.tuple_words * 8 + (static_cast<size_t>(rp.n_parts) * 3 + 1) * 4 + tile * 2 + 16;
+}
+size_t radix_smem_pass1(const RadixPlan& rp) { return rp.tile ? radix_tile_smem(rp) : static_cast<size_t>(rp.n_parts) * 4; }
+
+size_t radix_smem_pass2(const B2QQuery&, const RadixPlan& rp, int n_cta1) {
   const size_t SO = (size_t(1) << rp.log_s) + B2Q_RADIX_OV;
-  return SO * 8 * (1 + q.prog.n_accs) + (static_cast<size_t>(n_cta1) + 1) * 4 + 16;
+  return SO * (8 + rp.acc_bytes_total) + (static_cast<size_t>(n_cta1) + 1) * 4 + 16;
 }
 
 /* grid of pass 1 and the region capacity for a batch of `chunks` scan chunks */
@@ -565,6 +750,7 @@ cudaError_t launch_radix(const B2QQuery& q, const RadixPlan& rp, const DevLaunch
   a.scratch = buf.scratch;
   a.counts = buf.counts;
   a.ov = buf.ov;
+  a.ov_hi = buf.ov_hi;
   a.list = buf.list;
   a.list_count = buf.list_count;
   a.list_cap = buf.list_cap;
@@ -578,6 +764,10 @@ cudaError_t launch_radix(const B2QQuery& q, const RadixPlan& rp, const DevLaunch
   memcpy(a.val_col, rp.val_col, sizeof(a.val_col));
   memcpy(a.val_width, rp.val_width, sizeof(a.val_width));
   memcpy(a.acc_val, rp.acc_val, sizeof(a.acc_val));
+  memcpy(a.acc_bytes, rp.acc_bytes, sizeof(a.acc_bytes));
+  memcpy(a.acc_off, rp.acc_off, sizeof(a.acc_off));
+  a.acc_bytes_total = rp.acc_bytes_total;
+  a.pad_ = 0;
   a.chunk_begin = chunk_begin;
   a.chunk_end = chunk_end;
   const size_t smem2 = radix_smem_pass2(q, rp, n_cta1);
@@ -593,9 +783,32 @@ cudaError_t launch_radix(const B2QQuery& q, const RadixPlan& rp, const DevLaunch
   }
   cudaError_t e = cudaMemsetAsync(buf.work_counter, 0, 8, st); /* work_counter + list_count are adjacent words */
   if (e != cudaSuccess) return e;
-  const bool key32 = q.prog.key.width <= 4 && q.prog.key.width >= -2 && q.prog.key.width != 8;
-  const size_t smem1 = static_cast<size_t>(rp.n_parts) * 4;
-  if (key32) b2q_k_radix_partition<true><<<n_cta1, kRadixBlock, smem1, st>>>(a);
+  e = cudaMemsetAsync(buf.ov_hi, 0, buf.ov_hi_bytes, st);
+  if (e != cudaSuccess) return e;
+  const bool key32 = q.prog.key.width != 8;
+  const size_t smem1 = radix_smem_pass1(rp);
+  if (rp.tile) {
+    /* the four tile instantiations need the opt-in shared-memory limit, once per device */
+    static std::atomic<unsigned long long> tile_mask{0};
+    if (dev < 64 && !(tile_mask.load(std::memory_order_acquire) >> dev & 1ull)) {
+      int optin = 0;
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      const void* fns[4] = {reinterpret_cast<const void*>(b2q_k_radix_partition_tile<false, 1>), reinterpret_cast<const void*>(b2q_k_radix_partition_tile<false, 2>),
+                            reinterpret_cast<const void*>(b2q_k_radix_partition_tile<true, 1>), reinterpret_cast<const void*>(b2q_k_radix_partition_tile<true, 2>)};
+      for (const void* f : fns) {
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, f);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+        if (e != cudaSuccess) return e;
+      }
+      tile_mask.fetch_or(1ull << dev, std::memory_order_release);
+    }
+    if (key32 && rp.tuple_words == 1) b2q_k_radix_partition_tile<true, 1><<<n_cta1, kRadixBlock, smem1, st>>>(a);
+    else if (key32) b2q_k_radix_partition_tile<true, 2><<<n_cta1, kRadixBlock, smem1, st>>>(a);
+    else if (rp.tuple_words == 1) b2q_k_radix_partition_tile<false, 1><<<n_cta1, kRadixBlock, smem1, st>>>(a);
+    else b2q_k_radix_partition_tile<false, 2><<<n_cta1, kRadixBlock, smem1, st>>>(a);
+  } else if (key32) b2q_k_radix_partition<true><<<n_cta1, kRadixBlock, smem1, st>>>(a);
   else b2q_k_radix_partition<false><<<n_cta1, kRadixBlock, smem1, st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -21,12 +21,18 @@ struct RadixPlan {
   int8_t val_col[B2Q_RADIX_MAX_VALS + 1];   /* launch column of value word c */
   int8_t val_width[B2Q_RADIX_MAX_VALS + 1]; /* its width code */
   int8_t acc_val[B2Q_MAX_ACCS];             /* accumulator -> value word, -1: no argument */
+  int8_t acc_bytes[B2Q_MAX_ACCS];           /* pass 2, bytes per entry in shared memory: 4 (COUNT / integer SUM low word) or 8 */
+  int16_t acc_off[B2Q_MAX_ACCS];            /* byte offset per entry of the accumulator's array (8-byte arrays first) */
+  int32_t acc_bytes_total;
+  int32_t tile;                             /* pass 1 buckets each chunk in shared memory (tuples of <= 2 words) */
 };
 
 struct RadixBuffers {
   int64_t* scratch;      /* [n_parts][n_cta1][cap] tuples */
   uint32_t* counts;      /* [n_parts][n_cta1] */
   int64_t* ov;           /* [n_parts][B2Q_RADIX_OV] x {key, accumulators} */
+  int64_t* ov_hi;        /* [n_parts][B2Q_RADIX_OV][n_accs] high-word deltas of overflow-area entries (zeroed per launch) */
+  size_t ov_hi_bytes;
   int64_t* list;         /* raw tuples pass 2 could not place */
   uint32_t* work_counter;/* pass 2's partition queue; list_count is the next word */
   uint32_t* list_count;
@@ -39,6 +45,7 @@ struct RadixArgs {
   int64_t* scratch;
   uint32_t* counts;
   int64_t* ov;
+  int64_t* ov_hi;
   int64_t* list;
   uint32_t* list_count;
   uint32_t* work_counter;
@@ -49,10 +56,15 @@ struct RadixArgs {
   int8_t val_col[B2Q_RADIX_MAX_VALS + 1];
   int8_t val_width[B2Q_RADIX_MAX_VALS + 1];
   int8_t acc_val[B2Q_MAX_ACCS];
+  int8_t acc_bytes[B2Q_MAX_ACCS];
+  int16_t acc_off[B2Q_MAX_ACCS];
+  int32_t acc_bytes_total;
+  int32_t pad_;
   int64_t chunk_begin, chunk_end;
 };
 
 bool radix_plan(const B2QQuery& q, RadixPlan* rp);
+size_t radix_smem_pass1(const RadixPlan& rp);
 size_t radix_smem_pass2(const B2QQuery& q, const RadixPlan& rp, int n_cta1);
 void radix_geometry(const B2QQuery& q, const RadixPlan& rp, int64_t chunks, int* n_cta1, uint32_t* cap);
 int radix_chunk_rows();

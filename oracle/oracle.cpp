@@ -25,6 +25,9 @@
  *   (3) the ResultSetTest generator pattern (Tests/ResultSetTestUtils.h:33-70, ResultSetTest.cpp:1081-1098)
  *       for the reduction — tests/test_oracle_reduce.py.
  */
+#include <pthread.h>
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
@@ -1706,6 +1709,30 @@ void result_sort(OracleResult* r, const B2QOrderEntry* oes, int n, size_t top_n)
 }  // namespace
 
 static thread_local std::string g_last_error;
+
+/* Worker placement for the timed CPU arm (bench.py): with pinning on, worker t of oracle_execute and of
+ * oracle_gen_fragments runs on the t-th CPU of the process's affinity mask, so that the thread that scans fragment f is the
+ * one that first touched its pages (NUMA-local memory).  Off by default: the tests do not care. */
+static std::atomic<int> g_pin_threads{0};
+ORACLE_EXPORT void oracle_set_thread_pinning(int32_t on) { g_pin_threads = on; }
+static void pin_worker(int t) {
+  if (!g_pin_threads) return;
+  cpu_set_t mask;
+  if (sched_getaffinity(0, sizeof(mask), &mask) != 0) return;
+  const int n = CPU_COUNT(&mask);
+  if (n <= 0) return;
+  int want = t % n, seen = 0;
+  for (int c = 0; c < CPU_SETSIZE; ++c) {
+    if (!CPU_ISSET(c, &mask)) continue;
+    if (seen++ == want) {
+      cpu_set_t one;
+      CPU_ZERO(&one);
+      CPU_SET(c, &one);
+      pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+      return;
+    }
+  }
+}
 ORACLE_EXPORT void oracle_gen_column_strided(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
                                              int64_t count, int64_t lo, int64_t span, int64_t stride, int32_t num_threads);
 
@@ -1758,6 +1785,7 @@ ORACLE_EXPORT int32_t oracle_execute(const B2QExecUnit* u, const B2QTableInfo* t
     if (nf == 0) init_buffer(res->plan, bufs[0]);
     const int nt = std::max(1, std::min(num_threads, nf));
     auto work = [&](int tid) {
+      pin_worker(tid);
       for (int f = tid; f < nf; f += nt) {
         try {
           errs[f] = run_fragment(res->plan, *u, *tbl, tbl->fragments[f], bufs[f]);
@@ -1767,7 +1795,7 @@ ORACLE_EXPORT int32_t oracle_execute(const B2QExecUnit* u, const B2QTableInfo* t
         }
       }
     };
-    if (nt == 1) work(0);
+    if (nt == 1 && !g_pin_threads) work(0);
     else {
       std::vector<std::thread> ths;
       for (int t = 0; t < nt; ++t) ths.emplace_back(work, t);
@@ -2024,6 +2052,10 @@ ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue
 }
 
 /* ---- synthetic columns (bench / tests) ---- */
+/* whole fragments, fragment f by worker f % num_threads — the worker that oracle_execute gives the fragment to */
+ORACLE_EXPORT void oracle_gen_fragments(void* const* dst /* [nf * nc] */, const OracleGenCol* gen, int32_t nc, const int64_t* rows,
+                                        const int64_t* row0, int32_t nf, uint64_t seed, int32_t num_threads);
+
 ORACLE_EXPORT void oracle_gen_column_strided(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
                                              int64_t count, int64_t lo, int64_t span, int64_t stride, int32_t num_threads);
 ORACLE_EXPORT void oracle_gen_column(void* dst, int32_t sql_type, uint64_t seed, uint32_t col_tag, int64_t row0,
@@ -2053,5 +2085,19 @@ ORACLE_EXPORT void oracle_gen_column_strided(void* dst, int32_t sql_type, uint64
     const int64_t b = t * per, e = std::min(count, b + per);
     if (b < e) ths.emplace_back(work, b, e);
   }
+  for (auto& t : ths) t.join();
+}
+
+ORACLE_EXPORT void oracle_gen_fragments(void* const* dst, const OracleGenCol* gen, int32_t nc, const int64_t* rows,
+                                        const int64_t* row0, int32_t nf, uint64_t seed, int32_t num_threads) {
+  const int nt = std::max(1, std::min(num_threads, nf));
+  auto work = [&](int tid) {
+    pin_worker(tid);
+    for (int f = tid; f < nf; f += nt)
+      for (int c = 0; c < nc; ++c)
+        oracle_gen_column_strided(dst[static_cast<size_t>(f) * nc + c], gen[c].sql_type, seed, gen[c].col_tag, row0[f], rows[f], gen[c].lo, gen[c].span, gen[c].stride, 1);
+  };
+  std::vector<std::thread> ths;
+  for (int t = 0; t < nt; ++t) ths.emplace_back(work, t);
   for (auto& t : ths) t.join();
 }

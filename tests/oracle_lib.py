@@ -59,6 +59,9 @@ def lib():
         L.oracle_execute_generated.argtypes = [C.POINTER(abi.ExecUnit), C.POINTER(abi.TableInfo), C.POINTER(abi.ExecutionOptions),
                                                C.c_size_t, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(GenCol), C.c_int64,
                                                C.POINTER(C.c_void_p)]
+        L.oracle_set_thread_pinning.argtypes = [C.c_int32]
+        L.oracle_gen_fragments.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GenCol), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                           C.c_int32, C.c_uint64, C.c_int32]
         _lib = L
     return _lib
 
@@ -187,6 +190,20 @@ def execute_generated(unit: abi.BuiltUnit, table: abi.Table, gen_cols, seed, row
     if rc:
         raise OracleError(rc, lib().oracle_last_error().decode())
     return OracleResult(h)
+
+
+def set_thread_pinning(on: bool):
+    """Worker t of execute() / gen_fragments() runs on the t-th CPU of the process's affinity mask (NUMA-local first touch)."""
+    lib().oracle_set_thread_pinning(int(on))
+
+
+def gen_fragments(frag_arrays, gen_cols, rows, row0, seed, num_threads):
+    """Fill whole fragments (frag_arrays[f][c]: preallocated, untouched numpy arrays) with the counter-based generator, fragment f
+    by worker f % num_threads — the same worker execute() hands fragment f to."""
+    nf, nc = len(frag_arrays), len(gen_cols)
+    ptrs = (C.c_void_p * (nf * nc))(*[a.ctypes.data for fr in frag_arrays for a in fr])
+    arr = (GenCol * nc)(*[GenCol(int(t), int(tag), int(lo), int(span), int(stride)) for t, tag, lo, span, stride in gen_cols])
+    lib().oracle_gen_fragments(ptrs, arr, nc, (C.c_int64 * nf)(*rows), (C.c_int64 * nf)(*row0), nf, seed, num_threads)
 
 
 def gen_column(sql_type, seed, col_tag, row0, count, lo=0, span=1, threads=8, stride=1) -> np.ndarray:

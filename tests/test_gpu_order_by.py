@@ -17,6 +17,8 @@ pytestmark = pytest.mark.gpu
 def window(unit, n_sorted):
     """[first, first + count) of the oracle's permutation that the product materialises."""
     u = unit.unit
+    if u.has_limit and u.limit == 0:      # RelSort::isEmptyResult(): an empty result, not "no limit"
+        return 0, 0
     first = min(u.offset, n_sorted)
     count = n_sorted - first
     if u.has_limit and u.limit:
