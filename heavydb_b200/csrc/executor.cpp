@@ -345,22 +345,12 @@ static int32_t radix_prepare(B2QPartial& p, int64_t max_chunks, cudaStream_t st)
   if (tuples >= (size_t(1) << 32) - 2) return set_err(B2Q_ERR_OUT_OF_GPU_MEM, "radix scratch does not fit");
   const size_t b_scratch = DeviceBlock::pad(tuples * p.rp.tuple_words * 8);
   const size_t b_counts = DeviceBlock::pad(static_cast<size_t>(p.rp.n_parts) * n_cta1 * 4);
-  const size_t b_ov = DeviceBlock::pad(static_cast<size_t>(p.rp.n_parts) * B2Q_RADIX_OV * (1 + q.prog.n_accs) * 8);
-  const uint32_t list_cap = 1u << 18;
-  const size_t b_list = DeviceBlock::pad(static_cast<size_t>(list_cap) * p.rp.tuple_words * 8);
-  const size_t b_ovhi = DeviceBlock::pad(static_cast<size_t>(p.rp.n_parts) * B2Q_RADIX_OV * std::max(q.prog.n_accs, 1) * 8);
   int8_t* base = nullptr;
-  CU(cudaMallocAsync(reinterpret_cast<void**>(&base), b_scratch + b_counts + b_ov + b_list + b_ovhi + 256, st));
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&base), b_scratch + b_counts + 256, st));
   p.extra.push_back(base);
   p.rb.scratch = reinterpret_cast<int64_t*>(base);
   p.rb.counts = reinterpret_cast<uint32_t*>(base + b_scratch);
-  p.rb.ov = reinterpret_cast<int64_t*>(base + b_scratch + b_counts);
-  p.rb.list = reinterpret_cast<int64_t*>(base + b_scratch + b_counts + b_ov);
-  p.rb.ov_hi = reinterpret_cast<int64_t*>(base + b_scratch + b_counts + b_ov + b_list);
-  p.rb.ov_hi_bytes = b_ovhi;
-  p.rb.work_counter = reinterpret_cast<uint32_t*>(base + b_scratch + b_counts + b_ov + b_list + b_ovhi);
-  p.rb.list_count = p.rb.work_counter + 1;
-  p.rb.list_cap = list_cap;
+  p.rb.work_counter = reinterpret_cast<uint32_t*>(base + b_scratch + b_counts);
   p.radix_batch_chunks = batch;
   p.radix_n_cta1 = n_cta1;
   p.radix_cap = cap;
@@ -377,7 +367,7 @@ static int32_t radix_launch(B2QPartial& p, const DevLaunch& L, cudaStream_t st) 
       if (static_cast<size_t>(n_cta1) * cap > static_cast<size_t>(p.radix_n_cta1) * p.radix_cap) { n_cta1 = p.radix_n_cta1; cap = p.radix_cap; }
     }
     CU(launch_radix(p.q, p.rp, L, p.rb, c0, c1, n_cta1, cap, st));
-    p.launches += 3;
+    p.launches += 2;
   }
   return B2Q_OK;
 }

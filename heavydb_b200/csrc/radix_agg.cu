@@ -7,22 +7,21 @@
  * table — open addressing, h = MurmurHash3(key) % entry_count, every key reachable from its home slot by a linear probe
  * over occupied slots — but no row ever touches it in HBM:
  *
- *   pass 1  b2q_k_radix_partition   streams the fragments once (same coalesced column loads and filter program as
+ *   pass 1  b2q_k_radix_partition[_tile]   streams the fragments once (same coalesced column loads and filter program as
  *           b2q_k_scan), hashes the key and appends the tuple {key, argument values} of every passing row to the region
  *           of (partition = home slot / S, this CTA).  Regions are private to a CTA, so the append cursor is a shared-
- *           memory counter and the 16-byte tuple stores of one region land in consecutive addresses: the open 128-byte
- *           lines of all regions (148 x P x 128 B ~ 35 MB) stay in L2 until complete, HBM sees full lines once.
- *   pass 2  b2q_k_radix_aggregate   one CTA per partition: the partition's slice of the key / accumulator arrays
- *           (S entries) is bulk-copied into shared memory (cp.async.bulk, TMA), the partition's tuples are streamed
- *           through it — probe, claim and update are shared-memory operations —, and the slice is bulk-copied back.
- *           Keys whose probe runs off the end of the slice go to a small overflow area per partition.
- *   pass 3  b2q_k_radix_insert      merges the overflow areas (a few keys per partition) into the table in HBM with the
- *           reference's global-memory probe.
+ *           memory counter.  Tuples of one or two words are first bucketed by partition in shared memory, a chunk of
+ *           8192 rows at a time, and leave in runs of consecutive tuples (profiles/r2_scatter_bench.txt: one 16-byte
+ *           store per tuple straight to its place runs at 1.2 TB/s whatever the number of partitions; runs of ~9 tuples
+ *           at 2.8 TB/s).
+ *   pass 2  b2q_k_radix_aggregate   one CTA per partition: the partition's tuples are streamed through a private
+ *           shared-memory table — lookup, claim and update are shared-memory operations — whose occupied slots are then
+ *           merged into the table in HBM with the reference's probe, once per key instead of once per row.
  *
  * Algorithmic traffic: read columns + write tuples + read tuples ~ 3x the column bytes, sequential, instead of two
  * random 32-byte sectors per row (profiles/r1_scan_c4s_v2_ncu.txt: 9.7x, 514 instructions/row).
- * Rows a region has no room for (skewed keys) are inserted by pass 1 straight into the HBM table with the probe of the
- * old kernel — any input is handled, uniform ones fast.
+ * Rows a region has no room for (skewed keys) and keys the private table has no room for are inserted straight into the
+ * HBM table with the probe of the row-by-row kernel — any input is handled, uniform ones fast.
  */
 #include "scan_kernel.cuh"
 #include "radix_agg.h"
@@ -36,6 +35,18 @@ constexpr int kTupleBlock = 128;   /* pass 2: tuples a warp takes at a time (4 p
 __device__ __forceinline__ uint32_t home_slot(int64_t key, int hw, uint64_t magic, uint32_t n) {
   return (uint32_t)__umul64hi(magic * (uint64_t)murmur3_key(key, hw), (uint64_t)n); /* == MurmurHash3(key) % n */
 }
+
+/* The partition of a key and its bucket in pass 2's private table do NOT follow the reference's hash: MurmurHash3 + a 64-bit
+ * fast-mod is ~45 instructions, needed once per KEY when the private table is merged into the HBM table, not once per ROW.
+ * A 32-bit multiply-xorshift mix of the key picks the partition (its high bits, by multiply-shift) and the bucket (its
+ * re-multiplied low bits). */
+__device__ __forceinline__ uint32_t mix_key(int64_t key) {
+  uint32_t x = (uint32_t)key ^ ((uint32_t)((uint64_t)key >> 32) * 0x85ebca6bu);
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t part_of_mix(uint32_t mix, uint32_t n_parts) { return __umulhi(mix, n_parts); }
+__device__ __forceinline__ uint32_t bucket_of_mix(uint32_t mix, uint32_t nb_mask) { return ((mix * 0x9E3779B1u) >> 9) & nb_mask; }
 
 __device__ __forceinline__ int64_t global_probe(unsigned long long* keys, uint32_t n, uint32_t h, int64_t key) {
   const unsigned long long want = (unsigned long long)key;
@@ -94,7 +105,16 @@ __device__ __forceinline__ void global_insert_raw(const RadixArgs& A, int64_t ke
   }
 }
 
-/* ---- shared-memory slice (pass 2): 64-bit slots, 32-bit native atomics ---- */
+/* the high-word delta of a COUNT / integer SUM whose low word lives in shared memory: straight to the key's entry in HBM */
+__device__ __forceinline__ void global_add_hi(const RadixArgs& A, int64_t key, int a, int32_t hi) {
+  const DevProgram& P = A.prog;
+  const uint32_t n = (uint32_t)P.key.entry_count;
+  const int64_t e = global_probe(reinterpret_cast<unsigned long long*>(A.launch.keys), n, home_slot(key, P.key.hash_key_width, P.key.hash_magic, n), key);
+  if (e < 0) { atomicCAS(A.launch.error, 0, B2Q_ERR_OUT_OF_SLOTS); return; }
+  red_add_u64(A.launch.accs[a] + e, (uint64_t)(int64_t)hi << 32);
+}
+
+/* ---- private shared-memory table (pass 2): 64-bit slots, 32-bit native atomics ---- */
 __device__ __forceinline__ void smem_add64(int64_t* slot, int64_t v) {
   uint32_t* w = reinterpret_cast<uint32_t*>(slot);
   const uint32_t vl = (uint32_t)v;
@@ -141,9 +161,6 @@ __device__ __forceinline__ void partition_chunk(const RadixArgs& A, const int8_t
     if (KEY32) load32<true>(reinterpret_cast<int32_t(&)[R]>(k32), cols[P.key.col], P.key.width, row0, nthr, pass, pol);
     else load64<true>(reinterpret_cast<int64_t(&)[R]>(k64), cols[P.key.col], row0, nthr, pass, pol);
   }
-  const uint32_t n = (uint32_t)P.key.entry_count;
-  const uint64_t magic = P.key.hash_magic;
-  const int hw = P.key.hash_key_width;
   const int tw = A.tuple_words;
   const uint32_t region0 = blockIdx.x * A.cap;          /* this CTA's region inside a partition's block of regions */
   const uint32_t part_stride = gridDim.x * A.cap;
@@ -164,7 +181,7 @@ __device__ __forceinline__ void partition_chunk(const RadixArgs& A, const int8_t
       if (!(pass >> j & 1)) continue;
       int64_t key = B2Q_KEY_OF(j);
       if (key == P.key.null_val) key = P.key.null_logical; /* ENCODING FIXED: physical NULL -> logical NULL */
-      const uint32_t part = home_slot(key, hw, magic, n) >> A.log_s;
+      const uint32_t part = part_of_mix(mix_key(key), (uint32_t)A.n_parts);
       const uint32_t pos = atomicAdd(s_cnt + part, 1u);
       if (pos < A.cap) {
         int64_t* dst = A.scratch + ((uint64_t)part * part_stride + region0 + pos) * 2u;
@@ -183,7 +200,7 @@ __device__ __forceinline__ void partition_chunk(const RadixArgs& A, const int8_t
     if (!(pass >> j & 1)) continue;
     int64_t key = B2Q_KEY_OF(j);
     if (key == P.key.null_val) key = P.key.null_logical;
-    const uint32_t part = home_slot(key, hw, magic, n) >> A.log_s;
+    const uint32_t part = part_of_mix(mix_key(key), (uint32_t)A.n_parts);
     const uint32_t pos = atomicAdd(s_cnt + part, 1u);
     if (pos < A.cap) {
       place[j] = part * part_stride + region0 + pos;
@@ -286,9 +303,6 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_partition_tile(con
   __syncthreads();
   uint64_t pol;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  const uint32_t n = (uint32_t)P.key.entry_count;
-  const uint64_t magic = P.key.hash_magic;
-  const int hw = P.key.hash_key_width;
   const uint32_t region0 = blockIdx.x * A.cap;
   const uint32_t part_stride = gridDim.x * A.cap;
   const int per = (NP + nthr - 1) / nthr; /* scan: partitions per thread */
@@ -343,7 +357,7 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_partition_tile(con
       int64_t key = KEY32 ? (int64_t)k32[KEY32 ? j : 0] : k64[KEY32 ? 0 : j];
       if (key == P.key.null_val) key = P.key.null_logical; /* ENCODING FIXED: physical NULL -> logical NULL */
       if (KEY32) k32[KEY32 ? j : 0] = (int32_t)key; else k64[KEY32 ? 0 : j] = key;
-      const uint32_t part = home_slot(key, hw, magic, n) >> A.log_s;
+      const uint32_t part = part_of_mix(mix_key(key), (uint32_t)NP);
       pr[j] = part << 16 | atomicAdd(s_cnt + part, 1u);
     }
     __syncthreads();
@@ -400,63 +414,81 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_partition_tile(con
 }
 
 /* ==========================================================================================================
- * pass 2: aggregate one partition at a time in shared memory
+ * pass 2: aggregate one partition at a time in a private shared-memory table, then merge it into the table in HBM
  * ======================================================================================================== */
-__device__ __forceinline__ void tma_bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+/* The private table is NOT a slice of the reference's table: it is a bucketed table (4 slots per bucket, bucket = the key's
+ * home slot / 4 inside the partition's range, overflow into the following buckets) because probe LENGTHS decide the cost
+ * on a SIMT machine — ncu on the first version, which probed a slice of the reference's linear-probing layout in shared
+ * memory: mean probe length 2 at load 0.67, but the tail decays like 0.93^k, the longest of a warp's 32 probes was ~25
+ * steps, and 26 warp instructions per tuple went into waiting for it (profiles/r2_radix_pass2_linear_ncu.txt).  A lookup
+ * here reads one 32-byte bucket (two LDS.128) and nearly always ends there.  When the partition's tuples are through, every
+ * occupied slot is merged into the table in HBM with the reference's own probe (get_group_value, GroupByRuntime.cpp:25-48):
+ * ~1e7 probes per 1e9 rows.  A key that finds no room within kMaxBuckets buckets (more distinct keys in the range than the
+ * estimate behind entry_count promised) goes to the HBM table directly, row by row.
+ * Accumulators: COUNT / integer SUM as 32-bit low words (native ATOMS.ADD; a carry or a value wider than 32 bits is sent to
+ * the HBM entry at once, RED.ADD.64 of hi << 32), the others as 64-bit slots at their identity. */
+constexpr int kBucket = 4, kMaxBuckets = 8;
+
+__device__ __forceinline__ void lds128(const int64_t* p, int64_t& a, int64_t& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(smem_u32(p)) : "memory");
 }
 
-/* The slice of the KEY array is bulk-copied in and out (the probe needs the keys earlier launches and pass 1's direct
- * inserts left there).  Accumulators start at their identity in shared memory — COUNT / integer SUM as a 32-bit low word
- * (native ATOMS.ADD; the carry or a value wider than 32 bits goes straight to the HBM array as RED.ADD.64 of hi << 32, as in
- * b2q_k_scan), the others as 64-bit slots — and are merged into the HBM arrays entry by entry when the partition is done. */
+/* slot of `want` in the private table (claimed if new), or -1 when its buckets are full; starts at bucket b */
+__device__ __noinline__ int bucket_find(int64_t* s_keys, uint32_t nb_mask, uint32_t b, int64_t want) {
+  for (int step = 0; step < kMaxBuckets; ++step, b = (b + 1) & nb_mask) {
+    int64_t* bk = s_keys + (size_t)b * kBucket;
+    for (;;) {
+      int64_t k0, k1, k2, k3;
+      lds128(bk, k0, k1);
+      lds128(bk + 2, k2, k3);
+      const uint32_t hit = (uint32_t)(k0 == want) | (uint32_t)(k1 == want) << 1 | (uint32_t)(k2 == want) << 2 | (uint32_t)(k3 == want) << 3;
+      if (hit) return (int)(b * kBucket + (__ffs(hit) - 1));
+      const uint32_t empty = (uint32_t)(k0 == B2Q_I64_MAX) | (uint32_t)(k1 == B2Q_I64_MAX) << 1 | (uint32_t)(k2 == B2Q_I64_MAX) << 2 | (uint32_t)(k3 == B2Q_I64_MAX) << 3;
+      if (!empty) break; /* full bucket without the key: next bucket */
+      const int j = __ffs(empty) - 1;
+      const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(bk + j), (unsigned long long)B2Q_I64_MAX, (unsigned long long)want);
+      if (old == (unsigned long long)B2Q_I64_MAX || old == (unsigned long long)want) return (int)(b * kBucket + j);
+      /* lost the slot to another key: look at the bucket again */
+    }
+  }
+  return -1;
+}
+
 __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __grid_constant__ RadixArgs A) {
   extern __shared__ __align__(128) int8_t s_raw[];
   const DevProgram& P = A.prog;
   const DevLaunch& Lh = A.launch;
   const int tid = threadIdx.x, lane = tid & 31;
   constexpr int nthr = kRadixBlock;
-  const uint32_t S = 1u << A.log_s;
-  const uint32_t SO = S + B2Q_RADIX_OV;             /* slice + overflow area */
+  const uint32_t S = 1u << A.log_s;                 /* slots of the private table == home slots per partition */
   const int n_accs = P.n_accs;
   int64_t* s_keys = reinterpret_cast<int64_t*>(s_raw);
-  int8_t* s_acc = s_raw + (size_t)SO * 8;           /* accumulator a: s_acc + acc_off[a] * SO, 4 or 8 bytes per entry */
-  uint32_t* s_blk = reinterpret_cast<uint32_t*>(s_acc + (size_t)A.acc_bytes_total * SO); /* [n_cta1 + 1] block prefix of the partition's regions */
-  __shared__ uint64_t s_bar;
+  int8_t* s_acc = s_raw + (size_t)S * 8;            /* accumulator a: s_acc + acc_off[a] * S, 4 or 8 bytes per slot */
+  uint32_t* s_blk = reinterpret_cast<uint32_t*>(s_acc + (size_t)A.acc_bytes_total * S); /* [n_cta1 + 1] block prefix of the partition's regions */
   __shared__ uint32_t s_part, s_next;
   const uint32_t n = (uint32_t)P.key.entry_count;
   const uint64_t magic = P.key.hash_magic;
   const int hw = P.key.hash_key_width;
   const int tw = A.tuple_words;
   const int n_cta1 = A.n_cta1;
-  uint32_t phase = 0;
+  const uint32_t nb_mask = S / kBucket - 1;
+  /* the program is {one COUNT(*) or integer SUM without a NULL test}: one predicated ATOMS per tuple, no accumulator loop */
+  const bool fused = n_accs == 1 && A.acc_bytes[0] == 4 && !P.accs[0].skip1_en && !P.accs[0].skip2_en && tw <= 2;
+  const bool fused_count = fused && P.accs[0].op == ACC_COUNT;
   uint64_t pol;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
   for (;;) {
+    __syncthreads();
     if (tid == 0) { s_part = atomicAdd(A.work_counter, 1u); s_next = 0; }
     __syncthreads();
     const uint32_t part = s_part;
     if (part >= (uint32_t)A.n_parts) break;
-    const uint32_t first = part << A.log_s;
-    const uint32_t Sp = min(S, n - first);          /* entries of this slice (the last one may be short) */
-    const uint32_t bulk = (Sp * 8u) & ~15u;         /* bytes of the key slice that move as TMA bulk copies */
-    /* ---- key slice in: cp.async.bulk global -> shared ---- */
-    if (tid == 0 && bulk) {
-      mbar_expect_tx(&s_bar, bulk);
-      const int8_t* src = reinterpret_cast<const int8_t*>(Lh.keys + first);
-      for (uint32_t off = 0; off < bulk; off += 65536u) tma_bulk_g2s(reinterpret_cast<int8_t*>(s_keys) + off, src + off, min(bulk - off, 65536u), &s_bar);
-    }
-    if ((Sp & 1u) && tid == 0) s_keys[Sp - 1] = Lh.keys[first + Sp - 1]; /* the odd last entry of a short slice */
-    for (uint32_t i = tid; i < B2Q_RADIX_OV; i += nthr) s_keys[Sp + i] = B2Q_I64_MAX;
-    for (int a = 0; a < n_accs; ++a) { /* accumulators at their identity (slice and overflow area) */
-      int8_t* base = s_acc + (size_t)A.acc_off[a] * SO;
-      if (A.acc_bytes[a] == 4) for (uint32_t i = tid; i < Sp + B2Q_RADIX_OV; i += nthr) reinterpret_cast<uint32_t*>(base)[i] = 0u;
-      else { const int64_t id = b2q_acc_identity(P.accs[a].op); for (uint32_t i = tid; i < Sp + B2Q_RADIX_OV; i += nthr) reinterpret_cast<int64_t*>(base)[i] = id; }
+    /* ---- empty table ---- */
+    for (uint32_t i = tid; i < S; i += nthr) s_keys[i] = B2Q_I64_MAX;
+    for (int a = 0; a < n_accs; ++a) {
+      int8_t* base = s_acc + (size_t)A.acc_off[a] * S;
+      if (A.acc_bytes[a] == 4) for (uint32_t i = tid; i < S; i += nthr) reinterpret_cast<uint32_t*>(base)[i] = 0u;
+      else { const int64_t id = b2q_acc_identity(P.accs[a].op); for (uint32_t i = tid; i < S; i += nthr) reinterpret_cast<int64_t*>(base)[i] = id; }
     }
     if (tid < 32) { /* warp 0: inclusive scan of ceil(count / kTupleBlock) over the n_cta1 regions */
       uint32_t run = 0;
@@ -470,10 +502,8 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
       }
       if (lane == 0) s_blk[0] = 0;
     }
-    if (bulk) mbar_wait(&s_bar, phase);
-    phase ^= bulk ? 1u : 0u;
     __syncthreads();
-    /* ---- stream the partition's tuples through the slice ---- */
+    /* ---- stream the partition's tuples through the table ---- */
     const uint32_t total_blocks = s_blk[n_cta1];
     for (;;) {
       uint32_t b = 0;
@@ -500,110 +530,74 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
         }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) pos[u] = home_slot(key[u], hw, magic, n) - first;
+      for (int u = 0; u < U; ++u) pos[u] = bucket_of_mix(mix_key(key[u]), nb_mask);
+      /* the common case — the key sits in its first bucket — for all U tuples at once: 2 U independent 16-byte loads in
+       * flight, no claim, no second bucket, no divergence; whatever is left (a key's first appearance in the partition, a
+       * full bucket) takes the slow path afterwards */
+      int e[U];
+      uint32_t slow = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t* bk = s_keys + (size_t)pos[u] * kBucket;
+        const longlong2 ka = *reinterpret_cast<const longlong2*>(bk);
+        const longlong2 kb = *reinterpret_cast<const longlong2*>(bk + 2);
+        const uint32_t hit = (uint32_t)(ka.x == key[u]) | (uint32_t)(ka.y == key[u]) << 1 | (uint32_t)(kb.x == key[u]) << 2 | (uint32_t)(kb.y == key[u]) << 3;
+        e[u] = (int)(pos[u] * kBucket) + __ffs(hit) - 1;
+        slow |= (uint32_t)(hit == 0 && lane + 32u * u < m) << u;
+      }
+      if (slow) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (slow >> u & 1) e[u] = bucket_find(s_keys, nb_mask, pos[u], key[u]);
+      }
+      __syncwarp();
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const uint32_t i = lane + 32u * u;
         const bool live = i < m;
-        /* get_group_value's probe inside the slice: home slot, then linear; past the slice end -> the overflow area */
-        uint32_t e = pos[u];
-        bool found = false;
-        if (live) {
-          const unsigned long long want = (unsigned long long)key[u];
-          for (; e < Sp + B2Q_RADIX_OV; ++e) {
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_keys + e);
-            if (cur == (unsigned long long)B2Q_I64_MAX) cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_keys + e), (unsigned long long)B2Q_I64_MAX, want);
-            if (cur == (unsigned long long)B2Q_I64_MAX || cur == want) { found = true; break; }
-          }
-        }
-        __syncwarp(); /* probe lengths differ per lane: reconverge before the updates, or every lane group runs them on its own */
         const int64_t* vals = tp + (size_t)i * tw + 1;
-        if (live && !found) { /* a cluster longer than the overflow area: keep the raw tuple for pass 3 */
-          const uint32_t li = atomicAdd(A.list_count, 1u);
-          if (li < A.list_cap) {
-            int64_t* d = A.list + (size_t)li * tw;
-            d[0] = key[u];
-            for (int cidx = 0; cidx < A.n_vals; ++cidx) d[1 + cidx] = tw == 2 ? v0[u] : __ldcg(vals + cidx);
-          } else atomicCAS(Lh.error, 0, B2Q_RADIX_RETRY);
-        }
-        if (live && found) {
+        if (live && e[u] < 0) { /* no room in the private table: the row goes to the table in HBM */
+          int64_t rv[B2Q_RADIX_MAX_VALS];
+          for (int cidx = 0; cidx < A.n_vals; ++cidx) rv[cidx] = tw == 2 ? v0[u] : __ldcg(vals + cidx);
+          global_insert_raw(A, key[u], rv);
+        } else if (fused) {
+          const int64_t add = fused_count ? 1 : v0[u];
+          const uint32_t vl = (uint32_t)add;
+          uint32_t old = 0;
+          if (live) old = atomicAdd(reinterpret_cast<uint32_t*>(s_acc) + e[u], vl);
+          const int32_t hi32 = (int32_t)(add >> 32) + (int32_t)((uint32_t)(old + vl) < old);
+          if (live && hi32 != 0) global_add_hi(A, key[u], 0, hi32);
+        } else if (live) {
           for (int a = 0; a < n_accs; ++a) {
             const DevAcc& acc = P.accs[a];
             const int vi = A.acc_val[a];
             const int64_t v = vi < 0 ? 0 : (tw == 2 ? v0[u] : __ldcg(vals + vi));
             if (vi >= 0 && value_skipped(acc, v)) continue;
-            int8_t* base = s_acc + (size_t)A.acc_off[a] * SO;
-            if (A.acc_bytes[a] == 4) { /* COUNT / integer SUM: low word here, the rare high-word delta straight to HBM */
+            int8_t* base = s_acc + (size_t)A.acc_off[a] * S;
+            if (A.acc_bytes[a] == 4) {
               const int64_t add = acc.op == ACC_COUNT ? 1 : v;
               const uint32_t vl = (uint32_t)add;
-              const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(base) + e, vl);
-              const int32_t hi = (int32_t)(add >> 32) + (int32_t)((uint32_t)(old + vl) < old);
-              if (hi != 0) {
-                if (e < Sp) red_add_u64(Lh.accs[a] + first + e, (uint64_t)(int64_t)hi << 32);
-                else atomicAdd(reinterpret_cast<unsigned long long*>(A.ov_hi + ((size_t)part * B2Q_RADIX_OV + (e - Sp)) * n_accs + a), (unsigned long long)((uint64_t)(int64_t)hi << 32));
-              }
-            } else smem_acc_raw(acc.op, reinterpret_cast<int64_t*>(base) + e, v);
+              const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(base) + e[u], vl);
+              const int32_t hi32 = (int32_t)(add >> 32) + (int32_t)((uint32_t)(old + vl) < old);
+              if (hi32 != 0) global_add_hi(A, key[u], a, hi32);
+            } else smem_acc_raw(acc.op, reinterpret_cast<int64_t*>(base) + e[u], v);
           }
         }
       }
       __syncwarp();
     }
     __syncthreads();
-    /* ---- key slice out (TMA bulk shared -> global); accumulators merged into the HBM arrays; overflow area to its place ---- */
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes above -> visible to the bulk copy */
-    __syncthreads();
-    if (tid == 0 && bulk) {
-      int8_t* dst = reinterpret_cast<int8_t*>(Lh.keys + first);
-      for (uint32_t off = 0; off < bulk; off += 65536u) tma_bulk_s2g(dst + off, reinterpret_cast<const int8_t*>(s_keys) + off, min(bulk - off, 65536u));
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-    if ((Sp & 1u) && tid == 0) Lh.keys[first + Sp - 1] = s_keys[Sp - 1];
-    for (int a = 0; a < n_accs; ++a) {
-      const int8_t* base = s_acc + (size_t)A.acc_off[a] * SO;
-      const int op = P.accs[a].op;
-      int64_t* g = Lh.accs[a] + first;
-      if (A.acc_bytes[a] == 4) {
-        for (uint32_t i = tid; i < Sp; i += nthr) { const uint32_t x = reinterpret_cast<const uint32_t*>(base)[i]; if (x) red_add_u64(g + i, (uint64_t)x); }
-      } else {
-        for (uint32_t i = tid; i < Sp; i += nthr) global_acc_merge(op, g + i, reinterpret_cast<const int64_t*>(base)[i]);
-      }
-    }
-    for (uint32_t i = tid; i < B2Q_RADIX_OV; i += nthr) {
-      int64_t* o = A.ov + ((size_t)part * B2Q_RADIX_OV + i) * (size_t)(1 + n_accs);
-      o[0] = s_keys[Sp + i];
+    /* ---- merge the private table into the table in HBM: the reference's probe, once per key ---- */
+    for (uint32_t i = tid; i < S; i += nthr) {
+      const int64_t key = s_keys[i];
+      if (key == B2Q_I64_MAX) continue;
+      const int64_t e = global_probe(reinterpret_cast<unsigned long long*>(Lh.keys), n, home_slot(key, hw, magic, n), key);
+      if (e < 0) { atomicCAS(Lh.error, 0, B2Q_ERR_OUT_OF_SLOTS); continue; }
       for (int a = 0; a < n_accs; ++a) {
-        const int8_t* base = s_acc + (size_t)A.acc_off[a] * SO;
-        o[1 + a] = A.acc_bytes[a] == 4 ? (int64_t)(uint64_t)reinterpret_cast<const uint32_t*>(base)[Sp + i] : reinterpret_cast<const int64_t*>(base)[Sp + i];
+        const int8_t* base = s_acc + (size_t)A.acc_off[a] * S;
+        if (A.acc_bytes[a] == 4) { const uint32_t x = reinterpret_cast<const uint32_t*>(base)[i]; if (x) red_add_u64(Lh.accs[a] + e, (uint64_t)x); }
+        else global_acc_merge(P.accs[a].op, Lh.accs[a] + e, reinterpret_cast<const int64_t*>(base)[i]);
       }
     }
-    if (tid == 0 && bulk) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); /* shared memory may be overwritten */
-    __syncthreads();
-  }
-}
-
-/* ==========================================================================================================
- * pass 3: overflow areas (aggregated entries) and listed raw tuples -> the table in HBM
- * ======================================================================================================== */
-__global__ void b2q_k_radix_insert(const __grid_constant__ RadixArgs A) {
-  const DevProgram& P = A.prog;
-  const DevLaunch& Lh = A.launch;
-  const int n_accs = P.n_accs;
-  const uint32_t n = (uint32_t)P.key.entry_count;
-  const int64_t n_ov = (int64_t)A.n_parts * B2Q_RADIX_OV;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ov; i += stride) {
-    const int64_t* o = A.ov + (size_t)i * (size_t)(1 + n_accs);
-    const int64_t key = o[0];
-    if (key == B2Q_I64_MAX) continue;
-    const int64_t e = global_probe(reinterpret_cast<unsigned long long*>(Lh.keys), n, home_slot(key, P.key.hash_key_width, P.key.hash_magic, n), key);
-    if (e < 0) { atomicCAS(Lh.error, 0, B2Q_ERR_OUT_OF_SLOTS); continue; }
-    for (int a = 0; a < n_accs; ++a)
-      global_acc_merge(P.accs[a].op, Lh.accs[a] + e, A.acc_bytes[a] == 4 ? o[1 + a] + A.ov_hi[(size_t)i * n_accs + a] : o[1 + a]);
-  }
-  const uint32_t n_list = min(*A.list_count, A.list_cap);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_list; i += stride) {
-    const int64_t* t = A.list + (size_t)i * A.tuple_words;
-    global_insert_raw(A, t[0], t + 1);
   }
 }
 
@@ -704,8 +698,8 @@ bool radix_plan(const B2QQuery& q, RadixPlan* rp) {
   const int64_t entry_bytes = 8 + off;
   const int64_t budget = 208 * 1024;
   int log_s = 4;
-  while (log_s < 20 && ((int64_t(2) << log_s) + B2Q_RADIX_OV) * entry_bytes <= budget) ++log_s;
-  if (((int64_t(1) << log_s) + B2Q_RADIX_OV) * entry_bytes > budget) return false;
+  while (log_s < 20 && (int64_t(2) << log_s) * entry_bytes <= budget) ++log_s;
+  if ((int64_t(1) << log_s) * entry_bytes > budget) return false;
   rp->log_s = log_s;
   const int64_t S = int64_t(1) << log_s;
   rp->n_parts = static_cast<int32_t>((q.plan.entry_count + S - 1) / S);
@@ -722,8 +716,8 @@ static size_t radix_tile_smem(const RadixPlan& rp) {
 size_t radix_smem_pass1(const RadixPlan& rp) { return rp.tile ? radix_tile_smem(rp) : static_cast<size_t>(rp.n_parts) * 4; }
 
 size_t radix_smem_pass2(const B2QQuery&, const RadixPlan& rp, int n_cta1) {
-  const size_t SO = (size_t(1) << rp.log_s) + B2Q_RADIX_OV;
-  return SO * (8 + rp.acc_bytes_total) + (static_cast<size_t>(n_cta1) + 1) * 4 + 16;
+  const size_t S = size_t(1) << rp.log_s;
+  return S * (8 + rp.acc_bytes_total) + (static_cast<size_t>(n_cta1) + 1) * 4 + 16;
 }
 
 /* grid of pass 1 and the region capacity for a batch of `chunks` scan chunks */
@@ -749,11 +743,6 @@ cudaError_t launch_radix(const B2QQuery& q, const RadixPlan& rp, const DevLaunch
   a.launch = launch;
   a.scratch = buf.scratch;
   a.counts = buf.counts;
-  a.ov = buf.ov;
-  a.ov_hi = buf.ov_hi;
-  a.list = buf.list;
-  a.list_count = buf.list_count;
-  a.list_cap = buf.list_cap;
   a.work_counter = buf.work_counter;
   a.n_parts = rp.n_parts;
   a.log_s = rp.log_s;
@@ -781,9 +770,7 @@ cudaError_t launch_radix(const B2QQuery& q, const RadixPlan& rp, const DevLaunch
     if (e != cudaSuccess) return e;
     attr_mask.fetch_or(1ull << dev, std::memory_order_release);
   }
-  cudaError_t e = cudaMemsetAsync(buf.work_counter, 0, 8, st); /* work_counter + list_count are adjacent words */
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(buf.ov_hi, 0, buf.ov_hi_bytes, st);
+  cudaError_t e = cudaMemsetAsync(buf.work_counter, 0, 8, st);
   if (e != cudaSuccess) return e;
   const bool key32 = q.prog.key.width != 8;
   const size_t smem1 = radix_smem_pass1(rp);
@@ -816,9 +803,6 @@ cudaError_t launch_radix(const B2QQuery& q, const RadixPlan& rp, const DevLaunch
   b2q_k_radix_aggregate<<<grid2, kRadixBlock, smem2, st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int64_t n_ov = static_cast<int64_t>(rp.n_parts) * B2Q_RADIX_OV;
-  const int grid3 = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n_ov + 255) / 256, sm_count() * 8)));
-  b2q_k_radix_insert<<<grid3, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 

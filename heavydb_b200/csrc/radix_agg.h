@@ -8,14 +8,13 @@
 #include "b2q_internal.h"
 
 #define B2Q_RADIX_MAX_VALS 7   /* distinct aggregate-argument columns a tuple may carry */
-#define B2Q_RADIX_OV 32        /* overflow entries per partition (keys whose probe runs off the end of the slice) */
 #define B2Q_RADIX_RETRY 77001 /* device -> host: a structure of the radix path was too small; re-run with the per-row probe kernel */
 
 namespace b2q {
 
 struct RadixPlan {
   int32_t n_parts;     /* partitions = ceil(entry_count / 2^log_s), by home-slot range */
-  int32_t log_s;       /* log2(entries per slice) */
+  int32_t log_s;       /* log2(home slots per partition) == log2(slots of pass 2's private table) */
   int32_t n_vals;      /* value words per tuple */
   int32_t tuple_words; /* 1 + n_vals */
   int8_t val_col[B2Q_RADIX_MAX_VALS + 1];   /* launch column of value word c */
@@ -30,13 +29,7 @@ struct RadixPlan {
 struct RadixBuffers {
   int64_t* scratch;      /* [n_parts][n_cta1][cap] tuples */
   uint32_t* counts;      /* [n_parts][n_cta1] */
-  int64_t* ov;           /* [n_parts][B2Q_RADIX_OV] x {key, accumulators} */
-  int64_t* ov_hi;        /* [n_parts][B2Q_RADIX_OV][n_accs] high-word deltas of overflow-area entries (zeroed per launch) */
-  size_t ov_hi_bytes;
-  int64_t* list;         /* raw tuples pass 2 could not place */
-  uint32_t* work_counter;/* pass 2's partition queue; list_count is the next word */
-  uint32_t* list_count;
-  uint32_t list_cap;
+  uint32_t* work_counter;/* pass 2's partition queue */
 };
 
 struct RadixArgs {
@@ -44,13 +37,9 @@ struct RadixArgs {
   DevLaunch launch;
   int64_t* scratch;
   uint32_t* counts;
-  int64_t* ov;
-  int64_t* ov_hi;
-  int64_t* list;
-  uint32_t* list_count;
   uint32_t* work_counter;
-  uint32_t list_cap;
   uint32_t cap;          /* tuples per region */
+  uint32_t pad0_;
   int32_t n_parts, log_s, n_cta1;
   int32_t n_vals, tuple_words;
   int8_t val_col[B2Q_RADIX_MAX_VALS + 1];

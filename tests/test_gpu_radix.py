@@ -51,7 +51,7 @@ def test_radix_matches_oracle(n, ndv, frag_rows, nullable_v):
         unit = sqlmini.parse(sql, table, names)
         rs, _ = gu.run_both(unit, table, entry_guess=int(real_ndv * 1.5), has_card=True, dev_table=dev, oracle_threads=4)
         assert rs.getQueryMemDesc().kernel == abi.KERNEL_BASELINE_GLOBAL
-        assert rs.stats()["kernel_launches"] >= 5          # init + 3 radix passes + materialise
+        assert rs.stats()["kernel_launches"] >= 4          # init + 2 radix passes + materialise
 
 
 def test_radix_key32_and_host_resident():
