@@ -8,6 +8,7 @@
 #include "multi.h"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -19,10 +20,13 @@ const NcclApi* nccl_api(std::string* why) {
   static std::string err;
   static std::once_flag once;
   std::call_once(once, []() {
-    /* prefer the copy already in the process (one NCCL per process: torch's bundled one when it is loaded) */
-    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    /* Prefer the copy already in the process: a second library with the same SONAME cannot be loaded next to it, and the
+     * first one loaded wins for everybody — a host that bundles its own NCCL (torch does) must therefore have loaded it before
+     * the first b2q_comm_* call (heavydb_b200/executor.py imports torch first for that reason).  B2Q_NCCL_LIB names a file to use. */
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);
+    if (!h) { const char* env = getenv("B2Q_NCCL_LIB"); if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_LOCAL); }
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     if (!h) { const char* e = dlerror(); err = std::string("cannot load libnccl.so.2: ") + (e ? e : "?"); return; }
     auto sym = [&](const char* n) -> void* {
       void* p = dlsym(h, n);

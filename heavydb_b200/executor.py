@@ -463,7 +463,19 @@ class Comm:
         self.h = handle
 
     @staticmethod
+    def _host_nccl_first():
+        """libb2q binds whatever libnccl.so.2 the process holds.  torch ships its own and breaks if another copy with the same
+        SONAME got there first, so a Python host that has torch loads it before libb2q touches NCCL."""
+        try:
+            import torch  # noqa: F401  (plumbing: makes torch's bundled libnccl the process's NCCL)
+            import torch.cuda.nccl as _n
+            _n.version()
+        except Exception:
+            pass
+
+    @staticmethod
     def unique_id() -> bytes:
+        Comm._host_nccl_first()
         buf = C.create_string_buffer(abi.COMM_ID_BYTES)
         rc = lib().b2q_comm_unique_id(buf)
         if rc:
@@ -472,6 +484,7 @@ class Comm:
 
     @classmethod
     def init_rank(cls, unique_id: bytes, nranks: int, rank: int, device: int = -1) -> "Comm":
+        cls._host_nccl_first()
         h = C.c_void_p()
         rc = lib().b2q_comm_init_rank(C.c_char_p(unique_id), nranks, rank, device, C.byref(h))
         if rc:
@@ -480,6 +493,7 @@ class Comm:
 
     @classmethod
     def init_all(cls, devices: Sequence[int]):
+        cls._host_nccl_first()
         arr = (C.c_int32 * len(devices))(*devices)
         out = (C.c_void_p * len(devices))()
         rc = lib().b2q_comm_init_all(arr, len(devices), out)
