@@ -225,6 +225,8 @@ class Plan(C.Structure):
         ("join_entry_count", C.c_int64),
         ("join_outer_col", C.c_int32),
         ("join_inner_col", C.c_int32),
+        ("count_distinct_min", C.c_int64 * MAX_TARGETS),
+        ("count_distinct_bits", C.c_int64 * MAX_TARGETS),
     ]
 
     #: fields that must agree between the product planner and the oracle planner
@@ -246,9 +248,10 @@ class Plan(C.Structure):
         d["group_col_widths"] = list(self.group_col_widths[: self.num_group_cols])
         d["targets"] = [
             (t.is_agg, t.agg_kind, t.sql_type.type, t.sql_type.notnull, t.agg_arg_type.type,
-             t.agg_arg_type.notnull, t.skip_null_val, t.arg_col_id, t.first_slot, t.sql_type.scale, t.agg_arg_type.scale)
+             t.agg_arg_type.notnull, t.skip_null_val, t.arg_col_id, t.first_slot, t.sql_type.scale, t.agg_arg_type.scale, t.is_distinct)
             for t in self.targets[: self.num_targets]
         ]
+        d["count_distinct"] = [(self.count_distinct_min[i], self.count_distinct_bits[i]) for i in range(self.num_targets)]
         return d
 
 

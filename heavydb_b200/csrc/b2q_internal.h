@@ -68,6 +68,8 @@ enum {
   ACC_MIN_F64 = 5, /* stored as order-preserving int64 */
   ACC_MAX_F64 = 6,
   ACC_TOUCH = 7,   /* "some row reached this group": ONE BYTE per entry (the array holds uint8), merged with MAX */
+  ACC_BITMAP = 9,  /* COUNT(DISTINCT c): the array holds one bitmap of bm_words 32-bit words per entry; a value sets bit
+                      (v - bm_min) / bucket (agg_count_distinct_bitmap[_skip_val], RuntimeFunctions.cpp:366-376,1201-1210); merged with OR */
   ACC_NDV = 8      /* estimator query: the array is the linear-counting bitmap (plan.buffer_size bytes), one bit set per row
                       at MurmurHash3(tuple of DevProgram::keys) % bits (linear_probabilistic_count), merged with OR */
 };
@@ -83,6 +85,11 @@ struct DevAcc {
   int8_t skip2_en;
   int8_t skip2_trunc32;
   int8_t pad_[2];
+  /* ACC_BITMAP */
+  int64_t bm_min;      /* value of bit 0 */
+  int64_t bm_bits;     /* bits per entry */
+  int32_t bm_words;    /* 32-bit words per entry = align8(ceil(bits / 8)) / 4 (bitmapPaddedSizeBytes on the GPU) */
+  int32_t bm_bucket;   /* > 1: bit = (v - bm_min) / bucket */
 };
 
 /* ---- group key ------------------------------------------------------------------------------------------ */
@@ -171,7 +178,8 @@ enum {
   SLOT_COUNT = 1,      /* accs[a] as integer */
   SLOT_VALUE = 2,      /* accs[a] (int64 bits or double bits) ; if nn >= 0 and accs[nn] == 0 -> init (NULL sentinel) */
   SLOT_VALUE_ORD = 3,  /* like SLOT_VALUE but accs[a] holds an order-preserving int64 image of a double */
-  SLOT_NONE = 4        /* zero-width slot (baseline key reference) */
+  SLOT_NONE = 4,       /* zero-width slot (baseline key reference) */
+  SLOT_BITCOUNT = 5    /* COUNT(DISTINCT): number of bits set in the entry's bitmap of accs[a] (count_distinct_set_size) */
 };
 struct DevSlot {
   int64_t init_val;
@@ -185,6 +193,8 @@ struct DevSlot {
   int8_t key_comp;     /* SLOT_KEY of a multi-column key: which GROUP BY column */
   int8_t scale_day;    /* MIN / MAX over a days-encoded DATE chunk: the accumulator holds days, the slot seconds */
   int8_t pad_[4];
+  int32_t bm_words;    /* SLOT_BITCOUNT: 32-bit words per entry */
+  int32_t pad2_;
 };
 struct DevLayout {
   int64_t row_size;

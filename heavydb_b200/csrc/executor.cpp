@@ -268,6 +268,7 @@ static int merge_class(int op) {
 /* bytes of accumulator array a: entry_count x 8, except the estimator's bitmap */
 static size_t acc_array_bytes(const B2QQuery& q, int a) {
   if (q.prog.accs[a].op == ACC_NDV) return static_cast<size_t>(q.plan.buffer_size);
+  if (q.prog.accs[a].op == ACC_BITMAP) return std::max<size_t>(static_cast<size_t>(q.plan.entry_count), 1) * static_cast<size_t>(q.prog.accs[a].bm_words) * 4;
   return std::max<size_t>(static_cast<size_t>(q.plan.entry_count), 1) * 8;
 }
 
@@ -300,8 +301,8 @@ static int32_t alloc_partial(B2QPartial& p, size_t extra_bytes, cudaStream_t st)
   CU(cudaMemsetAsync(p.d_error, 0, sizeof(int32_t), st));
   CU(cudaEventRecord(p.ev[0], st));
   CU(launch_init(q, p.accs, p.keys, p.smem_image, st));
-  for (int a = 0; a < q.prog.n_accs; ++a) /* the estimator's bitmap starts all-zero */
-    if (q.prog.accs[a].op == ACC_NDV) CU(cudaMemsetAsync(p.accs[a], 0, acc_array_bytes(q, a), st));
+  for (int a = 0; a < q.prog.n_accs; ++a) /* the estimator's bitmap and the COUNT(DISTINCT) bitmaps start all-zero */
+    if (q.prog.accs[a].op == ACC_NDV || q.prog.accs[a].op == ACC_BITMAP) CU(cudaMemsetAsync(p.accs[a], 0, acc_array_bytes(q, a), st));
   CU(cudaEventRecord(p.ev[1], st));
   return B2Q_OK;
 }
@@ -1216,9 +1217,9 @@ int32_t b2q_partial_array(const B2QPartial* p, int32_t i, void** ptr, int64_t* c
   if (!p || i < 0 || i >= p->q.prog.n_accs) return set_err(B2Q_ERR_INVALID_ARGUMENT, "array index");
   const int op = p->q.prog.accs[i].op;
   if (ptr) *ptr = p->accs[i];
-  if (count) *count = op == ACC_NDV ? p->q.plan.buffer_size : p->q.plan.entry_count;
-  if (dtype) *dtype = op == ACC_SUM_F64 ? B2Q_DT_FLOAT64 : (op == ACC_TOUCH || op == ACC_NDV) ? B2Q_DT_UINT8 : B2Q_DT_INT64;
-  if (redop) *redop = op == ACC_NDV ? B2Q_RED_BOR : (op == ACC_MIN_I64 || op == ACC_MIN_F64) ? B2Q_RED_MIN : (op == ACC_MAX_I64 || op == ACC_MAX_F64 || op == ACC_TOUCH) ? B2Q_RED_MAX : B2Q_RED_SUM;
+  if (count) *count = op == ACC_NDV ? p->q.plan.buffer_size : op == ACC_BITMAP ? static_cast<int64_t>(acc_array_bytes(p->q, i)) : p->q.plan.entry_count;
+  if (dtype) *dtype = op == ACC_SUM_F64 ? B2Q_DT_FLOAT64 : (op == ACC_TOUCH || op == ACC_NDV || op == ACC_BITMAP) ? B2Q_DT_UINT8 : B2Q_DT_INT64;
+  if (redop) *redop = (op == ACC_NDV || op == ACC_BITMAP) ? B2Q_RED_BOR : (op == ACC_MIN_I64 || op == ACC_MIN_F64) ? B2Q_RED_MIN : (op == ACC_MAX_I64 || op == ACC_MAX_F64 || op == ACC_TOUCH) ? B2Q_RED_MAX : B2Q_RED_SUM;
   return B2Q_OK;
 }
 int32_t b2q_partial_is_mergeable(const B2QPartial* p) { return p && p->q.plan.kernel != B2Q_KERNEL_BASELINE_GLOBAL; }

@@ -88,8 +88,9 @@ __global__ void b2q_k_init(const __grid_constant__ InitArgs A) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.entry_count; i += stride) {
     for (int a = 0; a < A.n_accs; ++a) {
       const int64_t id = b2q_acc_identity(A.ops[a]);
-      if (A.ops[a] == ACC_TOUCH) reinterpret_cast<uint8_t*>(A.accs[a])[i] = 0; else A.accs[a][i] = id;
-      if (A.smem_image) {
+      if (A.ops[a] == ACC_TOUCH) reinterpret_cast<uint8_t*>(A.accs[a])[i] = 0;
+      else if (A.ops[a] != ACC_BITMAP && A.ops[a] != ACC_NDV) A.accs[a][i] = id; /* the bitmaps are zeroed with a memset */
+      if (A.smem_image && A.smem.acc_bytes[a] > 0) {
         int8_t* p = A.smem_image + A.smem.acc_off[a];
         if (A.smem.acc_bytes[a] == 1) reinterpret_cast<uint8_t*>(p)[i] = 0;
         else if (A.smem.acc_bytes[a] == 4) reinterpret_cast<uint32_t*>(p)[i] = 0u;
@@ -184,6 +185,13 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
         switch (sl.kind) {
           case SLOT_KEY: val = L.n_keys > 1 ? mkey_proj[sl.key_comp] : key; break;
           case SLOT_COUNT: val = A.accs[sl.acc][i]; break;
+          case SLOT_BITCOUNT: { /* count_distinct_set_size over the entry's bitmap (CountDistinct.h:54-70) */
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(A.accs[sl.acc]) + (size_t)i * (size_t)sl.bm_words;
+            int64_t n = 0;
+            for (int k = 0; k < sl.bm_words; ++k) n += __popc(w[k]);
+            val = n;
+            break;
+          }
           default: {
             const int64_t raw = A.accs[sl.acc][i];
             bool is_null = false;

@@ -90,6 +90,8 @@ struct TargetDesc {
   SqlType sql_type, arg_type; /* arg_type.type == 0: no argument */
   bool skip_null = false;
   bool constrained = false; /* the quals hold a top-level `arg IS NOT NULL` (constrained_not_null, OutputBufferInitialization.cpp:301-324) */
+  bool distinct = false;    /* COUNT(DISTINCT arg): CountDistinctDescriptor{Bitmap, cd_min, cd_bucket, cd_bits} */
+  int64_t cd_min = 0, cd_bits = 0, cd_bucket = 0;
   int arg_col = -1;
   int first_slot = 0;
   SqlType compact() const { /* get_compact_type */
@@ -132,6 +134,7 @@ class Planner {
     build_targets();
     plan_join(q.plan);
     choose_hash_type(q.plan);
+    count_distinct_descriptors(q.plan);
     layout_slots(q.plan);
     init_values(q.plan);
     publish_targets(q.plan);
@@ -332,7 +335,8 @@ class Planner {
         any_agg = true;
         if (e.op != B2Q_kCOUNT && e.op != B2Q_kSUM && e.op != B2Q_kMIN && e.op != B2Q_kMAX && e.op != B2Q_kAVG)
           reject(B2Q_ERR_UNSUPPORTED, "aggregate kind outside COUNT/SUM/MIN/MAX/AVG");
-        if (e.ival != 0) reject(B2Q_ERR_UNSUPPORTED, "DISTINCT aggregates (count-distinct bitmaps / sets) are outside this path");
+        if (e.ival != 0 && (e.op != B2Q_kCOUNT || e.left < 0)) reject(B2Q_ERR_UNSUPPORTED, "DISTINCT is on this path for COUNT(DISTINCT column) only");
+        d.distinct = e.ival != 0;
         if (e.left < 0) {
           if (e.op != B2Q_kCOUNT) reject(B2Q_ERR_INVALID_ARGUMENT, "aggregate without argument must be COUNT");
           d.sql_type = SqlType{bigint_count ? B2Q_kBIGINT : B2Q_kINT, e.ti.notnull != 0};
@@ -435,11 +439,50 @@ class Planner {
     }
   }
 
+  bool any_distinct() const { for (const TargetDesc& d : targets_) if (d.distinct) return true; return false; }
+  /* GroupByAndAggregate::getBaselineThreshold (:222-230): on the GPU a query with COUNT(DISTINCT) targets switches to
+   * baseline hash four times earlier (g_baseline_groupby_threshold = 1e6, Execute.cpp:111) */
+  int64_t baseline_threshold() const { return any_distinct() ? 1000000 / 4 : 1000000; }
+
+  /* init_count_distinct_descriptors (GroupByAndAggregate.cpp:650-855) for COUNT(DISTINCT column): the argument's range
+   * (get_expr_range_info: chunk stats narrowed by the simple quals) decides.  An integer range gives the Bitmap implementation
+   * with get_bucketed_cardinality_without_nulls bits (:379-395); fp arguments, ranges of g_bitmap_memory_limit (8e9) bits and
+   * more, and bitmaps that would total 8e9 bytes over the group range fall to the std::set implementation or an error in the
+   * reference — neither runs on its GPU (QueryMustRunOnCpu) and both are refused here.  check_total_bitmap_memory
+   * (QueryMemoryInitializer.cpp:40-66) is applied to the planned entry count as well. */
+  void count_distinct_descriptors(const B2QPlan& p) {
+    const int64_t limit = 8000000000ll; /* g_bitmap_memory_limit, QueryMemoryInitializer.cpp:28 */
+    int64_t bytes_per_group = 0;
+    for (TargetDesc& d : targets_) {
+      if (!d.distinct) continue;
+      if (d.arg_type.is_fp()) reject(B2Q_ERR_UNSUPPORTED, "COUNT(DISTINCT) of a floating-point column needs the set implementation (CPU only in the reference)");
+      if (is_days(d.arg_col)) reject(B2Q_ERR_UNSUPPORTED, "COUNT(DISTINCT) of a days-encoded DATE is outside this path");
+      ColRange r = leaf_range(d.arg_col);
+      narrow_by_simple_quals(d.arg_col, r);
+      if (r.imin > r.imax) { d.cd_min = 0; d.cd_bucket = r.bucket; d.cd_bits = 64; bytes_per_group += 8; continue; } /* isEmpty(): :735-744 */
+      uint64_t size = static_cast<uint64_t>(r.imax) - static_cast<uint64_t>(r.imin);
+      if (r.bucket) size /= static_cast<uint64_t>(r.bucket);
+      const int64_t bits = size >= static_cast<uint64_t>(INT64_MAX) ? 0 : static_cast<int64_t>(size + 1);
+      if (bits <= 0 || limit <= bits) reject(B2Q_ERR_UNSUPPORTED, "COUNT(DISTINCT): argument range too wide for a bitmap (set implementation, CPU only in the reference)");
+      const int64_t padded = align8((bits + 7) / 8); /* compute_bytes_per_group / bitmapPaddedSizeBytes on the GPU */
+      int64_t groups = 1;
+      if (grouped_) { /* maximum_num_groups over the GROUP BY range (:762-764); our composite ranges carry min 0 / max = product */
+        const int64_t bucket = std::max<int64_t>(p.bucket, 1);
+        groups = p.max_val >= p.min_val ? (p.max_val - p.min_val + 1) / bucket : 0;
+      }
+      if (groups > 0 && padded >= (limit + groups - 1) / groups) reject(B2Q_ERR_UNSUPPORTED, "COUNT(DISTINCT): bitmaps over the group range exceed g_bitmap_memory_limit (set implementation or an error in the reference)");
+      d.cd_min = r.imin; d.cd_bucket = r.bucket; d.cd_bits = bits;
+      bytes_per_group += padded;
+    }
+    if (bytes_per_group && p.entry_count > 0 && bytes_per_group >= (limit + p.entry_count - 1) / p.entry_count)
+      reject(B2Q_ERR_OUT_OF_GPU_MEM, "COUNT(DISTINCT) bitmaps exceed g_bitmap_memory_limit (OutOfHostMemory in the reference)");
+  }
+
   void keyless_info() {
     bool keyless = true, found = false;
     int index = 0;
     for (const TargetDesc& d : targets_) {
-      if (!found && d.is_agg) {
+      if (!found && d.is_agg && !d.distinct) { /* `!is_distinct_target(agg_info)`, GroupByAndAggregate.cpp:503 */
         const bool has_arg = d.arg_col >= 0;
         const ColRange r = has_arg ? leaf_range(d.arg_col) : ColRange{};
         switch (d.agg) {
@@ -511,7 +554,7 @@ class Planner {
         p.group_col_ids[i] = g.col_id;
         p.group_col_widths[i] = static_cast<int8_t>(col_type(g.col_id).size());
       }
-      if (!cardinality || cardinality > 1000000) reject(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
+      if (!cardinality || cardinality > baseline_threshold()) reject(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
       key_col_ = keycomps_[0].col;
       p.key_col_id = key_col_;
       p.group_col_width = p.group_col_widths[0];
@@ -539,7 +582,8 @@ class Planner {
     if (perfect) {
       p.min_val = r.imin; p.max_val = r.imax; p.bucket = r.bucket;
       const int64_t col_count = u_.num_groupby_exprs + u_.num_target_exprs;
-      const int64_t max_entries = (int64_t(1) << 30) / (col_count * 8); /* kMaxBufferSize, GroupByAndAggregate.cpp:57 */
+      int64_t max_entries = (int64_t(1) << 30) / (col_count * 8); /* kMaxBufferSize, GroupByAndAggregate.cpp:57 */
+      if (any_distinct()) max_entries = std::min(max_entries, baseline_threshold()); /* :307-309 */
       int64_t span;
       const bool too_big = __builtin_sub_overflow(r.imax, r.imin, &span) || span >= max_entries;
       if (kt.is_string() && !r.bucket) {
@@ -680,7 +724,9 @@ class Planner {
       B2QTargetInfo& o = p.targets[i];
       o.is_agg = d.is_agg; o.agg_kind = d.agg;
       o.sql_type = to_abi(d.sql_type); o.agg_arg_type = to_abi(d.arg_type);
-      o.skip_null_val = d.skip_null; o.is_distinct = 0; o.arg_col_id = d.arg_col; o.first_slot = d.first_slot;
+      o.skip_null_val = d.skip_null; o.is_distinct = d.distinct ? 1 : 0; o.arg_col_id = d.arg_col; o.first_slot = d.first_slot;
+      p.count_distinct_min[i] = d.distinct ? d.cd_min : 0;
+      p.count_distinct_bits[i] = d.distinct ? d.cd_bits : 0;
     }
   }
 
@@ -1402,6 +1448,22 @@ class Planner {
       };
       switch (d.agg) {
         case B2Q_kCOUNT: {
+          if (d.distinct) { /* codegenCountDistinct (GroupByAndAggregate.cpp:1889-1963): agg_count_distinct_bitmap[_skip_val] */
+            DevAcc a;
+            memset(&a, 0, sizeof(a));
+            a.op = ACC_BITMAP;
+            a.col = launch_col(q, d.arg_col);
+            a.width = static_cast<int8_t>(phys_width_code(d.arg_col));
+            if (d.skip_null) { a.skip1_en = 1; a.skip1_val = phys_int_null(d.arg_col); } /* inlineIntNull(arg_ti), as stored */
+            a.bm_min = d.cd_min;
+            a.bm_bits = d.cd_bits;
+            a.bm_words = static_cast<int32_t>(align8((d.cd_bits + 7) / 8) / 4);
+            a.bm_bucket = static_cast<int32_t>(d.cd_bucket);
+            sl.kind = SLOT_BITCOUNT;
+            sl.acc = find_or_add_acc(q, a);
+            sl.bm_words = a.bm_words;
+            break;
+          }
           sl.kind = SLOT_COUNT;
           const int nn = non_null_count();
           sl.acc = nn >= 0 ? nn : find_or_add_acc(q, make_acc(q, ACC_COUNT, nullptr));
@@ -1506,7 +1568,7 @@ class Planner {
     for (int pass = 0; pass < 2; ++pass)
       for (int a = 0; a < q.prog.n_accs; ++a) {
         const int op = q.prog.accs[a].op;
-        const int bytes = op == ACC_TOUCH ? 1 : (op == ACC_COUNT || op == ACC_SUM_I64) ? 4 : 8;
+        const int bytes = op == ACC_BITMAP ? 0 /* bitmaps stay in HBM */ : op == ACC_TOUCH ? 1 : (op == ACC_COUNT || op == ACC_SUM_I64) ? 4 : 8;
         if ((pass == 0) != (bytes == 8)) continue;
         sm.acc_bytes[a] = bytes;
         sm.acc_off[a] = off;

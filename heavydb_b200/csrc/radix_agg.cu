@@ -663,7 +663,7 @@ bool radix_plan(const B2QQuery& q, RadixPlan* rp) {
   int n_vals = 0;
   for (int a = 0; a < P.n_accs; ++a) {
     const DevAcc& acc = P.accs[a];
-    if (acc.op == ACC_TOUCH || acc.op == ACC_NDV) return false;
+    if (acc.op == ACC_TOUCH || acc.op == ACC_NDV || acc.op == ACC_BITMAP) return false;
     rp->acc_val[a] = -1;
     if (acc.col < 0) continue;
     int vi = -1;

@@ -884,6 +884,35 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       continue;
     }
 
+    if (op == ACC_BITMAP) {
+      /* COUNT(DISTINCT c): agg_count_distinct_bitmap[_skip_val] (RuntimeFunctions.cpp:366-376, :1201-1210) — bit
+       * (v - min) / bucket of the group's bitmap; the bitmaps live in HBM / L2 and saturate quickly, so a plain load filters
+       * out the bits that are already set before the atomic OR (as for the estimator's bitmap) */
+      int64_t v[R];
+      if (acc.width == 8) load64<true>(v, cols[acc.col], row0, nthr, arg_mask, pol, JX(acc.col));
+      else {
+        int32_t t32[R];
+        load32<true>(t32, cols[acc.col], acc.width, row0, nthr, arg_mask, pol, JX(acc.col));
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = t32[j];
+      }
+      const uint32_t m = not_skipped64(acc, v, pass);
+      uint32_t* bitmaps = reinterpret_cast<uint32_t*>(garr);
+      uint32_t bad = 0;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (!(m >> j & 1)) continue;
+        uint64_t idx = (uint64_t)(v[j] - acc.bm_min);
+        if (acc.bm_bucket > 1) idx /= (uint64_t)acc.bm_bucket;
+        if (idx >= (uint64_t)acc.bm_bits) { bad |= 1u << j; continue; } /* outside the chunk-stats range: the reference would write out of bounds */
+        uint32_t* w = bitmaps + (size_t)e[j] * (size_t)acc.bm_words + (size_t)(idx >> 5);
+        const uint32_t bit = 1u << (idx & 31u);
+        if (!(__ldcg(w) & bit)) atomicOr(w, bit);
+      }
+      if (bad) atomicCAS(Lh.error, 0, B2Q_ERR_KEY_OUT_OF_RANGE);
+      continue;
+    }
+
     if (op == ACC_COUNT && acc.col < 0) { /* COUNT(*) */
       if (WAGG) {
         const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(pass));
@@ -1153,7 +1182,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) b2q_k_scan(const __grid_c
       const int8_t* base = b2q_smem + A.smem.acc_off[a];
       for (int64_t i = tid; i < n; i += nthr) {
         switch (op) {
-          case ACC_NDV: break; /* lives in HBM only */
+          case ACC_NDV: case ACC_BITMAP: break; /* live in HBM only */
           case ACC_TOUCH: {
             uint32_t s = 0;
             for (int r = 0; r < nrep; ++r) s |= reinterpret_cast<const uint8_t*>(base + (size_t)r * rb)[i];

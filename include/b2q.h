@@ -42,7 +42,8 @@ extern "C" {
                                operands-before-node rule, b2q_columnar_results_*, host-phase stats;
                             4: DECIMAL / NUMERIC columns (B2QTypeInfo.scale), decimal_to_double of b2q_rs_get_next_row;
                             5: b2q_comm_* / b2q_execute_work_unit_dist / _multi (merge of the per-device tables inside the
-                               library, NCCL), B2Q_KERNEL_BASELINE_PROBE, LIMIT 0 = empty result */
+                               library, NCCL), B2Q_KERNEL_BASELINE_PROBE, LIMIT 0 = empty result, COUNT(DISTINCT) on bitmaps
+                               (B2QPlan.count_distinct_*) */
 
 /* ---- SQLTypes subset (Shared/sqltypes.h:65-99) -------------------------------------------------------- */
 enum {
@@ -324,6 +325,14 @@ typedef struct B2QPlan {
    * table column (id - num_cols). */
   int64_t join_min_key, join_max_key, join_entry_count;
   int32_t join_outer_col, join_inner_col; /* -1 without a join */
+  /* COUNT(DISTINCT c) targets — CountDistinctDescriptor with CountDistinctImplType::Bitmap (init_count_distinct_descriptors,
+   * GroupByAndAggregate.cpp:650-855): one bitmap of count_distinct_bits[t] bits per group, bit 0 = count_distinct_min[t];
+   * 0 bits = target t is not a distinct aggregate.  The reference keeps a POINTER to the group's bitmap in the target's slot
+   * and counts its bits when the value is read (count_distinct_set_size, ResultSetIteration.cpp:2178); here the bitmaps stay
+   * in HBM and the slot of the returned buffer holds the set size itself.  Descriptors the reference would serve with a
+   * std::set (fp argument, range too wide) cannot run on its GPU either (QueryMustRunOnCpu): B2Q_ERR_UNSUPPORTED. */
+  int64_t count_distinct_min[B2Q_MAX_TARGETS];
+  int64_t count_distinct_bits[B2Q_MAX_TARGETS];
 } B2QPlan;
 
 /* The 15-slot kernel parameter block of the reference's JIT entry (enums.h:64-79), device pointers. */

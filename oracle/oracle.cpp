@@ -370,6 +370,10 @@ struct Target {
   Ti arg_ti;      /* argument expression's own type info */
   int first_slot{0};
   bool arg_constrained_not_null{false}; /* constrained_not_null(agg_arg(target_expr), ra_exe_unit.quals) */
+  /* is_distinct_target: CountDistinctDescriptor{Bitmap, min_val, bucket_size, bitmap_sz_bits} (CountDistinctDescriptor.h) */
+  bool is_distinct{false};
+  int64_t cd_min{0}, cd_bits{0}, cd_bucket{0};
+  int64_t cd_tail{0}; /* ours: byte offset (past p.buffer_size) of this target's per-entry bitmaps while the query runs */
 };
 
 struct Range { /* ExpressionRange (Integer or Double or Invalid) */
@@ -398,6 +402,9 @@ struct Plan {
   std::shared_ptr<std::vector<int32_t>> join_buff;
   /* estimator query (QueryDescriptionType::Estimator): the argument tuple's (virtual) column ids */
   std::vector<int> estimator_cols;
+  /* COUNT(DISTINCT): bytes of bitmaps kept behind the result buffer while the query runs (the reference keeps them in the
+   * row set memory owner and a pointer in the slot; the slot here receives the set size when the query is done) */
+  int64_t cd_total{0};
 };
 
 const B2QExpr& expr_at(const B2QExecUnit& u, int idx) {
@@ -450,7 +457,8 @@ Target get_target_info(const B2QExecUnit& u, int expr_idx, bool bigint_count) {
   }
   t.is_agg = true;
   t.agg_kind = e.op;
-  if (e.ival != 0) fail(B2Q_ERR_UNSUPPORTED, "DISTINCT aggregates (count-distinct descriptors, GroupByAndAggregate.cpp:650-855) are not restated yet");
+  if (e.ival != 0 && (e.op != B2Q_kCOUNT || e.left < 0)) fail(B2Q_ERR_UNSUPPORTED, "DISTINCT is restated for COUNT(DISTINCT column) only");
+  t.is_distinct = e.ival != 0;
   if (e.left < 0) {
     if (e.op != B2Q_kCOUNT) fail(B2Q_ERR_INVALID_ARGUMENT, "only COUNT may have no argument");
     t.sql_type = Ti{bigint_count ? B2Q_kBIGINT : B2Q_kINT, notnull};
@@ -596,7 +604,7 @@ void get_keyless_info(const B2QExecUnit& u, const B2QTableInfo& tbl, const std::
   int32_t index = 0;
   for (const auto& agg_info : targets) {
     const Ti chosen_type = get_compact_type(agg_info);
-    if (!found && agg_info.is_agg) {
+    if (!found && agg_info.is_agg && !agg_info.is_distinct) { /* !is_distinct_target(agg_info) */
       const bool has_arg = agg_info.arg_col >= 0;
       switch (agg_info.agg_kind) {
         case B2Q_kAVG:
@@ -741,6 +749,12 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
   for (auto& t : plan.targets) any_agg |= t.is_agg;
   if (!any_agg) fail(B2Q_ERR_UNSUPPORTED, "projection queries are outside this path");
 
+  /* GroupByAndAggregate::getBaselineThreshold (:222-230): device_type is GPU on this path, so COUNT(DISTINCT) targets divide
+   * g_baseline_groupby_threshold (1e6) by four */
+  bool any_count_distinct = false;
+  for (const auto& t : plan.targets) any_count_distinct |= t.is_distinct;
+  const int64_t baseline_threshold = any_count_distinct ? 1000000 / 4 : 1000000;
+
   /* ---- hash type: GroupByAndAggregate::getColRangeInfo (:232-365) + get_expr_range_info (:181-218) ---- */
   int key_col = -1;
   Range key_range;
@@ -771,7 +785,7 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
       p.group_col_ids[i] = g.col_id;
       p.group_col_widths[i] = static_cast<int8_t>(type_size(tbl.col_types[g.col_id].type));
     }
-    if (!cardinality || cardinality > 1000000) fail(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
+    if (!cardinality || cardinality > baseline_threshold) fail(B2Q_ERR_UNSUPPORTED, "multi-column baseline hash is outside this path");
     p.query_desc_type = B2Q_GroupByPerfectHash;
     p.min_val = 0; p.max_val = cardinality; p.bucket = 0; p.has_nulls = has_nulls;
     key_col = plan.keys[0].col;
@@ -800,7 +814,8 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
     if (hash_type == B2Q_GroupByPerfectHash) {
       /* :298-304 max_entry_count, :131-139 is_column_range_too_big_for_perfect_hash */
       const int64_t col_count = u.num_groupby_exprs + u.num_target_exprs;
-      const int64_t max_entry_count = kMaxBufferSize / (col_count * static_cast<int64_t>(sizeof(int64_t)));
+      int64_t max_entry_count = kMaxBufferSize / (col_count * static_cast<int64_t>(sizeof(int64_t)));
+      if (any_count_distinct) max_entry_count = std::min(max_entry_count, baseline_threshold); /* :307-309 */
       bool too_big;
       int64_t diff;
       if (__builtin_sub_overflow(cmax, cmin, &diff)) too_big = true; else too_big = diff >= max_entry_count;
@@ -1013,7 +1028,49 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
     o.is_agg = t.is_agg; o.agg_kind = t.agg_kind;
     o.sql_type = B2QTypeInfo{t.sql_type.type, t.sql_type.notnull, t.sql_type.scale};
     o.agg_arg_type = B2QTypeInfo{t.agg_arg_type.type, t.agg_arg_type.notnull, t.agg_arg_type.scale};
-    o.skip_null_val = t.skip_null_val; o.is_distinct = 0; o.arg_col_id = t.arg_col; o.first_slot = t.first_slot;
+    o.skip_null_val = t.skip_null_val; o.is_distinct = t.is_distinct ? 1 : 0; o.arg_col_id = t.arg_col; o.first_slot = t.first_slot;
+  }
+  /* ---- init_count_distinct_descriptors (GroupByAndAggregate.cpp:650-855) for COUNT(DISTINCT column) on the GPU:
+   * arg_range_info = get_expr_range_info (:181-218: the column's chunk-stats range narrowed by the simple quals);
+   * empty range -> Bitmap of 64 bits at min 0 (:735-744); integer range -> Bitmap of get_bucketed_cardinality_without_nulls
+   * bits (:379-395) unless that is <= 0 or >= g_bitmap_memory_limit (8e9, QueryMemoryInitializer.cpp:28) or the bitmaps of
+   * the whole group range would reach the limit (:755-832) — then the std::set implementation or an exception; fp / invalid
+   * ranges are the set implementation from the start.  Sets do not run on the reference's GPU (QueryMustRunOnCpu), so they
+   * are refused.  check_total_bitmap_memory (QueryMemoryInitializer.cpp:40-66) bounds bytes per group x entry count. ---- */
+  {
+    const int64_t limit = 8000000000ll;
+    int64_t bytes_per_group = 0, tail = p.buffer_size;
+    for (size_t i = 0; i < plan.targets.size(); ++i) {
+      auto& t = plan.targets[i];
+      p.count_distinct_min[i] = p.count_distinct_bits[i] = 0;
+      if (!t.is_distinct) continue;
+      if (is_fp(tbl.col_types[t.arg_col].type)) fail(B2Q_ERR_UNSUPPORTED, "COUNT(DISTINCT) of a floating-point column: set implementation, CPU only");
+      if (is_date_in_days(tbl, t.arg_col)) fail(B2Q_ERR_UNSUPPORTED, "COUNT(DISTINCT) of a days-encoded DATE is outside the product path");
+      Range r = leaf_column_range(tbl, t.arg_col);
+      apply_simple_quals(u, t.arg_col, r);
+      if (r.kind != Range::Integer) fail(B2Q_ERR_UNSUPPORTED, "COUNT(DISTINCT): no integer range: set implementation, CPU only");
+      if (r.imin > r.imax) { t.cd_min = 0; t.cd_bucket = r.bucket; t.cd_bits = 64; }
+      else {
+        uint64_t size = static_cast<uint64_t>(r.imax) - static_cast<uint64_t>(r.imin);
+        if (r.bucket) size /= static_cast<uint64_t>(r.bucket);
+        const int64_t bits = size >= static_cast<uint64_t>(std::numeric_limits<int64_t>::max()) ? 0 : static_cast<int64_t>(size + 1);
+        if (bits <= 0 || limit <= bits) fail(B2Q_ERR_UNSUPPORTED, "COUNT(DISTINCT): range too wide for a bitmap: set implementation, CPU only");
+        const int64_t padded = align_to_int64((bits + 7) / 8);
+        int64_t groups = 1;
+        if (is_group_by) groups = p.max_val >= p.min_val ? (p.max_val - p.min_val + 1) / std::max<int64_t>(p.bucket, 1) : 0;
+        if (groups > 0 && padded >= (limit + groups - 1) / groups) fail(B2Q_ERR_UNSUPPORTED, "COUNT(DISTINCT): bitmaps over the group range reach g_bitmap_memory_limit: set implementation or an error");
+        t.cd_min = r.imin; t.cd_bucket = r.bucket; t.cd_bits = bits;
+      }
+      const int64_t padded = align_to_int64((t.cd_bits + 7) / 8);
+      bytes_per_group += padded;
+      t.cd_tail = tail;
+      tail += padded * std::max<int64_t>(p.entry_count, 1);
+      p.count_distinct_min[i] = t.cd_min;
+      p.count_distinct_bits[i] = t.cd_bits;
+    }
+    if (bytes_per_group && p.entry_count > 0 && bytes_per_group >= (limit + p.entry_count - 1) / p.entry_count)
+      fail(B2Q_ERR_OUT_OF_GPU_MEM, "COUNT(DISTINCT) bitmaps reach g_bitmap_memory_limit (OutOfHostMemory)");
+    plan.cd_total = tail - p.buffer_size;
   }
   p.kernel = 0;
   p.join_outer_col = p.join_inner_col = -1;
@@ -1332,6 +1389,17 @@ void update_target(const Plan& plan, const Target& t, int8_t* out, int64_t entry
     return;
   }
   if (t.agg_kind == B2Q_kCOUNT && t.arg_col < 0) { agg_count(a); return; }
+  if (t.is_distinct) {
+    /* agg_count_distinct_bitmap[_skip_val] (RuntimeFunctions.cpp:366-376, :1201-1210); *agg is the group's bitmap */
+    const int64_t v = decode_int_column(tbl, fr, t.arg_col, pos);
+    if (t.skip_null_val && v == inline_int_null_val(tbl.col_types[t.arg_col].type)) return;
+    uint64_t bitmap_idx = static_cast<uint64_t>(v - t.cd_min);
+    if (1 < t.cd_bucket) bitmap_idx /= static_cast<uint64_t>(t.cd_bucket);
+    if (bitmap_idx >= static_cast<uint64_t>(t.cd_bits)) fail(B2Q_ERR_KEY_OUT_OF_RANGE, "COUNT(DISTINCT) value outside the chunk-stats range");
+    int8_t* bitmap = out + t.cd_tail + entry * align_to_int64((t.cd_bits + 7) / 8);
+    bitmap[bitmap_idx >> 3] |= static_cast<int8_t>(1 << (bitmap_idx & 7));
+    return;
+  }
   const int ctype = tbl.col_types[t.arg_col].type;
   const bool arg_notnull = t.arg_ti.notnull;
   const bool need_skip_null = t.skip_null_val;
@@ -1384,7 +1452,7 @@ void update_target(const Plan& plan, const Target& t, int8_t* out, int64_t entry
 /* ---- buffer init: QueryMemoryInitializer::initRowGroups (QueryMemoryInitializer.cpp:620-700) ---- */
 void init_buffer(const Plan& plan, std::vector<int8_t>& buf) {
   const B2QPlan& p = plan.p;
-  buf.assign(static_cast<size_t>(p.buffer_size), 0);
+  buf.assign(static_cast<size_t>(p.buffer_size + plan.cd_total), 0); /* + zeroed COUNT(DISTINCT) bitmaps (allocateCountDistinctBuffers) */
   if (p.query_desc_type == B2Q_Estimator) return; /* the estimator buffer is a zeroed bitmap (QueryMemoryInitializer: allocateCountDistinct... / estimator_result_set_) */
   const bool has_key = p.query_desc_type != B2Q_NonGroupedAggregate && !p.keyless_hash;
   for (int64_t e = 0; e < p.entry_count; ++e) {
@@ -1556,6 +1624,13 @@ void reduce_one_row(const Plan& plan, int8_t* this_buf, int64_t this_e, const in
     int64_t b;
     memcpy(&b, op, 8);
     if (!t.is_agg) { if (b != init_val) *a = b; continue; } /* projection: :1585-1640 case 8 */
+    if (t.is_distinct) { /* count_distinct_set_union (CountDistinct.h:89-140): OR of the two bitmaps */
+      const int64_t bytes = align_to_int64((t.cd_bits + 7) / 8);
+      int8_t* x = this_buf + t.cd_tail + this_e * bytes;
+      const int8_t* y = that_buf + t.cd_tail + that_e * bytes;
+      for (int64_t k = 0; k < bytes; ++k) x[k] |= y[k];
+      continue;
+    }
     const bool fp = is_fp(get_compact_type(t).type);
     switch (t.agg_kind) {
       case B2Q_kCOUNT: agg_sum(a, b); break; /* AGGREGATE_ONE_COUNT */
@@ -1710,6 +1785,27 @@ void result_sort(OracleResult* r, const B2QOrderEntry* oes, int n, size_t top_n)
 
 static thread_local std::string g_last_error;
 
+/* COUNT(DISTINCT): the reference leaves a pointer to the group's bitmap in the slot and counts its bits when the value is read
+ * (count_distinct_set_size, CountDistinct.h:54-70; makeTargetValue, ResultSetIteration.cpp:2178-2181).  The boundary of the
+ * product carries no pointers, so its result buffer holds the set size itself; the oracle's final buffer is put in the same
+ * form here, after every reduce step has run on the bitmaps. */
+static void finalize_count_distinct(OracleResult* res) {
+  const B2QPlan& p = res->plan.p;
+  if (!res->plan.cd_total) return;
+  for (const auto& t : res->plan.targets) {
+    if (!t.is_distinct) continue;
+    const int64_t bytes = align_to_int64((t.cd_bits + 7) / 8);
+    for (int64_t e = 0; e < std::max<int64_t>(p.entry_count, 1); ++e) {
+      if (is_empty_entry(p, res->buf.data(), e)) continue;
+      const uint8_t* bm = reinterpret_cast<const uint8_t*>(res->buf.data()) + t.cd_tail + e * bytes;
+      int64_t n = 0;
+      for (int64_t k = 0; k < bytes; ++k) n += __builtin_popcount(bm[k]);
+      memcpy(slot_ptr(p, res->buf.data(), e, t.first_slot), &n, 8);
+    }
+  }
+  res->buf.resize(static_cast<size_t>(p.buffer_size));
+}
+
 /* Worker placement for the timed CPU arm (bench.py): with pinning on, worker t of oracle_execute and of
  * oracle_gen_fragments runs on the t-th CPU of the process's affinity mask, so that the thread that scans fragment f is the
  * one that first touched its pages (NUMA-local memory).  Off by default: the tests do not care. */
@@ -1808,6 +1904,7 @@ ORACLE_EXPORT int32_t oracle_execute(const B2QExecUnit* u, const B2QTableInfo* t
       std::vector<int8_t>().swap(bufs[f]);
     }
     res->buf = std::move(bufs[0]);
+    finalize_count_distinct(res);
     /* the tail of RelAlgExecutor::executeSort (RelAlgExecutor.cpp:3586-3610) when the unit carries sort_info */
     if (u->num_order_entries) result_sort(res, u->order_entries, u->num_order_entries, static_cast<size_t>((u->has_limit ? u->limit : 0) + u->offset));
     if (u->has_limit || u->offset) {
@@ -1917,6 +2014,7 @@ ORACLE_EXPORT int32_t oracle_execute_generated(const B2QExecUnit* u, const B2QTa
       }
     }
     res->buf = std::move(bufs[0]);
+    finalize_count_distinct(res);
     *out = holder.release();
     return 0;
   } catch (const OracleError& e) {

@@ -182,6 +182,8 @@ static int32_t run_program_impl(const B2QQuery* q, int32_t n_frags, const void* 
   std::vector<uint8_t> touch(static_cast<size_t>(n), 0);
   for (int a = 0; a < P.n_accs; ++a) for (int64_t i = 0; i < n; ++i) accs[a][i] = b2q_acc_identity(P.accs[a].op);
   std::vector<std::vector<double>> fsum(P.n_accs);
+  std::vector<std::vector<uint32_t>> bitmaps(P.n_accs); /* ACC_BITMAP: bm_words 32-bit words per entry */
+  for (int a = 0; a < P.n_accs; ++a) if (P.accs[a].op == ACC_BITMAP) bitmaps[a].assign(static_cast<size_t>(n) * P.accs[a].bm_words, 0u);
   for (int f = 0; f < n_frags; ++f) {
     for (int a = 0; a < P.n_accs; ++a) if (P.accs[a].op == ACC_SUM_F64) fsum[a].assign(static_cast<size_t>(n), 0.0);
     std::vector<uint8_t> ftouch(static_cast<size_t>(n), 0);
@@ -205,6 +207,13 @@ static int32_t run_program_impl(const B2QQuery* q, int32_t n_frags, const void* 
           const int8_t* col = static_cast<const int8_t*>(frag_cols[f][q->col_ids[A.col]]);
           v = A.is_fp ? load_int(col, 8, row) : load_int(col, A.width, row);
           if (skipped(A, v)) continue;
+        }
+        if (A.op == ACC_BITMAP) { /* as process_chunk: bit (v - min) / bucket of the entry's bitmap */
+          uint64_t idx = static_cast<uint64_t>(v - A.bm_min);
+          if (A.bm_bucket > 1) idx /= static_cast<uint64_t>(A.bm_bucket);
+          if (idx >= static_cast<uint64_t>(A.bm_bits)) return B2Q_ERR_KEY_OUT_OF_RANGE;
+          bitmaps[a][static_cast<size_t>(e) * A.bm_words + (idx >> 5)] |= 1u << (idx & 31);
+          continue;
         }
         int64_t& acc = accs[a][e];
         switch (A.op) {
@@ -263,6 +272,12 @@ static int32_t run_program_impl(const B2QQuery* q, int32_t n_frags, const void* 
         switch (sl.kind) {
           case SLOT_KEY: val = L.n_keys > 1 ? mkey_proj[sl.key_comp] : key; break;
           case SLOT_COUNT: val = accs[sl.acc][i]; break;
+          case SLOT_BITCOUNT: {
+            int64_t nbits = 0;
+            for (int k = 0; k < sl.bm_words; ++k) nbits += __builtin_popcount(bitmaps[sl.acc][static_cast<size_t>(i) * sl.bm_words + k]);
+            val = nbits;
+            break;
+          }
           default: {
             const int64_t raw = accs[sl.acc][i];
             bool is_null = false;

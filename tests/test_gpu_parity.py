@@ -13,7 +13,7 @@ import oracle_lib
 import ref_tables as rt
 import sqlmini
 from heavydb_b200 import abi, executor
-from test_oracle_golden import MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
+from test_oracle_golden import COUNT_DISTINCT_QUERIES, MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
 from test_planner_parity import EXTRA
 
 pytestmark = pytest.mark.gpu
@@ -25,7 +25,7 @@ def golden():
     return table, gu.DeviceTable(table)
 
 
-@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES)
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES + COUNT_DISTINCT_QUERIES)
 def test_golden_table_device_resident(golden, sql):
     table, dev = golden
     unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
@@ -194,6 +194,12 @@ RAND_QUERIES = [
     "SELECT k8, COUNT(*), SUM(a16) FROM r WHERE a8 < k8 OR a32 > a64 GROUP BY k8;",                       # column OP column: int8/int8, int32/int64
     "SELECT COUNT(*), MIN(d), MAX(dnn) FROM r WHERE d <= dnn AND NOT (a16 = nn32) AND (k16 >= nn32 OR big < a64);",   # double/double, int16/int32
     "SELECT nn64, COUNT(*) FROM r WHERE d > a32 AND nn32 <> nn64 GROUP BY nn64;",                       # double vs int32
+    # COUNT(DISTINCT): per-group bitmaps in HBM; shared-memory, HBM/L2, non-grouped and baseline-hash group tables
+    "SELECT k8, COUNT(DISTINCT a16), COUNT(DISTINCT nn32), COUNT(*) FROM r GROUP BY k8;",
+    "SELECT COUNT(DISTINCT a32), COUNT(DISTINCT k64), COUNT(DISTINCT a8), SUM(a16) FROM r WHERE nn32 < 250;",
+    "SELECT nn32, COUNT(DISTINCT k16), AVG(d) FROM r WHERE a16 BETWEEN -20000 AND 20000 AND k16 > 120 GROUP BY nn32;",
+    "SELECT sparse, COUNT(DISTINCT nn64), SUM(a32) FROM r GROUP BY sparse;",
+    "SELECT k8, nn64, COUNT(DISTINCT a8), MIN(big) FROM r GROUP BY k8, nn64;",
 ]
 
 

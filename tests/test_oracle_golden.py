@@ -118,13 +118,31 @@ NULL_LOGIC_QUERIES = [
 ]
 
 
+# COUNT(DISTINCT column) on per-group bitmaps (init_count_distinct_descriptors, GroupByAndAggregate.cpp:650-855;
+# agg_count_distinct_bitmap[_skip_val], RuntimeFunctions.cpp:366-376,1201-1210)
+COUNT_DISTINCT_QUERIES = [
+    "SELECT x, COUNT(DISTINCT x) FROM test GROUP BY x;",                      # verbatim, ExecuteTest.cpp:2781
+    "SELECT x, y, COUNT(DISTINCT x) FROM test GROUP BY x, y;",                # :2783
+    "SELECT COUNT(DISTINCT x) FROM test;",                                    # :3919
+    "SELECT COUNT(*), MIN(x), MAX(x), AVG(y), SUM(z), COUNT(DISTINCT x) FROM test;",          # :3924 without the alias
+    "SELECT y, COUNT(DISTINCT z) FROM test GROUP BY y;",
+    "SELECT z, AVG(z), COUNT(DISTINCT z) FROM test GROUP BY z;",              # :3931 on the integer key
+    "SELECT y, AVG(z), COUNT(DISTINCT x) FROM test GROUP BY y;",              # :3934 without HAVING
+    "SELECT COUNT(DISTINCT y), COUNT(DISTINCT w), COUNT(DISTINCT smallint_nulls), COUNT(y) FROM test;",       # nullable arguments: NULLs are skipped
+    "SELECT t, COUNT(DISTINCT y), COUNT(*), SUM(x) FROM test WHERE z > 0 GROUP BY t;",
+    "SELECT x, COUNT(DISTINCT ofd), COUNT(DISTINCT u) FROM test GROUP BY x;",   # u: all NULL -> empty range -> 64-bit bitmap, count 0
+    "SELECT ofq, COUNT(DISTINCT x), COUNT(*) FROM test WHERE ofq < 100 OR x > 100 GROUP BY ofq;",   # baseline-hash groups
+    "SELECT x, COUNT(DISTINCT y) FROM test WHERE y < 43 GROUP BY x;",         # simple qual narrows the bitmap's range
+]
+
+
 @pytest.fixture(scope="module")
 def env():
     rows = rt.test_rows()
     return rt.make_table(rows), rt.make_sqlite(rows)
 
 
-@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES)
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES + COUNT_DISTINCT_QUERIES)
 def test_oracle_vs_sqlite(env, sql):
     table, con = env
     unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
@@ -272,3 +290,23 @@ def test_constrained_not_null_plan(env, case):
     assert [p.targets[i].skip_null_val for i in range(p.num_targets)] == skips
     ref = [tuple(r) for r in con.execute(sql.rstrip(";")).fetchall()]
     rt.assert_rows_match(res.rows(), ref)
+
+
+def test_count_distinct_descriptors_by_hand(env):
+    """CountDistinctDescriptor{Bitmap, min_val, bitmap_sz_bits} as init_count_distinct_descriptors derives them from the golden
+    table's chunk stats (x in [7, 8], y in [42, 43] with NULLs, z in [-78, 102], u all NULL), and what the reference refuses on a GPU."""
+    table, _ = env
+    def plan(sql):
+        return oracle_lib.plan(sqlmini.parse(sql, table, rt.TEST_NAMES), table, entry_guess=64, has_card=True)
+    p = plan("SELECT x, COUNT(DISTINCT x), COUNT(DISTINCT z), COUNT(*) FROM test GROUP BY x;")
+    assert [(p.count_distinct_min[i], p.count_distinct_bits[i]) for i in range(4)] == [(0, 0), (7, 2), (-78, 181), (0, 0)]
+    assert [p.targets[i].is_distinct for i in range(4)] == [0, 1, 1, 0]
+    assert p.keyless_hash == 1 and p.idx_target_as_key == 3          # distinct targets never mark emptiness: COUNT(*) does
+    assert list(p.slot_padded_width[:4]) == [8, 8, 8, 8] and [p.init_vals[i] for i in range(4)] == [0, 0, 0, 0]
+    p = plan("SELECT COUNT(DISTINCT u), COUNT(DISTINCT y) FROM test WHERE y < 43;")
+    assert [(p.count_distinct_min[i], p.count_distinct_bits[i]) for i in range(2)] == [(0, 64), (42, 1)]
+    for sql in ["SELECT COUNT(DISTINCT d) FROM test;",            # fp argument: std::set implementation, CPU only (:3912-3913 run with dt = CPU)
+                "SELECT x, COUNT(DISTINCT ofq) FROM test GROUP BY x;"]:   # 2^63-wide range: no bitmap
+        with pytest.raises(oracle_lib.OracleError) as ei:
+            plan(sql)
+        assert ei.value.code == abi.ERR_UNSUPPORTED

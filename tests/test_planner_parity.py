@@ -7,14 +7,14 @@ import oracle_lib
 import ref_tables as rt
 import sqlmini
 from heavydb_b200 import abi, executor
-from test_oracle_golden import CONSTRAINED_NOT_NULL_PLANS, MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
+from test_oracle_golden import CONSTRAINED_NOT_NULL_PLANS, COUNT_DISTINCT_QUERIES, MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
 
 EXTRA = [
     "SELECT t, SUM(dn), AVG(dn), MIN(dn), MAX(dn), COUNT(dn) FROM test GROUP BY t;",
     "SELECT x, MIN(ufd), MAX(ufd), SUM(ufd) FROM test GROUP BY x;",
     "SELECT ofq, COUNT(*) FROM test GROUP BY ofq;",       # range too big for perfect hash -> baseline
     "SELECT ufq, COUNT(*), SUM(x) FROM test GROUP BY ufq;",
-] + [c[0] for c in CONSTRAINED_NOT_NULL_PLANS]   # `arg IS NOT NULL` quals: the plans are additionally pinned by hand in test_oracle_golden
+] + COUNT_DISTINCT_QUERIES + [c[0] for c in CONSTRAINED_NOT_NULL_PLANS]   # `arg IS NOT NULL` quals: the plans are additionally pinned by hand in test_oracle_golden
 
 
 @pytest.fixture(scope="module")
@@ -193,3 +193,17 @@ def test_date_keys_carry_the_day_bucket():
     # TIMESTAMP of the same range: no bucket, too big => baseline
     t = _stats_only_table([(abi.kTIMESTAMP, False), (abi.kINT, True)], [(18000 * day, 58000 * day, True), (0, 9, False)])
     assert _both_plans(sqlmini.parse("SELECT d, COUNT(*) FROM t GROUP BY d;", t, ["d", "x"]), t) == [("error", abi.ERR_CARDINALITY_ESTIMATION_REQUIRED)] * 2
+
+
+def test_count_distinct_refusals_agree(table):
+    """Descriptors the reference serves with a std::set (CPU only) are refused by both planners."""
+    for sql in ["SELECT COUNT(DISTINCT d) FROM test;", "SELECT x, COUNT(DISTINCT ofq) FROM test GROUP BY x;", "SELECT SUM(DISTINCT x) FROM test;"]:
+        try:
+            unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
+        except Exception:
+            continue
+        with pytest.raises(oracle_lib.OracleError) as ei:
+            oracle_lib.plan(unit, table, entry_guess=48, has_card=True)
+        assert ei.value.code == abi.ERR_UNSUPPORTED
+        with pytest.raises(executor.UnsupportedOnThisPath):
+            executor.Executor().plan(unit, table, max_groups_buffer_entry_guess=48, has_cardinality_estimation=True)
