@@ -85,10 +85,14 @@ STR_QUERIES = [
     "SELECT s8, COUNT(*), COUNT(dd) FROM s WHERE dd < dd16 OR dd IS NULL OR NOT (dd16 >= 864000000) GROUP BY s8;",
     "SELECT dd, COUNT(*) FROM s WHERE x <> 2 GROUP BY dd ORDER BY 1 DESC LIMIT 7;",
     "SELECT dd16, MIN(d), AVG(v) FROM s WHERE dd16 BETWEEN 863308800 AND 864950400 AND dd IS NOT NULL GROUP BY dd16 ORDER BY 1;",
+    # COUNT(DISTINCT) of dictionary ids (ExecuteTest.cpp:3921 `COUNT(distinct str)`), DICT(8) / DICT(16) chunks and a TIMESTAMP
+    "SELECT x, COUNT(DISTINCT str), COUNT(DISTINCT s8) FROM s GROUP BY x;",
+    "SELECT COUNT(DISTINCT str), COUNT(DISTINCT s16), COUNT(DISTINCT ts) FROM s WHERE s8 <> 7;",
 ]
 
 STR_REJECTED = [
-    "SELECT x, COUNT(DISTINCT str) FROM s GROUP BY x;",          # AggExpr::get_is_distinct(): refused, never counted as COUNT(str)
+    "SELECT x, COUNT(DISTINCT dd) FROM s GROUP BY x;",           # COUNT(DISTINCT) of a days-encoded DATE (count_distinct_on_encoded_date_arg_)
+    "SELECT x, SUM(DISTINCT v) FROM s GROUP BY x;",               # DISTINCT other than COUNT
     "SELECT COUNT(*) FROM s WHERE dd < dt;",                      # days-encoded vs seconds chunk
     "SELECT x, SUM(dd) FROM s GROUP BY x;",
     "SELECT s8, SUM(ts) FROM s GROUP BY s8;",
