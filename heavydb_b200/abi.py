@@ -61,15 +61,16 @@ NULL_SMALLINT = -(2**15)
 NULL_INT = -(2**31)
 NULL_BIGINT = -(2**63)
 NULL_DOUBLE = float(np.finfo(np.float64).tiny)  # DBL_MIN: smallest NORMAL double
+NULL_FLOAT = np.float32(np.finfo(np.float32).tiny)  # FLT_MIN
 EMPTY_KEY_64 = 2**63 - 1
 EMPTY_KEY_32 = 2**31 - 1
 
-NUMPY_OF = {kBOOLEAN: np.int8, kTINYINT: np.int8, kSMALLINT: np.int16, kINT: np.int32, kBIGINT: np.int64, kDOUBLE: np.float64,
+NUMPY_OF = {kBOOLEAN: np.int8, kTINYINT: np.int8, kSMALLINT: np.int16, kINT: np.int32, kBIGINT: np.int64, kDOUBLE: np.float64, kFLOAT: np.float32,
             kCHAR: np.int32, kVARCHAR: np.int32, kTEXT: np.int32, kTIME: np.int64, kTIMESTAMP: np.int64, kDATE: np.int64,
             kNUMERIC: np.int64, kDECIMAL: np.int64}
-SIZE_OF = {kBOOLEAN: 1, kTINYINT: 1, kSMALLINT: 2, kINT: 4, kBIGINT: 8, kDOUBLE: 8, kCHAR: 4, kVARCHAR: 4, kTEXT: 4, kTIME: 8, kTIMESTAMP: 8, kDATE: 8,
+SIZE_OF = {kBOOLEAN: 1, kTINYINT: 1, kSMALLINT: 2, kINT: 4, kBIGINT: 8, kDOUBLE: 8, kFLOAT: 4, kCHAR: 4, kVARCHAR: 4, kTEXT: 4, kTIME: 8, kTIMESTAMP: 8, kDATE: 8,
            kNUMERIC: 8, kDECIMAL: 8}
-NULL_OF = {kBOOLEAN: NULL_TINYINT, kTINYINT: NULL_TINYINT, kSMALLINT: NULL_SMALLINT, kINT: NULL_INT, kBIGINT: NULL_BIGINT, kDOUBLE: NULL_DOUBLE,
+NULL_OF = {kBOOLEAN: NULL_TINYINT, kTINYINT: NULL_TINYINT, kSMALLINT: NULL_SMALLINT, kINT: NULL_INT, kBIGINT: NULL_BIGINT, kDOUBLE: NULL_DOUBLE, kFLOAT: NULL_FLOAT,
            kCHAR: NULL_INT, kVARCHAR: NULL_INT, kTEXT: NULL_INT, kTIME: NULL_BIGINT, kTIMESTAMP: NULL_BIGINT, kDATE: NULL_BIGINT,
            kNUMERIC: NULL_BIGINT, kDECIMAL: NULL_BIGINT}
 
@@ -352,6 +353,8 @@ class UnitBuilder:
         n = _Node(EXPR_CONSTANT, sql_type, True, is_null=is_null, scale=scale)
         if sql_type == kDOUBLE:
             n.dval = float(value)
+        elif sql_type == kFLOAT:   # a FLOAT Datum: the literal rounded to float precision (Datum.floatval)
+            n.dval = float(np.float32(value))
         else:
             n.ival = int(value)
         self.nodes.append(n)
@@ -386,7 +389,7 @@ class UnitBuilder:
             if kind == kCOUNT:
                 ti = (kBIGINT if bigint_count else kINT, False)
             elif kind == kSUM:
-                ti = (at if at in DECIMAL_TYPES else kDOUBLE if at == kDOUBLE else kBIGINT, ann)   # SUM(DECIMAL) keeps type and scale
+                ti = (at if at in DECIMAL_TYPES or at in (kDOUBLE, kFLOAT) else kBIGINT, ann)   # SUM(DECIMAL) keeps type and scale; SUM(FLOAT) is FLOAT
                 scale = self.nodes[arg].scale
             elif kind == kAVG:
                 ti = (kDOUBLE, ann)
@@ -488,7 +491,7 @@ def chunk_stats(arr: np.ndarray, sql_type: int, notnull: bool, null=None) -> Chu
         mask = arr != null
         vals = arr[mask]
         st.has_nulls = int(vals.size != arr.size)
-    if sql_type == kDOUBLE:
+    if sql_type in (kDOUBLE, kFLOAT):
         if vals.size:
             st.fp_min, st.fp_max = float(vals.min()), float(vals.max())
         else:

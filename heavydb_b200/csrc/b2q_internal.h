@@ -192,7 +192,9 @@ struct DevSlot {
   int8_t width;        /* padded slot width: 0, 4 or 8 */
   int8_t key_comp;     /* SLOT_KEY of a multi-column key: which GROUP BY column */
   int8_t scale_day;    /* MIN / MAX over a days-encoded DATE chunk: the accumulator holds days, the slot seconds */
-  int8_t pad_[4];
+  int8_t as_float;     /* FLOAT argument (takes_float_argument, TargetInfo.h:106-110): the accumulator is a double; the slot gets
+                          its float image in the low 4 bytes, the high 4 bytes keep the init pattern's (agg_*_float write 32 bits) */
+  int8_t pad_[3];
   int32_t bm_words;    /* SLOT_BITCOUNT: 32-bit words per entry */
   int32_t pad2_;
 };

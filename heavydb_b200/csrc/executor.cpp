@@ -799,7 +799,7 @@ static int32_t partial_enqueue_error_copy(B2QPartial& p, cudaStream_t st) {
 
 /* logical size / NULL sentinel (dictionary-encoded strings are int32 ids, TIME-family types int64) */
 static bool is_dict_string(int t) { return t == B2Q_kTEXT || t == B2Q_kVARCHAR || t == B2Q_kCHAR; }
-static int type_size(int t) { return t == B2Q_kTINYINT ? 1 : t == B2Q_kSMALLINT ? 2 : (t == B2Q_kINT || is_dict_string(t)) ? 4 : 8; }
+static int type_size(int t) { return t == B2Q_kTINYINT ? 1 : t == B2Q_kSMALLINT ? 2 : (t == B2Q_kINT || t == B2Q_kFLOAT || is_dict_string(t)) ? 4 : 8; }
 static int64_t int_null(int t) { return t == B2Q_kTINYINT ? INT8_MIN : t == B2Q_kSMALLINT ? INT16_MIN : (t == B2Q_kINT || is_dict_string(t)) ? INT32_MIN : INT64_MIN; }
 
 /* ---- ORDER BY / LIMIT on the device (sort.cu) ---------------------------------------------------------------- */
@@ -1362,7 +1362,9 @@ static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* ro
       if (cnt == 0) { o.dval = DBL_MIN; o.is_null = 1; }
       else {
         double dividend;
-        if (t.sql_type.type == B2Q_kDOUBLE) memcpy(&dividend, &ival, 8); else dividend = static_cast<double>(ival);
+        if (t.sql_type.type == B2Q_kDOUBLE) memcpy(&dividend, &ival, 8);
+        else if (t.sql_type.type == B2Q_kFLOAT) { float f; memcpy(&f, ptr, 4); dividend = f; } /* float_argument_input: pair_to_double reads the sum as a float */
+        else dividend = static_cast<double>(ival);
         /* DECIMAL: one division by count x 10^scale, ResultSetBufferAccessors.h:222-225 */
         o.dval = is_decimal(t.sql_type.type) && t.sql_type.scale ? dividend / (static_cast<double>(cnt) * exp_to_scale(t.sql_type.scale))
                                                                  : dividend / static_cast<double>(cnt);
@@ -1374,6 +1376,14 @@ static void read_entry(const B2QResultSet* rs, int64_t entry, B2QTargetValue* ro
       o.is_fp = 1;
       memcpy(&o.dval, &ival, 8);
       o.is_null = o.dval == DBL_MIN;
+      continue;
+    }
+    if (compact_type == B2Q_kFLOAT) { /* make_target_value: a float read from the slot's low 4 bytes (ResultSetIteration.cpp:2140-2160) */
+      float f;
+      memcpy(&f, ptr, 4);
+      o.is_fp = 1;
+      o.dval = f;
+      o.is_null = f == FLT_MIN;
       continue;
     }
     if (is_decimal(compact_type)) { /* makeTargetValue, ResultSetIteration.cpp:2193-2210 */
@@ -1439,6 +1449,7 @@ int32_t b2q_columnar_results_create(const B2QResultSet* rs, int32_t num_threads,
       read_entry(rs, entries[first + r], row, false); /* decimals stay scaled int64 (ColumnarResults.cpp:155,550 getRowAtNoTranslations / getNextRow(false, false)) */
       for (int c = 0; c < nt; ++c) {
         int8_t* dst = cr->cols[c].data() + r * width[c];
+        if (row[c].is_fp && width[c] == 4) { const float f = row[c].is_null ? FLT_MIN : static_cast<float>(row[c].dval); memcpy(dst, &f, 4); continue; }
         if (row[c].is_fp) { memcpy(dst, &row[c].dval, 8); continue; }
         const int64_t v = row[c].ival;
         switch (width[c]) {

@@ -198,6 +198,8 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
             if (sl.nn >= 0) is_null = A.accs[sl.nn][i] == 0;
             else if (sl.nn == -2) is_null = raw == sl.identity;
             val = is_null ? sl.init_val : (sl.kind == SLOT_VALUE_ORD ? b2q_ord_to_f64(raw) : (sl.scale_day ? raw * 86400 : raw));
+            if (sl.as_float && !is_null) /* agg_*_float: 32 bits written, the slot's high word still holds the init pattern's */
+              val = (sl.init_val & (int64_t)0xFFFFFFFF00000000ll) | (int64_t)(uint32_t)__float_as_int((float)__longlong_as_double(val));
             break;
           }
         }

@@ -50,12 +50,13 @@ struct SqlType {
   bool is_decimal() const { return type == B2Q_kDECIMAL || type == B2Q_kNUMERIC; }
   bool is_int() const { return type == B2Q_kTINYINT || type == B2Q_kSMALLINT || type == B2Q_kINT || type == B2Q_kBIGINT || is_string() || is_time() || is_decimal(); }
   bool is_number() const { return is_int() && !is_string() && !is_time(); }
-  bool is_fp() const { return type == B2Q_kDOUBLE; }
+  bool is_fp() const { return type == B2Q_kDOUBLE || type == B2Q_kFLOAT; }
+  bool is_float() const { return type == B2Q_kFLOAT; } /* 4-byte chunks and slots; widened (exactly) to double on every load */
   int size() const { /* logical size */
     switch (type) {
       case B2Q_kTINYINT: return 1;
       case B2Q_kSMALLINT: return 2;
-      case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4;
+      case B2Q_kINT: case B2Q_kFLOAT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4;
       case B2Q_kBIGINT: case B2Q_kDOUBLE: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: case B2Q_kDECIMAL: case B2Q_kNUMERIC: return 8;
       default: return -1;
     }
@@ -76,6 +77,8 @@ int64_t dbl_bits(double d) { int64_t b; memcpy(&b, &d, 8); return b; }
 double bits_dbl(int64_t b) { double d; memcpy(&d, &b, 8); return d; }
 int64_t align8(int64_t v) { return (v + 7) & ~int64_t(7); }
 constexpr double kNullDouble = DBL_MIN;
+constexpr double kNullFloat = FLT_MIN; /* NULL_FLOAT (Shared/InlineNullValues.h), as the double it widens to */
+static bool fp_type(int t) { return t == B2Q_kDOUBLE || t == B2Q_kFLOAT; }
 
 struct ColRange {
   bool valid = false, fp = false, has_nulls = false;
@@ -132,6 +135,10 @@ class Planner {
       return;
     }
     build_targets();
+    for (int i = 0; i < u_.num_order_entries; ++i) { /* the device sort orders 8-byte images; float slots would need their own */
+      const TargetDesc& d = targets_[u_.order_entries[i].tle_no - 1];
+      if (d.compact().is_float()) reject(B2Q_ERR_UNSUPPORTED, "ORDER BY a FLOAT target is outside this path");
+    }
     plan_join(q.plan);
     choose_hash_type(q.plan);
     count_distinct_descriptors(q.plan);
@@ -399,7 +406,7 @@ class Planner {
       const B2QExpr& l = ex(q.left);
       const B2QExpr& c = ex(q.right);
       if (l.kind != B2Q_EXPR_COLUMN_VAR || l.col_id != col || c.kind != B2Q_EXPR_CONSTANT) continue;
-      const bool cfp = c.ti.type == B2Q_kDOUBLE;
+      const bool cfp = fp_type(c.ti.type);
       if (cfp != r.fp) continue; /* mixed int/fp comparisons are never simple quals in the reference (see sqlmini.py) */
       if (r.fp) {
         const double v = cfp ? c.dval : static_cast<double>(c.ival);
@@ -419,7 +426,19 @@ class Planner {
     }
   }
 
+  static double fp_null(const SqlType& t) { return t.is_float() ? kNullFloat : kNullDouble; }
+  static int64_t flt_bits(float f) { int32_t b; memcpy(&b, &f, 4); return b; } /* a float pattern in a 64-bit slot: its int32 image, sign-extended (get_agg_initial_val, OutputBufferInitialization.cpp:141-247) */
+
   static int64_t agg_init(int agg, const SqlType& ti, bool compaction, unsigned min_width) {
+    if (ti.is_float()) { /* float_argument_input: byte_width 4 whatever the padded slot width (init_agg_val_vec :66-76) */
+      switch (agg) {
+        case B2Q_kSUM: return ti.notnull ? flt_bits(0.f) : flt_bits(FLT_MIN);
+        case B2Q_kAVG: case B2Q_kCOUNT: return 0;
+        case B2Q_kMIN: return ti.notnull ? flt_bits(FLT_MAX) : flt_bits(FLT_MIN);
+        case B2Q_kMAX: return ti.notnull ? flt_bits(-FLT_MAX) : flt_bits(FLT_MIN);
+        default: reject(B2Q_ERR_UNSUPPORTED, "aggregate kind");
+      }
+    }
     const unsigned bw = compaction ? std::max<unsigned>(ti.size(), min_width) : 8u;
     const bool fp = ti.is_fp();
     switch (agg) {
@@ -736,7 +755,8 @@ class Planner {
     if (q.prog.n_cols >= B2Q_MAX_COLS) reject(B2Q_ERR_UNSUPPORTED, "too many referenced columns");
     q.col_ids[q.prog.n_cols] = table_col;
     q.prog.col_inner[q.prog.n_cols] = (join_ && table_col >= n_outer_) ? 1 : 0;
-    q.prog.col_null[q.prog.n_cols] = col_type(table_col).is_fp() ? dbl_bits(kNullDouble) : (t_.col_types[table_col].type == B2Q_kBOOLEAN ? 0 : phys_int_null(table_col));
+    /* what an unmatched LEFT-join row reads: the column's own NULL as STORED (a FLOAT is widened after the load) */
+    q.prog.col_null[q.prog.n_cols] = col_type(table_col).is_float() ? flt_bits(FLT_MIN) : col_type(table_col).is_fp() ? dbl_bits(kNullDouble) : (t_.col_types[table_col].type == B2Q_kBOOLEAN ? 0 : phys_int_null(table_col));
     q.prog.col_width[q.prog.n_cols] = static_cast<int8_t>(t_.col_types[table_col].type == B2Q_kBOOLEAN ? 1 : phys_size(table_col));
     return q.prog.n_cols++;
   }
@@ -761,10 +781,10 @@ class Planner {
     t.width = static_cast<int8_t>(phys_width_code(l.col_id));
     t.col_is_fp = ct.is_fp();
     if (ct.is_string() && e.op != B2Q_kEQ && e.op != B2Q_kNE) reject(B2Q_ERR_UNSUPPORTED, "dictionary-encoded strings compare by id: only = and <> are on this path");
-    if (ct.is_string() && c.ti.type == B2Q_kDOUBLE) reject(B2Q_ERR_INVALID_ARGUMENT, "string column compared with a floating-point constant");
+    if (ct.is_string() && fp_type(c.ti.type)) reject(B2Q_ERR_INVALID_ARGUMENT, "string column compared with a floating-point constant");
     const bool nullable = !ct.notnull;
-    t.null_bits = ct.is_fp() ? dbl_bits(kNullDouble) : phys_int_null(l.col_id);
-    const bool cfp = c.ti.type == B2Q_kDOUBLE;
+    t.null_bits = ct.is_fp() ? dbl_bits(fp_null(ct)) : phys_int_null(l.col_id);
+    const bool cfp = fp_type(c.ti.type);
     if (cfp && is_days(l.col_id)) reject(B2Q_ERR_UNSUPPORTED, "days-encoded DATE compared with a floating-point constant");
     t.cmp_fp = ct.is_fp() || cfp;
     bool negate = e.op == B2Q_kNE;
@@ -860,12 +880,12 @@ class Planner {
     t.col = launch_col(q, l.col_id);
     t.width = static_cast<int8_t>(phys_width_code(l.col_id));
     t.col_is_fp = lt.is_fp();
-    t.null_bits = lt.is_fp() ? dbl_bits(kNullDouble) : phys_int_null(l.col_id);
+    t.null_bits = lt.is_fp() ? dbl_bits(fp_null(lt)) : phys_int_null(l.col_id);
     t.nullable1 = !lt.notnull;
     t.col2 = launch_col(q, r.col_id);
     t.width2 = static_cast<int8_t>(phys_width_code(r.col_id));
     t.col2_is_fp = rt.is_fp();
-    t.null_bits2 = rt.is_fp() ? dbl_bits(kNullDouble) : phys_int_null(r.col_id);
+    t.null_bits2 = rt.is_fp() ? dbl_bits(fp_null(rt)) : phys_int_null(r.col_id);
     t.nullable2 = !rt.notnull;
     t.cmp_fp = lt.is_fp() || rt.is_fp();
     t.op2 = static_cast<int8_t>(e.op);
@@ -935,7 +955,7 @@ class Planner {
     const int op = it.negated ? inverse_cmp(e.op) : e.op;
     const B2QExpr& l = ex(e.left);
     const B2QExpr& c = ex(e.right);
-    if (l.kind != B2Q_EXPR_COLUMN_VAR || c.kind != B2Q_EXPR_CONSTANT || c.is_null || c.ti.type == B2Q_kDOUBLE) return false;
+    if (l.kind != B2Q_EXPR_COLUMN_VAR || c.kind != B2Q_EXPR_CONSTANT || c.is_null || fp_type(c.ti.type)) return false;
     if (col_type(l.col_id).is_fp()) return false;
     const int64_t k = c.ival;
     *col = l.col_id;
@@ -959,7 +979,7 @@ class Planner {
     const B2QExpr& l = ex(e.left);
     const B2QExpr& c = ex(e.right);
     if (l.kind != B2Q_EXPR_COLUMN_VAR || c.kind != B2Q_EXPR_CONSTANT || c.is_null || !col_type(l.col_id).is_fp()) return false;
-    const double k = c.ti.type == B2Q_kDOUBLE ? c.dval : static_cast<double>(c.ival);
+    const double k = fp_type(c.ti.type) ? c.dval : static_cast<double>(c.ival);
     if (std::isnan(k)) return false;
     const double inf = std::numeric_limits<double>::infinity();
     *col = l.col_id;
@@ -1182,7 +1202,7 @@ class Planner {
     t.width = static_cast<int8_t>(phys_width_code(l.col_id));
     t.col_is_fp = ct.is_fp();
     t.cmp_fp = ct.is_fp();
-    t.null_bits = ct.is_fp() ? dbl_bits(kNullDouble) : phys_int_null(l.col_id);
+    t.null_bits = ct.is_fp() ? dbl_bits(fp_null(ct)) : phys_int_null(l.col_id);
     t.null_check = 0;
     double sel;
     if (ct.notnull) { /* never NULL: "always in range" + negate encodes the constant FALSE */
@@ -1194,7 +1214,7 @@ class Planner {
     } else {
       const int64_t nullv = phys_int_null(l.col_id);
       t.lo = nullv; t.span = 0;
-      t.flo = t.fhi = kNullDouble;
+      t.flo = t.fhi = fp_null(ct);
       t.negate = negated;
       const ColRange cr = leaf_range(l.col_id);
       sel = cr.has_nulls ? 0.1 : 0.0;
@@ -1236,7 +1256,7 @@ class Planner {
     if (!d->skip_null) return a;
     if (at.is_fp()) { /* agg_*_double_skip_val: fp compare against NULL_DOUBLE */
       a.skip1_en = 1;
-      a.skip1_val = dbl_bits(kNullDouble);
+      a.skip1_val = dbl_bits(fp_null(at));
       return a;
     }
     if (d->agg == B2Q_kMIN || d->agg == B2Q_kMAX) { /* null = inlineIntNull(arg_ti) sign-extended */
@@ -1472,6 +1492,7 @@ class Planner {
         case B2Q_kSUM:
         case B2Q_kAVG: {
           sl.kind = SLOT_VALUE;
+          sl.as_float = d.arg_type.is_float() ? 1 : 0; /* takes_float_argument: a 4-byte float in the slot's low word */
           sl.acc = find_or_add_acc(q, make_acc(q, fp ? ACC_SUM_F64 : ACC_SUM_I64, &d));
           const int nn = non_null_count();
           sl.nn = nn;
@@ -1487,6 +1508,7 @@ class Planner {
         case B2Q_kMAX: {
           const int op = d.agg == B2Q_kMIN ? (fp ? ACC_MIN_F64 : ACC_MIN_I64) : (fp ? ACC_MAX_F64 : ACC_MAX_I64);
           sl.kind = fp ? SLOT_VALUE_ORD : SLOT_VALUE;
+          sl.as_float = d.arg_type.is_float() ? 1 : 0;
           sl.acc = find_or_add_acc(q, make_acc(q, op, &d));
           sl.identity = b2q_acc_identity(op);
           sl.scale_day = is_days(d.arg_col) ? 1 : 0;
@@ -1511,7 +1533,7 @@ class Planner {
     if (join_) { /* the first 1/2/4-byte inner column the program reads rides in the join table itself */
       static const bool pack = []() { const char* e = getenv("B2Q_JOIN_PACK"); return !e || atoi(e) != 0; }();
       for (int c = 0; c < g.n_cols && pack; ++c)
-        if (g.col_inner[c] && g.col_width[c] <= 4) {
+        if (g.col_inner[c] && g.col_width[c] <= 4 && !col_type(q.col_ids[c]).is_fp()) {
           g.join.packed_col = static_cast<int8_t>(c);
           g.join.packed_width = static_cast<int8_t>(phys_width_code(q.col_ids[c]));
           break;
@@ -1543,7 +1565,7 @@ class Planner {
       for (int a = 0; a < g.n_accs && ok; ++a) {
         const DevAcc& c = g.accs[a];
         if (c.op == ACC_COUNT && c.col < 0 && g.fused_cnt < 0) g.fused_cnt = static_cast<int8_t>(a);
-        else if ((c.op == ACC_SUM_I64 || c.op == ACC_SUM_F64) && !c.skip1_en && !c.skip2_en && g.fused_sum < 0) g.fused_sum = static_cast<int8_t>(a);
+        else if ((c.op == ACC_SUM_I64 || (c.op == ACC_SUM_F64 && c.width == 8)) && !c.skip1_en && !c.skip2_en && g.fused_sum < 0) g.fused_sum = static_cast<int8_t>(a);
         else ok = false;
       }
       g.fused = ok ? 1 : 0;

@@ -664,6 +664,7 @@ bool radix_plan(const B2QQuery& q, RadixPlan* rp) {
   for (int a = 0; a < P.n_accs; ++a) {
     const DevAcc& acc = P.accs[a];
     if (acc.op == ACC_TOUCH || acc.op == ACC_NDV || acc.op == ACC_BITMAP) return false;
+    if (acc.is_fp && acc.width != 8) return false; /* FLOAT arguments: tuples carry integer-widened words */
     rp->acc_val[a] = -1;
     if (acc.col < 0) continue;
     int vi = -1;

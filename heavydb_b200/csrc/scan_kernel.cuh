@@ -224,7 +224,13 @@ __device__ __forceinline__ uint32_t eval_term(const DevTerm& t, const int8_t* co
     const double lo = t.flo, hi = t.fhi;
     double d[R];
     uint32_t isnull = 0;
-    if (t.col_is_fp) {
+    if (t.col_is_fp && t.width == 4) { /* FLOAT chunk (fixed_width_float_decode, DecodersImpl.h:112-123): widened exactly */
+      int32_t v[R];
+      load32<!FULL>(v, cols[t.col], 4, row0, stride, valid, pol, jidx, jval, jnull);
+      const double nullv = __longlong_as_double(t.null_bits);
+#pragma unroll
+      for (int j = 0; j < R; ++j) { d[j] = (double)__int_as_float(v[j]); isnull |= (uint32_t)(d[j] == nullv) << j; }
+    } else if (t.col_is_fp) {
       int64_t v[R];
       load64<!FULL>(v, cols[t.col], row0, stride, valid, pol, jidx, nullptr, jnull);
       const double nullv = __longlong_as_double(t.null_bits);
@@ -261,14 +267,14 @@ __device__ __forceinline__ uint32_t eval_term2(const DevTerm& t, const int8_t* c
     int32_t x[R];
     load32<!FULL>(x, cols[t.col], t.width, row0, stride, valid, pol, jidx1, jval1, jnull1);
 #pragma unroll
-    for (int j = 0; j < R; ++j) a[j] = x[j];
+    for (int j = 0; j < R; ++j) a[j] = t.col_is_fp ? __double_as_longlong((double)__int_as_float(x[j])) : (int64_t)x[j];
   }
   if (t.width2 == 8) load64<!FULL>(b, cols[t.col2], row0, stride, valid, pol, jidx2, jval2, jnull2);
   else {
     int32_t x[R];
     load32<!FULL>(x, cols[t.col2], t.width2, row0, stride, valid, pol, jidx2, jval2, jnull2);
 #pragma unroll
-    for (int j = 0; j < R; ++j) b[j] = x[j];
+    for (int j = 0; j < R; ++j) b[j] = t.col2_is_fp ? __double_as_longlong((double)__int_as_float(x[j])) : (int64_t)x[j];
   }
   uint32_t isnull = 0, m = 0;
   const int op = t.op2;
@@ -945,7 +951,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       continue;
     }
 
-    const bool narrow = acc.width <= 4 && (op == ACC_COUNT || op == ACC_SUM_I64 || op == ACC_MIN_I64 || op == ACC_MAX_I64);
+    const bool narrow = acc.width <= 4 && !acc.is_fp && (op == ACC_COUNT || op == ACC_SUM_I64 || op == ACC_MIN_I64 || op == ACC_MAX_I64);
     if (narrow) {
       /* 1/2/4-byte integer argument: 32-bit registers */
       int32_t v[R];
@@ -988,14 +994,14 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       continue;
     }
 
-    /* 8-byte argument (BIGINT or DOUBLE), or a narrow column feeding a double aggregate (not produced by the planner) */
+    /* 8-byte argument (BIGINT or DOUBLE), or a FLOAT column: 4-byte chunk elements widened (exactly) to double */
     int64_t v[R];
     if (acc.width == 8) load64<true>(v, cols[acc.col], row0, nthr, arg_mask, pol, JX(acc.col));
     else {
       int32_t t32[R];
       load32<true>(t32, cols[acc.col], acc.width, row0, nthr, arg_mask, pol, JX(acc.col));
 #pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = t32[j];
+      for (int j = 0; j < R; ++j) v[j] = acc.is_fp ? __double_as_longlong((double)__int_as_float(t32[j])) : (int64_t)t32[j];
     }
     const uint32_t m = not_skipped64(acc, v, pass);
     if (WAGG) {

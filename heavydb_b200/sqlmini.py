@@ -100,6 +100,9 @@ class _P:
             if v != v.to_integral_value():
                 raise ValueError(f"literal {lit} has more fraction digits than DECIMAL scale {scale}")
             return self.b.cmp(col, op, int(v), tbl.col_types[col][0], rte, scale=scale)
+        if tbl.col_types[col][0] == abi.kFLOAT:
+            # common_numeric_type(FLOAT, <int / decimal literal>) = FLOAT: the literal is folded to a FLOAT Datum
+            return self.b.cmp(col, op, float(lit), abi.kFLOAT, rte)
         if re.fullmatch(r"-?\d+", lit):
             return self.b.cmp(col, op, int(lit), abi.kBIGINT, rte)
         return self.b.cmp(col, op, float(lit), abi.kDOUBLE, rte)
@@ -228,8 +231,8 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
             if simple:
                 # an integer column against an fp literal is `CAST(col AS DOUBLE) OP lit` in the reference; only
                 # int->int / timestamp casts survive BinOper::normalize_simple_predicate, so it is NOT a simple qual
-                col_fp = p.b.nodes[n.left].type == abi.kDOUBLE
-                lit_fp = p.b.nodes[n.right].type == abi.kDOUBLE
+                col_fp = p.b.nodes[n.left].type in (abi.kDOUBLE, abi.kFLOAT)
+                lit_fp = p.b.nodes[n.right].type in (abi.kDOUBLE, abi.kFLOAT)
                 simple = col_fp == lit_fp
             p.b.add_qual(c, simple=simple)
     if p.peek() and p.peek().upper() == "GROUP":

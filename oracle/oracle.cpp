@@ -56,6 +56,7 @@ constexpr int64_t kNullSmallint = INT16_MIN;
 constexpr int64_t kNullInt = INT32_MIN;
 constexpr int64_t kNullBigint = INT64_MIN;
 constexpr double kNullDouble = DBL_MIN; /* NULL_DOUBLE is the smallest NORMAL double */
+constexpr float kNullFloat = FLT_MIN;   /* NULL_FLOAT (Shared/InlineNullValues.h) */
 /* QueryEngine/GpuRtConstants.h: EMPTY_KEY_64 / EMPTY_KEY_32 */
 constexpr int64_t kEmptyKey64 = std::numeric_limits<int64_t>::max();
 constexpr int32_t kEmptyKey32 = std::numeric_limits<int32_t>::max();
@@ -74,12 +75,14 @@ bool is_time(int t) { return t == B2Q_kTIME || t == B2Q_kTIMESTAMP || t == B2Q_k
  * function that is not is_fp() treats it like BIGINT; the scale only matters at read-out) */
 bool is_decimal(int t) { return t == B2Q_kDECIMAL || t == B2Q_kNUMERIC; }
 bool is_integer(int t) { return t == B2Q_kTINYINT || t == B2Q_kSMALLINT || t == B2Q_kINT || t == B2Q_kBIGINT || is_string(t) || is_time(t) || is_decimal(t); }
-bool is_fp(int t) { return t == B2Q_kDOUBLE; }
+bool is_fp(int t) { return t == B2Q_kDOUBLE || t == B2Q_kFLOAT; }
+/* inline_fp_null_val widened to double: a FLOAT value reaches every comparison through an exact fpext */
+double fp_null_of(int t) { return t == B2Q_kFLOAT ? static_cast<double>(kNullFloat) : kNullDouble; }
 int type_size(int t) { /* SQLTypeInfo::get_size() for the fixed-width subset */
   switch (t) {
     case B2Q_kTINYINT: return 1;
     case B2Q_kSMALLINT: return 2;
-    case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4; /* logical size of a dictionary id */
+    case B2Q_kINT: case B2Q_kFLOAT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4; /* logical size of a dictionary id */
     case B2Q_kBIGINT: case B2Q_kTIME: case B2Q_kTIMESTAMP: case B2Q_kDATE: case B2Q_kDECIMAL: case B2Q_kNUMERIC: return 8;
     case B2Q_kDOUBLE: return 8;
     default: return -1;
@@ -350,10 +353,17 @@ int64_t decode_int_column(const B2QTableInfo& tbl, const B2QFragmentInfo& fr, in
   return v;
 }
 
-double decode_double_column(const B2QFragmentInfo& fr, int c, int64_t pos) {
-  if (outer_join_null(c)) return kNullDouble;
+/* fixed_width_double_decode / fixed_width_float_decode (DecodersImpl.h:112-136); a float is returned fpext-ed */
+double decode_double_column(int type, const B2QFragmentInfo& fr, int c, int64_t pos) {
+  if (outer_join_null(c)) return fp_null_of(type);
+  if (type == B2Q_kFLOAT) {
+    float f;
+    memcpy(&f, static_cast<const int8_t*>(fr.col_buffers[c]) + row_pos_of(c, pos) * 4, 4);
+    return f;
+  }
   return fixed_width_double_decode(static_cast<const int8_t*>(fr.col_buffers[c]), row_pos_of(c, pos));
 }
+int64_t float_bits(float f) { int32_t b; memcpy(&b, &f, 4); return b; } /* int32 image, sign-extended: how get_agg_initial_val returns 4-byte patterns */
 
 /* ===================================================================================================
  * Planner
@@ -579,6 +589,15 @@ int64_t get_agg_initial_val(int agg, const Ti& ti, bool enable_compaction, unsig
   auto int_min_of = [](unsigned w) -> int64_t {
     switch (w) { case 1: return INT8_MIN; case 2: return INT16_MIN; case 4: return INT32_MIN; default: return INT64_MIN; }
   };
+  if (ti.type == B2Q_kFLOAT) { /* byte_width 4 (float_argument_input, OutputBufferInitialization.cpp:66-76, :141-247): int32 patterns */
+    switch (agg) {
+      case B2Q_kSUM: return ti.notnull ? float_bits(0.f) : float_bits(kNullFloat);
+      case B2Q_kAVG: case B2Q_kCOUNT: return 0;
+      case B2Q_kMIN: return ti.notnull ? float_bits(std::numeric_limits<float>::max()) : float_bits(kNullFloat);
+      case B2Q_kMAX: return ti.notnull ? float_bits(-std::numeric_limits<float>::max()) : float_bits(kNullFloat);
+      default: abort();
+    }
+  }
   switch (agg) {
     case B2Q_kSUM:
       if (!ti.notnull) return fp ? bits_of(kNullDouble) : inline_int_null_val(ti.type);
@@ -748,6 +767,11 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
   bool any_agg = false;
   for (auto& t : plan.targets) any_agg |= t.is_agg;
   if (!any_agg) fail(B2Q_ERR_UNSUPPORTED, "projection queries are outside this path");
+  for (int i = 0; i < u.num_order_entries; ++i) {
+    const int tle = u.order_entries[i].tle_no;
+    if (tle >= 1 && tle <= static_cast<int>(plan.targets.size()) && get_compact_type(plan.targets[tle - 1]).type == B2Q_kFLOAT)
+      fail(B2Q_ERR_UNSUPPORTED, "ORDER BY a FLOAT target is outside the product path");
+  }
 
   /* GroupByAndAggregate::getBaselineThreshold (:222-230): device_type is GPU on this path, so COUNT(DISTINCT) targets divide
    * g_baseline_groupby_threshold (1e6) by four */
@@ -1252,7 +1276,7 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
       if (o.kind != B2Q_EXPR_COLUMN_VAR) fail(B2Q_ERR_UNSUPPORTED, "IS NULL operand must be a ColumnVar");
       const int ctype = tbl.col_types[o.col_id].type;
       if (tbl.col_types[o.col_id].notnull) return 0; /* inferred non-null: short-circuit to false */
-      if (is_fp(ctype)) return decode_double_column(fr, o.col_id, pos) == kNullDouble;
+      if (is_fp(ctype)) return decode_double_column(ctype, fr, o.col_id, pos) == fp_null_of(ctype);
       return decode_int_column(tbl, fr, o.col_id, pos) == inline_int_null_val(ctype);
     }
     fail(B2Q_ERR_UNSUPPORTED, "unary operator outside NOT / IS NULL");
@@ -1284,9 +1308,9 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
     if (is_fp(lt) || is_fp(rt)) {
       double a, b;
       bool an, bn;
-      if (is_fp(lt)) { a = decode_double_column(fr, l.col_id, pos); an = !lnn && a == kNullDouble; }
+      if (is_fp(lt)) { a = decode_double_column(lt, fr, l.col_id, pos); an = !lnn && a == fp_null_of(lt); }
       else { const int64_t v = decode_int_column(tbl, fr, l.col_id, pos); an = !lnn && v == inline_int_null_val(lt); a = static_cast<double>(v); }
-      if (is_fp(rt)) { b = decode_double_column(fr, r.col_id, pos); bn = !rnn && b == kNullDouble; }
+      if (is_fp(rt)) { b = decode_double_column(rt, fr, r.col_id, pos); bn = !rnn && b == fp_null_of(rt); }
       else { const int64_t v = decode_int_column(tbl, fr, r.col_id, pos); bn = !rnn && v == inline_int_null_val(rt); b = static_cast<double>(v); }
       if (an || bn) return kNullBool;
       switch (e.op) {
@@ -1317,7 +1341,7 @@ int8_t eval_bool(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QFragmen
     /* fp compare: the integer side is cast to double (CompareIR.cpp codegenCmp after normalisation) */
     double lv;
     bool lnull;
-    if (is_fp(ctype)) { lv = decode_double_column(fr, col, pos); lnull = !col_notnull && lv == kNullDouble; }
+    if (is_fp(ctype)) { lv = decode_double_column(ctype, fr, col, pos); lnull = !col_notnull && lv == fp_null_of(ctype); }
     else { const int64_t iv = decode_int_column(tbl, fr, col, pos); lnull = !col_notnull && iv == inline_int_null_val(ctype); lv = static_cast<double>(iv); }
     if (lnull) return kNullBool;
     const double rv = is_fp(r.ti.type) ? r.dval : static_cast<double>(r.ival);
@@ -1384,7 +1408,7 @@ void update_target(const Plan& plan, const Target& t, int8_t* out, int64_t entry
   int64_t* a = reinterpret_cast<int64_t*>(slot);
   if (!t.is_agg) { /* agg_id on the projected group key, sign-extended to the slot */
     const int ctype = tbl.col_types[t.arg_col].type;
-    if (is_fp(ctype)) agg_id(a, bits_of(decode_double_column(fr, t.arg_col, pos)));
+    if (is_fp(ctype)) agg_id(a, bits_of(decode_double_column(ctype, fr, t.arg_col, pos)));
     else agg_id(a, decode_int_column(tbl, fr, t.arg_col, pos));
     return;
   }
@@ -1403,9 +1427,32 @@ void update_target(const Plan& plan, const Target& t, int8_t* out, int64_t entry
   const int ctype = tbl.col_types[t.arg_col].type;
   const bool arg_notnull = t.arg_ti.notnull;
   const bool need_skip_null = t.skip_null_val;
+  if (ctype == B2Q_kFLOAT && t.agg_kind != B2Q_kCOUNT) {
+    /* takes_float_argument (TargetInfo.h:106-110): agg_{sum,min,max}_float[_skip_val] on the slot's low 4 bytes
+     * (RuntimeFunctions.cpp:1496-1518, DEF_SKIP_AGG :1558-1596); AVG keeps its count in the 8-byte slot that follows */
+    const float v = static_cast<float>(decode_double_column(ctype, fr, t.arg_col, pos));
+    int32_t* a32 = reinterpret_cast<int32_t*>(slot);
+    auto apply = [&](int kind) {
+      float cur;
+      memcpy(&cur, a32, 4);
+      const float r = kind == B2Q_kMIN ? std::min(cur, v) : kind == B2Q_kMAX ? std::max(cur, v) : cur + v;
+      memcpy(a32, &r, 4);
+    };
+    const int kind = t.agg_kind == B2Q_kAVG ? B2Q_kSUM : t.agg_kind;
+    if (need_skip_null) {
+      if (v != kNullFloat) { /* DEF_SKIP_AGG: the old value is compared bitwise with the skip pattern */
+        if (*a32 != static_cast<int32_t>(float_bits(kNullFloat))) apply(kind); else memcpy(a32, &v, 4);
+        if (t.agg_kind == B2Q_kAVG) agg_count(reinterpret_cast<int64_t*>(slot_ptr(p, out, entry, s + 1)));
+      }
+    } else {
+      apply(kind);
+      if (t.agg_kind == B2Q_kAVG) agg_count(reinterpret_cast<int64_t*>(slot_ptr(p, out, entry, s + 1)));
+    }
+    return;
+  }
   if (is_fp(ctype)) {
-    const double v = decode_double_column(fr, t.arg_col, pos);
-    const double null_v = kNullDouble; /* arg null == agg null for DOUBLE: no conversion needed */
+    const double v = decode_double_column(ctype, fr, t.arg_col, pos);
+    const double null_v = fp_null_of(ctype); /* arg null == agg null for DOUBLE; COUNT(float): value and NULL_FLOAT are fpext-ed (agg_count_double_skip_val) */
     switch (t.agg_kind) {
       case B2Q_kCOUNT: if (need_skip_null) agg_count_double_skip_val(a, v, null_v); else agg_count(a); break;
       case B2Q_kSUM: if (need_skip_null) agg_sum_double_skip_val(a, v, null_v); else agg_sum_double(a, v); break;
@@ -1629,6 +1676,28 @@ void reduce_one_row(const Plan& plan, int8_t* this_buf, int64_t this_e, const in
       int8_t* x = this_buf + t.cd_tail + this_e * bytes;
       const int8_t* y = that_buf + t.cd_tail + that_e * bytes;
       for (int64_t k = 0; k < bytes; ++k) x[k] |= y[k];
+      continue;
+    }
+    if (t.agg_arg_type.type == B2Q_kFLOAT && t.agg_kind != B2Q_kCOUNT) {
+      /* float_argument_input in reduceOneSlot (ResultSetReduction.cpp:1514, AGGREGATE_ONE_NULLABLE_VALUE on 4 bytes) */
+      int32_t* a32 = reinterpret_cast<int32_t*>(tp);
+      int32_t b32;
+      memcpy(&b32, op, 4);
+      float bv, cur;
+      memcpy(&bv, &b32, 4);
+      memcpy(&cur, a32, 4);
+      const int kind = t.agg_kind == B2Q_kAVG ? B2Q_kSUM : t.agg_kind;
+      if (t.agg_kind == B2Q_kAVG) {
+        int64_t bc;
+        memcpy(&bc, slot_ptr(p, that_buf, that_e, s + 1), 8);
+        agg_sum(reinterpret_cast<int64_t*>(slot_ptr(p, this_buf, this_e, s + 1)), bc);
+      }
+      const int32_t skip32 = static_cast<int32_t>(init_val);
+      if (t.skip_null_val && b32 == skip32) continue;       /* `that` holds no value */
+      float r;
+      if (t.skip_null_val && *a32 == skip32) r = bv;        /* `this` holds none yet */
+      else r = kind == B2Q_kMIN ? std::min(cur, bv) : kind == B2Q_kMAX ? std::max(cur, bv) : cur + bv;
+      memcpy(a32, &r, 4);
       continue;
     }
     const bool fp = is_fp(get_compact_type(t).type);
@@ -2114,11 +2183,20 @@ ORACLE_EXPORT int32_t oracle_result_get_next_row(OracleResult* r, B2QTargetValue
       o.is_fp = 1;
       if (cnt == 0) { o.dval = kNullDouble; o.is_null = 1; }
       else {
-        const double dividend = is_fp(t.sql_type.type) ? double_of(ival) : static_cast<double>(ival);
+        double dividend = is_fp(t.sql_type.type) ? double_of(ival) : static_cast<double>(ival);
+        if (t.sql_type.type == B2Q_kFLOAT) { float f; memcpy(&f, ptr, 4); dividend = f; } /* float_argument_input: pair_to_double (ResultSetBufferAccessors.h:205-214) */
         o.dval = is_decimal(t.sql_type.type) && t.sql_type.scale ? dividend / (static_cast<double>(cnt) * exp_to_scale(t.sql_type.scale))
                                                                  : dividend / static_cast<double>(cnt);
         o.is_null = o.dval == kNullDouble;
       }
+      continue;
+    }
+    if (chosen.type == B2Q_kFLOAT) { /* make_target_value: a float out of the slot's low 4 bytes */
+      float f;
+      memcpy(&f, ptr, 4);
+      o.is_fp = 1;
+      o.dval = f;
+      o.is_null = f == kNullFloat;
       continue;
     }
     if (is_fp(chosen.type)) {

@@ -25,6 +25,11 @@ int64_t load_int(const int8_t* base, int width, int64_t row) {
   }
 }
 double as_double(int64_t bits) { double d; memcpy(&d, &bits, 8); return d; }
+/* an fp column: double bits; a FLOAT chunk (width 4) widened exactly, as the kernels do on every load */
+int64_t load_fp_bits(const int8_t* base, int width, int64_t row) {
+  if (width == 4) { float f; memcpy(&f, base + row * 4, 4); const double d = f; int64_t b; memcpy(&b, &d, 8); return b; }
+  int64_t b; memcpy(&b, base + row * 8, 8); return b;
+}
 
 bool eval_term(const DevTerm& t, const int8_t* col, int64_t row) {
   const bool neg = t.negate;
@@ -41,7 +46,7 @@ bool eval_term(const DevTerm& t, const int8_t* col, int64_t row) {
   }
   double d;
   bool isnull;
-  if (t.col_is_fp) { int64_t bits; memcpy(&bits, col + row * 8, 8); d = as_double(bits); isnull = d == as_double(t.null_bits); }
+  if (t.col_is_fp) { d = as_double(load_fp_bits(col, t.width, row)); isnull = d == as_double(t.null_bits); }
   else {
     const int64_t v = load_int(col, t.width, row);
     d = static_cast<double>(v);
@@ -53,8 +58,8 @@ bool eval_term(const DevTerm& t, const int8_t* col, int64_t row) {
 }
 
 bool eval_term2(const DevTerm& t, const int8_t* c1, const int8_t* c2, int64_t row) {
-  const int64_t a = t.col_is_fp ? load_int(c1, 8, row) : load_int(c1, t.width, row);
-  const int64_t b = t.col2_is_fp ? load_int(c2, 8, row) : load_int(c2, t.width2, row);
+  const int64_t a = t.col_is_fp ? load_fp_bits(c1, t.width, row) : load_int(c1, t.width, row);
+  const int64_t b = t.col2_is_fp ? load_fp_bits(c2, t.width2, row) : load_int(c2, t.width2, row);
   bool isnull, r;
   const int op = t.op2;
   if (t.cmp_fp) {
@@ -205,7 +210,7 @@ static int32_t run_program_impl(const B2QQuery* q, int32_t n_frags, const void* 
         int64_t v = 0;
         if (A.col >= 0) {
           const int8_t* col = static_cast<const int8_t*>(frag_cols[f][q->col_ids[A.col]]);
-          v = A.is_fp ? load_int(col, 8, row) : load_int(col, A.width, row);
+          v = A.is_fp ? load_fp_bits(col, A.width, row) : load_int(col, A.width, row);
           if (skipped(A, v)) continue;
         }
         if (A.op == ACC_BITMAP) { /* as process_chunk: bit (v - min) / bucket of the entry's bitmap */
@@ -284,6 +289,11 @@ static int32_t run_program_impl(const B2QQuery* q, int32_t n_frags, const void* 
             if (sl.nn >= 0) is_null = accs[sl.nn][i] == 0;
             else if (sl.nn == -2) is_null = raw == sl.identity;
             val = is_null ? sl.init_val : (sl.kind == SLOT_VALUE_ORD ? b2q_ord_to_f64(raw) : (sl.scale_day ? raw * 86400 : raw));
+            if (sl.as_float && !is_null) { /* as b2q_k_materialize: float image in the low word, init pattern's high word */
+              const float f = static_cast<float>(as_double(val));
+              uint32_t fb; memcpy(&fb, &f, 4);
+              val = (sl.init_val & static_cast<int64_t>(0xFFFFFFFF00000000ll)) | static_cast<int64_t>(fb);
+            }
           }
         }
       }

@@ -8,9 +8,15 @@ import math
 import numpy as np
 
 import oracle_lib
+import ref_tables
 from heavydb_b200 import abi, executor
 
 FP_RTOL = 1e-6  # north_star: SUM/AVG(double) within 1e-6 relative; everything integer is bit-exact
+# SUM / AVG of a FLOAT column: the reference accumulates in float precision in whatever order its threads arrive
+# (agg_sum_float, atomicAdd(float) on its GPU); the product accumulates the exactly-widened values in double and rounds
+# once.  The two agree to float rounding of the partial sums, not to 1e-6; sums that cancel get the same fraction of a
+# typical partial sum as an absolute bound (ref_tables.float_sum_atol).
+FLOAT_SUM_RTOL = ref_tables.FLOAT_SUM_RTOL
 
 
 def _cudart():
@@ -46,14 +52,26 @@ class DeviceTable:
         torch.cuda.synchronize()
 
 
-def rows_equal(got, want, fp_rtol=FP_RTOL):
+def column_tolerances(plan, n_rows):
+    """(rtol, atol) per output column: 1e-6 relative, except SUM / AVG over a FLOAT argument."""
+    out = []
+    for t in plan.targets[: plan.num_targets]:
+        if t.is_agg and t.agg_kind in (abi.kSUM, abi.kAVG) and t.agg_arg_type.type == abi.kFLOAT:
+            out.append((FLOAT_SUM_RTOL, ref_tables.float_sum_atol(n_rows)))
+        else:
+            out.append((FP_RTOL, 0.0))
+    return out
+
+
+def rows_equal(got, want, fp_rtol=FP_RTOL, col_tol=None):
     def key(r):
         return tuple((0, 0) if v is None else (1, v) for v in r)
     g, w = sorted(got, key=key), sorted(want, key=key)
     assert len(g) == len(w), f"row count {len(g)} != {len(w)}\n got={g[:8]}\nwant={w[:8]}"
     for a, b in zip(g, w):
         assert len(a) == len(b)
-        for va, vb in zip(a, b):
+        for c, (va, vb) in enumerate(zip(a, b)):
+            rtol, atol = col_tol[c] if col_tol else (fp_rtol, 0.0)
             if va is None or vb is None:
                 assert va is None and vb is None, f"NULL mismatch: {a} vs {b}"
             elif isinstance(vb, float):
@@ -61,7 +79,7 @@ def rows_equal(got, want, fp_rtol=FP_RTOL):
                 if math.isnan(vb):
                     assert math.isnan(va)
                 else:
-                    assert va == vb or abs(va - vb) <= fp_rtol * abs(vb), f"{a} vs {b}"
+                    assert va == vb or abs(va - vb) <= rtol * abs(vb) + atol, f"{a} vs {b}"
             else:
                 assert va == vb, f"{a} vs {b}"
 
@@ -126,14 +144,14 @@ def compact_buffer_equal(got, gplan, want, wplan, perm, fp_rtol=FP_RTOL):
     assert np.array_equal(g[:, mask], w[:, mask]), "sorted/compacted buffer differs from the oracle's entries"
 
 
-def buffers_equal(got: np.ndarray, want: np.ndarray, plan: abi.Plan, fp_rtol=FP_RTOL, empty=None):
+def buffers_equal(got: np.ndarray, want: np.ndarray, plan: abi.Plan, fp_rtol=FP_RTOL, empty=None, float_atol=0.0):
     """Raw output buffers in the reference's row-wise layout.  Integer/bit-pattern slots must be identical; slots that
     hold a floating-point SUM (order of additions differs on a GPU) are compared within fp_rtol."""
     assert got.size == want.size == plan.buffer_size
     if plan.buffer_size == 0:
         return
     if plan.output_columnar:
-        return columnar_buffers_equal(got, want, plan, fp_rtol, empty)
+        return columnar_buffers_equal(got, want, plan, fp_rtol, empty, float_atol)
     rs = plan.row_size
     g = got.view(np.int8).reshape(-1, rs)
     w = want.view(np.int8).reshape(-1, rs)
@@ -142,6 +160,16 @@ def buffers_equal(got: np.ndarray, want: np.ndarray, plan: abi.Plan, fp_rtol=FP_
         if t.is_agg and t.agg_kind in (abi.kSUM, abi.kAVG) and t.agg_arg_type.type == abi.kDOUBLE:
             fp_sum_slots.add(t.first_slot)
     mask = np.ones(rs, dtype=bool)
+    for t in plan.targets[: plan.num_targets]:   # SUM / AVG of a FLOAT: a float32 in the slot's low 4 bytes, compared loosely
+        if t.is_agg and t.agg_kind in (abi.kSUM, abi.kAVG) and t.agg_arg_type.type == abi.kFLOAT:
+            off = plan.slot_offset[t.first_slot]
+            mask[off:off + 4] = False
+            a = np.ascontiguousarray(g[:, off:off + 4]).view(np.float32).ravel().astype(np.float64)
+            b = np.ascontiguousarray(w[:, off:off + 4]).view(np.float32).ravel().astype(np.float64)
+            if empty is not None:
+                a, b = a[~empty], b[~empty]
+            ok = (a == b) | (np.abs(a - b) <= FLOAT_SUM_RTOL * np.abs(b) + float_atol)
+            assert ok.all(), f"float SUM slot {t.first_slot}: {a[~ok][:4]} vs {b[~ok][:4]}"
     for s in fp_sum_slots:
         off = plan.slot_offset[s]
         mask[off:off + 8] = False
@@ -157,7 +185,7 @@ def buffers_equal(got: np.ndarray, want: np.ndarray, plan: abi.Plan, fp_rtol=FP_
     assert np.array_equal(g[:, mask], w[:, mask]), "integer part of the output buffer differs from the oracle"
 
 
-def columnar_buffers_equal(got, want, plan, fp_rtol, empty):
+def columnar_buffers_equal(got, want, plan, fp_rtol, empty, float_atol=0.0):
     """Columnar layout (ResultSet.h:72-84): int64 key columns (unless keyless), then one 8-byte-aligned column per slot."""
     n = plan.entry_count
     g, w = got.view(np.int8), want.view(np.int8)
@@ -170,6 +198,8 @@ def columnar_buffers_equal(got, want, plan, fp_rtol, empty):
             assert np.array_equal(a[keep], b[keep]), f"key column {c} differs from the oracle"
     fp_sum_slots = {t.first_slot for t in plan.targets[: plan.num_targets]
                     if t.is_agg and t.agg_kind in (abi.kSUM, abi.kAVG) and t.agg_arg_type.type == abi.kDOUBLE}
+    float_sum_slots = {t.first_slot for t in plan.targets[: plan.num_targets]
+                       if t.is_agg and t.agg_kind in (abi.kSUM, abi.kAVG) and t.agg_arg_type.type == abi.kFLOAT}
     for s in range(plan.num_slots):
         wd = plan.slot_padded_width[s]
         if wd == 0:
@@ -181,11 +211,17 @@ def columnar_buffers_equal(got, want, plan, fp_rtol, empty):
             a, b = a.view(np.float64), b.view(np.float64)
             ok = (a == b) | (np.abs(a - b) <= fp_rtol * np.abs(b))
             assert ok.all(), f"fp SUM slot {s}: {a[~ok][:4]} vs {b[~ok][:4]}"
+        elif s in float_sum_slots:
+            a32 = np.ascontiguousarray(a).view(np.float32)[0::2].astype(np.float64)
+            b32 = np.ascontiguousarray(b).view(np.float32)[0::2].astype(np.float64)
+            ok = (a32 == b32) | (np.abs(a32 - b32) <= FLOAT_SUM_RTOL * np.abs(b32) + float_atol)
+            assert ok.all(), f"float SUM slot {s}: {a32[~ok][:4]} vs {b32[~ok][:4]}"
+            assert np.array_equal(np.ascontiguousarray(a).view(np.int32)[1::2], np.ascontiguousarray(b).view(np.int32)[1::2])
         else:
             assert np.array_equal(a, b), f"slot column {s} differs from the oracle"
     if empty is None:
         mask = np.ones(g.size, dtype=bool)      # whole buffer incl. alignment padding, minus the fp SUM columns
-        for s in fp_sum_slots:
+        for s in fp_sum_slots | float_sum_slots:
             mask[plan.slot_offset[s]:plan.slot_offset[s] + 8 * n] = False
         assert np.array_equal(g[mask], w[mask]), "columnar buffer differs from the oracle outside the fp SUM columns"
 
@@ -210,7 +246,8 @@ def run_both(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=Fals
     assert rs.colCount() == ref.col_count()
     for i in range(rs.colCount()):
         assert rs.getColType(i) == ref.col_type(i)
-    rows_equal(rs.rows(), ref.rows())
+    n_rows = sum(f.num_tuples for f in table.fragments)
+    rows_equal(rs.rows(), ref.rows(), col_tol=column_tolerances(gp, n_rows))
     assert rs.rowCount() == ref.row_count()
     if compare_buffers and gp.query_desc_type != abi.GroupByBaselineHash:
         n = rs.entryCount()
@@ -222,5 +259,5 @@ def run_both(unit: abi.BuiltUnit, table: abi.Table, entry_guess=0, has_card=Fals
             assert np.array_equal(empty, empty_ref)
         else:
             empty = None
-        buffers_equal(rs.getStorageBuffer(), ref.buffer(), gp, empty=empty)
+        buffers_equal(rs.getStorageBuffer(), ref.buffer(), gp, empty=empty, float_atol=ref_tables.float_sum_atol(n_rows))
     return rs, ref

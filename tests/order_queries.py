@@ -63,7 +63,7 @@ def rows_of(table: abi.Table, cols):
             if not nn and v == abi.NULL_OF[t]:
                 r.append(None)
             else:
-                r.append(float(v) if t == abi.kDOUBLE else int(v))
+                r.append(float(v) if t in (abi.kDOUBLE, abi.kFLOAT) else int(v))
         out.append(tuple(r))
     return out
 

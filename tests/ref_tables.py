@@ -25,13 +25,16 @@ TEST_COLS = [
     ("ofq", abi.kBIGINT, False),
     ("ufq", abi.kBIGINT, True),
     ("smallint_nulls", abi.kSMALLINT, False),
+    ("f", abi.kFLOAT, False),
+    ("ff", abi.kFLOAT, False),
+    ("fn", abi.kFLOAT, False),
 ]
 TEST_NAMES = [c[0] for c in TEST_COLS]
 
 # values per INSERT template, in TEST_COLS order (None = NULL)
-_T1 = (7, -8, 42, 101, 1001, 2.2, None, None, 2147483647, -2147483648, None, -1, 32767)
-_T2 = (8, -7, 43, -78, 1002, 2.4, -2002.4, None, None, -2147483647, 9223372036854775807, -9223372036854775808, None)
-_T3 = (7, -7, 43, 102, 1002, 2.6, -220.6, None, 1, -1, 1, -9223372036854775808, 1)
+_T1 = (7, -8, 42, 101, 1001, 2.2, None, None, 2147483647, -2147483648, None, -1, 32767, 1.1, 1.1, None)
+_T2 = (8, -7, 43, -78, 1002, 2.4, -2002.4, None, None, -2147483647, 9223372036854775807, -9223372036854775808, None, 1.2, 101.2, -101.2)
+_T3 = (7, -7, 43, 102, 1002, 2.6, -220.6, None, 1, -1, 1, -9223372036854775808, 1, 1.3, 1000.3, -1000.3)
 G_NUM_ROWS = 10  # ExecuteTest.cpp:605
 
 
@@ -58,7 +61,7 @@ def make_table(rows, cols=TEST_COLS, fragment_size: int = 2) -> abi.Table:
 
 def make_sqlite(rows, cols=TEST_COLS, name="test"):
     con = sqlite3.connect(":memory:")
-    decl = ", ".join(f"{n} {'double' if t == abi.kDOUBLE else 'bigint'}" for n, t, _ in cols)
+    decl = ", ".join(f"{n} {'double' if t in (abi.kDOUBLE, abi.kFLOAT) else 'bigint'}" for n, t, _ in cols)
     con.execute(f"CREATE TABLE {name}({decl})")
     con.executemany(f"INSERT INTO {name} VALUES({','.join('?' * len(cols))})", rows)
     return con
@@ -67,7 +70,18 @@ def make_sqlite(rows, cols=TEST_COLS, name="test"):
 EPS = 1.25e-5  # ExecuteTest.cpp:311
 
 
-def assert_rows_match(ours, ref, fp_tol=EPS):
+# SUM / AVG over a FLOAT argument: the reference adds in float (agg_sum_float, RuntimeFunctions.cpp; atomicAdd(float) on
+# its GPU, in no fixed order), so two correct executions agree to float rounding of the partial sums only.  Relative
+# part for sums far from zero; absolute part = the same fraction of a TYPICAL partial sum of the test columns
+# (|x| ~ 50, random walk over n rows) for the sums that cancel.
+FLOAT_SUM_RTOL = 2e-4
+
+
+def float_sum_atol(n_rows: int) -> float:
+    return FLOAT_SUM_RTOL * 50.0 * math.sqrt(max(n_rows, 1))
+
+
+def assert_rows_match(ours, ref, fp_tol=EPS, fp_abs=0.0):
     """SQLiteComparator::compare_impl semantics (ExecuteTest.cpp:383-520): integers exact, fp within
     EPS*|ref|, NULL <-> NULL; rows compared as sorted multisets (our queries carry no ORDER BY)."""
     def key(r):
@@ -80,6 +94,6 @@ def assert_rows_match(ours, ref, fp_tol=EPS):
             if vb is None or va is None:
                 assert va is None and vb is None, f"NULL mismatch {a} vs {b}"
             elif isinstance(vb, float) or isinstance(va, float):
-                assert math.isclose(float(va), float(vb), rel_tol=fp_tol, abs_tol=0.0) or va == vb, f"{a} vs {b}"
+                assert math.isclose(float(va), float(vb), rel_tol=fp_tol, abs_tol=fp_abs) or va == vb, f"{a} vs {b}"
             else:
                 assert int(va) == int(vb), f"{a} vs {b}"

@@ -11,8 +11,9 @@ from test_gpu_parity import RAND_COLS, RAND_NAMES, random_table
 
 pytestmark = pytest.mark.gpu
 
-INT_COLS = [n for n, t, _ in RAND_COLS if t != abi.kDOUBLE and n != "sparse"]
-FP_COLS = ["d", "dnn"]
+INT_COLS = [n for n, t, _ in RAND_COLS if t not in (abi.kDOUBLE, abi.kFLOAT) and n != "sparse"]
+FP_COLS = ["d", "dnn", "f32", "fnn"]      # DOUBLE and FLOAT (4-byte chunks, widened to double in the kernel)
+FP_LIT = {"d": (-1500, 1500), "dnn": (-0.1, 1.1), "f32": (-120, 120), "fnn": (-1.5, 7.5)}
 KEY_COLS = ["k8", "k16", "k32", "k64", "nn32", "nn64", "a8", "sparse"]
 OPS = ["=", "<>", "<", ">", "<=", ">="]
 LIT = {"k8": (-6, 21), "k16": (90, 410), "k32": (-1100, 1100), "k64": (10**9 - 10, 10**9 + 5010), "nn32": (-5, 305),
@@ -29,7 +30,7 @@ def rand_cmp(rng):
             return f"{c} {rng.choice(OPS)} {lit + 0.5}"     # integer column against an fp literal
         return f"{c} {rng.choice(OPS)} {lit}"
     c = rng.choice(FP_COLS)
-    lit = rng.uniform(-1500, 1500) if c == "d" else rng.uniform(-0.1, 1.1)
+    lit = rng.uniform(*FP_LIT[c])
     return f"{c} {rng.choice(OPS)} {lit:.6f}"
 
 

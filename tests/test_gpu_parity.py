@@ -13,7 +13,7 @@ import oracle_lib
 import ref_tables as rt
 import sqlmini
 from heavydb_b200 import abi, executor
-from test_oracle_golden import COUNT_DISTINCT_QUERIES, MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
+from test_oracle_golden import COUNT_DISTINCT_QUERIES, FLOAT_QUERIES, MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
 from test_planner_parity import EXTRA
 
 pytestmark = pytest.mark.gpu
@@ -25,7 +25,7 @@ def golden():
     return table, gu.DeviceTable(table)
 
 
-@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES + COUNT_DISTINCT_QUERIES)
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + EXTRA + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES + COUNT_DISTINCT_QUERIES + FLOAT_QUERIES)
 def test_golden_table_device_resident(golden, sql):
     table, dev = golden
     unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
@@ -123,7 +123,7 @@ RAND_COLS = [
     ("k8", abi.kTINYINT, False), ("k16", abi.kSMALLINT, False), ("k32", abi.kINT, False), ("k64", abi.kBIGINT, False),
     ("nn32", abi.kINT, True), ("nn64", abi.kBIGINT, True), ("a8", abi.kTINYINT, False), ("a16", abi.kSMALLINT, True),
     ("a32", abi.kINT, False), ("a64", abi.kBIGINT, False), ("big", abi.kBIGINT, True), ("d", abi.kDOUBLE, False),
-    ("dnn", abi.kDOUBLE, True), ("sparse", abi.kBIGINT, True),
+    ("dnn", abi.kDOUBLE, True), ("sparse", abi.kBIGINT, True), ("f32", abi.kFLOAT, False), ("fnn", abi.kFLOAT, True),
 ]
 RAND_NAMES = [c[0] for c in RAND_COLS]
 
@@ -151,6 +151,8 @@ def random_table(n, seed, frag_rows):
         with_nulls(rng.normal(0, 1e3, n), abi.kDOUBLE),
         rng.random(n),
         rng.integers(0, 2000, n).astype(np.int64) * 7919 * 10**9,  # sparse keys -> baseline hash
+        with_nulls(rng.normal(0, 50, n).astype(np.float32), abi.kFLOAT),        # FLOAT chunks: 4 bytes, NULL_FLOAT = FLT_MIN
+        (rng.random(n) * 8 - 1).astype(np.float32),
     ]
     t = abi.Table([(ty, nn) for _, ty, nn in RAND_COLS])
     if n == 0:
@@ -194,6 +196,11 @@ RAND_QUERIES = [
     "SELECT k8, COUNT(*), SUM(a16) FROM r WHERE a8 < k8 OR a32 > a64 GROUP BY k8;",                       # column OP column: int8/int8, int32/int64
     "SELECT COUNT(*), MIN(d), MAX(dnn) FROM r WHERE d <= dnn AND NOT (a16 = nn32) AND (k16 >= nn32 OR big < a64);",   # double/double, int16/int32
     "SELECT nn64, COUNT(*) FROM r WHERE d > a32 AND nn32 <> nn64 GROUP BY nn64;",                       # double vs int32
+    # FLOAT arguments / filters: widened to double on load, 4-byte float images in the slots
+    "SELECT k8, COUNT(f32), MIN(f32), MAX(f32), SUM(fnn), AVG(f32) FROM r WHERE fnn > 0.5 GROUP BY k8;",
+    "SELECT COUNT(*), COUNT(f32), MIN(fnn), MAX(fnn), SUM(f32), AVG(fnn) FROM r WHERE f32 < 10 OR f32 IS NULL;",
+    "SELECT nn32, MAX(f32), MIN(f32) FROM r WHERE f32 <= d AND fnn <> 3 GROUP BY nn32;",
+    "SELECT sparse, SUM(fnn), MAX(f32) FROM r GROUP BY sparse;",
     # COUNT(DISTINCT): per-group bitmaps in HBM; shared-memory, HBM/L2, non-grouped and baseline-hash group tables
     "SELECT k8, COUNT(DISTINCT a16), COUNT(DISTINCT nn32), COUNT(*) FROM r GROUP BY k8;",
     "SELECT COUNT(DISTINCT a32), COUNT(DISTINCT k64), COUNT(DISTINCT a8), SUM(a16) FROM r WHERE nn32 < 250;",

@@ -2,6 +2,7 @@
 here — filter trees with NOT / IS NULL / IN, every aggregate over every column type, single / composite / baseline keys,
 INNER and LEFT star joins — against an independent SQL engine, the way Tests/ExecuteTest.cpp uses SQLite."""
 import random
+import re
 
 import pytest
 
@@ -24,6 +25,13 @@ def known_reference_quirk(unit, plan) -> bool:
         if t.first_slot == plan.idx_target_as_key or (t.agg_kind == abi.kAVG and t.first_slot + 1 == plan.idx_target_as_key):
             return t.is_agg and t.agg_kind in (abi.kMIN, abi.kMAX, abi.kSUM) and not t.agg_arg_type.notnull
     return False
+
+
+def float_sum_tol(sql: str, table) -> dict:
+    """Tolerances for a query that sums a FLOAT column (float accumulation, ref_tables.float_sum_atol)."""
+    if re.search(r"(SUM|AVG)\((f32|fnn)\)", sql):
+        return {"fp_abs": rt.float_sum_atol(sum(f.num_tuples for f in table.fragments))}
+    return {}
 
 
 def sqlite_overflows(sql: str) -> bool:
@@ -58,7 +66,7 @@ def test_single_table_queries(seed):
             continue
         ref = [tuple(r) for r in con.execute(sql.rstrip(";")).fetchall()]
         try:
-            rt.assert_rows_match(res.rows(), ref)
+            rt.assert_rows_match(res.rows(), ref, **float_sum_tol(sql, table))
         except AssertionError as e:
             raise AssertionError(f"query: {sql}\n{e}") from e
         checked += 1
@@ -145,7 +153,7 @@ def test_ordered_queries(seed):
             continue
         ref = [tuple(r) for r in con.execute(oq.sqlite_sql(sql, unit, "r")).fetchall()]
         try:
-            assert_ordered_rows_match(res.rows(), ref)
+            assert_ordered_rows_match(res.rows(), ref, **float_sum_tol(sql, table))
         except AssertionError as e:
             raise AssertionError(f"query: {sql}\n{e}") from e
         checked += 1

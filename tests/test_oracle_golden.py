@@ -136,13 +136,36 @@ COUNT_DISTINCT_QUERIES = [
 ]
 
 
+# FLOAT columns (fixed_width_float_decode, DecodersImpl.h:112-123; agg_*_float on 4-byte slots, RuntimeFunctions.cpp:1491-1596)
+FLOAT_QUERIES = [
+    "SELECT COUNT(smallint_nulls), COUNT(*), COUNT(fn) FROM test;",          # verbatim, ExecuteTest.cpp:1890
+    "SELECT MIN(ff) FROM test;",                                              # :1897
+    "SELECT MIN(fn) FROM test;",                                              # :1898
+    "SELECT SUM(ff) FROM test;",                                              # :1899
+    "SELECT SUM(fn) FROM test;",                                              # :1900
+    "SELECT MAX(f), MIN(f), AVG(f), AVG(fn), MAX(fn) FROM test;",
+    "SELECT COUNT(*) FROM test WHERE f > 1.1;",
+    "SELECT COUNT(*) FROM test WHERE f > 1.0 AND f < 1.2;",
+    "SELECT COUNT(*), SUM(x) FROM test WHERE fn < -500 OR fn IS NULL;",
+    "SELECT x, AVG(ff), COUNT(*) FROM test GROUP BY x;",                      # :2022 without the ORDER BY
+    "SELECT x, MAX(fn) FROM test WHERE fn IS NOT NULL GROUP BY x;",           # :2023
+    "SELECT x, SUM(f), MIN(ff), MAX(ff), COUNT(fn), SUM(fn) FROM test GROUP BY x;",
+    "SELECT y, MIN(ff), MAX(fn), AVG(fn) FROM test GROUP BY y;",              # a group whose fn are all NULL (MIN(fn) first would
+                                                                              # trip the keyless-MIN quirk, see test_reference_quirks)
+    "SELECT z, SUM(ff), AVG(f) FROM test WHERE ff > 100 GROUP BY z;",
+    "SELECT t, MIN(f), MAX(f) FROM test WHERE f <= d GROUP BY t;",            # float vs double column
+    "SELECT ofq, SUM(f), COUNT(ff) FROM test WHERE ofq < 100 OR x > 100 GROUP BY ofq;",   # baseline-hash groups
+    "SELECT x, y, MAX(ff), AVG(fn) FROM test GROUP BY x, y;",
+]
+
+
 @pytest.fixture(scope="module")
 def env():
     rows = rt.test_rows()
     return rt.make_table(rows), rt.make_sqlite(rows)
 
 
-@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES + COUNT_DISTINCT_QUERIES)
+@pytest.mark.parametrize("sql", REFERENCE_QUERIES + PATH_QUERIES + MULTI_KEY_QUERIES + NULL_LOGIC_QUERIES + COUNT_DISTINCT_QUERIES + FLOAT_QUERIES)
 def test_oracle_vs_sqlite(env, sql):
     table, con = env
     unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
@@ -227,6 +250,14 @@ def test_reference_quirks():
     assert res.plan.keyless_hash == 1 and res.plan.idx_target_as_key == 4
     got = res.rows()
     assert len(got) == 1 and got[0][0] == 1002 and got[0][5] == 10      # the t = 1001 group (all dn NULL) is dropped
+    # (1b) the same for a FLOAT argument, and wider: get_keyless_info reads the 4-byte init pattern (0x00800000 = NULL_FLOAT) as a
+    #      DOUBLE (`*reinterpret_cast<const double*>(&init_max)`, GroupByAndAggregate.cpp:575-578) — a denormal of ~4e-317 — so any
+    #      float argument whose maximum is <= 0 makes MIN the marker
+    unit = sqlmini.parse("SELECT y, MIN(fn), MAX(fn), AVG(fn) FROM test GROUP BY y;", table, rt.TEST_NAMES)
+    res = oracle_lib.execute(unit, table)
+    assert res.plan.keyless_hash == 1 and res.plan.idx_target_as_key == 1
+    got = res.rows()
+    assert len(got) == 1 and got[0][0] == 43            # the y = 42 group (all fn NULL) is dropped
     unit = sqlmini.parse("SELECT x, MIN(ufd), MAX(ufd), SUM(ufd) FROM test GROUP BY x;", table, rt.TEST_NAMES)
     got = sorted(oracle_lib.execute(unit, table).rows(), key=lambda r: r[0])
     assert got == [(7, None, -1, 10 * -2147483648 + 5 * -1), (8, -2147483647, -2147483647, 5 * -2147483647)]

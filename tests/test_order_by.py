@@ -11,7 +11,7 @@ from heavydb_b200 import abi, executor
 from test_gpu_parity import RAND_COLS, RAND_NAMES, random_table
 
 
-def assert_ordered_rows_match(ours, ref, eps=rt.EPS):
+def assert_ordered_rows_match(ours, ref, eps=rt.EPS, fp_abs=0.0):
     assert len(ours) == len(ref), f"{len(ours)} rows vs {len(ref)}\nours={ours[:6]}\nref={ref[:6]}"
     for a, b in zip(ours, ref):
         assert len(a) == len(b)
@@ -19,7 +19,7 @@ def assert_ordered_rows_match(ours, ref, eps=rt.EPS):
             if va is None or vb is None:
                 assert va is None and vb is None, f"{a} vs {b}"
             elif isinstance(vb, float) or isinstance(va, float):
-                assert va == vb or abs(va - vb) <= eps * abs(vb), f"{a} vs {b}"
+                assert va == vb or abs(va - vb) <= eps * abs(vb) + fp_abs, f"{a} vs {b}"
             else:
                 assert va == vb, f"{a} vs {b}"
 

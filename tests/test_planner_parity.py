@@ -7,14 +7,14 @@ import oracle_lib
 import ref_tables as rt
 import sqlmini
 from heavydb_b200 import abi, executor
-from test_oracle_golden import CONSTRAINED_NOT_NULL_PLANS, COUNT_DISTINCT_QUERIES, MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
+from test_oracle_golden import CONSTRAINED_NOT_NULL_PLANS, COUNT_DISTINCT_QUERIES, FLOAT_QUERIES, MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
 
 EXTRA = [
     "SELECT t, SUM(dn), AVG(dn), MIN(dn), MAX(dn), COUNT(dn) FROM test GROUP BY t;",
     "SELECT x, MIN(ufd), MAX(ufd), SUM(ufd) FROM test GROUP BY x;",
     "SELECT ofq, COUNT(*) FROM test GROUP BY ofq;",       # range too big for perfect hash -> baseline
     "SELECT ufq, COUNT(*), SUM(x) FROM test GROUP BY ufq;",
-] + COUNT_DISTINCT_QUERIES + [c[0] for c in CONSTRAINED_NOT_NULL_PLANS]   # `arg IS NOT NULL` quals: the plans are additionally pinned by hand in test_oracle_golden
+] + COUNT_DISTINCT_QUERIES + FLOAT_QUERIES + ["SELECT y, MIN(fn), MAX(fn), AVG(fn) FROM test GROUP BY y;"] + [c[0] for c in CONSTRAINED_NOT_NULL_PLANS]   # `arg IS NOT NULL` quals: the plans are additionally pinned by hand in test_oracle_golden
 
 
 @pytest.fixture(scope="module")

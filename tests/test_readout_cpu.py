@@ -15,11 +15,11 @@ import str_tables as stt
 from heavydb_b200 import abi, executor
 from test_filter_lowering import emu, run_program  # noqa: F401  (emu is a fixture)
 from test_gpu_parity import RAND_NAMES, RAND_QUERIES, random_table
-from test_oracle_golden import COLUMNAR_EXTRA, COUNT_DISTINCT_QUERIES, MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
+from test_oracle_golden import COLUMNAR_EXTRA, COUNT_DISTINCT_QUERIES, FLOAT_QUERIES, MULTI_KEY_QUERIES, NULL_LOGIC_QUERIES, PATH_QUERIES, REFERENCE_QUERIES
 
 
 def _cases():
-    yield "golden", rt.make_table(rt.test_rows()), rt.TEST_NAMES, list(REFERENCE_QUERIES) + list(MULTI_KEY_QUERIES) + list(PATH_QUERIES) + list(NULL_LOGIC_QUERIES) + list(COLUMNAR_EXTRA) + list(COUNT_DISTINCT_QUERIES)
+    yield "golden", rt.make_table(rt.test_rows()), rt.TEST_NAMES, list(REFERENCE_QUERIES) + list(MULTI_KEY_QUERIES) + list(PATH_QUERIES) + list(NULL_LOGIC_QUERIES) + list(COLUMNAR_EXTRA) + list(COUNT_DISTINCT_QUERIES) + list(FLOAT_QUERIES)
     yield "random", random_table(1500, seed=21, frag_rows=400), RAND_NAMES, list(RAND_QUERIES)
     yield "strings", stt.str_table(1200, seed=5, frag_rows=500), stt.STR_NAMES, list(stt.STR_QUERIES)
     yield "time", tt.make_table(tt.time_rows()), tt.TIME_NAMES, list(tt.TIME_QUERIES)

@@ -95,7 +95,7 @@ def main():
             if unit.unit.num_order_entries:
                 gu.rows_equal_ordered(rows, want)
             else:
-                gu.rows_equal(rows, want)
+                gu.rows_equal(rows, want, col_tol=gu.column_tolerances(ref.plan, sum(f.num_tuples for f in tbl.fragments)))
             assert rs.rowCount() == ref.row_count(), sql
         checked += 1
         del rs, part
