@@ -1148,6 +1148,17 @@ static int32_t execute_work_unit_rank(const B2QComm* comm, size_t* guess, const 
   return set_err(B2Q_ERR_CUDA, "internal: radix retry did not converge");
 }
 
+/* The entry points select eo->device_ordinal / the partial's / the communicator's device; the caller gets its own current
+ * device back when they return (the work they enqueued stays bound to its stream). */
+struct CallerDevice {
+  int dev = -1;
+  CallerDevice() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } }
+  ~CallerDevice() {
+    int now = -1;
+    if (dev >= 0 && cudaGetDevice(&now) == cudaSuccess && now != dev) cudaSetDevice(dev);
+  }
+};
+
 extern "C" {
 
 int32_t b2q_abi_version(void) { return B2Q_ABI_VERSION; }
@@ -1193,6 +1204,7 @@ void b2q_query_free(B2QQuery* q) { delete q; }
 int32_t b2q_execute_partial(size_t* guess, int32_t /*is_agg*/, const B2QTableInfo* tbl, const B2QExecUnit* u,
                             const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card,
                             void* stream, B2QPartial** out) {
+  CallerDevice restore;
   return execute_partial_impl(guess, tbl, u, co, eo, has_card, static_cast<cudaStream_t>(stream), out);
 }
 
@@ -1200,6 +1212,7 @@ int32_t b2q_execute_work_unit(size_t* guess, int32_t is_agg, const B2QTableInfo*
                               const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card,
                               B2QResultSet** out) {
   (void)is_agg;
+  CallerDevice restore;
   for (int attempt = 0; attempt < 2; ++attempt) {
     B2QPartial* p = nullptr;
     int32_t rc = execute_partial_attempt(guess, tbl, u, co, eo, has_card, nullptr, attempt == 0 && radix_enabled(), true, &p);
@@ -1225,7 +1238,10 @@ int32_t b2q_partial_array(const B2QPartial* p, int32_t i, void** ptr, int64_t* c
 int32_t b2q_partial_is_mergeable(const B2QPartial* p) { return p && p->q.plan.kernel != B2Q_KERNEL_BASELINE_GLOBAL; }
 const B2QPlan* b2q_partial_plan(const B2QPartial* p) { return p ? &p->q.plan : nullptr; }
 double b2q_partial_kernel_ms(const B2QPartial* p) { return p ? p->scan_ms : 0; }
-int32_t b2q_partial_finalize(B2QPartial* p, void* stream, B2QResultSet** out) { return finalize_impl(p, static_cast<cudaStream_t>(stream), out); }
+int32_t b2q_partial_finalize(B2QPartial* p, void* stream, B2QResultSet** out) {
+  CallerDevice restore;
+  return finalize_impl(p, static_cast<cudaStream_t>(stream), out);
+}
 void b2q_partial_free(B2QPartial* p) { delete p; }
 
 /* Inner entry: same parameter block as the reference's JIT kernel; writes the reference-layout buffer on the
@@ -1602,6 +1618,7 @@ int32_t b2q_comm_init_rank(const void* id128, int32_t nranks, int32_t rank, int3
   if (!api) return set_err(B2Q_ERR_UNSUPPORTED, why);
   if (!id128 || !out || nranks < 1 || rank < 0 || rank >= nranks) return set_err(B2Q_ERR_INVALID_ARGUMENT, "communicator arguments");
   if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible");
+  CallerDevice restore;
   if (device >= 0) CU(cudaSetDevice(device));
   std::unique_ptr<B2QComm> c(new B2QComm());
   CU(cudaGetDevice(&c->device));
@@ -1648,6 +1665,7 @@ int32_t b2q_execute_work_unit_dist(B2QComm* comm, size_t* guess, int32_t /*is_ag
                                    const B2QCompilationOptions* co, const B2QExecutionOptions* eo, int32_t has_card, void* stream,
                                    B2QResultSet** out) {
   if (!comm || !eo) return set_err(B2Q_ERR_INVALID_ARGUMENT, "null argument");
+  CallerDevice restore;
   return execute_work_unit_rank(comm, guess, tbl, u, co, eo, has_card, static_cast<cudaStream_t>(stream), true, out, nullptr);
 }
 

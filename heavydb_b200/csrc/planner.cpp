@@ -415,9 +415,9 @@ class Planner {
       } else {
         const int64_t v = cfp ? static_cast<int64_t>(c.dval) : c.ival;
         switch (q.op) {
-          case B2Q_kGT: r.imin = std::max(r.imin, v + 1); break;
+          case B2Q_kGT: r.imin = std::max(r.imin, static_cast<int64_t>(static_cast<uint64_t>(v) + 1)); break; /* apply_int_qual's const_val + 1 wraps for INT64_MAX: the same value without the signed-overflow UB */
           case B2Q_kGE: r.imin = std::max(r.imin, v); break;
-          case B2Q_kLT: r.imax = std::min(r.imax, v - 1); break;
+          case B2Q_kLT: r.imax = std::min(r.imax, static_cast<int64_t>(static_cast<uint64_t>(v) - 1)); break;
           case B2Q_kLE: r.imax = std::min(r.imax, v); break;
           case B2Q_kEQ: r.imin = std::max(r.imin, v); r.imax = std::min(r.imax, v); break;
           default: break;
@@ -624,7 +624,9 @@ class Planner {
       keyless_info();
       p.keyless_hash = (!p.bucket && keyless_) ? 1 : 0; /* QueryMemoryDescriptor.cpp:327-333; no sort hint, no baseline sort on this path */
       p.idx_target_as_key = keyless_idx_;
-      int64_t card = p.max_val - p.min_val;
+      int64_t card;
+      if (__builtin_sub_overflow(p.max_val, p.min_val, &card)) /* only a bucketed (DATE) range gets here with an overflowing span: getBucketedCardinality (:367-375) is undefined there */
+        reject(B2Q_ERR_UNSUPPORTED, "DATE key range wider than int64");
       if (p.bucket) card /= p.bucket; /* getBucketedCardinality (:367-375) */
       p.entry_count = std::max<int64_t>(card + 1 + (p.has_nulls ? 1 : 0), 1);
     } else {
@@ -1692,6 +1694,18 @@ static void build_joined_input(const B2QExecUnit& u, const B2QTableInfo& outer, 
   if (inner.num_fragments > 1) bad(B2Q_ERR_INVALID_ARGUMENT, "the inner table must come as one concatenated fragment (ColumnFetcher::getAllTableColumnFragments)");
   if (inner.deleted_column_plus1) bad(B2Q_ERR_UNSUPPORTED, "inner table with a deleted-rows column");
   if (inner.num_cols <= 0 || outer.num_cols <= 0) bad(B2Q_ERR_INVALID_ARGUMENT, "table without columns");
+  /* the same checks Planner::validate() makes on the outer table, before anything of the inner one is read */
+  if (!inner.col_types || !outer.col_types) bad(B2Q_ERR_INVALID_ARGUMENT, "col_types is null");
+  if (inner.num_fragments < 0 || (inner.num_fragments && !inner.fragments)) bad(B2Q_ERR_INVALID_ARGUMENT, "inner table: fragments");
+  if (inner.num_fragments) {
+    const B2QFragmentInfo& f0 = inner.fragments[0];
+    if (f0.num_tuples < 0) bad(B2Q_ERR_INVALID_ARGUMENT, "inner table: negative row count");
+    if (!f0.col_stats) bad(B2Q_ERR_INVALID_ARGUMENT, "inner table: fragment without chunk stats");
+    if (f0.num_tuples > 0 && !f0.col_buffers) bad(B2Q_ERR_INVALID_ARGUMENT, "inner table: fragment without column buffers");
+  }
+  if (outer.num_fragments < 0 || (outer.num_fragments && !outer.fragments)) bad(B2Q_ERR_INVALID_ARGUMENT, "fragments");
+  for (int f = 0; f < outer.num_fragments; ++f)
+    if (!outer.fragments[f].col_stats) bad(B2Q_ERR_INVALID_ARGUMENT, "fragment without chunk stats");
   ji.n_outer = outer.num_cols;
   ji.exprs.assign(u.exprs, u.exprs + std::max(u.num_exprs, 0));
   for (B2QExpr& e : ji.exprs) {

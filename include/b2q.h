@@ -255,7 +255,7 @@ typedef struct B2QExecutionOptions {
   int32_t output_columnar_hint;  /* --enable-columnar-output */
   int32_t bigint_count;          /* g_bigint_count (--bigint-count) */
   int32_t force_kernel;          /* 0 = planner's choice; else B2Q_KERNEL_* (for tests / benchmarks) */
-  int32_t device_ordinal;        /* CUDA device to run on (-1 = current) */
+  int32_t device_ordinal;        /* CUDA device to run on (-1 = current); the calling thread's current device is restored on return */
   int32_t pad_;
 } B2QExecutionOptions;
 

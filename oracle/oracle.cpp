@@ -566,9 +566,9 @@ void apply_simple_quals(const B2QExecUnit& u, int key_col_id, Range& r) { /* Exp
     } else if (r.kind == Range::Integer) {
       const int64_t v = is_fp(c.ti.type) ? static_cast<int64_t>(c.dval) : c.ival;
       switch (q.op) {
-        case B2Q_kGT: r.imin = std::max(r.imin, v + 1); break;
+        case B2Q_kGT: r.imin = std::max(r.imin, static_cast<int64_t>(static_cast<uint64_t>(v) + 1)); break; /* apply_int_qual's const_val + 1 wraps for INT64_MAX: the same value without the signed-overflow UB */
         case B2Q_kGE: r.imin = std::max(r.imin, v); break;
-        case B2Q_kLT: r.imax = std::min(r.imax, v - 1); break;
+        case B2Q_kLT: r.imax = std::min(r.imax, static_cast<int64_t>(static_cast<uint64_t>(v) - 1)); break;
         case B2Q_kLE: r.imax = std::min(r.imax, v); break;
         case B2Q_kEQ: r.imin = std::max(r.imin, v); r.imax = std::min(r.imax, v); break;
         default: break;
@@ -937,7 +937,8 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
       p.entry_count = p.max_val; /* col range info max contains the expected cardinality (QueryMemoryDescriptor.cpp:339-342) */
     } else {
       /* getBucketedCardinality (:367-375) */
-      int64_t card = p.max_val - p.min_val;
+      int64_t card;
+      if (__builtin_sub_overflow(p.max_val, p.min_val, &card)) fail(B2Q_ERR_UNSUPPORTED, "DATE key range wider than int64 (undefined in the reference)");
       if (p.bucket) card /= p.bucket;
       card += 1 + (p.has_nulls ? 1 : 0);
       p.entry_count = std::max<int64_t>(card, 1);

@@ -91,6 +91,27 @@ def test_refused_joins(env):
     _both_refuse(sqlmini.parse("SELECT COUNT(*) FROM t JOIN d ON t.d = d.w;", fact, jt.FACT_NAMES, inner=(dim, jt.DIM_NAMES)), fact)
 
 
+def test_malformed_inner_table_is_an_argument_error(env):
+    """The inner table gets the checks the outer one gets: a descriptor with missing pieces is INVALID_ARGUMENT, never a
+    dereference (the planner reads its chunk stats for the join table's range)."""
+    import ctypes as C
+    fact, dim, _ = env
+
+    def broken(mutate):
+        unit = parse("SELECT COUNT(*) FROM t JOIN d ON t.fk32 = d.id32;", fact, dim)
+        info = unit._inner_built.info
+        mutate(info)
+        with pytest.raises(executor.QueryExecutionError) as ei:
+            executor.Executor().plan(unit, fact)
+        assert ei.value.code == abi.ERR_INVALID_ARGUMENT
+
+    broken(lambda i: setattr(i.fragments[0], "col_stats", C.POINTER(abi.ChunkStats)()))
+    broken(lambda i: setattr(i.fragments[0], "col_buffers", C.POINTER(C.c_void_p)()))
+    broken(lambda i: setattr(i, "fragments", C.POINTER(abi.FragmentInfo)()))
+    broken(lambda i: setattr(i, "col_types", C.POINTER(abi.TypeInfo)()))
+    broken(lambda i: setattr(i.fragments[0], "num_tuples", -1))
+
+
 def test_empty_tables():
     dim = jt.dim_table()
     empty_fact = jt.fact_table(0, seed=1, frag_rows=10)
