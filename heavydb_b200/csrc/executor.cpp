@@ -605,9 +605,9 @@ static bool skip_fragment(const B2QExecUnit& u, const B2QTableInfo& tbl, const B
     if (c.kind != B2Q_EXPR_CONSTANT) return false;
     if (c.is_null || l.col_id < 0 || l.col_id >= tbl.num_cols) continue;
     const B2QChunkStats& st = fr.col_stats[l.col_id];
-    const bool col_fp = tbl.col_types[l.col_id].type == B2Q_kDOUBLE;
-    const bool const_fp = c.ti.type == B2Q_kDOUBLE;
-    if (col_fp) { /* canSkipFragmentForFpQual (Execute.cpp:4700-4774) */
+    const bool col_fp = tbl.col_types[l.col_id].type == B2Q_kDOUBLE || tbl.col_types[l.col_id].type == B2Q_kFLOAT;
+    const bool const_fp = c.ti.type == B2Q_kDOUBLE || c.ti.type == B2Q_kFLOAT; /* either carries its value in dval here */
+    if (col_fp) { /* canSkipFragmentForFpQual (Execute.cpp:4700-4774): FLOAT and DOUBLE chunks both keep fp min / max */
       const double mn = st.fp_min, mx = st.fp_max, v = const_fp ? c.dval : static_cast<double>(c.ival);
       if (mn > mx) return false;
       switch (q.op) {
@@ -648,7 +648,7 @@ static int32_t prepare_join(B2QPartial& p, const B2QExecUnit& u, cudaStream_t st
     switch (inner.col_types[c].type) {
       case B2Q_kTINYINT: case B2Q_kBOOLEAN: return 1;
       case B2Q_kSMALLINT: return 2;
-      case B2Q_kINT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4;
+      case B2Q_kINT: case B2Q_kFLOAT: case B2Q_kTEXT: case B2Q_kVARCHAR: case B2Q_kCHAR: return 4;
       default: return 8;
     }
   };

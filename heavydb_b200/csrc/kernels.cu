@@ -298,7 +298,8 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
   a.smem = q.smem;
   a.smem_image = smem_image;
   a.prefetch_distance = prefetch_distance;
-  a.pad_ = 0;
+  static const bool wp_knob = []() { const char* e = getenv("B2Q_WARP_PRIVATE"); return !e || atoi(e) != 0; }();
+  a.warp_private = (wp_knob && q.smem.use_smem && q.smem.replicas >= block / 32) ? 1 : 0;
   a.ndv_bitmap_bytes = q.plan.query_desc_type == B2Q_Estimator ? q.plan.buffer_size : 0;
   ScanConfig c;
   c.block = block;

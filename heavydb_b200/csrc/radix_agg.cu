@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_partition_tile(con
  * Accumulators: COUNT / integer SUM as 32-bit low words (native ATOMS.ADD; a carry or a value wider than 32 bits is sent to
  * the HBM entry at once, RED.ADD.64 of hi << 32), the others as 64-bit slots at their identity. */
 constexpr int kBucket = 4, kMaxBuckets = 8;
+constexpr int kQueue = 64; /* pass 2: parked tuples per warp */
 
 __device__ __forceinline__ void lds128(const int64_t* p, int64_t& a, int64_t& b) {
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(smem_u32(p)) : "memory");
@@ -465,6 +466,10 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
   int64_t* s_keys = reinterpret_cast<int64_t*>(s_raw);
   int8_t* s_acc = s_raw + (size_t)S * 8;            /* accumulator a: s_acc + acc_off[a] * S, 4 or 8 bytes per slot */
   uint32_t* s_blk = reinterpret_cast<uint32_t*>(s_acc + (size_t)A.acc_bytes_total * S); /* [n_cta1 + 1] block prefix of the partition's regions */
+  /* per warp: 64 parked tuples {key, value or tuple address} (at most 31 left over + 32 new before a drain) */
+  int64_t* q_key = reinterpret_cast<int64_t*>(s_raw + A.queue_off) + (size_t)(tid >> 5) * 2 * kQueue;
+  int64_t* q_aux = q_key + kQueue;
+  const uint32_t lt = (1u << lane) - 1u;
   __shared__ uint32_t s_part;
   const uint32_t n = (uint32_t)P.key.entry_count;
   const uint64_t magic = P.key.hash_magic;
@@ -505,6 +510,43 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
     __syncthreads();
     /* ---- stream the partition's tuples through the table ---- */
     const uint32_t total_blocks = s_blk[n_cta1];
+    uint32_t qn = 0; /* tuples parked in this warp's queue (warp-uniform) */
+    /* one tuple into the private table.  e >= 0: its slot is known; e == -2: find / claim it first (all lanes of the warp
+     * arrive together: the queue is drained 32 at a time); e == -3: nothing to do for this lane */
+    auto update = [&](int64_t k, int64_t aux, int e, bool find) {
+      if (find) {
+        if (e == -2) e = bucket_find(s_keys, nb_mask, bucket_of_mix(mix_key(k), nb_mask), k);
+        __syncwarp(); /* a few lanes visit a second bucket or retry a claim: reconverge before the updates */
+        if (e == -3) return;
+      }
+      const int64_t* vals = tw <= 2 ? nullptr : reinterpret_cast<const int64_t*>(aux) + 1;
+      if (e < 0) { /* no room in the private table: the row goes to the table in HBM */
+        int64_t rv[B2Q_RADIX_MAX_VALS];
+        for (int cidx = 0; cidx < A.n_vals; ++cidx) rv[cidx] = tw <= 2 ? aux : __ldcg(vals + cidx);
+        global_insert_raw(A, k, rv);
+      } else if (fused) {
+        const int64_t add = fused_count ? 1 : aux;
+        const uint32_t vl = (uint32_t)add;
+        const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(s_acc) + e, vl);
+        const int32_t hi32 = (int32_t)(add >> 32) + (int32_t)((uint32_t)(old + vl) < old);
+        if (hi32 != 0) global_add_hi(A, k, 0, hi32);
+      } else {
+        for (int a = 0; a < n_accs; ++a) {
+          const DevAcc& acc = P.accs[a];
+          const int vi = A.acc_val[a];
+          const int64_t v = vi < 0 ? 0 : (tw <= 2 ? aux : __ldcg(vals + vi));
+          if (vi >= 0 && value_skipped(acc, v)) continue;
+          int8_t* base = s_acc + (size_t)A.acc_off[a] * S;
+          if (A.acc_bytes[a] == 4) {
+            const int64_t add = acc.op == ACC_COUNT ? 1 : v;
+            const uint32_t vl = (uint32_t)add;
+            const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(base) + e, vl);
+            const int32_t hi32 = (int32_t)(add >> 32) + (int32_t)((uint32_t)(old + vl) < old);
+            if (hi32 != 0) global_add_hi(A, k, a, hi32);
+          } else smem_acc_raw(acc.op, reinterpret_cast<int64_t*>(base) + e, v);
+        }
+      }
+    };
     int c = 0; /* region of block b: blocks are taken in increasing order, so the region is a moving cursor */
     for (uint32_t b = tid >> 5; b < total_blocks; b += nthr / 32) {
       while (s_blk[c + 1] <= b) ++c;
@@ -527,10 +569,13 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
 #pragma unroll
       for (int u = 0; u < U; ++u) pos[u] = bucket_of_mix(mix_key(key[u]), nb_mask);
       /* the common case — the key sits in its first bucket — for all U tuples at once: 2 U independent 16-byte loads in
-       * flight, no claim, no second bucket, no divergence; whatever is left (a key's first appearance in the partition, a
-       * full bucket) takes the slow path afterwards */
+       * flight, no claim, no second bucket, no divergence.  Whatever is left (a key's first appearance in the partition, a
+       * full first bucket: ~6 % of the tuples, but at least one lane of 5 warps out of 6) is NOT resolved here — ncu on the
+       * version that called bucket_find for the odd lanes right away: 45 % of the kernel's warp instructions were that call,
+       * executed for one or two active lanes (profiles/r2_radix_c4s_full_ncu.txt).  Those tuples are parked in a queue of the
+       * warp in shared memory and resolved 32 at a time, one per lane. */
       int e[U];
-      uint32_t slow = 0;
+      uint32_t hits = 0;
 #pragma unroll
       for (int u = 0; u < U; ++u) { /* (checking the following bucket here as well was measured slower: 16.1 vs 13.5 ms per 1e9 tuples) */
         const int64_t* bk = s_keys + (size_t)pos[u] * kBucket;
@@ -538,46 +583,31 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
         const longlong2 kb = *reinterpret_cast<const longlong2*>(bk + 2);
         const uint32_t hit = (uint32_t)(ka.x == key[u]) | (uint32_t)(ka.y == key[u]) << 1 | (uint32_t)(kb.x == key[u]) << 2 | (uint32_t)(kb.y == key[u]) << 3;
         e[u] = (int)(pos[u] * kBucket) + __ffs(hit) - 1;
-        slow |= (uint32_t)(hit == 0 && lane + 32u * u < m) << u;
+        hits |= (uint32_t)(hit != 0) << u;
       }
-      if (slow) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) if (slow >> u & 1) e[u] = bucket_find(s_keys, nb_mask, pos[u], key[u]);
-      }
-      __syncwarp();
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const uint32_t i = lane + 32u * u;
-        const bool live = i < m;
-        const int64_t* vals = tp + (size_t)i * tw + 1;
-        if (live && e[u] < 0) { /* no room in the private table: the row goes to the table in HBM */
-          int64_t rv[B2Q_RADIX_MAX_VALS];
-          for (int cidx = 0; cidx < A.n_vals; ++cidx) rv[cidx] = tw == 2 ? v0[u] : __ldcg(vals + cidx);
-          global_insert_raw(A, key[u], rv);
-        } else if (fused) {
-          const int64_t add = fused_count ? 1 : v0[u];
-          const uint32_t vl = (uint32_t)add;
-          uint32_t old = 0;
-          if (live) old = atomicAdd(reinterpret_cast<uint32_t*>(s_acc) + e[u], vl);
-          const int32_t hi32 = (int32_t)(add >> 32) + (int32_t)((uint32_t)(old + vl) < old);
-          if (live && hi32 != 0) global_add_hi(A, key[u], 0, hi32);
-        } else if (live) {
-          for (int a = 0; a < n_accs; ++a) {
-            const DevAcc& acc = P.accs[a];
-            const int vi = A.acc_val[a];
-            const int64_t v = vi < 0 ? 0 : (tw == 2 ? v0[u] : __ldcg(vals + vi));
-            if (vi >= 0 && value_skipped(acc, v)) continue;
-            int8_t* base = s_acc + (size_t)A.acc_off[a] * S;
-            if (A.acc_bytes[a] == 4) {
-              const int64_t add = acc.op == ACC_COUNT ? 1 : v;
-              const uint32_t vl = (uint32_t)add;
-              const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(base) + e[u], vl);
-              const int32_t hi32 = (int32_t)(add >> 32) + (int32_t)((uint32_t)(old + vl) < old);
-              if (hi32 != 0) global_add_hi(A, key[u], a, hi32);
-            } else smem_acc_raw(acc.op, reinterpret_cast<int64_t*>(base) + e[u], v);
+        const bool live = i < m, hit = hits >> u & 1;
+        const int64_t aux = tw <= 2 ? v0[u] : (int64_t)(tp + (size_t)i * tw); /* the value itself, or where the tuple lies */
+        const bool park = live && !hit;
+        const uint32_t pm = __ballot_sync(0xffffffffu, park);
+        if (pm) {
+          if (park) {
+            const uint32_t at = qn + __popc(pm & lt);
+            q_key[at] = key[u];
+            q_aux[at] = aux;
           }
+          qn += __popc(pm);
+          __syncwarp();
+          if (qn >= 32) { qn -= 32; update(q_key[qn + lane], q_aux[qn + lane], -2, true); __syncwarp(); }
         }
+        if (live && hit) update(key[u], aux, e[u], false);
       }
+    }
+    if (qn) { /* what is left in the warp's queue */
+      update(lane < qn ? q_key[lane] : 0, lane < qn ? q_aux[lane] : 0, lane < qn ? -2 : -3, true);
+      qn = 0;
       __syncwarp();
     }
     __syncthreads();
@@ -692,7 +722,7 @@ bool radix_plan(const B2QQuery& q, RadixPlan* rp) {
   rp->acc_bytes_total = off;
   /* slice: the largest power of two of entries whose keys + accumulators (+ overflow area) fit the shared memory of a CTA */
   const int64_t entry_bytes = 8 + off;
-  const int64_t budget = 208 * 1024;
+  const int64_t budget = 193 * 1024; /* of the 227 KB a CTA may opt in to: 32 KB are the warps' queues, ~1 KB the block prefix */
   int log_s = 4;
   while (log_s < 20 && (int64_t(2) << log_s) * entry_bytes <= budget) ++log_s;
   if ((int64_t(1) << log_s) * entry_bytes > budget) return false;
@@ -711,9 +741,14 @@ static size_t radix_tile_smem(const RadixPlan& rp) {
 }
 size_t radix_smem_pass1(const RadixPlan& rp) { return rp.tile ? radix_tile_smem(rp) : static_cast<size_t>(rp.n_parts) * 4; }
 
+/* pass 2: [keys S x 8][accumulators][block prefix n_cta1 + 1][per-warp queues of parked tuples] */
+static size_t radix_queue_off(const RadixPlan& rp, int n_cta1) {
+  const size_t S = size_t(1) << rp.log_s;
+  return (S * (8 + rp.acc_bytes_total) + (static_cast<size_t>(n_cta1) + 1) * 4 + 15) / 16 * 16;
+}
 size_t radix_smem_pass2(const B2QQuery&, const RadixPlan& rp, int n_cta1) {
   const size_t S = size_t(1) << rp.log_s;
-  return S * (8 + rp.acc_bytes_total) + (static_cast<size_t>(n_cta1) + 1) * 4 + 16;
+  return radix_queue_off(rp, n_cta1) + static_cast<size_t>(kRadixBlock / 32) * 2 * kQueue * 8;
 }
 
 /* grid of pass 1 and the region capacity for a batch of `chunks` scan chunks */
@@ -752,7 +787,7 @@ cudaError_t launch_radix(const B2QQuery& q, const RadixPlan& rp, const DevLaunch
   memcpy(a.acc_bytes, rp.acc_bytes, sizeof(a.acc_bytes));
   memcpy(a.acc_off, rp.acc_off, sizeof(a.acc_off));
   a.acc_bytes_total = rp.acc_bytes_total;
-  a.pad_ = 0;
+  a.queue_off = static_cast<int32_t>(radix_queue_off(rp, n_cta1));
   a.chunk_begin = chunk_begin;
   a.chunk_end = chunk_end;
   const size_t smem2 = radix_smem_pass2(q, rp, n_cta1);

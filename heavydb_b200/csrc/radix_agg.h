@@ -48,7 +48,7 @@ struct RadixArgs {
   int8_t acc_bytes[B2Q_MAX_ACCS];
   int16_t acc_off[B2Q_MAX_ACCS];
   int32_t acc_bytes_total;
-  int32_t pad_;
+  int32_t queue_off;              /* pass 2: byte offset of the per-warp queues of parked tuples inside the dynamic shared memory */
   int64_t chunk_begin, chunk_end;
 };
 

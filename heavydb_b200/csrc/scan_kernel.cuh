@@ -539,7 +539,7 @@ struct ScanArgs {
   SmemPlan smem;
   const int8_t* smem_image; /* identity image of ONE replica in HBM (MODE_SMEM) */
   int32_t prefetch_distance; /* > 0: TMA bulk-prefetch the column slabs of the chunk this CTA will scan D iterations ahead into L2 */
-  int32_t pad_;
+  int32_t warp_private;      /* MODE_SMEM: every warp of the CTA has a replica of the group table to itself */
   int64_t ndv_bitmap_bytes;  /* estimator query: size of the ACC_NDV bitmap (a power of two) */
 };
 
@@ -798,6 +798,27 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       int64_t v[R];
       load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol, JX(sa.col));
       double* dsum = reinterpret_cast<double*>(sum_tab);
+      if (A.warp_private) {
+        /* the replica belongs to this warp alone: plain read-modify-write instead of the ATOMS.CAST.SPIN loop a shared
+         * double add compiles to.  Only lanes of THIS warp can collide: MATCH.ANY groups the lanes of a row by entry, the
+         * k-th lane of every group goes in round k (mostly one round: 32 lanes over 256 entries collide in ~2 pairs). */
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const bool act = pass >> j & 1;
+          const uint32_t peers = __match_any_sync(0xffffffffu, act ? e[j] : (0xFFFFFF00u | (uint32_t)lane));
+          const uint32_t rank = __popc(peers & lt);
+          const uint32_t rounds = __reduce_max_sync(0xffffffffu, rank);
+          for (uint32_t r = 0; r <= rounds; ++r) {
+            if (act && rank == r) {
+              dsum[e[j]] += __longlong_as_double(v[j]);
+              if (ic >= 0) cnt_tab[e[j]] += 1u;
+            }
+            __syncwarp();
+          }
+        }
+        return;
+      }
 #pragma unroll
       for (int j = 0; j < R; ++j)
         if (pass >> j & 1) {

@@ -23,7 +23,7 @@
  *       values computed by SQLite exactly as the reference's own comparator does
  *       (ExecuteTest.cpp:383-520) — tests/test_oracle_golden.py;
  *   (3) the ResultSetTest generator pattern (Tests/ResultSetTestUtils.h:33-70, ResultSetTest.cpp:1081-1098)
- *       for the reduction — tests/test_oracle_reduce.py.
+ *       for iteration and reduction over hand-filled storages — tests/test_resultset_vectors.py.
  */
 #include <pthread.h>
 #include <sched.h>
@@ -1651,14 +1651,16 @@ bool is_empty_entry(const B2QPlan& p, const int8_t* buf, int64_t entry) {
 /* ---- ResultSetStorage::reduceOneSlot (ResultSetReduction.cpp:1496-1566) with the AGGREGATE_ONE_* macros
  * (:1290-1437): COUNT merges as SUM, AVG merges (sum, count) separately, nullable values use *_skip_val with the
  * slot's init value as the skip value. ---- */
-void reduce_one_row(const Plan& plan, int8_t* this_buf, int64_t this_e, const int8_t* that_buf, int64_t that_e) {
+void reduce_one_row(const Plan& plan, int8_t* this_buf, int64_t this_e, const int8_t* that_buf, int64_t that_e,
+                    const B2QPlan* that_layout = nullptr) {
   const B2QPlan& p = plan.p;
+  const B2QPlan& q = that_layout ? *that_layout : p; /* `that` may have another entry count (ResultSetManager::reduce grows the baseline destination) */
   for (const auto& t : plan.targets) {
     const int s = t.first_slot;
     const int w = p.slot_padded_width[s];
     if (w == 0) continue;
     int8_t* tp = slot_ptr(p, this_buf, this_e, s);
-    const int8_t* op = slot_ptr(p, that_buf, that_e, s);
+    const int8_t* op = slot_ptr(q, that_buf, that_e, s);
     const int64_t init_val = p.init_vals[s];
     if (w == 4) {
       int32_t a, b;
@@ -1690,7 +1692,7 @@ void reduce_one_row(const Plan& plan, int8_t* this_buf, int64_t this_e, const in
       const int kind = t.agg_kind == B2Q_kAVG ? B2Q_kSUM : t.agg_kind;
       if (t.agg_kind == B2Q_kAVG) {
         int64_t bc;
-        memcpy(&bc, slot_ptr(p, that_buf, that_e, s + 1), 8);
+        memcpy(&bc, slot_ptr(q, that_buf, that_e, s + 1), 8);
         agg_sum(reinterpret_cast<int64_t*>(slot_ptr(p, this_buf, this_e, s + 1)), bc);
       }
       const int32_t skip32 = static_cast<int32_t>(init_val);
@@ -1707,7 +1709,7 @@ void reduce_one_row(const Plan& plan, int8_t* this_buf, int64_t this_e, const in
       case B2Q_kAVG: {
         int64_t* ac = reinterpret_cast<int64_t*>(slot_ptr(p, this_buf, this_e, s + 1));
         int64_t bc;
-        memcpy(&bc, slot_ptr(p, that_buf, that_e, s + 1), 8);
+        memcpy(&bc, slot_ptr(q, that_buf, that_e, s + 1), 8);
         agg_sum(ac, bc);
       } /* fall thru */
       case B2Q_kSUM:
@@ -1730,8 +1732,9 @@ void reduce_one_row(const Plan& plan, int8_t* this_buf, int64_t this_e, const in
 /* ResultSetStorage::reduce (ResultSetReduction.cpp:203-396): perfect hash => entry-wise
  * (reduceOneEntryNoCollisions :398-450: skip empty `that` entries, copy key); baseline => re-probe every
  * non-empty `that` entry into `this` (:698-828). */
-int32_t reduce_buffers(const Plan& plan, std::vector<int8_t>& this_buf, const std::vector<int8_t>& that_buf) {
+int32_t reduce_buffers(const Plan& plan, std::vector<int8_t>& this_buf, const std::vector<int8_t>& that_buf, const B2QPlan* that_layout = nullptr) {
   const B2QPlan& p = plan.p;
+  const B2QPlan& q = that_layout ? *that_layout : p;
   if (p.query_desc_type == B2Q_Estimator) { /* reduce_estimator_results (CardinalityEstimator.cpp:142-161) */
     for (size_t i = 0; i < this_buf.size(); ++i) this_buf[i] |= that_buf[i];
     return 0;
@@ -1740,16 +1743,16 @@ int32_t reduce_buffers(const Plan& plan, std::vector<int8_t>& this_buf, const st
     reduce_one_row(plan, this_buf.data(), 0, that_buf.data(), 0);
     return 0;
   }
-  for (int64_t e = 0; e < p.entry_count; ++e) {
-    if (is_empty_entry(p, that_buf.data(), e)) continue;
+  for (int64_t e = 0; e < q.entry_count; ++e) {
+    if (is_empty_entry(q, that_buf.data(), e)) continue;
     if (p.query_desc_type == B2Q_GroupByPerfectHash) {
       if (!p.keyless_hash) /* key copy (copyKeyColWise :452-476 when columnar) */
         for (int c = 0; c < std::max(p.num_group_cols, 1); ++c)
-          memcpy(key_ptr(p, this_buf.data(), e, c), key_ptr(p, that_buf.data(), e, c), p.output_columnar ? 8 : p.effective_key_width);
+          memcpy(key_ptr(p, this_buf.data(), e, c), key_ptr(q, that_buf.data(), e, c), p.output_columnar ? 8 : p.effective_key_width);
       reduce_one_row(plan, this_buf.data(), e, that_buf.data(), e);
     } else {
       int64_t keybuf = 0;
-      memcpy(&keybuf, key_ptr(p, that_buf.data(), e, 0), p.effective_key_width);
+      memcpy(&keybuf, key_ptr(q, that_buf.data(), e, 0), p.effective_key_width);
       int64_t this_e;
       if (p.output_columnar) {
         this_e = get_group_value_columnar_slot(reinterpret_cast<int64_t*>(this_buf.data()), static_cast<uint32_t>(p.entry_count), keybuf);
@@ -1760,7 +1763,7 @@ int32_t reduce_buffers(const Plan& plan, std::vector<int8_t>& this_buf, const st
         if (!slots) return B2Q_ERR_OUT_OF_SLOTS;
         this_e = (reinterpret_cast<int8_t*>(slots) - this_buf.data()) / p.row_size;
       }
-      reduce_one_row(plan, this_buf.data(), this_e, that_buf.data(), e);
+      reduce_one_row(plan, this_buf.data(), this_e, that_buf.data(), e, &q);
     }
   }
   return 0;
@@ -2086,6 +2089,78 @@ ORACLE_EXPORT int32_t oracle_execute_generated(const B2QExecUnit* u, const B2QTa
     res->buf = std::move(bufs[0]);
     finalize_count_distinct(res);
     *out = holder.release();
+    return 0;
+  } catch (const OracleError& e) {
+    g_last_error = e.msg;
+    return e.code;
+  }
+}
+
+/* A result set over a storage buffer the caller filled — ResultSet(targets, device_type, query_mem_desc, ...) +
+ * allocateStorage() as Tests/ResultSetTest.cpp:879-894 / :1026-1046 use it: the descriptor is the planned query's. */
+ORACLE_EXPORT int32_t oracle_result_from_storage(const B2QExecUnit* u, const B2QTableInfo* tbl, const B2QExecutionOptions* eo,
+                                                 size_t entry_guess, int32_t has_cardinality_estimation, const int8_t* storage,
+                                                 size_t size_bytes, OracleResult** out) {
+  try {
+    std::unique_ptr<OracleResult> res(new OracleResult());
+    JoinedInput ji;
+    res->plan = make_plan(*u, *tbl, *eo, entry_guess, has_cardinality_estimation != 0, &ji);
+    if (res->plan.cd_total) fail(B2Q_ERR_UNSUPPORTED, "storage of a COUNT(DISTINCT) query carries bitmap pointers");
+    if (size_bytes != static_cast<size_t>(res->plan.p.buffer_size)) fail(B2Q_ERR_INVALID_ARGUMENT, "storage size differs from the descriptor's buffer size");
+    res->buf.assign(storage, storage + size_bytes);
+    *out = res.release();
+    return 0;
+  } catch (const OracleError& e) {
+    g_last_error = e.msg;
+    return e.code;
+  }
+}
+
+/* ResultSetManager::reduce (ResultSetReduction.cpp:1055-1140): the first set's storage is the destination.  For baseline
+ * hash a storage with the SUM of the sets' entry counts is initialised first and the first set's entries are moved into it
+ * (moveEntriesToBuffer / moveOneEntryToBuffer :941-1050: every non-empty entry is re-probed into the bigger table and its
+ * slots copied); then every other set is reduced into the destination with ResultSetStorage::reduce. */
+ORACLE_EXPORT int32_t oracle_result_sets_reduce(OracleResult* const* sets, int32_t n, OracleResult** out) {
+  try {
+    if (!sets || n < 1 || !out) fail(B2Q_ERR_INVALID_ARGUMENT, "result sets");
+    std::unique_ptr<OracleResult> res(new OracleResult());
+    res->plan = sets[0]->plan;
+    B2QPlan& p = res->plan.p;
+    if (p.query_desc_type == B2Q_GroupByBaselineHash) {
+      if (res->plan.cd_total) fail(B2Q_ERR_UNSUPPORTED, "baseline growth with COUNT(DISTINCT) bitmaps");
+      int64_t total = 0;
+      for (int i = 0; i < n; ++i) total += sets[i]->plan.p.entry_count;
+      const B2QPlan first = p;
+      p.entry_count = total;
+      if (p.output_columnar) { /* the offsets of the columnar layout follow the entry count (getColOffInBytes :918-955) */
+        int64_t off = align_to_int64(8 * p.entry_count);
+        for (int s = 0; s < p.num_slots; ++s) { p.slot_offset[s] = off; off += align_to_int64(static_cast<int64_t>(p.slot_padded_width[s]) * p.entry_count); }
+        p.buffer_size = off;
+      } else p.buffer_size = p.row_size * p.entry_count;
+      init_buffer(res->plan, res->buf);
+      for (int64_t e = 0; e < first.entry_count; ++e) { /* moveOneEntryToBuffer: claim the key's slot in the new table, copy the value slots */
+        if (is_empty_entry(first, sets[0]->buf.data(), e)) continue;
+        int64_t key = 0;
+        memcpy(&key, key_ptr(first, sets[0]->buf.data(), e, 0), first.effective_key_width);
+        int64_t dst;
+        if (p.output_columnar) dst = get_group_value_columnar_slot(reinterpret_cast<int64_t*>(res->buf.data()), static_cast<uint32_t>(p.entry_count), key);
+        else {
+          int64_t* slots = get_group_value(reinterpret_cast<int64_t*>(res->buf.data()), static_cast<uint32_t>(p.entry_count), &key, 1,
+                                           static_cast<uint32_t>(p.effective_key_width), static_cast<uint32_t>(p.row_size / 8));
+          dst = slots ? (reinterpret_cast<int8_t*>(slots) - res->buf.data()) / p.row_size : -1;
+        }
+        if (dst < 0) fail(B2Q_ERR_OUT_OF_SLOTS, "moveEntriesToBuffer: no slot");
+        for (int s = 0; s < p.num_slots; ++s)
+          if (p.slot_padded_width[s]) memcpy(slot_ptr(p, res->buf.data(), dst, s), slot_ptr(first, sets[0]->buf.data(), e, s), p.slot_padded_width[s]);
+      }
+    } else {
+      res->buf = sets[0]->buf;
+    }
+    for (int i = 1; i < n; ++i) {
+      const int32_t rc = reduce_buffers(res->plan, res->buf, sets[i]->buf, &sets[i]->plan.p);
+      if (rc) fail(rc, "ResultSetStorage::reduce");
+    }
+    *out = res.release();
     return 0;
   } catch (const OracleError& e) {
     g_last_error = e.msg;

@@ -62,6 +62,11 @@ def lib():
         L.oracle_set_thread_pinning.argtypes = [C.c_int32]
         L.oracle_gen_fragments.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GenCol), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                            C.c_int32, C.c_uint64, C.c_int32]
+        L.oracle_result_from_storage.restype = C.c_int32
+        L.oracle_result_from_storage.argtypes = [C.POINTER(abi.ExecUnit), C.POINTER(abi.TableInfo), C.POINTER(abi.ExecutionOptions),
+                                                 C.c_size_t, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.oracle_result_sets_reduce.restype = C.c_int32
+        L.oracle_result_sets_reduce.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
         _lib = L
     return _lib
 
@@ -187,6 +192,31 @@ def execute_generated(unit: abi.BuiltUnit, table: abi.Table, gen_cols, seed, row
     eo = make_eo(bigint_count, output_columnar=output_columnar)
     rc = lib().oracle_execute_generated(C.byref(unit.unit), C.byref(bt.info), C.byref(eo), entry_guess, int(has_card), num_threads,
                                         seed, arr, rows_per_fragment_id, C.byref(h))
+    if rc:
+        raise OracleError(rc, lib().oracle_last_error().decode())
+    return OracleResult(h)
+
+
+def result_from_storage(unit: abi.BuiltUnit, table: abi.Table, storage: np.ndarray, entry_guess=0, has_card=False,
+                        bigint_count=False, output_columnar=False) -> OracleResult:
+    """ResultSet(targets, device_type, query_mem_desc, ...) + allocateStorage() over bytes the caller filled
+    (Tests/ResultSetTest.cpp:879-894): the descriptor is the planned query's."""
+    bt = table.build(abi.CPU_LEVEL)
+    h = C.c_void_p()
+    eo = make_eo(bigint_count, output_columnar=output_columnar)
+    buf = np.ascontiguousarray(storage).view(np.uint8)
+    rc = lib().oracle_result_from_storage(C.byref(unit.unit), C.byref(bt.info), C.byref(eo), entry_guess, int(has_card),
+                                          buf.ctypes.data, buf.size, C.byref(h))
+    if rc:
+        raise OracleError(rc, lib().oracle_last_error().decode())
+    return OracleResult(h)
+
+
+def reduce_result_sets(results) -> OracleResult:
+    """ResultSetManager::reduce (ResultSetReduction.cpp:1055-1140) over result sets of one descriptor."""
+    arr = (C.c_void_p * len(results))(*[r.h for r in results])
+    h = C.c_void_p()
+    rc = lib().oracle_result_sets_reduce(arr, len(results), C.byref(h))
     if rc:
         raise OracleError(rc, lib().oracle_last_error().decode())
     return OracleResult(h)
