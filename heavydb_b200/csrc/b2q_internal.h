@@ -210,7 +210,7 @@ struct DevLayout {
   int32_t touched_acc;   /* accumulator whose value != 0 marks a non-empty entry (non-keyless layouts) */
   int32_t keyless_marker;/* keyless: slot index whose init value marks an empty entry (idx_target_as_key), else -1 */
   int32_t n_keys;        /* > 1: multi-column perfect hash */
-  int32_t pad_k_;
+  int32_t touch_via_acc; /* accumulator (COUNT / integer SUM updated by every passing row) whose non-zero value also marks the entry, or -1 */
   DevKeyComp keys[B2Q_MAX_GROUP_COLS];
   int8_t has_key_col;    /* row starts with the group key(s) (non-keyless) */
   int8_t key_width;      /* 4 or 8 */
@@ -248,7 +248,7 @@ struct DevLaunch {
   const int64_t* frag_rows;        /* [n_frags] device */
   const int64_t* frag_chunk_start; /* [n_frags + 1] device: prefix sum of chunks per fragment */
   int32_t n_frags;
-  int32_t pad_;
+  int32_t split;                   /* HBM-table kernels: COUNT / integer SUM arrays are (lo[n] | hi[n]) 32-bit halves (1) or plain int64[] (0) */
   int64_t total_chunks;
   int64_t* accs[B2Q_MAX_ACCS];     /* dense accumulator arrays in HBM */
   int64_t* keys;                   /* baseline: open-addressing key array (EMPTY_KEY_64 initialised) */
@@ -308,4 +308,5 @@ struct B2QQuery {
   B2QOrderEntry order[B2Q_MAX_ORDER_ENTRIES];
   int32_t has_limit;
   int64_t limit, offset;
+  int64_t total_tuples;          /* rows of all fragments of the table (every device's) */
 };

@@ -25,7 +25,6 @@
 #include <mutex>
 #include <string>
 #include <thread>
-#include <chrono>
 #include <vector>
 
 #include "b2q_internal.h"
@@ -100,6 +99,29 @@ static bool have_device() {
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return false; }
   return n > 0;
 }
+
+/* B2Q_TRACE=1: wall-clock marks of one b2q_execute_work_unit call on stderr (where the host side of a step goes) */
+struct CallTrace {
+  bool on = false;
+  std::chrono::steady_clock::time_point last;
+  std::string line;
+  void begin() {
+    static const bool knob = []() { const char* e = getenv("B2Q_TRACE"); return e && atoi(e) != 0; }();
+    on = knob;
+    line.clear();
+    last = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof(buf), " %s %.0f us |", what, std::chrono::duration<double, std::micro>(now - last).count());
+    line += buf;
+    last = now;
+  }
+  void end() { if (on) fprintf(stderr, "[b2q]%s\n", line.c_str()); on = false; }
+};
+static thread_local CallTrace g_trace;
 
 /* ---------------------------------------------------------------------------------------------------------- */
 /* All device memory of one query comes from the CUDA stream-ordered pool in ONE allocation (the pool keeps freed
@@ -282,6 +304,7 @@ static size_t table_bytes(const B2QQuery& q) {
   return total;
 }
 
+static bool split_layout(const B2QQuery& q, bool radix);
 static int32_t alloc_partial(B2QPartial& p, size_t extra_bytes, cudaStream_t st) {
   const B2QQuery& q = p.q;
   configure_pool_once(p.device);
@@ -296,7 +319,7 @@ static int32_t alloc_partial(B2QPartial& p, size_t extra_bytes, cudaStream_t st)
   if (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL) p.keys = reinterpret_cast<int64_t*>(p.blk.take(n * 8));
   if (q.smem.use_smem) p.smem_image = p.blk.take(std::max<int>(q.smem.replica_bytes, 16));
   p.d_error = reinterpret_cast<int32_t*>(p.blk.take(256));
-  p.split = q.plan.kernel == B2Q_KERNEL_PERFECT_GLOBAL || (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL && !p.radix);
+  p.split = split_layout(q, p.radix);
   for (auto& e : p.ev) CU(cudaEventCreate(&e));
   CU(cudaMemsetAsync(p.d_error, 0, sizeof(int32_t), st));
   CU(cudaEventRecord(p.ev[0], st));
@@ -405,6 +428,7 @@ static int32_t scan_device_fragments(B2QPartial& p, int nf, const std::vector<co
   L.keys = p.keys;
   L.error = p.d_error;
   L.join_buff = p.join_buff;
+  L.split = p.split ? 1 : 0;
   if (p.radix) {
     const int32_t rc = radix_prepare(p, L.total_chunks, st);
     if (rc != B2Q_OK) return rc;
@@ -422,7 +446,26 @@ static int32_t scan_device_fragments(B2QPartial& p, int nf, const std::vector<co
   return B2Q_OK;
 }
 
-/* global-table kernels keep COUNT / integer SUM as (lo[n] | hi[n]); everything downstream (NCCL merge,
+/* HBM-table kernels: COUNT / integer SUM either as plain int64 words updated with RED.ADD.64, or — when those words would not
+ * stay L2-resident next to the column stream — as (lo[n] | hi[n]) halves of which only the low words are hot (a returning 32-bit
+ * atomic + the rare carry).  Measured on 1e9 rows over 1e7 groups (tools/atom_bench.cu, profiles/r2_atom_bench.txt): 80 MB of
+ * 8-byte words 7.5 ms, 40 MB of low words 9.8 ms; the 126 MB L2 holds the former, two such accumulators it would not. */
+static bool split_layout(const B2QQuery& q, bool radix) {
+  if (!(q.plan.kernel == B2Q_KERNEL_PERFECT_GLOBAL || (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL && !radix))) return false;
+  static const int knob = []() { const char* e = getenv("B2Q_GLOBAL_SPLIT"); return e ? atoi(e) : -1; }();
+  if (knob >= 0) return knob != 0;
+  int64_t hot = 0;
+  for (int a = 0; a < q.prog.n_accs; ++a) {
+    const int op = q.prog.accs[a].op;
+    if (op == ACC_COUNT || op == ACC_SUM_I64) hot += q.plan.entry_count * 8;
+    else if (op == ACC_TOUCH) hot += q.plan.entry_count;
+  }
+  /* without the returning atomic the touched flag rests on "a value in [1, 2^31) cannot sum to zero": fewer than 2^32 rows */
+  if (q.prog.touch_piggyback >= 0 && q.total_tuples >= (int64_t(1) << 32)) return true;
+  return hot > (int64_t(96) << 20);
+}
+
+/* the split layout is folded to plain int64 before anything downstream (NCCL merge,
  * materialise) wants plain int64 */
 static int32_t normalize_partial(B2QPartial& p, cudaStream_t st) {
   if (!p.split) return B2Q_OK;
@@ -564,6 +607,7 @@ static int32_t scan_host_table(B2QPartial& p, const B2QTableInfo& tbl, const B2Q
     L.keys = p.keys;
     L.error = p.d_error;
     L.join_buff = p.join_buff;
+    L.split = p.split ? 1 : 0;
     if (p.radix) {
       rc = radix_launch(p, L, st);
       if (rc != B2Q_OK) break;
@@ -736,6 +780,7 @@ static int32_t execute_partial_attempt(size_t* guess, const B2QTableInfo* tbl, c
   const size_t g = guess ? *guess : 0;
   int32_t rc = make_query(u, tbl, eo, g, has_card != 0, !co->ignore_deleted_column, &p->q, &err);
   if (rc != B2Q_OK) return set_err(rc, err);
+  g_trace.mark("plan");
   if (!have_device()) return set_err(B2Q_ERR_NO_DEVICE, "no CUDA device visible; this path has no CPU fallback");
   if (eo->device_ordinal >= 0) CU(cudaSetDevice(eo->device_ordinal));
   CU(cudaGetDevice(&p->device));
@@ -743,6 +788,7 @@ static int32_t execute_partial_attempt(size_t* guess, const B2QTableInfo* tbl, c
   const size_t extra = tbl->memory_level == B2Q_GPU_LEVEL ? launch_table_bytes(tbl->num_fragments, p->q.prog.n_cols) : 0;
   rc = alloc_partial(*p, extra, st);
   if (rc != B2Q_OK) return rc;
+  g_trace.mark("alloc+init");
   rc = prepare_join(*p, *u, st);
   if (rc != B2Q_OK) return rc;
   const B2QQuery& q = p->q;
@@ -773,6 +819,7 @@ static int32_t execute_partial_attempt(size_t* guess, const B2QTableInfo* tbl, c
   }
   rc = normalize_partial(*p, st);
   if (rc != B2Q_OK) return rc;
+  g_trace.mark("scan enqueued");
   if (defer && tbl->memory_level == B2Q_GPU_LEVEL) {
     p->h_err = reinterpret_cast<int32_t*>(pinned_cache().get(64, &p->h_err_cap));
     if (!p->h_err) return set_err(B2Q_ERR_INVALID_ARGUMENT, "out of (pinned) host memory");
@@ -997,12 +1044,15 @@ static int32_t finalize_core(B2QPartial* p, cudaStream_t st, B2QResultSet** out)
   if (nbytes) {
     rs->buf = pinned_cache().get(nbytes, &rs->buf_cap);
     if (!rs->buf) return set_err(B2Q_ERR_INVALID_ARGUMENT, "out of (pinned) host memory for the result buffer");
+    g_trace.mark("pinned buffer");
     int8_t* d_out = nullptr;
     CU(cudaMallocAsync(reinterpret_cast<void**>(&d_out), nbytes, st));
     cudaError_t e = launch_materialize(p->q, p->accs, p->keys, d_out, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(rs->buf, d_out, nbytes, cudaMemcpyDeviceToHost, st);
     cudaFreeAsync(d_out, st);
+    g_trace.mark("materialise + D2H enqueued");
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    g_trace.mark("stream synchronize");
     if (e != cudaSuccess) { cudaGetLastError(); return set_err(B2Q_ERR_CUDA, std::string("materialise: ") + cudaGetErrorString(e)); }
   }
   *out = rs.release();
@@ -1213,14 +1263,17 @@ int32_t b2q_execute_work_unit(size_t* guess, int32_t is_agg, const B2QTableInfo*
                               B2QResultSet** out) {
   (void)is_agg;
   CallerDevice restore;
+  g_trace.begin();
   for (int attempt = 0; attempt < 2; ++attempt) {
     B2QPartial* p = nullptr;
     int32_t rc = execute_partial_attempt(guess, tbl, u, co, eo, has_card, nullptr, attempt == 0 && radix_enabled(), true, &p);
     if (rc == B2Q_OK) {
       rc = finalize_impl(p, nullptr, out);
+      g_trace.mark("finalize");
       delete p;
+      g_trace.mark("release");
     }
-    if (rc != B2Q_RADIX_RETRY) return rc;
+    if (rc != B2Q_RADIX_RETRY) { g_trace.end(); return rc; }
   }
   return set_err(B2Q_ERR_CUDA, "internal: radix retry did not converge");
 }

@@ -147,14 +147,14 @@ __global__ void b2q_k_materialize(const __grid_constant__ MatArgs A) {
         mkey_stored[c] = is_null_comp ? kc.null_stored : kc.min_val + comp * kc.step; /* a NULL key is stored translated: max + (bucket ? bucket : 1) */
         mkey_proj[c] = is_null_comp ? kc.null_logical : kc.min_val + comp * kc.step;
       }
-      if (L.touched_acc >= 0) touched = reinterpret_cast<const uint8_t*>(A.accs[L.touched_acc])[i] != 0;
+      if (L.touched_acc >= 0) touched = reinterpret_cast<const uint8_t*>(A.accs[L.touched_acc])[i] != 0 || (L.touch_via_acc >= 0 && A.accs[L.touch_via_acc][i] != 0);
     } else if (L.baseline) {
       key = A.keys[i];
       touched = key != B2Q_I64_MAX;
       if (touched && L.key_width == 4) key = (int64_t)(int32_t)key;
     } else {
       key = (i == L.null_idx) ? L.key_null_val : L.key_min + i * L.key_step;
-      if (L.touched_acc >= 0) touched = reinterpret_cast<const uint8_t*>(A.accs[L.touched_acc])[i] != 0;
+      if (L.touched_acc >= 0) touched = reinterpret_cast<const uint8_t*>(A.accs[L.touched_acc])[i] != 0 || (L.touch_via_acc >= 0 && A.accs[L.touch_via_acc][i] != 0);
     }
     if (L.has_key_col && L.columnar) {
       /* int64 key columns (initColumnarGroups, QueryMemoryInitializer.cpp:729-735; keys written by
@@ -298,8 +298,7 @@ cudaError_t launch_scan(const B2QQuery& q, const DevLaunch& launch, const int8_t
   a.smem = q.smem;
   a.smem_image = smem_image;
   a.prefetch_distance = prefetch_distance;
-  static const bool wp_knob = []() { const char* e = getenv("B2Q_WARP_PRIVATE"); return !e || atoi(e) != 0; }();
-  a.warp_private = (wp_knob && q.smem.use_smem && q.smem.replicas >= block / 32) ? 1 : 0;
+  a.pad_ = 0;
   a.ndv_bitmap_bytes = q.plan.query_desc_type == B2Q_Estimator ? q.plan.buffer_size : 0;
   ScanConfig c;
   c.block = block;

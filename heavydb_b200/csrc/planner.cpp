@@ -152,6 +152,8 @@ class Planner {
     q.has_limit = u_.has_limit ? 1 : 0;
     q.limit = u_.limit;
     q.offset = u_.offset;
+    q.total_tuples = 0;
+    for (int f = 0; f < t_.num_fragments; ++f) q.total_tuples += t_.fragments[f].num_tuples;
   }
 
  private:
@@ -1369,6 +1371,7 @@ class Planner {
       EL.entry_count = 1;
       EL.n_slots = 0;
       EL.touched_acc = -1;
+      EL.touch_via_acc = -1;
       EL.keyless_marker = -1;
       for (int t = 0; t < g.filter.n_terms; ++t) { g.col_prefetch[g.filter.terms[t].col] = 1; if (g.filter.terms[t].col2 >= 0) g.col_prefetch[g.filter.terms[t].col2] = 1; }
       if (join_) g.col_prefetch[g.join.fk_col] = 1;
@@ -1432,6 +1435,7 @@ class Planner {
     L.key_width = static_cast<int8_t>(p.effective_key_width);
     L.baseline = p.query_desc_type == B2Q_GroupByBaselineHash;
     L.touched_acc = -1;
+    L.touch_via_acc = -1;
     L.n_keys = g.n_keys;
     for (int i = 0; i < g.n_keys; ++i) {
       L.keys[i] = g.keys[i];
@@ -1575,10 +1579,15 @@ class Planner {
     g.touch_acc = static_cast<int8_t>(L.touched_acc);
     g.touch_piggyback = -1;
     if (L.touched_acc >= 0)
-      for (int a = 0; a < g.n_accs; ++a) {
-        const DevAcc& c = g.accs[a];
-        if ((c.op == ACC_COUNT || c.op == ACC_SUM_I64) && !c.skip1_en && !c.skip2_en) { g.touch_piggyback = static_cast<int8_t>(a); break; }
+      for (int want : {ACC_COUNT, ACC_SUM_I64}) { /* a COUNT first: it is non-zero for every touched group whatever the values */
+        for (int a = 0; a < g.n_accs && g.touch_piggyback < 0; ++a) {
+          const DevAcc& c = g.accs[a];
+          if (c.op == want && !c.skip1_en && !c.skip2_en) g.touch_piggyback = static_cast<int8_t>(a);
+        }
       }
+    /* materialise: an entry is touched when its flag is set OR this accumulator is non-zero (the HBM-table kernels with plain
+     * 8-byte words only flag the rows whose value could leave the sum at zero: see global_split_add_touch) */
+    L.touch_via_acc = g.touch_piggyback;
   }
 
   void choose_kernel(B2QQuery& q) {

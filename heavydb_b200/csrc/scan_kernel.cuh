@@ -418,7 +418,22 @@ __device__ __forceinline__ uint32_t global_split_add(int64_t* arr, uint32_t e, i
 /* "group touched" flag piggy-backed on an accumulator that every passing row updates: the FIRST atomic on an entry
  * always returns the initial 0, so storing the flag whenever 0 comes back marks every touched group and costs no
  * extra L2 request for the (overwhelmingly common) rows that see a non-zero running value. */
+/* n < 0: the array is a plain int64[] (the table is small enough to stay L2-resident as 8-byte words): one RED.ADD.64 without a
+ * return trip — tools/atom_bench.cu, 1e9 rows over 1e7 groups: 7.5 ms against 9.8 ms for the returning 32-bit atomic on the
+ * split layout, and a flag byte read per row would give that back: 9.8 - 11.3 ms (profiles/r2_atom_bench.txt). */
 __device__ __forceinline__ void global_split_add_touch(int64_t* arr, uint8_t* flags, uint32_t e, int64_t n, uint32_t vl, int32_t vh, uint64_t pol_tab) {
+  if (n < 0) {
+    const uint64_t v = ((uint64_t)(uint32_t)vh << 32) + vl;
+    red_add_u64(arr + e, v);
+    /* touched = flag OR accumulator != 0 (b2q_k_materialize): a value in [1, 2^31) cannot leave the sum at zero while the launch
+     * set holds fewer than 2^32 rows (the executor checks), so only the other rows keep the flag — for a COUNT, none */
+    if (flags && v - 1 >= 0x7FFFFFFFull) {
+      uint32_t w;
+      asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(w) : "l"(flags + e));
+      if (!w) flags[e] = 1;
+    }
+    return;
+  }
   const uint32_t old = global_split_add(arr, e, n, vl, vh, pol_tab);
   if (flags && old == 0) flags[e] = 1;
 }
@@ -539,7 +554,7 @@ struct ScanArgs {
   SmemPlan smem;
   const int8_t* smem_image; /* identity image of ONE replica in HBM (MODE_SMEM) */
   int32_t prefetch_distance; /* > 0: TMA bulk-prefetch the column slabs of the chunk this CTA will scan D iterations ahead into L2 */
-  int32_t warp_private;      /* MODE_SMEM: every warp of the CTA has a replica of the group table to itself */
+  int32_t pad_;
   int64_t ndv_bitmap_bytes;  /* estimator query: size of the ACC_NDV bitmap (a power of two) */
 };
 
@@ -798,27 +813,9 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       int64_t v[R];
       load64<true>(v, cols[sa.col], row0, nthr, arg_mask, pol, JX(sa.col));
       double* dsum = reinterpret_cast<double*>(sum_tab);
-      if (A.warp_private) {
-        /* the replica belongs to this warp alone: plain read-modify-write instead of the ATOMS.CAST.SPIN loop a shared
-         * double add compiles to.  Only lanes of THIS warp can collide: MATCH.ANY groups the lanes of a row by entry, the
-         * k-th lane of every group goes in round k (mostly one round: 32 lanes over 256 entries collide in ~2 pairs). */
-        const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const bool act = pass >> j & 1;
-          const uint32_t peers = __match_any_sync(0xffffffffu, act ? e[j] : (0xFFFFFF00u | (uint32_t)lane));
-          const uint32_t rank = __popc(peers & lt);
-          const uint32_t rounds = __reduce_max_sync(0xffffffffu, rank);
-          for (uint32_t r = 0; r <= rounds; ++r) {
-            if (act && rank == r) {
-              dsum[e[j]] += __longlong_as_double(v[j]);
-              if (ic >= 0) cnt_tab[e[j]] += 1u;
-            }
-            __syncwarp();
-          }
-        }
-        return;
-      }
+      /* (measured and dropped: plain LDS / DADD / STS on the warp-private replica, lanes of a row grouped by entry with
+       * MATCH.ANY and serialised by rank — 8.2 ms against 3.5 ms for this CAS loop on C3: MATCH.ANY + REDUX per row costs
+       * more than the ATOMS.CAST.SPIN it saves) */
 #pragma unroll
       for (int j = 0; j < R; ++j)
         if (pass >> j & 1) {
@@ -872,6 +869,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
     int8_t* tab = (MODE == MODE_SMEM) ? my_tab + A.smem.acc_off[a] : nullptr;
     /* flags array when THIS accumulator carries the touched flag for the global-table kernels */
     uint8_t* pig = (MODE != MODE_SMEM && P.touch_piggyback == a) ? reinterpret_cast<uint8_t*>(Lh.accs[P.touch_acc]) : nullptr;
+    const int64_t n_split = Lh.split ? P.key.entry_count : int64_t(-1); /* (lo[n] | hi[n]) layout of COUNT / integer SUM, or plain int64[] */
 
     if (op == ACC_NDV) {
       /* estimator query: linear_probabilistic_count (RuntimeFunctions.cpp:2399-2408, cuda_mapd_rt.cu:1300-1308) over
@@ -950,7 +948,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         for (int j = 0; j < R; ++j) smem_inc_pred(tab32 + e[j] * 4u, pass >> j & 1);
       } else {
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (pass >> j & 1) global_split_add_touch(garr, pig, e[j], P.key.entry_count, 1u, 0, pol_tab);
+        for (int j = 0; j < R; ++j) if (pass >> j & 1) global_split_add_touch(garr, pig, e[j], n_split, 1u, 0, pol_tab);
       }
       continue;
     }
@@ -1010,7 +1008,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, pig, e[j], P.key.entry_count, (int64_t)v[j], pol_tab);
+        for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, pig, e[j], n_split, (int64_t)v[j], pol_tab);
       }
       continue;
     }
@@ -1093,7 +1091,7 @@ __device__ __forceinline__ void process_chunk(const ScanArgs& A, const int8_t* c
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, pig, e[j], P.key.entry_count, v[j], pol_tab);
+      for (int j = 0; j < R; ++j) if (m >> j & 1) global_update(op, garr, pig, e[j], n_split, v[j], pol_tab);
     }
   }
 }

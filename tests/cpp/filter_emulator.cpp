@@ -253,10 +253,10 @@ static int32_t run_program_impl(const B2QQuery* q, int32_t n_frags, const void* 
         mkey_stored[c] = is_null_comp ? kc.null_stored : kc.min_val + comp * kc.step;
         mkey_proj[c] = is_null_comp ? kc.null_logical : kc.min_val + comp * kc.step;
       }
-      if (L.touched_acc >= 0) touched = touch[i] != 0;
+      if (L.touched_acc >= 0) touched = touch[i] != 0 || (L.touch_via_acc >= 0 && accs[L.touch_via_acc][i] != 0);
     } else {
       key = (i == L.null_idx) ? L.key_null_val : L.key_min + i * L.key_step;
-      if (L.touched_acc >= 0) touched = touch[i] != 0;
+      if (L.touched_acc >= 0) touched = touch[i] != 0 || (L.touch_via_acc >= 0 && accs[L.touch_via_acc][i] != 0);
     }
     auto put64 = [](int8_t* p, int64_t v) { memcpy(p, &v, 8); };
     auto put32 = [](int8_t* p, int32_t v) { memcpy(p, &v, 4); };

@@ -11,6 +11,9 @@
  *   red64     red.add.u64 on an 8 B/group table (80 MB), evict_last policy on the table, evict_first on the stream
  *   red64n    the same without a cache policy on the table
  *   atom32x2  atom32 with 16 rows in flight per thread instead of 8
+ *   atom64    atom.add.u64 WITH return on the 8 B/group table (what a `touched` flag piggy-backed on the old value would need)
+ *   red64fb   red64 + a `touched` BYTE per group: ld.global.ca of the flag, st only when it reads 0 (10 MB of flags)
+ *   red64fw   red64 + a `touched` BIT per group: ld.global.ca of the word, atomicOr only when the bit reads 0 (1.25 MB)
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,11 +39,11 @@ __device__ __forceinline__ int64_t ld_stream(const int64_t* p, uint64_t pol) {
 }
 
 constexpr int BLOCK = 512;
-enum { V_STREAM, V_ATOM32, V_RED32, V_RED64, V_RED64N, V_ATOM32X2 };
+enum { V_STREAM, V_ATOM32, V_RED32, V_RED64, V_RED64N, V_ATOM32X2, V_ATOM64, V_RED64FB, V_RED64FW };
 
 template <int V, int R>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_agg(const int64_t* __restrict__ key, const int64_t* __restrict__ val, int64_t n,
-                                                             void* table, uint32_t G, unsigned long long* sink) {
+                                                             void* table, uint32_t G, unsigned long long* sink, uint8_t* flags) {
   uint64_t pol, polt;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(polt));
@@ -71,6 +74,33 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_agg(const int64_t* __re
     } else if (V == V_RED64) {
 #pragma unroll
       for (int j = 0; j < R; ++j) if (k[j] >= 0) asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(t64 + k[j]), "l"(v[j]), "l"(polt) : "memory");
+    } else if (V == V_ATOM64) {
+      unsigned long long old[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) { old[j] = 1; if (k[j] >= 0) old[j] = atomicAdd(t64 + k[j], (unsigned long long)v[j]); }
+#pragma unroll
+      for (int j = 0; j < R; ++j) if (old[j] == 0) flags[k[j]] = 1;
+    } else if (V == V_RED64FB) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) if (k[j] >= 0) asm volatile("red.global.add.u64 [%0], %1;" ::"l"(t64 + k[j]), "l"(v[j]) : "memory");
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (k[j] < 0) continue;
+        uint32_t w;
+        asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(w) : "l"(flags + k[j]));
+        if (!w) flags[k[j]] = 1;
+      }
+    } else if (V == V_RED64FW) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) if (k[j] >= 0) asm volatile("red.global.add.u64 [%0], %1;" ::"l"(t64 + k[j]), "l"(v[j]) : "memory");
+      uint32_t* bits = reinterpret_cast<uint32_t*>(flags);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (k[j] < 0) continue;
+        uint32_t w;
+        asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(w) : "l"(bits + (k[j] >> 5)));
+        if (!(w >> (k[j] & 31) & 1)) atomicOr(bits + (k[j] >> 5), 1u << (k[j] & 31));
+      }
     } else if (V == V_RED64N) {
 #pragma unroll
       for (int j = 0; j < R; ++j) if (k[j] >= 0) asm volatile("red.global.add.u64 [%0], %1;" ::"l"(t64 + k[j]), "l"(v[j]) : "memory");
@@ -81,13 +111,16 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) k_agg(const int64_t* __re
 
 template <int V, int R>
 static void run(const char* name, const int64_t* key, const int64_t* val, int64_t n, void* table, size_t table_bytes, uint32_t G, unsigned long long* sink, int sms) {
+  static uint8_t* flags = nullptr;
+  if (!flags) CK(cudaMalloc(&flags, (size_t)G + 64));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   float best = 1e9f;
   for (int rep = 0; rep < 4; ++rep) {
     CK(cudaMemsetAsync(table, 0, table_bytes));
+    CK(cudaMemsetAsync(flags, 0, (size_t)G + 64));
     CK(cudaEventRecord(e0));
-    k_agg<V, R><<<sms * (1024 / BLOCK), BLOCK>>>(key, val, n, table, G, sink);
+    k_agg<V, R><<<sms * (1024 / BLOCK), BLOCK>>>(key, val, n, table, G, sink, flags);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -117,7 +150,8 @@ int main(int argc, char** argv) {
   run<V_RED64, 8>("red64", key, val, n, table, table_bytes, G, sink, sms);
   run<V_RED64N, 8>("red64n", key, val, n, table, table_bytes, G, sink, sms);
   run<V_ATOM32X2, 16>("atom32x2", key, val, n, table, table_bytes, G, sink, sms);
-  run<V_RED32, 16>("red32", key, val, n, table, table_bytes, G, sink, sms);
-  run<V_RED64, 16>("red64", key, val, n, table, table_bytes, G, sink, sms);
+  run<V_ATOM64, 8>("atom64", key, val, n, table, table_bytes, G, sink, sms);
+  run<V_RED64FB, 8>("red64fb", key, val, n, table, table_bytes, G, sink, sms);
+  run<V_RED64FW, 8>("red64fw", key, val, n, table, table_bytes, G, sink, sms);
   return 0;
 }
