@@ -446,23 +446,19 @@ static int32_t scan_device_fragments(B2QPartial& p, int nf, const std::vector<co
   return B2Q_OK;
 }
 
-/* HBM-table kernels: COUNT / integer SUM either as plain int64 words updated with RED.ADD.64, or — when those words would not
- * stay L2-resident next to the column stream — as (lo[n] | hi[n]) halves of which only the low words are hot (a returning 32-bit
- * atomic + the rare carry).  Measured on 1e9 rows over 1e7 groups (tools/atom_bench.cu, profiles/r2_atom_bench.txt): 80 MB of
- * 8-byte words 7.5 ms, 40 MB of low words 9.8 ms; the 126 MB L2 holds the former, two such accumulators it would not. */
+/* HBM-table kernels: COUNT / integer SUM as (lo[n] | hi[n]) halves of which only the low words are hot (a returning 32-bit
+ * atomic + the rare carry), so that a 1e7-group table is 40 MB of L2 next to the column stream.  The alternative — plain int64
+ * words updated with RED.ADD.64, no return trip — wins in isolation (tools/atom_bench.cu: 7.8 ms against 9.8 ms per 1e9 rows
+ * over 1e7 groups with an evict_last hint on the table) but not inside the scan kernel: configs[3] 11.6 ms against 9.9 ms, the
+ * 80 MB of words do not stay resident (11.7 GB of table sectors written back per 1e9 rows; 27 GB and 16.6 ms without the hint:
+ * profiles/r2_atom_bench*.{txt,csv}).  B2Q_GLOBAL_SPLIT=0 keeps that layout selectable for tables the cache does hold. */
 static bool split_layout(const B2QQuery& q, bool radix) {
   if (!(q.plan.kernel == B2Q_KERNEL_PERFECT_GLOBAL || (q.plan.kernel == B2Q_KERNEL_BASELINE_GLOBAL && !radix))) return false;
-  static const int knob = []() { const char* e = getenv("B2Q_GLOBAL_SPLIT"); return e ? atoi(e) : -1; }();
-  if (knob >= 0) return knob != 0;
-  int64_t hot = 0;
-  for (int a = 0; a < q.prog.n_accs; ++a) {
-    const int op = q.prog.accs[a].op;
-    if (op == ACC_COUNT || op == ACC_SUM_I64) hot += q.plan.entry_count * 8;
-    else if (op == ACC_TOUCH) hot += q.plan.entry_count;
-  }
+  static const int knob = []() { const char* e = getenv("B2Q_GLOBAL_SPLIT"); return e ? atoi(e) : 1; }();
+  if (knob != 0) return true;
   /* without the returning atomic the touched flag rests on "a value in [1, 2^31) cannot sum to zero": fewer than 2^32 rows */
   if (q.prog.touch_piggyback >= 0 && q.total_tuples >= (int64_t(1) << 32)) return true;
-  return hot > (int64_t(96) << 20);
+  return false;
 }
 
 /* the split layout is folded to plain int64 before anything downstream (NCCL merge,

@@ -424,7 +424,9 @@ __device__ __forceinline__ uint32_t global_split_add(int64_t* arr, uint32_t e, i
 __device__ __forceinline__ void global_split_add_touch(int64_t* arr, uint8_t* flags, uint32_t e, int64_t n, uint32_t vl, int32_t vh, uint64_t pol_tab) {
   if (n < 0) {
     const uint64_t v = ((uint64_t)(uint32_t)vh << 32) + vl;
-    red_add_u64(arr + e, v);
+    /* evict_last on the table is what keeps its 8-byte words L2-resident next to the evict_first column stream: without the hint
+     * the same kernel writes 20 - 27 GB of table sectors back to DRAM per 1e9 rows (profiles/r2_atom_bench_ncu.csv) */
+    asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(arr + e), "l"(v), "l"(pol_tab) : "memory");
     /* touched = flag OR accumulator != 0 (b2q_k_materialize): a value in [1, 2^31) cannot leave the sum at zero while the launch
      * set holds fewer than 2^32 rows (the executor checks), so only the other rows keep the flag — for a COUNT, none */
     if (flags && v - 1 >= 0x7FFFFFFFull) {
