@@ -455,6 +455,10 @@ __device__ __noinline__ int bucket_find(int64_t* s_keys, uint32_t nb_mask, uint3
   return -1;
 }
 
+/* TWT: tuple words known at compile time (1 or 2), 0 = read from the arguments; FUSED: the program is {one COUNT(*) or integer SUM
+ * without a NULL test} — one predicated ATOMS per tuple, no accumulator loop.  (ncu's source view of the one generic kernel: ~20 %
+ * of its warp instructions were selects between the two tuple formats and re-reads of these loop invariants.) */
+template <int TWT, bool FUSED>
 __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __grid_constant__ RadixArgs A) {
   extern __shared__ __align__(128) int8_t s_raw[];
   const DevProgram& P = A.prog;
@@ -474,11 +478,10 @@ __global__ void __launch_bounds__(kRadixBlock, 1) b2q_k_radix_aggregate(const __
   const uint32_t n = (uint32_t)P.key.entry_count;
   const uint64_t magic = P.key.hash_magic;
   const int hw = P.key.hash_key_width;
-  const int tw = A.tuple_words;
+  const int tw = TWT ? TWT : A.tuple_words;
   const int n_cta1 = A.n_cta1;
   const uint32_t nb_mask = S / kBucket - 1;
-  /* the program is {one COUNT(*) or integer SUM without a NULL test}: one predicated ATOMS per tuple, no accumulator loop */
-  const bool fused = n_accs == 1 && A.acc_bytes[0] == 4 && !P.accs[0].skip1_en && !P.accs[0].skip2_en && tw <= 2;
+  constexpr bool fused = FUSED;
   const bool fused_count = fused && P.accs[0].op == ACC_COUNT;
   uint64_t pol;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -795,10 +798,14 @@ cudaError_t launch_radix(const B2QQuery& q, const RadixPlan& rp, const DevLaunch
     int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, b2q_k_radix_aggregate);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(b2q_k_radix_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
-    if (e != cudaSuccess) return e;
+    const void* fns2[3] = {reinterpret_cast<const void*>(b2q_k_radix_aggregate<0, false>), reinterpret_cast<const void*>(b2q_k_radix_aggregate<1, true>),
+                           reinterpret_cast<const void*>(b2q_k_radix_aggregate<2, true>)};
+    for (const void* f : fns2) {
+      cudaError_t e = cudaFuncGetAttributes(&fa, f);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+      if (e != cudaSuccess) return e;
+    }
     attr_mask.fetch_or(1ull << dev, std::memory_order_release);
   }
   cudaError_t e = cudaMemsetAsync(buf.work_counter, 0, 8, st);
@@ -831,7 +838,11 @@ cudaError_t launch_radix(const B2QQuery& q, const RadixPlan& rp, const DevLaunch
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int grid2 = std::max(1, std::min(sm_count(), rp.n_parts));
-  b2q_k_radix_aggregate<<<grid2, kRadixBlock, smem2, st>>>(a);
+  const DevProgram& P = q.prog;
+  const bool fused = P.n_accs == 1 && rp.acc_bytes[0] == 4 && !P.accs[0].skip1_en && !P.accs[0].skip2_en && rp.tuple_words <= 2;
+  if (fused && rp.tuple_words == 2) b2q_k_radix_aggregate<2, true><<<grid2, kRadixBlock, smem2, st>>>(a);
+  else if (fused) b2q_k_radix_aggregate<1, true><<<grid2, kRadixBlock, smem2, st>>>(a);
+  else b2q_k_radix_aggregate<0, false><<<grid2, kRadixBlock, smem2, st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return cudaGetLastError();

@@ -237,6 +237,43 @@ def test_random_table_forced_global_and_host():
         gu.run_both(unit, table, entry_guess=3001, has_card=True, device_resident=False)
 
 
+def test_plain_word_layout_of_the_hbm_table_kernels():
+    """B2Q_GLOBAL_SPLIT=0 (read once per process, hence the child): COUNT / integer SUM of the HBM-table kernels as plain int64
+    words updated with RED.ADD.64, the touched flag derived at materialise (flag | accumulator != 0) — same rows, same buffers."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B2Q_GLOBAL_SPLIT="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
+                        "tests/test_gpu_parity.py::test_random_table_forced_global_and_host",
+                        "tests/test_gpu_parity.py::test_touched_flag_cases_of_the_global_kernels"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+def test_touched_flag_cases_of_the_global_kernels():
+    """Keyed perfect-hash groups whose SUM is zero (all-zero values, cancelling values, a single zero) must still come out as
+    groups, and untouched entries must not: the HBM-table kernels see them through the touched flag."""
+    n = 4000
+    rng = np.random.default_rng(77)
+    k = rng.integers(0, 50, n).astype(np.int64)
+    v = rng.integers(-3, 4, n).astype(np.int64)
+    v[k == 7] = 0                      # group 7: only zeros
+    v[k == 9] = np.where(np.arange((k == 9).sum()) % 2 == 0, 5, -5)[: (k == 9).sum()]     # group 9: cancels (or +5)
+    keep = (k != 11) & (k != 12)       # groups 11 / 12 never appear: empty entries inside the range
+    k, v = k[keep], v[keep]
+    t = abi.Table([(abi.kBIGINT, True), (abi.kBIGINT, True)])
+    t.add_host_fragment([k, v])
+    for sql in ("SELECT k, SUM(v) FROM t GROUP BY k;", "SELECT k, SUM(v), MIN(v) FROM t GROUP BY k;",
+                "SELECT k, SUM(v) FROM t WHERE v <= 0 GROUP BY k;"):
+        unit = sqlmini.parse(sql, t, ["k", "v"])
+        p = executor.Executor().plan(unit, t)
+        assert p.query_desc_type == abi.GroupByPerfectHash and (not p.keyless_hash or "MIN" in sql)   # MIN(v) makes a keyless layout
+        gu.run_both(unit, t, force_kernel=abi.KERNEL_PERFECT_GLOBAL)
+        gu.run_both(unit, t)
+
+
 def test_baseline_out_of_slots():
     """Fewer entries than distinct keys: the reference returns -pos => OUT_OF_SLOTS (GroupByAndAggregate.cpp:1149-1154)."""
     table = random_table(5000, seed=9, frag_rows=5000)

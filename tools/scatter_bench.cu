@@ -11,6 +11,7 @@
  *   direct16L the same with an L2 evict_last policy on the stores
  *   pair32    tuples of a region are paired in shared memory (double-buffered parking slot) and leave as ONE 32-byte
  *             sector store (st.global.v4.b64): no partially written sector ever reaches L2
+ *   tile8kT   tile8k with the runs written by cp.async.bulk (TMA store) and not waited for: the next tile overlaps the drain
  *   tile      CTA-synchronous: a tile of rows is bucketed in shared memory (count, scan, place) and written out with
  *             consecutive lanes on consecutive tuples of a region (runs of ~tile/P tuples)
  */
@@ -183,6 +184,70 @@ __global__ void __launch_bounds__(BLOCK, 1) k_tile(const ulonglong2* in, ulonglo
   for (int i = threadIdx.x; i < P; i += BLOCK) counts[(size_t)i * gridDim.x + blockIdx.x] = min(s_cur[i], cap);
 }
 
+/* tileT: like tile, but the runs leave with ONE cp.async.bulk (TMA store, shared -> global) per partition instead of one
+ * 16-byte store per tuple, and the CTA does not wait for them: the next tile's loads, count + rank and scan run while the stores
+ * drain; only `place` (which overwrites the tile) waits for the bulk group to have READ its source. */
+template <int RT>
+__global__ void __launch_bounds__(BLOCK, 1) k_tile_tma(const ulonglong2* in, ulonglong2* out, int64_t n, uint32_t P, uint32_t cap, uint32_t* counts) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  constexpr int TILE = BLOCK * RT;
+  ulonglong2* tile = reinterpret_cast<ulonglong2*>(s_raw);
+  uint32_t* s_cur = reinterpret_cast<uint32_t*>(tile + TILE);
+  uint32_t* s_cnt = s_cur + P;
+  uint32_t* s_off = s_cnt + P;
+  __shared__ uint32_t s_warp[32];
+  for (int i = threadIdx.x; i < P; i += BLOCK) { s_cur[i] = 0; s_cnt[i] = 0; }
+  __syncthreads();
+  uint64_t pol; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t tile32 = (uint32_t)__cvta_generic_to_shared(tile);
+  for (int64_t base = (int64_t)blockIdx.x * TILE; base < n; base += (int64_t)gridDim.x * TILE) {
+    ulonglong2 v[RT];
+    uint32_t pr[RT], rk[RT];
+#pragma unroll
+    for (int j = 0; j < RT; ++j) { const int64_t i = base + threadIdx.x + (int64_t)j * BLOCK; v[j] = i < n ? ld_stream(in + i, pol) : make_ulonglong2(~0ull, 0); }
+#pragma unroll
+    for (int j = 0; j < RT; ++j) { pr[j] = v[j].x == ~0ull ? 0xFFFFFFFFu : part_of(v[j].x, P); rk[j] = pr[j] != 0xFFFFFFFFu ? atomicAdd(s_cnt + pr[j], 1u) : 0u; }
+    __syncthreads();
+    const int per = (P + BLOCK - 1) / BLOCK;
+    uint32_t loc = 0;
+    for (int q = 0; q < per; ++q) { const int i = threadIdx.x * per + q; if (i < (int)P) loc += s_cnt[i]; }
+    uint32_t inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) { uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      s_warp[lane] = w; }
+    /* the previous tile's bulk stores must have read the tile before `place` overwrites it */
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+    uint32_t run = inc - loc + (warp ? s_warp[warp - 1] : 0u);
+    for (int q = 0; q < per; ++q) { const int i = threadIdx.x * per + q; if (i < (int)P) { s_off[i] = run; run += s_cnt[i]; } }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RT; ++j) if (pr[j] != 0xFFFFFFFFu) tile[s_off[pr[j]] + rk[j]] = v[j];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy writes of the tile -> visible to the async proxy */
+    __syncthreads();
+    for (int p = threadIdx.x; p < (int)P; p += BLOCK) {
+      const uint32_t cnt = s_cnt[p], pos = s_cur[p];
+      const uint32_t ok = pos < cap ? min(cnt, cap - pos) : 0u;
+      if (ok) {
+        ulonglong2* dst = out + ((uint64_t)p * gridDim.x + blockIdx.x) * cap + pos;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tile32 + s_off[p] * 16u), "r"(ok * 16u) : "memory");
+      }
+      s_cur[p] = pos + cnt;
+      s_cnt[p] = 0;
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    __syncthreads();
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  for (int i = threadIdx.x; i < P; i += BLOCK) counts[(size_t)i * gridDim.x + blockIdx.x] = min(s_cur[i], cap);
+}
+
 __global__ void k_check(const ulonglong2* out, const uint32_t* counts, uint32_t P, uint32_t ncta, uint32_t cap, unsigned long long* sum, unsigned long long* cnt, unsigned long long* bad) {
   const uint64_t regions = (uint64_t)P * ncta;
   unsigned long long s = 0, c = 0, b = 0;
@@ -259,6 +324,9 @@ int main(int argc, char** argv) {
       const size_t sm8 = (size_t)BLOCK * 8 * 18 + (size_t)P * 12 + 16;
       CK(cudaFuncSetAttribute(k_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       if (sm8 <= 220 * 1024) { RUN("tile8k", (k_tile<8><<<ncta, BLOCK, sm8>>>(in, out, n, P, cap, counts)), true); }
+      const size_t smT = (size_t)BLOCK * 8 * 16 + (size_t)P * 12 + 16;
+      CK(cudaFuncSetAttribute(k_tile_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      if (smT <= 220 * 1024) { RUN("tile8kT", (k_tile_tma<8><<<ncta, BLOCK, smT>>>(in, out, n, P, cap, counts)), true); }
     }
   }
   return 0;
