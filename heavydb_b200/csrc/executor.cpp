@@ -1105,17 +1105,22 @@ static int32_t b2q_baseline_merge(B2QPartial& p, const B2QComm* comm, const Nccl
   const int64_t E = q.plan.entry_count;
   const int na = q.prog.n_accs;
   const size_t arr = static_cast<size_t>(E) * 8;
+  /* per-rank bytes of every gathered array: int64[E], except the COUNT(DISTINCT) bitmaps ([E][bm_words] 32-bit words) */
+  size_t bytes_of[B2Q_MAX_ACCS], total = arr;
+  for (int a = 0; a < na; ++a) { bytes_of[a] = DeviceBlock::pad(acc_array_bytes(q, a)); total += bytes_of[a]; }
   int8_t* stage = nullptr;
-  CU(cudaMallocAsync(reinterpret_cast<void**>(&stage), arr * comm->nranks * (1 + na) + 256, st));
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&stage), total * comm->nranks + 256, st));
   p.extra.push_back(stage);
   const int64_t* g_keys = reinterpret_cast<const int64_t*>(stage);
   const int64_t* g_accs[B2Q_MAX_ACCS];
   NC(api->GroupStart());
   NC(api->AllGather(p.keys, stage, static_cast<size_t>(E), ncclInt64, comm->comm, st));
+  int8_t* dst = stage + arr * comm->nranks;
   for (int a = 0; a < na; ++a) {
-    int8_t* dst = stage + arr * comm->nranks * (1 + a);
     g_accs[a] = reinterpret_cast<const int64_t*>(dst);
-    NC(api->AllGather(p.accs[a], dst, static_cast<size_t>(E), ncclInt64, comm->comm, st));
+    const size_t own = acc_array_bytes(q, a); /* the gathered blocks are packed at the array's own size: entry i of rank r sits at (r E + i) */
+    NC(api->AllGather(p.accs[a], dst, own, ncclUint8, comm->comm, st));
+    dst += bytes_of[a] * comm->nranks;
   }
   NC(api->AllReduce(p.d_error, p.d_error, 1, ncclInt32, ncclMax, comm->comm, st));
   NC(api->GroupEnd());

@@ -91,7 +91,7 @@ __device__ __forceinline__ bool value_skipped(const DevAcc& a, int64_t v) {
 }
 
 /* one raw tuple {key, vals[]} into the HBM table */
-__device__ __forceinline__ void global_insert_raw(const RadixArgs& A, int64_t key, const int64_t* vals) {
+__device__ __noinline__ void global_insert_raw(const RadixArgs& A, int64_t key, const int64_t* vals) { /* rare (skewed keys, a full private table): kept out of line so that the row loops stay small */
   const DevProgram& P = A.prog;
   const uint32_t n = (uint32_t)P.key.entry_count;
   const int64_t e = global_probe(reinterpret_cast<unsigned long long*>(A.launch.keys), n, home_slot(key, P.key.hash_key_width, P.key.hash_magic, n), key);
@@ -106,7 +106,7 @@ __device__ __forceinline__ void global_insert_raw(const RadixArgs& A, int64_t ke
 }
 
 /* the high-word delta of a COUNT / integer SUM whose low word lives in shared memory: straight to the key's entry in HBM */
-__device__ __forceinline__ void global_add_hi(const RadixArgs& A, int64_t key, int a, int32_t hi) {
+__device__ __noinline__ void global_add_hi(const RadixArgs& A, int64_t key, int a, int32_t hi) { /* rare: a carry out of a 32-bit low word, or a value wider than 32 bits */
   const DevProgram& P = A.prog;
   const uint32_t n = (uint32_t)P.key.entry_count;
   const int64_t e = global_probe(reinterpret_cast<unsigned long long*>(A.launch.keys), n, home_slot(key, P.key.hash_key_width, P.key.hash_magic, n), key);
@@ -643,6 +643,7 @@ struct MergeArgs {
   int64_t* accs[B2Q_MAX_ACCS];
   int32_t* error;
   int8_t ops[B2Q_MAX_ACCS];
+  int32_t bm_words[B2Q_MAX_ACCS];      /* ACC_BITMAP: 32-bit words per entry of the COUNT(DISTINCT) bitmaps (the arrays are [entries][bm_words]) */
   int32_t n_accs, hash_key_width;
   uint32_t entry_count;
   uint64_t hash_magic;
@@ -656,7 +657,14 @@ __global__ void b2q_k_baseline_merge(const __grid_constant__ MergeArgs A) {
     if (key == B2Q_I64_MAX) continue;
     const int64_t e = global_probe(reinterpret_cast<unsigned long long*>(A.keys), A.entry_count, home_slot(key, A.hash_key_width, A.hash_magic, A.entry_count), key);
     if (e < 0) { atomicCAS(A.error, 0, B2Q_ERR_OUT_OF_SLOTS); continue; }
-    for (int a = 0; a < A.n_accs; ++a) global_acc_merge(A.ops[a], A.accs[a] + e, A.src_accs[a][i]);
+    for (int a = 0; a < A.n_accs; ++a) {
+      if (A.ops[a] == ACC_BITMAP) { /* count_distinct_set_union (CountDistinct.h:89-140): OR the peer's bitmap of this group into ours */
+        const int w = A.bm_words[a];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(A.src_accs[a]) + (size_t)i * w;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(A.accs[a]) + (size_t)e * w;
+        for (int k = 0; k < w; ++k) { const uint32_t bits = src[k]; if (bits) atomicOr(dst + k, bits); }
+      } else global_acc_merge(A.ops[a], A.accs[a] + e, A.src_accs[a][i]);
+    }
   }
 }
 
@@ -677,7 +685,7 @@ cudaError_t launch_baseline_merge(const B2QQuery& q, const int64_t* src_keys, co
   a.keys = keys;
   a.error = error;
   a.n_accs = q.prog.n_accs;
-  for (int i = 0; i < q.prog.n_accs; ++i) { a.src_accs[i] = src_accs[i]; a.accs[i] = accs[i]; a.ops[i] = q.prog.accs[i].op; }
+  for (int i = 0; i < q.prog.n_accs; ++i) { a.src_accs[i] = src_accs[i]; a.accs[i] = accs[i]; a.ops[i] = q.prog.accs[i].op; a.bm_words[i] = q.prog.accs[i].bm_words; }
   a.hash_key_width = q.prog.key.hash_key_width;
   a.entry_count = static_cast<uint32_t>(q.prog.key.entry_count);
   a.hash_magic = q.prog.key.hash_magic;
