@@ -4,7 +4,7 @@ RelAlgExecutionUnit mirror, for the subset of the path:
     SELECT <col | COUNT(*) | COUNT(c) | SUM(c) | MIN(c) | MAX(c) | AVG(c)>, ...
     FROM <table> [[LEFT] JOIN <inner> ON <table>.<c> = <inner>.<c>] [WHERE <c OP literal | c IS [NOT] NULL | c [NOT] IN (l, ...) | c BETWEEN l AND l | NOT <factor>>
                   {AND|OR} ... with parentheses] [GROUP BY c {, c}]
-    [ORDER BY <position | target text> [ASC|DESC] [NULLS FIRST|LAST] {, ...}] [LIMIT n] [OFFSET m]
+    [ORDER BY <position | target text | target alias> [ASC|DESC] [NULLS FIRST|LAST] {, ...}] [LIMIT n] [OFFSET m]
 
 It plays the role Calcite + RelAlgTranslator play in the reference (kept, out of scope) and is test infrastructure.
 Like RelAlgTranslator/QualsConjunctiveForm, a top-level AND is split into separate quals, and a `col OP const`
@@ -203,12 +203,21 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
         assert inner is not None, "JOIN needs the inner table"
         p.inner_alias = toks[ji + 1].lower()
     p.eat("SELECT")
-    texts = [p.target_text()[0]]
-    targets = [p.target()]
-    while p.peek() == ",":
-        p.eat()
+    texts, targets, aliases = [], [], {}
+
+    def one_target():
         texts.append(p.target_text()[0])
         targets.append(p.target())
+        if p.peek() and p.peek().upper() == "AS":     # <target> AS alias — usable in ORDER BY
+            p.eat()
+            aliases[p.eat().upper()] = len(targets)
+        elif p.peek() and p.peek() != "," and p.peek().upper() != "FROM" and re.fullmatch(r"[A-Za-z_][A-Za-z_0-9]*", p.peek()):
+            aliases[p.eat().upper()] = len(targets)
+
+    one_target()
+    while p.peek() == ",":
+        p.eat()
+        one_target()
     p.eat("FROM")
     p.eat()  # table name
     if p.peek() and p.peek().upper() == "LEFT":
@@ -248,6 +257,8 @@ def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = Fal
         while True:
             if re.fullmatch(r"\d+", p.peek()):
                 tle = int(p.eat())
+            elif p.peek().upper() in aliases:
+                tle = aliases[p.eat().upper()]
             else:
                 text, nxt = p.target_text()
                 p.i = nxt
