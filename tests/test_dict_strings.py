@@ -54,3 +54,36 @@ def test_groupbytest_known_answers():
     assert res.plan.query_desc_type == abi.GroupByPerfectHash and res.rows() == [(1,)] and res.row_count() == 1
     unit = sqlmini.parse("SELECT COUNT(*) FROM t GROUP BY str;", t, ["x", "str"])
     assert oracle_lib.execute(unit, t).rows() == [(1,), (1,)]
+
+
+def high_cardinality_str_table():
+    """Tests/GroupByTest.cpp:160-171 + :192-194: table (x INT, str TEXT ENCODING DICT) with rows (1,'hi'), (2,'bye') whose cached
+    range of `str` is forced to [0, 134217728] — one value more than the perfect-hash buffer limit allows (setup_str_col_caching)."""
+    t = abi.Table([(abi.kINT, True), (abi.kTEXT, False)])
+    t.add_host_fragment([np.array([1, 2], dtype=np.int32), np.array([0, 1], dtype=np.int32)])   # 'hi' -> id 0, 'bye' -> id 1
+    st = t.fragments[0].stats[1]
+    st.int_min, st.int_max, st.has_nulls = 0, 134217728, 0
+    return t
+
+
+def test_groupbytest_baseline_fallback():
+    """Tests/GroupByTest.cpp:173-262 BaselineFallbackTest: COUNT(*) WHERE x = 1 GROUP BY str over a dictionary column whose range is
+    too big for a perfect-hash buffer, with a filter and no sort => baseline hash (GroupByAndAggregate.cpp:311-356):
+    executeWorkUnit(max_groups_buffer_entry_guess = 1, has_cardinality_estimation = false) throws CardinalityEstimationRequired, the
+    same call with has_cardinality_estimation = true returns ONE row whose value is 1.  Both sides, plans equal."""
+    t = high_cardinality_str_table()
+    unit = sqlmini.parse("SELECT COUNT(*) FROM t WHERE x = 1 GROUP BY str;", t, ["x", "str"])
+    with pytest.raises(oracle_lib.OracleError) as ei:
+        oracle_lib.execute(unit, t, entry_guess=1, has_card=False)
+    assert ei.value.code == abi.ERR_CARDINALITY_ESTIMATION_REQUIRED
+    with pytest.raises(executor.CardinalityEstimationRequired):
+        executor.Executor().plan(unit, t, max_groups_buffer_entry_guess=1, has_cardinality_estimation=False)
+    res = oracle_lib.execute(unit, t, entry_guess=1, has_card=True)
+    assert res.plan.query_desc_type == abi.GroupByBaselineHash and res.plan.entry_count == 1
+    assert res.row_count() == 1 and res.rows() == [(1,)]
+    got = executor.Executor().plan(unit, t, max_groups_buffer_entry_guess=1, has_cardinality_estimation=True).as_dict()
+    assert got == res.plan.as_dict()
+    # without the filter the same range stays perfect hash (dictionary ids are dense: :311-316), as BaselineNoFilters relies on
+    unit2 = sqlmini.parse("SELECT COUNT(*) FROM t GROUP BY str;", t, ["x", "str"])
+    assert oracle_lib.plan(unit2, t).query_desc_type == abi.GroupByPerfectHash
+

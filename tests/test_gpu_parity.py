@@ -556,3 +556,16 @@ def test_groupbytest_dictionary_key():
     assert rs.rowCount() == 1 and rs.rows() == [(1,)] and rs.getQueryMemDesc().query_desc_type == abi.GroupByPerfectHash
     rs, _ = gu.run_both(sqlmini.parse("SELECT str, COUNT(*) FROM t GROUP BY str;", t, ["x", "str"]), t)
     assert sorted(rs.rows()) == [(0, 1), (1, 1)]
+
+
+def test_groupbytest_baseline_fallback():
+    """Tests/GroupByTest.cpp:173-262 (BaselineFallbackTest) through the CUDA path: first CardinalityEstimationRequired, then — with
+    has_cardinality_estimation and max_groups_buffer_entry_guess = 1 — one row whose value is 1; radix passes and per-row probe."""
+    from test_dict_strings import high_cardinality_str_table
+    t = high_cardinality_str_table()
+    unit = sqlmini.parse("SELECT COUNT(*) FROM t WHERE x = 1 GROUP BY str;", t, ["x", "str"])
+    with pytest.raises(executor.CardinalityEstimationRequired):
+        executor.Executor().executeWorkUnit(1, True, t, unit, has_cardinality_estimation=False)
+    for force in (0, abi.KERNEL_BASELINE_PROBE):
+        rs, _ = gu.run_both(unit, t, entry_guess=1, has_card=True, force_kernel=force)
+        assert rs.rowCount() == 1 and rs.rows() == [(1,)] and rs.getQueryMemDesc().query_desc_type == abi.GroupByBaselineHash
