@@ -18,7 +18,7 @@ from typing import List, Tuple
 
 from heavydb_b200 import abi
 
-_TOK = re.compile(r"\s*(<>|<=|>=|!=|[(),*<>=]|[A-Za-z_][A-Za-z_0-9]*(?:\.[A-Za-z_][A-Za-z_0-9]*)?|-?\d+\.\d*(?:[eE][-+]?\d+)?|-?\d+)")
+_TOK = re.compile(r"\s*('(?:[^']|'')*'|<>|<=|>=|!=|[(),*<>=]|[A-Za-z_][A-Za-z_0-9]*(?:\.[A-Za-z_][A-Za-z_0-9]*)?|-?\d+\.\d*(?:[eE][-+]?\d+)?|-?\d+)")
 _OPS = {"=": abi.kEQ, "<>": abi.kNE, "!=": abi.kNE, "<": abi.kLT, ">": abi.kGT, "<=": abi.kLE, ">=": abi.kGE}
 _AGGS = {"COUNT": abi.kCOUNT, "SUM": abi.kSUM, "MIN": abi.kMIN, "MAX": abi.kMAX, "AVG": abi.kAVG}
 
@@ -36,8 +36,9 @@ def _tokens(s: str) -> List[str]:
 
 
 class _P:
-    def __init__(self, toks, table: abi.Table, names: List[str], bigint_count: bool, inner=None):
+    def __init__(self, toks, table: abi.Table, names: List[str], bigint_count: bool, inner=None, dicts=None):
         self.t, self.i = toks, 0
+        self.dicts = {k.lower(): v for k, v in (dicts or {}).items()}   # column name -> strings in dictionary-id order
         self.b = abi.UnitBuilder(table)
         self.names = [n.lower() for n in names]
         self.bigint_count = bigint_count
@@ -91,6 +92,18 @@ class _P:
 
     def literal_cmp(self, col, op, lit, rte=0):
         tbl = self.b.inner if rte else self.b.table
+        if lit.startswith("'"):
+            # a string literal against a dictionary-encoded column: the reference translates it to the column's dictionary id
+            # (StringDictionaryProxy::getIdOfString; an unknown string is INVALID_STR_ID = -1, which no row holds) and compares ids
+            # — for = and <> only; an ordering comparison needs the dictionary itself (CodeGenerator::codegenCmp -> string ops)
+            name = (self.inner_names if rte else self.names)[col]
+            if tbl.col_types[col][0] not in (abi.kTEXT, abi.kVARCHAR, abi.kCHAR) or name not in self.dicts:
+                raise ValueError(f"string literal {lit} against a column without a dictionary")
+            if op not in (abi.kEQ, abi.kNE):
+                raise ValueError("string ordering comparisons need the dictionary: outside the path")
+            text = lit[1:-1].replace("''", "'")
+            sid = self.dicts[name].index(text) if text in self.dicts[name] else -1
+            return self.b.cmp(col, op, sid, abi.kBIGINT, rte)
         if tbl.col_types[col][0] in abi.DECIMAL_TYPES:
             # the analyzer folds the literal to the common DECIMAL type: same scale as the column when the literal has no
             # more fraction digits than the column (Constant::do_cast); otherwise the COLUMN would be cast — not this path
@@ -151,6 +164,11 @@ class _P:
         rhs = self.eat()
         if re.fullmatch(r"[A-Za-z_][A-Za-z_0-9.]*", rhs):     # column OP column
             c2, rte2 = self.colref(rhs)
+            if self.dicts:   # ids of two dictionaries are not comparable: what the bridge's on_path() checks with getStringDictKey()
+                n1 = (self.inner_names if rte else self.names)[col]
+                n2 = (self.inner_names if rte2 else self.names)[c2]
+                if n1 in self.dicts and n2 in self.dicts and self.dicts[n1] is not self.dicts[n2]:
+                    raise ValueError(f"{n1} and {n2} use different dictionaries: string comparison, outside the path")
             return self.b.binop(op, self.b.col(col, rte), self.b.col(c2, rte2))
         return self.literal_cmp(col, op, rhs, rte)
 
@@ -188,10 +206,11 @@ def _conjuncts(b: abi.UnitBuilder, e: int) -> List[int]:
     return [e]
 
 
-def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = False, inner=None) -> abi.BuiltUnit:
-    """inner = (abi.Table, [names]) of the table named after JOIN (one concatenated fragment)."""
+def parse(sql: str, table: abi.Table, names: List[str], bigint_count: bool = False, inner=None, dicts=None) -> abi.BuiltUnit:
+    """inner = (abi.Table, [names]) of the table named after JOIN (one concatenated fragment); dicts = {column: [strings in id
+    order]} for string literals against dictionary-encoded columns."""
     toks = _tokens(sql)
-    p = _P(toks, table, names, bigint_count, inner)
+    p = _P(toks, table, names, bigint_count, inner, dicts)
     ups = [t.upper() for t in toks]
     fi = ups.index("FROM")
     p.outer_alias = toks[fi + 1].lower()

@@ -130,12 +130,16 @@ typedef struct B2QExpr {
   int32_t op;     /* BinOper: SQLOps; AggExpr: SQLAgg */
   int32_t left;   /* BinOper: left operand; AggExpr: argument (-1 = COUNT(*)) */
   int32_t right;  /* BinOper: right operand */
-  int64_t ival;   /* Constant: Datum for integer types; AggExpr: get_is_distinct() (COUNT(DISTINCT c) is refused on this path,
-                     not silently counted as COUNT(c)) */
+  int64_t ival;   /* Constant: Datum for integer types (a string literal against a dictionary column: its id in THAT column's
+                     dictionary, StringDictionaryProxy::getIdOfString; -1 = not in the dictionary); AggExpr: get_is_distinct() */
   double dval;    /* Constant: Datum for fp types */
   int32_t is_null;/* Constant::get_is_null() */
   int32_t rte_idx;/* ColumnVar::get_rte_idx(): 0 = the scanned (outer) table, 1 = the joined inner table */
 } B2QExpr;
+/* Dictionary-encoded strings are compared BY ID (= and <> only).  B2QTypeInfo does not carry the dictionary key, so a
+ * `ColumnVar OP ColumnVar` over two string columns is the caller's promise that both use ONE dictionary
+ * (SQLTypeInfo::getStringDictKey() equal — the id-compare branch of CodeGenerator::codegenCmp); columns of different dictionaries
+ * need the reference's string comparison and must not be routed here. */
 
 /* ---- Analyzer::OrderEntry (Analyzer/Analyzer.h:2960-2968) ------------------------------------------------ */
 typedef struct B2QOrderEntry {

@@ -93,6 +93,8 @@ def assert_rows_match(ours, ref, fp_tol=EPS, fp_abs=0.0):
         for va, vb in zip(a, b):
             if vb is None or va is None:
                 assert va is None and vb is None, f"NULL mismatch {a} vs {b}"
+            elif isinstance(vb, str) or isinstance(va, str):
+                assert va == vb, f"{a} vs {b}"
             elif isinstance(vb, float) or isinstance(va, float):
                 assert math.isclose(float(va), float(vb), rel_tol=fp_tol, abs_tol=fp_abs) or va == vb, f"{a} vs {b}"
             else:

@@ -4,7 +4,7 @@ device-resident fragments of the golden table (fragment_size = 2, ExecuteTest.cp
 import pytest
 
 import gpu_util as gu
-import ref_tables as rt
+import ref_full_table as ft
 import sqlmini
 from test_oracle_golden_harvest import QUERIES
 
@@ -13,14 +13,14 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def golden():
-    table = rt.make_table(rt.test_rows())
+    table = ft.make_table(ft.full_rows())
     return table, gu.DeviceTable(table)
 
 
 @pytest.mark.parametrize("sql", QUERIES)
 def test_reference_query_verbatim_on_the_gpu(golden, sql):
     table, dev = golden
-    unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
+    unit = sqlmini.parse(sql, table, ft.FULL_NAMES, dicts=ft.DICTS)
     if unit.unit.num_order_entries or unit.unit.has_limit or unit.unit.offset:
         from test_gpu_order_by import run_sorted     # rows in order + the compact buffer against the oracle's permutation
         run_sorted(unit, table, dev, entry_guess=48, has_card=True)

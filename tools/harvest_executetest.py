@@ -5,7 +5,8 @@ committed as tests/golden/executetest_harvest.json and replayed by tests/test_or
     python tools/harvest_executetest.py > tests/golden/executetest_harvest.json
 
 Tests/ExecuteTest.cpp holds ~1350 `c("SELECT ...", dt)` comparisons against SQLite.  A string is kept when
-  * it reads only table `test` and only the columns tests/ref_tables.py models (the numeric columns of the golden table),
+  * it reads only table `test` and only the columns tests/ref_full_table.py models (the numeric, dictionary-string and FIXED columns
+    of the golden table),
   * heavydb_b200.sqlmini parses it (one table, AND/OR/NOT of column-vs-constant / column-vs-column / IS NULL / IN / BETWEEN,
     GROUP BY columns, COUNT / SUM / MIN / MAX / AVG / COUNT(DISTINCT) of a column, ORDER BY / LIMIT / OFFSET),
   * the oracle plans it (the path's own refusals drop the rest), and
@@ -22,6 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import oracle_lib  # noqa: E402
+import ref_full_table as ft  # noqa: E402
 import ref_tables as rt  # noqa: E402
 import sqlmini  # noqa: E402
 from heavydb_b200 import abi  # noqa: E402
@@ -30,14 +32,22 @@ SRC = "/root/reference/Tests/ExecuteTest.cpp"
 
 
 def main():
-    text = open(SRC).read().splitlines()
-    rows = rt.test_rows()
-    table = rt.make_table(rows)
-    con = rt.make_sqlite(rows)
+    text = open(SRC).read()
+    rows = ft.full_rows()
+    table = ft.make_table(rows)
+    con = ft.make_sqlite(rows)
     seen, out, stats = set(), [], {"strings": 0, "table_test": 0, "parsed": 0, "planned": 0, "kept": 0}
-    for ln, line in enumerate(text, 1):
-        for m in re.finditer(r'c\("(SELECT[^"]*)"', line):
-            q = m.group(1).strip()
+    # c("..." "..." , dt) with adjacent literals concatenated, or c(R"(...)", dt); comparisons wrapped in EXPECT_THROW are negative tests
+    pat = re.compile(r'\bc\(\s*(?:R"\((.*?)\)"|((?:"(?:[^"\\]|\\.)*"\s*)+))\s*,', re.S)
+    for _ in (0,):
+        for m in pat.finditer(text):
+            if re.search(r"EXPECT_(ANY_)?THROW\(\s*$", text[max(0, m.start() - 40):m.start()]):
+                continue
+            q = m.group(1) if m.group(1) is not None else "".join(re.findall(r'"((?:[^"\\]|\\.)*)"', m.group(2)))
+            q = re.sub(r"\s+", " ", q).strip()
+            if not q.upper().startswith("SELECT"):
+                continue
+            ln = text.count("\n", 0, m.start()) + 1
             stats["strings"] += 1
             if not re.search(r"\bFROM test\b", q) or re.search(r"\b(JOIN|UNION|OVER|CASE|HAVING|EXTRACT|CAST|LIKE|DISTINCT ON)\b|,\s*test\b|\(SELECT", q, re.I):
                 continue
@@ -46,7 +56,7 @@ def main():
             if sql in seen:
                 continue
             try:
-                unit = sqlmini.parse(sql, table, rt.TEST_NAMES)
+                unit = sqlmini.parse(sql, table, ft.FULL_NAMES, dicts=ft.DICTS)
             except Exception:
                 continue
             stats["parsed"] += 1
