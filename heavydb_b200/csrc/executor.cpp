@@ -1406,6 +1406,18 @@ int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row, int32_t /*tra
   return 1;
 }
 
+/* ResultSet::getRowAt(logical_index) / getRowAtNoTranslations (ResultSetIteration.cpp:266-284): the row of entry
+ * permutation_[logical_index] (or logical_index itself when the set is not sorted); 0 = past entryCount() or an empty entry.
+ * Random access: it neither moves the getNextRow cursor nor looks at dropFirstN / keepFirstN (as in the reference). */
+int32_t b2q_rs_get_row_at(const B2QResultSet* rs, size_t logical_index, B2QTargetValue* row, int32_t /*translate_strings*/, int32_t decimal_to_double) {
+  if (!rs || !row || rs->q.plan.query_desc_type == B2Q_Estimator) return 0;
+  if (logical_index >= b2q_rs_entry_count(rs)) return 0;
+  const int64_t entry = rs->perm.empty() ? static_cast<int64_t>(logical_index) : static_cast<int64_t>(rs->perm[logical_index]);
+  if (rs_is_empty_entry(rs, entry)) return 0;
+  read_entry(rs, entry, row, decimal_to_double != 0);
+  return 1;
+}
+
 /* getRowAt / getTargetValueFromBufferRowwise|Colwise (ResultSetIteration.cpp:820-1000) for one storage entry */
 static bool is_decimal(int t) { return t == B2Q_kDECIMAL || t == B2Q_kNUMERIC; }
 static double exp_to_scale(int scale) { double d = 1; for (int i = 0; i < scale; ++i) d *= 10; return d; }

@@ -97,6 +97,8 @@ def lib():
         L.b2q_rs_get_col_type.argtypes = [C.c_void_p, C.c_size_t]
         L.b2q_rs_get_next_row.restype = C.c_int32
         L.b2q_rs_get_next_row.argtypes = [C.c_void_p, C.POINTER(abi.TargetValue), C.c_int32, C.c_int32]
+        L.b2q_rs_get_row_at.restype = C.c_int32
+        L.b2q_rs_get_row_at.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(abi.TargetValue), C.c_int32, C.c_int32]
         L.b2q_rs_move_to_begin.argtypes = [C.c_void_p]
         L.b2q_rs_is_row_at_empty.restype = C.c_int32
         L.b2q_rs_is_row_at_empty.argtypes = [C.c_void_p, C.c_size_t]
@@ -230,6 +232,14 @@ class ResultSet:
         while L.b2q_rs_get_next_row(self._h, row, 0, int(decimal_to_double)):
             out.append(tuple(v.py() for v in row))
         return out
+
+    def getRowAt(self, logical_index: int, translate_strings: bool = False, decimal_to_double: bool = True):
+        """ResultSet::getRowAt / getRowAtNoTranslations (ResultSetIteration.cpp:266-284): the row of one entry (through the
+        permutation when sorted) as a tuple, or () for an empty entry / an index past entryCount()."""
+        row = (abi.TargetValue * self.colCount())()
+        if not lib().b2q_rs_get_row_at(self._h, logical_index, row, int(translate_strings), int(decimal_to_double)):
+            return ()
+        return tuple(v.py() for v in row)
 
     def isRowAtEmpty(self, i: int) -> bool:
         return bool(lib().b2q_rs_is_row_at_empty(self._h, i))

@@ -464,6 +464,11 @@ B2QTypeInfo b2q_rs_get_col_type(const B2QResultSet* rs, size_t col_idx); /* Resu
  * target is a double (value / 10^scale, NULL_DOUBLE for NULL) under decimal_to_double, else the scaled int64.
  * b2q_rs_move_to_begin() == ResultSet::moveToBegin(). */
 int32_t b2q_rs_get_next_row(B2QResultSet* rs, B2QTargetValue* row, int32_t translate_strings, int32_t decimal_to_double);
+/* ResultSet::getRowAt(logical_index) / getRowAtNoTranslations(logical_index) (ResultSet.h:259-270, ResultSetIteration.cpp:266-284):
+ * random access by entry (through the permutation of a sorted set); returns 1 and fills `row`, 0 for an empty entry or an index
+ * past b2q_rs_entry_count().  Independent of the getNextRow cursor. */
+int32_t b2q_rs_get_row_at(const B2QResultSet* rs, size_t logical_index, B2QTargetValue* row, int32_t translate_strings,
+                          int32_t decimal_to_double);
 
 /* ColumnarResults (QueryEngine/ColumnarResults.h:60-232, .cpp:256-392): the rows of a result set, in iteration order
  * (ResultSet::sort permutation, OFFSET, LIMIT applied), as one contiguous array per target in the target type's own

@@ -200,6 +200,17 @@ class ResultSet {
     if (!b2q_rs_get_next_row(h_, row.data(), translate_strings, decimal_to_double)) row.clear();
     return row;
   }
+  /* ResultSet::getRowAt(logical_index) / getRowAtNoTranslations (ResultSet.h:259-270): empty vector for an empty entry */
+  std::vector<TargetValue> getRowAt(const size_t logical_index) const {
+    std::vector<TargetValue> row(colCount());
+    if (!b2q_rs_get_row_at(h_, logical_index, row.data(), 1, 0)) row.clear();
+    return row;
+  }
+  std::vector<TargetValue> getRowAtNoTranslations(const size_t logical_index) const {
+    std::vector<TargetValue> row(colCount());
+    if (!b2q_rs_get_row_at(h_, logical_index, row.data(), 0, 0)) row.clear();
+    return row;
+  }
   bool isRowAtEmpty(size_t i) const { return b2q_rs_is_row_at_empty(h_, i) != 0; }
   const int8_t* getUnderlyingBuffer(size_t* size_bytes) const { return b2q_rs_storage_buffer(h_, size_bytes); }
   const B2QPlan& getQueryMemDesc() const { return *b2q_rs_query_mem_desc(h_); }

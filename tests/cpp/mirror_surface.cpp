@@ -73,6 +73,8 @@ static int readout_over_hand_filled_storage() {
   const int64_t one_empty[10] = {7, 2, 11110, 11110, 1, 0, 0, INT64_MIN, 0, 0};
   auto rs2 = ex.resultSetFromStorage(reinterpret_cast<const int8_t*>(one_empty), sizeof(one_empty), 0, {info}, u, co, eo);
   if (rs2->rowCount() != 1 || rs2->isRowAtEmpty(0) || !rs2->isRowAtEmpty(1)) return 6;
+  /* getRowAt / getRowAtNoTranslations: random access by entry, an empty vector for an empty entry or past entryCount() */
+  if (rs2->getRowAt(0).size() != rs2->colCount() || !rs2->getRowAtNoTranslations(1).empty() || !rs2->getRowAt(rs2->entryCount()).empty()) return 8;
   ColumnarResults cols(*rs2, 4, {});
   if (cols.size() != 1 || reinterpret_cast<const int64_t*>(cols.getColumnBuffers()[2])[0] != 11110) return 7;
   try { /* a buffer of another size is not this descriptor's */

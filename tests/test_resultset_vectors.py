@@ -227,8 +227,16 @@ def test_reduce_perfect_hash(sql, columnar):
     red = oracle_lib.reduce_result_sets([r1, r2])
     want = [expected_row(plan, v, step) for v in range(0, 100, step) if not is_empty_by_marker(plan, v)]
     assert red.rows() == want
-    got, _ = product_rows(unit, table, red.buffer(), columnar)          # the product's read-out of the reduced bytes
+    got, rs = product_rows(unit, table, red.buffer(), columnar)         # the product's read-out of the reduced bytes
     assert got == want
+    # ... and entry by entry, as test_reduce reads it: getRowAtNoTranslations(row_idx), an empty row for an empty entry
+    for row_idx in range(100):
+        row = rs.getRowAt(row_idx)
+        if row_idx % step or is_empty_by_marker(plan, row_idx):
+            assert row == () and rs.isRowAtEmpty(row_idx)
+        else:
+            assert row == expected_row(plan, row_idx, step)
+    assert rs.getRowAt(100) == () and rs.getRowAt(10**9) == ()
     # three storages, as reduceMultiDeviceResultSets folds one per device: COUNT / SUM grow by v per storage
     red3 = oracle_lib.reduce_result_sets([r1, r2, oracle_lib.result_from_storage(unit, table, s1, output_columnar=columnar)])
     assert red3.rows() == [expected_row(plan, v, 3) for v in range(0, 100, step) if not is_empty_by_marker(plan, v)]
