@@ -665,7 +665,9 @@ class Planner {
     int8_t width = 0;
     if (eo_.bigint_count) width = 8;
     else {
-      int8_t compact = grouped_ ? 0 : 8;
+      /* QueryMemoryDescriptor.cpp:775-778: `groupby_exprs.size() != 1 || !groupby_exprs.front()` — non-grouped units and every
+       * multi-column GROUP BY keep 8-byte slots; only a single-column GROUP BY can compact to 4 */
+      int8_t compact = (grouped_ && u_.num_groupby_exprs == 1) ? 0 : 8;
       if (!compact) {
         for (int i = 0; i < u_.num_target_exprs && !compact; ++i) {
           const B2QExpr& e = ex(u_.target_exprs[i]);

@@ -894,7 +894,9 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
       min_slot_size = 8;
     } else {
       int8_t compact_width = 0;
-      if (!is_group_by) compact_width = crt_min_byte_width; /* groupby_exprs == {nullptr} (:775-778) */
+      /* :775-778: `groupby_exprs.size() != 1 || !groupby_exprs.front()` — the non-grouped unit ({nullptr}) AND every multi-column
+       * GROUP BY keep the 8-byte slots; only a single-column GROUP BY can compact to 4 */
+      if (!is_group_by || u.num_groupby_exprs != 1) compact_width = crt_min_byte_width;
       if (!compact_width) {
         for (int i = 0; i < u.num_target_exprs; ++i) {
           const B2QExpr& e = expr_at(u, u.target_exprs[i]);

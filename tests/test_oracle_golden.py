@@ -323,6 +323,35 @@ def test_constrained_not_null_plan(env, case):
     rt.assert_rows_match(res.rows(), ref)
 
 
+def test_slot_widths_by_hand(env):
+    """pick_target_compact_width (QueryMemoryDescriptor.cpp:748-842) read line by line: 4-byte slots ONLY for a single-column GROUP BY
+    whose targets are COUNT(*) and projections of integers of at most 4 bytes / dictionary strings, over at most 2^32 tuples, without
+    g_bigint_count; `groupby_exprs.size() != 1 || !groupby_exprs.front()` (:775-778) keeps 8 bytes for non-grouped units AND for
+    every multi-column GROUP BY — round 2 found planner and oracle both compacting the latter — any aggregate with an argument (:786-789)
+    and any wider projection (:813) too.  Oracle and product planner, same answers."""
+    table, _ = env
+    cases = [
+        ("SELECT x, COUNT(*) FROM test GROUP BY x;", False, [4, 4]),
+        ("SELECT COUNT(*), x FROM test GROUP BY x;", False, [4, 4]),
+        ("SELECT x, COUNT(*) FROM test GROUP BY x;", True, [8, 8]),               # g_bigint_count (:752-754)
+        ("SELECT x, w, COUNT(*) FROM test GROUP BY x, w;", False, [8, 8, 8]),      # two GROUP BY columns (:775-778)
+        ("SELECT w, x, z, COUNT(*) FROM test GROUP BY x, w, z;", False, [8, 8, 8, 8]),
+        ("SELECT COUNT(*) FROM test;", False, [8]),                               # groupby_exprs == {nullptr}
+        ("SELECT x, COUNT(y) FROM test GROUP BY x;", False, [8, 8]),              # an aggregate with an argument (:786-789)
+        ("SELECT x, COUNT(*), MIN(w) FROM test GROUP BY x;", False, [8, 8, 8]),
+        ("SELECT t, COUNT(*) FROM test GROUP BY t;", False, [8, 8]),              # BIGINT projection: not `no bigger than 4` (:813)
+        ("SELECT z, COUNT(*) FROM test GROUP BY z;", False, [4, 4]),              # SMALLINT key
+    ]
+    for sql, bigint_count, widths in cases:
+        unit = sqlmini.parse(sql, table, rt.TEST_NAMES, bigint_count=bigint_count)
+        p = oracle_lib.plan(unit, table, entry_guess=64, has_card=True, bigint_count=bigint_count)
+        assert list(p.slot_padded_width[: p.num_slots]) == widths, sql
+        from heavydb_b200 import executor
+        g = executor.Executor().plan(unit, table, eo=executor.execution_options(bigint_count=bigint_count),
+                                     max_groups_buffer_entry_guess=64, has_cardinality_estimation=True)
+        assert list(g.slot_padded_width[: g.num_slots]) == widths and g.as_dict() == p.as_dict(), sql
+
+
 def test_count_distinct_descriptors_by_hand(env):
     """CountDistinctDescriptor{Bitmap, min_val, bitmap_sz_bits} as init_count_distinct_descriptors derives them from the golden
     table's chunk stats (x in [7, 8], y in [42, 43] with NULLs, z in [-78, 102], u all NULL), and what the reference refuses on a GPU."""
