@@ -114,7 +114,9 @@ enum {
 typedef struct B2QTypeInfo {
   int32_t type;    /* B2Q_k* SQLTypes value */
   int32_t notnull; /* SQLTypeInfo::get_notnull() */
-  int32_t scale;   /* SQLTypeInfo::get_scale(): digits after the point of a DECIMAL / NUMERIC (0 for every other type) */
+  int32_t scale;   /* SQLTypeInfo::get_scale(): digits after the point of a DECIMAL / NUMERIC (0 for every other type).  The dimension of a
+                      TIMESTAMP is NOT carried: only TIMESTAMP(0) columns belong on this path (the reference plans high-precision
+                      timestamp keys differently, GroupByAndAggregate.cpp:288-298) */
 } B2QTypeInfo;
 
 /* ---- Analyzer::Expr subset (Analyzer/Analyzer.h:193 ColumnVar, :319 Constant, :434 BinOper, :1381 AggExpr)
