@@ -611,7 +611,9 @@ class Planner {
         /* :311-356 dictionary ids are dense: a too-big range stays perfect hash unless a filter can be expected to
          * thin it out — with filters and no sort, baseline when there is no estimate yet or 2 * estimate < range */
         const bool has_filters = u_.num_quals > 0 || u_.num_simple_quals > 0;
-        if (has_filters && too_big && u_.num_order_entries == 0) {
+        if (has_filters && too_big && u_.num_order_entries != 0) {
+          if (any_distinct()) perfect = false; /* :329-341: with a sort the range is kept, except under COUNT(DISTINCT) */
+        } else if (has_filters && too_big) {
           int64_t twice;
           const bool less = has_card_ && !__builtin_mul_overflow(static_cast<int64_t>(guess_), int64_t(2), &twice) && twice < span;
           if (!has_card_ || less) perfect = false;

@@ -847,7 +847,11 @@ Plan make_plan_single(const B2QExecUnit& u, const B2QTableInfo& tbl, const B2QEx
         /* :311-356 dictionary ids are dense, so a too-big range stays perfect hash unless a filter can be expected to
          * thin it out: with filters and no sort, baseline when there is no estimate yet or 2 * estimate < range */
         const bool has_filters = u.num_quals > 0 || u.num_simple_quals > 0;
-        if (has_filters && too_big && u.num_order_entries == 0) {
+        if (has_filters && too_big && u.num_order_entries != 0) {
+          /* :329-341 with a sort the original range is kept — except with COUNT(DISTINCT): "always use baseline hash for column
+           * range too big for perfect hash with count distinct descriptors" */
+          if (any_count_distinct) hash_type = B2Q_GroupByBaselineHash;
+        } else if (has_filters && too_big) {
           int64_t twice;
           const bool less = has_cardinality_estimation &&
                             !__builtin_mul_overflow(static_cast<int64_t>(max_groups_buffer_entry_guess), int64_t(2), &twice) && twice < diff;

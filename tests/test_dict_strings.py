@@ -87,3 +87,30 @@ def test_groupbytest_baseline_fallback():
     unit2 = sqlmini.parse("SELECT COUNT(*) FROM t GROUP BY str;", t, ["x", "str"])
     assert oracle_lib.plan(unit2, t).query_desc_type == abi.GroupByPerfectHash
 
+
+def test_dictionary_range_rule_with_a_sort():
+    """GroupByAndAggregate.cpp:313-356 read branch by branch on the forced range [0, 134217728] (too big for a perfect-hash buffer) with
+    a filter: no sort => baseline (estimate first); a sort keeps the original range => perfect hash; a sort AND a COUNT(DISTINCT)
+    target => baseline all the same (:331-338).  Planner and oracle, same decisions."""
+    t = high_cardinality_str_table()
+
+    def decide(sql, has_card):
+        unit = sqlmini.parse(sql, t, ["x", "str"])
+        try:
+            o = oracle_lib.plan(unit, t, entry_guess=4, has_card=has_card)
+        except oracle_lib.OracleError as e:
+            with pytest.raises(executor.QueryExecutionError) as ei:
+                executor.Executor().plan(unit, t, max_groups_buffer_entry_guess=4, has_cardinality_estimation=has_card)
+            assert ei.value.code == e.code
+            return e.code
+        g = executor.Executor().plan(unit, t, max_groups_buffer_entry_guess=4, has_cardinality_estimation=has_card)
+        assert g.as_dict() == o.as_dict()
+        return o.query_desc_type
+
+    assert decide("SELECT COUNT(*) FROM t WHERE x >= 1 GROUP BY str;", False) == abi.ERR_CARDINALITY_ESTIMATION_REQUIRED
+    assert decide("SELECT COUNT(*) FROM t WHERE x >= 1 GROUP BY str;", True) == abi.GroupByBaselineHash
+    assert decide("SELECT COUNT(*), SUM(x) FROM t WHERE x >= 1 GROUP BY str ORDER BY 2;", False) == abi.GroupByPerfectHash
+    assert decide("SELECT COUNT(*), COUNT(DISTINCT x) FROM t WHERE x >= 1 GROUP BY str ORDER BY 1;", False) == abi.ERR_CARDINALITY_ESTIMATION_REQUIRED
+    assert decide("SELECT COUNT(*), COUNT(DISTINCT x) FROM t WHERE x >= 1 GROUP BY str ORDER BY 1;", True) == abi.GroupByBaselineHash
+    assert decide("SELECT COUNT(*), COUNT(DISTINCT x) FROM t GROUP BY str ORDER BY 1;", False) in (abi.GroupByPerfectHash, abi.ERR_UNSUPPORTED)
+
