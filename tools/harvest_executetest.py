@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Harvest the reference's own golden query strings for this path (run HERE, where /root/reference exists; the result is
+"""TEST INFRASTRUCTURE (fixture generator; never imported by the product, tests, smoke() or bench.py — it is the committed script that
+made tests/golden/executetest_harvest.json).  Harvest the reference's own golden query strings for this path (run HERE, where /root/reference exists; the result is
 committed as tests/golden/executetest_harvest.json and replayed by tests/test_oracle_golden_harvest.py without the reference).
 
     python tools/harvest_executetest.py > tests/golden/executetest_harvest.json
